@@ -1,0 +1,39 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle for the ORB-SLAM3 hot path.
+//
+// This directory restates, on the CPU, the algorithm of the reference
+// (lturing/ORB_SLAM3_modified) for the path BASELINE.json names.  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load it; the product (orb_slam3_modified_b200/) never does.
+//
+// PARITY PINNING: the reference ships no tests or golden vectors for this path
+//  and cannot be compiled here (needs OpenCV C++, Eigen,
+// Boost, Pangolin, PCL -- all absent).  The OpenCV primitives restated here
+// (resize, FAST, GaussianBlur, fastAtan2, BFMatcher) are pinned against the
+// independent cv2 4.13 wheel in tests/ (fixtures under tests/golden/ made by
+// tools/make_golden.py); everything downstream of them is "parity unpinned"
+// by the reference itself and rests on this line-by-line restatement.
+#pragma once
+#include <cstdint>
+#include <cmath>
+#include <vector>
+
+namespace orbo {
+
+// Layout-compatible with cv::KeyPoint (28 bytes).
+struct KeyPoint {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int octave;
+    int class_id;
+};
+static_assert(sizeof(KeyPoint) == 28, "cv::KeyPoint layout");
+
+// cvRound(double/float): round-half-to-even (SSE cvtsd2si), OpenCV core/fast_math.hpp.
+static inline int cvRound(double v) { return (int)std::nearbyint(v); }
+static inline int cvRoundf(float v) { return (int)std::nearbyintf(v); }
+static inline int cvFloor(double v) { int i = (int)v; return i - (i > v); }
+static inline int cvCeil(double v) { int i = (int)v; return i + (i < v); }
+
+}  // namespace orbo
