@@ -1,0 +1,191 @@
+"""B200-native ORB-SLAM3 hot path: Python mirror of the reference class surfaces over the C-ABI.
+
+The compute lives in ``liborb_b200.so`` (hand-written sm_100a CUDA, ``csrc/``); this module only
+marshals numpy / torch buffers to the ``extern "C"`` entry points declared in ``include/orb_b200.h``.
+There is no CPU fallback: importing works anywhere, but creating any object without the built
+library or without a Blackwell GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'liborb_b200.so')
+
+ORB_OK, ORB_ERR_EMPTY, ORB_ERR_ARG, ORB_ERR_CAPACITY, ORB_ERR_CUDA, ORB_ERR_ASPECT = 0, -1, -2, -3, -4, -5
+
+#: numpy view of OrbKeyPoint / cv::KeyPoint (28 bytes)
+KP_DTYPE = np.dtype([('x', 'f4'), ('y', 'f4'), ('size', 'f4'), ('angle', 'f4'), ('response', 'f4'),
+                     ('octave', 'i4'), ('class_id', 'i4')])
+
+_lib = None
+
+
+class OrbError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        msg = lib().orb_last_error().decode() if _lib is not None else ''
+        super().__init__('%s failed with status %d: %s' % (where, code, msg))
+
+
+def lib():
+    """Load liborb_b200.so (built by ``__graft_entry__.build()``); raise if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('liborb_b200.so is not built (run `python -c "import __graft_entry__ as g; g.build()"`); '
+                               'this package has no fallback path')
+        L = C.CDLL(LIB_PATH)
+        L.orb_last_error.restype = C.c_char_p
+        vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+        L.orbx_create.argtypes = [C.POINTER(vp), i, f, i, i, i, i, i, i, i]
+        L.orbx_destroy.argtypes = [vp]
+        L.orbx_destroy.restype = None
+        L.orbx_get_levels.argtypes = [vp]
+        L.orbx_get_tables.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.orbx_max_keypoints.argtypes = [vp]
+        L.orbx_extract.argtypes = [vp, vp, i, i, sz, i, i, vp, vp, i, vp, vp]
+        L.orbx_extract_batch.argtypes = [vp, vp, i, i, i, sz, sz, i, i, vp, vp, i, vp, vp]
+        L.orbx_extract_batch_device.argtypes = [vp, vp, i, i, i, sz, sz, i, i, vp, vp, i, vp, vp, vp]
+        L.orbx_get_level_size.argtypes = [vp, i, vp, vp]
+        L.orbx_copy_level.argtypes = [vp, i, i, i, vp]
+        L.orbx_copy_candidates.argtypes = [vp, i, i, vp, i]
+        L.orbx_last_launch_count.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+class ORBextractor:
+    """Mirror of ``ORB_SLAM3::ORBextractor`` (reference include/ORBextractor.h:43-109).
+
+    ``ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)``; calling the object is
+    ``operator()``: ``mono_index, keypoints, descriptors = ex(image, vLappingArea)``.
+    """
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7,
+                 max_width=640, max_height=480, max_batch=1, device=0):
+        L = lib()
+        self._h = C.c_void_p()
+        self.nlevels = nlevels
+        self.max_batch = max_batch
+        rc = L.orbx_create(C.byref(self._h), nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST,
+                           max_width, max_height, max_batch, device)
+        if rc != ORB_OK:
+            self._h = None
+            raise OrbError(rc, 'orbx_create')
+        self.max_keypoints = L.orbx_max_keypoints(self._h)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().orbx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # --- getters (include/ORBextractor.h:60-82) ---
+    def GetLevels(self):
+        return lib().orbx_get_levels(self._h)
+
+    def _tables(self):
+        n = self.nlevels
+        s, i, g, ig = (np.zeros(n, np.float32) for _ in range(4))
+        f = np.zeros(n, np.int32)
+        lib().orbx_get_tables(self._h, _ptr(s), _ptr(i), _ptr(g), _ptr(ig), _ptr(f))
+        return s, i, g, ig, f
+
+    def GetScaleFactors(self):
+        return self._tables()[0]
+
+    def GetScaleFactor(self):
+        return float(self._tables()[0][1]) if self.nlevels > 1 else 1.0
+
+    def GetInverseScaleFactors(self):
+        return self._tables()[1]
+
+    def GetScaleSigmaSquares(self):
+        return self._tables()[2]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._tables()[3]
+
+    def features_per_level(self):
+        return self._tables()[4]
+
+    # --- operator() ---
+    def __call__(self, image, vLappingArea=(0, 0)):
+        """Returns (monoIndex, keypoints[K] as KP_DTYPE, descriptors[K,32] u8); monoIndex == -1 for an empty image."""
+        if image is None or image.size == 0:
+            return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2, 'CV_8UC1 expected (reference src/ORBextractor.cc:1094)'
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        cap = self.max_keypoints
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n, mono = C.c_int(0), C.c_int(0)
+        rc = lib().orbx_extract(self._h, _ptr(image), image.shape[0], image.shape[1], image.strides[0],
+                                int(vLappingArea[0]), int(vLappingArea[1]), _ptr(kps), _ptr(desc), cap,
+                                C.byref(n), C.byref(mono))
+        if rc == ORB_ERR_EMPTY:
+            return -1, kps[:0], desc[:0]
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbx_extract')
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images, vLappingArea=(0, 0)):
+        """images: [B, rows, cols] u8 host array.  Returns lists (mono, kps, desc) per frame."""
+        images = np.ascontiguousarray(images, np.uint8)
+        B, rows, cols = images.shape
+        cap = self.max_keypoints
+        kps = np.zeros((B, cap), KP_DTYPE)
+        desc = np.zeros((B, cap, 32), np.uint8)
+        n = np.zeros(B, np.int32)
+        mono = np.zeros(B, np.int32)
+        rc = lib().orbx_extract_batch(self._h, _ptr(images), B, rows, cols, images.strides[1], images.strides[0],
+                                      int(vLappingArea[0]), int(vLappingArea[1]), _ptr(kps), _ptr(desc), cap,
+                                      _ptr(n), _ptr(mono))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbx_extract_batch')
+        return ([int(m) for m in mono], [kps[b, :n[b]].copy() for b in range(B)], [desc[b, :n[b]].copy() for b in range(B)])
+
+    def extract_batch_device(self, d_images, d_kps, d_desc, d_n, d_mono, vLappingArea=(0, 0), stream=0):
+        """All-device variant (torch CUDA tensors): d_images [B, rows, cols] u8; slabs d_kps [B, cap, 7] (28-byte rows),
+        d_desc [B, cap, 32] u8, d_n / d_mono [B] i32.  Enqueues on ``stream`` and returns immediately."""
+        B, rows, cols = d_images.shape
+        cap = d_desc.shape[1]
+        rc = lib().orbx_extract_batch_device(self._h, _ptr(d_images), B, rows, cols, d_images.stride(1), d_images.stride(0),
+                                             int(vLappingArea[0]), int(vLappingArea[1]), _ptr(d_kps), _ptr(d_desc), cap,
+                                             _ptr(d_n), _ptr(d_mono), C.c_void_p(stream))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbx_extract_batch_device')
+
+    # --- inspection taps (mvImagePyramid is public in the reference, include/ORBextractor.h:84) ---
+    def level(self, level, frame=0, blurred=False):
+        w, h = C.c_int(), C.c_int()
+        rc = lib().orbx_get_level_size(self._h, level, C.byref(w), C.byref(h))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbx_get_level_size')
+        out = np.zeros((h.value, w.value), np.uint8)
+        rc = lib().orbx_copy_level(self._h, frame, level, int(blurred), _ptr(out))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbx_copy_level')
+        return out
+
+    def candidates(self, level, frame=0, cap=400000):
+        out = np.zeros((cap, 3), np.int32)
+        n = lib().orbx_copy_candidates(self._h, frame, level, _ptr(out), cap)
+        if n < 0:
+            raise OrbError(n, 'orbx_copy_candidates')
+        return out[:n].copy()
+
+    def last_launch_count(self):
+        return lib().orbx_last_launch_count(self._h)

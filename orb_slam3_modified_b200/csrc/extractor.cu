@@ -1,0 +1,490 @@
+// Host side of the batched B200 ORB extractor + its C-ABI (include/orb_b200.h).
+// Mirrors ORBextractor (reference include/ORBextractor.h:43-109, src/ORBextractor.cc).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/orb_b200.h"
+#include "extractor_kernels.cuh"
+
+namespace orbx {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+            return ORB_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+static const int8_t h_pattern[1024] = {
+#include "brief_pattern.inc"
+};
+
+static inline int cvRoundF(float v) { return (int)nearbyintf(v); }
+static inline int cvFloorD(double v) { int i = (int)v; return i - (i > v); }
+static inline int cvCeilD(double v) { int i = (int)v; return i + (i < v); }
+static inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Extractor {
+    // constructor arguments (reference src/ORBextractor.cc:409-413)
+    int nfeatures, nlevels, iniTh, minTh;
+    double scaleFactor;   // the reference keeps the float argument in a double member (ORBextractor.h:92)
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> featPerLevel;
+    int umax[HALF_PATCH + 1];
+    int device, maxW, maxH, maxBatch;
+    // current geometry
+    int rows = 0, cols = 0;
+    ExtractParams P;
+    std::vector<CellDesc> cells;
+    // device buffers
+    uint8_t *d_pyr = nullptr, *d_blur = nullptr;
+    CellDesc* d_cells = nullptr;
+    int* d_cellCount = nullptr;
+    uint32_t* d_cellList = nullptr;
+    uint32_t* d_cand = nullptr;
+    uint16_t* d_nodeOf = nullptr;
+    SelKp* d_sel = nullptr;
+    int *d_selCount = nullptr, *d_dstIndex = nullptr, *d_status = nullptr;
+    short4 *d_xtab = nullptr, *d_ytab = nullptr;
+    // staging for the host-pointer entry points
+    uint8_t* d_img = nullptr;      // maxBatch frames, tightly packed at level-0 pitch
+    OrbKeyPoint* d_outKp = nullptr; uint8_t* d_outDesc = nullptr; int *d_outN = nullptr, *d_outMono = nullptr;
+    int* h_counts = nullptr;       // pinned: n[maxBatch], mono[maxBatch], status[maxBatch]
+    int outCapInternal = 0;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    size_t smemFast = 0, smemQt = 0, smemAs = 0;
+    int launches = 0;
+    int maxKp = 0;
+
+    ~Extractor() { release(); }
+    void release() {
+        cudaSetDevice(device);
+        void* ptrs[] = {d_pyr, d_blur, d_cells, d_cellCount, d_cellList, d_cand, d_nodeOf, d_sel, d_selCount, d_dstIndex,
+                        d_status, d_xtab, d_ytab, d_img, d_outKp, d_outDesc, d_outN, d_outMono};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        if (h_counts) cudaFreeHost(h_counts);
+        if (stream) cudaStreamDestroy(stream);
+        if (stream2) cudaStreamDestroy(stream2);
+        if (evFork) cudaEventDestroy(evFork);
+        if (evJoin) cudaEventDestroy(evJoin);
+    }
+
+    // ORBextractor::ORBextractor, src/ORBextractor.cc:409-469
+    void init_tables() {
+        scale.resize(nlevels); sigma2.resize(nlevels); invScale.resize(nlevels); invSigma2.resize(nlevels);
+        scale[0] = 1.0f; sigma2[0] = 1.0f;
+        for (int i = 1; i < nlevels; ++i) {
+            scale[i] = (float)(scale[i - 1] * scaleFactor);
+            sigma2[i] = scale[i] * scale[i];
+        }
+        for (int i = 0; i < nlevels; ++i) { invScale[i] = 1.0f / scale[i]; invSigma2[i] = 1.0f / sigma2[i]; }
+        featPerLevel.resize(nlevels);
+        float factor = (float)(1.0f / scaleFactor);
+        float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+        int sum = 0;
+        for (int l = 0; l < nlevels - 1; ++l) {
+            featPerLevel[l] = cvRoundF(nDesired);
+            sum += featPerLevel[l];
+            nDesired *= factor;
+        }
+        featPerLevel[nlevels - 1] = std::max(nfeatures - sum, 0);
+        int v, v0, vmax = cvFloorD(HALF_PATCH * sqrtf(2.f) / 2 + 1);
+        int vmin = cvCeilD(HALF_PATCH * sqrtf(2.f) / 2);
+        const double hp2 = HALF_PATCH * HALF_PATCH;
+        for (v = 0; v <= vmax; ++v) umax[v] = (int)nearbyint(sqrt(hp2 - v * v));
+        for (v = HALF_PATCH, v0 = 0; v >= vmin; --v) {
+            while (umax[v0] == umax[v0 + 1]) ++v0;
+            umax[v] = v0;
+            ++v0;
+        }
+    }
+
+    // Level geometry for a rows x cols image: pyramid sizes (src/ORBextractor.cc:1174-1175), FAST cell
+    // grid (:789-824), quadtree roots (:559-561), resize coefficient tables.
+    int configure(int r, int c, std::vector<short4>& xtab, std::vector<short4>& ytab) {
+        memset(&P, 0, sizeof(P));
+        P.nlevels = nlevels; P.iniTh = iniTh; P.minTh = minTh; P.rows = r; P.cols = c;
+        cells.clear(); xtab.clear(); ytab.clear();
+        size_t planeOff = 0, listOff = 0, candOff = 0;
+        int selOff = 0, blurTiles = 0, maxNodes = 0, maxCells = 0;
+        maxKp = 0;
+        smemFast = 0;
+        for (int l = 0; l < nlevels; ++l) {
+            LevelGeom& G = P.lv[l];
+            G.w = cvRoundF((float)c * invScale[l]);
+            G.h = cvRoundF((float)r * invScale[l]);
+            if (G.w > 4095 || G.h > 4095) { set_error("image larger than 4095 px is not supported"); return ORB_ERR_ARG; }
+            G.pitch = (int)alignUp(G.w, 32);
+            G.planeOff = (uint32_t)planeOff;
+            planeOff += alignUp((size_t)G.pitch * G.h, 256);
+            G.minBX = EDGE_THRESHOLD - 3; G.minBY = G.minBX;
+            G.maxBX = G.w - EDGE_THRESHOLD + 3; G.maxBY = G.h - EDGE_THRESHOLD + 3;
+            const float width = (float)(G.maxBX - G.minBX), height = (float)(G.maxBY - G.minBY);
+            const float W = 35;
+            G.nCols = (int)(width / W); G.nRows = (int)(height / W);
+            if (G.nCols < 1 || G.nRows < 1) { set_error("image too small for the number of pyramid levels"); return ORB_ERR_ARG; }
+            G.wCell = (int)ceil(width / G.nCols); G.hCell = (int)ceil(height / G.nRows);
+            G.cellCap = ((G.wCell + 1) / 2) * ((G.hCell + 1) / 2);
+            G.cellBase = (int)cells.size();
+            for (int i = 0; i < G.nRows; ++i) {
+                const float iniY = (float)(G.minBY + i * G.hCell);
+                float maxY = iniY + G.hCell + 6;
+                if (iniY >= G.maxBY - 3) continue;
+                if (maxY > G.maxBY) maxY = (float)G.maxBY;
+                for (int j = 0; j < G.nCols; ++j) {
+                    const float iniX = (float)(G.minBX + j * G.wCell);
+                    float maxX = iniX + G.wCell + 6;
+                    if (iniX >= G.maxBX - 6) continue;
+                    if (maxX > G.maxBX) maxX = (float)G.maxBX;
+                    CellDesc cd;
+                    cd.level = (uint16_t)l; cd.x0 = (uint16_t)iniX; cd.y0 = (uint16_t)iniY;
+                    cd.rw = (uint16_t)((int)maxX - (int)iniX); cd.rh = (uint16_t)((int)maxY - (int)iniY);
+                    cd.offX = (uint16_t)(j * G.wCell); cd.offY = (uint16_t)(i * G.hCell); cd.pad = 0;
+                    cd.listOff = (uint32_t)listOff;
+                    listOff += G.cellCap;
+                    cells.push_back(cd);
+                    const int tp = (cd.rw + 3) & ~3, iw = cd.rw - 6, ih = cd.rh - 6;
+                    if (iw > 0 && ih > 0) {
+                        size_t sm = (((size_t)cd.rh * tp + 15) & ~15) + ((((size_t)ih + 2) * (iw + 2) + 15) & ~15) + 2 * (size_t)iw * ih;
+                        smemFast = std::max(smemFast, sm);
+                    }
+                }
+            }
+            G.nCells = (int)cells.size() - G.cellBase;
+            maxCells = std::max(maxCells, G.nCells);
+            G.candOff = (uint32_t)candOff; G.candCap = (uint32_t)G.nCells * G.cellCap;
+            candOff += alignUp(G.candCap, 64);
+            G.nDesired = featPerLevel[l];
+            G.nIni = (int)roundf((float)(G.maxBX - G.minBX) / (G.maxBY - G.minBY));
+            if (G.nIni < 1) { set_error("aspect ratio < 0.5: reference divides by zero (ORBextractor.cc:559-561)"); return ORB_ERR_ASPECT; }
+            G.hX = (float)(G.maxBX - G.minBX) / G.nIni;
+            const int nodes = std::max(G.nDesired + 3, 4 * G.nIni) + 4;
+            maxNodes = std::max(maxNodes, nodes);
+            G.selCap = std::max(G.nDesired + 3, 4 * G.nIni);
+            G.selOff = selOff; selOff += G.selCap;
+            maxKp += G.selCap;
+            G.scale = scale[l];
+            G.sizeScaled = (float)(int)(PATCH_SIZE * scale[l]);
+            G.blurTileBase = blurTiles;
+            G.blurTilesX = (G.w + BL_TW - 1) / BL_TW; G.blurTilesY = (G.h + BL_TH - 1) / BL_TH;
+            blurTiles += G.blurTilesX * G.blurTilesY;
+            G.area2x = 0;
+            G.xtabOff = (uint32_t)xtab.size(); G.ytabOff = (uint32_t)ytab.size();
+            if (l > 0) {
+                const LevelGeom& S = P.lv[l - 1];
+                if (S.w == 2 * G.w && S.h == 2 * G.h) G.area2x = 1;
+                const double sx_ = (double)S.w / G.w, sy_ = (double)S.h / G.h;
+                for (int dx = 0; dx < G.w; ++dx) {
+                    float fx = (float)((dx + 0.5) * sx_ - 0.5);
+                    int sx = cvFloorD(fx);
+                    fx -= sx;
+                    if (sx < 0) { fx = 0; sx = 0; }
+                    if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+                    short4 t;
+                    t.x = (short)sx; t.y = (short)std::min(sx + 1, S.w - 1);
+                    t.z = (short)cvRoundF((1.f - fx) * 2048); t.w = (short)cvRoundF(fx * 2048);
+                    xtab.push_back(t);
+                }
+                for (int dy = 0; dy < G.h; ++dy) {
+                    float fy = (float)((dy + 0.5) * sy_ - 0.5);
+                    int sy = cvFloorD(fy);
+                    fy -= sy;
+                    short4 t;
+                    t.x = (short)std::min(std::max(sy, 0), S.h - 1); t.y = (short)std::min(std::max(sy + 1, 0), S.h - 1);
+                    t.z = (short)cvRoundF((1.f - fy) * 2048); t.w = (short)cvRoundF(fy * 2048);
+                    ytab.push_back(t);
+                }
+            }
+        }
+        P.pyrFrameStride = planeOff;
+        P.nCellsTotal = (int)cells.size();
+        P.cellCountStride = alignUp(cells.size(), 32);
+        P.cellListStride = alignUp(listOff, 64);
+        P.candStride = alignUp(candOff, 64);
+        P.selStride = (size_t)selOff;
+        P.blurTilesTotal = blurTiles;
+        P.maxNodes = maxNodes;
+        P.maxCellsPerLevel = maxCells;
+        smemQt = (size_t)maxNodes * (2 * sizeof(QtNode) + 2 * 4 + 3 * 4 + 3 * 16 + sizeof(QtSort) + 8) + 16 + 4 * ((size_t)maxCells + 1);
+        smemAs = 2 * P.selStride * sizeof(int);
+        rows = r; cols = c;
+        return ORB_OK;
+    }
+
+    int allocate() {
+        // geometry + buffers are sized for the largest image; smaller images reuse them
+        std::vector<short4> xtab, ytab;
+        int rc = configure(maxH, maxW, xtab, ytab);
+        if (rc) return rc;
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) { set_error("device is not sm_100+ (Blackwell); this library has no other code path"); return ORB_ERR_CUDA; }
+        const size_t B = (size_t)maxBatch;
+        CK(cudaMalloc(&d_pyr, P.pyrFrameStride * B));
+        CK(cudaMalloc(&d_blur, P.pyrFrameStride * B));
+        capPyr = P.pyrFrameStride; capCells = cells.size() + cells.size() / 4 + 64; capCellCount = alignUp(capCells, 32);
+        capCellList = P.cellListStride + P.cellListStride / 8; capCand = P.candStride + P.candStride / 8;
+        capSel = P.selStride + 64; capX = xtab.size() + 64; capY = ytab.size() + 64;
+        CK(cudaMalloc(&d_cells, sizeof(CellDesc) * capCells));
+        CK(cudaMalloc(&d_cellCount, sizeof(int) * capCellCount * B));
+        CK(cudaMalloc(&d_cellList, sizeof(uint32_t) * capCellList * B));
+        CK(cudaMalloc(&d_cand, sizeof(uint32_t) * capCand * B));
+        CK(cudaMalloc(&d_nodeOf, sizeof(uint16_t) * capCand * B));
+        CK(cudaMalloc(&d_sel, sizeof(SelKp) * capSel * B));
+        CK(cudaMalloc(&d_selCount, sizeof(int) * kMaxLevels * B));
+        CK(cudaMalloc(&d_dstIndex, sizeof(int) * capSel * B));
+        CK(cudaMalloc(&d_status, sizeof(int) * B));
+        CK(cudaMalloc(&d_xtab, sizeof(short4) * capX));
+        CK(cudaMalloc(&d_ytab, sizeof(short4) * capY));
+        CK(cudaMalloc(&d_img, (size_t)P.lv[0].pitch * maxH * B));
+        outCapInternal = (int)capSel;
+        CK(cudaMalloc(&d_outKp, sizeof(OrbKeyPoint) * outCapInternal * B));
+        CK(cudaMalloc(&d_outDesc, (size_t)32 * outCapInternal * B));
+        CK(cudaMalloc(&d_outN, sizeof(int) * B));
+        CK(cudaMalloc(&d_outMono, sizeof(int) * B));
+        CK(cudaMallocHost(&h_counts, sizeof(int) * 3 * B));
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&evJoin, cudaEventDisableTiming));
+        CK(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
+        CK(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
+        maxSmemFast = 40 * 1024;   // worst-case cell is 76x76 (cells are < 70 px wide): ~21 KB
+        maxSmemQt = smemQt + 16 * 1024; maxSmemAs = 2 * capSel * sizeof(int);
+        if (maxSmemQt > 200 * 1024) { set_error("nfeatures too large for the quadtree kernel's shared memory"); return ORB_ERR_ARG; }
+        CK(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmemFast));
+        CK(cudaFuncSetAttribute(quadtree_orient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmemQt));
+        CK(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(maxSmemAs, 1024)));
+        maxKpAlloc = (int)capSel;
+        rows = cols = 0;   // force set_size on first use
+        return set_size(maxH, maxW);
+    }
+    size_t maxSmemFast = 0, maxSmemQt = 0, maxSmemAs = 0;
+    size_t capPyr = 0, capCells = 0, capCellCount = 0, capCellList = 0, capCand = 0, capSel = 0, capX = 0, capY = 0;
+    int maxKpAlloc = 0;
+
+    int set_size(int r, int c) {
+        if (r == rows && c == cols) return ORB_OK;
+        if (r > maxH || c > maxW) { set_error("image larger than max_width x max_height given to orbx_create"); return ORB_ERR_ARG; }
+        std::vector<short4> xtab, ytab;
+        int rc = configure(r, c, xtab, ytab);
+        if (rc) { rows = cols = 0; return rc; }
+        if (P.pyrFrameStride > capPyr || cells.size() > capCells || P.cellCountStride > capCellCount || P.cellListStride > capCellList ||
+            P.candStride > capCand || P.selStride > capSel || xtab.size() > capX || ytab.size() > capY || smemQt > maxSmemQt ||
+            smemFast > maxSmemFast || smemAs > maxSmemAs) {
+            rows = cols = 0;
+            set_error("image geometry exceeds the buffers sized at orbx_create (aspect ratio very different from max_width x max_height?)");
+            return ORB_ERR_ARG;
+        }
+        CK(cudaSetDevice(device));
+        CK(cudaStreamSynchronize(stream));
+        if (!cells.empty()) CK(cudaMemcpy(d_cells, cells.data(), sizeof(CellDesc) * cells.size(), cudaMemcpyHostToDevice));
+        if (!xtab.empty()) CK(cudaMemcpy(d_xtab, xtab.data(), sizeof(short4) * xtab.size(), cudaMemcpyHostToDevice));
+        if (!ytab.empty()) CK(cudaMemcpy(d_ytab, ytab.data(), sizeof(short4) * ytab.size(), cudaMemcpyHostToDevice));
+        P.pyr = d_pyr; P.blur = d_blur; P.cells = d_cells; P.cellCount = d_cellCount; P.cellList = d_cellList;
+        P.cand = d_cand; P.nodeOf = d_nodeOf; P.sel = d_sel; P.selCount = d_selCount; P.dstIndex = d_dstIndex;
+        P.status = d_status; P.xtab = d_xtab; P.ytab = d_ytab;
+        return ORB_OK;
+    }
+
+    // Enqueue the whole pipeline for `batch` frames whose level-0 planes are described by (lv0, pitch, stride).
+    int enqueue(const uint8_t* lv0, size_t lv0Pitch, size_t lv0Stride, int batch, int lap0, int lap1,
+                OrbKeyPoint* outKp, uint8_t* outDesc, int cap, int* outN, int* outMono, cudaStream_t st) {
+        ExtractParams Q = P;
+        Q.batch = batch; Q.lap0 = lap0; Q.lap1 = lap1;
+        Q.lv0 = lv0; Q.lv0Pitch = lv0Pitch; Q.lv0FrameStride = lv0Stride;
+        Q.outKp = outKp; Q.outDesc = outDesc; Q.outCap = cap; Q.outN = outN; Q.outMono = outMono;
+        launches = 0;
+        CK(cudaMemsetAsync(d_status, 0, sizeof(int) * batch, st));
+        // pyramid: levels depend on each other
+        for (int l = 1; l < nlevels; ++l) {
+            dim3 blk(32, 8), grd((Q.lv[l].w + 127) / 128, (Q.lv[l].h + 7) / 8, batch);
+            pyr_resize_kernel<<<grd, blk, 0, st>>>(Q, l);
+            ++launches;
+        }
+        // blur runs on a forked stream, concurrently with detection
+        CK(cudaEventRecord(evFork, st));
+        CK(cudaStreamWaitEvent(stream2, evFork, 0));
+        blur_kernel<<<dim3(Q.blurTilesTotal, batch), BL_NT, 0, stream2>>>(Q);
+        ++launches;
+        CK(cudaEventRecord(evJoin, stream2));
+        fast_cells_kernel<<<dim3(Q.nCellsTotal, batch), FAST_NT, smemFast, st>>>(Q);
+        ++launches;
+        quadtree_orient_kernel<<<dim3(nlevels, batch), QT_NT, smemQt, st>>>(Q);
+        ++launches;
+        assemble_kernel<<<batch, AS_NT, smemAs, st>>>(Q);
+        ++launches;
+        CK(cudaStreamWaitEvent(st, evJoin, 0));
+        describe_kernel<<<dim3((unsigned)((Q.selStride + DS_NT / 32 - 1) / (DS_NT / 32)), batch), DS_NT, 0, st>>>(Q);
+        ++launches;
+        CK(cudaGetLastError());
+        return ORB_OK;
+    }
+};
+
+}  // namespace orbx
+
+using namespace orbx;
+
+struct orbx_handle { Extractor e; };
+
+extern "C" {
+
+const char* orb_last_error(void) { return g_err.c_str(); }
+int orb_abi_version(void) { return 1; }
+int orb_compiled_sm(void) { return 100; }
+
+int orbx_create(orbx_handle** out, int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+                int max_width, int max_height, int max_batch, int device) {
+    if (!out || nfeatures < 1 || nlevels < 1 || nlevels > kMaxLevels || !(scaleFactor > 1.0f) || max_width < 1 || max_height < 1 ||
+        max_batch < 1 || iniThFAST < 1 || minThFAST < 1 || minThFAST > iniThFAST) {
+        set_error("orbx_create: bad argument");
+        return ORB_ERR_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (this library has no CPU path)"); return ORB_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { set_error("orbx_create: bad device index"); return ORB_ERR_ARG; }
+    orbx_handle* h = new orbx_handle();
+    Extractor& e = h->e;
+    e.nfeatures = nfeatures; e.nlevels = nlevels; e.iniTh = iniThFAST; e.minTh = minThFAST; e.scaleFactor = scaleFactor;
+    e.device = device; e.maxW = max_width; e.maxH = max_height; e.maxBatch = max_batch;
+    e.init_tables();
+    int rc = e.allocate();
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return ORB_OK;
+}
+
+void orbx_destroy(orbx_handle* h) { delete h; }
+
+int orbx_get_levels(const orbx_handle* h) { return h ? h->e.nlevels : ORB_ERR_ARG; }
+
+int orbx_get_tables(const orbx_handle* h, float* s, float* is, float* g, float* ig, int* fpl) {
+    if (!h) return ORB_ERR_ARG;
+    const Extractor& e = h->e;
+    for (int i = 0; i < e.nlevels; ++i) {
+        if (s) s[i] = e.scale[i];
+        if (is) is[i] = e.invScale[i];
+        if (g) g[i] = e.sigma2[i];
+        if (ig) ig[i] = e.invSigma2[i];
+        if (fpl) fpl[i] = e.featPerLevel[i];
+    }
+    return ORB_OK;
+}
+
+int orbx_max_keypoints(const orbx_handle* h) { return h ? h->e.maxKpAlloc : ORB_ERR_ARG; }
+
+int orbx_extract_batch_device(orbx_handle* h, const uint8_t* d_images, int batch, int rows, int cols, size_t step,
+                              size_t frame_stride, int lap0, int lap1, OrbKeyPoint* d_kps, uint8_t* d_desc, int cap,
+                              int* d_n, int* d_mono, void* stream) {
+    if (!h || !d_kps || !d_desc || !d_n || !d_mono || cap < 1) { set_error("orbx_extract_batch_device: bad argument"); return ORB_ERR_ARG; }
+    if (!d_images || rows <= 0 || cols <= 0 || batch <= 0) return ORB_ERR_EMPTY;
+    Extractor& e = h->e;
+    if (batch > e.maxBatch) { set_error("batch larger than max_batch"); return ORB_ERR_ARG; }
+    if (step < (size_t)cols) { set_error("step < cols"); return ORB_ERR_ARG; }
+    CK(cudaSetDevice(e.device));
+    int rc = e.set_size(rows, cols);
+    if (rc) return rc;
+    return e.enqueue(d_images, step, frame_stride, batch, lap0, lap1, d_kps, d_desc, cap, d_n, d_mono, (cudaStream_t)stream);
+}
+
+int orbx_extract_batch(orbx_handle* h, const uint8_t* images, int batch, int rows, int cols, size_t step, size_t frame_stride,
+                       int lap0, int lap1, OrbKeyPoint* kps, uint8_t* desc, int cap, int* n, int* mono) {
+    if (!h || !kps || !desc || !n || !mono || cap < 1) { set_error("orbx_extract_batch: bad argument"); return ORB_ERR_ARG; }
+    if (!images || rows <= 0 || cols <= 0 || batch <= 0) return ORB_ERR_EMPTY;
+    Extractor& e = h->e;
+    if (batch > e.maxBatch) { set_error("batch larger than max_batch"); return ORB_ERR_ARG; }
+    if (step < (size_t)cols) { set_error("step < cols"); return ORB_ERR_ARG; }
+    CK(cudaSetDevice(e.device));
+    int rc = e.set_size(rows, cols);
+    if (rc) return rc;
+    const size_t pitch = e.P.lv[0].pitch, fstride = pitch * rows;
+    cudaStream_t st = e.stream;
+    if (batch > 1 && frame_stride == step * rows) {
+        CK(cudaMemcpy2DAsync(e.d_img, pitch, images, step, cols, (size_t)rows * batch, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int f = 0; f < batch; ++f)
+            CK(cudaMemcpy2DAsync(e.d_img + f * fstride, pitch, images + f * frame_stride, step, cols, rows, cudaMemcpyHostToDevice, st));
+    }
+    const int icap = e.outCapInternal;
+    rc = e.enqueue(e.d_img, pitch, fstride, batch, lap0, lap1, e.d_outKp, e.d_outDesc, icap, e.d_outN, e.d_outMono, st);
+    if (rc) return rc;
+    int* hn = e.h_counts; int* hm = hn + e.maxBatch; int* hs = hm + e.maxBatch;
+    CK(cudaMemcpyAsync(hn, e.d_outN, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hm, e.d_outMono, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hs, e.d_status, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int worst = ORB_OK;
+    for (int f = 0; f < batch; ++f) {
+        n[f] = hn[f]; mono[f] = hm[f];
+        if (hs[f] || hn[f] > cap) { worst = ORB_ERR_CAPACITY; set_error("keypoint capacity exceeded"); continue; }
+        if (hn[f] > 0) {
+            CK(cudaMemcpyAsync(kps + (size_t)f * cap, e.d_outKp + (size_t)f * icap, sizeof(OrbKeyPoint) * hn[f], cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(desc + (size_t)f * cap * 32, e.d_outDesc + (size_t)f * icap * 32, (size_t)32 * hn[f], cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    return worst;
+}
+
+int orbx_extract(orbx_handle* h, const uint8_t* image, int rows, int cols, size_t step, int lap0, int lap1,
+                 OrbKeyPoint* kps, uint8_t* desc, int cap, int* n, int* mono) {
+    return orbx_extract_batch(h, image, 1, rows, cols, step, step * (size_t)(rows > 0 ? rows : 0), lap0, lap1, kps, desc, cap, n, mono);
+}
+
+int orbx_get_level_size(const orbx_handle* h, int level, int* w, int* hh) {
+    if (!h || level < 0 || level >= h->e.nlevels || h->e.rows == 0) return ORB_ERR_ARG;
+    *w = h->e.P.lv[level].w; *hh = h->e.P.lv[level].h;
+    return ORB_OK;
+}
+
+int orbx_copy_level(orbx_handle* h, int frame, int level, int blurred, uint8_t* dst) {
+    if (!h || !dst || level < 0 || level >= h->e.nlevels || frame < 0 || frame >= h->e.maxBatch || h->e.rows == 0) return ORB_ERR_ARG;
+    Extractor& e = h->e;
+    CK(cudaSetDevice(e.device));
+    const LevelGeom& G = e.P.lv[level];
+    const uint8_t* src;
+    size_t pitch = G.pitch;
+    if (level == 0 && !blurred) { src = e.d_img + (size_t)frame * G.pitch * e.rows; }
+    else src = (blurred ? e.d_blur : e.d_pyr) + (size_t)frame * e.P.pyrFrameStride + G.planeOff;
+    CK(cudaMemcpy2D(dst, G.w, src, pitch, G.w, G.h, cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+int orbx_copy_candidates(orbx_handle* h, int frame, int level, int* xys, int cap) {
+    if (!h || !xys || level < 0 || level >= h->e.nlevels || frame < 0 || frame >= h->e.maxBatch || h->e.rows == 0) return ORB_ERR_ARG;
+    Extractor& e = h->e;
+    CK(cudaSetDevice(e.device));
+    const LevelGeom& G = e.P.lv[level];
+    std::vector<int> counts(G.nCells);
+    if (G.nCells == 0) return 0;
+    CK(cudaMemcpy(counts.data(), e.d_cellCount + (size_t)frame * e.P.cellCountStride + G.cellBase, sizeof(int) * G.nCells, cudaMemcpyDeviceToHost));
+    int total = 0;
+    std::vector<uint32_t> buf(G.cellCap);
+    for (int c = 0; c < G.nCells; ++c) {
+        const int cnt = counts[c];
+        if (cnt > G.cellCap) return ORB_ERR_CAPACITY;
+        if (cnt) CK(cudaMemcpy(buf.data(), e.d_cellList + (size_t)frame * e.P.cellListStride + e.cells[G.cellBase + c].listOff, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < cnt; ++k) {
+            if (total < cap) { xys[3 * total] = cand_x(buf[k]); xys[3 * total + 1] = cand_y(buf[k]); xys[3 * total + 2] = cand_s(buf[k]); }
+            ++total;
+        }
+    }
+    return total;
+}
+
+int orbx_last_launch_count(const orbx_handle* h) { return h ? h->e.launches : ORB_ERR_ARG; }
+
+}  // extern "C"

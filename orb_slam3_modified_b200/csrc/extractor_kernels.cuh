@@ -1,0 +1,715 @@
+// Hand-written sm_100a kernels of the batched ORB extractor.  Every kernel carries a
+// batch (frame) dimension in blockIdx.y / blockIdx.z so that one launch covers all streams.
+//
+// Reference semantics (file:line in /root/reference) are cited per kernel; the
+// bit-exact scalar pieces live in exact_math.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "exact_math.h"
+#include "extractor_types.h"
+
+namespace orbx {
+
+__constant__ int8_t c_pattern[1024];      // 256 pairs x (x0,y0,x1,y1), reference src/ORBextractor.cc:149-407
+__constant__ int c_umax[HALF_PATCH + 1];  // :453-468
+
+// ------------------------------------------------------------------------------------------
+// plane addressing: level 0 may alias the caller's image
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ const uint8_t* plane_ptr(const ExtractParams& P, int f, int l, int& pitch) {
+    if (l == 0) { pitch = (int)P.lv0Pitch; return P.lv0 + (size_t)f * P.lv0FrameStride; }
+    pitch = P.lv[l].pitch;
+    return P.pyr + (size_t)f * P.pyrFrameStride + P.lv[l].planeOff;
+}
+__device__ __forceinline__ const uint8_t* blur_ptr(const ExtractParams& P, int f, int l, int& pitch) {
+    pitch = P.lv[l].pitch;
+    return P.blur + (size_t)f * P.pyrFrameStride + P.lv[l].planeOff;
+}
+
+// ------------------------------------------------------------------------------------------
+// block-wide exclusive scan of an int array living in shared memory (in place).
+// Returns the total.  `warpTmp` needs 33 ints.  All threads of the block must call.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_excl_scan(int* data, int m, int* warpTmp) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    int carry = 0;
+    for (int base = 0; base < m; base += nt) {
+        const int i = base + tid;
+        const int v = i < m ? data[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warpTmp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = lane < nw ? warpTmp[lane] : 0;
+            int winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warpTmp[lane] = winc - w;       // exclusive warp offsets
+            if (lane == 31) warpTmp[32] = winc;  // tile total
+        }
+        __syncthreads();
+        if (i < m) data[i] = carry + warpTmp[wid] + inc - v;
+        carry += warpTmp[32];
+        __syncthreads();
+    }
+    return carry;
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: copy the caller's image into the level-0 plane (only when level 0 cannot alias it).
+// ------------------------------------------------------------------------------------------
+__global__ void copy_level0_kernel(ExtractParams P) {
+    const int f = blockIdx.z;
+    const int y = blockIdx.y;
+    const uint8_t* s = P.src + (size_t)f * P.srcFrameStride + (size_t)y * P.srcStep;
+    uint8_t* d = P.pyr + (size_t)f * P.pyrFrameStride + P.lv[0].planeOff + (size_t)y * P.lv[0].pitch;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < P.cols; x += gridDim.x * blockDim.x) d[x] = s[x];
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: pyramid level l from level l-1.  cv::resize(INTER_LINEAR) restated in integer
+// fixed point (reference call site src/ORBextractor.cc:1183).  Each thread
+// produces 4 horizontally adjacent pixels and stores them as one 32-bit word.
+// The 19-px reflected border the reference also writes (:1185-1191) is never read on this
+// path (SURVEY.md 8a reach analysis) and is not materialised.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pyr_resize_kernel(ExtractParams P, int l) {
+    const LevelGeom& G = P.lv[l];
+    const int f = blockIdx.z;
+    const int dy = blockIdx.y * blockDim.y + threadIdx.y;
+    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (dy >= G.h || dx0 >= G.w) return;
+    int spitch;
+    const uint8_t* src = plane_ptr(P, f, l - 1, spitch);
+    uint8_t* dst = P.pyr + (size_t)f * P.pyrFrameStride + G.planeOff + (size_t)dy * G.pitch;
+    uint32_t out = 0;
+    if (G.area2x) {
+        const uint8_t* r0 = src + (size_t)(2 * dy) * spitch;
+        const uint8_t* r1 = r0 + spitch;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int dx = dx0 + k;
+            if (dx < G.w) {
+                int v = (r0[2 * dx] + r0[2 * dx + 1] + r1[2 * dx] + r1[2 * dx + 1] + 2) >> 2;
+                out |= (uint32_t)v << (8 * k);
+            }
+        }
+    } else {
+        const short4 yt = P.ytab[G.ytabOff + dy];  // {sy0, sy1, b0, b1}
+        const uint8_t* r0 = src + (size_t)yt.x * spitch;
+        const uint8_t* r1 = src + (size_t)yt.y * spitch;
+        const int b0 = yt.z, b1 = yt.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int dx = dx0 + k;
+            if (dx < G.w) {
+                const short4 xt = __ldg(&P.xtab[G.xtabOff + dx]);  // {sx0, sx1, a0, a1}
+                const int s0 = r0[xt.x] * xt.z + r0[xt.y] * xt.w;
+                const int s1 = r1[xt.x] * xt.z + r1[xt.y] * xt.w;
+                const int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+                out |= (uint32_t)(v & 0xFF) << (8 * k);
+            }
+        }
+    }
+    *reinterpret_cast<uint32_t*>(dst + dx0) = out;   // pitch is a multiple of 32: in-bounds even for the tail
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: FAST-9/16 per cell with the two-threshold fallback and cell-local NMS.
+// Reference: ORBextractor::ComputeKeyPointsOctTree src/ORBextractor.cc:805-873 calling
+// cv::FAST(cellROI, th, nonmax=true).  One CTA per (cell, frame).
+//   score = max over the 16 nine-pixel arcs of max(min(v-p), min(p-v)) - 1; corner at T <=> score >= T;
+//   NMS: strict 8-neighbour maximum, neighbours outside the ROI interior count as 0.
+// A strict local maximum of the th=minTh score map with score >= T is exactly what
+// cv::FAST(T) keeps, so one score map serves both passes.
+// Output: per cell a count and a row-major (y, x) list of packed (x+offX, y+offY, score).
+// ------------------------------------------------------------------------------------------
+constexpr int FAST_NT = 256;
+
+__device__ __forceinline__ int fast_score_at(const uint8_t* t, const int* off) {
+    // d_k = v - p_k (darker ring), e_k = p_k - v (brighter ring) for the 16 ring pixels.
+    // NOTE: both polarities are written as min-trees over separately subtracted arrays on purpose.
+    // The shorter form max(min9(d), -max9(d)) is miscompiled by ptxas 12.9 for sm_100a (the negation is
+    // dropped when it is folded into a VIMNMX3 operand); see DESIGN.md "toolchain findings".
+    const int v = t[0];
+    int d[16], e[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { const int p = t[off[k]]; d[k] = v - p; e[k] = p - v; }
+    // min over every window of 9 consecutive (cyclic) ring positions via two levels of 3-input minima
+    int a3[16], b3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        a3[k] = min(d[k], min(d[(k + 1) & 15], d[(k + 2) & 15]));
+        b3[k] = min(e[k], min(e[(k + 1) & 15], e[(k + 2) & 15]));
+    }
+    int best = -512;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int a9 = min(a3[k], min(a3[(k + 3) & 15], a3[(k + 6) & 15]));
+        const int b9 = min(b3[k], min(b3[(k + 3) & 15], b3[(k + 6) & 15]));
+        best = max(best, max(a9, b9));
+    }
+    return best;  // corner at T <=> best > T, score = best - 1
+}
+
+__global__ void __launch_bounds__(FAST_NT) fast_cells_kernel(ExtractParams P) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int f = blockIdx.y;
+    const CellDesc cd = P.cells[blockIdx.x];
+    const int rw = cd.rw, rh = cd.rh;
+    int* outCount = P.cellCount + (size_t)f * P.cellCountStride + blockIdx.x;
+    if (rw < 7 || rh < 7) { if (threadIdx.x == 0) *outCount = 0; return; }
+    const int tp = (rw + 3) & ~3;               // tile pitch
+    const int iw = rw - 6, ih = rh - 6;         // detection interior
+    const int sp = iw + 2;                      // score-map pitch (1-px zero ring)
+    uint8_t* tile = smem_raw;                                   // rh * tp
+    uint8_t* score = tile + ((rh * tp + 15) & ~15);             // (ih+2) * sp
+    uint16_t* list = reinterpret_cast<uint16_t*>(score + (((ih + 2) * sp + 15) & ~15));  // iw*ih
+    __shared__ int s_nCand, s_cntHi, s_warp[33];
+    const int tid = threadIdx.x;
+
+    int pitch;
+    const uint8_t* img = plane_ptr(P, f, cd.level, pitch);
+    img += (size_t)cd.y0 * pitch + cd.x0;
+    for (int i = tid; i < rh * rw; i += FAST_NT) {
+        const int y = i / rw, x = i - y * rw;
+        tile[y * tp + x] = img[(size_t)y * pitch + x];
+    }
+    for (int i = tid; i < (ih + 2) * sp; i += FAST_NT) score[i] = 0;
+    if (tid == 0) { s_nCand = 0; s_cntHi = 0; }
+    __syncthreads();
+
+    // phase 1: cheap rejection (any 9-arc contains pixel k or k+8 for every k) + compaction
+    const int th = P.minTh;
+    const int npix = iw * ih;
+    for (int base = 0; base < npix; base += FAST_NT) {
+        const int i = base + tid;
+        bool cand = false;
+        if (i < npix) {
+            const int y = i / iw, x = i - y * iw;
+            const uint8_t* t = tile + (y + 3) * tp + (x + 3);
+            const int v = t[0], lo = v - th, hi = v + th;
+            const int p0 = t[3 * tp], p8 = t[-3 * tp], p4 = t[3], p12 = t[-3];
+            bool dark = (p0 < lo || p8 < lo) && (p4 < lo || p12 < lo);
+            bool brig = (p0 > hi || p8 > hi) && (p4 > hi || p12 > hi);
+            if (dark || brig) {
+                const int p2 = t[2 * tp + 2], p10 = t[-2 * tp - 2], p6 = t[-2 * tp + 2], p14 = t[2 * tp - 2];
+                dark = dark && (p2 < lo || p10 < lo) && (p6 < lo || p14 < lo);
+                brig = brig && (p2 > hi || p10 > hi) && (p6 > hi || p14 > hi);
+                cand = dark || brig;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (m) {
+            int wbase = 0;
+            if ((tid & 31) == 0) wbase = atomicAdd(&s_nCand, __popc(m));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (cand) list[wbase + __popc(m & ((1u << (tid & 31)) - 1))] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+
+    // phase 2: exact score for the survivors
+    {
+        int off[16];
+        const int dxs[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+        const int dys[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) off[k] = dys[k] * tp + dxs[k];
+        const int nc = s_nCand;
+        for (int c = tid; c < nc; c += FAST_NT) {
+            const int i = list[c];
+            const int y = i / iw, x = i - y * iw;
+            const int b = fast_score_at(tile + (y + 3) * tp + (x + 3), off);
+            if (b > th) score[(y + 1) * sp + (x + 1)] = (uint8_t)(b - 1);
+        }
+    }
+    __syncthreads();
+
+    // phase 3: strict local maxima; each thread owns a run of R consecutive row-major pixels
+    const int R = (npix + FAST_NT - 1) / FAST_NT;   // <= 32 for interiors up to 8192 px
+    const int i0 = tid * R;
+    unsigned mHi = 0, mLo = 0;
+    for (int r = 0; r < R; ++r) {
+        const int i = i0 + r;
+        if (i >= npix) break;
+        const int y = i / iw, x = i - y * iw;
+        const uint8_t* s = score + (y + 1) * sp + (x + 1);
+        const int v = s[0];
+        if (v == 0) continue;
+        const bool mx = v > s[-1] && v > s[1] && v > s[-sp - 1] && v > s[-sp] && v > s[-sp + 1] &&
+                        v > s[sp - 1] && v > s[sp] && v > s[sp + 1];
+        if (mx) {
+            mLo |= 1u << r;                       // score >= minTh by construction
+            if (v >= P.iniTh) mHi |= 1u << r;
+        }
+    }
+    if (mHi) atomicAdd(&s_cntHi, __popc(mHi));
+    __syncthreads();
+    const unsigned mk = s_cntHi > 0 ? mHi : mLo;    // fallback to minTh only if the cell is empty at iniTh (:843-859)
+    // block scan of per-thread counts (FAST_NT == 256 -> one tile)
+    __shared__ int s_cnt[FAST_NT];
+    s_cnt[tid] = __popc(mk);
+    __syncthreads();
+    const int total = block_excl_scan(s_cnt, FAST_NT, s_warp);
+    uint32_t* out = P.cellList + (size_t)f * P.cellListStride + cd.listOff;
+    int o = s_cnt[tid];
+    for (unsigned m = mk; m; m &= m - 1) {
+        const int r = __ffs(m) - 1;
+        const int i = i0 + r;
+        const int y = i / iw, x = i - y * iw;
+        out[o++] = pack_cand(x + 3 + cd.offX, y + 3 + cd.offY, score[(y + 1) * sp + (x + 1)]);
+    }
+    if (tid == 0) *outCount = total;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: quadtree distribution + orientation.  One CTA per (level, frame).
+// Reference: ORBextractor::DistributeOctTree src/ORBextractor.cc:555-779,
+// ExtractorNode::DivideNode :480-536, compareNodes :538-553, IC_Angle :76-103.
+//
+// The std::list / push_front choreography of the reference is restated as a rebuild of the
+// whole node list per pass ("split a set of nodes in processing order, children blocks go to the
+// front in reverse processing order, unsplit nodes keep their relative order"); the only
+// sequential piece is the libstdc++ std::sort emulation that decides ties in the final phase.
+// ------------------------------------------------------------------------------------------
+constexpr int QT_NT = 256;
+
+struct QtNode { int16_t ulx, uly, brx, bry; };
+struct QtSort { int size; int ulx; int node; };
+
+struct QtShared {
+    QtNode* bnd[2];
+    int* cnt[2];
+    int* proc;        // per list node: processing index or -1
+    int* procNode;    // per processing index: list node
+    int* childCnt;    // 4 per processing index
+    int* childPos;    // 4 per processing index: new list position (or -1)
+    int* keepPos;     // per list node: new position when unsplit
+    int* scanA;       // scratch, 4*maxNodes
+    QtSort* v;        // expandable children in creation order
+    unsigned long long* best;
+};
+
+__device__ __forceinline__ int qt_child(const QtNode& n, int px, int py, int& midx, int& midy) {
+    const int halfX = (int)ceilf((float)(n.brx - n.ulx) / 2);
+    const int halfY = (int)ceilf((float)(n.bry - n.uly) / 2);
+    midx = n.ulx + halfX; midy = n.uly + halfY;
+    return (px < midx ? 0 : 1) + (py < midy ? 0 : 2);
+}
+
+__global__ void __launch_bounds__(QT_NT) quadtree_orient_kernel(ExtractParams P) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const LevelGeom& G = P.lv[l];
+    const int MN = P.maxNodes;
+    __shared__ int s_warp[33];
+    __shared__ int s_P;
+
+    // carve shared memory
+    QtShared S;
+    uint8_t* p = smem_raw;
+    S.bnd[0] = (QtNode*)p; p += sizeof(QtNode) * MN;
+    S.bnd[1] = (QtNode*)p; p += sizeof(QtNode) * MN;
+    S.cnt[0] = (int*)p; p += 4 * MN;
+    S.cnt[1] = (int*)p; p += 4 * MN;
+    S.proc = (int*)p; p += 4 * MN;
+    S.procNode = (int*)p; p += 4 * MN;
+    S.keepPos = (int*)p; p += 4 * MN;
+    S.childCnt = (int*)p; p += 16 * MN;
+    S.childPos = (int*)p; p += 16 * MN;
+    S.scanA = (int*)p; p += 16 * MN;
+    S.v = (QtSort*)p; p += sizeof(QtSort) * MN;
+    p = (uint8_t*)(((uintptr_t)p + 7) & ~(uintptr_t)7);
+    S.best = (unsigned long long*)p; p += 8 * MN;
+    int* cellOff = (int*)p;   // maxCellsPerLevel + 1
+
+    uint32_t* cand = P.cand + (size_t)f * P.candStride + G.candOff;
+    uint16_t* nodeOf = P.nodeOf + (size_t)f * P.candStride + G.candOff;
+    SelKp* sel = P.sel + (size_t)f * P.selStride + G.selOff;
+
+    // ---- gather the per-cell lists into candidate order (cell row-major, then y, x) ----
+    const int* cellCount = P.cellCount + (size_t)f * P.cellCountStride + G.cellBase;
+    for (int c = tid; c < G.nCells; c += QT_NT) cellOff[c] = cellCount[c];
+    __syncthreads();
+    const int n = block_excl_scan(cellOff, G.nCells, s_warp);
+    {
+        const uint32_t* lists = P.cellList + (size_t)f * P.cellListStride;
+        const int wid = tid >> 5, lane = tid & 31;
+        for (int c = wid; c < G.nCells; c += QT_NT / 32) {
+            const int cnt = cellCount[c], o = cellOff[c];
+            const uint32_t* src = lists + P.cells[G.cellBase + c].listOff;
+            for (int k = lane; k < cnt; k += 32) cand[o + k] = src[k];
+        }
+    }
+    __syncthreads();
+
+    int cur = 0;
+    // ---- root nodes (:559-598) ----
+    for (int i = tid; i < G.nIni; i += QT_NT) {
+        QtNode nd;
+        nd.ulx = (int16_t)(int)fmul(G.hX, (float)i); nd.uly = 0;
+        nd.brx = (int16_t)(int)fmul(G.hX, (float)(i + 1)); nd.bry = (int16_t)(G.maxBY - G.minBY);
+        S.bnd[0][i] = nd; S.cnt[0][i] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += QT_NT) {
+        const int r = (int)fdiv((float)cand_x(cand[i]), G.hX);
+        nodeOf[i] = (uint16_t)r;
+        atomicAdd(&S.cnt[0][r], 1);
+    }
+    __syncthreads();
+    // erase empty roots, keep order
+    for (int i = tid; i < G.nIni; i += QT_NT) S.scanA[i] = S.cnt[0][i] > 0;
+    __syncthreads();
+    int m = block_excl_scan(S.scanA, G.nIni, s_warp);
+    for (int i = tid; i < G.nIni; i += QT_NT) {
+        S.keepPos[i] = S.cnt[0][i] > 0 ? S.scanA[i] : -1;
+        if (S.cnt[0][i] > 0) { S.bnd[1][S.scanA[i]] = S.bnd[0][i]; S.cnt[1][S.scanA[i]] = S.cnt[0][i]; }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += QT_NT) nodeOf[i] = (uint16_t)S.keepPos[nodeOf[i]];
+    cur = 1;
+    __syncthreads();
+
+    const int N = G.nDesired;
+    bool finish = (n == 0);
+    bool careful = false;
+    int q = 0;   // size of S.v
+    while (!finish) {
+        const int prevSize = m;
+        QtNode* bndC = S.bnd[cur]; int* cntC = S.cnt[cur];
+        QtNode* bndN = S.bnd[cur ^ 1]; int* cntN = S.cnt[cur ^ 1];
+        // --- A. processing order of the nodes to split ---
+        int P0;
+        if (!careful) {
+            for (int s = tid; s < m; s += QT_NT) S.scanA[s] = cntC[s] > 1;
+            __syncthreads();
+            P0 = block_excl_scan(S.scanA, m, s_warp);
+            for (int s = tid; s < m; s += QT_NT) {
+                if (cntC[s] > 1) { S.proc[s] = S.scanA[s]; S.procNode[S.scanA[s]] = s; }
+                else S.proc[s] = -1;
+            }
+        } else {
+            if (tid == 0) {   // std::sort(vPrev.begin(), vPrev.end(), compareNodes) (:705)
+                libstdcxx_sort(S.v, q, [](const QtSort& a, const QtSort& b) {
+                    return a.size < b.size || (a.size == b.size && a.ulx < b.ulx);
+                });
+            }
+            for (int s = tid; s < m; s += QT_NT) S.proc[s] = -1;
+            __syncthreads();
+            P0 = q;
+            for (int j = tid; j < q; j += QT_NT) {   // processed from the back (:706)
+                const int pi = q - 1 - j;
+                S.proc[S.v[j].node] = pi; S.procNode[pi] = S.v[j].node;
+            }
+        }
+        for (int i = tid; i < 4 * P0; i += QT_NT) S.childCnt[i] = 0;
+        __syncthreads();
+        // --- C. distribute the keys of every split node to its four children (:512-526) ---
+        for (int i = tid; i < n; i += QT_NT) {
+            const int s = nodeOf[i], pi = S.proc[s];
+            if (pi >= 0) {
+                int mx, my;
+                const uint32_t c = cand[i];
+                const int ch = qt_child(bndC[s], cand_x(c), cand_y(c), mx, my);
+                atomicAdd(&S.childCnt[4 * pi + ch], 1);
+            }
+        }
+        __syncthreads();
+        // --- D. in the careful phase stop as soon as the list reaches N nodes (:755-756) ---
+        int Pn = P0;
+        for (int pi = tid; pi < P0; pi += QT_NT) {
+            const int* cc = S.childCnt + 4 * pi;
+            S.scanA[pi] = (cc[0] > 0) + (cc[1] > 0) + (cc[2] > 0) + (cc[3] > 0);
+        }
+        __syncthreads();
+        // exclusive scan of k -> scanA; keep k in childPos scratch? recompute instead
+        const int totalK = block_excl_scan(S.scanA, P0, s_warp);
+        if (careful) {
+            if (tid == 0) s_P = P0;
+            __syncthreads();
+            for (int pi = tid; pi < P0; pi += QT_NT) {
+                const int* cc = S.childCnt + 4 * pi;
+                const int k = (cc[0] > 0) + (cc[1] > 0) + (cc[2] > 0) + (cc[3] > 0);
+                const int sizeAfter = prevSize + (S.scanA[pi] + k) - (pi + 1);
+                if (sizeAfter >= N) atomicMin(&s_P, pi + 1);
+            }
+            __syncthreads();
+            Pn = s_P;
+            for (int pi = Pn + tid; pi < P0; pi += QT_NT) S.proc[S.procNode[pi]] = -1;
+            __syncthreads();
+        }
+        // children of the first Pn processed nodes: inclusive prefix at Pn-1
+        int totalChildren;
+        if (Pn == P0) totalChildren = totalK;
+        else totalChildren = S.scanA[Pn];   // exclusive prefix at Pn == sum over pi < Pn
+        // --- E/G. positions of the children: blocks in reverse processing order, n4..n1 inside ---
+        for (int pi = tid; pi < Pn; pi += QT_NT) {
+            const int* cc = S.childCnt + 4 * pi;
+            const int k = (cc[0] > 0) + (cc[1] > 0) + (cc[2] > 0) + (cc[3] > 0);
+            const int blockStart = totalChildren - (S.scanA[pi] + k);
+            int after = 0;
+            const QtNode pn = bndC[S.procNode[pi]];
+            int mx, my;
+            qt_child(pn, 0, 0, mx, my);
+            for (int ch = 3; ch >= 0; --ch) {
+                if (cc[ch] > 0) {
+                    const int pos = blockStart + after;
+                    ++after;
+                    S.childPos[4 * pi + ch] = pos;
+                    QtNode c;
+                    c.ulx = (ch & 1) ? (int16_t)mx : pn.ulx; c.brx = (ch & 1) ? pn.brx : (int16_t)mx;
+                    c.uly = (ch & 2) ? (int16_t)my : pn.uly; c.bry = (ch & 2) ? pn.bry : (int16_t)my;
+                    bndN[pos] = c; cntN[pos] = cc[ch];
+                } else S.childPos[4 * pi + ch] = -1;
+            }
+        }
+        // --- F. unsplit nodes keep their order behind the new blocks ---
+        for (int s = tid; s < m; s += QT_NT) S.keepPos[s] = S.proc[s] < 0;
+        __syncthreads();
+        const int nKeep = block_excl_scan(S.keepPos, m, s_warp);
+        for (int s = tid; s < m; s += QT_NT) {
+            if (S.proc[s] < 0) {
+                const int pos = totalChildren + S.keepPos[s];
+                S.keepPos[s] = pos;
+                bndN[pos] = bndC[s]; cntN[pos] = cntC[s];
+            }
+        }
+        // --- new expandable list in creation order (processing order, n1..n4) (:634-668) ---
+        for (int i = tid; i < 4 * Pn; i += QT_NT) S.scanA[i] = S.childCnt[i] > 1;
+        __syncthreads();
+        const int qNew = block_excl_scan(S.scanA, 4 * Pn, s_warp);
+        for (int i = tid; i < 4 * Pn; i += QT_NT) {
+            if (S.childCnt[i] > 1) {
+                QtSort e; e.size = S.childCnt[i]; e.node = S.childPos[i]; e.ulx = bndN[e.node].ulx;
+                S.v[S.scanA[i]] = e;
+            }
+        }
+        // --- H. re-home the keys ---
+        for (int i = tid; i < n; i += QT_NT) {
+            const int s = nodeOf[i], pi = S.proc[s];
+            if (pi >= 0) {
+                int mx, my;
+                const uint32_t c = cand[i];
+                const int ch = qt_child(bndC[s], cand_x(c), cand_y(c), mx, my);
+                nodeOf[i] = (uint16_t)S.childPos[4 * pi + ch];
+            } else nodeOf[i] = (uint16_t)S.keepPos[s];
+        }
+        __syncthreads();
+        m = totalChildren + nKeep;
+        q = qNew;
+        cur ^= 1;
+        // --- termination (:684-764) ---
+        if (m >= N || m == prevSize) finish = true;
+        else if (!careful && m + 3 * q > N) careful = true;
+    }
+
+    // ---- best response per node, first maximum in candidate order (:767-783) ----
+    for (int s = tid; s < m; s += QT_NT) S.best[s] = 0ull;
+    __syncthreads();
+    for (int i = tid; i < n; i += QT_NT) {
+        const unsigned long long key = ((unsigned long long)cand_s(cand[i]) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)i);
+        atomicMax(&S.best[nodeOf[i]], key);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        P.selCount[f * kMaxLevels + l] = m;
+        if (m > G.selCap) atomicOr(&P.status[f], 1);
+    }
+    const int mOut = min(m, G.selCap);
+    // ---- orientation: one warp per keypoint, lane = row of the radius-15 disc (:76-103) ----
+    int pitch;
+    const uint8_t* img = plane_ptr(P, f, l, pitch);
+    const int wid = tid >> 5, lane = tid & 31;
+    for (int s = wid; s < mOut; s += QT_NT / 32) {
+        const unsigned idx = 0xFFFFFFFFu - (unsigned)(S.best[s] & 0xFFFFFFFFull);
+        const uint32_t c = cand[idx];
+        const int x = cand_x(c) + G.minBX, y = cand_y(c) + G.minBY;
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+            const int v = lane - HALF_PATCH;
+            const int d = c_umax[v < 0 ? -v : v];
+            const uint8_t* row = img + (size_t)(y + v) * pitch + x;
+            int rs = 0;
+            for (int u = -d; u <= d; ++u) { const int px = row[u]; m10 += u * px; rs += px; }
+            m01 = v * rs;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        if (lane == 0) {
+            SelKp k; k.x = (int16_t)x; k.y = (int16_t)y; k.response = cand_s(c);
+            k.angle = fast_atan2_deg((float)m01, (float)m10);
+            sel[s] = k;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: 7x7 sigma=2 Gaussian blur of every level (cv::GaussianBlur, fixed-point kernel
+// [18,34,48,56,48,34,18]/256, BORDER_REFLECT_101; reference call site src/ORBextractor.cc:1133,
+// SURVEY.md 9E).  Tile 64x32 per CTA, all levels in one launch.
+// ------------------------------------------------------------------------------------------
+constexpr int BL_TW = 64, BL_TH = 32, BL_NT = 256;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(BL_NT) blur_kernel(ExtractParams P) {
+    __shared__ uint8_t tile[(BL_TH + 6)][BL_TW + 8];
+    __shared__ uint16_t hb[(BL_TH + 6)][BL_TW];
+    const int f = blockIdx.y;
+    int l = 0;
+    while (l + 1 < P.nlevels && (int)blockIdx.x >= P.lv[l + 1].blurTileBase) ++l;
+    const LevelGeom& G = P.lv[l];
+    const int t = blockIdx.x - G.blurTileBase;
+    const int ty = t / G.blurTilesX, tx = t - ty * G.blurTilesX;
+    const int x0 = tx * BL_TW, y0 = ty * BL_TH;
+    int pitch;
+    const uint8_t* img = plane_ptr(P, f, l, pitch);
+    for (int i = threadIdx.x; i < (BL_TH + 6) * (BL_TW + 6); i += BL_NT) {
+        const int yy = i / (BL_TW + 6), xx = i - yy * (BL_TW + 6);
+        const int sx = reflect101(min(x0 + xx - 3, G.w + 2), G.w), sy = reflect101(min(y0 + yy - 3, G.h + 2), G.h);
+        tile[yy][xx] = img[(size_t)sy * pitch + sx];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (BL_TH + 6) * BL_TW; i += BL_NT) {
+        const int yy = i / BL_TW, xx = i - yy * BL_TW;
+        const uint8_t* r = &tile[yy][xx];
+        hb[yy][xx] = (uint16_t)(18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3]);
+    }
+    __syncthreads();
+    int bpitch;
+    uint8_t* out = const_cast<uint8_t*>(blur_ptr(P, f, l, bpitch));
+    for (int i = threadIdx.x; i < BL_TH * BL_TW; i += BL_NT) {
+        const int yy = i / BL_TW, xx = i - yy * BL_TW;
+        const int x = x0 + xx, y = y0 + yy;
+        if (x < G.w && y < G.h) {
+            const uint32_t v = 18u * (hb[yy][xx] + hb[yy + 6][xx]) + 34u * (hb[yy + 1][xx] + hb[yy + 5][xx]) +
+                               48u * (hb[yy + 2][xx] + hb[yy + 4][xx]) + 56u * hb[yy + 3][xx];
+            out[(size_t)y * bpitch + x] = (uint8_t)((v + 32768u) >> 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: output assembly.  One CTA per frame: scale coordinates, split lapping / non-lapping
+// keypoints (front / back fill), write the cv::KeyPoint-layout slab and the row map.
+// Reference: ORBextractor::operator() src/ORBextractor.cc:1120-1164.
+// ------------------------------------------------------------------------------------------
+constexpr int AS_NT = 256;
+
+__global__ void __launch_bounds__(AS_NT) assemble_kernel(ExtractParams P) {
+    extern __shared__ int s_flags[];   // selStride ints
+    __shared__ int s_warp[33];
+    __shared__ int s_lvOff[kMaxLevels + 1];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        int o = 0;
+        for (int l = 0; l < P.nlevels; ++l) { s_lvOff[l] = o; o += min(P.selCount[f * kMaxLevels + l], P.lv[l].selCap); }
+        s_lvOff[P.nlevels] = o;
+    }
+    __syncthreads();
+    const int K = s_lvOff[P.nlevels];
+    const SelKp* sel = P.sel + (size_t)f * P.selStride;
+    // flag = keypoint lies in the lapping area (scaled x within [lap0, lap1])
+    for (int e = tid; e < K; e += AS_NT) {
+        int l = 0;
+        while (e >= s_lvOff[l + 1]) ++l;
+        const SelKp k = sel[P.lv[l].selOff + (e - s_lvOff[l])];
+        float x = (float)k.x;
+        if (l != 0) x = fmul(x, P.lv[l].scale);
+        s_flags[e] = (x >= (float)P.lap0 && x <= (float)P.lap1) ? 1 : 0;
+    }
+    __syncthreads();
+    // exclusive scan -> number of lapping keypoints before e
+    int* s_scan = s_flags + P.selStride;
+    for (int e = tid; e < K; e += AS_NT) s_scan[e] = s_flags[e];
+    __syncthreads();
+    const int nLap = block_excl_scan(s_scan, K, s_warp);
+    int* dstIndex = P.dstIndex + (size_t)f * P.selStride;
+    OrbKeyPoint* out = reinterpret_cast<OrbKeyPoint*>(P.outKp) + (size_t)f * P.outCap;
+    const bool fits = K <= P.outCap;
+    for (int e = tid; e < K; e += AS_NT) {
+        int l = 0;
+        while (e >= s_lvOff[l + 1]) ++l;
+        const int src = P.lv[l].selOff + (e - s_lvOff[l]);
+        const SelKp k = sel[src];
+        const int at = s_flags[e] ? (K - 1 - s_scan[e]) : (e - s_scan[e]);
+        dstIndex[src] = fits ? at : -1;
+        if (fits) {
+            OrbKeyPoint o;
+            o.x = (float)k.x; o.y = (float)k.y;
+            if (l != 0) { o.x = fmul(o.x, P.lv[l].scale); o.y = fmul(o.y, P.lv[l].scale); }
+            o.size = P.lv[l].sizeScaled; o.angle = k.angle; o.response = (float)k.response;
+            o.octave = l; o.class_id = -1;
+            out[at] = o;
+        }
+    }
+    if (tid == 0) {
+        P.outN[f] = K;
+        P.outMono[f] = K - nLap;
+        if (!fits) atomicOr(&P.status[f], 2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: rotated BRIEF.  One warp per keypoint, lane = descriptor byte.
+// Reference: computeOrbDescriptor src/ORBextractor.cc:107-146 on the blurred plane.
+// ------------------------------------------------------------------------------------------
+constexpr int DS_NT = 256;
+
+__global__ void __launch_bounds__(DS_NT) describe_kernel(ExtractParams P) {
+    __shared__ char4 s_pat[8][32];   // [pair-in-byte][byte] -> conflict-free across lanes
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 256; i += DS_NT) {
+        const int byte = i >> 3, k = i & 7;
+        s_pat[k][byte] = make_char4(c_pattern[4 * i], c_pattern[4 * i + 1], c_pattern[4 * i + 2], c_pattern[4 * i + 3]);
+    }
+    __syncthreads();
+    const int slot = blockIdx.x * (DS_NT / 32) + (tid >> 5);   // index into the frame's sel array
+    if (slot >= (int)P.selStride) return;
+    int l = 0;
+    while (l + 1 < P.nlevels && slot >= P.lv[l + 1].selOff) ++l;
+    const int idx = slot - P.lv[l].selOff;
+    if (idx >= min(P.selCount[f * kMaxLevels + l], P.lv[l].selCap)) return;
+    const int at = P.dstIndex[(size_t)f * P.selStride + slot];
+    if (at < 0) return;
+    const SelKp k = P.sel[(size_t)f * P.selStride + slot];
+    const float factorPI = 0.01745329238474369049072265625f;   // (float)(CV_PI/180.f), :106
+    float a, b;
+    sincosf_glibc(fmul(k.angle, factorPI), &b, &a);
+    int pitch;
+    const uint8_t* img = blur_ptr(P, f, l, pitch);
+    const uint8_t* c = img + (size_t)k.y * pitch + k.x;
+    int val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const char4 q = s_pat[j][lane];
+        const float x0 = (float)q.x, y0 = (float)q.y, x1 = (float)q.z, y1 = (float)q.w;
+        const int r0 = round_half_even(ffma(x0, b, fmul(y0, a)));
+        const int c0 = round_half_even(ffma(x0, a, -fmul(y0, b)));
+        const int r1 = round_half_even(ffma(x1, b, fmul(y1, a)));
+        const int c1 = round_half_even(ffma(x1, a, -fmul(y1, b)));
+        const int t0 = c[r0 * pitch + c0], t1 = c[r1 * pitch + c1];
+        val |= (t0 < t1) << j;
+    }
+    P.outDesc[((size_t)f * P.outCap + at) * 32 + lane] = (uint8_t)val;
+}
+
+}  // namespace orbx
