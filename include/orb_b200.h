@@ -102,6 +102,91 @@ int orbx_copy_candidates(orbx_handle* h, int frame, int level, int* xys, int cap
 /* Number of kernels launched by the last extract call (for bench.py's gpu_launches). */
 int orbx_last_launch_count(const orbx_handle* h);
 
+/* ------------------------------------------------------------------------------------------
+ * ORBmatcher (reference include/ORBmatcher.h:36-103): the per-frame projection matchers, the Hamming
+ * primitive and the brute-force kNN used by the reference.  All inputs are flat arrays: the host shim
+ * flattens Frame / MapPoint fields exactly as listed in SURVEY.md 8a' ("Matcher in").
+ * ------------------------------------------------------------------------------------------ */
+typedef struct orbm_handle orbm_handle;
+
+/* Scratch for up to max_batch frames of max_keypoints keypoints matched against max_mappoints map points. */
+int orbm_create(orbm_handle** out, int max_batch, int max_keypoints, int max_mappoints, int device);
+void orbm_destroy(orbm_handle* h);
+
+/* Current frame as seen by the matchers (Frame::mvKeysUn, mDescriptors, image bounds mnMinX.., mvScaleFactors;
+ * the 64x48 grid of Frame::AssignFeaturesToGrid, src/Frame.cc:385-416, is rebuilt on the device). */
+typedef struct OrbmFrame {
+    int K;                        /* number of keypoints */
+    const OrbKeyPoint* keypoints; /* K */
+    const uint8_t* descriptors;   /* K x 32 */
+    float minX, minY, maxX, maxY; /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+    const float* scaleFactors;    /* mvScaleFactors, nlevels entries */
+    int nlevels;
+} OrbmFrame;
+
+/* Map points for ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)
+ * (src/ORBmatcher.cc:43-213, mono branch): the tracking fields Frame::isInFrustum wrote (src/Frame.cc:563-571). */
+typedef struct OrbmLocalPoints {
+    int M;
+    const uint8_t* inView;     /* mbTrackInView */
+    const uint8_t* bad;        /* isBad() */
+    const float* depth;        /* mTrackDepth */
+    const float* projX;        /* mTrackProjX */
+    const float* projY;        /* mTrackProjY */
+    const int32_t* level;      /* mnTrackScaleLevel */
+    const float* viewCos;      /* mTrackViewCos */
+    const uint8_t* hasObs;     /* Observations() > 0 */
+    const uint8_t* descriptors;/* GetDescriptor(), M x 32 */
+} OrbmLocalPoints;
+
+/* Last-frame map points for ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono=true)
+ * (src/ORBmatcher.cc:1676-1887): index i runs over LastFrame.N. */
+typedef struct OrbmLastFrame {
+    int M;
+    const uint8_t* valid;      /* LastFrame.mvpMapPoints[i] != NULL && !LastFrame.mvbOutlier[i] */
+    const float* xyz;          /* GetWorldPos(), M x 3 */
+    const int32_t* octave;     /* LastFrame.mvKeys[i].octave */
+    const float* angle;        /* LastFrame.mvKeysUn[i].angle */
+    const uint8_t* hasObs;     /* Observations() > 0 */
+    const uint8_t* descriptors;/* GetDescriptor(), M x 32 */
+} OrbmLastFrame;
+
+/* Both searches return the reference's `int nmatches` in *nmatches and update, per keypoint of the current frame,
+ * match[K] (index of the assigned map point in the input arrays, -1 = none; the host re-attaches MapPoint*) and
+ * claimed[K] (assigned point has Observations()>0: such keypoints are skipped by later candidates,
+ * src/ORBmatcher.cc:84-86,1747-1749).  Both arrays are in/out (the reference reads Frame::mvpMapPoints). Host pointers. */
+int orbm_search_local_map(orbm_handle* h, const OrbmFrame* frame, const OrbmLocalPoints* pts, float th, float nnratio,
+                          int bFarPoints, float thFarPoints, int32_t* match, uint8_t* claimed, int* nmatches);
+/* Tcw: unit quaternion (w,x,y,z) + translation (CurrentFrame.GetPose()); cam: fx, fy, cx, cy (Pinhole). */
+int orbm_search_last_frame(orbm_handle* h, const OrbmFrame* frame, const OrbmLastFrame* last, const float* Tcw7,
+                           const float* cam4, float th, int checkOrientation, int32_t* match, uint8_t* claimed,
+                           int* nmatches);
+
+/* Device-resident, batched last-frame search: `batch` independent streams.  All pointers are device pointers into
+ * fixed-capacity slabs (stride = capacity per stream): current frame slabs as written by orbx_extract_batch_device
+ * (kps[batch][kcap], desc[batch][kcap][32], nK[batch]); last-frame slabs [batch][mcap]; Tcw [batch][7].
+ * match/claimed [batch][kcap] must be initialised by the caller (e.g. -1 / 0); nmatches [batch].  Enqueues on `stream`. */
+typedef struct OrbmBatchDevice {
+    int batch, kcap, mcap, nlevels;
+    const OrbKeyPoint* kps; const uint8_t* desc; const int32_t* nK;
+    float minX, minY, maxX, maxY;
+    const float* scaleFactors;          /* device, nlevels */
+    const int32_t* nM;                  /* [batch] */
+    const uint8_t* valid; const float* xyz; const int32_t* octave; const float* angle; const uint8_t* hasObs;
+    const uint8_t* mpDesc;
+    const float* Tcw7;                  /* [batch][7] */
+    float cam[4];
+} OrbmBatchDevice;
+int orbm_search_last_frame_batch_device(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOrientation,
+                                        int32_t* d_match, uint8_t* d_claimed, int32_t* d_nmatches, void* stream);
+
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) as used at src/Frame.cc:1144: idx/dist are Q x 2,
+ * ordered by (distance, lower train index); missing neighbours are -1.  Host pointers. */
+int orbm_bf_knn2(orbm_handle* h, const uint8_t* query, int Q, const uint8_t* train, int T, int32_t* idx, int32_t* dist);
+/* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2058-2074) for n descriptor pairs a[i], b[i].  Host pointers. */
+int orbm_descriptor_distance(orbm_handle* h, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
+int orbm_last_launch_count(const orbm_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,246 @@
+// TEST INFRASTRUCTURE ONLY (see oracle_common.h).  CPU restatement of the per-frame matchers:
+//   ORBmatcher::DescriptorDistance                       reference src/ORBmatcher.cc:2058-2074
+//   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFar, thFar)   :43-213 (mono branch)
+//   ORBmatcher::RadiusByViewingCos                       :215-221
+//   ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)                     :1676-1887 (mono branch)
+//   ORBmatcher::ComputeThreeMaxima                       :2012-2053
+//   Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea   src/Frame.cc:385-416,725-735,657-723
+//   Pinhole::project(Vector3f)                           src/CameraModels/Pinhole.cpp:43-49
+//   Sophus SO3f * point, SE3f * point                    Thirdparty/Sophus/sophus/so3.hpp:358-367, se3.hpp:321-324
+//   cv::BFMatcher(NORM_HAMMING).knnMatch(k=2)            use at src/Frame.cc:1144 (pinned vs cv2 in tests)
+//
+// Floating point contract: every float operation below rounds individually, in the written order
+// (-ffp-contract=off).  The reference evaluates the pose transform through Eigen expression templates
+// whose contraction under -O3 -march=native cannot be reproduced without Eigen; that last-ulp choice is
+// "parity unpinned" (DESIGN.md).  Everything after the projection is integer / comparison logic.
+#include "oracle_common.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace orbo {
+
+static const int TH_HIGH = 100;       // src/ORBmatcher.cc:35
+static const int HISTO_LENGTH = 30;   // :37
+static const int GRID_COLS = 64, GRID_ROWS = 48;   // include/Frame.h:44-45
+
+static int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    const uint32_t* pa = (const uint32_t*)a;
+    const uint32_t* pb = (const uint32_t*)b;
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t v = pa[i] ^ pb[i];
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+struct FrameView {
+    int K;
+    const KeyPoint* kps;     // mvKeysUn (== mvKeys with zero distortion)
+    const uint8_t* desc;     // K x 32
+    float minX, minY, maxX, maxY, gridWInv, gridHInv;
+    const float* scaleFactors;
+    std::vector<int> grid[GRID_COLS][GRID_ROWS];
+
+    void build_grid() {   // Frame::AssignFeaturesToGrid
+        for (int i = 0; i < K; ++i) {
+            int px = (int)std::round((kps[i].x - minX) * gridWInv);
+            int py = (int)std::round((kps[i].y - minY) * gridHInv);
+            if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+            grid[px][py].push_back(i);
+        }
+    }
+    // Frame::GetFeaturesInArea (mono)
+    void features_in_area(float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) const {
+        out.clear();
+        const float factorX = r, factorY = r;
+        const int nMinCellX = std::max(0, (int)std::floor((x - minX - factorX) * gridWInv));
+        if (nMinCellX >= GRID_COLS) return;
+        const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((x - minX + factorX) * gridWInv));
+        if (nMaxCellX < 0) return;
+        const int nMinCellY = std::max(0, (int)std::floor((y - minY - factorY) * gridHInv));
+        if (nMinCellY >= GRID_ROWS) return;
+        const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((y - minY + factorY) * gridHInv));
+        if (nMaxCellY < 0) return;
+        const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+            for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+                for (int idx : grid[ix][iy]) {
+                    const KeyPoint& kp = kps[idx];
+                    if (bCheckLevels) {
+                        if (kp.octave < minLevel) continue;
+                        if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                    }
+                    const float dx = kp.x - x, dy = kp.y - y;
+                    if (std::fabs(dx) < factorX && std::fabs(dy) < factorY) out.push_back(idx);
+                }
+    }
+};
+
+}  // namespace orbo
+
+using namespace orbo;
+
+extern "C" {
+
+int orbo_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+
+// Local-map matcher.  Per map point: inView (mbTrackInView), bad, depth (mTrackDepth), projX/projY,
+// level (mnTrackScaleLevel), viewCos, hasObs (Observations()>0), descriptor.
+// curMatch[K] in/out: map-point index assigned to each keypoint (-1 none); curClaimed[K] in/out: the assigned
+// map point has Observations()>0 (such keypoints are skipped, :84-86).
+int orbo_search_local_map(int K, const KeyPoint* kps, const uint8_t* desc, const float* bounds /*minX,minY,maxX,maxY*/,
+                          const float* scaleFactors, int M, const uint8_t* inView, const uint8_t* bad, const float* depth,
+                          const float* projX, const float* projY, const int* level, const float* viewCos, const uint8_t* hasObs,
+                          const uint8_t* mpDesc, float th, float nnratio, int bFarPoints, float thFarPoints,
+                          int* curMatch, uint8_t* curClaimed) {
+    FrameView F;
+    F.K = K; F.kps = kps; F.desc = desc;
+    F.minX = bounds[0]; F.minY = bounds[1]; F.maxX = bounds[2]; F.maxY = bounds[3];
+    F.gridWInv = (float)GRID_COLS / (F.maxX - F.minX);
+    F.gridHInv = (float)GRID_ROWS / (F.maxY - F.minY);
+    F.scaleFactors = scaleFactors;
+    F.build_grid();
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    std::vector<int> vIndices;
+    for (int i = 0; i < M; ++i) {
+        if (!inView[i]) continue;
+        if (bFarPoints && depth[i] > thFarPoints) continue;
+        if (bad[i]) continue;
+        const int lvl = level[i];
+        float r = viewCos[i] > 0.998 ? 2.5f : 4.0f;   // RadiusByViewingCos (float vs double literal compare)
+        if (bFactor) r *= th;
+        F.features_in_area(projX[i], projY[i], r * scaleFactors[lvl], lvl - 1, lvl, vIndices);
+        if (vIndices.empty()) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (curMatch[idx] >= 0 && curClaimed[idx]) continue;
+            const int dist = descriptor_distance(mpDesc + (size_t)i * 32, desc + (size_t)idx * 32);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = kps[idx].octave;
+                bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = kps[idx].octave;
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            curMatch[bestIdx] = i;
+            curClaimed[bestIdx] = hasObs[i];
+            ++nmatches;
+        }
+    }
+    return nmatches;
+}
+
+// Last-frame matcher (mono).  Tcw = (qw,qx,qy,qz,tx,ty,tz), cam = (fx,fy,cx,cy).
+// Per last-frame index i: valid (pMP && !outlier), world position, octave, angle, hasObs, descriptor of the map point.
+int orbo_search_last_frame(int K, const KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors,
+                           const float* Tcw, const float* cam, int M, const uint8_t* valid, const float* xyz,
+                           const int* lastOctave, const float* lastAngle, const uint8_t* hasObs, const uint8_t* mpDesc,
+                           float th, int checkOrientation, int* curMatch, uint8_t* curClaimed) {
+    FrameView F;
+    F.K = K; F.kps = kps; F.desc = desc;
+    F.minX = bounds[0]; F.minY = bounds[1]; F.maxX = bounds[2]; F.maxY = bounds[3];
+    F.gridWInv = (float)GRID_COLS / (F.maxX - F.minX);
+    F.gridHInv = (float)GRID_ROWS / (F.maxY - F.minY);
+    F.scaleFactors = scaleFactors;
+    F.build_grid();
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    const float qw = Tcw[0], qx = Tcw[1], qy = Tcw[2], qz = Tcw[3];
+    std::vector<int> vIndices;
+    for (int i = 0; i < M; ++i) {
+        if (!valid[i]) continue;
+        const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+        // SO3 * p: uv = q.vec x p; uv += uv; p + w*uv + q.vec x uv   (so3.hpp:358-367)
+        float ux = qy * pz - qz * py, uy = qz * px - qx * pz, uz = qx * py - qy * px;
+        ux += ux; uy += uy; uz += uz;
+        const float cx_ = qy * uz - qz * uy, cy_ = qz * ux - qx * uz, cz_ = qx * uy - qy * ux;
+        const float xc = (px + qw * ux) + cx_ + Tcw[4];
+        const float yc = (py + qw * uy) + cy_ + Tcw[5];
+        const float zc = (pz + qw * uz) + cz_ + Tcw[6];
+        const float invzc = (float)(1.0 / zc);
+        if (invzc < 0) continue;
+        const float u = cam[0] * xc / zc + cam[2];
+        const float v = cam[1] * yc / zc + cam[3];
+        if (u < F.minX || u > F.maxX) continue;
+        if (v < F.minY || v > F.maxY) continue;
+        const int oct = lastOctave[i];
+        const float radius = th * scaleFactors[oct];
+        F.features_in_area(u, v, radius, oct - 1, oct + 1, vIndices);
+        if (vIndices.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices) {
+            if (curMatch[i2] >= 0 && curClaimed[i2]) continue;
+            const int dist = descriptor_distance(mpDesc + (size_t)i * 32, desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            curMatch[bestIdx2] = i;
+            curClaimed[bestIdx2] = hasObs[i];
+            ++nmatches;
+            if (checkOrientation) {
+                float rot = lastAngle[i] - kps[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (checkOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;   // ComputeThreeMaxima
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx : rotHist[i]) { curMatch[idx] = -1; curClaimed[idx] = 0; --nmatches; }
+    }
+    return nmatches;
+}
+
+// cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2): exact top-2 by (distance, lower train index).
+void orbo_bf_knn2(const uint8_t* q, int Q, const uint8_t* t, int T, int* idx, int* dist) {
+    for (int i = 0; i < Q; ++i) {
+        int b1 = 1 << 30, i1 = -1, b2 = 1 << 30, i2 = -1;
+        for (int j = 0; j < T; ++j) {
+            const int d = descriptor_distance(q + (size_t)i * 32, t + (size_t)j * 32);
+            if (d < b1) { b2 = b1; i2 = i1; b1 = d; i1 = j; }
+            else if (d < b2) { b2 = d; i2 = j; }
+        }
+        idx[2 * i] = i1; idx[2 * i + 1] = i2;
+        dist[2 * i] = i1 >= 0 ? b1 : -1; dist[2 * i + 1] = i2 >= 0 ? b2 : -1;
+    }
+}
+
+// Frame::GetFeaturesInArea alone (for unit tests of the grid)
+int orbo_features_in_area(int K, const KeyPoint* kps, const float* bounds, float x, float y, float r, int minLevel, int maxLevel,
+                          int* out, int cap) {
+    FrameView F;
+    F.K = K; F.kps = kps; F.desc = nullptr;
+    F.minX = bounds[0]; F.minY = bounds[1]; F.maxX = bounds[2]; F.maxY = bounds[3];
+    F.gridWInv = (float)GRID_COLS / (F.maxX - F.minX);
+    F.gridHInv = (float)GRID_ROWS / (F.maxY - F.minY);
+    F.build_grid();
+    std::vector<int> v;
+    F.features_in_area(x, y, r, minLevel, maxLevel, v);
+    for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = v[i];
+    return (int)v.size();
+}
+
+}  // extern "C"

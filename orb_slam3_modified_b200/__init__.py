@@ -189,3 +189,156 @@ class ORBextractor:
 
     def last_launch_count(self):
         return lib().orbx_last_launch_count(self._h)
+
+
+# =============================================================================================
+# ORBmatcher (reference include/ORBmatcher.h:36-103)
+# =============================================================================================
+class _OrbmFrame(C.Structure):
+    _fields_ = [('K', C.c_int), ('keypoints', C.c_void_p), ('descriptors', C.c_void_p), ('minX', C.c_float), ('minY', C.c_float),
+                ('maxX', C.c_float), ('maxY', C.c_float), ('scaleFactors', C.c_void_p), ('nlevels', C.c_int)]
+
+
+class _OrbmLocalPoints(C.Structure):
+    _fields_ = [('M', C.c_int)] + [(n, C.c_void_p) for n in ('inView', 'bad', 'depth', 'projX', 'projY', 'level', 'viewCos', 'hasObs', 'descriptors')]
+
+
+class _OrbmLastFrame(C.Structure):
+    _fields_ = [('M', C.c_int)] + [(n, C.c_void_p) for n in ('valid', 'xyz', 'octave', 'angle', 'hasObs', 'descriptors')]
+
+
+class _OrbmBatchDevice(C.Structure):
+    _fields_ = [('batch', C.c_int), ('kcap', C.c_int), ('mcap', C.c_int), ('nlevels', C.c_int),
+                ('kps', C.c_void_p), ('desc', C.c_void_p), ('nK', C.c_void_p),
+                ('minX', C.c_float), ('minY', C.c_float), ('maxX', C.c_float), ('maxY', C.c_float),
+                ('scaleFactors', C.c_void_p), ('nM', C.c_void_p),
+                ('valid', C.c_void_p), ('xyz', C.c_void_p), ('octave', C.c_void_p), ('angle', C.c_void_p), ('hasObs', C.c_void_p),
+                ('mpDesc', C.c_void_p), ('Tcw7', C.c_void_p), ('cam', C.c_float * 4)]
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+class Frame:
+    """The slice of ``ORB_SLAM3::Frame`` the matchers read: mvKeysUn, mDescriptors, image bounds, mvScaleFactors,
+    and the in/out ``mvpMapPoints`` state as (match index, claimed flag) per keypoint."""
+
+    def __init__(self, keypoints, descriptors, bounds, scale_factors):
+        self.keypoints = _c(keypoints, KP_DTYPE)
+        self.descriptors = _c(descriptors, np.uint8).reshape(-1, 32)
+        self.bounds = tuple(float(b) for b in bounds)   # mnMinX, mnMinY, mnMaxX, mnMaxY
+        self.scale_factors = _c(scale_factors, np.float32)
+        self.match = np.full(len(self.keypoints), -1, np.int32)     # mvpMapPoints[i] as an index, -1 = NULL
+        self.claimed = np.zeros(len(self.keypoints), np.uint8)      # mvpMapPoints[i]->Observations() > 0
+
+    def _struct(self):
+        return _OrbmFrame(len(self.keypoints), _ptr(self.keypoints), _ptr(self.descriptors), *self.bounds,
+                          _ptr(self.scale_factors), len(self.scale_factors))
+
+
+class ORBmatcher:
+    """Mirror of ``ORB_SLAM3::ORBmatcher`` (reference include/ORBmatcher.h:36-103) for the per-frame hot functions."""
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30   # src/ORBmatcher.cc:35-37
+
+    def __init__(self, nnratio=0.6, checkOri=True, max_batch=1, max_keypoints=2048, max_mappoints=8192, device=0):
+        L = lib()
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        L.orbm_create.argtypes = [C.POINTER(vp), i, i, i, i]
+        L.orbm_destroy.argtypes = [vp]
+        L.orbm_destroy.restype = None
+        L.orbm_search_local_map.argtypes = [vp, vp, vp, f, f, i, f, vp, vp, vp]
+        L.orbm_search_last_frame.argtypes = [vp, vp, vp, vp, vp, f, i, vp, vp, vp]
+        L.orbm_search_last_frame_batch_device.argtypes = [vp, vp, f, i, vp, vp, vp, vp]
+        L.orbm_bf_knn2.argtypes = [vp, vp, i, vp, i, vp, vp]
+        L.orbm_descriptor_distance.argtypes = [vp, vp, vp, i, vp]
+        L.orbm_last_launch_count.argtypes = [vp]
+        self.mfNNratio, self.mbCheckOrientation = float(nnratio), bool(checkOri)
+        self._h = C.c_void_p()
+        rc = L.orbm_create(C.byref(self._h), max_batch, max_keypoints, max_mappoints, device)
+        if rc != ORB_OK:
+            self._h = None
+            raise OrbError(rc, 'orbm_create')
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().orbm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def DescriptorDistance(self, a, b):
+        """ORBmatcher::DescriptorDistance for one pair or for n pairs ([n,32] arrays)."""
+        a = _c(a, np.uint8).reshape(-1, 32)
+        b = _c(b, np.uint8).reshape(-1, 32)
+        out = np.zeros(len(a), np.int32)
+        rc = lib().orbm_descriptor_distance(self._h, _ptr(a), _ptr(b), len(a), _ptr(out))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_descriptor_distance')
+        return int(out[0]) if len(out) == 1 else out
+
+    def SearchByProjection(self, F, *args, **kw):
+        """Overloads by argument type as in the reference: (F, map_points: dict, th, bFarPoints=False, thFarPoints=50)
+        or (CurrentFrame, last_frame: dict, th, bMono, Tcw=..., cam=...)."""
+        pts = args[0]
+        if 'projX' in pts:
+            return self._search_local_map(F, pts, *args[1:], **kw)
+        return self._search_last_frame(F, pts, *args[1:], **kw)
+
+    def _search_local_map(self, F, pts, th=1.0, bFarPoints=False, thFarPoints=50.0):
+        M = len(pts['projX'])
+        keep = dict(inView=_c(pts['inView'], np.uint8), bad=_c(pts['bad'], np.uint8), depth=_c(pts['depth'], np.float32),
+                    projX=_c(pts['projX'], np.float32), projY=_c(pts['projY'], np.float32), level=_c(pts['level'], np.int32),
+                    viewCos=_c(pts['viewCos'], np.float32), hasObs=_c(pts['hasObs'], np.uint8),
+                    descriptors=_c(pts['descriptors'], np.uint8))
+        s = _OrbmLocalPoints(M, *[_ptr(keep[k]) for k in ('inView', 'bad', 'depth', 'projX', 'projY', 'level', 'viewCos', 'hasObs', 'descriptors')])
+        fs = F._struct()
+        n = C.c_int(0)
+        rc = lib().orbm_search_local_map(self._h, C.byref(fs), C.byref(s), th, self.mfNNratio, int(bFarPoints), thFarPoints,
+                                         _ptr(F.match), _ptr(F.claimed), C.byref(n))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_search_local_map')
+        return n.value
+
+    def _search_last_frame(self, F, last, th, bMono=True, Tcw=None, cam=None):
+        assert bMono, 'only the monocular branch is on the hot path (SURVEY.md 8a row a10)'
+        M = len(last['valid'])
+        keep = dict(valid=_c(last['valid'], np.uint8), xyz=_c(last['xyz'], np.float32), octave=_c(last['octave'], np.int32),
+                    angle=_c(last['angle'], np.float32), hasObs=_c(last['hasObs'], np.uint8), descriptors=_c(last['descriptors'], np.uint8))
+        s = _OrbmLastFrame(M, *[_ptr(keep[k]) for k in ('valid', 'xyz', 'octave', 'angle', 'hasObs', 'descriptors')])
+        T = _c(Tcw, np.float32)
+        cm = _c(cam, np.float32)
+        fs = F._struct()
+        n = C.c_int(0)
+        rc = lib().orbm_search_last_frame(self._h, C.byref(fs), C.byref(s), _ptr(T), _ptr(cm), th, int(self.mbCheckOrientation),
+                                          _ptr(F.match), _ptr(F.claimed), C.byref(n))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_search_last_frame')
+        return n.value
+
+    def search_last_frame_batch_device(self, d, th, d_match, d_claimed, d_nmatches, stream=0):
+        """Device-resident batch (torch CUDA tensors in dict ``d``; see OrbmBatchDevice in include/orb_b200.h)."""
+        s = _OrbmBatchDevice()
+        s.batch, s.kcap, s.mcap, s.nlevels = d['batch'], d['kcap'], d['mcap'], d['nlevels']
+        for k in ('kps', 'desc', 'nK', 'scaleFactors', 'nM', 'valid', 'xyz', 'octave', 'angle', 'hasObs', 'mpDesc', 'Tcw7'):
+            setattr(s, k, d[k].data_ptr())
+        s.minX, s.minY, s.maxX, s.maxY = d['bounds']
+        s.cam = (C.c_float * 4)(*d['cam'])
+        rc = lib().orbm_search_last_frame_batch_device(self._h, C.byref(s), th, int(self.mbCheckOrientation), _ptr(d_match),
+                                                       _ptr(d_claimed), _ptr(d_nmatches), C.c_void_p(stream))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_search_last_frame_batch_device')
+
+    def knnMatch2(self, query, train):
+        """cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) (src/Frame.cc:1144): (idx[Q,2], dist[Q,2])."""
+        q = _c(query, np.uint8).reshape(-1, 32)
+        t = _c(train, np.uint8).reshape(-1, 32)
+        idx = np.full((len(q), 2), -1, np.int32)
+        dist = np.full((len(q), 2), -1, np.int32)
+        rc = lib().orbm_bf_knn2(self._h, _ptr(q), len(q), _ptr(t), len(t), _ptr(idx), _ptr(dist))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_bf_knn2')
+        return idx, dist
+
+    def last_launch_count(self):
+        return lib().orbm_last_launch_count(self._h)

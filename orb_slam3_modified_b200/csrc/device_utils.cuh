@@ -1,0 +1,55 @@
+// Small device-side helpers shared by the kernels of this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace orbx {
+
+// ------------------------------------------------------------------------------------------
+// block-wide exclusive scan of an int array living in shared memory (in place).
+// Returns the total.  `warpTmp` needs 33 ints.  All threads of the block must call.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_excl_scan(int* data, int m, int* warpTmp) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    int carry = 0;
+    for (int base = 0; base < m; base += nt) {
+        const int i = base + tid;
+        const int v = i < m ? data[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warpTmp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = lane < nw ? warpTmp[lane] : 0;
+            int winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warpTmp[lane] = winc - w;       // exclusive warp offsets
+            if (lane == 31) warpTmp[32] = winc;  // tile total
+        }
+        __syncthreads();
+        if (i < m) data[i] = carry + warpTmp[wid] + inc - v;
+        carry += warpTmp[32];
+        __syncthreads();
+    }
+    return carry;
+}
+
+
+// 256-bit Hamming distance of two 32-byte descriptors held as 8 words (ORBmatcher::DescriptorDistance,
+// reference src/ORBmatcher.cc:2058-2074; the SWAR popcount there == __popc).
+__device__ __forceinline__ int hamming256(const uint32_t* a, const uint32_t* b) {
+    int d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d += __popc(a[i] ^ b[i]);
+    return d;
+}
+
+}  // namespace orbx

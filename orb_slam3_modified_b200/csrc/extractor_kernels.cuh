@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "exact_math.h"
+#include "device_utils.cuh"
 #include "extractor_types.h"
 
 namespace orbx {
@@ -25,43 +26,6 @@ __device__ __forceinline__ const uint8_t* plane_ptr(const ExtractParams& P, int 
 __device__ __forceinline__ const uint8_t* blur_ptr(const ExtractParams& P, int f, int l, int& pitch) {
     pitch = P.lv[l].pitch;
     return P.blur + (size_t)f * P.pyrFrameStride + P.lv[l].planeOff;
-}
-
-// ------------------------------------------------------------------------------------------
-// block-wide exclusive scan of an int array living in shared memory (in place).
-// Returns the total.  `warpTmp` needs 33 ints.  All threads of the block must call.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int block_excl_scan(int* data, int m, int* warpTmp) {
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    int carry = 0;
-    for (int base = 0; base < m; base += nt) {
-        const int i = base + tid;
-        const int v = i < m ? data[i] : 0;
-        int inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) warpTmp[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            int w = lane < nw ? warpTmp[lane] : 0;
-            int winc = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
-            }
-            warpTmp[lane] = winc - w;       // exclusive warp offsets
-            if (lane == 31) warpTmp[32] = winc;  // tile total
-        }
-        __syncthreads();
-        if (i < m) data[i] = carry + warpTmp[wid] + inc - v;
-        carry += warpTmp[32];
-        __syncthreads();
-    }
-    return carry;
 }
 
 // ------------------------------------------------------------------------------------------

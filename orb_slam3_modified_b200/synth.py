@@ -64,3 +64,47 @@ def frame(t=0, width=640, height=480, seed=0):
 
 def frames(n, width=640, height=480, seed=0, t0=0):
     return np.stack([frame(t0 + i, width, height, seed) for i in range(n)])
+
+
+# ---------------------------------------------------------------------------------------------
+# Camera geometry of frame(): the similarity view of the plane z = 0 is exactly a pinhole camera
+# (fx = fy = F, principal point at the image centre, zero distortion) looking down +z from
+# C = (mu*cx, mu*cy, -Zc), rotated by `ang` about the optical axis, with Zc = mu * zoom * F.
+# ---------------------------------------------------------------------------------------------
+F_PIX = 458.0
+MU = 3.0 / F_PIX   # metres per world-plane pixel: ~3 m depth at zoom 1
+
+
+def _view(t, seed, size=2048):
+    ang = 0.15 * np.sin(0.05 * t + seed)
+    zoom = 1.0 + 0.2 * np.sin(0.031 * t + 1.0)
+    cx = size / 2 + 300 * np.sin(0.02 * t + 0.3 * seed)
+    cy = size / 2 + 300 * np.cos(0.017 * t)
+    return ang, zoom, cx, cy
+
+
+def camera(width=640, height=480):
+    """(fx, fy, cx, cy) of the synthetic pinhole camera."""
+    return np.array([F_PIX, F_PIX, width / 2.0, height / 2.0], np.float32)
+
+
+def pose(t, seed=0):
+    """Tcw of frame t as (qw, qx, qy, qz, tx, ty, tz), float64."""
+    ang, zoom, cx, cy = _view(t, seed)
+    zc = MU * zoom * F_PIX
+    C = np.array([MU * cx, MU * cy, -zc])
+    ca, sa = np.cos(-ang), np.sin(-ang)
+    Rcw = np.array([[ca, -sa, 0], [sa, ca, 0], [0, 0, 1.0]])
+    tcw = -Rcw @ C
+    return np.array([np.cos(-ang / 2), 0, 0, np.sin(-ang / 2), tcw[0], tcw[1], tcw[2]])
+
+
+def backproject(xy, t, seed=0, width=640, height=480):
+    """World coordinates (on the plane z = 0) of pixel positions xy [n, 2] seen in frame t."""
+    ang, zoom, cx, cy = _view(t, seed)
+    xs = xy[:, 0].astype(np.float64) - width / 2
+    ys = xy[:, 1].astype(np.float64) - height / 2
+    c, s = np.cos(ang) * zoom, np.sin(ang) * zoom
+    wx = c * xs - s * ys + cx
+    wy = s * xs + c * ys + cy
+    return np.stack([MU * wx, MU * wy, np.zeros_like(wx)], 1)

@@ -123,3 +123,55 @@ def sincosf(a):
     c = np.zeros_like(a)
     lib().orbo_sincosf_n(_p(a), _p(s), _p(c), len(a))
     return s, c
+
+
+# ---------------------------------------------------------------------------------------------
+# matchers
+# ---------------------------------------------------------------------------------------------
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+def descriptor_distance(a, b):
+    a = _c(a, np.uint8)
+    b = _c(b, np.uint8)
+    return lib().orbo_descriptor_distance(_p(a), _p(b))
+
+
+def search_local_map(kps, desc, bounds, scale_factors, pts, th, nnratio, b_far, th_far, match, claimed):
+    kps = _c(kps, KP_DTYPE); desc = _c(desc, np.uint8); b = _c(bounds, np.float32); sf = _c(scale_factors, np.float32)
+    a = {k: _c(pts[k], dt) for k, dt in (('inView', np.uint8), ('bad', np.uint8), ('depth', np.float32), ('projX', np.float32),
+                                          ('projY', np.float32), ('level', np.int32), ('viewCos', np.float32), ('hasObs', np.uint8),
+                                          ('descriptors', np.uint8))}
+    L = lib()
+    L.orbo_search_local_map.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 9 + [C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    return L.orbo_search_local_map(len(kps), _p(kps), _p(desc), _p(b), _p(sf), len(a['projX']), _p(a['inView']), _p(a['bad']), _p(a['depth']),
+                                   _p(a['projX']), _p(a['projY']), _p(a['level']), _p(a['viewCos']), _p(a['hasObs']), _p(a['descriptors']),
+                                   th, nnratio, int(b_far), th_far, _p(match), _p(claimed))
+
+
+def search_last_frame(kps, desc, bounds, scale_factors, Tcw, cam, last, th, check_ori, match, claimed):
+    kps = _c(kps, KP_DTYPE); desc = _c(desc, np.uint8); b = _c(bounds, np.float32); sf = _c(scale_factors, np.float32)
+    T = _c(Tcw, np.float32); cm = _c(cam, np.float32)
+    a = {k: _c(last[k], dt) for k, dt in (('valid', np.uint8), ('xyz', np.float32), ('octave', np.int32), ('angle', np.float32),
+                                           ('hasObs', np.uint8), ('descriptors', np.uint8))}
+    L = lib()
+    L.orbo_search_last_frame.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    return L.orbo_search_last_frame(len(kps), _p(kps), _p(desc), _p(b), _p(sf), _p(T), _p(cm), len(a['valid']), _p(a['valid']), _p(a['xyz']),
+                                    _p(a['octave']), _p(a['angle']), _p(a['hasObs']), _p(a['descriptors']), th, int(check_ori), _p(match), _p(claimed))
+
+
+def bf_knn2(q, t):
+    q = _c(q, np.uint8).reshape(-1, 32); t = _c(t, np.uint8).reshape(-1, 32)
+    idx = np.zeros((len(q), 2), np.int32); dist = np.zeros((len(q), 2), np.int32)
+    lib().orbo_bf_knn2(_p(q), len(q), _p(t), len(t), _p(idx), _p(dist))
+    return idx, dist
+
+
+def features_in_area(kps, bounds, x, y, r, min_level, max_level):
+    kps = _c(kps, KP_DTYPE); b = _c(bounds, np.float32)
+    out = np.zeros(len(kps) + 1, np.int32)
+    L = lib()
+    L.orbo_features_in_area.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = L.orbo_features_in_area(len(kps), _p(kps), _p(b), x, y, r, min_level, max_level, _p(out), len(out))
+    return out[:n].copy()

@@ -1,0 +1,158 @@
+"""GPU parity tests of the matchers (through the C-ABI) vs the CPU oracle: identical match arrays."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import matcher_scenes as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def orb():
+    import orb_slam3_modified_b200 as m
+    m.lib()
+    return m
+
+
+@pytest.fixture(scope='module')
+def matcher(orb):
+    return orb.ORBmatcher(0.8, True, max_batch=4, max_keypoints=2048, max_mappoints=8192)
+
+
+def test_descriptor_distance(matcher):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (1000, 32)).astype(np.uint8)
+    b = rng.integers(0, 256, (1000, 32)).astype(np.uint8)
+    b[:10] = a[:10]
+    got = matcher.DescriptorDistance(a, b)
+    assert np.array_equal(got, np.unpackbits(a ^ b, axis=1).sum(1))
+    assert matcher.DescriptorDistance(a[0], b[500]) == O.descriptor_distance(a[0], b[500])
+
+
+def test_bf_knn2(matcher):
+    rng = np.random.default_rng(1)
+    for Q, T in ((300, 400), (1000, 1000), (5, 1), (7, 2), (1, 3000)):
+        q = rng.integers(0, 256, (Q, 32)).astype(np.uint8)
+        t = rng.integers(0, 256, (T, 32)).astype(np.uint8)
+        if T > 200:
+            t[100:200] = t[:100]
+            q[:min(Q, 50)] = t[:min(Q, 50)]
+        idx, dist = matcher.knnMatch2(q, t)
+        oi, od = O.bf_knn2(q, t)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od), (Q, T)
+
+
+def _run_last(orb, matcher, s, th, ori, init=None):
+    F = orb.Frame(s['kps'], s['desc'], s['bounds'], s['sf'])
+    om = np.full(len(s['kps']), -1, np.int32)
+    oc = np.zeros(len(s['kps']), np.uint8)
+    if init is not None:
+        F.match[:], F.claimed[:] = init
+        om[:], oc[:] = init
+    matcher.mbCheckOrientation = ori
+    n = matcher.SearchByProjection(F, s['last'], th, True, Tcw=s['Tcw'], cam=s['cam'])
+    on = O.search_last_frame(s['kps'], s['desc'], s['bounds'], s['sf'], s['Tcw'], s['cam'], s['last'], th, ori, om, oc)
+    assert n == on, (n, on)
+    assert np.array_equal(F.match, om), int((F.match != om).sum())
+    assert np.array_equal(F.claimed, oc)
+    return n
+
+
+@pytest.mark.parametrize('t', [5, 12, 30])
+def test_search_last_frame(orb, matcher, t):
+    s = S.last_frame_scene(t, seed=t % 2)
+    n = _run_last(orb, matcher, s, 15.0, True)
+    assert n > 200
+    _run_last(orb, matcher, s, 30.0, True)      # the 2*th retry of Tracking.cc:2897: much more contention
+    _run_last(orb, matcher, s, 15.0, False)
+
+
+def test_search_last_frame_contention_and_initial_state(orb, matcher):
+    """Heavy claim contention: every map point duplicated 3x + keypoints pre-assigned before the call."""
+    s = S.last_frame_scene(8)
+    L = s['last']
+    rng = np.random.default_rng(3)
+    rep = {k: np.concatenate([v, v, v]) for k, v in L.items()}
+    rep['hasObs'] = (rng.random(len(rep['valid'])) > 0.3).astype(np.uint8)
+    s2 = dict(s, last=rep)
+    K = len(s['kps'])
+    init = (np.where(rng.random(K) < 0.2, 7, -1).astype(np.int32), (rng.random(K) < 0.5).astype(np.uint8))
+    _run_last(orb, matcher, s2, 15.0, True, init)
+    _run_last(orb, matcher, s2, 40.0, True)
+
+
+def test_search_last_frame_degenerate(orb, matcher):
+    s = S.last_frame_scene(9)
+    empty = {k: v[:0] for k, v in s['last'].items()}
+    assert _run_last(orb, matcher, dict(s, last=empty), 15.0, True) == 0
+    behind = dict(s['last'])
+    behind['xyz'] = behind['xyz'].copy()
+    behind['xyz'][:, 2] = -50.0        # behind the camera -> invzc < 0
+    assert _run_last(orb, matcher, dict(s, last=behind), 15.0, True) == 0
+    nokp = dict(s, kps=s['kps'][:0], desc=s['desc'][:0])
+    assert _run_last(orb, matcher, nokp, 15.0, True) == 0
+
+
+def _run_local(orb, matcher, s, th, nnratio, far=False, thfar=50.0, init=None):
+    F = orb.Frame(s['kps'], s['desc'], s['bounds'], s['sf'])
+    om = np.full(len(s['kps']), -1, np.int32)
+    oc = np.zeros(len(s['kps']), np.uint8)
+    if init is not None:
+        F.match[:], F.claimed[:] = init
+        om[:], oc[:] = init
+    matcher.mfNNratio = nnratio
+    n = matcher.SearchByProjection(F, s['pts'], th, far, thfar)
+    on = O.search_local_map(s['kps'], s['desc'], s['bounds'], s['sf'], s['pts'], th, nnratio, far, thfar, om, oc)
+    assert n == on, (n, on)
+    assert np.array_equal(F.match, om), int((F.match != om).sum())
+    assert np.array_equal(F.claimed, oc)
+    return n
+
+
+@pytest.mark.parametrize('t', [6, 20])
+def test_search_local_map(orb, matcher, t):
+    s = S.local_map_scene(t, seed=t % 3)
+    assert _run_local(orb, matcher, s, 1.0, 0.8) > 100
+    _run_local(orb, matcher, s, 3.0, 0.8)             # th=3 as after relocalisation (Tracking.cc:3409-3414)
+    _run_local(orb, matcher, s, 5.0, 0.9)
+    _run_local(orb, matcher, s, 1.0, 0.8, True, 3.4)  # bFarPoints
+    rng = np.random.default_rng(t)
+    K = len(s['kps'])
+    _run_local(orb, matcher, s, 3.0, 0.8, init=(np.where(rng.random(K) < 0.3, 11, -1).astype(np.int32), (rng.random(K) < 0.6).astype(np.uint8)))
+
+
+def test_batch_device_matches_host(orb, matcher):
+    """Batched device entry point == per-stream host calls."""
+    import torch
+    B = 3
+    scenes = [S.last_frame_scene(5 + 7 * b, seed=b % 2) for b in range(B)]
+    kcap, mcap = 1100, 1100
+    dev = torch.device('cuda')
+    kps = np.zeros((B, kcap), orb.KP_DTYPE); desc = np.zeros((B, kcap, 32), np.uint8); nK = np.zeros(B, np.int32)
+    nM = np.zeros(B, np.int32); valid = np.zeros((B, mcap), np.uint8); xyz = np.zeros((B, mcap, 3), np.float32)
+    octv = np.zeros((B, mcap), np.int32); ang = np.zeros((B, mcap), np.float32); obs = np.zeros((B, mcap), np.uint8)
+    mpd = np.zeros((B, mcap, 32), np.uint8); Tcw = np.zeros((B, 7), np.float32)
+    for b, s in enumerate(scenes):
+        k, m = len(s['kps']), len(s['last']['valid'])
+        nK[b], nM[b] = k, m
+        kps[b, :k], desc[b, :k] = s['kps'], s['desc']
+        L = s['last']
+        valid[b, :m], xyz[b, :m], octv[b, :m], ang[b, :m], obs[b, :m], mpd[b, :m] = L['valid'], L['xyz'], L['octave'], L['angle'], L['hasObs'], L['descriptors']
+        Tcw[b] = s['Tcw']
+    tt = lambda a: torch.from_numpy(a.view(np.uint8) if a.dtype == orb.KP_DTYPE else a).to(dev)
+    d = dict(batch=B, kcap=kcap, mcap=mcap, nlevels=8, kps=tt(kps), desc=tt(desc), nK=tt(nK), scaleFactors=tt(scenes[0]['sf']), nM=tt(nM),
+             valid=tt(valid), xyz=tt(xyz), octave=tt(octv), angle=tt(ang), hasObs=tt(obs), mpDesc=tt(mpd), Tcw7=tt(Tcw),
+             bounds=(0.0, 0.0, 640.0, 480.0), cam=[float(c) for c in scenes[0]['cam']])
+    d_match = torch.full((B, kcap), -1, dtype=torch.int32, device=dev)
+    d_claimed = torch.zeros((B, kcap), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    matcher.mbCheckOrientation = True
+    matcher.search_last_frame_batch_device(d, 15.0, d_match, d_claimed, d_n, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for b, s in enumerate(scenes):
+        k = len(s['kps'])
+        om = np.full(k, -1, np.int32); oc = np.zeros(k, np.uint8)
+        on = O.search_last_frame(s['kps'], s['desc'], s['bounds'], s['sf'], s['Tcw'], s['cam'], s['last'], 15.0, True, om, oc)
+        assert int(d_n[b]) == on
+        assert np.array_equal(d_match[b, :k].cpu().numpy(), om) and np.array_equal(d_claimed[b, :k].cpu().numpy(), oc)
