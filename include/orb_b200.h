@@ -187,6 +187,49 @@ int orbm_bf_knn2(orbm_handle* h, const uint8_t* query, int Q, const uint8_t* tra
 int orbm_descriptor_distance(orbm_handle* h, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
 int orbm_last_launch_count(const orbm_handle* h);
 
+/* ------------------------------------------------------------------------------------------
+ * Optimizer::LocalBundleAdjustment (reference include/Optimizer.h:71, src/Optimizer.cc:1116-1498): the numeric
+ * core between graph construction and write-back, i.e. optimizer.initializeOptimization(); optimizer.optimize(10)
+ * (:1410-1411) with g2o's BlockSolver_6_3 + Levenberg-Marquardt semantics, and the per-edge values the outlier
+ * test reads (:1417-1430).  The host shim flattens the pointer graph exactly as :1213-1403 builds it
+ * (SURVEY.md 8a' "LBA in"); arrays are in g2o's Hessian order (poses by id, then points by id).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lba_handle lba_handle;
+
+typedef struct LbaProblem {
+    int nPoses;                  /* local + fixed keyframes (VertexSE3Expmap) */
+    const double* poses;         /* nPoses x 7: unit quaternion (w,x,y,z) + translation of Tcw (float->double cast, :1217-1218) */
+    const uint8_t* poseFixed;    /* vSE3->setFixed(...): InitKF or member of lFixedCameras */
+    const float* cam;            /* nPoses x 4: fx, fy, cx, cy of pKFi->mpCamera (Pinhole, float parameters) */
+    int nPoints;                 /* VertexSBAPointXYZ, all marginalized (:1289) */
+    const double* points;        /* nPoints x 3 */
+    int nEdges;                  /* EdgeSE3ProjectXYZ (mono observations, :1305-1331) */
+    const int32_t* edgePoint;    /* vertex 0 */
+    const int32_t* edgePose;     /* vertex 1 */
+    const double* obs;           /* nEdges x 2: kpUn.pt (:1307-1309) */
+    const float* invSigma2;      /* nEdges: pKFi->mvInvLevelSigma2[kpUn.octave] (:1316) */
+    double huberDelta;           /* thHuberMono = (float)sqrt(5.991) (:1275,:1321) */
+    int iterations;              /* optimizer.optimize(10) */
+    double userLambdaInit;       /* solver->setUserLambdaInit(100.0) for inertial maps (:1197-1198), else 0 */
+    const volatile int* stopFlag;/* pbStopFlag (mbAbortBA), polled like SparseOptimizer::terminate(); may be NULL */
+} LbaProblem;
+
+typedef struct LbaResult {
+    double* poses;               /* nPoses x 7, optimised (fixed ones unchanged) */
+    double* points;              /* nPoints x 3 */
+    double* edgeChi2;            /* nEdges: e->chi2() as the outlier test sees it (errors of the last evaluated state) */
+    uint8_t* edgeDepthPositive;  /* nEdges: e->isDepthPositive() at the final state */
+    int iterations;              /* return value of SparseOptimizer::optimize */
+    int trials;                  /* total LM trials */
+    double lambda, chi2, initialChi2;
+    int gpuLaunches;
+} LbaResult;
+
+int lba_create(lba_handle** out, int max_poses, int max_points, int max_edges, int device);
+void lba_destroy(lba_handle* h);
+/* Host pointers in and out; returns ORB_OK, or ORB_ERR_ARG for malformed graphs (index out of range, no free vertex). */
+int lba_solve(lba_handle* h, const LbaProblem* problem, LbaResult* result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -342,3 +342,60 @@ class ORBmatcher:
 
     def last_launch_count(self):
         return lib().orbm_last_launch_count(self._h)
+
+
+# =============================================================================================
+# Optimizer (reference include/Optimizer.h:46-102)
+# =============================================================================================
+class _LbaProblem(C.Structure):
+    _fields_ = [('nPoses', C.c_int), ('poses', C.c_void_p), ('poseFixed', C.c_void_p), ('cam', C.c_void_p),
+                ('nPoints', C.c_int), ('points', C.c_void_p), ('nEdges', C.c_int), ('edgePoint', C.c_void_p),
+                ('edgePose', C.c_void_p), ('obs', C.c_void_p), ('invSigma2', C.c_void_p), ('huberDelta', C.c_double),
+                ('iterations', C.c_int), ('userLambdaInit', C.c_double), ('stopFlag', C.c_void_p)]
+
+
+class _LbaResult(C.Structure):
+    _fields_ = [('poses', C.c_void_p), ('points', C.c_void_p), ('edgeChi2', C.c_void_p), ('edgeDepthPositive', C.c_void_p),
+                ('iterations', C.c_int), ('trials', C.c_int), ('lambda_', C.c_double), ('chi2', C.c_double),
+                ('initialChi2', C.c_double), ('gpuLaunches', C.c_int)]
+
+
+class Optimizer:
+    """Mirror of the static ``ORB_SLAM3::Optimizer`` functions on the hot path.  The pointer-graph walk of
+    ``LocalBundleAdjustment`` (src/Optimizer.cc:1125-1403) stays with the caller; this object runs the numeric core
+    on flat arrays (``synth.lba_problem`` has the layout) and returns what the write-back / outlier test reads."""
+
+    def __init__(self, max_poses=64, max_points=8192, max_edges=65536, device=0):
+        L = lib()
+        L.lba_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.lba_destroy.argtypes = [C.c_void_p]
+        L.lba_destroy.restype = None
+        L.lba_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._h = C.c_void_p()
+        rc = L.lba_create(C.byref(self._h), max_poses, max_points, max_edges, device)
+        if rc != ORB_OK:
+            self._h = None
+            raise OrbError(rc, 'lba_create')
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().lba_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def LocalBundleAdjustment(self, prob, iterations=10, user_lambda_init=0.0, stop_flag=None):
+        keep = dict(poses=_c(prob['poses'], np.float64), fixed=_c(prob['fixed'], np.uint8), cam=_c(prob['cam'], np.float32),
+                    points=_c(prob['points'], np.float64), ep=_c(prob['edge_point'], np.int32), ek=_c(prob['edge_pose'], np.int32),
+                    obs=_c(prob['obs'], np.float64), isg=_c(prob['inv_sigma2'], np.float32))
+        nP, nL, nE = len(keep['poses']), len(keep['points']), len(keep['ep'])
+        p = _LbaProblem(nP, _ptr(keep['poses']), _ptr(keep['fixed']), _ptr(keep['cam']), nL, _ptr(keep['points']), nE, _ptr(keep['ep']),
+                        _ptr(keep['ek']), _ptr(keep['obs']), _ptr(keep['isg']), float(prob['huber_delta']), iterations, user_lambda_init,
+                        _ptr(stop_flag) if stop_flag is not None else None)
+        out = dict(poses=np.zeros((nP, 7)), points=np.zeros((nL, 3)), chi2=np.zeros(nE), depth_pos=np.zeros(nE, np.uint8))
+        r = _LbaResult(_ptr(out['poses']), _ptr(out['points']), _ptr(out['chi2']), _ptr(out['depth_pos']))
+        rc = lib().lba_solve(self._h, C.byref(p), C.byref(r))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'lba_solve')
+        out.update(iters=r.iterations, trials=r.trials, lambda_=r.lambda_, final_chi2=r.chi2, initial_chi2=r.initialChi2, launches=r.gpuLaunches)
+        return out

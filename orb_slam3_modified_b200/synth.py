@@ -108,3 +108,82 @@ def backproject(xy, t, seed=0, width=640, height=480):
     wx = c * xs - s * ys + cx
     wy = s * xs + c * ys + cy
     return np.stack([MU * wx, MU * wy, np.zeros_like(wx)], 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# Local bundle adjustment problems (BASELINE config 4): flat arrays in g2o's Hessian order.
+# ---------------------------------------------------------------------------------------------
+def _quat_from_rotvec(rv):
+    th = np.linalg.norm(rv)
+    if th < 1e-12:
+        return np.array([1.0, 0, 0, 0])
+    ax = rv / th
+    return np.concatenate([[np.cos(th / 2)], np.sin(th / 2) * ax])
+
+
+def _qmul(a, b):
+    return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                     a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3], a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1]])
+
+
+def _qrot(q, v):
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return v @ R.T
+
+
+def lba_problem(n_kf=20, n_pts=5000, obs_per_pt=8, n_fixed=1, seed=0, width=640, height=480, outlier_frac=0.05,
+                pose_noise=(0.01, 0.5), point_noise=0.02):
+    """Returns a dict of flat arrays: poses [n_kf,7] (qw,qx,qy,qz,t), fixed [n_kf], cam [n_kf,4] f32, points [n_pts,3],
+    edge_point / edge_pose [n_e], obs [n_e,2], inv_sigma2 [n_e] f32 (+ ground truth).  Edges are grouped by point."""
+    rng = np.random.default_rng(seed)
+    cam = np.tile(np.array([F_PIX, F_PIX, width / 2.0, height / 2.0], np.float32), (n_kf, 1))
+    # ground-truth keyframes: a slow sideways arc looking down +z
+    gt = np.zeros((n_kf, 7))
+    for i in range(n_kf):
+        q = _quat_from_rotvec(np.array([0.03 * np.sin(0.4 * i), 0.02 * i - 0.2, 0.02 * np.cos(0.3 * i)]))
+        c = np.array([0.25 * i - 0.125 * n_kf, 0.05 * np.sin(0.5 * i), 0.1 * np.cos(0.2 * i)])   # camera centre in world
+        qc = q * np.array([1, -1, -1, -1])    # Rcw = Rwc^T
+        gt[i, :4] = qc
+        gt[i, 4:] = -_qrot(qc, c)
+    inv_sigma2_tab = (1.0 / (np.float32(1.2) ** np.arange(8, dtype=np.float32)) ** 2).astype(np.float32)
+    level_p = np.array([217, 181, 151, 126, 105, 87, 73, 60], np.float64)
+    level_p /= level_p.sum()
+    pts = np.zeros((n_pts, 3))
+    e_pt, e_kf, obs, isg = [], [], [], []
+    span = max(1, n_kf - obs_per_pt + 1)
+    for j in range(n_pts):
+        s = j % span
+        kfs = list(range(s, min(n_kf, s + obs_per_pt)))
+        mid = kfs[len(kfs) // 2]
+        # a point in front of the middle keyframe of its window
+        z = rng.uniform(4.0, 10.0)
+        u, v = rng.uniform(60, width - 60), rng.uniform(60, height - 60)
+        pc = np.array([(u - width / 2) * z / F_PIX, (v - height / 2) * z / F_PIX, z])
+        qc, t = gt[mid, :4], gt[mid, 4:]
+        pw = _qrot(qc * np.array([1, -1, -1, -1]), pc - t)
+        pts[j] = pw
+        for k in kfs:
+            xc = _qrot(gt[k, :4], pw) + gt[k, 4:]
+            if xc[2] <= 0.1:
+                continue
+            oct_ = rng.choice(8, p=level_p)
+            sig = 1.2 ** oct_
+            uv = np.array([F_PIX * xc[0] / xc[2] + width / 2, F_PIX * xc[1] / xc[2] + height / 2]) + rng.normal(0, sig, 2)
+            if rng.random() < outlier_frac:
+                uv += rng.choice([-1, 1], 2) * rng.uniform(10, 20, 2)
+            e_pt.append(j); e_kf.append(k); obs.append(uv.astype(np.float32).astype(np.float64)); isg.append(inv_sigma2_tab[oct_])
+    poses = gt.copy()
+    for i in range(n_fixed, n_kf):
+        dq = _quat_from_rotvec(rng.normal(0, np.deg2rad(pose_noise[1]), 3))
+        poses[i, :4] = _qmul(dq, gt[i, :4])
+        poses[i, 4:] = gt[i, 4:] + rng.normal(0, pose_noise[0], 3)
+    # float -> double casts as in Optimizer.cc:1217-1218,1286
+    poses = poses.astype(np.float32).astype(np.float64)
+    points = (pts + rng.normal(0, point_noise, pts.shape)).astype(np.float32).astype(np.float64)
+    fixed = np.zeros(n_kf, np.uint8)
+    fixed[:n_fixed] = 1
+    return dict(poses=poses, fixed=fixed, cam=cam, points=points, edge_point=np.array(e_pt, np.int32), edge_pose=np.array(e_kf, np.int32),
+                obs=np.array(obs, np.float64).reshape(-1, 2), inv_sigma2=np.array(isg, np.float32), gt_poses=gt, gt_points=pts,
+                huber_delta=float(np.float32(np.sqrt(5.991))))

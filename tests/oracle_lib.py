@@ -175,3 +175,31 @@ def features_in_area(kps, bounds, x, y, r, min_level, max_level):
     L.orbo_features_in_area.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
     n = L.orbo_features_in_area(len(kps), _p(kps), _p(b), x, y, r, min_level, max_level, _p(out), len(out))
     return out[:n].copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# local bundle adjustment
+# ---------------------------------------------------------------------------------------------
+def lba_solve(prob, iterations=10, user_lambda_init=0.0, stop_flag=None):
+    """Runs the oracle LBA on a synth.lba_problem dict; returns dict(poses, points, chi2, depth_pos, iters, stats)."""
+    poses = _c(prob['poses'], np.float64).copy(); points = _c(prob['points'], np.float64).copy()
+    fixed = _c(prob['fixed'], np.uint8); cam = _c(prob['cam'], np.float32)
+    ep = _c(prob['edge_point'], np.int32); ek = _c(prob['edge_pose'], np.int32)
+    obs = _c(prob['obs'], np.float64); isg = _c(prob['inv_sigma2'], np.float32)
+    nE = len(ep)
+    chi2 = np.zeros(nE, np.float64); dpos = np.zeros(nE, np.uint8); stats = np.zeros(8, np.float64)
+    L = lib()
+    L.orbo_lba_solve.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    sf = _p(stop_flag) if stop_flag is not None else None
+    it = L.orbo_lba_solve(len(poses), _p(poses), _p(fixed), _p(cam), len(points), _p(points), nE, _p(ep), _p(ek), _p(obs), _p(isg),
+                          float(prob['huber_delta']), iterations, user_lambda_init, sf, _p(chi2), _p(dpos), _p(stats))
+    return dict(poses=poses, points=points, chi2=chi2, depth_pos=dpos, iters=it, stats=stats)
+
+
+def lba_residuals(prob, poses, points):
+    poses = _c(poses, np.float64); points = _c(points, np.float64); cam = _c(prob['cam'], np.float32)
+    ep = _c(prob['edge_point'], np.int32); ek = _c(prob['edge_pose'], np.int32); obs = _c(prob['obs'], np.float64)
+    res = np.zeros((len(ep), 2), np.float64)
+    lib().orbo_lba_residuals(len(poses), _p(poses), _p(cam), len(points), _p(points), len(ep), _p(ep), _p(ek), _p(obs), _p(res))
+    return res

@@ -1,0 +1,70 @@
+"""GPU parity tests of LocalBundleAdjustment: reprojection residuals within 1e-4 px of the oracle (north_star bar),
+identical LM control flow (iterations, trials) and identical outlier classification."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from orb_slam3_modified_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL_PX = 1e-4   # BASELINE.json north_star: "LBA reprojection residuals within 1e-4 px"
+
+
+@pytest.fixture(scope='module')
+def opt():
+    import orb_slam3_modified_b200 as m
+    m.lib()
+    return m.Optimizer(max_poses=64, max_points=8192, max_edges=65536)
+
+
+def _check(opt, p, **kw):
+    ref = O.lba_solve(p, **kw)
+    out = opt.LocalBundleAdjustment(p, **kw)
+    assert out['iters'] == ref['iters'], (out['iters'], ref['iters'])
+    assert out['trials'] == int(ref['stats'][3])
+    r_ref = O.lba_residuals(p, ref['poses'], ref['points'])
+    r_gpu = O.lba_residuals(p, out['poses'], out['points'])
+    assert np.abs(r_ref - r_gpu).max() < TOL_PX, float(np.abs(r_ref - r_gpu).max())
+    assert np.allclose(out['poses'], ref['poses'], atol=1e-9) and np.allclose(out['points'], ref['points'], atol=1e-8)
+    assert np.allclose(out['chi2'], ref['chi2'], rtol=1e-6, atol=1e-7)
+    near = np.abs(ref['chi2'] - 5.991) < 1e-6
+    assert np.array_equal((out['chi2'] > 5.991)[~near], (ref['chi2'] > 5.991)[~near])
+    assert np.array_equal(out['depth_pos'], ref['depth_pos'])
+    assert abs(out['final_chi2'] - ref['stats'][1]) <= 1e-9 * max(1.0, ref['stats'][1])
+    return out
+
+
+def test_config4_20kf_5000pts_40k_edges(opt):
+    """BASELINE config 4."""
+    p = synth.lba_problem(n_kf=20, n_pts=5000, obs_per_pt=8, seed=0)
+    assert len(p['edge_point']) == 40000
+    out = _check(opt, p)
+    assert out['iters'] >= 5 and out['launches'] > 0
+
+
+@pytest.mark.parametrize('seed,n_kf,n_pts,obs,n_fixed', [(1, 8, 600, 5, 1), (2, 6, 300, 6, 2), (5, 30, 2000, 10, 3), (7, 3, 50, 3, 1), (9, 12, 800, 12, 11)])
+def test_other_sizes(opt, seed, n_kf, n_pts, obs, n_fixed):
+    _check(opt, synth.lba_problem(n_kf=n_kf, n_pts=n_pts, obs_per_pt=obs, seed=seed, n_fixed=n_fixed))
+
+
+def test_control_flow_variants(opt):
+    p = synth.lba_problem(n_kf=8, n_pts=500, obs_per_pt=5, seed=11)
+    _check(opt, p, user_lambda_init=100.0)          # inertial map initial lambda
+    _check(opt, p, iterations=1)
+    _check(opt, p, iterations=0)
+    out = opt.LocalBundleAdjustment(p, stop_flag=np.ones(1, np.int32))
+    assert out['iters'] == 0 and np.allclose(out['points'], p['points'])
+    # badly perturbed start: forces rejected LM trials (lambda escalation + pop)
+    q = synth.lba_problem(n_kf=8, n_pts=500, obs_per_pt=5, seed=12, pose_noise=(0.3, 8.0), point_noise=0.5)
+    _check(opt, q)
+
+
+def test_all_poses_fixed_and_bad_graphs(opt):
+    import orb_slam3_modified_b200 as m
+    p = synth.lba_problem(n_kf=4, n_pts=80, obs_per_pt=4, seed=13, n_fixed=4)   # only landmarks move
+    _check(opt, p)
+    bad = dict(p)
+    bad['edge_pose'] = p['edge_pose'].copy()
+    bad['edge_pose'][0] = 99
+    with pytest.raises(m.OrbError):
+        opt.LocalBundleAdjustment(bad)
