@@ -67,13 +67,32 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def make_frames(n, seed):
+DISTINCT = 32   # distinct synthetic streams; larger batches replicate them (separate buffers, same content)
+TH_PROJ = 15.0  # SearchByProjection window for mono tracking (reference src/Tracking.cc:2884-2889)
+
+
+def stream_time(s, k):
+    """Frame index of stream s at parity k (0: 'previous', 1: 'next')."""
+    return 5 * s + k
+
+
+def make_frames(n, k, rank=0):
+    """Frame k (0/1) of n streams: stream s shows synth.frame(t = 5 s + k, seed = s % 4 + 4 rank)."""
     from orb_slam3_modified_b200 import synth
     import numpy as np
-    base = synth.frames(min(n, 16), W, H, seed=seed, t0=0)
-    reps = (n + len(base) - 1) // len(base)
-    out = np.concatenate([np.roll(base, 7 * r, axis=2) for r in range(reps)])[:n]   # distinct content per slot
-    return np.ascontiguousarray(out)
+    d = min(n, DISTINCT)
+    base = np.stack([synth.frame(stream_time(s, k), W, H, seed=s % 4 + 4 * rank) for s in range(d)])
+    return np.ascontiguousarray(np.concatenate([base] * ((n + d - 1) // d))[:n])
+
+
+def stream_pose(s, k, rank=0, noise=0.003):
+    """Motion-model prior of Tcw for stream s at parity k: the exact synthetic pose plus a seeded perturbation."""
+    from orb_slam3_modified_b200 import synth
+    import numpy as np
+    rng = np.random.default_rng(1000 * rank + 2 * s + k)
+    T = synth.pose(stream_time(s % DISTINCT, k), seed=(s % DISTINCT) % 4 + 4 * rank)
+    T[4:] += rng.normal(0, noise, 3)
+    return T.astype(np.float32)
 
 
 def cpu_oracle_throughput(frames, seconds_budget, threads):

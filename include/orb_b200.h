@@ -226,9 +226,19 @@ typedef struct LbaResult {
 } LbaResult;
 
 int lba_create(lba_handle** out, int max_poses, int max_points, int max_edges, int device);
+/* Same, sized for up to max_batch independent problems solved by one kernel launch (one per stream / local map). */
+int lba_create_batch(lba_handle** out, int max_poses, int max_points, int max_edges, int max_batch, int device);
 void lba_destroy(lba_handle* h);
 /* Host pointers in and out; returns ORB_OK, or ORB_ERR_ARG for malformed graphs (index out of range, no free vertex). */
 int lba_solve(lba_handle* h, const LbaProblem* problem, LbaResult* result);
+int lba_solve_batch(lba_handle* h, int count, const LbaProblem* problems, LbaResult* results);
+/* Split form of lba_solve_batch: upload the flattened graphs once (host pointers), run the whole LM loop for all of
+ * them from the uploaded initial estimates on `stream` (device-resident, asynchronous, repeatable), download results. */
+int lba_upload_batch(lba_handle* h, int count, const LbaProblem* problems);
+int lba_run_batch_device(lba_handle* h, void* stream);
+int lba_download_batch(lba_handle* h, int count, LbaResult* results);
+/* Thread-block-cluster size (CTAs per problem) the last run used. */
+int lba_last_cluster_size(const lba_handle* h);
 
 #ifdef __cplusplus
 }

@@ -365,14 +365,19 @@ class Optimizer:
     ``LocalBundleAdjustment`` (src/Optimizer.cc:1125-1403) stays with the caller; this object runs the numeric core
     on flat arrays (``synth.lba_problem`` has the layout) and returns what the write-back / outlier test reads."""
 
-    def __init__(self, max_poses=64, max_points=8192, max_edges=65536, device=0):
+    def __init__(self, max_poses=64, max_points=8192, max_edges=65536, max_batch=1, device=0):
         L = lib()
-        L.lba_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.lba_create_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.lba_destroy.argtypes = [C.c_void_p]
         L.lba_destroy.restype = None
         L.lba_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lba_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.lba_upload_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.lba_run_batch_device.argtypes = [C.c_void_p, C.c_void_p]
+        L.lba_download_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.lba_last_cluster_size.argtypes = [C.c_void_p]
         self._h = C.c_void_p()
-        rc = L.lba_create(C.byref(self._h), max_poses, max_points, max_edges, device)
+        rc = L.lba_create_batch(C.byref(self._h), max_poses, max_points, max_edges, max_batch, device)
         if rc != ORB_OK:
             self._h = None
             raise OrbError(rc, 'lba_create')
@@ -383,6 +388,56 @@ class Optimizer:
             self._h = None
 
     __del__ = close
+
+    @staticmethod
+    def _pack(prob, iterations, user_lambda_init, stop_flag):
+        keep = dict(poses=_c(prob['poses'], np.float64), fixed=_c(prob['fixed'], np.uint8), cam=_c(prob['cam'], np.float32),
+                    points=_c(prob['points'], np.float64), ep=_c(prob['edge_point'], np.int32), ek=_c(prob['edge_pose'], np.int32),
+                    obs=_c(prob['obs'], np.float64), isg=_c(prob['inv_sigma2'], np.float32))
+        nP, nL, nE = len(keep['poses']), len(keep['points']), len(keep['ep'])
+        p = _LbaProblem(nP, _ptr(keep['poses']), _ptr(keep['fixed']), _ptr(keep['cam']), nL, _ptr(keep['points']), nE, _ptr(keep['ep']),
+                        _ptr(keep['ek']), _ptr(keep['obs']), _ptr(keep['isg']), float(prob['huber_delta']), iterations, user_lambda_init,
+                        _ptr(stop_flag) if stop_flag is not None else None)
+        out = dict(poses=np.zeros((nP, 7)), points=np.zeros((nL, 3)), chi2=np.zeros(nE), depth_pos=np.zeros(nE, np.uint8))
+        r = _LbaResult(_ptr(out['poses']), _ptr(out['points']), _ptr(out['chi2']), _ptr(out['depth_pos']))
+        return keep, p, out, r
+
+    @staticmethod
+    def _finish(out, r):
+        out.update(iters=r.iterations, trials=r.trials, lambda_=r.lambda_, final_chi2=r.chi2, initial_chi2=r.initialChi2, launches=r.gpuLaunches)
+        return out
+
+    def LocalBundleAdjustmentBatch(self, probs, iterations=10, user_lambda_init=0.0):
+        """One LocalBundleAdjustment per stream / local map, all solved by one kernel launch."""
+        packs = [self._pack(p, iterations, user_lambda_init, None) for p in probs]
+        P = (_LbaProblem * len(probs))(*[k[1] for k in packs])
+        R = (_LbaResult * len(probs))(*[k[3] for k in packs])
+        rc = lib().lba_solve_batch(self._h, len(probs), P, R)
+        if rc != ORB_OK:
+            raise OrbError(rc, 'lba_solve_batch')
+        return [self._finish(k[2], R[i]) for i, k in enumerate(packs)]
+
+    def upload(self, probs, iterations=10, user_lambda_init=0.0):
+        self._packs = [self._pack(p, iterations, user_lambda_init, None) for p in probs]
+        P = (_LbaProblem * len(probs))(*[k[1] for k in self._packs])
+        rc = lib().lba_upload_batch(self._h, len(probs), P)
+        if rc != ORB_OK:
+            raise OrbError(rc, 'lba_upload_batch')
+
+    def run_device(self, stream=0):
+        rc = lib().lba_run_batch_device(self._h, C.c_void_p(stream))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'lba_run_batch_device')
+
+    def download(self):
+        R = (_LbaResult * len(self._packs))(*[k[3] for k in self._packs])
+        rc = lib().lba_download_batch(self._h, len(self._packs), R)
+        if rc != ORB_OK:
+            raise OrbError(rc, 'lba_download_batch')
+        return [self._finish(k[2], R[i]) for i, k in enumerate(self._packs)]
+
+    def last_cluster_size(self):
+        return lib().lba_last_cluster_size(self._h)
 
     def LocalBundleAdjustment(self, prob, iterations=10, user_lambda_init=0.0, stop_flag=None):
         keep = dict(poses=_c(prob['poses'], np.float64), fixed=_c(prob['fixed'], np.uint8), cam=_c(prob['cam'], np.float32),

@@ -68,3 +68,38 @@ def test_all_poses_fixed_and_bad_graphs(opt):
     bad['edge_pose'][0] = 99
     with pytest.raises(m.OrbError):
         opt.LocalBundleAdjustment(bad)
+
+
+def test_batch_of_problems_one_launch():
+    """Several local maps (different sizes) solved by one persistent-kernel launch == individual solves."""
+    import orb_slam3_modified_b200 as m
+    optb = m.Optimizer(max_poses=32, max_points=6000, max_edges=48000, max_batch=24)
+    probs = [synth.lba_problem(n_kf=6 + b % 5, n_pts=200 + 37 * b, obs_per_pt=4 + b % 3, seed=20 + b) for b in range(20)]
+    probs[3] = synth.lba_problem(n_kf=20, n_pts=5000, obs_per_pt=8, seed=0)
+    outs = optb.LocalBundleAdjustmentBatch(probs)
+    assert optb.last_cluster_size() in (1, 2, 4, 8)
+    for p, out in zip(probs, outs):
+        ref = O.lba_solve(p)
+        assert out['iters'] == ref['iters'] and out['trials'] == int(ref['stats'][3])
+        r_ref = O.lba_residuals(p, ref['poses'], ref['points'])
+        r_gpu = O.lba_residuals(p, out['poses'], out['points'])
+        assert np.abs(r_ref - r_gpu).max() < TOL_PX
+    # resident re-run: upload once, run twice, same answer (state restarts from the uploaded estimates)
+    optb.upload(probs[:4])
+    optb.run_device()
+    a = optb.download()
+    optb.run_device()
+    b = optb.download()
+    for x, y in zip(a, b):
+        assert np.array_equal(x['poses'], y['poses']) and np.array_equal(x['points'], y['points']) and np.array_equal(x['chi2'], y['chi2'])
+
+
+def test_large_window_matrix_in_global_memory():
+    """60 free keyframes: the 360x360 reduced camera system does not fit in shared memory -> global/L2 path."""
+    import orb_slam3_modified_b200 as m
+    optl = m.Optimizer(max_poses=64, max_points=3000, max_edges=40000)
+    p = synth.lba_problem(n_kf=61, n_pts=2500, obs_per_pt=12, seed=31)
+    ref = O.lba_solve(p)
+    out = optl.LocalBundleAdjustment(p)
+    assert out['iters'] == ref['iters'] and out['trials'] == int(ref['stats'][3])
+    assert np.abs(O.lba_residuals(p, ref['poses'], ref['points']) - O.lba_residuals(p, out['poses'], out['points'])).max() < TOL_PX
