@@ -1,11 +1,15 @@
 #!/usr/bin/env python3
 """bench.py -- frames/sec of the ORB-SLAM3 hot path (BASELINE.json metric) on N B200s.
 
-One "step" = one pass of the hot path over one batch of synthetic 640x480 frames per GPU
-(BASELINE configs[1]: 640x480 mono stream, 1000 feats/frame).  `value` is whole-job frames/s with the
-frames already resident in HBM; `e2e` is the same metric through the reference-facing C-ABI with
-HOST buffers (pinned), H2D/D2H inside the timed region.  --impl reference times the CPU oracle
-(the reference itself cannot be built here: needs OpenCV C++/Eigen) on all host cores.
+One "step" = one pass of the hot path over one batch of synthetic 640x480 mono frames per GPU
+(BASELINE configs[1]: 640x480 mono stream, 1000 feats/frame, extended by the LBA share of configs[3]):
+  * every stream contributes one frame: ORBextractor::operator() + SearchByProjection(current, last frame);
+  * every KF_INTERVAL-th frame of a stream is a keyframe and triggers one LocalBundleAdjustment of the
+    configs[3] size (20 keyframes x 5000 points x 40000 edges) on the mapping side -> B / KF_INTERVAL LBAs per step.
+`value` is whole-job frames/s with all inputs already resident in HBM; `e2e` is the same metric through the
+reference-facing C-ABI with HOST buffers (pinned), host<->device copies inside the timed region.
+--impl reference times the CPU oracle (the reference itself cannot be built here: needs OpenCV C++/Eigen)
+on all host cores for the same work mix.
 """
 import argparse
 import json
@@ -21,8 +25,18 @@ sys.path.insert(0, ROOT)
 METRIC = 'frames/sec (extract+match+LBA) 640x480 mono-inertial'
 UNIT = 'frames/s'
 W, H, NFEAT = 640, 480, 1000
-# algorithmic bytes per extracted frame = 5S - A0 - A7 + 1321*K, 640x480, K=1000
+KF_INTERVAL = 10     # one keyframe (-> one LBA) per 10 frames of a stream
+LBA_CFG = dict(n_kf=20, n_pts=5000, obs_per_pt=8)   # BASELINE configs[3]
+STAGES = ['extract', 'match(SearchByProjection last frame)', 'LBA(1 per %d frames)' % KF_INTERVAL]
+WORKLOAD = 'configs[1]: 640x480 mono stream, 1000 feats/frame, extract+SearchByProjection, + configs[3]-sized LBA every %d frames' % KF_INTERVAL
+# SURVEY.md 8d algorithmic bytes, 640x480, K = 1000 keypoints (S = 950,532 px over the 8 levels, A0 = 307,200, A7 = 23,986)
+ALG = {'pyramid': 926546 + 643332, 'blur': 2 * 950532, 'fast_cells': 950532, 'quadtree_orient': 749 * 1000, 'assemble': 60 * 1000,
+       'brief': 512 * 1000 + 32 * 1000}
 ALG_BYTES_EXTRACT = 5742474
+ALG_BYTES_MATCH = 552000
+ALG_BYTES_LBA_PER_TRIAL = 13.6e6
+DISTINCT = 32        # distinct synthetic streams; larger batches replicate them (separate buffers, same content)
+TH_PROJ = 15.0       # SearchByProjection window for mono tracking (reference src/Tracking.cc:2884-2889)
 
 
 def _peaks():
@@ -41,7 +55,7 @@ class ClockSampler:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(index), '--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
                  'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap',
-                 '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -67,17 +81,15 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-DISTINCT = 32   # distinct synthetic streams; larger batches replicate them (separate buffers, same content)
-TH_PROJ = 15.0  # SearchByProjection window for mono tracking (reference src/Tracking.cc:2884-2889)
-
-
+# ------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------
 def stream_time(s, k):
-    """Frame index of stream s at parity k (0: 'previous', 1: 'next')."""
+    """Frame index of distinct stream s at parity k (consecutive frames t, t+1)."""
     return 5 * s + k
 
 
 def make_frames(n, k, rank=0):
-    """Frame k (0/1) of n streams: stream s shows synth.frame(t = 5 s + k, seed = s % 4 + 4 rank)."""
     from orb_slam3_modified_b200 import synth
     import numpy as np
     d = min(n, DISTINCT)
@@ -89,64 +101,112 @@ def stream_pose(s, k, rank=0, noise=0.003):
     """Motion-model prior of Tcw for stream s at parity k: the exact synthetic pose plus a seeded perturbation."""
     from orb_slam3_modified_b200 import synth
     import numpy as np
-    rng = np.random.default_rng(1000 * rank + 2 * s + k)
-    T = synth.pose(stream_time(s % DISTINCT, k), seed=(s % DISTINCT) % 4 + 4 * rank)
+    d = s % DISTINCT
+    rng = np.random.default_rng(1000 * rank + 2 * d + k)
+    T = synth.pose(stream_time(d, k), seed=d % 4 + 4 * rank)
     T[4:] += rng.normal(0, noise, 3)
     return T.astype(np.float32)
 
 
-def cpu_oracle_throughput(frames, seconds_budget, threads):
-    """frames/s of the CPU oracle (port of the reference path) on `threads` host threads."""
+def last_frame_slabs(kps_list, desc_list, k_last, cap, rank=0):
+    """Map points of the 'last frame' (parity k_last) of every stream as fixed-capacity host slabs."""
+    from orb_slam3_modified_b200 import synth
+    import numpy as np
+    B = len(kps_list)
+    out = dict(nM=np.zeros(B, np.int32), valid=np.zeros((B, cap), np.uint8), xyz=np.zeros((B, cap, 3), np.float32),
+               octave=np.zeros((B, cap), np.int32), angle=np.zeros((B, cap), np.float32), hasObs=np.zeros((B, cap), np.uint8),
+               mpDesc=np.zeros((B, cap, 32), np.uint8))
+    for b in range(B):
+        k, d = kps_list[b], desc_list[b]
+        m = len(k)
+        sd = b % DISTINCT
+        out['nM'][b] = m
+        out['valid'][b, :m] = 1
+        out['xyz'][b, :m] = synth.backproject(np.stack([k['x'], k['y']], 1), stream_time(sd, k_last), sd % 4 + 4 * rank, W, H)
+        out['octave'][b, :m] = k['octave']
+        out['angle'][b, :m] = k['angle']
+        out['hasObs'][b, :m] = 1
+        out['mpDesc'][b, :m] = d
+    return out
+
+
+def lba_problems(n, rank=0):
+    from orb_slam3_modified_b200 import synth
+    base = [synth.lba_problem(seed=100 * rank + i, **LBA_CFG) for i in range(min(n, 4))]
+    return [base[i % len(base)] for i in range(n)]
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference path)
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_mix(frames0, frames1, poses1, lba_prob, n_frames, threads):
+    """Runs extract + SearchByProjection on n_frames frames and n_frames/KF_INTERVAL LBAs with the CPU oracle on `threads` threads.
+    Returns (frames/s, seconds)."""
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import numpy as np
     import oracle_lib as O
+    from orb_slam3_modified_b200 import synth
     from concurrent.futures import ThreadPoolExecutor
     exs = [O.OracleExtractor(NFEAT, 1.2, 8, 20, 7) for _ in range(threads)]
-    exs[0](frames[0], (0, 1000))
-    t0 = time.perf_counter()
-    exs[0](frames[0], (0, 1000))
-    per = max(time.perf_counter() - t0, 1e-4)
-    n = max(threads, min(len(frames) * 4, int(seconds_budget / per) * threads))
-    n -= n % threads
+    sf = exs[0].tables()['scale']
+    cam = synth.camera(W, H)
+    nsrc = len(frames0)
+    last = [None] * nsrc
+    for s in range(min(nsrc, n_frames)):     # untimed: the last frame's features / map points
+        _, k, d = exs[0](frames0[s], (0, 1000))
+        last[s] = dict(valid=np.ones(len(k), np.uint8), xyz=synth.backproject(np.stack([k['x'], k['y']], 1), stream_time(s, 0), s % 4, W, H).astype(np.float32),
+                       octave=k['octave'].astype(np.int32), angle=k['angle'].astype(np.float32), hasObs=np.ones(len(k), np.uint8), descriptors=d)
+    n_lba = n_frames // KF_INTERVAL
 
-    def work(k):
-        e = exs[k]
-        for i in range(k, n, threads):
-            e(frames[i % len(frames)], (0, 1000))
+    def work(tid):
+        e = exs[tid]
+        for i in range(tid, n_frames, threads):
+            s = i % nsrc
+            _, k, d = e(frames1[s], (0, 1000))
+            match = np.full(len(k), -1, np.int32)
+            claimed = np.zeros(len(k), np.uint8)
+            O.search_last_frame(k, d, (0.0, 0.0, float(W), float(H)), sf, poses1[s], cam, last[s], TH_PROJ, True, match, claimed)
+        for i in range(tid, n_lba, threads):
+            O.lba_solve(lba_prob)
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as pool:
         list(pool.map(work, range(threads)))
     dt = time.perf_counter() - t0
-    return n / dt, n, dt
+    return n_frames / dt, dt
 
 
 def run_reference(args):
-    """Reference arm: the CPU implementation of the path on all host cores (oracle port; kind='port')."""
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
+    """Reference arm: the CPU implementation of the path (oracle port; kind='port') on all host cores."""
+    if int(os.environ.get('RANK', '0')) != 0:
         return
+    import numpy as np
     cores = os.cpu_count() or 1
-    frames = make_frames(32, seed=0)
-    t_all, n_all = 0.0, 0
-    for _ in range(args.warmup):
-        cpu_oracle_throughput(frames, 0.5, cores)
+    nsrc = 16
+    f0, f1 = make_frames(nsrc, 0), make_frames(nsrc, 1)
+    poses1 = [stream_pose(s, 1) for s in range(nsrc)]
+    prob = lba_problems(1)[0]
+    n_frames = max(KF_INTERVAL * cores, 80)
+    n_frames -= n_frames % KF_INTERVAL
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_mix(f0, f1, poses1, prob, KF_INTERVAL * cores, cores)
+    t_all = 0.0
     for _ in range(args.steps):
-        fps, n, dt = cpu_oracle_throughput(frames, 3.0, cores)
+        _, dt = cpu_oracle_mix(f0, f1, poses1, prob, n_frames, cores)
         t_all += dt
-        n_all += n
-    fps = n_all / t_all
-    sample = '%d frames of 640x480 per step on %d threads (extract only; matcher/LBA stages as in the GPU arm are added as they land)' % (n_all // max(args.steps, 1), cores)
+    fps = n_frames * args.steps / t_all
+    sample = '%d frames (extract+SearchByProjection) + %d LBAs (20 KF x 5000 pts x 40k edges) per step on %d threads' % (n_frames, n_frames // KF_INTERVAL, cores)
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * t_all / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'u8', 'data': 'synthetic', 'config': {'workload': 'configs[1]: 640x480 mono stream, 1000 feats/frame', 'stages': STAGES},
+        'dtype': 'u8 (extract/match), f64 (LBA)', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'stages': STAGES},
         'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
-STAGES = ['extract']
-
-
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -155,6 +215,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='frames (streams) per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -174,28 +235,65 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     B = args.batch
+    NLBA = max(1, B // KF_INTERVAL)
     dev = torch.device('cuda', local)
     ex = orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, W, H, B, local)
     cap = ex.max_keypoints
+    matcher = orb.ORBmatcher(0.9, True, max_batch=B, max_keypoints=cap, max_mappoints=cap, device=local)
+    opt = orb.Optimizer(max_poses=LBA_CFG['n_kf'], max_points=LBA_CFG['n_pts'], max_edges=LBA_CFG['n_pts'] * LBA_CFG['obs_per_pt'],
+                        max_batch=NLBA, device=local)
+    sf = ex.GetScaleFactors()
+    from orb_slam3_modified_b200 import synth
+    cam = [float(c) for c in synth.camera(W, H)]
 
-    # two alternating input sets so that consecutive steps never re-read the same frames from L2
-    # (2 x B x 307 KB; with B=256 that is 157 MB > the 126 MB L2, and the per-step working set is ~1.3 GB)
-    host_sets = [torch.from_numpy(make_frames(B, seed=rank * 2 + s)).pin_memory() for s in range(2)]
+    # ---- inputs: two alternating sets (consecutive frames t / t+1 of every stream); step i extracts set i&1 and matches it
+    # against the map points of set (i+1)&1.  2 x B x 307 KB (157 MB at B=256) > 126 MB L2, per-step working set ~1.3 GB.
+    host_sets = [torch.from_numpy(make_frames(B, k, rank)).pin_memory() for k in range(2)]
     dev_sets = [h.to(dev) for h in host_sets]
+    poses_h = [np.stack([stream_pose(s, k, rank) for s in range(B)]) for k in range(2)]
     d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device=dev)
     d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
     d_n = torch.zeros(B, dtype=torch.int32, device=dev)
     d_mono = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_match = torch.full((B, cap), -1, dtype=torch.int32, device=dev)
+    d_claimed = torch.zeros((B, cap), dtype=torch.uint8, device=dev)
+    d_nmatch = torch.zeros(B, dtype=torch.int32, device=dev)
+    # untimed set-up: features of both sets -> last-frame map points (the map state the tracker would already hold)
+    last_h, last_d = [], []
+    for k in range(2):
+        monos, kl, dl = ex.extract_batch(host_sets[k].numpy(), (0, 1000))
+        slabs = last_frame_slabs(kl, dl, k, cap, rank)
+        last_h.append(slabs)
+        last_d.append({n: torch.from_numpy(v).to(dev) for n, v in slabs.items()})
+    d_sf = torch.from_numpy(sf).to(dev)
+    d_Tcw = [torch.from_numpy(p).to(dev) for p in poses_h]
+    probs = lba_problems(NLBA, rank)
+    opt.upload(probs)                      # flattened graphs resident in HBM for the `value` measurement
     gathered = None
     if world > 1:
         gathered = [torch.empty((world,) + t.shape, dtype=t.dtype, device=dev) for t in (d_kps, d_desc, d_n)]
     stream = torch.cuda.current_stream()
+    lba_stream = torch.cuda.Stream(device=dev)      # LocalMapping runs beside Tracking in the reference (src/System.cc:197)
+    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+
+    def match_args(i):
+        cur, lst = i & 1, (i + 1) & 1
+        L = last_d[lst]
+        return dict(batch=B, kcap=cap, mcap=cap, nlevels=8, kps=d_kps, desc=d_desc, nK=d_n, scaleFactors=d_sf, nM=L['nM'], valid=L['valid'],
+                    xyz=L['xyz'], octave=L['octave'], angle=L['angle'], hasObs=L['hasObs'], mpDesc=L['mpDesc'], Tcw7=d_Tcw[cur],
+                    bounds=(0.0, 0.0, float(W), float(H)), cam=cam, reset=1)
 
     def step_device(i):
+        ev_fork.record(stream)
+        lba_stream.wait_event(ev_fork)
+        opt.run_device(lba_stream.cuda_stream)                       # B / KF_INTERVAL LBAs, one persistent kernel
         ex.extract_batch_device(dev_sets[i & 1], d_kps, d_desc, d_n, d_mono, (0, 1000), stream.cuda_stream)
-        if world > 1:   # shared-map exchange: one all-gather of the fixed-capacity slabs
+        matcher.search_last_frame_batch_device(match_args(i), TH_PROJ, d_match, d_claimed, d_nmatch, stream.cuda_stream)
+        if world > 1:   # shared-map exchange: one all-gather of the fixed-capacity keypoint/descriptor slabs
             for src, dst in zip((d_kps, d_desc, d_n), gathered):
                 dist.all_gather_into_tensor(dst, src)
+        ev_join.record(lba_stream)
+        stream.wait_event(ev_join)
 
     def barrier():
         if world > 1:
@@ -214,7 +312,7 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = ex.last_launch_count() * args.steps
+    launches = (ex.last_launch_count() + matcher.last_launch_count() + 1) * args.steps
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -222,47 +320,117 @@ def main():
     clk = clocks.stop() if clocks else None
     value = world * B * args.steps / (ms * 1e-3)
     mean_kp = float(d_n.float().mean().item())
+    mean_matches = float(d_nmatch.float().mean().item())
+
+    # ---------------- per-stage split (events on the launching stream) + roofline of the dominant kernel ----------------
+    stage = {}
+    if rank == 0:
+        ex.set_profiling(True)
+        acc = {}
+        reps = 3
+        for i in range(reps):
+            ex.extract_batch_device(dev_sets[i & 1], d_kps, d_desc, d_n, d_mono, (0, 1000), stream.cuda_stream)
+            for k, v in ex.stage_ms().items():
+                acc[k] = acc.get(k, 0.0) + v / reps
+        ex.set_profiling(False)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for i in range(reps):
+            matcher.search_last_frame_batch_device(match_args(i), TH_PROJ, d_match, d_claimed, d_nmatch, stream.cuda_stream)
+        a1.record(stream)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        for i in range(reps):
+            opt.run_device(stream.cuda_stream)
+        b1.record(stream)
+        torch.cuda.synchronize()
+        stage = {k: v for k, v in acc.items()}
+        stage['match(3 kernels)'] = a0.elapsed_time(a1) / reps
+        stage['lba_cluster_kernel'] = b0.elapsed_time(b1) / reps
+        lba_out = opt.download()
+        mean_trials = float(np.mean([o['trials'] for o in lba_out]))
+    torch.cuda.synchronize()
 
     # ---------------- end to end through the host C-ABI (`e2e`) ----------------
-    def step_host(i):
-        return ex.extract_batch(host_sets[i & 1].numpy(), (0, 1000))
+    e2e, e2e_steps, h2d, d2h = None, 0, 0, 0
+    if not args.no_e2e:
+        match_h = np.full((B, cap), -1, np.int32)
+        claimed_h = np.zeros((B, cap), np.uint8)
+        nmatch_h = np.zeros(B, np.int32)
 
-    for i in range(max(1, min(args.warmup, 2))):
-        step_host(i)
-    barrier()
-    e2e_steps = max(2, min(args.steps, 6))
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        monos, kps, descs = step_host(i)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = world * B * e2e_steps / float(t.item())
-    d2h = int(sum(len(k) for k in kps) * 60 + 12 * B)
+        def step_host(i):
+            cur, lst = i & 1, (i + 1) & 1
+            monos, kl, dl = ex.extract_batch(host_sets[cur].numpy(), (0, 1000))
+            kps_h = np.zeros((B, cap), orb.KP_DTYPE)
+            desc_h = np.zeros((B, cap, 32), np.uint8)
+            nK = np.zeros(B, np.int32)
+            for b in range(B):
+                nK[b] = len(kl[b])
+                kps_h[b, :nK[b]] = kl[b]
+                desc_h[b, :nK[b]] = dl[b]
+            L = last_h[lst]
+            d = dict(batch=B, kcap=cap, mcap=cap, nlevels=8, kps=kps_h, desc=desc_h, nK=nK, scaleFactors=sf, nM=L['nM'], valid=L['valid'], xyz=L['xyz'],
+                     octave=L['octave'], angle=L['angle'], hasObs=L['hasObs'], mpDesc=L['mpDesc'], Tcw7=poses_h[cur],
+                     bounds=(0.0, 0.0, float(W), float(H)), cam=cam, reset=1)
+            matcher.search_last_frame_batch(d, TH_PROJ, match_h, claimed_h, nmatch_h)
+            outs = opt.LocalBundleAdjustmentBatch(probs)
+            return int(nK.sum()), outs
+
+        step_host(0)
+        barrier()
+        e2e_steps = max(2, min(args.steps, 4))
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            nk, outs = step_host(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = world * B * e2e_steps / float(t.item())
+        p0 = probs[0]
+        lba_h2d = NLBA * (p0['poses'].nbytes + p0['points'].nbytes + p0['obs'].nbytes + 3 * 4 * len(p0['edge_point']) + p0['cam'].nbytes)
+        lba_d2h = NLBA * (p0['poses'].nbytes + p0['points'].nbytes + 9 * len(p0['edge_point']))
+        h2d = B * W * H + B * cap * (28 + 32 + 5) + sum(v.nbytes for v in last_h[0].values()) + lba_h2d
+        d2h = nk * 60 + 12 * B + B * cap * 5 + lba_d2h
 
     if rank == 0:
         peak, how = _peaks()
-        ach = ALG_BYTES_EXTRACT * (value / world) / 1e9
+        dom = max((k for k in stage if k in ALG), key=lambda k: stage[k]) if stage else None
+        cand = {k: stage[k] for k in stage}
+        top = max(cand, key=cand.get)
+        if top == 'lba_cluster_kernel':
+            alg_bytes = ALG_BYTES_LBA_PER_TRIAL * mean_trials * NLBA
+            per = 'LBA launch: %.1f LM trials x 13.6 MB x %d problems' % (mean_trials, NLBA)
+        elif top.startswith('match'):
+            alg_bytes = ALG_BYTES_MATCH * B
+            per = '552,000 B/frame x %d frames' % B
+        else:
+            alg_bytes = ALG[top] * B
+            per = '%d B/frame x %d frames' % (ALG[top], B)
+        ach = alg_bytes / (stage[top] * 1e-3) / 1e9
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'u8', 'data': 'synthetic',
-            'config': {'workload': 'configs[1]: 640x480 mono stream, 1000 feats/frame', 'stages': STAGES, 'frames_per_gpu_per_step': B,
-                       'l2': 'inputs alternate between two %d-frame sets (2 x %.0f MB) > 126 MB L2' % (B, B * W * H / 1e6),
-                       'mean_keypoints_per_frame': mean_kp},
+            'dtype': 'u8 (extract/match), f64 (LBA)', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'stages': STAGES, 'frames_per_gpu_per_step': B, 'lba_per_gpu_per_step': NLBA,
+                       'l2': 'inputs alternate between two %d-frame sets (2 x %.0f MB) > 126 MB L2; per-step working set > 1 GB' % (B, B * W * H / 1e6),
+                       'mean_keypoints_per_frame': mean_kp, 'mean_matches_per_frame': mean_matches, 'lba_cluster_size': opt.last_cluster_size(),
+                       'lba_mean_trials': mean_trials},
             'clocks': clk, 'gpu_launches': launches,
-            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': B * W * H, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps},
-            'roofline': {'bound': 'hbm', 'kernel': 'whole extract step (per-kernel split in profiles/)', 'achieved': ach, 'peak': peak,
-                         'unit': 'GB/s', 'frac': ach / peak, 'traffic': None, 'peak_source': how,
-                         'algorithmic_bytes_per_frame': ALG_BYTES_EXTRACT},
+            'stage_ms_per_step': stage,
+            'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+                         'peak_source': how, 'algorithmic_bytes_per_launch': alg_bytes, 'per': per, 'launch_ms': stage[top],
+                         'whole_step_frac': (ALG_BYTES_EXTRACT + ALG_BYTES_MATCH + ALG_BYTES_LBA_PER_TRIAL * mean_trials / KF_INTERVAL) * (value / world) / 1e9 / peak},
         }
+        if e2e is not None:
+            out['e2e'] = {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps}
         if world == 1 and not args.no_cpu_baseline:
-            frames = host_sets[0].numpy()[:32]
-            fps1, n1, dt1 = cpu_oracle_throughput(frames, 8.0, 1)
+            nsrc = 8
+            f0, f1 = host_sets[0].numpy()[:nsrc], host_sets[1].numpy()[:nsrc]
+            fps1, dt1 = cpu_oracle_mix(f0, f1, [poses_h[1][s] for s in range(nsrc)], probs[0], 2 * KF_INTERVAL, 1)
             out['cpu_baseline'] = {'value': fps1, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-                                   'sample': '%d frames of 640x480, oracle ORBextractor, 1 thread (the reference mono path is single-threaded)' % n1}
+                                   'sample': '%d frames extract+SearchByProjection + %d LBA, oracle, 1 thread (%.1f s)' % (2 * KF_INTERVAL, 2, dt1)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

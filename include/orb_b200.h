@@ -101,6 +101,11 @@ int orbx_copy_level(orbx_handle* h, int frame, int level, int blurred, uint8_t* 
 int orbx_copy_candidates(orbx_handle* h, int frame, int level, int* xys, int cap);
 /* Number of kernels launched by the last extract call (for bench.py's gpu_launches). */
 int orbx_last_launch_count(const orbx_handle* h);
+/* Per-kernel device times of the pipeline (the reference's REGISTER_TIMES analogue, include/Settings.h:24): with profiling on,
+ * CUDA events bracket each stage on the launching stream (the blur then runs in line instead of on its forked stream).
+ * ms6 = pyramid, blur, FAST cells, quadtree+orientation, assemble, BRIEF of the last profiled call. */
+int orbx_set_profiling(orbx_handle* h, int on);
+int orbx_get_stage_ms(orbx_handle* h, float* ms6);
 
 /* ------------------------------------------------------------------------------------------
  * ORBmatcher (reference include/ORBmatcher.h:36-103): the per-frame projection matchers, the Hamming
@@ -176,9 +181,14 @@ typedef struct OrbmBatchDevice {
     const uint8_t* mpDesc;
     const float* Tcw7;                  /* [batch][7] */
     float cam[4];
+    int resetState;                     /* 1: start from match = -1, claimed = 0 (fill(mvpMapPoints, NULL), Tracking.cc:2876) instead of reading them */
 } OrbmBatchDevice;
 int orbm_search_last_frame_batch_device(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOrientation,
                                         int32_t* d_match, uint8_t* d_claimed, int32_t* d_nmatches, void* stream);
+
+/* Same batched search with HOST pointers in `in` and in match / claimed / nmatches (copies in, runs, copies back). */
+int orbm_search_last_frame_batch(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOrientation,
+                                 int32_t* match, uint8_t* claimed, int32_t* nmatches);
 
 /* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) as used at src/Frame.cc:1144: idx/dist are Q x 2,
  * ordered by (distance, lower train index); missing neighbours are -1.  Host pointers. */

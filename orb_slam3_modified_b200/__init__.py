@@ -190,6 +190,20 @@ class ORBextractor:
     def last_launch_count(self):
         return lib().orbx_last_launch_count(self._h)
 
+    STAGES = ('pyramid', 'blur', 'fast_cells', 'quadtree_orient', 'assemble', 'brief')
+
+    def set_profiling(self, on):
+        lib().orbx_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        lib().orbx_set_profiling(self._h, int(on))
+
+    def stage_ms(self):
+        lib().orbx_get_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
+        ms = np.zeros(6, np.float32)
+        rc = lib().orbx_get_stage_ms(self._h, _ptr(ms))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbx_get_stage_ms')
+        return dict(zip(self.STAGES, (float(m) for m in ms)))
+
 
 # =============================================================================================
 # ORBmatcher (reference include/ORBmatcher.h:36-103)
@@ -213,7 +227,7 @@ class _OrbmBatchDevice(C.Structure):
                 ('minX', C.c_float), ('minY', C.c_float), ('maxX', C.c_float), ('maxY', C.c_float),
                 ('scaleFactors', C.c_void_p), ('nM', C.c_void_p),
                 ('valid', C.c_void_p), ('xyz', C.c_void_p), ('octave', C.c_void_p), ('angle', C.c_void_p), ('hasObs', C.c_void_p),
-                ('mpDesc', C.c_void_p), ('Tcw7', C.c_void_p), ('cam', C.c_float * 4)]
+                ('mpDesc', C.c_void_p), ('Tcw7', C.c_void_p), ('cam', C.c_float * 4), ('resetState', C.c_int)]
 
 
 def _c(a, dt):
@@ -324,10 +338,25 @@ class ORBmatcher:
             setattr(s, k, d[k].data_ptr())
         s.minX, s.minY, s.maxX, s.maxY = d['bounds']
         s.cam = (C.c_float * 4)(*d['cam'])
+        s.resetState = int(d.get('reset', 0))
         rc = lib().orbm_search_last_frame_batch_device(self._h, C.byref(s), th, int(self.mbCheckOrientation), _ptr(d_match),
                                                        _ptr(d_claimed), _ptr(d_nmatches), C.c_void_p(stream))
         if rc != ORB_OK:
             raise OrbError(rc, 'orbm_search_last_frame_batch_device')
+
+    def search_last_frame_batch(self, d, th, match, claimed, nmatches):
+        """Host-buffer batch (numpy arrays in dict ``d``, same keys as the device variant); in/out arrays are numpy."""
+        s = _OrbmBatchDevice()
+        s.batch, s.kcap, s.mcap, s.nlevels = d['batch'], d['kcap'], d['mcap'], d['nlevels']
+        for k in ('kps', 'desc', 'nK', 'scaleFactors', 'nM', 'valid', 'xyz', 'octave', 'angle', 'hasObs', 'mpDesc', 'Tcw7'):
+            setattr(s, k, d[k].ctypes.data)
+        s.minX, s.minY, s.maxX, s.maxY = d['bounds']
+        s.cam = (C.c_float * 4)(*d['cam'])
+        s.resetState = int(d.get('reset', 0))
+        lib().orbm_search_last_frame_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = lib().orbm_search_last_frame_batch(self._h, C.byref(s), th, int(self.mbCheckOrientation), _ptr(match), _ptr(claimed), _ptr(nmatches))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_search_last_frame_batch')
 
     def knnMatch2(self, query, train):
         """cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) (src/Frame.cc:1144): (idx[Q,2], dist[Q,2])."""

@@ -63,6 +63,8 @@ struct Extractor {
     int outCapInternal = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    bool profiling = false; cudaEvent_t evStage[8] = {};   // pyramid | blur | fast | quadtree | assemble | describe
+    float stageMs[6] = {0, 0, 0, 0, 0, 0};
     size_t smemFast = 0, smemQt = 0, smemAs = 0;
     int launches = 0;
     int maxKp = 0;
@@ -78,6 +80,7 @@ struct Extractor {
         if (stream2) cudaStreamDestroy(stream2);
         if (evFork) cudaEventDestroy(evFork);
         if (evJoin) cudaEventDestroy(evJoin);
+        for (cudaEvent_t e : evStage) if (e) cudaEventDestroy(e);
     }
 
     // ORBextractor::ORBextractor, src/ORBextractor.cc:409-469
@@ -308,27 +311,38 @@ struct Extractor {
         Q.outKp = outKp; Q.outDesc = outDesc; Q.outCap = cap; Q.outN = outN; Q.outMono = outMono;
         launches = 0;
         CK(cudaMemsetAsync(d_status, 0, sizeof(int) * batch, st));
+        if (profiling) for (int i = 0; i < 7; ++i) if (!evStage[i]) CK(cudaEventCreate(&evStage[i]));
+        if (profiling) CK(cudaEventRecord(evStage[0], st));
         // pyramid: levels depend on each other
         for (int l = 1; l < nlevels; ++l) {
             dim3 blk(32, 8), grd((Q.lv[l].w + 127) / 128, (Q.lv[l].h + 7) / 8, batch);
             pyr_resize_kernel<<<grd, blk, 0, st>>>(Q, l);
             ++launches;
         }
-        // blur runs on a forked stream, concurrently with detection
-        CK(cudaEventRecord(evFork, st));
-        CK(cudaStreamWaitEvent(stream2, evFork, 0));
-        blur_kernel<<<dim3(Q.blurTilesTotal, batch), BL_NT, 0, stream2>>>(Q);
+        if (profiling) CK(cudaEventRecord(evStage[1], st));
+        // blur runs on a forked stream, concurrently with detection (in line when profiling, so that events bracket it)
+        cudaStream_t sb = profiling ? st : stream2;
+        if (!profiling) {
+            CK(cudaEventRecord(evFork, st));
+            CK(cudaStreamWaitEvent(stream2, evFork, 0));
+        }
+        blur_kernel<<<dim3(Q.blurTilesTotal, batch), BL_NT, 0, sb>>>(Q);
         ++launches;
-        CK(cudaEventRecord(evJoin, stream2));
+        if (!profiling) CK(cudaEventRecord(evJoin, stream2));
+        if (profiling) CK(cudaEventRecord(evStage[2], st));
         fast_cells_kernel<<<dim3(Q.nCellsTotal, batch), FAST_NT, smemFast, st>>>(Q);
         ++launches;
+        if (profiling) CK(cudaEventRecord(evStage[3], st));
         quadtree_orient_kernel<<<dim3(nlevels, batch), QT_NT, smemQt, st>>>(Q);
         ++launches;
+        if (profiling) CK(cudaEventRecord(evStage[4], st));
         assemble_kernel<<<batch, AS_NT, smemAs, st>>>(Q);
         ++launches;
-        CK(cudaStreamWaitEvent(st, evJoin, 0));
+        if (profiling) CK(cudaEventRecord(evStage[5], st));
+        if (!profiling) CK(cudaStreamWaitEvent(st, evJoin, 0));
         describe_kernel<<<dim3((unsigned)((Q.selStride + DS_NT / 32 - 1) / (DS_NT / 32)), batch), DS_NT, 0, st>>>(Q);
         ++launches;
+        if (profiling) CK(cudaEventRecord(evStage[6], st));
         CK(cudaGetLastError());
         return ORB_OK;
     }
@@ -486,5 +500,20 @@ int orbx_copy_candidates(orbx_handle* h, int frame, int level, int* xys, int cap
 }
 
 int orbx_last_launch_count(const orbx_handle* h) { return h ? h->e.launches : ORB_ERR_ARG; }
+
+int orbx_set_profiling(orbx_handle* h, int on) {
+    if (!h) return ORB_ERR_ARG;
+    h->e.profiling = on != 0;
+    return ORB_OK;
+}
+
+int orbx_get_stage_ms(orbx_handle* h, float* ms6) {
+    if (!h || !ms6 || !h->e.evStage[6]) { set_error("orbx_get_stage_ms: no profiled call yet"); return ORB_ERR_ARG; }
+    Extractor& e = h->e;
+    CK(cudaSetDevice(e.device));
+    CK(cudaEventSynchronize(e.evStage[6]));
+    for (int i = 0; i < 6; ++i) CK(cudaEventElapsedTime(&ms6[i], e.evStage[i], e.evStage[i + 1]));
+    return ORB_OK;
+}
 
 }  // extern "C"

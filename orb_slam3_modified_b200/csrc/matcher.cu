@@ -55,7 +55,7 @@ struct MatchParams {
     const int *level, *octave;
     float cam[4];
     float th, nnratio, thFar;
-    int bFar, checkOri;
+    int bFar, checkOri, resetState;
     // scratch
     int* cellStart;      // [batch][GRID_CELLS + 1]
     uint16_t* cellIdx;   // [batch][kcap]
@@ -81,6 +81,11 @@ __global__ void __launch_bounds__(GB_NT) grid_build_kernel(MatchParams P) {
     int* cellStart = P.cellStart + (size_t)f * (GRID_CELLS + 1);
     uint16_t* cellIdx = P.cellIdx + (size_t)f * P.kcap;
     for (int c = tid; c < GRID_CELLS; c += GB_NT) s_cnt[c] = 0;
+    if (P.resetState) {
+        int* match = P.match + (size_t)f * P.kcap;
+        uint8_t* claimed = P.claimed + (size_t)f * P.kcap;
+        for (int i = tid; i < P.kcap; i += GB_NT) { match[i] = -1; claimed[i] = 0; }
+    }
     __syncthreads();
     for (int i = tid; i < K; i += GB_NT) {
         const int px = (int)roundf(fmul(fsub(kps[i].x, P.minX), P.gridWInv));
@@ -396,11 +401,12 @@ struct Matcher {
     // staging for the host entry points (batch = 1) -- one arena
     uint8_t* d_arena = nullptr; size_t arenaBytes = 0;
     uint8_t* h_arena = nullptr;
+    uint8_t* d_batch = nullptr; size_t batchBytes = 0;   // device staging for the host-pointer batch entry point
     int launches = 0;
 
     ~Matcher() {
         cudaSetDevice(device);
-        void* ptrs[] = {d_cellStart, d_cellIdx, d_query, d_result, d_evBin, d_evIdx, d_status, d_arena};
+        void* ptrs[] = {d_cellStart, d_cellIdx, d_query, d_result, d_evBin, d_evIdx, d_status, d_arena, d_batch};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (h_arena) cudaFreeHost(h_arena);
         if (stream) cudaStreamDestroy(stream);
@@ -424,6 +430,8 @@ struct Matcher {
         arenaBytes = std::max(arenaBytes, bf);
         CK(cudaMalloc(&d_arena, arenaBytes));
         CK(cudaMallocHost(&h_arena, arenaBytes));
+        batchBytes = B * ((size_t)kcap * (28 + 32 + 4 + 1) + (size_t)mcap * (1 + 12 + 4 + 4 + 1 + 32) + 28 + 16 + 13 * 256) + 4096;
+        CK(cudaMalloc(&d_batch, batchBytes));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaFuncSetAttribute(match_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
         return ORB_OK;
@@ -581,9 +589,42 @@ int orbm_search_last_frame_batch_device(orbm_handle* h, const OrbmBatchDevice* i
     P.scaleFactors = in->scaleFactors; P.nM = in->nM;
     P.valid = in->valid; P.xyz = in->xyz; P.octave = in->octave; P.angle = in->angle; P.hasObs = in->hasObs; P.mpDesc = in->mpDesc;
     P.Tcw7 = in->Tcw7; memcpy(P.cam, in->cam, sizeof(float) * 4);
-    P.th = th; P.checkOri = checkOri;
+    P.th = th; P.checkOri = checkOri; P.resetState = in->resetState;
     P.match = d_match; P.claimed = d_claimed; P.nmatches = d_nmatches;
     return m.run(P, (cudaStream_t)stream);
+}
+
+int orbm_search_last_frame_batch(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOri, int32_t* match, uint8_t* claimed,
+                                 int32_t* nmatches) {
+    if (!h || !in || !match || !claimed || !nmatches || in->batch < 1 || in->batch > h->m.maxBatch || in->kcap > h->m.kcap ||
+        in->mcap > h->m.mcap || in->nlevels < 1) { set_error("orbm_search_last_frame_batch: bad argument"); return ORB_ERR_ARG; }
+    Matcher& m = h->m;
+    CK(cudaSetDevice(m.device));
+    cudaStream_t st = m.stream;
+    const size_t B = in->batch, K = in->kcap, M = in->mcap;
+    size_t off = 0;
+    OrbmBatchDevice d = *in;
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+        off = (off + 255) & ~(size_t)255;
+        if (off + bytes > m.batchBytes) { set_error("orbm_search_last_frame_batch: staging too small"); return ORB_ERR_CAPACITY; }
+        if (src) { cudaError_t e = cudaMemcpyAsync(m.d_batch + off, src, bytes, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return ORB_ERR_CUDA; } }
+        *dst = m.d_batch + off; off += bytes;
+        return ORB_OK;
+    };
+    int rc;
+    const void *dm, *dc, *dn;
+#define UP(field, bytes) if ((rc = up(in->field, bytes, (const void**)&d.field))) return rc
+    UP(kps, B * K * 28); UP(desc, B * K * 32); UP(nK, B * 4); UP(scaleFactors, (size_t)in->nlevels * 4); UP(nM, B * 4);
+    UP(valid, B * M); UP(xyz, B * M * 12); UP(octave, B * M * 4); UP(angle, B * M * 4); UP(hasObs, B * M); UP(mpDesc, B * M * 32); UP(Tcw7, B * 28);
+#undef UP
+    if ((rc = up(match, B * K * 4, &dm)) || (rc = up(claimed, B * K, &dc)) || (rc = up(nullptr, B * 4, &dn))) return rc;
+    rc = orbm_search_last_frame_batch_device(h, &d, th, checkOri, (int32_t*)dm, (uint8_t*)dc, (int32_t*)dn, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(match, dm, B * K * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(claimed, dc, B * K, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nmatches, dn, B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORB_OK;
 }
 
 int orbm_bf_knn2(orbm_handle* h, const uint8_t* query, int Q, const uint8_t* train, int T, int32_t* idx, int32_t* dist) {
