@@ -46,23 +46,30 @@ struct Dev {
     const float* cam;                 // nP x 4
     const int* hidx;                  // nP: Hessian block index or -1
     const int* freePose;              // nF: pose index of Hessian block
+    // edges in INTERNAL order = sorted by point (the edges of a point are contiguous)
     const int *ePt, *ePose;           // nE
+    const int* eOrig;                 // nE: caller's edge index
     const double* obs;                // nE x 2
     const float* invSigma2;           // nE
-    const int *ptStart, *ptEdges;     // CSR by point
-    const int *poseStart, *poseEdges; // CSR by pose (all poses)
-    const int* edgeAt;                // nL x nF: edge of (point, free pose) or -1
+    const int* ptStart;               // nL + 1
+    const int *poseStart, *poseEdges; // CSR by pose (internal edge ids, ascending)
+    const int* blockStart;            // nF(nF-1)/2 + 1: off-diagonal Schur blocks (i1 < i2), row-major over the strict upper triangle
+    const int2* pairs;                // (edge of pose i1, edge of pose i2) observing the same point
+    // Schur work list: tasks 0..nF-1 = diagonal blocks (items = edges of the pose), nF.. = off-diagonal blocks (items = pairs);
+    // every task is cut into chunks of SCH items so that all warps of the cluster get the same amount of work
+    int nChunks; const int* chunkTask; const int* chunkFirst; const int* taskChunkStart;   // nChunks, nChunks, nTasks + 1
+    double* Spart;                    // nChunks x 42 partial sums (36 block entries + 6 rhs entries for diagonal tasks)
     double* err;                      // nE x 2
     double* W;                        // nE x 18 (6x3 Hpl block, zero for fixed poses)
     double* Y;                        // nE x 18 (W Hll^-1)
     double *Hpp, *bp;                 // nF x 36, nF x 6
     double *Hll, *bl;                 // nL x 9, nL x 3
     double *Dinv, *db;                // nL x 9, nL x 3
-    double *Hs, *bs;                  // n x n, n
+    double *Hs, *bs;                  // n x n (only when it does not fit in shared memory), n
     double* x;                        // n + 3 nL
     double* partial;                  // 4 rotating slots x 16 doubles: per-CTA partial sums + broadcast words
-    double* stats;                    // out: [0] iterations [1] trials [2] lambda [3] chi2 [4] initial chi2
-    double* outChi2; uint8_t* outDepthPos;   // nE
+    double* stats;                    // out: [0] iterations [1] trials [2] lambda [3] chi2 [4] initial chi2, [8..17] phase ns (CTA 0)
+    double* outChi2; uint8_t* outDepthPos;   // nE, caller's edge order
     double delta, dsqr, userLambdaInit;
     int iterations;
 };
@@ -139,15 +146,6 @@ __device__ void pose_oplus(double* T, const double* upd) {
     T[4] = te[0] + rt[0]; T[5] = te[1] + rt[1]; T[6] = te[2] + rt[2];
 }
 
-__device__ __forceinline__ void project_edge(const Dev& D, int e, double* Xc, double* uv) {
-    const int ic = D.ePose[e];
-    const double* T = D.poses + 7 * (size_t)ic;
-    double r[3]; qrot(T, D.pts + 3 * (size_t)D.ePt[e], r);
-    Xc[0] = r[0] + T[4]; Xc[1] = r[1] + T[5]; Xc[2] = r[2] + T[6];
-    const float* c = D.cam + 4 * (size_t)ic;
-    uv[0] = (double)c[0] * Xc[0] / Xc[2] + (double)c[2];   // Pinhole::project(Vector3d), float params promoted
-    uv[1] = (double)c[1] * Xc[1] / Xc[2] + (double)c[3];
-}
 __device__ __forceinline__ void robustify(const Dev& D, double e2, double& rho0, double& rho1) {   // RobustKernelHuber
     if (e2 <= D.dsqr) { rho0 = e2; rho1 = 1.; }
     else { const double s = sqrt(e2); rho0 = 2 * s * D.delta - D.dsqr; rho1 = D.delta / s; }
@@ -155,34 +153,36 @@ __device__ __forceinline__ void robustify(const Dev& D, double e2, double& rho0,
 
 
 namespace cg = cooperative_groups;
-constexpr int NT = 256;
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+constexpr int NT = 512;
+constexpr int NWARP = NT / 32;
 constexpr int MAXC = 8;            // largest cluster
 constexpr int PSLOT = 16;          // doubles per partial slot
-
-// ordered block reduction of one double per thread; every thread returns the sum
-__device__ __forceinline__ double block_sum(double v, double* sm) {
-    const int tid = threadIdx.x;
-    sm[tid] = v;
-    __syncthreads();
-#pragma unroll
-    for (int s = NT / 2; s > 0; s >>= 1) {
-        if (tid < s) sm[tid] += sm[tid + s];
-        __syncthreads();
-    }
-    const double r = sm[0];
-    __syncthreads();
-    return r;
-}
+constexpr int PC = 20;             // doubles per cached pose: q(4) t(3) R(9) fx fy cx cy
 
 struct Ctx {
     int crank, csize, tid;
     int wid, nw;           // worker id / count over the cluster
     int slot;              // rotating partial slot
-    double* sm;            // NT doubles
+    double* sm;            // NT doubles of scratch
+    const double* pc;      // pose cache in shared memory, PC doubles per pose
 };
 
-// cluster-wide ordered sum: per-CTA partials -> global slot -> cluster barrier -> every thread adds them in rank order.
-// `flagIn` (only meaningful on CTA 0 / thread 0) is broadcast alongside and returned in flagOut.
+// ordered block reduction of one double per thread; every thread returns the sum
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) sm[tid >> 5] = v;
+    __syncthreads();
+    double r = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) r += sm[w];
+    __syncthreads();
+    return r;
+}
+// cluster-wide ordered sum (per-CTA partials -> global slot -> cluster barrier -> added in rank order by every thread);
+// `flagIn` of CTA 0 / thread 0 is broadcast alongside.
 __device__ __forceinline__ double cluster_sum(const Dev& D, Ctx& c, double local, int flagIn, int& flagOut) {
     const double s = block_sum(local, c.sm);
     double* slot = D.partial + (size_t)(c.slot & 3) * PSLOT;
@@ -199,14 +199,36 @@ __device__ __forceinline__ double cluster_sum(const Dev& D, Ctx& c, double local
 }
 __device__ __forceinline__ void csync() { cg::this_cluster().sync(); }
 
-// ---- residuals + robust chi2 (SparseOptimizer::computeActiveErrors + activeRobustChi2) ----
+// (re)load every pose into the CTA's shared-memory cache: quaternion, translation, rotation matrix, camera
+__device__ void load_pose_cache(const Dev& D, double* pc) {
+    for (int i = threadIdx.x; i < D.nP; i += NT) {
+        double* o = pc + PC * i;
+        const double* T = D.poses + 7 * (size_t)i;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) o[k] = T[k];
+        qtoR(T, o + 7);
+        const float* cm = D.cam + 4 * (size_t)i;
+        o[16] = (double)cm[0]; o[17] = (double)cm[1]; o[18] = (double)cm[2]; o[19] = (double)cm[3];   // float params promoted (Pinhole.cpp:35-41)
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void project_edge(const Dev& D, const Ctx& c, int e, double* Xc, double* uv) {
+    const double* P = c.pc + PC * D.ePose[e];
+    double r[3]; qrot(P, D.pts + 3 * (size_t)D.ePt[e], r);      // SE3Quat::map: _r * xyz + _t
+    Xc[0] = r[0] + P[4]; Xc[1] = r[1] + P[5]; Xc[2] = r[2] + P[6];
+    uv[0] = P[16] * Xc[0] / Xc[2] + P[18];                      // Pinhole::project(Vector3d)
+    uv[1] = P[17] * Xc[1] / Xc[2] + P[19];
+}
+
+// ---- residuals + robust chi2 (SparseOptimizer::computeActiveErrors + activeRobustChi2), thread per edge ----
 __device__ double phase_errors(const Dev& D, const Ctx& c) {
     double acc = 0;
     for (int e = c.wid; e < D.nE; e += c.nw) {
         double Xc[3], uv[2];
-        project_edge(D, e, Xc, uv);
+        project_edge(D, c, e, Xc, uv);
         const double e0 = D.obs[2 * (size_t)e] - uv[0], e1 = D.obs[2 * (size_t)e + 1] - uv[1];
-        D.err[2 * (size_t)e] = e0; D.err[2 * (size_t)e + 1] = e1;
+        *reinterpret_cast<double2*>(D.err + 2 * (size_t)e) = make_double2(e0, e1);
         double r0, r1;
         robustify(D, (double)D.invSigma2[e] * (e0 * e0 + e1 * e1), r0, r1);
         acc += r0;
@@ -215,84 +237,83 @@ __device__ double phase_errors(const Dev& D, const Ctx& c) {
 }
 
 // Jacobians of one edge (EdgeSE3ProjectXYZ::linearizeOplus): A = dE/dpoint (2x3), B = dE/dpose (2x6)
-__device__ __forceinline__ void edge_jacobians(const Dev& D, int e, double* A, double* B, double& w, double& r0, double& r1) {
-    const int ic = D.ePose[e];
+__device__ __forceinline__ void edge_jacobians(const Dev& D, const Ctx& c, int e, double* A, double* B, double& w, double& r0, double& r1) {
+    const double* P = c.pc + PC * D.ePose[e];
     double Xc[3], uv[2];
-    project_edge(D, e, Xc, uv);
-    const float* c = D.cam + 4 * (size_t)ic;
+    project_edge(D, c, e, Xc, uv);
     const double x = Xc[0], y = Xc[1], z = Xc[2];
-    const double fx = (double)c[0], fy = (double)c[1];
-    const double J00 = -(fx / z), J02 = fx * x / (z * z), J11 = -(fy / z), J12 = fy * y / (z * z);   // -projectJac
-    double R[9]; qtoR(D.poses + 7 * (size_t)ic, R);
+    const double fx = P[16], fy = P[17];
+    const double J00 = -(fx / z), J02 = fx * x / (z * z), J11 = -(fy / z), J12 = fy * y / (z * z);   // -projectJac (Pinhole.cpp:71-81)
+    const double* R = P + 7;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { A[k] = J00 * R[k] + J02 * R[6 + k]; A[3 + k] = J11 * R[3 + k] + J12 * R[6 + k]; }
     // SE3deriv = [0 z -y 1 0 0; -z 0 x 0 1 0; y -x 0 0 0 1]
     B[0] = J02 * y;            B[1] = J00 * z - J02 * x;  B[2] = -J00 * y;  B[3] = J00; B[4] = 0;   B[5] = J02;
     B[6] = -J11 * z + J12 * y; B[7] = -J12 * x;           B[8] = J11 * x;   B[9] = 0;   B[10] = J11; B[11] = J12;
     const double is2 = (double)D.invSigma2[e];
-    const double e0 = D.err[2 * (size_t)e], e1 = D.err[2 * (size_t)e + 1];
+    const double2 er = *reinterpret_cast<const double2*>(D.err + 2 * (size_t)e);
     double rho0, rho1;
-    robustify(D, is2 * (e0 * e0 + e1 * e1), rho0, rho1);
+    robustify(D, is2 * (er.x * er.x + er.y * er.y), rho0, rho1);
     w = rho1 * is2;
-    r0 = -is2 * e0 * rho1; r1 = -is2 * e1 * rho1;
+    r0 = -is2 * er.x * rho1; r1 = -is2 * er.y * rho1;
 }
 
-// ---- per point Hll, bl and the Hpl blocks W of its edges; one warp per point, lanes over edges ----
+// ---- per point Hll, bl and the Hpl blocks W of its edges; 8 lanes per point (edges of a point are contiguous) ----
 __device__ void phase_build_points(const Dev& D, const Ctx& c) {
-    const int lane = c.tid & 31, wpb = NT / 32;
-    for (int p = c.crank * wpb + (c.tid >> 5); p < D.nL; p += c.csize * wpb) {
+    const int sl = c.tid & 7;
+    const unsigned gmask = 0xFFu << (c.tid & 24);
+    for (int p = c.wid >> 3; p < D.nL; p += c.nw >> 3) {
         const int a = D.ptStart[p], b = D.ptStart[p + 1];
-        double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-        for (int k = a + lane; k < b; k += 32) {
-            const int e = D.ptEdges[k];
+        double h[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+        for (int e = a + sl; e < b; e += 8) {
             double A[6], B[12], w, r0, r1;
-            edge_jacobians(D, e, A, B, w, r0, r1);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                g[i] += A[i] * r0 + A[3 + i] * r1;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) h[i * 3 + j] += w * (A[i] * A[j] + A[3 + i] * A[3 + j]);
-            }
-            double* We = D.W + 18 * (size_t)e;
+            edge_jacobians(D, c, e, A, B, w, r0, r1);
+            g[0] += A[0] * r0 + A[3] * r1; g[1] += A[1] * r0 + A[4] * r1; g[2] += A[2] * r0 + A[5] * r1;
+            h[0] += w * (A[0] * A[0] + A[3] * A[3]); h[1] += w * (A[0] * A[1] + A[3] * A[4]); h[2] += w * (A[0] * A[2] + A[3] * A[5]);
+            h[3] += w * (A[1] * A[1] + A[4] * A[4]); h[4] += w * (A[1] * A[2] + A[4] * A[5]); h[5] += w * (A[2] * A[2] + A[5] * A[5]);
+            double2* We = reinterpret_cast<double2*>(D.W + 18 * (size_t)e);
             if (D.hidx[D.ePose[e]] >= 0) {
+                double v[18];
 #pragma unroll
                 for (int i = 0; i < 6; ++i)
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) We[i * 3 + j] = w * (B[i] * A[j] + B[6 + i] * A[3 + j]);
+                    for (int j = 0; j < 3; ++j) v[i * 3 + j] = w * (B[i] * A[j] + B[6 + i] * A[3 + j]);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) We[i] = make_double2(v[2 * i], v[2 * i + 1]);
             } else {
 #pragma unroll
-                for (int i = 0; i < 18; ++i) We[i] = 0.0;
+                for (int i = 0; i < 9; ++i) We[i] = make_double2(0.0, 0.0);
             }
         }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
+        for (int o = 4; o; o >>= 1) {
 #pragma unroll
-            for (int i = 0; i < 9; ++i) h[i] += __shfl_xor_sync(0xffffffffu, h[i], o);
+            for (int i = 0; i < 6; ++i) h[i] += __shfl_xor_sync(gmask, h[i], o);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) g[i] += __shfl_xor_sync(0xffffffffu, g[i], o);
+            for (int i = 0; i < 3; ++i) g[i] += __shfl_xor_sync(gmask, g[i], o);
         }
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) D.Hll[9 * (size_t)p + i] = h[i];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) D.bl[3 * (size_t)p + i] = g[i];
+        if (sl == 0) {
+            double* H = D.Hll + 9 * (size_t)p;
+            H[0] = h[0]; H[1] = h[1]; H[2] = h[2]; H[3] = h[1]; H[4] = h[3]; H[5] = h[4]; H[6] = h[2]; H[7] = h[4]; H[8] = h[5];
+            D.bl[3 * (size_t)p] = g[0]; D.bl[3 * (size_t)p + 1] = g[1]; D.bl[3 * (size_t)p + 2] = g[2];
         }
     }
 }
 
-// ---- per free pose Hpp, bp; one warp per pose, lanes over its edges ----
+// ---- per free pose Hpp, bp; one CTA per pose (round-robin over the cluster), threads over its edges ----
 __device__ void phase_build_poses(const Dev& D, const Ctx& c) {
-    const int lane = c.tid & 31, wpb = NT / 32;
-    for (int hI = c.crank * wpb + (c.tid >> 5); hI < D.nF; hI += c.csize * wpb) {
+    const int lane = c.tid & 31, warp = c.tid >> 5;
+    double* red = c.sm;                      // NWARP x 27 <= NT doubles
+    for (int hI = c.crank; hI < D.nF; hI += c.csize) {
         const int ic = D.freePose[hI];
         const int a = D.poseStart[ic], b = D.poseStart[ic + 1];
         double acc[27];
 #pragma unroll
         for (int i = 0; i < 27; ++i) acc[i] = 0;
-        for (int k = a + lane; k < b; k += 32) {
+        for (int k = a + c.tid; k < b; k += NT) {
             const int e = D.poseEdges[k];
             double A[6], B[12], w, r0, r1;
-            edge_jacobians(D, e, A, B, w, r0, r1);
+            edge_jacobians(D, c, e, A, B, w, r0, r1);
             int t = 0;
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
@@ -307,14 +328,24 @@ __device__ void phase_build_poses(const Dev& D, const Ctx& c) {
 #pragma unroll
             for (int i = 0; i < 27; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
         }
+        __syncthreads();
         if (lane == 0) {
-            int t = 0;
-            double* H = D.Hpp + 36 * (size_t)hI;
-            for (int i = 0; i < 6; ++i)
-                for (int j = i; j < 6; ++j) { H[i * 6 + j] = acc[t]; H[j * 6 + i] = acc[t]; ++t; }
-            for (int i = 0; i < 6; ++i) D.bp[6 * (size_t)hI + i] = acc[21 + i];
+#pragma unroll
+            for (int i = 0; i < 27; ++i) red[warp * 27 + i] = acc[i];
+        }
+        __syncthreads();
+        if (c.tid < 27) {
+            double s = 0;
+            for (int w2 = 0; w2 < NWARP; ++w2) s += red[w2 * 27 + c.tid];
+            if (c.tid < 21) {
+                int i = 0, t = c.tid;           // unrank (i, j), i <= j
+                while (t >= 6 - i) { t -= 6 - i; ++i; }
+                const int j = i + t;
+                D.Hpp[36 * (size_t)hI + i * 6 + j] = s; D.Hpp[36 * (size_t)hI + j * 6 + i] = s;
+            } else D.bp[6 * (size_t)hI + (c.tid - 21)] = s;
         }
     }
+    __syncthreads();
 }
 
 // ---- max |diag| over all Hessian blocks (computeLambdaInit); every CTA computes it redundantly ----
@@ -322,159 +353,285 @@ __device__ double phase_maxdiag(const Dev& D, const Ctx& c) {
     double m = 0;
     for (int i = c.tid; i < D.n; i += NT) m = fmax(m, fabs(D.Hpp[36 * (size_t)(i / 6) + 7 * (i % 6)]));
     for (int i = c.tid; i < 3 * D.nL; i += NT) m = fmax(m, fabs(D.Hll[9 * (size_t)(i / 3) + 4 * (i % 3)]));
-    c.sm[c.tid] = m;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     __syncthreads();
-    for (int s = NT / 2; s > 0; s >>= 1) { if (c.tid < s) c.sm[c.tid] = fmax(c.sm[c.tid], c.sm[c.tid + s]); __syncthreads(); }
-    const double r = c.sm[0];
+    if ((c.tid & 31) == 0) c.sm[c.tid >> 5] = m;
+    __syncthreads();
+    double r = 0;
+    for (int w = 0; w < NWARP; ++w) r = fmax(r, c.sm[w]);
     __syncthreads();
     return r;
 }
 
-// ---- Hll^-1 (lambda on the diagonal) and Hll^-1 bl per point (block_solver.hpp:381-394) ----
+// ---- Hll^-1 (lambda on the diagonal), Hll^-1 bl, and Y = W Hll^-1; thread per edge, the inverse is recomputed per edge
+//      (cheaper than a barrier), the first edge of a point stores it (block_solver.hpp:381-394) ----
 __device__ void phase_point_prep(const Dev& D, const Ctx& c, double lambda) {
-    for (int p = c.wid; p < D.nL; p += c.nw) {
+    for (int e = c.wid; e < D.nE; e += c.nw) {
+        const int p = D.ePt[e];
         double m[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) m[i] = D.Hll[9 * (size_t)p + i];
         m[0] += lambda; m[4] += lambda; m[8] += lambda;
         const double c00 = m[4] * m[8] - m[5] * m[7], c10 = m[5] * m[6] - m[3] * m[8], c20 = m[3] * m[7] - m[4] * m[6];
-        const double id = 1.0 / (m[0] * c00 + m[1] * c10 + m[2] * c20);
+        const double id = 1.0 / (m[0] * c00 + m[1] * c10 + m[2] * c20);   // Eigen 3x3 inverse: cofactors / determinant
         double o[9];
         o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
         o[3] = c10 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
         o[6] = c20 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+        if (e == D.ptStart[p]) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) D.Dinv[9 * (size_t)p + i] = o[i];
-        const double* b3 = D.bl + 3 * (size_t)p;
+            for (int i = 0; i < 9; ++i) D.Dinv[9 * (size_t)p + i] = o[i];
+            const double* b3 = D.bl + 3 * (size_t)p;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) D.db[3 * (size_t)p + i] = o[i * 3] * b3[0] + o[i * 3 + 1] * b3[1] + o[i * 3 + 2] * b3[2];
-        // Y = W Hll^-1 for the edges of this point
-        for (int k = D.ptStart[p]; k < D.ptStart[p + 1]; ++k) {
-            const int e = D.ptEdges[k];
-            const double* Wd = D.W + 18 * (size_t)e;
-            double* Yd = D.Y + 18 * (size_t)e;
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-                for (int b = 0; b < 3; ++b) Yd[a * 3 + b] = Wd[a * 3] * o[b] + Wd[a * 3 + 1] * o[3 + b] + Wd[a * 3 + 2] * o[6 + b];
+            for (int i = 0; i < 3; ++i) D.db[3 * (size_t)p + i] = o[i * 3] * b3[0] + o[i * 3 + 1] * b3[1] + o[i * 3 + 2] * b3[2];
         }
+        const double2* Wd = reinterpret_cast<const double2*>(D.W + 18 * (size_t)e);
+        double wv[18];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { const double2 t = Wd[i]; wv[2 * i] = t.x; wv[2 * i + 1] = t.y; }
+        double yv[18];
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) yv[a * 3 + b] = wv[a * 3] * o[b] + wv[a * 3 + 1] * o[3 + b] + wv[a * 3 + 2] * o[6 + b];
+        double2* Yd = reinterpret_cast<double2*>(D.Y + 18 * (size_t)e);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Yd[i] = make_double2(yv[2 * i], yv[2 * i + 1]);
     }
 }
-// ---- Schur complement, one warp per block pair (i1 <= i2) (block_solver.hpp:396-431) ----
-__device__ void phase_schur(const Dev& D, const Ctx& c, double lambda, double* Hs, int ld) {
-    const int lane = c.tid & 31, wpb = NT / 32;
-    const int nPairs = D.nF * (D.nF + 1) / 2;
-    for (int pr = c.crank * wpb + (c.tid >> 5); pr < nPairs; pr += c.csize * wpb) {
-        int i1 = 0, rem = pr;   // unrank (i1, i2), i1 <= i2, row-major over the upper triangle
-        while (rem >= D.nF - i1) { rem -= D.nF - i1; ++i1; }
-        const int i2 = i1 + rem;
-        const int ic = D.freePose[i1];
-        const int a = D.poseStart[ic], b = D.poseStart[ic + 1];
-        double acc[36];
+
+__device__ __forceinline__ void load18(const double* p, double* v) {
+    const double2* q = reinterpret_cast<const double2*>(p);
 #pragma unroll
-        for (int i = 0; i < 36; ++i) acc[i] = 0;
-        double bacc[6] = {0, 0, 0, 0, 0, 0};
-        for (int k = a + lane; k < b; k += 32) {
-            const int e1 = D.poseEdges[k];
-            const int p = D.ePt[e1];
-            const int e2 = (i1 == i2) ? e1 : D.edgeAt[(size_t)p * D.nF + i2];
-            if (e2 < 0) continue;
-            const double* Y1 = D.Y + 18 * (size_t)e1;
-            const double* W2 = D.W + 18 * (size_t)e2;
+    for (int i = 0; i < 9; ++i) { const double2 t = q[i]; v[2 * i] = t.x; v[2 * i + 1] = t.y; }
+}
+// ---- Schur complement (block_solver.hpp:396-431), two steps.
+//   partial: the work list (diagonal block i: edges of pose i, contributes Y_e W_e^T and W_e Hll^-1 bl;
+//            off-diagonal block (i1 < i2): the precomputed (e1, e2) pairs, contributes Y_e1 W_e2^T) is cut into chunks of
+//            SCH items; one warp per chunk, two lanes share one item (each owns three rows of the 6x6 product), 16 items
+//            in flight per warp; the chunk's sums go to Spart.
+//   combine: thread per (task, entry): ordered sum of the task's chunks -> lower triangle of the reduced camera system
+//            (diagonal: Hpp_i + lambda I - sum, bs_i = bp_i - sum; off-diagonal: block (i2, i1) = -(sum)^T). ----
+constexpr int SCH = 128;
+__device__ void phase_schur_partial(const Dev& D, const Ctx& c) {
+    const int lane = c.tid & 31, half = lane & 1, slot = lane >> 1;
+    for (int ch = c.crank * NWARP + (c.tid >> 5); ch < D.nChunks; ch += c.csize * NWARP) {
+        const int task = D.chunkTask[ch], first = D.chunkFirst[ch];
+        double acc[18], bacc[3] = {0, 0, 0};
 #pragma unroll
-            for (int r = 0; r < 6; ++r)
+        for (int i = 0; i < 18; ++i) acc[i] = 0;
+        if (task >= D.nF) {
+            const int blk = task - D.nF;
+            const int k0 = D.blockStart[blk] + first, k1 = min(k0 + SCH, D.blockStart[blk + 1]);
+            int2 pr[SCH / 16];
 #pragma unroll
-                for (int q = 0; q < 6; ++q) acc[r * 6 + q] += Y1[r * 3] * W2[q * 3] + Y1[r * 3 + 1] * W2[q * 3 + 1] + Y1[r * 3 + 2] * W2[q * 3 + 2];
-            if (i1 == i2) {
-                const double* dbp = D.db + 3 * (size_t)p;
+            for (int j = 0; j < SCH / 16; ++j) { const int k = k0 + slot + 16 * j; pr[j] = k < k1 ? D.pairs[k] : make_int2(-1, -1); }
+#pragma unroll 2
+            for (int j = 0; j < SCH / 16; ++j) {
+                if (pr[j].x < 0) continue;
+                const double* yp = D.Y + 18 * (size_t)pr[j].x + 9 * half;
+                double y[9], w[18];
 #pragma unroll
-                for (int r = 0; r < 6; ++r) bacc[r] += W2[r * 3] * dbp[0] + W2[r * 3 + 1] * dbp[1] + W2[r * 3 + 2] * dbp[2];
+                for (int i = 0; i < 9; ++i) y[i] = yp[i];
+                load18(D.W + 18 * (size_t)pr[j].y, w);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) acc[r * 6 + q] += y[r * 3] * w[q * 3] + y[r * 3 + 1] * w[q * 3 + 1] + y[r * 3 + 2] * w[q * 3 + 2];
             }
-        }
+        } else {
+            const int ic = D.freePose[task];
+            const int k0 = D.poseStart[ic] + first, k1 = min(k0 + SCH, D.poseStart[ic + 1]);
+            int ed[SCH / 16];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
+            for (int j = 0; j < SCH / 16; ++j) { const int k = k0 + slot + 16 * j; ed[j] = k < k1 ? D.poseEdges[k] : -1; }
+#pragma unroll 2
+            for (int j = 0; j < SCH / 16; ++j) {
+                const int e = ed[j];
+                if (e < 0) continue;
+                const double* yp = D.Y + 18 * (size_t)e + 9 * half;
+                double y[9], w[18];
 #pragma unroll
-            for (int i = 0; i < 36; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+                for (int i = 0; i < 9; ++i) y[i] = yp[i];
+                load18(D.W + 18 * (size_t)e, w);
+                const double* dbp = D.db + 3 * (size_t)D.ePt[e];
+                const double d0 = dbp[0], d1 = dbp[1], d2 = dbp[2];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) bacc[i] += __shfl_xor_sync(0xffffffffu, bacc[i], o);
-        }
-        // lanes 0..35 each write one entry (+ mirror); all lanes hold the reduced values
+                for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int i = 0; i < 36; ++i) {
-            if (lane == (i & 31)) {
-                const int r = i / 6, q = i % 6;
-                double v = -acc[i];
-                if (i1 == i2) {
-                    v += D.Hpp[36 * (size_t)i1 + i] + (r == q ? lambda : 0.0);
-                    if (r >= q) Hs[(size_t)(6 * i1 + r) * ld + 6 * i1 + q] = v;       // lower triangle is what ldlt reads
-                } else {
-                    Hs[(size_t)(6 * i2 + q) * ld + 6 * i1 + r] = v;                    // block (i2, i1), lower triangle
+                    for (int q = 0; q < 6; ++q) acc[r * 6 + q] += y[r * 3] * w[q * 3] + y[r * 3 + 1] * w[q * 3 + 1] + y[r * 3 + 2] * w[q * 3 + 2];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double w0 = half ? w[9 + 3 * r] : w[3 * r], w1 = half ? w[10 + 3 * r] : w[1 + 3 * r], w2 = half ? w[11 + 3 * r] : w[2 + 3 * r];
+                    bacc[r] += w0 * d0 + w1 * d1 + w2 * d2;
                 }
             }
         }
-        if (i1 == i2 && lane < 6) D.bs[6 * i1 + lane] = D.bp[6 * (size_t)i1 + lane] - bacc[lane];
+#pragma unroll
+        for (int o = 16; o >= 2; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 18; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) bacc[i] += __shfl_xor_sync(0xffffffffu, bacc[i], o);
+        }
+        if (slot == 0) {
+            double* out = D.Spart + 42 * (size_t)ch;
+#pragma unroll
+            for (int i = 0; i < 18; ++i) out[18 * half + i] = acc[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) out[36 + 3 * half + i] = bacc[i];
+        }
     }
 }
-// ---- dense LDL^T (no pivoting) + solve, one CTA; A is the lower triangle with leading dimension ld ----
+__device__ void phase_schur_combine(const Dev& D, const Ctx& c, double lambda, double* Hs, int ld) {
+    const int nOff = D.nF * (D.nF - 1) / 2, nTasks = D.nF + nOff;
+    for (int idx = c.wid; idx < nTasks * 42; idx += c.nw) {
+        const int task = idx / 42, ent = idx - task * 42;
+        if (task >= D.nF && ent >= 36) continue;
+        double s = 0;
+        for (int ch = D.taskChunkStart[task]; ch < D.taskChunkStart[task + 1]; ++ch) s += D.Spart[42 * (size_t)ch + ent];
+        if (task < D.nF) {
+            const int i1 = task;
+            if (ent < 36) {
+                const int r = ent / 6, q = ent % 6;
+                if (q <= r) Hs[(size_t)(6 * i1 + r) * ld + 6 * i1 + q] = D.Hpp[36 * (size_t)i1 + ent] + (r == q ? lambda : 0.0) - s;
+            } else D.bs[6 * i1 + (ent - 36)] = D.bp[6 * (size_t)i1 + (ent - 36)] - s;
+        } else {
+            int i1 = 0, rem = task - D.nF;
+            while (rem >= D.nF - 1 - i1) { rem -= D.nF - 1 - i1; ++i1; }
+            const int i2 = i1 + 1 + rem;
+            const int r = ent / 6, q = ent % 6;
+            Hs[(size_t)(6 * i2 + q) * ld + 6 * i1 + r] = -s;       // block (i2, i1) = -(sum)^T
+        }
+    }
+}
+// ---- dense LDL^T (no pivoting) + solve, one CTA; A = lower triangle, leading dimension ld (shared memory when it fits).
+// Blocked by the natural 6x6 pose blocks: every thread that owns a row below the diagonal block re-factors that block in
+// registers (no barrier between "factor" and "panel"), then all warps apply the rank-6 trailing update.
 // (LinearSolverEigen::solve: SimplicialLDLT fails only on an exactly zero pivot.)  Returns 1 on success (uniform).
-__device__ int phase_ldlt(const Dev& D, const Ctx& c, double* A, int ld) {
-    const int n = D.n, tid = c.tid;
-    __shared__ int s_ok;
-    if (tid == 0) s_ok = 1;
+// xrow: n x 6 scratch (unscaled panel), in shared memory. ----
+__device__ int phase_ldlt(const Dev& D, const Ctx& c, double* A, int ld, double* xrow) {
+    const int n = D.n, tid = c.tid, lane = tid & 31, warp = tid >> 5;
+    __shared__ double s_L[36], s_dinv[6];
+    __shared__ int s_fail;
+    if (tid == 0) s_fail = 0;
     __syncthreads();
-    for (int k = 0; k < n; ++k) {
-        const double d = A[(size_t)k * ld + k];
-        if (d == 0.0) { if (tid == 0) s_ok = 0; break; }      // uniform: every thread reads the same d
-        const int m = n - k - 1;
-        // trailing update of the lower triangle with the unscaled column k
-        for (int idx = tid; idx < m * m; idx += NT) {
-            const int i = k + 1 + idx / m, j = k + 1 + idx % m;
-            if (j <= i) A[(size_t)i * ld + j] -= A[(size_t)i * ld + k] * A[(size_t)j * ld + k] / d;
+    for (int k0 = 0; k0 < n; k0 += 6) {
+        // (1) one thread factors the 6x6 diagonal block: L11 unit lower, d[6]; one reciprocal per pivot
+        if (tid == 0) {
+            double L[36], d[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) L[i * 6 + j] = A[(size_t)(k0 + i) * ld + k0 + j];
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                double dk = L[k * 6 + k];
+#pragma unroll
+                for (int j = 0; j < k; ++j) dk -= L[k * 6 + j] * L[k * 6 + j] * d[j];
+                d[k] = dk;
+                if (dk == 0.0) bad = true;
+                const double inv = 1.0 / dk;
+                s_dinv[k] = inv;
+#pragma unroll
+                for (int i = k + 1; i < 6; ++i) {
+                    double v = L[i * 6 + k];
+#pragma unroll
+                    for (int j = 0; j < k; ++j) v -= L[i * 6 + j] * L[k * 6 + j] * d[j];
+                    L[i * 6 + k] = v * inv;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                A[(size_t)(k0 + i) * ld + k0 + i] = d[i];
+#pragma unroll
+                for (int j = 0; j < i; ++j) { A[(size_t)(k0 + i) * ld + k0 + j] = L[i * 6 + j]; s_L[i * 6 + j] = L[i * 6 + j]; }
+            }
+            if (bad) s_fail = 1;
         }
         __syncthreads();
-        for (int i = k + 1 + tid; i < n; i += NT) A[(size_t)i * ld + k] /= d;
+        if (s_fail) return 0;
+        // (2) panel: row i below the block: X = A21 L11^-T (unscaled), L21 = X D^-1
+        for (int i = k0 + 6 + tid; i < n; i += NT) {
+            double xr[6];
+#pragma unroll
+            for (int cidx = 0; cidx < 6; ++cidx) {
+                double v = A[(size_t)i * ld + k0 + cidx];
+#pragma unroll
+                for (int j = 0; j < cidx; ++j) v -= xr[j] * s_L[cidx * 6 + j];
+                xr[cidx] = v;
+            }
+#pragma unroll
+            for (int cidx = 0; cidx < 6; ++cidx) { xrow[i * 6 + cidx] = xr[cidx]; A[(size_t)i * ld + k0 + cidx] = xr[cidx] * s_dinv[cidx]; }
+        }
+        __syncthreads();
+        // (3) trailing update: A22[i][j] -= sum_c X[i][c] * L21[j][c], warp per row
+        for (int i = k0 + 6 + warp; i < n; i += NWARP) {
+            double xi[6];
+#pragma unroll
+            for (int cidx = 0; cidx < 6; ++cidx) xi[cidx] = xrow[i * 6 + cidx];
+            for (int j = k0 + 6 + lane; j <= i; j += 32) {
+                const double* lj = A + (size_t)j * ld + k0;
+                double sacc = 0;
+#pragma unroll
+                for (int cidx = 0; cidx < 6; ++cidx) sacc += xi[cidx] * lj[cidx];
+                A[(size_t)i * ld + j] -= sacc;
+            }
+        }
         __syncthreads();
     }
-    __syncthreads();
-    const int ok = s_ok;
-    __syncthreads();
-    if (!ok) return 0;
-    // solve L D L^T x = bs; y kept in D.x (pose part), column-oriented substitutions
-    double* y = D.x;
-    for (int i = tid; i < n; i += NT) y[i] = D.bs[i];
-    __syncthreads();
-    for (int k = 0; k < n; ++k) {          // forward: y_i -= L_ik y_k
-        const double yk = y[k];
-        for (int i = k + 1 + tid; i < n; i += NT) y[i] -= A[(size_t)i * ld + k] * yk;
-        __syncthreads();
+    // L D L^T x = bs by warp 0 alone (warp-synchronous column-oriented substitutions), y kept in shared memory
+    double* y = xrow;   // the panel scratch is free now (n <= 6 n doubles)
+    if (warp == 0) {
+        for (int i = lane; i < n; i += 32) y[i] = D.bs[i];
+        __syncwarp();
+        for (int k = 0; k < n; ++k) {
+            const double yk = y[k];
+            for (int i = k + 1 + lane; i < n; i += 32) y[i] -= A[(size_t)i * ld + k] * yk;
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32) y[i] /= A[(size_t)i * ld + i];
+        __syncwarp();
+        for (int k = n - 1; k >= 0; --k) {
+            const double yk = y[k];
+            for (int j = lane; j < k; j += 32) y[j] -= A[(size_t)k * ld + j] * yk;
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32) D.x[i] = y[i];
     }
-    for (int i = tid; i < n; i += NT) y[i] /= A[(size_t)i * ld + i];
     __syncthreads();
-    for (int k = n - 1; k >= 0; --k) {     // backward: y_j -= L_kj y_k for j < k
-        const double yk = y[k];
-        for (int j = tid; j < k; j += NT) y[j] -= A[(size_t)k * ld + j] * yk;
-        __syncthreads();
-    }
     return 1;
 }
-// ---- landmark back-substitution x_l = Hll^-1 (bl - W^T x_p)  (block_solver.hpp:461-483) ----
+// ---- landmark back-substitution x_l = Hll^-1 (bl - W^T x_p)  (block_solver.hpp:461-483); 8 lanes per point ----
 __device__ void phase_backsub(const Dev& D, const Ctx& c) {
-    for (int p = c.wid; p < D.nL; p += c.nw) {
-        double cl[3] = {D.bl[3 * (size_t)p], D.bl[3 * (size_t)p + 1], D.bl[3 * (size_t)p + 2]};
-        for (int k = D.ptStart[p]; k < D.ptStart[p + 1]; ++k) {
-            const int e = D.ptEdges[k];
+    const int sl = c.tid & 7;
+    const unsigned gmask = 0xFFu << (c.tid & 24);
+    for (int p = c.wid >> 3; p < D.nL; p += c.nw >> 3) {
+        double cl[3] = {0, 0, 0};
+        for (int e = D.ptStart[p] + sl; e < D.ptStart[p + 1]; e += 8) {
             const int h = D.hidx[D.ePose[e]];
             if (h < 0) continue;
-            const double* Wd = D.W + 18 * (size_t)e;
+            double w[18];
+            load18(D.W + 18 * (size_t)e, w);
             const double* xp = D.x + 6 * (size_t)h;
 #pragma unroll
             for (int b = 0; b < 3; ++b)
 #pragma unroll
-                for (int a = 0; a < 6; ++a) cl[b] -= Wd[a * 3 + b] * xp[a];
+                for (int a = 0; a < 6; ++a) cl[b] -= w[a * 3 + b] * xp[a];
         }
-        const double* Di = D.Dinv + 9 * (size_t)p;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) D.x[D.n + 3 * (size_t)p + a] = Di[a * 3] * cl[0] + Di[a * 3 + 1] * cl[1] + Di[a * 3 + 2] * cl[2];
+        for (int o = 4; o; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) cl[i] += __shfl_xor_sync(gmask, cl[i], o);
+        }
+        if (sl < 3) {
+            const double* Di = D.Dinv + 9 * (size_t)p;
+            const double* b3 = D.bl + 3 * (size_t)p;
+            const double c0 = cl[0] + b3[0], c1 = cl[1] + b3[1], c2 = cl[2] + b3[2];
+            D.x[D.n + 3 * (size_t)p + sl] = Di[sl * 3] * c0 + Di[sl * 3 + 1] * c1 + Di[sl * 3 + 2] * c2;
+        }
     }
 }
 // ---- push + update (SparseOptimizer::push / update) and the partial sum of computeScale ----
@@ -516,10 +673,11 @@ __device__ void phase_restore(const Dev& D, const Ctx& c) {   // pop
 __device__ void phase_finalize(const Dev& D, const Ctx& c) {
     for (int e = c.wid; e < D.nE; e += c.nw) {
         const double e0 = D.err[2 * (size_t)e], e1 = D.err[2 * (size_t)e + 1];
-        D.outChi2[e] = (double)D.invSigma2[e] * (e0 * e0 + e1 * e1);   // e->chi2() from the last computed _error (Optimizer.cc:1425)
+        const int o = D.eOrig[e];
+        D.outChi2[o] = (double)D.invSigma2[e] * (e0 * e0 + e1 * e1);   // e->chi2() from the last computed _error (Optimizer.cc:1425)
         double Xc[3], uv[2];
-        project_edge(D, e, Xc, uv);
-        D.outDepthPos[e] = Xc[2] > 0.0;
+        project_edge(D, c, e, Xc, uv);
+        D.outDepthPos[o] = Xc[2] > 0.0;
     }
 }
 
@@ -527,41 +685,56 @@ __device__ void phase_finalize(const Dev& D, const Ctx& c) {
 // The persistent kernel: SparseOptimizer::optimize (sparse_optimizer.cpp:354-418) around
 // OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-168), one cluster per problem.
 // Every thread carries the (uniform) LM state; decisions use values every CTA reads identically after a cluster barrier.
+// Dynamic shared memory: pose cache (PC x maxP doubles) | LDLT panel scratch (6 maxP x 6) | reduced camera system (smemMatrixN^2).
 // =============================================================================================
-__global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restrict__ probs, const volatile int* stop, int smemMatrixN) {
-    extern __shared__ double s_mat[];          // reduced camera system (CTA 0) when it fits: smemMatrixN^2 doubles
+__global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restrict__ probs, const volatile int* stop, int smemMatrixN, int maxP) {
+    extern __shared__ double s_dyn[];
     __shared__ double s_red[NT];
     cg::cluster_group cluster = cg::this_cluster();
     Ctx c;
     c.crank = (int)cluster.block_rank(); c.csize = (int)cluster.num_blocks(); c.tid = threadIdx.x;
     c.wid = c.crank * NT + c.tid; c.nw = c.csize * NT; c.slot = 0; c.sm = s_red;
+    double* s_pc = s_dyn;
+    double* s_col = s_pc + PC * maxP;
+    double* s_mat = s_col + 36 * maxP;
+    c.pc = s_pc;
     const Dev D = probs[blockIdx.x / c.csize];
-    const bool matInSmem = D.n <= smemMatrixN;
-    // reduced camera system: CTA 0's shared memory, reached from the other CTAs of the cluster as distributed shared memory
-    double* Hs = matInSmem ? cluster.map_shared_rank(s_mat, 0) : D.Hs;
+    const bool matInSmem = D.n <= smemMatrixN && D.n > 0;
+    // reduced camera system: CTA 0's shared memory; the other CTAs of the cluster reach it as distributed shared memory
+    double* HsRemote = matInSmem ? cluster.map_shared_rank(s_mat, 0) : D.Hs;
+    double* HsLocal = matInSmem ? s_mat : D.Hs;
     const int ld = D.n;
     const int stopIdx = blockIdx.x / c.csize;
+    const bool poller = c.crank == 0 && c.tid == 0;
 
     for (int i = c.wid; i < D.nP; i += c.nw) qnormalize(D.poses + 7 * (size_t)i);   // SE3Quat(q, t) constructor
     for (int i = c.wid; i < 2 * D.nE; i += c.nw) D.err[i] = 0.0;
     for (int i = c.wid; i < D.n + 3 * D.nL; i += c.nw) D.x[i] = 0.0;
     int term = 0, dummy;
-    // initial terminate() poll (+ makes the normalised poses visible cluster-wide)
-    cluster_sum(D, c, 0.0, (stop && stop[stopIdx]) ? 1 : 0, term);
+    cluster_sum(D, c, 0.0, (poller && stop && stop[stopIdx]) ? 1 : 0, term);   // initial terminate() poll + publishes the poses
+    load_pose_cache(D, s_pc);
 
     double lambda = -1, ni = 2, currentChi = 0, firstChi = 0;
     int nBad = 0, cj = 0, trials = 0;
     const int maxTrials = 10;
     const double goodUpper = 2. / 3., goodLower = 1. / 3., tau = 1e-5;
     bool ok = true;
+    unsigned long long tph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0;
+#define TICK() t0 = globaltimer_ns()
+#define TOCK(i) tph[i] += globaltimer_ns() - t0
     for (int it = 0; it < D.iterations && !term && ok; ++it) {
+        TICK();
         currentChi = cluster_sum(D, c, phase_errors(D, c), 0, dummy);
+        TOCK(0);
         double tempChi = currentChi;
         const double iniChi = currentChi;
         if (it == 0) firstChi = iniChi;
+        TICK();
         phase_build_points(D, c);
+        TOCK(1); TICK();
         phase_build_poses(D, c);
         csync();
+        TOCK(2);
         if (it == 0) {
             if (D.userLambdaInit > 0) lambda = D.userLambdaInit;
             else lambda = tau * phase_maxdiag(D, c);
@@ -570,23 +743,35 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
         double rho = 0;
         int qmax = 0;
         do {
+            TICK();
             phase_point_prep(D, c, lambda);
             csync();
+            TOCK(3);
             int ok2 = 1;
             if (D.nF) {
-                phase_schur(D, c, lambda, Hs, ld);   // every CTA writes its block pairs (into CTA 0's shared memory through DSMEM)
+                TICK();
+                phase_schur_partial(D, c);
                 csync();
+                phase_schur_combine(D, c, lambda, HsRemote, ld);   // every CTA writes entries into CTA 0's shared memory through DSMEM
+                csync();
+                TOCK(4); TICK();
                 if (c.crank == 0) {
-                    ok2 = phase_ldlt(D, c, Hs, ld);
+                    ok2 = phase_ldlt(D, c, HsLocal, ld, s_col);
                     if (c.tid == 0) D.partial[4 * PSLOT] = (double)ok2;
                 }
                 csync();
                 ok2 = (int)D.partial[4 * PSLOT];
+                TOCK(5);
             }
+            TICK();
             phase_backsub(D, c);
             csync();
+            TOCK(6); TICK();
             const double scale0 = cluster_sum(D, c, phase_update(D, c, lambda), 0, dummy);
-            tempChi = cluster_sum(D, c, phase_errors(D, c), (stop && stop[stopIdx]) ? 1 : 0, term);
+            load_pose_cache(D, s_pc);
+            TOCK(7); TICK();
+            tempChi = cluster_sum(D, c, phase_errors(D, c), (poller && stop && stop[stopIdx]) ? 1 : 0, term);
+            TOCK(8);
             if (!ok2) tempChi = DBL_MAX;
             rho = currentChi - tempChi;
             const double scale = scale0 + 1e-3;
@@ -603,6 +788,7 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
                 ni *= 2;
                 phase_restore(D, c);
                 csync();
+                load_pose_cache(D, s_pc);
             }
             ++qmax; ++trials;
         } while (rho < 0 && qmax < maxTrials && !term);
@@ -614,9 +800,9 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
         }
     }
     phase_finalize(D, c);
+    if (c.wid == 0) for (int i = 0; i < 10; ++i) D.stats[8 + i] = (double)tph[i];
     if (c.wid == 0) { D.stats[0] = cj; D.stats[1] = trials; D.stats[2] = lambda; D.stats[3] = currentChi; D.stats[4] = firstChi; }
 }
-
 
 // =============================================================================================
 // host side
@@ -635,6 +821,7 @@ struct Solver {
     int* h_stop = nullptr; int* d_stop = nullptr;   // mapped pinned stop flags, one per problem
     cudaEvent_t evDone = nullptr;
     int nLoaded = 0, launches = 0, smemN = 0, numSMs = 148;
+    size_t fixedSmem = 0;
     ~Solver() {
         cudaSetDevice(device);
         if (d_arena) cudaFree(d_arena);
@@ -651,10 +838,16 @@ struct Solver {
         b += 2 * al(56 * nP) + 2 * al(24 * nL) + al(56 * nP) + al(24 * nL);      // poses, bk, pts, bk, initial copies
         b += al(16 * nP) + 2 * al(4 * nP);                                        // cam, hidx, freePose
         b += 2 * al(4 * nE) + al(16 * nE) + al(4 * nE);                           // ePt, ePose, obs, invSigma2
-        b += al(4 * (nL + 1)) + al(4 * nE) + al(4 * (nP + 1)) + al(4 * nE) + al(4 * nL * nP);   // CSR + edgeAt
+        b += al(4 * (nL + 1)) + al(4 * nE) + al(4 * (nP + 1)) + al(4 * nE);                     // CSR, eOrig
+        b += al(4 * (nP * nP / 2 + 2)) + al(8 * (nE * (nP > 1 ? nP - 1 : 1) / 2 + 1));              // Schur block starts + (e1, e2) pair lists
         b += al(16 * nE) + 2 * al(144 * nE);                                      // err, W, Y
         b += al(288 * nP) + al(48 * nP) + 2 * al(72 * nL) + 2 * al(24 * nL);      // Hpp, bp, Hll, Dinv, bl, db
-        b += al(8 * n * n) + al(8 * n) + al(8 * (n + 3 * nL)) + al(8 * (4 * PSLOT + 8)) + al(64);   // Hs, bs, x, partial, stats
+        b += al(8 * n * n) + al(8 * n) + al(8 * (n + 3 * nL)) + al(8 * (4 * PSLOT + 8)) + al(256);   // Hs, bs, x, partial, stats
+        {   // Schur chunk tables + partial sums: at most (#tasks + #items / SCH) chunks
+            const size_t items = nE + nE * (nP > 1 ? nP - 1 : 1) / 2 + 1, tasks = nP + nP * nP / 2 + 2;
+            const size_t ch = tasks + items / SCH + 1;
+            b += 2 * al(4 * ch) + al(4 * (tasks + 1)) + al(8 * 42 * ch);
+        }
         b += al(8 * nE) + al(nE);                                                 // outputs
         return b;
     }
@@ -673,11 +866,13 @@ struct Solver {
         CK(cudaHostGetDevicePointer(&d_stop, h_stop, 0));
         CK(cudaEventCreateWithFlags(&evDone, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        // shared-memory budget for the reduced camera system: up to 200 KB of the 227 KB opt-in limit
-        const int maxDyn = 200 * 1024;
-        smemN = (int)floor(sqrt((double)maxDyn / 8.0));
+        // dynamic shared memory: pose cache + two LDLT column buffers + (when it fits) the reduced camera system,
+        // within 200 KB of the 227 KB opt-in limit
+        fixedSmem = 8 * (size_t)(PC + 36) * maxP;
+        const size_t maxDyn = 200 * 1024;
+        smemN = fixedSmem < maxDyn ? (int)floor(sqrt((double)(maxDyn - fixedSmem) / 8.0)) : 0;
         smemN = std::min(smemN, 6 * maxP);
-        CK(cudaFuncSetAttribute(lba_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(8 * (size_t)smemN * smemN, 1024)));
+        CK(cudaFuncSetAttribute(lba_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fixedSmem + 8 * (size_t)smemN * smemN)));
         h_probs.resize(maxBatch); packed.resize(maxBatch);
         return ORB_OK;
     }
@@ -694,7 +889,8 @@ struct Solver {
         for (int i = 0; i < nP; ++i) if (!P->poseFixed[i]) { hidx[i] = (int)freePose.size(); freePose.push_back(i); }
         const int nF = (int)freePose.size(), n = 6 * nF;
         if (nF + nL == 0) { set_error("lba: 0 vertices to optimize"); return ORB_ERR_ARG; }
-        std::vector<int> ptStart(nL + 1, 0), poseStart(nP + 1, 0), ptEdges(nE), poseEdges(nE);
+        // internal edge order: stable sort by point, so that the edges of a point are contiguous
+        std::vector<int> ptStart(nL + 1, 0), poseStart(nP + 1, 0), eOrig(nE), inv(nE), poseEdges(nE);
         for (int e = 0; e < nE; ++e) {
             const int p = P->edgePoint[e], c = P->edgePose[e];
             if (p < 0 || p >= nL || c < 0 || c >= nP) { set_error("lba: edge index out of range"); return ORB_ERR_ARG; }
@@ -703,9 +899,60 @@ struct Solver {
         for (int i = 0; i < nL; ++i) ptStart[i + 1] += ptStart[i];
         for (int i = 0; i < nP; ++i) poseStart[i + 1] += poseStart[i];
         {
-            std::vector<int> a(ptStart.begin(), ptStart.end() - 1), b(poseStart.begin(), poseStart.end() - 1);
-            for (int e = 0; e < nE; ++e) { ptEdges[a[P->edgePoint[e]]++] = e; poseEdges[b[P->edgePose[e]]++] = e; }
+            std::vector<int> a(ptStart.begin(), ptStart.end() - 1);
+            for (int e = 0; e < nE; ++e) { const int k = a[P->edgePoint[e]]++; eOrig[k] = e; inv[e] = k; }
+            std::vector<int> b(poseStart.begin(), poseStart.end() - 1);
+            for (int k = 0; k < nE; ++k) poseEdges[b[P->edgePose[eOrig[k]]]++] = k;     // ascending internal ids per pose
         }
+        std::vector<int> ePt(nE), ePose(nE); std::vector<double> obs(2 * (size_t)nE); std::vector<float> is2(nE);
+        for (int k = 0; k < nE; ++k) {
+            const int e = eOrig[k];
+            ePt[k] = P->edgePoint[e]; ePose[k] = P->edgePose[e]; obs[2 * (size_t)k] = P->obs[2 * (size_t)e]; obs[2 * (size_t)k + 1] = P->obs[2 * (size_t)e + 1];
+            is2[k] = P->invSigma2[e];
+        }
+        // Schur structure: for every point, every pair of its free-pose edges (i1 < i2) goes to block (i1, i2)
+        const int nOff = nF * (nF - 1) / 2;
+        auto blockOf = [&](int i1, int i2) { return i1 * (nF - 1) - i1 * (i1 - 1) / 2 + (i2 - i1 - 1); };
+        std::vector<int> blockStart(nOff + 1, 0);
+        std::vector<int> fe;   // free edges of the current point: (hidx, internal id)
+        size_t nPairs = 0;
+        for (int p = 0; p < nL; ++p) {
+            fe.clear();
+            for (int k = ptStart[p]; k < ptStart[p + 1]; ++k) if (hidx[ePose[k]] >= 0) fe.push_back(k);
+            for (size_t a2 = 0; a2 < fe.size(); ++a2)
+                for (size_t b2 = a2 + 1; b2 < fe.size(); ++b2) {
+                    const int h1 = hidx[ePose[fe[a2]]], h2 = hidx[ePose[fe[b2]]];
+                    if (h1 == h2) { set_error("lba: duplicate (point, keyframe) observation"); return ORB_ERR_ARG; }
+                    ++blockStart[blockOf(std::min(h1, h2), std::max(h1, h2)) + 1];
+                    ++nPairs;
+                }
+        }
+        if (nPairs > (size_t)nE * (nP > 1 ? nP - 1 : 1) / 2 + 1) { set_error("lba: pair list larger than sized"); return ORB_ERR_CAPACITY; }
+        for (int i = 0; i < nOff; ++i) blockStart[i + 1] += blockStart[i];
+        std::vector<int2> pairs(nPairs);
+        {
+            std::vector<int> cur(blockStart.begin(), blockStart.end() - 1);
+            for (int p = 0; p < nL; ++p) {
+                fe.clear();
+                for (int k = ptStart[p]; k < ptStart[p + 1]; ++k) if (hidx[ePose[k]] >= 0) fe.push_back(k);
+                for (size_t a2 = 0; a2 < fe.size(); ++a2)
+                    for (size_t b2 = a2 + 1; b2 < fe.size(); ++b2) {
+                        int k1 = fe[a2], k2 = fe[b2];
+                        if (hidx[ePose[k1]] > hidx[ePose[k2]]) std::swap(k1, k2);
+                        const int blk = blockOf(hidx[ePose[k1]], hidx[ePose[k2]]);
+                        pairs[cur[blk]++] = make_int2(k1, k2);
+                    }
+            }
+        }
+        // Schur work list cut into chunks of SCH items
+        std::vector<int> chunkTask, chunkFirst, taskChunkStart(nF + nOff + 1, 0);
+        for (int t = 0; t < nF + nOff; ++t) {
+            const int len = t < nF ? poseStart[freePose[t] + 1] - poseStart[freePose[t]] : blockStart[t - nF + 1] - blockStart[t - nF];
+            taskChunkStart[t] = (int)chunkTask.size();
+            for (int f = 0; f < len; f += SCH) { chunkTask.push_back(t); chunkFirst.push_back(f); }
+        }
+        taskChunkStart[nF + nOff] = (int)chunkTask.size();
+        const int nChunks = (int)chunkTask.size();
         const size_t base = perProblem * (size_t)slot;
         size_t off = base;
         auto carve = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
@@ -721,29 +968,20 @@ struct Solver {
         o = carve(16 * (size_t)nP); put(o, P->cam, 16 * (size_t)nP); D.cam = (const float*)(d_arena + o);
         o = carve(4 * (size_t)nP); put(o, hidx.data(), 4 * (size_t)nP); D.hidx = (const int*)(d_arena + o);
         o = carve(4 * (size_t)std::max(nF, 1)); put(o, freePose.data(), 4 * (size_t)nF); D.freePose = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)nE); put(o, P->edgePoint, 4 * (size_t)nE); D.ePt = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)nE); put(o, P->edgePose, 4 * (size_t)nE); D.ePose = (const int*)(d_arena + o);
-        o = carve(16 * (size_t)nE); put(o, P->obs, 16 * (size_t)nE); D.obs = (const double*)(d_arena + o);
-        o = carve(4 * (size_t)nE); put(o, P->invSigma2, 4 * (size_t)nE); D.invSigma2 = (const float*)(d_arena + o);
+        o = carve(4 * (size_t)nE); put(o, ePt.data(), 4 * (size_t)nE); D.ePt = (const int*)(d_arena + o);
+        o = carve(4 * (size_t)nE); put(o, ePose.data(), 4 * (size_t)nE); D.ePose = (const int*)(d_arena + o);
+        o = carve(4 * (size_t)nE); put(o, eOrig.data(), 4 * (size_t)nE); D.eOrig = (const int*)(d_arena + o);
+        o = carve(16 * (size_t)nE); put(o, obs.data(), 16 * (size_t)nE); D.obs = (const double*)(d_arena + o);
+        o = carve(4 * (size_t)nE); put(o, is2.data(), 4 * (size_t)nE); D.invSigma2 = (const float*)(d_arena + o);
         o = carve(4 * (size_t)(nL + 1)); put(o, ptStart.data(), 4 * (size_t)(nL + 1)); D.ptStart = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)nE); put(o, ptEdges.data(), 4 * (size_t)nE); D.ptEdges = (const int*)(d_arena + o);
         o = carve(4 * (size_t)(nP + 1)); put(o, poseStart.data(), 4 * (size_t)(nP + 1)); D.poseStart = (const int*)(d_arena + o);
         o = carve(4 * (size_t)nE); put(o, poseEdges.data(), 4 * (size_t)nE); D.poseEdges = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)nL * std::max(nF, 1));
-        {
-            int* ea = (int*)(h_arena + o);
-            const size_t cnt = (size_t)nL * std::max(nF, 1);
-            for (size_t i = 0; i < cnt; ++i) ea[i] = -1;
-            for (int e = 0; e < nE; ++e) {
-                const int hI = hidx[P->edgePose[e]];
-                if (hI >= 0) {
-                    int& s = ea[(size_t)P->edgePoint[e] * nF + hI];
-                    if (s >= 0) { set_error("lba: duplicate (point, keyframe) observation"); return ORB_ERR_ARG; }
-                    s = e;
-                }
-            }
-            D.edgeAt = (const int*)(d_arena + o);
-        }
+        o = carve(4 * (size_t)(nOff + 1)); put(o, blockStart.data(), 4 * (size_t)(nOff + 1)); D.blockStart = (const int*)(d_arena + o);
+        o = carve(8 * std::max<size_t>(nPairs, 1)); put(o, pairs.data(), 8 * nPairs); D.pairs = (const int2*)(d_arena + o);
+        D.nChunks = nChunks;
+        o = carve(4 * (size_t)std::max(nChunks, 1)); put(o, chunkTask.data(), 4 * (size_t)nChunks); D.chunkTask = (const int*)(d_arena + o);
+        o = carve(4 * (size_t)std::max(nChunks, 1)); put(o, chunkFirst.data(), 4 * (size_t)nChunks); D.chunkFirst = (const int*)(d_arena + o);
+        o = carve(4 * (size_t)(nF + nOff + 1)); put(o, taskChunkStart.data(), 4 * (size_t)(nF + nOff + 1)); D.taskChunkStart = (const int*)(d_arena + o);
         uploadBytes[slot] = off - base;
         // --- device-only scratch / state / outputs ---
         K.posesOff = carve(56 * (size_t)nP); D.poses = (double*)(d_arena + K.posesOff);
@@ -755,10 +993,11 @@ struct Solver {
         D.Hpp = (double*)(d_arena + carve(288 * (size_t)std::max(nF, 1))); D.bp = (double*)(d_arena + carve(48 * (size_t)std::max(nF, 1)));
         D.Hll = (double*)(d_arena + carve(72 * (size_t)nL)); D.bl = (double*)(d_arena + carve(24 * (size_t)nL));
         D.Dinv = (double*)(d_arena + carve(72 * (size_t)nL)); D.db = (double*)(d_arena + carve(24 * (size_t)nL));
+        D.Spart = (double*)(d_arena + carve(8 * 42 * (size_t)std::max(nChunks, 1)));
         D.Hs = (double*)(d_arena + carve(8 * (size_t)n * n)); D.bs = (double*)(d_arena + carve(8 * (size_t)std::max(n, 1)));
         D.x = (double*)(d_arena + carve(8 * ((size_t)n + 3 * (size_t)nL)));
         D.partial = (double*)(d_arena + carve(8 * (4 * PSLOT + 8)));
-        K.statsOff = carve(64); D.stats = (double*)(d_arena + K.statsOff);
+        K.statsOff = carve(256); D.stats = (double*)(d_arena + K.statsOff);
         K.chi2Off = carve(8 * (size_t)nE); D.outChi2 = (double*)(d_arena + K.chi2Off);
         K.dposOff = carve((size_t)nE); D.outDepthPos = (uint8_t*)(d_arena + K.dposOff);
         if (off - base > perProblem) { set_error("lba: arena too small (internal sizing error)"); return ORB_ERR_CAPACITY; }
@@ -775,6 +1014,7 @@ struct Solver {
         for (int i = 0; i < count; ++i)
             CK(cudaMemcpyAsync(d_arena + perProblem * (size_t)i, h_arena + perProblem * (size_t)i, uploadBytes[i], cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_probs, h_probs.data(), sizeof(Dev) * count, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // the resident copy must be complete before a run on any other stream
         nLoaded = count;
         return ORB_OK;
     }
@@ -794,14 +1034,14 @@ struct Solver {
         const int matN = maxN <= smemN ? maxN : 0;   // matrix in shared memory only when every problem of the batch fits
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(nLoaded * csize); cfg.blockDim = dim3(NT);
-        cfg.dynamicSmemBytes = std::max<size_t>(8 * (size_t)matN * matN, 16);
+        cfg.dynamicSmemBytes = fixedSmem + 8 * (size_t)matN * matN;
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        const Dev* dp = d_probs; const volatile int* ds = d_stop; int mn = matN;
-        CK(cudaLaunchKernelEx(&cfg, lba_cluster_kernel, dp, ds, mn));
+        const Dev* dp = d_probs; const volatile int* ds = d_stop; int mn = matN, mp = maxP;
+        CK(cudaLaunchKernelEx(&cfg, lba_cluster_kernel, dp, ds, mn, mp));
         launches = 1;
         lastCluster = csize;
         return ORB_OK;
@@ -818,7 +1058,7 @@ struct Solver {
                 CK(cudaMemcpyAsync(R.edgeChi2, d_arena + K.chi2Off, 8 * (size_t)K.nE, cudaMemcpyDeviceToHost, s));
                 CK(cudaMemcpyAsync(R.edgeDepthPositive, d_arena + K.dposOff, (size_t)K.nE, cudaMemcpyDeviceToHost, s));
             }
-            CK(cudaMemcpyAsync(h_arena + K.statsOff, d_arena + K.statsOff, 64, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(h_arena + K.statsOff, d_arena + K.statsOff, 256, cudaMemcpyDeviceToHost, s));
         }
         CK(cudaStreamSynchronize(s));
         for (int i = 0; i < count; ++i) {
@@ -869,6 +1109,13 @@ int lba_download_batch(lba_handle* h, int count, LbaResult* results) {
     return h->s.download(count, results, h->s.st);
 }
 int lba_last_cluster_size(const lba_handle* h) { return h ? h->s.lastCluster : ORB_ERR_ARG; }
+/* ns spent by CTA 0 of problem `i` in each phase of the last downloaded run: errors, build_points, build_poses, point_prep, schur, ldlt, backsub, update, errors(trial) */
+int lba_get_phase_ns(const lba_handle* h, int i, double* ns10) {
+    if (!h || !ns10 || i < 0 || i >= h->s.nLoaded) return ORB_ERR_ARG;
+    const double* stt = (const double*)(h->s.h_arena + h->s.packed[i].statsOff);
+    for (int k = 0; k < 10; ++k) ns10[k] = stt[8 + k];
+    return ORB_OK;
+}
 
 int lba_solve_batch(lba_handle* h, int count, const LbaProblem* problems, LbaResult* results) {
     if (!h || !problems || !results) { set_error("lba_solve_batch: bad argument"); return ORB_ERR_ARG; }
