@@ -284,14 +284,16 @@ def main():
                     bounds=(0.0, 0.0, float(W), float(H)), cam=cam, reset=1)
 
     def step_device(i):
-        ev_fork.record(stream)
-        lba_stream.wait_event(ev_fork)
+        # LocalMapping is asynchronous to Tracking in the reference (own thread, src/System.cc:197): the LBAs of step i are
+        # enqueued on their own stream and only joined at the end of the timed region (all of them finish inside it).
         opt.run_device(lba_stream.cuda_stream)                       # B / KF_INTERVAL LBAs, one persistent kernel
         ex.extract_batch_device(dev_sets[i & 1], d_kps, d_desc, d_n, d_mono, (0, 1000), stream.cuda_stream)
         matcher.search_last_frame_batch_device(match_args(i), TH_PROJ, d_match, d_claimed, d_nmatch, stream.cuda_stream)
         if world > 1:   # shared-map exchange: one all-gather of the fixed-capacity keypoint/descriptor slabs
             for src, dst in zip((d_kps, d_desc, d_n), gathered):
                 dist.all_gather_into_tensor(dst, src)
+
+    def join_lba():
         ev_join.record(lba_stream)
         stream.wait_event(ev_join)
 
@@ -303,12 +305,16 @@ def main():
     # ---------------- device-resident timing (`value`) ----------------
     for i in range(args.warmup):
         step_device(i)
+    join_lba()
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_fork.record(stream)
+    lba_stream.wait_event(ev_fork)
     e0.record(stream)
     for i in range(args.steps):
         step_device(i)
+    join_lba()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)

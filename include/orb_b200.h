@@ -249,6 +249,8 @@ int lba_run_batch_device(lba_handle* h, void* stream);
 int lba_download_batch(lba_handle* h, int count, LbaResult* results);
 /* Thread-block-cluster size (CTAs per problem) the last run used. */
 int lba_last_cluster_size(const lba_handle* h);
+/* Force the cluster size (1, 2, 4, 8 CTAs per problem; 0 = automatic: the largest that lets the whole batch run at once). */
+int lba_set_cluster_size(lba_handle* h, int ctas);
 /* Device-side phase timers (ns, CTA 0) of problem i of the last downloaded run: errors, build_points, build_poses, point_prep,
  * schur, ldlt, backsub, update, errors(trial), spare. */
 int lba_get_phase_ns(const lba_handle* h, int i, double* ns10);

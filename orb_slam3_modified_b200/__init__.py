@@ -468,6 +468,12 @@ class Optimizer:
     def last_cluster_size(self):
         return lib().lba_last_cluster_size(self._h)
 
+    def set_cluster_size(self, ctas):
+        lib().lba_set_cluster_size.argtypes = [C.c_void_p, C.c_int]
+        rc = lib().lba_set_cluster_size(self._h, ctas)
+        if rc != ORB_OK:
+            raise OrbError(rc, 'lba_set_cluster_size')
+
     def LocalBundleAdjustment(self, prob, iterations=10, user_lambda_init=0.0, stop_flag=None):
         keep = dict(poses=_c(prob['poses'], np.float64), fixed=_c(prob['fixed'], np.uint8), cam=_c(prob['cam'], np.float32),
                     points=_c(prob['points'], np.float64), ep=_c(prob['edge_point'], np.int32), ek=_c(prob['edge_pose'], np.int32),

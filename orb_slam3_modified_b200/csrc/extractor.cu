@@ -159,7 +159,8 @@ struct Extractor {
                     cells.push_back(cd);
                     const int tp = (cd.rw + 3) & ~3, iw = cd.rw - 6, ih = cd.rh - 6;
                     if (iw > 0 && ih > 0) {
-                        size_t sm = (((size_t)cd.rh * tp + 15) & ~15) + ((((size_t)ih + 2) * (iw + 2) + 15) & ~15) + 2 * (size_t)iw * ih;
+                        const size_t spm = ((size_t)iw + 2 + 3) & ~(size_t)3;
+                        size_t sm = (((size_t)cd.rh * tp + 15) & ~15) + ((((size_t)ih + 2) * spm + 15) & ~15) + 2 * (size_t)iw * ih;
                         smemFast = std::max(smemFast, sm);
                     }
                 }

@@ -133,51 +133,51 @@ __global__ void __launch_bounds__(FAST_NT) fast_cells_kernel(ExtractParams P) {
     int* outCount = P.cellCount + (size_t)f * P.cellCountStride + blockIdx.x;
     if (rw < 7 || rh < 7) { if (threadIdx.x == 0) *outCount = 0; return; }
     const int tp = (rw + 3) & ~3;               // tile pitch
-    const int iw = rw - 6, ih = rh - 6;         // detection interior
-    const int sp = iw + 2;                      // score-map pitch (1-px zero ring)
+    const int iw = rw - 6, ih = rh - 6;         // detection interior (<= 70 x 70)
+    const int sp = (iw + 2 + 3) & ~3;           // score-map pitch (1-px zero ring), word aligned
     uint8_t* tile = smem_raw;                                   // rh * tp
     uint8_t* score = tile + ((rh * tp + 15) & ~15);             // (ih+2) * sp
-    uint16_t* list = reinterpret_cast<uint16_t*>(score + (((ih + 2) * sp + 15) & ~15));  // iw*ih
+    uint16_t* list = reinterpret_cast<uint16_t*>(score + (((ih + 2) * sp + 15) & ~15));  // iw*ih candidates (y << 7 | x)
     __shared__ int s_nCand, s_cntHi, s_warp[33];
-    const int tid = threadIdx.x;
+    __shared__ uint32_t s_hi[72 * 3], s_lo[72 * 3];             // per-row keep bitmaps (<= 70 rows x 96 columns)
+    __shared__ int s_rowOff[96];
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;  // 32 x 8 threads
 
     int pitch;
     const uint8_t* img = plane_ptr(P, f, cd.level, pitch);
     img += (size_t)cd.y0 * pitch + cd.x0;
-    for (int i = tid; i < rh * rw; i += FAST_NT) {
-        const int y = i / rw, x = i - y * rw;
-        tile[y * tp + x] = img[(size_t)y * pitch + x];
-    }
-    for (int i = tid; i < (ih + 2) * sp; i += FAST_NT) score[i] = 0;
+    for (int y = ty; y < rh; y += 8)
+        for (int x = tx; x < rw; x += 32) tile[y * tp + x] = img[(size_t)y * pitch + x];
+    for (int i = tid; i < ((ih + 2) * sp) >> 2; i += FAST_NT) reinterpret_cast<uint32_t*>(score)[i] = 0;
     if (tid == 0) { s_nCand = 0; s_cntHi = 0; }
     __syncthreads();
 
-    // phase 1: cheap rejection (any 9-arc contains pixel k or k+8 for every k) + compaction
+    // phase 1: cheap rejection (any 9-arc contains ring pixel k or k+8 for every k) + compaction of the survivors
     const int th = P.minTh;
-    const int npix = iw * ih;
-    for (int base = 0; base < npix; base += FAST_NT) {
-        const int i = base + tid;
-        bool cand = false;
-        if (i < npix) {
-            const int y = i / iw, x = i - y * iw;
-            const uint8_t* t = tile + (y + 3) * tp + (x + 3);
-            const int v = t[0], lo = v - th, hi = v + th;
-            const int p0 = t[3 * tp], p8 = t[-3 * tp], p4 = t[3], p12 = t[-3];
-            bool dark = (p0 < lo || p8 < lo) && (p4 < lo || p12 < lo);
-            bool brig = (p0 > hi || p8 > hi) && (p4 > hi || p12 > hi);
-            if (dark || brig) {
-                const int p2 = t[2 * tp + 2], p10 = t[-2 * tp - 2], p6 = t[-2 * tp + 2], p14 = t[2 * tp - 2];
-                dark = dark && (p2 < lo || p10 < lo) && (p6 < lo || p14 < lo);
-                brig = brig && (p2 > hi || p10 > hi) && (p6 > hi || p14 > hi);
-                cand = dark || brig;
+    for (int y = ty; y < ih; y += 8) {
+        for (int xb = 0; xb < iw; xb += 32) {
+            const int x = xb + tx;
+            bool cand = false;
+            if (x < iw) {
+                const uint8_t* t = tile + (y + 3) * tp + (x + 3);
+                const int v = t[0], lo = v - th, hi = v + th;
+                const int p0 = t[3 * tp], p8 = t[-3 * tp], p4 = t[3], p12 = t[-3];
+                bool dark = (p0 < lo || p8 < lo) && (p4 < lo || p12 < lo);
+                bool brig = (p0 > hi || p8 > hi) && (p4 > hi || p12 > hi);
+                if (dark || brig) {
+                    const int p2 = t[2 * tp + 2], p10 = t[-2 * tp - 2], p6 = t[-2 * tp + 2], p14 = t[2 * tp - 2];
+                    dark = dark && (p2 < lo || p10 < lo) && (p6 < lo || p14 < lo);
+                    brig = brig && (p2 > hi || p10 > hi) && (p6 > hi || p14 > hi);
+                    cand = dark || brig;
+                }
             }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (m) {
-            int wbase = 0;
-            if ((tid & 31) == 0) wbase = atomicAdd(&s_nCand, __popc(m));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (cand) list[wbase + __popc(m & ((1u << (tid & 31)) - 1))] = (uint16_t)i;
+            const unsigned m = __ballot_sync(0xffffffffu, cand);
+            if (m) {
+                int wbase = 0;
+                if (tx == 0) wbase = atomicAdd(&s_nCand, __popc(m));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (cand) list[wbase + __popc(m & ((1u << tx) - 1))] = (uint16_t)((y << 7) | x);
+            }
         }
     }
     __syncthreads();
@@ -191,47 +191,52 @@ __global__ void __launch_bounds__(FAST_NT) fast_cells_kernel(ExtractParams P) {
         for (int k = 0; k < 16; ++k) off[k] = dys[k] * tp + dxs[k];
         const int nc = s_nCand;
         for (int c = tid; c < nc; c += FAST_NT) {
-            const int i = list[c];
-            const int y = i / iw, x = i - y * iw;
+            const int yx = list[c];
+            const int y = yx >> 7, x = yx & 127;
             const int b = fast_score_at(tile + (y + 3) * tp + (x + 3), off);
             if (b > th) score[(y + 1) * sp + (x + 1)] = (uint8_t)(b - 1);
         }
     }
     __syncthreads();
 
-    // phase 3: strict local maxima; each thread owns a run of R consecutive row-major pixels
-    const int R = (npix + FAST_NT - 1) / FAST_NT;   // <= 32 for interiors up to 8192 px
-    const int i0 = tid * R;
-    unsigned mHi = 0, mLo = 0;
-    for (int r = 0; r < R; ++r) {
-        const int i = i0 + r;
-        if (i >= npix) break;
-        const int y = i / iw, x = i - y * iw;
-        const uint8_t* s = score + (y + 1) * sp + (x + 1);
-        const int v = s[0];
-        if (v == 0) continue;
-        const bool mx = v > s[-1] && v > s[1] && v > s[-sp - 1] && v > s[-sp] && v > s[-sp + 1] &&
-                        v > s[sp - 1] && v > s[sp] && v > s[sp + 1];
-        if (mx) {
-            mLo |= 1u << r;                       // score >= minTh by construction
-            if (v >= P.iniTh) mHi |= 1u << r;
+    // phase 3: strict 8-neighbour maxima -> per-row bitmaps for both thresholds (a ballot is one bitmap word)
+    int cntHi = 0;
+    for (int y = ty; y < ih; y += 8) {
+        for (int xb = 0; xb < iw; xb += 32) {
+            const int x = xb + tx;
+            bool kLo = false, kHi = false;
+            if (x < iw) {
+                const uint8_t* sc = score + (y + 1) * sp + (x + 1);
+                const int v = sc[0];
+                if (v != 0) {
+                    kLo = v > sc[-1] && v > sc[1] && v > sc[-sp - 1] && v > sc[-sp] && v > sc[-sp + 1] &&
+                          v > sc[sp - 1] && v > sc[sp] && v > sc[sp + 1];          // score >= minTh by construction
+                    kHi = kLo && v >= P.iniTh;
+                }
+            }
+            const unsigned mLo = __ballot_sync(0xffffffffu, kLo), mHi = __ballot_sync(0xffffffffu, kHi);
+            if (tx == 0) { s_lo[y * 3 + (xb >> 5)] = mLo; s_hi[y * 3 + (xb >> 5)] = mHi; cntHi += __popc(mHi); }
         }
     }
-    if (mHi) atomicAdd(&s_cntHi, __popc(mHi));
+    if (tx == 0 && cntHi) atomicAdd(&s_cntHi, cntHi);
     __syncthreads();
-    const unsigned mk = s_cntHi > 0 ? mHi : mLo;    // fallback to minTh only if the cell is empty at iniTh (:843-859)
-    // block scan of per-thread counts (FAST_NT == 256 -> one tile)
-    __shared__ int s_cnt[FAST_NT];
-    s_cnt[tid] = __popc(mk);
+    // fallback to minTh only if the cell is empty at iniTh (:843-859); ordered (row-major) emission, one thread per row
+    const uint32_t* bits = s_cntHi > 0 ? s_hi : s_lo;
+    const int nwr = (iw + 31) >> 5;
+    int myCnt = 0;
+    if (tid < ih) for (int w = 0; w < nwr; ++w) myCnt += __popc(bits[tid * 3 + w]);
+    if (tid < 96) s_rowOff[tid] = tid < ih ? myCnt : 0;
     __syncthreads();
-    const int total = block_excl_scan(s_cnt, FAST_NT, s_warp);
-    uint32_t* out = P.cellList + (size_t)f * P.cellListStride + cd.listOff;
-    int o = s_cnt[tid];
-    for (unsigned m = mk; m; m &= m - 1) {
-        const int r = __ffs(m) - 1;
-        const int i = i0 + r;
-        const int y = i / iw, x = i - y * iw;
-        out[o++] = pack_cand(x + 3 + cd.offX, y + 3 + cd.offY, score[(y + 1) * sp + (x + 1)]);
+    const int total = block_excl_scan(s_rowOff, 96, s_warp);
+    if (tid < ih && myCnt) {
+        uint32_t* out = P.cellList + (size_t)f * P.cellListStride + cd.listOff;
+        int o = s_rowOff[tid];
+        const int y = tid;
+        for (int w = 0; w < nwr; ++w)
+            for (unsigned m = bits[y * 3 + w]; m; m &= m - 1) {
+                const int x = (w << 5) + __ffs(m) - 1;
+                out[o++] = pack_cand(x + 3 + cd.offX, y + 3 + cd.offY, score[(y + 1) * sp + (x + 1)]);
+            }
     }
     if (tid == 0) *outCount = total;
 }
@@ -526,7 +531,8 @@ __global__ void __launch_bounds__(QT_NT) quadtree_orient_kernel(ExtractParams P)
 // [18,34,48,56,48,34,18]/256, BORDER_REFLECT_101; reference call site src/ORBextractor.cc:1133,
 // SURVEY.md 9E).  Tile 64x32 per CTA, all levels in one launch.
 // ------------------------------------------------------------------------------------------
-constexpr int BL_TW = 64, BL_TH = 32, BL_NT = 256;
+constexpr int BL_TW = 128, BL_TH = 64, BL_NT = 256;   // tile per CTA; thread = 4 columns x 8 rows
+constexpr int BL_SP = BL_TW + 8;                       // smem row pitch in bytes: columns x0-4 .. x0+TW+3
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
@@ -534,39 +540,76 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
+// One thread produces a 4 (columns) x 8 (rows) strip.  Horizontal pass on pairs of pixels packed as 2 x 16 bit
+// (k*p <= 56*255 and the 7-tap sum <= 65280 fit 16 bits, so one IMAD serves two pixels), vertical pass in 32 bit,
+// result (v + 32768) >> 16 -- bit-identical to cv::GaussianBlur's fixed-point path.
 __global__ void __launch_bounds__(BL_NT) blur_kernel(ExtractParams P) {
-    __shared__ uint8_t tile[(BL_TH + 6)][BL_TW + 8];
-    __shared__ uint16_t hb[(BL_TH + 6)][BL_TW];
+    __shared__ __align__(16) uint8_t tile[(BL_TH + 6) * BL_SP];
     const int f = blockIdx.y;
     int l = 0;
     while (l + 1 < P.nlevels && (int)blockIdx.x >= P.lv[l + 1].blurTileBase) ++l;
     const LevelGeom& G = P.lv[l];
     const int t = blockIdx.x - G.blurTileBase;
-    const int ty = t / G.blurTilesX, tx = t - ty * G.blurTilesX;
-    const int x0 = tx * BL_TW, y0 = ty * BL_TH;
+    const int tyb = t / G.blurTilesX, txb = t - tyb * G.blurTilesX;
+    const int x0 = txb * BL_TW, y0 = tyb * BL_TH;
     int pitch;
     const uint8_t* img = plane_ptr(P, f, l, pitch);
-    for (int i = threadIdx.x; i < (BL_TH + 6) * (BL_TW + 6); i += BL_NT) {
-        const int yy = i / (BL_TW + 6), xx = i - yy * (BL_TW + 6);
-        const int sx = reflect101(min(x0 + xx - 3, G.w + 2), G.w), sy = reflect101(min(y0 + yy - 3, G.h + 2), G.h);
-        tile[yy][xx] = img[(size_t)sy * pitch + sx];
+    const int tid = threadIdx.x;
+    // ---- tile load: rows y0-3 .. y0+TH+2, columns x0-4 .. x0+TW+3 (reflect-101 at the image border) ----
+    const bool interiorX = x0 >= 4 && x0 + BL_TW + 4 <= G.w && ((reinterpret_cast<uintptr_t>(img) + x0) & 3) == 0 && (pitch & 3) == 0;
+    for (int i = tid; i < (BL_TH + 6) * 34; i += BL_NT) {
+        const int r = i / 34, wq = i - r * 34;
+        const int sy = reflect101(min(y0 + r - 3, G.h + 2), G.h);
+        const uint8_t* row = img + (size_t)sy * pitch;
+        uint32_t v;
+        if (interiorX) v = *reinterpret_cast<const uint32_t*>(row + x0 - 4 + 4 * wq);
+        else {
+            v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v |= (uint32_t)row[reflect101(min(x0 - 4 + 4 * wq + k, G.w + 3), G.w)] << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(tile + r * BL_SP + 4 * wq) = v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (BL_TH + 6) * BL_TW; i += BL_NT) {
-        const int yy = i / BL_TW, xx = i - yy * BL_TW;
-        const uint8_t* r = &tile[yy][xx];
-        hb[yy][xx] = (uint16_t)(18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3]);
+    const int tx = tid & 31, ty = tid >> 5;          // 32 x 8 threads
+    const int xo = x0 + 4 * tx, yo = y0 + 8 * ty;
+    if (xo >= G.w || yo >= G.h) return;
+    // horizontal pass for the 14 input rows of this strip: h01 / h23 = packed (h(x), h(x+1)), (h(x+2), h(x+3))
+    uint32_t h01[14], h23[14];
+#pragma unroll
+    for (int r = 0; r < 14; ++r) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(tile + (8 * ty + r) * BL_SP + 4 * tx);
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];   // bytes b0..b11 = columns xo-4 .. xo+7
+        // pair words Ps = b_s | b_{s+1} << 16 (two pixels as 2 x 16 bit), s = 1..9: 32-bit window at byte s, then spread bytes 0,1
+#define ORBX_PAIR(lo, hi, sh) __byte_perm(__funnelshift_r(lo, hi, sh), 0u, 0x4140)
+        const uint32_t P1 = ORBX_PAIR(w0, w1, 8), P2 = ORBX_PAIR(w0, w1, 16), P3 = ORBX_PAIR(w0, w1, 24);
+        const uint32_t P4 = ORBX_PAIR(w1, w2, 0), P5 = ORBX_PAIR(w1, w2, 8), P6 = ORBX_PAIR(w1, w2, 16), P7 = ORBX_PAIR(w1, w2, 24);
+        const uint32_t P8 = ORBX_PAIR(w2, 0u, 0), P9 = ORBX_PAIR(w2, 0u, 8);
+#undef ORBX_PAIR
+        h01[r] = 18u * (P1 + P7) + 34u * (P2 + P6) + 48u * (P3 + P5) + 56u * P4;
+        h23[r] = 18u * (P3 + P9) + 34u * (P4 + P8) + 48u * (P5 + P7) + 56u * P6;
     }
-    __syncthreads();
     int bpitch;
     uint8_t* out = const_cast<uint8_t*>(blur_ptr(P, f, l, bpitch));
-    for (int i = threadIdx.x; i < BL_TH * BL_TW; i += BL_NT) {
-        const int yy = i / BL_TW, xx = i - yy * BL_TW;
-        const int x = x0 + xx, y = y0 + yy;
-        if (x < G.w && y < G.h) {
-            const uint32_t v = 18u * (hb[yy][xx] + hb[yy + 6][xx]) + 34u * (hb[yy + 1][xx] + hb[yy + 5][xx]) +
-                               48u * (hb[yy + 2][xx] + hb[yy + 4][xx]) + 56u * hb[yy + 3][xx];
-            out[(size_t)y * bpitch + x] = (uint8_t)((v + 32768u) >> 16);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (yo + r >= G.h) break;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const uint32_t kj = j == 0 || j == 6 ? 18u : (j == 1 || j == 5 ? 34u : (j == 2 || j == 4 ? 48u : 56u));
+            v[0] += kj * (h01[r + j] & 0xFFFFu); v[1] += kj * (h01[r + j] >> 16);
+            v[2] += kj * (h23[r + j] & 0xFFFFu); v[3] += kj * (h23[r + j] >> 16);
+        }
+        uint32_t pk = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pk |= ((v[k] + 32768u) >> 16) << (8 * k);
+        uint8_t* o = out + (size_t)(yo + r) * bpitch + xo;
+        if (xo + 3 < G.w) *reinterpret_cast<uint32_t*>(o) = pk;     // bpitch and xo are multiples of 4
+        else {
+            for (int k = 0; k < 4 && xo + k < G.w; ++k) o[k] = (uint8_t)(pk >> (8 * k));
         }
     }
 }

@@ -1031,6 +1031,7 @@ struct Solver {
         }
         int csize = 1;
         for (int cand = MAXC; cand >= 1; cand >>= 1) if (nLoaded * cand <= numSMs) { csize = cand; break; }
+        if (forcedCluster > 0) csize = forcedCluster;
         const int matN = maxN <= smemN ? maxN : 0;   // matrix in shared memory only when every problem of the batch fits
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(nLoaded * csize); cfg.blockDim = dim3(NT);
@@ -1046,7 +1047,7 @@ struct Solver {
         lastCluster = csize;
         return ORB_OK;
     }
-    int lastCluster = 1;
+    int lastCluster = 1, forcedCluster = 0;
     int download(int count, LbaResult* res, cudaStream_t s) {
         for (int i = 0; i < count; ++i) {
             const Packed& K = packed[i];
@@ -1109,6 +1110,11 @@ int lba_download_batch(lba_handle* h, int count, LbaResult* results) {
     return h->s.download(count, results, h->s.st);
 }
 int lba_last_cluster_size(const lba_handle* h) { return h ? h->s.lastCluster : ORB_ERR_ARG; }
+int lba_set_cluster_size(lba_handle* h, int ctas) {
+    if (!h || (ctas != 0 && ctas != 1 && ctas != 2 && ctas != 4 && ctas != 8)) { set_error("lba_set_cluster_size: 0 (auto), 1, 2, 4 or 8"); return ORB_ERR_ARG; }
+    h->s.forcedCluster = ctas;
+    return ORB_OK;
+}
 /* ns spent by CTA 0 of problem `i` in each phase of the last downloaded run: errors, build_points, build_poses, point_prep, schur, ldlt, backsub, update, errors(trial) */
 int lba_get_phase_ns(const lba_handle* h, int i, double* ns10) {
     if (!h || !ns10 || i < 0 || i >= h->s.nLoaded) return ORB_ERR_ARG;

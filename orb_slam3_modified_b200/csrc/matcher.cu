@@ -275,19 +275,41 @@ __global__ void __launch_bounds__(32) match_commit_kernel(MatchParams P) {
     __syncwarp();
     int nmatches = 0, nEvents = 0;
     const float factor = 1.0f / HISTO_LENGTH;
+    const bool hist = P.mode == 1 && P.checkOri;
+    auto rot_bin = [&](float lastAngle, float curAngle) {   // rotation histogram bin (:1779-1789)
+        float rot = fsub(lastAngle, curAngle);
+        if (rot < 0.0f) rot = fadd(rot, 360.0f);
+        int bin = (int)roundf(fmul(rot, factor));
+        if (bin == HISTO_LENGTH) bin = 0;
+        return min(max(bin, 0), HISTO_LENGTH - 1);
+    };
     for (int base = 0; base < M; base += 32) {
+        // every lane prefetches everything the serial part needs for "its" map point (gathers run in parallel)
         const int i = base + lane;
         const size_t o = (size_t)f * P.mcap + i;
         int4 res = make_int4(-1, 256, -1, 256);
-        int hasObs = 0;
-        if (i < M) { res = P.result[o]; hasObs = P.hasObs[o]; }
+        int hasObs = 0, l1 = -1, l2 = -1, bin = 0;
+        float lastAngle = 0.f;
+        if (i < M) {
+            res = P.result[o]; hasObs = P.hasObs[o];
+            if (hist) lastAngle = P.angle[o];
+            if (res.x >= 0) {
+                const OrbKeyPoint kb = kps[res.x];
+                l1 = kb.octave;
+                if (hist) bin = rot_bin(lastAngle, kb.angle);
+                if (res.z >= 0) l2 = kps[res.z].octave;
+            }
+        }
         const int cnt = min(32, M - base);
         for (int j = 0; j < cnt; ++j) {
-            int bIdx = __shfl_sync(0xffffffffu, res.x, j), bDist = __shfl_sync(0xffffffffu, res.y, j);
-            int sIdx = __shfl_sync(0xffffffffu, res.z, j), sDist = __shfl_sync(0xffffffffu, res.w, j);
-            const int obs = __shfl_sync(0xffffffffu, hasObs, j);
+            int bIdx = __shfl_sync(0xffffffffu, res.x, j);
             if (bIdx < 0) continue;
-            const bool stale = ((s_bits[bIdx >> 5] >> (bIdx & 31)) & 1u) || (sIdx >= 0 && ((s_bits[sIdx >> 5] >> (sIdx & 31)) & 1u));
+            int bDist = __shfl_sync(0xffffffffu, res.y, j), sIdx = __shfl_sync(0xffffffffu, res.z, j), sDist = __shfl_sync(0xffffffffu, res.w, j);
+            const int obs = __shfl_sync(0xffffffffu, hasObs, j);
+            int lv1 = __shfl_sync(0xffffffffu, l1, j), lv2 = __shfl_sync(0xffffffffu, l2, j), bn = __shfl_sync(0xffffffffu, bin, j);
+            // the second-best candidate only matters for the local-map ratio test (mode 0)
+            const bool stale = ((s_bits[bIdx >> 5] >> (bIdx & 31)) & 1u) ||
+                               (P.mode == 0 && sIdx >= 0 && ((s_bits[sIdx >> 5] >> (sIdx & 31)) & 1u));
             if (stale) {   // rescan this map point against the current claims
                 const size_t oj = (size_t)f * P.mcap + base + j;
                 const float4 q = P.query[oj];
@@ -299,26 +321,19 @@ __global__ void __launch_bounds__(32) match_commit_kernel(MatchParams P) {
                 bIdx = t.i1; bDist = t.i1 >= 0 ? (int)(t.k1 >> 40) : 256;
                 sIdx = t.i2; sDist = t.i2 >= 0 ? (int)(t.k2 >> 40) : 256;
                 if (bIdx < 0) continue;
+                lv1 = kps[bIdx].octave; lv2 = sIdx >= 0 ? kps[sIdx].octave : -1;
+                if (hist) bn = rot_bin(P.angle[oj], kps[bIdx].angle);
             }
             if (bDist > TH_HIGH) continue;
             if (P.mode == 0) {   // ratio test only when best and second come from the same level (:123-128)
-                const int l1 = kps[bIdx].octave, l2 = sIdx >= 0 ? kps[sIdx].octave : -1;
-                if (l1 == l2 && (float)bDist > fmul(P.nnratio, (float)sDist)) continue;
+                if (lv1 == lv2 && (float)bDist > fmul(P.nnratio, (float)sDist)) continue;
             }
             if (lane == 0) {
                 match[bIdx] = base + j;
                 claimed[bIdx] = (uint8_t)obs;
                 if (obs) s_bits[bIdx >> 5] |= 1u << (bIdx & 31);
                 else s_bits[bIdx >> 5] &= ~(1u << (bIdx & 31));
-                if (P.mode == 1 && P.checkOri) {   // rotation histogram (:1779-1791)
-                    float rot = fsub(P.angle[(size_t)f * P.mcap + base + j], kps[bIdx].angle);
-                    if (rot < 0.0f) rot = fadd(rot, 360.0f);
-                    int bin = (int)roundf(fmul(rot, factor));
-                    if (bin == HISTO_LENGTH) bin = 0;
-                    bin = min(max(bin, 0), HISTO_LENGTH - 1);
-                    evBin[nEvents] = (uint8_t)bin; evIdx[nEvents] = (uint16_t)bIdx;
-                    s_hist[bin]++;
-                }
+                if (hist) { evBin[nEvents] = (uint8_t)bn; evIdx[nEvents] = (uint16_t)bIdx; s_hist[bn]++; }
             }
             ++nmatches; ++nEvents;
             __syncwarp();

@@ -7,6 +7,7 @@ opt = orb.Optimizer(20, 5000, 40000, max_batch=n)
 p = synth.lba_problem()
 import torch
 opt.upload([p]*n)
+if len(sys.argv) > 2: opt.set_cluster_size(int(sys.argv[2]))
 for _ in range(2): opt.run_device()
 torch.cuda.synchronize()
 e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
