@@ -269,9 +269,8 @@ def main():
     d_Tcw = [torch.from_numpy(p).to(dev) for p in poses_h]
     probs = lba_problems(NLBA, rank)
     opt.upload(probs)                      # flattened graphs resident in HBM for the `value` measurement
-    gathered = None
-    if world > 1:
-        gathered = [torch.empty((world,) + t.shape, dtype=t.dtype, device=dev) for t in (d_kps, d_desc, d_n)]
+    from orb_slam3_modified_b200 import sharding
+    gather = sharding.SlabGather(dist, world, d_kps, d_desc, d_n) if world > 1 else None
     stream = torch.cuda.current_stream()
     lba_stream = torch.cuda.Stream(device=dev)      # LocalMapping runs beside Tracking in the reference (src/System.cc:197)
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
@@ -290,8 +289,7 @@ def main():
         ex.extract_batch_device(dev_sets[i & 1], d_kps, d_desc, d_n, d_mono, (0, 1000), stream.cuda_stream)
         matcher.search_last_frame_batch_device(match_args(i), TH_PROJ, d_match, d_claimed, d_nmatch, stream.cuda_stream)
         if world > 1:   # shared-map exchange: one all-gather of the fixed-capacity keypoint/descriptor slabs
-            for src, dst in zip((d_kps, d_desc, d_n), gathered):
-                dist.all_gather_into_tensor(dst, src)
+            gather(d_kps, d_desc, d_n)
 
     def join_lba():
         ev_join.record(lba_stream)
