@@ -255,6 +255,19 @@ int lba_set_cluster_size(lba_handle* h, int ctas);
  * schur, ldlt, backsub, update, errors(trial), spare. */
 int lba_get_phase_ns(const lba_handle* h, int i, double* ns10);
 
+/* ------------------------------------------------------------------------------------------
+ * int Optimizer::PoseOptimization(Frame* pFrame) (reference include/Optimizer.h:62, src/Optimizer.cc:814-1114), monocular
+ * branch, for `count` frames at once (one CTA per frame).  Per frame f (slots of `cap` entries, N[f] used):
+ *   pose7 [count][7]: pFrame->GetPose() as unit quaternion (w,x,y,z) + translation, cast to double (:829-830)
+ *   cam4  [count][4]: fx, fy, cx, cy;  Xw [count][cap][3]: pMP->GetWorldPos() (:884);  obs [count][cap][2]: mvKeysUn[i].pt
+ *   invSigma2 [count][cap]: mvInvLevelSigma2[octave] (:877);  huberDelta = (float)sqrt(5.991)
+ * Out: poseOut [count][7] (pFrame->SetPose), outlier [count][cap] (pFrame->mvbOutlier), nInliers[count] = the return value
+ * nInitialCorrespondences - nBad.  Host pointers.
+ * ------------------------------------------------------------------------------------------ */
+int pose_optimization_batch(int count, int cap, const int32_t* N, const double* pose7, const float* cam4, const double* Xw,
+                            const double* obs, const float* invSigma2, double huberDelta, double* poseOut, uint8_t* outlier,
+                            int32_t* nInliers, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -390,4 +390,100 @@ void orbo_lba_residuals(int nP, const double* poses7, const float* cam4, int nL,
     (void)nP; (void)nL;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Optimizer::PoseOptimization (reference src/Optimizer.cc:814-1114, monocular branch): one VertexSE3Expmap,
+// EdgeSE3ProjectXYZOnlyPose per matched keypoint (include/OptimizableTypes.h:31-57, src/OptimizableTypes.cpp:49-63),
+// BaseUnaryEdge::constructQuadraticForm (g2o/core/base_unary_edge.hpp:43-72), LinearSolverDense (6x6 LDLT).
+// 4 rounds x optimize(10), every round restarts from the frame's pose; outliers (chi2 > 5.991) leave the active set
+// (level 1) and can come back; the Huber kernel is removed after the third round (:1040-1041).
+// Returns nInitialCorrespondences - nBad.  pose7 in/out, outlier[N] out.
+// ---------------------------------------------------------------------------------------------------------
+int orbo_pose_optimization(double* pose7, const float* cam4, int N, const double* Xw3, const double* obs2, const float* invSigma2,
+                           double huberDelta, uint8_t* outlier, double* stats) {
+    Quat q0 = {pose7[0], pose7[1], pose7[2], pose7[3]};
+    Pose T0; T0.q = q0; qnormalize(T0.q); T0.t[0] = pose7[4]; T0.t[1] = pose7[5]; T0.t[2] = pose7[6];
+    Pose T = T0;
+    std::vector<double> err(2 * (size_t)N, 0.0);
+    std::vector<uint8_t> level(N, 0), robust(N, 1);
+    for (int i = 0; i < N; ++i) outlier[i] = 0;
+    const double dsqr = huberDelta * huberDelta;
+    auto compute_error = [&](int e) {
+        double r[3]; qrot(T.q, Xw3 + 3 * (size_t)e, r);
+        const double X = r[0] + T.t[0], Y = r[1] + T.t[1], Z = r[2] + T.t[2];
+        err[2 * (size_t)e] = obs2[2 * (size_t)e] - ((double)cam4[0] * X / Z + (double)cam4[2]);
+        err[2 * (size_t)e + 1] = obs2[2 * (size_t)e + 1] - ((double)cam4[1] * Y / Z + (double)cam4[3]);
+    };
+    auto chi2 = [&](int e) { return (double)invSigma2[e] * (err[2 * (size_t)e] * err[2 * (size_t)e] + err[2 * (size_t)e + 1] * err[2 * (size_t)e + 1]); };
+    auto robustify = [&](int e, double e2, double* rho) {
+        if (!robust[e] || e2 <= dsqr) { rho[0] = e2; rho[1] = 1.; }
+        else { const double s = std::sqrt(e2); rho[0] = 2 * s * huberDelta - dsqr; rho[1] = huberDelta / s; }
+    };
+    auto active_chi2 = [&]() { double c = 0, rho[2]; for (int e = 0; e < N; ++e) if (!level[e]) { robustify(e, chi2(e), rho); c += rho[0]; } return c; };
+    int nBad = 0, totalTrials = 0;
+    double xs[6] = {0, 0, 0, 0, 0, 0};   // the solver's x vector keeps its previous content when the factorisation fails
+    for (int round = 0; round < 4; ++round) {
+        T = T0;
+        int nActive = 0;
+        for (int e = 0; e < N; ++e) nActive += !level[e];
+        // optimizer.optimize(10)
+        double lambda = -1, ni = 2; int nBadLM = 0; bool ok = true;
+        for (int it = 0; it < 10 && ok && nActive > 0; ++it) {
+            for (int e = 0; e < N; ++e) if (!level[e]) compute_error(e);
+            double currentChi = active_chi2(), tempChi = currentChi; const double iniChi = currentChi;
+            double H[36] = {0}, b[6] = {0};
+            for (int e = 0; e < N; ++e) {
+                if (level[e]) continue;
+                double r[3]; qrot(T.q, Xw3 + 3 * (size_t)e, r);
+                const double x = r[0] + T.t[0], y = r[1] + T.t[1], z = r[2] + T.t[2];
+                const double fx = cam4[0], fy = cam4[1];
+                const double J00 = -(fx / z), J02 = fx * x / (z * z), J11 = -(fy / z), J12 = fy * y / (z * z);
+                const double B[12] = {J02 * y, J00 * z - J02 * x, -J00 * y, J00, 0, J02, -J11 * z + J12 * y, -J12 * x, J11 * x, 0, J11, J12};
+                double rho[2]; robustify(e, chi2(e), rho);
+                const double w = rho[1] * (double)invSigma2[e];
+                const double r0 = (double)invSigma2[e] * err[2 * (size_t)e], r1 = (double)invSigma2[e] * err[2 * (size_t)e + 1];
+                for (int a = 0; a < 6; ++a) {
+                    b[a] -= rho[1] * (B[a] * r0 + B[6 + a] * r1);
+                    for (int c = 0; c < 6; ++c) H[a * 6 + c] += w * (B[a] * B[c] + B[6 + a] * B[6 + c]);
+                }
+            }
+            if (it == 0) { double md = 0; for (int a = 0; a < 6; ++a) md = std::max(md, std::fabs(H[a * 7])); lambda = 1e-5 * md; ni = 2; nBadLM = 0; }
+            double rho = 0; int qmax = 0;
+            do {
+                const Pose Tbk = T;
+                std::vector<double> A(H, H + 36); for (int a = 0; a < 6; ++a) A[a * 7] += lambda;
+                double x6[6] = {0, 0, 0, 0, 0, 0};
+                bool ok2 = ldlt_solve(A, 6, b, x6);
+                if (ok2) for (int a = 0; a < 6; ++a) if (A[a * 7] < 0) ok2 = false;     // Eigen::LDLT::isPositive()
+                if (ok2) for (int a = 0; a < 6; ++a) xs[a] = x6[a];
+                pose_oplus(T, ok2 ? x6 : xs);
+                for (int e = 0; e < N; ++e) if (!level[e]) compute_error(e);
+                tempChi = active_chi2();
+                if (!ok2) tempChi = DBL_MAX;
+                rho = currentChi - tempChi;
+                double scale = 0; for (int a = 0; a < 6; ++a) scale += (ok2 ? x6 : xs)[a] * (lambda * (ok2 ? x6 : xs)[a] + b[a]);
+                scale += 1e-3; rho /= scale;
+                if (rho > 0 && std::isfinite(tempChi)) {
+                    double alpha = 1. - std::pow((2 * rho - 1), 3); alpha = std::min(alpha, 2. / 3.);
+                    lambda *= std::max(1. / 3., alpha); ni = 2; currentChi = tempChi;
+                } else { lambda *= ni; ni *= 2; T = Tbk; }
+                ++qmax; ++totalTrials;
+            } while (rho < 0 && qmax < 10);
+            if (qmax == 10 || rho == 0) ok = false;
+            else { if ((iniChi - currentChi) * 1e3 < iniChi) ++nBadLM; else nBadLM = 0; if (nBadLM >= 3) ok = false; }
+        }
+        nBad = 0;
+        for (int e = 0; e < N; ++e) {
+            if (outlier[e]) compute_error(e);
+            if (chi2(e) > 5.991) { outlier[e] = 1; level[e] = 1; ++nBad; }
+            else { outlier[e] = 0; level[e] = 0; }
+            if (round == 2) robust[e] = 0;
+        }
+        if (N < 10) break;
+    }
+    pose7[0] = T.q.w; pose7[1] = T.q.x; pose7[2] = T.q.y; pose7[3] = T.q.z; pose7[4] = T.t[0]; pose7[5] = T.t[1]; pose7[6] = T.t[2];
+    if (stats) { stats[0] = totalTrials; }
+    return N - nBad;
+}
+
 }  // extern "C"

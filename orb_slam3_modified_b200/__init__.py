@@ -489,3 +489,24 @@ class Optimizer:
             raise OrbError(rc, 'lba_solve')
         out.update(iters=r.iterations, trials=r.trials, lambda_=r.lambda_, final_chi2=r.chi2, initial_chi2=r.initialChi2, launches=r.gpuLaunches)
         return out
+
+
+def PoseOptimization(frames, device=0):
+    """``Optimizer::PoseOptimization`` for a list of frames (dicts: pose [7], cam [4], Xw [N,3], obs [N,2], inv_sigma2 [N]).
+    Returns a list of dicts(pose, outlier, inliers)."""
+    count = len(frames)
+    cap = max(1, max(len(f['obs']) for f in frames))
+    N = np.array([len(f['obs']) for f in frames], np.int32)
+    pose = np.stack([_c(f['pose'], np.float64) for f in frames])
+    cam = np.stack([_c(f['cam'], np.float32) for f in frames])
+    Xw = np.zeros((count, cap, 3)); obs = np.zeros((count, cap, 2)); isg = np.ones((count, cap), np.float32)
+    for i, f in enumerate(frames):
+        Xw[i, :N[i]] = f['Xw']; obs[i, :N[i]] = f['obs']; isg[i, :N[i]] = f['inv_sigma2']
+    out_pose = np.zeros((count, 7)); outl = np.zeros((count, cap), np.uint8); ninl = np.zeros(count, np.int32)
+    L = lib()
+    L.pose_optimization_batch.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_double] + [C.c_void_p] * 3 + [C.c_int]
+    rc = L.pose_optimization_batch(count, cap, _ptr(N), _ptr(pose), _ptr(cam), _ptr(Xw), _ptr(obs), _ptr(isg),
+                                   float(np.float32(np.sqrt(5.991))), _ptr(out_pose), _ptr(outl), _ptr(ninl), device)
+    if rc != ORB_OK:
+        raise OrbError(rc, 'pose_optimization_batch')
+    return [dict(pose=out_pose[i], outlier=outl[i, :N[i]].copy(), inliers=int(ninl[i])) for i in range(count)]

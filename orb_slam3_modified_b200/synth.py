@@ -187,3 +187,23 @@ def lba_problem(n_kf=20, n_pts=5000, obs_per_pt=8, n_fixed=1, seed=0, width=640,
     return dict(poses=poses, fixed=fixed, cam=cam, points=points, edge_point=np.array(e_pt, np.int32), edge_pose=np.array(e_kf, np.int32),
                 obs=np.array(obs, np.float64).reshape(-1, 2), inv_sigma2=np.array(isg, np.float32), gt_poses=gt, gt_points=pts,
                 huber_delta=float(np.float32(np.sqrt(5.991))))
+
+
+def pose_opt_problem(n=400, seed=0, width=640, height=480, outlier_frac=0.15, pose_noise=(0.03, 1.5)):
+    """A tracked frame for Optimizer::PoseOptimization: map points, their (noisy) observations, a perturbed initial pose."""
+    rng = np.random.default_rng(seed)
+    gt = np.concatenate([_quat_from_rotvec(rng.normal(0, 0.1, 3)), rng.normal(0, 0.3, 3)])
+    z = rng.uniform(3, 12, n)
+    u, v = rng.uniform(20, width - 20, n), rng.uniform(20, height - 20, n)
+    pc = np.stack([(u - width / 2) * z / F_PIX, (v - height / 2) * z / F_PIX, z], 1)
+    Xw = _qrot(gt[:4] * np.array([1, -1, -1, -1]), pc - gt[4:])
+    octv = rng.integers(0, 8, n)
+    obs = np.stack([u, v], 1) + rng.normal(0, 1, (n, 2)) * (1.2 ** octv)[:, None]
+    bad = rng.random(n) < outlier_frac
+    obs[bad] += rng.uniform(8, 30, (int(bad.sum()), 2)) * rng.choice([-1, 1], (int(bad.sum()), 2))
+    pose = gt.copy()
+    pose[:4] = _qmul(_quat_from_rotvec(rng.normal(0, np.deg2rad(pose_noise[1]), 3)), gt[:4])
+    pose[4:] += rng.normal(0, pose_noise[0], 3)
+    inv_sigma2 = (1.0 / (np.float32(1.2) ** octv.astype(np.float32)) ** 2).astype(np.float32)
+    return dict(pose=pose.astype(np.float32).astype(np.float64), cam=np.array([F_PIX, F_PIX, width / 2, height / 2], np.float32),
+                Xw=Xw.astype(np.float32).astype(np.float64), obs=obs.astype(np.float32).astype(np.float64), inv_sigma2=inv_sigma2, gt_pose=gt)

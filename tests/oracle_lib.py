@@ -203,3 +203,14 @@ def lba_residuals(prob, poses, points):
     res = np.zeros((len(ep), 2), np.float64)
     lib().orbo_lba_residuals(len(poses), _p(poses), _p(cam), len(points), _p(points), len(ep), _p(ep), _p(ek), _p(obs), _p(res))
     return res
+
+
+def pose_optimization(frame):
+    pose = _c(frame['pose'], np.float64).copy(); cam = _c(frame['cam'], np.float32)
+    Xw = _c(frame['Xw'], np.float64); obs = _c(frame['obs'], np.float64); isg = _c(frame['inv_sigma2'], np.float32)
+    N = len(obs)
+    outl = np.zeros(max(N, 1), np.uint8); stats = np.zeros(8)
+    L = lib()
+    L.orbo_pose_optimization.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    n = L.orbo_pose_optimization(_p(pose), _p(cam), N, _p(Xw), _p(obs), _p(isg), float(np.float32(np.sqrt(5.991))), _p(outl), _p(stats))
+    return dict(pose=pose, outlier=outl[:N].copy(), inliers=n, trials=int(stats[0]))

@@ -40,3 +40,11 @@ def test_lba_user_lambda_init_changes_first_step():
     a = O.lba_solve(p, iterations=1)
     b = O.lba_solve(p, iterations=1, user_lambda_init=100.0)   # inertial maps (Optimizer.cc:1197-1198)
     assert not np.allclose(a['points'], b['points'])
+
+
+def test_pose_optimization_oracle_recovers_pose_and_flags_outliers():
+    f = synth.pose_opt_problem(n=500, seed=3, outlier_frac=0.2)
+    out = O.pose_optimization(f)
+    assert 350 <= out['inliers'] <= 420
+    assert 0.1 < out['outlier'].mean() < 0.3
+    assert np.abs(out['pose'][4:] - f['gt_pose'][4:]).max() < 0.03
