@@ -1,8 +1,10 @@
 // Host side of the batched B200 ORB extractor + its C-ABI (include/orb_b200.h).
 // Mirrors ORBextractor (reference include/ORBextractor.h:43-109, src/ORBextractor.cc).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -33,6 +35,31 @@ static inline int cvRoundF(float v) { return (int)nearbyintf(v); }
 static inline int cvFloorD(double v) { int i = (int)v; return i - (i > v); }
 static inline int cvCeilD(double v) { int i = (int)v; return i + (i < v); }
 static inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// 3-D u8 tensor {x, y, frame}: x contiguous, row pitch, frame stride; box {bw, bh, 1}; out-of-bounds reads return 0
+static bool encode_plane_map(CUtensorMap* m, const void* base, int w, int h, int frames, size_t pitch, size_t frameStride, int bw, int bh) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    if (((uintptr_t)base & 15) || (pitch & 15) || (frameStride & 15)) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frameStride};
+    cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 struct Extractor {
     // constructor arguments (reference src/ORBextractor.cc:409-413)
@@ -68,12 +95,14 @@ struct Extractor {
     size_t smemFast = 0, smemQt = 0, smemAs = 0;
     int launches = 0;
     int maxKp = 0;
+    TmaMaps maps;            // per-level TMA descriptors of the internal pyramid planes (level 0: internal copy)
+    CUtensorMap* d_maps = nullptr;   // device copy of `maps`
 
     ~Extractor() { release(); }
     void release() {
         cudaSetDevice(device);
         void* ptrs[] = {d_pyr, d_blur, d_cells, d_cellCount, d_cellList, d_cand, d_nodeOf, d_sel, d_selCount, d_dstIndex,
-                        d_status, d_xtab, d_ytab, d_img, d_outKp, d_outDesc, d_outN, d_outMono};
+                        d_status, d_xtab, d_ytab, d_img, d_outKp, d_outDesc, d_outN, d_outMono, d_maps};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (h_counts) cudaFreeHost(h_counts);
         if (stream) cudaStreamDestroy(stream);
@@ -157,15 +186,22 @@ struct Extractor {
                     cd.listOff = (uint32_t)listOff;
                     listOff += G.cellCap;
                     cells.push_back(cd);
-                    const int tp = (cd.rw + 3) & ~3, iw = cd.rw - 6, ih = cd.rh - 6;
-                    if (iw > 0 && ih > 0) {
-                        const size_t spm = ((size_t)iw + 2 + 3) & ~(size_t)3;
-                        size_t sm = (((size_t)cd.rh * tp + 15) & ~15) + ((((size_t)ih + 2) * spm + 15) & ~15) + 2 * (size_t)iw * ih;
-                        smemFast = std::max(smemFast, sm);
-                    }
                 }
             }
             G.nCells = (int)cells.size() - G.cellBase;
+            {   // TMA box covering the largest ROI of the level (width rounded up to 16 bytes)
+                int mw = 7, mh = 7;
+                int mwOff = 7;   // widest (x0 & 15) + rw: the box starts 16-byte aligned
+                for (int ci = G.cellBase; ci < (int)cells.size(); ++ci) {
+                    mw = std::max<int>(mw, cells[ci].rw); mh = std::max<int>(mh, cells[ci].rh);
+                    mwOff = std::max<int>(mwOff, (cells[ci].x0 & 15) + cells[ci].rw);
+                }
+                G.fastBoxW = (int)alignUp(mwOff, 16); G.fastBoxH = mh;
+                const int iwm = mw - 6, ihm = mh - 6;
+                const size_t spm = ((size_t)iwm + 2 + 3) & ~(size_t)3;
+                const size_t sm = alignUp((size_t)G.fastBoxW * G.fastBoxH, 128) + alignUp(((size_t)ihm + 2) * spm, 16) + 2 * (size_t)iwm * ihm;
+                smemFast = std::max(smemFast, sm);
+            }
             maxCells = std::max(maxCells, G.nCells);
             G.candOff = (uint32_t)candOff; G.candCap = (uint32_t)G.nCells * G.cellCap;
             candOff += alignUp(G.candCap, 64);
@@ -250,6 +286,7 @@ struct Extractor {
         CK(cudaMalloc(&d_selCount, sizeof(int) * kMaxLevels * B));
         CK(cudaMalloc(&d_dstIndex, sizeof(int) * capSel * B));
         CK(cudaMalloc(&d_status, sizeof(int) * B));
+        CK(cudaMalloc(&d_maps, sizeof(TmaMaps)));
         CK(cudaMalloc(&d_xtab, sizeof(short4) * capX));
         CK(cudaMalloc(&d_ytab, sizeof(short4) * capY));
         CK(cudaMalloc(&d_img, (size_t)P.lv[0].pitch * maxH * B));
@@ -265,7 +302,7 @@ struct Extractor {
         CK(cudaEventCreateWithFlags(&evJoin, cudaEventDisableTiming));
         CK(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
         CK(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
-        maxSmemFast = 40 * 1024;   // worst-case cell is 76x76 (cells are < 70 px wide): ~21 KB
+        maxSmemFast = 48 * 1024;   // worst-case cell is 76x76 in a 96-byte wide box: ~25 KB
         maxSmemQt = smemQt + 16 * 1024; maxSmemAs = 2 * capSel * sizeof(int);
         if (maxSmemQt > 200 * 1024) { set_error("nfeatures too large for the quadtree kernel's shared memory"); return ORB_ERR_ARG; }
         CK(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmemFast));
@@ -300,6 +337,15 @@ struct Extractor {
         P.pyr = d_pyr; P.blur = d_blur; P.cells = d_cells; P.cellCount = d_cellCount; P.cellList = d_cellList;
         P.cand = d_cand; P.nodeOf = d_nodeOf; P.sel = d_sel; P.selCount = d_selCount; P.dstIndex = d_dstIndex;
         P.status = d_status; P.xtab = d_xtab; P.ytab = d_ytab;
+        for (int l = 0; l < nlevels; ++l) {
+            const LevelGeom& G = P.lv[l];
+            if (!encode_plane_map(&maps.lv[l], d_pyr + G.planeOff, G.w, G.h, maxBatch, G.pitch, P.pyrFrameStride, G.fastBoxW, G.fastBoxH)) {
+                set_error("cuTensorMapEncodeTiled failed for a pyramid level (TMA descriptors are required)");
+                rows = cols = 0;
+                return ORB_ERR_CUDA;
+            }
+        }
+        CK(cudaMemcpy(d_maps, &maps, sizeof(TmaMaps), cudaMemcpyHostToDevice));
         return ORB_OK;
     }
 
@@ -312,6 +358,15 @@ struct Extractor {
         Q.outKp = outKp; Q.outDesc = outDesc; Q.outCap = cap; Q.outN = outN; Q.outMono = outMono;
         launches = 0;
         CK(cudaMemsetAsync(d_status, 0, sizeof(int) * batch, st));
+        // level 0: TMA straight from the caller's frames when base / strides are 16-byte aligned, else from an internal copy
+        CUtensorMap map0;
+        if (!encode_plane_map(&map0, lv0, Q.lv[0].w, Q.lv[0].h, batch, lv0Pitch, lv0Stride, Q.lv[0].fastBoxW, Q.lv[0].fastBoxH)) {
+            Q.src = lv0; Q.srcStep = lv0Pitch; Q.srcFrameStride = lv0Stride;
+            copy_level0_kernel<<<dim3((Q.cols + 255) / 256, Q.rows, batch), 256, 0, st>>>(Q);
+            ++launches;
+            Q.lv0 = d_pyr + Q.lv[0].planeOff; Q.lv0Pitch = Q.lv[0].pitch; Q.lv0FrameStride = Q.pyrFrameStride;
+            map0 = maps.lv[0];
+        }
         if (profiling) for (int i = 0; i < 7; ++i) if (!evStage[i]) CK(cudaEventCreate(&evStage[i]));
         if (profiling) CK(cudaEventRecord(evStage[0], st));
         // pyramid: levels depend on each other
@@ -331,7 +386,7 @@ struct Extractor {
         ++launches;
         if (!profiling) CK(cudaEventRecord(evJoin, stream2));
         if (profiling) CK(cudaEventRecord(evStage[2], st));
-        fast_cells_kernel<<<dim3(Q.nCellsTotal, batch), FAST_NT, smemFast, st>>>(Q);
+        fast_cells_kernel<<<dim3(Q.nCellsTotal, batch), FAST_NT, smemFast, st>>>(Q, map0, d_maps);
         ++launches;
         if (profiling) CK(cudaEventRecord(evStage[3], st));
         quadtree_orient_kernel<<<dim3(nlevels, batch), QT_NT, smemQt, st>>>(Q);

@@ -4,6 +4,7 @@
 // Reference semantics (file:line in /root/reference) are cited per kernel; the
 // bit-exact scalar pieces live in exact_math.h.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "exact_math.h"
@@ -125,59 +126,93 @@ __device__ __forceinline__ int fast_score_at(const uint8_t* t, const int* off) {
     return best;  // corner at T <=> best > T, score = best - 1
 }
 
-__global__ void __launch_bounds__(FAST_NT) fast_cells_kernel(ExtractParams P) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+// TMA descriptors: one 3-D tensor {x, y, frame} per pyramid level.  Levels >= 1 live in a global-memory table; level 0 (which
+// may alias the caller's frames and so changes per call) travels as a __grid_constant__ kernel parameter.
+struct alignas(64) TmaMaps { CUtensorMap lv[kMaxLevels]; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// cp.async.bulk.tensor (TMA) 3-D tile load: box {bw, bh, 1} at (x, y, frame) -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(FAST_NT) fast_cells_kernel(ExtractParams P, const __grid_constant__ CUtensorMap map0, const CUtensorMap* __restrict__ maps) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
     const int f = blockIdx.y;
     const CellDesc cd = P.cells[blockIdx.x];
     const int rw = cd.rw, rh = cd.rh;
     int* outCount = P.cellCount + (size_t)f * P.cellCountStride + blockIdx.x;
     if (rw < 7 || rh < 7) { if (threadIdx.x == 0) *outCount = 0; return; }
-    const int tp = (rw + 3) & ~3;               // tile pitch
+    const LevelGeom& G = P.lv[cd.level];
+    const int tp = G.fastBoxW;                  // tile pitch = TMA box width (multiple of 16)
     const int iw = rw - 6, ih = rh - 6;         // detection interior (<= 70 x 70)
     const int sp = (iw + 2 + 3) & ~3;           // score-map pitch (1-px zero ring), word aligned
-    uint8_t* tile = smem_raw;                                   // rh * tp
-    uint8_t* score = tile + ((rh * tp + 15) & ~15);             // (ih+2) * sp
+    // TMA tile mode needs a 16-byte aligned box start (unaligned inner coordinates fault: measured), so the box
+    // starts at x0 & ~15 and the ROI begins `xoff` bytes into every tile row
+    const int xoff = cd.x0 & 15;
+    uint8_t* tileBase = smem_raw;                                               // fastBoxH * tp, 128-byte aligned
+    const uint8_t* tile = tileBase + xoff;
+    uint8_t* score = tileBase + ((G.fastBoxH * tp + 127) & ~127);               // (ih+2) * sp
     uint16_t* list = reinterpret_cast<uint16_t*>(score + (((ih + 2) * sp + 15) & ~15));  // iw*ih candidates (y << 7 | x)
     __shared__ int s_nCand, s_cntHi, s_warp[33];
     __shared__ uint32_t s_hi[72 * 3], s_lo[72 * 3];             // per-row keep bitmaps (<= 70 rows x 96 columns)
     __shared__ int s_rowOff[96];
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;  // 32 x 8 threads
+    const int tid = threadIdx.x, lane = tid & 31;
 
-    int pitch;
-    const uint8_t* img = plane_ptr(P, f, cd.level, pitch);
-    img += (size_t)cd.y0 * pitch + cd.x0;
-    for (int y = ty; y < rh; y += 8)
-        for (int x = tx; x < rw; x += 32) tile[y * tp + x] = img[(size_t)y * pitch + x];
+    // ---- tile: one TMA bulk-tensor load of the whole ROI (image pyramid staged into shared memory) ----
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_expect_tx(&s_bar, (uint32_t)(tp * G.fastBoxH));
+        tma_load_3d(tileBase, cd.level == 0 ? &map0 : maps + cd.level, cd.x0 - xoff, cd.y0, f, &s_bar);
+        s_nCand = 0; s_cntHi = 0;
+    }
     for (int i = tid; i < ((ih + 2) * sp) >> 2; i += FAST_NT) reinterpret_cast<uint32_t*>(score)[i] = 0;
-    if (tid == 0) { s_nCand = 0; s_cntHi = 0; }
-    __syncthreads();
+    const unsigned magic = 0xFFFFFFFFu / (unsigned)iw + 1u;     // i / iw == __umulhi(i, magic) for i < 2^16
+    __syncthreads();                                            // barrier init visible + score zeroed
+    mbar_wait(&s_bar, 0);
 
     // phase 1: cheap rejection (any 9-arc contains ring pixel k or k+8 for every k) + compaction of the survivors
     const int th = P.minTh;
-    for (int y = ty; y < ih; y += 8) {
-        for (int xb = 0; xb < iw; xb += 32) {
-            const int x = xb + tx;
-            bool cand = false;
-            if (x < iw) {
-                const uint8_t* t = tile + (y + 3) * tp + (x + 3);
-                const int v = t[0], lo = v - th, hi = v + th;
-                const int p0 = t[3 * tp], p8 = t[-3 * tp], p4 = t[3], p12 = t[-3];
-                bool dark = (p0 < lo || p8 < lo) && (p4 < lo || p12 < lo);
-                bool brig = (p0 > hi || p8 > hi) && (p4 > hi || p12 > hi);
-                if (dark || brig) {
-                    const int p2 = t[2 * tp + 2], p10 = t[-2 * tp - 2], p6 = t[-2 * tp + 2], p14 = t[2 * tp - 2];
-                    dark = dark && (p2 < lo || p10 < lo) && (p6 < lo || p14 < lo);
-                    brig = brig && (p2 > hi || p10 > hi) && (p6 > hi || p14 > hi);
-                    cand = dark || brig;
-                }
+    const int npix = iw * ih;
+    for (int base = 0; base < npix; base += FAST_NT) {
+        const int i = base + tid;
+        bool cand = false;
+        int y = 0, x = 0;
+        if (i < npix) {
+            y = (int)__umulhi((unsigned)i, magic); x = i - y * iw;
+            const uint8_t* t = tile + (y + 3) * tp + (x + 3);
+            const int v = t[0], lo = v - th, hi = v + th;
+            const int p0 = t[3 * tp], p8 = t[-3 * tp], p4 = t[3], p12 = t[-3];
+            bool dark = (p0 < lo || p8 < lo) && (p4 < lo || p12 < lo);
+            bool brig = (p0 > hi || p8 > hi) && (p4 > hi || p12 > hi);
+            if (dark || brig) {
+                const int p2 = t[2 * tp + 2], p10 = t[-2 * tp - 2], p6 = t[-2 * tp + 2], p14 = t[2 * tp - 2];
+                dark = dark && (p2 < lo || p10 < lo) && (p6 < lo || p14 < lo);
+                brig = brig && (p2 > hi || p10 > hi) && (p6 > hi || p14 > hi);
+                cand = dark || brig;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, cand);
-            if (m) {
-                int wbase = 0;
-                if (tx == 0) wbase = atomicAdd(&s_nCand, __popc(m));
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (cand) list[wbase + __popc(m & ((1u << tx) - 1))] = (uint16_t)((y << 7) | x);
-            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (m) {
+            int wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&s_nCand, __popc(m));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (cand) list[wbase + __popc(m & ((1u << lane) - 1))] = (uint16_t)((y << 7) | x);
         }
     }
     __syncthreads();
@@ -199,11 +234,11 @@ __global__ void __launch_bounds__(FAST_NT) fast_cells_kernel(ExtractParams P) {
     }
     __syncthreads();
 
-    // phase 3: strict 8-neighbour maxima -> per-row bitmaps for both thresholds (a ballot is one bitmap word)
+    // phase 3: strict 8-neighbour maxima -> per-row bitmaps for both thresholds; warp per row, ballot = bitmap word
     int cntHi = 0;
-    for (int y = ty; y < ih; y += 8) {
+    for (int y = tid >> 5; y < ih; y += FAST_NT / 32) {
         for (int xb = 0; xb < iw; xb += 32) {
-            const int x = xb + tx;
+            const int x = xb + lane;
             bool kLo = false, kHi = false;
             if (x < iw) {
                 const uint8_t* sc = score + (y + 1) * sp + (x + 1);
@@ -215,10 +250,10 @@ __global__ void __launch_bounds__(FAST_NT) fast_cells_kernel(ExtractParams P) {
                 }
             }
             const unsigned mLo = __ballot_sync(0xffffffffu, kLo), mHi = __ballot_sync(0xffffffffu, kHi);
-            if (tx == 0) { s_lo[y * 3 + (xb >> 5)] = mLo; s_hi[y * 3 + (xb >> 5)] = mHi; cntHi += __popc(mHi); }
+            if (lane == 0) { s_lo[y * 3 + (xb >> 5)] = mLo; s_hi[y * 3 + (xb >> 5)] = mHi; cntHi += __popc(mHi); }
         }
     }
-    if (tx == 0 && cntHi) atomicAdd(&s_cntHi, cntHi);
+    if (lane == 0 && cntHi) atomicAdd(&s_cntHi, cntHi);
     __syncthreads();
     // fallback to minTh only if the cell is empty at iniTh (:843-859); ordered (row-major) emission, one thread per row
     const uint32_t* bits = s_cntHi > 0 ? s_hi : s_lo;
@@ -277,7 +312,7 @@ __device__ __forceinline__ int qt_child(const QtNode& n, int px, int py, int& mi
 }
 
 __global__ void __launch_bounds__(QT_NT) quadtree_orient_kernel(ExtractParams P) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     const LevelGeom& G = P.lv[l];
     const int MN = P.maxNodes;

@@ -25,6 +25,7 @@ struct LevelGeom {
     int area2x;               // level is an exact 2x decimation of the previous (cv::resize -> INTER_AREA)
     uint32_t xtabOff, ytabOff;        // resize coefficient tables (entries, not bytes)
     int blurTileBase, blurTilesX, blurTilesY;   // flattened tile index range of the blur launch
+    int fastBoxW, fastBoxH;   // TMA box of the FAST cell ROI: width (multiple of 16 bytes) x height
 };
 
 // One active FAST cell (cells skipped by the reference's `continue`s are not listed).
@@ -68,6 +69,7 @@ struct ExtractParams {
     void* outKp; uint8_t* outDesc; int outCap; int* outN; int* outMono;
     int* status;                                    // [batch] sticky error flags
     int maxNodes, maxCellsPerLevel;
+    int dbg;
 };
 
 // candidate packing: x (12 bits) | y (12 bits) << 12 | score << 24
