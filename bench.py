@@ -358,27 +358,25 @@ def main():
     # ---------------- end to end through the host C-ABI (`e2e`) ----------------
     e2e, e2e_steps, h2d, d2h = None, 0, 0, 0
     if not args.no_e2e:
-        match_h = np.full((B, cap), -1, np.int32)
-        claimed_h = np.zeros((B, cap), np.uint8)
-        nmatch_h = np.zeros(B, np.int32)
+        from concurrent.futures import ThreadPoolExecutor
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+        kps_h = pin((B, cap, 7), torch.float32).view(np.uint8).reshape(B, cap, 28).view(orb.KP_DTYPE).reshape(B, cap)
+        desc_h = pin((B, cap, 32), torch.uint8)
+        nK_h, mono_h, nmatch_h = pin((B,), torch.int32), pin((B,), torch.int32), pin((B,), torch.int32)
+        match_h, claimed_h = pin((B, cap), torch.int32), pin((B, cap), torch.uint8)
+        mapper = ThreadPoolExecutor(1)      # the LocalMapping thread of the reference (src/System.cc:197)
 
         def step_host(i):
             cur, lst = i & 1, (i + 1) & 1
-            monos, kl, dl = ex.extract_batch(host_sets[cur].numpy(), (0, 1000))
-            kps_h = np.zeros((B, cap), orb.KP_DTYPE)
-            desc_h = np.zeros((B, cap, 32), np.uint8)
-            nK = np.zeros(B, np.int32)
-            for b in range(B):
-                nK[b] = len(kl[b])
-                kps_h[b, :nK[b]] = kl[b]
-                desc_h[b, :nK[b]] = dl[b]
+            lba_job = mapper.submit(opt.LocalBundleAdjustmentBatch, probs)           # host graphs in, optimised state out
+            ex.extract_batch_slabs(host_sets[cur].numpy(), kps_h, desc_h, nK_h, mono_h, (0, 1000))   # host frames in, host slabs out
             L = last_h[lst]
-            d = dict(batch=B, kcap=cap, mcap=cap, nlevels=8, kps=kps_h, desc=desc_h, nK=nK, scaleFactors=sf, nM=L['nM'], valid=L['valid'], xyz=L['xyz'],
+            d = dict(batch=B, kcap=cap, mcap=cap, nlevels=8, kps=kps_h, desc=desc_h, nK=nK_h, scaleFactors=sf, nM=L['nM'], valid=L['valid'], xyz=L['xyz'],
                      octave=L['octave'], angle=L['angle'], hasObs=L['hasObs'], mpDesc=L['mpDesc'], Tcw7=poses_h[cur],
                      bounds=(0.0, 0.0, float(W), float(H)), cam=cam, reset=1)
             matcher.search_last_frame_batch(d, TH_PROJ, match_h, claimed_h, nmatch_h)
-            outs = opt.LocalBundleAdjustmentBatch(probs)
-            return int(nK.sum()), outs
+            outs = lba_job.result()
+            return int(nK_h.sum()), outs
 
         step_host(0)
         barrier()

@@ -157,6 +157,17 @@ class ORBextractor:
             raise OrbError(rc, 'orbx_extract_batch')
         return ([int(m) for m in mono], [kps[b, :n[b]].copy() for b in range(B)], [desc[b, :n[b]].copy() for b in range(B)])
 
+    def extract_batch_slabs(self, images, kps, desc, n, mono, vLappingArea=(0, 0)):
+        """Batched operator() into caller-owned fixed-capacity slabs (numpy, ideally pinned): kps [B, cap] KP_DTYPE,
+        desc [B, cap, 32] u8, n / mono [B] i32 with cap == max_keypoints.  No per-frame copies."""
+        B, rows, cols = images.shape
+        assert kps.shape[1] == self.max_keypoints and images.strides[2] == 1
+        rc = lib().orbx_extract_batch(self._h, _ptr(images), B, rows, cols, images.strides[1], images.strides[0],
+                                      int(vLappingArea[0]), int(vLappingArea[1]), _ptr(kps), _ptr(desc), self.max_keypoints,
+                                      _ptr(n), _ptr(mono))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbx_extract_batch')
+
     def extract_batch_device(self, d_images, d_kps, d_desc, d_n, d_mono, vLappingArea=(0, 0), stream=0):
         """All-device variant (torch CUDA tensors): d_images [B, rows, cols] u8; slabs d_kps [B, cap, 7] (28-byte rows),
         d_desc [B, cap, 32] u8, d_n / d_mono [B] i32.  Enqueues on ``stream`` and returns immediately."""

@@ -497,10 +497,18 @@ int orbx_extract_batch(orbx_handle* h, const uint8_t* images, int batch, int row
     CK(cudaMemcpyAsync(hs, e.d_status, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     int worst = ORB_OK;
+    bool anyBad = false;
     for (int f = 0; f < batch; ++f) {
         n[f] = hn[f]; mono[f] = hm[f];
-        if (hs[f] || hn[f] > cap) { worst = ORB_ERR_CAPACITY; set_error("keypoint capacity exceeded"); continue; }
-        if (hn[f] > 0) {
+        if (hs[f] || hn[f] > cap) { worst = ORB_ERR_CAPACITY; set_error("keypoint capacity exceeded"); anyBad = true; }
+    }
+    if (!anyBad && cap == icap && batch > 1) {
+        // slab-to-slab: the caller's buffers have the internal capacity -> two bulk copies (rows beyond n[f] are unspecified)
+        CK(cudaMemcpyAsync(kps, e.d_outKp, sizeof(OrbKeyPoint) * (size_t)icap * batch, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(desc, e.d_outDesc, (size_t)32 * icap * batch, cudaMemcpyDeviceToHost, st));
+    } else {
+        for (int f = 0; f < batch; ++f) {
+            if (hs[f] || hn[f] > cap || hn[f] <= 0) continue;
             CK(cudaMemcpyAsync(kps + (size_t)f * cap, e.d_outKp + (size_t)f * icap, sizeof(OrbKeyPoint) * hn[f], cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(desc + (size_t)f * cap * 32, e.d_outDesc + (size_t)f * icap * 32, (size_t)32 * hn[f], cudaMemcpyDeviceToHost, st));
         }

@@ -19,7 +19,9 @@
 #include <math.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/orb_b200.h"
@@ -1009,7 +1011,21 @@ struct Solver {
     int upload(int count, const LbaProblem* probs) {
         if (count < 1 || count > maxBatch) { set_error("lba: batch larger than max_batch"); return ORB_ERR_ARG; }
         uploadBytes.assign(maxBatch, 0);
-        for (int i = 0; i < count; ++i) { int rc = pack(i, probs + i); if (rc) return rc; }
+        {   // BlockSolver::buildStructure for every problem, on the host cores (problems are independent)
+            const int nth = std::max(1, std::min<int>({count, (int)std::thread::hardware_concurrency(), 16}));
+            std::atomic<int> next(0), firstErr(ORB_OK);
+            auto worker = [&]() {
+                for (int i = next.fetch_add(1); i < count; i = next.fetch_add(1)) {
+                    const int rc = pack(i, probs + i);
+                    if (rc) { int exp = ORB_OK; firstErr.compare_exchange_strong(exp, rc); }
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nth; ++t) pool.emplace_back(worker);
+            worker();
+            for (auto& t : pool) t.join();
+            if (firstErr.load()) { set_error("lba: malformed problem in the batch (index out of range, duplicate observation, or larger than the handle)"); return firstErr.load(); }
+        }
         CK(cudaSetDevice(device));
         for (int i = 0; i < count; ++i)
             CK(cudaMemcpyAsync(d_arena + perProblem * (size_t)i, h_arena + perProblem * (size_t)i, uploadBytes[i], cudaMemcpyHostToDevice, st));
