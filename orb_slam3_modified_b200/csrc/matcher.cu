@@ -60,7 +60,7 @@ struct MatchParams {
     int* cellStart;      // [batch][GRID_CELLS + 1]
     uint16_t* cellIdx;   // [batch][kcap]
     float4* query;       // [batch][mcap]  u, v, r, bits(minLevel+1 | (maxLevel+1) << 8 | valid << 16)
-    int4* result;        // [batch][mcap]  bestIdx, bestDist, secondIdx, secondDist
+    int4 *resultIdx, *resultDist;   // [batch][mcap]  the four best (keypoint index, distance) of pass 1, ascending
     uint8_t* evBin; uint16_t* evIdx;   // [batch][mcap] rotation-histogram events
     // in/out
     int* match; uint8_t* claimed; int* nmatches;
@@ -123,18 +123,43 @@ __global__ void __launch_bounds__(GB_NT) grid_build_kernel(MatchParams P) {
 // Keeps the two smallest (distance, order) keys among keypoints that are not claimed.
 // key = dist << 40 | cellRank << 20 | j ; returns idx/dist of best and second (idx -1 when absent).
 // ---------------------------------------------------------------------------------------------
-struct Top2 { unsigned long long k1, k2; int i1, i2; };
+template <int K>
+struct TopK {   // the K smallest keys seen, ascending
+    unsigned long long k[K];
+    int i[K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < K; ++j) { k[j] = ~0ull; i[j] = -1; }
+    }
+    __device__ __forceinline__ void insert(unsigned long long key, int idx) {
+        if (key >= k[K - 1]) return;
+        k[K - 1] = key; i[K - 1] = idx;
+#pragma unroll
+        for (int j = K - 1; j > 0; --j) {
+            if (k[j] < k[j - 1]) {
+                const unsigned long long tk = k[j]; k[j] = k[j - 1]; k[j - 1] = tk;
+                const int ti = i[j]; i[j] = i[j - 1]; i[j - 1] = ti;
+            }
+        }
+    }
+    __device__ __forceinline__ void warp_merge() {   // afterwards every lane holds the K smallest of the whole warp
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            unsigned long long ok[K]; int oi[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) { ok[j] = __shfl_xor_sync(0xffffffffu, k[j], o); oi[j] = __shfl_xor_sync(0xffffffffu, i[j], o); }
+#pragma unroll
+            for (int j = 0; j < K; ++j) insert(ok[j], oi[j]);
+        }
+    }
+};
+typedef TopK<2> Top2;
 
-__device__ __forceinline__ void top2_insert(Top2& t, unsigned long long k, int i) {
-    if (k < t.k1) { t.k2 = t.k1; t.i2 = t.i1; t.k1 = k; t.i1 = i; }
-    else if (k < t.k2) { t.k2 = k; t.i2 = i; }
-}
-
-template <class ClaimFn>
-__device__ __forceinline__ Top2 scan_candidates(const MatchParams& P, int f, float u, float v, float r, int minLevel, int maxLevel,
-                                                const uint32_t* mpd, ClaimFn isClaimed) {
+template <int K, class ClaimFn>
+__device__ __forceinline__ TopK<K> scan_candidates(const MatchParams& P, int f, float u, float v, float r, int minLevel, int maxLevel,
+                                                   const uint32_t* mpd, ClaimFn isClaimed) {
     const int lane = threadIdx.x & 31;
-    Top2 t; t.k1 = t.k2 = ~0ull; t.i1 = t.i2 = -1;
+    TopK<K> t; t.init();
     const int nMinCellX = max(0, (int)floorf(fmul(fsub(fsub(u, P.minX), r), P.gridWInv)));
     const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf(fmul(fadd(fsub(u, P.minX), r), P.gridWInv)));
     const int nMinCellY = max(0, (int)floorf(fmul(fsub(fsub(v, P.minY), r), P.gridHInv)));
@@ -164,18 +189,11 @@ __device__ __forceinline__ Top2 scan_candidates(const MatchParams& P, int f, flo
                 const uint4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
                 const uint32_t dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
                 const int dist = hamming256(mpd, dd);
-                top2_insert(t, ((unsigned long long)dist << 40) | ((unsigned long long)c << 20) | (unsigned)(e - a), idx);
+                t.insert(((unsigned long long)dist << 40) | ((unsigned long long)c << 20) | (unsigned)(e - a), idx);
             }
         }
     }
-    // merge the per-lane pairs
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const unsigned long long ok1 = __shfl_xor_sync(0xffffffffu, t.k1, o), ok2 = __shfl_xor_sync(0xffffffffu, t.k2, o);
-        const int oi1 = __shfl_xor_sync(0xffffffffu, t.i1, o), oi2 = __shfl_xor_sync(0xffffffffu, t.i2, o);
-        top2_insert(t, ok1, oi1);
-        top2_insert(t, ok2, oi2);
-    }
+    t.warp_merge();
     return t;
 }
 
@@ -235,18 +253,20 @@ __global__ void __launch_bounds__(MC_NT) match_candidates_kernel(MatchParams P) 
     const size_t o = (size_t)f * P.mcap + i;
     float u = 0, v = 0, r = 0; int minL = 0, maxL = 0;
     const bool ok = make_query(P, f, i, u, v, r, minL, maxL);
-    int4 res = make_int4(-1, 256, -1, 256);
+    int4 ri = make_int4(-1, -1, -1, -1), rd = make_int4(256, 256, 256, 256);
     if (ok) {
         uint32_t mpd[8];
         load_mp_desc(P, f, i, mpd);
         const int* match = P.match + (size_t)f * P.kcap;
         const uint8_t* claimed = P.claimed + (size_t)f * P.kcap;
-        const Top2 t = scan_candidates(P, f, u, v, r, minL, maxL, mpd, [&](int idx) { return match[idx] >= 0 && claimed[idx]; });
-        if (t.i1 >= 0) { res.x = t.i1; res.y = (int)(t.k1 >> 40); }
-        if (t.i2 >= 0) { res.z = t.i2; res.w = (int)(t.k2 >> 40); }
+        const bool reset = P.resetState != 0;
+        const TopK<4> t = scan_candidates<4>(P, f, u, v, r, minL, maxL, mpd, [&](int idx) { return !reset && match[idx] >= 0 && claimed[idx]; });
+        ri = make_int4(t.i[0], t.i[1], t.i[2], t.i[3]);
+        rd = make_int4(t.i[0] >= 0 ? (int)(t.k[0] >> 40) : 256, t.i[1] >= 0 ? (int)(t.k[1] >> 40) : 256,
+                       t.i[2] >= 0 ? (int)(t.k[2] >> 40) : 256, t.i[3] >= 0 ? (int)(t.k[3] >> 40) : 256);
     }
     if (lane == 0) {
-        P.result[o] = res;
+        P.resultIdx[o] = ri; P.resultDist[o] = rd;
         P.query[o] = make_float4(u, v, r, __int_as_float((minL + 1) | ((maxL + 1) << 8) | ((ok ? 1 : 0) << 16)));
     }
 }
@@ -283,47 +303,62 @@ __global__ void __launch_bounds__(32) match_commit_kernel(MatchParams P) {
         if (bin == HISTO_LENGTH) bin = 0;
         return min(max(bin, 0), HISTO_LENGTH - 1);
     };
+    auto is_claimed = [&](int idx) { return (bool)((s_bits[idx >> 5] >> (idx & 31)) & 1u); };
     for (int base = 0; base < M; base += 32) {
         // every lane prefetches everything the serial part needs for "its" map point (gathers run in parallel)
         const int i = base + lane;
         const size_t o = (size_t)f * P.mcap + i;
-        int4 res = make_int4(-1, 256, -1, 256);
-        int hasObs = 0, l1 = -1, l2 = -1, bin = 0;
-        float lastAngle = 0.f;
+        int4 ri = make_int4(-1, -1, -1, -1), rd = make_int4(256, 256, 256, 256);
+        int hasObs = 0;
+        unsigned lv = 0, bn = 0;   // 4 x 8 bit: octave / histogram bin of the four candidates
         if (i < M) {
-            res = P.result[o]; hasObs = P.hasObs[o];
-            if (hist) lastAngle = P.angle[o];
-            if (res.x >= 0) {
-                const OrbKeyPoint kb = kps[res.x];
-                l1 = kb.octave;
-                if (hist) bin = rot_bin(lastAngle, kb.angle);
-                if (res.z >= 0) l2 = kps[res.z].octave;
+            ri = P.resultIdx[o]; rd = P.resultDist[o]; hasObs = P.hasObs[o];
+            const float lastAngle = hist ? P.angle[o] : 0.f;
+            const int ids[4] = {ri.x, ri.y, ri.z, ri.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (ids[c] >= 0) {
+                    const OrbKeyPoint kb = kps[ids[c]];
+                    lv |= (unsigned)(kb.octave & 0xff) << (8 * c);
+                    if (hist) bn |= (unsigned)rot_bin(lastAngle, kb.angle) << (8 * c);
+                }
             }
         }
         const int cnt = min(32, M - base);
         for (int j = 0; j < cnt; ++j) {
-            int bIdx = __shfl_sync(0xffffffffu, res.x, j);
-            if (bIdx < 0) continue;
-            int bDist = __shfl_sync(0xffffffffu, res.y, j), sIdx = __shfl_sync(0xffffffffu, res.z, j), sDist = __shfl_sync(0xffffffffu, res.w, j);
+            const int c0 = __shfl_sync(0xffffffffu, ri.x, j);
+            if (c0 < 0) continue;                                     // no candidate at all
+            const int ids[4] = {c0, __shfl_sync(0xffffffffu, ri.y, j), __shfl_sync(0xffffffffu, ri.z, j), __shfl_sync(0xffffffffu, ri.w, j)};
+            const int ds[4] = {__shfl_sync(0xffffffffu, rd.x, j), __shfl_sync(0xffffffffu, rd.y, j), __shfl_sync(0xffffffffu, rd.z, j),
+                               __shfl_sync(0xffffffffu, rd.w, j)};
             const int obs = __shfl_sync(0xffffffffu, hasObs, j);
-            int lv1 = __shfl_sync(0xffffffffu, l1, j), lv2 = __shfl_sync(0xffffffffu, l2, j), bn = __shfl_sync(0xffffffffu, bin, j);
-            // the second-best candidate only matters for the local-map ratio test (mode 0)
-            const bool stale = ((s_bits[bIdx >> 5] >> (bIdx & 31)) & 1u) ||
-                               (P.mode == 0 && sIdx >= 0 && ((s_bits[sIdx >> 5] >> (sIdx & 31)) & 1u));
-            if (stale) {   // rescan this map point against the current claims
+            const unsigned lvs = __shfl_sync(0xffffffffu, lv, j), bns = __shfl_sync(0xffffffffu, bn, j);
+            // first (and, for the local-map ratio test, second) candidate that is still unclaimed
+            int bIdx = -1, bDist = 256, sIdx = -1, sDist = 256, lv1 = -1, lv2 = -1, bnb = 0;
+            bool exhausted = false;                                   // true: the list ended before 4 entries
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (ids[c] < 0) { exhausted = true; continue; }
+                if (is_claimed(ids[c])) continue;
+                if (bIdx < 0) { bIdx = ids[c]; bDist = ds[c]; lv1 = (int)((lvs >> (8 * c)) & 0xff); bnb = (int)((bns >> (8 * c)) & 0xff); }
+                else if (sIdx < 0) { sIdx = ids[c]; sDist = ds[c]; lv2 = (int)((lvs >> (8 * c)) & 0xff); }
+            }
+            const bool need2 = P.mode == 0;
+            if (!exhausted && (bIdx < 0 || (need2 && sIdx < 0))) {   // the four were not enough: rescan against the current claims
                 const size_t oj = (size_t)f * P.mcap + base + j;
                 const float4 q = P.query[oj];
                 const int bits = __float_as_int(q.w);
                 uint32_t mpd[8];
                 load_mp_desc(P, f, base + j, mpd);
-                const Top2 t = scan_candidates(P, f, q.x, q.y, q.z, (bits & 0xff) - 1, ((bits >> 8) & 0xff) - 1, mpd,
-                                               [&](int idx) { return (bool)((s_bits[idx >> 5] >> (idx & 31)) & 1u); });
-                bIdx = t.i1; bDist = t.i1 >= 0 ? (int)(t.k1 >> 40) : 256;
-                sIdx = t.i2; sDist = t.i2 >= 0 ? (int)(t.k2 >> 40) : 256;
-                if (bIdx < 0) continue;
-                lv1 = kps[bIdx].octave; lv2 = sIdx >= 0 ? kps[sIdx].octave : -1;
-                if (hist) bn = rot_bin(P.angle[oj], kps[bIdx].angle);
+                const Top2 t = scan_candidates<2>(P, f, q.x, q.y, q.z, (bits & 0xff) - 1, ((bits >> 8) & 0xff) - 1, mpd, is_claimed);
+                bIdx = t.i[0]; bDist = t.i[0] >= 0 ? (int)(t.k[0] >> 40) : 256;
+                sIdx = t.i[1]; sDist = t.i[1] >= 0 ? (int)(t.k[1] >> 40) : 256;
+                if (bIdx >= 0) {
+                    lv1 = kps[bIdx].octave; lv2 = sIdx >= 0 ? kps[sIdx].octave : -1;
+                    if (hist) bnb = rot_bin(P.angle[oj], kps[bIdx].angle);
+                }
             }
+            if (bIdx < 0) continue;
             if (bDist > TH_HIGH) continue;
             if (P.mode == 0) {   // ratio test only when best and second come from the same level (:123-128)
                 if (lv1 == lv2 && (float)bDist > fmul(P.nnratio, (float)sDist)) continue;
@@ -333,7 +368,7 @@ __global__ void __launch_bounds__(32) match_commit_kernel(MatchParams P) {
                 claimed[bIdx] = (uint8_t)obs;
                 if (obs) s_bits[bIdx >> 5] |= 1u << (bIdx & 31);
                 else s_bits[bIdx >> 5] &= ~(1u << (bIdx & 31));
-                if (hist) { evBin[nEvents] = (uint8_t)bn; evIdx[nEvents] = (uint16_t)bIdx; s_hist[bn]++; }
+                if (hist) { evBin[nEvents] = (uint8_t)bnb; evIdx[nEvents] = (uint16_t)bIdx; s_hist[bnb]++; }
             }
             ++nmatches; ++nEvents;
             __syncwarp();
@@ -375,24 +410,18 @@ __global__ void __launch_bounds__(BF_NT) bf_knn2_kernel(const uint8_t* __restric
     const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)qi * 32);
     const uint4 a = __ldg(qp), b = __ldg(qp + 1);
     const uint32_t qd[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    Top2 tt; tt.k1 = tt.k2 = ~0ull; tt.i1 = tt.i2 = -1;
+    Top2 tt; tt.init();
     for (int j = lane; j < T; j += 32) {
         const uint4* tp = reinterpret_cast<const uint4*>(t + (size_t)j * 32);
         const uint4 c = __ldg(tp), d = __ldg(tp + 1);
         const uint32_t td[8] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
-        top2_insert(tt, ((unsigned long long)hamming256(qd, td) << 32) | (unsigned)j, j);
+        tt.insert(((unsigned long long)hamming256(qd, td) << 32) | (unsigned)j, j);
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const unsigned long long ok1 = __shfl_xor_sync(0xffffffffu, tt.k1, o), ok2 = __shfl_xor_sync(0xffffffffu, tt.k2, o);
-        const int oi1 = __shfl_xor_sync(0xffffffffu, tt.i1, o), oi2 = __shfl_xor_sync(0xffffffffu, tt.i2, o);
-        top2_insert(tt, ok1, oi1);
-        top2_insert(tt, ok2, oi2);
-    }
+    tt.warp_merge();
     if (lane == 0) {
-        idx[2 * qi] = tt.i1; idx[2 * qi + 1] = tt.i2;
-        dist[2 * qi] = tt.i1 >= 0 ? (int)(tt.k1 >> 32) : -1;
-        dist[2 * qi + 1] = tt.i2 >= 0 ? (int)(tt.k2 >> 32) : -1;
+        idx[2 * qi] = tt.i[0]; idx[2 * qi + 1] = tt.i[1];
+        dist[2 * qi] = tt.i[0] >= 0 ? (int)(tt.k[0] >> 32) : -1;
+        dist[2 * qi + 1] = tt.i[1] >= 0 ? (int)(tt.k[1] >> 32) : -1;
     }
 }
 
@@ -411,7 +440,7 @@ struct Matcher {
     int device, maxBatch, kcap, mcap;
     cudaStream_t stream = nullptr;
     // scratch
-    int* d_cellStart = nullptr; uint16_t* d_cellIdx = nullptr; float4* d_query = nullptr; int4* d_result = nullptr;
+    int* d_cellStart = nullptr; uint16_t* d_cellIdx = nullptr; float4* d_query = nullptr; int4 *d_resultIdx = nullptr, *d_resultDist = nullptr;
     uint8_t* d_evBin = nullptr; uint16_t* d_evIdx = nullptr; int* d_status = nullptr;
     // staging for the host entry points (batch = 1) -- one arena
     uint8_t* d_arena = nullptr; size_t arenaBytes = 0;
@@ -421,7 +450,7 @@ struct Matcher {
 
     ~Matcher() {
         cudaSetDevice(device);
-        void* ptrs[] = {d_cellStart, d_cellIdx, d_query, d_result, d_evBin, d_evIdx, d_status, d_arena, d_batch};
+        void* ptrs[] = {d_cellStart, d_cellIdx, d_query, d_resultIdx, d_resultDist, d_evBin, d_evIdx, d_status, d_arena, d_batch};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (h_arena) cudaFreeHost(h_arena);
         if (stream) cudaStreamDestroy(stream);
@@ -435,7 +464,8 @@ struct Matcher {
         CK(cudaMalloc(&d_cellStart, sizeof(int) * (GRID_CELLS + 1) * B));
         CK(cudaMalloc(&d_cellIdx, sizeof(uint16_t) * kcap * B));
         CK(cudaMalloc(&d_query, sizeof(float4) * mcap * B));
-        CK(cudaMalloc(&d_result, sizeof(int4) * mcap * B));
+        CK(cudaMalloc(&d_resultIdx, sizeof(int4) * mcap * B));
+        CK(cudaMalloc(&d_resultDist, sizeof(int4) * mcap * B));
         CK(cudaMalloc(&d_evBin, mcap * B));
         CK(cudaMalloc(&d_evIdx, sizeof(uint16_t) * mcap * B));
         CK(cudaMalloc(&d_status, sizeof(int) * B));
@@ -454,7 +484,7 @@ struct Matcher {
     int run(MatchParams& P, cudaStream_t st) {
         P.gridWInv = (float)GRID_COLS / (P.maxX - P.minX);   // src/Frame.cc:342-343
         P.gridHInv = (float)GRID_ROWS / (P.maxY - P.minY);
-        P.cellStart = d_cellStart; P.cellIdx = d_cellIdx; P.query = d_query; P.result = d_result;
+        P.cellStart = d_cellStart; P.cellIdx = d_cellIdx; P.query = d_query; P.resultIdx = d_resultIdx; P.resultDist = d_resultDist;
         P.evBin = d_evBin; P.evIdx = d_evIdx; P.status = d_status;
         launches = 0;
         grid_build_kernel<<<P.batch, GB_NT, 0, st>>>(P);
