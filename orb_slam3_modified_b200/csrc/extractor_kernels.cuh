@@ -182,37 +182,85 @@ __global__ void __launch_bounds__(FAST_NT) fast_cells_kernel(ExtractParams P, co
         s_nCand = 0; s_cntHi = 0;
     }
     for (int i = tid; i < ((ih + 2) * sp) >> 2; i += FAST_NT) reinterpret_cast<uint32_t*>(score)[i] = 0;
-    const unsigned magic = 0xFFFFFFFFu / (unsigned)iw + 1u;     // i / iw == __umulhi(i, magic) for i < 2^16
+    if (tid < 72 * 3) { s_hi[tid] = 0; s_lo[tid] = 0; }
     __syncthreads();                                            // barrier init visible + score zeroed
     mbar_wait(&s_bar, 0);
 
-    // phase 1: cheap rejection (any 9-arc contains ring pixel k or k+8 for every k) + compaction of the survivors
+    // phase 1: cheap rejection (any 9-arc contains ring pixel k or k+8 for every k) + compaction of the survivors.
+    // One thread tests four horizontally adjacent pixels; pixels travel in pairs as 2 x 16-bit lanes so that one
+    // VIADD.16x2 / LOP3 serves two pixels: with NLO = T - v and NHI1 = -(v + T + 1) per lane,
+    //   p < v - T  <=>  sign(p + NLO) set,      p > v + T  <=>  sign(p + NHI1) clear.
     const int th = P.minTh;
-    const int npix = iw * ih;
-    for (int base = 0; base < npix; base += FAST_NT) {
-        const int i = base + tid;
-        bool cand = false;
-        int y = 0, x = 0;
-        if (i < npix) {
-            y = (int)__umulhi((unsigned)i, magic); x = i - y * iw;
-            const uint8_t* t = tile + (y + 3) * tp + (x + 3);
-            const int v = t[0], lo = v - th, hi = v + th;
-            const int p0 = t[3 * tp], p8 = t[-3 * tp], p4 = t[3], p12 = t[-3];
-            bool dark = (p0 < lo || p8 < lo) && (p4 < lo || p12 < lo);
-            bool brig = (p0 > hi || p8 > hi) && (p4 > hi || p12 > hi);
-            if (dark || brig) {
-                const int p2 = t[2 * tp + 2], p10 = t[-2 * tp - 2], p6 = t[-2 * tp + 2], p14 = t[2 * tp - 2];
-                dark = dark && (p2 < lo || p10 < lo) && (p6 < lo || p14 < lo);
-                brig = brig && (p2 > hi || p10 > hi) && (p6 > hi || p14 > hi);
-                cand = dark || brig;
+    {
+        const int nq = (iw + 3) >> 2, nQ = nq * ih;
+        const unsigned qmagic = 0xFFFFFFFFu / (unsigned)nq + 1u;
+        const uint32_t TT = (uint32_t)th * 0x10001u, TT1 = (uint32_t)(th + 1) * 0x10001u;
+        const int shC = ((xoff) & 3) * 8;            // byte phase of column (4q + xoff) inside an aligned word
+        for (int base = 0; base < nQ; base += FAST_NT) {
+            const int qi = base + tid;
+            uint32_t c01 = 0, c23 = 0;
+            int y = 0, q = 0;
+            if (qi < nQ) {
+                y = (int)__umulhi((unsigned)qi, qmagic); q = qi - y * nq;
+                // aligned word address of tile byte (row y+3, column 4q + xoff) = first of the 10 bytes c0-3 .. c0+6, c0 = 4q + 3 + xoff
+                const uint32_t* rc = reinterpret_cast<const uint32_t*>(tileBase + (y + 3) * tp + ((4 * q + xoff) & ~3));
+                const int tpw = tp >> 2;
+                // three 4-byte windows per row: bytes [c0-3, c0], [c0+1, c0+4], [c0+5, c0+8]
+#define ORBX_WIN3(r, A, B, C) { const uint32_t w0 = (r)[0], w1 = (r)[1], w2 = (r)[2], w3 = (r)[3]; \
+                                A = __funnelshift_r(w0, w1, shC); B = __funnelshift_r(w1, w2, shC); C = __funnelshift_r(w2, w3, shC); }
+                uint32_t A0, B0, C0, Au, Bu, Cu, Ad, Bd, Cd;
+                ORBX_WIN3(rc, A0, B0, C0);                         // centre row
+                ORBX_WIN3(rc + 2 * tpw, Au, Bu, Cu);               // row +2
+                ORBX_WIN3(rc - 2 * tpw, Ad, Bd, Cd);               // row -2
+                uint32_t t3a, t3b;                                 // rows +-3: bytes c0 .. c0+3 = window offset 3..6
+                { const uint32_t* r3 = rc + 3 * tpw; const uint32_t w0 = r3[0], w1 = r3[1], w2 = r3[2];
+                  t3a = __funnelshift_r(__funnelshift_r(w0, w1, shC), __funnelshift_r(w1, w2, shC), 24); }
+                { const uint32_t* r3 = rc - 3 * tpw; const uint32_t w0 = r3[0], w1 = r3[1], w2 = r3[2];
+                  t3b = __funnelshift_r(__funnelshift_r(w0, w1, shC), __funnelshift_r(w1, w2, shC), 24); }
+#undef ORBX_WIN3
+                // window byte offsets (relative to c0-3): centre = 3..6, p12 (x-3) = 0..3, p4 (x+3) = 6..9, x-2 = 1..4, x+2 = 5..8
+                const uint32_t ctr = __funnelshift_r(A0, B0, 24);                 // bytes c0 .. c0+3
+                const uint32_t p12 = A0;                                           // bytes c0-3 .. c0
+                const uint32_t p4 = __funnelshift_r(B0, C0, 16);                  // bytes c0+3 .. c0+6
+                const uint32_t p2 = __funnelshift_r(Bu, Cu, 8), p14 = __funnelshift_r(Au, Bu, 8);    // row +2: x+2 (5..8), x-2 (1..4)
+                const uint32_t p6 = __funnelshift_r(Bd, Cd, 8), p10 = __funnelshift_r(Ad, Bd, 8);    // row -2: x+2, x-2
+                const uint32_t p0 = t3a, p8 = t3b;
+#define ORBX_LO(w) __byte_perm((w), 0u, 0x4140)   /* bytes 0,1 -> two 16-bit lanes */
+#define ORBX_HI(w) __byte_perm((w), 0u, 0x4342)   /* bytes 2,3 */
+                const uint32_t V01 = ORBX_LO(ctr), V23 = ORBX_HI(ctr);
+                const uint32_t NLO01 = __vsub2(TT, V01), NLO23 = __vsub2(TT, V23);                 // T - v
+                const uint32_t NHI01 = __vsub2(0u, __vadd2(V01, TT1)), NHI23 = __vsub2(0u, __vadd2(V23, TT1));   // -(v + T + 1)
+                uint32_t dk01 = 0xFFFFFFFFu, dk23 = 0xFFFFFFFFu, br01 = 0u, br23 = 0u;
+#define ORBX_OPP(pa, pb) { \
+                    const uint32_t a01 = ORBX_LO(pa), a23 = ORBX_HI(pa), b01 = ORBX_LO(pb), b23 = ORBX_HI(pb); \
+                    dk01 &= __vadd2(a01, NLO01) | __vadd2(b01, NLO01); dk23 &= __vadd2(a23, NLO23) | __vadd2(b23, NLO23); \
+                    br01 |= __vadd2(a01, NHI01) & __vadd2(b01, NHI01); br23 |= __vadd2(a23, NHI23) & __vadd2(b23, NHI23); }
+                ORBX_OPP(p0, p8); ORBX_OPP(p4, p12); ORBX_OPP(p2, p10); ORBX_OPP(p6, p14);
+#undef ORBX_OPP
+#undef ORBX_LO
+#undef ORBX_HI
+                c01 = (dk01 | ~br01) & 0x80008000u;
+                c23 = (dk23 | ~br23) & 0x80008000u;
+                const int xr = iw - 4 * q;     // pixels of this quad inside the interior
+                if (xr < 4) { c23 = xr <= 2 ? 0u : (c23 & 0x8000u); if (xr < 2) c01 &= 0x8000u; }
             }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (m) {
-            int wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&s_nCand, __popc(m));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (cand) list[wbase + __popc(m & ((1u << lane) - 1))] = (uint16_t)((y << 7) | x);
+            // compaction: up to four candidates per lane, in (y, x) packed form
+            const int n4 = ((c01 >> 15) & 1) + (c01 >> 31) + ((c23 >> 15) & 1) + (c23 >> 31);
+            int incl = n4;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+            if (wtot) {
+                int wbase = 0;
+                if (lane == 31) wbase = atomicAdd(&s_nCand, wtot);
+                wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                int o = wbase + incl - n4;
+                const int yx = (y << 7) | (4 * q);
+                if (c01 & 0x8000u) list[o++] = (uint16_t)yx;
+                if (c01 & 0x80000000u) list[o++] = (uint16_t)(yx + 1);
+                if (c23 & 0x8000u) list[o++] = (uint16_t)(yx + 2);
+                if (c23 & 0x80000000u) list[o++] = (uint16_t)(yx + 3);
+            }
         }
     }
     __syncthreads();
@@ -234,26 +282,26 @@ __global__ void __launch_bounds__(FAST_NT) fast_cells_kernel(ExtractParams P, co
     }
     __syncthreads();
 
-    // phase 3: strict 8-neighbour maxima -> per-row bitmaps for both thresholds; warp per row, ballot = bitmap word
-    int cntHi = 0;
-    for (int y = tid >> 5; y < ih; y += FAST_NT / 32) {
-        for (int xb = 0; xb < iw; xb += 32) {
-            const int x = xb + lane;
-            bool kLo = false, kHi = false;
-            if (x < iw) {
-                const uint8_t* sc = score + (y + 1) * sp + (x + 1);
-                const int v = sc[0];
-                if (v != 0) {
-                    kLo = v > sc[-1] && v > sc[1] && v > sc[-sp - 1] && v > sc[-sp] && v > sc[-sp + 1] &&
-                          v > sc[sp - 1] && v > sc[sp] && v > sc[sp + 1];          // score >= minTh by construction
-                    kHi = kLo && v >= P.iniTh;
-                }
+    // phase 3: strict 8-neighbour maxima among the scored candidates only (corners are sparse) -> per-row keep bitmaps
+    // for both thresholds via shared-memory atomicOr
+    {
+        const int nc = s_nCand;
+        int cntHi = 0;
+        for (int c = tid; c < nc; c += FAST_NT) {
+            const int yx = list[c];
+            const int y = yx >> 7, x = yx & 127;
+            const uint8_t* sc = score + (y + 1) * sp + (x + 1);
+            const int v = sc[0];
+            if (v == 0) continue;
+            const bool keep = v > sc[-1] && v > sc[1] && v > sc[-sp - 1] && v > sc[-sp] && v > sc[-sp + 1] &&
+                              v > sc[sp - 1] && v > sc[sp] && v > sc[sp + 1];          // score >= minTh by construction
+            if (keep) {
+                atomicOr(&s_lo[y * 3 + (x >> 5)], 1u << (x & 31));
+                if (v >= P.iniTh) { atomicOr(&s_hi[y * 3 + (x >> 5)], 1u << (x & 31)); ++cntHi; }
             }
-            const unsigned mLo = __ballot_sync(0xffffffffu, kLo), mHi = __ballot_sync(0xffffffffu, kHi);
-            if (lane == 0) { s_lo[y * 3 + (xb >> 5)] = mLo; s_hi[y * 3 + (xb >> 5)] = mHi; cntHi += __popc(mHi); }
         }
+        if (cntHi) atomicAdd(&s_cntHi, cntHi);
     }
-    if (lane == 0 && cntHi) atomicAdd(&s_cntHi, cntHi);
     __syncthreads();
     // fallback to minTh only if the cell is empty at iniTh (:843-859); ordered (row-major) emission, one thread per row
     const uint32_t* bits = s_cntHi > 0 ? s_hi : s_lo;
