@@ -103,18 +103,28 @@ static inline int reflect101(int i, int n) {
 static void blur7(const uint8_t* src, int w, int h, int sstep, uint8_t* dst, int dstep) {
     static const int k[7] = {18, 34, 48, 56, 48, 34, 18};
     std::vector<uint16_t> hbuf((size_t)w * h);
-    for (int y = 0; y < h; ++y)
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* r = src + (size_t)y * sstep;
+        uint16_t* hb = &hbuf[(size_t)y * w];
         for (int x = 0; x < w; ++x) {
-            int s = 0;
-            for (int i = 0; i < 7; ++i) s += k[i] * src[(size_t)y * sstep + reflect101(x + i - 3, w)];
-            hbuf[(size_t)y * w + x] = (uint16_t)s;
+            if (x >= 3 && x + 3 < w) {   // interior: no reflection
+                hb[x] = (uint16_t)(18 * (r[x - 3] + r[x + 3]) + 34 * (r[x - 2] + r[x + 2]) + 48 * (r[x - 1] + r[x + 1]) + 56 * r[x]);
+            } else {
+                int s = 0;
+                for (int i = 0; i < 7; ++i) s += k[i] * r[reflect101(x + i - 3, w)];
+                hb[x] = (uint16_t)s;
+            }
         }
-    for (int y = 0; y < h; ++y)
+    }
+    for (int y = 0; y < h; ++y) {
+        const uint16_t* rows[7];
+        for (int i = 0; i < 7; ++i) rows[i] = &hbuf[(size_t)reflect101(y + i - 3, h) * w];
+        uint8_t* d = dst + (size_t)y * dstep;
         for (int x = 0; x < w; ++x) {
-            uint32_t s = 0;
-            for (int i = 0; i < 7; ++i) s += (uint32_t)k[i] * hbuf[(size_t)reflect101(y + i - 3, h) * w + x];
-            dst[(size_t)y * dstep + x] = (uint8_t)((s + 32768u) >> 16);
+            const uint32_t s = 18u * (rows[0][x] + rows[6][x]) + 34u * (rows[1][x] + rows[5][x]) + 48u * (rows[2][x] + rows[4][x]) + 56u * rows[3][x];
+            d[x] = (uint8_t)((s + 32768u) >> 16);
         }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -147,7 +157,14 @@ static void fast9_nms(const uint8_t* roi, int w, int h, int step, int T, std::ve
     std::vector<uint8_t> sc((size_t)w * h, 0);
     for (int y = 3; y < h - 3; ++y)
         for (int x = 3; x < w - 3; ++x) {
-            int m = fast_arc_max(roi + (size_t)y * step + x, step);
+            // early rejection as in OpenCV's FAST_t (a 9-arc contains ring pixel k or k+8 for every k): exact, only saves time
+            const uint8_t* p = roi + (size_t)y * step + x;
+            const int v = p[0], lo = v - T, hi = v + T;
+            const int p0 = p[3 * step], p8 = p[-3 * step], p4 = p[3], p12 = p[-3];
+            const bool dark = (p0 < lo || p8 < lo) && (p4 < lo || p12 < lo);
+            const bool brig = (p0 > hi || p8 > hi) && (p4 > hi || p12 > hi);
+            if (!dark && !brig) continue;
+            int m = fast_arc_max(p, step);
             if (m > T) sc[(size_t)y * w + x] = (uint8_t)(m - 1);
         }
     for (int y = 3; y < h - 3; ++y)
