@@ -5,12 +5,18 @@
 // (1..8 CTAs, chosen so that the batch fills the 148 SMs); the whole Levenberg-Marquardt loop -- accept/reject,
 // lambda schedule, stop rules, stop-flag polling -- runs on the device, phases are separated by cluster barriers,
 // and the host only uploads the flattened graph and downloads the result.  All arithmetic is FP64 (g2o is double).
+// The linearisation is kept FACTORED: an edge stores only (x/z, y/z, 1/z, robust weight) at the linearisation point (32 B);
+// its Jacobians are A = -S t (2x3, t = [R0 - xn R2; R1 - yn R2], S = diag(fx, fy)/z) and B = F b (2x6, F = diag(fx, fy),
+// b a polynomial in xn, yn, 1/z), so the Hpl block W = w B^T A is rank 2 and is never materialised: every product that
+// g2o forms with W (Schur complement, rhs, back-substitution) is evaluated from the factors.  Per LM trial the working
+// set is ~1.5 MB per problem (L2 resident for a whole batch) instead of 11.5 MB of W / W Hll^-1 blocks.
 // Phases of one LM trial (workers = all threads of the cluster):
-//   residual   thread/edge      EdgeSE3ProjectXYZ::computeError + Huber rho            (HOT LOOP A)
-//   build      warp/point, CTA/pose   linearizeOplus + constructQuadraticForm: Hll, bl, W=Hpl blocks, Hpp, bp   (HOT LOOP B)
-//   schur      thread/point, thread/edge, warp/pose-pair   Hll^-1, Y = W Hll^-1, Hschur = Hpp - sum Y W^T       (HOT LOOP C)
-//   ldlt       CTA 0, matrix in shared memory   dense LDL^T of the reduced camera system + solve
-//   backsub    thread/point     x_l = Hll^-1 (b_l - W^T x_p)
+//   residual   thread/edge      EdgeSE3ProjectXYZ::computeError + Huber rho, edge factors   (HOT LOOP A)
+//   build      8 lanes/point: Hll, bl;  warp/chunk of a pose's edges: Hpp, bp               (HOT LOOP B)
+//   schur      thread/point: (Hll + lambda I)^-1;  warp/chunk of (e1, e2) pairs of one pose pair:
+//              Hschur = Hpp - sum B1^T (w1 w2 A1 Hll^-1 A2^T) B2                            (HOT LOOP C)
+//   ldlt       CTA 0, matrix in shared memory: blocked LDL^T with look-ahead, rhs carried as an extra row
+//   backsub    8 lanes/point    x_l = Hll^-1 (b_l - W^T x_p)
 //   update     thread/vertex    T <- exp(dx) T, p <- p + dx  (+ backup for the LM "pop")
 // Every reduction is ordered (no floating-point atomics), so results are reproducible run to run.
 #include <cooperative_groups.h>
@@ -57,16 +63,16 @@ struct Dev {
     const int *poseStart, *poseEdges; // CSR by pose (internal edge ids, ascending)
     const int* blockStart;            // nF(nF-1)/2 + 1: off-diagonal Schur blocks (i1 < i2), row-major over the strict upper triangle
     const int2* pairs;                // (edge of pose i1, edge of pose i2) observing the same point
+    const int* pairPt;                // that point
     // Schur work list: tasks 0..nF-1 = diagonal blocks (items = edges of the pose), nF.. = off-diagonal blocks (items = pairs);
     // every task is cut into chunks of SCH items so that all warps of the cluster get the same amount of work
     int nChunks; const int* chunkTask; const int* chunkFirst; const int* taskChunkStart;   // nChunks, nChunks, nTasks + 1
     double* Spart;                    // nChunks x 42 partial sums (36 block entries + 6 rhs entries for diagonal tasks)
     double* err;                      // nE x 2
-    double* W;                        // nE x 18 (6x3 Hpl block, zero for fixed poses)
-    double* Y;                        // nE x 18 (W Hll^-1)
+    double *E4a, *E4b;                // nE x 4 edge factors (x/z, y/z, 1/z, w): linearisation point / trial state (swapped on accept)
     double *Hpp, *bp;                 // nF x 36, nF x 6
-    double *Hll, *bl;                 // nL x 9, nL x 3
-    double *Dinv, *db;                // nL x 9, nL x 3
+    double *Hll, *bl;                 // nL x 6 (00 01 02 11 12 22), nL x 3
+    double *DinvS, *db;               // nL x 8 (upper triangle of (Hll + lambda I)^-1, 2 pad), nL x 3
     double *Hs, *bs;                  // n x n (only when it does not fit in shared memory), n
     double* x;                        // n + 3 nL
     double* partial;                  // 4 rotating slots x 16 doubles: per-CTA partial sums + broadcast words
@@ -223,69 +229,90 @@ __device__ __forceinline__ void project_edge(const Dev& D, const Ctx& c, int e, 
     uv[1] = P[17] * Xc[1] / Xc[2] + P[19];
 }
 
-// ---- residuals + robust chi2 (SparseOptimizer::computeActiveErrors + activeRobustChi2), thread per edge ----
-__device__ double phase_errors(const Dev& D, const Ctx& c) {
+// ---- residuals + robust chi2 (SparseOptimizer::computeActiveErrors + activeRobustChi2), thread per edge.
+//      Also leaves the edge factors (x/z, y/z, 1/z, rho' / sigma^2) of this state in Eout. ----
+__device__ double phase_errors(const Dev& D, const Ctx& c, double* __restrict__ Eout) {
     double acc = 0;
     for (int e = c.wid; e < D.nE; e += c.nw) {
         double Xc[3], uv[2];
         project_edge(D, c, e, Xc, uv);
         const double e0 = D.obs[2 * (size_t)e] - uv[0], e1 = D.obs[2 * (size_t)e + 1] - uv[1];
         *reinterpret_cast<double2*>(D.err + 2 * (size_t)e) = make_double2(e0, e1);
+        const double is2 = (double)D.invSigma2[e];
         double r0, r1;
-        robustify(D, (double)D.invSigma2[e] * (e0 * e0 + e1 * e1), r0, r1);
+        robustify(D, is2 * (e0 * e0 + e1 * e1), r0, r1);
         acc += r0;
+        const double iz = 1.0 / Xc[2];
+        double2* o = reinterpret_cast<double2*>(Eout + 4 * (size_t)e);
+        o[0] = make_double2(Xc[0] * iz, Xc[1] * iz);
+        o[1] = make_double2(iz, r1 * is2);
     }
     return acc;
 }
 
-// Jacobians of one edge (EdgeSE3ProjectXYZ::linearizeOplus): A = dE/dpoint (2x3), B = dE/dpose (2x6)
-__device__ __forceinline__ void edge_jacobians(const Dev& D, const Ctx& c, int e, double* A, double* B, double& w, double& r0, double& r1) {
-    const double* P = c.pc + PC * D.ePose[e];
-    double Xc[3], uv[2];
-    project_edge(D, c, e, Xc, uv);
-    const double x = Xc[0], y = Xc[1], z = Xc[2];
-    const double fx = P[16], fy = P[17];
-    const double J00 = -(fx / z), J02 = fx * x / (z * z), J11 = -(fy / z), J12 = fy * y / (z * z);   // -projectJac (Pinhole.cpp:71-81)
-    const double* R = P + 7;
+// Edge factors.  With xn = x/z, yn = y/z, iz = 1/z (camera frame) and R the keyframe rotation, the Jacobians of
+// EdgeSE3ProjectXYZ::linearizeOplus (-projectJac * R and -projectJac * [-[Xc]x | I], Pinhole.cpp:71-81) are
+//   A = -diag(fx iz, fy iz) t,   t = [R0 - xn R2 ; R1 - yn R2]                           (2x3)
+//   B =  diag(fx, fy) b,         b = [xn yn, -(1 + xn^2), yn, -iz, 0, xn iz ; 1 + yn^2, -xn yn, -xn, 0, -iz, yn iz]   (2x6)
+__device__ __forceinline__ void load_e4(const double* __restrict__ E, int e, double& xn, double& yn, double& iz, double& w) {
+    const double2* q = reinterpret_cast<const double2*>(E + 4 * (size_t)e);
+    const double2 a = q[0], b = q[1];
+    xn = a.x; yn = a.y; iz = b.x; w = b.y;
+}
+__device__ __forceinline__ void edge_t(const double* R, double xn, double yn, double* t) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { A[k] = J00 * R[k] + J02 * R[6 + k]; A[3 + k] = J11 * R[3 + k] + J12 * R[6 + k]; }
-    // SE3deriv = [0 z -y 1 0 0; -z 0 x 0 1 0; y -x 0 0 0 1]
-    B[0] = J02 * y;            B[1] = J00 * z - J02 * x;  B[2] = -J00 * y;  B[3] = J00; B[4] = 0;   B[5] = J02;
-    B[6] = -J11 * z + J12 * y; B[7] = -J12 * x;           B[8] = J11 * x;   B[9] = 0;   B[10] = J11; B[11] = J12;
-    const double is2 = (double)D.invSigma2[e];
-    const double2 er = *reinterpret_cast<const double2*>(D.err + 2 * (size_t)e);
-    double rho0, rho1;
-    robustify(D, is2 * (er.x * er.x + er.y * er.y), rho0, rho1);
-    w = rho1 * is2;
-    r0 = -is2 * er.x * rho1; r1 = -is2 * er.y * rho1;
+    for (int k = 0; k < 3; ++k) { t[k] = R[k] - xn * R[6 + k]; t[3 + k] = R[3 + k] - yn * R[6 + k]; }
+}
+__device__ __forceinline__ void edge_b(double xn, double yn, double iz, double* b0, double* b1) {   // b0[4] and b1[3] are zero
+    const double xy = xn * yn;
+    b0[0] = xy;                 b0[1] = -(1.0 + xn * xn); b0[2] = yn;  b0[3] = -iz; b0[4] = 0.0; b0[5] = xn * iz;
+    b1[0] = 1.0 + yn * yn;      b1[1] = -xy;              b1[2] = -xn; b1[3] = 0.0; b1[4] = -iz; b1[5] = yn * iz;
 }
 
-// ---- per point Hll, bl and the Hpl blocks W of its edges; 8 lanes per point (edges of a point are contiguous) ----
-__device__ void phase_build_points(const Dev& D, const Ctx& c) {
+// Reduce-scatter of V register values over the 32 lanes of a warp: afterwards lane `lane` holds the totals of entries
+// [lo, lo + n) in v[0..n), n <= 2.  Fixed butterfly (halve the vector at every level), ~V shuffles instead of 5 V.
+template <int N, int H>
+__device__ __forceinline__ void rs_level(double* v, bool up, int o) {
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const double a = v[i];
+        const double b = (i + H < N) ? v[i + H] : 0.0;
+        const double keep = up ? b : a, send = up ? a : b;
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+}
+template <int V>
+__device__ __forceinline__ void warp_reduce_scatter(double* v, int lane, int& lo, int& n) {
+    constexpr int H1 = (V + 1) / 2, H2 = (H1 + 1) / 2, H3 = (H2 + 1) / 2, H4 = (H3 + 1) / 2, H5 = (H4 + 1) / 2;
+    static_assert(H5 <= 2, "vector too long");
+    lo = 0; n = V;
+    bool up;
+    up = lane & 16; rs_level<V, H1>(v, up, 16); if (up) { lo += H1; n -= H1; } else n = min(n, H1);
+    up = lane & 8;  rs_level<H1, H2>(v, up, 8); if (up) { lo += H2; n -= H2; } else n = min(n, H2);
+    up = lane & 4;  rs_level<H2, H3>(v, up, 4); if (up) { lo += H3; n -= H3; } else n = min(n, H3);
+    up = lane & 2;  rs_level<H3, H4>(v, up, 2); if (up) { lo += H4; n -= H4; } else n = min(n, H4);
+    up = lane & 1;  rs_level<H4, H5>(v, up, 1); if (up) { lo += H5; n -= H5; } else n = min(n, H5);
+}
+
+// ---- per point Hll, bl; 8 lanes per point (the edges of a point are contiguous) ----
+__device__ void phase_build_points(const Dev& D, const Ctx& c, const double* __restrict__ E) {
     const int sl = c.tid & 7;
     const unsigned gmask = 0xFFu << (c.tid & 24);
     for (int p = c.wid >> 3; p < D.nL; p += c.nw >> 3) {
         const int a = D.ptStart[p], b = D.ptStart[p + 1];
         double h[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
         for (int e = a + sl; e < b; e += 8) {
-            double A[6], B[12], w, r0, r1;
-            edge_jacobians(D, c, e, A, B, w, r0, r1);
-            g[0] += A[0] * r0 + A[3] * r1; g[1] += A[1] * r0 + A[4] * r1; g[2] += A[2] * r0 + A[5] * r1;
-            h[0] += w * (A[0] * A[0] + A[3] * A[3]); h[1] += w * (A[0] * A[1] + A[3] * A[4]); h[2] += w * (A[0] * A[2] + A[3] * A[5]);
-            h[3] += w * (A[1] * A[1] + A[4] * A[4]); h[4] += w * (A[1] * A[2] + A[4] * A[5]); h[5] += w * (A[2] * A[2] + A[5] * A[5]);
-            double2* We = reinterpret_cast<double2*>(D.W + 18 * (size_t)e);
-            if (D.hidx[D.ePose[e]] >= 0) {
-                double v[18];
-#pragma unroll
-                for (int i = 0; i < 6; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) v[i * 3 + j] = w * (B[i] * A[j] + B[6 + i] * A[3 + j]);
-#pragma unroll
-                for (int i = 0; i < 9; ++i) We[i] = make_double2(v[2 * i], v[2 * i + 1]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) We[i] = make_double2(0.0, 0.0);
-            }
+            const double* P = c.pc + PC * D.ePose[e];
+            double xn, yn, iz, w, t[6];
+            load_e4(E, e, xn, yn, iz, w);
+            edge_t(P + 7, xn, yn, t);
+            const double2 er = *reinterpret_cast<const double2*>(D.err + 2 * (size_t)e);
+            const double s0 = P[16] * iz, s1 = P[17] * iz;
+            const double c0 = w * s0 * s0, c1 = w * s1 * s1;          // w A^T A = c0 t0^T t0 + c1 t1^T t1
+            const double q0 = s0 * w * er.x, q1 = s1 * w * er.y;      // A^T r, r = -w err
+            g[0] += t[0] * q0 + t[3] * q1; g[1] += t[1] * q0 + t[4] * q1; g[2] += t[2] * q0 + t[5] * q1;
+            h[0] += c0 * t[0] * t[0] + c1 * t[3] * t[3]; h[1] += c0 * t[0] * t[1] + c1 * t[3] * t[4]; h[2] += c0 * t[0] * t[2] + c1 * t[3] * t[5];
+            h[3] += c0 * t[1] * t[1] + c1 * t[4] * t[4]; h[4] += c0 * t[1] * t[2] + c1 * t[4] * t[5]; h[5] += c0 * t[2] * t[2] + c1 * t[5] * t[5];
         }
 #pragma unroll
         for (int o = 4; o; o >>= 1) {
@@ -295,66 +322,71 @@ __device__ void phase_build_points(const Dev& D, const Ctx& c) {
             for (int i = 0; i < 3; ++i) g[i] += __shfl_xor_sync(gmask, g[i], o);
         }
         if (sl == 0) {
-            double* H = D.Hll + 9 * (size_t)p;
-            H[0] = h[0]; H[1] = h[1]; H[2] = h[2]; H[3] = h[1]; H[4] = h[3]; H[5] = h[4]; H[6] = h[2]; H[7] = h[4]; H[8] = h[5];
+            double2* H = reinterpret_cast<double2*>(D.Hll + 6 * (size_t)p);
+            H[0] = make_double2(h[0], h[1]); H[1] = make_double2(h[2], h[3]); H[2] = make_double2(h[4], h[5]);
             D.bl[3 * (size_t)p] = g[0]; D.bl[3 * (size_t)p + 1] = g[1]; D.bl[3 * (size_t)p + 2] = g[2];
         }
     }
 }
 
-// ---- per free pose Hpp, bp; one CTA per pose (round-robin over the cluster), threads over its edges ----
-__device__ void phase_build_poses(const Dev& D, const Ctx& c) {
-    const int lane = c.tid & 31, warp = c.tid >> 5;
-    double* red = c.sm;                      // NWARP x 27 <= NT doubles
-    for (int hI = c.crank; hI < D.nF; hI += c.csize) {
-        const int ic = D.freePose[hI];
-        const int a = D.poseStart[ic], b = D.poseStart[ic + 1];
+constexpr int SCH = 128;           // items per chunk of the pose / pose-pair work lists
+constexpr int IPL = SCH / 32;      // items per lane
+
+// ---- per free pose Hpp, bp.  partial: warp per chunk of the pose's edges (the chunks of the diagonal Schur tasks), lane per
+//      edge, 21 + 6 sums reduce-scattered to Spart; combine: thread per (pose, entry), chunks added in order ----
+__device__ void phase_build_poses_partial(const Dev& D, const Ctx& c, const double* __restrict__ E) {
+    const int lane = c.tid & 31;
+    const int nDiag = D.taskChunkStart[D.nF];
+    for (int ch = c.crank * NWARP + (c.tid >> 5); ch < nDiag; ch += c.csize * NWARP) {
+        const int ic = D.freePose[D.chunkTask[ch]];
+        const double* P = c.pc + PC * ic;
+        const double fx = P[16], fy = P[17];
+        const int k0 = D.poseStart[ic] + D.chunkFirst[ch], k1 = min(k0 + SCH, D.poseStart[ic + 1]);
         double acc[27];
 #pragma unroll
         for (int i = 0; i < 27; ++i) acc[i] = 0;
-        for (int k = a + c.tid; k < b; k += NT) {
+        for (int k = k0 + lane; k < k1; k += 32) {
             const int e = D.poseEdges[k];
-            double A[6], B[12], w, r0, r1;
-            edge_jacobians(D, c, e, A, B, w, r0, r1);
+            double xn, yn, iz, w, b0[6], b1[6];
+            load_e4(E, e, xn, yn, iz, w);
+            edge_b(xn, yn, iz, b0, b1);
+            const double2 er = *reinterpret_cast<const double2*>(D.err + 2 * (size_t)e);
+            const double c0 = w * fx * fx, c1 = w * fy * fy;          // w B^T B = c0 b0^T b0 + c1 b1^T b1
+            const double q0 = fx * w * er.x, q1 = fy * w * er.y;      // B^T r = -(b0 q0 + b1 q1)
             int t = 0;
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
+                const double u0 = c0 * b0[i], u1 = c1 * b1[i];
 #pragma unroll
-                for (int j = i; j < 6; ++j) acc[t++] += w * (B[i] * B[j] + B[6 + i] * B[6 + j]);
+                for (int j = i; j < 6; ++j) acc[t++] += u0 * b0[j] + u1 * b1[j];
             }
 #pragma unroll
-            for (int i = 0; i < 6; ++i) acc[21 + i] += B[i] * r0 + B[6 + i] * r1;
+            for (int i = 0; i < 6; ++i) acc[21 + i] -= b0[i] * q0 + b1[i] * q1;
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-#pragma unroll
-            for (int i = 0; i < 27; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-        }
-        __syncthreads();
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < 27; ++i) red[warp * 27 + i] = acc[i];
-        }
-        __syncthreads();
-        if (c.tid < 27) {
-            double s = 0;
-            for (int w2 = 0; w2 < NWARP; ++w2) s += red[w2 * 27 + c.tid];
-            if (c.tid < 21) {
-                int i = 0, t = c.tid;           // unrank (i, j), i <= j
-                while (t >= 6 - i) { t -= 6 - i; ++i; }
-                const int j = i + t;
-                D.Hpp[36 * (size_t)hI + i * 6 + j] = s; D.Hpp[36 * (size_t)hI + j * 6 + i] = s;
-            } else D.bp[6 * (size_t)hI + (c.tid - 21)] = s;
-        }
+        int lo, n;
+        warp_reduce_scatter<27>(acc, lane, lo, n);
+        if (n > 0) D.Spart[42 * (size_t)ch + lo] = acc[0];
     }
-    __syncthreads();
+}
+__device__ void phase_build_poses_combine(const Dev& D, const Ctx& c) {
+    for (int idx = c.wid; idx < D.nF * 27; idx += c.nw) {
+        const int hI = idx / 27, ent = idx - hI * 27;
+        double s = 0;
+        for (int ch = D.taskChunkStart[hI]; ch < D.taskChunkStart[hI + 1]; ++ch) s += D.Spart[42 * (size_t)ch + ent];
+        if (ent < 21) {
+            int i = 0, t = ent;             // unrank (i, j), i <= j
+            while (t >= 6 - i) { t -= 6 - i; ++i; }
+            const int j = i + t;
+            D.Hpp[36 * (size_t)hI + i * 6 + j] = s; D.Hpp[36 * (size_t)hI + j * 6 + i] = s;
+        } else D.bp[6 * (size_t)hI + (ent - 21)] = s;
+    }
 }
 
 // ---- max |diag| over all Hessian blocks (computeLambdaInit); every CTA computes it redundantly ----
 __device__ double phase_maxdiag(const Dev& D, const Ctx& c) {
     double m = 0;
     for (int i = c.tid; i < D.n; i += NT) m = fmax(m, fabs(D.Hpp[36 * (size_t)(i / 6) + 7 * (i % 6)]));
-    for (int i = c.tid; i < 3 * D.nL; i += NT) m = fmax(m, fabs(D.Hll[9 * (size_t)(i / 3) + 4 * (i % 3)]));
+    for (int i = c.tid; i < 3 * D.nL; i += NT) { const int k = i % 3; m = fmax(m, fabs(D.Hll[6 * (size_t)(i / 3) + (k == 0 ? 0 : k == 1 ? 3 : 5)])); }
 #pragma unroll
     for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     __syncthreads();
@@ -366,124 +398,130 @@ __device__ double phase_maxdiag(const Dev& D, const Ctx& c) {
     return r;
 }
 
-// ---- Hll^-1 (lambda on the diagonal), Hll^-1 bl, and Y = W Hll^-1; thread per edge, the inverse is recomputed per edge
-//      (cheaper than a barrier), the first edge of a point stores it (block_solver.hpp:381-394) ----
+// ---- (Hll + lambda I)^-1 and (Hll + lambda I)^-1 bl, thread per point (block_solver.hpp:381-394) ----
 __device__ void phase_point_prep(const Dev& D, const Ctx& c, double lambda) {
-    for (int e = c.wid; e < D.nE; e += c.nw) {
-        const int p = D.ePt[e];
-        double m[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) m[i] = D.Hll[9 * (size_t)p + i];
-        m[0] += lambda; m[4] += lambda; m[8] += lambda;
-        const double c00 = m[4] * m[8] - m[5] * m[7], c10 = m[5] * m[6] - m[3] * m[8], c20 = m[3] * m[7] - m[4] * m[6];
-        const double id = 1.0 / (m[0] * c00 + m[1] * c10 + m[2] * c20);   // Eigen 3x3 inverse: cofactors / determinant
-        double o[9];
-        o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
-        o[3] = c10 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
-        o[6] = c20 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
-        if (e == D.ptStart[p]) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) D.Dinv[9 * (size_t)p + i] = o[i];
-            const double* b3 = D.bl + 3 * (size_t)p;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) D.db[3 * (size_t)p + i] = o[i * 3] * b3[0] + o[i * 3 + 1] * b3[1] + o[i * 3 + 2] * b3[2];
-        }
-        const double2* Wd = reinterpret_cast<const double2*>(D.W + 18 * (size_t)e);
-        double wv[18];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { const double2 t = Wd[i]; wv[2 * i] = t.x; wv[2 * i + 1] = t.y; }
-        double yv[18];
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) yv[a * 3 + b] = wv[a * 3] * o[b] + wv[a * 3 + 1] * o[3 + b] + wv[a * 3 + 2] * o[6 + b];
-        double2* Yd = reinterpret_cast<double2*>(D.Y + 18 * (size_t)e);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Yd[i] = make_double2(yv[2 * i], yv[2 * i + 1]);
+    for (int p = c.wid; p < D.nL; p += c.nw) {
+        const double2* H = reinterpret_cast<const double2*>(D.Hll + 6 * (size_t)p);
+        const double2 h01 = H[0], h23 = H[1], h45 = H[2];
+        const double m0 = h01.x + lambda, m1 = h01.y, m2 = h23.x, m4 = h23.y + lambda, m5 = h45.x, m8 = h45.y + lambda;
+        const double c00 = m4 * m8 - m5 * m5, c10 = m5 * m2 - m1 * m8, c20 = m1 * m5 - m4 * m2;
+        const double id = 1.0 / (m0 * c00 + m1 * c10 + m2 * c20);     // Eigen 3x3 inverse: cofactors / determinant
+        const double o0 = c00 * id, o1 = c10 * id, o2 = c20 * id;
+        const double o4 = (m0 * m8 - m2 * m2) * id, o5 = (m2 * m1 - m0 * m5) * id, o8 = (m0 * m4 - m1 * m1) * id;
+        double2* O = reinterpret_cast<double2*>(D.DinvS + 8 * (size_t)p);
+        O[0] = make_double2(o0, o1); O[1] = make_double2(o2, o4); O[2] = make_double2(o5, o8);
+        const double* b3 = D.bl + 3 * (size_t)p;
+        const double b0 = b3[0], b1 = b3[1], b2 = b3[2];
+        D.db[3 * (size_t)p] = o0 * b0 + o1 * b1 + o2 * b2;
+        D.db[3 * (size_t)p + 1] = o1 * b0 + o4 * b1 + o5 * b2;
+        D.db[3 * (size_t)p + 2] = o2 * b0 + o5 * b1 + o8 * b2;
     }
 }
 
-__device__ __forceinline__ void load18(const double* p, double* v) {
-    const double2* q = reinterpret_cast<const double2*>(p);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { const double2 t = q[i]; v[2 * i] = t.x; v[2 * i + 1] = t.y; }
-}
 // ---- Schur complement (block_solver.hpp:396-431), two steps.
-//   partial: the work list (diagonal block i: edges of pose i, contributes Y_e W_e^T and W_e Hll^-1 bl;
-//            off-diagonal block (i1 < i2): the precomputed (e1, e2) pairs, contributes Y_e1 W_e2^T) is cut into chunks of
-//            SCH items; one warp per chunk, two lanes share one item (each owns three rows of the 6x6 product), 16 items
-//            in flight per warp; the chunk's sums go to Spart.
+//   partial: the work list (diagonal block i: edges of pose i; off-diagonal block (i1 < i2): the precomputed (e1, e2) pairs)
+//            is cut into chunks of SCH items; one warp per chunk, one lane per item.  An item adds
+//                b1^T M b2,   M[k][l] = g1_k g2_l (t1_k Hll^-1 t2_l^T),   g_k = w f_k^2 / z
+//            (= W1 Hll^-1 W2^T with W = w B^T A) into the lane's 36 accumulators; diagonal items also add
+//            W Hll^-1 bl = -sum_k b_k g_k (t_k . db).  The lanes' sums are reduce-scattered into Spart.
 //   combine: thread per (task, entry): ordered sum of the task's chunks -> lower triangle of the reduced camera system
 //            (diagonal: Hpp_i + lambda I - sum, bs_i = bp_i - sum; off-diagonal: block (i2, i1) = -(sum)^T). ----
-constexpr int SCH = 128;
-__device__ void phase_schur_partial(const Dev& D, const Ctx& c) {
-    const int lane = c.tid & 31, half = lane & 1, slot = lane >> 1;
+__device__ __forceinline__ void schur_item(const double* t1, const double* t2, const double* dv, double g10, double g11, double g20, double g21,
+                                           const double* b10, const double* b11, const double* b20, const double* b21, double* acc) {
+    // u = t1 Dinv (2x3), dv = 00 01 02 11 12 22
+    const double u00 = t1[0] * dv[0] + t1[1] * dv[1] + t1[2] * dv[2], u01 = t1[0] * dv[1] + t1[1] * dv[3] + t1[2] * dv[4], u02 = t1[0] * dv[2] + t1[1] * dv[4] + t1[2] * dv[5];
+    const double u10 = t1[3] * dv[0] + t1[4] * dv[1] + t1[5] * dv[2], u11 = t1[3] * dv[1] + t1[4] * dv[3] + t1[5] * dv[4], u12 = t1[3] * dv[2] + t1[4] * dv[4] + t1[5] * dv[5];
+    const double m00 = (u00 * t2[0] + u01 * t2[1] + u02 * t2[2]) * (g10 * g20), m01 = (u00 * t2[3] + u01 * t2[4] + u02 * t2[5]) * (g10 * g21);
+    const double m10 = (u10 * t2[0] + u11 * t2[1] + u12 * t2[2]) * (g11 * g20), m11 = (u10 * t2[3] + u11 * t2[4] + u12 * t2[5]) * (g11 * g21);
+    // T = M b2 (2x6); b20[4] = b21[3] = 0
+    double T0[6], T1[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        if (q == 3) { T0[q] = m00 * b20[q]; T1[q] = m10 * b20[q]; }
+        else if (q == 4) { T0[q] = m01 * b21[q]; T1[q] = m11 * b21[q]; }
+        else { T0[q] = m00 * b20[q] + m01 * b21[q]; T1[q] = m10 * b20[q] + m11 * b21[q]; }
+    }
+    // acc += b1^T T; b10[4] = b11[3] = 0
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            if (a == 3) acc[a * 6 + q] += b10[a] * T0[q];
+            else if (a == 4) acc[a * 6 + q] += b11[a] * T1[q];
+            else acc[a * 6 + q] += b10[a] * T0[q] + b11[a] * T1[q];
+        }
+}
+__device__ void phase_schur_partial(const Dev& D, const Ctx& c, const double* __restrict__ E) {
+    const int lane = c.tid & 31;
     for (int ch = c.crank * NWARP + (c.tid >> 5); ch < D.nChunks; ch += c.csize * NWARP) {
         const int task = D.chunkTask[ch], first = D.chunkFirst[ch];
-        double acc[18], bacc[3] = {0, 0, 0};
+        double acc[42];
 #pragma unroll
-        for (int i = 0; i < 18; ++i) acc[i] = 0;
+        for (int i = 0; i < 42; ++i) acc[i] = 0;
+        int lo, n;
         if (task >= D.nF) {
             const int blk = task - D.nF;
             const int k0 = D.blockStart[blk] + first, k1 = min(k0 + SCH, D.blockStart[blk + 1]);
-            int2 pr[SCH / 16];
+            const int2 pr0 = D.pairs[k0];
+            const double* P1 = c.pc + PC * D.ePose[pr0.x];
+            const double* P2 = c.pc + PC * D.ePose[pr0.y];
+            const double f10 = P1[16] * P1[16], f11 = P1[17] * P1[17], f20 = P2[16] * P2[16], f21 = P2[17] * P2[17];
+            int2 pr[IPL]; int pp[IPL];
 #pragma unroll
-            for (int j = 0; j < SCH / 16; ++j) { const int k = k0 + slot + 16 * j; pr[j] = k < k1 ? D.pairs[k] : make_int2(-1, -1); }
-#pragma unroll 2
-            for (int j = 0; j < SCH / 16; ++j) {
-                if (pr[j].x < 0) continue;
-                const double* yp = D.Y + 18 * (size_t)pr[j].x + 9 * half;
-                double y[9], w[18];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) y[i] = yp[i];
-                load18(D.W + 18 * (size_t)pr[j].y, w);
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) acc[r * 6 + q] += y[r * 3] * w[q * 3] + y[r * 3 + 1] * w[q * 3 + 1] + y[r * 3 + 2] * w[q * 3 + 2];
+            for (int j = 0; j < IPL; ++j) {
+                const int k = k0 + lane + 32 * j;
+                if (k < k1) { pr[j] = D.pairs[k]; pp[j] = D.pairPt[k]; } else { pr[j] = make_int2(-1, -1); pp[j] = 0; }
             }
+#pragma unroll 2
+            for (int j = 0; j < IPL; ++j) {
+                if (pr[j].x < 0) continue;
+                double xn1, yn1, iz1, w1, xn2, yn2, iz2, w2, dv[6];
+                load_e4(E, pr[j].x, xn1, yn1, iz1, w1);
+                load_e4(E, pr[j].y, xn2, yn2, iz2, w2);
+                const double2* dq = reinterpret_cast<const double2*>(D.DinvS + 8 * (size_t)pp[j]);
+                const double2 d01 = dq[0], d23 = dq[1], d45 = dq[2];
+                dv[0] = d01.x; dv[1] = d01.y; dv[2] = d23.x; dv[3] = d23.y; dv[4] = d45.x; dv[5] = d45.y;
+                double t1[6], t2[6], b10[6], b11[6], b20[6], b21[6];
+                edge_t(P1 + 7, xn1, yn1, t1); edge_t(P2 + 7, xn2, yn2, t2);
+                edge_b(xn1, yn1, iz1, b10, b11); edge_b(xn2, yn2, iz2, b20, b21);
+                const double q1 = iz1 * w1, q2 = iz2 * w2;
+                schur_item(t1, t2, dv, f10 * q1, f11 * q1, f20 * q2, f21 * q2, b10, b11, b20, b21, acc);
+            }
+            warp_reduce_scatter<36>(acc, lane, lo, n);
         } else {
             const int ic = D.freePose[task];
+            const double* P1 = c.pc + PC * ic;
+            const double f10 = P1[16] * P1[16], f11 = P1[17] * P1[17];
             const int k0 = D.poseStart[ic] + first, k1 = min(k0 + SCH, D.poseStart[ic + 1]);
-            int ed[SCH / 16];
+            int ed[IPL];
 #pragma unroll
-            for (int j = 0; j < SCH / 16; ++j) { const int k = k0 + slot + 16 * j; ed[j] = k < k1 ? D.poseEdges[k] : -1; }
+            for (int j = 0; j < IPL; ++j) { const int k = k0 + lane + 32 * j; ed[j] = k < k1 ? D.poseEdges[k] : -1; }
 #pragma unroll 2
-            for (int j = 0; j < SCH / 16; ++j) {
+            for (int j = 0; j < IPL; ++j) {
                 const int e = ed[j];
                 if (e < 0) continue;
-                const double* yp = D.Y + 18 * (size_t)e + 9 * half;
-                double y[9], w[18];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) y[i] = yp[i];
-                load18(D.W + 18 * (size_t)e, w);
-                const double* dbp = D.db + 3 * (size_t)D.ePt[e];
+                const int p = D.ePt[e];
+                double xn, yn, iz, w, dv[6];
+                load_e4(E, e, xn, yn, iz, w);
+                const double2* dq = reinterpret_cast<const double2*>(D.DinvS + 8 * (size_t)p);
+                const double2 d01 = dq[0], d23 = dq[1], d45 = dq[2];
+                dv[0] = d01.x; dv[1] = d01.y; dv[2] = d23.x; dv[3] = d23.y; dv[4] = d45.x; dv[5] = d45.y;
+                const double* dbp = D.db + 3 * (size_t)p;
                 const double d0 = dbp[0], d1 = dbp[1], d2 = dbp[2];
+                double t1[6], b10[6], b11[6];
+                edge_t(P1 + 7, xn, yn, t1);
+                edge_b(xn, yn, iz, b10, b11);
+                const double q1 = iz * w, g0 = f10 * q1, g1 = f11 * q1;
+                schur_item(t1, t1, dv, g0, g1, g0, g1, b10, b11, b10, b11, acc);
+                const double y0 = g0 * (t1[0] * d0 + t1[1] * d1 + t1[2] * d2), y1 = g1 * (t1[3] * d0 + t1[4] * d1 + t1[5] * d2);
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) acc[r * 6 + q] += y[r * 3] * w[q * 3] + y[r * 3 + 1] * w[q * 3 + 1] + y[r * 3 + 2] * w[q * 3 + 2];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const double w0 = half ? w[9 + 3 * r] : w[3 * r], w1 = half ? w[10 + 3 * r] : w[1 + 3 * r], w2 = half ? w[11 + 3 * r] : w[2 + 3 * r];
-                    bacc[r] += w0 * d0 + w1 * d1 + w2 * d2;
-                }
+                for (int a = 0; a < 6; ++a) acc[36 + a] -= b10[a] * y0 + b11[a] * y1;
             }
+            warp_reduce_scatter<42>(acc, lane, lo, n);
         }
-#pragma unroll
-        for (int o = 16; o >= 2; o >>= 1) {
-#pragma unroll
-            for (int i = 0; i < 18; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) bacc[i] += __shfl_xor_sync(0xffffffffu, bacc[i], o);
-        }
-        if (slot == 0) {
-            double* out = D.Spart + 42 * (size_t)ch;
-#pragma unroll
-            for (int i = 0; i < 18; ++i) out[18 * half + i] = acc[i];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) out[36 + 3 * half + i] = bacc[i];
-        }
+        double* out = D.Spart + 42 * (size_t)ch + lo;
+        if (n > 0) out[0] = acc[0];
+        if (n > 1) out[1] = acc[1];
     }
 }
 __device__ void phase_schur_combine(const Dev& D, const Ctx& c, double lambda, double* Hs, int ld) {
@@ -509,119 +547,141 @@ __device__ void phase_schur_combine(const Dev& D, const Ctx& c, double lambda, d
     }
 }
 // ---- dense LDL^T (no pivoting) + solve, one CTA; A = lower triangle, leading dimension ld (shared memory when it fits).
-// Blocked by the natural 6x6 pose blocks: every thread that owns a row below the diagonal block re-factors that block in
-// registers (no barrier between "factor" and "panel"), then all warps apply the rank-6 trailing update.
+// Right-looking, blocked by the natural 6x6 pose blocks, with look-ahead: while warps 1.. apply the rank-6 trailing update
+// of block step k, warp 0 updates the next diagonal block first and factors it (the serial chain of 6 reciprocals),
+// so the only barriers are panel | update.  The rhs rides along as row n of the matrix (`brow`): after the last step it
+// holds z = D^-1 L^-1 bs, and only the backward substitution L^T x = z remains.
 // (LinearSolverEigen::solve: SimplicialLDLT fails only on an exactly zero pivot.)  Returns 1 on success (uniform).
-// xrow: n x 6 scratch (unscaled panel), in shared memory. ----
-__device__ int phase_ldlt(const Dev& D, const Ctx& c, double* A, int ld, double* xrow) {
+// xrow: (n + 1) x 6 scratch (unscaled panel), brow: n doubles, both in shared memory. ----
+__device__ __forceinline__ void ldlt_factor6(double* A, int ld, int k0, double* sL, double* sDinv, int* sFail) {   // one thread
+    double a[21];            // lower triangle, row-major packed: (i, j) -> i (i + 1) / 2 + j
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) a[i * (i + 1) / 2 + j] = A[(size_t)(k0 + i) * ld + k0 + j];
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double dk = a[k * (k + 1) / 2 + k];
+        if (dk == 0.0) bad = true;
+        const double inv = 1.0 / dk;
+        sDinv[k] = inv;
+        double l[6];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) l[i] = a[i * (i + 1) / 2 + k] * inv;
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i)
+#pragma unroll
+            for (int j = k + 1; j <= i; ++j) a[i * (i + 1) / 2 + j] -= l[i] * a[j * (j + 1) / 2 + k];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) a[i * (i + 1) / 2 + k] = l[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            A[(size_t)(k0 + i) * ld + k0 + j] = a[i * (i + 1) / 2 + j];
+            if (j < i) sL[i * 6 + j] = a[i * (i + 1) / 2 + j];
+        }
+    if (bad) *sFail = 1;
+}
+__device__ int phase_ldlt(const Dev& D, const Ctx& c, double* A, int ld, double* xrow, double* brow) {
     const int n = D.n, tid = c.tid, lane = tid & 31, warp = tid >> 5;
     __shared__ double s_L[36], s_dinv[6];
     __shared__ int s_fail;
-    if (tid == 0) s_fail = 0;
+    for (int i = tid; i < n; i += NT) brow[i] = D.bs[i];
+    if (tid == 0) { s_fail = 0; ldlt_factor6(A, ld, 0, s_L, s_dinv, &s_fail); }
     __syncthreads();
+    if (s_fail) return 0;
     for (int k0 = 0; k0 < n; k0 += 6) {
-        // (1) one thread factors the 6x6 diagonal block: L11 unit lower, d[6]; one reciprocal per pivot
-        if (tid == 0) {
-            double L[36], d[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) L[i * 6 + j] = A[(size_t)(k0 + i) * ld + k0 + j];
-            bool bad = false;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                double dk = L[k * 6 + k];
-#pragma unroll
-                for (int j = 0; j < k; ++j) dk -= L[k * 6 + j] * L[k * 6 + j] * d[j];
-                d[k] = dk;
-                if (dk == 0.0) bad = true;
-                const double inv = 1.0 / dk;
-                s_dinv[k] = inv;
-#pragma unroll
-                for (int i = k + 1; i < 6; ++i) {
-                    double v = L[i * 6 + k];
-#pragma unroll
-                    for (int j = 0; j < k; ++j) v -= L[i * 6 + j] * L[k * 6 + j] * d[j];
-                    L[i * 6 + k] = v * inv;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                A[(size_t)(k0 + i) * ld + k0 + i] = d[i];
-#pragma unroll
-                for (int j = 0; j < i; ++j) { A[(size_t)(k0 + i) * ld + k0 + j] = L[i * 6 + j]; s_L[i * 6 + j] = L[i * 6 + j]; }
-            }
-            if (bad) s_fail = 1;
-        }
-        __syncthreads();
-        if (s_fail) return 0;
-        // (2) panel: row i below the block: X = A21 L11^-T (unscaled), L21 = X D^-1
-        for (int i = k0 + 6 + tid; i < n; i += NT) {
+        // (1) panel: row i below the block (and the rhs row, i == n): X = A21 L11^-T (unscaled), L21 = X D^-1
+        for (int i = k0 + 6 + tid; i <= n; i += NT) {
+            double* row = i < n ? A + (size_t)i * ld : brow;
             double xr[6];
 #pragma unroll
             for (int cidx = 0; cidx < 6; ++cidx) {
-                double v = A[(size_t)i * ld + k0 + cidx];
+                double v = row[k0 + cidx];
 #pragma unroll
                 for (int j = 0; j < cidx; ++j) v -= xr[j] * s_L[cidx * 6 + j];
                 xr[cidx] = v;
             }
 #pragma unroll
-            for (int cidx = 0; cidx < 6; ++cidx) { xrow[i * 6 + cidx] = xr[cidx]; A[(size_t)i * ld + k0 + cidx] = xr[cidx] * s_dinv[cidx]; }
+            for (int cidx = 0; cidx < 6; ++cidx) { xrow[i * 6 + cidx] = xr[cidx]; row[k0 + cidx] = xr[cidx] * s_dinv[cidx]; }
         }
         __syncthreads();
-        // (3) trailing update: A22[i][j] -= sum_c X[i][c] * L21[j][c], warp per row
-        for (int i = k0 + 6 + warp; i < n; i += NWARP) {
-            double xi[6];
+        // (2) trailing update A22[i][j] -= sum_c X[i][c] L21[j][c];  warp 0: next diagonal block, then its factorisation
+        const int r0 = k0 + 6;
+        if (warp == 0) {
+            if (r0 < n) {
+                if (lane < 21) {
+                    int i = 0, t = lane;
+                    while (t > i) { t -= i + 1; ++i; }      // lane -> (i, j = t), j <= i
+                    const double* xi = xrow + (r0 + i) * 6;
+                    const double* lj = A + (size_t)(r0 + t) * ld + k0;
+                    double sacc = 0;
 #pragma unroll
-            for (int cidx = 0; cidx < 6; ++cidx) xi[cidx] = xrow[i * 6 + cidx];
-            for (int j = k0 + 6 + lane; j <= i; j += 32) {
-                const double* lj = A + (size_t)j * ld + k0;
-                double sacc = 0;
+                    for (int cidx = 0; cidx < 6; ++cidx) sacc += xi[cidx] * lj[cidx];
+                    A[(size_t)(r0 + i) * ld + r0 + t] -= sacc;
+                }
+                __syncwarp();
+                if (lane == 0) ldlt_factor6(A, ld, r0, s_L, s_dinv, &s_fail);
+            }
+        } else {
+            for (int i = r0 + 6 + (warp - 1); i <= n; i += NWARP - 1) {
+                double* row = i < n ? A + (size_t)i * ld : brow;
+                double xi[6];
 #pragma unroll
-                for (int cidx = 0; cidx < 6; ++cidx) sacc += xi[cidx] * lj[cidx];
-                A[(size_t)i * ld + j] -= sacc;
+                for (int cidx = 0; cidx < 6; ++cidx) xi[cidx] = xrow[i * 6 + cidx];
+                const int jend = i < n ? i : n - 1;
+                for (int j = r0 + lane; j <= jend; j += 32) {
+                    const double* lj = A + (size_t)j * ld + k0;
+                    double sacc = 0;
+#pragma unroll
+                    for (int cidx = 0; cidx < 6; ++cidx) sacc += xi[cidx] * lj[cidx];
+                    row[j] -= sacc;
+                }
             }
         }
         __syncthreads();
+        if (s_fail) return 0;
     }
-    // L D L^T x = bs by warp 0 alone (warp-synchronous column-oriented substitutions), y kept in shared memory
-    double* y = xrow;   // the panel scratch is free now (n <= 6 n doubles)
+    // L^T x = z by warp 0 (column-oriented, warp-synchronous)
     if (warp == 0) {
-        for (int i = lane; i < n; i += 32) y[i] = D.bs[i];
-        __syncwarp();
-        for (int k = 0; k < n; ++k) {
-            const double yk = y[k];
-            for (int i = k + 1 + lane; i < n; i += 32) y[i] -= A[(size_t)i * ld + k] * yk;
-            __syncwarp();
-        }
-        for (int i = lane; i < n; i += 32) y[i] /= A[(size_t)i * ld + i];
-        __syncwarp();
         for (int k = n - 1; k >= 0; --k) {
-            const double yk = y[k];
-            for (int j = lane; j < k; j += 32) y[j] -= A[(size_t)k * ld + j] * yk;
+            const double yk = brow[k];
+            const double* Lk = A + (size_t)k * ld;
+            for (int j = lane; j < k; j += 32) brow[j] -= Lk[j] * yk;
             __syncwarp();
         }
-        for (int i = lane; i < n; i += 32) D.x[i] = y[i];
+        for (int i = lane; i < n; i += 32) D.x[i] = brow[i];
     }
     __syncthreads();
     return 1;
 }
-// ---- landmark back-substitution x_l = Hll^-1 (bl - W^T x_p)  (block_solver.hpp:461-483); 8 lanes per point ----
-__device__ void phase_backsub(const Dev& D, const Ctx& c) {
+// ---- landmark back-substitution x_l = Hll^-1 (bl - W^T x_p)  (block_solver.hpp:461-483); 8 lanes per point.
+//      W^T x_p = w A^T (B x_p) = -sum_k t_k g_k (b_k . x_p) ----
+__device__ void phase_backsub(const Dev& D, const Ctx& c, const double* __restrict__ E) {
     const int sl = c.tid & 7;
     const unsigned gmask = 0xFFu << (c.tid & 24);
     for (int p = c.wid >> 3; p < D.nL; p += c.nw >> 3) {
         double cl[3] = {0, 0, 0};
         for (int e = D.ptStart[p] + sl; e < D.ptStart[p + 1]; e += 8) {
-            const int h = D.hidx[D.ePose[e]];
+            const int ic = D.ePose[e];
+            const int h = D.hidx[ic];
             if (h < 0) continue;
-            double w[18];
-            load18(D.W + 18 * (size_t)e, w);
+            const double* P = c.pc + PC * ic;
+            double xn, yn, iz, w, t[6], b0[6], b1[6];
+            load_e4(E, e, xn, yn, iz, w);
+            edge_t(P + 7, xn, yn, t);
+            edge_b(xn, yn, iz, b0, b1);
             const double* xp = D.x + 6 * (size_t)h;
+            double be0 = 0, be1 = 0;
 #pragma unroll
-            for (int b = 0; b < 3; ++b)
+            for (int a = 0; a < 6; ++a) { const double xa = xp[a]; be0 += b0[a] * xa; be1 += b1[a] * xa; }
+            const double q = iz * w;
+            be0 *= P[16] * P[16] * q; be1 *= P[17] * P[17] * q;
 #pragma unroll
-                for (int a = 0; a < 6; ++a) cl[b] -= w[a * 3 + b] * xp[a];
+            for (int b = 0; b < 3; ++b) cl[b] += t[b] * be0 + t[3 + b] * be1;
         }
 #pragma unroll
         for (int o = 4; o; o >>= 1) {
@@ -629,10 +689,13 @@ __device__ void phase_backsub(const Dev& D, const Ctx& c) {
             for (int i = 0; i < 3; ++i) cl[i] += __shfl_xor_sync(gmask, cl[i], o);
         }
         if (sl < 3) {
-            const double* Di = D.Dinv + 9 * (size_t)p;
+            const double* Di = D.DinvS + 8 * (size_t)p;     // 00 01 02 11 12 22
             const double* b3 = D.bl + 3 * (size_t)p;
             const double c0 = cl[0] + b3[0], c1 = cl[1] + b3[1], c2 = cl[2] + b3[2];
-            D.x[D.n + 3 * (size_t)p + sl] = Di[sl * 3] * c0 + Di[sl * 3 + 1] * c1 + Di[sl * 3 + 2] * c2;
+            const double r0 = sl == 0 ? Di[0] : sl == 1 ? Di[1] : Di[2];
+            const double r1 = sl == 0 ? Di[1] : sl == 1 ? Di[3] : Di[4];
+            const double r2 = sl == 0 ? Di[2] : sl == 1 ? Di[4] : Di[5];
+            D.x[D.n + 3 * (size_t)p + sl] = r0 * c0 + r1 * c1 + r2 * c2;
         }
     }
 }
@@ -697,8 +760,9 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
     c.crank = (int)cluster.block_rank(); c.csize = (int)cluster.num_blocks(); c.tid = threadIdx.x;
     c.wid = c.crank * NT + c.tid; c.nw = c.csize * NT; c.slot = 0; c.sm = s_red;
     double* s_pc = s_dyn;
-    double* s_col = s_pc + PC * maxP;
-    double* s_mat = s_col + 36 * maxP;
+    double* s_col = s_pc + PC * maxP;            // (6 maxP + 1) x 6 panel scratch
+    double* s_rhs = s_col + 36 * maxP + 6;       // 6 maxP: rhs row of the LDLT
+    double* s_mat = s_rhs + 6 * maxP + 2;
     c.pc = s_pc;
     const Dev D = probs[blockIdx.x / c.csize];
     const bool matInSmem = D.n <= smemMatrixN && D.n > 0;
@@ -708,6 +772,8 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
     const int ld = D.n;
     const int stopIdx = blockIdx.x / c.csize;
     const bool poller = c.crank == 0 && c.tid == 0;
+    double* Elin = D.E4a;       // edge factors at the linearisation point
+    double* Etrial = D.E4b;     // ... at the trial state (becomes the next linearisation point when the step is accepted)
 
     for (int i = c.wid; i < D.nP; i += c.nw) qnormalize(D.poses + 7 * (size_t)i);   // SE3Quat(q, t) constructor
     for (int i = c.wid; i < 2 * D.nE; i += c.nw) D.err[i] = 0.0;
@@ -725,21 +791,26 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
 #define TICK() t0 = globaltimer_ns()
 #define TOCK(i) tph[i] += globaltimer_ns() - t0
     for (int it = 0; it < D.iterations && !term && ok; ++it) {
-        TICK();
-        currentChi = cluster_sum(D, c, phase_errors(D, c), 0, dummy);
-        TOCK(0);
+        // computeActiveErrors at the start of solve(): after an accepted step the state, the errors and the edge factors are
+        // exactly those of the accepted trial (same arithmetic, same order), so only the first iteration evaluates them
+        if (it == 0) {
+            TICK();
+            currentChi = cluster_sum(D, c, phase_errors(D, c, Elin), 0, dummy);
+            TOCK(0);
+        }
         double tempChi = currentChi;
         const double iniChi = currentChi;
         if (it == 0) firstChi = iniChi;
         TICK();
-        phase_build_points(D, c);
+        phase_build_points(D, c, Elin);
         TOCK(1); TICK();
-        phase_build_poses(D, c);
+        phase_build_poses_partial(D, c, Elin);
         csync();
+        phase_build_poses_combine(D, c);
         TOCK(2);
         if (it == 0) {
             if (D.userLambdaInit > 0) lambda = D.userLambdaInit;
-            else lambda = tau * phase_maxdiag(D, c);
+            else { csync(); lambda = tau * phase_maxdiag(D, c); }
             ni = 2; nBad = 0;
         }
         double rho = 0;
@@ -752,13 +823,13 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
             int ok2 = 1;
             if (D.nF) {
                 TICK();
-                phase_schur_partial(D, c);
+                phase_schur_partial(D, c, Elin);
                 csync();
                 phase_schur_combine(D, c, lambda, HsRemote, ld);   // every CTA writes entries into CTA 0's shared memory through DSMEM
                 csync();
                 TOCK(4); TICK();
                 if (c.crank == 0) {
-                    ok2 = phase_ldlt(D, c, HsLocal, ld, s_col);
+                    ok2 = phase_ldlt(D, c, HsLocal, ld, s_col, s_rhs);
                     if (c.tid == 0) D.partial[4 * PSLOT] = (double)ok2;
                 }
                 csync();
@@ -766,13 +837,13 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
                 TOCK(5);
             }
             TICK();
-            phase_backsub(D, c);
+            phase_backsub(D, c, Elin);
             csync();
             TOCK(6); TICK();
             const double scale0 = cluster_sum(D, c, phase_update(D, c, lambda), 0, dummy);
             load_pose_cache(D, s_pc);
             TOCK(7); TICK();
-            tempChi = cluster_sum(D, c, phase_errors(D, c), (poller && stop && stop[stopIdx]) ? 1 : 0, term);
+            tempChi = cluster_sum(D, c, phase_errors(D, c, Etrial), (poller && stop && stop[stopIdx]) ? 1 : 0, term);
             TOCK(8);
             if (!ok2) tempChi = DBL_MAX;
             rho = currentChi - tempChi;
@@ -785,6 +856,7 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
                 lambda *= scaleFactor;
                 ni = 2;
                 currentChi = tempChi;
+                double* sw = Elin; Elin = Etrial; Etrial = sw;
             } else {
                 lambda *= ni;
                 ni *= 2;
@@ -841,9 +913,9 @@ struct Solver {
         b += al(16 * nP) + 2 * al(4 * nP);                                        // cam, hidx, freePose
         b += 2 * al(4 * nE) + al(16 * nE) + al(4 * nE);                           // ePt, ePose, obs, invSigma2
         b += al(4 * (nL + 1)) + al(4 * nE) + al(4 * (nP + 1)) + al(4 * nE);                     // CSR, eOrig
-        b += al(4 * (nP * nP / 2 + 2)) + al(8 * (nE * (nP > 1 ? nP - 1 : 1) / 2 + 1));              // Schur block starts + (e1, e2) pair lists
-        b += al(16 * nE) + 2 * al(144 * nE);                                      // err, W, Y
-        b += al(288 * nP) + al(48 * nP) + 2 * al(72 * nL) + 2 * al(24 * nL);      // Hpp, bp, Hll, Dinv, bl, db
+        b += al(4 * (nP * nP / 2 + 2)) + al(12 * (nE * (nP > 1 ? nP - 1 : 1) / 2 + 1)) + 256;        // Schur block starts + (e1, e2) pair lists + their points
+        b += al(16 * nE) + 2 * al(32 * nE);                                       // err, edge factors x 2
+        b += al(288 * nP) + al(48 * nP) + al(48 * nL) + al(64 * nL) + 2 * al(24 * nL);   // Hpp, bp, Hll, DinvS, bl, db
         b += al(8 * n * n) + al(8 * n) + al(8 * (n + 3 * nL)) + al(8 * (4 * PSLOT + 8)) + al(256);   // Hs, bs, x, partial, stats
         {   // Schur chunk tables + partial sums: at most (#tasks + #items / SCH) chunks
             const size_t items = nE + nE * (nP > 1 ? nP - 1 : 1) / 2 + 1, tasks = nP + nP * nP / 2 + 2;
@@ -870,7 +942,7 @@ struct Solver {
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         // dynamic shared memory: pose cache + two LDLT column buffers + (when it fits) the reduced camera system,
         // within 200 KB of the 227 KB opt-in limit
-        fixedSmem = 8 * (size_t)(PC + 36) * maxP;
+        fixedSmem = 8 * ((size_t)(PC + 36 + 6) * maxP + 8);
         const size_t maxDyn = 200 * 1024;
         smemN = fixedSmem < maxDyn ? (int)floor(sqrt((double)(maxDyn - fixedSmem) / 8.0)) : 0;
         smemN = std::min(smemN, 6 * maxP);
@@ -931,7 +1003,7 @@ struct Solver {
         }
         if (nPairs > (size_t)nE * (nP > 1 ? nP - 1 : 1) / 2 + 1) { set_error("lba: pair list larger than sized"); return ORB_ERR_CAPACITY; }
         for (int i = 0; i < nOff; ++i) blockStart[i + 1] += blockStart[i];
-        std::vector<int2> pairs(nPairs);
+        std::vector<int2> pairs(nPairs); std::vector<int> pairPt(nPairs);
         {
             std::vector<int> cur(blockStart.begin(), blockStart.end() - 1);
             for (int p = 0; p < nL; ++p) {
@@ -942,7 +1014,7 @@ struct Solver {
                         int k1 = fe[a2], k2 = fe[b2];
                         if (hidx[ePose[k1]] > hidx[ePose[k2]]) std::swap(k1, k2);
                         const int blk = blockOf(hidx[ePose[k1]], hidx[ePose[k2]]);
-                        pairs[cur[blk]++] = make_int2(k1, k2);
+                        pairPt[cur[blk]] = p; pairs[cur[blk]++] = make_int2(k1, k2);
                     }
             }
         }
@@ -980,6 +1052,7 @@ struct Solver {
         o = carve(4 * (size_t)nE); put(o, poseEdges.data(), 4 * (size_t)nE); D.poseEdges = (const int*)(d_arena + o);
         o = carve(4 * (size_t)(nOff + 1)); put(o, blockStart.data(), 4 * (size_t)(nOff + 1)); D.blockStart = (const int*)(d_arena + o);
         o = carve(8 * std::max<size_t>(nPairs, 1)); put(o, pairs.data(), 8 * nPairs); D.pairs = (const int2*)(d_arena + o);
+        o = carve(4 * std::max<size_t>(nPairs, 1)); put(o, pairPt.data(), 4 * nPairs); D.pairPt = (const int*)(d_arena + o);
         D.nChunks = nChunks;
         o = carve(4 * (size_t)std::max(nChunks, 1)); put(o, chunkTask.data(), 4 * (size_t)nChunks); D.chunkTask = (const int*)(d_arena + o);
         o = carve(4 * (size_t)std::max(nChunks, 1)); put(o, chunkFirst.data(), 4 * (size_t)nChunks); D.chunkFirst = (const int*)(d_arena + o);
@@ -991,10 +1064,10 @@ struct Solver {
         K.ptsOff = carve(24 * (size_t)nL); D.pts = (double*)(d_arena + K.ptsOff);
         D.ptsBk = (double*)(d_arena + carve(24 * (size_t)nL));
         D.err = (double*)(d_arena + carve(16 * (size_t)nE));
-        D.W = (double*)(d_arena + carve(144 * (size_t)nE)); D.Y = (double*)(d_arena + carve(144 * (size_t)nE));
+        D.E4a = (double*)(d_arena + carve(32 * (size_t)nE)); D.E4b = (double*)(d_arena + carve(32 * (size_t)nE));
         D.Hpp = (double*)(d_arena + carve(288 * (size_t)std::max(nF, 1))); D.bp = (double*)(d_arena + carve(48 * (size_t)std::max(nF, 1)));
-        D.Hll = (double*)(d_arena + carve(72 * (size_t)nL)); D.bl = (double*)(d_arena + carve(24 * (size_t)nL));
-        D.Dinv = (double*)(d_arena + carve(72 * (size_t)nL)); D.db = (double*)(d_arena + carve(24 * (size_t)nL));
+        D.Hll = (double*)(d_arena + carve(48 * (size_t)nL)); D.bl = (double*)(d_arena + carve(24 * (size_t)nL));
+        D.DinvS = (double*)(d_arena + carve(64 * (size_t)nL)); D.db = (double*)(d_arena + carve(24 * (size_t)nL));
         D.Spart = (double*)(d_arena + carve(8 * 42 * (size_t)std::max(nChunks, 1)));
         D.Hs = (double*)(d_arena + carve(8 * (size_t)n * n)); D.bs = (double*)(d_arena + carve(8 * (size_t)std::max(n, 1)));
         D.x = (double*)(d_arena + carve(8 * ((size_t)n + 3 * (size_t)nL)));
