@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liborb_b200.so')
+LIB_PATH = os.environ.get('ORB_B200_LIB', os.path.join(_HERE, 'liborb_b200.so'))   # override: kernel-variant experiments
 
 ORB_OK, ORB_ERR_EMPTY, ORB_ERR_ARG, ORB_ERR_CAPACITY, ORB_ERR_CUDA, ORB_ERR_ASPECT = 0, -1, -2, -3, -4, -5
 

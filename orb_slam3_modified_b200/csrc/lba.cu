@@ -50,7 +50,7 @@ namespace lba {
 
 struct Dev {
     int nP, nL, nE, nF, n;            // n = 6 nF
-    double *poses, *posesBk, *pts, *ptsBk;      // nP x 7, nL x 3
+    double *poses, *posesB, *pts, *ptsB;        // nP x 7, nL x 3: estimate / second buffer (trial state; the two swap when a step is accepted)
     const float* cam;                 // nP x 4
     const int* hidx;                  // nP: Hessian block index or -1
     const int* freePose;              // nF: pose index of Hessian block
@@ -66,13 +66,15 @@ struct Dev {
     const int* pairPt;                // that point
     // Schur work list: tasks 0..nF-1 = diagonal blocks (items = edges of the pose), nF.. = off-diagonal blocks (items = pairs);
     // every task is cut into chunks of SCH items so that all warps of the cluster get the same amount of work
-    int nChunks; const int* chunkTask; const int* chunkFirst; const int* taskChunkStart;   // nChunks, nChunks, nTasks + 1
+    int nChunks; const int4* chunkHdr; const int* taskChunkStart;   // nChunks x (first item, items, pose A, pose B or -1), nTasks + 1
+    const int* poseEdgePt;            // nE: point of poseEdges[k]
     double* Spart;                    // nChunks x 42 partial sums (36 block entries + 6 rhs entries for diagonal tasks)
+    double* Ppart;                    // (chunks of the diagonal tasks) x 28: partial sums of Hpp (21) and bp (6)
     double* err;                      // nE x 2
     double *E4a, *E4b;                // nE x 4 edge factors (x/z, y/z, 1/z, w): linearisation point / trial state (swapped on accept)
     double *Hpp, *bp;                 // nF x 36, nF x 6
     double *Hll, *bl;                 // nL x 6 (00 01 02 11 12 22), nL x 3
-    double *DinvS, *db;               // nL x 8 (upper triangle of (Hll + lambda I)^-1, 2 pad), nL x 3
+    double* PT;                       // nL x 12 point records: upper triangle of (Hll + lambda I)^-1 (6), (Hll + lambda I)^-1 bl (3), 3 pad
     double *Hs, *bs;                  // n x n (only when it does not fit in shared memory), n
     double* x;                        // n + 3 nL
     double* partial;                  // 4 rotating slots x 16 doubles: per-CTA partial sums + broadcast words
@@ -162,10 +164,19 @@ __device__ __forceinline__ void robustify(const Dev& D, double e2, double& rho0,
 
 namespace cg = cooperative_groups;
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-constexpr int NT = 512;
+#ifndef LBA_NT
+#define LBA_NT 512
+#endif
+#ifndef LBA_SCH
+#define LBA_SCH 128
+#endif
+#ifndef LBA_UNR
+#define LBA_UNR 4
+#endif
+constexpr int NT = LBA_NT;
 constexpr int NWARP = NT / 32;
 constexpr int MAXC = 8;            // largest cluster
-constexpr int PSLOT = 16;          // doubles per partial slot
+constexpr int PSLOT = 24;          // doubles per partial slot: A[0..7], flag[8], B[9..16]
 constexpr int PC = 20;             // doubles per cached pose: q(4) t(3) R(9) fx fy cx cy
 
 struct Ctx {
@@ -173,7 +184,8 @@ struct Ctx {
     int wid, nw;           // worker id / count over the cluster
     int slot;              // rotating partial slot
     double* sm;            // NT doubles of scratch
-    const double* pc;      // pose cache in shared memory, PC doubles per pose
+    const double* pc;      // pose cache in shared memory (state at the linearisation point), PC doubles per pose
+    const double* pts;     // point estimates of that state
 };
 
 // ordered block reduction of one double per thread; every thread returns the sum
@@ -205,13 +217,33 @@ __device__ __forceinline__ double cluster_sum(const Dev& D, Ctx& c, double local
     ++c.slot;
     return tot;
 }
+// the same for two sums at once
+__device__ __forceinline__ void cluster_sum2(const Dev& D, Ctx& c, double a, double b, int flagIn, int& flagOut, double& totA, double& totB) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if ((tid & 31) == 0) { c.sm[tid >> 5] = a; c.sm[NWARP + (tid >> 5)] = b; }
+    __syncthreads();
+    double* slot = D.partial + (size_t)(c.slot & 3) * PSLOT;
+    if (tid == 0) {
+        double ra = 0, rb = 0;
+        for (int w = 0; w < NWARP; ++w) { ra += c.sm[w]; rb += c.sm[NWARP + w]; }
+        slot[c.crank] = ra; slot[MAXC + 1 + c.crank] = rb;
+        if (c.crank == 0) slot[MAXC] = (double)flagIn;
+    }
+    cg::this_cluster().sync();
+    totA = 0; totB = 0;
+    for (int r = 0; r < c.csize; ++r) { totA += slot[r]; totB += slot[MAXC + 1 + r]; }
+    flagOut = (int)slot[MAXC];
+    ++c.slot;
+}
 __device__ __forceinline__ void csync() { cg::this_cluster().sync(); }
 
 // (re)load every pose into the CTA's shared-memory cache: quaternion, translation, rotation matrix, camera
-__device__ void load_pose_cache(const Dev& D, double* pc) {
+__device__ void load_pose_cache(const Dev& D, const double* poses, double* pc) {
     for (int i = threadIdx.x; i < D.nP; i += NT) {
         double* o = pc + PC * i;
-        const double* T = D.poses + 7 * (size_t)i;
+        const double* T = poses + 7 * (size_t)i;
 #pragma unroll
         for (int k = 0; k < 7; ++k) o[k] = T[k];
         qtoR(T, o + 7);
@@ -221,32 +253,27 @@ __device__ void load_pose_cache(const Dev& D, double* pc) {
     __syncthreads();
 }
 
-__device__ __forceinline__ void project_edge(const Dev& D, const Ctx& c, int e, double* Xc, double* uv) {
-    const double* P = c.pc + PC * D.ePose[e];
-    double r[3]; qrot(P, D.pts + 3 * (size_t)D.ePt[e], r);      // SE3Quat::map: _r * xyz + _t
-    Xc[0] = r[0] + P[4]; Xc[1] = r[1] + P[5]; Xc[2] = r[2] + P[6];
-    uv[0] = P[16] * Xc[0] / Xc[2] + P[18];                      // Pinhole::project(Vector3d)
-    uv[1] = P[17] * Xc[1] / Xc[2] + P[19];
+// one edge at pose P (cached: q t R cam) and point X: residual, robust chi2 and the edge factors of this state
+__device__ __forceinline__ double edge_error(const Dev& D, const double* P, const double* X, int e, double* __restrict__ Eout) {
+    double r[3]; qrot(P, X, r);                                     // SE3Quat::map: _r * xyz + _t
+    const double xc = r[0] + P[4], yc = r[1] + P[5], zc = r[2] + P[6];
+    const double u = P[16] * xc / zc + P[18], v = P[17] * yc / zc + P[19];      // Pinhole::project(Vector3d)
+    const double e0 = D.obs[2 * (size_t)e] - u, e1 = D.obs[2 * (size_t)e + 1] - v;
+    *reinterpret_cast<double2*>(D.err + 2 * (size_t)e) = make_double2(e0, e1);
+    const double is2 = (double)D.invSigma2[e];
+    double r0, r1;
+    robustify(D, is2 * (e0 * e0 + e1 * e1), r0, r1);
+    const double iz = 1.0 / zc;
+    double2* o = reinterpret_cast<double2*>(Eout + 4 * (size_t)e);
+    o[0] = make_double2(xc * iz, yc * iz);
+    o[1] = make_double2(iz, r1 * is2);
+    return r0;
 }
-
 // ---- residuals + robust chi2 (SparseOptimizer::computeActiveErrors + activeRobustChi2), thread per edge.
 //      Also leaves the edge factors (x/z, y/z, 1/z, rho' / sigma^2) of this state in Eout. ----
 __device__ double phase_errors(const Dev& D, const Ctx& c, double* __restrict__ Eout) {
     double acc = 0;
-    for (int e = c.wid; e < D.nE; e += c.nw) {
-        double Xc[3], uv[2];
-        project_edge(D, c, e, Xc, uv);
-        const double e0 = D.obs[2 * (size_t)e] - uv[0], e1 = D.obs[2 * (size_t)e + 1] - uv[1];
-        *reinterpret_cast<double2*>(D.err + 2 * (size_t)e) = make_double2(e0, e1);
-        const double is2 = (double)D.invSigma2[e];
-        double r0, r1;
-        robustify(D, is2 * (e0 * e0 + e1 * e1), r0, r1);
-        acc += r0;
-        const double iz = 1.0 / Xc[2];
-        double2* o = reinterpret_cast<double2*>(Eout + 4 * (size_t)e);
-        o[0] = make_double2(Xc[0] * iz, Xc[1] * iz);
-        o[1] = make_double2(iz, r1 * is2);
-    }
+    for (int e = c.wid; e < D.nE; e += c.nw) acc += edge_error(D, c.pc + PC * D.ePose[e], c.pts + 3 * (size_t)D.ePt[e], e, Eout);
     return acc;
 }
 
@@ -254,10 +281,13 @@ __device__ double phase_errors(const Dev& D, const Ctx& c, double* __restrict__ 
 // EdgeSE3ProjectXYZ::linearizeOplus (-projectJac * R and -projectJac * [-[Xc]x | I], Pinhole.cpp:71-81) are
 //   A = -diag(fx iz, fy iz) t,   t = [R0 - xn R2 ; R1 - yn R2]                           (2x3)
 //   B =  diag(fx, fy) b,         b = [xn yn, -(1 + xn^2), yn, -iz, 0, xn iz ; 1 + yn^2, -xn yn, -xn, 0, -iz, yn iz]   (2x6)
+// 256-bit global load (LDG.E.256, sm_100+): one L1 tag look-up per lane for a 32-byte record -- the gathers of the Schur
+// phase are bound by look-ups per instruction, not by bytes
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 __device__ __forceinline__ void load_e4(const double* __restrict__ E, int e, double& xn, double& yn, double& iz, double& w) {
-    const double2* q = reinterpret_cast<const double2*>(E + 4 * (size_t)e);
-    const double2 a = q[0], b = q[1];
-    xn = a.x; yn = a.y; iz = b.x; w = b.y;
+    ld256(E + 4 * (size_t)e, xn, yn, iz, w);
 }
 __device__ __forceinline__ void edge_t(const double* R, double xn, double yn, double* t) {
 #pragma unroll
@@ -294,8 +324,10 @@ __device__ __forceinline__ void warp_reduce_scatter(double* v, int lane, int& lo
     up = lane & 1;  rs_level<H4, H5>(v, up, 1); if (up) { lo += H5; n -= H5; } else n = min(n, H5);
 }
 
-// ---- per point Hll, bl; 8 lanes per point (the edges of a point are contiguous) ----
-__device__ void phase_build_points(const Dev& D, const Ctx& c, const double* __restrict__ E) {
+__device__ __forceinline__ void point_record(const Dev& D, int p, const double* h, const double* bl3, double lambda);
+// ---- per point Hll, bl (and, when lambda is already known, the point record of phase_point_prep); 8 lanes per point
+//      (the edges of a point are contiguous) ----
+__device__ void phase_build_points(const Dev& D, const Ctx& c, const double* __restrict__ E, double lambda) {
     const int sl = c.tid & 7;
     const unsigned gmask = 0xFFu << (c.tid & 24);
     for (int p = c.wid >> 3; p < D.nL; p += c.nw >> 3) {
@@ -325,12 +357,15 @@ __device__ void phase_build_points(const Dev& D, const Ctx& c, const double* __r
             double2* H = reinterpret_cast<double2*>(D.Hll + 6 * (size_t)p);
             H[0] = make_double2(h[0], h[1]); H[1] = make_double2(h[2], h[3]); H[2] = make_double2(h[4], h[5]);
             D.bl[3 * (size_t)p] = g[0]; D.bl[3 * (size_t)p + 1] = g[1]; D.bl[3 * (size_t)p + 2] = g[2];
+            if (lambda >= 0) point_record(D, p, h, g, lambda);
         }
     }
 }
 
-constexpr int SCH = 128;           // items per chunk of the pose / pose-pair work lists
+constexpr int SCH = LBA_SCH;       // items per chunk of the pose / pose-pair work lists
 constexpr int IPL = SCH / 32;      // items per lane
+constexpr int UNR = LBA_UNR;       // items in flight per lane in the Schur chunk loops
+constexpr int PTR = 12;            // doubles per point record: d00 d01 d02 d11 | d12 d22 db0 db1 | db2 - - -   (Dinv = (Hll + lambda I)^-1, db = Dinv bl)
 
 // ---- per free pose Hpp, bp.  partial: warp per chunk of the pose's edges (the chunks of the diagonal Schur tasks), lane per
 //      edge, 21 + 6 sums reduce-scattered to Spart; combine: thread per (pose, entry), chunks added in order ----
@@ -338,15 +373,14 @@ __device__ void phase_build_poses_partial(const Dev& D, const Ctx& c, const doub
     const int lane = c.tid & 31;
     const int nDiag = D.taskChunkStart[D.nF];
     for (int ch = c.crank * NWARP + (c.tid >> 5); ch < nDiag; ch += c.csize * NWARP) {
-        const int ic = D.freePose[D.chunkTask[ch]];
-        const double* P = c.pc + PC * ic;
+        const int4 h = D.chunkHdr[ch];
+        const double* P = c.pc + PC * h.z;
         const double fx = P[16], fy = P[17];
-        const int k0 = D.poseStart[ic] + D.chunkFirst[ch], k1 = min(k0 + SCH, D.poseStart[ic + 1]);
         double acc[27];
 #pragma unroll
         for (int i = 0; i < 27; ++i) acc[i] = 0;
-        for (int k = k0 + lane; k < k1; k += 32) {
-            const int e = D.poseEdges[k];
+        for (int i = lane; i < h.y; i += 32) {
+            const int e = D.poseEdges[h.x + i];
             double xn, yn, iz, w, b0[6], b1[6];
             load_e4(E, e, xn, yn, iz, w);
             edge_b(xn, yn, iz, b0, b1);
@@ -355,24 +389,24 @@ __device__ void phase_build_poses_partial(const Dev& D, const Ctx& c, const doub
             const double q0 = fx * w * er.x, q1 = fy * w * er.y;      // B^T r = -(b0 q0 + b1 q1)
             int t = 0;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const double u0 = c0 * b0[i], u1 = c1 * b1[i];
+            for (int a = 0; a < 6; ++a) {
+                const double u0 = c0 * b0[a], u1 = c1 * b1[a];
 #pragma unroll
-                for (int j = i; j < 6; ++j) acc[t++] += u0 * b0[j] + u1 * b1[j];
+                for (int j = a; j < 6; ++j) acc[t++] += u0 * b0[j] + u1 * b1[j];
             }
 #pragma unroll
-            for (int i = 0; i < 6; ++i) acc[21 + i] -= b0[i] * q0 + b1[i] * q1;
+            for (int a = 0; a < 6; ++a) acc[21 + a] -= b0[a] * q0 + b1[a] * q1;
         }
         int lo, n;
         warp_reduce_scatter<27>(acc, lane, lo, n);
-        if (n > 0) D.Spart[42 * (size_t)ch + lo] = acc[0];
+        if (n > 0) D.Ppart[28 * (size_t)ch + lo] = acc[0];
     }
 }
 __device__ void phase_build_poses_combine(const Dev& D, const Ctx& c) {
     for (int idx = c.wid; idx < D.nF * 27; idx += c.nw) {
         const int hI = idx / 27, ent = idx - hI * 27;
         double s = 0;
-        for (int ch = D.taskChunkStart[hI]; ch < D.taskChunkStart[hI + 1]; ++ch) s += D.Spart[42 * (size_t)ch + ent];
+        for (int ch = D.taskChunkStart[hI]; ch < D.taskChunkStart[hI + 1]; ++ch) s += D.Ppart[28 * (size_t)ch + ent];
         if (ent < 21) {
             int i = 0, t = ent;             // unrank (i, j), i <= j
             while (t >= 6 - i) { t -= 6 - i; ++i; }
@@ -399,22 +433,25 @@ __device__ double phase_maxdiag(const Dev& D, const Ctx& c) {
 }
 
 // ---- (Hll + lambda I)^-1 and (Hll + lambda I)^-1 bl, thread per point (block_solver.hpp:381-394) ----
+__device__ __forceinline__ void point_record(const Dev& D, int p, const double* h, const double* bl3, double lambda) {
+    const double m0 = h[0] + lambda, m1 = h[1], m2 = h[2], m4 = h[3] + lambda, m5 = h[4], m8 = h[5] + lambda;
+    const double c00 = m4 * m8 - m5 * m5, c10 = m5 * m2 - m1 * m8, c20 = m1 * m5 - m4 * m2;
+    const double id = 1.0 / (m0 * c00 + m1 * c10 + m2 * c20);     // Eigen 3x3 inverse: cofactors / determinant
+    const double o0 = c00 * id, o1 = c10 * id, o2 = c20 * id;
+    const double o4 = (m0 * m8 - m2 * m2) * id, o5 = (m2 * m1 - m0 * m5) * id, o8 = (m0 * m4 - m1 * m1) * id;
+    const double b0 = bl3[0], b1 = bl3[1], b2 = bl3[2];
+    double2* O = reinterpret_cast<double2*>(D.PT + PTR * (size_t)p);
+    O[0] = make_double2(o0, o1); O[1] = make_double2(o2, o4); O[2] = make_double2(o5, o8);
+    O[3] = make_double2(o0 * b0 + o1 * b1 + o2 * b2, o1 * b0 + o4 * b1 + o5 * b2);
+    O[4] = make_double2(o2 * b0 + o5 * b1 + o8 * b2, 0.0);
+}
 __device__ void phase_point_prep(const Dev& D, const Ctx& c, double lambda) {
     for (int p = c.wid; p < D.nL; p += c.nw) {
         const double2* H = reinterpret_cast<const double2*>(D.Hll + 6 * (size_t)p);
         const double2 h01 = H[0], h23 = H[1], h45 = H[2];
-        const double m0 = h01.x + lambda, m1 = h01.y, m2 = h23.x, m4 = h23.y + lambda, m5 = h45.x, m8 = h45.y + lambda;
-        const double c00 = m4 * m8 - m5 * m5, c10 = m5 * m2 - m1 * m8, c20 = m1 * m5 - m4 * m2;
-        const double id = 1.0 / (m0 * c00 + m1 * c10 + m2 * c20);     // Eigen 3x3 inverse: cofactors / determinant
-        const double o0 = c00 * id, o1 = c10 * id, o2 = c20 * id;
-        const double o4 = (m0 * m8 - m2 * m2) * id, o5 = (m2 * m1 - m0 * m5) * id, o8 = (m0 * m4 - m1 * m1) * id;
-        double2* O = reinterpret_cast<double2*>(D.DinvS + 8 * (size_t)p);
-        O[0] = make_double2(o0, o1); O[1] = make_double2(o2, o4); O[2] = make_double2(o5, o8);
-        const double* b3 = D.bl + 3 * (size_t)p;
-        const double b0 = b3[0], b1 = b3[1], b2 = b3[2];
-        D.db[3 * (size_t)p] = o0 * b0 + o1 * b1 + o2 * b2;
-        D.db[3 * (size_t)p + 1] = o1 * b0 + o4 * b1 + o5 * b2;
-        D.db[3 * (size_t)p + 2] = o2 * b0 + o5 * b1 + o8 * b2;
+        const double h[6] = {h01.x, h01.y, h23.x, h23.y, h45.x, h45.y};
+        const double b3[3] = {D.bl[3 * (size_t)p], D.bl[3 * (size_t)p + 1], D.bl[3 * (size_t)p + 2]};
+        point_record(D, p, h, b3, lambda);
     }
 }
 
@@ -423,7 +460,10 @@ __device__ void phase_point_prep(const Dev& D, const Ctx& c, double lambda) {
 //            is cut into chunks of SCH items; one warp per chunk, one lane per item.  An item adds
 //                b1^T M b2,   M[k][l] = g1_k g2_l (t1_k Hll^-1 t2_l^T),   g_k = w f_k^2 / z
 //            (= W1 Hll^-1 W2^T with W = w B^T A) into the lane's 36 accumulators; diagonal items also add
-//            W Hll^-1 bl = -sum_k b_k g_k (t_k . db).  The lanes' sums are reduce-scattered into Spart.
+//            W Hll^-1 bl = -sum_k b_k g_k (t_k . db).  The item's three records (two edges, one point) are per-lane
+//            gathers -- the phase is bound by L1 look-ups (~39 clk per 32-lane LDG.256 of 32 distinct lines), so the
+//            chunk's indices sit in a warp-private shared-memory buffer and the gathers of item j + 1 are issued before
+//            the arithmetic of item j.  The lanes' sums are reduce-scattered into Spart.
 //   combine: thread per (task, entry): ordered sum of the task's chunks -> lower triangle of the reduced camera system
 //            (diagonal: Hpp_i + lambda I - sum, bs_i = bp_i - sum; off-diagonal: block (i2, i1) = -(sum)^T). ----
 __device__ __forceinline__ void schur_item(const double* t1, const double* t2, const double* dv, double g10, double g11, double g20, double g21,
@@ -451,77 +491,104 @@ __device__ __forceinline__ void schur_item(const double* t1, const double* t2, c
             else acc[a * 6 + q] += b10[a] * T0[q] + b11[a] * T1[q];
         }
 }
-__device__ void phase_schur_partial(const Dev& D, const Ctx& c, const double* __restrict__ E) {
-    const int lane = c.tid & 31;
-    for (int ch = c.crank * NWARP + (c.tid >> 5); ch < D.nChunks; ch += c.csize * NWARP) {
-        const int task = D.chunkTask[ch], first = D.chunkFirst[ch];
-        double acc[42];
+struct PairOps { double a[4], b[4], dv[6]; };          // edge 1, edge 2 (x/z, y/z, 1/z, w), Dinv
+struct DiagOps { double a[4], dv[6], db[3]; };
+#define SCHUR_FN __device__ __forceinline__
+SCHUR_FN void schur_chunk_offdiag(const int2* __restrict__ pairs, const int* __restrict__ pairPt, const double* __restrict__ PT, const double* __restrict__ E,
+                                                  const double* pcache, double* out42, int4 h) {
+    const int lane = threadIdx.x & 31;
+    const int cnt = h.y;
+    int2 rpr[IPL]; int rpt[IPL];
 #pragma unroll
-        for (int i = 0; i < 42; ++i) acc[i] = 0;
-        int lo, n;
-        if (task >= D.nF) {
-            const int blk = task - D.nF;
-            const int k0 = D.blockStart[blk] + first, k1 = min(k0 + SCH, D.blockStart[blk + 1]);
-            const int2 pr0 = D.pairs[k0];
-            const double* P1 = c.pc + PC * D.ePose[pr0.x];
-            const double* P2 = c.pc + PC * D.ePose[pr0.y];
-            const double f10 = P1[16] * P1[16], f11 = P1[17] * P1[17], f20 = P2[16] * P2[16], f21 = P2[17] * P2[17];
-            int2 pr[IPL]; int pp[IPL];
+    for (int j = 0; j < IPL; ++j) { const int i = lane + 32 * j; if (i < cnt) { rpr[j] = pairs[h.x + i]; rpt[j] = pairPt[h.x + i]; } else { rpr[j] = make_int2(0, 0); rpt[j] = 0; } }
+    const double* P1 = pcache + PC * h.z;
+    const double* P2 = pcache + PC * h.w;
+    const double f10 = P1[16] * P1[16], f11 = P1[17] * P1[17], f20 = P2[16] * P2[16], f21 = P2[17] * P2[17];
+    double acc[36];
 #pragma unroll
-            for (int j = 0; j < IPL; ++j) {
-                const int k = k0 + lane + 32 * j;
-                if (k < k1) { pr[j] = D.pairs[k]; pp[j] = D.pairPt[k]; } else { pr[j] = make_int2(-1, -1); pp[j] = 0; }
-            }
-#pragma unroll 2
-            for (int j = 0; j < IPL; ++j) {
-                if (pr[j].x < 0) continue;
-                double xn1, yn1, iz1, w1, xn2, yn2, iz2, w2, dv[6];
-                load_e4(E, pr[j].x, xn1, yn1, iz1, w1);
-                load_e4(E, pr[j].y, xn2, yn2, iz2, w2);
-                const double2* dq = reinterpret_cast<const double2*>(D.DinvS + 8 * (size_t)pp[j]);
-                const double2 d01 = dq[0], d23 = dq[1], d45 = dq[2];
-                dv[0] = d01.x; dv[1] = d01.y; dv[2] = d23.x; dv[3] = d23.y; dv[4] = d45.x; dv[5] = d45.y;
-                double t1[6], t2[6], b10[6], b11[6], b20[6], b21[6];
-                edge_t(P1 + 7, xn1, yn1, t1); edge_t(P2 + 7, xn2, yn2, t2);
-                edge_b(xn1, yn1, iz1, b10, b11); edge_b(xn2, yn2, iz2, b20, b21);
-                const double q1 = iz1 * w1, q2 = iz2 * w2;
-                schur_item(t1, t2, dv, f10 * q1, f11 * q1, f20 * q2, f21 * q2, b10, b11, b20, b21, acc);
-            }
-            warp_reduce_scatter<36>(acc, lane, lo, n);
-        } else {
-            const int ic = D.freePose[task];
-            const double* P1 = c.pc + PC * ic;
-            const double f10 = P1[16] * P1[16], f11 = P1[17] * P1[17];
-            const int k0 = D.poseStart[ic] + first, k1 = min(k0 + SCH, D.poseStart[ic + 1]);
-            int ed[IPL];
-#pragma unroll
-            for (int j = 0; j < IPL; ++j) { const int k = k0 + lane + 32 * j; ed[j] = k < k1 ? D.poseEdges[k] : -1; }
-#pragma unroll 2
-            for (int j = 0; j < IPL; ++j) {
-                const int e = ed[j];
-                if (e < 0) continue;
-                const int p = D.ePt[e];
-                double xn, yn, iz, w, dv[6];
-                load_e4(E, e, xn, yn, iz, w);
-                const double2* dq = reinterpret_cast<const double2*>(D.DinvS + 8 * (size_t)p);
-                const double2 d01 = dq[0], d23 = dq[1], d45 = dq[2];
-                dv[0] = d01.x; dv[1] = d01.y; dv[2] = d23.x; dv[3] = d23.y; dv[4] = d45.x; dv[5] = d45.y;
-                const double* dbp = D.db + 3 * (size_t)p;
-                const double d0 = dbp[0], d1 = dbp[1], d2 = dbp[2];
-                double t1[6], b10[6], b11[6];
-                edge_t(P1 + 7, xn, yn, t1);
-                edge_b(xn, yn, iz, b10, b11);
-                const double q1 = iz * w, g0 = f10 * q1, g1 = f11 * q1;
-                schur_item(t1, t1, dv, g0, g1, g0, g1, b10, b11, b10, b11, acc);
-                const double y0 = g0 * (t1[0] * d0 + t1[1] * d1 + t1[2] * d2), y1 = g1 * (t1[3] * d0 + t1[4] * d1 + t1[5] * d2);
-#pragma unroll
-                for (int a = 0; a < 6; ++a) acc[36 + a] -= b10[a] * y0 + b11[a] * y1;
-            }
-            warp_reduce_scatter<42>(acc, lane, lo, n);
+    for (int i = 0; i < 36; ++i) acc[i] = 0;
+#pragma unroll UNR
+    for (int j = 0; j < IPL; ++j) {
+        const int i = lane + 32 * j;
+        if (i < cnt) {
+            PairOps o;
+            const int e1 = rpr[j].x, e2 = rpr[j].y, ip = rpt[j];
+            ld256(E + 4 * (size_t)e1, o.a[0], o.a[1], o.a[2], o.a[3]);
+            ld256(E + 4 * (size_t)e2, o.b[0], o.b[1], o.b[2], o.b[3]);
+            const double* pt = PT + PTR * (size_t)ip;
+            ld256(pt, o.dv[0], o.dv[1], o.dv[2], o.dv[3]);
+            const double2 t = *reinterpret_cast<const double2*>(pt + 4);
+            o.dv[4] = t.x; o.dv[5] = t.y;
+            double t1[6], t2[6], b10[6], b11[6], b20[6], b21[6];
+            edge_t(P1 + 7, o.a[0], o.a[1], t1); edge_t(P2 + 7, o.b[0], o.b[1], t2);
+            edge_b(o.a[0], o.a[1], o.a[2], b10, b11); edge_b(o.b[0], o.b[1], o.b[2], b20, b21);
+            const double q1 = o.a[2] * o.a[3], q2 = o.b[2] * o.b[3];
+            schur_item(t1, t2, o.dv, f10 * q1, f11 * q1, f20 * q2, f21 * q2, b10, b11, b20, b21, acc);
         }
-        double* out = D.Spart + 42 * (size_t)ch + lo;
-        if (n > 0) out[0] = acc[0];
-        if (n > 1) out[1] = acc[1];
+    }
+    int lo, n;
+    warp_reduce_scatter<36>(acc, lane, lo, n);
+    double* out = out42 + lo;
+    if (n > 0) out[0] = acc[0];
+    if (n > 1) out[1] = acc[1];
+}
+SCHUR_FN void schur_chunk_diag(const int* __restrict__ poseEdges, const int* __restrict__ poseEdgePt, const double* __restrict__ PT, const double* __restrict__ E,
+                                               const double* pcache, double* out42, int4 h) {
+    const int lane = threadIdx.x & 31;
+    const int cnt = h.y;
+    int red[IPL], rpt[IPL];
+#pragma unroll
+    for (int j = 0; j < IPL; ++j) { const int i = lane + 32 * j; if (i < cnt) { red[j] = poseEdges[h.x + i]; rpt[j] = poseEdgePt[h.x + i]; } else { red[j] = 0; rpt[j] = 0; } }
+    const double* P1 = pcache + PC * h.z;
+    const double f10 = P1[16] * P1[16], f11 = P1[17] * P1[17];
+    double acc[42];
+#pragma unroll
+    for (int i = 0; i < 42; ++i) acc[i] = 0;
+#pragma unroll UNR
+    for (int j = 0; j < IPL; ++j) {
+        const int i = lane + 32 * j;
+        if (i < cnt) {
+            DiagOps o;
+            const int e1 = red[j], ip = rpt[j];
+            ld256(E + 4 * (size_t)e1, o.a[0], o.a[1], o.a[2], o.a[3]);
+            const double* pt = PT + PTR * (size_t)ip;
+            ld256(pt, o.dv[0], o.dv[1], o.dv[2], o.dv[3]);
+            ld256(pt + 4, o.dv[4], o.dv[5], o.db[0], o.db[1]);
+            o.db[2] = pt[8];
+            double t1[6], b10[6], b11[6];
+            edge_t(P1 + 7, o.a[0], o.a[1], t1);
+            edge_b(o.a[0], o.a[1], o.a[2], b10, b11);
+            const double q1 = o.a[2] * o.a[3], g0 = f10 * q1, g1 = f11 * q1;
+            schur_item(t1, t1, o.dv, g0, g1, g0, g1, b10, b11, b10, b11, acc);
+            const double y0 = g0 * (t1[0] * o.db[0] + t1[1] * o.db[1] + t1[2] * o.db[2]), y1 = g1 * (t1[3] * o.db[0] + t1[4] * o.db[1] + t1[5] * o.db[2]);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) acc[36 + a] -= b10[a] * y0 + b11[a] * y1;
+        }
+    }
+    int lo, n;
+    warp_reduce_scatter<42>(acc, lane, lo, n);
+    double* out = out42 + lo;
+    if (n > 0) out[0] = acc[0];
+    if (n > 1) out[1] = acc[1];
+}
+#ifndef LBA_RSYNC
+#define LBA_RSYNC 0
+#endif
+__device__ void phase_schur_partial(const Dev& D, const Ctx& c, const double* __restrict__ E) {
+    // The warps of a CTA work on neighbouring chunks (same pose pair or the next one), whose gathers hit many of the same
+    // lines (the edges of pose A, nearby points).  Keeping the warps in step -- a CTA barrier at entry and per round --
+    // keeps those lines in L1 while they are hot: measured 3x on this phase against free-running warps.
+    const int stride = c.csize * NWARP;
+    const int rounds = (D.nChunks + stride - 1) / stride;
+    __syncthreads();
+    for (int r = 0; r < rounds; ++r) {
+        const int ch = r * stride + c.crank * NWARP + (c.tid >> 5);
+        if (ch < D.nChunks) {
+            const int4 h = D.chunkHdr[ch];      // first item, items, pose A, pose B (-1: diagonal task)
+            if (h.w >= 0) schur_chunk_offdiag(D.pairs, D.pairPt, D.PT, E, c.pc, D.Spart + 42 * (size_t)ch, h);
+            else schur_chunk_diag(D.poseEdges, D.poseEdgePt, D.PT, E, c.pc, D.Spart + 42 * (size_t)ch, h);
+        }
+        if (LBA_RSYNC) __syncthreads();
     }
 }
 __device__ void phase_schur_combine(const Dev& D, const Ctx& c, double lambda, double* Hs, int ld) {
@@ -552,7 +619,7 @@ __device__ void phase_schur_combine(const Dev& D, const Ctx& c, double lambda, d
 // so the only barriers are panel | update.  The rhs rides along as row n of the matrix (`brow`): after the last step it
 // holds z = D^-1 L^-1 bs, and only the backward substitution L^T x = z remains.
 // (LinearSolverEigen::solve: SimplicialLDLT fails only on an exactly zero pivot.)  Returns 1 on success (uniform).
-// xrow: (n + 1) x 6 scratch (unscaled panel), brow: n doubles, both in shared memory. ----
+// scratch: 2 x 6 x (n + 1) doubles (unscaled and scaled panel), brow: n doubles, both in shared memory. ----
 __device__ __forceinline__ void ldlt_factor6(double* A, int ld, int k0, double* sL, double* sDinv, int* sFail) {   // one thread
     double a[21];            // lower triangle, row-major packed: (i, j) -> i (i + 1) / 2 + j
 #pragma unroll
@@ -585,8 +652,11 @@ __device__ __forceinline__ void ldlt_factor6(double* A, int ld, int k0, double* 
         }
     if (bad) *sFail = 1;
 }
-__device__ int phase_ldlt(const Dev& D, const Ctx& c, double* A, int ld, double* xrow, double* brow) {
+__device__ int phase_ldlt(const Dev& D, const Ctx& c, double* A, int ld, double* scratch, double* brow) {
     const int n = D.n, tid = c.tid, lane = tid & 31, warp = tid >> 5;
+    const int n1 = n + 1;
+    double* Xs = scratch;               // 6 x (n + 1): unscaled panel, column-major by panel column (conflict-free for lanes over rows)
+    double* Ls = scratch + 6 * n1;      // 6 x (n + 1): scaled panel (= the final L entries)
     __shared__ double s_L[36], s_dinv[6];
     __shared__ int s_fail;
     for (int i = tid; i < n; i += NT) brow[i] = D.bs[i];
@@ -606,7 +676,10 @@ __device__ int phase_ldlt(const Dev& D, const Ctx& c, double* A, int ld, double*
                 xr[cidx] = v;
             }
 #pragma unroll
-            for (int cidx = 0; cidx < 6; ++cidx) { xrow[i * 6 + cidx] = xr[cidx]; row[k0 + cidx] = xr[cidx] * s_dinv[cidx]; }
+            for (int cidx = 0; cidx < 6; ++cidx) {
+                const double l = xr[cidx] * s_dinv[cidx];
+                Xs[cidx * n1 + i] = xr[cidx]; Ls[cidx * n1 + i] = l; row[k0 + cidx] = l;
+            }
         }
         __syncthreads();
         // (2) trailing update A22[i][j] -= sum_c X[i][c] L21[j][c];  warp 0: next diagonal block, then its factorisation
@@ -616,11 +689,9 @@ __device__ int phase_ldlt(const Dev& D, const Ctx& c, double* A, int ld, double*
                 if (lane < 21) {
                     int i = 0, t = lane;
                     while (t > i) { t -= i + 1; ++i; }      // lane -> (i, j = t), j <= i
-                    const double* xi = xrow + (r0 + i) * 6;
-                    const double* lj = A + (size_t)(r0 + t) * ld + k0;
                     double sacc = 0;
 #pragma unroll
-                    for (int cidx = 0; cidx < 6; ++cidx) sacc += xi[cidx] * lj[cidx];
+                    for (int cidx = 0; cidx < 6; ++cidx) sacc += Xs[cidx * n1 + r0 + i] * Ls[cidx * n1 + r0 + t];
                     A[(size_t)(r0 + i) * ld + r0 + t] -= sacc;
                 }
                 __syncwarp();
@@ -631,14 +702,22 @@ __device__ int phase_ldlt(const Dev& D, const Ctx& c, double* A, int ld, double*
                 double* row = i < n ? A + (size_t)i * ld : brow;
                 double xi[6];
 #pragma unroll
-                for (int cidx = 0; cidx < 6; ++cidx) xi[cidx] = xrow[i * 6 + cidx];
+                for (int cidx = 0; cidx < 6; ++cidx) xi[cidx] = Xs[cidx * n1 + i];
                 const int jend = i < n ? i : n - 1;
-                for (int j = r0 + lane; j <= jend; j += 32) {
-                    const double* lj = A + (size_t)j * ld + k0;
-                    double sacc = 0;
+                for (int j0 = r0 + lane; j0 <= jend; j0 += 128) {
+                    double sacc[4], old[4];
 #pragma unroll
-                    for (int cidx = 0; cidx < 6; ++cidx) sacc += xi[cidx] * lj[cidx];
-                    row[j] -= sacc;
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = j0 + 32 * u;
+                        sacc[u] = 0; old[u] = 0;
+                        if (j <= jend) {
+                            old[u] = row[j];
+#pragma unroll
+                            for (int cidx = 0; cidx < 6; ++cidx) sacc[u] += xi[cidx] * Ls[cidx * n1 + j];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int j = j0 + 32 * u; if (j <= jend) row[j] = old[u] - sacc[u]; }
                 }
             }
         }
@@ -658,14 +737,51 @@ __device__ int phase_ldlt(const Dev& D, const Ctx& c, double* A, int ld, double*
     __syncthreads();
     return 1;
 }
-// ---- landmark back-substitution x_l = Hll^-1 (bl - W^T x_p)  (block_solver.hpp:461-483); 8 lanes per point.
-//      W^T x_p = w A^T (B x_p) = -sum_k t_k g_k (b_k . x_p) ----
-__device__ void phase_backsub(const Dev& D, const Ctx& c, const double* __restrict__ E) {
+// ---- the trial state of one LM step, part 1: every CTA applies the pose increments (SparseOptimizer::update,
+//      VertexSE3Expmap::oplusImpl) to ALL poses into its own trial pose cache (so that no barrier is needed before the
+//      residuals); CTA 0 also writes them to the trial buffer and returns the poses' share of computeScale ----
+__device__ double phase_pose_trial(const Dev& D, const Ctx& c, const double* __restrict__ Pcur, double* __restrict__ Ptr, double* pcTr, double lambda) {
+    double acc = 0;
+    for (int v = c.tid; v < D.nP; v += NT) {
+        double T[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) T[i] = Pcur[7 * (size_t)v + i];
+        const int h = D.hidx[v];
+        if (h >= 0) {
+            const double* u = D.x + 6 * (size_t)h;
+            pose_oplus(T, u);
+            if (c.crank == 0) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) acc += u[i] * (lambda * u[i] + D.bp[6 * (size_t)h + i]);
+            }
+        }
+        if (c.crank == 0) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) Ptr[7 * (size_t)v + i] = T[i];
+        }
+        double* o = pcTr + PC * v;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) o[k] = T[k];
+        qtoR(T, o + 7);
+        const float* cm = D.cam + 4 * (size_t)v;
+        o[16] = (double)cm[0]; o[17] = (double)cm[1]; o[18] = (double)cm[2]; o[19] = (double)cm[3];
+    }
+    __syncthreads();
+    return acc;
+}
+// ---- part 2, 8 lanes per point, one pass: landmark back-substitution x_l = Hll^-1 (bl - W^T x_p)
+//      (block_solver.hpp:461-483; W^T x_p = w A^T (B x_p) = -sum_k t_k g_k (b_k . x_p)), the point update into the trial
+//      buffer, its share of computeScale, and the residuals / robust chi2 / edge factors of the point's edges at the
+//      trial state (computeActiveErrors + activeRobustChi2).  Returns (scale share, chi2 share). ----
+__device__ double2 phase_points_trial(const Dev& D, const Ctx& c, const double* __restrict__ E, double* __restrict__ Eout, double* __restrict__ Xtr,
+                                      const double* pcTr, double lambda) {
     const int sl = c.tid & 7;
     const unsigned gmask = 0xFFu << (c.tid & 24);
+    double accS = 0, accC = 0;
     for (int p = c.wid >> 3; p < D.nL; p += c.nw >> 3) {
+        const int a = D.ptStart[p], b = D.ptStart[p + 1];
         double cl[3] = {0, 0, 0};
-        for (int e = D.ptStart[p] + sl; e < D.ptStart[p + 1]; e += 8) {
+        for (int e = a + sl; e < b; e += 8) {
             const int ic = D.ePose[e];
             const int h = D.hidx[ic];
             if (h < 0) continue;
@@ -677,80 +793,50 @@ __device__ void phase_backsub(const Dev& D, const Ctx& c, const double* __restri
             const double* xp = D.x + 6 * (size_t)h;
             double be0 = 0, be1 = 0;
 #pragma unroll
-            for (int a = 0; a < 6; ++a) { const double xa = xp[a]; be0 += b0[a] * xa; be1 += b1[a] * xa; }
+            for (int k = 0; k < 6; ++k) { const double xa = xp[k]; be0 += b0[k] * xa; be1 += b1[k] * xa; }
             const double q = iz * w;
             be0 *= P[16] * P[16] * q; be1 *= P[17] * P[17] * q;
 #pragma unroll
-            for (int b = 0; b < 3; ++b) cl[b] += t[b] * be0 + t[3 + b] * be1;
+            for (int k = 0; k < 3; ++k) cl[k] += t[k] * be0 + t[3 + k] * be1;
         }
 #pragma unroll
         for (int o = 4; o; o >>= 1) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) cl[i] += __shfl_xor_sync(gmask, cl[i], o);
         }
-        if (sl < 3) {
-            const double* Di = D.DinvS + 8 * (size_t)p;     // 00 01 02 11 12 22
-            const double* b3 = D.bl + 3 * (size_t)p;
-            const double c0 = cl[0] + b3[0], c1 = cl[1] + b3[1], c2 = cl[2] + b3[2];
-            const double r0 = sl == 0 ? Di[0] : sl == 1 ? Di[1] : Di[2];
-            const double r1 = sl == 0 ? Di[1] : sl == 1 ? Di[3] : Di[4];
-            const double r2 = sl == 0 ? Di[2] : sl == 1 ? Di[4] : Di[5];
-            D.x[D.n + 3 * (size_t)p + sl] = r0 * c0 + r1 * c1 + r2 * c2;
+        const double* Di = D.PT + PTR * (size_t)p;      // 00 01 02 11 12 22
+        const double* b3 = D.bl + 3 * (size_t)p;
+        const double bl0 = b3[0], bl1 = b3[1], bl2 = b3[2];
+        const double c0 = cl[0] + bl0, c1 = cl[1] + bl1, c2 = cl[2] + bl2;
+        const double u0 = Di[0] * c0 + Di[1] * c1 + Di[2] * c2, u1 = Di[1] * c0 + Di[3] * c1 + Di[4] * c2, u2 = Di[2] * c0 + Di[4] * c1 + Di[5] * c2;
+        const double* X0 = c.pts + 3 * (size_t)p;
+        double X[3] = {X0[0] + u0, X0[1] + u1, X0[2] + u2};
+        if (sl == 0) {
+            Xtr[3 * (size_t)p] = X[0]; Xtr[3 * (size_t)p + 1] = X[1]; Xtr[3 * (size_t)p + 2] = X[2];
+            accS += u0 * (lambda * u0 + bl0) + u1 * (lambda * u1 + bl1) + u2 * (lambda * u2 + bl2);
         }
+        for (int e = a + sl; e < b; e += 8) accC += edge_error(D, pcTr + PC * D.ePose[e], X, e, Eout);
     }
-}
-// ---- push + update (SparseOptimizer::push / update) and the partial sum of computeScale ----
-__device__ double phase_update(const Dev& D, const Ctx& c, double lambda) {
-    double acc = 0;
-    const int total = D.nP + D.nL;
-    for (int v = c.wid; v < total; v += c.nw) {
-        if (v < D.nP) {
-            double T[7];
-#pragma unroll
-            for (int i = 0; i < 7; ++i) { T[i] = D.poses[7 * (size_t)v + i]; D.posesBk[7 * (size_t)v + i] = T[i]; }
-            const int h = D.hidx[v];
-            if (h >= 0) {
-                const double* u = D.x + 6 * (size_t)h;
-                pose_oplus(T, u);
-#pragma unroll
-                for (int i = 0; i < 7; ++i) D.poses[7 * (size_t)v + i] = T[i];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) acc += u[i] * (lambda * u[i] + D.bp[6 * (size_t)h + i]);
-            }
-        } else {
-            const int p = v - D.nP;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const double u = D.x[D.n + 3 * (size_t)p + i];
-                const double old = D.pts[3 * (size_t)p + i];
-                D.ptsBk[3 * (size_t)p + i] = old;
-                D.pts[3 * (size_t)p + i] = old + u;
-                acc += u * (lambda * u + D.bl[3 * (size_t)p + i]);
-            }
-        }
-    }
-    return acc;
-}
-__device__ void phase_restore(const Dev& D, const Ctx& c) {   // pop
-    for (int i = c.wid; i < 7 * D.nP; i += c.nw) D.poses[i] = D.posesBk[i];
-    for (int i = c.wid; i < 3 * D.nL; i += c.nw) D.pts[i] = D.ptsBk[i];
+    return make_double2(accS, accC);
 }
 __device__ void phase_finalize(const Dev& D, const Ctx& c) {
     for (int e = c.wid; e < D.nE; e += c.nw) {
         const double e0 = D.err[2 * (size_t)e], e1 = D.err[2 * (size_t)e + 1];
         const int o = D.eOrig[e];
         D.outChi2[o] = (double)D.invSigma2[e] * (e0 * e0 + e1 * e1);   // e->chi2() from the last computed _error (Optimizer.cc:1425)
-        double Xc[3], uv[2];
-        project_edge(D, c, e, Xc, uv);
-        D.outDepthPos[o] = Xc[2] > 0.0;
+        const double* P = c.pc + PC * D.ePose[e];
+        double r[3]; qrot(P, c.pts + 3 * (size_t)D.ePt[e], r);
+        D.outDepthPos[o] = r[2] + P[6] > 0.0;
     }
+    // the estimate ends in whichever buffer was current last; the caller reads D.poses / D.pts
+    if (c.pts != D.pts) for (int i = c.wid; i < 3 * D.nL; i += c.nw) D.pts[i] = c.pts[i];
 }
 
 // =============================================================================================
 // The persistent kernel: SparseOptimizer::optimize (sparse_optimizer.cpp:354-418) around
 // OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-168), one cluster per problem.
 // Every thread carries the (uniform) LM state; decisions use values every CTA reads identically after a cluster barrier.
-// Dynamic shared memory: pose cache (PC x maxP doubles) | LDLT panel scratch (6 maxP x 6) | reduced camera system (smemMatrixN^2).
+// Dynamic shared memory: 2 pose caches (PC x maxP doubles each) | LDLT panel scratch (2 x 6 x (6 maxP + 1)) | rhs row | reduced camera system (smemMatrixN^2).
 // =============================================================================================
 __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restrict__ probs, const volatile int* stop, int smemMatrixN, int maxP) {
     extern __shared__ double s_dyn[];
@@ -759,11 +845,11 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
     Ctx c;
     c.crank = (int)cluster.block_rank(); c.csize = (int)cluster.num_blocks(); c.tid = threadIdx.x;
     c.wid = c.crank * NT + c.tid; c.nw = c.csize * NT; c.slot = 0; c.sm = s_red;
-    double* s_pc = s_dyn;
-    double* s_col = s_pc + PC * maxP;            // (6 maxP + 1) x 6 panel scratch
-    double* s_rhs = s_col + 36 * maxP + 6;       // 6 maxP: rhs row of the LDLT
+    double* s_pc = s_dyn;                        // pose cache, linearisation state
+    double* s_pcT = s_pc + PC * maxP;            // pose cache, trial state
+    double* s_col = s_pcT + PC * maxP;           // 2 x 6 x (6 maxP + 1) panel scratch
+    double* s_rhs = s_col + 72 * maxP + 12;      // 6 maxP: rhs row of the LDLT
     double* s_mat = s_rhs + 6 * maxP + 2;
-    c.pc = s_pc;
     const Dev D = probs[blockIdx.x / c.csize];
     const bool matInSmem = D.n <= smemMatrixN && D.n > 0;
     // reduced camera system: CTA 0's shared memory; the other CTAs of the cluster reach it as distributed shared memory
@@ -772,27 +858,33 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
     const int ld = D.n;
     const int stopIdx = blockIdx.x / c.csize;
     const bool poller = c.crank == 0 && c.tid == 0;
-    double* Elin = D.E4a;       // edge factors at the linearisation point
-    double* Etrial = D.E4b;     // ... at the trial state (becomes the next linearisation point when the step is accepted)
+    // double-buffered state: the trial of an LM step is written next to the current estimate and the two swap when the
+    // step is accepted, so a rejected step needs no restore ("pop") pass
+    double *Elin = D.E4a, *Etrial = D.E4b;       // edge factors at the linearisation point / at the trial state
+    double *Pcur = D.poses, *Ptr = D.posesB;     // poses
+    double *Xcur = D.pts, *Xtr = D.ptsB;         // points
+    c.pc = s_pc; c.pts = Xcur;
 
     for (int i = c.wid; i < D.nP; i += c.nw) qnormalize(D.poses + 7 * (size_t)i);   // SE3Quat(q, t) constructor
     for (int i = c.wid; i < 2 * D.nE; i += c.nw) D.err[i] = 0.0;
-    for (int i = c.wid; i < D.n + 3 * D.nL; i += c.nw) D.x[i] = 0.0;
+    for (int i = c.wid; i < D.n; i += c.nw) D.x[i] = 0.0;
     int term = 0, dummy;
     cluster_sum(D, c, 0.0, (poller && stop && stop[stopIdx]) ? 1 : 0, term);   // initial terminate() poll + publishes the poses
-    load_pose_cache(D, s_pc);
+    load_pose_cache(D, Pcur, s_pc);
 
     double lambda = -1, ni = 2, currentChi = 0, firstChi = 0;
     int nBad = 0, cj = 0, trials = 0;
     const int maxTrials = 10;
     const double goodUpper = 2. / 3., goodLower = 1. / 3., tau = 1e-5;
     bool ok = true;
-    unsigned long long tph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0;
-#define TICK() t0 = globaltimer_ns()
-#define TOCK(i) tph[i] += globaltimer_ns() - t0
+    __shared__ unsigned long long s_tph[11];     // per-phase ns of CTA 0 (thread 0), [10] = tick
+    if (c.tid < 11) s_tph[c.tid] = 0;
+    __syncthreads();
+#define TICK() do { if (c.wid == 0) s_tph[10] = globaltimer_ns(); } while (0)
+#define TOCK(i) do { if (c.wid == 0) s_tph[i] += globaltimer_ns() - s_tph[10]; } while (0)
     for (int it = 0; it < D.iterations && !term && ok; ++it) {
         // computeActiveErrors at the start of solve(): after an accepted step the state, the errors and the edge factors are
-        // exactly those of the accepted trial (same arithmetic, same order), so only the first iteration evaluates them
+        // exactly those of the accepted trial (same arithmetic), so only the first iteration evaluates them
         if (it == 0) {
             TICK();
             currentChi = cluster_sum(D, c, phase_errors(D, c, Elin), 0, dummy);
@@ -801,33 +893,38 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
         double tempChi = currentChi;
         const double iniChi = currentChi;
         if (it == 0) firstChi = iniChi;
+        const bool lambdaKnown = it > 0 || D.userLambdaInit > 0;
+        if (it == 0 && lambdaKnown) lambda = D.userLambdaInit;
         TICK();
-        phase_build_points(D, c, Elin);
+        phase_build_points(D, c, Elin, lambdaKnown ? lambda : -1.0);
         TOCK(1); TICK();
         phase_build_poses_partial(D, c, Elin);
         csync();
         phase_build_poses_combine(D, c);
         TOCK(2);
         if (it == 0) {
-            if (D.userLambdaInit > 0) lambda = D.userLambdaInit;
-            else { csync(); lambda = tau * phase_maxdiag(D, c); }
+            if (!lambdaKnown) { csync(); lambda = tau * phase_maxdiag(D, c); }
             ni = 2; nBad = 0;
         }
+        bool needPrep = !lambdaKnown;
         double rho = 0;
         int qmax = 0;
         do {
-            TICK();
-            phase_point_prep(D, c, lambda);
-            csync();
-            TOCK(3);
+            if (needPrep) {
+                TICK();
+                phase_point_prep(D, c, lambda);
+                csync();
+                TOCK(3);
+            }
             int ok2 = 1;
             if (D.nF) {
                 TICK();
                 phase_schur_partial(D, c, Elin);
                 csync();
+                TOCK(4); TICK();
                 phase_schur_combine(D, c, lambda, HsRemote, ld);   // every CTA writes entries into CTA 0's shared memory through DSMEM
                 csync();
-                TOCK(4); TICK();
+                TOCK(6); TICK();
                 if (c.crank == 0) {
                     ok2 = phase_ldlt(D, c, HsLocal, ld, s_col, s_rhs);
                     if (c.tid == 0) D.partial[4 * PSLOT] = (double)ok2;
@@ -837,13 +934,11 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
                 TOCK(5);
             }
             TICK();
-            phase_backsub(D, c, Elin);
-            csync();
-            TOCK(6); TICK();
-            const double scale0 = cluster_sum(D, c, phase_update(D, c, lambda), 0, dummy);
-            load_pose_cache(D, s_pc);
+            const double sP = phase_pose_trial(D, c, Pcur, Ptr, s_pcT, lambda);
             TOCK(7); TICK();
-            tempChi = cluster_sum(D, c, phase_errors(D, c, Etrial), (poller && stop && stop[stopIdx]) ? 1 : 0, term);
+            const double2 sc = phase_points_trial(D, c, Elin, Etrial, Xtr, s_pcT, lambda);
+            double scale0;
+            cluster_sum2(D, c, sP + sc.x, sc.y, (poller && stop && stop[stopIdx]) ? 1 : 0, term, scale0, tempChi);
             TOCK(8);
             if (!ok2) tempChi = DBL_MAX;
             rho = currentChi - tempChi;
@@ -856,14 +951,18 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
                 lambda *= scaleFactor;
                 ni = 2;
                 currentChi = tempChi;
-                double* sw = Elin; Elin = Etrial; Etrial = sw;
+                double* sw;
+                sw = Elin; Elin = Etrial; Etrial = sw;
+                sw = Pcur; Pcur = Ptr; Ptr = sw;
+                sw = Xcur; Xcur = Xtr; Xtr = sw;
+                c.pts = Xcur;
+                for (int i = c.tid; i < PC * D.nP; i += NT) s_pc[i] = s_pcT[i];
+                __syncthreads();
             } else {
-                lambda *= ni;
+                lambda *= ni;                                   // the trial buffers are simply abandoned (pop)
                 ni *= 2;
-                phase_restore(D, c);
-                csync();
-                load_pose_cache(D, s_pc);
             }
+            needPrep = true;
             ++qmax; ++trials;
         } while (rho < 0 && qmax < maxTrials && !term);
         ++cj;
@@ -874,7 +973,8 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
         }
     }
     phase_finalize(D, c);
-    if (c.wid == 0) for (int i = 0; i < 10; ++i) D.stats[8 + i] = (double)tph[i];
+    if (Pcur != D.poses) for (int i = c.wid; i < 7 * D.nP; i += c.nw) D.poses[i] = Pcur[i];
+    if (c.wid == 0) for (int i = 0; i < 10; ++i) D.stats[8 + i] = (double)s_tph[i];
     if (c.wid == 0) { D.stats[0] = cj; D.stats[1] = trials; D.stats[2] = lambda; D.stats[3] = currentChi; D.stats[4] = firstChi; }
 }
 
@@ -915,12 +1015,12 @@ struct Solver {
         b += al(4 * (nL + 1)) + al(4 * nE) + al(4 * (nP + 1)) + al(4 * nE);                     // CSR, eOrig
         b += al(4 * (nP * nP / 2 + 2)) + al(12 * (nE * (nP > 1 ? nP - 1 : 1) / 2 + 1)) + 256;        // Schur block starts + (e1, e2) pair lists + their points
         b += al(16 * nE) + 2 * al(32 * nE);                                       // err, edge factors x 2
-        b += al(288 * nP) + al(48 * nP) + al(48 * nL) + al(64 * nL) + 2 * al(24 * nL);   // Hpp, bp, Hll, DinvS, bl, db
-        b += al(8 * n * n) + al(8 * n) + al(8 * (n + 3 * nL)) + al(8 * (4 * PSLOT + 8)) + al(256);   // Hs, bs, x, partial, stats
+        b += al(288 * nP) + al(48 * nP) + al(48 * nL) + al(96 * nL) + al(24 * nL);   // Hpp, bp, Hll, PT, bl
+        b += al(8 * n * n) + al(8 * n) + al(8 * (n + 3 * nL)) + al(8 * (4 * PSLOT + 8)) + al(512);   // Hs, bs, x, partial, stats
         {   // Schur chunk tables + partial sums: at most (#tasks + #items / SCH) chunks
             const size_t items = nE + nE * (nP > 1 ? nP - 1 : 1) / 2 + 1, tasks = nP + nP * nP / 2 + 2;
             const size_t ch = tasks + items / SCH + 1;
-            b += 2 * al(4 * ch) + al(4 * (tasks + 1)) + al(8 * 42 * ch);
+            b += al(16 * ch) + al(4 * (tasks + 1)) + al(8 * 42 * ch) + al(4 * nE) + al(8 * 28 * (nP + nE / SCH + 1));   // chunk headers, task chunk starts, Spart, poseEdgePt, Ppart
         }
         b += al(8 * nE) + al(nE);                                                 // outputs
         return b;
@@ -942,7 +1042,7 @@ struct Solver {
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         // dynamic shared memory: pose cache + two LDLT column buffers + (when it fits) the reduced camera system,
         // within 200 KB of the 227 KB opt-in limit
-        fixedSmem = 8 * ((size_t)(PC + 36 + 6) * maxP + 8);
+        fixedSmem = 8 * ((size_t)(2 * PC + 72 + 6) * maxP + 16);
         const size_t maxDyn = 200 * 1024;
         smemN = fixedSmem < maxDyn ? (int)floor(sqrt((double)(maxDyn - fixedSmem) / 8.0)) : 0;
         smemN = std::min(smemN, 6 * maxP);
@@ -1019,14 +1119,21 @@ struct Solver {
             }
         }
         // Schur work list cut into chunks of SCH items
-        std::vector<int> chunkTask, chunkFirst, taskChunkStart(nF + nOff + 1, 0);
-        for (int t = 0; t < nF + nOff; ++t) {
-            const int len = t < nF ? poseStart[freePose[t] + 1] - poseStart[freePose[t]] : blockStart[t - nF + 1] - blockStart[t - nF];
-            taskChunkStart[t] = (int)chunkTask.size();
-            for (int f = 0; f < len; f += SCH) { chunkTask.push_back(t); chunkFirst.push_back(f); }
+        std::vector<int4> chunkHdr; std::vector<int> taskChunkStart(nF + nOff + 1, 0);
+        {
+            int t = 0;
+            auto cut = [&](int first, int len, int poseA, int poseB) {
+                taskChunkStart[t++] = (int)chunkHdr.size();
+                for (int f = 0; f < len; f += SCH) chunkHdr.push_back(make_int4(first + f, std::min(SCH, len - f), poseA, poseB));
+            };
+            for (int i = 0; i < nF; ++i) cut(poseStart[freePose[i]], poseStart[freePose[i] + 1] - poseStart[freePose[i]], freePose[i], -1);
+            for (int i1 = 0; i1 < nF; ++i1)
+                for (int i2 = i1 + 1; i2 < nF; ++i2) { const int blk = blockOf(i1, i2); cut(blockStart[blk], blockStart[blk + 1] - blockStart[blk], freePose[i1], freePose[i2]); }
+            taskChunkStart[nF + nOff] = (int)chunkHdr.size();
         }
-        taskChunkStart[nF + nOff] = (int)chunkTask.size();
-        const int nChunks = (int)chunkTask.size();
+        const int nChunks = (int)chunkHdr.size();
+        std::vector<int> poseEdgePt(nE);
+        for (int k = 0; k < nE; ++k) poseEdgePt[k] = ePt[poseEdges[k]];
         const size_t base = perProblem * (size_t)slot;
         size_t off = base;
         auto carve = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
@@ -1054,25 +1161,26 @@ struct Solver {
         o = carve(8 * std::max<size_t>(nPairs, 1)); put(o, pairs.data(), 8 * nPairs); D.pairs = (const int2*)(d_arena + o);
         o = carve(4 * std::max<size_t>(nPairs, 1)); put(o, pairPt.data(), 4 * nPairs); D.pairPt = (const int*)(d_arena + o);
         D.nChunks = nChunks;
-        o = carve(4 * (size_t)std::max(nChunks, 1)); put(o, chunkTask.data(), 4 * (size_t)nChunks); D.chunkTask = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)std::max(nChunks, 1)); put(o, chunkFirst.data(), 4 * (size_t)nChunks); D.chunkFirst = (const int*)(d_arena + o);
+        o = carve(16 * (size_t)std::max(nChunks, 1)); put(o, chunkHdr.data(), 16 * (size_t)nChunks); D.chunkHdr = (const int4*)(d_arena + o);
+        o = carve(4 * (size_t)nE); put(o, poseEdgePt.data(), 4 * (size_t)nE); D.poseEdgePt = (const int*)(d_arena + o);
         o = carve(4 * (size_t)(nF + nOff + 1)); put(o, taskChunkStart.data(), 4 * (size_t)(nF + nOff + 1)); D.taskChunkStart = (const int*)(d_arena + o);
         uploadBytes[slot] = off - base;
         // --- device-only scratch / state / outputs ---
         K.posesOff = carve(56 * (size_t)nP); D.poses = (double*)(d_arena + K.posesOff);
-        D.posesBk = (double*)(d_arena + carve(56 * (size_t)nP));
+        D.posesB = (double*)(d_arena + carve(56 * (size_t)nP));
         K.ptsOff = carve(24 * (size_t)nL); D.pts = (double*)(d_arena + K.ptsOff);
-        D.ptsBk = (double*)(d_arena + carve(24 * (size_t)nL));
+        D.ptsB = (double*)(d_arena + carve(24 * (size_t)nL));
         D.err = (double*)(d_arena + carve(16 * (size_t)nE));
         D.E4a = (double*)(d_arena + carve(32 * (size_t)nE)); D.E4b = (double*)(d_arena + carve(32 * (size_t)nE));
         D.Hpp = (double*)(d_arena + carve(288 * (size_t)std::max(nF, 1))); D.bp = (double*)(d_arena + carve(48 * (size_t)std::max(nF, 1)));
         D.Hll = (double*)(d_arena + carve(48 * (size_t)nL)); D.bl = (double*)(d_arena + carve(24 * (size_t)nL));
-        D.DinvS = (double*)(d_arena + carve(64 * (size_t)nL)); D.db = (double*)(d_arena + carve(24 * (size_t)nL));
+        D.PT = (double*)(d_arena + carve(96 * (size_t)nL));
         D.Spart = (double*)(d_arena + carve(8 * 42 * (size_t)std::max(nChunks, 1)));
+        D.Ppart = (double*)(d_arena + carve(8 * 28 * (size_t)std::max(taskChunkStart[nF], 1)));
         D.Hs = (double*)(d_arena + carve(8 * (size_t)n * n)); D.bs = (double*)(d_arena + carve(8 * (size_t)std::max(n, 1)));
         D.x = (double*)(d_arena + carve(8 * ((size_t)n + 3 * (size_t)nL)));
         D.partial = (double*)(d_arena + carve(8 * (4 * PSLOT + 8)));
-        K.statsOff = carve(256); D.stats = (double*)(d_arena + K.statsOff);
+        K.statsOff = carve(512); D.stats = (double*)(d_arena + K.statsOff);
         K.chi2Off = carve(8 * (size_t)nE); D.outChi2 = (double*)(d_arena + K.chi2Off);
         K.dposOff = carve((size_t)nE); D.outDepthPos = (uint8_t*)(d_arena + K.dposOff);
         if (off - base > perProblem) { set_error("lba: arena too small (internal sizing error)"); return ORB_ERR_CAPACITY; }
@@ -1148,7 +1256,7 @@ struct Solver {
                 CK(cudaMemcpyAsync(R.edgeChi2, d_arena + K.chi2Off, 8 * (size_t)K.nE, cudaMemcpyDeviceToHost, s));
                 CK(cudaMemcpyAsync(R.edgeDepthPositive, d_arena + K.dposOff, (size_t)K.nE, cudaMemcpyDeviceToHost, s));
             }
-            CK(cudaMemcpyAsync(h_arena + K.statsOff, d_arena + K.statsOff, 256, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(h_arena + K.statsOff, d_arena + K.statsOff, 512, cudaMemcpyDeviceToHost, s));
         }
         CK(cudaStreamSynchronize(s));
         for (int i = 0; i < count; ++i) {
@@ -1205,6 +1313,11 @@ int lba_set_cluster_size(lba_handle* h, int ctas) {
     return ORB_OK;
 }
 /* ns spent by CTA 0 of problem `i` in each phase of the last downloaded run: errors, build_points, build_poses, point_prep, schur, ldlt, backsub, update, errors(trial) */
+int lba_get_stats64(const lba_handle* h, int i, double* out64) {
+    if (!h || !out64 || i < 0 || i >= h->s.nLoaded) return ORB_ERR_ARG;
+    memcpy(out64, h->s.h_arena + h->s.packed[i].statsOff, 512);
+    return ORB_OK;
+}
 int lba_get_phase_ns(const lba_handle* h, int i, double* ns10) {
     if (!h || !ns10 || i < 0 || i >= h->s.nLoaded) return ORB_ERR_ARG;
     const double* stt = (const double*)(h->s.h_arena + h->s.packed[i].statsOff);

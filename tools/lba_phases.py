@@ -16,6 +16,6 @@ out = opt.download()
 ns = np.zeros(10)
 L = orb.lib(); L.lba_get_phase_ns.argtypes=[C.c_void_p,C.c_int,C.c_void_p]
 L.lba_get_phase_ns(opt._h, 0, ns.ctypes.data_as(C.c_void_p))
-names=['errors','build_points','build_poses','point_prep','schur','ldlt','backsub','update','errors_trial','-']
+names=['errors(it0)','build_points','build_poses','point_prep','schur_partial','ldlt','schur_combine','pose_trial','points_trial','-']
 print('batch',n,'cluster',opt.last_cluster_size(),'kernel ms',e0.elapsed_time(e1),'iters',out[0]['iters'],'trials',out[0]['trials'])
 for k,v in zip(names,ns): print('  %-14s %8.1f us total  %7.1f us/trial'%(k,v/1e3,v/1e3/max(out[0]['trials'],1)))
