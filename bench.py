@@ -207,6 +207,25 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Run this process on the CPUs the GPU is attached to (sysfs local_cpulist), so that pinned host memory is NUMA-local."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bus = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for tok in open('/sys/bus/pci/devices/%s/local_cpulist' % bus).read().strip().split(','):
+            a, _, b = tok.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return '%s: %d cpus' % (bus, len(cpus))
+    except (OSError, ValueError, AttributeError):
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -230,6 +249,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU path in the product)')
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)     # pinned buffers (ours and the library's) land on the GPU's socket: ~53 vs ~20 GB/s over PCIe
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -418,7 +438,7 @@ def main():
             'config': {'workload': WORKLOAD, 'stages': STAGES, 'frames_per_gpu_per_step': B, 'lba_per_gpu_per_step': NLBA,
                        'l2': 'inputs alternate between two %d-frame sets (2 x %.0f MB) > 126 MB L2; per-step working set > 1 GB' % (B, B * W * H / 1e6),
                        'mean_keypoints_per_frame': mean_kp, 'mean_matches_per_frame': mean_matches, 'lba_cluster_size': opt.last_cluster_size(),
-                       'lba_mean_trials': mean_trials},
+                       'lba_mean_trials': mean_trials, 'host_numa_binding': numa},
             'clocks': clk, 'gpu_launches': launches,
             'stage_ms_per_step': stage,
             'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,

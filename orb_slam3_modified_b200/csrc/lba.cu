@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../../include/orb_b200.h"
+#include "host_affinity.h"
 
 namespace orbx {
 void set_error(const std::string& s);
@@ -51,6 +52,11 @@ namespace lba {
 struct Dev {
     int nP, nL, nE, nF, n;            // n = 6 nF
     double *poses, *posesB, *pts, *ptsB;        // nP x 7, nL x 3: estimate / second buffer (trial state; the two swap when a step is accepted)
+    const double *initPoses, *initPts;          // the uploaded initial estimates (a run always restarts from them)
+    // the caller's graph as uploaded (caller's edge order); lba_build_structure_kernel derives everything below from it
+    const int *rawEdgePoint, *rawEdgePose; const double* rawObs; const float* rawInvSigma2;
+    int *bCnt, *bCursor, *bTmp, *bEid, *bTaskLen, *bItemStart;   // build scratch: nL + 1, nL + 1, nE, nF x nL, nTasks, nTasks
+    int pairCap, chunkCap;
     const float* cam;                 // nP x 4
     const int* hidx;                  // nP: Hessian block index or -1
     const int* freePose;              // nF: pose index of Hessian block
@@ -60,8 +66,7 @@ struct Dev {
     const double* obs;                // nE x 2
     const float* invSigma2;           // nE
     const int* ptStart;               // nL + 1
-    const int *poseStart, *poseEdges; // CSR by pose (internal edge ids, ascending)
-    const int* blockStart;            // nF(nF-1)/2 + 1: off-diagonal Schur blocks (i1 < i2), row-major over the strict upper triangle
+    const int* poseEdges;             // edge lists of the free poses (internal edge ids, ascending), back to back
     const int2* pairs;                // (edge of pose i1, edge of pose i2) observing the same point
     const int* pairPt;                // that point
     // Schur work list: tasks 0..nF-1 = diagonal blocks (items = edges of the pose), nF.. = off-diagonal blocks (items = pairs);
@@ -865,7 +870,13 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
     double *Xcur = D.pts, *Xtr = D.ptsB;         // points
     c.pc = s_pc; c.pts = Xcur;
 
-    for (int i = c.wid; i < D.nP; i += c.nw) qnormalize(D.poses + 7 * (size_t)i);   // SE3Quat(q, t) constructor
+    for (int i = c.wid; i < D.nP; i += c.nw) {
+        double* T = D.poses + 7 * (size_t)i;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) T[k] = D.initPoses[7 * (size_t)i + k];
+        qnormalize(T);                                              // SE3Quat(q, t) constructor
+    }
+    for (int i = c.wid; i < 3 * D.nL; i += c.nw) D.pts[i] = D.initPts[i];
     for (int i = c.wid; i < 2 * D.nE; i += c.nw) D.err[i] = 0.0;
     for (int i = c.wid; i < D.n; i += c.nw) D.x[i] = 0.0;
     int term = 0, dummy;
@@ -979,6 +990,181 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
 }
 
 // =============================================================================================
+// BlockSolver::buildStructure (block_solver.hpp:143-295) on the device: one CTA per problem turns the caller's edge list
+// into the index structures of the LM kernel -- edges sorted by point (stable), the (free pose, point) -> edge table, the
+// per-pose edge lists, the (e1, e2) pair list of every off-diagonal Schur block, and the chunked work list.  Only the raw
+// graph (28 B per edge) crosses PCIe; the derived lists (~2.3 MB per 40k-edge problem) never exist on the host.
+// Every list is in a deterministic order (by point, ties by the caller's edge index).
+// status: 0 ok, 1 edge index out of range, 2 duplicate (point, keyframe) observation, 3 pair list larger than sized.
+// =============================================================================================
+constexpr int BT = 1024;
+__device__ __forceinline__ int bt_excl_scan(int v, int* sm, int& total) {   // exclusive scan of one int per thread over the CTA
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) sm[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int x = sm[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+        sm[lane] = x;
+    }
+    __syncthreads();
+    const int base = w ? sm[w - 1] : 0;
+    total = sm[31];
+    __syncthreads();
+    return base + inc - v;
+}
+__global__ void __launch_bounds__(BT) lba_build_structure_kernel(Dev* probs, int* status) {
+    Dev& D = probs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nL = D.nL, nE = D.nE, nF = D.nF, nP = D.nP;
+    const int nOff = nF * (nF - 1) / 2, nTasks = nF + nOff;
+    __shared__ int s_sm[32];
+    __shared__ int s_err;
+    int* ptStart = const_cast<int*>(D.ptStart);
+    int* ePt = const_cast<int*>(D.ePt); int* ePose = const_cast<int*>(D.ePose); int* eOrig = const_cast<int*>(D.eOrig);
+    double* obs = const_cast<double*>(D.obs); float* is2 = const_cast<float*>(D.invSigma2);
+    int* poseEdges = const_cast<int*>(D.poseEdges); int* poseEdgePt = const_cast<int*>(D.poseEdgePt);
+    int2* pairs = const_cast<int2*>(D.pairs); int* pairPt = const_cast<int*>(D.pairPt);
+    int4* chunkHdr = const_cast<int4*>(D.chunkHdr); int* taskChunkStart = const_cast<int*>(D.taskChunkStart);
+    if (tid == 0) s_err = 0;
+    for (int i = tid; i <= nL; i += BT) D.bCnt[i] = 0;
+    for (size_t i = tid; i < (size_t)nF * nL; i += BT) D.bEid[i] = -1;
+    __syncthreads();
+    // 1. edges per point
+    for (int e = tid; e < nE; e += BT) {
+        const int p = D.rawEdgePoint[e], c = D.rawEdgePose[e];
+        if (p < 0 || p >= nL || c < 0 || c >= nP) s_err = 1;
+        else atomicAdd(&D.bCnt[p], 1);
+    }
+    __syncthreads();
+    if (s_err) { if (tid == 0) status[blockIdx.x] = s_err; return; }
+    // 2. ptStart = exclusive scan
+    {
+        int carry = 0;
+        for (int b0 = 0; b0 < nL; b0 += BT) {
+            const int i = b0 + tid;
+            const int v = i < nL ? D.bCnt[i] : 0;
+            int total;
+            const int ex = bt_excl_scan(v, s_sm, total);
+            if (i < nL) { ptStart[i] = carry + ex; D.bCursor[i] = carry + ex; }
+            carry += total;
+        }
+        if (tid == 0) ptStart[nL] = carry;
+    }
+    __syncthreads();
+    // 3. group by point (arbitrary order), then order every point's slice by the caller's edge index (stable sort by point)
+    for (int e = tid; e < nE; e += BT) D.bTmp[atomicAdd(&D.bCursor[D.rawEdgePoint[e]], 1)] = e;
+    __syncthreads();
+    for (int p = tid; p < nL; p += BT) {
+        const int a = ptStart[p], b = ptStart[p + 1];
+        for (int i = a + 1; i < b; ++i) {
+            const int v = D.bTmp[i];
+            int j = i - 1;
+            while (j >= a && D.bTmp[j] > v) { D.bTmp[j + 1] = D.bTmp[j]; --j; }
+            D.bTmp[j + 1] = v;
+        }
+    }
+    __syncthreads();
+    for (int p = tid; p < nL; p += BT)
+        for (int k = ptStart[p]; k < ptStart[p + 1]; ++k) {
+            const int e = D.bTmp[k], c = D.rawEdgePose[e];
+            ePt[k] = p; ePose[k] = c; eOrig[k] = e;
+            obs[2 * (size_t)k] = D.rawObs[2 * (size_t)e]; obs[2 * (size_t)k + 1] = D.rawObs[2 * (size_t)e + 1];
+            is2[k] = D.rawInvSigma2[e];
+            const int h = D.hidx[c];
+            if (h >= 0 && atomicCAS(&D.bEid[(size_t)h * nL + p], -1, k) != -1) s_err = 2;
+        }
+    __syncthreads();
+    if (s_err) { if (tid == 0) status[blockIdx.x] = s_err; return; }
+    // 4. items per task: edges of a free pose / points shared by a pair of free poses; warp per task, ballot over points
+    auto taskRows = [&](int t, const int*& r1, const int*& r2) {
+        if (t < nF) { r1 = D.bEid + (size_t)t * nL; r2 = r1; return; }
+        int i1 = 0, rem = t - nF;
+        while (rem >= nF - 1 - i1) { rem -= nF - 1 - i1; ++i1; }
+        r1 = D.bEid + (size_t)i1 * nL; r2 = D.bEid + (size_t)(i1 + 1 + rem) * nL;
+    };
+    for (int t = warp; t < nTasks; t += BT / 32) {
+        const int *r1, *r2;
+        taskRows(t, r1, r2);
+        int cnt = 0;
+#pragma unroll 4
+        for (int p0 = 0; p0 < nL; p0 += 32) {
+            const int p = p0 + lane;
+            const bool f = p < nL && r1[p] >= 0 && r2[p] >= 0;
+            cnt += __popc(__ballot_sync(0xffffffffu, f));
+        }
+        if (lane == 0) D.bTaskLen[t] = cnt;
+    }
+    __syncthreads();
+    // 5. where every task's items and chunks start (pose lists and pair lists are separate arrays)
+    int nChunks = 0;
+    {
+        int carry = 0, tot;
+        for (int b0 = 0; b0 < nF; b0 += BT) {                  // pose lists
+            const int t = b0 + tid;
+            const int ex = bt_excl_scan(t < nF ? D.bTaskLen[t] : 0, s_sm, tot);
+            if (t < nF) D.bItemStart[t] = carry + ex;
+            carry += tot;
+        }
+        carry = 0;
+        for (int b0 = nF; b0 < nTasks; b0 += BT) {             // pair lists
+            const int t = b0 + tid;
+            const int ex = bt_excl_scan(t < nTasks ? D.bTaskLen[t] : 0, s_sm, tot);
+            if (t < nTasks) D.bItemStart[t] = carry + ex;
+            carry += tot;
+        }
+        if (carry > D.pairCap) s_err = 3;
+        carry = 0;
+        for (int b0 = 0; b0 < nTasks; b0 += BT) {              // chunks
+            const int t = b0 + tid;
+            const int ex = bt_excl_scan(t < nTasks ? (D.bTaskLen[t] + SCH - 1) / SCH : 0, s_sm, tot);
+            if (t < nTasks) taskChunkStart[t] = carry + ex;
+            carry += tot;
+        }
+        nChunks = carry;
+        if (tid == 0) taskChunkStart[nTasks] = nChunks;
+        if (nChunks > D.chunkCap) s_err = 3;
+    }
+    __syncthreads();
+    if (s_err) { if (tid == 0) status[blockIdx.x] = s_err; return; }
+    // 6. the lists themselves (ascending point = ascending internal edge id) and the chunk headers
+    for (int t = warp; t < nTasks; t += BT / 32) {
+        const int *r1, *r2;
+        taskRows(t, r1, r2);
+        int pos = D.bItemStart[t];
+        for (int p0 = 0; p0 < nL; p0 += 32) {
+            const int p = p0 + lane;
+            const int e1 = p < nL ? r1[p] : -1, e2 = p < nL ? r2[p] : -1;
+            const bool f = e1 >= 0 && e2 >= 0;
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            if (f) {
+                const int k = pos + __popc(m & ((1u << lane) - 1));
+                if (t < nF) { poseEdges[k] = e1; poseEdgePt[k] = p; }
+                else { pairs[k] = make_int2(e1, e2); pairPt[k] = p; }
+            }
+            pos += __popc(m);
+        }
+    }
+    for (int t = tid; t < nTasks; t += BT) {
+        int poseA, poseB = -1;
+        if (t < nF) poseA = D.freePose[t];
+        else {
+            int i1 = 0, rem = t - nF;
+            while (rem >= nF - 1 - i1) { rem -= nF - 1 - i1; ++i1; }
+            poseA = D.freePose[i1]; poseB = D.freePose[i1 + 1 + rem];
+        }
+        const int len = D.bTaskLen[t], first = D.bItemStart[t];
+        int ch = taskChunkStart[t];
+        for (int f = 0; f < len; f += SCH) chunkHdr[ch++] = make_int4(first + f, min(SCH, len - f), poseA, poseB);
+    }
+    if (tid == 0) { D.nChunks = nChunks; status[blockIdx.x] = 0; }
+}
+
+// =============================================================================================
 // host side
 // =============================================================================================
 struct Packed {             // one uploaded problem: where its pieces live inside the arena
@@ -993,6 +1179,7 @@ struct Solver {
     Dev* d_probs = nullptr; std::vector<Dev> h_probs;
     std::vector<Packed> packed;
     int* h_stop = nullptr; int* d_stop = nullptr;   // mapped pinned stop flags, one per problem
+    int* h_status = nullptr; int* d_status = nullptr;   // mapped pinned status words of the structure kernel
     cudaEvent_t evDone = nullptr;
     int nLoaded = 0, launches = 0, smemN = 0, numSMs = 148;
     size_t fixedSmem = 0;
@@ -1002,27 +1189,28 @@ struct Solver {
         if (h_arena) cudaFreeHost(h_arena);
         if (d_probs) cudaFree(d_probs);
         if (h_stop) cudaFreeHost(h_stop);
+        if (h_status) cudaFreeHost(h_status);
         if (evDone) cudaEventDestroy(evDone);
         if (st) cudaStreamDestroy(st);
     }
     static size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
+    static size_t outBlock(size_t nP, size_t nL, size_t nE) { return al(56 * nP) + al(24 * nL) + al(8 * nE) + al(nE) + al(512); }
+    static size_t pairCapOf(size_t nP, size_t nE) { return nE * (nP > 1 ? nP - 1 : 1) / 2 + 1; }
+    static size_t chunkCapOf(size_t nP, size_t nE) { return nP + nP * nP / 2 + 2 + (nE + pairCapOf(nP, nE)) / SCH + 1; }
     static size_t need(size_t nP, size_t nL, size_t nE) {
-        const size_t n = 6 * nP;
-        size_t b = 0;
-        b += 2 * al(56 * nP) + 2 * al(24 * nL) + al(56 * nP) + al(24 * nL);      // poses, bk, pts, bk, initial copies
-        b += al(16 * nP) + 2 * al(4 * nP);                                        // cam, hidx, freePose
-        b += 2 * al(4 * nE) + al(16 * nE) + al(4 * nE);                           // ePt, ePose, obs, invSigma2
-        b += al(4 * (nL + 1)) + al(4 * nE) + al(4 * (nP + 1)) + al(4 * nE);                     // CSR, eOrig
-        b += al(4 * (nP * nP / 2 + 2)) + al(12 * (nE * (nP > 1 ? nP - 1 : 1) / 2 + 1)) + 256;        // Schur block starts + (e1, e2) pair lists + their points
+        const size_t n = 6 * nP, pc = pairCapOf(nP, nE), cc = chunkCapOf(nP, nE), tasks = nP + nP * nP / 2 + 2;
+        size_t b = outBlock(nP, nL, nE);                                          // poses, pts, chi2, depth flags, stats (downloaded in one copy)
+        b += al(56 * nP) + al(24 * nL) + al(16 * nP) + 2 * al(4 * nP);            // uploaded: initial estimates, cam, hidx, freePose
+        b += 2 * al(4 * nE) + al(16 * nE) + al(4 * nE);                           // uploaded: the caller's edges (point, pose, obs, invSigma2)
+        b += 3 * al(4 * nE) + al(16 * nE) + al(4 * nE) + al(4 * (nL + 1));        // edges sorted by point: ePt, ePose, eOrig, obs, invSigma2; ptStart
+        b += 2 * al(4 * nE) + al(8 * pc) + al(4 * pc);                            // poseEdges, poseEdgePt, pairs, pairPt
+        b += al(16 * cc) + al(4 * (tasks + 1));                                   // chunk headers, task chunk starts
+        b += 2 * al(4 * (nL + 1)) + al(4 * nE) + al(4 * nP * nL) + 2 * al(4 * tasks);   // structure-build scratch
+        b += al(56 * nP) + al(24 * nL);                                           // second state buffers
         b += al(16 * nE) + 2 * al(32 * nE);                                       // err, edge factors x 2
         b += al(288 * nP) + al(48 * nP) + al(48 * nL) + al(96 * nL) + al(24 * nL);   // Hpp, bp, Hll, PT, bl
-        b += al(8 * n * n) + al(8 * n) + al(8 * (n + 3 * nL)) + al(8 * (4 * PSLOT + 8)) + al(512);   // Hs, bs, x, partial, stats
-        {   // Schur chunk tables + partial sums: at most (#tasks + #items / SCH) chunks
-            const size_t items = nE + nE * (nP > 1 ? nP - 1 : 1) / 2 + 1, tasks = nP + nP * nP / 2 + 2;
-            const size_t ch = tasks + items / SCH + 1;
-            b += al(16 * ch) + al(4 * (tasks + 1)) + al(8 * 42 * ch) + al(4 * nE) + al(8 * 28 * (nP + nE / SCH + 1));   // chunk headers, task chunk starts, Spart, poseEdgePt, Ppart
-        }
-        b += al(8 * nE) + al(nE);                                                 // outputs
+        b += al(8 * 42 * cc) + al(8 * 28 * (nP + nE / SCH + 1));                  // Spart, Ppart
+        b += al(8 * n * n) + al(8 * n) + al(8 * (n + 3 * nL)) + al(8 * (4 * PSLOT + 8));   // Hs, bs, x, partial
         return b;
     }
     int init() {
@@ -1034,10 +1222,15 @@ struct Solver {
         perProblem = need(maxP, maxL, maxE);
         arenaBytes = perProblem * (size_t)maxBatch;
         CK(cudaMalloc(&d_arena, arenaBytes));
-        CK(cudaMallocHost(&h_arena, arenaBytes));
+        {
+            orbx::ScopedGpuAffinity numaLocal(device);     // pinned pages on the GPU's NUMA node (host_affinity.h)
+            CK(cudaMallocHost(&h_arena, arenaBytes));
+        }
         CK(cudaMalloc(&d_probs, sizeof(Dev) * maxBatch));
         CK(cudaHostAlloc(&h_stop, sizeof(int) * maxBatch, cudaHostAllocMapped));
         CK(cudaHostGetDevicePointer(&d_stop, h_stop, 0));
+        CK(cudaHostAlloc(&h_status, sizeof(int) * maxBatch, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer(&d_status, h_status, 0));
         CK(cudaEventCreateWithFlags(&evDone, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         // dynamic shared memory: pose cache + two LDLT column buffers + (when it fits) the reduced camera system,
@@ -1051,8 +1244,8 @@ struct Solver {
         return ORB_OK;
     }
 
-    // BlockSolver::buildStructure (block_solver.hpp:143-295) on the host: index maps, CSR lists, the (point, pose) -> edge table;
-    // packs one problem into slot `slot` of the pinned arena.
+    // Lays one problem out in slot `slot` of the arena and copies the caller's graph into the pinned mirror; the index
+    // structures are derived on the device (lba_build_structure_kernel).
     int pack(int slot, const LbaProblem* P) {
         const int nP = P->nPoses, nL = P->nPoints, nE = P->nEdges;
         if (nP < 1 || nL < 0 || nE < 0 || nP > maxP || nL > maxL || nE > maxE || !P->poses || !P->poseFixed || !P->cam ||
@@ -1063,77 +1256,8 @@ struct Solver {
         for (int i = 0; i < nP; ++i) if (!P->poseFixed[i]) { hidx[i] = (int)freePose.size(); freePose.push_back(i); }
         const int nF = (int)freePose.size(), n = 6 * nF;
         if (nF + nL == 0) { set_error("lba: 0 vertices to optimize"); return ORB_ERR_ARG; }
-        // internal edge order: stable sort by point, so that the edges of a point are contiguous
-        std::vector<int> ptStart(nL + 1, 0), poseStart(nP + 1, 0), eOrig(nE), inv(nE), poseEdges(nE);
-        for (int e = 0; e < nE; ++e) {
-            const int p = P->edgePoint[e], c = P->edgePose[e];
-            if (p < 0 || p >= nL || c < 0 || c >= nP) { set_error("lba: edge index out of range"); return ORB_ERR_ARG; }
-            ++ptStart[p + 1]; ++poseStart[c + 1];
-        }
-        for (int i = 0; i < nL; ++i) ptStart[i + 1] += ptStart[i];
-        for (int i = 0; i < nP; ++i) poseStart[i + 1] += poseStart[i];
-        {
-            std::vector<int> a(ptStart.begin(), ptStart.end() - 1);
-            for (int e = 0; e < nE; ++e) { const int k = a[P->edgePoint[e]]++; eOrig[k] = e; inv[e] = k; }
-            std::vector<int> b(poseStart.begin(), poseStart.end() - 1);
-            for (int k = 0; k < nE; ++k) poseEdges[b[P->edgePose[eOrig[k]]]++] = k;     // ascending internal ids per pose
-        }
-        std::vector<int> ePt(nE), ePose(nE); std::vector<double> obs(2 * (size_t)nE); std::vector<float> is2(nE);
-        for (int k = 0; k < nE; ++k) {
-            const int e = eOrig[k];
-            ePt[k] = P->edgePoint[e]; ePose[k] = P->edgePose[e]; obs[2 * (size_t)k] = P->obs[2 * (size_t)e]; obs[2 * (size_t)k + 1] = P->obs[2 * (size_t)e + 1];
-            is2[k] = P->invSigma2[e];
-        }
-        // Schur structure: for every point, every pair of its free-pose edges (i1 < i2) goes to block (i1, i2)
-        const int nOff = nF * (nF - 1) / 2;
-        auto blockOf = [&](int i1, int i2) { return i1 * (nF - 1) - i1 * (i1 - 1) / 2 + (i2 - i1 - 1); };
-        std::vector<int> blockStart(nOff + 1, 0);
-        std::vector<int> fe;   // free edges of the current point: (hidx, internal id)
-        size_t nPairs = 0;
-        for (int p = 0; p < nL; ++p) {
-            fe.clear();
-            for (int k = ptStart[p]; k < ptStart[p + 1]; ++k) if (hidx[ePose[k]] >= 0) fe.push_back(k);
-            for (size_t a2 = 0; a2 < fe.size(); ++a2)
-                for (size_t b2 = a2 + 1; b2 < fe.size(); ++b2) {
-                    const int h1 = hidx[ePose[fe[a2]]], h2 = hidx[ePose[fe[b2]]];
-                    if (h1 == h2) { set_error("lba: duplicate (point, keyframe) observation"); return ORB_ERR_ARG; }
-                    ++blockStart[blockOf(std::min(h1, h2), std::max(h1, h2)) + 1];
-                    ++nPairs;
-                }
-        }
-        if (nPairs > (size_t)nE * (nP > 1 ? nP - 1 : 1) / 2 + 1) { set_error("lba: pair list larger than sized"); return ORB_ERR_CAPACITY; }
-        for (int i = 0; i < nOff; ++i) blockStart[i + 1] += blockStart[i];
-        std::vector<int2> pairs(nPairs); std::vector<int> pairPt(nPairs);
-        {
-            std::vector<int> cur(blockStart.begin(), blockStart.end() - 1);
-            for (int p = 0; p < nL; ++p) {
-                fe.clear();
-                for (int k = ptStart[p]; k < ptStart[p + 1]; ++k) if (hidx[ePose[k]] >= 0) fe.push_back(k);
-                for (size_t a2 = 0; a2 < fe.size(); ++a2)
-                    for (size_t b2 = a2 + 1; b2 < fe.size(); ++b2) {
-                        int k1 = fe[a2], k2 = fe[b2];
-                        if (hidx[ePose[k1]] > hidx[ePose[k2]]) std::swap(k1, k2);
-                        const int blk = blockOf(hidx[ePose[k1]], hidx[ePose[k2]]);
-                        pairPt[cur[blk]] = p; pairs[cur[blk]++] = make_int2(k1, k2);
-                    }
-            }
-        }
-        // Schur work list cut into chunks of SCH items
-        std::vector<int4> chunkHdr; std::vector<int> taskChunkStart(nF + nOff + 1, 0);
-        {
-            int t = 0;
-            auto cut = [&](int first, int len, int poseA, int poseB) {
-                taskChunkStart[t++] = (int)chunkHdr.size();
-                for (int f = 0; f < len; f += SCH) chunkHdr.push_back(make_int4(first + f, std::min(SCH, len - f), poseA, poseB));
-            };
-            for (int i = 0; i < nF; ++i) cut(poseStart[freePose[i]], poseStart[freePose[i] + 1] - poseStart[freePose[i]], freePose[i], -1);
-            for (int i1 = 0; i1 < nF; ++i1)
-                for (int i2 = i1 + 1; i2 < nF; ++i2) { const int blk = blockOf(i1, i2); cut(blockStart[blk], blockStart[blk + 1] - blockStart[blk], freePose[i1], freePose[i2]); }
-            taskChunkStart[nF + nOff] = (int)chunkHdr.size();
-        }
-        const int nChunks = (int)chunkHdr.size();
-        std::vector<int> poseEdgePt(nE);
-        for (int k = 0; k < nE; ++k) poseEdgePt[k] = ePt[poseEdges[k]];
+        const int nOff = nF * (nF - 1) / 2, nTasks = nF + nOff;
+        const size_t pc = pairCapOf(nP, nE), cc = chunkCapOf(nP, nE);
         const size_t base = perProblem * (size_t)slot;
         size_t off = base;
         auto carve = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
@@ -1141,63 +1265,67 @@ struct Solver {
         Dev& D = h_probs[slot]; memset(&D, 0, sizeof(D));
         Packed& K = packed[slot];
         K.nP = nP; K.nL = nL; K.nE = nE; K.nF = nF;
-        D.nP = nP; D.nL = nL; D.nE = nE; D.nF = nF; D.n = n;
-        // --- uploaded block (host content matters) ---
-        K.initPosesOff = carve(56 * (size_t)nP); put(K.initPosesOff, P->poses, 56 * (size_t)nP);
-        K.initPtsOff = carve(24 * (size_t)nL); put(K.initPtsOff, P->points, 24 * (size_t)nL);
+        D.nP = nP; D.nL = nL; D.nE = nE; D.nF = nF; D.n = n; D.pairCap = (int)pc; D.chunkCap = (int)cc;
+        // --- output block: fixed layout (sized by the handle's maxima) so that one strided copy downloads every problem ---
+        K.posesOff = carve(56 * (size_t)maxP); D.poses = (double*)(d_arena + K.posesOff);
+        K.ptsOff = carve(24 * (size_t)maxL); D.pts = (double*)(d_arena + K.ptsOff);
+        K.chi2Off = carve(8 * (size_t)maxE); D.outChi2 = (double*)(d_arena + K.chi2Off);
+        K.dposOff = carve((size_t)maxE); D.outDepthPos = (uint8_t*)(d_arena + K.dposOff);
+        K.statsOff = carve(512); D.stats = (double*)(d_arena + K.statsOff);
+        // --- uploaded block: the caller's graph ---
+        const size_t upBase = off;
         size_t o;
+        o = carve(56 * (size_t)nP); put(o, P->poses, 56 * (size_t)nP); D.initPoses = (const double*)(d_arena + o);
+        o = carve(24 * (size_t)nL); put(o, P->points, 24 * (size_t)nL); D.initPts = (const double*)(d_arena + o);
         o = carve(16 * (size_t)nP); put(o, P->cam, 16 * (size_t)nP); D.cam = (const float*)(d_arena + o);
         o = carve(4 * (size_t)nP); put(o, hidx.data(), 4 * (size_t)nP); D.hidx = (const int*)(d_arena + o);
         o = carve(4 * (size_t)std::max(nF, 1)); put(o, freePose.data(), 4 * (size_t)nF); D.freePose = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)nE); put(o, ePt.data(), 4 * (size_t)nE); D.ePt = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)nE); put(o, ePose.data(), 4 * (size_t)nE); D.ePose = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)nE); put(o, eOrig.data(), 4 * (size_t)nE); D.eOrig = (const int*)(d_arena + o);
-        o = carve(16 * (size_t)nE); put(o, obs.data(), 16 * (size_t)nE); D.obs = (const double*)(d_arena + o);
-        o = carve(4 * (size_t)nE); put(o, is2.data(), 4 * (size_t)nE); D.invSigma2 = (const float*)(d_arena + o);
-        o = carve(4 * (size_t)(nL + 1)); put(o, ptStart.data(), 4 * (size_t)(nL + 1)); D.ptStart = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)(nP + 1)); put(o, poseStart.data(), 4 * (size_t)(nP + 1)); D.poseStart = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)nE); put(o, poseEdges.data(), 4 * (size_t)nE); D.poseEdges = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)(nOff + 1)); put(o, blockStart.data(), 4 * (size_t)(nOff + 1)); D.blockStart = (const int*)(d_arena + o);
-        o = carve(8 * std::max<size_t>(nPairs, 1)); put(o, pairs.data(), 8 * nPairs); D.pairs = (const int2*)(d_arena + o);
-        o = carve(4 * std::max<size_t>(nPairs, 1)); put(o, pairPt.data(), 4 * nPairs); D.pairPt = (const int*)(d_arena + o);
-        D.nChunks = nChunks;
-        o = carve(16 * (size_t)std::max(nChunks, 1)); put(o, chunkHdr.data(), 16 * (size_t)nChunks); D.chunkHdr = (const int4*)(d_arena + o);
-        o = carve(4 * (size_t)nE); put(o, poseEdgePt.data(), 4 * (size_t)nE); D.poseEdgePt = (const int*)(d_arena + o);
-        o = carve(4 * (size_t)(nF + nOff + 1)); put(o, taskChunkStart.data(), 4 * (size_t)(nF + nOff + 1)); D.taskChunkStart = (const int*)(d_arena + o);
-        uploadBytes[slot] = off - base;
-        // --- device-only scratch / state / outputs ---
-        K.posesOff = carve(56 * (size_t)nP); D.poses = (double*)(d_arena + K.posesOff);
+        o = carve(4 * (size_t)nE); put(o, P->edgePoint, 4 * (size_t)nE); D.rawEdgePoint = (const int*)(d_arena + o);
+        o = carve(4 * (size_t)nE); put(o, P->edgePose, 4 * (size_t)nE); D.rawEdgePose = (const int*)(d_arena + o);
+        o = carve(16 * (size_t)nE); put(o, P->obs, 16 * (size_t)nE); D.rawObs = (const double*)(d_arena + o);
+        o = carve(4 * (size_t)nE); put(o, P->invSigma2, 4 * (size_t)nE); D.rawInvSigma2 = (const float*)(d_arena + o);
+        uploadOff[slot] = upBase; uploadBytes[slot] = off - upBase;
+        // --- derived on the device ---
+        D.ePt = (const int*)(d_arena + carve(4 * (size_t)nE)); D.ePose = (const int*)(d_arena + carve(4 * (size_t)nE)); D.eOrig = (const int*)(d_arena + carve(4 * (size_t)nE));
+        D.obs = (const double*)(d_arena + carve(16 * (size_t)nE)); D.invSigma2 = (const float*)(d_arena + carve(4 * (size_t)nE));
+        D.ptStart = (const int*)(d_arena + carve(4 * (size_t)(nL + 1)));
+        D.poseEdges = (const int*)(d_arena + carve(4 * (size_t)nE)); D.poseEdgePt = (const int*)(d_arena + carve(4 * (size_t)nE));
+        D.pairs = (const int2*)(d_arena + carve(8 * pc)); D.pairPt = (const int*)(d_arena + carve(4 * pc));
+        D.chunkHdr = (const int4*)(d_arena + carve(16 * cc)); D.taskChunkStart = (const int*)(d_arena + carve(4 * (size_t)(nTasks + 1)));
+        D.bCnt = (int*)(d_arena + carve(4 * (size_t)(nL + 1))); D.bCursor = (int*)(d_arena + carve(4 * (size_t)(nL + 1)));
+        D.bTmp = (int*)(d_arena + carve(4 * (size_t)nE)); D.bEid = (int*)(d_arena + carve(4 * (size_t)std::max(nF, 1) * (size_t)std::max(nL, 1)));
+        D.bTaskLen = (int*)(d_arena + carve(4 * (size_t)std::max(nTasks, 1))); D.bItemStart = (int*)(d_arena + carve(4 * (size_t)std::max(nTasks, 1)));
+        // --- state / scratch of the LM kernel ---
         D.posesB = (double*)(d_arena + carve(56 * (size_t)nP));
-        K.ptsOff = carve(24 * (size_t)nL); D.pts = (double*)(d_arena + K.ptsOff);
         D.ptsB = (double*)(d_arena + carve(24 * (size_t)nL));
         D.err = (double*)(d_arena + carve(16 * (size_t)nE));
         D.E4a = (double*)(d_arena + carve(32 * (size_t)nE)); D.E4b = (double*)(d_arena + carve(32 * (size_t)nE));
         D.Hpp = (double*)(d_arena + carve(288 * (size_t)std::max(nF, 1))); D.bp = (double*)(d_arena + carve(48 * (size_t)std::max(nF, 1)));
         D.Hll = (double*)(d_arena + carve(48 * (size_t)nL)); D.bl = (double*)(d_arena + carve(24 * (size_t)nL));
         D.PT = (double*)(d_arena + carve(96 * (size_t)nL));
-        D.Spart = (double*)(d_arena + carve(8 * 42 * (size_t)std::max(nChunks, 1)));
-        D.Ppart = (double*)(d_arena + carve(8 * 28 * (size_t)std::max(taskChunkStart[nF], 1)));
+        D.Spart = (double*)(d_arena + carve(8 * 42 * cc));
+        D.Ppart = (double*)(d_arena + carve(8 * 28 * ((size_t)nP + (size_t)nE / SCH + 1)));
         D.Hs = (double*)(d_arena + carve(8 * (size_t)n * n)); D.bs = (double*)(d_arena + carve(8 * (size_t)std::max(n, 1)));
         D.x = (double*)(d_arena + carve(8 * ((size_t)n + 3 * (size_t)nL)));
         D.partial = (double*)(d_arena + carve(8 * (4 * PSLOT + 8)));
-        K.statsOff = carve(512); D.stats = (double*)(d_arena + K.statsOff);
-        K.chi2Off = carve(8 * (size_t)nE); D.outChi2 = (double*)(d_arena + K.chi2Off);
-        K.dposOff = carve((size_t)nE); D.outDepthPos = (uint8_t*)(d_arena + K.dposOff);
         if (off - base > perProblem) { set_error("lba: arena too small (internal sizing error)"); return ORB_ERR_CAPACITY; }
         D.delta = P->huberDelta; D.dsqr = P->huberDelta * P->huberDelta; D.userLambdaInit = P->userLambdaInit; D.iterations = P->iterations;
         return ORB_OK;
     }
-    std::vector<size_t> uploadBytes = std::vector<size_t>(1);
+    std::vector<size_t> uploadBytes = std::vector<size_t>(1), uploadOff = std::vector<size_t>(1);
 
     int upload(int count, const LbaProblem* probs) {
         if (count < 1 || count > maxBatch) { set_error("lba: batch larger than max_batch"); return ORB_ERR_ARG; }
-        uploadBytes.assign(maxBatch, 0);
-        {   // BlockSolver::buildStructure for every problem, on the host cores (problems are independent)
-            const int nth = std::max(1, std::min<int>({count, (int)std::thread::hardware_concurrency(), 16}));
+        uploadBytes.assign(maxBatch, 0); uploadOff.assign(maxBatch, 0);
+        {   // stage the callers' graphs in the pinned mirror on a few host threads; every worker queues the host-to-device
+            // copy of a problem as soon as it is staged, so the copies overlap the staging of the next problems
+            const int nth = std::max(1, std::min<int>({count, (int)std::thread::hardware_concurrency(), 8}));
             std::atomic<int> next(0), firstErr(ORB_OK);
             auto worker = [&]() {
+                cudaSetDevice(device);
                 for (int i = next.fetch_add(1); i < count; i = next.fetch_add(1)) {
-                    const int rc = pack(i, probs + i);
+                    int rc = pack(i, probs + i);
+                    if (!rc && cudaMemcpyAsync(d_arena + uploadOff[i], h_arena + uploadOff[i], uploadBytes[i], cudaMemcpyHostToDevice, st) != cudaSuccess) rc = ORB_ERR_CUDA;
                     if (rc) { int exp = ORB_OK; firstErr.compare_exchange_strong(exp, rc); }
                 }
             };
@@ -1205,13 +1333,21 @@ struct Solver {
             for (int t = 1; t < nth; ++t) pool.emplace_back(worker);
             worker();
             for (auto& t : pool) t.join();
-            if (firstErr.load()) { set_error("lba: malformed problem in the batch (index out of range, duplicate observation, or larger than the handle)"); return firstErr.load(); }
+            if (firstErr.load()) { cudaStreamSynchronize(st); return firstErr.load(); }
         }
         CK(cudaSetDevice(device));
-        for (int i = 0; i < count; ++i)
-            CK(cudaMemcpyAsync(d_arena + perProblem * (size_t)i, h_arena + perProblem * (size_t)i, uploadBytes[i], cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_probs, h_probs.data(), sizeof(Dev) * count, cudaMemcpyHostToDevice, st));
+        for (int i = 0; i < count; ++i) h_status[i] = -1;
+        lba_build_structure_kernel<<<count, BT, 0, st>>>(d_probs, d_status);     // BlockSolver::buildStructure, one CTA per problem
+        CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));   // the resident copy must be complete before a run on any other stream
+        for (int i = 0; i < count; ++i) {
+            if (h_status[i] == 0) continue;
+            nLoaded = 0;
+            if (h_status[i] == 1) { set_error("lba: edge index out of range"); return ORB_ERR_ARG; }
+            if (h_status[i] == 2) { set_error("lba: duplicate (point, keyframe) observation"); return ORB_ERR_ARG; }
+            set_error("lba: pair / chunk list larger than sized"); return ORB_ERR_CAPACITY;
+        }
         nLoaded = count;
         return ORB_OK;
     }
@@ -1220,12 +1356,7 @@ struct Solver {
         if (nLoaded < 1) { set_error("lba: nothing uploaded"); return ORB_ERR_ARG; }
         CK(cudaSetDevice(device));
         int maxN = 0;
-        for (int i = 0; i < nLoaded; ++i) {
-            const Packed& K = packed[i];
-            CK(cudaMemcpyAsync(d_arena + K.posesOff, d_arena + K.initPosesOff, 56 * (size_t)K.nP, cudaMemcpyDeviceToDevice, s));
-            if (K.nL) CK(cudaMemcpyAsync(d_arena + K.ptsOff, d_arena + K.initPtsOff, 24 * (size_t)K.nL, cudaMemcpyDeviceToDevice, s));
-            maxN = std::max(maxN, 6 * K.nF);
-        }
+        for (int i = 0; i < nLoaded; ++i) maxN = std::max(maxN, 6 * packed[i].nF);     // the kernel itself restarts from the uploaded estimates
         int csize = 1;
         for (int cand = MAXC; cand >= 1; cand >>= 1) if (nLoaded * cand <= numSMs) { csize = cand; break; }
         if (forcedCluster > 0) csize = forcedCluster;
@@ -1246,23 +1377,21 @@ struct Solver {
     }
     int lastCluster = 1, forcedCluster = 0;
     int download(int count, LbaResult* res, cudaStream_t s) {
+        for (int i = 0; i < count; ++i)
+            if (!res[i].poses || !res[i].points || !res[i].edgeChi2 || !res[i].edgeDepthPositive) { set_error("lba: null result arrays"); return ORB_ERR_ARG; }
+        // the output blocks sit at the start of every slot with one layout: a single strided copy into the pinned mirror
+        const size_t ob = outBlock(maxP, maxL, maxE);
+        CK(cudaMemcpy2DAsync(h_arena, perProblem, d_arena, perProblem, ob, (size_t)count, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
         for (int i = 0; i < count; ++i) {
             const Packed& K = packed[i];
             LbaResult& R = res[i];
-            if (!R.poses || !R.points || !R.edgeChi2 || !R.edgeDepthPositive) { set_error("lba: null result arrays"); return ORB_ERR_ARG; }
-            CK(cudaMemcpyAsync(R.poses, d_arena + K.posesOff, 56 * (size_t)K.nP, cudaMemcpyDeviceToHost, s));
-            if (K.nL) CK(cudaMemcpyAsync(R.points, d_arena + K.ptsOff, 24 * (size_t)K.nL, cudaMemcpyDeviceToHost, s));
-            if (K.nE) {
-                CK(cudaMemcpyAsync(R.edgeChi2, d_arena + K.chi2Off, 8 * (size_t)K.nE, cudaMemcpyDeviceToHost, s));
-                CK(cudaMemcpyAsync(R.edgeDepthPositive, d_arena + K.dposOff, (size_t)K.nE, cudaMemcpyDeviceToHost, s));
-            }
-            CK(cudaMemcpyAsync(h_arena + K.statsOff, d_arena + K.statsOff, 512, cudaMemcpyDeviceToHost, s));
-        }
-        CK(cudaStreamSynchronize(s));
-        for (int i = 0; i < count; ++i) {
-            const double* stt = (const double*)(h_arena + packed[i].statsOff);
-            res[i].iterations = (int)stt[0]; res[i].trials = (int)stt[1]; res[i].lambda = stt[2]; res[i].chi2 = stt[3]; res[i].initialChi2 = stt[4];
-            res[i].gpuLaunches = 1;
+            memcpy(R.poses, h_arena + K.posesOff, 56 * (size_t)K.nP);
+            if (K.nL) memcpy(R.points, h_arena + K.ptsOff, 24 * (size_t)K.nL);
+            if (K.nE) { memcpy(R.edgeChi2, h_arena + K.chi2Off, 8 * (size_t)K.nE); memcpy(R.edgeDepthPositive, h_arena + K.dposOff, (size_t)K.nE); }
+            const double* stt = (const double*)(h_arena + K.statsOff);
+            R.iterations = (int)stt[0]; R.trials = (int)stt[1]; R.lambda = stt[2]; R.chi2 = stt[3]; R.initialChi2 = stt[4];
+            R.gpuLaunches = 1;
         }
         return ORB_OK;
     }

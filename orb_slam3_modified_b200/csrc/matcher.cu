@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/orb_b200.h"
+#include "host_affinity.h"
 #include "device_utils.cuh"
 #include "exact_math.h"
 
@@ -474,7 +475,10 @@ struct Matcher {
         const size_t bf = (size_t)(kcap + mcap) * 32 + (size_t)std::max(kcap, mcap) * 16 + 4096;
         arenaBytes = std::max(arenaBytes, bf);
         CK(cudaMalloc(&d_arena, arenaBytes));
-        CK(cudaMallocHost(&h_arena, arenaBytes));
+        {
+            orbx::ScopedGpuAffinity numaLocal(device);     // pinned pages on the GPU's NUMA node (host_affinity.h)
+            CK(cudaMallocHost(&h_arena, arenaBytes));
+        }
         batchBytes = B * ((size_t)kcap * (28 + 32 + 4 + 1) + (size_t)mcap * (1 + 12 + 4 + 4 + 1 + 32) + 28 + 16 + 13 * 256) + 4096;
         CK(cudaMalloc(&d_batch, batchBytes));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));

@@ -1,3 +1,4 @@
+"""Where the end-to-end (host buffers in, host buffers out) step of bench.py spends its time: each C-ABI call timed alone."""
 import sys, time; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
 import numpy as np, torch
 import bench as Bn
@@ -15,15 +16,16 @@ last=[]
 for k in range(2):
     m,kl,dl=ex.extract_batch(host[k].numpy(),(0,1000)); last.append(Bn.last_frame_slabs(kl,dl,k,cap))
 probs=Bn.lba_problems(NL)
+pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+kps_h = pin((B, cap, 7), torch.float32).view(np.uint8).reshape(B, cap, 28).view(orb.KP_DTYPE).reshape(B, cap)
+desc_h = pin((B, cap, 32), torch.uint8)
+nK_h, mono_h, nmatch_h = pin((B,), torch.int32), pin((B,), torch.int32), pin((B,), torch.int32)
+match_h, claimed_h = pin((B, cap), torch.int32), pin((B, cap), torch.uint8)
 def T(): torch.cuda.synchronize(); return time.perf_counter()
-for it in range(3):
-    t0=T(); monos,kl,dl=ex.extract_batch(host[it&1].numpy(),(0,1000)); t1=T()
-    kps_h=np.zeros((B,cap),orb.KP_DTYPE); desc_h=np.zeros((B,cap,32),np.uint8); nK=np.zeros(B,np.int32)
-    for b in range(B): nK[b]=len(kl[b]); kps_h[b,:nK[b]]=kl[b]; desc_h[b,:nK[b]]=dl[b]
-    t2=T()
+for it in range(4):
+    t0=T(); ex.extract_batch_slabs(host[it&1].numpy(), kps_h, desc_h, nK_h, mono_h, (0,1000)); t1=T()
     L=last[(it+1)&1]
-    d=dict(batch=B,kcap=cap,mcap=cap,nlevels=8,kps=kps_h,desc=desc_h,nK=nK,scaleFactors=sf,nM=L['nM'],valid=L['valid'],xyz=L['xyz'],octave=L['octave'],angle=L['angle'],hasObs=L['hasObs'],mpDesc=L['mpDesc'],Tcw7=poses[it&1],bounds=(0.,0.,640.,480.),cam=cam,reset=1)
-    mh=np.full((B,cap),-1,np.int32); ch=np.zeros((B,cap),np.uint8); nm=np.zeros(B,np.int32)
-    matcher.search_last_frame_batch(d,15.0,mh,ch,nm); t3=T()
-    outs=opt.LocalBundleAdjustmentBatch(probs); t4=T()
-    print('extract_batch %.1f ms | python slab copy %.1f | match_batch %.1f | lba_batch %.1f | total %.1f'%((t1-t0)*1e3,(t2-t1)*1e3,(t3-t2)*1e3,(t4-t3)*1e3,(t4-t0)*1e3))
+    d=dict(batch=B,kcap=cap,mcap=cap,nlevels=8,kps=kps_h,desc=desc_h,nK=nK_h,scaleFactors=sf,nM=L['nM'],valid=L['valid'],xyz=L['xyz'],octave=L['octave'],angle=L['angle'],hasObs=L['hasObs'],mpDesc=L['mpDesc'],Tcw7=poses[it&1],bounds=(0.,0.,640.,480.),cam=cam,reset=1)
+    matcher.search_last_frame_batch(d,15.0,match_h,claimed_h,nmatch_h); t2=T()
+    ta=time.perf_counter(); opt.upload(probs); tb=T(); opt.run_device(); tc=T(); outs=opt.download(); td=T()
+    print('extract_batch_slabs %.2f ms | match_batch %.2f | lba upload(pack+H2D) %.2f run %.2f download %.2f | sum %.2f'%((t1-t0)*1e3,(t2-t1)*1e3,(tb-ta)*1e3,(tc-tb)*1e3,(td-tc)*1e3,(td-t0)*1e3))
