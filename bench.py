@@ -464,18 +464,32 @@ def main():
 
     if rank == 0:
         peak, how = _peaks()
-        dom = max((k for k in stage if k in ALG), key=lambda k: stage[k]) if stage else None
-        cand = {k: stage[k] for k in stage}
-        top = max(cand, key=cand.get)
-        if top == 'lba_cluster_kernel':
-            alg_bytes = ALG_BYTES_LBA_PER_TRIAL * mean_trials * NLBA
-            per = 'LBA launch: %.1f LM trials x 13.6 MB x %d problems' % (mean_trials, NLBA)
-        elif top.startswith('match'):
-            alg_bytes = ALG_BYTES_MATCH * B
-            per = '552,000 B/frame x %d frames' % B
-        else:
-            alg_bytes = ALG[top] * B
-            per = '%d B/frame x %d frames' % (ALG[top], B)
+        traffic_tab = {}
+        try:
+            traffic_tab = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
+        except (OSError, ValueError):
+            pass
+
+        def alg_of(k):
+            if k == 'lba_cluster_kernel':
+                return ALG_BYTES_LBA_PER_TRIAL * mean_trials * NLBA, 'LBA launch: %.1f LM trials x 13.6 MB x %d problems' % (mean_trials, NLBA)
+            if k.startswith('match'):
+                return ALG_BYTES_MATCH * B, '552,000 B/frame x %d frames' % B
+            return ALG[k] * B, '%d B/frame x %d frames' % (ALG[k], B)
+
+        def traffic_of(k):
+            t = traffic_tab.get(k)
+            # the table holds ncu DRAM bytes per launch of THIS workload (256 frames / 25 problems per launch); scale if --batch differs
+            if not t:
+                return None
+            return t['bytes'] * (NLBA / 25.0 if k == 'lba_cluster_kernel' else B / 256.0)
+
+        per_kernel = {}
+        for k in stage:
+            ab, _ = alg_of(k)
+            per_kernel[k] = {'achieved': ab / (stage[k] * 1e-3) / 1e9, 'frac': ab / (stage[k] * 1e-3) / 1e9 / peak, 'traffic': traffic_of(k)}
+        top = max(stage, key=stage.get)
+        alg_bytes, per = alg_of(top)
         ach = alg_bytes / (stage[top] * 1e-3) / 1e9
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -487,8 +501,11 @@ def main():
                        'lba_mean_trials': mean_trials, 'host_numa_binding': numa},
             'clocks': clk, 'gpu_launches': launches,
             'stage_ms_per_step': stage,
-            'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+            'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic_of(top),
+                         'traffic_source': (traffic_tab.get(top) or {}).get('source'),
                          'peak_source': how, 'algorithmic_bytes_per_launch': alg_bytes, 'per': per, 'launch_ms': stage[top],
+                         'note': 'FP64 LM solver bound by L1 look-ups of per-lane gathers and by cluster barriers, not by DRAM (DESIGN.md 5); frac is against the HBM copy peak as the contract asks',
+                         'per_kernel': per_kernel,
                          'whole_step_frac': (ALG_BYTES_EXTRACT + ALG_BYTES_MATCH + ALG_BYTES_LBA_PER_TRIAL * mean_trials / KF_INTERVAL) * (value / world) / 1e9 / peak},
         }
         if e2e is not None:

@@ -103,3 +103,26 @@ def test_large_window_matrix_in_global_memory():
     out = optl.LocalBundleAdjustment(p)
     assert out['iters'] == ref['iters'] and out['trials'] == int(ref['stats'][3])
     assert np.abs(O.lba_residuals(p, ref['poses'], ref['points']) - O.lba_residuals(p, out['poses'], out['points'])).max() < TOL_PX
+
+
+def test_device_structure_build_any_edge_order_and_rejects_bad_graphs(opt):
+    """BlockSolver::buildStructure runs on the device: the caller's edges may come in any order (per-edge outputs come back in the
+    caller's order), duplicate (point, keyframe) observations and out-of-range indices are refused."""
+    import orb_slam3_modified_b200 as m
+    p = synth.lba_problem(n_kf=9, n_pts=700, obs_per_pt=6, seed=41, n_fixed=2)
+    perm = np.random.default_rng(5).permutation(len(p['edge_point']))
+    q = dict(p)
+    for k in ('edge_point', 'edge_pose', 'obs', 'inv_sigma2'):
+        q[k] = np.ascontiguousarray(p[k][perm])
+    _check(opt, q)
+    dup = dict(p)
+    for k in ('edge_point', 'edge_pose', 'obs', 'inv_sigma2'):
+        dup[k] = np.concatenate([p[k], p[k][:1]])
+    with pytest.raises(m.OrbError):
+        opt.LocalBundleAdjustment(dup)
+    bad = dict(p)
+    bad['edge_point'] = p['edge_point'].copy()
+    bad['edge_point'][5] = len(p['points'])
+    with pytest.raises(m.OrbError):
+        opt.LocalBundleAdjustment(bad)
+    _check(opt, p)      # the handle is usable after a refused graph
