@@ -234,6 +234,7 @@ def main():
     ap.add_argument('--batch', type=int, default=256, help='frames (streams) per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--dev-groups', type=int, default=4, help='stream groups (own handles + CUDA stream) in the device-resident measurement')
     ap.add_argument('--e2e-groups', type=int, default=2, help='stream groups (host threads with their own handles) in flight in the e2e measurement')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -295,21 +296,50 @@ def main():
     lba_stream = torch.cuda.Stream(device=dev)      # LocalMapping runs beside Tracking in the reference (src/System.cc:197)
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
-    def match_args(i):
+    # The B streams are served as DG groups, each with its own extractor / matcher handles on its own CUDA stream: the latency-bound
+    # kernels of one group (quadtree, ordered commit) overlap the throughput-bound ones of the other (FAST, blur).
+    DG = max(1, min(args.dev_groups, B))
+    gb = [(g * B // DG, (g + 1) * B // DG) for g in range(DG)]
+    if DG == 1:
+        g_ex, g_mt, g_st = [ex], [matcher], [stream]
+    else:
+        g_ex = [orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, W, H, b1 - b0, local) for b0, b1 in gb]
+        g_mt = [orb.ORBmatcher(0.9, True, max_batch=b1 - b0, max_keypoints=cap, max_mappoints=cap, device=local) for b0, b1 in gb]
+        g_st = [torch.cuda.Stream(device=dev) for _ in gb]
+    g_ev = [torch.cuda.Event() for _ in gb]
+
+    def match_args(i, b0=0, b1=None):
+        b1 = B if b1 is None else b1
         cur, lst = i & 1, (i + 1) & 1
         L = last_d[lst]
-        return dict(batch=B, kcap=cap, mcap=cap, nlevels=8, kps=d_kps, desc=d_desc, nK=d_n, scaleFactors=d_sf, nM=L['nM'], valid=L['valid'],
-                    xyz=L['xyz'], octave=L['octave'], angle=L['angle'], hasObs=L['hasObs'], mpDesc=L['mpDesc'], Tcw7=d_Tcw[cur],
-                    bounds=(0.0, 0.0, float(W), float(H)), cam=cam, reset=1)
+        return dict(batch=b1 - b0, kcap=cap, mcap=cap, nlevels=8, kps=d_kps[b0:b1], desc=d_desc[b0:b1], nK=d_n[b0:b1], scaleFactors=d_sf,
+                    nM=L['nM'][b0:b1], valid=L['valid'][b0:b1], xyz=L['xyz'][b0:b1], octave=L['octave'][b0:b1], angle=L['angle'][b0:b1],
+                    hasObs=L['hasObs'][b0:b1], mpDesc=L['mpDesc'][b0:b1], Tcw7=d_Tcw[cur][b0:b1], bounds=(0.0, 0.0, float(W), float(H)), cam=cam, reset=1)
 
     def step_device(i):
         # LocalMapping is asynchronous to Tracking in the reference (own thread, src/System.cc:197): the LBAs of step i are
         # enqueued on their own stream and only joined at the end of the timed region (all of them finish inside it).
         opt.run_device(lba_stream.cuda_stream)                       # B / KF_INTERVAL LBAs, one persistent kernel
-        ex.extract_batch_device(dev_sets[i & 1], d_kps, d_desc, d_n, d_mono, (0, 1000), stream.cuda_stream)
-        matcher.search_last_frame_batch_device(match_args(i), TH_PROJ, d_match, d_claimed, d_nmatch, stream.cuda_stream)
+        for g, (b0, b1) in enumerate(gb):
+            st = g_st[g]
+            g_ex[g].extract_batch_device(dev_sets[i & 1][b0:b1], d_kps[b0:b1], d_desc[b0:b1], d_n[b0:b1], d_mono[b0:b1], (0, 1000), st.cuda_stream)
+            g_mt[g].search_last_frame_batch_device(match_args(i, b0, b1), TH_PROJ, d_match[b0:b1], d_claimed[b0:b1], d_nmatch[b0:b1], st.cuda_stream)
         if world > 1:   # shared-map exchange: one all-gather of the fixed-capacity keypoint/descriptor slabs
+            join_groups()
             gather(d_kps, d_desc, d_n)
+            fork_groups()        # the next step's kernels overwrite the slabs: after the gather
+
+    def fork_groups():
+        if DG > 1:
+            ev_fork.record(stream)
+            for st in g_st:
+                st.wait_event(ev_fork)
+
+    def join_groups():
+        if DG > 1:
+            for g, st in enumerate(g_st):
+                g_ev[g].record(st)
+                stream.wait_event(g_ev[g])
 
     def join_lba():
         ev_join.record(lba_stream)
@@ -323,6 +353,7 @@ def main():
     # ---------------- device-resident timing (`value`) ----------------
     for i in range(args.warmup):
         step_device(i)
+    join_groups()
     join_lba()
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
@@ -330,13 +361,15 @@ def main():
     ev_fork.record(stream)
     lba_stream.wait_event(ev_fork)
     e0.record(stream)
+    fork_groups()
     for i in range(args.steps):
         step_device(i)
+    join_groups()
     join_lba()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = (ex.last_launch_count() + matcher.last_launch_count() + 1) * args.steps
+    launches = (sum(e.last_launch_count() for e in g_ex) + sum(m_.last_launch_count() for m_ in g_mt) + 1) * args.steps
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -498,7 +531,7 @@ def main():
             'config': {'workload': WORKLOAD, 'stages': STAGES, 'frames_per_gpu_per_step': B, 'lba_per_gpu_per_step': NLBA,
                        'l2': 'inputs alternate between two %d-frame sets (2 x %.0f MB) > 126 MB L2; per-step working set > 1 GB' % (B, B * W * H / 1e6),
                        'mean_keypoints_per_frame': mean_kp, 'mean_matches_per_frame': mean_matches, 'lba_cluster_size': opt.last_cluster_size(),
-                       'lba_mean_trials': mean_trials, 'host_numa_binding': numa},
+                       'lba_mean_trials': mean_trials, 'host_numa_binding': numa, 'device_stream_groups': DG},
             'clocks': clk, 'gpu_launches': launches,
             'stage_ms_per_step': stage,
             'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic_of(top),

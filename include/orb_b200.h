@@ -167,6 +167,31 @@ int orbm_search_last_frame(orbm_handle* h, const OrbmFrame* frame, const OrbmLas
                            const float* cam4, float th, int checkOrientation, int32_t* match, uint8_t* claimed,
                            int* nmatches);
 
+/* Frame::isInFrustum (src/Frame.cc:512-574, monocular branch Nleft == -1) with MapPoint::PredictScale
+ * (src/MapPoint.cc:531-546) for the M local map points of one frame: what Tracking::SearchLocalPoints
+ * (src/Tracking.cc:3346) runs before the local-map SearchByProjection.  Host pointers. */
+typedef struct OrbmFrustumIn {
+    int M;
+    const float* worldPos;        /* GetWorldPos(), M x 3 */
+    const float* normal;          /* GetNormal(), M x 3 */
+    const float* minDistInv;      /* GetMinDistanceInvariance() = 0.8f * mfMinDistance */
+    const float* maxDistInv;      /* GetMaxDistanceInvariance() = 1.2f * mfMaxDistance */
+    const float* maxDistance;     /* mfMaxDistance (PredictScale divides it by the current distance) */
+    float Rcw[9], tcw[3], Ow[3];  /* mRcw (row-major), mtcw, mOw */
+    float cam[4];                 /* fx fy cx cy (Pinhole::project) */
+    float minX, minY, maxX, maxY; /* mnMinX ... mnMaxY */
+    float mbf;                    /* for mTrackProjXR */
+    float logScaleFactor;         /* Frame::mfLogScaleFactor */
+    int nScaleLevels;             /* Frame::mnScaleLevels */
+    float viewingCosLimit;        /* 0.5 in SearchLocalPoints */
+} OrbmFrustumIn;
+/* Outputs, one per map point: inView = mbTrackInView (the return value); projX / projY = mTrackProjX / Y (-1 when the
+ * point is behind the camera or outside the image; set as soon as the bounds test passes, like the reference);
+ * projXR, depth (= |Pc|), level (mnTrackScaleLevel), viewCos are written only for points in view (0 / -1 otherwise: the
+ * reference leaves those fields untouched). */
+int orbm_frustum_project(orbm_handle* h, const OrbmFrustumIn* in, uint8_t* inView, float* projX, float* projY, float* projXR,
+                         float* depth, int32_t* level, float* viewCos);
+
 /* Device-resident, batched last-frame search: `batch` independent streams.  All pointers are device pointers into
  * fixed-capacity slabs (stride = capacity per stream): current frame slabs as written by orbx_extract_batch_device
  * (kps[batch][kcap], desc[batch][kcap][32], nK[batch]); last-frame slabs [batch][mcap]; Tcw [batch][7].

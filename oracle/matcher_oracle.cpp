@@ -243,4 +243,39 @@ int orbo_features_in_area(int K, const KeyPoint* kps, const float* bounds, float
     return (int)v.size();
 }
 
+// Frame::isInFrustum, monocular branch (src/Frame.cc:512-574), + MapPoint::PredictScale(const float&, Frame*) (src/MapPoint.cc:531-546)
+// for M map points.  Eigen's 3-vector products are written out in one fixed order with every operation rounded individually
+// (the reference's -O3 -march=native build may contract them differently: unpinned at the last ulp, like the last-frame
+// transform above); `log(ratio)` is std::log(float) = glibc logf; Pinhole::project(Vector3f) is src/CameraModels/Pinhole.cpp:35-41.
+// Outputs as documented in include/orb_b200.h (orbm_frustum_project).
+void orbo_is_in_frustum(int M, const float* P, const float* N, const float* minDistInv, const float* maxDistInv, const float* maxDistance,
+                        const float* Rcw, const float* tcw, const float* Ow, const float* cam, const float* bounds, float mbf,
+                        float logScaleFactor, int nScaleLevels, float viewingCosLimit,
+                        uint8_t* inView, float* projX, float* projY, float* projXR, float* depth, int* level, float* viewCos) {
+    for (int i = 0; i < M; ++i) {
+        inView[i] = 0; projX[i] = -1.f; projY[i] = -1.f; projXR[i] = 0.f; depth[i] = 0.f; level[i] = -1; viewCos[i] = 0.f;   // :515-517
+        const float X = P[3 * i], Y = P[3 * i + 1], Z = P[3 * i + 2];
+        const float xc = ((Rcw[0] * X + Rcw[1] * Y) + Rcw[2] * Z) + tcw[0];                 // :523 Pc = mRcw * P + mtcw
+        const float yc = ((Rcw[3] * X + Rcw[4] * Y) + Rcw[5] * Z) + tcw[1];
+        const float zc = ((Rcw[6] * X + Rcw[7] * Y) + Rcw[8] * Z) + tcw[2];
+        const float pcDist = sqrtf((xc * xc + yc * yc) + zc * zc);                          // :524
+        const float invz = 1.0f / zc;                                                       // :528
+        if (zc < 0.0f) continue;                                                            // :529
+        const float u = cam[0] * xc / zc + cam[2], v = cam[1] * yc / zc + cam[3];           // :532 mpCamera->project(Pc)
+        if (u < bounds[0] || u > bounds[2]) continue;                                       // :534
+        if (v < bounds[1] || v > bounds[3]) continue;                                       // :536
+        projX[i] = u; projY[i] = v;                                                         // :539-540
+        const float ox = X - Ow[0], oy = Y - Ow[1], oz = Z - Ow[2];                         // :545
+        const float dist = sqrtf((ox * ox + oy * oy) + oz * oz);                            // :546
+        if (dist < minDistInv[i] || dist > maxDistInv[i]) continue;                         // :548
+        const float c = ((ox * N[3 * i] + oy * N[3 * i + 1]) + oz * N[3 * i + 2]) / dist;   // :554
+        if (c < viewingCosLimit) continue;                                                  // :556
+        const float ratio = maxDistance[i] / dist;                                          // MapPoint.cc:536
+        int nScale = (int)std::ceil(std::log(ratio) / logScaleFactor);                      // :539 (float overloads)
+        if (nScale < 0) nScale = 0;
+        else if (nScale >= nScaleLevels) nScale = nScaleLevels - 1;
+        inView[i] = 1; projXR[i] = u - mbf * invz; depth[i] = pcDist; level[i] = nScale; viewCos[i] = c;   // :563-571
+    }
+}
+
 }  // extern "C"

@@ -228,6 +228,13 @@ class _OrbmLocalPoints(C.Structure):
     _fields_ = [('M', C.c_int)] + [(n, C.c_void_p) for n in ('inView', 'bad', 'depth', 'projX', 'projY', 'level', 'viewCos', 'hasObs', 'descriptors')]
 
 
+class _OrbmFrustumIn(C.Structure):
+    _fields_ = ([('M', C.c_int)] + [(n, C.c_void_p) for n in ('worldPos', 'normal', 'minDistInv', 'maxDistInv', 'maxDistance')] +
+                [('Rcw', C.c_float * 9), ('tcw', C.c_float * 3), ('Ow', C.c_float * 3), ('cam', C.c_float * 4),
+                 ('minX', C.c_float), ('minY', C.c_float), ('maxX', C.c_float), ('maxY', C.c_float), ('mbf', C.c_float),
+                 ('logScaleFactor', C.c_float), ('nScaleLevels', C.c_int), ('viewingCosLimit', C.c_float)])
+
+
 class _OrbmLastFrame(C.Structure):
     _fields_ = [('M', C.c_int)] + [(n, C.c_void_p) for n in ('valid', 'xyz', 'octave', 'angle', 'hasObs', 'descriptors')]
 
@@ -301,6 +308,27 @@ class ORBmatcher:
         if rc != ORB_OK:
             raise OrbError(rc, 'orbm_descriptor_distance')
         return int(out[0]) if len(out) == 1 else out
+
+    def isInFrustum(self, pts, Rcw, tcw, Ow, cam, bounds, log_scale_factor, n_levels, viewingCosLimit=0.5, mbf=0.0):
+        """``Frame::isInFrustum`` + ``MapPoint::PredictScale`` (src/Frame.cc:512-574, src/MapPoint.cc:531-546) for all local map
+        points of one frame. ``pts``: worldPos [M,3], normal [M,3], minDistInv, maxDistInv, maxDistance [M]. Returns the tracking
+        fields (inView, projX, projY, projXR, depth, level, viewCos) that the local-map SearchByProjection reads."""
+        keep = {k: _c(pts[k], np.float32) for k in ('worldPos', 'normal', 'minDistInv', 'maxDistInv', 'maxDistance')}
+        M = len(keep['minDistInv'])
+        s = _OrbmFrustumIn(M, *[_ptr(keep[k]) for k in ('worldPos', 'normal', 'minDistInv', 'maxDistInv', 'maxDistance')],
+                           (C.c_float * 9)(*[float(v) for v in np.asarray(Rcw, np.float32).reshape(9)]),
+                           (C.c_float * 3)(*[float(v) for v in np.asarray(tcw, np.float32).reshape(3)]),
+                           (C.c_float * 3)(*[float(v) for v in np.asarray(Ow, np.float32).reshape(3)]),
+                           (C.c_float * 4)(*[float(v) for v in cam]), *[float(b) for b in bounds], float(mbf),
+                           float(np.float32(log_scale_factor)), int(n_levels), float(viewingCosLimit))
+        out = dict(inView=np.zeros(M, np.uint8), projX=np.zeros(M, np.float32), projY=np.zeros(M, np.float32), projXR=np.zeros(M, np.float32),
+                   depth=np.zeros(M, np.float32), level=np.zeros(M, np.int32), viewCos=np.zeros(M, np.float32))
+        L = lib()
+        L.orbm_frustum_project.argtypes = [C.c_void_p] * 9
+        rc = L.orbm_frustum_project(self._h, C.byref(s), *[_ptr(out[k]) for k in ('inView', 'projX', 'projY', 'projXR', 'depth', 'level', 'viewCos')])
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_frustum_project')
+        return out
 
     def SearchByProjection(self, F, *args, **kw):
         """Overloads by argument type as in the reference: (F, map_points: dict, th, bFarPoints=False, thFarPoints=50)

@@ -113,6 +113,41 @@ ORB_HD void sincosf_glibc(float y, float* sinp, float* cosp) {
     else       { *sinp = sv;  *cosp = cvv; }
 }
 
+// glibc 2.39 logf (sysdeps/ieee754/flt-32/e_logf.c with logf_data.c, __logf_fma variant: every a*b + c of the C source is
+// one fused multiply-add).  `MapPoint::PredictScale` calls it through std::log(float) (src/MapPoint.cc:531-546).
+// Valid for positive normal finite x (the caller passes a distance ratio).
+ORB_HD float logf_glibc(float x) {
+    const double T[16][2] = {
+        {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+        {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+        {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+        {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+        {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+        {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+        {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+        {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+    const double Ln2 = 0x1.62e42fefa39efp-1;
+    const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
+    union { float f; uint32_t u; } cv;
+    cv.f = x;
+    const uint32_t ix = cv.u;
+    if (ix == 0x3f800000u) return 0.0f;
+    // x = 2^k z; z in [OFF, 2 OFF); the range is split into 16 subintervals, the ratio of the endpoints is close to 1 / invc
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const int k = (int32_t)tmp >> 23;
+    cv.u = ix - (tmp & 0xff800000u);
+    const double z = (double)cv.f;
+    const double invc = T[i][0], logc = T[i][1];
+    const double r = dfma(z, invc, -1.0);
+    const double y0 = dfma((double)k, Ln2, logc);
+    const double r2 = dmul(r, r);
+    double y = dfma(A1, r, A2);
+    y = dfma(A0, r2, y);
+    y = dfma(y, r2, y0 + r);
+    return d2f(y);
+}
+
 // ---------------------------------------------------------------------------
 // libstdc++ std::sort emulation (bits/stl_algo.h: __sort -> __introsort_loop +
 // __final_insertion_sort, _S_threshold = 16, median-of-3 to first, unguarded

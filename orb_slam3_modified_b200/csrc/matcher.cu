@@ -503,6 +503,48 @@ struct Matcher {
 };
 
 // bump allocator over the paired host/device arenas
+// ---- Frame::isInFrustum + MapPoint::PredictScale, thread per map point (src/Frame.cc:512-574, src/MapPoint.cc:531-546).
+//      Every float operation is individually rounded in the order fixed by the oracle; std::log(float) is glibc's logf
+//      (exact_math.h: logf_glibc). ----
+struct FrustumParams {
+    int M;
+    const float *P, *N, *minD, *maxD, *maxRaw;
+    float R[9], t[3], Ow[3], cam[4], minX, minY, maxX, maxY, mbf, logSF, cosLimit;
+    int nLevels;
+    uint8_t* inView; float *projX, *projY, *projXR, *depth, *viewCos; int* level;
+};
+__global__ void frustum_project_kernel(FrustumParams Q) {
+    using namespace orbx;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q.M) return;
+    uint8_t in = 0; float px = -1.f, py = -1.f, pxr = 0.f, dep = 0.f, vc = 0.f; int lvl = -1;
+    const float X = Q.P[3 * i], Y = Q.P[3 * i + 1], Z = Q.P[3 * i + 2];
+    const float xc = fadd(fadd(fadd(fmul(Q.R[0], X), fmul(Q.R[1], Y)), fmul(Q.R[2], Z)), Q.t[0]);
+    const float yc = fadd(fadd(fadd(fmul(Q.R[3], X), fmul(Q.R[4], Y)), fmul(Q.R[5], Z)), Q.t[1]);
+    const float zc = fadd(fadd(fadd(fmul(Q.R[6], X), fmul(Q.R[7], Y)), fmul(Q.R[8], Z)), Q.t[2]);
+    const float pcDist = __fsqrt_rn(fadd(fadd(fmul(xc, xc), fmul(yc, yc)), fmul(zc, zc)));
+    const float invz = fdiv(1.0f, zc);
+    if (!(zc < 0.0f)) {
+        const float u = fadd(fdiv(fmul(Q.cam[0], xc), zc), Q.cam[2]);
+        const float v = fadd(fdiv(fmul(Q.cam[1], yc), zc), Q.cam[3]);
+        if (!(u < Q.minX || u > Q.maxX) && !(v < Q.minY || v > Q.maxY)) {
+            px = u; py = v;
+            const float ox = fsub(X, Q.Ow[0]), oy = fsub(Y, Q.Ow[1]), oz = fsub(Z, Q.Ow[2]);
+            const float dist = __fsqrt_rn(fadd(fadd(fmul(ox, ox), fmul(oy, oy)), fmul(oz, oz)));
+            if (!(dist < Q.minD[i] || dist > Q.maxD[i])) {
+                const float c = fdiv(fadd(fadd(fmul(ox, Q.N[3 * i]), fmul(oy, Q.N[3 * i + 1])), fmul(oz, Q.N[3 * i + 2])), dist);
+                if (!(c < Q.cosLimit)) {
+                    const float ratio = fdiv(Q.maxRaw[i], dist);
+                    int n = (int)ceilf(fdiv(logf_glibc(ratio), Q.logSF));
+                    if (n < 0) n = 0; else if (n >= Q.nLevels) n = Q.nLevels - 1;
+                    in = 1; pxr = fsub(u, fmul(Q.mbf, invz)); dep = pcDist; lvl = n; vc = c;
+                }
+            }
+        }
+    }
+    Q.inView[i] = in; Q.projX[i] = px; Q.projY[i] = py; Q.projXR[i] = pxr; Q.depth[i] = dep; Q.level[i] = lvl; Q.viewCos[i] = vc;
+}
+
 struct Arena {
     uint8_t *h, *d; size_t off = 0, cap;
     Arena(uint8_t* h_, uint8_t* d_, size_t c) : h(h_), d(d_), cap(c) {}
@@ -673,6 +715,46 @@ int orbm_search_last_frame_batch(orbm_handle* h, const OrbmBatchDevice* in, floa
     CK(cudaMemcpyAsync(claimed, dc, B * K, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(nmatches, dn, B * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_frustum_project(orbm_handle* h, const OrbmFrustumIn* in, uint8_t* inView, float* projX, float* projY, float* projXR,
+                         float* depth, int32_t* level, float* viewCos) {
+    if (!h || !in || in->M < 0 || !inView || !projX || !projY || !projXR || !depth || !level || !viewCos ||
+        (in->M && (!in->worldPos || !in->normal || !in->minDistInv || !in->maxDistInv || !in->maxDistance)) || in->nScaleLevels < 1) {
+        set_error("orbm_frustum_project: bad argument"); return ORB_ERR_ARG;
+    }
+    Matcher& m = h->m;
+    CK(cudaSetDevice(m.device));
+    const size_t M = in->M;
+    if (M == 0) return ORB_OK;
+    Arena A(m.h_arena, m.d_arena, m.arenaBytes);
+    FrustumParams Q; memset(&Q, 0, sizeof(Q));
+    Q.M = in->M;
+    bool ok = A.put(in->worldPos, M * 3, &Q.P) && A.put(in->normal, M * 3, &Q.N) && A.put(in->minDistInv, M, &Q.minD) &&
+              A.put(in->maxDistInv, M, &Q.maxD) && A.put(in->maxDistance, M, &Q.maxRaw);
+    const size_t inBytes = A.off;
+    const uint8_t* dIn; const float *dX, *dY, *dXR, *dD, *dC; const int* dL;
+    ok = ok && A.put((const float*)nullptr, M, &dX) && A.put((const float*)nullptr, M, &dY) && A.put((const float*)nullptr, M, &dXR) &&
+         A.put((const float*)nullptr, M, &dD) && A.put((const float*)nullptr, M, &dC) && A.put((const int*)nullptr, M, &dL) &&
+         A.put((const uint8_t*)nullptr, M, &dIn);
+    if (!ok) { set_error("orbm_frustum_project: more map points than the staging arena holds (max_mappoints)"); return ORB_ERR_CAPACITY; }
+    memcpy(Q.R, in->Rcw, sizeof(Q.R)); memcpy(Q.t, in->tcw, sizeof(Q.t)); memcpy(Q.Ow, in->Ow, sizeof(Q.Ow)); memcpy(Q.cam, in->cam, sizeof(Q.cam));
+    Q.minX = in->minX; Q.minY = in->minY; Q.maxX = in->maxX; Q.maxY = in->maxY; Q.mbf = in->mbf; Q.logSF = in->logScaleFactor;
+    Q.cosLimit = in->viewingCosLimit; Q.nLevels = in->nScaleLevels;
+    Q.inView = const_cast<uint8_t*>(dIn); Q.projX = const_cast<float*>(dX); Q.projY = const_cast<float*>(dY); Q.projXR = const_cast<float*>(dXR);
+    Q.depth = const_cast<float*>(dD); Q.viewCos = const_cast<float*>(dC); Q.level = const_cast<int*>(dL);
+    cudaStream_t st = m.stream;
+    CK(cudaMemcpyAsync(m.d_arena, m.h_arena, inBytes, cudaMemcpyHostToDevice, st));
+    frustum_project_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(Q);
+    m.launches = 1;
+    CK(cudaGetLastError());
+    const size_t outOff = (const uint8_t*)dX - m.d_arena, outBytes = A.off - outOff;
+    CK(cudaMemcpyAsync(m.h_arena + outOff, m.d_arena + outOff, outBytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    auto hp = [&](const void* d) { return m.h_arena + ((const uint8_t*)d - m.d_arena); };
+    memcpy(projX, hp(dX), 4 * M); memcpy(projY, hp(dY), 4 * M); memcpy(projXR, hp(dXR), 4 * M); memcpy(depth, hp(dD), 4 * M);
+    memcpy(viewCos, hp(dC), 4 * M); memcpy(level, hp(dL), 4 * M); memcpy(inView, hp(dIn), M);
     return ORB_OK;
 }
 

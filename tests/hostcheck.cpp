@@ -26,6 +26,17 @@ long hc_sincosf_sweep(uint32_t lo, uint32_t hi, uint32_t* first_bad) {
     return bad;
 }
 
+// exhaustive sweep over all floats with bit patterns [lo, hi): mismatch count of logf_glibc vs the host libm logf
+long hc_logf_sweep(uint32_t lo, uint32_t hi, uint32_t* first_bad) {
+    long bad = 0;
+    for (uint32_t u = lo; u < hi; ++u) {
+        float y; std::memcpy(&y, &u, 4);
+        const float a = logf(y), b = orbx::logf_glibc(y);
+        if (std::memcmp(&a, &b, 4)) { if (!bad && first_bad) *first_bad = u; ++bad; }
+    }
+    return bad;
+}
+
 void hc_fast_atan2_n(const float* y, const float* x, float* out, int n) {
     for (int i = 0; i < n; ++i) out[i] = orbx::fast_atan2_deg(y[i], x[i]);
 }

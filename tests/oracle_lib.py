@@ -150,6 +150,22 @@ def search_local_map(kps, desc, bounds, scale_factors, pts, th, nnratio, b_far, 
                                    th, nnratio, int(b_far), th_far, _p(match), _p(claimed))
 
 
+def is_in_frustum(pts, Rcw, tcw, Ow, cam, bounds, log_scale_factor, n_levels, viewing_cos_limit=0.5, mbf=0.0):
+    a = {k: _c(pts[k], np.float32) for k in ('worldPos', 'normal', 'minDistInv', 'maxDistInv', 'maxDistance')}
+    M = len(a['minDistInv'])
+    R = _c(np.asarray(Rcw, np.float32).reshape(9), np.float32); t = _c(tcw, np.float32); o = _c(Ow, np.float32)
+    cm = _c(cam, np.float32); b = _c(bounds, np.float32)
+    out = dict(inView=np.zeros(M, np.uint8), projX=np.zeros(M, np.float32), projY=np.zeros(M, np.float32), projXR=np.zeros(M, np.float32),
+               depth=np.zeros(M, np.float32), level=np.zeros(M, np.int32), viewCos=np.zeros(M, np.float32))
+    L = lib()
+    L.orbo_is_in_frustum.restype = None
+    L.orbo_is_in_frustum.argtypes = [C.c_int] + [C.c_void_p] * 10 + [C.c_float, C.c_float, C.c_int, C.c_float] + [C.c_void_p] * 7
+    L.orbo_is_in_frustum(M, _p(a['worldPos']), _p(a['normal']), _p(a['minDistInv']), _p(a['maxDistInv']), _p(a['maxDistance']), _p(R), _p(t), _p(o),
+                         _p(cm), _p(b), float(mbf), float(np.float32(log_scale_factor)), int(n_levels), float(viewing_cos_limit),
+                         *[_p(out[k]) for k in ('inView', 'projX', 'projY', 'projXR', 'depth', 'level', 'viewCos')])
+    return out
+
+
 def search_last_frame(kps, desc, bounds, scale_factors, Tcw, cam, last, th, check_ori, match, claimed):
     kps = _c(kps, KP_DTYPE); desc = _c(desc, np.uint8); b = _c(bounds, np.float32); sf = _c(scale_factors, np.float32)
     T = _c(Tcw, np.float32); cm = _c(cam, np.float32)
