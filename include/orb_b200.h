@@ -276,8 +276,9 @@ int lba_download_batch(lba_handle* h, int count, LbaResult* results);
 int lba_last_cluster_size(const lba_handle* h);
 /* Force the cluster size (1, 2, 4, 8 CTAs per problem; 0 = automatic: the largest that lets the whole batch run at once). */
 int lba_set_cluster_size(lba_handle* h, int ctas);
-/* Device-side phase timers (ns, CTA 0) of problem i of the last downloaded run: errors, build_points, build_poses, point_prep,
- * schur, ldlt, backsub, update, errors(trial), spare. */
+/* Device-side phase timers (ns, CTA 0) of problem i of the last downloaded run: errors (first iteration), build_points,
+ * build_poses, point_prep (after a rejected step), schur_partial, ldlt, schur_combine, pose_trial, points_trial (back-substitution +
+ * update + residuals), spare. */
 int lba_get_phase_ns(const lba_handle* h, int i, double* ns10);
 
 /* ------------------------------------------------------------------------------------------

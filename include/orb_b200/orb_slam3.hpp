@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <cmath>
 #include <vector>
 
 #include "../orb_b200.h"
@@ -143,6 +144,17 @@ public:
                                          CurrentFrame.mvbClaimed.data(), &n), "orbm_search_last_frame");
         return n;
     }
+    // bool Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) for all local map points of a frame (Tracking::SearchLocalPoints,
+    // src/Tracking.cc:3346): fills the per-point tracking fields that the local-map SearchByProjection above reads.
+    struct TrackFields { std::vector<uint8_t> inView; std::vector<float> projX, projY, projXR, depth, viewCos; std::vector<int32_t> level; };
+    void isInFrustum(const OrbmFrustumIn& points, TrackFields& out) {
+        const size_t M = (size_t)(points.M > 0 ? points.M : 0);
+        out.inView.assign(M, 0); out.projX.assign(M, -1.f); out.projY.assign(M, -1.f); out.projXR.assign(M, 0.f); out.depth.assign(M, 0.f);
+        out.viewCos.assign(M, 0.f); out.level.assign(M, -1);
+        if (!M) return;
+        orb_check(orbm_frustum_project(h_, &points, out.inView.data(), out.projX.data(), out.projY.data(), out.projXR.data(), out.depth.data(),
+                                       out.level.data(), out.viewCos.data()), "orbm_frustum_project");
+    }
     // cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, matches, 2)
     void knnMatch(const Descriptors& query, const Descriptors& train, std::vector<int32_t>& idx, std::vector<int32_t>& dist) {
         idx.assign((size_t)query.rows * 2, -1); dist.assign((size_t)query.rows * 2, -1);
@@ -171,6 +183,15 @@ public:
         const int rc = lba_solve(h, &graph, &out);
         lba_destroy(h);
         orb_check(rc, "lba_solve");
+    }
+    // int static PoseOptimization(Frame* pFrame)  (src/Optimizer.cc:814-1113, monocular branch): the caller flattens the frame's map
+    // point associations (:862-905); returns nInitialCorrespondences - nBad, writes the pose and the outlier flags.
+    static int PoseOptimization(int N, const double pose7[7], const float cam4[4], const double* Xw, const double* obs, const float* invSigma2,
+                                double poseOut[7], uint8_t* mvbOutlier, int device = 0) {
+        int32_t n = N, inliers = 0;
+        orb_check(pose_optimization_batch(1, N > 0 ? N : 1, &n, pose7, cam4, Xw, obs, invSigma2, (double)(float)std::sqrt(5.991) /* deltaMono, :852 */, poseOut, mvbOutlier, &inliers, device),
+                  "pose_optimization_batch");
+        return inliers;
     }
 };
 
