@@ -498,8 +498,7 @@ __device__ __forceinline__ void schur_item(const double* t1, const double* t2, c
 }
 struct PairOps { double a[4], b[4], dv[6]; };          // edge 1, edge 2 (x/z, y/z, 1/z, w), Dinv
 struct DiagOps { double a[4], dv[6], db[3]; };
-#define SCHUR_FN __device__ __forceinline__
-SCHUR_FN void schur_chunk_offdiag(const int2* __restrict__ pairs, const int* __restrict__ pairPt, const double* __restrict__ PT, const double* __restrict__ E,
+__device__ __forceinline__ void schur_chunk_offdiag(const int2* __restrict__ pairs, const int* __restrict__ pairPt, const double* __restrict__ PT, const double* __restrict__ E,
                                                   const double* pcache, double* out42, int4 h) {
     const int lane = threadIdx.x & 31;
     const int cnt = h.y;
@@ -537,7 +536,7 @@ SCHUR_FN void schur_chunk_offdiag(const int2* __restrict__ pairs, const int* __r
     if (n > 0) out[0] = acc[0];
     if (n > 1) out[1] = acc[1];
 }
-SCHUR_FN void schur_chunk_diag(const int* __restrict__ poseEdges, const int* __restrict__ poseEdgePt, const double* __restrict__ PT, const double* __restrict__ E,
+__device__ __forceinline__ void schur_chunk_diag(const int* __restrict__ poseEdges, const int* __restrict__ poseEdgePt, const double* __restrict__ PT, const double* __restrict__ E,
                                                const double* pcache, double* out42, int4 h) {
     const int lane = threadIdx.x & 31;
     const int cnt = h.y;
@@ -576,24 +575,14 @@ SCHUR_FN void schur_chunk_diag(const int* __restrict__ poseEdges, const int* __r
     if (n > 0) out[0] = acc[0];
     if (n > 1) out[1] = acc[1];
 }
-#ifndef LBA_RSYNC
-#define LBA_RSYNC 0
-#endif
 __device__ void phase_schur_partial(const Dev& D, const Ctx& c, const double* __restrict__ E) {
-    // The warps of a CTA work on neighbouring chunks (same pose pair or the next one), whose gathers hit many of the same
-    // lines (the edges of pose A, nearby points).  Keeping the warps in step -- a CTA barrier at entry and per round --
-    // keeps those lines in L1 while they are hot: measured 3x on this phase against free-running warps.
-    const int stride = c.csize * NWARP;
-    const int rounds = (D.nChunks + stride - 1) / stride;
+    // CTA barrier at entry: the previous phase (combine of the pose sums) leaves the warps of a CTA out of step, and warps that
+    // enter this gather-bound phase out of step ran it 3x slower (measured); a barrier per round of chunks on top was slower again.
     __syncthreads();
-    for (int r = 0; r < rounds; ++r) {
-        const int ch = r * stride + c.crank * NWARP + (c.tid >> 5);
-        if (ch < D.nChunks) {
-            const int4 h = D.chunkHdr[ch];      // first item, items, pose A, pose B (-1: diagonal task)
-            if (h.w >= 0) schur_chunk_offdiag(D.pairs, D.pairPt, D.PT, E, c.pc, D.Spart + 42 * (size_t)ch, h);
-            else schur_chunk_diag(D.poseEdges, D.poseEdgePt, D.PT, E, c.pc, D.Spart + 42 * (size_t)ch, h);
-        }
-        if (LBA_RSYNC) __syncthreads();
+    for (int ch = c.crank * NWARP + (c.tid >> 5); ch < D.nChunks; ch += c.csize * NWARP) {
+        const int4 h = D.chunkHdr[ch];      // first item, items, pose A, pose B (-1: diagonal task)
+        if (h.w >= 0) schur_chunk_offdiag(D.pairs, D.pairPt, D.PT, E, c.pc, D.Spart + 42 * (size_t)ch, h);
+        else schur_chunk_diag(D.poseEdges, D.poseEdgePt, D.PT, E, c.pc, D.Spart + 42 * (size_t)ch, h);
     }
 }
 __device__ void phase_schur_combine(const Dev& D, const Ctx& c, double lambda, double* Hs, int ld) {
@@ -1442,11 +1431,6 @@ int lba_set_cluster_size(lba_handle* h, int ctas) {
     return ORB_OK;
 }
 /* ns spent by CTA 0 of problem `i` in each phase of the last downloaded run: errors, build_points, build_poses, point_prep, schur, ldlt, backsub, update, errors(trial) */
-int lba_get_stats64(const lba_handle* h, int i, double* out64) {
-    if (!h || !out64 || i < 0 || i >= h->s.nLoaded) return ORB_ERR_ARG;
-    memcpy(out64, h->s.h_arena + h->s.packed[i].statsOff, 512);
-    return ORB_OK;
-}
 int lba_get_phase_ns(const lba_handle* h, int i, double* ns10) {
     if (!h || !ns10 || i < 0 || i >= h->s.nLoaded) return ORB_ERR_ARG;
     const double* stt = (const double*)(h->s.h_arena + h->s.packed[i].statsOff);

@@ -116,8 +116,9 @@ def test_device_structure_build_any_edge_order_and_rejects_bad_graphs(opt):
         q[k] = np.ascontiguousarray(p[k][perm])
     _check(opt, q)
     dup = dict(p)
+    e = int(np.flatnonzero(np.asarray(p['fixed'])[p['edge_pose']] == 0)[0])      # an observation by a free keyframe, given twice
     for k in ('edge_point', 'edge_pose', 'obs', 'inv_sigma2'):
-        dup[k] = np.concatenate([p[k], p[k][:1]])
+        dup[k] = np.concatenate([p[k], p[k][e:e + 1]])
     with pytest.raises(m.OrbError):
         opt.LocalBundleAdjustment(dup)
     bad = dict(p)
