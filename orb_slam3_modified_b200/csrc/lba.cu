@@ -692,26 +692,40 @@ __device__ int phase_ldlt(const Dev& D, const Ctx& c, double* A, int ld, double*
                 if (lane == 0) ldlt_factor6(A, ld, r0, s_L, s_dinv, &s_fail);
             }
         } else {
-            for (int i = r0 + 6 + (warp - 1); i <= n; i += NWARP - 1) {
-                double* row = i < n ? A + (size_t)i * ld : brow;
-                double xi[6];
+            // two rows per warp and pass: the scaled panel entries L21[j][:] are loaded once for both
+            for (int ia = r0 + 6 + (warp - 1); ia <= n; ia += 2 * (NWARP - 1)) {
+                const int ib = ia + (NWARP - 1);
+                const bool hasB = ib <= n;
+                double* rowA = ia < n ? A + (size_t)ia * ld : brow;
+                double* rowB = !hasB ? rowA : (ib < n ? A + (size_t)ib * ld : brow);
+                double xa[6], xb[6];
 #pragma unroll
-                for (int cidx = 0; cidx < 6; ++cidx) xi[cidx] = Xs[cidx * n1 + i];
-                const int jend = i < n ? i : n - 1;
-                for (int j0 = r0 + lane; j0 <= jend; j0 += 128) {
-                    double sacc[4], old[4];
+                for (int cidx = 0; cidx < 6; ++cidx) { xa[cidx] = Xs[cidx * n1 + ia]; xb[cidx] = hasB ? Xs[cidx * n1 + ib] : 0.0; }
+                const int jendA = ia < n ? ia : n - 1;
+                const int jendB = hasB ? (ib < n ? ib : n - 1) : -1;
+                const int jmax = jendA > jendB ? jendA : jendB;
+                for (int j0 = r0 + lane; j0 <= jmax; j0 += 128) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int j = j0 + 32 * u;
-                        sacc[u] = 0; old[u] = 0;
-                        if (j <= jend) {
-                            old[u] = row[j];
+                        if (j <= jmax) {
+                            double l[6];
 #pragma unroll
-                            for (int cidx = 0; cidx < 6; ++cidx) sacc[u] += xi[cidx] * Ls[cidx * n1 + j];
+                            for (int cidx = 0; cidx < 6; ++cidx) l[cidx] = Ls[cidx * n1 + j];
+                            if (j <= jendA) {
+                                double sacc = 0;
+#pragma unroll
+                                for (int cidx = 0; cidx < 6; ++cidx) sacc += xa[cidx] * l[cidx];
+                                rowA[j] -= sacc;
+                            }
+                            if (j <= jendB) {
+                                double sacc = 0;
+#pragma unroll
+                                for (int cidx = 0; cidx < 6; ++cidx) sacc += xb[cidx] * l[cidx];
+                                rowB[j] -= sacc;
+                            }
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int j = j0 + 32 * u; if (j <= jend) row[j] = old[u] - sacc[u]; }
                 }
             }
         }
