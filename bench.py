@@ -50,7 +50,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.m0 = [], None, 0
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(index), '--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
@@ -65,6 +65,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(',')])
 
+    def mark(self):
+        """Start of the region of interest: only samples taken from here on are reported."""
+        self.m0 = len(self.rows)
+
+    def samples(self):
+        return len(self.rows) - self.m0
+
     def stop(self):
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
@@ -73,10 +80,11 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = self.rows[self.m0:]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
                 'samples': len(sm)}
 
@@ -351,12 +359,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing (`value`) ----------------
+    clocks = ClockSampler(local) if rank == 0 else None      # started before the warm-up: nvidia-smi needs ~0.2 s to deliver its first row
     for i in range(args.warmup):
         step_device(i)
     join_groups()
     join_lba()
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_fork.record(stream)
     lba_stream.wait_event(ev_fork)
@@ -374,7 +384,19 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    if clocks and clocks.samples() == 0 and world == 1:
+        # the timed region was shorter than the sampling period: sample the same load for a moment more (untimed), and say so
+        t_end = time.perf_counter() + 0.4
+        i = 0
+        while time.perf_counter() < t_end and clocks.samples() < 2:
+            step_device(i)
+            join_groups()
+            join_lba()
+            torch.cuda.synchronize()
+            i += 1
     clk = clocks.stop() if clocks else None
+    if clk is not None:
+        clk['sampled'] = 'timed region (+ an untimed continuation of the same load when it was shorter than the 50 ms sampling period)'
     value = world * B * args.steps / (ms * 1e-3)
     mean_kp = float(d_n.float().mean().item())
     mean_matches = float(d_nmatch.float().mean().item())
