@@ -184,6 +184,18 @@ def cpu_oracle_mix(frames0, frames1, poses1, lba_prob, n_frames, threads):
     return n_frames / dt, dt
 
 
+def cpu_info():
+    model = None
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                model = line.split(':', 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {'model': model, 'nproc': os.cpu_count()}
+
+
 def run_reference(args):
     """Reference arm: the CPU implementation of the path (oracle port; kind='port') on all host cores."""
     if int(os.environ.get('RANK', '0')) != 0:
@@ -207,7 +219,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * t_all / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'u8 (extract/match), f64 (LBA)', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'stages': STAGES},
-        'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample, 'host': cpu_info()},
         'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
@@ -571,7 +583,7 @@ def main():
             f0, f1 = host_sets[0].numpy()[:nsrc], host_sets[1].numpy()[:nsrc]
             n_cpu = 64 * KF_INTERVAL                 # ~15-20 s of single-thread CPU work
             fps1, dt1 = cpu_oracle_mix(f0, f1, [poses_h[1][s] for s in range(nsrc)], probs[0], n_cpu, 1)
-            out['cpu_baseline'] = {'value': fps1, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            out['cpu_baseline'] = {'value': fps1, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'host': cpu_info(),
                                    'sample': '%d frames extract+SearchByProjection + %d LBA, oracle, 1 thread (%.1f s)' % (n_cpu, n_cpu // KF_INTERVAL, dt1)}
         print(json.dumps(out))
     if world > 1:
