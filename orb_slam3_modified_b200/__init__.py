@@ -89,7 +89,11 @@ class ORBextractor:
             lib().orbx_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     # --- getters (include/ORBextractor.h:60-82) ---
     def GetLevels(self):
@@ -297,7 +301,11 @@ class ORBmatcher:
             lib().orbm_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     def DescriptorDistance(self, a, b):
         """ORBmatcher::DescriptorDistance for one pair or for n pairs ([n,32] arrays)."""
@@ -455,7 +463,11 @@ class Optimizer:
             lib().lba_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     @staticmethod
     def _pack(prob, iterations, user_lambda_init, stop_flag):
