@@ -1,8 +1,13 @@
 // TEST INFRASTRUCTURE ONLY (see oracle_common.h).  CPU restatement of
 // ORBextractor (reference src/ORBextractor.cc, include/ORBextractor.h) plus the
-// five OpenCV primitives it calls (pinned against cv2 4.13
-// by tests/test_oracle_primitives.py).  Every function cites the reference
-// lines it follows.  Build: see oracle/Makefile (-O2 -ffp-contract=off; the one
+// five OpenCV primitives it calls.  Every function cites the
+// reference lines it follows.  Pinned by (tests/): the primitives bit for bit
+// against cv2 4.13 (test_oracle_cpu.py + golden fixtures); the pyramid chain and the
+// per-cell FAST loop against a cv2 transcription (test_cells_vs_cv2_cpu.py); IC_Angle
+// against the definition + cv2.fastAtan2 (test_orientation_cpu.py); the steered BRIEF
+// against numpy and cv2.ORB (test_brief_vs_cv2_cpu.py).  PARITY UNPINNED by the
+// reference (it ships no vectors and cannot be built here): DistributeOctTree order and
+// the output assembly.  Build: see oracle/Makefile (-O3 -ffp-contract=off; the one
 // place where the reference's -march=native build fuses a multiply-add, the
 // BRIEF sample rotation, is written with an explicit fmaf()).
 #include "oracle_common.h"

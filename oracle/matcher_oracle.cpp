@@ -8,6 +8,8 @@
 //   Pinhole::project(Vector3f)                           src/CameraModels/Pinhole.cpp:43-49
 //   Sophus SO3f * point, SE3f * point                    Thirdparty/Sophus/sophus/so3.hpp:358-367, se3.hpp:321-324
 //   cv::BFMatcher(NORM_HAMMING).knnMatch(k=2)            use at src/Frame.cc:1144 (pinned vs cv2 in tests)
+//   Frame::isInFrustum + MapPoint::PredictScale          src/Frame.cc:512-574, src/MapPoint.cc:531-546
+// PARITY UNPINNED by the reference (no vectors, not buildable here) for everything but the brute-force matcher.
 //
 // Floating point contract: every float operation below rounds individually, in the written order
 // (-ffp-contract=off).  The reference evaluates the pose transform through Eigen expression templates
