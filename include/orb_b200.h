@@ -264,7 +264,9 @@ int lba_create(lba_handle** out, int max_poses, int max_points, int max_edges, i
 /* Same, sized for up to max_batch independent problems solved by one kernel launch (one per stream / local map). */
 int lba_create_batch(lba_handle** out, int max_poses, int max_points, int max_edges, int max_batch, int device);
 void lba_destroy(lba_handle* h);
-/* Host pointers in and out; returns ORB_OK, or ORB_ERR_ARG for malformed graphs (index out of range, no free vertex). */
+/* Host pointers in and out; edges may come in any order (per-edge results come back in the caller's order); the index structures of
+ * BlockSolver::buildStructure are derived on the device.  Returns ORB_OK, or ORB_ERR_ARG for malformed graphs (index out of range,
+ * the same point observed twice by one free keyframe, no free vertex), ORB_ERR_CAPACITY for a problem larger than the handle. */
 int lba_solve(lba_handle* h, const LbaProblem* problem, LbaResult* result);
 int lba_solve_batch(lba_handle* h, int count, const LbaProblem* problems, LbaResult* results);
 /* Split form of lba_solve_batch: upload the flattened graphs once (host pointers), run the whole LM loop for all of
