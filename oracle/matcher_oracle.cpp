@@ -18,6 +18,7 @@
 #include "oracle_common.h"
 
 #include <algorithm>
+#include <cstdint>
 #include <cstring>
 #include <vector>
 
@@ -243,6 +244,75 @@ int orbo_features_in_area(int K, const KeyPoint* kps, const float* bounds, float
     F.features_in_area(x, y, r, minLevel, maxLevel, v);
     for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = v[i];
     return (int)v.size();
+}
+
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:648-763): windowed search between the two frames of the monocular
+// initialiser (only level-0 keypoints of F1; candidates of F2 at level 0 inside windowSize around vbPrevMatched[i1]; best / second
+// best among candidates whose current match is not at least as good (vMatchedDistance), TH_LOW, ratio test, re-assignment of an
+// already matched F2 keypoint, rotation histogram on F1 indices).  prevMatched (K1 x 2) is updated like vbPrevMatched (:757-759).
+// Oracle only so far: the sm_100a kernel for this init-time function is the first item of the next round.
+int orbo_search_for_initialization(int K1, const KeyPoint* kps1, const uint8_t* desc1, int K2, const KeyPoint* kps2, const uint8_t* desc2,
+                                   const float* bounds, const float* scaleFactors, float* prevMatched, int windowSize, float nnratio,
+                                   int checkOrientation, int* matches12) {
+    static const int TH_LOW = 50;   // src/ORBmatcher.cc:36
+    FrameView F2;
+    F2.K = K2; F2.kps = kps2; F2.desc = desc2;
+    F2.minX = bounds[0]; F2.minY = bounds[1]; F2.maxX = bounds[2]; F2.maxY = bounds[3];
+    F2.gridWInv = (float)GRID_COLS / (F2.maxX - F2.minX);
+    F2.gridHInv = (float)GRID_ROWS / (F2.maxY - F2.minY);
+    F2.scaleFactors = scaleFactors;
+    F2.build_grid();
+    int nmatches = 0;
+    for (int i = 0; i < K1; ++i) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vMatchedDistance(K2, INT32_MAX), vnMatches21(K2, -1), vIndices2;
+    for (int i1 = 0; i1 < K1; ++i1) {
+        const int level1 = kps1[i1].octave;
+        if (level1 > 0) continue;
+        F2.features_in_area(prevMatched[2 * i1], prevMatched[2 * i1 + 1], (float)windowSize, level1, level1, vIndices2);
+        if (vIndices2.empty()) continue;
+        int bestDist = INT32_MAX, bestDist2 = INT32_MAX, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            const int dist = descriptor_distance(desc1 + (size_t)i1 * 32, desc2 + (size_t)i2 * 32);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW && bestDist < (float)bestDist2 * nnratio) {
+            if (vnMatches21[bestIdx2] >= 0) { matches12[vnMatches21[bestIdx2]] = -1; --nmatches; }
+            matches12[i1] = bestIdx2;
+            vnMatches21[bestIdx2] = i1;
+            vMatchedDistance[bestIdx2] = bestDist;
+            ++nmatches;
+            if (checkOrientation) {
+                float rot = kps1[i1].angle - kps2[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(i1);
+            }
+        }
+    }
+    if (checkOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;   // ComputeThreeMaxima
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            const int sz = (int)rotHist[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i])
+                if (matches12[idx1] >= 0) { matches12[idx1] = -1; --nmatches; }
+        }
+    }
+    for (int i1 = 0; i1 < K1; ++i1)
+        if (matches12[i1] >= 0) { prevMatched[2 * i1] = kps2[matches12[i1]].x; prevMatched[2 * i1 + 1] = kps2[matches12[i1]].y; }
+    return nmatches;
 }
 
 // Frame::isInFrustum, monocular branch (src/Frame.cc:512-574), + MapPoint::PredictScale(const float&, Frame*) (src/MapPoint.cc:531-546)

@@ -150,6 +150,19 @@ def search_local_map(kps, desc, bounds, scale_factors, pts, th, nnratio, b_far, 
                                    th, nnratio, int(b_far), th_far, _p(match), _p(claimed))
 
 
+def search_for_initialization(kps1, desc1, kps2, desc2, bounds, scale_factors, prev_matched, window=100, nnratio=0.9, check_ori=True):
+    kps1 = _c(kps1, KP_DTYPE); kps2 = _c(kps2, KP_DTYPE); d1 = _c(desc1, np.uint8); d2 = _c(desc2, np.uint8)
+    b = _c(bounds, np.float32); sf = _c(scale_factors, np.float32)
+    pm = _c(prev_matched, np.float32).copy()
+    m12 = np.full(len(kps1), -1, np.int32)
+    L = lib()
+    L.orbo_search_for_initialization.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = L.orbo_search_for_initialization(len(kps1), _p(kps1), _p(d1), len(kps2), _p(kps2), _p(d2), _p(b), _p(sf), _p(pm), int(window), nnratio,
+                                         int(check_ori), _p(m12))
+    return n, m12, pm
+
+
 def is_in_frustum(pts, Rcw, tcw, Ow, cam, bounds, log_scale_factor, n_levels, viewing_cos_limit=0.5, mbf=0.0):
     a = {k: _c(pts[k], np.float32) for k in ('worldPos', 'normal', 'minDistInv', 'maxDistInv', 'maxDistance')}
     M = len(a['minDistInv'])
