@@ -491,86 +491,92 @@ def main():
     # copies overlap the other's kernels), and the local maps' bundle adjustments by G mapping threads (the LocalMapping
     # thread of the reference, src/System.cc:197).  A step is complete when every group has its host results.
     e2e, e2e_steps, h2d, d2h = None, 0, 0, 0
+    e2e_err = None
     if not args.no_e2e:
-        from concurrent.futures import ThreadPoolExecutor
-        G = max(1, min(args.e2e_groups, B, NLBA))
-        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
-        kps_h = pin((B, cap, 7), torch.float32).view(np.uint8).reshape(B, cap, 28).view(orb.KP_DTYPE).reshape(B, cap)
-        desc_h = pin((B, cap, 32), torch.uint8)
-        nK_h, mono_h, nmatch_h = pin((B,), torch.int32), pin((B,), torch.int32), pin((B,), torch.int32)
-        match_h, claimed_h = pin((B, cap), torch.int32), pin((B, cap), torch.uint8)
-        bounds = [(g * B // G, (g + 1) * B // G) for g in range(G)]
-        lbounds = [(g * NLBA // G, (g + 1) * NLBA // G) for g in range(G)]
-        if G == 1:
-            exs, mts, opts = [ex], [matcher], [opt]
-        else:
-            exs = [orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, W, H, b1 - b0, local) for b0, b1 in bounds]
-            mts = [orb.ORBmatcher(0.9, True, max_batch=b1 - b0, max_keypoints=cap, max_mappoints=cap, device=local) for b0, b1 in bounds]
-            opts = [orb.Optimizer(max_poses=LBA_CFG['n_kf'], max_points=LBA_CFG['n_pts'], max_edges=LBA_CFG['n_pts'] * LBA_CFG['obs_per_pt'],
-                                  max_batch=l1 - l0, device=local) for l0, l1 in lbounds]
-        pool = ThreadPoolExecutor(2 * G)
+        try:
+            from concurrent.futures import ThreadPoolExecutor
+            G = max(1, min(args.e2e_groups, B, NLBA))
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+            kps_h = pin((B, cap, 7), torch.float32).view(np.uint8).reshape(B, cap, 28).view(orb.KP_DTYPE).reshape(B, cap)
+            desc_h = pin((B, cap, 32), torch.uint8)
+            nK_h, mono_h, nmatch_h = pin((B,), torch.int32), pin((B,), torch.int32), pin((B,), torch.int32)
+            match_h, claimed_h = pin((B, cap), torch.int32), pin((B, cap), torch.uint8)
+            bounds = [(g * B // G, (g + 1) * B // G) for g in range(G)]
+            lbounds = [(g * NLBA // G, (g + 1) * NLBA // G) for g in range(G)]
+            if G == 1:
+                exs, mts, opts = [ex], [matcher], [opt]
+            else:
+                exs = [orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, W, H, b1 - b0, local) for b0, b1 in bounds]
+                mts = [orb.ORBmatcher(0.9, True, max_batch=b1 - b0, max_keypoints=cap, max_mappoints=cap, device=local) for b0, b1 in bounds]
+                opts = [orb.Optimizer(max_poses=LBA_CFG['n_kf'], max_points=LBA_CFG['n_pts'], max_edges=LBA_CFG['n_pts'] * LBA_CFG['obs_per_pt'],
+                                      max_batch=l1 - l0, device=local) for l0, l1 in lbounds]
+            pool = ThreadPoolExecutor(2 * G)
 
-        trace = [] if os.environ.get('BENCH_E2E_TRACE') else None
+            trace = [] if os.environ.get('BENCH_E2E_TRACE') else None
 
-        def frames_job(g, i):
-            cur, lst = i & 1, (i + 1) & 1
-            b0, b1 = bounds[g]
-            tq = time.perf_counter()
-            exs[g].extract_batch_slabs(host_sets[cur].numpy()[b0:b1], kps_h[b0:b1], desc_h[b0:b1], nK_h[b0:b1], mono_h[b0:b1], (0, 1000))
-            L = last_h[lst]
-            d = dict(batch=b1 - b0, kcap=cap, mcap=cap, nlevels=8, kps=kps_h[b0:b1], desc=desc_h[b0:b1], nK=nK_h[b0:b1], scaleFactors=sf,
-                     nM=L['nM'][b0:b1], valid=L['valid'][b0:b1], xyz=L['xyz'][b0:b1], octave=L['octave'][b0:b1], angle=L['angle'][b0:b1],
-                     hasObs=L['hasObs'][b0:b1], mpDesc=L['mpDesc'][b0:b1], Tcw7=poses_h[cur][b0:b1], bounds=(0.0, 0.0, float(W), float(H)), cam=cam, reset=1)
-            tm = time.perf_counter()
-            mts[g].search_last_frame_batch(d, TH_PROJ, match_h[b0:b1], claimed_h[b0:b1], nmatch_h[b0:b1])
-            if trace is not None:
-                trace.append(('frames', g, i, tq, tm, time.perf_counter()))
-            return int(nK_h[b0:b1].sum())
+            def frames_job(g, i):
+                cur, lst = i & 1, (i + 1) & 1
+                b0, b1 = bounds[g]
+                tq = time.perf_counter()
+                exs[g].extract_batch_slabs(host_sets[cur].numpy()[b0:b1], kps_h[b0:b1], desc_h[b0:b1], nK_h[b0:b1], mono_h[b0:b1], (0, 1000))
+                L = last_h[lst]
+                d = dict(batch=b1 - b0, kcap=cap, mcap=cap, nlevels=8, kps=kps_h[b0:b1], desc=desc_h[b0:b1], nK=nK_h[b0:b1], scaleFactors=sf,
+                         nM=L['nM'][b0:b1], valid=L['valid'][b0:b1], xyz=L['xyz'][b0:b1], octave=L['octave'][b0:b1], angle=L['angle'][b0:b1],
+                         hasObs=L['hasObs'][b0:b1], mpDesc=L['mpDesc'][b0:b1], Tcw7=poses_h[cur][b0:b1], bounds=(0.0, 0.0, float(W), float(H)), cam=cam, reset=1)
+                tm = time.perf_counter()
+                mts[g].search_last_frame_batch(d, TH_PROJ, match_h[b0:b1], claimed_h[b0:b1], nmatch_h[b0:b1])
+                if trace is not None:
+                    trace.append(('frames', g, i, tq, tm, time.perf_counter()))
+                return int(nK_h[b0:b1].sum())
 
-        def lba_job(g):
-            l0, l1 = lbounds[g]
-            tq = time.perf_counter()
-            r = opts[g].LocalBundleAdjustmentBatch(probs[l0:l1])        # host graphs in, optimised state out
-            if trace is not None:
-                trace.append(('lba', g, -1, tq, tq, time.perf_counter()))
-            return r
+            def lba_job(g):
+                l0, l1 = lbounds[g]
+                tq = time.perf_counter()
+                r = opts[g].LocalBundleAdjustmentBatch(probs[l0:l1])        # host graphs in, optimised state out
+                if trace is not None:
+                    trace.append(('lba', g, -1, tq, tq, time.perf_counter()))
+                return r
 
-        pending = []          # bundle adjustments of the previous step: LocalMapping runs beside Tracking, one step behind
+            pending = []          # bundle adjustments of the previous step: LocalMapping runs beside Tracking, one step behind
 
-        def step_host(i):
-            nonlocal pending
-            lba = [pool.submit(lba_job, g) for g in range(G)]
-            fr = [pool.submit(frames_job, g, i) for g in range(G)]
-            nk = sum(j.result() for j in fr)
+            def step_host(i):
+                nonlocal pending
+                lba = [pool.submit(lba_job, g) for g in range(G)]
+                fr = [pool.submit(frames_job, g, i) for g in range(G)]
+                nk = sum(j.result() for j in fr)
+                outs = [j.result() for j in pending]
+                pending = lba
+                return nk, outs
+
+            step_host(0)
+            step_host(1)
+            barrier()
+            e2e_steps = max(2, min(args.steps, 8))
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                nk, outs = step_host(i)
+            torch.cuda.synchronize()
+            # every step of the timed region submitted one batch of bundle adjustments and collected one (the one submitted a
+            # step earlier); the batches still in flight are collected outside the timed region
+            dt = time.perf_counter() - t0
             outs = [j.result() for j in pending]
-            pending = lba
-            return nk, outs
-
-        step_host(0)
-        step_host(1)
-        barrier()
-        e2e_steps = max(2, min(args.steps, 8))
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            nk, outs = step_host(i)
-        torch.cuda.synchronize()
-        # every step of the timed region submitted one batch of bundle adjustments and collected one (the one submitted a
-        # step earlier); the batches still in flight are collected outside the timed region
-        dt = time.perf_counter() - t0
-        outs = [j.result() for j in pending]
-        if trace is not None and rank == 0:
-            for kind, g, i, a, m, b in sorted(trace, key=lambda r: r[3])[-6 * G:]:
-                print('# %-6s g%d step %2d start %8.2f ms  first call %6.2f  total %6.2f' % (kind, g, i, (a - t0) * 1e3, (m - a) * 1e3, (b - a) * 1e3), file=sys.stderr)
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = world * B * e2e_steps / float(t.item())
-        p0 = probs[0]
-        lba_h2d = NLBA * (p0['poses'].nbytes + p0['points'].nbytes + p0['obs'].nbytes + 3 * 4 * len(p0['edge_point']) + p0['cam'].nbytes)
-        lba_d2h = NLBA * (p0['poses'].nbytes + p0['points'].nbytes + 9 * len(p0['edge_point']))
-        h2d = B * W * H + B * cap * (28 + 32 + 5) + sum(v.nbytes for v in last_h[0].values()) + lba_h2d
-        d2h = nk * 60 + 12 * B + B * cap * 5 + lba_d2h
-        pool.shutdown()
+            if trace is not None and rank == 0:
+                for kind, g, i, a, m, b in sorted(trace, key=lambda r: r[3])[-6 * G:]:
+                    print('# %-6s g%d step %2d start %8.2f ms  first call %6.2f  total %6.2f' % (kind, g, i, (a - t0) * 1e3, (m - a) * 1e3, (b - a) * 1e3), file=sys.stderr)
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e = world * B * e2e_steps / float(t.item())
+            p0 = probs[0]
+            lba_h2d = NLBA * (p0['poses'].nbytes + p0['points'].nbytes + p0['obs'].nbytes + 3 * 4 * len(p0['edge_point']) + p0['cam'].nbytes)
+            lba_d2h = NLBA * (p0['poses'].nbytes + p0['points'].nbytes + 9 * len(p0['edge_point']))
+            h2d = B * W * H + B * cap * (28 + 32 + 5) + sum(v.nbytes for v in last_h[0].values()) + lba_h2d
+            d2h = nk * 60 + 12 * B + B * cap * 5 + lba_d2h
+            pool.shutdown()
+        except Exception as exc:     # the device-resident result is still reported (single GPU); with several ranks a failure must stay fatal
+            if world > 1:
+                raise
+            e2e, e2e_err = None, repr(exc)[:300]
 
     if rank == 0:
         peak, how = _peaks()
@@ -618,6 +624,8 @@ def main():
                          'per_kernel': per_kernel,
                          'whole_step_frac': (ALG_BYTES_EXTRACT + ALG_BYTES_MATCH + ALG_BYTES_LBA_PER_TRIAL * mean_trials / KF_INTERVAL) * (value / world) / 1e9 / peak},
         }
+        if e2e_err:
+            out['e2e'], out['e2e_error'] = None, e2e_err
         if e2e is not None:
             out['e2e'] = {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps,
                           'stream_groups': max(1, min(args.e2e_groups, B, NLBA))}
@@ -625,9 +633,13 @@ def main():
             nsrc = 8
             f0, f1 = host_sets[0].numpy()[:nsrc], host_sets[1].numpy()[:nsrc]
             n_cpu = 64 * KF_INTERVAL                 # ~15-20 s of single-thread CPU work
-            fps1, dt1 = cpu_oracle_mix(f0, f1, [poses_h[1][s] for s in range(nsrc)], probs[0], n_cpu, 1)
-            out['cpu_baseline'] = {'value': fps1, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'host': cpu_info(),
-                                   'sample': '%d frames extract+SearchByProjection + %d LBA, oracle, 1 thread (%.1f s)' % (n_cpu, n_cpu // KF_INTERVAL, dt1)}
+            try:
+                fps1, dt1 = cpu_oracle_mix(f0, f1, [poses_h[1][s] for s in range(nsrc)], probs[0], n_cpu, 1)
+                out['cpu_baseline'] = {'value': fps1, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'host': cpu_info(),
+                                       'sample': '%d frames extract+SearchByProjection + %d LBA, oracle, 1 thread (%.1f s)' % (n_cpu, n_cpu // KF_INTERVAL, dt1)}
+            except Exception as exc:
+                out['cpu_baseline'] = None
+                out['cpu_baseline_error'] = repr(exc)[:300]
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
