@@ -1336,7 +1336,13 @@ struct Solver {
             for (int t = 1; t < nth; ++t) pool.emplace_back(worker);
             worker();
             for (auto& t : pool) t.join();
-            if (firstErr.load()) { cudaStreamSynchronize(st); return firstErr.load(); }
+            if (firstErr.load()) {
+                cudaStreamSynchronize(st);
+                // the workers' own messages live in their thread-local error strings: restate it for the calling thread
+                set_error(firstErr.load() == ORB_ERR_CUDA ? "lba: host-to-device copy failed"
+                                                          : "lba: a problem is larger than the handle, has null arrays or no vertex to optimize");
+                return firstErr.load();
+            }
         }
         CK(cudaSetDevice(device));
         CK(cudaMemcpyAsync(d_probs, h_probs.data(), sizeof(Dev) * count, cudaMemcpyHostToDevice, st));
