@@ -1466,11 +1466,17 @@ int lba_solve_batch(lba_handle* h, int count, const LbaProblem* problems, LbaRes
     for (int i = 0; i < count; ++i) S.h_stop[i] = (problems[i].stopFlag && *problems[i].stopFlag) ? 1 : 0;
     rc = S.run(S.st);
     if (rc) return rc;
-    CK(cudaEventRecord(S.evDone, S.st));
-    // forward the callers' stop flags (SparseOptimizer::terminate() polls *pbStopFlag) while the kernel runs
-    while (cudaEventQuery(S.evDone) == cudaErrorNotReady)
-        for (int i = 0; i < count; ++i)
-            if (problems[i].stopFlag && *problems[i].stopFlag) S.h_stop[i] = 1;
+    bool anyFlag = false;
+    for (int i = 0; i < count; ++i) anyFlag = anyFlag || problems[i].stopFlag;
+    if (anyFlag) {
+        CK(cudaEventRecord(S.evDone, S.st));
+        // forward the callers' stop flags (SparseOptimizer::terminate() polls *pbStopFlag) while the kernel runs
+        while (cudaEventQuery(S.evDone) == cudaErrorNotReady) {
+            for (int i = 0; i < count; ++i)
+                if (problems[i].stopFlag && *problems[i].stopFlag) S.h_stop[i] = 1;
+            std::this_thread::yield();
+        }
+    }
     CK(cudaGetLastError());
     return S.download(count, results, S.st);
 }
