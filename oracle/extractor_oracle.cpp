@@ -5,9 +5,9 @@
 // against cv2 4.13 (test_oracle_cpu.py + golden fixtures); the pyramid chain and the
 // per-cell FAST loop against a cv2 transcription (test_cells_vs_cv2_cpu.py); IC_Angle
 // against the definition + cv2.fastAtan2 (test_orientation_cpu.py); the steered BRIEF
-// against numpy and cv2.ORB (test_brief_vs_cv2_cpu.py).  PARITY UNPINNED by the
-// reference (it ships no vectors and cannot be built here): DistributeOctTree order and
-// the output assembly.  Build: see oracle/Makefile (-O3 -ffp-contract=off; the one
+// against numpy and cv2.ORB (test_brief_vs_cv2_cpu.py); DistributeOctTree against a second
+// transcription with the real std::sort (test_quadtree_transcription_cpu.py).  PARITY
+// UNPINNED by the reference (it ships no vectors and cannot be built here).  Build: see oracle/Makefile (-O3 -ffp-contract=off; the one
 // place where the reference's -march=native build fuses a multiply-add, the
 // BRIEF sample rotation, is written with an explicit fmaf()).
 #include "oracle_common.h"

@@ -42,6 +42,19 @@ void hc_fast_atan2_n(const float* y, const float* x, float* out, int n) {
 }
 
 struct SK { int size; int ulx; int id; };
+// the permutation REAL libstdc++ std::sort produces for (size, UL.x) keys under the reference's compareNodes
+// (src/ORBextractor.cc:538-553: size ascending, then UL.x ascending, everything else a tie)
+void hc_std_sort_order(const int* size, const int* ulx, int n, int* order_out) {
+    std::vector<SK> b(n);
+    for (int i = 0; i < n; ++i) b[i] = {size[i], ulx[i], i};
+    std::sort(b.begin(), b.end(), [](const SK& e1, const SK& e2) {
+        if (e1.size < e2.size) return true;
+        else if (e1.size > e2.size) return false;
+        else return e1.ulx < e2.ulx;
+    });
+    for (int i = 0; i < n; ++i) order_out[i] = b[i].id;
+}
+
 // sorts keys with the emulation and with std::sort using the reference's comparator shape; returns 0 if equal
 int hc_sort_check(const int* size, const int* ulx, int n, int* order_out) {
     std::vector<SK> a(n), b(n);
