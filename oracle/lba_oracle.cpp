@@ -14,7 +14,8 @@
 // Summation order over edges is free (the reference's own order depends on pointer values, SURVEY.md 8a'); control
 // flow (accept/reject, lambda schedule, stop rules, stale errors after a rejected last trial) is reproduced exactly.
 // PARITY UNPINNED by the reference (no vectors, not buildable here); one LM step is checked against an independent dense solve
-// with numerical Jacobians (tests/test_lba_dense_cpu.py).
+// with numerical Jacobians (tests/test_lba_dense_cpu.py) and the whole LM loop against a second transcription
+// (tests/test_lba_lm_transcription_cpu.py).
 #include "oracle_common.h"
 
 #include <cfloat>
