@@ -478,7 +478,7 @@ int orbo_pose_optimization(double* pose7, const float* cam4, int N, const double
         nBad = 0;
         for (int e = 0; e < N; ++e) {
             if (outlier[e]) compute_error(e);
-            if (chi2(e) > 5.991) { outlier[e] = 1; level[e] = 1; ++nBad; }
+            if ((float)chi2(e) > 5.991f) { outlier[e] = 1; level[e] = 1; ++nBad; }     // const float chi2 = e->chi2(); chi2 > chi2Mono[it] (:1025-1027)
             else { outlier[e] = 0; level[e] = 0; }
             if (round == 2) robust[e] = 0;
         }

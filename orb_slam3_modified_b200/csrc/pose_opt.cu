@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(NT) pose_opt_kernel(Params P) {
         for (int e = tid; e < N; e += NT) {
             if (outlier[e]) compute_error(e);
             const double c2 = (double)is2[e] * (err[2 * e] * err[2 * e] + err[2 * e + 1] * err[2 * e + 1]);
-            if (c2 > 5.991) { outlier[e] = 1; ++bad; } else outlier[e] = 0;
+            if ((float)c2 > 5.991f) { outlier[e] = 1; ++bad; } else outlier[e] = 0;     // const float chi2 = e->chi2(); chi2 > chi2Mono[it] (float, :1025-1027)
         }
         nBad = (int)block_sum((double)bad, s_red);
         if (round == 2) robust = false;                                   // e->setRobustKernel(0) (:1040-1041)
