@@ -57,3 +57,41 @@ def test_oracle_is_in_frustum_fields():
     dist = np.linalg.norm(P - sc['Ow'].astype(np.float64), axis=1)
     lvl = np.clip(np.ceil(np.log(sc['pts']['maxDistance'] / dist) / np.log(1.2)), 0, 7)
     assert (out['level'][iv] == lvl[iv]).mean() > 0.999      # float vs double log: equal except on exact level boundaries
+
+
+def test_oracle_is_in_frustum_equals_float32_numpy_restatement():
+    """Frame::isInFrustum + PredictScale once more, vectorised in numpy float32 (every operation rounds to float like the C++ float
+    expressions; logf from the host libm): all seven output fields equal the oracle's bit for bit."""
+    f32 = np.float32
+    libm = C.CDLL('libm.so.6'); libm.logf.restype = C.c_float; libm.logf.argtypes = [C.c_float]
+    for seed in (4, 8):
+        sc = frustum_scenes.scene(5000, seed=seed)
+        out = O.is_in_frustum(**sc)
+        P, Nn = sc['pts']['worldPos'], sc['pts']['normal']
+        R, t, Ow = sc['Rcw'].astype(f32), sc['tcw'].astype(f32), sc['Ow'].astype(f32)
+        fx, fy, cx, cy = (f32(v) for v in sc['cam'])
+        X, Y, Z = P[:, 0], P[:, 1], P[:, 2]
+        xc = ((R[0, 0] * X + R[0, 1] * Y) + R[0, 2] * Z) + t[0]
+        yc = ((R[1, 0] * X + R[1, 1] * Y) + R[1, 2] * Z) + t[1]
+        zc = ((R[2, 0] * X + R[2, 1] * Y) + R[2, 2] * Z) + t[2]
+        pc = np.sqrt((xc * xc + yc * yc) + zc * zc)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            invz = f32(1) / zc
+            u, v = fx * xc / zc + cx, fy * yc / zc + cy
+        a = ~(zc < 0)
+        b = a & ~((u < f32(0)) | (u > f32(640))) & ~((v < f32(0)) | (v > f32(480)))
+        ox, oy, oz = X - Ow[0], Y - Ow[1], Z - Ow[2]
+        dist = np.sqrt((ox * ox + oy * oy) + oz * oz)
+        c = b & ~((dist < sc['pts']['minDistInv']) | (dist > sc['pts']['maxDistInv']))
+        with np.errstate(divide='ignore', invalid='ignore'):
+            vc = ((ox * Nn[:, 0] + oy * Nn[:, 1]) + oz * Nn[:, 2]) / dist
+            ratio = sc['pts']['maxDistance'] / dist
+        d = c & ~(vc < f32(0.5))
+        lvl = np.full(len(P), -1, np.int32)
+        for i in np.flatnonzero(d):
+            n = int(np.ceil(f32(libm.logf(float(ratio[i]))) / f32(sc['log_scale_factor'])))
+            lvl[i] = min(max(n, 0), 7)
+        assert np.array_equal(out['inView'], d.astype(np.uint8))
+        assert np.array_equal(out['projX'], np.where(b, u, f32(-1))) and np.array_equal(out['projY'], np.where(b, v, f32(-1)))
+        assert np.array_equal(out['projXR'], np.where(d, u - f32(sc['mbf']) * invz, f32(0))) and np.array_equal(out['depth'], np.where(d, pc, f32(0)))
+        assert np.array_equal(out['viewCos'], np.where(d, vc, f32(0))) and np.array_equal(out['level'], lvl)
