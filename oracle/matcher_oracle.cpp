@@ -319,6 +319,8 @@ int orbo_search_for_initialization(int K1, const KeyPoint* kps1, const uint8_t* 
 // for M map points.  Eigen's 3-vector products are written out in one fixed order with every operation rounded individually
 // (the reference's -O3 -march=native build may contract them differently: unpinned at the last ulp, like the last-frame
 // transform above); `log(ratio)` is std::log(float) = glibc logf; Pinhole::project(Vector3f) is src/CameraModels/Pinhole.cpp:35-41.
+// `uv(0) - mbf*invz` (:565) is one fused multiply-add in the reference's -O3 -march=native build (found by comparing with
+// oracle/_ref, which compiles the reference's own text with contraction on): written as fmaf here.
 // Outputs as documented in include/orb_b200.h (orbm_frustum_project).
 void orbo_is_in_frustum(int M, const float* P, const float* N, const float* minDistInv, const float* maxDistInv, const float* maxDistance,
                         const float* Rcw, const float* tcw, const float* Ow, const float* cam, const float* bounds, float mbf,
@@ -346,7 +348,7 @@ void orbo_is_in_frustum(int M, const float* P, const float* N, const float* minD
         int nScale = (int)std::ceil(std::log(ratio) / logScaleFactor);                      // :539 (float overloads)
         if (nScale < 0) nScale = 0;
         else if (nScale >= nScaleLevels) nScale = nScaleLevels - 1;
-        inView[i] = 1; projXR[i] = u - mbf * invz; depth[i] = pcDist; level[i] = nScale; viewCos[i] = c;   // :563-571
+        inView[i] = 1; projXR[i] = fmaf(-mbf, invz, u); depth[i] = pcDist; level[i] = nScale; viewCos[i] = c;   // :563-571
     }
 }
 

@@ -1,0 +1,37 @@
+"""TEST INFRASTRUCTURE.  Build-time helper of oracle/Makefile: writes the listed LINE RANGES of the reference's sources
+(read where they lie under <ref>) into <out>/*.inc so that ref_wrap_matcher.cpp can #include them verbatim.  <out> is
+oracle/_ref/gen/ -- git-ignored; no reference text is ever committed.  Each range is guarded by an anchor that must
+appear on its first line, so a drifted checkout fails the build instead of compiling something else."""
+import os
+import sys
+
+RANGES = [
+    # out name, file, first, last (1-based, inclusive), anchor on first line
+    ('matcher_consts.inc', 'src/ORBmatcher.cc', 35, 41, 'const int ORBmatcher::TH_HIGH'),
+    ('matcher_local_map.inc', 'src/ORBmatcher.cc', 43, 221, 'int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>'),
+    ('matcher_init.inc', 'src/ORBmatcher.cc', 648, 763, 'int ORBmatcher::SearchForInitialization'),
+    ('matcher_last_frame.inc', 'src/ORBmatcher.cc', 1676, 1887, 'int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame'),
+    ('matcher_maxima_distance.inc', 'src/ORBmatcher.cc', 2012, 2074, 'void ORBmatcher::ComputeThreeMaxima'),
+    ('frame_assign_grid.inc', 'src/Frame.cc', 385, 416, 'void Frame::AssignFeaturesToGrid()'),
+    ('frame_in_frustum_mono.inc', 'src/Frame.cc', 512, 574, 'bool Frame::isInFrustum(MapPoint *pMP, float viewingCosLimit)'),
+    ('frame_features_in_area.inc', 'src/Frame.cc', 657, 735, 'vector<size_t> Frame::GetFeaturesInArea'),
+    ('mappoint_invariance.inc', 'src/MapPoint.cc', 502, 512, 'float MapPoint::GetMinDistanceInvariance()'),
+    ('mappoint_predict_scale.inc', 'src/MapPoint.cc', 531, 546, 'int MapPoint::PredictScale(const float &currentDist, Frame* pF)'),
+    ('pinhole_project.inc', 'src/CameraModels/Pinhole.cpp', 43, 49, 'Eigen::Vector2f Pinhole::project(const Eigen::Vector3f &v3D)'),
+]
+
+
+def main(ref, out):
+    os.makedirs(out, exist_ok=True)
+    for name, rel, a, b, anchor in RANGES:
+        lines = open(os.path.join(ref, rel), encoding='utf-8', errors='replace').read().split('\n')
+        if anchor not in lines[a - 1]:
+            sys.exit('extract_ranges: %s:%d does not start with %r (reference drifted?)' % (rel, a, anchor))
+        with open(os.path.join(out, name), 'w') as f:
+            f.write('// generated from %s:%d-%d of the reference at build time -- do not commit\n' % (rel, a, b))
+            f.write('#line %d "%s"\n' % (a, os.path.join(ref, rel)))
+            f.write('\n'.join(lines[a - 1:b]) + '\n')
+
+
+if __name__ == '__main__':
+    main(sys.argv[1], sys.argv[2])

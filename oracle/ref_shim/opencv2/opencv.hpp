@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE: forwards <opencv2/opencv.hpp> to the minimal type stand-in (see minicv.hpp).
+#pragma once
+#include "../minicv.hpp"

@@ -1,0 +1,172 @@
+// TEST INFRASTRUCTURE ONLY -- declarations that let LINE RANGES of the reference's matcher-side sources
+// (src/ORBmatcher.cc, src/Frame.cc, src/MapPoint.cc, src/CameraModels/Pinhole.cpp; the ranges are listed in
+// extract_ranges.py and written, at build time only, to oracle/_ref/gen/) compile verbatim without Eigen, Sophus,
+// DBoW2 or the rest of the SLAM object graph.  The classes below carry exactly the members those function bodies
+// touch, under the reference's member names (include/Frame.h, include/MapPoint.h, include/ORBmatcher.h,
+// include/CameraModels/Pinhole.h); no function body of the reference is restated here.
+//
+// Arithmetic that the reference gets from Eigen / Sophus expression templates is written out once, in the order the
+// oracle documents (oracle/matcher_oracle.cpp header): Matrix3f * Vector3f row-wise left to right, norm / dot left to
+// right, SO3f * point in Sophus' quaternion form (Thirdparty/Sophus/sophus/so3.hpp:358-367).  Those few operators live out of
+// line in ref_slam_types.cpp, compiled with -ffp-contract=off so they stay individually rounded; the reference's own text
+// (everything that includes this header) is compiled with the reference's flags, contraction included.
+#pragma once
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <set>
+#include <vector>
+#include "minicv.hpp"
+
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+namespace Eigen {
+template <typename T, int R, int C> struct Matrix;
+template <> struct Matrix<float, 3, 1> {
+    float v[3];
+    Matrix() : v{0, 0, 0} {}
+    Matrix(float a, float b, float c) : v{a, b, c} {}
+    float& operator()(int i) { return v[i]; }
+    const float& operator()(int i) const { return v[i]; }
+    float& operator[](int i) { return v[i]; }
+    const float& operator[](int i) const { return v[i]; }
+    // out of line in ref_slam_types.cpp (compiled with -ffp-contract=off, see the header comment)
+    Matrix operator+(const Matrix& o) const;
+    Matrix operator-(const Matrix& o) const;
+    float dot(const Matrix& o) const;
+    float norm() const;
+};
+template <> struct Matrix<float, 2, 1> {
+    float v[2];
+    Matrix() : v{0, 0} {}
+    float& operator()(int i) { return v[i]; }
+    const float& operator()(int i) const { return v[i]; }
+    float& operator[](int i) { return v[i]; }
+    const float& operator[](int i) const { return v[i]; }
+};
+template <> struct Matrix<float, 3, 3> {
+    float m[9];   // row-major
+    Matrix() : m{1, 0, 0, 0, 1, 0, 0, 0, 1} {}
+    Matrix<float, 3, 1> operator*(const Matrix<float, 3, 1>& p) const;
+};
+typedef Matrix<float, 3, 1> Vector3f;
+typedef Matrix<float, 2, 1> Vector2f;
+typedef Matrix<float, 3, 3> Matrix3f;
+}  // namespace Eigen
+
+namespace Sophus {
+template <typename T> struct SE3;
+template <> struct SE3<float> {
+    float qw, qx, qy, qz;   // unit quaternion
+    Eigen::Vector3f t;
+    SE3() : qw(1), qx(0), qy(0), qz(0) {}
+    // so3.hpp:358-367 then se3.hpp:321-324 (+ translation)
+    Eigen::Vector3f rotate(const Eigen::Vector3f& p) const;
+    Eigen::Vector3f operator*(const Eigen::Vector3f& p) const;
+    SE3 inverse() const;
+    const Eigen::Vector3f& translation() const { return t; }
+};
+typedef SE3<float> SE3f;
+template <typename T> struct Sim3 {};
+typedef Sim3<float> Sim3f;
+}  // namespace Sophus
+
+#define FRAME_GRID_ROWS 48
+#define FRAME_GRID_COLS 64
+
+namespace ORB_SLAM3 {
+using std::vector;
+using std::pair;
+
+class Frame;
+class KeyFrame;
+
+class GeometricCamera {
+public:
+    virtual ~GeometricCamera() {}
+    virtual Eigen::Vector2f project(const Eigen::Vector3f& v3D) = 0;
+    std::vector<float> mvParameters;
+};
+class Pinhole : public GeometricCamera {
+public:
+    Eigen::Vector2f project(const Eigen::Vector3f& v3D);   // body: src/CameraModels/Pinhole.cpp:43-49
+};
+
+class MapPoint {
+public:
+    // flattened state (what the reference reads under mutexes)
+    Eigen::Vector3f mWorldPos, mNormalVector;
+    cv::Mat mDescriptor;
+    int nObs = 0;
+    bool mbBad = false;
+    float mfMinDistance = 0, mfMaxDistance = 0;
+    std::mutex mMutexPos;
+    int index = -1;   // position in the wrapper's flat arrays
+
+    Eigen::Vector3f GetWorldPos() { return mWorldPos; }
+    Eigen::Vector3f GetNormal() { return mNormalVector; }
+    cv::Mat GetDescriptor() { return mDescriptor.clone(); }
+    int Observations() { return nObs; }
+    bool isBad() { return mbBad; }
+    float GetMinDistanceInvariance();                          // bodies: src/MapPoint.cc:502-512
+    float GetMaxDistanceInvariance();
+    int PredictScale(const float& currentDist, Frame* pF);     // body: src/MapPoint.cc:531-546
+
+    float mTrackProjX = 0, mTrackProjY = 0, mTrackDepth = 0, mTrackDepthR = 0, mTrackProjXR = 0, mTrackProjYR = 0;
+    bool mbTrackInView = false, mbTrackInViewR = false;
+    int mnTrackScaleLevel = 0, mnTrackScaleLevelR = 0;
+    float mTrackViewCos = 0, mTrackViewCosR = 0;
+};
+
+class Frame {
+public:
+    int N = 0, Nleft = -1;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    std::vector<float> mvuRight;
+    cv::Mat mDescriptors;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
+    float mb = 0, mbf = 0;
+    std::vector<float> mvScaleFactors;
+    int mnScaleLevels = 0;
+    float mfLogScaleFactor = 0;
+    float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;      // static in the reference; per object here
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    GeometricCamera* mpCamera = nullptr;
+    Eigen::Matrix<float, 3, 1> mOw;
+    Eigen::Matrix<float, 3, 3> mRcw;
+    Eigen::Matrix<float, 3, 1> mtcw;
+    Sophus::SE3<float> mTcw;
+
+    Sophus::SE3<float> GetPose() const { return mTcw; }
+    Sophus::SE3f GetRelativePoseTrl() { return Sophus::SE3f(); }
+    void AssignFeaturesToGrid();                                // body: src/Frame.cc:385-416
+    bool isInFrustum(MapPoint* pMP, float viewingCosLimit);     // body: src/Frame.cc:512-573 (monocular branch)
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);   // body: src/Frame.cc:725-735
+    vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1,
+                                     const bool bRight = false) const;   // body: src/Frame.cc:657-723
+};
+
+class ORBmatcher {
+public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true);
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
+                           const float thFarPoints = 50.0f);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
+    static const int TH_LOW;
+    static const int TH_HIGH;
+    static const int HISTO_LENGTH;
+    float RadiusByViewingCos(const float& viewCos);
+    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
+    float mfNNratio;
+    bool mbCheckOrientation;
+};
+
+}  // namespace ORB_SLAM3

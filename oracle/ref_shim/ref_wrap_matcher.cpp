@@ -1,0 +1,188 @@
+// TEST INFRASTRUCTURE ONLY -- C entry points over the REFERENCE's own matcher-side function bodies.  The bodies are
+// #included verbatim from oracle/_ref/gen/*.inc, which oracle/Makefile generates at build time from line ranges of
+// /root/reference/src/{ORBmatcher.cc,Frame.cc,MapPoint.cc,CameraModels/Pinhole.cpp} (extract_ranges.py; nothing of it is
+// committed).  This file only flattens arrays into the stand-in Frame / MapPoint objects (ref_slam_types.hpp) and back,
+// with the same flat signatures as the orbo_* functions of oracle/matcher_oracle.cpp so that tests can compare 1:1.
+#include "ref_slam_types.hpp"
+
+using namespace std;
+
+namespace ORB_SLAM3 {
+#include "matcher_consts.inc"
+#include "matcher_local_map.inc"
+#include "matcher_init.inc"
+#include "matcher_last_frame.inc"
+#include "matcher_maxima_distance.inc"
+#include "pinhole_project.inc"
+}  // namespace ORB_SLAM3
+namespace ORB_SLAM3 {
+#include "frame_assign_grid.inc"
+#include "frame_in_frustum_mono.inc"
+    return false;   // the reference continues with the two-camera branch (src/Frame.cc:574-...), not on the monocular path
+}
+#include "frame_features_in_area.inc"
+#include "mappoint_invariance.inc"
+#include "mappoint_predict_scale.inc"
+}  // namespace ORB_SLAM3
+
+using namespace ORB_SLAM3;
+
+namespace {
+void fill_frame(Frame& F, int K, const cv::KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors, int nlevels) {
+    F.N = K; F.Nleft = -1;
+    F.mvKeys.assign(kps, kps + K);
+    F.mvKeysUn.assign(kps, kps + K);           // zero distortion: mvKeysUn == mvKeys (src/Frame.cc:749)
+    F.mvuRight.assign(K, -1.f);                // monocular (src/Frame.cc:326)
+    F.mDescriptors = K ? cv::Mat(K, 32, CV_8UC1, (void*)desc, 32) : cv::Mat();
+    F.mvpMapPoints.assign(K, (MapPoint*)nullptr);
+    F.mvbOutlier.assign(K, false);
+    F.mnMinX = bounds[0]; F.mnMinY = bounds[1]; F.mnMaxX = bounds[2]; F.mnMaxY = bounds[3];
+    // src/Frame.cc:342-343
+    F.mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(F.mnMaxX - F.mnMinX);
+    F.mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(F.mnMaxY - F.mnMinY);
+    if (scaleFactors) F.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    F.AssignFeaturesToGrid();
+}
+// state carried in from earlier searches: keypoint k holds map point curMatch[k], whose Observations()>0 iff curClaimed[k]
+void load_state(Frame& F, std::vector<MapPoint>& prior, const int* curMatch, const uint8_t* curClaimed) {
+    for (int k = 0; k < F.N; ++k)
+        if (curMatch[k] >= 0) {
+            prior[k].index = curMatch[k];
+            prior[k].nObs = curClaimed[k] ? 1 : 0;
+            F.mvpMapPoints[k] = &prior[k];
+        }
+}
+void store_state(const Frame& F, int* curMatch, uint8_t* curClaimed) {
+    for (int k = 0; k < F.N; ++k) {
+        MapPoint* p = F.mvpMapPoints[k];
+        curMatch[k] = p ? p->index : -1;
+        curClaimed[k] = p ? (p->nObs > 0) : 0;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    return ORBmatcher::DescriptorDistance(cv::Mat(1, 32, CV_8UC1, (void*)a, 32), cv::Mat(1, 32, CV_8UC1, (void*)b, 32));
+}
+
+void ref_compute_three_maxima(const int* histoSizes, int L, int* ind3) {
+    std::vector<std::vector<int>> h(L);
+    for (int i = 0; i < L; ++i) h[i].assign(histoSizes[i], 0);
+    ORBmatcher m;
+    ind3[0] = ind3[1] = ind3[2] = -1;
+    m.ComputeThreeMaxima(h.data(), L, ind3[0], ind3[1], ind3[2]);
+}
+
+int ref_features_in_area(int K, const cv::KeyPoint* kps, const float* bounds, float x, float y, float r, int minLevel, int maxLevel,
+                         int* out, int cap) {
+    Frame F;
+    fill_frame(F, K, kps, nullptr, bounds, nullptr, 0);
+    vector<size_t> v = F.GetFeaturesInArea(x, y, r, minLevel, maxLevel);
+    for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = (int)v[i];
+    return (int)v.size();
+}
+
+int ref_search_local_map(int K, const cv::KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors, int M,
+                         const uint8_t* inView, const uint8_t* bad, const float* depth, const float* projX, const float* projY,
+                         const int* level, const float* viewCos, const uint8_t* hasObs, const uint8_t* mpDesc, float th, float nnratio,
+                         int bFarPoints, float thFarPoints, int* curMatch, uint8_t* curClaimed) {
+    Frame F;
+    fill_frame(F, K, kps, desc, bounds, scaleFactors, 64);   // nlevels is not part of this flat signature: take what is there
+    std::vector<MapPoint> prior(K);   // MapPoint holds a mutex: sized once, never moved
+    load_state(F, prior, curMatch, curClaimed);
+    std::vector<MapPoint> mps(M);
+    std::vector<MapPoint*> vp(M);
+    for (int i = 0; i < M; ++i) {
+        MapPoint& p = mps[i];
+        p.index = i; p.mbTrackInView = inView[i]; p.mbBad = bad[i]; p.mTrackDepth = depth[i]; p.mTrackProjX = projX[i];
+        p.mTrackProjY = projY[i]; p.mnTrackScaleLevel = level[i]; p.mTrackViewCos = viewCos[i]; p.nObs = hasObs[i] ? 1 : 0;
+        p.mDescriptor = cv::Mat(1, 32, CV_8UC1, (void*)(mpDesc + (size_t)i * 32), 32);
+        vp[i] = &p;
+    }
+    ORBmatcher matcher(nnratio, true);
+    int n = matcher.SearchByProjection(F, vp, th, bFarPoints != 0, thFarPoints);
+    store_state(F, curMatch, curClaimed);
+    return n;
+}
+
+int ref_search_last_frame(int K, const cv::KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors,
+                          const float* Tcw, const float* cam, int M, const uint8_t* valid, const float* xyz, const int* lastOctave,
+                          const float* lastAngle, const uint8_t* hasObs, const uint8_t* mpDesc, float th, int checkOrientation,
+                          int* curMatch, uint8_t* curClaimed) {
+    Frame Cur, Last;
+    fill_frame(Cur, K, kps, desc, bounds, scaleFactors, 64);
+    std::vector<MapPoint> prior(K);
+    load_state(Cur, prior, curMatch, curClaimed);
+    Pinhole camera;
+    camera.mvParameters.assign(cam, cam + 4);
+    Cur.mpCamera = &camera;
+    Cur.mTcw.qw = Tcw[0]; Cur.mTcw.qx = Tcw[1]; Cur.mTcw.qy = Tcw[2]; Cur.mTcw.qz = Tcw[3];
+    Cur.mTcw.t = Eigen::Vector3f(Tcw[4], Tcw[5], Tcw[6]);
+    Last.N = M; Last.Nleft = -1;
+    Last.mvKeys.resize(M); Last.mvKeysUn.resize(M);
+    Last.mvpMapPoints.assign(M, (MapPoint*)nullptr);
+    Last.mvbOutlier.assign(M, false);
+    std::vector<MapPoint> mps(M);
+    for (int i = 0; i < M; ++i) {
+        Last.mvKeys[i].octave = lastOctave[i]; Last.mvKeysUn[i].octave = lastOctave[i];
+        Last.mvKeys[i].angle = lastAngle[i]; Last.mvKeysUn[i].angle = lastAngle[i];
+        MapPoint& p = mps[i];
+        p.index = i; p.nObs = hasObs[i] ? 1 : 0;
+        p.mWorldPos = Eigen::Vector3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        p.mDescriptor = cv::Mat(1, 32, CV_8UC1, (void*)(mpDesc + (size_t)i * 32), 32);
+        if (valid[i]) Last.mvpMapPoints[i] = &p;
+    }
+    ORBmatcher matcher(0.9f, checkOrientation != 0);
+    int n = matcher.SearchByProjection(Cur, Last, th, true);
+    store_state(Cur, curMatch, curClaimed);
+    return n;
+}
+
+int ref_search_for_initialization(int K1, const cv::KeyPoint* kps1, const uint8_t* desc1, int K2, const cv::KeyPoint* kps2,
+                                  const uint8_t* desc2, const float* bounds, const float* scaleFactors, float* prevMatched, int windowSize,
+                                  float nnratio, int checkOrientation, int* matches12) {
+    Frame F1, F2;
+    fill_frame(F1, K1, kps1, desc1, bounds, scaleFactors, 64);
+    fill_frame(F2, K2, kps2, desc2, bounds, scaleFactors, 64);
+    std::vector<cv::Point2f> prev(K1);
+    for (int i = 0; i < K1; ++i) prev[i] = cv::Point2f(prevMatched[2 * i], prevMatched[2 * i + 1]);
+    std::vector<int> m12;
+    ORBmatcher matcher(nnratio, checkOrientation != 0);
+    int n = matcher.SearchForInitialization(F1, F2, prev, m12, windowSize);
+    for (int i = 0; i < K1; ++i) { matches12[i] = m12[i]; prevMatched[2 * i] = prev[i].x; prevMatched[2 * i + 1] = prev[i].y; }
+    return n;
+}
+
+// minDistance / maxDistance are the RAW mfMinDistance / mfMaxDistance: the 0.8f / 1.2f invariance factors are applied by the
+// reference's own getters (src/MapPoint.cc:502-512).
+void ref_is_in_frustum(int M, const float* P, const float* N, const float* minDistance, const float* maxDistance,
+                       const float* Rcw, const float* tcw, const float* Ow, const float* cam, const float* bounds, float mbf,
+                       float logScaleFactor, int nScaleLevels, float viewingCosLimit, uint8_t* inView, float* projX, float* projY,
+                       float* projXR, float* depth, int* level, float* viewCos) {
+    Frame F;
+    F.Nleft = -1;
+    Pinhole camera;
+    camera.mvParameters.assign(cam, cam + 4);
+    F.mpCamera = &camera;
+    for (int i = 0; i < 9; ++i) F.mRcw.m[i] = Rcw[i];
+    F.mtcw = Eigen::Vector3f(tcw[0], tcw[1], tcw[2]);
+    F.mOw = Eigen::Vector3f(Ow[0], Ow[1], Ow[2]);
+    F.mnMinX = bounds[0]; F.mnMinY = bounds[1]; F.mnMaxX = bounds[2]; F.mnMaxY = bounds[3];
+    F.mbf = mbf; F.mfLogScaleFactor = logScaleFactor; F.mnScaleLevels = nScaleLevels;
+    for (int i = 0; i < M; ++i) {
+        MapPoint p;
+        p.mWorldPos = Eigen::Vector3f(P[3 * i], P[3 * i + 1], P[3 * i + 2]);
+        p.mNormalVector = Eigen::Vector3f(N[3 * i], N[3 * i + 1], N[3 * i + 2]);
+        p.mfMaxDistance = maxDistance[i];
+        p.mfMinDistance = minDistance[i];
+        // fields the reference leaves untouched for points out of view: documented defaults of orbm_frustum_project
+        p.mTrackProjXR = 0.f; p.mTrackDepth = 0.f; p.mnTrackScaleLevel = -1; p.mTrackViewCos = 0.f;
+        inView[i] = F.isInFrustum(&p, viewingCosLimit) ? 1 : 0;
+        projX[i] = p.mTrackProjX; projY[i] = p.mTrackProjY; projXR[i] = p.mTrackProjXR; depth[i] = p.mTrackDepth;
+        level[i] = p.mnTrackScaleLevel; viewCos[i] = p.mTrackViewCos;
+    }
+}
+
+}  // extern "C"

@@ -537,7 +537,7 @@ __global__ void frustum_project_kernel(FrustumParams Q) {
                     const float ratio = fdiv(Q.maxRaw[i], dist);
                     int n = (int)ceilf(fdiv(logf_glibc(ratio), Q.logSF));
                     if (n < 0) n = 0; else if (n >= Q.nLevels) n = Q.nLevels - 1;
-                    in = 1; pxr = fsub(u, fmul(Q.mbf, invz)); dep = pcDist; lvl = n; vc = c;
+                    in = 1; pxr = __fmaf_rn(-Q.mbf, invz, u) /* one FMA in the reference build, see oracle */; dep = pcDist; lvl = n; vc = c;
                 }
             }
         }

@@ -25,7 +25,8 @@ def scene(M=3000, seed=0, W=640, H=480):
     n[flip] *= -1
     dmax = (dist * rng.uniform(0.6, 3.0, M)).astype(np.float32)                       # mfMaxDistance
     dmin = (dmax / np.float32(1.2 ** 7) * rng.uniform(0.5, 1.5, M)).astype(np.float32)
-    pts = dict(worldPos=P, normal=n.astype(np.float32), minDistInv=np.float32(0.8) * dmin, maxDistInv=np.float32(1.2) * dmax, maxDistance=dmax)
+    pts = dict(worldPos=P, normal=n.astype(np.float32), minDistInv=np.float32(0.8) * dmin, maxDistInv=np.float32(1.2) * dmax, maxDistance=dmax,
+               minDistance=dmin)   # raw mfMinDistance: only oracle/_ref (the reference's own getters) reads it
     return dict(pts=pts, Rcw=R, tcw=t, Ow=Ow, cam=cam, bounds=(0.0, 0.0, float(W), float(H)),
                 log_scale_factor=np.float32(np.log(np.float32(1.2))), n_levels=8, mbf=40.0)
 

@@ -1,0 +1,170 @@
+"""ctypes loader for oracle/_ref/libref_orb.so: the REFERENCE's own sources (src/ORBextractor.cc whole; line ranges of
+src/ORBmatcher.cc, src/Frame.cc, src/MapPoint.cc, src/CameraModels/Pinhole.cpp) compiled where they lie under /root/reference
+against the type stand-ins of oracle/ref_shim/ (recipe: oracle/Makefile).  Test infrastructure; used to pin the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle_lib import KP_DTYPE, _p, _c
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, 'oracle', '_ref', 'libref_orb.so')
+_lib = None
+
+
+def available():
+    if not os.path.exists(_SO) and os.path.exists('/root/reference/src/ORBextractor.cc'):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(_ROOT, 'oracle')])
+    return os.path.exists(_SO)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if os.path.exists('/root/reference/src/ORBextractor.cc'):
+            subprocess.check_call(['make', '-s', '-C', os.path.join(_ROOT, 'oracle')])   # rebuilds when the shim or the recipe changed
+        _lib = C.CDLL(_SO)
+        _lib.ref_orbx_create.restype = C.c_void_p
+        _lib.ref_orbx_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        _lib.ref_orbx_destroy.argtypes = [C.c_void_p]
+        _lib.ref_ic_angle.restype = C.c_float
+        _lib.ref_ic_angle.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+        _lib.ref_orb_descriptor.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    return _lib
+
+
+class RefExtractor:
+    """ORB_SLAM3::ORBextractor itself (reference include/ORBextractor.h:43-109)."""
+
+    def __init__(self, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = lib()
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self.h = C.c_void_p(self.L.ref_orbx_create(nfeatures, scale, nlevels, ini_th, min_th))
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            self.L.ref_orbx_destroy(self.h)
+            self.h = None
+
+    def __call__(self, img, lap=(0, 0)):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.nfeatures + 64 * self.nlevels + 4096
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        rows, cols = (img.shape[0], img.shape[1]) if img.size else (0, 0)
+        mono = self.L.ref_orbx_extract(self.h, _p(img), rows, cols, img.strides[0] if img.size else 0, lap[0], lap[1], _p(kps), _p(desc), cap, C.byref(n))
+        return mono, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def tables(self):
+        nl = self.nlevels
+        s, i, g, ig = (np.zeros(nl, np.float32) for _ in range(4))
+        f = np.zeros(nl, np.int32)
+        u = np.zeros(16, np.int32)
+        self.L.ref_orbx_tables(self.h, _p(s), _p(i), _p(g), _p(ig), _p(f), _p(u))
+        return dict(scale=s, inv_scale=i, sigma2=g, inv_sigma2=ig, features_per_level=f, umax=u)
+
+    def level(self, l, border=0):
+        w, h = C.c_int(), C.c_int()
+        self.L.ref_orbx_level_size(self.h, l, C.byref(w), C.byref(h))
+        out = np.zeros((h.value + 2 * border, w.value + 2 * border), np.uint8)
+        self.L.ref_orbx_level_copy(self.h, l, border, _p(out))
+        return out
+
+    def distribute(self, cands, minX, maxX, minY, maxY, N):
+        cands = np.ascontiguousarray(cands, KP_DTYPE)
+        out = np.zeros(len(cands) + 8, KP_DTYPE)
+        n = self.L.ref_orbx_distribute(self.h, _p(cands), len(cands), minX, maxX, minY, maxY, N, _p(out), len(out))
+        return out[:n].copy()
+
+    def ic_angle(self, img, x, y):
+        img = np.ascontiguousarray(img, np.uint8)
+        return self.L.ref_ic_angle(self.h, _p(img), img.shape[0], img.shape[1], img.strides[0], x, y)
+
+    def descriptor(self, img, x, y, angle):
+        img = np.ascontiguousarray(img, np.uint8)
+        d = np.zeros(32, np.uint8)
+        self.L.ref_orb_descriptor(self.h, _p(img), img.shape[0], img.shape[1], img.strides[0], x, y, angle, _p(d))
+        return d
+
+
+def descriptor_distance(a, b):
+    a = _c(a, np.uint8); b = _c(b, np.uint8)
+    return lib().ref_descriptor_distance(_p(a), _p(b))
+
+
+def compute_three_maxima(sizes):
+    s = _c(sizes, np.int32)
+    out = np.zeros(3, np.int32)
+    lib().ref_compute_three_maxima(_p(s), len(s), _p(out))
+    return tuple(int(v) for v in out)
+
+
+def features_in_area(kps, bounds, x, y, r, min_level, max_level):
+    kps = _c(kps, KP_DTYPE); b = _c(bounds, np.float32)
+    out = np.zeros(len(kps) + 1, np.int32)
+    L = lib()
+    L.ref_features_in_area.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = L.ref_features_in_area(len(kps), _p(kps), _p(b), x, y, r, min_level, max_level, _p(out), len(out))
+    return out[:n].copy()
+
+
+def _pad_sf(sf):
+    out = np.ones(64, np.float32)     # the wrapper copies 64 entries of mvScaleFactors
+    out[:len(sf)] = sf
+    return out
+
+
+def search_local_map(kps, desc, bounds, scale_factors, pts, th, nnratio, b_far, th_far, match, claimed):
+    kps = _c(kps, KP_DTYPE); desc = _c(desc, np.uint8); b = _c(bounds, np.float32); sf = _pad_sf(_c(scale_factors, np.float32))
+    a = {k: _c(pts[k], dt) for k, dt in (('inView', np.uint8), ('bad', np.uint8), ('depth', np.float32), ('projX', np.float32),
+                                          ('projY', np.float32), ('level', np.int32), ('viewCos', np.float32), ('hasObs', np.uint8),
+                                          ('descriptors', np.uint8))}
+    L = lib()
+    L.ref_search_local_map.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 9 + [C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    return L.ref_search_local_map(len(kps), _p(kps), _p(desc), _p(b), _p(sf), len(a['projX']), _p(a['inView']), _p(a['bad']), _p(a['depth']),
+                                  _p(a['projX']), _p(a['projY']), _p(a['level']), _p(a['viewCos']), _p(a['hasObs']), _p(a['descriptors']),
+                                  th, nnratio, int(b_far), th_far, _p(match), _p(claimed))
+
+
+def search_last_frame(kps, desc, bounds, scale_factors, Tcw, cam, last, th, check_ori, match, claimed):
+    kps = _c(kps, KP_DTYPE); desc = _c(desc, np.uint8); b = _c(bounds, np.float32); sf = _pad_sf(_c(scale_factors, np.float32))
+    T = _c(Tcw, np.float32); cm = _c(cam, np.float32)
+    a = {k: _c(last[k], dt) for k, dt in (('valid', np.uint8), ('xyz', np.float32), ('octave', np.int32), ('angle', np.float32),
+                                           ('hasObs', np.uint8), ('descriptors', np.uint8))}
+    L = lib()
+    L.ref_search_last_frame.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    return L.ref_search_last_frame(len(kps), _p(kps), _p(desc), _p(b), _p(sf), _p(T), _p(cm), len(a['valid']), _p(a['valid']), _p(a['xyz']),
+                                   _p(a['octave']), _p(a['angle']), _p(a['hasObs']), _p(a['descriptors']), th, int(check_ori), _p(match), _p(claimed))
+
+
+def search_for_initialization(kps1, desc1, kps2, desc2, bounds, scale_factors, prev_matched, window=100, nnratio=0.9, check_ori=True):
+    kps1 = _c(kps1, KP_DTYPE); kps2 = _c(kps2, KP_DTYPE); d1 = _c(desc1, np.uint8); d2 = _c(desc2, np.uint8)
+    b = _c(bounds, np.float32); sf = _pad_sf(_c(scale_factors, np.float32))
+    pm = _c(prev_matched, np.float32).copy()
+    m12 = np.full(len(kps1), -1, np.int32)
+    L = lib()
+    L.ref_search_for_initialization.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = L.ref_search_for_initialization(len(kps1), _p(kps1), _p(d1), len(kps2), _p(kps2), _p(d2), _p(b), _p(sf), _p(pm), int(window), nnratio,
+                                        int(check_ori), _p(m12))
+    return n, m12, pm
+
+
+def is_in_frustum(pts, Rcw, tcw, Ow, cam, bounds, log_scale_factor, n_levels, viewing_cos_limit=0.5, mbf=0.0):
+    a = {k: _c(pts[k], np.float32) for k in ('worldPos', 'normal', 'minDistance', 'maxDistance')}
+    M = len(a['minDistance'])
+    R = _c(np.asarray(Rcw, np.float32).reshape(9), np.float32); t = _c(tcw, np.float32); o = _c(Ow, np.float32)
+    cm = _c(cam, np.float32); b = _c(bounds, np.float32)
+    out = dict(inView=np.zeros(M, np.uint8), projX=np.zeros(M, np.float32), projY=np.zeros(M, np.float32), projXR=np.zeros(M, np.float32),
+               depth=np.zeros(M, np.float32), level=np.zeros(M, np.int32), viewCos=np.zeros(M, np.float32))
+    L = lib()
+    L.ref_is_in_frustum.restype = None
+    L.ref_is_in_frustum.argtypes = [C.c_int] + [C.c_void_p] * 9 + [C.c_float, C.c_float, C.c_int, C.c_float] + [C.c_void_p] * 7
+    L.ref_is_in_frustum(M, _p(a['worldPos']), _p(a['normal']), _p(a['minDistance']), _p(a['maxDistance']), _p(R), _p(t), _p(o),
+                        _p(cm), _p(b), float(mbf), float(np.float32(log_scale_factor)), int(n_levels), float(viewing_cos_limit),
+                        *[_p(out[k]) for k in ('inView', 'projX', 'projY', 'projXR', 'depth', 'level', 'viewCos')])
+    return out

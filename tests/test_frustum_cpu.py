@@ -13,6 +13,13 @@ import oracle_lib as O
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def _fnmadd(a, b, c):
+    """float32 fma(-a, b, c) element-wise through the host libm's fmaf (one rounding, like the FMA the reference build emits)."""
+    libm = C.CDLL('libm.so.6'); libm.fmaf.restype = C.c_float; libm.fmaf.argtypes = [C.c_float] * 3
+    with np.errstate(all='ignore'):
+        return np.array([libm.fmaf(-float(a), float(bi), float(ci)) for bi, ci in zip(b, c)], np.float32)
+
+
 def _bits(f):
     return struct.unpack('<I', struct.pack('<f', f))[0]
 
@@ -93,5 +100,5 @@ def test_oracle_is_in_frustum_equals_float32_numpy_restatement():
             lvl[i] = min(max(n, 0), 7)
         assert np.array_equal(out['inView'], d.astype(np.uint8))
         assert np.array_equal(out['projX'], np.where(b, u, f32(-1))) and np.array_equal(out['projY'], np.where(b, v, f32(-1)))
-        assert np.array_equal(out['projXR'], np.where(d, u - f32(sc['mbf']) * invz, f32(0))) and np.array_equal(out['depth'], np.where(d, pc, f32(0)))
+        assert np.array_equal(out['projXR'], np.where(d, _fnmadd(f32(sc['mbf']), invz, u), f32(0))) and np.array_equal(out['depth'], np.where(d, pc, f32(0)))
         assert np.array_equal(out['viewCos'], np.where(d, vc, f32(0))) and np.array_equal(out['level'], lvl)

@@ -1,0 +1,172 @@
+"""The oracle is pinned by the REFERENCE ITSELF: oracle/_ref/libref_orb.so is /root/reference/src/ORBextractor.cc (the whole
+file: ctor tables, ComputePyramid, ComputeKeyPointsOctTree, DivideNode / compareNodes / DistributeOctTree, IC_Angle,
+computeOrbDescriptor, operator()) and the matcher-side function bodies (both SearchByProjection overloads, SearchForInitialization,
+ComputeThreeMaxima, DescriptorDistance, Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid / isInFrustum,
+MapPoint::PredictScale, Pinhole::project) compiled verbatim with the reference's flags (-O3, FMA contraction on) against type
+stand-ins; the five OpenCV image primitives underneath are the cv2-pinned ones (tests/test_oracle_cpu.py).  Everything is compared
+bit for bit with the restated oracle that the GPU parity tests use."""
+import numpy as np
+import pytest
+
+import frustum_scenes
+import matcher_scenes
+import oracle_lib as O
+import ref_lib as R
+from orb_slam3_modified_b200 import synth
+
+pytestmark = pytest.mark.skipif(not R.available(), reason='oracle/_ref not built (needs /root/reference at build time)')
+
+
+def _same_extraction(a, b):
+    (m1, k1, d1), (m2, k2, d2) = a, b
+    assert m1 == m2 and len(k1) == len(k2)
+    assert k1.tobytes() == k2.tobytes()
+    assert np.array_equal(d1, d2)
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(w=640, h=480, nf=1000, lap=(0, 1000), ts=(0, 1, 7, 12, 40)),
+    dict(w=640, h=480, nf=1000, lap=(200, 400), ts=(3,)),
+    dict(w=1280, h=720, nf=1000, lap=(0, 1000), ts=(5,)),
+    dict(w=640, h=480, nf=5000, lap=(0, 1000), ts=(2,)),          # the 5x extractor of the monocular initialiser (Tracking.cc:603)
+    dict(w=600, h=800, nf=1500, lap=(0, 0), ts=(4,)),             # portrait
+    dict(w=1241, h=376, nf=2000, lap=(0, 0), ts=(6,)),            # KITTI aspect: two initial quadtree nodes... (nIni = 3)
+    dict(w=640, h=480, nf=1000, lap=(0, 1000), ts=(9,), scale=1.3, nlevels=6, ini=15, mn=5),
+], ids=lambda c: '%dx%d_n%d' % (c['w'], c['h'], c['nf']))
+def test_operator_call_equals_reference(cfg):
+    args = (cfg['nf'], cfg.get('scale', 1.2), cfg.get('nlevels', 8), cfg.get('ini', 20), cfg.get('mn', 7))
+    ref, ora = R.RefExtractor(*args), O.OracleExtractor(*args)
+    tr, to = ref.tables(), ora.tables()
+    for k in tr:
+        assert np.array_equal(tr[k], to[k]), k
+    for t in cfg['ts']:
+        img = synth.frame(t, cfg['w'], cfg['h'])
+        _same_extraction(ref(img, cfg['lap']), ora(img, cfg['lap']))
+        for l in range(args[2]):
+            assert np.array_equal(ref.level(l), ora.level(l)), ('pyramid', l)
+
+
+def test_degenerate_images_equal_reference():
+    ref, ora = R.RefExtractor(), O.OracleExtractor()
+    rng = np.random.default_rng(5)
+    flat = np.full((480, 640), 77, np.uint8)
+    noise = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    grad = (np.add.outer(np.arange(480), np.arange(640)) // 5).astype(np.uint8)
+    low = (128 + rng.integers(-6, 7, (480, 640))).astype(np.uint8)
+    for img in (flat, noise, grad, low):
+        _same_extraction(ref(img, (0, 1000)), ora(img, (0, 1000)))
+    assert ref(np.zeros((0, 0), np.uint8))[0] == -1 == ora(np.zeros((0, 0), np.uint8))[0]
+
+
+def test_distribute_oct_tree_equals_reference_on_random_candidates():
+    # DistributeOctTree / DivideNode / compareNodes on candidate sets the images above do not produce: heavy ties in
+    # (node size, UL.x), clustered points, fewer candidates than N
+    ref, ora = R.RefExtractor(), O.OracleExtractor()
+    rng = np.random.default_rng(11)
+    for case in range(60):
+        n = int(rng.integers(1, 4000))
+        W, H = int(rng.integers(120, 1300)), int(rng.integers(100, 760))
+        if W < H // 2 + 1:
+            W = H
+        c = np.zeros(n, O.KP_DTYPE)
+        if case % 3 == 0:     # clusters
+            cx, cy = rng.uniform(0, W, 6), rng.uniform(0, H, 6)
+            k = rng.integers(0, 6, n)
+            c['x'] = np.clip(np.round(cx[k] + rng.normal(0, 12, n)), 0, W - 1)
+            c['y'] = np.clip(np.round(cy[k] + rng.normal(0, 12, n)), 0, H - 1)
+        else:
+            c['x'] = rng.integers(0, W, n)
+            c['y'] = rng.integers(0, H, n)
+        c['response'] = rng.integers(7, 60, n)    # few distinct responses: ties inside nodes too
+        c['size'] = 7; c['angle'] = -1; c['class_id'] = -1
+        N = int(rng.integers(1, 1200))
+        a = ref.distribute(c, 0, W, 0, H, N)
+        b = ora.distribute(c, 0, W, 0, H, N)
+        assert a.tobytes() == b.tobytes(), case
+
+
+def test_ic_angle_and_descriptor_equal_reference_on_keypoints():
+    # file-static helpers of src/ORBextractor.cc called directly: angle on the level plane, descriptor on the blurred plane
+    ref, ora = R.RefExtractor(), O.OracleExtractor()
+    img = synth.frame(21)
+    _, kps, desc = ora(img, (0, 0))          # lap (0,0): keypoints fill from the front, level order
+    l0 = kps[kps['octave'] == 0]
+    d0 = desc[kps['octave'] == 0]
+    blurred = O.blur7(img)
+    for i in range(0, len(l0), 7):
+        k = l0[i]
+        assert np.float32(ref.ic_angle(img, float(k['x']), float(k['y']))) == k['angle']
+        assert np.array_equal(ref.descriptor(blurred, float(k['x']), float(k['y']), float(k['angle'])), d0[i])
+
+
+def test_descriptor_distance_and_three_maxima_equal_reference():
+    rng = np.random.default_rng(2)
+    d = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    for i in range(0, 299):
+        assert R.descriptor_distance(d[i], d[i + 1]) == O.descriptor_distance(d[i], d[i + 1]) == int(np.unpackbits(d[i] ^ d[i + 1]).sum())
+    assert R.compute_three_maxima([0] * 30) == (-1, -1, -1)
+    assert R.compute_three_maxima([5, 0, 100, 9, 50] + [0] * 25) == (2, 4, -1)
+    assert R.compute_three_maxima([5, 0, 100, 10, 50] + [0] * 25) == (2, 4, 3)
+
+
+def test_features_in_area_equals_reference():
+    kps, _ = matcher_scenes.extract(4)
+    rng = np.random.default_rng(8)
+    b = (0.0, 0.0, 640.0, 480.0)
+    for _ in range(300):
+        x, y, r = float(rng.uniform(-30, 670)), float(rng.uniform(-30, 510)), float(rng.uniform(1, 60))
+        lo, hi = int(rng.integers(-1, 7)), int(rng.integers(-1, 8))
+        assert np.array_equal(R.features_in_area(kps, b, x, y, r, lo, hi), O.features_in_area(kps, b, x, y, r, lo, hi))
+
+
+@pytest.mark.parametrize('t,check_ori,th', [(3, 1, 15.0), (8, 0, 7.0), (15, 1, 30.0), (22, 1, 15.0)])
+def test_search_last_frame_equals_reference(t, check_ori, th):
+    sc = matcher_scenes.last_frame_scene(t)
+    K = len(sc['kps'])
+    rng = np.random.default_rng(t)
+    res = []
+    for fn in (R.search_last_frame, O.search_last_frame):
+        match = np.full(K, -1, np.int32); claimed = np.zeros(K, np.uint8)
+        pre = np.random.default_rng(t + 100).random(K) < 0.05          # some keypoints already hold points from an earlier search
+        match[pre] = 5000 + np.arange(pre.sum()); claimed[pre] = (np.random.default_rng(t + 101).random(pre.sum()) < 0.5)
+        n = fn(sc['kps'], sc['desc'], sc['bounds'], sc['sf'], sc['Tcw'], sc['cam'], sc['last'], th, check_ori, match, claimed)
+        res.append((n, match, claimed))
+    assert res[0][0] == res[1][0] and res[0][0] > 100
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+
+
+@pytest.mark.parametrize('t,th,far', [(4, 1.0, 0), (9, 3.0, 0), (14, 3.0, 1), (20, 5.0, 0)])
+def test_search_local_map_equals_reference(t, th, far):
+    sc = matcher_scenes.local_map_scene(t)
+    K = len(sc['kps'])
+    res = []
+    for fn in (R.search_local_map, O.search_local_map):
+        match = np.full(K, -1, np.int32); claimed = np.zeros(K, np.uint8)
+        pre = np.random.default_rng(t + 7).random(K) < 0.3             # as after TrackWithMotionModel: part of the frame is matched
+        match[pre] = 9000 + np.arange(pre.sum()); claimed[pre] = (np.random.default_rng(t + 8).random(pre.sum()) < 0.8)
+        n = fn(sc['kps'], sc['desc'], sc['bounds'], sc['sf'], sc['pts'], th, 0.8, far, 6.0, match, claimed)
+        res.append((n, match, claimed))
+    assert res[0][0] == res[1][0] and res[0][0] > 50
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+
+
+@pytest.mark.parametrize('t,window,ori', [(2, 100, True), (6, 30, True), (11, 100, False)])
+def test_search_for_initialization_equals_reference(t, window, ori):
+    k1, d1 = matcher_scenes.extract(t)
+    k2, d2 = matcher_scenes.extract(t + 1)
+    sf = O.OracleExtractor().tables()['scale']
+    prev = np.stack([k1['x'], k1['y']], 1)
+    a = R.search_for_initialization(k1, d1, k2, d2, (0.0, 0.0, 640.0, 480.0), sf, prev, window, 0.9, ori)
+    b = O.search_for_initialization(k1, d1, k2, d2, (0.0, 0.0, 640.0, 480.0), sf, prev, window, 0.9, ori)
+    assert a[0] == b[0] and a[0] > 30
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize('seed', [0, 3, 9])
+def test_is_in_frustum_equals_reference(seed):
+    sc = frustum_scenes.scene(5000, seed=seed)
+    a = R.is_in_frustum(**sc)
+    b = O.is_in_frustum(**sc)
+    assert 0.1 < a['inView'].mean() < 0.9
+    for k in ('inView', 'projX', 'projY', 'depth', 'level', 'viewCos', 'projXR'):
+        assert a[k].tobytes() == b[k].tobytes(), k
