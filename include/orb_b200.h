@@ -215,6 +215,14 @@ int orbm_search_last_frame_batch_device(orbm_handle* h, const OrbmBatchDevice* i
 int orbm_search_last_frame_batch(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOrientation,
                                  int32_t* match, uint8_t* claimed, int32_t* nmatches);
 
+/* int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12,
+ * int windowSize) (include/ORBmatcher.h:74, src/ORBmatcher.cc:648-763): the windowed brute-force search of the monocular
+ * initialiser (Tracking::MonocularInitialization, src/Tracking.cc:2494-2495, nnratio 0.9, window 100).  F1.K <= max_mappoints and
+ * F2.K <= max_keypoints of the handle.  prevMatched [F1.K][2] is vbPrevMatched (in/out, updated like :757-759); matches12 [F1.K] is
+ * vnMatches12 (-1 = none); *nmatches is the return value.  Host pointers. */
+int orbm_search_for_initialization(orbm_handle* h, const OrbmFrame* F1, const OrbmFrame* F2, float* prevMatched, int windowSize,
+                                   float nnratio, int checkOrientation, int32_t* matches12, int* nmatches);
+
 /* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) as used at src/Frame.cc:1144: idx/dist are Q x 2,
  * ordered by (distance, lower train index); missing neighbours are -1.  Host pointers. */
 int orbm_bf_knn2(orbm_handle* h, const uint8_t* query, int Q, const uint8_t* train, int T, int32_t* idx, int32_t* dist);
@@ -246,7 +254,8 @@ typedef struct LbaProblem {
     double huberDelta;           /* thHuberMono = (float)sqrt(5.991) (:1275,:1321) */
     int iterations;              /* optimizer.optimize(10) */
     double userLambdaInit;       /* solver->setUserLambdaInit(100.0) for inertial maps (:1197-1198), else 0 */
-    const volatile int* stopFlag;/* pbStopFlag (mbAbortBA), polled like SparseOptimizer::terminate(); may be NULL */
+    const volatile uint8_t* stopFlag; /* bool* pbStopFlag (&mbAbortBA, src/LocalMapping.cc:154): one byte, so that the caller's own bool can be
+                                       * handed over as it is; polled like SparseOptimizer::terminate(); may be NULL */
 } LbaProblem;
 
 typedef struct LbaResult {
@@ -270,13 +279,15 @@ void lba_destroy(lba_handle* h);
 int lba_solve(lba_handle* h, const LbaProblem* problem, LbaResult* result);
 int lba_solve_batch(lba_handle* h, int count, const LbaProblem* problems, LbaResult* results);
 /* Split form of lba_solve_batch: upload the flattened graphs once (host pointers), run the whole LM loop for all of
- * them from the uploaded initial estimates on `stream` (device-resident, asynchronous, repeatable), download results. */
+ * them from the uploaded initial estimates on `stream` (device-resident, asynchronous, repeatable), download results.
+ * Ordering: lba_download_batch and the next lba_upload_batch wait (on the device, through an event) for the last
+ * lba_run_batch_device whatever stream it was given, so no synchronisation is required from the caller in between. */
 int lba_upload_batch(lba_handle* h, int count, const LbaProblem* problems);
 int lba_run_batch_device(lba_handle* h, void* stream);
 int lba_download_batch(lba_handle* h, int count, LbaResult* results);
 /* Thread-block-cluster size (CTAs per problem) the last run used. */
 int lba_last_cluster_size(const lba_handle* h);
-/* Force the cluster size (1, 2, 4, 8 CTAs per problem; 0 = automatic: the largest that lets the whole batch run at once). */
+/* Force the cluster size (1..8 CTAs per problem; 0 = automatic: the largest for which every problem's cluster is resident at once). */
 int lba_set_cluster_size(lba_handle* h, int ctas);
 /* Device-side phase timers (ns, CTA 0) of problem i of the last downloaded run: errors (first iteration), build_points,
  * build_poses, point_prep (after a rejected step), schur_partial, ldlt, schur_combine, pose_trial, points_trial (back-substitution +

@@ -404,6 +404,11 @@ void orbo_lba_residuals(int nP, const double* poses7, const float* cam4, int nL,
 // ---------------------------------------------------------------------------------------------------------
 int orbo_pose_optimization(double* pose7, const float* cam4, int N, const double* Xw3, const double* obs2, const float* invSigma2,
                            double huberDelta, uint8_t* outlier, double* stats) {
+    if (N < 3) {   // if(nInitialCorrespondences<3) return 0; (src/Optimizer.cc:996-997): the frame's pose is not touched
+        for (int i = 0; i < N; ++i) outlier[i] = 0;
+        if (stats) stats[0] = 0;
+        return 0;
+    }
     Quat q0 = {pose7[0], pose7[1], pose7[2], pose7[3]};
     Pose T0; T0.q = q0; qnormalize(T0.q); T0.t[0] = pose7[4]; T0.t[1] = pose7[5]; T0.t[2] = pose7[6];
     Pose T = T0;

@@ -405,6 +405,21 @@ class ORBmatcher:
         if rc != ORB_OK:
             raise OrbError(rc, 'orbm_search_last_frame_batch')
 
+    def SearchForInitialization(self, F1, F2, vbPrevMatched, windowSize=10):
+        """``int ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)`` (src/ORBmatcher.cc:648-763).
+        ``vbPrevMatched`` [K1, 2] float32 is updated in place; returns (nmatches, vnMatches12 [K1] i32, -1 = none)."""
+        assert vbPrevMatched.dtype == np.float32 and vbPrevMatched.flags.c_contiguous and vbPrevMatched.shape == (len(F1.keypoints), 2)
+        m12 = np.full(len(F1.keypoints), -1, np.int32)
+        n = C.c_int(0)
+        f1, f2 = F1._struct(), F2._struct()
+        L = lib()
+        L.orbm_search_for_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        rc = L.orbm_search_for_initialization(self._h, C.byref(f1), C.byref(f2), _ptr(vbPrevMatched), int(windowSize), self.mfNNratio,
+                                              int(self.mbCheckOrientation), _ptr(m12), C.byref(n))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_search_for_initialization')
+        return n.value, m12
+
     def knnMatch2(self, query, train):
         """cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) (src/Frame.cc:1144): (idx[Q,2], dist[Q,2])."""
         q = _c(query, np.uint8).reshape(-1, 32)

@@ -3,7 +3,30 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+
 namespace orbx {
+
+void set_error(const std::string& s);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the (function, device) pair, not of a handle: several handles of
+// different sizes share it.  Keep a process-wide monotonic maximum per kernel and device and only ever raise it, so that a
+// smaller handle created later can never lower the limit under a larger one (the launch would fail with invalid-value).
+template <class Kernel>
+inline int ensure_dynamic_smem(Kernel* kernel, size_t bytes, int device) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> current;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = current[std::make_pair((const void*)kernel, device)];
+    if (bytes <= cur || bytes <= 48 * 1024) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): ") + cudaGetErrorString(e)); return -4; }
+    cur = bytes;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // block-wide exclusive scan of an int array living in shared memory (in place).

@@ -305,9 +305,9 @@ struct Extractor {
         maxSmemFast = 48 * 1024;   // worst-case cell is 76x76 in a 96-byte wide box: ~25 KB
         maxSmemQt = smemQt + 16 * 1024; maxSmemAs = 2 * capSel * sizeof(int);
         if (maxSmemQt > 200 * 1024) { set_error("nfeatures too large for the quadtree kernel's shared memory"); return ORB_ERR_ARG; }
-        CK(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmemFast));
-        CK(cudaFuncSetAttribute(quadtree_orient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmemQt));
-        CK(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(maxSmemAs, 1024)));
+        // process-wide monotonic maxima (device_utils.cuh): a smaller handle created later must not lower another handle's limit
+        if (ensure_dynamic_smem(fast_cells_kernel, maxSmemFast, device) || ensure_dynamic_smem(quadtree_orient_kernel, maxSmemQt, device) ||
+            ensure_dynamic_smem(assemble_kernel, std::max<size_t>(maxSmemAs, 1024), device)) return ORB_ERR_CUDA;
         maxKpAlloc = (int)capSel;
         rows = cols = 0;   // force set_size on first use
         return set_size(maxH, maxW);

@@ -32,10 +32,8 @@
 
 #include "../../include/orb_b200.h"
 #include "host_affinity.h"
+#include "device_utils.cuh"
 
-namespace orbx {
-void set_error(const std::string& s);
-}
 using orbx::set_error;
 
 #define CK(call)                                                                   \
@@ -844,9 +842,10 @@ __device__ void phase_finalize(const Dev& D, const Ctx& c) {
 // The persistent kernel: SparseOptimizer::optimize (sparse_optimizer.cpp:354-418) around
 // OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-168), one cluster per problem.
 // Every thread carries the (uniform) LM state; decisions use values every CTA reads identically after a cluster barrier.
-// Dynamic shared memory: 2 pose caches (PC x maxP doubles each) | LDLT panel scratch (2 x 6 x (6 maxP + 1)) | rhs row | reduced camera system (smemMatrixN^2).
+// Dynamic shared memory: 2 pose caches (PC x maxP doubles each, maxP = most poses of any loaded problem, fixed keyframes included) |
+// LDLT panel scratch (2 x 6 x (6 maxF + 1), maxF = most FREE poses) | rhs row (6 maxF) | reduced camera system (smemMatrixN^2).
 // =============================================================================================
-__global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restrict__ probs, const volatile int* stop, int smemMatrixN, int maxP) {
+__global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restrict__ probs, const volatile int* stop, int smemMatrixN, int maxP, int maxF) {
     extern __shared__ double s_dyn[];
     __shared__ double s_red[NT];
     cg::cluster_group cluster = cg::this_cluster();
@@ -855,9 +854,9 @@ __global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restric
     c.wid = c.crank * NT + c.tid; c.nw = c.csize * NT; c.slot = 0; c.sm = s_red;
     double* s_pc = s_dyn;                        // pose cache, linearisation state
     double* s_pcT = s_pc + PC * maxP;            // pose cache, trial state
-    double* s_col = s_pcT + PC * maxP;           // 2 x 6 x (6 maxP + 1) panel scratch
-    double* s_rhs = s_col + 72 * maxP + 12;      // 6 maxP: rhs row of the LDLT
-    double* s_mat = s_rhs + 6 * maxP + 2;
+    double* s_col = s_pcT + PC * maxP;           // 2 x 6 x (6 maxF + 1) panel scratch
+    double* s_rhs = s_col + 72 * maxF + 12;      // 6 maxF: rhs row of the LDLT
+    double* s_mat = s_rhs + 6 * maxF + 2;
     const Dev D = probs[blockIdx.x / c.csize];
     const bool matInSmem = D.n <= smemMatrixN && D.n > 0;
     // reduced camera system: CTA 0's shared memory; the other CTAs of the cluster reach it as distributed shared memory
@@ -1183,9 +1182,9 @@ struct Solver {
     std::vector<Packed> packed;
     int* h_stop = nullptr; int* d_stop = nullptr;   // mapped pinned stop flags, one per problem
     int* h_status = nullptr; int* d_status = nullptr;   // mapped pinned status words of the structure kernel
-    cudaEvent_t evDone = nullptr;
-    int nLoaded = 0, launches = 0, smemN = 0, numSMs = 148;
-    size_t fixedSmem = 0;
+    cudaEvent_t evDone = nullptr, evRun = nullptr;   // evRun: end of the last run, on whatever stream the caller launched it
+    bool ranOnce = false;
+    int nLoaded = 0, launches = 0, numSMs = 148;
     ~Solver() {
         cudaSetDevice(device);
         if (d_arena) cudaFree(d_arena);
@@ -1194,6 +1193,7 @@ struct Solver {
         if (h_stop) cudaFreeHost(h_stop);
         if (h_status) cudaFreeHost(h_status);
         if (evDone) cudaEventDestroy(evDone);
+        if (evRun) cudaEventDestroy(evRun);
         if (st) cudaStreamDestroy(st);
     }
     static size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -1236,13 +1236,7 @@ struct Solver {
         CK(cudaHostGetDevicePointer(&d_status, h_status, 0));
         CK(cudaEventCreateWithFlags(&evDone, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        // dynamic shared memory: pose cache + two LDLT column buffers + (when it fits) the reduced camera system,
-        // within 200 KB of the 227 KB opt-in limit
-        fixedSmem = 8 * ((size_t)(2 * PC + 72 + 6) * maxP + 16);
-        const size_t maxDyn = 200 * 1024;
-        smemN = fixedSmem < maxDyn ? (int)floor(sqrt((double)(maxDyn - fixedSmem) / 8.0)) : 0;
-        smemN = std::min(smemN, 6 * maxP);
-        CK(cudaFuncSetAttribute(lba_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fixedSmem + 8 * (size_t)smemN * smemN)));
+        CK(cudaEventCreateWithFlags(&evRun, cudaEventDisableTiming));
         h_probs.resize(maxBatch); packed.resize(maxBatch);
         return ORB_OK;
     }
@@ -1320,6 +1314,8 @@ struct Solver {
     int upload(int count, const LbaProblem* probs) {
         if (count < 1 || count > maxBatch) { set_error("lba: batch larger than max_batch"); return ORB_ERR_ARG; }
         uploadBytes.assign(maxBatch, 0); uploadOff.assign(maxBatch, 0);
+        CK(cudaSetDevice(device));
+        if (ranOnce) CK(cudaStreamWaitEvent(st, evRun, 0));   // a run may still be reading the arena on the caller's stream
         {   // stage the callers' graphs in the pinned mirror on a few host threads; every worker queues the host-to-device
             // copy of a problem as soon as it is staged, so the copies overlap the staging of the next problems
             const int nth = std::max(1, std::min<int>({count, (int)std::thread::hardware_concurrency(), 8}));
@@ -1364,22 +1360,48 @@ struct Solver {
     int run(cudaStream_t s) {
         if (nLoaded < 1) { set_error("lba: nothing uploaded"); return ORB_ERR_ARG; }
         CK(cudaSetDevice(device));
-        int maxN = 0;
-        for (int i = 0; i < nLoaded; ++i) maxN = std::max(maxN, 6 * packed[i].nF);     // the kernel itself restarts from the uploaded estimates
-        int csize = 1;
-        for (int cand = MAXC; cand >= 1; cand >>= 1) if (nLoaded * cand <= numSMs) { csize = cand; break; }
-        if (forcedCluster > 0) csize = forcedCluster;
+        int maxN = 0, mp = 1, mf = 1;
+        for (int i = 0; i < nLoaded; ++i) {                             // the kernel itself restarts from the uploaded estimates
+            maxN = std::max(maxN, 6 * packed[i].nF); mp = std::max(mp, packed[i].nP); mf = std::max(mf, packed[i].nF);
+        }
+        // dynamic shared memory: the pose caches hold every pose of the window (fixed keyframes included, the reference puts no
+        // bound on lFixedCameras), the LDLT panels and rhs only the free ones; the reduced camera system joins them when it fits
+        const size_t fixedSmem = 8 * ((size_t)2 * PC * mp + (size_t)78 * mf + 16);
+        const size_t maxDyn = 200 * 1024;                               // of the 227 KB opt-in limit; the kernel has ~5 KB static
+        if (fixedSmem > maxDyn) {
+            set_error("lba: window too large for the shared-memory pose caches (about 600 keyframes incl. fixed ones)");
+            return ORB_ERR_CAPACITY;
+        }
+        const int smemN = (int)floor(sqrt((double)(maxDyn - fixedSmem) / 8.0));
         const int matN = maxN <= smemN ? maxN : 0;   // matrix in shared memory only when every problem of the batch fits
+        const size_t dyn = fixedSmem + 8 * (size_t)matN * matN;
+        if (orbx::ensure_dynamic_smem(lba_cluster_kernel, dyn, device)) return ORB_ERR_CUDA;
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(nLoaded * csize); cfg.blockDim = dim3(NT);
-        cfg.dynamicSmemBytes = fixedSmem + 8 * (size_t)matN * matN;
+        cfg.blockDim = dim3(NT);
+        cfg.dynamicSmemBytes = dyn;
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        const Dev* dp = d_probs; const volatile int* ds = d_stop; int mn = matN, mp = maxP;
-        CK(cudaLaunchKernelEx(&cfg, lba_cluster_kernel, dp, ds, mn, mp));
+        // cluster size: the largest (any size up to 8, not only powers of two) for which every problem's cluster is resident at
+        // once -- asked from the occupancy calculator, because clusters cannot straddle GPCs (24 clusters of 6 fit 148 SMs, 25 do not)
+        int csize = 1;
+        for (int cand = MAXC; cand >= 1; --cand) {
+            if ((long)nLoaded * cand > numSMs) continue;
+            attr[0].val.clusterDim.x = cand;
+            cfg.gridDim = dim3(nLoaded * cand);
+            int nClusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nClusters, lba_cluster_kernel, &cfg) == cudaSuccess && nClusters >= nLoaded) { csize = cand; break; }
+        }
+        (void)cudaGetLastError();
+        if (forcedCluster > 0) csize = forcedCluster;
+        attr[0].val.clusterDim.x = csize;
+        cfg.gridDim = dim3(nLoaded * csize);
+        const Dev* dp = d_probs; const volatile int* ds = d_stop; int mn = matN;
+        CK(cudaLaunchKernelEx(&cfg, lba_cluster_kernel, dp, ds, mn, mp, mf));
+        CK(cudaEventRecord(evRun, s));
+        ranOnce = true;
         launches = 1;
         lastCluster = csize;
         return ORB_OK;
@@ -1390,6 +1412,7 @@ struct Solver {
             if (!res[i].poses || !res[i].points || !res[i].edgeChi2 || !res[i].edgeDepthPositive) { set_error("lba: null result arrays"); return ORB_ERR_ARG; }
         // the output blocks sit at the start of every slot with one layout: a single strided copy into the pinned mirror
         const size_t ob = outBlock(maxP, maxL, maxE);
+        if (ranOnce) CK(cudaStreamWaitEvent(s, evRun, 0));    // the run may be on another stream than this copy
         CK(cudaMemcpy2DAsync(h_arena, perProblem, d_arena, perProblem, ob, (size_t)count, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         for (int i = 0; i < count; ++i) {
@@ -1446,7 +1469,7 @@ int lba_download_batch(lba_handle* h, int count, LbaResult* results) {
 }
 int lba_last_cluster_size(const lba_handle* h) { return h ? h->s.lastCluster : ORB_ERR_ARG; }
 int lba_set_cluster_size(lba_handle* h, int ctas) {
-    if (!h || (ctas != 0 && ctas != 1 && ctas != 2 && ctas != 4 && ctas != 8)) { set_error("lba_set_cluster_size: 0 (auto), 1, 2, 4 or 8"); return ORB_ERR_ARG; }
+    if (!h || ctas < 0 || ctas > MAXC) { set_error("lba_set_cluster_size: 0 (auto) or 1..8"); return ORB_ERR_ARG; }
     h->s.forcedCluster = ctas;
     return ORB_OK;
 }

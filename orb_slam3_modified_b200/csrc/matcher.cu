@@ -12,6 +12,7 @@
 //   pass 2 (one warp per stream, map points in index order): a pass-1 result is still exact unless its best or
 //           second-best keypoint has been claimed meanwhile -- only then the warp rescans that map point against
 //           the current claim state.  Claims live in a shared-memory bitset.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <string.h>
@@ -40,6 +41,7 @@ using orbx::set_error;
 namespace orbm {
 
 using namespace orbx;
+namespace cg = cooperative_groups;
 
 constexpr int GRID_COLS = 64, GRID_ROWS = 48, GRID_CELLS = GRID_COLS * GRID_ROWS;   // include/Frame.h:44-45
 constexpr int TH_HIGH = 100;       // src/ORBmatcher.cc:35
@@ -57,73 +59,83 @@ struct MatchParams {
     float cam[4];
     float th, nnratio, thFar;
     int bFar, checkOri, resetState;
+    int ks, ms, descInSmem;   // shared-memory capacities of match_frame_kernel (keypoints, map points) and where the descriptors live
     // scratch
-    int* cellStart;      // [batch][GRID_CELLS + 1]
-    uint16_t* cellIdx;   // [batch][kcap]
     float4* query;       // [batch][mcap]  u, v, r, bits(minLevel+1 | (maxLevel+1) << 8 | valid << 16)
     int4 *resultIdx, *resultDist;   // [batch][mcap]  the four best (keypoint index, distance) of pass 1, ascending
-    uint8_t* evBin; uint16_t* evIdx;   // [batch][mcap] rotation-histogram events
     // in/out
     int* match; uint8_t* claimed; int* nmatches;
     int* status;
 };
 
 // ---------------------------------------------------------------------------------------------
-// Frame::AssignFeaturesToGrid + PosInGrid: counting sort of the keypoints into the 64x48 grid, cell lists in
-// increasing keypoint index (= the reference's push_back order).  One CTA per stream.
+// Fused per-frame matcher.  One thread-block CLUSTER per frame (stream); every CTA of the cluster holds the frame in
+// shared memory -- the 64x48 grid of Frame::AssignFeaturesToGrid (src/Frame.cc:385-416, cell lists in keypoint order
+// = the reference's push_back order), keypoint positions / octaves and (when they fit) the descriptors -- and scans
+// its share of the map points (pass 1, warp per map point).  CTA 0 of the cluster then resolves the reference's
+// sequential claim rule in parallel (pass 2) and applies the rotation-histogram filter.
+//
+// Pass 1: the four smallest (Hamming distance, Frame::GetFeaturesInArea enumeration order) keys of every map point
+//         among the keypoints that are not claimed at entry.
+// Pass 2: the reference visits map points in index order; a keypoint assigned to a map point with observations is
+//         skipped by all later map points (src/ORBmatcher.cc:84-86, :1747-1749).  With s_i the choice of map point i,
+//         s_i = first candidate of i that no j < i with observations chose.  That recurrence is solved by fixed-point
+//         iteration: every map point re-decides in parallel against minClaimer[c] = min{ j : s_j = c, j has
+//         observations }; after iteration t the first t map points are final, and an iteration without a change is the
+//         sequential result (induction over i).  Contention is rare, so it converges in a handful of sweeps instead of
+//         the M dependent steps of a serial walk.  A map point whose four candidates are all taken (while more exist)
+//         is rescanned by a warp against the current claims -- removing keys ranked after the second never changes
+//         (best, second), so this is exact.
 // ---------------------------------------------------------------------------------------------
-constexpr int GB_NT = 256;
-__global__ void __launch_bounds__(GB_NT) grid_build_kernel(MatchParams P) {
-    __shared__ int s_cnt[GRID_CELLS];
-    __shared__ int s_warp[33];
-    const int f = blockIdx.x, tid = threadIdx.x;
-    const int K = min(P.nK[f], P.kcap);
-    const OrbKeyPoint* kps = P.kps + (size_t)f * P.kcap;
-    int* cellStart = P.cellStart + (size_t)f * (GRID_CELLS + 1);
-    uint16_t* cellIdx = P.cellIdx + (size_t)f * P.kcap;
-    for (int c = tid; c < GRID_CELLS; c += GB_NT) s_cnt[c] = 0;
-    if (P.resetState) {
-        int* match = P.match + (size_t)f * P.kcap;
-        uint8_t* claimed = P.claimed + (size_t)f * P.kcap;
-        for (int i = tid; i < P.kcap; i += GB_NT) { match[i] = -1; claimed[i] = 0; }
-    }
-    __syncthreads();
-    for (int i = tid; i < K; i += GB_NT) {
-        const int px = (int)roundf(fmul(fsub(kps[i].x, P.minX), P.gridWInv));
-        const int py = (int)roundf(fmul(fsub(kps[i].y, P.minY), P.gridHInv));
-        if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) atomicAdd(&s_cnt[px * GRID_ROWS + py], 1);
-    }
-    __syncthreads();
-    const int total = block_excl_scan(s_cnt, GRID_CELLS, s_warp);
-    for (int c = tid; c < GRID_CELLS; c += GB_NT) cellStart[c] = s_cnt[c];
-    if (tid == 0) cellStart[GRID_CELLS] = total;
-    __syncthreads();
-    for (int i = tid; i < K; i += GB_NT) {
-        const int px = (int)roundf(fmul(fsub(kps[i].x, P.minX), P.gridWInv));
-        const int py = (int)roundf(fmul(fsub(kps[i].y, P.minY), P.gridHInv));
-        if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) {
-            const int pos = atomicAdd(&s_cnt[px * GRID_ROWS + py], 1);
-            cellIdx[pos] = (uint16_t)i;
-        }
-    }
-    __syncthreads();
-    // restore insertion order inside each cell (lists are short)
-    for (int c = tid; c < GRID_CELLS; c += GB_NT) {
-        const int a = cellStart[c], b = s_cnt[c];   // s_cnt now holds the end offset
-        for (int i = a + 1; i < b; ++i) {
-            const uint16_t v = cellIdx[i];
-            int j = i - 1;
-            while (j >= a && cellIdx[j] > v) { cellIdx[j + 1] = cellIdx[j]; --j; }
-            cellIdx[j + 1] = v;
-        }
-    }
+constexpr int MF_NT = 512;
+constexpr unsigned NONE16 = 0xFFFFu;
+
+struct FrameSmem {          // carved from dynamic shared memory (layout computed by frame_smem_bytes)
+    int* cnt;               // [GRID_CELLS] build counters; reused as histogram / scratch afterwards
+    uint16_t* cellStart;    // [GRID_CELLS + 1]
+    uint16_t* cellIdx;      // [Ks]
+    float *kx, *ky;         // [Ks]
+    uint8_t* koct;          // [Ks]
+    uint32_t* initBits;     // [(Ks + 31) / 32] claimed at entry
+    int* minClaimer;        // [Ks]
+    uint16_t* choice;       // [Ms] chosen keypoint of every map point (NONE16: none / not accepted)
+    uint8_t* mflags;        // [Ms] bit0 = has observations, bits 2.. = rotation bin + 1 (0: none)
+    uint16_t* queue;        // [Ms] map points that need a rescan in the current sweep
+    uint32_t* desc;         // [Ks][8] or nullptr (descriptors stay in global memory)
+};
+
+__host__ __device__ inline size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t frame_smem_bytes(int Ks, int Ms, bool descInSmem) {
+    size_t b = 0;
+    b += al16(sizeof(int) * GRID_CELLS);
+    b += al16(sizeof(uint16_t) * (GRID_CELLS + 1));
+    b += al16(sizeof(uint16_t) * Ks);
+    b += 2 * al16(sizeof(float) * Ks);
+    b += al16(Ks);
+    b += al16(sizeof(uint32_t) * ((Ks + 31) / 32));
+    b += al16(sizeof(int) * Ks);
+    b += 2 * al16(sizeof(uint16_t) * Ms);
+    b += al16(Ms);
+    if (descInSmem) b += al16((size_t)32 * Ks);
+    return b;
+}
+__device__ __forceinline__ FrameSmem carve_frame_smem(uint8_t* p, int Ks, int Ms, bool descInSmem) {
+    FrameSmem S;
+    S.cnt = (int*)p; p += al16(sizeof(int) * GRID_CELLS);
+    S.cellStart = (uint16_t*)p; p += al16(sizeof(uint16_t) * (GRID_CELLS + 1));
+    S.cellIdx = (uint16_t*)p; p += al16(sizeof(uint16_t) * Ks);
+    S.kx = (float*)p; p += al16(sizeof(float) * Ks);
+    S.ky = (float*)p; p += al16(sizeof(float) * Ks);
+    S.koct = p; p += al16(Ks);
+    S.initBits = (uint32_t*)p; p += al16(sizeof(uint32_t) * ((Ks + 31) / 32));
+    S.minClaimer = (int*)p; p += al16(sizeof(int) * Ks);
+    S.choice = (uint16_t*)p; p += al16(sizeof(uint16_t) * Ms);
+    S.mflags = p; p += al16(Ms);
+    S.queue = (uint16_t*)p; p += al16(sizeof(uint16_t) * Ms);
+    S.desc = descInSmem ? (uint32_t*)p : nullptr;
+    return S;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Warp-wide scan of the candidates of one map point: Frame::GetFeaturesInArea order = (ix, iy, position in cell).
-// Keeps the two smallest (distance, order) keys among keypoints that are not claimed.
-// key = dist << 40 | cellRank << 20 | j ; returns idx/dist of best and second (idx -1 when absent).
-// ---------------------------------------------------------------------------------------------
 template <int K>
 struct TopK {   // the K smallest keys seen, ascending
     unsigned long long k[K];
@@ -156,9 +168,12 @@ struct TopK {   // the K smallest keys seen, ascending
 };
 typedef TopK<2> Top2;
 
-template <int K, class ClaimFn>
-__device__ __forceinline__ TopK<K> scan_candidates(const MatchParams& P, int f, float u, float v, float r, int minLevel, int maxLevel,
-                                                   const uint32_t* mpd, ClaimFn isClaimed) {
+// Warp-wide scan of the candidates of one query in Frame::GetFeaturesInArea order (src/Frame.cc:657-723): (ix, iy, position in
+// the cell).  key = dist << 40 | cellRank << 20 | position; keeps the K smallest keys among keypoints that pass `usable`.
+struct AnyDist { __device__ __forceinline__ bool operator()(int, int) const { return true; } };
+template <int K, class UsableFn, class UsableDistFn = AnyDist>
+__device__ __forceinline__ TopK<K> scan_candidates(const MatchParams& P, const FrameSmem& S, int f, float u, float v, float r, int minLevel,
+                                                   int maxLevel, const uint32_t* mpd, UsableFn usable, UsableDistFn usableDist = AnyDist()) {
     const int lane = threadIdx.x & 31;
     TopK<K> t; t.init();
     const int nMinCellX = max(0, (int)floorf(fmul(fsub(fsub(u, P.minX), r), P.gridWInv)));
@@ -167,29 +182,33 @@ __device__ __forceinline__ TopK<K> scan_candidates(const MatchParams& P, int f, 
     const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf(fmul(fadd(fsub(v, P.minY), r), P.gridHInv)));
     if (nMinCellX < GRID_COLS && nMaxCellX >= 0 && nMinCellY < GRID_ROWS && nMaxCellY >= 0) {
         const int ny = nMaxCellY - nMinCellY + 1, nx = nMaxCellX - nMinCellX + 1;
-        const int* cellStart = P.cellStart + (size_t)f * (GRID_CELLS + 1);
-        const uint16_t* cellIdx = P.cellIdx + (size_t)f * P.kcap;
-        const OrbKeyPoint* kps = P.kps + (size_t)f * P.kcap;
-        const uint8_t* desc = P.desc + (size_t)f * P.kcap * 32;
+        const uint8_t* gdesc = P.desc + (size_t)f * P.kcap * 32;
         const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
         for (int c = lane; c < nx * ny; c += 32) {
             const int ix = nMinCellX + c / ny, iy = nMinCellY + c % ny;
             const int cell = ix * GRID_ROWS + iy;
-            const int a = cellStart[cell], b = cellStart[cell + 1];
+            const int a = S.cellStart[cell], b = S.cellStart[cell + 1];
             for (int e = a; e < b; ++e) {
-                const int idx = cellIdx[e];
-                const OrbKeyPoint kp = kps[idx];
+                const int idx = S.cellIdx[e];
+                const int oct = S.koct[idx];
                 if (bCheckLevels) {
-                    if (kp.octave < minLevel) continue;
-                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                    if (oct < minLevel) continue;
+                    if (maxLevel >= 0 && oct > maxLevel) continue;
                 }
-                const float dx = fsub(kp.x, u), dy = fsub(kp.y, v);
+                const float dx = fsub(S.kx[idx], u), dy = fsub(S.ky[idx], v);
                 if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
-                if (isClaimed(idx)) continue;
-                const uint4* dp = reinterpret_cast<const uint4*>(desc + (size_t)idx * 32);
-                const uint4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+                if (!usable(idx)) continue;
+                uint4 d0, d1;
+                if (S.desc) {
+                    const uint4* dp = reinterpret_cast<const uint4*>(S.desc + (size_t)idx * 8);
+                    d0 = dp[0]; d1 = dp[1];
+                } else {
+                    const uint4* dp = reinterpret_cast<const uint4*>(gdesc + (size_t)idx * 32);
+                    d0 = __ldg(dp); d1 = __ldg(dp + 1);
+                }
                 const uint32_t dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
                 const int dist = hamming256(mpd, dd);
+                if (!usableDist(idx, dist)) continue;
                 t.insert(((unsigned long long)dist << 40) | ((unsigned long long)c << 20) | (unsigned)(e - a), idx);
             }
         }
@@ -211,7 +230,7 @@ __device__ __forceinline__ bool make_query(const MatchParams& P, int f, int i, f
         if (!P.inView[o]) return false;
         if (P.bFar && P.depth[o] > P.thFar) return false;
         if (P.bad[o]) return false;
-        const int lvl = P.level[o];
+        const int lvl = min(max(P.level[o], 0), P.nlevels - 1);   // the host entry points reject out-of-range levels; device callers are clamped
         float rr = ((double)P.viewCos[o] > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos :215-221
         if (P.th != 1.0f) rr = fmul(rr, P.th);
         u = P.projX[o]; v = P.projY[o];
@@ -237,149 +256,210 @@ __device__ __forceinline__ bool make_query(const MatchParams& P, int f, int i, f
     if (u < P.minX || u > P.maxX) return false;
     if (v < P.minY || v > P.maxY) return false;
     if (!(u == u) || !(v == v)) return false;   // NaN projections (zc == 0) fail every comparison above in the reference too
-    const int oct = P.octave[o];
+    const int oct = min(max(P.octave[o], 0), P.nlevels - 1);
     r = fmul(P.th, P.scaleFactors[oct]);
     minL = oct - 1; maxL = oct + 1;
     return true;
 }
 
-// pass 1: warp per map point
-constexpr int MC_NT = 256;
-__global__ void __launch_bounds__(MC_NT) match_candidates_kernel(MatchParams P) {
-    const int f = blockIdx.y;
-    const int i = blockIdx.x * (MC_NT / 32) + (threadIdx.x >> 5);
-    const int M = min(P.nM[f], P.mcap);
-    if (i >= M) return;
-    const int lane = threadIdx.x & 31;
-    const size_t o = (size_t)f * P.mcap + i;
-    float u = 0, v = 0, r = 0; int minL = 0, maxL = 0;
-    const bool ok = make_query(P, f, i, u, v, r, minL, maxL);
-    int4 ri = make_int4(-1, -1, -1, -1), rd = make_int4(256, 256, 256, 256);
-    if (ok) {
-        uint32_t mpd[8];
-        load_mp_desc(P, f, i, mpd);
-        const int* match = P.match + (size_t)f * P.kcap;
-        const uint8_t* claimed = P.claimed + (size_t)f * P.kcap;
-        const bool reset = P.resetState != 0;
-        const TopK<4> t = scan_candidates<4>(P, f, u, v, r, minL, maxL, mpd, [&](int idx) { return !reset && match[idx] >= 0 && claimed[idx]; });
-        ri = make_int4(t.i[0], t.i[1], t.i[2], t.i[3]);
-        rd = make_int4(t.i[0] >= 0 ? (int)(t.k[0] >> 40) : 256, t.i[1] >= 0 ? (int)(t.k[1] >> 40) : 256,
-                       t.i[2] >= 0 ? (int)(t.k[2] >> 40) : 256, t.i[3] >= 0 ? (int)(t.k[3] >> 40) : 256);
-    }
-    if (lane == 0) {
-        P.resultIdx[o] = ri; P.resultDist[o] = rd;
-        P.query[o] = make_float4(u, v, r, __int_as_float((minL + 1) | ((maxL + 1) << 8) | ((ok ? 1 : 0) << 16)));
-    }
+// rotation histogram bin (:1779-1789)
+__device__ __forceinline__ int rot_bin(float lastAngle, float curAngle) {
+    float rot = fsub(lastAngle, curAngle);
+    if (rot < 0.0f) rot = fadd(rot, 360.0f);
+    int bin = (int)roundf(fmul(rot, 1.0f / HISTO_LENGTH));
+    if (bin == HISTO_LENGTH) bin = 0;
+    return min(max(bin, 0), HISTO_LENGTH - 1);
 }
 
-// pass 2: one warp per stream, map points in index order
-__global__ void __launch_bounds__(32) match_commit_kernel(MatchParams P) {
-    extern __shared__ uint32_t s_bits[];   // claim bitset, ceil(kcap/32) words
-    __shared__ int s_hist[HISTO_LENGTH];
-    const int f = blockIdx.x, lane = threadIdx.x;
+// Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:385-416, :725-735): counting sort of the keypoints into the 64x48 grid held in
+// shared memory, cell lists in increasing keypoint index (= the reference's push_back order); also stages positions, octaves and
+// (when S.desc is set) the descriptors.  All threads of the CTA call; ends with a barrier.
+__device__ void build_frame_smem(const FrameSmem& S, const OrbKeyPoint* kps, const uint8_t* gdesc, int K, float minX, float minY, float gridWInv,
+                                 float gridHInv, int* s_warp) {
+    const int tid = threadIdx.x;
+    for (int c = tid; c < GRID_CELLS; c += MF_NT) S.cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < K; i += MF_NT) {
+        const OrbKeyPoint kp = kps[i];
+        S.kx[i] = kp.x; S.ky[i] = kp.y; S.koct[i] = (uint8_t)min(max(kp.octave, 0), 255);
+        const int px = (int)roundf(fmul(fsub(kp.x, minX), gridWInv));
+        const int py = (int)roundf(fmul(fsub(kp.y, minY), gridHInv));
+        if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) atomicAdd(&S.cnt[px * GRID_ROWS + py], 1);
+    }
+    if (S.desc) {
+        const uint4* src = reinterpret_cast<const uint4*>(gdesc);
+        uint4* dst = reinterpret_cast<uint4*>(S.desc);
+        for (int i = tid; i < 2 * K; i += MF_NT) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int total = block_excl_scan(S.cnt, GRID_CELLS, s_warp);
+    for (int c = tid; c < GRID_CELLS; c += MF_NT) S.cellStart[c] = (uint16_t)S.cnt[c];
+    if (tid == 0) S.cellStart[GRID_CELLS] = (uint16_t)total;
+    __syncthreads();
+    for (int i = tid; i < K; i += MF_NT) {
+        const int px = (int)roundf(fmul(fsub(S.kx[i], minX), gridWInv));
+        const int py = (int)roundf(fmul(fsub(S.ky[i], minY), gridHInv));
+        if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) S.cellIdx[atomicAdd(&S.cnt[px * GRID_ROWS + py], 1)] = (uint16_t)i;
+    }
+    __syncthreads();
+    for (int c = tid; c < GRID_CELLS; c += MF_NT) {    // restore insertion order inside each cell (lists are short)
+        const int a = S.cellStart[c], b = S.cnt[c];     // cnt now holds the end offset
+        for (int i = a + 1; i < b; ++i) {
+            const uint16_t v = S.cellIdx[i];
+            int j = i - 1;
+            while (j >= a && S.cellIdx[j] > v) { S.cellIdx[j + 1] = S.cellIdx[j]; --j; }
+            S.cellIdx[j + 1] = v;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(MF_NT) match_frame_kernel(MatchParams P) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int s_warp[33];
+    __shared__ int s_changed, s_nq, s_nAcc, s_nRemoved, s_ind[3];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int f = blockIdx.x / C, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int K = min(P.nK[f], P.kcap), M = min(P.nM[f], P.mcap);
+    const FrameSmem S = carve_frame_smem(smem_raw, P.ks, P.ms, P.descInSmem != 0);
+    const OrbKeyPoint* kps = P.kps + (size_t)f * P.kcap;
     int* match = P.match + (size_t)f * P.kcap;
     uint8_t* claimed = P.claimed + (size_t)f * P.kcap;
-    const OrbKeyPoint* kps = P.kps + (size_t)f * P.kcap;
-    uint8_t* evBin = P.evBin + (size_t)f * P.mcap;
-    uint16_t* evIdx = P.evIdx + (size_t)f * P.mcap;
-    const int nw = (P.kcap + 31) / 32;
-    for (int w = lane; w < nw; w += 32) {
-        uint32_t bits = 0;
-        for (int b = 0; b < 32; ++b) {
-            const int idx = w * 32 + b;
-            if (idx < K && match[idx] >= 0 && claimed[idx]) bits |= 1u << b;
-        }
-        s_bits[w] = bits;
+    const bool reset = P.resetState != 0;
+
+    // ---- the frame in shared memory: grid, positions, octaves, descriptors; claims at entry ----
+    for (int w = tid; w < (P.ks + 31) / 32; w += MF_NT) S.initBits[w] = 0;
+    build_frame_smem(S, kps, P.desc + (size_t)f * P.kcap * 32, K, P.minX, P.minY, P.gridWInv, P.gridHInv, s_warp);
+    if (!reset) {
+        for (int i = tid; i < K; i += MF_NT)
+            if (match[i] >= 0 && claimed[i]) atomicOr(&S.initBits[i >> 5], 1u << (i & 31));
+        __syncthreads();
     }
-    if (lane < HISTO_LENGTH) s_hist[lane] = 0;
-    __syncwarp();
-    int nmatches = 0, nEvents = 0;
-    const float factor = 1.0f / HISTO_LENGTH;
-    const bool hist = P.mode == 1 && P.checkOri;
-    auto rot_bin = [&](float lastAngle, float curAngle) {   // rotation histogram bin (:1779-1789)
-        float rot = fsub(lastAngle, curAngle);
-        if (rot < 0.0f) rot = fadd(rot, 360.0f);
-        int bin = (int)roundf(fmul(rot, factor));
-        if (bin == HISTO_LENGTH) bin = 0;
-        return min(max(bin, 0), HISTO_LENGTH - 1);
-    };
-    auto is_claimed = [&](int idx) { return (bool)((s_bits[idx >> 5] >> (idx & 31)) & 1u); };
-    for (int base = 0; base < M; base += 32) {
-        // every lane prefetches everything the serial part needs for "its" map point (gathers run in parallel)
-        const int i = base + lane;
+
+    // ---- pass 1: this CTA's share of the map points, warp per map point ----
+    auto notInit = [&](int idx) { return !((S.initBits[idx >> 5] >> (idx & 31)) & 1u); };
+    for (int i = rank * (MF_NT / 32) + wid; i < M; i += C * (MF_NT / 32)) {
         const size_t o = (size_t)f * P.mcap + i;
+        float u = 0, v = 0, r = 0; int minL = 0, maxL = 0;
+        const bool ok = make_query(P, f, i, u, v, r, minL, maxL);
         int4 ri = make_int4(-1, -1, -1, -1), rd = make_int4(256, 256, 256, 256);
-        int hasObs = 0;
-        unsigned lv = 0, bn = 0;   // 4 x 8 bit: octave / histogram bin of the four candidates
-        if (i < M) {
-            ri = P.resultIdx[o]; rd = P.resultDist[o]; hasObs = P.hasObs[o];
-            const float lastAngle = hist ? P.angle[o] : 0.f;
-            const int ids[4] = {ri.x, ri.y, ri.z, ri.w};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (ids[c] >= 0) {
-                    const OrbKeyPoint kb = kps[ids[c]];
-                    lv |= (unsigned)(kb.octave & 0xff) << (8 * c);
-                    if (hist) bn |= (unsigned)rot_bin(lastAngle, kb.angle) << (8 * c);
-                }
-            }
+        if (ok) {
+            uint32_t mpd[8];
+            load_mp_desc(P, f, i, mpd);
+            const TopK<4> t = scan_candidates<4>(P, S, f, u, v, r, minL, maxL, mpd, notInit);
+            ri = make_int4(t.i[0], t.i[1], t.i[2], t.i[3]);
+            rd = make_int4(t.i[0] >= 0 ? (int)(t.k[0] >> 40) : 256, t.i[1] >= 0 ? (int)(t.k[1] >> 40) : 256,
+                           t.i[2] >= 0 ? (int)(t.k[2] >> 40) : 256, t.i[3] >= 0 ? (int)(t.k[3] >> 40) : 256);
         }
-        const int cnt = min(32, M - base);
-        for (int j = 0; j < cnt; ++j) {
-            const int c0 = __shfl_sync(0xffffffffu, ri.x, j);
-            if (c0 < 0) continue;                                     // no candidate at all
-            const int ids[4] = {c0, __shfl_sync(0xffffffffu, ri.y, j), __shfl_sync(0xffffffffu, ri.z, j), __shfl_sync(0xffffffffu, ri.w, j)};
-            const int ds[4] = {__shfl_sync(0xffffffffu, rd.x, j), __shfl_sync(0xffffffffu, rd.y, j), __shfl_sync(0xffffffffu, rd.z, j),
-                               __shfl_sync(0xffffffffu, rd.w, j)};
-            const int obs = __shfl_sync(0xffffffffu, hasObs, j);
-            const unsigned lvs = __shfl_sync(0xffffffffu, lv, j), bns = __shfl_sync(0xffffffffu, bn, j);
-            // first (and, for the local-map ratio test, second) candidate that is still unclaimed
-            int bIdx = -1, bDist = 256, sIdx = -1, sDist = 256, lv1 = -1, lv2 = -1, bnb = 0;
-            bool exhausted = false;                                   // true: the list ended before 4 entries
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (ids[c] < 0) { exhausted = true; continue; }
-                if (is_claimed(ids[c])) continue;
-                if (bIdx < 0) { bIdx = ids[c]; bDist = ds[c]; lv1 = (int)((lvs >> (8 * c)) & 0xff); bnb = (int)((bns >> (8 * c)) & 0xff); }
-                else if (sIdx < 0) { sIdx = ids[c]; sDist = ds[c]; lv2 = (int)((lvs >> (8 * c)) & 0xff); }
-            }
-            const bool need2 = P.mode == 0;
-            if (!exhausted && (bIdx < 0 || (need2 && sIdx < 0))) {   // the four were not enough: rescan against the current claims
-                const size_t oj = (size_t)f * P.mcap + base + j;
-                const float4 q = P.query[oj];
-                const int bits = __float_as_int(q.w);
-                uint32_t mpd[8];
-                load_mp_desc(P, f, base + j, mpd);
-                const Top2 t = scan_candidates<2>(P, f, q.x, q.y, q.z, (bits & 0xff) - 1, ((bits >> 8) & 0xff) - 1, mpd, is_claimed);
-                bIdx = t.i[0]; bDist = t.i[0] >= 0 ? (int)(t.k[0] >> 40) : 256;
-                sIdx = t.i[1]; sDist = t.i[1] >= 0 ? (int)(t.k[1] >> 40) : 256;
-                if (bIdx >= 0) {
-                    lv1 = kps[bIdx].octave; lv2 = sIdx >= 0 ? kps[sIdx].octave : -1;
-                    if (hist) bnb = rot_bin(P.angle[oj], kps[bIdx].angle);
-                }
-            }
-            if (bIdx < 0) continue;
-            if (bDist > TH_HIGH) continue;
-            if (P.mode == 0) {   // ratio test only when best and second come from the same level (:123-128)
-                if (lv1 == lv2 && (float)bDist > fmul(P.nnratio, (float)sDist)) continue;
-            }
-            if (lane == 0) {
-                match[bIdx] = base + j;
-                claimed[bIdx] = (uint8_t)obs;
-                if (obs) s_bits[bIdx >> 5] |= 1u << (bIdx & 31);
-                else s_bits[bIdx >> 5] &= ~(1u << (bIdx & 31));
-                if (hist) { evBin[nEvents] = (uint8_t)bnb; evIdx[nEvents] = (uint16_t)bIdx; s_hist[bnb]++; }
-            }
-            ++nmatches; ++nEvents;
-            __syncwarp();
+        if (lane == 0) {
+            P.resultIdx[o] = ri; P.resultDist[o] = rd;
+            P.query[o] = make_float4(u, v, r, __int_as_float((minL + 1) | ((maxL + 1) << 8) | ((ok ? 1 : 0) << 16)));
         }
     }
-    if (P.mode == 1 && P.checkOri) {   // ComputeThreeMaxima (:2012-2053) + removal (:1868-1884)
-        __syncwarp();
-        int ind1 = -1, ind2 = -1, ind3 = -1;
-        if (lane == 0) {
-            int max1 = 0, max2 = 0, max3 = 0;
+    if (C > 1) { __threadfence(); cluster.sync(); }     // the lists of all CTAs are visible to CTA 0
+    else __syncthreads();
+    if (rank != 0) return;
+
+    // ---- pass 2 (CTA 0): fixed-point resolution of the sequential claim rule ----
+    const int4* RI = P.resultIdx + (size_t)f * P.mcap;
+    const int4* RD = P.resultDist + (size_t)f * P.mcap;
+    for (int i = tid; i < M; i += MF_NT) { S.choice[i] = (uint16_t)NONE16; S.mflags[i] = P.hasObs[(size_t)f * P.mcap + i] ? 1 : 0; }
+    for (int c = tid; c < K; c += MF_NT) S.minClaimer[c] = 0x7fffffff;
+    if (tid == 0) { s_changed = 0; s_nq = 0; }
+    __syncthreads();
+    // decision of map point i from (best, second) among the usable candidates
+    auto decide = [&](int bIdx, int bDist, int sIdx, int sDist) -> unsigned {
+        if (bIdx < 0 || bDist > TH_HIGH) return NONE16;
+        if (P.mode == 0) {   // ratio test only when best and second come from the same level (:123-128)
+            const int lv1 = S.koct[bIdx], lv2 = sIdx >= 0 ? (int)S.koct[sIdx] : -1;
+            if (lv1 == lv2 && (float)bDist > fmul(P.nnratio, (float)sDist)) return NONE16;
+        }
+        return (unsigned)bIdx;
+    };
+    const bool need2 = P.mode == 0;
+    for (int sweep = 0; sweep <= M; ++sweep) {
+        // A. thread per map point: walk the four candidates against the claims of lower-index map points
+        for (int i = tid; i < M; i += MF_NT) {
+            const int4 ri = RI[i];
+            unsigned ch = NONE16;
+            if (ri.x >= 0) {
+                const int4 rd = RD[i];
+                const int ids[4] = {ri.x, ri.y, ri.z, ri.w};
+                const int ds[4] = {rd.x, rd.y, rd.z, rd.w};
+                int bIdx = -1, bDist = 256, sIdx = -1, sDist = 256;
+                bool exhausted = false;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (ids[c] < 0) { exhausted = true; continue; }
+                    if (S.minClaimer[ids[c]] < i) continue;
+                    if (bIdx < 0) { bIdx = ids[c]; bDist = ds[c]; }
+                    else if (sIdx < 0) { sIdx = ids[c]; sDist = ds[c]; }
+                }
+                if (!exhausted && (bIdx < 0 || (need2 && sIdx < 0))) {
+                    S.queue[atomicAdd(&s_nq, 1)] = (uint16_t)i;            // decided in phase B
+                    continue;
+                }
+                ch = decide(bIdx, bDist, sIdx, sDist);
+            }
+            if (ch != S.choice[i]) { S.choice[i] = (uint16_t)ch; s_changed = 1; }
+        }
+        __syncthreads();
+        // B. warp per queued map point: exact rescan against the current claims
+        const int nq = s_nq;
+        for (int q = wid; q < nq; q += MF_NT / 32) {
+            const int i = S.queue[q];
+            const float4 qq = P.query[(size_t)f * P.mcap + i];
+            const int bits = __float_as_int(qq.w);
+            uint32_t mpd[8];
+            load_mp_desc(P, f, i, mpd);
+            const Top2 t = scan_candidates<2>(P, S, f, qq.x, qq.y, qq.z, (bits & 0xff) - 1, ((bits >> 8) & 0xff) - 1, mpd,
+                                              [&](int idx) { return notInit(idx) && !(S.minClaimer[idx] < i); });
+            const unsigned ch = decide(t.i[0], t.i[0] >= 0 ? (int)(t.k[0] >> 40) : 256, t.i[1], t.i[1] >= 0 ? (int)(t.k[1] >> 40) : 256);
+            if (lane == 0 && ch != S.choice[i]) { S.choice[i] = (uint16_t)ch; s_changed = 1; }
+        }
+        __syncthreads();
+        const int changed = s_changed;
+        __syncthreads();
+        if (!changed) break;
+        // C. claims of this sweep's choices
+        for (int c = tid; c < K; c += MF_NT) S.minClaimer[c] = 0x7fffffff;
+        if (tid == 0) { s_changed = 0; s_nq = 0; }
+        __syncthreads();
+        for (int i = tid; i < M; i += MF_NT) {
+            const unsigned ch = S.choice[i];
+            if (ch != NONE16 && (S.mflags[i] & 1)) atomicMin(&S.minClaimer[ch], i);
+        }
+        __syncthreads();
+    }
+
+    // ---- outcome: nmatches++ per accepted map point (:1762-1776), rotation histogram, ComputeThreeMaxima (:2012-2053) ----
+    const bool hist = P.mode == 1 && P.checkOri;
+    int* s_hist = S.cnt;                      // [HISTO_LENGTH]
+    int* lastWriter = S.minClaimer;           // [K] highest-index accepted map point that chose the keypoint
+    uint32_t* removedBits = S.initBits;       // [K bits] keypoints cleared by the rotation filter
+    if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+    if (tid == 0) { s_nAcc = 0; s_nRemoved = 0; }
+    for (int c = tid; c < K; c += MF_NT) lastWriter[c] = -1;
+    for (int w = tid; w < (K + 31) / 32; w += MF_NT) removedBits[w] = 0;
+    __syncthreads();
+    int nAcc = 0;
+    for (int i = tid; i < M; i += MF_NT) {
+        const unsigned ch = S.choice[i];
+        if (ch == NONE16) continue;
+        ++nAcc;
+        atomicMax(&lastWriter[ch], i);
+        if (hist) {
+            const int b = rot_bin(P.angle[(size_t)f * P.mcap + i], kps[ch].angle);
+            S.mflags[i] = (uint8_t)((S.mflags[i] & 1) | ((b + 1) << 2));
+            atomicAdd(&s_hist[b], 1);
+        }
+    }
+    if (nAcc) atomicAdd(&s_nAcc, nAcc);
+    __syncthreads();
+    if (hist) {
+        if (tid == 0) {
+            int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
             for (int b = 0; b < HISTO_LENGTH; ++b) {
                 const int s = s_hist[b];
                 if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = b; }
@@ -388,18 +468,156 @@ __global__ void __launch_bounds__(32) match_commit_kernel(MatchParams P) {
             }
             if ((float)max2 < fmul(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
             else if ((float)max3 < fmul(0.1f, (float)max1)) { ind3 = -1; }
+            s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
         }
-        ind1 = __shfl_sync(0xffffffffu, ind1, 0); ind2 = __shfl_sync(0xffffffffu, ind2, 0); ind3 = __shfl_sync(0xffffffffu, ind3, 0);
+        __syncthreads();
         int removed = 0;
-        for (int e = lane; e < nEvents; e += 32) {
-            const int b = evBin[e];
-            if (b != ind1 && b != ind2 && b != ind3) { match[evIdx[e]] = -1; claimed[evIdx[e]] = 0; ++removed; }
+        for (int i = tid; i < M; i += MF_NT) {      // every event of a rejected bin clears its keypoint (:1868-1884)
+            const unsigned ch = S.choice[i];
+            if (ch == NONE16) continue;
+            const int b = (S.mflags[i] >> 2) - 1;
+            if (b != s_ind[0] && b != s_ind[1] && b != s_ind[2]) { atomicOr(&removedBits[ch >> 5], 1u << (ch & 31)); ++removed; }
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
-        nmatches -= removed;
+        if (removed) atomicAdd(&s_nRemoved, removed);
+        __syncthreads();
     }
-    if (lane == 0) P.nmatches[f] = nmatches;
+    for (int c = tid; c < K; c += MF_NT) {
+        const int w = lastWriter[c];
+        if ((removedBits[c >> 5] >> (c & 31)) & 1u) { match[c] = -1; claimed[c] = 0; }
+        else if (w >= 0) { match[c] = w; claimed[c] = S.mflags[w] & 1; }
+        else if (reset) { match[c] = -1; claimed[c] = 0; }
+    }
+    if (reset) for (int c = K + tid; c < P.kcap; c += MF_NT) { match[c] = -1; claimed[c] = 0; }
+    if (tid == 0) P.nmatches[f] = s_nAcc - s_nRemoved;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:648-763): windowed brute force between the two frames of the monocular
+// initialiser.  Same cluster layout as match_frame_kernel with F2 as the frame in shared memory:
+//   pass 1 (all CTAs, warp per level-0 keypoint of F1): the four smallest (distance, enumeration order) keys among the level-0
+//           keypoints of F2 inside the window around vbPrevMatched[i1];
+//   pass 2 (one warp of CTA 0, F1 keypoints in index order -- the vMatchedDistance / vnMatches21 overwrite rule is order dependent):
+//           best and second-best among the candidates i2 whose current match is worse (vMatchedDistance[i2] > dist, :686), TH_LOW,
+//           ratio test, re-assignment of an already matched F2 keypoint (:706-714); a keypoint whose four candidates do not
+//           settle it is rescanned against the live vMatchedDistance;
+//   then the rotation histogram on F1 indices (:716-726, :733-754) and the vbPrevMatched update (:757-759).
+// MatchParams reuse: kps/desc/nK = F2, mpDesc/nM = descriptors / count of F1, projX/projY = vbPrevMatched (in), level = F1 octaves,
+// angle = F1 angles, th = windowSize, nnratio; outputs: match = vnMatches12 [K1], query = updated vbPrevMatched (xy), nmatches.
+// ---------------------------------------------------------------------------------------------
+constexpr int TH_LOW = 50;         // src/ORBmatcher.cc:36
+__global__ void __launch_bounds__(MF_NT) init_match_kernel(MatchParams P) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int s_warp[33];
+    __shared__ int s_hist[HISTO_LENGTH], s_ind[3], s_nm;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int K2 = min(P.nK[0], P.kcap), K1 = min(P.nM[0], P.mcap);
+    const FrameSmem S = carve_frame_smem(smem_raw, P.ks, P.ms, P.descInSmem != 0);
+    uint16_t* m21 = reinterpret_cast<uint16_t*>(smem_raw + frame_smem_bytes(P.ks, P.ms, P.descInSmem != 0));   // vnMatches21 [K2]
+    int* matchedDist = S.minClaimer;                                                                             // vMatchedDistance [K2]
+    build_frame_smem(S, P.kps, P.desc, K2, P.minX, P.minY, P.gridWInv, P.gridHInv, s_warp);
+    auto anyIdx = [](int) { return true; };
+    // ---- pass 1 ----
+    for (int i = rank * (MF_NT / 32) + wid; i < K1; i += C * (MF_NT / 32)) {
+        int4 ri = make_int4(-1, -1, -1, -1), rd = make_int4(256, 256, 256, 256);
+        const int level1 = P.level[i];
+        if (!(level1 > 0)) {                                        // :663-665
+            uint32_t mpd[8];
+            load_mp_desc(P, 0, i, mpd);
+            const TopK<4> t = scan_candidates<4>(P, S, 0, P.projX[i], P.projY[i], P.th, level1, level1, mpd, anyIdx);
+            ri = make_int4(t.i[0], t.i[1], t.i[2], t.i[3]);
+            rd = make_int4(t.i[0] >= 0 ? (int)(t.k[0] >> 40) : 256, t.i[1] >= 0 ? (int)(t.k[1] >> 40) : 256,
+                           t.i[2] >= 0 ? (int)(t.k[2] >> 40) : 256, t.i[3] >= 0 ? (int)(t.k[3] >> 40) : 256);
+        }
+        if (lane == 0) { P.resultIdx[i] = ri; P.resultDist[i] = rd; }
+    }
+    if (C > 1) { __threadfence(); cluster.sync(); }
+    else __syncthreads();
+    if (rank != 0) return;
+    // ---- pass 2 ----
+    for (int c = tid; c < K2; c += MF_NT) { matchedDist[c] = 0x7fffffff; m21[c] = (uint16_t)NONE16; }
+    for (int i = tid; i < K1; i += MF_NT) { S.choice[i] = (uint16_t)NONE16; S.mflags[i] = 0; }
+    if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+    if (tid == 0) s_nm = 0;
+    __syncthreads();
+    if (wid == 0) {
+        for (int base = 0; base < K1; base += 32) {
+            const int i = base + lane;
+            int4 ri = make_int4(-1, -1, -1, -1), rd = make_int4(256, 256, 256, 256);
+            if (i < K1) { ri = P.resultIdx[i]; rd = P.resultDist[i]; }
+            const int cnt = min(32, K1 - base);
+            for (int j = 0; j < cnt; ++j) {
+                const int c0 = __shfl_sync(0xffffffffu, ri.x, j);
+                if (c0 < 0) continue;                                 // level > 0 or no candidate (:671-672)
+                const int ids[4] = {c0, __shfl_sync(0xffffffffu, ri.y, j), __shfl_sync(0xffffffffu, ri.z, j), __shfl_sync(0xffffffffu, ri.w, j)};
+                const int ds[4] = {__shfl_sync(0xffffffffu, rd.x, j), __shfl_sync(0xffffffffu, rd.y, j), __shfl_sync(0xffffffffu, rd.z, j),
+                                   __shfl_sync(0xffffffffu, rd.w, j)};
+                const int i1 = base + j;
+                int bIdx = -1, bDist = 0x7fffffff, sDist = 0x7fffffff, found = 0;
+                bool exhausted = false;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (ids[c] < 0) { exhausted = true; continue; }
+                    if (matchedDist[ids[c]] <= ds[c]) continue;       // :686-687
+                    if (found == 0) { bIdx = ids[c]; bDist = ds[c]; }
+                    else if (found == 1) sDist = ds[c];
+                    ++found;
+                }
+                if (!exhausted && found < 2) {                        // the four do not settle best and second: exact rescan
+                    uint32_t mpd[8];
+                    load_mp_desc(P, 0, i1, mpd);
+                    const int level1 = P.level[i1];
+                    const Top2 t = scan_candidates<2>(P, S, 0, P.projX[i1], P.projY[i1], P.th, level1, level1, mpd, anyIdx,
+                                                      [&](int idx, int dist) { return !(matchedDist[idx] <= dist); });
+                    bIdx = t.i[0]; bDist = t.i[0] >= 0 ? (int)(t.k[0] >> 40) : 0x7fffffff;
+                    sDist = t.i[1] >= 0 ? (int)(t.k[1] >> 40) : 0x7fffffff;
+                }
+                if (bIdx < 0 || bDist > TH_LOW) continue;             // :702
+                if (!((float)bDist < fmul((float)sDist, P.nnratio))) continue;    // :704
+                if (lane == 0) {
+                    const unsigned prev = m21[bIdx];
+                    if (prev != NONE16) S.choice[prev] = (uint16_t)NONE16;        // :706-710
+                    S.choice[i1] = (uint16_t)bIdx; m21[bIdx] = (uint16_t)i1; matchedDist[bIdx] = bDist;
+                    if (P.checkOri) {                                             // :716-726
+                        const int b = rot_bin(P.angle[i1], P.kps[bIdx].angle);
+                        S.mflags[i1] = (uint8_t)(b + 1);
+                        s_hist[b]++;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    if (P.checkOri && tid == 0) {   // ComputeThreeMaxima (:2012-2053)
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int b = 0; b < HISTO_LENGTH; ++b) {
+            const int sz = s_hist[b];
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = b; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = b; }
+            else if (sz > max3) { max3 = sz; ind3 = b; }
+        }
+        if ((float)max2 < fmul(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < fmul(0.1f, (float)max1)) { ind3 = -1; }
+        s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+    }
+    __syncthreads();
+    int n = 0;
+    for (int i = tid; i < K1; i += MF_NT) {
+        unsigned ch = S.choice[i];
+        if (ch != NONE16 && P.checkOri) {                             // :733-754: events of rejected bins lose their match if they still hold one
+            const int b = (int)S.mflags[i] - 1;
+            if (b != s_ind[0] && b != s_ind[1] && b != s_ind[2]) ch = NONE16;
+        }
+        P.match[i] = ch == NONE16 ? -1 : (int)ch;
+        float px = P.projX[i], py = P.projY[i];
+        if (ch != NONE16) { ++n; px = S.kx[ch]; py = S.ky[ch]; }      // :757-759
+        P.query[i] = make_float4(px, py, 0.f, 0.f);
+    }
+    if (n) atomicAdd(&s_nm, n);
+    __syncthreads();
+    if (tid == 0) P.nmatches[0] = s_nm;
 }
 
 // cv::BFMatcher(NORM_HAMMING).knnMatch(k=2): warp per query, lanes over train rows
@@ -441,8 +659,9 @@ struct Matcher {
     int device, maxBatch, kcap, mcap;
     cudaStream_t stream = nullptr;
     // scratch
-    int* d_cellStart = nullptr; uint16_t* d_cellIdx = nullptr; float4* d_query = nullptr; int4 *d_resultIdx = nullptr, *d_resultDist = nullptr;
-    uint8_t* d_evBin = nullptr; uint16_t* d_evIdx = nullptr; int* d_status = nullptr;
+    float4* d_query = nullptr; int4 *d_resultIdx = nullptr, *d_resultDist = nullptr;
+    int* d_status = nullptr;
+    int numSMs = 148;
     // staging for the host entry points (batch = 1) -- one arena
     uint8_t* d_arena = nullptr; size_t arenaBytes = 0;
     uint8_t* h_arena = nullptr;
@@ -451,7 +670,7 @@ struct Matcher {
 
     ~Matcher() {
         cudaSetDevice(device);
-        void* ptrs[] = {d_cellStart, d_cellIdx, d_query, d_resultIdx, d_resultDist, d_evBin, d_evIdx, d_status, d_arena, d_batch};
+        void* ptrs[] = {d_query, d_resultIdx, d_resultDist, d_status, d_arena, d_batch};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (h_arena) cudaFreeHost(h_arena);
         if (stream) cudaStreamDestroy(stream);
@@ -462,13 +681,10 @@ struct Matcher {
         CK(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) { set_error("device is not sm_100+ (Blackwell); this library has no other code path"); return ORB_ERR_CUDA; }
         const size_t B = maxBatch;
-        CK(cudaMalloc(&d_cellStart, sizeof(int) * (GRID_CELLS + 1) * B));
-        CK(cudaMalloc(&d_cellIdx, sizeof(uint16_t) * kcap * B));
+        numSMs = prop.multiProcessorCount;
         CK(cudaMalloc(&d_query, sizeof(float4) * mcap * B));
         CK(cudaMalloc(&d_resultIdx, sizeof(int4) * mcap * B));
         CK(cudaMalloc(&d_resultDist, sizeof(int4) * mcap * B));
-        CK(cudaMalloc(&d_evBin, mcap * B));
-        CK(cudaMalloc(&d_evIdx, sizeof(uint16_t) * mcap * B));
         CK(cudaMalloc(&d_status, sizeof(int) * B));
         arenaBytes = (size_t)kcap * (28 + 32 + 4 + 1) + (size_t)mcap * (32 + 12 + 4 * 6 + 4) + 4096 + 64 * 64;
         arenaBytes = (arenaBytes + 255) & ~(size_t)255;
@@ -482,22 +698,60 @@ struct Matcher {
         batchBytes = B * ((size_t)kcap * (28 + 32 + 4 + 1) + (size_t)mcap * (1 + 12 + 4 + 4 + 1 + 32) + 28 + 16 + 13 * 256) + 4096;
         CK(cudaMalloc(&d_batch, batchBytes));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        CK(cudaFuncSetAttribute(match_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
         return ORB_OK;
     }
-    int run(MatchParams& P, cudaStream_t st) {
+    // kUse / mUse: the largest keypoint / map-point count any frame of this call can have (the slab capacities when the
+    // counts live on the device): they size the kernel's shared memory.
+    int run(MatchParams& P, int kUse, int mUse, cudaStream_t st) {
         P.gridWInv = (float)GRID_COLS / (P.maxX - P.minX);   // src/Frame.cc:342-343
         P.gridHInv = (float)GRID_ROWS / (P.maxY - P.minY);
-        P.cellStart = d_cellStart; P.cellIdx = d_cellIdx; P.query = d_query; P.resultIdx = d_resultIdx; P.resultDist = d_resultDist;
-        P.evBin = d_evBin; P.evIdx = d_evIdx; P.status = d_status;
-        launches = 0;
-        grid_build_kernel<<<P.batch, GB_NT, 0, st>>>(P);
-        match_candidates_kernel<<<dim3((P.mcap + MC_NT / 32 - 1) / (MC_NT / 32), P.batch), MC_NT, 0, st>>>(P);
-        const size_t sm = sizeof(uint32_t) * ((P.kcap + 31) / 32);
-        if (sm > 48 * 1024) { set_error("kcap too large for the claim bitset"); return ORB_ERR_ARG; }
-        match_commit_kernel<<<P.batch, 32, sm, st>>>(P);
-        launches = 3;
-        CK(cudaGetLastError());
+        P.query = d_query; P.resultIdx = d_resultIdx; P.resultDist = d_resultDist; P.status = d_status;
+        P.ks = std::max(kUse, 1); P.ms = std::max(mUse, 1);
+        if (P.ks > 65535 || P.ms > 65535) { set_error("more than 65535 keypoints or map points per frame"); return ORB_ERR_CAPACITY; }
+        const size_t limit = 227 * 1024 - 2048;              // opt-in maximum minus the kernel's static shared memory
+        P.descInSmem = frame_smem_bytes(P.ks, P.ms, true) <= 100 * 1024 ? 1 : 0;   // two CTAs per SM when the descriptors are staged
+        const size_t sm = frame_smem_bytes(P.ks, P.ms, P.descInSmem != 0);
+        if (sm > limit) { set_error("frame too large for the matcher's shared-memory grid (keypoints + map points)"); return ORB_ERR_CAPACITY; }
+        int rc = ensure_dynamic_smem(match_frame_kernel, sm, device);
+        if (rc) return rc;
+        // cluster size: as many CTAs per frame as keeps the whole call resident at once (pass 1 is spread over the cluster)
+        int C = 1;
+        while (C < 8 && (long)P.batch * (C * 2) <= (long)numSMs * (sm > 100 * 1024 ? 1 : 2)) C *= 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(P.batch * C)); cfg.blockDim = dim3(MF_NT); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, match_frame_kernel, P));
+        launches = 1;
+        lastCluster = C;
+        return ORB_OK;
+    }
+    int lastCluster = 1;
+
+    // SearchForInitialization: F2 in shared memory (K2 keypoints), K1 keypoints of F1 as the queries
+    int run_init(MatchParams& P, int K2, int K1, cudaStream_t st) {
+        P.gridWInv = (float)GRID_COLS / (P.maxX - P.minX);
+        P.gridHInv = (float)GRID_ROWS / (P.maxY - P.minY);
+        P.query = d_query; P.resultIdx = d_resultIdx; P.resultDist = d_resultDist; P.status = d_status;
+        P.ks = std::max(K2, 1); P.ms = std::max(K1, 1);
+        if (P.ks > 65535 || P.ms > 65535) { set_error("more than 65535 keypoints per frame"); return ORB_ERR_CAPACITY; }
+        const size_t limit = 227 * 1024 - 2048;
+        auto bytes = [&](bool d) { return frame_smem_bytes(P.ks, P.ms, d) + al16(sizeof(uint16_t) * (size_t)P.ks); };
+        P.descInSmem = bytes(true) <= limit ? 1 : 0;
+        const size_t sm = bytes(P.descInSmem != 0);
+        if (sm > limit) { set_error("frames too large for the matcher's shared-memory grid"); return ORB_ERR_CAPACITY; }
+        int rc = ensure_dynamic_smem(init_match_kernel, sm, device);
+        if (rc) return rc;
+        cudaLaunchConfig_t cfg = {};
+        const int C = 8;                                   // one pair of frames: pass 1 spread over a full cluster
+        cfg.gridDim = dim3(C); cfg.blockDim = dim3(MF_NT); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, init_match_kernel, P));
+        launches = 1;
+        lastCluster = C;
         return ORB_OK;
     }
 };
@@ -601,12 +855,12 @@ static int stage_frame(Matcher& m, Arena& A, const OrbmFrame* fr, MatchParams& P
     return ORB_OK;
 }
 
-static int finish_host(Matcher& m, Arena& A, MatchParams& P, int K, int* dMatch, uint8_t* dClaimed, int* dN, int32_t* match,
+static int finish_host(Matcher& m, Arena& A, MatchParams& P, int K, int mUse, int* dMatch, uint8_t* dClaimed, int* dN, int32_t* match,
                        uint8_t* claimed, int* nmatches) {
     cudaStream_t st = m.stream;
     CK(cudaMemcpyAsync(m.d_arena, m.h_arena, A.off, cudaMemcpyHostToDevice, st));
     P.match = dMatch; P.claimed = dClaimed; P.nmatches = dN + 1;
-    int rc = m.run(P, st);
+    int rc = m.run(P, K, mUse, st);
     if (rc) return rc;
     // results come back through the same arena offsets
     const size_t oM = (uint8_t*)dMatch - m.d_arena, oC = (uint8_t*)dClaimed - m.d_arena, oN = (uint8_t*)dN - m.d_arena;
@@ -641,7 +895,7 @@ int orbm_search_local_map(orbm_handle* h, const OrbmFrame* fr, const OrbmLocalPo
     for (size_t i = 0; i < M; ++i)
         if (pts->inView[i] && !pts->bad[i] && (pts->level[i] < 0 || pts->level[i] >= fr->nlevels)) { set_error("map point level out of range"); return ORB_ERR_ARG; }
     P.mcap = m.mcap; P.mode = 0; P.th = th; P.nnratio = nnratio; P.bFar = bFar; P.thFar = thFar;
-    return finish_host(m, A, P, fr->K, dMatch, dClaimed, dN, match, claimed, nmatches);
+    return finish_host(m, A, P, fr->K, pts->M, dMatch, dClaimed, dN, match, claimed, nmatches);
 }
 
 int orbm_search_last_frame(orbm_handle* h, const OrbmFrame* fr, const OrbmLastFrame* last, const float* Tcw7, const float* cam4,
@@ -664,7 +918,7 @@ int orbm_search_last_frame(orbm_handle* h, const OrbmFrame* fr, const OrbmLastFr
         if (last->valid[i] && (last->octave[i] < 0 || last->octave[i] >= fr->nlevels)) { set_error("last-frame octave out of range"); return ORB_ERR_ARG; }
     memcpy(P.cam, cam4, sizeof(float) * 4);
     P.mcap = m.mcap; P.mode = 1; P.th = th; P.checkOri = checkOri;
-    return finish_host(m, A, P, fr->K, dMatch, dClaimed, dN, match, claimed, nmatches);
+    return finish_host(m, A, P, fr->K, last->M, dMatch, dClaimed, dN, match, claimed, nmatches);
 }
 
 int orbm_search_last_frame_batch_device(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOri, int32_t* d_match,
@@ -682,7 +936,7 @@ int orbm_search_last_frame_batch_device(orbm_handle* h, const OrbmBatchDevice* i
     P.Tcw7 = in->Tcw7; memcpy(P.cam, in->cam, sizeof(float) * 4);
     P.th = th; P.checkOri = checkOri; P.resetState = in->resetState;
     P.match = d_match; P.claimed = d_claimed; P.nmatches = d_nmatches;
-    return m.run(P, (cudaStream_t)stream);
+    return m.run(P, in->kcap, in->mcap, (cudaStream_t)stream);
 }
 
 int orbm_search_last_frame_batch(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOri, int32_t* match, uint8_t* claimed,
@@ -715,6 +969,48 @@ int orbm_search_last_frame_batch(orbm_handle* h, const OrbmBatchDevice* in, floa
     CK(cudaMemcpyAsync(claimed, dc, B * K, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(nmatches, dn, B * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_search_for_initialization(orbm_handle* h, const OrbmFrame* F1, const OrbmFrame* F2, float* prevMatched, int windowSize, float nnratio,
+                                   int checkOrientation, int32_t* matches12, int* nmatches) {
+    if (!h || !F1 || !F2 || !prevMatched || !matches12 || !nmatches || F1->K < 0 || F2->K < 0 || F1->K > h->m.mcap || F2->K > h->m.kcap ||
+        F2->nlevels < 1 || !(F2->maxX > F2->minX) || !(F2->maxY > F2->minY) || windowSize < 0) {
+        set_error("orbm_search_for_initialization: bad argument (F1.K <= max_mappoints, F2.K <= max_keypoints)"); return ORB_ERR_ARG;
+    }
+    Matcher& m = h->m;
+    CK(cudaSetDevice(m.device));
+    const size_t K1 = F1->K, K2 = F2->K;
+    *nmatches = 0;
+    for (size_t i = 0; i < K1; ++i) matches12[i] = -1;              // vnMatches12 = vector<int>(F1.mvKeysUn.size(),-1), :651
+    if (K1 == 0) return ORB_OK;
+    MatchParams P; memset(&P, 0, sizeof(P));
+    Arena A(m.h_arena, m.d_arena, m.arenaBytes);
+    std::vector<float> px(K1), py(K1), ang(K1); std::vector<int> lvl(K1);
+    for (size_t i = 0; i < K1; ++i) { px[i] = prevMatched[2 * i]; py[i] = prevMatched[2 * i + 1]; ang[i] = F1->keypoints[i].angle; lvl[i] = F1->keypoints[i].octave; }
+    int counts[2] = {F2->K, F1->K};
+    const int* dCounts; const int32_t* dMatch; const int* dN;
+    bool ok = A.put(F2->keypoints, K2, &P.kps) && A.put(F2->descriptors, K2 * 32, &P.desc) && A.put(F1->descriptors, K1 * 32, &P.mpDesc) &&
+              A.put(px.data(), K1, &P.projX) && A.put(py.data(), K1, &P.projY) && A.put(ang.data(), K1, &P.angle) && A.put(lvl.data(), K1, &P.level) &&
+              A.put(counts, (size_t)2, &dCounts);
+    const size_t inBytes = A.off;
+    ok = ok && A.put((const int32_t*)nullptr, K1, &dMatch) && A.put((const int*)nullptr, (size_t)1, &dN);
+    if (!ok) { set_error("matcher staging arena too small"); return ORB_ERR_CAPACITY; }
+    P.nK = dCounts; P.nM = dCounts + 1;
+    P.batch = 1; P.kcap = m.kcap; P.mcap = m.mcap; P.nlevels = F2->nlevels; P.mode = 2;
+    P.minX = F2->minX; P.minY = F2->minY; P.maxX = F2->maxX; P.maxY = F2->maxY;
+    P.th = (float)windowSize; P.nnratio = nnratio; P.checkOri = checkOrientation;
+    P.match = const_cast<int32_t*>(dMatch); P.nmatches = const_cast<int*>(dN);
+    cudaStream_t st = m.stream;
+    CK(cudaMemcpyAsync(m.d_arena, m.h_arena, inBytes, cudaMemcpyHostToDevice, st));
+    int rc = m.run_init(P, F2->K, F1->K, st);
+    if (rc) return rc;
+    std::vector<float4> q(K1);
+    CK(cudaMemcpyAsync(matches12, dMatch, 4 * K1, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nmatches, dN, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(q.data(), m.d_query, sizeof(float4) * K1, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < K1; ++i) { prevMatched[2 * i] = q[i].x; prevMatched[2 * i + 1] = q[i].y; }
     return ORB_OK;
 }
 

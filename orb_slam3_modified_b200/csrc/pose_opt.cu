@@ -127,6 +127,12 @@ __global__ void __launch_bounds__(NT) pose_opt_kernel(Params P) {
     __shared__ int s_ok2;
     const int f = blockIdx.x, tid = threadIdx.x;
     const int N = min(P.N[f], P.cap);
+    if (N < 3) {   // if(nInitialCorrespondences<3) return 0; (src/Optimizer.cc:996-997): pose and outlier flags stay as they are
+        if (tid < 7) P.poseOut[7 * (size_t)f + tid] = P.pose7[7 * (size_t)f + tid];
+        for (int e = tid; e < N; e += NT) P.outlier[(size_t)f * P.cap + e] = 0;
+        if (tid == 0) P.nInliers[f] = 0;
+        return;
+    }
     const double* Xw = P.Xw + (size_t)f * P.cap * 3;
     const double* obs = P.obs + (size_t)f * P.cap * 2;
     const float* is2 = P.invSigma2 + (size_t)f * P.cap;

@@ -52,7 +52,7 @@ def test_control_flow_variants(opt):
     _check(opt, p, user_lambda_init=100.0)          # inertial map initial lambda
     _check(opt, p, iterations=1)
     _check(opt, p, iterations=0)
-    out = opt.LocalBundleAdjustment(p, stop_flag=np.ones(1, np.int32))
+    out = opt.LocalBundleAdjustment(p, stop_flag=np.ones(1, np.uint8))
     assert out['iters'] == 0 and np.allclose(out['points'], p['points'])
     # badly perturbed start: forces rejected LM trials (lambda escalation + pop)
     q = synth.lba_problem(n_kf=8, n_pts=500, obs_per_pt=5, seed=12, pose_noise=(0.3, 8.0), point_noise=0.5)
@@ -77,7 +77,7 @@ def test_batch_of_problems_one_launch():
     probs = [synth.lba_problem(n_kf=6 + b % 5, n_pts=200 + 37 * b, obs_per_pt=4 + b % 3, seed=20 + b) for b in range(20)]
     probs[3] = synth.lba_problem(n_kf=20, n_pts=5000, obs_per_pt=8, seed=0)
     outs = optb.LocalBundleAdjustmentBatch(probs)
-    assert optb.last_cluster_size() in (1, 2, 4, 8)
+    assert 1 <= optb.last_cluster_size() <= 8
     for p, out in zip(probs, outs):
         ref = O.lba_solve(p)
         assert out['iters'] == ref['iters'] and out['trials'] == int(ref['stats'][3])
@@ -85,13 +85,29 @@ def test_batch_of_problems_one_launch():
         r_gpu = O.lba_residuals(p, out['poses'], out['points'])
         assert np.abs(r_ref - r_gpu).max() < TOL_PX
     # resident re-run: upload once, run twice, same answer (state restarts from the uploaded estimates)
-    optb.upload(probs[:4])
+    # Different problems than the ones slots 0..3 still hold from the call above, and no host synchronisation between run and
+    # download: a download that does not wait for the run (it is on another stream) would return stale or half-written results.
+    optb.upload(probs[4:8])
     optb.run_device()
     a = optb.download()
     optb.run_device()
     b = optb.download()
-    for x, y in zip(a, b):
+    for x, y, first in zip(a, b, outs[4:8]):
         assert np.array_equal(x['poses'], y['poses']) and np.array_equal(x['points'], y['points']) and np.array_equal(x['chi2'], y['chi2'])
+        assert np.array_equal(x['poses'], first['poses']) and np.array_equal(x['chi2'], first['chi2']) and x['trials'] == first['trials']
+    import torch
+    side = torch.cuda.Stream()                         # run on a caller stream, upload + download on the handle's own
+    optb.upload(probs[8:12])
+    optb.run_device(side.cuda_stream)
+    c = optb.download()
+    for x, first in zip(c, outs[8:12]):
+        assert np.array_equal(x['poses'], first['poses']) and np.array_equal(x['chi2'], first['chi2'])
+    optb.run_device(side.cuda_stream)
+    optb.upload(probs[12:16])                          # must not overwrite the arena under the running kernel
+    optb.run_device(side.cuda_stream)
+    d = optb.download()
+    for x, first in zip(d, outs[12:16]):
+        assert np.array_equal(x['poses'], first['poses']) and np.array_equal(x['chi2'], first['chi2'])
 
 
 def test_large_window_matrix_in_global_memory():
@@ -103,6 +119,25 @@ def test_large_window_matrix_in_global_memory():
     out = optl.LocalBundleAdjustment(p)
     assert out['iters'] == ref['iters'] and out['trials'] == int(ref['stats'][3])
     assert np.abs(O.lba_residuals(p, ref['poses'], ref['points']) - O.lba_residuals(p, out['poses'], out['points'])).max() < TOL_PX
+
+
+def test_many_fixed_keyframes_and_handle_creation_order():
+    """The reference puts no bound on lFixedCameras (src/Optimizer.cc:1166-1186): a window with hundreds of fixed keyframes must
+    run (pose caches hold all poses, the LDLT panels only the free ones).  And the shared-memory opt-in of the kernel is a
+    per-function attribute: a smaller handle created after a larger one must not break the larger one."""
+    import orb_slam3_modified_b200 as m
+    big = m.Optimizer(max_poses=300, max_points=2000, max_edges=20000)
+    p = synth.lba_problem(n_kf=280, n_pts=1500, obs_per_pt=10, seed=51, n_fixed=268)
+    small = m.Optimizer(max_poses=4, max_points=100, max_edges=400)
+    q = synth.lba_problem(n_kf=4, n_pts=80, obs_per_pt=4, seed=52)
+    for opt_, prob in ((small, q), (big, p), (small, q), (big, p)):
+        ref = O.lba_solve(prob)
+        out = opt_.LocalBundleAdjustment(prob)
+        assert out['iters'] == ref['iters'] and out['trials'] == int(ref['stats'][3])
+        assert np.abs(O.lba_residuals(prob, ref['poses'], ref['points']) - O.lba_residuals(prob, out['poses'], out['points'])).max() < TOL_PX
+    with pytest.raises(m.OrbError):       # beyond the shared-memory pose caches: a clear capacity error, not a launch failure
+        huge = m.Optimizer(max_poses=900, max_points=1000, max_edges=9000)
+        huge.LocalBundleAdjustment(synth.lba_problem(n_kf=900, n_pts=900, obs_per_pt=8, seed=53, n_fixed=890))
 
 
 def test_device_structure_build_any_edge_order_and_rejects_bad_graphs(opt):

@@ -156,3 +156,57 @@ def test_batch_device_matches_host(orb, matcher):
         on = O.search_last_frame(s['kps'], s['desc'], s['bounds'], s['sf'], s['Tcw'], s['cam'], s['last'], 15.0, True, om, oc)
         assert int(d_n[b]) == on
         assert np.array_equal(d_match[b, :k].cpu().numpy(), om) and np.array_equal(d_claimed[b, :k].cpu().numpy(), oc)
+
+
+@pytest.mark.parametrize('t,window,ori,nf', [(2, 100, True, 1000), (6, 30, True, 1000), (11, 100, False, 1000), (4, 100, True, 5000), (9, 10, True, 1000)])
+def test_search_for_initialization(orb, t, window, ori, nf):
+    """a13, second call site: ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:648-763) vs the oracle (which equals the reference's
+    own function body, tests/test_ref_pins_oracle_cpu.py): vnMatches12, the return value and the updated vbPrevMatched."""
+    k1, d1 = S.extract(t, nf=nf)
+    k2, d2 = S.extract(t + 1, nf=nf)
+    sf = O.OracleExtractor().tables()['scale']
+    b = (0.0, 0.0, 640.0, 480.0)
+    m = orb.ORBmatcher(0.9, ori, max_batch=1, max_keypoints=8192, max_mappoints=8192)
+    prev = np.ascontiguousarray(np.stack([k1['x'], k1['y']], 1), np.float32)
+    rng = np.random.default_rng(t)
+    prev += rng.normal(0, 3.0, prev.shape).astype(np.float32)            # vbPrevMatched drifts while the initialiser retries
+    on, om, oprev = O.search_for_initialization(k1, d1, k2, d2, b, sf, prev, window, 0.9, ori)
+    F1, F2 = orb.Frame(k1, d1, b, sf), orb.Frame(k2, d2, b, sf)
+    gp = prev.copy()
+    n, m12 = m.SearchForInitialization(F1, F2, gp, window)
+    assert n == on and (window < 30 or n > 30), (n, on)
+    assert np.array_equal(m12, om) and np.array_equal(gp, oprev)
+    # second attempt with the updated vbPrevMatched (Tracking::MonocularInitialization keeps it across frames)
+    on2, om2, oprev2 = O.search_for_initialization(k1, d1, k2, d2, b, sf, oprev, window, 0.9, ori)
+    n2, m122 = m.SearchForInitialization(F1, F2, gp, window)
+    assert n2 == on2 and np.array_equal(m122, om2) and np.array_equal(gp, oprev2)
+
+
+def test_search_for_initialization_heavy_rematching(orb):
+    """Many F1 keypoints compete for few F2 keypoints (descriptors duplicated): exercises the vMatchedDistance overwrite rule, the
+    displacement of earlier matches and the rescan path."""
+    k1, d1 = S.extract(13)
+    k2, d2 = S.extract(14)
+    sf = O.OracleExtractor().tables()['scale']
+    b = (0.0, 0.0, 640.0, 480.0)
+    rng = np.random.default_rng(3)
+    l0 = np.flatnonzero(k2['octave'] == 0)
+    d2 = d2.copy()
+    src = rng.choice(l0, 25)
+    for i in l0:                                   # level-0 descriptors of F2 collapse onto 25 prototypes (+ a few bit flips)
+        d2[i] = d2[src[rng.integers(0, 25)]]
+        for bit in rng.integers(0, 256, rng.integers(0, 4)):
+            d2[i, bit >> 3] ^= np.uint8(1 << (bit & 7))
+    d1 = d1.copy()
+    l01 = np.flatnonzero(k1['octave'] == 0)
+    for i in l01:
+        d1[i] = d2[src[rng.integers(0, 25)]]
+        for bit in rng.integers(0, 256, rng.integers(0, 12)):
+            d1[i, bit >> 3] ^= np.uint8(1 << (bit & 7))
+    prev = np.ascontiguousarray(np.stack([k1['x'], k1['y']], 1), np.float32)
+    for ratio in (0.9, 1.5):
+        m = orb.ORBmatcher(ratio, True, max_batch=1, max_keypoints=2048, max_mappoints=2048)
+        on, om, oprev = O.search_for_initialization(k1, d1, k2, d2, b, sf, prev, 100, ratio, True)
+        gp = prev.copy()
+        n, m12 = m.SearchForInitialization(orb.Frame(k1, d1, b, sf), orb.Frame(k2, d2, b, sf), gp, 100)
+        assert n == on and np.array_equal(m12, om) and np.array_equal(gp, oprev), (ratio, n, on)
