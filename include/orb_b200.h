@@ -92,6 +92,12 @@ int orbx_extract_batch_device(orbx_handle* h, const uint8_t* d_images, int batch
                               size_t frame_stride, int lap0, int lap1, OrbKeyPoint* d_keypoints,
                               uint8_t* d_descriptors, int cap, int* d_nkeypoints, int* d_monoIndex, void* stream);
 
+/* The host-buffer calls above also leave their results in the handle's device slabs ([batch][cap] keypoints, [batch][cap][32]
+ * descriptors, [batch] counts, cap = orbx_max_keypoints()).  These pointers stay valid until the next call on the handle, so a
+ * matcher call that follows (orbm_search_last_frame_batch_resident) does not have to ship the current frame back to the device. */
+int orbx_resident_slabs(const orbx_handle* h, const OrbKeyPoint** d_keypoints, const uint8_t** d_descriptors, const int** d_nkeypoints,
+                        int* cap);
+
 /* Debug/inspection taps used by the parity tests (mvImagePyramid is a public member of the reference class,
  * include/ORBextractor.h:84).  Copies level `level` of frame `frame` of the last call, unbordered, tightly packed. */
 int orbx_get_level_size(const orbx_handle* h, int level, int* width, int* height);
@@ -114,7 +120,10 @@ int orbx_get_stage_ms(orbx_handle* h, float* ms6);
  * ------------------------------------------------------------------------------------------ */
 typedef struct orbm_handle orbm_handle;
 
-/* Scratch for up to max_batch frames of max_keypoints keypoints matched against max_mappoints map points. */
+/* Scratch for up to max_batch frames of max_keypoints keypoints matched against max_mappoints map points (both <= 65535).
+ * One call in flight per handle: the per-frame scratch (candidate lists, queries) belongs to the handle, so two concurrent calls --
+ * also on different streams -- need two handles (bench.py gives every stream group its own).  Device-side octave / level values
+ * outside [0, nlevels) are clamped; the host entry points reject them. */
 int orbm_create(orbm_handle** out, int max_batch, int max_keypoints, int max_mappoints, int device);
 void orbm_destroy(orbm_handle* h);
 
@@ -222,6 +231,11 @@ int orbm_search_last_frame_batch(orbm_handle* h, const OrbmBatchDevice* in, floa
  * vnMatches12 (-1 = none); *nmatches is the return value.  Host pointers. */
 int orbm_search_for_initialization(orbm_handle* h, const OrbmFrame* F1, const OrbmFrame* F2, float* prevMatched, int windowSize,
                                    float nnratio, int checkOrientation, int32_t* matches12, int* nmatches);
+
+/* Same with the CURRENT FRAME already on the device (in->kps, in->desc, in->nK are device pointers with stride in->kcap, e.g. from
+ * orbx_resident_slabs()); everything else as in orbm_search_last_frame_batch (host pointers). */
+int orbm_search_last_frame_batch_resident(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOrientation, int32_t* match,
+                                          uint8_t* claimed, int32_t* nmatches);
 
 /* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) as used at src/Frame.cc:1144: idx/dist are Q x 2,
  * ordered by (distance, lower train index); missing neighbours are -1.  Host pointers. */

@@ -172,6 +172,15 @@ class ORBextractor:
         if rc != ORB_OK:
             raise OrbError(rc, 'orbx_extract_batch')
 
+    def resident_slabs(self):
+        """Device addresses (ints) of the slabs the last host-buffer call left in the handle: (kps, desc, n, cap)."""
+        k, d, n, cap = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
+        lib().orbx_resident_slabs.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        rc = lib().orbx_resident_slabs(self._h, C.byref(k), C.byref(d), C.byref(n), C.byref(cap))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbx_resident_slabs')
+        return k.value, d.value, n.value, cap.value
+
     def extract_batch_device(self, d_images, d_kps, d_desc, d_n, d_mono, vLappingArea=(0, 0), stream=0):
         """All-device variant (torch CUDA tensors): d_images [B, rows, cols] u8; slabs d_kps [B, cap, 7] (28-byte rows),
         d_desc [B, cap, 32] u8, d_n / d_mono [B] i32.  Enqueues on ``stream`` and returns immediately."""
@@ -391,17 +400,26 @@ class ORBmatcher:
         if rc != ORB_OK:
             raise OrbError(rc, 'orbm_search_last_frame_batch_device')
 
-    def search_last_frame_batch(self, d, th, match, claimed, nmatches):
-        """Host-buffer batch (numpy arrays in dict ``d``, same keys as the device variant); in/out arrays are numpy."""
+    def search_last_frame_batch(self, d, th, match, claimed, nmatches, resident=None):
+        """Host-buffer batch (numpy arrays in dict ``d``, same keys as the device variant); in/out arrays are numpy.
+        ``resident`` = ``ORBextractor.resident_slabs()`` of the extractor that just produced the frames: the current frame is then read
+        from the device slabs (d['kps'], d['desc'], d['nK'] are ignored) instead of being uploaded again."""
         s = _OrbmBatchDevice()
         s.batch, s.kcap, s.mcap, s.nlevels = d['batch'], d['kcap'], d['mcap'], d['nlevels']
-        for k in ('kps', 'desc', 'nK', 'scaleFactors', 'nM', 'valid', 'xyz', 'octave', 'angle', 'hasObs', 'mpDesc', 'Tcw7'):
+        for k in ('scaleFactors', 'nM', 'valid', 'xyz', 'octave', 'angle', 'hasObs', 'mpDesc', 'Tcw7'):
             setattr(s, k, d[k].ctypes.data)
+        if resident is not None:
+            s.kps, s.desc, s.nK = resident[0], resident[1], resident[2]
+            assert resident[3] == d['kcap']
+        else:
+            for k in ('kps', 'desc', 'nK'):
+                setattr(s, k, d[k].ctypes.data)
         s.minX, s.minY, s.maxX, s.maxY = d['bounds']
         s.cam = (C.c_float * 4)(*d['cam'])
         s.resetState = int(d.get('reset', 0))
-        lib().orbm_search_last_frame_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        rc = lib().orbm_search_last_frame_batch(self._h, C.byref(s), th, int(self.mbCheckOrientation), _ptr(match), _ptr(claimed), _ptr(nmatches))
+        fn = lib().orbm_search_last_frame_batch_resident if resident is not None else lib().orbm_search_last_frame_batch
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = fn(self._h, C.byref(s), th, int(self.mbCheckOrientation), _ptr(match), _ptr(claimed), _ptr(nmatches))
         if rc != ORB_OK:
             raise OrbError(rc, 'orbm_search_last_frame_batch')
 

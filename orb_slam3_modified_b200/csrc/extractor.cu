@@ -495,25 +495,27 @@ int orbx_extract_batch(orbx_handle* h, const uint8_t* images, int batch, int row
     CK(cudaMemcpyAsync(hn, e.d_outN, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hm, e.d_outMono, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hs, e.d_status, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    int worst = ORB_OK;
-    bool anyBad = false;
-    for (int f = 0; f < batch; ++f) {
-        n[f] = hn[f]; mono[f] = hm[f];
-        if (hs[f] || hn[f] > cap) { worst = ORB_ERR_CAPACITY; set_error("keypoint capacity exceeded"); anyBad = true; }
-    }
-    if (!anyBad && cap == icap && batch > 1) {
-        // slab-to-slab: the caller's buffers have the internal capacity -> two bulk copies (rows beyond n[f] are unspecified)
+    const bool slabToSlab = cap == icap && batch > 1;
+    if (slabToSlab) {
+        // the caller's buffers have the internal capacity -> two bulk copies queued behind the kernels, ONE synchronisation per call
+        // (rows beyond n[f] are unspecified; on a capacity error the buffers hold whatever the device wrote)
         CK(cudaMemcpyAsync(kps, e.d_outKp, sizeof(OrbKeyPoint) * (size_t)icap * batch, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(desc, e.d_outDesc, (size_t)32 * icap * batch, cudaMemcpyDeviceToHost, st));
-    } else {
+    }
+    CK(cudaStreamSynchronize(st));
+    int worst = ORB_OK;
+    for (int f = 0; f < batch; ++f) {
+        n[f] = hn[f]; mono[f] = hm[f];
+        if (hs[f] || hn[f] > cap) { worst = ORB_ERR_CAPACITY; set_error("keypoint capacity exceeded"); }
+    }
+    if (!slabToSlab) {
         for (int f = 0; f < batch; ++f) {
             if (hs[f] || hn[f] > cap || hn[f] <= 0) continue;
             CK(cudaMemcpyAsync(kps + (size_t)f * cap, e.d_outKp + (size_t)f * icap, sizeof(OrbKeyPoint) * hn[f], cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(desc + (size_t)f * cap * 32, e.d_outDesc + (size_t)f * icap * 32, (size_t)32 * hn[f], cudaMemcpyDeviceToHost, st));
         }
+        CK(cudaStreamSynchronize(st));
     }
-    CK(cudaStreamSynchronize(st));
     return worst;
 }
 
@@ -561,6 +563,12 @@ int orbx_copy_candidates(orbx_handle* h, int frame, int level, int* xys, int cap
         }
     }
     return total;
+}
+
+int orbx_resident_slabs(const orbx_handle* h, const OrbKeyPoint** d_keypoints, const uint8_t** d_descriptors, const int** d_nkeypoints, int* cap) {
+    if (!h || !d_keypoints || !d_descriptors || !d_nkeypoints || !cap) return ORB_ERR_ARG;
+    *d_keypoints = h->e.d_outKp; *d_descriptors = h->e.d_outDesc; *d_nkeypoints = h->e.d_outN; *cap = h->e.outCapInternal;
+    return ORB_OK;
 }
 
 int orbx_last_launch_count(const orbx_handle* h) { return h ? h->e.launches : ORB_ERR_ARG; }

@@ -170,6 +170,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long l
 #ifndef LBA_NT
 #define LBA_NT 512
 #endif
+#ifndef LBA_MINB
+#define LBA_MINB 1     /* __launch_bounds__ min blocks: with LBA_NT=256, 2 caps the kernel at 128 registers = half an SM's file */
+#endif
 #ifndef LBA_SCH
 #define LBA_SCH 128
 #endif
@@ -845,7 +848,7 @@ __device__ void phase_finalize(const Dev& D, const Ctx& c) {
 // Dynamic shared memory: 2 pose caches (PC x maxP doubles each, maxP = most poses of any loaded problem, fixed keyframes included) |
 // LDLT panel scratch (2 x 6 x (6 maxF + 1), maxF = most FREE poses) | rhs row (6 maxF) | reduced camera system (smemMatrixN^2).
 // =============================================================================================
-__global__ void __launch_bounds__(NT, 1) lba_cluster_kernel(const Dev* __restrict__ probs, const volatile int* stop, int smemMatrixN, int maxP, int maxF) {
+__global__ void __launch_bounds__(NT, LBA_MINB) lba_cluster_kernel(const Dev* __restrict__ probs, const volatile int* stop, int smemMatrixN, int maxP, int maxF) {
     extern __shared__ double s_dyn[];
     __shared__ double s_red[NT];
     cg::cluster_group cluster = cg::this_cluster();

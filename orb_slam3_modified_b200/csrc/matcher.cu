@@ -155,15 +155,28 @@ struct TopK {   // the K smallest keys seen, ascending
             }
         }
     }
-    __device__ __forceinline__ void warp_merge() {   // afterwards every lane holds the K smallest of the whole warp
+    // Afterwards every lane holds the K smallest keys of the whole warp.  Keys are unique (they carry the candidate's enumeration
+    // rank), every lane's list is sorted, so the warp minimum is the minimum of the heads: K rounds of a 64-bit warp minimum (two
+    // REDUX.MIN on the halves), the winning lane pops its head.
+    __device__ __forceinline__ void warp_merge() {
+        unsigned long long rk[K]; int ri[K];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            unsigned long long ok[K]; int oi[K];
+        for (int j = 0; j < K; ++j) {
+            const unsigned hi = (unsigned)(k[0] >> 32), lo = (unsigned)k[0];
+            const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+            const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+            const unsigned long long mk = ((unsigned long long)mhi << 32) | mlo;
+            const bool won = k[0] == mk;
+            const int src = __ffs(__ballot_sync(0xffffffffu, won)) - 1;
+            rk[j] = mk; ri[j] = __shfl_sync(0xffffffffu, i[0], src);
+            if (won && mk != ~0ull) {
 #pragma unroll
-            for (int j = 0; j < K; ++j) { ok[j] = __shfl_xor_sync(0xffffffffu, k[j], o); oi[j] = __shfl_xor_sync(0xffffffffu, i[j], o); }
-#pragma unroll
-            for (int j = 0; j < K; ++j) insert(ok[j], oi[j]);
+                for (int q = 0; q + 1 < K; ++q) { k[q] = k[q + 1]; i[q] = i[q + 1]; }
+                k[K - 1] = ~0ull; i[K - 1] = -1;
+            }
         }
+#pragma unroll
+        for (int j = 0; j < K; ++j) { k[j] = rk[j]; i[j] = ri[j]; }
     }
 };
 typedef TopK<2> Top2;
@@ -184,8 +197,10 @@ __device__ __forceinline__ TopK<K> scan_candidates(const MatchParams& P, const F
         const int ny = nMaxCellY - nMinCellY + 1, nx = nMaxCellX - nMinCellX + 1;
         const uint8_t* gdesc = P.desc + (size_t)f * P.kcap * 32;
         const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        const unsigned nyMagic = 0xFFFFFFFFu / (unsigned)ny + 1u;          // c / ny by multiply-high (exact: c * ny < 2^32)
         for (int c = lane; c < nx * ny; c += 32) {
-            const int ix = nMinCellX + c / ny, iy = nMinCellY + c % ny;
+            const int cq = (int)__umulhi((unsigned)c, nyMagic);
+            const int ix = nMinCellX + cq, iy = nMinCellY + (c - cq * ny);
             const int cell = ix * GRID_ROWS + iy;
             const int a = S.cellStart[cell], b = S.cellStart[cell + 1];
             for (int e = a; e < b; ++e) {
@@ -924,7 +939,10 @@ int orbm_search_last_frame(orbm_handle* h, const OrbmFrame* fr, const OrbmLastFr
 int orbm_search_last_frame_batch_device(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOri, int32_t* d_match,
                                         uint8_t* d_claimed, int32_t* d_nmatches, void* stream) {
     if (!h || !in || !d_match || !d_claimed || !d_nmatches || in->batch < 1 || in->batch > h->m.maxBatch || in->kcap > 65535 ||
-        in->kcap > h->m.kcap || in->mcap > h->m.mcap) { set_error("orbm_search_last_frame_batch_device: bad argument"); return ORB_ERR_ARG; }
+        in->kcap > h->m.kcap || in->mcap > h->m.mcap || in->kcap < 1 || in->mcap < 1 || in->nlevels < 1 || !(in->maxX > in->minX) ||
+        !(in->maxY > in->minY) || !in->kps || !in->desc || !in->nK || !in->nM || !in->scaleFactors) {
+        set_error("orbm_search_last_frame_batch_device: bad argument (sizes, image bounds or null slabs)"); return ORB_ERR_ARG;
+    }
     Matcher& m = h->m;
     CK(cudaSetDevice(m.device));
     MatchParams P; memset(&P, 0, sizeof(P));
@@ -939,8 +957,8 @@ int orbm_search_last_frame_batch_device(orbm_handle* h, const OrbmBatchDevice* i
     return m.run(P, in->kcap, in->mcap, (cudaStream_t)stream);
 }
 
-int orbm_search_last_frame_batch(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOri, int32_t* match, uint8_t* claimed,
-                                 int32_t* nmatches) {
+static int search_last_frame_batch_host(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOri, int32_t* match, uint8_t* claimed,
+                                       int32_t* nmatches, bool frameOnDevice) {
     if (!h || !in || !match || !claimed || !nmatches || in->batch < 1 || in->batch > h->m.maxBatch || in->kcap > h->m.kcap ||
         in->mcap > h->m.mcap || in->nlevels < 1) { set_error("orbm_search_last_frame_batch: bad argument"); return ORB_ERR_ARG; }
     Matcher& m = h->m;
@@ -959,10 +977,13 @@ int orbm_search_last_frame_batch(orbm_handle* h, const OrbmBatchDevice* in, floa
     int rc;
     const void *dm, *dc, *dn;
 #define UP(field, bytes) if ((rc = up(in->field, bytes, (const void**)&d.field))) return rc
-    UP(kps, B * K * 28); UP(desc, B * K * 32); UP(nK, B * 4); UP(scaleFactors, (size_t)in->nlevels * 4); UP(nM, B * 4);
+    if (!frameOnDevice) { UP(kps, B * K * 28); UP(desc, B * K * 32); UP(nK, B * 4); }
+    UP(scaleFactors, (size_t)in->nlevels * 4); UP(nM, B * 4);
     UP(valid, B * M); UP(xyz, B * M * 12); UP(octave, B * M * 4); UP(angle, B * M * 4); UP(hasObs, B * M); UP(mpDesc, B * M * 32); UP(Tcw7, B * 28);
 #undef UP
-    if ((rc = up(match, B * K * 4, &dm)) || (rc = up(claimed, B * K, &dc)) || (rc = up(nullptr, B * 4, &dn))) return rc;
+    // with resetState the incoming match / claimed arrays are not read: do not ship them
+    if ((rc = up(in->resetState ? nullptr : match, B * K * 4, &dm)) || (rc = up(in->resetState ? nullptr : claimed, B * K, &dc)) ||
+        (rc = up(nullptr, B * 4, &dn))) return rc;
     rc = orbm_search_last_frame_batch_device(h, &d, th, checkOri, (int32_t*)dm, (uint8_t*)dc, (int32_t*)dn, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(match, dm, B * K * 4, cudaMemcpyDeviceToHost, st));
@@ -1012,6 +1033,15 @@ int orbm_search_for_initialization(orbm_handle* h, const OrbmFrame* F1, const Or
     CK(cudaStreamSynchronize(st));
     for (size_t i = 0; i < K1; ++i) { prevMatched[2 * i] = q[i].x; prevMatched[2 * i + 1] = q[i].y; }
     return ORB_OK;
+}
+
+int orbm_search_last_frame_batch(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOri, int32_t* match, uint8_t* claimed,
+                                 int32_t* nmatches) {
+    return search_last_frame_batch_host(h, in, th, checkOri, match, claimed, nmatches, false);
+}
+int orbm_search_last_frame_batch_resident(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOri, int32_t* match, uint8_t* claimed,
+                                          int32_t* nmatches) {
+    return search_last_frame_batch_host(h, in, th, checkOri, match, claimed, nmatches, true);
 }
 
 int orbm_frustum_project(orbm_handle* h, const OrbmFrustumIn* in, uint8_t* inView, float* projX, float* projY, float* projXR,

@@ -38,9 +38,19 @@ def test_reference_arm_json_contract():
                                   cwd=ROOT, preexec_fn=lambda: os.sched_setaffinity(0, two), timeout=600).decode().strip().splitlines()
     d = json.loads(out[-1])
     assert d['impl'] == 'reference' and d['unit'] == 'frames/s' and d['higher_is_better'] is True and d['value'] > 0
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] == len(two) and d['cpu_baseline']['value'] == d['value']
+    have_ref = os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'libref_orb.so'))
+    cb = d['cpu_baseline']
+    assert cb['kind'] == ('reference' if have_ref else 'port') and cb['kind_per_stage']['lba'] == 'port'
+    assert cb['cores'] == len(two) and cb['value'] == d['value'] and 1.0 <= cb['effective_cores_measured'] <= 2.6
+    assert cb['split']['extract_ms_per_frame'] > 1 and cb['split']['lba_ms_per_problem'] > 10
     assert d['e2e'] == {'value': d['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['metric'].startswith('frames/sec') and d['config']['workload'].startswith('configs[1]')
+
+
+def test_host_cores_respects_affinity():
+    import bench
+    n, how = bench.host_cores()
+    assert 1 <= n <= len(os.sched_getaffinity(0)) and isinstance(how, str)
 
 
 def test_reference_arm_other_ranks_do_nothing():

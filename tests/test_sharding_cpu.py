@@ -1,4 +1,4 @@
-"""CPU tests of the N>1 path with the gloo backend (world_size 2): slab gather == concatenation, max-over-ranks timing,
+"""CPU tests of the N>1 path with the gloo backend (world_size 2): packed per-group slab gather == the ranks' slabs, max-over-ranks timing,
 stream sharding."""
 import os
 import socket
@@ -21,15 +21,26 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     from orb_slam3_modified_b200 import sharding
-    B, cap = 3, 16
-    g = torch.Generator().manual_seed(100 + rank)
-    kps = torch.rand((B, cap, 7), generator=g)
-    desc = torch.randint(0, 256, (B, cap, 32), generator=g, dtype=torch.uint8)
-    n = torch.randint(0, cap, (B,), generator=g, dtype=torch.int32)
-    gather = sharding.SlabGather(dist, world, kps, desc, n)
-    gk, gd, gn = gather(kps, desc, n)
+    nb, cap, G = 3, 16, 2
+    gen = torch.Generator().manual_seed(100 + rank)
+    slabs = [[sharding.PackedSlab(nb, cap, torch.device('cpu')) for _ in range(2)] for _ in range(G)]
+    for pair in slabs:
+        for s in pair:
+            s.kps.copy_(torch.rand((nb, cap, 7), generator=gen))
+            s.desc.copy_(torch.randint(0, 256, (nb, cap, 32), generator=gen, dtype=torch.uint8))
+            s.n.copy_(torch.randint(0, cap, (nb,), generator=gen, dtype=torch.int32))
+            s.mono.copy_(torch.randint(0, cap, (nb,), generator=gen, dtype=torch.int32))
+    gather = sharding.GroupSlabGather(dist, world, slabs)
+    for d in range(2):                    # two rounds in flight per group, as in bench.py
+        for g in range(G):
+            gather.wait(g, d)
+            gather.gather(g, d)
+    gather.drain()
+    # what this rank holds for (group 1, set 0) after the exchange, unpacked per source rank
+    got = [tuple(v.numpy().copy() for v in sharding.PackedSlab.views_of(gather.out[1][0][r], nb, cap)) for r in range(world)]
+    mine = tuple(v.numpy().copy() for v in (slabs[1][0].kps, slabs[1][0].desc, slabs[1][0].n, slabs[1][0].mono))
     t = sharding.max_over_ranks(dist, 1.0 + rank, torch.device('cpu'))
-    q.put((rank, kps.numpy(), desc.numpy(), n.numpy(), gk.numpy(), gd.numpy(), gn.numpy(), t))
+    q.put((rank, mine, got, t))
     dist.destroy_process_group()
 
 
@@ -44,10 +55,11 @@ def test_slab_gather_two_ranks():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    cat_k = np.stack([r[1] for r in res]); cat_d = np.stack([r[2] for r in res]); cat_n = np.stack([r[3] for r in res])
     for r in res:
-        assert r[4].tobytes() == cat_k.tobytes() and r[5].tobytes() == cat_d.tobytes() and r[6].tobytes() == cat_n.tobytes()
-        assert r[7] == 2.0      # max over ranks
+        for src in range(world):          # every rank sees every rank's slab, field by field, bit for bit
+            for a, b in zip(r[2][src], res[src][1]):
+                assert a.dtype == b.dtype and a.tobytes() == b.tobytes()
+        assert r[3] == 2.0      # max over ranks
 
 
 def test_shard_streams():
