@@ -106,22 +106,55 @@ struct FrameView {
     }
 };
 
+namespace detail {
+// The reference constructs ORBmatcher as a stack temporary per use (src/Tracking.cc:2494,2730,2859,3393,3631) and Optimizer's
+// functions are static: neither can own device scratch.  The handles therefore live in per-thread caches (Tracking and
+// LocalMapping are different threads, src/System.cc:197) that grow on demand and are reused by every later call.
+struct MatcherSlot {
+    orbm_handle* h = nullptr; int maxK = 0, maxM = 0, device = -1;
+    ~MatcherSlot() { if (h) orbm_destroy(h); }
+};
+inline orbm_handle* matcher_handle(int needK, int needM, int device) {
+    thread_local MatcherSlot s;
+    if (!s.h || s.device != device || needK > s.maxK || needM > s.maxM) {
+        if (s.h) { orbm_destroy(s.h); s.h = nullptr; }
+        s.maxK = needK > s.maxK ? needK + needK / 2 : s.maxK; if (s.maxK < 4096) s.maxK = 4096; if (s.maxK > 65535) s.maxK = 65535;
+        s.maxM = needM > s.maxM ? needM + needM / 2 : s.maxM; if (s.maxM < 16384) s.maxM = 16384; if (s.maxM > 65535) s.maxM = 65535;
+        s.device = device;
+        orb_check(orbm_create(&s.h, 1, s.maxK, s.maxM, device), "orbm_create");
+    }
+    return s.h;
+}
+struct LbaSlot {
+    lba_handle* h = nullptr; int maxP = 0, maxL = 0, maxE = 0, device = -1;
+    ~LbaSlot() { if (h) lba_destroy(h); }
+};
+inline lba_handle* lba_handle_for(int nP, int nL, int nE, int device) {
+    thread_local LbaSlot s;
+    if (!s.h || s.device != device || nP > s.maxP || nL > s.maxL || nE > s.maxE) {
+        if (s.h) { lba_destroy(s.h); s.h = nullptr; }
+        auto grow = [](int need, int have, int floor_) { int v = need > have ? need + need / 2 : have; return v < floor_ ? floor_ : v; };
+        s.maxP = grow(nP, s.maxP, 32); s.maxL = grow(nL, s.maxL, 4096); s.maxE = grow(nE, s.maxE, 32768); s.device = device;
+        orb_check(lba_create(&s.h, s.maxP, s.maxL, s.maxE, device), "lba_create");
+    }
+    return s.h;
+}
+}  // namespace detail
+
 class ORBmatcher {
 public:
     static const int TH_LOW = 50, TH_HIGH = 100, HISTO_LENGTH = 30;   // src/ORBmatcher.cc:35-37
-    ORBmatcher(float nnratio = 0.6, bool checkOri = true, int maxKeypoints = 4096, int maxMapPoints = 16384, int device = 0)
-        : mfNNratio(nnratio), mbCheckOrientation(checkOri) {
-        orb_check(orbm_create(&h_, 1, maxKeypoints, maxMapPoints, device), "orbm_create");
-    }
-    ~ORBmatcher() { orbm_destroy(h_); }
-    ORBmatcher(const ORBmatcher&) = delete;
-    ORBmatcher& operator=(const ORBmatcher&) = delete;
+    // ORBmatcher(float nnratio=0.6, bool checkOri=true): two scalars, like the reference -- cheap to construct per use
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true, int device = 0) : mfNNratio(nnratio), mbCheckOrientation(checkOri), device_(device) {}
 
-    // static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b) -- needs a handle here (device popcount)
-    int DescriptorDistance(const uint8_t* a, const uint8_t* b) {
-        int32_t d = 0;
-        orb_check(orbm_descriptor_distance(h_, a, b, 1, &d), "orbm_descriptor_distance");
-        return d;
+    // static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b): the device popcount is exposed for parity checks; a host caller
+    // that needs one distance uses this portable form (the reference's SWAR popcount, src/ORBmatcher.cc:2058-2074)
+    static int DescriptorDistance(const uint8_t* a, const uint8_t* b) {
+        const uint32_t* pa = reinterpret_cast<const uint32_t*>(a); const uint32_t* pb = reinterpret_cast<const uint32_t*>(b);
+        int dist = 0;
+        for (int i = 0; i < 8; ++i) { uint32_t v = pa[i] ^ pb[i]; v = v - ((v >> 1) & 0x55555555); v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+                                      dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24; }
+        return dist;
     }
     // int SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th, const bool bFarPoints, const float thFarPoints)
     int SearchByProjection(FrameView& F, const OrbmLocalPoints& vpMapPoints, const float th = 3, const bool bFarPoints = false,
@@ -129,8 +162,8 @@ public:
         prepare(F);
         const OrbmFrame f = F.c_struct();
         int n = 0;
-        orb_check(orbm_search_local_map(h_, &f, &vpMapPoints, th, mfNNratio, bFarPoints, thFarPoints, F.mvpMapPoints.data(), F.mvbClaimed.data(), &n),
-                  "orbm_search_local_map");
+        orb_check(orbm_search_local_map(detail::matcher_handle(f.K, vpMapPoints.M, device_), &f, &vpMapPoints, th, mfNNratio, bFarPoints, thFarPoints,
+                                        F.mvpMapPoints.data(), F.mvbClaimed.data(), &n), "orbm_search_local_map");
         return n;
     }
     // int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)  (mono branch)
@@ -140,8 +173,20 @@ public:
         prepare(CurrentFrame);
         const OrbmFrame f = CurrentFrame.c_struct();
         int n = 0;
-        orb_check(orbm_search_last_frame(h_, &f, &LastFrame, Tcw, cam, th, mbCheckOrientation, CurrentFrame.mvpMapPoints.data(),
-                                         CurrentFrame.mvbClaimed.data(), &n), "orbm_search_last_frame");
+        orb_check(orbm_search_last_frame(detail::matcher_handle(f.K, LastFrame.M, device_), &f, &LastFrame, Tcw, cam, th, mbCheckOrientation,
+                                         CurrentFrame.mvpMapPoints.data(), CurrentFrame.mvbClaimed.data(), &n), "orbm_search_last_frame");
+        return n;
+    }
+    // int SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12, int windowSize=10)
+    // vbPrevMatched: F1.N x 2 floats (x, y), updated like the reference (src/ORBmatcher.cc:757-759)
+    int SearchForInitialization(const FrameView& F1, const FrameView& F2, std::vector<float>& vbPrevMatched, std::vector<int>& vnMatches12,
+                                int windowSize = 10) {
+        const OrbmFrame f1 = F1.c_struct(), f2 = F2.c_struct();
+        if (vbPrevMatched.size() != (size_t)f1.K * 2) throw std::invalid_argument("vbPrevMatched must hold one point per keypoint of F1");
+        vnMatches12.assign((size_t)f1.K, -1);
+        int n = 0;
+        orb_check(orbm_search_for_initialization(detail::matcher_handle(f2.K, f1.K, device_), &f1, &f2, vbPrevMatched.data(), windowSize, mfNNratio,
+                                                 mbCheckOrientation, vnMatches12.data(), &n), "orbm_search_for_initialization");
         return n;
     }
     // bool Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) for all local map points of a frame (Tracking::SearchLocalPoints,
@@ -152,13 +197,14 @@ public:
         out.inView.assign(M, 0); out.projX.assign(M, -1.f); out.projY.assign(M, -1.f); out.projXR.assign(M, 0.f); out.depth.assign(M, 0.f);
         out.viewCos.assign(M, 0.f); out.level.assign(M, -1);
         if (!M) return;
-        orb_check(orbm_frustum_project(h_, &points, out.inView.data(), out.projX.data(), out.projY.data(), out.projXR.data(), out.depth.data(),
-                                       out.level.data(), out.viewCos.data()), "orbm_frustum_project");
+        orb_check(orbm_frustum_project(detail::matcher_handle(1, points.M, device_), &points, out.inView.data(), out.projX.data(), out.projY.data(),
+                                       out.projXR.data(), out.depth.data(), out.level.data(), out.viewCos.data()), "orbm_frustum_project");
     }
     // cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, matches, 2)
     void knnMatch(const Descriptors& query, const Descriptors& train, std::vector<int32_t>& idx, std::vector<int32_t>& dist) {
         idx.assign((size_t)query.rows * 2, -1); dist.assign((size_t)query.rows * 2, -1);
-        orb_check(orbm_bf_knn2(h_, query.data.data(), query.rows, train.data.data(), train.rows, idx.data(), dist.data()), "orbm_bf_knn2");
+        orb_check(orbm_bf_knn2(detail::matcher_handle(query.rows, train.rows, device_), query.data.data(), query.rows, train.data.data(), train.rows,
+                               idx.data(), dist.data()), "orbm_bf_knn2");
     }
 
 protected:
@@ -168,7 +214,7 @@ protected:
     }
     float mfNNratio;
     bool mbCheckOrientation;
-    orbm_handle* h_ = nullptr;
+    int device_;
 };
 
 class Optimizer {
@@ -176,13 +222,11 @@ public:
     // void static LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, int& num_fixedKF, int& num_OptKF, int& num_MPs, int& num_edges)
     // The pointer-graph walk (src/Optimizer.cc:1125-1403) and the write-back (:1464-1497) stay with the caller; this is
     // optimizer.initializeOptimization(); optimizer.optimize(10); and the values the outlier test at :1417-1430 reads.
+    // graph.stopFlag takes the caller's own `bool* pbStopFlag` (one byte).  The device arena is kept per thread and reused.
     static void LocalBundleAdjustment(const LbaProblem& graph, LbaResult& out, int device = 0) {
         if (graph.stopFlag && *graph.stopFlag) return;               // :1406-1408
-        lba_handle* h = nullptr;
-        orb_check(lba_create(&h, graph.nPoses, graph.nPoints > 0 ? graph.nPoints : 1, graph.nEdges > 0 ? graph.nEdges : 1, device), "lba_create");
-        const int rc = lba_solve(h, &graph, &out);
-        lba_destroy(h);
-        orb_check(rc, "lba_solve");
+        orb_check(lba_solve(detail::lba_handle_for(graph.nPoses, graph.nPoints > 0 ? graph.nPoints : 1, graph.nEdges > 0 ? graph.nEdges : 1, device),
+                            &graph, &out), "lba_solve");
     }
     // int static PoseOptimization(Frame* pFrame)  (src/Optimizer.cc:814-1113, monocular branch): the caller flattens the frame's map
     // point associations (:862-905); returns nInitialCorrespondences - nBad, writes the pose and the outlier flags.

@@ -307,14 +307,25 @@ int pose_optimization_batch(int count, int cap, const int32_t* N, const double* 
     if (device < 0 || device >= ndev) { set_error("pose_optimization_batch: bad device index"); return ORB_ERR_ARG; }
     CK(cudaSetDevice(device));
     const size_t C = count, K = cap;
-    uint8_t* d = nullptr;
+    // device scratch + stream are kept per host thread and device (PoseOptimization is a static function in the reference: no object
+    // to own them) and grow on demand: a call costs copies + one launch, not a cudaMalloc / cudaFree pair
+    struct Scratch { int device = -1; uint8_t* d = nullptr; size_t cap = 0; cudaStream_t st = nullptr;
+                     ~Scratch() { if (d) { cudaSetDevice(device); cudaFree(d); } if (st) cudaStreamDestroy(st); } };
+    thread_local Scratch S;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t oN = take(4 * C), oP = take(56 * C), oC = take(16 * C), oX = take(24 * C * K), oO = take(16 * C * K), oS = take(4 * C * K),
                  oE = take(16 * C * K), oPo = take(56 * C), oOut = take(C * K), oNi = take(4 * C);
-    CK(cudaMalloc(&d, off));
-    cudaStream_t st;
-    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (S.device != device || off > S.cap) {
+        if (S.d) { cudaSetDevice(S.device); cudaFree(S.d); S.d = nullptr; S.cap = 0; CK(cudaSetDevice(device)); }
+        if (S.st && S.device != device) { cudaStreamDestroy(S.st); S.st = nullptr; }
+        S.device = device;
+        CK(cudaMalloc(&S.d, off + off / 2));
+        S.cap = off + off / 2;
+    }
+    if (!S.st) CK(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+    uint8_t* d = S.d;
+    cudaStream_t st = S.st;
     int rc = ORB_OK;
     do {
 #define TRY(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error(cudaGetErrorString(e_)); rc = ORB_ERR_CUDA; break; } }
@@ -336,8 +347,6 @@ int pose_optimization_batch(int count, int cap, const int32_t* N, const double* 
         TRY(cudaStreamSynchronize(st));
 #undef TRY
     } while (0);
-    cudaStreamDestroy(st);
-    cudaFree(d);
     return rc;
 }
 
