@@ -321,6 +321,45 @@ int pose_optimization_batch(int count, int cap, const int32_t* N, const double* 
                             const double* obs, const float* invSigma2, double huberDelta, double* poseOut, uint8_t* outlier,
                             int32_t* nInliers, int device);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Inertial edges: what Optimizer::LocalInertialBA (reference include/Optimizer.h:96, src/Optimizer.cc:2383-2958)
+ * and PoseInertialOptimizationLast{KeyFrame,Frame} (:4491, :4875) evaluate in every iteration, batched over all streams of a GPU.
+ * The 15-DoF block solver around them is not part of this library yet; these entry points return residuals, Jacobians, chi2 and
+ * robust weights in g2o's conventions.  Host pointers.
+ * ------------------------------------------------------------------------------------------ */
+/* One IMU::Preintegrated (reference include/ImuTypes.h:159-240) as 292 floats:
+ *   [0] dT | [1..9] dR | [10..12] dV | [13..15] dP | [16..24] JRg | [25..33] JVg | [34..42] JVa | [43..51] JPg | [52..60] JPa |
+ *   [61..66] b = (bax, bay, baz, bwx, bwy, bwz) | [67..291] C (15 x 15 covariance, row-major).  3 x 3 blocks are row-major. */
+#define IMU_PREINT_FLOATS 292
+/* Preintegrated::Initialize(b) + IntegrateNewMeasurement (src/ImuTypes.cc:177-240) for `count` intervals (one per stream / keyframe pair):
+ * acc, gyr [count][maxMeas][3], dt [count][maxMeas], nMeas [count], bias6 [count][6] = (bax, bay, baz, bwx, bwy, bwz);
+ * noise4 = (ng, na, ngw, naw) as given to IMU::Calib::Set (:395-407).  preint [count][IMU_PREINT_FLOATS]. */
+int imu_preintegrate_batch(int count, const int32_t* nMeas, int maxMeas, const float* acc, const float* gyr, const float* dt, const float* bias6,
+                           const float* noise4, float* preint, int device);
+/* EdgeInertial's information matrix (src/G2oTypes.cc:499-507: inverse of C.block<9,9>, symmetrised, eigenvalues < 1e-12 clamped) and the
+ * EdgeGyroRW / EdgeAccRW informations (src/Optimizer.cc:551,559: inverses of C.block<3,3>(9,9) / (12,12)).  info9 [count][81], infoG / infoA [count][9]. */
+int imu_information_batch(int count, const float* preint, double* info9, double* infoG, double* infoA, int device);
+/* EdgeInertial::computeError + linearizeOplus (src/G2oTypes.cc:514-594) for `count` edges; edge e uses preint[e].
+ * states36 [count][36]: Rwb1 9 | twb1 3 | v1 3 | gyro bias 3 | acc bias 3 | Rwb2 9 | twb2 3 | v2 3 (estimates of the six vertices).
+ * err9 [count][9] = (er, ev, ep); J9x24 [count][9][24] (may be NULL), columns: pose 1 (rotation 3, translation 3; tangent of
+ * ImuCamPose::Update) | velocity 1 | gyro bias | acc bias | pose 2 | velocity 2.  With info9: chi2 [count] = e^T Omega e and, if rho is
+ * given, the Huber weight rho'(chi2) for huberDelta (sqrt(16.92) in LocalInertialBA, src/Optimizer.cc:540-542; <= 0: no kernel). */
+int imu_inertial_edges(int count, const float* preint, const double* states36, const double* info9, double huberDelta, double* err9, double* J9x24,
+                       double* chi2, double* rho, int device);
+/* EdgeMono (include/G2oTypes.h:342-385, src/G2oTypes.cc:349-373) over VertexPose = ImuCamPose (body pose + camera extrinsics, src/G2oTypes.cc:148-220). */
+typedef struct ImuMonoEdges {
+    int nPoses;  const double* poses;       /* [nPoses][12]: Rwb 9 | twb 3 */
+    const double* extrinsics;               /* [24]: Rcb 9 | tcb 3 | Rbc 9 | tbc 3 (camera 0, IMU::Calib mTcb / mTbc) */
+    const float* cam;                       /* [nPoses][4]: fx fy cx cy */
+    int nPoints; const double* points;      /* [nPoints][3] */
+    int nEdges;  const int32_t* edgePoint; const int32_t* edgePose; const double* obs /* [nEdges][2] */; const float* invSigma2 /* [nEdges] */;
+    double huberDelta;                      /* thHuberMono = sqrt(5.991); <= 0: no kernel */
+} ImuMonoEdges;
+/* err2 [nEdges][2]; Jpoint2x3 [nEdges][6] / Jpose2x6 [nEdges][12] (both or neither may be NULL); chi2, rho (may be NULL) [nEdges];
+ * depthPositive [nEdges] = EdgeMono::isDepthPositive(). */
+int imu_mono_edges(const ImuMonoEdges* in, double* err2, double* Jpoint2x3, double* Jpose2x6, double* chi2, double* rho, uint8_t* depthPositive, int device);
+
 #ifdef __cplusplus
 }
 #endif

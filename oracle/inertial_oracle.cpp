@@ -1,0 +1,367 @@
+// TEST INFRASTRUCTURE ONLY (see oracle_common.h).  CPU restatement of the inertial part of the path:
+//   IMU::Preintegrated::IntegrateNewMeasurement / IntegratedRotation        reference src/ImuTypes.cc:177-240, :84-107   (float, as the reference)
+//   IMU::Preintegrated::GetDeltaRotation / GetDeltaVelocity / GetDeltaPosition / GetDeltaBias     :276-307
+//   IMU::NormalizeRotation (Eigen::JacobiSVD U V^T)                                               :34-37
+//   EdgeInertial ctor (information = inverse of the 9x9 covariance, symmetrised, eigenvalues < 1e-12 clamped)  src/G2oTypes.cc:492-509
+//   EdgeInertial::computeError / linearizeOplus                                                   :514-594
+//   EdgeMono::computeError (include/G2oTypes.h:353-358), linearizeOplus (src/G2oTypes.cc:349-373), ImuCamPose::Project :170-175
+//   EdgeGyroRW / EdgeAccRW (include/G2oTypes.h:635-700): error = b2 - b1, information = inverse of the 3x3 walk covariance
+//   ExpSO3 / LogSO3 / RightJacobianSO3 / InverseRightJacobianSO3                                  :777-861
+//   ImuCamPose::Update (VertexPose::oplusImpl)                                                    :192-220
+// PARITY: G2oTypes / ImuTypes need Eigen and Sophus and cannot be compiled here (no oracle/_ref for them): the analytic Jacobians
+// below are pinned by numerical differentiation of the residuals under the reference's own update rules
+// (tests/test_inertial_cpu.py), the SVD / eigen pieces by their defining properties.  "parity unpinned" by the reference itself.
+#include "oracle_common.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace orbo {
+namespace imu {
+
+template <class T> static void mat3_mul(const T* A, const T* B, T* C) {
+    T r[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+    for (int i = 0; i < 9; ++i) C[i] = r[i];
+}
+template <class T> static void mat3_T(const T* A, T* B) { T r[9]; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r[i * 3 + j] = A[j * 3 + i]; for (int i = 0; i < 9; ++i) B[i] = r[i]; }
+template <class T> static void mat3_vec(const T* A, const T* v, T* o) { T r[3]; for (int i = 0; i < 3; ++i) r[i] = A[i * 3] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2]; for (int i = 0; i < 3; ++i) o[i] = r[i]; }
+template <class T> static void hat(const T* w, T* W) { W[0] = 0; W[1] = -w[2]; W[2] = w[1]; W[3] = w[2]; W[4] = 0; W[5] = -w[0]; W[6] = -w[1]; W[7] = w[0]; W[8] = 0; }
+
+// One-sided Jacobi SVD of a 3x3 matrix (what Eigen::JacobiSVD computes, up to rounding): returns U V^T = the nearest rotation.
+template <class T> static void normalize_rotation(const T* R, T* out) {
+    T A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i < 9; ++i) A[i] = R[i];
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        T off = 0;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                T alpha = 0, beta = 0, gamma = 0;       // column p, q of A
+                for (int i = 0; i < 3; ++i) { alpha += A[i * 3 + p] * A[i * 3 + p]; beta += A[i * 3 + q] * A[i * 3 + q]; gamma += A[i * 3 + p] * A[i * 3 + q]; }
+                off = std::max(off, (T)std::fabs(gamma) / (T)std::sqrt(std::max(alpha * beta, sizeof(T) == 4 ? (T)1e-30 : (T)1e-300)));
+                if (gamma == 0) continue;
+                const T zeta = (beta - alpha) / (2 * gamma);
+                const T t = (zeta >= 0 ? (T)1 : (T)-1) / ((T)std::fabs(zeta) + (T)std::sqrt(1 + zeta * zeta));
+                const T c = 1 / (T)std::sqrt(1 + t * t), s = c * t;
+                for (int i = 0; i < 3; ++i) {
+                    const T ap = A[i * 3 + p], aq = A[i * 3 + q];
+                    A[i * 3 + p] = c * ap - s * aq; A[i * 3 + q] = s * ap + c * aq;
+                    const T vp = V[i * 3 + p], vq = V[i * 3 + q];
+                    V[i * 3 + p] = c * vp - s * vq; V[i * 3 + q] = s * vp + c * vq;
+                }
+            }
+        if (off < (sizeof(T) == 4 ? (T)1e-7 : (T)1e-15)) break;
+    }
+    T U[9];   // columns of A are sigma_j u_j
+    for (int j = 0; j < 3; ++j) {
+        T n = 0;
+        for (int i = 0; i < 3; ++i) n += A[i * 3 + j] * A[i * 3 + j];
+        n = (T)std::sqrt(n);
+        for (int i = 0; i < 3; ++i) U[i * 3 + j] = n > 0 ? A[i * 3 + j] / n : (i == j ? 1 : 0);
+    }
+    T Vt[9];
+    mat3_T(V, Vt);
+    mat3_mul(U, Vt, out);
+}
+
+// src/G2oTypes.cc:782-798 (double) / Sophus::SO3f::exp(...).matrix() (float: Rodrigues through the quaternion; same rotation to rounding)
+template <class T> static void exp_so3(const T* w, T* R, bool normalise) {
+    const T x = w[0], y = w[1], z = w[2];
+    const T d2 = x * x + y * y + z * z, d = (T)std::sqrt(d2);
+    T W[9], W2[9];
+    hat(w, W);
+    mat3_mul(W, W, W2);
+    T res[9];
+    for (int i = 0; i < 9; ++i) {
+        const T I = (i % 4 == 0) ? 1 : 0;
+        res[i] = d < (T)1e-5 ? I + W[i] + (T)0.5 * W2[i] : I + W[i] * (T)std::sin(d) / d + W2[i] * ((T)1.0 - (T)std::cos(d)) / d2;
+    }
+    if (normalise) normalize_rotation(res, R);
+    else for (int i = 0; i < 9; ++i) R[i] = res[i];
+}
+static void log_so3(const double* R, double* w) {   // :800-814
+    const double tr = R[0] + R[4] + R[8];
+    w[0] = (R[7] - R[5]) / 2; w[1] = (R[2] - R[6]) / 2; w[2] = (R[3] - R[1]) / 2;
+    const double costheta = (tr - 1.0) * 0.5f;
+    if (costheta > 1 || costheta < -1) return;
+    const double theta = std::acos(costheta);
+    const double s = std::sin(theta);
+    if (std::fabs(s) < 1e-5) return;
+    for (int i = 0; i < 3; ++i) w[i] = theta * w[i] / s;
+}
+template <class T> static void right_jacobian(const T* v, T* J, T eps) {   // G2oTypes.cc:839-854 / ImuTypes.cc:39-55
+    const T d2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], d = (T)std::sqrt(d2);
+    T W[9], W2[9];
+    hat(v, W); mat3_mul(W, W, W2);
+    for (int i = 0; i < 9; ++i) {
+        const T I = (i % 4 == 0) ? 1 : 0;
+        J[i] = d < eps ? I : I - W[i] * ((T)1.0 - (T)std::cos(d)) / d2 + W2[i] * (d - (T)std::sin(d)) / (d2 * d);
+    }
+}
+static void inv_right_jacobian(const double* v, double* J) {   // G2oTypes.cc:821-832
+    const double d2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], d = std::sqrt(d2);
+    double W[9], W2[9];
+    hat(v, W); mat3_mul(W, W, W2);
+    for (int i = 0; i < 9; ++i) {
+        const double I = (i % 4 == 0) ? 1 : 0;
+        J[i] = d < 1e-5 ? I : I + W[i] / 2 + W2[i] * (1.0 / d2 - (1.0 + std::cos(d)) / (2.0 * d * std::sin(d)));
+    }
+}
+
+}  // namespace imu
+}  // namespace orbo
+
+using namespace orbo::imu;
+
+extern "C" {
+
+// Layout of one IMU::Preintegrated as 292 floats (include/orb_b200.h: ImuPreintegrated):
+//   [0] dT | [1..9] dR | [10..12] dV | [13..15] dP | [16..24] JRg | [25..33] JVg | [34..42] JVa | [43..51] JPg | [52..60] JPa |
+//   [61..66] b = (bax, bay, baz, bwx, bwy, bwz) | [67..291] C (15 x 15, row-major)
+enum { P_DT = 0, P_DR = 1, P_DV = 10, P_DP = 13, P_JRG = 16, P_JVG = 25, P_JVA = 34, P_JPG = 43, P_JPA = 52, P_B = 61, P_C = 67, P_SIZE = 292 };
+
+// Preintegrated::Initialize(b) + IntegrateNewMeasurement for n measurements (acc, gyro, dt); noise4 = (ng, na, ngw, naw) of IMU::Calib::Set.
+void orbo_imu_preintegrate(int n, const float* acc, const float* gyr, const float* dts, const float* bias6, const float* noise4, float* P) {
+    std::memset(P, 0, sizeof(float) * P_SIZE);
+    float* dR = P + P_DR; float* dV = P + P_DV; float* dP = P + P_DP;
+    float *JRg = P + P_JRG, *JVg = P + P_JVG, *JVa = P + P_JVA, *JPg = P + P_JPG, *JPa = P + P_JPA, *C = P + P_C;
+    dR[0] = dR[4] = dR[8] = 1.f;
+    for (int i = 0; i < 6; ++i) P[P_B + i] = bias6[i];
+    const float ng2 = noise4[0] * noise4[0], na2 = noise4[1] * noise4[1], ngw2 = noise4[2] * noise4[2], naw2 = noise4[3] * noise4[3];
+    const float Nga[6] = {ng2, ng2, ng2, na2, na2, na2}, Walk[6] = {ngw2, ngw2, ngw2, naw2, naw2, naw2};
+    float dT = 0.f;
+    for (int m = 0; m < n; ++m) {
+        const float dt = dts[m];
+        float A[81], B[54];
+        for (int i = 0; i < 81; ++i) A[i] = (i % 10 == 0) ? 1.f : 0.f;
+        for (int i = 0; i < 54; ++i) B[i] = 0.f;
+        const float a[3] = {acc[3 * m] - bias6[0], acc[3 * m + 1] - bias6[1], acc[3 * m + 2] - bias6[2]};
+        float Ra[3];
+        mat3_vec(dR, a, Ra);
+        for (int i = 0; i < 3; ++i) { dP[i] = dP[i] + dV[i] * dt + 0.5f * Ra[i] * dt * dt; }
+        for (int i = 0; i < 3; ++i) dV[i] = dV[i] + Ra[i] * dt;
+        float Wacc[9], RW[9];
+        hat(a, Wacc);
+        mat3_mul(dR, Wacc, RW);
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+            A[(3 + i) * 9 + j] = -RW[i * 3 + j] * dt;                 // A.block<3,3>(3,0) = -dR*dt*Wacc
+            A[(6 + i) * 9 + j] = -0.5f * RW[i * 3 + j] * dt * dt;     // A.block<3,3>(6,0)
+            A[(6 + i) * 9 + 3 + j] = i == j ? dt : 0.f;               // A.block<3,3>(6,3)
+            B[(3 + i) * 6 + 3 + j] = dR[i * 3 + j] * dt;              // B.block<3,3>(3,3)
+            B[(6 + i) * 6 + 3 + j] = 0.5f * dR[i * 3 + j] * dt * dt;  // B.block<3,3>(6,3)
+        }
+        float RWJ[9];
+        mat3_mul(RW, JRg, RWJ);
+        for (int i = 0; i < 9; ++i) {
+            JPa[i] = JPa[i] + JVa[i] * dt - 0.5f * dR[i] * dt * dt;
+            JPg[i] = JPg[i] + JVg[i] * dt - 0.5f * RWJ[i] * dt * dt;
+            JVa[i] = JVa[i] - dR[i] * dt;
+            JVg[i] = JVg[i] - RWJ[i] * dt;
+        }
+        // IntegratedRotation (ImuTypes.cc:84-107)
+        const float w[3] = {(gyr[3 * m] - bias6[3]) * dt, (gyr[3 * m + 1] - bias6[4]) * dt, (gyr[3 * m + 2] - bias6[5]) * dt};
+        const float d2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], d = std::sqrt(d2);
+        float W[9], W2[9], deltaR[9], rightJ[9];
+        hat(w, W); mat3_mul(W, W, W2);
+        for (int i = 0; i < 9; ++i) {
+            const float I = (i % 4 == 0) ? 1.f : 0.f;
+            if (d < 1e-4f) { deltaR[i] = I + W[i]; rightJ[i] = I; }
+            else { deltaR[i] = I + W[i] * std::sin(d) / d + W2[i] * (1.0f - std::cos(d)) / d2; rightJ[i] = I - W[i] * (1.0f - std::cos(d)) / d2 + W2[i] * (d - std::sin(d)) / (d2 * d); }
+        }
+        float Rn[9];
+        mat3_mul(dR, deltaR, Rn);
+        normalize_rotation(Rn, dR);
+        float dRt[9];
+        mat3_T(deltaR, dRt);
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i * 9 + j] = dRt[i * 3 + j]; B[i * 6 + j] = rightJ[i * 3 + j] * dt; }
+        // C.block<9,9>(0,0) = A C A^T + B Nga B^T ; C.block<6,6>(9,9) += NgaWalk
+        float C9[81], AC[81], N9[81];
+        for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) C9[i * 9 + j] = C[i * 15 + j];
+        for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) { float s = 0; for (int k = 0; k < 9; ++k) s += A[i * 9 + k] * C9[k * 9 + j]; AC[i * 9 + j] = s; }
+        for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) {
+            float s = 0; for (int k = 0; k < 9; ++k) s += AC[i * 9 + k] * A[j * 9 + k];
+            float t = 0; for (int k = 0; k < 6; ++k) t += B[i * 6 + k] * Nga[k] * B[j * 6 + k];
+            N9[i * 9 + j] = s + t;
+        }
+        for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) C[i * 15 + j] = N9[i * 9 + j];
+        for (int k = 0; k < 6; ++k) C[(9 + k) * 15 + 9 + k] += Walk[k];
+        float T1[9];
+        mat3_mul(dRt, JRg, T1);
+        for (int i = 0; i < 9; ++i) JRg[i] = T1[i] - rightJ[i] * dt;
+        dT += dt;
+    }
+    P[P_DT] = dT;
+}
+
+// GetDeltaRotation / Velocity / Position (b1), float like the reference, returned as the doubles EdgeInertial casts them to.
+void orbo_imu_delta(const float* P, const double* bg, const double* ba, double* dR9, double* dV3, double* dP3) {
+    // const IMU::Bias b1(VA1[0..2], VG1[0..2]): double -> float
+    const float b1[6] = {(float)ba[0], (float)ba[1], (float)ba[2], (float)bg[0], (float)bg[1], (float)bg[2]};
+    const float dbg[3] = {b1[3] - P[P_B + 3], b1[4] - P[P_B + 4], b1[5] - P[P_B + 5]};
+    const float dba[3] = {b1[0] - P[P_B], b1[1] - P[P_B + 1], b1[2] - P[P_B + 2]};
+    float w[3], E[9], M[9], Rn[9];
+    mat3_vec(P + P_JRG, dbg, w);
+    exp_so3(w, E, false);
+    mat3_mul(P + P_DR, E, M);
+    normalize_rotation(M, Rn);
+    float g1[3], a1[3], g2[3], a2[3];
+    mat3_vec(P + P_JVG, dbg, g1); mat3_vec(P + P_JVA, dba, a1); mat3_vec(P + P_JPG, dbg, g2); mat3_vec(P + P_JPA, dba, a2);
+    for (int i = 0; i < 9; ++i) dR9[i] = (double)Rn[i];
+    for (int i = 0; i < 3; ++i) { dV3[i] = (double)(P[P_DV + i] + g1[i] + a1[i]); dP3[i] = (double)(P[P_DP + i] + g2[i] + a2[i]); }
+}
+
+// symmetric eigen-decomposition by cyclic Jacobi (n <= 9): A = V diag(w) V^T
+static void jacobi_eig(int n, double* A, double* V, double* w) {
+    for (int i = 0; i < n * n; ++i) V[i] = (i % (n + 1) == 0) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0;
+        for (int p = 0; p < n; ++p) for (int q = p + 1; q < n; ++q) off += A[p * n + q] * A[p * n + q];
+        if (off < 1e-300) break;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[p * n + q];
+                if (apq == 0) continue;
+                const double theta = (A[q * n + q] - A[p * n + p]) / (2 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+                const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+                for (int k = 0; k < n; ++k) { const double akp = A[k * n + p], akq = A[k * n + q]; A[k * n + p] = c * akp - s * akq; A[k * n + q] = s * akp + c * akq; }
+                for (int k = 0; k < n; ++k) { const double apk = A[p * n + k], aqk = A[q * n + k]; A[p * n + k] = c * apk - s * aqk; A[q * n + k] = s * apk + c * aqk; }
+                for (int k = 0; k < n; ++k) { const double vkp = V[k * n + p], vkq = V[k * n + q]; V[k * n + p] = c * vkp - s * vkq; V[k * n + q] = s * vkp + c * vkq; }
+            }
+    }
+    for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
+}
+static bool invert(int n, const double* A, double* out) {   // Gauss-Jordan with partial pivoting (Eigen: PartialPivLU)
+    double M[9 * 18];
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { M[i * 2 * n + j] = A[i * n + j]; M[i * 2 * n + n + j] = i == j ? 1.0 : 0.0; }
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r) if (std::fabs(M[r * 2 * n + c]) > std::fabs(M[piv * 2 * n + c])) piv = r;
+        if (M[piv * 2 * n + c] == 0) return false;
+        if (piv != c) for (int j = 0; j < 2 * n; ++j) std::swap(M[c * 2 * n + j], M[piv * 2 * n + j]);
+        const double inv = 1.0 / M[c * 2 * n + c];
+        for (int j = 0; j < 2 * n; ++j) M[c * 2 * n + j] *= inv;
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const double f = M[r * 2 * n + c];
+            if (f != 0) for (int j = 0; j < 2 * n; ++j) M[r * 2 * n + j] -= f * M[c * 2 * n + j];
+        }
+    }
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) out[i * n + j] = M[i * 2 * n + n + j];
+    return true;
+}
+// EdgeInertial ctor (G2oTypes.cc:499-507): Info (9x9) ; EdgeGyroRW / EdgeAccRW information (Optimizer.cc:551,559): InfoG, InfoA (3x3)
+void orbo_imu_information(const float* P, double* Info9, double* InfoG3, double* InfoA3) {
+    double C9[81], Inv[81], V[81], w[9];
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) C9[i * 9 + j] = (double)P[P_C + i * 15 + j];
+    invert(9, C9, Inv);
+    for (int i = 0; i < 9; ++i) for (int j = i; j < 9; ++j) { const double s = (Inv[i * 9 + j] + Inv[j * 9 + i]) / 2; Inv[i * 9 + j] = Inv[j * 9 + i] = s; }
+    double A[81];
+    std::memcpy(A, Inv, sizeof(A));
+    jacobi_eig(9, A, V, w);
+    for (int i = 0; i < 9; ++i) if (w[i] < 1e-12) w[i] = 0;
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) { double s = 0; for (int k = 0; k < 9; ++k) s += V[i * 9 + k] * w[k] * V[j * 9 + k]; Info9[i * 9 + j] = s; }
+    double G[9], Aa[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { G[i * 3 + j] = (double)P[P_C + (9 + i) * 15 + 9 + j]; Aa[i * 3 + j] = (double)P[P_C + (12 + i) * 15 + 12 + j]; }
+    invert(3, G, InfoG3); invert(3, Aa, InfoA3);
+}
+
+// EdgeInertial::computeError + linearizeOplus for one edge.  State: Rwb1[9], twb1[3], v1[3], bg[3], ba[3], Rwb2[9], twb2[3], v2[3].
+// err[9] = (er, ev, ep); J[9][24] columns: pose1 (rot 3, trans 3) | v1 | gyro bias | acc bias | pose2 (rot 3, trans 3) | v2.
+void orbo_imu_edge_inertial(const float* P, const double* Rwb1, const double* twb1, const double* v1, const double* bg, const double* ba,
+                            const double* Rwb2, const double* twb2, const double* v2, double* err, double* J) {
+    double dR[9], dV[3], dP[3];
+    orbo_imu_delta(P, bg, ba, dR, dV, dP);
+    const double dt = (double)P[P_DT];
+    const double g[3] = {0, 0, -(double)9.81f};                 // g << 0, 0, -IMU::GRAVITY_VALUE (const float 9.81)
+    double Rbw1[9], dRt[9], T[9], eR[9], er[3];
+    mat3_T(Rwb1, Rbw1); mat3_T(dR, dRt);
+    mat3_mul(dRt, Rbw1, T); mat3_mul(T, Rwb2, eR);
+    log_so3(eR, er);
+    double dv[3], dp[3], rv[3], rp[3];
+    for (int i = 0; i < 3; ++i) { dv[i] = v2[i] - v1[i] - g[i] * dt; dp[i] = twb2[i] - twb1[i] - v1[i] * dt - g[i] * dt * dt / 2; }
+    mat3_vec(Rbw1, dv, rv); mat3_vec(Rbw1, dp, rp);
+    for (int i = 0; i < 3; ++i) { err[i] = er[i]; err[3 + i] = rv[i] - dV[i]; err[6 + i] = rp[i] - dP[i]; }
+    if (!J) return;
+    for (int i = 0; i < 9 * 24; ++i) J[i] = 0;
+    double invJr[9];
+    inv_right_jacobian(er, invJr);
+    // dbg of GetDeltaBias(b1) (float), JRg etc. cast to double
+    const float b1g[3] = {(float)bg[0], (float)bg[1], (float)bg[2]};
+    const double dbg[3] = {(double)(b1g[0] - P[P_B + 3]), (double)(b1g[1] - P[P_B + 4]), (double)(b1g[2] - P[P_B + 5])};
+    double JRg[9], JVg[9], JVa[9], JPg[9], JPa[9];
+    for (int i = 0; i < 9; ++i) { JRg[i] = P[P_JRG + i]; JVg[i] = P[P_JVG + i]; JVa[i] = P[P_JVA + i]; JPg[i] = P[P_JPG + i]; JPa[i] = P[P_JPA + i]; }
+    auto put = [&](int r0, int c0, const double* M, double s) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J[(r0 + i) * 24 + c0 + j] = s * M[i * 3 + j]; };
+    double Rwb2t[9], A[9], H[9];
+    mat3_T(Rwb2, Rwb2t);
+    mat3_mul(Rwb2t, Rwb1, A); mat3_mul(invJr, A, A);
+    put(0, 0, A, -1.0);                                         // -invJr*Rwb2^T*Rwb1
+    hat(rv, H); put(3, 0, H, 1.0);                              // hat(Rbw1*(v2 - v1 - g dt))
+    // NOTE the reference uses 0.5*g*dt*dt here and g*dt*dt/2 in computeError: the same value
+    hat(rp, H); put(6, 0, H, 1.0);
+    const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    put(6, 3, I3, -1.0);
+    put(3, 6, Rbw1, -1.0); put(6, 6, Rbw1, -dt);                // velocity 1
+    double w[3], Jr[9], eRt[9];
+    mat3_vec(JRg, dbg, w);
+    right_jacobian(w, Jr, 1e-5);
+    mat3_T(eR, eRt);
+    mat3_mul(invJr, eRt, A); mat3_mul(A, Jr, A); mat3_mul(A, JRg, A);
+    put(0, 9, A, -1.0); put(3, 9, JVg, -1.0); put(6, 9, JPg, -1.0);   // gyro bias
+    put(3, 12, JVa, -1.0); put(6, 12, JPa, -1.0);               // acc bias
+    put(0, 15, invJr, 1.0);                                     // pose 2
+    mat3_mul(Rbw1, Rwb2, A); put(6, 18, A, 1.0);
+    put(3, 21, Rbw1, 1.0);                                      // velocity 2
+}
+
+// EdgeMono for one edge.  Body pose (Rwb, twb), extrinsics Tcb = (Rcb, tcb), Tbc = (Rbc, tbc); pinhole cam4 (float promoted).
+// err[2]; Jpoint[2][3] (_jacobianOplusXi); Jpose[2][6] (_jacobianOplusXj, tangent = (rotation, translation) of ImuCamPose::Update).
+void orbo_imu_edge_mono(const double* Rwb, const double* twb, const double* Rcb, const double* tcb, const double* Rbc, const double* tbc,
+                        const float* cam4, const double* Xw, const double* obs, double* err, double* Jpoint, double* Jpose, int* depthPositive) {
+    double Rbw[9], tbw[3], Rcw[9], tcw[3];
+    mat3_T(Rwb, Rbw);
+    mat3_vec(Rbw, twb, tbw);
+    for (int i = 0; i < 3; ++i) tbw[i] = -tbw[i];
+    mat3_mul(Rcb, Rbw, Rcw);                                    // ImuCamPose::Update: Rcw = Rcb*Rbw, tcw = Rcb*tbw + tcb
+    mat3_vec(Rcb, tbw, tcw);
+    for (int i = 0; i < 3; ++i) tcw[i] += tcb[i];
+    double Xc[3];
+    mat3_vec(Rcw, Xw, Xc);
+    for (int i = 0; i < 3; ++i) Xc[i] += tcw[i];
+    const double fx = cam4[0], fy = cam4[1], cx = cam4[2], cy = cam4[3];
+    err[0] = obs[0] - (fx * Xc[0] / Xc[2] + cx);
+    err[1] = obs[1] - (fy * Xc[1] / Xc[2] + cy);
+    if (depthPositive) *depthPositive = (Rcw[6] * Xw[0] + Rcw[7] * Xw[1] + Rcw[8] * Xw[2] + tcw[2]) > 0.0;
+    if (!Jpoint) return;
+    // Pinhole::projectJac (src/CameraModels/Pinhole.cpp:71-81)
+    const double pj[6] = {fx / Xc[2], 0, -fx * Xc[0] / (Xc[2] * Xc[2]), 0, fy / Xc[2], -fy * Xc[1] / (Xc[2] * Xc[2])};
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) Jpoint[i * 3 + j] = -(pj[i * 3] * Rcw[j] + pj[i * 3 + 1] * Rcw[3 + j] + pj[i * 3 + 2] * Rcw[6 + j]);
+    double Xb[3];
+    mat3_vec(Rbc, Xc, Xb);
+    for (int i = 0; i < 3; ++i) Xb[i] += tbc[i];
+    const double x = Xb[0], y = Xb[1], z = Xb[2];
+    const double S[18] = {0.0, z, -y, 1.0, 0.0, 0.0, -z, 0.0, x, 0.0, 1.0, 0.0, y, -x, 0.0, 0.0, 0.0, 1.0};
+    double PR[6];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) PR[i * 3 + j] = pj[i * 3] * Rcb[j] + pj[i * 3 + 1] * Rcb[3 + j] + pj[i * 3 + 2] * Rcb[6 + j];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 6; ++j) Jpose[i * 6 + j] = PR[i * 3] * S[j] + PR[i * 3 + 1] * S[6 + j] + PR[i * 3 + 2] * S[12 + j];
+}
+
+// ImuCamPose::Update (VertexPose::oplusImpl): twb += Rwb*ut; Rwb = Rwb*ExpSO3(ur)   (the periodic re-normalisation left out)
+void orbo_imu_pose_update(double* Rwb, double* twb, const double* pu) {
+    double t[3], E[9];
+    mat3_vec(Rwb, pu + 3, t);
+    for (int i = 0; i < 3; ++i) twb[i] += t[i];
+    exp_so3(pu, E, true);
+    mat3_mul(Rwb, E, Rwb);
+}
+
+void orbo_so3(int what, const double* in, double* out) {   // 0 Exp, 1 Log, 2 RightJacobian, 3 InverseRightJacobian, 4 NormalizeRotation
+    if (what == 0) exp_so3(in, out, true);
+    else if (what == 1) log_so3(in, out);
+    else if (what == 2) right_jacobian(in, out, 1e-5);
+    else if (what == 3) inv_right_jacobian(in, out);
+    else normalize_rotation(in, out);
+}
+
+}  // extern "C"

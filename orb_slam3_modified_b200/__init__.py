@@ -594,3 +594,72 @@ def PoseOptimization(frames, device=0):
     if rc != ORB_OK:
         raise OrbError(rc, 'pose_optimization_batch')
     return [dict(pose=out_pose[i], outlier=outl[i, :N[i]].copy(), inliers=int(ninl[i])) for i in range(count)]
+
+
+# =============================================================================================
+# Inertial edges (reference src/G2oTypes.cc, src/ImuTypes.cc)
+# =============================================================================================
+IMU_PREINT_FLOATS = 292
+
+
+class _ImuMonoEdges(C.Structure):
+    _fields_ = [('nPoses', C.c_int), ('poses', C.c_void_p), ('extrinsics', C.c_void_p), ('cam', C.c_void_p), ('nPoints', C.c_int), ('points', C.c_void_p),
+                ('nEdges', C.c_int), ('edgePoint', C.c_void_p), ('edgePose', C.c_void_p), ('obs', C.c_void_p), ('invSigma2', C.c_void_p), ('huberDelta', C.c_double)]
+
+
+def imu_preintegrate(acc, gyr, dt, n_meas, bias6, noise4, device=0):
+    """``IMU::Preintegrated`` of `count` intervals: acc / gyr [count, maxMeas, 3], dt [count, maxMeas], n_meas [count], bias6 [count, 6]."""
+    acc = _c(acc, np.float32); gyr = _c(gyr, np.float32); dt = _c(dt, np.float32); n = _c(n_meas, np.int32); b = _c(bias6, np.float32); nz = _c(noise4, np.float32)
+    count, mm = dt.shape
+    out = np.zeros((count, IMU_PREINT_FLOATS), np.float32)
+    L = lib()
+    L.imu_preintegrate_batch.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int]
+    rc = L.imu_preintegrate_batch(count, _ptr(n), mm, _ptr(acc), _ptr(gyr), _ptr(dt), _ptr(b), _ptr(nz), _ptr(out), device)
+    if rc != ORB_OK:
+        raise OrbError(rc, 'imu_preintegrate_batch')
+    return out
+
+
+def imu_information(preint, device=0):
+    P = _c(preint, np.float32).reshape(-1, IMU_PREINT_FLOATS)
+    n = len(P)
+    info = np.zeros((n, 9, 9)); ig = np.zeros((n, 3, 3)); ia = np.zeros((n, 3, 3))
+    L = lib()
+    L.imu_information_batch.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int]
+    rc = L.imu_information_batch(n, _ptr(P), _ptr(info), _ptr(ig), _ptr(ia), device)
+    if rc != ORB_OK:
+        raise OrbError(rc, 'imu_information_batch')
+    return info, ig, ia
+
+
+def imu_inertial_edges(preint, states36, info9=None, huber_delta=0.0, jac=True, device=0):
+    """``EdgeInertial::computeError`` / ``linearizeOplus`` for n edges.  Returns dict(err [n,9], J [n,9,24] | None, chi2, rho)."""
+    P = _c(preint, np.float32).reshape(-1, IMU_PREINT_FLOATS); S = _c(states36, np.float64).reshape(-1, 36)
+    n = len(S)
+    err = np.zeros((n, 9)); J = np.zeros((n, 9, 24)) if jac else None
+    info = _c(info9, np.float64) if info9 is not None else None
+    chi2 = np.zeros(n); rho = np.zeros(n)
+    L = lib()
+    L.imu_inertial_edges.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = L.imu_inertial_edges(n, _ptr(P), _ptr(S), _ptr(info), float(huber_delta), _ptr(err), _ptr(J), _ptr(chi2), _ptr(rho), device)
+    if rc != ORB_OK:
+        raise OrbError(rc, 'imu_inertial_edges')
+    return dict(err=err, J=J, chi2=chi2 if info is not None else None, rho=rho if info is not None else None)
+
+
+def imu_mono_edges(poses12, extrinsics24, cam, points, edge_point, edge_pose, obs, inv_sigma2, huber_delta=0.0, jac=True, device=0):
+    """``EdgeMono`` over ``ImuCamPose`` vertices.  Returns dict(err [n,2], Jpoint [n,2,3], Jpose [n,2,6], chi2, rho, depth_pos)."""
+    po = _c(poses12, np.float64).reshape(-1, 12); ex = _c(extrinsics24, np.float64).reshape(24); cm = _c(cam, np.float32).reshape(-1, 4)
+    pt = _c(points, np.float64).reshape(-1, 3); ep = _c(edge_point, np.int32); ek = _c(edge_pose, np.int32); ob = _c(obs, np.float64).reshape(-1, 2)
+    isg = _c(inv_sigma2, np.float32)
+    n = len(ep)
+    s = _ImuMonoEdges(len(po), po.ctypes.data, ex.ctypes.data, cm.ctypes.data, len(pt), pt.ctypes.data, n, ep.ctypes.data, ek.ctypes.data, ob.ctypes.data,
+                      isg.ctypes.data, float(huber_delta))
+    err = np.zeros((n, 2)); Jp = np.zeros((n, 2, 3)) if jac else None; Jx = np.zeros((n, 2, 6)) if jac else None
+    chi2 = np.zeros(n); rho = np.zeros(n); dp = np.zeros(n, np.uint8)
+    L = lib()
+    L.imu_mono_edges.argtypes = [C.c_void_p] * 7 + [C.c_int]
+    rc = L.imu_mono_edges(C.byref(s), _ptr(err), _ptr(Jp), _ptr(Jx), _ptr(chi2), _ptr(rho), _ptr(dp), device)
+    if rc != ORB_OK:
+        raise OrbError(rc, 'imu_mono_edges')
+    return dict(err=err, Jpoint=Jp, Jpose=Jx, chi2=chi2, rho=rho, depth_pos=dp)

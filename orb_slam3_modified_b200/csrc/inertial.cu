@@ -1,0 +1,555 @@
+// B200 kernels + C-ABI for the inertial edges of the path: what Optimizer::LocalInertialBA
+// (reference src/Optimizer.cc:2383-2958) and PoseInertialOptimizationLast{KeyFrame,Frame} (:4491, :4875) evaluate per iteration.
+//   IMU::Preintegrated::IntegrateNewMeasurement (src/ImuTypes.cc:177-240)             imu_preintegrate_kernel   thread per interval
+//   EdgeInertial ctor information matrix (src/G2oTypes.cc:499-507), EdgeGyroRW / EdgeAccRW information (src/Optimizer.cc:551,559)
+//                                                                                       imu_information_kernel    thread per edge
+//   EdgeInertial::computeError / linearizeOplus (src/G2oTypes.cc:514-594) + robust chi2  inertial_edges_kernel     thread per edge
+//   EdgeMono::computeError / linearizeOplus (include/G2oTypes.h:353, src/G2oTypes.cc:349-373) + robust chi2
+//                                                                                       mono_imu_edges_kernel     thread per edge
+// Units of work are independent (one interval / edge per thread, batched over all streams of a GPU); the preintegrated terms are
+// float like the reference's IMU::Preintegrated, the edges double like g2o.  NormalizeRotation (Eigen::JacobiSVD, U V^T) is a
+// one-sided Jacobi SVD; results agree with the CPU oracle to rounding (tests/test_inertial_gpu.py states the tolerances).
+// The 15-DoF block solver around these edges is not built yet.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/orb_b200.h"
+#include "device_utils.cuh"
+
+using orbx::set_error;
+
+#define CK(call)                                                                   \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) {                                                   \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));         \
+            return ORB_ERR_CUDA;                                                   \
+        }                                                                          \
+    } while (0)
+
+namespace imu {
+
+enum { P_DT = 0, P_DR = 1, P_DV = 10, P_DP = 13, P_JRG = 16, P_JVG = 25, P_JVA = 34, P_JPG = 43, P_JPA = 52, P_B = 61, P_C = 67, P_SIZE = IMU_PREINT_FLOATS };
+
+template <class T> __device__ __forceinline__ void m3mul(const T* A, const T* B, T* C) {
+    T r[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) C[i] = r[i];
+}
+template <class T> __device__ __forceinline__ void m3T(const T* A, T* B) {
+    T r[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r[i * 3 + j] = A[j * 3 + i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) B[i] = r[i];
+}
+template <class T> __device__ __forceinline__ void m3vec(const T* A, const T* v, T* o) {
+    T r[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r[i] = A[i * 3] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = r[i];
+}
+template <class T> __device__ __forceinline__ void hat(const T* w, T* W) {
+    W[0] = 0; W[1] = -w[2]; W[2] = w[1]; W[3] = w[2]; W[4] = 0; W[5] = -w[0]; W[6] = -w[1]; W[7] = w[0]; W[8] = 0;
+}
+// NormalizeRotation (src/ImuTypes.cc:34-37, Eigen::JacobiSVD): U V^T by one-sided Jacobi
+template <class T> __device__ void normalize_rotation(const T* R, T* out) {
+    T A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = R[i];
+    const T tol = sizeof(T) == 4 ? (T)1e-7 : (T)1e-15;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        T off = 0;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 3; ++q) {
+                T alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { alpha += A[i * 3 + p] * A[i * 3 + p]; beta += A[i * 3 + q] * A[i * 3 + q]; gamma += A[i * 3 + p] * A[i * 3 + q]; }
+                const T ab = alpha * beta, tiny = sizeof(T) == 4 ? (T)1e-30 : (T)1e-300;
+                off = fmax(off, (T)fabs(gamma) / (T)sqrt(ab > tiny ? ab : tiny));
+                if (gamma != 0) {
+                    const T zeta = (beta - alpha) / (2 * gamma);
+                    const T t = (zeta >= 0 ? (T)1 : (T)-1) / ((T)fabs(zeta) + (T)sqrt(1 + zeta * zeta));
+                    const T c = 1 / (T)sqrt(1 + t * t), s = c * t;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const T ap = A[i * 3 + p], aq = A[i * 3 + q];
+                        A[i * 3 + p] = c * ap - s * aq; A[i * 3 + q] = s * ap + c * aq;
+                        const T vp = V[i * 3 + p], vq = V[i * 3 + q];
+                        V[i * 3 + p] = c * vp - s * vq; V[i * 3 + q] = s * vp + c * vq;
+                    }
+                }
+            }
+        if (off < tol) break;
+    }
+    T U[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        T n = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) n += A[i * 3 + j] * A[i * 3 + j];
+        n = (T)sqrt(n);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) U[i * 3 + j] = n > 0 ? A[i * 3 + j] / n : (T)(i == j);
+    }
+    T Vt[9];
+    m3T(V, Vt);
+    m3mul(U, Vt, out);
+}
+
+// ---- Preintegrated::Initialize + IntegrateNewMeasurement over the measurements of one interval; thread per interval ----
+__global__ void imu_preintegrate_kernel(int count, const int* __restrict__ nMeas, int maxMeas, const float* __restrict__ acc, const float* __restrict__ gyr,
+                                        const float* __restrict__ dts, const float* __restrict__ bias6, float ng2, float na2, float ngw2, float naw2,
+                                        float* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    float dR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, dV[3] = {0, 0, 0}, dP[3] = {0, 0, 0};
+    float JRg[9], JVg[9], JVa[9], JPg[9], JPa[9], C9[81];
+    for (int i = 0; i < 9; ++i) JRg[i] = JVg[i] = JVa[i] = JPg[i] = JPa[i] = 0.f;
+    for (int i = 0; i < 81; ++i) C9[i] = 0.f;
+    float walk[6] = {0, 0, 0, 0, 0, 0};
+    const float* b = bias6 + 6 * (size_t)e;
+    const float Nga[6] = {ng2, ng2, ng2, na2, na2, na2}, Walk[6] = {ngw2, ngw2, ngw2, naw2, naw2, naw2};
+    float dT = 0.f;
+    const int n = min(nMeas[e], maxMeas);
+    for (int m = 0; m < n; ++m) {
+        const size_t o = (size_t)e * maxMeas + m;
+        const float dt = dts[o];
+        const float a[3] = {acc[3 * o] - b[0], acc[3 * o + 1] - b[1], acc[3 * o + 2] - b[2]};
+        float Ra[3];
+        m3vec(dR, a, Ra);
+        for (int i = 0; i < 3; ++i) dP[i] = dP[i] + dV[i] * dt + 0.5f * Ra[i] * dt * dt;
+        for (int i = 0; i < 3; ++i) dV[i] = dV[i] + Ra[i] * dt;
+        float Wacc[9], RW[9], RWJ[9];
+        hat(a, Wacc);
+        m3mul(dR, Wacc, RW);
+        m3mul(RW, JRg, RWJ);
+        // A = [dRi^T 0 0; -dR dt Wacc, I, 0; -0.5 dR dt^2 Wacc, dt I, I], B = [rightJ dt, 0; 0, dR dt; 0, 0.5 dR dt^2]  (built after the rotation step)
+        float A10[9], A20[9], B11[9], B21[9];
+        for (int i = 0; i < 9; ++i) { A10[i] = -RW[i] * dt; A20[i] = -0.5f * RW[i] * dt * dt; B11[i] = dR[i] * dt; B21[i] = 0.5f * dR[i] * dt * dt; }
+        for (int i = 0; i < 9; ++i) {
+            JPa[i] = JPa[i] + JVa[i] * dt - 0.5f * dR[i] * dt * dt;
+            JPg[i] = JPg[i] + JVg[i] * dt - 0.5f * RWJ[i] * dt * dt;
+            JVa[i] = JVa[i] - dR[i] * dt;
+            JVg[i] = JVg[i] - RWJ[i] * dt;
+        }
+        // IntegratedRotation (:84-107)
+        const float w[3] = {(gyr[3 * o] - b[3]) * dt, (gyr[3 * o + 1] - b[4]) * dt, (gyr[3 * o + 2] - b[5]) * dt};
+        const float d2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], d = sqrtf(d2);
+        float W[9], W2[9], deltaR[9], rightJ[9];
+        hat(w, W); m3mul(W, W, W2);
+        for (int i = 0; i < 9; ++i) {
+            const float I = (i % 4 == 0) ? 1.f : 0.f;
+            if (d < 1e-4f) { deltaR[i] = I + W[i]; rightJ[i] = I; }
+            else { deltaR[i] = I + W[i] * sinf(d) / d + W2[i] * (1.0f - cosf(d)) / d2; rightJ[i] = I - W[i] * (1.0f - cosf(d)) / d2 + W2[i] * (d - sinf(d)) / (d2 * d); }
+        }
+        float Rn[9], dRt[9];
+        m3mul(dR, deltaR, Rn);
+        normalize_rotation(Rn, dR);
+        m3T(deltaR, dRt);
+        // C9 <- A C9 A^T + B Nga B^T with the block structure of A and B written out row-block by row-block
+        float A[81], B[54];
+        for (int i = 0; i < 81; ++i) A[i] = (i % 10 == 0) ? 1.f : 0.f;
+        for (int i = 0; i < 54; ++i) B[i] = 0.f;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                A[i * 9 + j] = dRt[i * 3 + j]; A[(3 + i) * 9 + j] = A10[i * 3 + j]; A[(6 + i) * 9 + j] = A20[i * 3 + j]; A[(6 + i) * 9 + 3 + j] = i == j ? dt : 0.f;
+                B[i * 6 + j] = rightJ[i * 3 + j] * dt; B[(3 + i) * 6 + 3 + j] = B11[i * 3 + j]; B[(6 + i) * 6 + 3 + j] = B21[i * 3 + j];
+            }
+        float AC[81];
+        for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) { float s = 0; for (int k = 0; k < 9; ++k) s += A[i * 9 + k] * C9[k * 9 + j]; AC[i * 9 + j] = s; }
+        for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) {
+            float s = 0; for (int k = 0; k < 9; ++k) s += AC[i * 9 + k] * A[j * 9 + k];
+            float t = 0; for (int k = 0; k < 6; ++k) t += B[i * 6 + k] * Nga[k] * B[j * 6 + k];
+            C9[i * 9 + j] = s + t;
+        }
+        for (int k = 0; k < 6; ++k) walk[k] += Walk[k];
+        float T1[9];
+        m3mul(dRt, JRg, T1);
+        for (int i = 0; i < 9; ++i) JRg[i] = T1[i] - rightJ[i] * dt;
+        dT += dt;
+    }
+    float* P = out + (size_t)P_SIZE * e;
+    for (int i = 0; i < P_SIZE; ++i) P[i] = 0.f;
+    P[P_DT] = dT;
+    for (int i = 0; i < 9; ++i) { P[P_DR + i] = dR[i]; P[P_JRG + i] = JRg[i]; P[P_JVG + i] = JVg[i]; P[P_JVA + i] = JVa[i]; P[P_JPG + i] = JPg[i]; P[P_JPA + i] = JPa[i]; }
+    for (int i = 0; i < 3; ++i) { P[P_DV + i] = dV[i]; P[P_DP + i] = dP[i]; }
+    for (int i = 0; i < 6; ++i) P[P_B + i] = b[i];
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) P[P_C + i * 15 + j] = C9[i * 9 + j];
+    for (int k = 0; k < 6; ++k) P[P_C + (9 + k) * 15 + 9 + k] = walk[k];
+}
+
+// ---- information matrices: inverse of the covariance blocks (Gauss-Jordan with partial pivoting, like Eigen's PartialPivLU inverse),
+//      symmetrised, eigenvalues below 1e-12 clamped to zero (cyclic Jacobi eigen-decomposition) ----
+template <int N> __device__ bool invert_n(const double* A, double* out) {
+    double M[N * 2 * N];
+    for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) { M[i * 2 * N + j] = A[i * N + j]; M[i * 2 * N + N + j] = i == j ? 1.0 : 0.0; }
+    for (int c = 0; c < N; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < N; ++r) if (fabs(M[r * 2 * N + c]) > fabs(M[piv * 2 * N + c])) piv = r;
+        if (M[piv * 2 * N + c] == 0) return false;
+        if (piv != c) for (int j = 0; j < 2 * N; ++j) { const double t = M[c * 2 * N + j]; M[c * 2 * N + j] = M[piv * 2 * N + j]; M[piv * 2 * N + j] = t; }
+        const double inv = 1.0 / M[c * 2 * N + c];
+        for (int j = 0; j < 2 * N; ++j) M[c * 2 * N + j] *= inv;
+        for (int r = 0; r < N; ++r) {
+            if (r == c) continue;
+            const double f = M[r * 2 * N + c];
+            if (f != 0) for (int j = 0; j < 2 * N; ++j) M[r * 2 * N + j] -= f * M[c * 2 * N + j];
+        }
+    }
+    for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) out[i * N + j] = M[i * 2 * N + N + j];
+    return true;
+}
+__global__ void imu_information_kernel(int count, const float* __restrict__ preint, double* __restrict__ info9, double* __restrict__ infoG, double* __restrict__ infoA) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const float* P = preint + (size_t)P_SIZE * e;
+    double C9[81], A[81], V[81], w[9];
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) C9[i * 9 + j] = (double)P[P_C + i * 15 + j];
+    invert_n<9>(C9, A);
+    for (int i = 0; i < 9; ++i) for (int j = i; j < 9; ++j) { const double s = (A[i * 9 + j] + A[j * 9 + i]) / 2; A[i * 9 + j] = A[j * 9 + i] = s; }
+    for (int i = 0; i < 81; ++i) V[i] = (i % 10 == 0) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0;
+        for (int p = 0; p < 9; ++p) for (int q = p + 1; q < 9; ++q) off += A[p * 9 + q] * A[p * 9 + q];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 9; ++p)
+            for (int q = p + 1; q < 9; ++q) {
+                const double apq = A[p * 9 + q];
+                if (apq == 0) continue;
+                const double theta = (A[q * 9 + q] - A[p * 9 + p]) / (2 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+                const double c = 1 / sqrt(t * t + 1), s = t * c;
+                for (int k = 0; k < 9; ++k) { const double akp = A[k * 9 + p], akq = A[k * 9 + q]; A[k * 9 + p] = c * akp - s * akq; A[k * 9 + q] = s * akp + c * akq; }
+                for (int k = 0; k < 9; ++k) { const double apk = A[p * 9 + k], aqk = A[q * 9 + k]; A[p * 9 + k] = c * apk - s * aqk; A[q * 9 + k] = s * apk + c * aqk; }
+                for (int k = 0; k < 9; ++k) { const double vkp = V[k * 9 + p], vkq = V[k * 9 + q]; V[k * 9 + p] = c * vkp - s * vkq; V[k * 9 + q] = s * vkp + c * vkq; }
+            }
+    }
+    for (int i = 0; i < 9; ++i) { w[i] = A[i * 9 + i]; if (w[i] < 1e-12) w[i] = 0; }
+    double* I9 = info9 + 81 * (size_t)e;
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) { double s = 0; for (int k = 0; k < 9; ++k) s += V[i * 9 + k] * w[k] * V[j * 9 + k]; I9[i * 9 + j] = s; }
+    double G[9], Aa[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { G[i * 3 + j] = (double)P[P_C + (9 + i) * 15 + 9 + j]; Aa[i * 3 + j] = (double)P[P_C + (12 + i) * 15 + 12 + j]; }
+    invert_n<3>(G, infoG + 9 * (size_t)e);
+    invert_n<3>(Aa, infoA + 9 * (size_t)e);
+}
+
+// ---- SO3 helpers in double (src/G2oTypes.cc:777-861) ----
+__device__ void log_so3(const double* R, double* w) {
+    const double tr = R[0] + R[4] + R[8];
+    w[0] = (R[7] - R[5]) / 2; w[1] = (R[2] - R[6]) / 2; w[2] = (R[3] - R[1]) / 2;
+    const double costheta = (tr - 1.0) * 0.5f;
+    if (costheta > 1 || costheta < -1) return;
+    const double theta = acos(costheta);
+    const double s = sin(theta);
+    if (fabs(s) < 1e-5) return;
+    for (int i = 0; i < 3; ++i) w[i] = theta * w[i] / s;
+}
+__device__ void right_jacobian(const double* v, double* J) {
+    const double d2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], d = sqrt(d2);
+    double W[9], W2[9];
+    hat(v, W); m3mul(W, W, W2);
+    for (int i = 0; i < 9; ++i) {
+        const double I = (i % 4 == 0) ? 1 : 0;
+        J[i] = d < 1e-5 ? I : I - W[i] * (1.0 - cos(d)) / d2 + W2[i] * (d - sin(d)) / (d2 * d);
+    }
+}
+__device__ void inv_right_jacobian(const double* v, double* J) {
+    const double d2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], d = sqrt(d2);
+    double W[9], W2[9];
+    hat(v, W); m3mul(W, W, W2);
+    for (int i = 0; i < 9; ++i) {
+        const double I = (i % 4 == 0) ? 1 : 0;
+        J[i] = d < 1e-5 ? I : I + W[i] / 2 + W2[i] * (1.0 / d2 - (1.0 + cos(d)) / (2.0 * d * sin(d)));
+    }
+}
+
+// ---- EdgeInertial: residual, Jacobians, chi2 and robust weight; thread per edge.  states [count][36] doubles:
+//      Rwb1 9 | twb1 3 | v1 3 | bg 3 | ba 3 | Rwb2 9 | twb2 3 | v2 3 ----
+__global__ void inertial_edges_kernel(int count, const float* __restrict__ preint, const int* __restrict__ preintIndex, const double* __restrict__ states,
+                                      const double* __restrict__ info9, double huberDelta, double* __restrict__ errOut, double* __restrict__ Jout,
+                                      double* __restrict__ chi2Out, double* __restrict__ rhoOut) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const int pi = preintIndex ? preintIndex[e] : e;
+    const float* P = preint + (size_t)P_SIZE * pi;
+    const double* S = states + 36 * (size_t)e;
+    const double *Rwb1 = S, *twb1 = S + 9, *v1 = S + 12, *bg = S + 15, *ba = S + 18, *Rwb2 = S + 21, *twb2 = S + 30, *v2 = S + 33;
+    // GetDeltaRotation / Velocity / Position(b1): float, like IMU::Preintegrated (src/ImuTypes.cc:283-307)
+    const float b1[6] = {(float)ba[0], (float)ba[1], (float)ba[2], (float)bg[0], (float)bg[1], (float)bg[2]};
+    const float dbgf[3] = {b1[3] - P[P_B + 3], b1[4] - P[P_B + 4], b1[5] - P[P_B + 5]};
+    const float dbaf[3] = {b1[0] - P[P_B], b1[1] - P[P_B + 1], b1[2] - P[P_B + 2]};
+    double dR[9], dV[3], dP[3];
+    {
+        float w[3], W[9], W2[9], E[9], M[9], Rn[9];
+        m3vec(P + P_JRG, dbgf, w);
+        const float d2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], d = sqrtf(d2);
+        hat(w, W); m3mul(W, W, W2);
+        for (int i = 0; i < 9; ++i) {
+            const float I = (i % 4 == 0) ? 1.f : 0.f;
+            E[i] = d < 1e-5f ? I + W[i] + 0.5f * W2[i] : I + W[i] * sinf(d) / d + W2[i] * (1.0f - cosf(d)) / d2;
+        }
+        m3mul(P + P_DR, E, M);
+        normalize_rotation(M, Rn);
+        float g1[3], a1[3], g2[3], a2[3];
+        m3vec(P + P_JVG, dbgf, g1); m3vec(P + P_JVA, dbaf, a1); m3vec(P + P_JPG, dbgf, g2); m3vec(P + P_JPA, dbaf, a2);
+        for (int i = 0; i < 9; ++i) dR[i] = (double)Rn[i];
+        for (int i = 0; i < 3; ++i) { dV[i] = (double)(P[P_DV + i] + g1[i] + a1[i]); dP[i] = (double)(P[P_DP + i] + g2[i] + a2[i]); }
+    }
+    const double dt = (double)P[P_DT];
+    const double g[3] = {0, 0, -(double)9.81f};
+    double Rbw1[9], dRt[9], T[9], eR[9], er[3];
+    m3T(Rwb1, Rbw1); m3T(dR, dRt);
+    m3mul(dRt, Rbw1, T); m3mul(T, Rwb2, eR);
+    log_so3(eR, er);
+    double dv[3], dp[3], rv[3], rp[3], err[9];
+    for (int i = 0; i < 3; ++i) { dv[i] = v2[i] - v1[i] - g[i] * dt; dp[i] = twb2[i] - twb1[i] - v1[i] * dt - g[i] * dt * dt / 2; }
+    m3vec(Rbw1, dv, rv); m3vec(Rbw1, dp, rp);
+    for (int i = 0; i < 3; ++i) { err[i] = er[i]; err[3 + i] = rv[i] - dV[i]; err[6 + i] = rp[i] - dP[i]; }
+    for (int i = 0; i < 9; ++i) errOut[9 * (size_t)e + i] = err[i];
+    if (info9) {   // chi2 = e^T Omega e, Huber rho' (RobustKernelHuber with delta = sqrt(16.92), src/Optimizer.cc:540-542)
+        const double* Om = info9 + 81 * (size_t)pi;
+        double c2 = 0;
+        for (int i = 0; i < 9; ++i) { double s = 0; for (int j = 0; j < 9; ++j) s += Om[i * 9 + j] * err[j]; c2 += err[i] * s; }
+        chi2Out[e] = c2;
+        if (rhoOut) { const double dsq = huberDelta * huberDelta; rhoOut[e] = (huberDelta <= 0 || c2 <= dsq) ? 1.0 : huberDelta / sqrt(c2); }
+    }
+    if (!Jout) return;
+    double* J = Jout + 216 * (size_t)e;
+    for (int i = 0; i < 216; ++i) J[i] = 0;
+    double invJr[9], A[9], H[9], Rwb2t[9];
+    inv_right_jacobian(er, invJr);
+    auto put = [&](int r0, int c0, const double* M, double s) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J[(r0 + i) * 24 + c0 + j] = s * M[i * 3 + j]; };
+    m3T(Rwb2, Rwb2t);
+    m3mul(Rwb2t, Rwb1, A); m3mul(invJr, A, A);
+    put(0, 0, A, -1.0);
+    hat(rv, H); put(3, 0, H, 1.0);
+    hat(rp, H); put(6, 0, H, 1.0);
+    const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    put(6, 3, I3, -1.0);
+    put(3, 6, Rbw1, -1.0); put(6, 6, Rbw1, -dt);
+    double JRg[9], M9[9], w[3], Jr[9], eRt[9];
+    const double dbg[3] = {(double)dbgf[0], (double)dbgf[1], (double)dbgf[2]};
+    for (int i = 0; i < 9; ++i) JRg[i] = (double)P[P_JRG + i];
+    m3vec(JRg, dbg, w);
+    right_jacobian(w, Jr);
+    m3T(eR, eRt);
+    m3mul(invJr, eRt, A); m3mul(A, Jr, A); m3mul(A, JRg, A);
+    put(0, 9, A, -1.0);
+    for (int i = 0; i < 9; ++i) M9[i] = (double)P[P_JVG + i];
+    put(3, 9, M9, -1.0);
+    for (int i = 0; i < 9; ++i) M9[i] = (double)P[P_JPG + i];
+    put(6, 9, M9, -1.0);
+    for (int i = 0; i < 9; ++i) M9[i] = (double)P[P_JVA + i];
+    put(3, 12, M9, -1.0);
+    for (int i = 0; i < 9; ++i) M9[i] = (double)P[P_JPA + i];
+    put(6, 12, M9, -1.0);
+    put(0, 15, invJr, 1.0);
+    m3mul(Rbw1, Rwb2, A); put(6, 18, A, 1.0);
+    put(3, 21, Rbw1, 1.0);
+}
+
+// ---- EdgeMono with ImuCamPose (body pose + camera extrinsics): residual, Jacobians, chi2, depth sign; thread per edge ----
+struct MonoParams {
+    int nEdges;
+    const double* poses;       // [nPoses][12]: Rwb 9 | twb 3
+    const double* extr;        // [24]: Rcb 9 | tcb 3 | Rbc 9 | tbc 3   (Tcb / Tbc of camera 0, IMU::Calib)
+    const float* cam;          // [nPoses][4]
+    const double* points;      // [nPoints][3]
+    const int *edgePoint, *edgePose;
+    const double* obs;         // [nEdges][2]
+    const float* invSigma2;    // [nEdges]
+    double huberDelta;
+    double *err, *Jpoint, *Jpose, *chi2, *rho; uint8_t* depthPositive;
+};
+__global__ void mono_imu_edges_kernel(MonoParams Q) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Q.nEdges) return;
+    const double* Pz = Q.poses + 12 * (size_t)Q.edgePose[e];
+    const double *Rwb = Pz, *twb = Pz + 9, *Rcb = Q.extr, *tcb = Q.extr + 9, *Rbc = Q.extr + 12, *tbc = Q.extr + 21;
+    const double* Xw = Q.points + 3 * (size_t)Q.edgePoint[e];
+    const float* cm = Q.cam + 4 * (size_t)Q.edgePose[e];
+    double Rbw[9], tbw[3], Rcw[9], tcw[3], Xc[3];
+    m3T(Rwb, Rbw);
+    m3vec(Rbw, twb, tbw);
+    for (int i = 0; i < 3; ++i) tbw[i] = -tbw[i];
+    m3mul(Rcb, Rbw, Rcw);
+    m3vec(Rcb, tbw, tcw);
+    for (int i = 0; i < 3; ++i) tcw[i] += tcb[i];
+    m3vec(Rcw, Xw, Xc);
+    for (int i = 0; i < 3; ++i) Xc[i] += tcw[i];
+    const double fx = cm[0], fy = cm[1], cx = cm[2], cy = cm[3];
+    const double e0 = Q.obs[2 * (size_t)e] - (fx * Xc[0] / Xc[2] + cx), e1 = Q.obs[2 * (size_t)e + 1] - (fy * Xc[1] / Xc[2] + cy);
+    Q.err[2 * (size_t)e] = e0; Q.err[2 * (size_t)e + 1] = e1;
+    const double c2 = (double)Q.invSigma2[e] * (e0 * e0 + e1 * e1);
+    Q.chi2[e] = c2;
+    if (Q.rho) { const double dsq = Q.huberDelta * Q.huberDelta; Q.rho[e] = (Q.huberDelta <= 0 || c2 <= dsq) ? 1.0 : Q.huberDelta / sqrt(c2); }
+    Q.depthPositive[e] = (Rcw[6] * Xw[0] + Rcw[7] * Xw[1] + Rcw[8] * Xw[2] + tcw[2]) > 0.0;
+    if (!Q.Jpoint) return;
+    const double pj[6] = {fx / Xc[2], 0, -fx * Xc[0] / (Xc[2] * Xc[2]), 0, fy / Xc[2], -fy * Xc[1] / (Xc[2] * Xc[2])};
+    double* Jp = Q.Jpoint + 6 * (size_t)e;
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) Jp[i * 3 + j] = -(pj[i * 3] * Rcw[j] + pj[i * 3 + 1] * Rcw[3 + j] + pj[i * 3 + 2] * Rcw[6 + j]);
+    double Xb[3];
+    m3vec(Rbc, Xc, Xb);
+    for (int i = 0; i < 3; ++i) Xb[i] += tbc[i];
+    const double x = Xb[0], y = Xb[1], z = Xb[2];
+    const double Sd[18] = {0.0, z, -y, 1.0, 0.0, 0.0, -z, 0.0, x, 0.0, 1.0, 0.0, y, -x, 0.0, 0.0, 0.0, 1.0};
+    double PR[6];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) PR[i * 3 + j] = pj[i * 3] * Rcb[j] + pj[i * 3 + 1] * Rcb[3 + j] + pj[i * 3 + 2] * Rcb[6 + j];
+    double* Jx = Q.Jpose + 12 * (size_t)e;
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 6; ++j) Jx[i * 6 + j] = PR[i * 3] * Sd[j] + PR[i * 3 + 1] * Sd[6 + j] + PR[i * 3 + 2] * Sd[12 + j];
+}
+
+// host plumbing: one device arena per host thread and device, grown on demand (these are static functions in the reference)
+struct Scratch {
+    int device = -1; uint8_t* d = nullptr; size_t cap = 0; cudaStream_t st = nullptr;
+    ~Scratch() { if (d) { cudaSetDevice(device); cudaFree(d); } if (st) cudaStreamDestroy(st); }
+};
+static int scratch_for(int device, size_t bytes, Scratch** out) {
+    thread_local Scratch S;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (this library has no CPU path)"); return ORB_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { set_error("bad device index"); return ORB_ERR_ARG; }
+    CK(cudaSetDevice(device));
+    if (S.device != device || bytes > S.cap) {
+        if (S.d) { cudaSetDevice(S.device); cudaFree(S.d); S.d = nullptr; S.cap = 0; CK(cudaSetDevice(device)); }
+        if (S.st && S.device != device) { cudaStreamDestroy(S.st); S.st = nullptr; }
+        S.device = device;
+        CK(cudaMalloc(&S.d, bytes + bytes / 2 + 256));
+        S.cap = bytes + bytes / 2 + 256;
+    }
+    if (!S.st) CK(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+    *out = &S;
+    return ORB_OK;
+}
+struct Bump {
+    uint8_t* base; size_t off = 0;
+    explicit Bump(uint8_t* b) : base(b) {}
+    size_t take(size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; }
+};
+
+}  // namespace imu
+
+using namespace imu;
+
+extern "C" {
+
+int imu_preintegrate_batch(int count, const int32_t* nMeas, int maxMeas, const float* acc, const float* gyr, const float* dt, const float* bias6,
+                           const float* noise4, float* preint, int device) {
+    if (count < 1 || maxMeas < 1 || !nMeas || !acc || !gyr || !dt || !bias6 || !noise4 || !preint) { set_error("imu_preintegrate_batch: bad argument"); return ORB_ERR_ARG; }
+    const size_t C = count, M = maxMeas;
+    Bump B(nullptr);
+    const size_t oN = B.take(4 * C), oA = B.take(12 * C * M), oG = B.take(12 * C * M), oT = B.take(4 * C * M), oB = B.take(24 * C), oP = B.take(4 * P_SIZE * C);
+    Scratch* S;
+    int rc = scratch_for(device, B.off, &S);
+    if (rc) return rc;
+    uint8_t* d = S->d; cudaStream_t st = S->st;
+    CK(cudaMemcpyAsync(d + oN, nMeas, 4 * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oA, acc, 12 * C * M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oG, gyr, 12 * C * M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oT, dt, 4 * C * M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oB, bias6, 24 * C, cudaMemcpyHostToDevice, st));
+    // IMU::Calib::Set (src/ImuTypes.cc:395-407): squares in float
+    const float ng2 = noise4[0] * noise4[0], na2 = noise4[1] * noise4[1], ngw2 = noise4[2] * noise4[2], naw2 = noise4[3] * noise4[3];
+    imu_preintegrate_kernel<<<(count + 63) / 64, 64, 0, st>>>(count, (const int*)(d + oN), maxMeas, (const float*)(d + oA), (const float*)(d + oG),
+                                                              (const float*)(d + oT), (const float*)(d + oB), ng2, na2, ngw2, naw2, (float*)(d + oP));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(preint, d + oP, 4 * P_SIZE * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int imu_information_batch(int count, const float* preint, double* info9, double* infoG, double* infoA, int device) {
+    if (count < 1 || !preint || !info9 || !infoG || !infoA) { set_error("imu_information_batch: bad argument"); return ORB_ERR_ARG; }
+    const size_t C = count;
+    Bump B(nullptr);
+    const size_t oP = B.take(4 * P_SIZE * C), oI = B.take(648 * C), oG = B.take(72 * C), oA = B.take(72 * C);
+    Scratch* S;
+    int rc = scratch_for(device, B.off, &S);
+    if (rc) return rc;
+    uint8_t* d = S->d; cudaStream_t st = S->st;
+    CK(cudaMemcpyAsync(d + oP, preint, 4 * P_SIZE * C, cudaMemcpyHostToDevice, st));
+    imu_information_kernel<<<(count + 31) / 32, 32, 0, st>>>(count, (const float*)(d + oP), (double*)(d + oI), (double*)(d + oG), (double*)(d + oA));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(info9, d + oI, 648 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(infoG, d + oG, 72 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(infoA, d + oA, 72 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int imu_inertial_edges(int count, const float* preint, const double* states36, const double* info9, double huberDelta, double* err9, double* J9x24,
+                       double* chi2, double* rho, int device) {
+    if (count < 1 || !preint || !states36 || !err9 || (info9 && !chi2)) { set_error("imu_inertial_edges: bad argument"); return ORB_ERR_ARG; }
+    const size_t C = count;
+    Bump B(nullptr);
+    const size_t oP = B.take(4 * P_SIZE * C), oS = B.take(288 * C), oI = B.take(648 * C), oE = B.take(72 * C), oJ = B.take(1728 * C), oC = B.take(8 * C), oR = B.take(8 * C);
+    Scratch* S;
+    int rc = scratch_for(device, B.off, &S);
+    if (rc) return rc;
+    uint8_t* d = S->d; cudaStream_t st = S->st;
+    CK(cudaMemcpyAsync(d + oP, preint, 4 * P_SIZE * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oS, states36, 288 * C, cudaMemcpyHostToDevice, st));
+    if (info9) CK(cudaMemcpyAsync(d + oI, info9, 648 * C, cudaMemcpyHostToDevice, st));
+    inertial_edges_kernel<<<(count + 31) / 32, 32, 0, st>>>(count, (const float*)(d + oP), nullptr, (const double*)(d + oS), info9 ? (const double*)(d + oI) : nullptr,
+                                                            huberDelta, (double*)(d + oE), J9x24 ? (double*)(d + oJ) : nullptr, (double*)(d + oC), rho ? (double*)(d + oR) : nullptr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(err9, d + oE, 72 * C, cudaMemcpyDeviceToHost, st));
+    if (J9x24) CK(cudaMemcpyAsync(J9x24, d + oJ, 1728 * C, cudaMemcpyDeviceToHost, st));
+    if (info9) CK(cudaMemcpyAsync(chi2, d + oC, 8 * C, cudaMemcpyDeviceToHost, st));
+    if (info9 && rho) CK(cudaMemcpyAsync(rho, d + oR, 8 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int imu_mono_edges(const ImuMonoEdges* in, double* err2, double* Jpoint2x3, double* Jpose2x6, double* chi2, double* rho, uint8_t* depthPositive, int device) {
+    if (!in || in->nEdges < 1 || in->nPoses < 1 || in->nPoints < 1 || !in->poses || !in->extrinsics || !in->cam || !in->points || !in->edgePoint || !in->edgePose ||
+        !in->obs || !in->invSigma2 || !err2 || !chi2 || !depthPositive || ((Jpoint2x3 == nullptr) != (Jpose2x6 == nullptr))) {
+        set_error("imu_mono_edges: bad argument"); return ORB_ERR_ARG;
+    }
+    for (int e = 0; e < in->nEdges; ++e)
+        if (in->edgePoint[e] < 0 || in->edgePoint[e] >= in->nPoints || in->edgePose[e] < 0 || in->edgePose[e] >= in->nPoses) { set_error("imu_mono_edges: edge index out of range"); return ORB_ERR_ARG; }
+    const size_t E = in->nEdges, NP = in->nPoses, NL = in->nPoints;
+    Bump B(nullptr);
+    const size_t oPo = B.take(96 * NP), oX = B.take(192), oCm = B.take(16 * NP), oPt = B.take(24 * NL), oEp = B.take(4 * E), oEk = B.take(4 * E), oOb = B.take(16 * E),
+                 oIs = B.take(4 * E), oEr = B.take(16 * E), oJp = B.take(48 * E), oJx = B.take(96 * E), oC2 = B.take(8 * E), oRh = B.take(8 * E), oDp = B.take(E);
+    Scratch* S;
+    int rc = scratch_for(device, B.off, &S);
+    if (rc) return rc;
+    uint8_t* d = S->d; cudaStream_t st = S->st;
+    CK(cudaMemcpyAsync(d + oPo, in->poses, 96 * NP, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oX, in->extrinsics, 192, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oCm, in->cam, 16 * NP, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oPt, in->points, 24 * NL, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oEp, in->edgePoint, 4 * E, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oEk, in->edgePose, 4 * E, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oOb, in->obs, 16 * E, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oIs, in->invSigma2, 4 * E, cudaMemcpyHostToDevice, st));
+    MonoParams Q;
+    Q.nEdges = in->nEdges; Q.poses = (const double*)(d + oPo); Q.extr = (const double*)(d + oX); Q.cam = (const float*)(d + oCm); Q.points = (const double*)(d + oPt);
+    Q.edgePoint = (const int*)(d + oEp); Q.edgePose = (const int*)(d + oEk); Q.obs = (const double*)(d + oOb); Q.invSigma2 = (const float*)(d + oIs);
+    Q.huberDelta = in->huberDelta; Q.err = (double*)(d + oEr); Q.Jpoint = Jpoint2x3 ? (double*)(d + oJp) : nullptr; Q.Jpose = Jpose2x6 ? (double*)(d + oJx) : nullptr;
+    Q.chi2 = (double*)(d + oC2); Q.rho = rho ? (double*)(d + oRh) : nullptr; Q.depthPositive = d + oDp;
+    mono_imu_edges_kernel<<<(in->nEdges + 127) / 128, 128, 0, st>>>(Q);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(err2, d + oEr, 16 * E, cudaMemcpyDeviceToHost, st));
+    if (Jpoint2x3) { CK(cudaMemcpyAsync(Jpoint2x3, d + oJp, 48 * E, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(Jpose2x6, d + oJx, 96 * E, cudaMemcpyDeviceToHost, st)); }
+    CK(cudaMemcpyAsync(chi2, d + oC2, 8 * E, cudaMemcpyDeviceToHost, st));
+    if (rho) CK(cudaMemcpyAsync(rho, d + oRh, 8 * E, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(depthPositive, d + oDp, E, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+}  // extern "C"

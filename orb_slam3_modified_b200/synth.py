@@ -207,3 +207,57 @@ def pose_opt_problem(n=400, seed=0, width=640, height=480, outlier_frac=0.15, po
     inv_sigma2 = (1.0 / (np.float32(1.2) ** octv.astype(np.float32)) ** 2).astype(np.float32)
     return dict(pose=pose.astype(np.float32).astype(np.float64), cam=np.array([F_PIX, F_PIX, width / 2, height / 2], np.float32),
                 Xw=Xw.astype(np.float32).astype(np.float64), obs=obs.astype(np.float32).astype(np.float64), inv_sigma2=inv_sigma2, gt_pose=gt)
+
+
+# ---------------------------------------------------------------------------------------------
+# Inertial data (300 Hz accel + gyro from an analytic trajectory + gravity, EuRoC-like noise)
+# ---------------------------------------------------------------------------------------------
+IMU_NOISE = (1.7e-4 * np.sqrt(200.0), 2.0e-3 * np.sqrt(200.0), 1.9393e-5 / np.sqrt(200.0), 3.0e-3 / np.sqrt(200.0))   # ng, na, ngw, naw as Tracking builds them from EuRoC.yaml (NoiseGyro * sqrt(freq), ...)
+
+
+def _rodrigues(w):
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+
+
+def imu_trajectory(t):
+    """Body pose in the world (Rwb, twb), velocity, body angular velocity and world acceleration of a smooth trajectory at time t [s]."""
+    w = np.array([0.2 * np.sin(0.7 * t), 0.15 * np.cos(0.5 * t), 0.1 * np.sin(0.3 * t + 1.0)])          # rotation vector of Rwb(t)
+    eps = 1e-5
+    R = _rodrigues(w)
+    w2 = np.array([0.2 * np.sin(0.7 * (t + eps)), 0.15 * np.cos(0.5 * (t + eps)), 0.1 * np.sin(0.3 * (t + eps) + 1.0)])
+    dR = R.T @ _rodrigues(w2)
+    omega = np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]]) / (2 * eps)       # body rate
+    p = np.array([0.5 * np.sin(0.4 * t), 0.3 * np.cos(0.3 * t), 0.2 * np.sin(0.2 * t)])
+    v = np.array([0.2 * np.cos(0.4 * t), -0.09 * np.sin(0.3 * t), 0.04 * np.cos(0.2 * t)])
+    a = np.array([-0.08 * np.sin(0.4 * t), -0.027 * np.cos(0.3 * t), -0.008 * np.sin(0.2 * t)])
+    return R, p, v, omega, a
+
+
+def imu_interval(t0, t1, rate=300.0, seed=0, bias=(0.02, -0.01, 0.03, 0.002, -0.001, 0.0015), noise=True):
+    """IMU samples (acc [n,3], gyro [n,3], dt [n]) between two frame times: specific force in the body frame = Rbw (a - g_w), g_w = (0,0,-9.81),
+    + bias (bax..baz, bwx..bwz) + white noise."""
+    rng = np.random.default_rng(seed)
+    n = max(1, int(round((t1 - t0) * rate)))
+    dt = (t1 - t0) / n
+    acc, gyr = [], []
+    for i in range(n):
+        R, p, v, om, a = imu_trajectory(t0 + (i + 0.5) * dt)
+        f = R.T @ (a - np.array([0, 0, -9.81]))
+        acc.append(f + np.array(bias[:3]) + (rng.normal(0, IMU_NOISE[1], 3) if noise else 0))
+        gyr.append(om + np.array(bias[3:]) + (rng.normal(0, IMU_NOISE[0], 3) if noise else 0))
+    return np.array(acc, np.float32), np.array(gyr, np.float32), np.full(n, dt, np.float32)
+
+
+def inertial_edge_state(t0, t1, seed=0, perturb=1.0):
+    """Vertex estimates of one EdgeInertial (keyframes at t0, t1): ground truth + a seeded perturbation."""
+    rng = np.random.default_rng(seed + 77)
+    R1, p1, v1, _, _ = imu_trajectory(t0)
+    R2, p2, v2, _, _ = imu_trajectory(t1)
+    s = dict(Rwb1=R1 @ _rodrigues(perturb * rng.normal(0, 0.01, 3)), twb1=p1 + perturb * rng.normal(0, 0.01, 3), v1=v1 + perturb * rng.normal(0, 0.02, 3),
+             bg=np.array([0.002, -0.001, 0.0015]) + perturb * rng.normal(0, 1e-3, 3), ba=np.array([0.02, -0.01, 0.03]) + perturb * rng.normal(0, 1e-2, 3),
+             Rwb2=R2 @ _rodrigues(perturb * rng.normal(0, 0.01, 3)), twb2=p2 + perturb * rng.normal(0, 0.01, 3), v2=v2 + perturb * rng.normal(0, 0.02, 3))
+    return {k: np.ascontiguousarray(v, np.float64) for k, v in s.items()}

@@ -243,3 +243,61 @@ def pose_optimization(frame):
     L.orbo_pose_optimization.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
     n = L.orbo_pose_optimization(_p(pose), _p(cam), N, _p(Xw), _p(obs), _p(isg), float(np.float32(np.sqrt(5.991))), _p(outl), _p(stats))
     return dict(pose=pose, outlier=outl[:N].copy(), inliers=n, trials=int(stats[0]))
+
+
+# ---------------------------------------------------------------------------------------------
+# inertial edges
+# ---------------------------------------------------------------------------------------------
+IMU_P_SIZE = 292
+
+
+def imu_preintegrate(acc, gyr, dts, bias6, noise4):
+    acc = _c(acc, np.float32); gyr = _c(gyr, np.float32); dts = _c(dts, np.float32); b = _c(bias6, np.float32); nz = _c(noise4, np.float32)
+    P = np.zeros(IMU_P_SIZE, np.float32)
+    lib().orbo_imu_preintegrate(len(dts), _p(acc), _p(gyr), _p(dts), _p(b), _p(nz), _p(P))
+    return P
+
+
+def imu_information(P):
+    P = _c(P, np.float32)
+    info = np.zeros((9, 9)); ig = np.zeros((3, 3)); ia = np.zeros((3, 3))
+    lib().orbo_imu_information(_p(P), _p(info), _p(ig), _p(ia))
+    return info, ig, ia
+
+
+def imu_delta(P, bg, ba):
+    P = _c(P, np.float32); bg = _c(bg, np.float64); ba = _c(ba, np.float64)
+    dR = np.zeros((3, 3)); dV = np.zeros(3); dP = np.zeros(3)
+    lib().orbo_imu_delta(_p(P), _p(bg), _p(ba), _p(dR), _p(dV), _p(dP))
+    return dR, dV, dP
+
+
+def imu_edge_inertial(P, s, jac=True):
+    """s: dict Rwb1 [3,3], twb1, v1, bg, ba, Rwb2, twb2, v2 (float64).  Returns (err [9], J [9,24] or None)."""
+    P = _c(P, np.float32)
+    a = {k: _c(s[k], np.float64) for k in ('Rwb1', 'twb1', 'v1', 'bg', 'ba', 'Rwb2', 'twb2', 'v2')}
+    err = np.zeros(9); J = np.zeros((9, 24)) if jac else None
+    lib().orbo_imu_edge_inertial(_p(P), _p(a['Rwb1']), _p(a['twb1']), _p(a['v1']), _p(a['bg']), _p(a['ba']), _p(a['Rwb2']), _p(a['twb2']), _p(a['v2']),
+                                 _p(err), _p(J) if jac else None)
+    return err, J
+
+
+def imu_edge_mono(Rwb, twb, Rcb, tcb, Rbc, tbc, cam4, Xw, obs, jac=True):
+    a = [_c(v, np.float64) for v in (Rwb, twb, Rcb, tcb, Rbc, tbc)]
+    cam = _c(cam4, np.float32); X = _c(Xw, np.float64); o = _c(obs, np.float64)
+    err = np.zeros(2); Jp = np.zeros((2, 3)); Jx = np.zeros((2, 6)); dp = C.c_int(0)
+    lib().orbo_imu_edge_mono(*[_p(v) for v in a], _p(cam), _p(X), _p(o), _p(err), _p(Jp) if jac else None, _p(Jx) if jac else None, C.byref(dp))
+    return err, Jp, Jx, bool(dp.value)
+
+
+def imu_pose_update(Rwb, twb, pu):
+    R = _c(Rwb, np.float64).copy(); t = _c(twb, np.float64).copy(); u = _c(pu, np.float64)
+    lib().orbo_imu_pose_update(_p(R), _p(t), _p(u))
+    return R, t
+
+
+def so3(what, v):
+    v = _c(v, np.float64)
+    out = np.zeros(3 if what == 'log' else (3, 3))
+    lib().orbo_so3({'exp': 0, 'log': 1, 'Jr': 2, 'invJr': 3, 'normalize': 4}[what], _p(v), _p(out))
+    return out
