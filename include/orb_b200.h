@@ -98,6 +98,22 @@ int orbx_extract_batch_device(orbx_handle* h, const uint8_t* d_images, int batch
 int orbx_resident_slabs(const orbx_handle* h, const OrbKeyPoint** d_keypoints, const uint8_t** d_descriptors, const int** d_nkeypoints,
                         int* cap);
 
+/* void Frame::ComputeStereoMatches() (reference src/Frame.cc:811-982), the stereo consumer of ORBextractor::mvImagePyramid
+ * (src/Frame.cc:122-125 runs two extractors on the left / right image, then :126 calls this): for every left keypoint the best right
+ * keypoint on its row band by Hamming distance, an 11 x 11 SAD refinement over 11 shifts on the two pyramids, parabola fit, and the
+ * 1.5 * 1.4 * median SAD outlier cut.  `left` and `right` must have extracted the pair's images in their last call (`batch` pairs, pair f =
+ * frame f of both); mb / mbf as in Frame.  uRight / depth [batch][cap] receive mvuRight / mvDepth (-1 = no match).
+ * Host form: keypoints come from both handles' resident slabs (last call = orbx_extract[_batch]); cap = orbx_max_keypoints(left). */
+int orbx_stereo_matches(orbx_handle* left, orbx_handle* right, int batch, float mb, float mbf, float* uRight, float* depth, int cap);
+/* Device form: keypoint / descriptor / count slabs as written by orbx_extract_batch_device of the two handles; enqueues on `stream`
+ * (the stream both extractions were enqueued on, or one that waits for them). */
+int orbx_stereo_matches_device(orbx_handle* left, orbx_handle* right, int batch, const OrbKeyPoint* d_kpsL, const uint8_t* d_descL, const int* d_nL,
+                               int capL, const OrbKeyPoint* d_kpsR, const uint8_t* d_descR, const int* d_nR, int capR, float mb, float mbf,
+                               float* d_uRight, float* d_depth, void* stream);
+/* mvImagePyramid[level] of frame `frame` of the last call including the reflected frame of `border` pixels (19 in the reference,
+ * src/ORBextractor.cc:1185-1191) that ComputePyramid keeps around every level: (w + 2 border) x (h + 2 border) bytes, tightly packed. */
+int orbx_copy_level_bordered(orbx_handle* h, int frame, int level, int border, uint8_t* dst);
+
 /* Debug/inspection taps used by the parity tests (mvImagePyramid is a public member of the reference class,
  * include/ORBextractor.h:84).  Copies level `level` of frame `frame` of the last call, unbordered, tightly packed. */
 int orbx_get_level_size(const orbx_handle* h, int level, int* width, int* height);

@@ -14,6 +14,7 @@ RANGES = [
     ('matcher_maxima_distance.inc', 'src/ORBmatcher.cc', 2012, 2074, 'void ORBmatcher::ComputeThreeMaxima'),
     ('frame_assign_grid.inc', 'src/Frame.cc', 385, 416, 'void Frame::AssignFeaturesToGrid()'),
     ('frame_in_frustum_mono.inc', 'src/Frame.cc', 512, 574, 'bool Frame::isInFrustum(MapPoint *pMP, float viewingCosLimit)'),
+    ('frame_stereo_matches.inc', 'src/Frame.cc', 811, 982, 'void Frame::ComputeStereoMatches()'),
     ('frame_features_in_area.inc', 'src/Frame.cc', 657, 735, 'vector<size_t> Frame::GetFeaturesInArea'),
     ('mappoint_invariance.inc', 'src/MapPoint.cc', 502, 512, 'float MapPoint::GetMinDistanceInvariance()'),
     ('mappoint_predict_scale.inc', 'src/MapPoint.cc', 531, 546, 'int MapPoint::PredictScale(const float &currentDist, Frame* pF)'),

@@ -168,6 +168,18 @@ inline void Mat::copyTo(const _OutputArray& dst) const {
     for (int r = 0; r < rows; ++r) std::memmove(d.data + (size_t)r * d.step, data + (size_t)r * step, (size_t)cols);
 }
 
+enum { NORM_L1 = 2 };
+// cv::norm(a, b, NORM_L1) for two 8-bit single-channel matrices of the same size: sum of absolute differences (exact integer)
+inline double norm(const Mat& a, const Mat& b, int normType) {
+    assert(normType == NORM_L1 && a.rows == b.rows && a.cols == b.cols);
+    long s = 0;
+    for (int r = 0; r < a.rows; ++r) {
+        const uchar* pa = a.data + (size_t)r * a.step; const uchar* pb = b.data + (size_t)r * b.step;
+        for (int c = 0; c < a.cols; ++c) s += pa[c] > pb[c] ? pa[c] - pb[c] : pb[c] - pa[c];
+    }
+    return (double)s;
+}
+
 // the five primitives: implemented in minicv.cpp on top of the cv2-pinned oracle primitives
 void FAST(InputArray image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression = true);
 void resize(InputArray src, OutputArray dst, Size dsize, double fx = 0, double fy = 0, int interpolation = INTER_LINEAR);

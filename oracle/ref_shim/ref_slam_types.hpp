@@ -19,6 +19,7 @@
 #include <set>
 #include <vector>
 #include "minicv.hpp"
+#include "ORBextractor.h"   // the reference's own header (resolved through -I $(REF)/include): Frame::ComputeStereoMatches reads mvImagePyramid
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
 
@@ -82,6 +83,7 @@ using std::pair;
 
 class Frame;
 class KeyFrame;
+class ORBmatcher;
 
 class GeometricCamera {
 public:
@@ -124,7 +126,10 @@ class Frame {
 public:
     int N = 0, Nleft = -1;
     std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
-    std::vector<float> mvuRight;
+    std::vector<float> mvuRight, mvDepth;
+    cv::Mat mDescriptorsRight;
+    std::vector<float> mvInvScaleFactors;
+    ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
     cv::Mat mDescriptors;
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<bool> mvbOutlier;
@@ -146,6 +151,7 @@ public:
     Sophus::SE3<float> GetPose() const { return mTcw; }
     Sophus::SE3f GetRelativePoseTrl() { return Sophus::SE3f(); }
     void AssignFeaturesToGrid();                                // body: src/Frame.cc:385-416
+    void ComputeStereoMatches();                                // body: src/Frame.cc:811-982
     bool isInFrustum(MapPoint* pMP, float viewingCosLimit);     // body: src/Frame.cc:512-573 (monocular branch)
     bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);   // body: src/Frame.cc:725-735
     vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1,

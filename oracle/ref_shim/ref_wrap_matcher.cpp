@@ -21,6 +21,7 @@ namespace ORB_SLAM3 {
     return false;   // the reference continues with the two-camera branch (src/Frame.cc:574-...), not on the monocular path
 }
 #include "frame_features_in_area.inc"
+#include "frame_stereo_matches.inc"
 #include "mappoint_invariance.inc"
 #include "mappoint_predict_scale.inc"
 }  // namespace ORB_SLAM3
@@ -153,6 +154,23 @@ int ref_search_for_initialization(int K1, const cv::KeyPoint* kps1, const uint8_
     int n = matcher.SearchForInitialization(F1, F2, prev, m12, windowSize);
     for (int i = 0; i < K1; ++i) { matches12[i] = m12[i]; prevMatched[2 * i] = prev[i].x; prevMatched[2 * i + 1] = prev[i].y; }
     return n;
+}
+
+// Frame::ComputeStereoMatches (src/Frame.cc:811-982) on two of the reference's own extractors (handles of ref_orbx_create, each after its
+// operator() on the left / right image of the pair): mvKeys / mvKeysRight + descriptors in, mvuRight / mvDepth out.
+void ref_stereo_matches(void* exLeft, void* exRight, int N, const cv::KeyPoint* kl, const uint8_t* dl, int Nr, const cv::KeyPoint* kr, const uint8_t* dr,
+                        const float* scaleFactors, const float* invScaleFactors, int nlevels, float mb, float mbf, float* uRight, float* depth) {
+    Frame F;
+    F.N = N;
+    F.mvKeys.assign(kl, kl + N); F.mvKeysRight.assign(kr, kr + Nr);
+    F.mDescriptors = N ? cv::Mat(N, 32, CV_8UC1, (void*)dl, 32) : cv::Mat();
+    F.mDescriptorsRight = Nr ? cv::Mat(Nr, 32, CV_8UC1, (void*)dr, 32) : cv::Mat();
+    F.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    F.mvInvScaleFactors.assign(invScaleFactors, invScaleFactors + nlevels);
+    F.mb = mb; F.mbf = mbf;
+    F.mpORBextractorLeft = (ORBextractor*)exLeft; F.mpORBextractorRight = (ORBextractor*)exRight;
+    F.ComputeStereoMatches();
+    for (int i = 0; i < N; ++i) { uRight[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; }
 }
 
 // minDistance / maxDistance are the RAW mfMinDistance / mfMaxDistance: the 0.8f / 1.2f invariance factors are applied by the

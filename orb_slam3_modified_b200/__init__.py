@@ -204,6 +204,28 @@ class ORBextractor:
             raise OrbError(rc, 'orbx_copy_level')
         return out
 
+    def level_bordered(self, level, frame=0, border=19):
+        """mvImagePyramid[level] with the reflected frame ComputePyramid keeps around it (src/ORBextractor.cc:1185-1191)."""
+        w, h = C.c_int(), C.c_int()
+        lib().orbx_get_level_size(self._h, level, C.byref(w), C.byref(h))
+        out = np.zeros((h.value + 2 * border, w.value + 2 * border), np.uint8)
+        lib().orbx_copy_level_bordered.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        rc = lib().orbx_copy_level_bordered(self._h, frame, level, border, _ptr(out))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbx_copy_level_bordered')
+        return out
+
+    def ComputeStereoMatches(self, right, mb, mbf, batch=1):
+        """``Frame::ComputeStereoMatches`` (src/Frame.cc:811-982) for the pairs both extractors processed in their last host-buffer call
+        (self = left).  Returns (mvuRight, mvDepth) as [batch, cap] float32, -1 = no match."""
+        cap = self.max_keypoints
+        ur = np.zeros((batch, cap), np.float32); dep = np.zeros((batch, cap), np.float32)
+        lib().orbx_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
+        rc = lib().orbx_stereo_matches(self._h, right._h, batch, mb, mbf, _ptr(ur), _ptr(dep), cap)
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbx_stereo_matches')
+        return ur, dep
+
     def candidates(self, level, frame=0, cap=400000):
         out = np.zeros((cap, 3), np.int32)
         n = lib().orbx_copy_candidates(self._h, frame, level, _ptr(out), cap)

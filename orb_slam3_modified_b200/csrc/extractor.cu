@@ -95,6 +95,8 @@ struct Extractor {
     size_t smemFast = 0, smemQt = 0, smemAs = 0;
     int launches = 0;
     int maxKp = 0;
+    ExtractParams lastQ; bool hasLast = false;   // geometry + plane pointers of the last enqueued call (the pyramid the stereo matcher reads)
+    int* d_stereoSad = nullptr; float *d_stereoU = nullptr, *d_stereoD = nullptr; int* h_stereoStatus = nullptr;
     TmaMaps maps;            // per-level TMA descriptors of the internal pyramid planes (level 0: internal copy)
     CUtensorMap* d_maps = nullptr;   // device copy of `maps`
 
@@ -102,9 +104,10 @@ struct Extractor {
     void release() {
         cudaSetDevice(device);
         void* ptrs[] = {d_pyr, d_blur, d_cells, d_cellCount, d_cellList, d_cand, d_nodeOf, d_sel, d_selCount, d_dstIndex,
-                        d_status, d_xtab, d_ytab, d_img, d_outKp, d_outDesc, d_outN, d_outMono, d_maps};
+                        d_status, d_xtab, d_ytab, d_img, d_outKp, d_outDesc, d_outN, d_outMono, d_maps, d_stereoSad, d_stereoU, d_stereoD};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (h_counts) cudaFreeHost(h_counts);
+        if (h_stereoStatus) cudaFreeHost(h_stereoStatus);
         if (stream) cudaStreamDestroy(stream);
         if (stream2) cudaStreamDestroy(stream2);
         if (evFork) cudaEventDestroy(evFork);
@@ -296,6 +299,7 @@ struct Extractor {
         CK(cudaMalloc(&d_outN, sizeof(int) * B));
         CK(cudaMalloc(&d_outMono, sizeof(int) * B));
         CK(cudaMallocHost(&h_counts, sizeof(int) * 3 * B));
+        CK(cudaMallocHost(&h_stereoStatus, sizeof(int) * B));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
@@ -400,6 +404,7 @@ struct Extractor {
         ++launches;
         if (profiling) CK(cudaEventRecord(evStage[6], st));
         CK(cudaGetLastError());
+        lastQ = Q; hasLast = true;
         return ORB_OK;
     }
 };
@@ -563,6 +568,71 @@ int orbx_copy_candidates(orbx_handle* h, int frame, int level, int* xys, int cap
         }
     }
     return total;
+}
+
+int orbx_stereo_matches_device(orbx_handle* left, orbx_handle* right, int batch, const OrbKeyPoint* d_kpsL, const uint8_t* d_descL, const int* d_nL, int capL,
+                               const OrbKeyPoint* d_kpsR, const uint8_t* d_descR, const int* d_nR, int capR, float mb, float mbf, float* d_uRight,
+                               float* d_depth, void* stream) {
+    if (!left || !right || batch < 1 || !d_kpsL || !d_descL || !d_nL || !d_kpsR || !d_descR || !d_nR || capL < 1 || capR < 1 || capR > 65535 || !d_uRight || !d_depth ||
+        !(mb > 0) || !(mbf > 0)) { set_error("orbx_stereo_matches_device: bad argument"); return ORB_ERR_ARG; }
+    Extractor &L = left->e, &R = right->e;
+    if (!L.hasLast || !R.hasLast || L.lastQ.batch < batch || R.lastQ.batch < batch || L.rows != R.rows || L.cols != R.cols || L.nlevels != R.nlevels ||
+        L.scaleFactor != R.scaleFactor || L.device != R.device || batch > L.maxBatch) {
+        set_error("orbx_stereo_matches: both extractors must have processed the pair's images (same size, levels and scale factor) in their last call");
+        return ORB_ERR_ARG;
+    }
+    CK(cudaSetDevice(L.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!L.d_stereoSad) CK(cudaMalloc(&L.d_stereoSad, sizeof(int) * L.capSel * (size_t)L.maxBatch));
+    if (capL > (int)L.capSel) { set_error("orbx_stereo_matches: capL larger than the left extractor's keypoint capacity"); return ORB_ERR_CAPACITY; }
+    StereoParams Q;
+    Q.L = L.lastQ; Q.R = R.lastQ;
+    Q.kpsL = d_kpsL; Q.kpsR = d_kpsR; Q.descL = d_descL; Q.descR = d_descR; Q.nL = d_nL; Q.nR = d_nR; Q.capL = capL; Q.capR = capR;
+    Q.mb = mb; Q.mbf = mbf; Q.uRight = d_uRight; Q.depth = d_depth; Q.sad = L.d_stereoSad; Q.status = L.d_status;
+    CK(cudaMemsetAsync(L.d_status, 0, sizeof(int) * batch, st));
+    stereo_matches_kernel<<<batch, ST_NT, 0, st>>>(Q);
+    CK(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orbx_stereo_matches(orbx_handle* left, orbx_handle* right, int batch, float mb, float mbf, float* uRight, float* depth, int cap) {
+    if (!left || !right || !uRight || !depth || batch < 1) { set_error("orbx_stereo_matches: bad argument"); return ORB_ERR_ARG; }
+    Extractor &L = left->e, &R = right->e;
+    if (cap != L.outCapInternal) { set_error("orbx_stereo_matches: cap must equal orbx_max_keypoints(left)"); return ORB_ERR_ARG; }
+    CK(cudaSetDevice(L.device));
+    const size_t n = (size_t)L.outCapInternal * L.maxBatch;
+    if (!L.d_stereoU) { CK(cudaMalloc(&L.d_stereoU, sizeof(float) * n)); CK(cudaMalloc(&L.d_stereoD, sizeof(float) * n)); }
+    cudaStream_t st = L.stream;
+    int rc = orbx_stereo_matches_device(left, right, batch, L.d_outKp, L.d_outDesc, L.d_outN, L.outCapInternal, R.d_outKp, R.d_outDesc, R.d_outN,
+                                        R.outCapInternal, mb, mbf, L.d_stereoU, L.d_stereoD, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(uRight, L.d_stereoU, sizeof(float) * (size_t)cap * batch, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(depth, L.d_stereoD, sizeof(float) * (size_t)cap * batch, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(L.h_stereoStatus, L.d_status, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int f = 0; f < batch; ++f)
+        if (L.h_stereoStatus[f] & 4) { set_error("orbx_stereo_matches: a correlation window left the pyramid plane (keypoints not from this extractor?)"); return ORB_ERR_ARG; }
+    return ORB_OK;
+}
+
+// mvImagePyramid[level] of the last call WITH the reflected frame ComputePyramid writes around it (src/ORBextractor.cc:1185-1191):
+// (w + 2 border) x (h + 2 border), tightly packed.  The mono path never reads that frame, so it is materialised on request.
+int orbx_copy_level_bordered(orbx_handle* h, int frame, int level, int border, uint8_t* dst) {
+    if (!h || !dst || level < 0 || level >= h->e.nlevels || frame < 0 || frame >= h->e.maxBatch || border < 0 || border > 64 || !h->e.hasLast) {
+        set_error("orbx_copy_level_bordered: bad argument"); return ORB_ERR_ARG;
+    }
+    Extractor& e = h->e;
+    CK(cudaSetDevice(e.device));
+    const LevelGeom& G = e.P.lv[level];
+    const int W = G.w + 2 * border, H = G.h + 2 * border;
+    uint8_t* d_tmp = nullptr;
+    CK(cudaMalloc(&d_tmp, (size_t)W * H));
+    border_copy_kernel<<<dim3((W + 255) / 256, H), 256, 0, e.stream>>>(e.lastQ, frame, level, border, d_tmp);
+    cudaError_t err = cudaMemcpyAsync(dst, d_tmp, (size_t)W * H, cudaMemcpyDeviceToHost, e.stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e.stream);
+    cudaFree(d_tmp);
+    if (err != cudaSuccess) { set_error(cudaGetErrorString(err)); return ORB_ERR_CUDA; }
+    return ORB_OK;
 }
 
 int orbx_resident_slabs(const orbx_handle* h, const OrbKeyPoint** d_keypoints, const uint8_t** d_descriptors, const int** d_nkeypoints, int* cap) {

@@ -806,4 +806,150 @@ __global__ void __launch_bounds__(DS_NT) describe_kernel(ExtractParams P) {
     P.outDesc[((size_t)f * P.outCap + at) * 32 + lane] = (uint8_t)val;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K7: Frame::ComputeStereoMatches (reference src/Frame.cc:811-982), the stereo consumer of mvImagePyramid.  One CTA per rectified
+// pair; a warp per left keypoint: (1) best right keypoint on the same row band (|dy| <= 2 * scale of the right keypoint, level
+// within +-1, disparity window) by Hamming distance, ties to the lower right index (= the reference's row-table order);
+// (2) 11 x 11 SAD refinement over 11 shifts on the pyramid planes of the left keypoint's level, parabola fit, disparity / depth;
+// then (3) the CTA removes matches whose SAD is >= 1.5 * 1.4 * median.  Float arithmetic is individually rounded like the oracle's.
+// The 19-px reflected frame the reference keeps around every plane is not needed: for keypoints the extractor can produce the
+// windows stay >= 5 px inside the planes; a window that would leave the plane flags status bit 4 instead of reading.
+// ------------------------------------------------------------------------------------------
+// copyMakeBorder(level, BORDER_REFLECT_101) around one pyramid plane (src/ORBextractor.cc:1185-1191), written on request only
+__global__ void border_copy_kernel(ExtractParams P, int f, int l, int border, uint8_t* __restrict__ dst) {
+    const LevelGeom& G = P.lv[l];
+    const int W = G.w + 2 * border;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    int pitch;
+    const uint8_t* img = plane_ptr(P, f, l, pitch);
+    dst[(size_t)y * W + x] = img[(size_t)reflect101(y - border, G.h) * pitch + reflect101(x - border, G.w)];
+}
+
+constexpr int ST_NT = 256;
+struct StereoParams {
+    ExtractParams L, R;                    // geometry + pyramid pointers of the two extractors (same image size)
+    const OrbKeyPoint *kpsL, *kpsR; const uint8_t *descL, *descR; const int *nL, *nR; int capL, capR;
+    float mb, mbf;
+    float* uRight; float* depth;           // [batch][capL]
+    int* sad;                              // scratch [batch][capL]
+    int* status;                           // [batch]
+};
+
+__global__ void __launch_bounds__(ST_NT) stereo_matches_kernel(StereoParams Q) {
+    __shared__ int s_cnt, s_median;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int N = min(Q.nL[f], Q.capL), Nr = min(Q.nR[f], Q.capR);
+    const OrbKeyPoint* kl = Q.kpsL + (size_t)f * Q.capL; const OrbKeyPoint* kr = Q.kpsR + (size_t)f * Q.capR;
+    const uint8_t* dl = Q.descL + (size_t)f * Q.capL * 32; const uint8_t* dr = Q.descR + (size_t)f * Q.capR * 32;
+    float* uRight = Q.uRight + (size_t)f * Q.capL; float* depth = Q.depth + (size_t)f * Q.capL;
+    int* sad = Q.sad + (size_t)f * Q.capL;
+    const float minD = 0.f, maxD = fdiv(Q.mbf, Q.mb);
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (int iL = wid; iL < N; iL += ST_NT / 32) {
+        const OrbKeyPoint kpL = kl[iL];
+        float outU = -1.0f, outD = -1.0f; int outSad = -1;
+        const float uL = kpL.x, vL = kpL.y;
+        const int rowL = (int)vL;                                    // vRowIndices[vL]: float -> index by truncation
+        const float minU = fsub(uL, maxD), maxU = fsub(uL, minD);
+        unsigned best = 0xFFFFFFFFu;
+        if (!(maxU < 0)) {
+            const uint4* pl = reinterpret_cast<const uint4*>(dl + (size_t)iL * 32);
+            const uint4 a0 = __ldg(pl), a1 = __ldg(pl + 1);
+            const uint32_t da[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            for (int iR = lane; iR < Nr; iR += 32) {
+                const OrbKeyPoint kpR = kr[iR];
+                const float r = fmul(2.0f, Q.L.lv[min(max(kpR.octave, 0), Q.L.nlevels - 1)].scale);
+                const int maxr = (int)ceilf(fadd(kpR.y, r)), minr = (int)floorf(fsub(kpR.y, r));
+                if (rowL < minr || rowL > maxr) continue;
+                if (kpR.octave < kpL.octave - 1 || kpR.octave > kpL.octave + 1) continue;
+                if (!(kpR.x >= minU && kpR.x <= maxU)) continue;
+                const uint4* pr = reinterpret_cast<const uint4*>(dr + (size_t)iR * 32);
+                const uint4 b0 = __ldg(pr), b1 = __ldg(pr + 1);
+                const uint32_t db[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const unsigned dist = (unsigned)hamming256(da, db);
+                if (dist < 100u) best = min(best, (dist << 16) | (unsigned)iR);      // bestDist starts at TH_HIGH, strict <
+            }
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (best != 0xFFFFFFFFu && (int)(best >> 16) < (100 + 50) / 2) {             // thOrbDist
+            const int bestIdxR = (int)(best & 0xFFFFu);
+            const int lvl = min(max(kpL.octave, 0), Q.L.nlevels - 1);
+            const float uR0 = kr[bestIdxR].x;
+            const float scaleFactor = fdiv(1.0f, Q.L.lv[lvl].scale);                  // mvInvScaleFactors[octave] = 1.0f / mvScaleFactor[octave]
+            const float scaleduL = roundf(fmul(kpL.x, scaleFactor)), scaledvL = roundf(fmul(kpL.y, scaleFactor)), scaleduR0 = roundf(fmul(uR0, scaleFactor));
+            const int w = 5, Lr = 5;
+            const LevelGeom& G = Q.L.lv[lvl];
+            const float iniu = fsub(fadd(scaleduR0, (float)Lr), (float)w), endu = fadd(fadd(fadd(scaleduR0, (float)Lr), (float)w), 1.0f);
+            if (!(iniu < 0 || endu >= (float)G.w)) {
+                const int y0 = (int)fsub(scaledvL, (float)w), xL0 = (int)fsub(scaleduL, (float)w), xR00 = (int)scaleduR0 - Lr - w;
+                if (y0 < 0 || y0 + 2 * w + 1 > G.h || xL0 < 0 || xL0 + 2 * w + 1 > G.w || xR00 < 0) { if (lane == 0) atomicOr(&Q.status[f], 4); }
+                else {
+                    int pitchL, pitchR;
+                    const uint8_t* IL = plane_ptr(Q.L, f, lvl, pitchL);
+                    const uint8_t* IR = plane_ptr(Q.R, f, lvl, pitchR);
+                    // this lane's pixels of the 11 x 11 left window
+                    int pa[4], rr[4], cc[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int p = lane + 32 * k;
+                        rr[k] = p / 11; cc[k] = p - rr[k] * 11;
+                        pa[k] = p < 121 ? IL[(size_t)(y0 + rr[k]) * pitchL + xL0 + cc[k]] : 0;
+                    }
+                    int bestSad = 0x7fffffff, bestincR = 0;
+                    float vDists[11];
+#pragma unroll
+                    for (int incR = -5; incR <= 5; ++incR) {
+                        const int xR0 = (int)fsub(fadd(scaleduR0, (float)incR), (float)w);
+                        int s = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int p = lane + 32 * k;
+                            if (p < 121) { const int b = IR[(size_t)(y0 + rr[k]) * pitchR + xR0 + cc[k]]; s += abs(pa[k] - b); }
+                        }
+                        s = __reduce_add_sync(0xffffffffu, s);
+                        const float dist = (float)s;
+                        if (dist < (float)bestSad) { bestSad = (int)dist; bestincR = incR; }
+                        vDists[incR + 5] = dist;
+                    }
+                    if (!(bestincR == -Lr || bestincR == Lr)) {
+                        float dist1 = 0, dist2 = 0, dist3 = 0;
+#pragma unroll
+                        for (int k = 1; k < 10; ++k) if (k == bestincR + 5) { dist1 = vDists[k - 1]; dist2 = vDists[k]; dist3 = vDists[k + 1]; }
+                        const float deltaR = fdiv(fsub(dist1, dist3), fmul(2.0f, fsub(fadd(dist1, dist3), fmul(2.0f, dist2))));
+                        if (!(deltaR < -1 || deltaR > 1)) {
+                            float bestuR = fmul(G.scale, fadd(fadd(scaleduR0, (float)bestincR), deltaR));
+                            float disparity = fsub(uL, bestuR);
+                            if (disparity >= minD && disparity < maxD) {
+                                if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
+                                outD = fdiv(Q.mbf, disparity); outU = bestuR; outSad = bestSad;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (lane == 0) { uRight[iL] = outU; depth[iL] = outD; sad[iL] = outSad; if (outSad >= 0) atomicAdd(&s_cnt, 1); }
+    }
+    __syncthreads();
+    // median of the SAD distances of the accepted matches: element size/2 of the (distance, iL)-sorted list (:964-966)
+    const int cnt = s_cnt;
+    if (cnt == 0) return;
+    for (int i = tid; i < N; i += ST_NT) {
+        const int di = sad[i];
+        if (di < 0) continue;
+        int rank = 0;
+        for (int j = 0; j < N; ++j) { const int dj = sad[j]; rank += dj >= 0 && (dj < di || (dj == di && j < i)); }
+        if (rank == cnt / 2) s_median = di;
+    }
+    __syncthreads();
+    const float thDist = fmul(1.5f * 1.4f, (float)s_median);
+    for (int i = tid; i < N; i += ST_NT) {
+        const int di = sad[i];
+        if (di >= 0 && !((float)di < thDist)) { uRight[i] = -1.0f; depth[i] = -1.0f; }
+    }
+}
+
 }  // namespace orbx

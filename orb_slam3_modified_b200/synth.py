@@ -261,3 +261,13 @@ def inertial_edge_state(t0, t1, seed=0, perturb=1.0):
              bg=np.array([0.002, -0.001, 0.0015]) + perturb * rng.normal(0, 1e-3, 3), ba=np.array([0.02, -0.01, 0.03]) + perturb * rng.normal(0, 1e-2, 3),
              Rwb2=R2 @ _rodrigues(perturb * rng.normal(0, 0.01, 3)), twb2=p2 + perturb * rng.normal(0, 0.01, 3), v2=v2 + perturb * rng.normal(0, 0.02, 3))
     return {k: np.ascontiguousarray(v, np.float64) for k, v in s.items()}
+
+
+def stereo_pair(t=0, width=640, height=480, seed=0, baseline_px=22.0):
+    """Left / right frames of a rectified stereo rig looking at the scene plane: the right view is the left one shifted by the disparity of
+    the plane (all points share one depth in frame(), so the disparity is constant: mbf / Z = baseline_px) + independent sensor noise."""
+    left = frame(t, width + 64, height, seed)
+    rng = np.random.default_rng(1000 + seed * 31 + t)
+    d = int(round(baseline_px))
+    right = left[:, 32 + d:32 + d + width].astype(np.int16) + rng.integers(-2, 3, (height, width))
+    return np.ascontiguousarray(left[:, 32:32 + width]), np.clip(right, 0, 255).astype(np.uint8)

@@ -301,3 +301,23 @@ def so3(what, v):
     out = np.zeros(3 if what == 'log' else (3, 3))
     lib().orbo_so3({'exp': 0, 'log': 1, 'Jr': 2, 'invJr': 3, 'normalize': 4}[what], _p(v), _p(out))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# stereo (Frame::ComputeStereoMatches, the consumer of ORBextractor::mvImagePyramid)
+# ---------------------------------------------------------------------------------------------
+def stereo_matches(planes_l, planes_r, kl, dl, kr, dr, scale, inv_scale, mb, mbf):
+    """planes_*: lists of the unbordered pyramid planes of the left / right extractor (OracleExtractor.level(l))."""
+    nl = len(planes_l)
+    pl = [np.ascontiguousarray(p, np.uint8) for p in planes_l]; pr = [np.ascontiguousarray(p, np.uint8) for p in planes_r]
+    PL = (C.c_void_p * nl)(*[p.ctypes.data for p in pl]); PR = (C.c_void_p * nl)(*[p.ctypes.data for p in pr])
+    w = np.array([p.shape[1] for p in pl], np.int32); h = np.array([p.shape[0] for p in pl], np.int32)
+    kl = _c(kl, KP_DTYPE); kr = _c(kr, KP_DTYPE); dl = _c(dl, np.uint8); dr = _c(dr, np.uint8)
+    sf = _c(scale, np.float32); isf = _c(inv_scale, np.float32)
+    ur = np.zeros(len(kl), np.float32); dep = np.zeros(len(kl), np.float32)
+    L = lib()
+    L.orbo_stereo_matches.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    n = L.orbo_stereo_matches(nl, PL, PR, _p(w), _p(h), len(kl), _p(kl), _p(dl), len(kr), _p(kr), _p(dr), _p(sf), _p(isf), mb, mbf, _p(ur), _p(dep))
+    assert n >= 0, 'a SAD window left the pyramid plane'
+    return ur, dep

@@ -168,3 +168,16 @@ def is_in_frustum(pts, Rcw, tcw, Ow, cam, bounds, log_scale_factor, n_levels, vi
                         _p(cm), _p(b), float(mbf), float(np.float32(log_scale_factor)), int(n_levels), float(viewing_cos_limit),
                         *[_p(out[k]) for k in ('inView', 'projX', 'projY', 'projXR', 'depth', 'level', 'viewCos')])
     return out
+
+
+def stereo_matches(ex_left, ex_right, kl, dl, kr, dr, scale, inv_scale, mb, mbf):
+    """Frame::ComputeStereoMatches on two RefExtractor objects (each after its own call on the left / right image)."""
+    kl = _c(kl, KP_DTYPE); kr = _c(kr, KP_DTYPE); dl = _c(dl, np.uint8); dr = _c(dr, np.uint8)
+    sf = _c(scale, np.float32); isf = _c(inv_scale, np.float32)
+    ur = np.zeros(len(kl), np.float32); dep = np.zeros(len(kl), np.float32)
+    L = lib()
+    L.ref_stereo_matches.restype = None
+    L.ref_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.ref_stereo_matches(ex_left.h, ex_right.h, len(kl), _p(kl), _p(dl), len(kr), _p(kr), _p(dr), _p(sf), _p(isf), len(sf), mb, mbf, _p(ur), _p(dep))
+    return ur, dep

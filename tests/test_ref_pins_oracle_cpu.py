@@ -170,3 +170,24 @@ def test_is_in_frustum_equals_reference(seed):
     assert 0.1 < a['inView'].mean() < 0.9
     for k in ('inView', 'projX', 'projY', 'depth', 'level', 'viewCos', 'projXR'):
         assert a[k].tobytes() == b[k].tobytes(), k
+
+
+@pytest.mark.parametrize('t,w,h', [(3, 640, 480), (11, 752, 480)])
+def test_compute_stereo_matches_equals_reference(t, w, h):
+    """Frame::ComputeStereoMatches (src/Frame.cc:811-982), the stereo consumer of mvImagePyramid: the reference's own body on the reference's own
+    extractors vs the oracle restatement on the oracle's pyramid planes -- mvuRight and mvDepth bit for bit."""
+    left, right = synth.stereo_pair(t, w, h)
+    rl, rr = R.RefExtractor(1200, 1.2, 8, 20, 7), R.RefExtractor(1200, 1.2, 8, 20, 7)
+    ol, orr = O.OracleExtractor(1200, 1.2, 8, 20, 7), O.OracleExtractor(1200, 1.2, 8, 20, 7)
+    _, kl, dl = rl(left, (0, 0)); _, kr, dr = rr(right, (0, 0))
+    _same_extraction((0, kl, dl), (0,) + ol(left, (0, 0))[1:]); _same_extraction((0, kr, dr), (0,) + orr(right, (0, 0))[1:])
+    tb = ol.tables()
+    mbf, mb = 22.0 * 8.0, 22.0 * 8.0 / 458.0 * 1.0     # disparity 22 px at depth 8 (arbitrary units): maxD = mbf / mb = 458 px
+    a = R.stereo_matches(rl, rr, kl, dl, kr, dr, tb['scale'], tb['inv_scale'], mb, mbf)
+    b = O.stereo_matches([ol.level(l) for l in range(8)], [orr.level(l) for l in range(8)], kl, dl, kr, dr, tb['scale'], tb['inv_scale'], mb, mbf)
+    assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
+    ok = a[0] >= 0
+    assert ok.sum() > 300 and np.abs((kl['x'][ok] - a[0][ok]) - 22.0).max() < 2.0      # the plane's disparity is recovered
+    # the reflected 19-px frame ComputePyramid writes around every level (src/ORBextractor.cc:1185-1191): reflect-101 of the plane
+    for l in (0, 3, 7):
+        assert np.array_equal(rl.level(l, border=19), np.pad(ol.level(l), 19, mode='reflect'))
