@@ -376,6 +376,38 @@ typedef struct ImuMonoEdges {
  * depthPositive [nEdges] = EdgeMono::isDepthPositive(). */
 int imu_mono_edges(const ImuMonoEdges* in, double* err2, double* Jpoint2x3, double* Jpose2x6, double* chi2, double* rho, uint8_t* depthPositive, int device);
 
+
+/* ------------------------------------------------------------------------------------------
+ * DBoW2 transform: Frame::ComputeBoW / KeyFrame::ComputeBoW (reference src/Frame.cc:738-745) call
+ * ORBVocabulary::transform(vCurrentDesc, mBowVec, mFeatVec, 4) = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform
+ * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1259).  The vocabulary tree is handed over once as flat arrays (the host shim
+ * flattens m_nodes after loadFromTextFile) and stays in HBM; a call transforms the descriptors of `batch` frames.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct orbv_handle orbv_handle;
+typedef struct OrbVocabulary {
+    int nNodes;                   /* m_nodes.size(); node 0 is the root */
+    int L;                        /* m_L (6 for ORBvoc) */
+    int weighting;                /* m_weighting: 0 TF_IDF (ORB-SLAM3), 1 TF, 2 IDF, 3 BINARY */
+    int norm;                     /* what m_scoring_object->mustNormalize gives: 0 none, 1 L1 (L1_NORM, ORB-SLAM3), 2 L2 */
+    const int32_t* childStart;    /* [nNodes + 1]: children of node n are children[childStart[n] .. childStart[n+1]) */
+    const int32_t* children;      /* node ids in the order of m_nodes[n].children */
+    const uint8_t* descriptors;   /* [nNodes][32]: m_nodes[n].descriptor */
+    const double* weight;         /* [nNodes]: m_nodes[n].weight (idf of a word; 0 = stopped) */
+    const int32_t* wordId;        /* [nNodes]: m_nodes[n].word_id for leaves, -1 otherwise */
+} OrbVocabulary;
+int orbv_create(orbv_handle** out, const OrbVocabulary* voc, int device);
+void orbv_destroy(orbv_handle* h);
+/* transform() for `batch` frames; frame f has n[f] descriptors in desc [batch][cap][32].  Outputs in the iteration order of the reference's
+ * std::map containers: BowVector as wordId / wordValue [batch][cap] (nWords[f] entries, ascending word id; values are DBoW2's doubles bit
+ * for bit), FeatureVector as parallel arrays fvNode / fvFeature [batch][cap] (nEntries[f] entries: ascending node id, feature indices
+ * ascending within a node).  levelsup = 4 in the reference.  Host pointers. */
+int orbv_transform_batch(orbv_handle* h, int batch, const uint8_t* desc, const int32_t* n, int cap, int levelsup, int32_t* wordId, double* wordValue,
+                         int32_t* nWords, int32_t* fvNode, int32_t* fvFeature, int32_t* nEntries);
+/* Device form: all pointers device pointers; d_scratch* are [batch][cap] work arrays owned by the caller; enqueues on `stream`. */
+int orbv_transform_batch_device(orbv_handle* h, int batch, const uint8_t* d_desc, const int* d_n, int cap, int levelsup, int* d_scratchWord,
+                                double* d_scratchWeight, int* d_scratchNode, int* d_wordId, double* d_wordValue, int* d_nWords, int* d_fvNode,
+                                int* d_fvFeature, int* d_nEntries, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

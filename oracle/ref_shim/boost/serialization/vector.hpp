@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE: forwards <boost/serialization/vector.hpp> to the stand-in (see _common.hpp).
+#pragma once
+#include "_common.hpp"

@@ -13,7 +13,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <iostream>
 #include <memory>
+#include <sstream>   // the real opencv2/core pulls these in; DBoW2's TemplatedVocabulary.h relies on it
+#include <string>
 #include <vector>
 
 typedef unsigned char uchar;
@@ -102,7 +105,7 @@ public:
         step = st ? st : (size_t)c;
     }
     void create(int r, int c, int type) {
-        assert(type == CV_8UC1);
+        assert(type == CV_8UC1);   // CV_32F (FORB::toMat32F) parses but is never executed here
         if (data && r == rows && c == cols) return;
         rows = r; cols = c; step = (size_t)c;
         buf = std::shared_ptr<uchar>(new uchar[(size_t)std::max(r, 0) * std::max(c, 0) + 1], std::default_delete<uchar[]>());
@@ -179,6 +182,32 @@ inline double norm(const Mat& a, const Mat& b, int normType) {
     }
     return (double)s;
 }
+
+// cv::FileStorage / cv::FileNode: DBoW2's TemplatedVocabulary.h (compiled verbatim into oracle/_ref for its transform()) names them in its
+// YAML save / load members.  Those members are never called here; these declarations only let the header parse.
+struct FileNode {
+    enum { NONE = 0, SEQ = 5, MAP = 6 };
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    int type() const { return NONE; }
+    size_t size() const { return 0; }
+    operator int() const { return 0; }
+    operator double() const { return 0; }
+    operator float() const { return 0; }
+    operator std::string() const { return std::string(); }
+};
+struct FileStorage {
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+};
+template <class T> inline FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }
+#define CV_32F 5
 
 // the five primitives: implemented in minicv.cpp on top of the cv2-pinned oracle primitives
 void FAST(InputArray image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression = true);

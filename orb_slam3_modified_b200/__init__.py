@@ -685,3 +685,56 @@ def imu_mono_edges(poses12, extrinsics24, cam, points, edge_point, edge_pose, ob
     if rc != ORB_OK:
         raise OrbError(rc, 'imu_mono_edges')
     return dict(err=err, Jpoint=Jp, Jpose=Jx, chi2=chi2, rho=rho, depth_pos=dp)
+
+
+# =============================================================================================
+# DBoW2 vocabulary transform (reference Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h)
+# =============================================================================================
+class _OrbVocabulary(C.Structure):
+    _fields_ = [('nNodes', C.c_int), ('L', C.c_int), ('weighting', C.c_int), ('norm', C.c_int), ('childStart', C.c_void_p), ('children', C.c_void_p),
+                ('descriptors', C.c_void_p), ('weight', C.c_void_p), ('wordId', C.c_void_p)]
+
+
+class ORBVocabulary:
+    """Mirror of ``ORB_SLAM3::ORBVocabulary`` (= ``DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>``) for ``transform``: the tree is
+    given as flat arrays (child_start, children, desc, weight, word_id) and stays on the device."""
+
+    def __init__(self, L, child_start, children, desc, weight, word_id, weighting=0, norm=1, device=0):
+        self._keep = [_c(child_start, np.int32), _c(children, np.int32), _c(desc, np.uint8), _c(weight, np.float64), _c(word_id, np.int32)]
+        s = _OrbVocabulary(len(self._keep[4]), int(L), int(weighting), int(norm), *[a.ctypes.data for a in self._keep])
+        self._h = C.c_void_p()
+        lib().orbv_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]
+        rc = lib().orbv_create(C.byref(self._h), C.byref(s), device)
+        if rc != ORB_OK:
+            self._h = None
+            raise OrbError(rc, 'orbv_create')
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().orbv_destroy.argtypes = [C.c_void_p]
+            lib().orbv_destroy.restype = None
+            lib().orbv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def transform(self, desc_list, levelsup=4):
+        """``transform(features, BowVector, FeatureVector, levelsup)`` for a list of frames (each [n, 32] u8).  Returns per frame
+        (word_id [w] i32, word_value [w] f64, fv_node [e] i32, fv_feature [e] i32) in the reference's std::map order."""
+        B = len(desc_list)
+        cap = max(1, max(len(d) for d in desc_list))
+        desc = np.zeros((B, cap, 32), np.uint8); n = np.zeros(B, np.int32)
+        for b, d in enumerate(desc_list):
+            n[b] = len(d); desc[b, :len(d)] = d
+        wid = np.zeros((B, cap), np.int32); wv = np.zeros((B, cap)); nw = np.zeros(B, np.int32)
+        fn = np.zeros((B, cap), np.int32); ff = np.zeros((B, cap), np.int32); ne = np.zeros(B, np.int32)
+        L = lib()
+        L.orbv_transform_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+        rc = L.orbv_transform_batch(self._h, B, _ptr(desc), _ptr(n), cap, int(levelsup), _ptr(wid), _ptr(wv), _ptr(nw), _ptr(fn), _ptr(ff), _ptr(ne))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbv_transform_batch')
+        return [(wid[b, :nw[b]].copy(), wv[b, :nw[b]].copy(), fn[b, :ne[b]].copy(), ff[b, :ne[b]].copy()) for b in range(B)]

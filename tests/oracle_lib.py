@@ -321,3 +321,58 @@ def stereo_matches(planes_l, planes_r, kl, dl, kr, dr, scale, inv_scale, mb, mbf
     n = L.orbo_stereo_matches(nl, PL, PR, _p(w), _p(h), len(kl), _p(kl), _p(dl), len(kr), _p(kr), _p(dr), _p(sf), _p(isf), mb, mbf, _p(ur), _p(dep))
     assert n >= 0, 'a SAD window left the pyramid plane'
     return ur, dep
+
+
+# ---------------------------------------------------------------------------------------------
+# DBoW2 transform (Frame::ComputeBoW)
+# ---------------------------------------------------------------------------------------------
+def synthetic_vocabulary(k=10, L=3, seed=0, stop_frac=0.02):
+    """A random vocabulary tree in the flat layout of include/orb_b200.h (OrbVocabulary): node 0 is the root, every inner node has k children whose
+    descriptors are bit-flipped copies of the parent's, leaves carry idf-like weights (a few are 0 = stopped words)."""
+    rng = np.random.default_rng(seed)
+    parent, desc, level = [0], [np.zeros(32, np.uint8)], [0]
+    frontier = [0]
+    for lv in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            for _ in range(k):
+                d = desc[p].copy() if lv > 1 else rng.integers(0, 256, 32).astype(np.uint8)
+                for b in rng.integers(0, 256, 60 // lv):
+                    d[b >> 3] ^= np.uint8(1 << (b & 7))
+                parent.append(p); desc.append(d); level.append(lv); nxt.append(len(parent) - 1)
+        frontier = nxt
+    n = len(parent)
+    children = [[] for _ in range(n)]
+    for i in range(1, n):
+        children[parent[i]].append(i)
+    child_start = np.zeros(n + 1, np.int32)
+    for i in range(n):
+        child_start[i + 1] = child_start[i] + len(children[i])
+    flat_children = np.array([c for ch in children for c in ch], np.int32)
+    word_id = np.full(n, -1, np.int32)
+    leaves = [i for i in range(1, n) if not children[i]]
+    word_id[leaves] = np.arange(len(leaves))
+    weight = np.zeros(n)
+    weight[leaves] = rng.uniform(0.5, 9.0, len(leaves))
+    weight[rng.choice(leaves, max(1, int(stop_frac * len(leaves))), replace=False)] = 0.0
+    return dict(k=k, L=L, parent=np.array(parent, np.int32), desc=np.stack(desc), weight=weight, child_start=child_start, children=flat_children,
+                word_id=word_id, n_words=len(leaves))
+
+
+def bow_transform(voc, feats, levelsup=4, weighting=0, norm=1):
+    feats = _c(feats, np.uint8).reshape(-1, 32)
+    N = len(feats)
+    ow = np.zeros(max(N, 1), np.int32); ov = np.zeros(max(N, 1)); fn = np.zeros(max(N, 1), np.int32); ff = np.zeros(max(N, 1), np.int32); nf = C.c_int(0)
+    L = lib()
+    L.orbo_bow_transform.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = L.orbo_bow_transform(voc['L'], weighting, norm, _p(voc['child_start']), _p(voc['children']), _p(_c(voc['desc'], np.uint8)), _p(_c(voc['weight'], np.float64)),
+                             _p(voc['word_id']), N, _p(feats), levelsup, _p(ow), _p(ov), len(ow), _p(fn), _p(ff), C.byref(nf))
+    return ow[:n].copy(), ov[:n].copy(), fn[:nf.value].copy(), ff[:nf.value].copy()
+
+
+def bow_score_l1(a, b):
+    i1, v1 = _c(a[0], np.int32), _c(a[1], np.float64); i2, v2 = _c(b[0], np.int32), _c(b[1], np.float64)
+    L = lib()
+    L.orbo_bow_score_l1.restype = C.c_double
+    L.orbo_bow_score_l1.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    return L.orbo_bow_score_l1(len(i1), _p(i1), _p(v1), len(i2), _p(i2), _p(v2))

@@ -181,3 +181,34 @@ def stereo_matches(ex_left, ex_right, kl, dl, kr, dr, scale, inv_scale, mb, mbf)
                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     L.ref_stereo_matches(ex_left.h, ex_right.h, len(kl), _p(kl), _p(dl), len(kr), _p(kr), _p(dr), _p(sf), _p(isf), len(sf), mb, mbf, _p(ur), _p(dep))
     return ur, dep
+
+
+class RefVocabulary:
+    """DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> itself (the reference's ORBVocabulary), filled from flat arrays."""
+
+    def __init__(self, voc, weighting=0, scoring=0):
+        self.L = lib()
+        self.L.ref_bow_create.restype = C.c_void_p
+        self.L.ref_bow_create.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3
+        self.h = C.c_void_p(self.L.ref_bow_create(voc['k'], voc['L'], weighting, scoring, len(voc['parent']), _p(voc['parent']), _p(_c(voc['desc'], np.uint8)),
+                                                  _p(_c(voc['weight'], np.float64))))
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            self.L.ref_bow_destroy.argtypes = [C.c_void_p]
+            self.L.ref_bow_destroy(self.h)
+            self.h = None
+
+    def transform(self, feats, levelsup=4):
+        feats = _c(feats, np.uint8).reshape(-1, 32)
+        N = len(feats)
+        ow = np.zeros(max(N, 1), np.int32); ov = np.zeros(max(N, 1)); fn = np.zeros(max(N, 1), np.int32); ff = np.zeros(max(N, 1), np.int32); nf = C.c_int(0)
+        self.L.ref_bow_transform.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        n = self.L.ref_bow_transform(self.h, N, _p(feats), levelsup, _p(ow), _p(ov), len(ow), _p(fn), _p(ff), C.byref(nf))
+        return ow[:n].copy(), ov[:n].copy(), fn[:nf.value].copy(), ff[:nf.value].copy()
+
+    def score(self, a, b):
+        i1, v1 = _c(a[0], np.int32), _c(a[1], np.float64); i2, v2 = _c(b[0], np.int32), _c(b[1], np.float64)
+        self.L.ref_bow_score.restype = C.c_double
+        self.L.ref_bow_score.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        return self.L.ref_bow_score(self.h, len(i1), _p(i1), _p(v1), len(i2), _p(i2), _p(v2))

@@ -191,3 +191,23 @@ def test_compute_stereo_matches_equals_reference(t, w, h):
     # the reflected 19-px frame ComputePyramid writes around every level (src/ORBextractor.cc:1185-1191): reflect-101 of the plane
     for l in (0, 3, 7):
         assert np.array_equal(rl.level(l, border=19), np.pad(ol.level(l), 19, mode='reflect'))
+
+
+@pytest.mark.parametrize('k,L,levelsup,weighting,scoring', [(10, 3, 1, 0, 0), (10, 4, 2, 0, 0), (6, 5, 4, 0, 0), (10, 3, 4, 2, 0), (8, 3, 2, 1, 0), (9, 3, 1, 3, 0), (10, 3, 1, 2, 1), (10, 3, 2, 0, 1)])
+def test_dbow2_transform_equals_reference(k, L, levelsup, weighting, scoring):
+    """TemplatedVocabulary::transform (the reference's own DBoW2 sources in oracle/_ref) vs the oracle restatement on synthetic vocabulary trees:
+    BowVector (word ids, values bit for bit), FeatureVector (node ids, feature lists) and the L1 score of two frames."""
+    voc = O.synthetic_vocabulary(k, L, seed=L * 7 + k)
+    ref = R.RefVocabulary(voc, weighting=weighting, scoring=scoring)    # 0 = L1_NORM as ORB-SLAM3 configures it, 1 = L2_NORM
+    outs = []
+    for t in (4, 5):
+        _, desc = matcher_scenes.extract(t)
+        a = ref.transform(desc, levelsup)
+        b = O.bow_transform(voc, desc, levelsup, weighting, 1 + scoring)
+        assert np.array_equal(a[0], b[0]) and a[1].tobytes() == b[1].tobytes() and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+        assert len(a[0]) > 50 and abs((a[1].sum() if scoring == 0 else (a[1] ** 2).sum()) - 1.0) < 1e-12 and len(a[3]) <= len(desc)
+        outs.append(a)
+    if scoring:
+        return
+    s = ref.score(outs[0], outs[1])
+    assert s == O.bow_score_l1(outs[0], outs[1]) and 0 < s < 1 and abs(ref.score(outs[0], outs[0]) - 1.0) < 1e-12
