@@ -481,7 +481,7 @@ def main():
     g_match = [torch.full((b1 - b0, cap), -1, dtype=torch.int32, device=dev) for b0, b1 in gb]
     g_claimed = [torch.zeros((b1 - b0, cap), dtype=torch.uint8, device=dev) for b0, b1 in gb]
     g_nmatch = [torch.zeros(b1 - b0, dtype=torch.int32, device=dev) for b0, b1 in gb]
-    gather = sharding.GroupSlabGather(dist, world, g_slab) if world > 1 else None
+    gather = sharding.GroupSlabGather(dist, world, g_slab) if world > 1 and os.environ.get('BENCH_DIAG', '') != 'nogather' else None
 
     EXCL = not args.lba_concurrent
     ev_lba = torch.cuda.Event()
@@ -517,6 +517,10 @@ def main():
             # the GPU to itself between two rounds -- the mapping stream waits for the groups, and the groups for the mapping stream.
             if EXCL:
                 for g, st in enumerate(g_st):
+                    if gather:     # the collectives in flight finish first: an NCCL kernel starved of SMs by the LBA kernel stalls its peer rank too
+                        with torch.cuda.stream(st):
+                            gather.wait(g, 0)
+                            gather.wait(g, 1)
                     g_ev[g].record(st)
                     lba_stream.wait_event(g_ev[g])
             opt.run_device(lba_stream.cuda_stream)
@@ -572,7 +576,10 @@ def main():
     value = world * B * n_rounds / (ms * 1e-3)
 
     if DIAG:
-        print(json.dumps({'INVALID_diagnostic_run': DIAG, 'ms_per_round': ms / n_rounds}))
+        if rank == 0:
+            print(json.dumps({'INVALID_diagnostic_run': DIAG, 'ms_per_round': ms / n_rounds}))
+        if world > 1:
+            dist.destroy_process_group()
         return
     # ---------------- parity gate 1: what the timed loop left in the slabs, against the CPU oracle ----------------
     i_last = n_rounds - 1
