@@ -409,7 +409,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the BASELINE configs[0] / configs[2] latency lines')
     ap.add_argument('--dev-groups', type=int, default=2, help='stream groups (own handles + CUDA stream) in the device-resident measurement')
-    ap.add_argument('--e2e-groups', type=int, default=2, help='stream groups (host threads with their own handles) in flight in the e2e measurement')
+    ap.add_argument('--e2e-groups', type=int, default=4, help='stream groups (host threads with their own handles) in flight in the e2e measurement')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -655,7 +655,8 @@ def main():
             hb = [(g * B // G, (g + 1) * B // G) for g in range(G)]
             exs = [orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, W, H, b1 - b0, local) for b0, b1 in hb]
             mts = [orb.ORBmatcher(0.9, True, max_batch=b1 - b0, max_keypoints=cap, max_mappoints=cap, device=local) for b0, b1 in hb]
-            pool = ThreadPoolExecutor(G + 1)
+            pool = ThreadPoolExecutor(G + 2)
+            E2E_EXCL = os.environ.get('BENCH_E2E_LBA', 'concurrent') == 'exclusive'
 
             def frames_job(g, i):
                 cur, lst = i & 1, (i + 1) & 1
@@ -668,20 +669,35 @@ def main():
                 mts[g].search_last_frame_batch(d, TH_PROJ, match_h[b0:b1], claimed_h[b0:b1], nmatch_h[b0:b1], resident=exs[g].resident_slabs())
                 return int(nK_h[b0:b1].sum())
 
-            def lba_job():
-                return opt.LocalBundleAdjustmentBatch(probs)        # host graphs of LR rounds' keyframes in, optimised state out
-
-            pending = None        # the mapping thread's batch in flight: LocalMapping runs beside Tracking (src/System.cc:197)
+            # Mapping side, like the device-resident loop: the graphs of the next batch are uploaded and the results of the previous one
+            # downloaded by a mapping thread WHILE the frames of the following rounds run; only the persistent kernel itself gets the
+            # GPU to itself, between two rounds (it does not share SMs: see round_device).  Two handles alternate.
+            opt_pair = [opt, orb.Optimizer(max_poses=LBA_CFG['n_kf'], max_points=LBA_CFG['n_pts'], max_edges=LBA_CFG['n_pts'] * LBA_CFG['obs_per_pt'],
+                                           max_batch=NLBA * LR, device=local)]
+            up = [None, None]       # upload future per handle
+            down = [None, None]     # download future per handle
             outs = None
+            nbatch = 0
 
             def round_host(i):
-                nonlocal pending, outs
-                if i % LR == 0:                                     # one batch submitted and one collected every LR rounds
-                    if pending is not None:
-                        outs = pending.result()
-                    pending = pool.submit(lba_job)
+                nonlocal outs, nbatch
+                if i % LR == 0:                                     # graphs of this batch's keyframes: upload in the background
+                    k = nbatch & 1
+                    if down[k] is not None:
+                        outs = down[k].result()                     # the handle's previous results are out before it is reused
+                        down[k] = None
+                    up[k] = pool.submit(opt_pair[k].upload, probs)
                 fr = [pool.submit(frames_job, g, i) for g in range(G)]
-                return sum(j.result() for j in fr)
+                nk = sum(j.result() for j in fr)
+                if i % LR == LR - 1:
+                    k = nbatch & 1
+                    up[k].result()
+                    opt_pair[k].run_device(lba_stream.cuda_stream)
+                    if E2E_EXCL:
+                        lba_stream.synchronize()                    # the kernel alone on the GPU (no PCIe traffic of the frames meanwhile)
+                    down[k] = pool.submit(opt_pair[k].download)     # waits for the kernel on the device (event inside the library)
+                    nbatch += 1
+                return nk
 
             for i in range(2 * LR):
                 round_host(i)
@@ -692,10 +708,11 @@ def main():
             for i in range(nr):
                 nk = round_host(i)
             torch.cuda.synchronize()
-            # every LR rounds of the timed region submitted one batch of bundle adjustments and collected one (the one submitted LR
-            # rounds earlier); the batch still in flight is collected outside the timed region
+            # every LR rounds of the timed region uploaded, solved and started to download one batch of bundle adjustments; the last
+            # download may complete just outside the timed region (its kernel ran inside)
             dt = time.perf_counter() - t0
-            tail = pending.result()
+            tail = [d.result() for d in down if d is not None]
+            tail = tail[-1] if tail else None
             dt = sharding.max_over_ranks(dist, dt, dev)
             e2e = world * B * nr / dt
             # parity gate 2: the host buffers of the last timed round
@@ -703,7 +720,7 @@ def main():
             L = last_h[(nr) & 1]
             nchk = check_frames_against_oracle('e2e loop', host_sets[cur].numpy(), kps_h, desc_h, nK_h, match_h, nmatch_h, L, poses_h[cur], sf, cam,
                                                [0, B // 2 - 1, B // 2, B - 1])
-            dl = check_lba_against_oracle('e2e loop', probs[0], (outs or tail)[0])
+            dl = check_lba_against_oracle('e2e loop', probs[0], (tail or outs)[0])
             parity['e2e_loop'] = {'frames_checked': nchk, 'lba_checked': 1, 'lba_max_residual_diff_px': dl, 'ok': True}
             p0 = probs[0]
             lba_h2d = NLBA * (p0['poses'].nbytes + p0['points'].nbytes + p0['obs'].nbytes + 3 * 4 * len(p0['edge_point']) + p0['cam'].nbytes)
