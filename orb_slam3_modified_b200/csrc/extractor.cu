@@ -99,12 +99,14 @@ struct Extractor {
     int* d_stereoSad = nullptr; float *d_stereoU = nullptr, *d_stereoD = nullptr; int* h_stereoStatus = nullptr;
     TmaMaps maps;            // per-level TMA descriptors of the internal pyramid planes (level 0: internal copy)
     CUtensorMap* d_maps = nullptr;   // device copy of `maps`
+    TmaMaps blurMaps;        // the same planes with the blur tile box (BL_SP x (BL_TH + 6))
+    CUtensorMap* d_blurMaps = nullptr;
 
     ~Extractor() { release(); }
     void release() {
         cudaSetDevice(device);
         void* ptrs[] = {d_pyr, d_blur, d_cells, d_cellCount, d_cellList, d_cand, d_nodeOf, d_sel, d_selCount, d_dstIndex,
-                        d_status, d_xtab, d_ytab, d_img, d_outKp, d_outDesc, d_outN, d_outMono, d_maps, d_stereoSad, d_stereoU, d_stereoD};
+                        d_status, d_xtab, d_ytab, d_img, d_outKp, d_outDesc, d_outN, d_outMono, d_maps, d_blurMaps, d_stereoSad, d_stereoU, d_stereoD};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (h_counts) cudaFreeHost(h_counts);
         if (h_stereoStatus) cudaFreeHost(h_stereoStatus);
@@ -290,6 +292,7 @@ struct Extractor {
         CK(cudaMalloc(&d_dstIndex, sizeof(int) * capSel * B));
         CK(cudaMalloc(&d_status, sizeof(int) * B));
         CK(cudaMalloc(&d_maps, sizeof(TmaMaps)));
+        CK(cudaMalloc(&d_blurMaps, sizeof(TmaMaps)));
         CK(cudaMalloc(&d_xtab, sizeof(short4) * capX));
         CK(cudaMalloc(&d_ytab, sizeof(short4) * capY));
         CK(cudaMalloc(&d_img, (size_t)P.lv[0].pitch * maxH * B));
@@ -350,6 +353,15 @@ struct Extractor {
             }
         }
         CK(cudaMemcpy(d_maps, &maps, sizeof(TmaMaps), cudaMemcpyHostToDevice));
+        for (int l = 0; l < nlevels; ++l) {
+            const LevelGeom& G = P.lv[l];
+            if (!encode_plane_map(&blurMaps.lv[l], d_pyr + G.planeOff, G.w, G.h, maxBatch, G.pitch, P.pyrFrameStride, BL_SP, BL_TH + 6)) {
+                set_error("cuTensorMapEncodeTiled failed for a pyramid level (blur tile)");
+                rows = cols = 0;
+                return ORB_ERR_CUDA;
+            }
+        }
+        CK(cudaMemcpy(d_blurMaps, &blurMaps, sizeof(TmaMaps), cudaMemcpyHostToDevice));
         return ORB_OK;
     }
 
@@ -363,13 +375,15 @@ struct Extractor {
         launches = 0;
         CK(cudaMemsetAsync(d_status, 0, sizeof(int) * batch, st));
         // level 0: TMA straight from the caller's frames when base / strides are 16-byte aligned, else from an internal copy
-        CUtensorMap map0;
-        if (!encode_plane_map(&map0, lv0, Q.lv[0].w, Q.lv[0].h, batch, lv0Pitch, lv0Stride, Q.lv[0].fastBoxW, Q.lv[0].fastBoxH)) {
+        CUtensorMap map0, mapBlur0;
+        if (!encode_plane_map(&map0, lv0, Q.lv[0].w, Q.lv[0].h, batch, lv0Pitch, lv0Stride, Q.lv[0].fastBoxW, Q.lv[0].fastBoxH) ||
+            !encode_plane_map(&mapBlur0, lv0, Q.lv[0].w, Q.lv[0].h, batch, lv0Pitch, lv0Stride, BL_SP, BL_TH + 6)) {
             Q.src = lv0; Q.srcStep = lv0Pitch; Q.srcFrameStride = lv0Stride;
             copy_level0_kernel<<<dim3((Q.cols + 255) / 256, Q.rows, batch), 256, 0, st>>>(Q);
             ++launches;
             Q.lv0 = d_pyr + Q.lv[0].planeOff; Q.lv0Pitch = Q.lv[0].pitch; Q.lv0FrameStride = Q.pyrFrameStride;
             map0 = maps.lv[0];
+            mapBlur0 = blurMaps.lv[0];
         }
         if (profiling) for (int i = 0; i < 7; ++i) if (!evStage[i]) CK(cudaEventCreate(&evStage[i]));
         if (profiling) CK(cudaEventRecord(evStage[0], st));
@@ -386,7 +400,7 @@ struct Extractor {
             CK(cudaEventRecord(evFork, st));
             CK(cudaStreamWaitEvent(stream2, evFork, 0));
         }
-        blur_kernel<<<dim3(Q.blurTilesTotal, batch), BL_NT, 0, sb>>>(Q);
+        blur_kernel<<<dim3(Q.blurTilesTotal, batch), BL_NT, 0, sb>>>(Q, mapBlur0, d_blurMaps, 1);
         ++launches;
         if (!profiling) CK(cudaEventRecord(evJoin, stream2));
         if (profiling) CK(cudaEventRecord(evStage[2], st));

@@ -363,7 +363,7 @@ __device__ __forceinline__ int qt_child(const QtNode& n, int px, int py, int& mi
     return (px < midx ? 0 : 1) + (py < midy ? 0 : 2);
 }
 
-__global__ void __launch_bounds__(QT_NT) quadtree_orient_kernel(ExtractParams P) {
+__global__ void __launch_bounds__(QT_NT, 4) quadtree_orient_kernel(ExtractParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     const LevelGeom& G = P.lv[l];
@@ -591,14 +591,21 @@ __global__ void __launch_bounds__(QT_NT) quadtree_orient_kernel(ExtractParams P)
         const unsigned idx = 0xFFFFFFFFu - (unsigned)(S.best[s] & 0xFFFFFFFFull);
         const uint32_t c = cand[idx];
         const int x = cand_x(c) + G.minBX, y = cand_y(c) + G.minBY;
+        // lane = column u of the radius-15 disc, rows walked together: every load instruction of the warp reads one contiguous 31-byte
+        // row segment (one or two sectors) instead of 31 different rows (ncu r2a: 28 % of the kernel's stall samples sat on the
+        // row-per-lane form of this loop, all long-scoreboard)
         int m10 = 0, m01 = 0;
-        if (lane < 31) {
-            const int v = lane - HALF_PATCH;
-            const int d = c_umax[v < 0 ? -v : v];
-            const uint8_t* row = img + (size_t)(y + v) * pitch + x;
-            int rs = 0;
-            for (int u = -d; u <= d; ++u) { const int px = row[u]; m10 += u * px; rs += px; }
-            m01 = v * rs;
+        {
+            const int u = lane - HALF_PATCH;
+            const int au = u < 0 ? -u : u;
+            const uint8_t* centre = img + (size_t)y * pitch + x + (lane < 31 ? u : 0);
+            int colsum = 0;
+#pragma unroll
+            for (int v = -HALF_PATCH; v <= HALF_PATCH; ++v) {
+                const int px = (lane < 31 && au <= c_umax[v < 0 ? -v : v]) ? centre[v * pitch] : 0;
+                colsum += px; m01 += v * px;
+            }
+            m10 = u * colsum;
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
@@ -619,7 +626,8 @@ __global__ void __launch_bounds__(QT_NT) quadtree_orient_kernel(ExtractParams P)
 // SURVEY.md 9E).  Tile 64x32 per CTA, all levels in one launch.
 // ------------------------------------------------------------------------------------------
 constexpr int BL_TW = 128, BL_TH = 64, BL_NT = 256;   // tile per CTA; thread = 4 columns x 8 rows
-constexpr int BL_SP = BL_TW + 8;                       // smem row pitch in bytes: columns x0-4 .. x0+TW+3
+constexpr int BL_SP = BL_TW + 32;                      // smem row pitch = TMA box width: columns x0-16 .. x0+TW+15 (the box must start 16-byte aligned)
+constexpr int BL_C0 = 12;                              // tile byte of column x0-4, the first one the filter reads
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
@@ -630,8 +638,9 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // One thread produces a 4 (columns) x 8 (rows) strip.  Horizontal pass on pairs of pixels packed as 2 x 16 bit
 // (k*p <= 56*255 and the 7-tap sum <= 65280 fit 16 bits, so one IMAD serves two pixels), vertical pass in 32 bit,
 // result (v + 32768) >> 16 -- bit-identical to cv::GaussianBlur's fixed-point path.
-__global__ void __launch_bounds__(BL_NT) blur_kernel(ExtractParams P) {
-    __shared__ __align__(16) uint8_t tile[(BL_TH + 6) * BL_SP];
+__global__ void __launch_bounds__(BL_NT) blur_kernel(ExtractParams P, const __grid_constant__ CUtensorMap map0, const CUtensorMap* __restrict__ maps, int useTma) {
+    __shared__ __align__(128) uint8_t tile[(BL_TH + 6) * BL_SP];
+    __shared__ __align__(8) uint64_t s_bar;
     const int f = blockIdx.y;
     int l = 0;
     while (l + 1 < P.nlevels && (int)blockIdx.x >= P.lv[l + 1].blurTileBase) ++l;
@@ -639,33 +648,69 @@ __global__ void __launch_bounds__(BL_NT) blur_kernel(ExtractParams P) {
     const int t = blockIdx.x - G.blurTileBase;
     const int tyb = t / G.blurTilesX, txb = t - tyb * G.blurTilesX;
     const int x0 = txb * BL_TW, y0 = tyb * BL_TH;
-    int pitch;
-    const uint8_t* img = plane_ptr(P, f, l, pitch);
     const int tid = threadIdx.x;
-    // ---- tile load: rows y0-3 .. y0+TH+2, columns x0-4 .. x0+TW+3 (reflect-101 at the image border) ----
-    const bool interiorX = x0 >= 4 && x0 + BL_TW + 4 <= G.w && ((reinterpret_cast<uintptr_t>(img) + x0) & 3) == 0 && (pitch & 3) == 0;
-    for (int i = tid; i < (BL_TH + 6) * 34; i += BL_NT) {
-        const int r = i / 34, wq = i - r * 34;
-        const int sy = reflect101(min(y0 + r - 3, G.h + 2), G.h);
-        const uint8_t* row = img + (size_t)sy * pitch;
-        uint32_t v;
-        if (interiorX) v = *reinterpret_cast<const uint32_t*>(row + x0 - 4 + 4 * wq);
-        else {
-            v = 0;
+    if (useTma && G.w >= 8 && G.h >= 8) {
+        // ---- tile: ONE TMA bulk-tensor load of rows y0-3 .. y0+TH+2, columns x0-16 .. x0+TW+15 of the pyramid plane (out-of-range
+        //      elements arrive as 0); tiles on the image border then mirror the 3-px halo in shared memory (BORDER_REFLECT_101) ----
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_expect_tx(&s_bar, (uint32_t)((BL_TH + 6) * BL_SP));
+            tma_load_3d(tile, l == 0 ? &map0 : maps + l, x0 - 16, y0 - 3, f, &s_bar);
+        }
+        __syncthreads();
+        mbar_wait(&s_bar, 0);
+        const bool left = x0 == 0, right = x0 + BL_TW + 3 >= G.w, top = y0 == 0, bottom = y0 + BL_TH + 3 >= G.h;
+        if (left || right) {
+            for (int i = tid; i < (BL_TH + 6) * 8; i += BL_NT) {           // per row: 4 halo columns on either side
+                const int r = i >> 3, k = i & 7;
+                if (k < 4) { if (left) { const int x = -4 + k; tile[r * BL_SP + 16 + x] = tile[r * BL_SP + 16 - x]; } }
+                else if (right) {
+                    const int x = G.w + (k - 4);                           // columns w .. w+3
+                    if (x - x0 < BL_TW + 4) tile[r * BL_SP + 16 + x - x0] = tile[r * BL_SP + 16 + (2 * G.w - 2 - x) - x0];
+                }
+            }
+            __syncthreads();
+        }
+        if (top || bottom) {
+            for (int i = tid; i < 6 * (BL_SP / 4); i += BL_NT) {           // 3 halo rows above / below, whole rows as words
+                const int k = i / (BL_SP / 4), wq = i - k * (BL_SP / 4);
+                int y;
+                if (k < 3) { if (!top) continue; y = -3 + k; }
+                else { if (!bottom) continue; y = G.h + (k - 3); if (y - y0 + 3 >= BL_TH + 6) continue; }
+                const int ys = y < 0 ? -y : 2 * G.h - 2 - y;
+                reinterpret_cast<uint32_t*>(tile + (y - y0 + 3) * BL_SP)[wq] = reinterpret_cast<const uint32_t*>(tile + (ys - y0 + 3) * BL_SP)[wq];
+            }
+            __syncthreads();
+        }
+    } else {
+        int pitch;
+        const uint8_t* img = plane_ptr(P, f, l, pitch);
+        // ---- fallback tile load (level 0 not TMA-addressable, or a plane smaller than the halo logic assumes) ----
+        for (int i = tid; i < (BL_TH + 6) * 34; i += BL_NT) {
+            const int r = i / 34, wq = i - r * 34;
+            const int sy = reflect101(min(y0 + r - 3, G.h + 2), G.h);
+            const uint8_t* row = img + (size_t)sy * pitch;
+            uint32_t v = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) v |= (uint32_t)row[reflect101(min(x0 - 4 + 4 * wq + k, G.w + 3), G.w)] << (8 * k);
+            *reinterpret_cast<uint32_t*>(tile + r * BL_SP + BL_C0 + 4 * wq) = v;
         }
-        *reinterpret_cast<uint32_t*>(tile + r * BL_SP + 4 * wq) = v;
+        __syncthreads();
     }
-    __syncthreads();
     const int tx = tid & 31, ty = tid >> 5;          // 32 x 8 threads
     const int xo = x0 + 4 * tx, yo = y0 + 8 * ty;
     if (xo >= G.w || yo >= G.h) return;
-    // horizontal pass for the 14 input rows of this strip: h01 / h23 = packed (h(x), h(x+1)), (h(x+2), h(x+3))
-    uint32_t h01[14], h23[14];
+    // Fused H + V: the 14 input rows of the strip are walked once.  Horizontal pass on pairs of pixels packed as 2 x 16 bit; every
+    // horizontal sum is unpacked ONCE and scattered with its tap weight into the (up to 7) output rows it contributes to -- the
+    // accumulators of the 8 x 4 outputs stay in registers (the earlier form unpacked every sum once per output row: 7x the work).
+    uint32_t acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[r][k] = 0;
 #pragma unroll
     for (int r = 0; r < 14; ++r) {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(tile + (8 * ty + r) * BL_SP + 4 * tx);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(tile + (8 * ty + r) * BL_SP + BL_C0 + 4 * tx);
         const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];   // bytes b0..b11 = columns xo-4 .. xo+7
         // pair words Ps = b_s | b_{s+1} << 16 (two pixels as 2 x 16 bit), s = 1..9: 32-bit window at byte s, then spread bytes 0,1
 #define ORBX_PAIR(lo, hi, sh) __byte_perm(__funnelshift_r(lo, hi, sh), 0u, 0x4140)
@@ -673,26 +718,27 @@ __global__ void __launch_bounds__(BL_NT) blur_kernel(ExtractParams P) {
         const uint32_t P4 = ORBX_PAIR(w1, w2, 0), P5 = ORBX_PAIR(w1, w2, 8), P6 = ORBX_PAIR(w1, w2, 16), P7 = ORBX_PAIR(w1, w2, 24);
         const uint32_t P8 = ORBX_PAIR(w2, 0u, 0), P9 = ORBX_PAIR(w2, 0u, 8);
 #undef ORBX_PAIR
-        h01[r] = 18u * (P1 + P7) + 34u * (P2 + P6) + 48u * (P3 + P5) + 56u * P4;
-        h23[r] = 18u * (P3 + P9) + 34u * (P4 + P8) + 48u * (P5 + P7) + 56u * P6;
+        const uint32_t h01 = 18u * (P1 + P7) + 34u * (P2 + P6) + 48u * (P3 + P5) + 56u * P4;
+        const uint32_t h23 = 18u * (P3 + P9) + 34u * (P4 + P8) + 48u * (P5 + P7) + 56u * P6;
+        const uint32_t h[4] = {h01 & 0xFFFFu, h01 >> 16, h23 & 0xFFFFu, h23 >> 16};
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const int o = r - j;                         // input row r is tap j of output row r - j
+            if (o >= 0 && o < 8) {
+                const uint32_t kj = j == 0 || j == 6 ? 18u : (j == 1 || j == 5 ? 34u : (j == 2 || j == 4 ? 48u : 56u));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[o][k] += kj * h[k];
+            }
+        }
     }
     int bpitch;
     uint8_t* out = const_cast<uint8_t*>(blur_ptr(P, f, l, bpitch));
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         if (yo + r >= G.h) break;
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = 0;
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            const uint32_t kj = j == 0 || j == 6 ? 18u : (j == 1 || j == 5 ? 34u : (j == 2 || j == 4 ? 48u : 56u));
-            v[0] += kj * (h01[r + j] & 0xFFFFu); v[1] += kj * (h01[r + j] >> 16);
-            v[2] += kj * (h23[r + j] & 0xFFFFu); v[3] += kj * (h23[r + j] >> 16);
-        }
         uint32_t pk = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) pk |= ((v[k] + 32768u) >> 16) << (8 * k);
+        for (int k = 0; k < 4; ++k) pk |= ((acc[r][k] + 32768u) >> 16) << (8 * k);
         uint8_t* o = out + (size_t)(yo + r) * bpitch + xo;
         if (xo + 3 < G.w) *reinterpret_cast<uint32_t*>(o) = pk;     // bpitch and xo are multiples of 4
         else {
