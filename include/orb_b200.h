@@ -253,6 +253,23 @@ int orbm_search_for_initialization(orbm_handle* h, const OrbmFrame* F1, const Or
 int orbm_search_last_frame_batch_resident(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOrientation, int32_t* match,
                                           uint8_t* claimed, int32_t* nmatches);
 
+/* int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (include/ORBmatcher.h:68, src/ORBmatcher.cc:223-425,
+ * monocular branch): Tracking::TrackReferenceKeyFrame (src/Tracking.cc:2730) and relocalisation.  A frame / keyframe is its keypoints,
+ * descriptors and DBoW2::FeatureVector as parallel (node id, feature index) arrays in map order (what orbv_transform_batch returns).
+ * kfPoint [KF.N]: 0 = no map point at that keyframe feature, 1 = a map point, 2 = a bad one.  match [F.N] receives the index of the keyframe
+ * feature whose map point is assigned to each frame feature (-1 = none), *nmatches the return value.  KF.N <= max_mappoints and
+ * F.N <= max_keypoints of the handle.  Host pointers. */
+typedef struct OrbmBowFrame {
+    int N; const OrbKeyPoint* keypoints; const uint8_t* descriptors;
+    int nEntries; const int32_t* fvNode; const int32_t* fvFeature;
+} OrbmBowFrame;
+int orbm_search_by_bow(orbm_handle* h, const OrbmBowFrame* KF, const uint8_t* kfPoint, const OrbmBowFrame* F, float nnratio, int checkOrientation,
+                       int32_t* match, int* nmatches);
+/* void MapPoint::ComputeDistinctiveDescriptors() (src/MapPoint.cc:329-403) for nPoints map points at once (LocalMapping::ProcessNewKeyFrame /
+ * CreateNewMapPoints call it per point): the observed descriptors of point p are rows obsStart[p] .. obsStart[p+1] of `descriptors`;
+ * best[p] = row (relative to obsStart[p]) with the least median Hamming distance to the others, -1 for a point without observations. */
+int orbm_distinctive_descriptors(orbm_handle* h, int nPoints, const int32_t* obsStart, const uint8_t* descriptors, int32_t* best);
+
 /* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) as used at src/Frame.cc:1144: idx/dist are Q x 2,
  * ordered by (distance, lower train index); missing neighbours are -1.  Host pointers. */
 int orbm_bf_knn2(orbm_handle* h, const uint8_t* query, int Q, const uint8_t* train, int T, int32_t* idx, int32_t* dist);

@@ -352,4 +352,82 @@ void orbo_is_in_frustum(int M, const float* P, const float* N, const float* minD
     }
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (src/ORBmatcher.cc:223-425), monocular branch
+// (F.Nleft == -1, pKF->mpCamera2 == NULL): matching restricted to features of the same vocabulary node; a frame feature that already holds a
+// match is skipped by later keyframe features (:275-276); TH_LOW, ratio test, rotation histogram on frame indices.
+// Feature vectors: parallel (node id, feature index) arrays in DBoW2::FeatureVector order.  kfPoint[i]: 0 no map point, 1 map point, 2 bad.
+int orbo_search_by_bow(int nKF, const KeyPoint* kpsKF, const uint8_t* descKF, const uint8_t* kfPoint, int eKF, const int* fvNodeKF, const int* fvFeatKF,
+                       int nF, const KeyPoint* kpsF, const uint8_t* descF, int eF, const int* fvNodeF, const int* fvFeatF, float nnratio, int checkOri,
+                       int* matchF) {
+    static const int TH_LOW = 50;
+    for (int i = 0; i < nF; ++i) matchF[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int a = 0, b = 0;
+    while (a < eKF && b < eF) {
+        if (fvNodeKF[a] == fvNodeF[b]) {
+            int a1 = a, b1 = b;
+            while (a1 < eKF && fvNodeKF[a1] == fvNodeKF[a]) ++a1;
+            while (b1 < eF && fvNodeF[b1] == fvNodeF[b]) ++b1;
+            for (int iKF = a; iKF < a1; ++iKF) {
+                const int realIdxKF = fvFeatKF[iKF];
+                if (kfPoint[realIdxKF] != 1) continue;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int iF = b; iF < b1; ++iF) {
+                    const int realIdxF = fvFeatF[iF];
+                    if (matchF[realIdxF] >= 0) continue;
+                    const int dist = descriptor_distance(descKF + (size_t)realIdxKF * 32, descF + (size_t)realIdxF * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= TH_LOW && static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                    matchF[bestIdxF] = realIdxKF;
+                    if (checkOri) {
+                        float rot = kpsKF[realIdxKF].angle - kpsF[bestIdxF].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(bestIdxF);
+                    }
+                    ++nmatches;
+                }
+            }
+            a = a1; b = b1;
+        } else if (fvNodeKF[a] < fvNodeF[b]) { const int t = fvNodeF[b]; while (a < eKF && fvNodeKF[a] < t) ++a; }
+        else { const int t = fvNodeKF[a]; while (b < eF && fvNodeF[b] < t) ++b; }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            const int sz = (int)rotHist[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rotHist[i]) { matchF[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:329-403) for one map point: n observed descriptors -> index of the one with the
+// least median Hamming distance to the others (first minimum; the median is element (int)(0.5 * (n - 1)) of the sorted row).
+int orbo_distinctive_descriptor(int n, const uint8_t* desc) {
+    if (n <= 0) return -1;
+    int BestMedian = INT32_MAX, BestIdx = 0;
+    std::vector<int> vDists(n);
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) vDists[j] = i == j ? 0 : descriptor_distance(desc + (size_t)i * 32, desc + (size_t)j * 32);
+        std::sort(vDists.begin(), vDists.end());
+        const int median = vDists[(size_t)(0.5 * (n - 1))];
+        if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    return BestIdx;
+}
+
 }  // extern "C"

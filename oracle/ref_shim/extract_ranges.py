@@ -9,6 +9,7 @@ RANGES = [
     # out name, file, first, last (1-based, inclusive), anchor on first line
     ('matcher_consts.inc', 'src/ORBmatcher.cc', 35, 41, 'const int ORBmatcher::TH_HIGH'),
     ('matcher_local_map.inc', 'src/ORBmatcher.cc', 43, 221, 'int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>'),
+    ('matcher_bow_kf_frame.inc', 'src/ORBmatcher.cc', 223, 425, 'int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F'),
     ('matcher_init.inc', 'src/ORBmatcher.cc', 648, 763, 'int ORBmatcher::SearchForInitialization'),
     ('matcher_last_frame.inc', 'src/ORBmatcher.cc', 1676, 1887, 'int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame'),
     ('matcher_maxima_distance.inc', 'src/ORBmatcher.cc', 2012, 2074, 'void ORBmatcher::ComputeThreeMaxima'),
@@ -16,6 +17,7 @@ RANGES = [
     ('frame_in_frustum_mono.inc', 'src/Frame.cc', 512, 574, 'bool Frame::isInFrustum(MapPoint *pMP, float viewingCosLimit)'),
     ('frame_stereo_matches.inc', 'src/Frame.cc', 811, 982, 'void Frame::ComputeStereoMatches()'),
     ('frame_features_in_area.inc', 'src/Frame.cc', 657, 735, 'vector<size_t> Frame::GetFeaturesInArea'),
+    ('mappoint_distinctive.inc', 'src/MapPoint.cc', 329, 403, 'void MapPoint::ComputeDistinctiveDescriptors()'),
     ('mappoint_invariance.inc', 'src/MapPoint.cc', 502, 512, 'float MapPoint::GetMinDistanceInvariance()'),
     ('mappoint_predict_scale.inc', 'src/MapPoint.cc', 531, 546, 'int MapPoint::PredictScale(const float &currentDist, Frame* pF)'),
     ('pinhole_project.inc', 'src/CameraModels/Pinhole.cpp', 43, 49, 'Eigen::Vector2f Pinhole::project(const Eigen::Vector3f &v3D)'),

@@ -17,8 +17,10 @@
 #include <map>
 #include <mutex>
 #include <set>
+#include <tuple>
 #include <vector>
 #include "minicv.hpp"
+#include "DBoW2/FeatureVector.h"   // the reference's own DBoW2 classes (-I $(REF)/Thirdparty/DBoW2): SearchByBoW walks two FeatureVectors
 #include "ORBextractor.h"   // the reference's own header (resolved through -I $(REF)/include): Frame::ComputeStereoMatches reads mvImagePyramid
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
@@ -83,6 +85,7 @@ using std::pair;
 
 class Frame;
 class KeyFrame;
+class MapPoint;
 class ORBmatcher;
 
 class GeometricCamera {
@@ -96,8 +99,24 @@ public:
     Eigen::Vector2f project(const Eigen::Vector3f& v3D);   // body: src/CameraModels/Pinhole.cpp:43-49
 };
 
+class KeyFrame {
+public:
+    std::vector<MapPoint*> mvpMapPoints;
+    DBoW2::FeatureVector mFeatVec;
+    cv::Mat mDescriptors;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
+    int NLeft = -1;
+    bool mbBad = false;
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    bool isBad() { return mbBad; }
+};
+
 class MapPoint {
 public:
+    std::map<KeyFrame*, std::tuple<int, int>> mObservations;
+    std::mutex mMutexFeatures;
+    void ComputeDistinctiveDescriptors();                      // body: src/MapPoint.cc:329-403
     // flattened state (what the reference reads under mutexes)
     Eigen::Vector3f mWorldPos, mNormalVector;
     cv::Mat mDescriptor;
@@ -134,6 +153,8 @@ public:
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<bool> mvbOutlier;
     std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
+    DBoW2::FeatureVector mFeatVec;
+    GeometricCamera* mpCamera2 = nullptr;
     float mb = 0, mbf = 0;
     std::vector<float> mvScaleFactors;
     int mnScaleLevels = 0;
@@ -165,6 +186,7 @@ public:
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
                            const float thFarPoints = 50.0f);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     static const int TH_LOW;
     static const int TH_HIGH;

@@ -10,6 +10,7 @@ using namespace std;
 namespace ORB_SLAM3 {
 #include "matcher_consts.inc"
 #include "matcher_local_map.inc"
+#include "matcher_bow_kf_frame.inc"
 #include "matcher_init.inc"
 #include "matcher_last_frame.inc"
 #include "matcher_maxima_distance.inc"
@@ -22,6 +23,7 @@ namespace ORB_SLAM3 {
 }
 #include "frame_features_in_area.inc"
 #include "frame_stereo_matches.inc"
+#include "mappoint_distinctive.inc"
 #include "mappoint_invariance.inc"
 #include "mappoint_predict_scale.inc"
 }  // namespace ORB_SLAM3
@@ -171,6 +173,46 @@ void ref_stereo_matches(void* exLeft, void* exRight, int N, const cv::KeyPoint* 
     F.mpORBextractorLeft = (ORBextractor*)exLeft; F.mpORBextractorRight = (ORBextractor*)exRight;
     F.ComputeStereoMatches();
     for (int i = 0; i < N; ++i) { uRight[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; }
+}
+
+// int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (src/ORBmatcher.cc:223-425).  Feature vectors as
+// parallel (node id, feature index) arrays; kfPoint[i]: 0 = no map point, 1 = map point, 2 = bad map point.  matchF[nF] = KF feature index or -1.
+int ref_search_by_bow(int nKF, const cv::KeyPoint* kpsKF, const uint8_t* descKF, const uint8_t* kfPoint, int eKF, const int* fvNodeKF, const int* fvFeatKF,
+                      int nF, const cv::KeyPoint* kpsF, const uint8_t* descF, int eF, const int* fvNodeF, const int* fvFeatF, float nnratio, int checkOri,
+                      int* matchF) {
+    KeyFrame KF;
+    std::vector<MapPoint> mps(nKF);
+    KF.mvpMapPoints.assign(nKF, (MapPoint*)nullptr);
+    for (int i = 0; i < nKF; ++i) { mps[i].index = i; mps[i].mbBad = kfPoint[i] == 2; if (kfPoint[i]) KF.mvpMapPoints[i] = &mps[i]; }
+    KF.mDescriptors = nKF ? cv::Mat(nKF, 32, CV_8UC1, (void*)descKF, 32) : cv::Mat();
+    KF.mvKeysUn.assign(kpsKF, kpsKF + nKF); KF.mvKeys = KF.mvKeysUn;
+    for (int e = 0; e < eKF; ++e) KF.mFeatVec.addFeature(fvNodeKF[e], fvFeatKF[e]);
+    Frame F;
+    F.N = nF; F.Nleft = -1;
+    F.mDescriptors = nF ? cv::Mat(nF, 32, CV_8UC1, (void*)descF, 32) : cv::Mat();
+    F.mvKeys.assign(kpsF, kpsF + nF);
+    for (int e = 0; e < eF; ++e) F.mFeatVec.addFeature(fvNodeF[e], fvFeatF[e]);
+    std::vector<MapPoint*> out;
+    ORBmatcher matcher(nnratio, checkOri != 0);
+    const int n = matcher.SearchByBoW(&KF, F, out);
+    for (int i = 0; i < nF; ++i) matchF[i] = out[i] ? out[i]->index : -1;
+    return n;
+}
+
+// void MapPoint::ComputeDistinctiveDescriptors() (src/MapPoint.cc:329-403) for one map point with n observations (descriptor rows); returns the
+// index of the chosen observation (the reference stores a clone of that row in mDescriptor).
+int ref_distinctive_descriptor(int n, const uint8_t* desc) {
+    std::vector<KeyFrame> kfs(n);
+    MapPoint mp;
+    for (int i = 0; i < n; ++i) {
+        kfs[i].mDescriptors = cv::Mat(1, 32, CV_8UC1, (void*)(desc + (size_t)i * 32), 32);
+        mp.mObservations[&kfs[i]] = std::make_tuple(0, -1);       // the map iterates in pointer order = array order
+    }
+    mp.mDescriptor = cv::Mat();
+    mp.ComputeDistinctiveDescriptors();
+    if (mp.mDescriptor.empty()) return -1;
+    for (int i = 0; i < n; ++i) if (!memcmp(mp.mDescriptor.data, desc + (size_t)i * 32, 32)) return i;   // first row with the chosen bytes
+    return -2;
 }
 
 // minDistance / maxDistance are the RAW mfMinDistance / mfMaxDistance: the 0.8f / 1.2f invariance factors are applied by the

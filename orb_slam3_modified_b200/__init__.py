@@ -460,6 +460,39 @@ class ORBmatcher:
             raise OrbError(rc, 'orbm_search_for_initialization')
         return n.value, m12
 
+    def SearchByBoW(self, kf_kps, kf_desc, kf_point, kf_fv, f_kps, f_desc, f_fv):
+        """``int ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)`` (src/ORBmatcher.cc:223-425).  ``*_fv`` = (node ids, feature indices) of
+        the DBoW2 FeatureVector; ``kf_point`` [nKF]: 0 none / 1 map point / 2 bad.  Returns (nmatches, match [nF] = keyframe feature index or -1)."""
+        class _BF(C.Structure):
+            _fields_ = [('N', C.c_int), ('keypoints', C.c_void_p), ('descriptors', C.c_void_p), ('nEntries', C.c_int), ('fvNode', C.c_void_p), ('fvFeature', C.c_void_p)]
+        keep = [_c(kf_kps, KP_DTYPE), _c(kf_desc, np.uint8), _c(kf_fv[0], np.int32), _c(kf_fv[1], np.int32), _c(f_kps, KP_DTYPE), _c(f_desc, np.uint8),
+                _c(f_fv[0], np.int32), _c(f_fv[1], np.int32), _c(kf_point, np.uint8)]
+        a = _BF(len(keep[0]), keep[0].ctypes.data, keep[1].ctypes.data, len(keep[2]), keep[2].ctypes.data, keep[3].ctypes.data)
+        b = _BF(len(keep[4]), keep[4].ctypes.data, keep[5].ctypes.data, len(keep[6]), keep[6].ctypes.data, keep[7].ctypes.data)
+        match = np.full(len(keep[4]), -1, np.int32)
+        n = C.c_int(0)
+        L = lib()
+        L.orbm_search_by_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        rc = L.orbm_search_by_bow(self._h, C.byref(a), _ptr(keep[8]), C.byref(b), self.mfNNratio, int(self.mbCheckOrientation), _ptr(match), C.byref(n))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_search_by_bow')
+        return n.value, match
+
+    def ComputeDistinctiveDescriptors(self, obs_list):
+        """``MapPoint::ComputeDistinctiveDescriptors`` for a list of map points (each an [n, 32] u8 array of observed descriptors): index of the chosen row."""
+        start = np.zeros(len(obs_list) + 1, np.int32)
+        for i, o in enumerate(obs_list):
+            start[i + 1] = start[i] + len(o)
+        desc = np.concatenate([_c(o, np.uint8).reshape(-1, 32) for o in obs_list]) if start[-1] else np.zeros((0, 32), np.uint8)
+        desc = np.ascontiguousarray(desc)
+        best = np.zeros(len(obs_list), np.int32)
+        L = lib()
+        L.orbm_distinctive_descriptors.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = L.orbm_distinctive_descriptors(self._h, len(obs_list), _ptr(start), _ptr(desc), _ptr(best))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_distinctive_descriptors')
+        return best
+
     def knnMatch2(self, query, train):
         """cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) (src/Frame.cc:1144): (idx[Q,2], dist[Q,2])."""
         q = _c(query, np.uint8).reshape(-1, 32)

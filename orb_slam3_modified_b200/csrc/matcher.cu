@@ -635,6 +635,137 @@ __global__ void __launch_bounds__(MF_NT) init_match_kernel(MatchParams P) {
     if (tid == 0) P.nmatches[0] = s_nm;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:223-425, monocular branch; Tracking::TrackReferenceKeyFrame
+// src/Tracking.cc:2730 and relocalisation).  Features are matched only inside the same vocabulary node, so nodes are independent: one warp per
+// keyframe node walks its features in order (the claim rule "a frame feature that already holds a match is skipped" is sequential inside a
+// node only), lanes over the frame features of that node: top-2 by (distance, position).  The rotation histogram is resolved by the CTA.
+// One CTA per (keyframe, frame) pair.
+// ---------------------------------------------------------------------------------------------
+struct BowMatchParams {
+    int nKF, nF, eKF, eF;
+    const OrbKeyPoint *kpsKF, *kpsF; const uint8_t *descKF, *descF, *kfPoint;
+    const int *fvNodeKF, *fvFeatKF, *fvNodeF, *fvFeatF;
+    float nnratio; int checkOri;
+    int* match; int* nmatches; int* groupStart; uint8_t* evBin;   // match [nF]; scratch: groupStart [eKF + 1], evBin [nF]
+};
+constexpr int BM_NT = 256;
+__global__ void __launch_bounds__(BM_NT) bow_match_kernel(BowMatchParams Q) {
+    __shared__ int s_hist[HISTO_LENGTH], s_ind[3], s_acc, s_rem, s_ng;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < Q.nF; i += BM_NT) { Q.match[i] = -1; Q.evBin[i] = 0; }
+    if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+    if (tid == 0) { s_acc = 0; s_rem = 0; s_ng = 0; }
+    __syncthreads();
+    // group heads of the keyframe's feature vector (entries are sorted by node id)
+    for (int e = tid; e < Q.eKF; e += BM_NT)
+        if (e == 0 || Q.fvNodeKF[e] != Q.fvNodeKF[e - 1]) Q.groupStart[atomicAdd(&s_ng, 1)] = e;     // order of groups is irrelevant: nodes are independent
+    __syncthreads();
+    const int ng = s_ng;
+    int acc = 0;
+    for (int g = wid; g < ng; g += BM_NT / 32) {
+        const int a = Q.groupStart[g];
+        const int node = Q.fvNodeKF[a];
+        int a1 = a;
+        while (a1 < Q.eKF && Q.fvNodeKF[a1] == node) ++a1;
+        int lo = 0, hi = Q.eF;                                   // lower_bound / upper_bound of `node` in the frame's vector
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (Q.fvNodeF[mid] < node) lo = mid + 1; else hi = mid; }
+        const int b = lo;
+        hi = Q.eF;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (Q.fvNodeF[mid] <= node) lo = mid + 1; else hi = mid; }
+        const int b1 = lo;
+        if (b1 == b) continue;
+        for (int iKF = a; iKF < a1; ++iKF) {
+            const int realIdxKF = Q.fvFeatKF[iKF];
+            if (Q.kfPoint[realIdxKF] != 1) continue;             // no map point, or a bad one (:255-259)
+            const uint4* pk = reinterpret_cast<const uint4*>(Q.descKF + (size_t)realIdxKF * 32);
+            const uint4 k0 = __ldg(pk), k1 = __ldg(pk + 1);
+            const uint32_t dk[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+            Top2 t; t.init();
+            for (int iF = b + lane; iF < b1; iF += 32) {
+                const int realIdxF = Q.fvFeatF[iF];
+                if (Q.match[realIdxF] >= 0) continue;            // already matched by an earlier keyframe feature of this node (:275-276)
+                const uint4* pf = reinterpret_cast<const uint4*>(Q.descF + (size_t)realIdxF * 32);
+                const uint4 f0 = __ldg(pf), f1 = __ldg(pf + 1);
+                const uint32_t dfw[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                t.insert(((unsigned long long)hamming256(dk, dfw) << 32) | (unsigned)(iF - b), realIdxF);
+            }
+            t.warp_merge();
+            const int bestDist1 = t.i[0] >= 0 ? (int)(t.k[0] >> 32) : 256, bestDist2 = t.i[1] >= 0 ? (int)(t.k[1] >> 32) : 256;
+            if (bestDist1 <= TH_LOW && (float)bestDist1 < fmul(Q.nnratio, (float)bestDist2)) {
+                if (lane == 0) {
+                    Q.match[t.i[0]] = realIdxKF;
+                    if (Q.checkOri) {
+                        const int bin = rot_bin(Q.kpsKF[realIdxKF].angle, Q.kpsF[t.i[0]].angle);
+                        Q.evBin[t.i[0]] = (uint8_t)(bin + 1);
+                        atomicAdd(&s_hist[bin], 1);
+                    }
+                }
+                ++acc;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && acc) atomicAdd(&s_acc, acc);
+    __syncthreads();
+    if (Q.checkOri) {
+        if (tid == 0) {
+            int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+            for (int bb = 0; bb < HISTO_LENGTH; ++bb) {
+                const int sz = s_hist[bb];
+                if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = bb; }
+                else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = bb; }
+                else if (sz > max3) { max3 = sz; ind3 = bb; }
+            }
+            if ((float)max2 < fmul(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < fmul(0.1f, (float)max1)) { ind3 = -1; }
+            s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+        }
+        __syncthreads();
+        int rem = 0;
+        for (int i = tid; i < Q.nF; i += BM_NT) {
+            const int bb = (int)Q.evBin[i] - 1;
+            if (bb >= 0 && bb != s_ind[0] && bb != s_ind[1] && bb != s_ind[2]) { Q.match[i] = -1; ++rem; }
+        }
+        if (rem) atomicAdd(&s_rem, rem);
+        __syncthreads();
+    }
+    if (tid == 0) *Q.nmatches = s_acc - s_rem;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:329-403) for a batch of map points: warp per map point, lane per observation row;
+// the row's median distance (element (int)(0.5 (n - 1)) of the sorted row) by bisection on the distance value; first minimum wins.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) distinctive_kernel(int nPoints, const int* __restrict__ ptStart, const uint8_t* __restrict__ desc, int* __restrict__ best) {
+    const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= nPoints) return;
+    const int a = ptStart[p], n = ptStart[p + 1] - a;
+    if (n <= 0) { if (lane == 0) best[p] = -1; return; }
+    const int k = (int)(0.5 * (double)(n - 1));
+    unsigned bestKey = 0xFFFFFFFFu;
+    for (int i = lane; i < n; i += 32) {
+        const uint4* pi = reinterpret_cast<const uint4*>(desc + (size_t)(a + i) * 32);
+        const uint4 x0 = __ldg(pi), x1 = __ldg(pi + 1);
+        const uint32_t di[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        int lo = 0, hi = 256;                                    // smallest v with #{j : d(i, j) <= v} >= k + 1
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int cnt = 0;
+            for (int j = 0; j < n; ++j) {
+                const uint4* pj = reinterpret_cast<const uint4*>(desc + (size_t)(a + j) * 32);
+                const uint4 y0 = __ldg(pj), y1 = __ldg(pj + 1);
+                const uint32_t dj[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+                cnt += (i == j ? 0 : hamming256(di, dj)) <= mid;
+            }
+            if (cnt >= k + 1) hi = mid; else lo = mid + 1;
+        }
+        bestKey = min(bestKey, ((unsigned)lo << 16) | (unsigned)i);
+    }
+    bestKey = __reduce_min_sync(0xffffffffu, bestKey);
+    if (lane == 0) best[p] = (int)(bestKey & 0xFFFFu);
+}
+
 // cv::BFMatcher(NORM_HAMMING).knnMatch(k=2): warp per query, lanes over train rows
 constexpr int BF_NT = 256;
 __global__ void __launch_bounds__(BF_NT) bf_knn2_kernel(const uint8_t* __restrict__ q, int Q, const uint8_t* __restrict__ t, int T,
@@ -705,6 +836,7 @@ struct Matcher {
         arenaBytes = (arenaBytes + 255) & ~(size_t)255;
         const size_t bf = (size_t)(kcap + mcap) * 32 + (size_t)std::max(kcap, mcap) * 16 + 4096;
         arenaBytes = std::max(arenaBytes, bf);
+        arenaBytes = std::max(arenaBytes, (size_t)(kcap + mcap) * (28 + 32 + 1 + 8 + 4 + 4 + 1) + 8192);   // SearchByBoW: keyframe + frame staged together
         CK(cudaMalloc(&d_arena, arenaBytes));
         {
             orbx::ScopedGpuAffinity numaLocal(device);     // pinned pages on the GPU's NUMA node (host_affinity.h)
@@ -1042,6 +1174,70 @@ int orbm_search_last_frame_batch(orbm_handle* h, const OrbmBatchDevice* in, floa
 int orbm_search_last_frame_batch_resident(orbm_handle* h, const OrbmBatchDevice* in, float th, int checkOri, int32_t* match, uint8_t* claimed,
                                           int32_t* nmatches) {
     return search_last_frame_batch_host(h, in, th, checkOri, match, claimed, nmatches, true);
+}
+
+int orbm_search_by_bow(orbm_handle* h, const OrbmBowFrame* KF, const uint8_t* kfPoint, const OrbmBowFrame* F, float nnratio, int checkOrientation,
+                       int32_t* match, int* nmatches) {
+    if (!h || !KF || !F || !kfPoint || !match || !nmatches || KF->N < 0 || F->N < 0 || KF->nEntries < 0 || F->nEntries < 0 || KF->nEntries > KF->N ||
+        F->nEntries > F->N || KF->N > h->m.mcap || F->N > h->m.kcap) {
+        set_error("orbm_search_by_bow: bad argument (KF.N <= max_mappoints, F.N <= max_keypoints of the handle)"); return ORB_ERR_ARG;
+    }
+    for (int e = 0; e < KF->nEntries; ++e) if (KF->fvFeature[e] < 0 || KF->fvFeature[e] >= KF->N || (e && KF->fvNode[e] < KF->fvNode[e - 1])) { set_error("orbm_search_by_bow: keyframe feature vector not sorted / out of range"); return ORB_ERR_ARG; }
+    for (int e = 0; e < F->nEntries; ++e) if (F->fvFeature[e] < 0 || F->fvFeature[e] >= F->N || (e && F->fvNode[e] < F->fvNode[e - 1])) { set_error("orbm_search_by_bow: frame feature vector not sorted / out of range"); return ORB_ERR_ARG; }
+    Matcher& m = h->m;
+    CK(cudaSetDevice(m.device));
+    *nmatches = 0;
+    for (int i = 0; i < F->N; ++i) match[i] = -1;
+    if (F->N == 0 || KF->N == 0) return ORB_OK;
+    Arena A(m.h_arena, m.d_arena, m.arenaBytes);
+    BowMatchParams Q; memset(&Q, 0, sizeof(Q));
+    Q.nKF = KF->N; Q.nF = F->N; Q.eKF = KF->nEntries; Q.eF = F->nEntries; Q.nnratio = nnratio; Q.checkOri = checkOrientation;
+    bool ok = A.put(KF->keypoints, (size_t)KF->N, &Q.kpsKF) && A.put(KF->descriptors, (size_t)KF->N * 32, &Q.descKF) && A.put(kfPoint, (size_t)KF->N, &Q.kfPoint) &&
+              A.put(KF->fvNode, (size_t)KF->nEntries, &Q.fvNodeKF) && A.put(KF->fvFeature, (size_t)KF->nEntries, &Q.fvFeatKF) &&
+              A.put(F->keypoints, (size_t)F->N, &Q.kpsF) && A.put(F->descriptors, (size_t)F->N * 32, &Q.descF) &&
+              A.put(F->fvNode, (size_t)F->nEntries, &Q.fvNodeF) && A.put(F->fvFeature, (size_t)F->nEntries, &Q.fvFeatF);
+    const size_t inBytes = A.off;
+    const int *dMatch, *dN, *dGs; const uint8_t* dEv;
+    ok = ok && A.put((const int*)nullptr, (size_t)F->N, &dMatch) && A.put((const int*)nullptr, (size_t)1, &dN) && A.put((const int*)nullptr, (size_t)KF->nEntries + 1, &dGs) &&
+         A.put((const uint8_t*)nullptr, (size_t)F->N, &dEv);
+    if (!ok) { set_error("matcher staging arena too small"); return ORB_ERR_CAPACITY; }
+    Q.match = const_cast<int*>(dMatch); Q.nmatches = const_cast<int*>(dN); Q.groupStart = const_cast<int*>(dGs); Q.evBin = const_cast<uint8_t*>(dEv);
+    cudaStream_t st = m.stream;
+    CK(cudaMemcpyAsync(m.d_arena, m.h_arena, inBytes, cudaMemcpyHostToDevice, st));
+    bow_match_kernel<<<1, BM_NT, 0, st>>>(Q);
+    m.launches = 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(match, dMatch, 4 * (size_t)F->N, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nmatches, dN, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_distinctive_descriptors(orbm_handle* h, int nPoints, const int32_t* obsStart, const uint8_t* descriptors, int32_t* best) {
+    if (!h || nPoints < 0 || !obsStart || !best || (nPoints && obsStart[nPoints] > 0 && !descriptors)) { set_error("orbm_distinctive_descriptors: bad argument"); return ORB_ERR_ARG; }
+    if (nPoints == 0) return ORB_OK;
+    for (int p = 0; p < nPoints; ++p) if (obsStart[p + 1] < obsStart[p] || obsStart[p + 1] - obsStart[p] > 65535) { set_error("orbm_distinctive_descriptors: obsStart must be non-decreasing (<= 65535 observations per point)"); return ORB_ERR_ARG; }
+    Matcher& m = h->m;
+    CK(cudaSetDevice(m.device));
+    const size_t total = (size_t)obsStart[nPoints];
+    const size_t need = 4 * ((size_t)nPoints + 1) + 32 * total + 4 * (size_t)nPoints + 1024;
+    if (need > m.batchBytes) {                                  // grow the device staging (cudaMemcpy from pageable host memory: rare, mapping-side call)
+        if (m.d_batch) cudaFree(m.d_batch);
+        m.d_batch = nullptr; m.batchBytes = 0;
+        CK(cudaMalloc(&m.d_batch, need));
+        m.batchBytes = need;
+    }
+    uint8_t* d = m.d_batch;
+    const size_t oS = 0, oD = (4 * ((size_t)nPoints + 1) + 255) & ~(size_t)255, oB = (oD + 32 * total + 255) & ~(size_t)255;
+    cudaStream_t st = m.stream;
+    CK(cudaMemcpyAsync(d + oS, obsStart, 4 * ((size_t)nPoints + 1), cudaMemcpyHostToDevice, st));
+    if (total) CK(cudaMemcpyAsync(d + oD, descriptors, 32 * total, cudaMemcpyHostToDevice, st));
+    distinctive_kernel<<<(nPoints + 7) / 8, 256, 0, st>>>(nPoints, (const int*)(d + oS), d + oD, (int*)(d + oB));
+    m.launches = 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(best, d + oB, 4 * (size_t)nPoints, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORB_OK;
 }
 
 int orbm_frustum_project(orbm_handle* h, const OrbmFrustumIn* in, uint8_t* inView, float* projX, float* projY, float* projXR,

@@ -376,3 +376,22 @@ def bow_score_l1(a, b):
     L.orbo_bow_score_l1.restype = C.c_double
     L.orbo_bow_score_l1.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return L.orbo_bow_score_l1(len(i1), _p(i1), _p(v1), len(i2), _p(i2), _p(v2))
+
+
+def search_by_bow(kps_kf, desc_kf, kf_point, fv_kf, kps_f, desc_f, fv_f, nnratio=0.7, check_ori=True, _lib=None, _name='orbo_search_by_bow'):
+    """fv_*: (node ids, feature indices) parallel arrays in DBoW2::FeatureVector order.  Returns (nmatches, match [nF] = KF feature index or -1)."""
+    kk = _c(kps_kf, KP_DTYPE); dk = _c(desc_kf, np.uint8); kp = _c(kf_point, np.uint8); kf_ = _c(kps_f, KP_DTYPE); df = _c(desc_f, np.uint8)
+    nk, fk = _c(fv_kf[0], np.int32), _c(fv_kf[1], np.int32); nf, ff = _c(fv_f[0], np.int32), _c(fv_f[1], np.int32)
+    match = np.full(len(kf_), -1, np.int32)
+    L = _lib or lib()
+    fn = getattr(L, _name)
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                   C.c_float, C.c_int, C.c_void_p]
+    n = fn(len(kk), _p(kk), _p(dk), _p(kp), len(nk), _p(nk), _p(fk), len(kf_), _p(kf_), _p(df), len(nf), _p(nf), _p(ff), nnratio, int(check_ori), _p(match))
+    return n, match
+
+
+def distinctive_descriptor(desc, _lib=None, _name='orbo_distinctive_descriptor'):
+    d = _c(desc, np.uint8).reshape(-1, 32)
+    L = _lib or lib()
+    return getattr(L, _name)(len(d), _p(d))

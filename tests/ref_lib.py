@@ -212,3 +212,13 @@ class RefVocabulary:
         self.L.ref_bow_score.restype = C.c_double
         self.L.ref_bow_score.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         return self.L.ref_bow_score(self.h, len(i1), _p(i1), _p(v1), len(i2), _p(i2), _p(v2))
+
+
+def search_by_bow(*a, **kw):
+    import oracle_lib as O
+    return O.search_by_bow(*a, _lib=lib(), _name='ref_search_by_bow', **kw)
+
+
+def distinctive_descriptor(desc):
+    import oracle_lib as O
+    return O.distinctive_descriptor(desc, _lib=lib(), _name='ref_distinctive_descriptor')

@@ -210,3 +210,35 @@ def test_search_for_initialization_heavy_rematching(orb):
         gp = prev.copy()
         n, m12 = m.SearchForInitialization(orb.Frame(k1, d1, b, sf), orb.Frame(k2, d2, b, sf), gp, 100)
         assert n == on and np.array_equal(m12, om) and np.array_equal(gp, oprev), (ratio, n, on)
+
+
+@pytest.mark.parametrize('t,k,L,levelsup,ratio,ori', [(3, 10, 4, 2, 0.7, True), (8, 10, 3, 2, 0.75, True), (15, 6, 4, 3, 0.9, False), (21, 10, 3, 1, 0.7, True)])
+def test_search_by_bow(orb, t, k, L, levelsup, ratio, ori):
+    """f2: ORBmatcher::SearchByBoW(KeyFrame*, Frame&) vs the oracle (= the reference's own body, tests/test_ref_pins_oracle_cpu.py)."""
+    voc = O.synthetic_vocabulary(k, L, seed=k + L)
+    rng = np.random.default_rng(t)
+    kk, dk = S.extract(t); kf, df = S.extract(t + 1)
+    fvk = O.bow_transform(voc, dk, levelsup)[2:]; fvf = O.bow_transform(voc, df, levelsup)[2:]
+    kf_point = rng.choice([0, 1, 1, 1, 1, 2], len(kk)).astype(np.uint8)
+    m = orb.ORBmatcher(ratio, ori, max_batch=1, max_keypoints=2048, max_mappoints=2048)
+    n, match = m.SearchByBoW(kk, dk, kf_point, fvk, kf, df, fvf)
+    on, om = O.search_by_bow(kk, dk, kf_point, fvk, kf, df, fvf, nnratio=ratio, check_ori=ori)
+    assert n == on and np.array_equal(match, om) and n > 20, (n, on)
+
+
+def test_compute_distinctive_descriptors(orb, matcher):
+    rng = np.random.default_rng(6)
+    _, desc = S.extract(5)
+    obs_list = []
+    for n in list(range(0, 12)) + [17, 32, 33, 64, 100] + list(rng.integers(2, 30, 300)):
+        base = desc[rng.integers(0, len(desc))]
+        obs = np.tile(base, (int(n), 1))
+        for i in range(int(n)):
+            for bit in rng.integers(0, 256, rng.integers(0, 40)):
+                obs[i, bit >> 3] ^= np.uint8(1 << (bit & 7))
+        if n > 3:
+            obs[2] = obs[1]
+        obs_list.append(obs)
+    best = matcher.ComputeDistinctiveDescriptors(obs_list)
+    for o, b in zip(obs_list, best):
+        assert b == O.distinctive_descriptor(o), (len(o), b)

@@ -211,3 +211,35 @@ def test_dbow2_transform_equals_reference(k, L, levelsup, weighting, scoring):
         return
     s = ref.score(outs[0], outs[1])
     assert s == O.bow_score_l1(outs[0], outs[1]) and 0 < s < 1 and abs(ref.score(outs[0], outs[0]) - 1.0) < 1e-12
+
+
+def _bow_scene(t, voc, levelsup=2, seed=0):
+    rng = np.random.default_rng(seed)
+    kk, dk = matcher_scenes.extract(t); kf, df = matcher_scenes.extract(t + 1)
+    fvk = O.bow_transform(voc, dk, levelsup)[2:]; fvf = O.bow_transform(voc, df, levelsup)[2:]
+    kf_point = rng.choice([0, 1, 1, 1, 1, 2], len(kk)).astype(np.uint8)
+    return kk, dk, kf_point, fvk, kf, df, fvf
+
+
+@pytest.mark.parametrize('t,k,L,levelsup,ratio,ori', [(3, 10, 4, 2, 0.7, True), (8, 10, 3, 2, 0.75, True), (15, 6, 4, 3, 0.9, False), (21, 10, 3, 1, 0.7, True)])
+def test_search_by_bow_equals_reference(t, k, L, levelsup, ratio, ori):
+    voc = O.synthetic_vocabulary(k, L, seed=k + L)
+    sc = _bow_scene(t, voc, levelsup, seed=t)
+    a = R.search_by_bow(*sc, nnratio=ratio, check_ori=ori)
+    b = O.search_by_bow(*sc, nnratio=ratio, check_ori=ori)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[0] > 20, (a[0], b[0])
+
+
+def test_compute_distinctive_descriptors_equals_reference():
+    rng = np.random.default_rng(6)
+    _, desc = matcher_scenes.extract(5)
+    for n in list(range(1, 12)) + [17, 32, 33, 64]:
+        base = desc[rng.integers(0, len(desc))]
+        obs = np.tile(base, (n, 1))
+        for i in range(n):
+            for bit in rng.integers(0, 256, rng.integers(0, 40)):
+                obs[i, bit >> 3] ^= np.uint8(1 << (bit & 7))
+        if n > 3:
+            obs[2] = obs[1]            # duplicates: ties between medians -> the first row wins
+        a, b = R.distinctive_descriptor(obs), O.distinctive_descriptor(obs)
+        assert np.array_equal(obs[a], obs[b]), (n, a, b)      # the reference keeps a clone of the chosen row: compare bytes
