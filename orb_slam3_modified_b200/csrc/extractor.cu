@@ -99,6 +99,7 @@ struct Extractor {
     int* d_stereoSad = nullptr; float *d_stereoU = nullptr, *d_stereoD = nullptr; int* h_stereoStatus = nullptr;
     TmaMaps maps;            // per-level TMA descriptors of the internal pyramid planes (level 0: internal copy)
     CUtensorMap* d_maps = nullptr;   // device copy of `maps`
+    TmaMaps pyrMaps;         // pyrMaps.lv[l]: level l-1 with the source box of level l's resize tiles (host copy: passed by value per launch)
     TmaMaps blurMaps;        // the same planes with the blur tile box (BL_SP x (BL_TH + 6))
     CUtensorMap* d_blurMaps = nullptr;
 
@@ -250,6 +251,14 @@ struct Extractor {
                     t.z = (short)cvRoundF((1.f - fy) * 2048); t.w = (short)cvRoundF(fy * 2048);
                     ytab.push_back(t);
                 }
+                // TMA box that covers the sources of any 128 x 8 destination tile (start column aligned down to 16 bytes)
+                int bw = 16, bh = 2;
+                for (int dx0 = 0; dx0 < G.w; dx0 += 128) {
+                    const int first = xtab[G.xtabOff + dx0].x & ~15, last = xtab[G.xtabOff + std::min(dx0 + 127, G.w - 1)].y;
+                    bw = std::max(bw, last - first + 1);
+                }
+                for (int dy0 = 0; dy0 < G.h; dy0 += 8) bh = std::max(bh, ytab[G.ytabOff + std::min(dy0 + 7, G.h - 1)].y - ytab[G.ytabOff + dy0].x + 1);
+                G.pyrBoxW = (int)alignUp(bw, 16); G.pyrBoxH = bh;
             }
         }
         P.pyrFrameStride = planeOff;
@@ -362,6 +371,11 @@ struct Extractor {
             }
         }
         CK(cudaMemcpy(d_blurMaps, &blurMaps, sizeof(TmaMaps), cudaMemcpyHostToDevice));
+        for (int l = 2; l < nlevels; ++l) {     // level 1 reads level 0, which may alias the caller's frames: encoded per call
+            const LevelGeom& S = P.lv[l - 1];
+            if (P.lv[l].area2x || P.lv[l].pyrBoxW > 256 || P.lv[l].pyrBoxH > 256 ||
+                !encode_plane_map(&pyrMaps.lv[l], d_pyr + S.planeOff, S.w, S.h, maxBatch, S.pitch, P.pyrFrameStride, P.lv[l].pyrBoxW, P.lv[l].pyrBoxH)) P.lv[l].pyrBoxW = 0;
+        }
         return ORB_OK;
     }
 
@@ -390,7 +404,12 @@ struct Extractor {
         // pyramid: levels depend on each other
         for (int l = 1; l < nlevels; ++l) {
             dim3 blk(32, 8), grd((Q.lv[l].w + 127) / 128, (Q.lv[l].h + 7) / 8, batch);
-            pyr_resize_kernel<<<grd, blk, 0, st>>>(Q, l);
+            CUtensorMap srcMap;
+            bool tma = Q.lv[l].pyrBoxW > 0 && !Q.lv[l].area2x && Q.lv[l].pyrBoxW <= 256 && Q.lv[l].pyrBoxH <= 256;
+            if (tma && l == 1) tma = encode_plane_map(&srcMap, Q.lv0, Q.lv[0].w, Q.lv[0].h, batch, Q.lv0Pitch, Q.lv0FrameStride, Q.lv[1].pyrBoxW, Q.lv[1].pyrBoxH);
+            else if (tma) srcMap = pyrMaps.lv[l];
+            if (tma) pyr_resize_tma_kernel<<<grd, blk, (size_t)Q.lv[l].pyrBoxW * Q.lv[l].pyrBoxH, st>>>(Q, l, srcMap);
+            else pyr_resize_kernel<<<grd, blk, 0, st>>>(Q, l);     // exact 2x decimation (INTER_AREA promotion) or a box TMA cannot express
             ++launches;
         }
         if (profiling) CK(cudaEventRecord(evStage[1], st));

@@ -328,6 +328,52 @@ __global__ void __launch_bounds__(FAST_NT) fast_cells_kernel(ExtractParams P, co
     if (tid == 0) *outCount = total;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K1 (TMA form): pyramid level l from level l-1 with the source rows of a 128 x 8 destination tile staged into shared memory by ONE
+// TMA bulk-tensor load (box pyrBoxW x pyrBoxH of level l-1, start aligned to 16 bytes); the fixed-point bilinear taps then read
+// shared memory instead of gathering bytes from global memory.  Same integer arithmetic as pyr_resize_kernel (cv::resize INTER_LINEAR).
+// ------------------------------------------------------------------------------------------
+constexpr int PYR_TILE_W = 128, PYR_TILE_H = 8;
+__global__ void __launch_bounds__(256) pyr_resize_tma_kernel(ExtractParams P, int l, const __grid_constant__ CUtensorMap srcMap) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    const LevelGeom& G = P.lv[l];
+    const int f = blockIdx.z;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int dxT = blockIdx.x * PYR_TILE_W, dyT = blockIdx.y * PYR_TILE_H;
+    const int cx0 = (int)P.xtab[G.xtabOff + dxT].x & ~15;                 // first source column of the tile, aligned down
+    const int ry0 = (int)P.ytab[G.ytabOff + dyT].x;
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_expect_tx(&s_bar, (uint32_t)(G.pyrBoxW * G.pyrBoxH));
+        tma_load_3d(smem_raw, &srcMap, cx0, ry0, f, &s_bar);
+    }
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
+    const int dy = dyT + threadIdx.y;
+    const int dx0 = dxT + threadIdx.x * 4;
+    if (dy >= G.h || dx0 >= G.w) return;
+    const short4 yt = P.ytab[G.ytabOff + dy];  // {sy0, sy1, b0, b1}
+    const uint8_t* r0 = smem_raw + (yt.x - ry0) * G.pyrBoxW - cx0;
+    const uint8_t* r1 = smem_raw + (yt.y - ry0) * G.pyrBoxW - cx0;
+    const int b0 = yt.z, b1 = yt.w;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int dx = dx0 + k;
+        if (dx < G.w) {
+            const short4 xt = __ldg(&P.xtab[G.xtabOff + dx]);  // {sx0, sx1, a0, a1}
+            const int s0 = r0[xt.x] * xt.z + r0[xt.y] * xt.w;
+            const int s1 = r1[xt.x] * xt.z + r1[xt.y] * xt.w;
+            const int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+            out |= (uint32_t)(v & 0xFF) << (8 * k);
+        }
+    }
+    uint8_t* dst = P.pyr + (size_t)f * P.pyrFrameStride + G.planeOff + (size_t)dy * G.pitch;
+    *reinterpret_cast<uint32_t*>(dst + dx0) = out;   // pitch is a multiple of 32: in-bounds even for the tail
+}
+
 // ------------------------------------------------------------------------------------------
 // K3: quadtree distribution + orientation.  One CTA per (level, frame).
 // Reference: ORBextractor::DistributeOctTree src/ORBextractor.cc:555-779,
