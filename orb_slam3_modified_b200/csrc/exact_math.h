@@ -223,6 +223,36 @@ ORB_HD void sx_insertion_sort(T* first, T* last, Less less) {
     }
 }
 
+// One __introsort_loop iteration on [lo, hi): __move_median_to_first(first, first+1, mid, last-1) + __unguarded_partition(first+1, last,
+// pivot = *first); returns the cut.
+template <class T, class Less>
+ORB_HD int sx_partition_step(T* a, int lo, int hi, Less less) {
+    T* first = a + lo;
+    T* A = first + 1;
+    T* B = first + (hi - lo) / 2;
+    T* C = a + hi - 1;
+    T* med;
+    if (less(*A, *B)) {
+        if (less(*B, *C)) med = B;
+        else if (less(*A, *C)) med = C;
+        else med = A;
+    } else if (less(*A, *C)) med = A;
+    else if (less(*B, *C)) med = C;
+    else med = B;
+    { T t = *first; *first = *med; *med = t; }
+    T* l = first + 1;
+    T* r = a + hi;
+    while (true) {
+        while (less(*l, *first)) ++l;
+        --r;
+        while (less(*first, *r)) --r;
+        if (!(l < r)) break;
+        T t = *l; *l = *r; *r = t;
+        ++l;
+    }
+    return (int)(l - a);
+}
+
 template <class T, class Less>
 ORB_HD void libstdcxx_sort(T* a, int n, Less less) {
     if (n < 2) return;
@@ -243,32 +273,7 @@ ORB_HD void libstdcxx_sort(T* a, int n, Less less) {
                 break;
             }
             --d;
-            // __move_median_to_first(first, first+1, mid, last-1)
-            T* first = a + lo;
-            T* A = first + 1;
-            T* B = first + (hi - lo) / 2;
-            T* C = a + hi - 1;
-            T* med;
-            if (less(*A, *B)) {
-                if (less(*B, *C)) med = B;
-                else if (less(*A, *C)) med = C;
-                else med = A;
-            } else if (less(*A, *C)) med = A;
-            else if (less(*B, *C)) med = C;
-            else med = B;
-            { T t = *first; *first = *med; *med = t; }
-            // __unguarded_partition(first+1, last, pivot = *first)
-            T* l = first + 1;
-            T* r = a + hi;
-            while (true) {
-                while (less(*l, *first)) ++l;
-                --r;
-                while (less(*first, *r)) --r;
-                if (!(l < r)) break;
-                T t = *l; *l = *r; *r = t;
-                ++l;
-            }
-            int cut = (int)(l - a);
+            const int cut = sx_partition_step(a, lo, hi, less);
             // recurse on [cut, hi) first: emulate by pushing the LEFT part and continuing... no:
             // libstdc++ calls __introsort_loop(cut, last) recursively, then loops on [first, cut).
             // The two parts are disjoint, so the order in which they are finished does not matter;
@@ -284,6 +289,46 @@ ORB_HD void libstdcxx_sort(T* a, int n, Less less) {
     } else {
         sx_insertion_sort(a, a + n, less);
     }
+}
+
+
+// ---------------------------------------------------------------------------
+// The same sort as a sequence of ROUNDS of independent tasks (what quadtree_orient_kernel runs with one thread per task):
+//   round r: every pending range longer than 16 does ONE partition step (or the heapsort fallback when its depth budget is spent) and
+//            hands its two parts to the next round; parts of <= 16 elements become leaves;
+//   finally every leaf is insertion-sorted on its own.
+// Equal to libstdcxx_sort: the parts of a partition are disjoint, so the order in which they are processed is irrelevant; and the final
+// insertion sort of std::sort never moves an element across a partition boundary (left part <= pivot <= right part, and it stops at the
+// first element that is not greater), so it decomposes into independent insertion sorts of the leaves.  Checked against std::sort on the
+// host (tests/hostcheck.cpp: hc_sort_check_rounds).  `task` holds (lo, hi, depth) triples: 2 x capacity ints x 3; `leaf` (lo, hi) pairs.
+// ---------------------------------------------------------------------------
+struct SxTask { int lo, hi, d; };
+template <class T, class Less>
+ORB_HD void sx_round_task(T* a, SxTask t, Less less, SxTask* next, int* nNext, SxTask* leaf, int* nLeaf) {
+    // sequential helper used by the host model; the device driver inlines the same steps with atomic counters
+    if (t.hi - t.lo <= 16) { leaf[(*nLeaf)++] = t; return; }
+    if (t.d == 0) { sx_heapsort(a + t.lo, t.hi - t.lo, less); return; }          // sorted: not a leaf, nothing left to do
+    const int cut = sx_partition_step(a, t.lo, t.hi, less);
+    const SxTask right = {cut, t.hi, t.d - 1}, left = {t.lo, cut, t.d - 1};
+    if (right.hi - right.lo > 16) next[(*nNext)++] = right; else leaf[(*nLeaf)++] = right;
+    if (left.hi - left.lo > 16) next[(*nNext)++] = left; else leaf[(*nLeaf)++] = left;
+}
+template <class T, class Less>
+inline void libstdcxx_sort_rounds_host(T* a, int n, Less less, SxTask* q0, SxTask* q1, SxTask* leaf) {
+    if (n < 2) return;
+    int depth = 0;
+    for (int t = n; t > 1; t >>= 1) depth++;
+    depth *= 2;
+    int nCur = 1, nLeaf = 0;
+    q0[0] = SxTask{0, n, depth};
+    SxTask *cur = q0, *nxt = q1;
+    while (nCur) {
+        int nNext = 0;
+        for (int i = 0; i < nCur; ++i) sx_round_task(a, cur[i], less, nxt, &nNext, leaf, &nLeaf);
+        SxTask* t = cur; cur = nxt; nxt = t;
+        nCur = nNext;
+    }
+    for (int i = 0; i < nLeaf; ++i) sx_insertion_sort(a + leaf[i].lo, a + leaf[i].hi, less);
 }
 
 }  // namespace orbx

@@ -409,6 +409,42 @@ __device__ __forceinline__ int qt_child(const QtNode& n, int px, int py, int& mi
     return (px < midx ? 0 : 1) + (py < midy ? 0 : 2);
 }
 
+
+// std::sort emulation by the whole CTA (see exact_math.h: rounds of independent tasks).  leaf: capacity n entries; qA / qB: n / 17 + 1 each.
+__device__ void cta_libstdcxx_sort(QtSort* a, int n, SxTask* leaf, SxTask* qA, SxTask* qB, int* cnt /* shared: nCur, nNext, nLeaf */) {
+    const auto less = [](const QtSort& x, const QtSort& y) { return x.size < y.size || (x.size == y.size && x.ulx < y.ulx); };
+    const int tid = threadIdx.x;
+    if (n < 2) return;
+    if (n <= 16) { if (tid == 0) sx_insertion_sort(a, a + n, less); __syncthreads(); return; }
+    if (tid == 0) {
+        int depth = 0;
+        for (int t = n; t > 1; t >>= 1) depth++;
+        qA[0] = SxTask{0, n, 2 * depth};
+        cnt[0] = 1; cnt[1] = 0; cnt[2] = 0;
+    }
+    __syncthreads();
+    SxTask *cur = qA, *nxt = qB;
+    for (;;) {
+        const int nc = cnt[0];
+        if (nc == 0) break;
+        for (int i = tid; i < nc; i += blockDim.x) {
+            const SxTask t = cur[i];
+            if (t.d == 0) { sx_heapsort(a + t.lo, t.hi - t.lo, less); continue; }
+            const int cut = sx_partition_step(a, t.lo, t.hi, less);
+            const SxTask right = {cut, t.hi, t.d - 1}, left = {t.lo, cut, t.d - 1};
+            if (right.hi - right.lo > 16) nxt[atomicAdd(&cnt[1], 1)] = right; else if (right.hi - right.lo > 1) leaf[atomicAdd(&cnt[2], 1)] = right;
+            if (left.hi - left.lo > 16) nxt[atomicAdd(&cnt[1], 1)] = left; else if (left.hi - left.lo > 1) leaf[atomicAdd(&cnt[2], 1)] = left;
+        }
+        __syncthreads();
+        if (tid == 0) { cnt[0] = cnt[1]; cnt[1] = 0; }
+        SxTask* sw = cur; cur = nxt; nxt = sw;
+        __syncthreads();
+    }
+    const int nl = cnt[2];
+    for (int i = tid; i < nl; i += blockDim.x) sx_insertion_sort(a + leaf[i].lo, a + leaf[i].hi, less);
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(QT_NT, 4) quadtree_orient_kernel(ExtractParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
@@ -416,6 +452,7 @@ __global__ void __launch_bounds__(QT_NT, 4) quadtree_orient_kernel(ExtractParams
     const int MN = P.maxNodes;
     __shared__ int s_warp[33];
     __shared__ int s_P;
+    __shared__ int s_sortCnt[3];
 
     // carve shared memory
     QtShared S;
@@ -502,11 +539,11 @@ __global__ void __launch_bounds__(QT_NT, 4) quadtree_orient_kernel(ExtractParams
                 else S.proc[s] = -1;
             }
         } else {
-            if (tid == 0) {   // std::sort(vPrev.begin(), vPrev.end(), compareNodes) (:705)
-                libstdcxx_sort(S.v, q, [](const QtSort& a, const QtSort& b) {
-                    return a.size < b.size || (a.size == b.size && a.ulx < b.ulx);
-                });
-            }
+            // std::sort(vPrev.begin(), vPrev.end(), compareNodes) (:705): the libstdc++ introsort, whose order among equal keys the result
+            // depends on, run as rounds of independent partition steps (one thread per pending range) + independent leaf insertion
+            // sorts -- exact_math.h: libstdcxx_sort_rounds_host is the same sequence, checked against std::sort on the host
+            cta_libstdcxx_sort(S.v, q, reinterpret_cast<SxTask*>(S.scanA), reinterpret_cast<SxTask*>(S.scanA + 3 * MN),
+                               reinterpret_cast<SxTask*>(S.scanA + 3 * MN) + MN / 6, s_sortCnt);
             for (int s = tid; s < m; s += QT_NT) S.proc[s] = -1;
             __syncthreads();
             P0 = q;

@@ -55,6 +55,19 @@ void hc_std_sort_order(const int* size, const int* ulx, int n, int* order_out) {
     for (int i = 0; i < n; ++i) order_out[i] = b[i].id;
 }
 
+// the round-based form of the emulation (one partition step per pending range and round, leaves insertion-sorted independently: what the
+// kernel runs with one thread per task) against std::sort; returns 0 if equal
+int hc_sort_check_rounds(const int* size, const int* ulx, int n) {
+    std::vector<SK> a(n), b(n);
+    for (int i = 0; i < n; ++i) { a[i] = {size[i], ulx[i], i}; b[i] = a[i]; }
+    auto less = [](const SK& p, const SK& q) { return p.size < q.size || (p.size == q.size && p.ulx < q.ulx); };
+    std::vector<orbx::SxTask> q0(n + 2), q1(n + 2), leaf(n + 2);
+    orbx::libstdcxx_sort_rounds_host(a.data(), n, less, q0.data(), q1.data(), leaf.data());
+    std::sort(b.begin(), b.end(), less);
+    for (int i = 0; i < n; ++i) if (a[i].id != b[i].id) return 1;
+    return 0;
+}
+
 // sorts keys with the emulation and with std::sort using the reference's comparator shape; returns 0 if equal
 int hc_sort_check(const int* size, const int* ulx, int n, int* order_out) {
     std::vector<SK> a(n), b(n);

@@ -74,11 +74,13 @@ def test_sort_emulation_vs_libstdcxx(hc):
         size = rng.integers(2, 2 + int(rng.integers(1, 12)), n).astype(np.int32)
         ulx = (rng.integers(0, 1 + int(rng.integers(1, 40)), n) * 7).astype(np.int32)
         bad += hc.hc_sort_check(_p(size), _p(ulx), n, None)
+        bad += hc.hc_sort_check_rounds(_p(size), _p(ulx), n)
     for n in (17, 100, 1000, 5000):   # adversarial shapes incl. the heapsort fallback
         for arr in (np.arange(n), np.arange(n)[::-1], np.r_[np.arange(n // 2), np.arange(n - n // 2)[::-1]], np.zeros(n), np.arange(n) % 3):
             size = np.ascontiguousarray(arr, dtype=np.int32)
             ulx = np.ascontiguousarray((np.arange(n) * 7919) % 13, dtype=np.int32)
             bad += hc.hc_sort_check(_p(size), _p(ulx), n, None)
+            bad += hc.hc_sort_check_rounds(_p(size), _p(ulx), n)
     assert bad == 0
 
 
