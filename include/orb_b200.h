@@ -265,6 +265,21 @@ typedef struct OrbmBowFrame {
 } OrbmBowFrame;
 int orbm_search_by_bow(orbm_handle* h, const OrbmBowFrame* KF, const uint8_t* kfPoint, const OrbmBowFrame* F, float nnratio, int checkOrientation,
                        int32_t* match, int* nmatches);
+/* int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th, const bool bRight) (include/ORBmatcher.h:99,
+ * src/ORBmatcher.cc:1148-1338, monocular keyframe; LocalMapping::SearchInNeighbors, src/LocalMapping.cc:878-1021): the SEARCH of every map
+ * point -- projection with the keyframe pose, KeyFrame::IsInImage, distance / viewing-angle tests, MapPoint::PredictScale, the radius search
+ * of KeyFrame::GetFeaturesInArea with the level window and the chi-square gate, best Hamming distance.  bestIdx[i] = keyframe keypoint
+ * (-1: none), bestDist[i] its distance (256: none).  Fuse's return value is the number of i with bestDist[i] <= TH_LOW (50); for those the
+ * caller applies :1310-1330 in map-point order (Replace the point with fewer observations, or AddObservation + AddMapPoint): that walk
+ * mutates the pointer graph and does not feed back into any search.  state[i]: 0 = NULL, 1 = searched, 2 = isBad(), 3 = IsInKeyFrame(pKF).
+ * minDistance / maxDistance are the RAW mfMinDistance / mfMaxDistance (the 0.8f / 1.2f of the getters are applied inside).
+ * KF.K <= max_keypoints of the handle; M is unbounded.  Host pointers. */
+typedef struct OrbmFusePoints {
+    int M; const uint8_t* state; const float* worldPos; const float* normal; const float* minDistance; const float* maxDistance;
+    const uint8_t* descriptors;
+} OrbmFusePoints;
+int orbm_fuse_search(orbm_handle* h, const OrbmFrame* KF, const float* invLevelSigma2, float logScaleFactor, const float* Tcw7, const float* Ow3,
+                     const float* cam4, const OrbmFusePoints* pts, float th, int32_t* bestIdx, int32_t* bestDist);
 /* void MapPoint::ComputeDistinctiveDescriptors() (src/MapPoint.cc:329-403) for nPoints map points at once (LocalMapping::ProcessNewKeyFrame /
  * CreateNewMapPoints call it per point): the observed descriptors of point p are rows obsStart[p] .. obsStart[p+1] of `descriptors`;
  * best[p] = row (relative to obsStart[p]) with the least median Hamming distance to the others, -1 for a point without observations. */

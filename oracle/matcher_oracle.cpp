@@ -430,4 +430,57 @@ int orbo_distinctive_descriptor(int n, const uint8_t* desc) {
     return BestIdx;
 }
 
+// ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th, bRight = false) (src/ORBmatcher.cc:1148-1338), monocular keyframe:
+// the SEARCH of every map point (projection, image / distance / viewing-angle tests, scale prediction, radius search with the chi-square gate,
+// best Hamming distance).  What Fuse then does with a hit (AddObservation / Replace, :1310-1330) mutates the pointer graph and stays with the
+// caller; no map point's search depends on it.  state[i]: 0 NULL, 1 ok, 2 bad, 3 already in the keyframe.  bestIdx -1 / bestDist 256: no candidate.
+// `ex*ex+ey*ey` (:1280) is one FMA in the reference's -O3 -march=native build (checked against oracle/_ref).
+void orbo_fuse_search(int K, const KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors, const float* invLevelSigma2, int nlevels,
+                      float logScaleFactor, const float* Tcw, const float* Ow, const float* cam, int M, const uint8_t* state, const float* xyz,
+                      const float* normal, const float* minDistance, const float* maxDistance, const uint8_t* mpDesc, float th, int* bestIdxOut, int* bestDistOut) {
+    FrameView F;
+    F.K = K; F.kps = kps; F.desc = desc;
+    F.minX = bounds[0]; F.minY = bounds[1]; F.maxX = bounds[2]; F.maxY = bounds[3];
+    F.gridWInv = (float)GRID_COLS / (F.maxX - F.minX);
+    F.gridHInv = (float)GRID_ROWS / (F.maxY - F.minY);
+    F.scaleFactors = scaleFactors;
+    F.build_grid();
+    const float qw = Tcw[0], qx = Tcw[1], qy = Tcw[2], qz = Tcw[3];
+    std::vector<int> vIndices;
+    for (int i = 0; i < M; ++i) {
+        bestIdxOut[i] = -1; bestDistOut[i] = 256;
+        if (state[i] != 1) continue;
+        const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+        float ux = qy * pz - qz * py, uy = qz * px - qx * pz, uz = qx * py - qy * px;
+        ux += ux; uy += uy; uz += uz;
+        const float cx_ = qy * uz - qz * uy, cy_ = qz * ux - qx * uz, cz_ = qx * uy - qy * ux;
+        const float xc = (px + qw * ux) + cx_ + Tcw[4], yc = (py + qw * uy) + cy_ + Tcw[5], zc = (pz + qw * uz) + cz_ + Tcw[6];
+        if (zc < 0.0f) continue;
+        const float u = cam[0] * xc / zc + cam[2], v = cam[1] * yc / zc + cam[3];
+        if (!(u >= F.minX && u < F.maxX && v >= F.minY && v < F.maxY)) continue;                    // KeyFrame::IsInImage
+        const float maxD = 1.2f * maxDistance[i], minD = 0.8f * minDistance[i];
+        const float ox = px - Ow[0], oy = py - Ow[1], oz = pz - Ow[2];
+        const float dist3D = sqrtf((ox * ox + oy * oy) + oz * oz);
+        if (dist3D < minD || dist3D > maxD) continue;
+        const float dot = (ox * normal[3 * i] + oy * normal[3 * i + 1]) + oz * normal[3 * i + 2];
+        if (dot < 0.5 * dist3D) continue;
+        const float ratio = maxDistance[i] / dist3D;
+        int lvl = (int)std::ceil(std::log(ratio) / logScaleFactor);
+        if (lvl < 0) lvl = 0; else if (lvl >= nlevels) lvl = nlevels - 1;
+        const float radius = th * scaleFactors[lvl];
+        F.features_in_area(u, v, radius, -1, -1, vIndices);          // KeyFrame::GetFeaturesInArea has no level filter
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            const int kpLevel = kps[idx].octave;
+            if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+            const float ex = u - kps[idx].x, ey = v - kps[idx].y;
+            const float e2 = fmaf(ex, ex, ey * ey);
+            if (e2 * invLevelSigma2[kpLevel] > 5.99) continue;
+            const int dist = descriptor_distance(mpDesc + (size_t)i * 32, desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        bestIdxOut[i] = bestIdx; bestDistOut[i] = bestDist;
+    }
+}
+
 }  // extern "C"

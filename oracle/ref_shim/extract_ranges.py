@@ -11,6 +11,7 @@ RANGES = [
     ('matcher_local_map.inc', 'src/ORBmatcher.cc', 43, 221, 'int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>'),
     ('matcher_bow_kf_frame.inc', 'src/ORBmatcher.cc', 223, 425, 'int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F'),
     ('matcher_init.inc', 'src/ORBmatcher.cc', 648, 763, 'int ORBmatcher::SearchForInitialization'),
+    ('matcher_fuse.inc', 'src/ORBmatcher.cc', 1148, 1338, 'int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints'),
     ('matcher_last_frame.inc', 'src/ORBmatcher.cc', 1676, 1887, 'int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame'),
     ('matcher_maxima_distance.inc', 'src/ORBmatcher.cc', 2012, 2074, 'void ORBmatcher::ComputeThreeMaxima'),
     ('frame_assign_grid.inc', 'src/Frame.cc', 385, 416, 'void Frame::AssignFeaturesToGrid()'),
@@ -18,6 +19,8 @@ RANGES = [
     ('frame_stereo_matches.inc', 'src/Frame.cc', 811, 982, 'void Frame::ComputeStereoMatches()'),
     ('frame_features_in_area.inc', 'src/Frame.cc', 657, 735, 'vector<size_t> Frame::GetFeaturesInArea'),
     ('mappoint_distinctive.inc', 'src/MapPoint.cc', 329, 403, 'void MapPoint::ComputeDistinctiveDescriptors()'),
+    ('keyframe_features_in_area.inc', 'src/KeyFrame.cc', 704, 753, 'vector<size_t> KeyFrame::GetFeaturesInArea'),
+    ('mappoint_predict_scale_kf.inc', 'src/MapPoint.cc', 514, 529, 'int MapPoint::PredictScale(const float &currentDist, KeyFrame* pKF)'),
     ('mappoint_invariance.inc', 'src/MapPoint.cc', 502, 512, 'float MapPoint::GetMinDistanceInvariance()'),
     ('mappoint_predict_scale.inc', 'src/MapPoint.cc', 531, 546, 'int MapPoint::PredictScale(const float &currentDist, Frame* pF)'),
     ('pinhole_project.inc', 'src/CameraModels/Pinhole.cpp', 43, 49, 'Eigen::Vector2f Pinhole::project(const Eigen::Vector3f &v3D)'),

@@ -110,6 +110,23 @@ public:
     bool mbBad = false;
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
     bool isBad() { return mbBad; }
+    // --- what ORBmatcher::Fuse reads (include/KeyFrame.h) ---
+    int N = 0, mnScaleLevels = 0;
+    int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+    float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mfLogScaleFactor = 0;
+    float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0, mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    std::vector<float> mvScaleFactors, mvInvLevelSigma2, mvuRight;
+    std::vector<std::vector<std::vector<size_t>>> mGrid, mGridRight;
+    Sophus::SE3f mTcw;
+    Eigen::Vector3f mOw;
+    Sophus::SE3f GetPose() { return mTcw; }
+    Sophus::SE3f GetRightPose() { return mTcw; }
+    Eigen::Vector3f GetCameraCenter() { return mOw; }
+    Eigen::Vector3f GetRightCameraCenter() { return mOw; }
+    bool IsInImage(const float& x, const float& y) const;                       // body: src/KeyFrame.cc:750-753
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;   // body: src/KeyFrame.cc:704-748
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
 };
 
 class MapPoint {
@@ -134,12 +151,30 @@ public:
     float GetMinDistanceInvariance();                          // bodies: src/MapPoint.cc:502-512
     float GetMaxDistanceInvariance();
     int PredictScale(const float& currentDist, Frame* pF);     // body: src/MapPoint.cc:531-546
+    int PredictScale(const float& currentDist, KeyFrame* pKF); // body: src/MapPoint.cc:514-529
+    // Fuse's view of the map: which keyframes observe the point, and a log of what Fuse did with it (the wrapper reads the log back)
+    std::set<KeyFrame*> inKF;
+    // slot: the keypoint of the (one) keyframe under Fuse that holds this point, -1 if none.  fuseAction / fuseIdx log what Fuse did for the
+    // searched map point: 1 = AddObservation(pKF, idx); 2 = it was Replace()d by the keyframe's point at idx; 3 = it Replace()d the point at idx.
+    int slot = -1, fuseAction = 0, fuseIdx = -1;
+    KeyFrame* slotKF = nullptr;
+    bool IsInKeyFrame(KeyFrame* pKF) { return inKF.count(pKF) != 0; }
+    void AddObservation(KeyFrame* pKF, int idx) { fuseAction = 1; fuseIdx = idx; slot = idx; slotKF = pKF; inKF.insert(pKF); ++nObs; }
+    // MapPoint::Replace (src/MapPoint.cc:232-291) as Fuse sees it: this point goes bad; where the keyframe held it, it now holds pMP
+    void Replace(MapPoint* pMP) {
+        mbBad = true;
+        if (slot >= 0) { pMP->fuseAction = 3; pMP->fuseIdx = slot; pMP->slot = slot; pMP->slotKF = slotKF; pMP->inKF.insert(slotKF); ++pMP->nObs; replace_in_keyframe(pMP); slot = -1; }
+        else { fuseAction = 2; fuseIdx = pMP->slot; }
+    }
+    void replace_in_keyframe(MapPoint* pMP);
 
     float mTrackProjX = 0, mTrackProjY = 0, mTrackDepth = 0, mTrackDepthR = 0, mTrackProjXR = 0, mTrackProjYR = 0;
     bool mbTrackInView = false, mbTrackInViewR = false;
     int mnTrackScaleLevel = 0, mnTrackScaleLevelR = 0;
     float mTrackViewCos = 0, mTrackViewCosR = 0;
 };
+
+inline void MapPoint::replace_in_keyframe(MapPoint* pMP) { slotKF->mvpMapPoints[slot] = pMP; }
 
 class Frame {
 public:
@@ -187,6 +222,7 @@ public:
                            const float thFarPoints = 50.0f);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0, const bool bRight = false);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     static const int TH_LOW;
     static const int TH_HIGH;

@@ -12,6 +12,7 @@ namespace ORB_SLAM3 {
 #include "matcher_local_map.inc"
 #include "matcher_bow_kf_frame.inc"
 #include "matcher_init.inc"
+#include "matcher_fuse.inc"
 #include "matcher_last_frame.inc"
 #include "matcher_maxima_distance.inc"
 #include "pinhole_project.inc"
@@ -24,6 +25,8 @@ namespace ORB_SLAM3 {
 #include "frame_features_in_area.inc"
 #include "frame_stereo_matches.inc"
 #include "mappoint_distinctive.inc"
+#include "keyframe_features_in_area.inc"
+#include "mappoint_predict_scale_kf.inc"
 #include "mappoint_invariance.inc"
 #include "mappoint_predict_scale.inc"
 }  // namespace ORB_SLAM3
@@ -197,6 +200,59 @@ int ref_search_by_bow(int nKF, const cv::KeyPoint* kpsKF, const uint8_t* descKF,
     const int n = matcher.SearchByBoW(&KF, F, out);
     for (int i = 0; i < nF; ++i) matchF[i] = out[i] ? out[i]->index : -1;
     return n;
+}
+
+// int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th, bRight = false) (src/ORBmatcher.cc:1148-1338), monocular keyframe.
+// Map points: state[i] (0 NULL, 1 ok, 2 bad, 3 already observed by the keyframe), world position, normal, RAW min / max distance, descriptor, nObs.
+// kfPoint[k]: -1 = keyframe keypoint k has no map point, else the Observations() of the map point it holds (>= 0); kfPointBad[k].
+// Out per map point: action (0 none, 1 added as observation of keypoint idx, 2 replaced by the keyframe's point at idx, 3 replaces the keyframe's
+// point at idx, 4 counted but nothing done: the keyframe's point at that keypoint is bad) and idx; returns nFused.
+int ref_fuse(int K, const cv::KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors, const float* invLevelSigma2, int nlevels,
+             float logScaleFactor, const float* Tcw, const float* Ow, const float* cam, const int* kfPoint, const uint8_t* kfPointBad, int M,
+             const uint8_t* state, const float* xyz, const float* normal, const float* minDistance, const float* maxDistance, const uint8_t* mpDesc,
+             const int* mpObs, float th, int* action, int* actionIdx) {
+    KeyFrame KF;
+    KF.N = K; KF.NLeft = -1;
+    KF.mvKeysUn.assign(kps, kps + K); KF.mvKeys = KF.mvKeysUn;
+    KF.mvuRight.assign(K, -1.f);
+    KF.mDescriptors = K ? cv::Mat(K, 32, CV_8UC1, (void*)desc, 32) : cv::Mat();
+    KF.mnMinX = bounds[0]; KF.mnMinY = bounds[1]; KF.mnMaxX = bounds[2]; KF.mnMaxY = bounds[3];
+    KF.mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (KF.mnMaxX - KF.mnMinX);
+    KF.mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (KF.mnMaxY - KF.mnMinY);
+    KF.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels); KF.mvInvLevelSigma2.assign(invLevelSigma2, invLevelSigma2 + nlevels);
+    KF.mnScaleLevels = nlevels; KF.mfLogScaleFactor = logScaleFactor;
+    KF.fx = cam[0]; KF.fy = cam[1]; KF.cx = cam[2]; KF.cy = cam[3]; KF.mbf = 0.f;
+    Pinhole camera; camera.mvParameters.assign(cam, cam + 4); KF.mpCamera = &camera;
+    KF.mTcw.qw = Tcw[0]; KF.mTcw.qx = Tcw[1]; KF.mTcw.qy = Tcw[2]; KF.mTcw.qz = Tcw[3]; KF.mTcw.t = Eigen::Vector3f(Tcw[4], Tcw[5], Tcw[6]);
+    KF.mOw = Eigen::Vector3f(Ow[0], Ow[1], Ow[2]);
+    // the keyframe's grid = the frame's (KeyFrame copies Frame::mGrid, src/KeyFrame.cc:60-75): built with the reference's AssignFeaturesToGrid
+    {
+        Frame F;
+        fill_frame(F, K, kps, desc, bounds, scaleFactors, nlevels);
+        KF.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+        for (int i = 0; i < FRAME_GRID_COLS; ++i) for (int j = 0; j < FRAME_GRID_ROWS; ++j) KF.mGrid[i][j] = F.mGrid[i][j];
+        KF.mGridRight = KF.mGrid;
+    }
+    std::vector<MapPoint> kfMps(K);
+    KF.mvpMapPoints.assign(K, (MapPoint*)nullptr);
+    for (int k = 0; k < K; ++k) if (kfPoint[k] >= 0) { kfMps[k].index = k; kfMps[k].slot = k; kfMps[k].slotKF = &KF; kfMps[k].inKF.insert(&KF); kfMps[k].nObs = kfPoint[k]; kfMps[k].mbBad = kfPointBad[k] != 0; KF.mvpMapPoints[k] = &kfMps[k]; }
+    std::vector<MapPoint> mps(M);
+    std::vector<MapPoint*> vp(M, (MapPoint*)nullptr);
+    for (int i = 0; i < M; ++i) {
+        MapPoint& p = mps[i];
+        p.index = i; p.mbBad = state[i] == 2; p.nObs = mpObs[i];
+        if (state[i] == 3) p.inKF.insert(&KF);
+        p.mWorldPos = Eigen::Vector3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        p.mNormalVector = Eigen::Vector3f(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
+        p.mfMinDistance = minDistance[i]; p.mfMaxDistance = maxDistance[i];
+        p.mDescriptor = cv::Mat(1, 32, CV_8UC1, (void*)(mpDesc + (size_t)i * 32), 32);
+        if (state[i]) vp[i] = &p;
+    }
+    ORBmatcher matcher(0.6f, true);
+    const int nFused = matcher.Fuse(&KF, vp, th, false);
+    for (int i = 0; i < M; ++i) { action[i] = 0; actionIdx[i] = -1; }
+    for (int i = 0; i < M; ++i) { action[i] = mps[i].fuseAction; actionIdx[i] = mps[i].fuseIdx; }
+    return nFused;
 }
 
 // void MapPoint::ComputeDistinctiveDescriptors() (src/MapPoint.cc:329-403) for one map point with n observations (descriptor rows); returns the

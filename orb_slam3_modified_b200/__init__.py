@@ -478,6 +478,28 @@ class ORBmatcher:
             raise OrbError(rc, 'orbm_search_by_bow')
         return n.value, match
 
+    def FuseSearch(self, kf_kps, kf_desc, bounds, scale_factors, inv_level_sigma2, log_scale_factor, Tcw7, Ow, cam4, state, xyz, normal, min_d, max_d,
+                   mp_desc, th=3.0):
+        """The search of ``int ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th)`` (src/ORBmatcher.cc:1148-1338): (bestIdx [M], bestDist [M]);
+        Fuse's return value is ``(bestDist <= 50).sum()``; see include/orb_b200.h: orbm_fuse_search."""
+        class _Fr(C.Structure):
+            _fields_ = [('K', C.c_int), ('keypoints', C.c_void_p), ('descriptors', C.c_void_p), ('minX', C.c_float), ('minY', C.c_float), ('maxX', C.c_float),
+                        ('maxY', C.c_float), ('scaleFactors', C.c_void_p), ('nlevels', C.c_int)]
+        class _Pt(C.Structure):
+            _fields_ = [('M', C.c_int)] + [(n, C.c_void_p) for n in ('state', 'worldPos', 'normal', 'minDistance', 'maxDistance', 'descriptors')]
+        k = [_c(kf_kps, KP_DTYPE), _c(kf_desc, np.uint8), _c(scale_factors, np.float32), _c(inv_level_sigma2, np.float32)]
+        m = [_c(state, np.uint8), _c(xyz, np.float32), _c(normal, np.float32), _c(min_d, np.float32), _c(max_d, np.float32), _c(mp_desc, np.uint8)]
+        o = [_c(Tcw7, np.float32), _c(Ow, np.float32), _c(cam4, np.float32)]
+        fr = _Fr(len(k[0]), k[0].ctypes.data, k[1].ctypes.data, *[float(b) for b in bounds], k[2].ctypes.data, len(k[2]))
+        pt = _Pt(len(m[0]), *[a.ctypes.data for a in m])
+        bi = np.zeros(len(m[0]), np.int32); bd = np.zeros(len(m[0]), np.int32)
+        L = lib()
+        L.orbm_fuse_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+        rc = L.orbm_fuse_search(self._h, C.byref(fr), _ptr(k[3]), float(log_scale_factor), _ptr(o[0]), _ptr(o[1]), _ptr(o[2]), C.byref(pt), float(th), _ptr(bi), _ptr(bd))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_fuse_search')
+        return bi, bd
+
     def ComputeDistinctiveDescriptors(self, obs_list):
         """``MapPoint::ComputeDistinctiveDescriptors`` for a list of map points (each an [n, 32] u8 array of observed descriptors): index of the chosen row."""
         start = np.zeros(len(obs_list) + 1, np.int32)

@@ -734,6 +734,76 @@ __global__ void __launch_bounds__(BM_NT) bow_match_kernel(BowMatchParams Q) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// ORBmatcher::Fuse(KeyFrame*, vector<MapPoint*>, th) (src/ORBmatcher.cc:1148-1338), the search: the keyframe's grid in shared memory (every CTA
+// builds its own copy), one warp per map point: projection with the keyframe pose, KeyFrame::IsInImage, distance and viewing-angle tests,
+// MapPoint::PredictScale, then the radius search of KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:704-753) with the level window
+// [predicted - 1, predicted] and the chi-square gate e2 * invSigma2 > 5.99; first smallest distance wins.  No search depends on what Fuse does
+// with another map point's hit, so the AddObservation / Replace bookkeeping stays with the caller (in map-point order).
+// ---------------------------------------------------------------------------------------------
+struct FuseParams {
+    MatchParams P;          // keyframe: kps, desc, bounds, scaleFactors, nlevels, ks, descInSmem
+    int K, M;
+    const uint8_t *state, *mpDesc;
+    const float *xyz, *normal, *minD, *maxD, *invSigma2;
+    float Tcw[7], Ow[3], logSF;
+    int *bestIdx, *bestDist;
+};
+__global__ void __launch_bounds__(MF_NT) fuse_search_kernel(FuseParams Q) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int s_warp[33];
+    const MatchParams& P = Q.P;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const FrameSmem S = carve_frame_smem(smem_raw, P.ks, 1, P.descInSmem != 0);
+    build_frame_smem(S, P.kps, P.desc, Q.K, P.minX, P.minY, P.gridWInv, P.gridHInv, s_warp);
+    const int nw = gridDim.x * (MF_NT / 32);
+    for (int i = blockIdx.x * (MF_NT / 32) + (tid >> 5); i < Q.M; i += nw) {
+        int bestIdx = -1, bestDist = 256;
+        bool go = Q.state[i] == 1;
+        float u = 0.f, v = 0.f, r = 0.f; int lvl = 0;
+        if (go) {
+            const float qw = Q.Tcw[0], qx = Q.Tcw[1], qy = Q.Tcw[2], qz = Q.Tcw[3];
+            const float px = Q.xyz[3 * i], py = Q.xyz[3 * i + 1], pz = Q.xyz[3 * i + 2];
+            float ux = fsub(fmul(qy, pz), fmul(qz, py)), uy = fsub(fmul(qz, px), fmul(qx, pz)), uz = fsub(fmul(qx, py), fmul(qy, px));
+            ux = fadd(ux, ux); uy = fadd(uy, uy); uz = fadd(uz, uz);
+            const float cx_ = fsub(fmul(qy, uz), fmul(qz, uy)), cy_ = fsub(fmul(qz, ux), fmul(qx, uz)), cz_ = fsub(fmul(qx, uy), fmul(qy, ux));
+            const float xc = fadd(fadd(fadd(px, fmul(qw, ux)), cx_), Q.Tcw[4]);
+            const float yc = fadd(fadd(fadd(py, fmul(qw, uy)), cy_), Q.Tcw[5]);
+            const float zc = fadd(fadd(fadd(pz, fmul(qw, uz)), cz_), Q.Tcw[6]);
+            go = !(zc < 0.0f);
+            u = fadd(fdiv(fmul(P.cam[0], xc), zc), P.cam[2]);
+            v = fadd(fdiv(fmul(P.cam[1], yc), zc), P.cam[3]);
+            go = go && (u >= P.minX && u < P.maxX && v >= P.minY && v < P.maxY);                                     // KeyFrame::IsInImage
+            const float maxRaw = Q.maxD[i];
+            const float maxDist = fmul(1.2f, maxRaw), minDist = fmul(0.8f, Q.minD[i]);
+            const float ox = fsub(px, Q.Ow[0]), oy = fsub(py, Q.Ow[1]), oz = fsub(pz, Q.Ow[2]);
+            const float dist3D = __fsqrt_rn(fadd(fadd(fmul(ox, ox), fmul(oy, oy)), fmul(oz, oz)));
+            go = go && !(dist3D < minDist || dist3D > maxDist);
+            const float dot = fadd(fadd(fmul(ox, Q.normal[3 * i]), fmul(oy, Q.normal[3 * i + 1])), fmul(oz, Q.normal[3 * i + 2]));
+            go = go && !((double)dot < 0.5 * (double)dist3D);
+            if (go) {
+                lvl = (int)ceilf(fdiv(orbx::logf_glibc(fdiv(maxRaw, dist3D)), Q.logSF));
+                if (lvl < 0) lvl = 0; else if (lvl >= P.nlevels) lvl = P.nlevels - 1;
+                r = fmul(P.th, P.scaleFactors[lvl]);
+            }
+        }
+        if (go) {      // warp-uniform: every lane computed the same query
+            uint32_t mpd[8];
+            const uint4* dp = reinterpret_cast<const uint4*>(Q.mpDesc + (size_t)i * 32);
+            const uint4 a = __ldg(dp), b = __ldg(dp + 1);
+            mpd[0] = a.x; mpd[1] = a.y; mpd[2] = a.z; mpd[3] = a.w; mpd[4] = b.x; mpd[5] = b.y; mpd[6] = b.z; mpd[7] = b.w;
+            const float* isg = Q.invSigma2;
+            const TopK<1> t = scan_candidates<1>(P, S, 0, u, v, r, lvl - 1, lvl, mpd, [&](int idx) {
+                const float ex = fsub(u, S.kx[idx]), ey = fsub(v, S.ky[idx]);
+                const float e2 = __fmaf_rn(ex, ex, fmul(ey, ey));                     // one FMA in the reference build, see oracle
+                return !((double)fmul(e2, isg[S.koct[idx]]) > 5.99);
+            });
+            if (t.i[0] >= 0) { bestIdx = t.i[0]; bestDist = (int)(t.k[0] >> 40); }
+        }
+        if (lane == 0) { Q.bestIdx[i] = bestIdx; Q.bestDist[i] = bestDist; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:329-403) for a batch of map points: warp per map point, lane per observation row;
 // the row's median distance (element (int)(0.5 (n - 1)) of the sorted row) by bisection on the distance value; first minimum wins.
 // ---------------------------------------------------------------------------------------------
@@ -1209,6 +1279,67 @@ int orbm_search_by_bow(orbm_handle* h, const OrbmBowFrame* KF, const uint8_t* kf
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(match, dMatch, 4 * (size_t)F->N, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(nmatches, dN, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_fuse_search(orbm_handle* h, const OrbmFrame* KF, const float* invLevelSigma2, float logScaleFactor, const float* Tcw7, const float* Ow3,
+                     const float* cam4, const OrbmFusePoints* pts, float th, int32_t* bestIdx, int32_t* bestDist) {
+    if (!h || !KF || !invLevelSigma2 || !Tcw7 || !Ow3 || !cam4 || !pts || !bestIdx || !bestDist || pts->M < 0 || KF->K < 0 || KF->K > h->m.kcap ||
+        !KF->scaleFactors || KF->nlevels < 1 || KF->nlevels > 256 || !(KF->maxX > KF->minX) || !(KF->maxY > KF->minY)) {
+        set_error("orbm_fuse_search: bad argument (KF.K <= max_keypoints of the handle)"); return ORB_ERR_ARG;
+    }
+    Matcher& m = h->m;
+    CK(cudaSetDevice(m.device));
+    const size_t M = (size_t)pts->M, K = (size_t)KF->K;
+    for (size_t i = 0; i < M; ++i) { bestIdx[i] = -1; bestDist[i] = 256; }
+    if (M == 0 || K == 0) return ORB_OK;
+    for (size_t k = 0; k < K; ++k) if (KF->keypoints[k].octave < 0 || KF->keypoints[k].octave >= KF->nlevels) { set_error("orbm_fuse_search: keypoint octave out of range"); return ORB_ERR_ARG; }
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t oKp = take(K * sizeof(OrbKeyPoint)), oDe = take(K * 32), oSf = take(4 * (size_t)KF->nlevels), oIs = take(4 * (size_t)KF->nlevels), oSt = take(M),
+                 oXy = take(12 * M), oNo = take(12 * M), oMi = take(4 * M), oMa = take(4 * M), oMd = take(32 * M), oBi = take(4 * M), oBd = take(4 * M);
+    if (off > m.batchBytes) {                                   // grow the device staging (mapping-side call: pageable copies are fine)
+        if (m.d_batch) cudaFree(m.d_batch);
+        m.d_batch = nullptr; m.batchBytes = 0;
+        CK(cudaMalloc(&m.d_batch, off));
+        m.batchBytes = off;
+    }
+    uint8_t* d = m.d_batch;
+    cudaStream_t st = m.stream;
+    CK(cudaMemcpyAsync(d + oKp, KF->keypoints, K * sizeof(OrbKeyPoint), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oDe, KF->descriptors, K * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oSf, KF->scaleFactors, 4 * (size_t)KF->nlevels, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oIs, invLevelSigma2, 4 * (size_t)KF->nlevels, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oSt, pts->state, M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oXy, pts->worldPos, 12 * M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oNo, pts->normal, 12 * M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oMi, pts->minDistance, 4 * M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oMa, pts->maxDistance, 4 * M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oMd, pts->descriptors, 32 * M, cudaMemcpyHostToDevice, st));
+    FuseParams Q; memset(&Q, 0, sizeof(Q));
+    MatchParams& P = Q.P;
+    P.kps = (const OrbKeyPoint*)(d + oKp); P.desc = d + oDe; P.scaleFactors = (const float*)(d + oSf); P.kcap = m.kcap; P.nlevels = KF->nlevels; P.batch = 1;
+    P.minX = KF->minX; P.minY = KF->minY; P.maxX = KF->maxX; P.maxY = KF->maxY;
+    P.gridWInv = (float)GRID_COLS / (P.maxX - P.minX); P.gridHInv = (float)GRID_ROWS / (P.maxY - P.minY);
+    P.th = th; memcpy(P.cam, cam4, 16);
+    P.ks = (int)K; P.ms = 1;
+    const size_t limit = 227 * 1024 - 2048;
+    P.descInSmem = frame_smem_bytes(P.ks, 1, true) <= limit ? 1 : 0;
+    const size_t sm = frame_smem_bytes(P.ks, 1, P.descInSmem != 0);
+    if (sm > limit) { set_error("keyframe too large for the matcher's shared-memory grid"); return ORB_ERR_CAPACITY; }
+    int rc = ensure_dynamic_smem(fuse_search_kernel, sm, m.device);
+    if (rc) return rc;
+    Q.K = (int)K; Q.M = (int)M; Q.state = d + oSt; Q.mpDesc = d + oMd; Q.xyz = (const float*)(d + oXy); Q.normal = (const float*)(d + oNo);
+    Q.minD = (const float*)(d + oMi); Q.maxD = (const float*)(d + oMa); Q.invSigma2 = (const float*)(d + oIs);
+    memcpy(Q.Tcw, Tcw7, 28); memcpy(Q.Ow, Ow3, 12); Q.logSF = logScaleFactor;
+    Q.bestIdx = (int*)(d + oBi); Q.bestDist = (int*)(d + oBd);
+    const int grid = (int)std::min<size_t>(16, (M + 127) / 128);          // every CTA rebuilds the grid: a few CTAs, ~8 map points per warp
+    fuse_search_kernel<<<grid, MF_NT, sm, st>>>(Q);
+    m.launches = 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(bestIdx, d + oBi, 4 * M, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(bestDist, d + oBd, 4 * M, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return ORB_OK;
 }

@@ -395,3 +395,49 @@ def distinctive_descriptor(desc, _lib=None, _name='orbo_distinctive_descriptor')
     d = _c(desc, np.uint8).reshape(-1, 32)
     L = _lib or lib()
     return getattr(L, _name)(len(d), _p(d))
+
+
+def fuse_scene(t, seed=0, M=3000):
+    """A keyframe (frame t) and map points seen from neighbouring frames, for ORBmatcher::Fuse."""
+    import matcher_scenes
+    from orb_slam3_modified_b200 import synth
+    rng = np.random.default_rng(seed + 13 * t)
+    kps, desc = matcher_scenes.extract(t)
+    T = synth.pose(t)
+    w, x, y, z = T[:4]
+    Rm = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                   [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    Ow = -Rm.T @ T[4:]
+    P, D, Oc = [], [], []
+    for dt in (-2, -1, 1, 2):
+        k, d = matcher_scenes.extract(t + dt)
+        P.append(synth.backproject(np.stack([k['x'], k['y']], 1), t + dt) + rng.normal(0, 0.004, (len(k), 3))); D.append(d); Oc.append(k['octave'])
+    P, D, Oc = np.concatenate(P), np.concatenate(D), np.concatenate(Oc)
+    sel = rng.permutation(len(P))[:M]
+    P, D, Oc = P[sel], D[sel], Oc[sel]
+    PO = P - Ow
+    dist = np.linalg.norm(PO, axis=1)
+    n = PO / dist[:, None] + rng.normal(0, 0.25, P.shape)
+    n /= np.linalg.norm(n, axis=1)[:, None]
+    dmax = (dist * 1.2 ** Oc * rng.uniform(0.8, 1.3, len(P))).astype(np.float32)
+    dmin = (dmax / np.float32(1.2 ** 7)).astype(np.float32)
+    state = rng.choice([0, 1, 1, 1, 1, 1, 1, 2, 3], len(P)).astype(np.uint8)
+    kf_point = np.where(rng.random(len(kps)) < 0.5, rng.integers(0, 6, len(kps)), -1).astype(np.int32)
+    sf = OracleExtractor().tables()
+    return dict(kps=kps, desc=desc, bounds=(0.0, 0.0, 640.0, 480.0), sf=sf['scale'], isg=sf['inv_sigma2'], log_sf=np.float32(np.log(np.float32(1.2))),
+                Tcw=T.astype(np.float32), Ow=Ow.astype(np.float32), cam=synth.camera(), kf_point=kf_point, kf_point_bad=np.zeros(len(kps), np.uint8),
+                state=state, xyz=P.astype(np.float32), normal=n.astype(np.float32), min_d=dmin, max_d=dmax, mp_desc=D,
+                mp_obs=rng.integers(1, 6, len(P)).astype(np.int32))
+
+
+def fuse_search(sc, th=3.0):
+    M = len(sc['state'])
+    bi = np.zeros(M, np.int32); bd = np.zeros(M, np.int32)
+    L = lib()
+    L.orbo_fuse_search.restype = None
+    L.orbo_fuse_search.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_float] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_void_p, C.c_void_p]
+    a = [_c(sc['kps'], KP_DTYPE), _c(sc['desc'], np.uint8), _c(sc['bounds'], np.float32), _c(sc['sf'], np.float32), _c(sc['isg'], np.float32)]
+    b = [_c(sc['Tcw'], np.float32), _c(sc['Ow'], np.float32), _c(sc['cam'], np.float32)]
+    c = [_c(sc['state'], np.uint8), _c(sc['xyz'], np.float32), _c(sc['normal'], np.float32), _c(sc['min_d'], np.float32), _c(sc['max_d'], np.float32), _c(sc['mp_desc'], np.uint8)]
+    L.orbo_fuse_search(len(a[0]), *[_p(v) for v in a], len(a[3]), float(sc['log_sf']), *[_p(v) for v in b], M, *[_p(v) for v in c], th, _p(bi), _p(bd))
+    return bi, bd

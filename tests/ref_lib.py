@@ -222,3 +222,17 @@ def search_by_bow(*a, **kw):
 def distinctive_descriptor(desc):
     import oracle_lib as O
     return O.distinctive_descriptor(desc, _lib=lib(), _name='ref_distinctive_descriptor')
+
+
+def fuse(sc, th=3.0):
+    """ORBmatcher::Fuse itself; returns (nFused, action [M], action_idx [M]) -- see ref_wrap_matcher.cpp: ref_fuse."""
+    M = len(sc['state'])
+    act = np.zeros(M, np.int32); idx = np.zeros(M, np.int32)
+    L = lib()
+    L.ref_fuse.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_float] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p]
+    a = [_c(sc['kps'], KP_DTYPE), _c(sc['desc'], np.uint8), _c(sc['bounds'], np.float32), _c(sc['sf'], np.float32), _c(sc['isg'], np.float32)]
+    b = [_c(sc['Tcw'], np.float32), _c(sc['Ow'], np.float32), _c(sc['cam'], np.float32), _c(sc['kf_point'], np.int32), _c(sc['kf_point_bad'], np.uint8)]
+    c = [_c(sc['state'], np.uint8), _c(sc['xyz'], np.float32), _c(sc['normal'], np.float32), _c(sc['min_d'], np.float32), _c(sc['max_d'], np.float32), _c(sc['mp_desc'], np.uint8),
+         _c(sc['mp_obs'], np.int32)]
+    n = L.ref_fuse(len(a[0]), *[_p(v) for v in a], len(a[3]), float(sc['log_sf']), *[_p(v) for v in b], M, *[_p(v) for v in c], th, _p(act), _p(idx))
+    return n, act, idx

@@ -242,3 +242,22 @@ def test_compute_distinctive_descriptors(orb, matcher):
     best = matcher.ComputeDistinctiveDescriptors(obs_list)
     for o, b in zip(obs_list, best):
         assert b == O.distinctive_descriptor(o), (len(o), b)
+
+
+@pytest.mark.parametrize('t,th,M', [(6, 3.0, 3000), (14, 3.0, 9000), (23, 5.0, 300), (9, 3.0, 0)])
+def test_fuse_search(orb, t, th, M):
+    """f2: the search of ORBmatcher::Fuse(KeyFrame*, vector<MapPoint*>, th) vs the oracle, which tests/test_ref_pins_oracle_cpu.py holds against the
+    reference's own Fuse body (every logged AddObservation / Replace names the oracle's best keypoint)."""
+    sc = O.fuse_scene(t, M=max(M, 1))
+    if M == 0:
+        for k in ('state', 'xyz', 'normal', 'min_d', 'max_d', 'mp_desc'):
+            sc[k] = sc[k][:0]
+    m = orb.ORBmatcher(0.6, True, max_batch=1, max_keypoints=2048, max_mappoints=64)       # M is not bounded by the handle
+    bi, bd = m.FuseSearch(sc['kps'], sc['desc'], sc['bounds'], sc['sf'], sc['isg'], sc['log_sf'], sc['Tcw'], sc['Ow'], sc['cam'], sc['state'], sc['xyz'],
+                          sc['normal'], sc['min_d'], sc['max_d'], sc['mp_desc'], th)
+    if M == 0:
+        assert len(bi) == 0
+        return
+    obi, obd = O.fuse_search(sc, th)
+    assert np.array_equal(bi, obi) and np.array_equal(bd, obd)
+    assert (bd <= 50).sum() > M // 20

@@ -243,3 +243,20 @@ def test_compute_distinctive_descriptors_equals_reference():
             obs[2] = obs[1]            # duplicates: ties between medians -> the first row wins
         a, b = R.distinctive_descriptor(obs), O.distinctive_descriptor(obs)
         assert np.array_equal(obs[a], obs[b]), (n, a, b)      # the reference keeps a clone of the chosen row: compare bytes
+
+
+@pytest.mark.parametrize('t,th', [(6, 3.0), (14, 3.0), (23, 5.0)])
+def test_fuse_search_equals_reference(t, th):
+    """ORBmatcher::Fuse (src/ORBmatcher.cc:1148-1338): the reference's own body run on stand-in KeyFrame / MapPoint objects that log what Fuse did,
+    against the oracle's per-map-point search result (best keypoint, best distance): every logged action names the oracle's best keypoint, and the
+    return value is the number of oracle hits within TH_LOW."""
+    sc = O.fuse_scene(t)
+    n, act, idx = R.fuse(sc, th)
+    bi, bd = O.fuse_search(sc, th)
+    hit = bd <= 50
+    assert n == int(hit.sum()) and n > 100, (n, int(hit.sum()))
+    # every hit is one logged action at the oracle's best keypoint (a point the loop made bad earlier by Replace is still searched: the reference
+    # tests isBad() once, before the search), and nothing else is logged
+    assert np.array_equal(act > 0, hit) and np.array_equal(idx[hit], bi[hit])
+    assert {1, 2, 3} <= set(act[hit].tolist())
+    assert not hit[sc['state'] != 1].any()
