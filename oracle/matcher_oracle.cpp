@@ -434,7 +434,7 @@ int orbo_distinctive_descriptor(int n, const uint8_t* desc) {
 // the SEARCH of every map point (projection, image / distance / viewing-angle tests, scale prediction, radius search with the chi-square gate,
 // best Hamming distance).  What Fuse then does with a hit (AddObservation / Replace, :1310-1330) mutates the pointer graph and stays with the
 // caller; no map point's search depends on it.  state[i]: 0 NULL, 1 ok, 2 bad, 3 already in the keyframe.  bestIdx -1 / bestDist 256: no candidate.
-// `ex*ex+ey*ey` (:1280) is one FMA in the reference's -O3 -march=native build (checked against oracle/_ref).
+// `ex*ex+ey*ey` (:1292) is one FMA in the reference's -O3 -march=native build (checked against oracle/_ref).
 void orbo_fuse_search(int K, const KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors, const float* invLevelSigma2, int nlevels,
                       float logScaleFactor, const float* Tcw, const float* Ow, const float* cam, int M, const uint8_t* state, const float* xyz,
                       const float* normal, const float* minDistance, const float* maxDistance, const uint8_t* mpDesc, float th, int* bestIdxOut, int* bestDistOut) {
