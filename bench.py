@@ -465,7 +465,7 @@ def main():
     probs = lba_problems(NLBA * LR, rank)   # the keyframes of LR rounds: one LocalBundleAdjustment each, solved by ONE kernel launch
     opt.upload(probs)                      # flattened graphs resident in HBM for the `value` measurement
     stream = torch.cuda.current_stream()
-    lba_stream = torch.cuda.Stream(device=dev)      # LocalMapping runs beside Tracking in the reference (src/System.cc:197)
+    lba_stream = torch.cuda.Stream(device=dev, priority=-1 if os.environ.get('BENCH_LBA_PRIO') else 0)      # LocalMapping runs beside Tracking in the reference (src/System.cc:197)
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
     # The B streams are served as DG groups, each with its own extractor / matcher handles on its own CUDA stream: the latency-bound
@@ -676,45 +676,101 @@ def main():
                                            max_batch=NLBA * LR, device=local)]
             up = [None, None]       # upload future per handle
             down = [None, None]     # download future per handle
-            outs = None
-            nbatch = 0
+            # Streams are independent SLAM instances: every group's host thread free-runs through its rounds (no join between rounds, so one
+            # group's PCIe copies always overlap another group's kernels); the mapping thread waits only for the keyframes it optimises.
+            import threading
+            # A host thread coming back from a C-ABI call must re-take the interpreter lock; with CPython's default 5 ms switch interval it can
+            # wait that long behind another thread's Python glue (GPU idle meanwhile).  Hand the lock over promptly instead.
+            sys.setswitchinterval(float(os.environ.get('BENCH_SWITCH_INTERVAL', '5e-5')))
+            cv = threading.Condition()
+            done = [0] * G                                          # rounds finished per group (absolute round counter)
+            state = {'outs': None, 'nbatch': 0, 'err': None, 'lba_wants': False, 'frames_in_flight': 0}
 
-            def round_host(i):
-                nonlocal outs, nbatch
-                if i % LR == 0:                                     # graphs of this batch's keyframes: upload in the background
-                    k = nbatch & 1
-                    if down[k] is not None:
-                        outs = down[k].result()                     # the handle's previous results are out before it is reused
-                        down[k] = None
-                    up[k] = pool.submit(opt_pair[k].upload, probs)
-                fr = [pool.submit(frames_job, g, i) for g in range(G)]
-                nk = sum(j.result() for j in fr)
-                if i % LR == LR - 1:
-                    k = nbatch & 1
-                    up[k].result()
-                    opt_pair[k].run_device(lba_stream.cuda_stream)
-                    if E2E_EXCL:
-                        lba_stream.synchronize()                    # the kernel alone on the GPU (no PCIe traffic of the frames meanwhile)
-                    down[k] = pool.submit(opt_pair[k].download)     # waits for the kernel on the device (event inside the library)
-                    nbatch += 1
-                return nk
+            def group_loop(g, r0, r1):
+                try:
+                    for i in range(r0, r1):
+                        if E2E_EXCL:                                # gate: no frame call starts while a bundle-adjustment launch owns the GPU
+                            with cv:
+                                cv.wait_for(lambda: not state['lba_wants'])
+                                state['frames_in_flight'] += 1
+                        frames_job(g, i)
+                        with cv:
+                            if E2E_EXCL:
+                                state['frames_in_flight'] -= 1
+                            done[g] = i + 1
+                            cv.notify_all()
+                except BaseException as exc:                       # surfaced by the main thread
+                    with cv:
+                        state['err'] = exc
+                        done[g] = 1 << 60
+                        cv.notify_all()
 
-            for i in range(2 * LR):
-                round_host(i)
+            def mapping_loop(r0, r1):
+                try:
+                    for i in range(r0, r1):
+                        if i % LR == 0:                             # graphs of this batch's keyframes: uploaded while their frames run
+                            k = state['nbatch'] & 1
+                            if down[k] is not None:
+                                state['outs'] = down[k].result()    # the handle's previous results are out before it is reused
+                                down[k] = None
+                            up[k] = pool.submit(opt_pair[k].upload, probs)
+                        if i % LR == LR - 1:
+                            with cv:
+                                cv.wait_for(lambda: min(done) >= i + 1)     # the batch's keyframes exist
+                            k = state['nbatch'] & 1
+                            up[k].result()
+                            if E2E_EXCL:
+                                with cv:
+                                    state['lba_wants'] = True
+                                    cv.wait_for(lambda: state['frames_in_flight'] == 0)
+                            opt_pair[k].run_device(lba_stream.cuda_stream)
+                            if E2E_EXCL:
+                                lba_stream.synchronize()
+                                with cv:
+                                    state['lba_wants'] = False
+                                    cv.notify_all()
+                            down[k] = pool.submit(opt_pair[k].download)     # waits for the kernel on the device (event inside the library)
+                            state['nbatch'] += 1
+                except BaseException as exc:
+                    with cv:
+                        state['err'] = exc
+
+            def run_rounds(r0, r1):
+                ediag = os.environ.get('BENCH_E2E_DIAG', '')          # diagnosis only: 'nolba' / 'noframes' (half of the work skipped -> line marked invalid)
+                th = [threading.Thread(target=group_loop, args=(g, r0, r1)) for g in range(G)] if ediag != 'noframes' else []
+                if ediag == 'noframes':
+                    with cv:
+                        for g in range(G):
+                            done[g] = 1 << 60
+                if ediag != 'nolba':
+                    th.append(threading.Thread(target=mapping_loop, args=(r0, r1)))
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+                if state['err'] is not None:
+                    raise state['err']
+
+            run_rounds(0, 2 * LR)
+            torch.cuda.synchronize()
             barrier()
             e2e_steps = max(1, args.steps)
             nr = e2e_steps * R
             t0 = time.perf_counter()
-            for i in range(nr):
-                nk = round_host(i)
+            run_rounds(2 * LR, 2 * LR + nr)                         # 2 LR is even: the input sets alternate as in the warm-up
             torch.cuda.synchronize()
             # every LR rounds of the timed region uploaded, solved and started to download one batch of bundle adjustments; the last
             # download may complete just outside the timed region (its kernel ran inside)
             dt = time.perf_counter() - t0
+            outs = state['outs']
             tail = [d.result() for d in down if d is not None]
             tail = tail[-1] if tail else None
             dt = sharding.max_over_ranks(dist, dt, dev)
             e2e = world * B * nr / dt
+            if os.environ.get('BENCH_E2E_DIAG'):
+                if rank == 0:
+                    print(json.dumps({'INVALID_diagnostic_run': 'e2e ' + os.environ['BENCH_E2E_DIAG'], 'groups': G, 'e2e_frames_per_s_equiv': e2e, 'ms_per_round': 1e3 * dt / nr}))
+                os._exit(0)
             # parity gate 2: the host buffers of the last timed round
             cur = (nr - 1) & 1
             L = last_h[(nr) & 1]
