@@ -280,6 +280,20 @@ typedef struct OrbmFusePoints {
 } OrbmFusePoints;
 int orbm_fuse_search(orbm_handle* h, const OrbmFrame* KF, const float* invLevelSigma2, float logScaleFactor, const float* Tcw7, const float* Ow3,
                      const float* cam4, const OrbmFusePoints* pts, float th, int32_t* bestIdx, int32_t* bestDist);
+/* int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs, const bool bOnlyStereo,
+ * const bool bCoarse) (include/ORBmatcher.h:84-85, src/ORBmatcher.cc:907-1146; monocular keyframes, bOnlyStereo = false) for ONE new keyframe
+ * against nKF2 neighbours in one launch (LocalMapping::CreateNewMapPoints loops over vpNeighKFs, src/LocalMapping.cc:296-344).
+ * A keyframe is its undistorted keypoints, descriptors, hasMapPoint[i] (GetMapPoint(i) != NULL) and DBoW2::FeatureVector as (node id, feature
+ * index) arrays in map order.  ep2 [nKF2][2]: the epipole pKF2->mpCamera->project(T2w * Cw) (:913-919); F12 [nKF2][9] row-major: the
+ * fundamental matrix of Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:109-112) -- both are Eigen / Sophus expressions the caller
+ * evaluates.  scaleFactors / levelSigma2: mvScaleFactors / mvLevelSigma2 (the same extractor settings for all keyframes).
+ * matches12 [nKF2][KF1.N]: vMatchedPairs scattered (index in KF2 or -1); nmatches [nKF2]: the return values.  Host pointers. */
+typedef struct OrbmTriFrame {
+    int N; const OrbKeyPoint* keypoints; const uint8_t* descriptors; const uint8_t* hasMapPoint;
+    int nEntries; const int32_t* fvNode; const int32_t* fvFeature;
+} OrbmTriFrame;
+int orbm_search_for_triangulation(orbm_handle* h, const OrbmTriFrame* KF1, int nKF2, const OrbmTriFrame* KF2, const float* scaleFactors, const float* levelSigma2,
+                                  int nlevels, const float* ep2, const float* F12, int bCoarse, int checkOrientation, int32_t* matches12, int32_t* nmatches);
 /* void MapPoint::ComputeDistinctiveDescriptors() (src/MapPoint.cc:329-403) for nPoints map points at once (LocalMapping::ProcessNewKeyFrame /
  * CreateNewMapPoints call it per point): the observed descriptors of point p are rows obsStart[p] .. obsStart[p+1] of `descriptors`;
  * best[p] = row (relative to obsStart[p]) with the least median Hamming distance to the others, -1 for a point without observations. */

@@ -483,4 +483,88 @@ void orbo_fuse_search(int K, const KeyPoint* kps, const uint8_t* desc, const flo
     }
 }
 
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo = false, bCoarse) (src/ORBmatcher.cc:907-1146), monocular keyframes,
+// with Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:107-129).  The epipole `ep` (:919) and the fundamental matrix F12 (Pinhole.cpp:112,
+// constant per keyframe pair although the reference recomputes it per candidate) are INPUTS: they come out of Eigen/Sophus expression templates
+// in the caller.  Only features WITHOUT a map point take part; a KF2 feature may be matched by several KF1 features (vbMatched2 is never set in
+// the reference).  Among the candidates of the same vocabulary node that pass the epipole-distance and epipolar tests the smallest distance
+// <= TH_LOW wins, the LAST one on ties (`dist>bestDist` is strict, :1008).  The scalar float expressions are contracted by the reference's
+// -O3 -march=native build exactly as written here with fmaf (checked against oracle/_ref).
+int orbo_search_for_triangulation(int N1, const KeyPoint* kps1, const uint8_t* desc1, const uint8_t* hasMP1, int E1, const int* fvNode1, const int* fvFeat1,
+                                  int N2, const KeyPoint* kps2, const uint8_t* desc2, const uint8_t* hasMP2, int E2, const int* fvNode2, const int* fvFeat2,
+                                  const float* scaleFactors2, const float* levelSigma2_2, const float* ep, const float* F12, int bCoarse, int checkOri,
+                                  int* matches12) {
+    static const int TH_LOW = 50;
+    (void)N2;
+    for (int i = 0; i < N1; ++i) matches12[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int a = 0, b = 0;
+    while (a < E1 && b < E2) {
+        if (fvNode1[a] == fvNode2[b]) {
+            int a1 = a, b1 = b;
+            while (a1 < E1 && fvNode1[a1] == fvNode1[a]) ++a1;
+            while (b1 < E2 && fvNode2[b1] == fvNode2[b]) ++b1;
+            for (int i1 = a; i1 < a1; ++i1) {
+                const int idx1 = fvFeat1[i1];
+                if (hasMP1[idx1]) continue;
+                const KeyPoint& kp1 = kps1[idx1];
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int i2 = b; i2 < b1; ++i2) {
+                    const int idx2 = fvFeat2[i2];
+                    if (hasMP2[idx2]) continue;
+                    const int dist = descriptor_distance(desc1 + (size_t)idx1 * 32, desc2 + (size_t)idx2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const KeyPoint& kp2 = kps2[idx2];
+                    const float distex = ep[0] - kp2.x, distey = ep[1] - kp2.y;
+                    if (fmaf(distex, distex, distey * distey) < 100 * scaleFactors2[kp2.octave]) continue;
+                    bool ok = bCoarse != 0;
+                    if (!ok) {
+                        const float ea = fmaf(kp1.x, F12[0], kp1.y * F12[3]) + F12[6];
+                        const float eb = fmaf(kp1.x, F12[1], kp1.y * F12[4]) + F12[7];
+                        const float ec = fmaf(kp1.x, F12[2], kp1.y * F12[5]) + F12[8];
+                        const float num = fmaf(ea, kp2.x, eb * kp2.y) + ec;
+                        const float den = fmaf(ea, ea, eb * eb);
+                        if (den != 0) {
+                            const float dsqr = num * num / den;
+                            ok = dsqr < 3.84 * levelSigma2_2[kp2.octave];
+                        }
+                    }
+                    if (ok) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    matches12[idx1] = bestIdx2;
+                    ++nmatches;
+                    if (checkOri) {
+                        float rot = kp1.angle - kps2[bestIdx2].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(idx1);
+                    }
+                }
+            }
+            a = a1; b = b1;
+        } else if (fvNode1[a] < fvNode2[b]) { const int t = fvNode2[b]; while (a < E1 && fvNode1[a] < t) ++a; }
+        else { const int t = fvNode1[a]; while (b < E2 && fvNode2[b] < t) ++b; }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            const int sz = (int)rotHist[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rotHist[i]) { matches12[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

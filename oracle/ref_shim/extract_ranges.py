@@ -11,6 +11,8 @@ RANGES = [
     ('matcher_local_map.inc', 'src/ORBmatcher.cc', 43, 221, 'int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>'),
     ('matcher_bow_kf_frame.inc', 'src/ORBmatcher.cc', 223, 425, 'int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F'),
     ('matcher_init.inc', 'src/ORBmatcher.cc', 648, 763, 'int ORBmatcher::SearchForInitialization'),
+    ('matcher_triangulation.inc', 'src/ORBmatcher.cc', 907, 1146, 'int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2'),
+    ('pinhole_epipolar.inc', 'src/CameraModels/Pinhole.cpp', 107, 129, 'bool Pinhole::epipolarConstrain(GeometricCamera* pCamera2'),
     ('matcher_fuse.inc', 'src/ORBmatcher.cc', 1148, 1338, 'int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints'),
     ('matcher_last_frame.inc', 'src/ORBmatcher.cc', 1676, 1887, 'int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame'),
     ('matcher_maxima_distance.inc', 'src/ORBmatcher.cc', 2012, 2074, 'void ORBmatcher::ComputeThreeMaxima'),

@@ -11,6 +11,27 @@ Vector3f Matrix3f::operator*(const Vector3f& p) const {
     return Vector3f((m[0] * p.v[0] + m[1] * p.v[1]) + m[2] * p.v[2], (m[3] * p.v[0] + m[4] * p.v[1]) + m[5] * p.v[2],
                     (m[6] * p.v[0] + m[7] * p.v[1]) + m[8] * p.v[2]);
 }
+Matrix3f Matrix3f::operator*(const Matrix3f& o) const {
+    Matrix3f r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r.m[3 * i + j] = (m[3 * i] * o.m[j] + m[3 * i + 1] * o.m[3 + j]) + m[3 * i + 2] * o.m[6 + j];
+    return r;
+}
+Matrix3f Matrix3f::transpose() const {
+    Matrix3f r;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[3 * i + j] = m[3 * j + i];
+    return r;
+}
+Matrix3f Matrix3f::inverse() const {   // cofactor (i, j) of the transpose over the determinant expanded along the first row
+    const float c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+    const float det = (m[0] * c00 + m[1] * c01) + m[2] * c02;
+    const float id = 1.0f / det;
+    Matrix3f r;
+    r.m[0] = c00 * id; r.m[1] = (m[2] * m[7] - m[1] * m[8]) * id; r.m[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    r.m[3] = c01 * id; r.m[4] = (m[0] * m[8] - m[2] * m[6]) * id; r.m[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    r.m[6] = c02 * id; r.m[7] = (m[1] * m[6] - m[0] * m[7]) * id; r.m[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+    return r;
+}
 }  // namespace Eigen
 
 namespace Sophus {
@@ -28,5 +49,28 @@ SE3f SE3f::inverse() const {
     Eigen::Vector3f rt = r.rotate(t);
     r.t = Eigen::Vector3f(-rt.v[0], -rt.v[1], -rt.v[2]);
     return r;
+}
+SE3f SE3f::operator*(const SE3f& o) const {
+    SE3f r;
+    r.qw = ((qw * o.qw - qx * o.qx) - qy * o.qy) - qz * o.qz;
+    r.qx = ((qw * o.qx + qx * o.qw) + qy * o.qz) - qz * o.qy;
+    r.qy = ((qw * o.qy + qy * o.qw) + qz * o.qx) - qx * o.qz;
+    r.qz = ((qw * o.qz + qz * o.qw) + qx * o.qy) - qy * o.qx;
+    r.t = rotate(o.t) + t;
+    return r;
+}
+Eigen::Matrix3f SE3f::rotationMatrix() const {     // Eigen::QuaternionBase::toRotationMatrix
+    const float tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+    const float twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    Eigen::Matrix3f R;
+    R(0, 0) = 1 - (tyy + tzz); R(0, 1) = txy - twz; R(0, 2) = txz + twy;
+    R(1, 0) = txy + twz; R(1, 1) = 1 - (txx + tzz); R(1, 2) = tyz - twx;
+    R(2, 0) = txz - twy; R(2, 1) = tyz + twx; R(2, 2) = 1 - (txx + tyy);
+    return R;
+}
+Eigen::Matrix3f SO3f::hat(const Eigen::Vector3f& w) {
+    Eigen::Matrix3f O;
+    O(0, 0) = 0; O(0, 1) = -w(2); O(0, 2) = w(1); O(1, 0) = w(2); O(1, 1) = 0; O(1, 2) = -w(0); O(2, 0) = -w(1); O(2, 1) = w(0); O(2, 2) = 0;
+    return O;
 }
 }  // namespace Sophus

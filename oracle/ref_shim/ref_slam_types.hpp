@@ -53,6 +53,13 @@ template <> struct Matrix<float, 3, 3> {
     float m[9];   // row-major
     Matrix() : m{1, 0, 0, 0, 1, 0, 0, 0, 1} {}
     Matrix<float, 3, 1> operator*(const Matrix<float, 3, 1>& p) const;
+    const float& operator()(int i, int j) const { return m[3 * i + j]; }
+    float& operator()(int i, int j) { return m[3 * i + j]; }
+    // what Pinhole::epipolarConstrain's fundamental-matrix line needs (out of line, individually rounded; the C-ABI takes F12 as an
+    // INPUT computed by the caller's own Eigen code, so this stand-in only has to be one fixed arithmetic, not Eigen's)
+    Matrix operator*(const Matrix& o) const;   // row-major triple loop, left to right
+    Matrix transpose() const;
+    Matrix inverse() const;                    // cofactors / determinant
 };
 typedef Matrix<float, 3, 1> Vector3f;
 typedef Matrix<float, 2, 1> Vector2f;
@@ -70,8 +77,13 @@ template <> struct SE3<float> {
     Eigen::Vector3f operator*(const Eigen::Vector3f& p) const;
     SE3 inverse() const;
     const Eigen::Vector3f& translation() const { return t; }
+    SE3 operator*(const SE3& o) const;         // quaternion product (not renormalised, so3.hpp:316-331), translation t + R o.t
+    Eigen::Matrix3f rotationMatrix() const;    // Eigen::Quaternion::toRotationMatrix
 };
 typedef SE3<float> SE3f;
+template <typename T> struct SO3;
+template <> struct SO3<float> { static Eigen::Matrix3f hat(const Eigen::Vector3f& w); };   // so3.hpp:631-640
+typedef SO3<float> SO3f;
 template <typename T> struct Sim3 {};
 typedef Sim3<float> Sim3f;
 }  // namespace Sophus
@@ -92,11 +104,22 @@ class GeometricCamera {
 public:
     virtual ~GeometricCamera() {}
     virtual Eigen::Vector2f project(const Eigen::Vector3f& v3D) = 0;
+    virtual Eigen::Matrix3f toK_() = 0;
+    virtual bool epipolarConstrain(GeometricCamera* pCamera2, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const Eigen::Matrix3f& R12,
+                                   const Eigen::Vector3f& t12, const float sigmaLevel, const float unc) = 0;
     std::vector<float> mvParameters;
 };
 class Pinhole : public GeometricCamera {
 public:
     Eigen::Vector2f project(const Eigen::Vector3f& v3D);   // body: src/CameraModels/Pinhole.cpp:43-49
+    Eigen::Matrix3f toK_() {                                // src/CameraModels/Pinhole.cpp:100-104 (a comma initialiser, no arithmetic)
+        Eigen::Matrix3f K;
+        K(0, 0) = mvParameters[0]; K(0, 1) = 0.f; K(0, 2) = mvParameters[2]; K(1, 0) = 0.f; K(1, 1) = mvParameters[1]; K(1, 2) = mvParameters[3];
+        K(2, 0) = 0.f; K(2, 1) = 0.f; K(2, 2) = 1.f;
+        return K;
+    }
+    bool epipolarConstrain(GeometricCamera* pCamera2, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const Eigen::Matrix3f& R12,
+                           const Eigen::Vector3f& t12, const float sigmaLevel, const float unc);   // body: src/CameraModels/Pinhole.cpp:107-129
 };
 
 class KeyFrame {
@@ -115,12 +138,14 @@ public:
     int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
     float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mfLogScaleFactor = 0;
     float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0, mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
-    std::vector<float> mvScaleFactors, mvInvLevelSigma2, mvuRight;
+    std::vector<float> mvScaleFactors, mvInvLevelSigma2, mvLevelSigma2, mvuRight;
     std::vector<std::vector<std::vector<size_t>>> mGrid, mGridRight;
     Sophus::SE3f mTcw;
     Eigen::Vector3f mOw;
     Sophus::SE3f GetPose() { return mTcw; }
     Sophus::SE3f GetRightPose() { return mTcw; }
+    Sophus::SE3f GetPoseInverse() { return mTcw.inverse(); }        // the reference caches mTwc = mTcw.inverse() (src/KeyFrame.cc:115)
+    Sophus::SE3f GetRightPoseInverse() { return mTcw.inverse(); }
     Eigen::Vector3f GetCameraCenter() { return mOw; }
     Eigen::Vector3f GetRightCameraCenter() { return mOw; }
     bool IsInImage(const float& x, const float& y) const;                       // body: src/KeyFrame.cc:750-753
@@ -223,6 +248,7 @@ public:
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0, const bool bRight = false);
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<pair<size_t, size_t>>& vMatchedPairs, const bool bOnlyStereo, const bool bCoarse = false);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     static const int TH_LOW;
     static const int TH_HIGH;

@@ -13,9 +13,11 @@ namespace ORB_SLAM3 {
 #include "matcher_bow_kf_frame.inc"
 #include "matcher_init.inc"
 #include "matcher_fuse.inc"
+#include "matcher_triangulation.inc"
 #include "matcher_last_frame.inc"
 #include "matcher_maxima_distance.inc"
 #include "pinhole_project.inc"
+#include "pinhole_epipolar.inc"
 }  // namespace ORB_SLAM3
 namespace ORB_SLAM3 {
 #include "frame_assign_grid.inc"
@@ -199,6 +201,49 @@ int ref_search_by_bow(int nKF, const cv::KeyPoint* kpsKF, const uint8_t* descKF,
     ORBmatcher matcher(nnratio, checkOri != 0);
     const int n = matcher.SearchByBoW(&KF, F, out);
     for (int i = 0; i < nF; ++i) matchF[i] = out[i] ? out[i]->index : -1;
+    return n;
+}
+
+// int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vMatchedPairs, bOnlyStereo = false, bCoarse) (src/ORBmatcher.cc:907-1146),
+// monocular keyframes (Pinhole::epipolarConstrain, src/CameraModels/Pinhole.cpp:107-129).  hasMP[i]: the keyframe holds a map point at feature i.
+// matches12 [N1]: vMatchedPairs scattered back (-1 = none).  epOut / F12Out: the epipole and fundamental matrix the body works with, recomputed here
+// with the same stand-in operators in the same order (the C-ABI takes both as inputs: the caller forms them with its own Eigen code).
+static void fill_tri_kf(KeyFrame& KF, std::vector<MapPoint>& mps, Pinhole& camera, int N, const cv::KeyPoint* kps, const uint8_t* desc, const uint8_t* hasMP, int E,
+                        const int* fvNode, const int* fvFeat, const float* scaleFactors, const float* levelSigma2, int nlevels, const float* Tcw, const float* cam) {
+    KF.N = N; KF.NLeft = -1;
+    KF.mvpMapPoints.assign(N, (MapPoint*)nullptr);                 // mps: N stand-in map points, pre-sized by the caller (not movable)
+    for (int i = 0; i < N; ++i) if (hasMP[i]) KF.mvpMapPoints[i] = &mps[i];
+    KF.mDescriptors = N ? cv::Mat(N, 32, CV_8UC1, (void*)desc, 32) : cv::Mat();
+    KF.mvKeysUn.assign(kps, kps + N); KF.mvKeys = KF.mvKeysUn;
+    KF.mvuRight.assign(N, -1.f);
+    for (int e = 0; e < E; ++e) KF.mFeatVec.addFeature(fvNode[e], fvFeat[e]);
+    KF.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels); KF.mvLevelSigma2.assign(levelSigma2, levelSigma2 + nlevels);
+    KF.mTcw.qw = Tcw[0]; KF.mTcw.qx = Tcw[1]; KF.mTcw.qy = Tcw[2]; KF.mTcw.qz = Tcw[3]; KF.mTcw.t = Eigen::Vector3f(Tcw[4], Tcw[5], Tcw[6]);
+    KF.mOw = KF.mTcw.inverse().translation();             // GetCameraCenter() = mTwc.translation() (src/KeyFrame.cc:143-147)
+    camera.mvParameters.assign(cam, cam + 4); KF.mpCamera = &camera;
+}
+int ref_search_for_triangulation(int N1, const cv::KeyPoint* kps1, const uint8_t* desc1, const uint8_t* hasMP1, int E1, const int* fvNode1, const int* fvFeat1,
+                                 int N2, const cv::KeyPoint* kps2, const uint8_t* desc2, const uint8_t* hasMP2, int E2, const int* fvNode2, const int* fvFeat2,
+                                 const float* scaleFactors, const float* levelSigma2, int nlevels, const float* T1w, const float* T2w, const float* cam1,
+                                 const float* cam2, int bCoarse, int checkOri, int* matches12, float* epOut, float* F12Out) {
+    KeyFrame KF1, KF2;
+    std::vector<MapPoint> mps1(N1), mps2(N2);
+    Pinhole c1, c2;
+    fill_tri_kf(KF1, mps1, c1, N1, kps1, desc1, hasMP1, E1, fvNode1, fvFeat1, scaleFactors, levelSigma2, nlevels, T1w, cam1);
+    fill_tri_kf(KF2, mps2, c2, N2, kps2, desc2, hasMP2, E2, fvNode2, fvFeat2, scaleFactors, levelSigma2, nlevels, T2w, cam2);
+    {
+        const Eigen::Vector3f C2 = KF2.GetPose() * KF1.GetCameraCenter();
+        const Eigen::Vector2f ep = KF2.mpCamera->project(C2);
+        epOut[0] = ep(0); epOut[1] = ep(1);
+        const Sophus::SE3f T12 = KF1.GetPose() * KF2.GetPoseInverse();
+        const Eigen::Matrix3f F12 = c1.toK_().transpose().inverse() * Sophus::SO3f::hat(T12.translation()) * T12.rotationMatrix() * c2.toK_().inverse();
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) F12Out[3 * i + j] = F12(i, j);
+    }
+    std::vector<std::pair<size_t, size_t>> pairs;
+    ORBmatcher matcher(0.6f, checkOri != 0);
+    const int n = matcher.SearchForTriangulation(&KF1, &KF2, pairs, false, bCoarse != 0);
+    for (int i = 0; i < N1; ++i) matches12[i] = -1;
+    for (auto& pr : pairs) matches12[pr.first] = (int)pr.second;
     return n;
 }
 

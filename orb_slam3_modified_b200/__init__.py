@@ -500,6 +500,33 @@ class ORBmatcher:
             raise OrbError(rc, 'orbm_fuse_search')
         return bi, bd
 
+    def SearchForTriangulation(self, kf1, kf2_list, scale_factors, level_sigma2, ep, F12, coarse=False):
+        """``int ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, false, bCoarse)`` (src/ORBmatcher.cc:907-1146) for one keyframe against
+        several neighbours.  A keyframe is a dict(kps, desc, has_mp, fv=(nodes, features)); ep [n, 2], F12 [n, 9].  Returns (nmatches [n], matches12 [n, N1])."""
+        class _TF(C.Structure):
+            _fields_ = [('N', C.c_int), ('keypoints', C.c_void_p), ('descriptors', C.c_void_p), ('hasMapPoint', C.c_void_p), ('nEntries', C.c_int),
+                        ('fvNode', C.c_void_p), ('fvFeature', C.c_void_p)]
+        keep = []
+
+        def mk(kf):
+            a = [_c(kf['kps'], KP_DTYPE), _c(kf['desc'], np.uint8), _c(kf['has_mp'], np.uint8), _c(kf['fv'][0], np.int32), _c(kf['fv'][1], np.int32)]
+            keep.append(a)
+            return _TF(len(a[0]), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, len(a[3]), a[3].ctypes.data, a[4].ctypes.data)
+        f1 = mk(kf1)
+        n2 = len(kf2_list)
+        f2 = (_TF * max(n2, 1))(*[mk(k) for k in kf2_list])
+        sf, sg = _c(scale_factors, np.float32), _c(level_sigma2, np.float32)
+        epa, Fa = _c(ep, np.float32).reshape(-1, 2), _c(F12, np.float32).reshape(-1, 9)
+        m12 = np.full((n2, f1.N), -1, np.int32); nm = np.zeros(n2, np.int32)
+        L = lib()
+        L.orbm_search_for_triangulation.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                    C.c_void_p, C.c_void_p]
+        rc = L.orbm_search_for_triangulation(self._h, C.byref(f1), n2, f2, _ptr(sf), _ptr(sg), len(sf), _ptr(epa), _ptr(Fa), int(coarse), int(self.mbCheckOrientation),
+                                             _ptr(m12), _ptr(nm))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_search_for_triangulation')
+        return nm, m12
+
     def ComputeDistinctiveDescriptors(self, obs_list):
         """``MapPoint::ComputeDistinctiveDescriptors`` for a list of map points (each an [n, 32] u8 array of observed descriptors): index of the chosen row."""
         start = np.zeros(len(obs_list) + 1, np.int32)

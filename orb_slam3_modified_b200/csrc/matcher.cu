@@ -804,6 +804,121 @@ __global__ void __launch_bounds__(MF_NT) fuse_search_kernel(FuseParams Q) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo = false, bCoarse) (src/ORBmatcher.cc:907-1146, monocular keyframes;
+// LocalMapping::CreateNewMapPoints, src/LocalMapping.cc:340-344) with Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:107-129).
+// One CTA per (KF1, KF2) pair, one warp per KF1 feature without a map point: lanes over the KF2 features of the same vocabulary node (binary
+// search in KF2's feature vector); a candidate passes with distance <= TH_LOW, no map point, the epipole-distance test and the epipolar test;
+// the smallest distance wins, the last candidate on ties (:1008 is strict).  The reference never sets vbMatched2, so KF1 features are
+// independent.  The epipole and the fundamental matrix are inputs (Eigen / Sophus expressions in the caller); the scalar float expressions
+// are contracted as the reference's build contracts them (oracle/matcher_oracle.cpp: orbo_search_for_triangulation).
+// ---------------------------------------------------------------------------------------------
+struct TriPair {
+    int N2, E2;
+    const OrbKeyPoint* kps2; const uint8_t *desc2, *hasMP2; const int *fvNode2, *fvFeat2;
+    float ep[2], F12[9];
+    int* matches12; int* nmatches; uint8_t* evBin;
+};
+struct TriParams {
+    int N1, E1, coarse, checkOri;
+    const OrbKeyPoint* kps1; const uint8_t *desc1, *hasMP1; const int *fvNode1, *fvFeat1;
+    const float *scaleFactors, *levelSigma2;
+    const TriPair* pairs;
+};
+constexpr int TM_NT = 256;
+__global__ void __launch_bounds__(TM_NT) tri_match_kernel(TriParams Q) {
+    __shared__ int s_hist[HISTO_LENGTH], s_ind[3], s_acc, s_rem;
+    const TriPair R = Q.pairs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < Q.N1; i += TM_NT) { R.matches12[i] = -1; R.evBin[i] = 0; }
+    if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+    if (tid == 0) { s_acc = 0; s_rem = 0; }
+    __syncthreads();
+    int acc = 0;
+    for (int e1 = wid; e1 < Q.E1; e1 += TM_NT / 32) {
+        const int idx1 = Q.fvFeat1[e1];
+        if (Q.hasMP1[idx1]) continue;
+        const int node = Q.fvNode1[e1];
+        int lo = 0, hi = R.E2;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (R.fvNode2[mid] < node) lo = mid + 1; else hi = mid; }
+        const int b = lo;
+        hi = R.E2;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (R.fvNode2[mid] <= node) lo = mid + 1; else hi = mid; }
+        const int b1 = lo;
+        if (b1 == b) continue;
+        const OrbKeyPoint kp1 = Q.kps1[idx1];
+        const uint4* p1 = reinterpret_cast<const uint4*>(Q.desc1 + (size_t)idx1 * 32);
+        const uint4 k0 = __ldg(p1), k1 = __ldg(p1 + 1);
+        const uint32_t d1[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+        // epipolar line of kp1 in the second image, l = x1' F12 = [a b c]
+        const float ea = fadd(__fmaf_rn(kp1.x, R.F12[0], fmul(kp1.y, R.F12[3])), R.F12[6]);
+        const float eb = fadd(__fmaf_rn(kp1.x, R.F12[1], fmul(kp1.y, R.F12[4])), R.F12[7]);
+        const float ec = fadd(__fmaf_rn(kp1.x, R.F12[2], fmul(kp1.y, R.F12[5])), R.F12[8]);
+        const float den = __fmaf_rn(ea, ea, fmul(eb, eb));
+        unsigned long long best = ~0ull;
+        for (int i2 = b + lane; i2 < b1; i2 += 32) {
+            const int idx2 = R.fvFeat2[i2];
+            if (R.hasMP2[idx2]) continue;
+            const uint4* p2 = reinterpret_cast<const uint4*>(R.desc2 + (size_t)idx2 * 32);
+            const uint4 f0 = __ldg(p2), f1 = __ldg(p2 + 1);
+            const uint32_t d2[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            const int dist = hamming256(d1, d2);
+            if (dist > TH_LOW) continue;
+            const OrbKeyPoint kp2 = R.kps2[idx2];
+            const int oct = min(max(kp2.octave, 0), 255);
+            const float distex = fsub(R.ep[0], kp2.x), distey = fsub(R.ep[1], kp2.y);
+            if (__fmaf_rn(distex, distex, fmul(distey, distey)) < fmul(100.0f, Q.scaleFactors[oct])) continue;
+            if (!Q.coarse) {
+                if (den == 0.0f) continue;
+                const float num = fadd(__fmaf_rn(ea, kp2.x, fmul(eb, kp2.y)), ec);
+                const float dsqr = fdiv(fmul(num, num), den);
+                if (!((double)dsqr < 3.84 * (double)Q.levelSigma2[oct])) continue;
+            }
+            const unsigned long long key = ((unsigned long long)dist << 32) | (0xFFFFFFFFu - (unsigned)(i2 - b));
+            best = key < best ? key : best;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t < best ? t : best; }
+        if (best != ~0ull) {
+            if (lane == 0) {
+                const int idx2 = R.fvFeat2[b + (int)(0xFFFFFFFFu - (unsigned)best)];
+                R.matches12[idx1] = idx2;
+                if (Q.checkOri) {
+                    const int bin = rot_bin(kp1.angle, R.kps2[idx2].angle);
+                    R.evBin[idx1] = (uint8_t)(bin + 1);
+                    atomicAdd(&s_hist[bin], 1);
+                }
+            }
+            ++acc;
+        }
+    }
+    if (lane == 0 && acc) atomicAdd(&s_acc, acc);
+    __syncthreads();
+    if (Q.checkOri) {
+        if (tid == 0) {
+            int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+            for (int bb = 0; bb < HISTO_LENGTH; ++bb) {
+                const int sz = s_hist[bb];
+                if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = bb; }
+                else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = bb; }
+                else if (sz > max3) { max3 = sz; ind3 = bb; }
+            }
+            if ((float)max2 < fmul(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < fmul(0.1f, (float)max1)) { ind3 = -1; }
+            s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+        }
+        __syncthreads();
+        int rem = 0;
+        for (int i = tid; i < Q.N1; i += TM_NT) {
+            const int bb = (int)R.evBin[i] - 1;
+            if (bb >= 0 && bb != s_ind[0] && bb != s_ind[1] && bb != s_ind[2]) { R.matches12[i] = -1; ++rem; }
+        }
+        if (rem) atomicAdd(&s_rem, rem);
+        __syncthreads();
+    }
+    if (tid == 0) *R.nmatches = s_acc - s_rem;
+}
+
+// ---------------------------------------------------------------------------------------------
 // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:329-403) for a batch of map points: warp per map point, lane per observation row;
 // the row's median distance (element (int)(0.5 (n - 1)) of the sorted row) by bisection on the distance value; first minimum wins.
 // ---------------------------------------------------------------------------------------------
@@ -1340,6 +1455,79 @@ int orbm_fuse_search(orbm_handle* h, const OrbmFrame* KF, const float* invLevelS
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(bestIdx, d + oBi, 4 * M, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(bestDist, d + oBd, 4 * M, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+static bool tri_frame_ok(const OrbmTriFrame* f) {
+    if (!f || f->N < 0 || f->nEntries < 0 || f->nEntries > f->N) return false;
+    if (f->N && (!f->keypoints || !f->descriptors || !f->hasMapPoint)) return false;
+    if (f->nEntries && (!f->fvNode || !f->fvFeature)) return false;
+    for (int e = 0; e < f->nEntries; ++e) if (f->fvFeature[e] < 0 || f->fvFeature[e] >= f->N || (e && f->fvNode[e] < f->fvNode[e - 1])) return false;
+    return true;
+}
+int orbm_search_for_triangulation(orbm_handle* h, const OrbmTriFrame* KF1, int nKF2, const OrbmTriFrame* KF2, const float* scaleFactors, const float* levelSigma2,
+                                  int nlevels, const float* ep2, const float* F12, int bCoarse, int checkOrientation, int32_t* matches12, int32_t* nmatches) {
+    if (!h || nKF2 < 0 || !tri_frame_ok(KF1) || (nKF2 && (!KF2 || !ep2 || !F12 || !matches12 || !nmatches)) || !scaleFactors || !levelSigma2 || nlevels < 1 || nlevels > 256) {
+        set_error("orbm_search_for_triangulation: bad argument (feature vectors must be sorted by node id, indices in range)"); return ORB_ERR_ARG;
+    }
+    for (int k = 0; k < nKF2; ++k) {
+        if (!tri_frame_ok(KF2 + k)) { set_error("orbm_search_for_triangulation: bad KF2 entry"); return ORB_ERR_ARG; }
+        for (int i = 0; i < KF2[k].N; ++i) if (KF2[k].keypoints[i].octave < 0 || KF2[k].keypoints[i].octave >= nlevels) { set_error("orbm_search_for_triangulation: keypoint octave out of range"); return ORB_ERR_ARG; }
+    }
+    if (nKF2 == 0) return ORB_OK;
+    Matcher& m = h->m;
+    CK(cudaSetDevice(m.device));
+    const size_t N1 = (size_t)KF1->N, E1 = (size_t)KF1->nEntries;
+    for (size_t i = 0; i < (size_t)nKF2 * N1; ++i) matches12[i] = -1;
+    for (int k = 0; k < nKF2; ++k) nmatches[k] = 0;
+    if (N1 == 0) return ORB_OK;
+    // one staging buffer: tables | KF1 | per pair: KF2 arrays, outputs | pair table
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t oSf = take(4 * (size_t)nlevels), oSg = take(4 * (size_t)nlevels);
+    const size_t oK1 = take(N1 * sizeof(OrbKeyPoint)), oD1 = take(N1 * 32), oM1 = take(N1), oN1 = take(4 * E1), oF1 = take(4 * E1);
+    struct Off { size_t kp, de, mp, fn, ff, out, ev; };
+    std::vector<Off> po(nKF2);
+    for (int k = 0; k < nKF2; ++k) {
+        const size_t N2 = (size_t)KF2[k].N, E2 = (size_t)KF2[k].nEntries;
+        po[k] = {take(N2 * sizeof(OrbKeyPoint)), take(N2 * 32), take(N2), take(4 * E2), take(4 * E2), take(4 * N1), take(N1)};
+    }
+    const size_t oCnt = take(4 * (size_t)nKF2), oTab = take(sizeof(TriPair) * (size_t)nKF2);
+    if (off > m.batchBytes) {                                   // grow the device staging (mapping-side call: pageable copies are fine)
+        if (m.d_batch) cudaFree(m.d_batch);
+        m.d_batch = nullptr; m.batchBytes = 0;
+        CK(cudaMalloc(&m.d_batch, off));
+        m.batchBytes = off;
+    }
+    uint8_t* d = m.d_batch;
+    cudaStream_t st = m.stream;
+    auto up = [&](size_t o, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
+    CK(up(oSf, scaleFactors, 4 * (size_t)nlevels)); CK(up(oSg, levelSigma2, 4 * (size_t)nlevels));
+    CK(up(oK1, KF1->keypoints, N1 * sizeof(OrbKeyPoint))); CK(up(oD1, KF1->descriptors, N1 * 32)); CK(up(oM1, KF1->hasMapPoint, N1));
+    CK(up(oN1, KF1->fvNode, 4 * E1)); CK(up(oF1, KF1->fvFeature, 4 * E1));
+    std::vector<TriPair> tab(nKF2);
+    for (int k = 0; k < nKF2; ++k) {
+        const size_t N2 = (size_t)KF2[k].N, E2 = (size_t)KF2[k].nEntries;
+        CK(up(po[k].kp, KF2[k].keypoints, N2 * sizeof(OrbKeyPoint))); CK(up(po[k].de, KF2[k].descriptors, N2 * 32)); CK(up(po[k].mp, KF2[k].hasMapPoint, N2));
+        CK(up(po[k].fn, KF2[k].fvNode, 4 * E2)); CK(up(po[k].ff, KF2[k].fvFeature, 4 * E2));
+        TriPair& T = tab[k];
+        T.N2 = (int)N2; T.E2 = (int)E2;
+        T.kps2 = (const OrbKeyPoint*)(d + po[k].kp); T.desc2 = d + po[k].de; T.hasMP2 = d + po[k].mp; T.fvNode2 = (const int*)(d + po[k].fn); T.fvFeat2 = (const int*)(d + po[k].ff);
+        memcpy(T.ep, ep2 + 2 * (size_t)k, 8); memcpy(T.F12, F12 + 9 * (size_t)k, 36);
+        T.matches12 = (int*)(d + po[k].out); T.nmatches = (int*)(d + oCnt) + k; T.evBin = d + po[k].ev;
+    }
+    CK(cudaMemcpyAsync(d + oTab, tab.data(), sizeof(TriPair) * (size_t)nKF2, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                              // `tab` is pageable host memory: the copy must be done before it goes out of scope
+    TriParams Q; memset(&Q, 0, sizeof(Q));
+    Q.N1 = (int)N1; Q.E1 = (int)E1; Q.coarse = bCoarse; Q.checkOri = checkOrientation;
+    Q.kps1 = (const OrbKeyPoint*)(d + oK1); Q.desc1 = d + oD1; Q.hasMP1 = d + oM1; Q.fvNode1 = (const int*)(d + oN1); Q.fvFeat1 = (const int*)(d + oF1);
+    Q.scaleFactors = (const float*)(d + oSf); Q.levelSigma2 = (const float*)(d + oSg); Q.pairs = (const TriPair*)(d + oTab);
+    tri_match_kernel<<<nKF2, TM_NT, 0, st>>>(Q);
+    m.launches = 1;
+    CK(cudaGetLastError());
+    for (int k = 0; k < nKF2; ++k) CK(cudaMemcpyAsync(matches12 + (size_t)k * N1, d + po[k].out, 4 * N1, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nmatches, d + oCnt, 4 * (size_t)nKF2, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return ORB_OK;
 }

@@ -441,3 +441,50 @@ def fuse_search(sc, th=3.0):
     c = [_c(sc['state'], np.uint8), _c(sc['xyz'], np.float32), _c(sc['normal'], np.float32), _c(sc['min_d'], np.float32), _c(sc['max_d'], np.float32), _c(sc['mp_desc'], np.uint8)]
     L.orbo_fuse_search(len(a[0]), *[_p(v) for v in a], len(a[3]), float(sc['log_sf']), *[_p(v) for v in b], M, *[_p(v) for v in c], th, _p(bi), _p(bd))
     return bi, bd
+
+
+def triangulation_scene(t, dt=3, k=10, L=4, levelsup=2, seed=0):
+    """Two keyframes (frames t and t + dt of the synthetic stream) for ORBmatcher::SearchForTriangulation: keypoints, descriptors,
+    which features hold a map point, DBoW2 feature vectors, poses, camera, level tables."""
+    import matcher_scenes
+    from orb_slam3_modified_b200 import synth
+    rng = np.random.default_rng(seed + 31 * t + dt)
+    voc = synthetic_vocabulary(k, L, seed=k + L)
+    k1, d1 = matcher_scenes.extract(t); k2, d2 = matcher_scenes.extract(t + dt)
+    tab = OracleExtractor().tables()
+    return dict(k1=k1, d1=d1, k2=k2, d2=d2, mp1=(rng.random(len(k1)) < 0.4).astype(np.uint8), mp2=(rng.random(len(k2)) < 0.4).astype(np.uint8),
+                fv1=bow_transform(voc, d1, levelsup)[2:], fv2=bow_transform(voc, d2, levelsup)[2:], sf=tab['scale'], sigma2=tab['sigma2'],
+                T1w=synth.pose(t).astype(np.float32), T2w=synth.pose(t + dt).astype(np.float32), cam=synth.camera())
+
+
+def search_for_triangulation(sc, ep, F12, coarse=False, check_ori=True):
+    a = [_c(sc['k1'], KP_DTYPE), _c(sc['d1'], np.uint8), _c(sc['mp1'], np.uint8), _c(sc['fv1'][0], np.int32), _c(sc['fv1'][1], np.int32)]
+    b = [_c(sc['k2'], KP_DTYPE), _c(sc['d2'], np.uint8), _c(sc['mp2'], np.uint8), _c(sc['fv2'][0], np.int32), _c(sc['fv2'][1], np.int32)]
+    c = [_c(sc['sf'], np.float32), _c(sc['sigma2'], np.float32), _c(ep, np.float32), _c(F12, np.float32)]
+    m12 = np.full(len(a[0]), -1, np.int32)
+    L = lib()
+    L.orbo_search_for_triangulation.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] * 2 + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p]
+    n = L.orbo_search_for_triangulation(len(a[0]), _p(a[0]), _p(a[1]), _p(a[2]), len(a[3]), _p(a[3]), _p(a[4]),
+                                        len(b[0]), _p(b[0]), _p(b[1]), _p(b[2]), len(b[3]), _p(b[3]), _p(b[4]), *[_p(v) for v in c], int(coarse), int(check_ori), _p(m12))
+    return n, m12
+
+
+def triangulation_geometry(sc):
+    """Epipole of KF1's centre in KF2 and the fundamental matrix F12 = K1^-T [t12]x R12 K2^-1 (src/ORBmatcher.cc:913-929, Pinhole.cpp:109-112) in numpy
+    float64, rounded to float32: inputs of the search (the reference evaluates them with Eigen / Sophus)."""
+    def Rt(T):
+        w, x, y, z = [float(v) for v in T[:4]]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        return R, np.asarray(T[4:], np.float64)
+    R1, t1 = Rt(sc['T1w']); R2, t2 = Rt(sc['T2w'])
+    fx, fy, cx, cy = [float(v) for v in sc['cam']]
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    Cw = -R1.T @ t1
+    C2 = R2 @ Cw + t2
+    ep = np.array([fx * C2[0] / C2[2] + cx, fy * C2[1] / C2[2] + cy])
+    R12 = R1 @ R2.T
+    t12 = t1 - R12 @ t2
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    F12 = np.linalg.inv(K.T) @ tx @ R12 @ np.linalg.inv(K)
+    return ep.astype(np.float32), F12.astype(np.float32).reshape(9)

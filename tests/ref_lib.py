@@ -236,3 +236,20 @@ def fuse(sc, th=3.0):
          _c(sc['mp_obs'], np.int32)]
     n = L.ref_fuse(len(a[0]), *[_p(v) for v in a], len(a[3]), float(sc['log_sf']), *[_p(v) for v in b], M, *[_p(v) for v in c], th, _p(act), _p(idx))
     return n, act, idx
+
+
+def search_for_triangulation(sc, coarse=False, check_ori=True):
+    """ORBmatcher::SearchForTriangulation itself (+ Pinhole::epipolarConstrain); returns (nmatches, matches12, ep [2], F12 [9]) -- the epipole and
+    fundamental matrix are the ones the body worked with (ref_wrap_matcher.cpp)."""
+    a = [_c(sc['k1'], KP_DTYPE), _c(sc['d1'], np.uint8), _c(sc['mp1'], np.uint8), _c(sc['fv1'][0], np.int32), _c(sc['fv1'][1], np.int32)]
+    b = [_c(sc['k2'], KP_DTYPE), _c(sc['d2'], np.uint8), _c(sc['mp2'], np.uint8), _c(sc['fv2'][0], np.int32), _c(sc['fv2'][1], np.int32)]
+    c = [_c(sc['sf'], np.float32), _c(sc['sigma2'], np.float32)]
+    d = [_c(sc['T1w'], np.float32), _c(sc['T2w'], np.float32), _c(sc['cam'], np.float32), _c(sc['cam'], np.float32)]
+    m12 = np.full(len(a[0]), -1, np.int32); ep = np.zeros(2, np.float32); F12 = np.zeros(9, np.float32)
+    L = lib()
+    L.ref_search_for_triangulation.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] * 2 + [C.c_void_p, C.c_void_p, C.c_int] + \
+        [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = L.ref_search_for_triangulation(len(a[0]), _p(a[0]), _p(a[1]), _p(a[2]), len(a[3]), _p(a[3]), _p(a[4]),
+                                       len(b[0]), _p(b[0]), _p(b[1]), _p(b[2]), len(b[3]), _p(b[3]), _p(b[4]), _p(c[0]), _p(c[1]), len(c[0]),
+                                       *[_p(v) for v in d], int(coarse), int(check_ori), _p(m12), _p(ep), _p(F12))
+    return n, m12, ep, F12

@@ -261,3 +261,23 @@ def test_fuse_search(orb, t, th, M):
     obi, obd = O.fuse_search(sc, th)
     assert np.array_equal(bi, obi) and np.array_equal(bd, obd)
     assert (bd <= 50).sum() > M // 20
+
+
+@pytest.mark.parametrize('t,dts,coarse,ori', [(4, (3, -2, 5), False, True), (11, (2,), False, False), (17, (5, 1), True, True), (22, (), False, True)])
+def test_search_for_triangulation(orb, t, dts, coarse, ori):
+    """f2: ORBmatcher::SearchForTriangulation for one keyframe against several neighbours in one launch vs the oracle (which
+    tests/test_ref_pins_oracle_cpu.py holds against the reference's own body + Pinhole::epipolarConstrain)."""
+    scs = [O.triangulation_scene(t, dt) for dt in dts] or [O.triangulation_scene(t, 1)]
+    kf1 = dict(kps=scs[0]['k1'], desc=scs[0]['d1'], has_mp=scs[0]['mp1'], fv=scs[0]['fv1'])
+    for sc in scs:
+        sc['mp1'] = scs[0]['mp1']                     # one KF1 for all pairs
+    geo = [O.triangulation_geometry(sc) for sc in scs] if dts else []
+    kf2 = [dict(kps=sc['k2'], desc=sc['d2'], has_mp=sc['mp2'], fv=sc['fv2']) for sc in scs] if dts else []
+    m = orb.ORBmatcher(0.6, ori, max_batch=1, max_keypoints=2048, max_mappoints=2048)
+    nm, m12 = m.SearchForTriangulation(kf1, kf2, scs[0]['sf'], scs[0]['sigma2'], np.array([g[0] for g in geo], np.float32).reshape(-1, 2),
+                                       np.array([g[1] for g in geo], np.float32).reshape(-1, 9), coarse)
+    assert len(nm) == len(dts)
+    for k, sc in enumerate(scs if dts else []):
+        on, om = O.search_for_triangulation(sc, geo[k][0], geo[k][1], coarse, ori)
+        assert nm[k] == on and np.array_equal(m12[k], om), (k, nm[k], on)
+        assert on > 30

@@ -260,3 +260,15 @@ def test_fuse_search_equals_reference(t, th):
     assert np.array_equal(act > 0, hit) and np.array_equal(idx[hit], bi[hit])
     assert {1, 2, 3} <= set(act[hit].tolist())
     assert not hit[sc['state'] != 1].any()
+
+
+@pytest.mark.parametrize('t,dt,coarse,ori', [(4, 3, False, True), (11, 2, False, True), (17, 5, False, False), (22, 3, True, True), (9, -4, False, True)])
+def test_search_for_triangulation_equals_reference(t, dt, coarse, ori):
+    """ORBmatcher::SearchForTriangulation + Pinhole::epipolarConstrain (src/ORBmatcher.cc:907-1146, src/CameraModels/Pinhole.cpp:107-129): the
+    reference's own bodies against the oracle, given the epipole and fundamental matrix the bodies worked with."""
+    sc = O.triangulation_scene(t, dt)
+    n, m12, ep, F12 = R.search_for_triangulation(sc, coarse, ori)
+    on, om = O.search_for_triangulation(sc, ep, F12, coarse, ori)
+    assert n == on and np.array_equal(m12, om), (n, on, int((m12 != om).sum()))
+    assert n > 30
+    assert not sc['mp1'][m12 >= 0].any() and not sc['mp2'][m12[m12 >= 0]].any()

@@ -3,9 +3,9 @@ run() {
   env "$1" python bench.py --steps 4 --warmup 2 --no-extra --no-cpu-baseline "${@:2}" 2>&1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('%-60s value %.0f e2e %s' % ('$*', d['value'], d.get('e2e')))"
+print('%-60s value %.0f e2e %.0f cluster %s' % ('$*', d['value'], d['e2e']['value'], d['config']['lba_cluster_size']))"
 }
-run X=1 --e2e-groups 4
-run X=1 --e2e-groups 8
-run BENCH_SWITCH_INTERVAL=5e-3 --e2e-groups 4
-run BENCH_E2E_LBA=exclusive --e2e-groups 4
+run X=1 --lba-rounds 1
+run X=1 --lba-rounds 2
+run X=1 --lba-rounds 6
+run X=1 --lba-rounds 3 --e2e-groups 3
