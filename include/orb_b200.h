@@ -265,6 +265,11 @@ typedef struct OrbmBowFrame {
 } OrbmBowFrame;
 int orbm_search_by_bow(orbm_handle* h, const OrbmBowFrame* KF, const uint8_t* kfPoint, const OrbmBowFrame* F, float nnratio, int checkOrientation,
                        int32_t* match, int* nmatches);
+/* int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (include/ORBmatcher.h:69, src/ORBmatcher.cc:765-905;
+ * LoopClosing): both sides are keyframes (point1 / point2: 0 none, 1 map point, 2 bad), the distance test is strict (bestDist1 < TH_LOW).
+ * match12 [KF1.N] = feature of KF2 whose map point goes to vpMatches12[idx1] (-1 = NULL).  KF1.N <= max_mappoints, KF2.N <= max_keypoints. */
+int orbm_search_by_bow_kf(orbm_handle* h, const OrbmBowFrame* KF1, const uint8_t* point1, const OrbmBowFrame* KF2, const uint8_t* point2, float nnratio,
+                          int checkOrientation, int32_t* match12, int* nmatches);
 /* int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th, const bool bRight) (include/ORBmatcher.h:99,
  * src/ORBmatcher.cc:1148-1338, monocular keyframe; LocalMapping::SearchInNeighbors, src/LocalMapping.cc:878-1021): the SEARCH of every map
  * point -- projection with the keyframe pose, KeyFrame::IsInImage, distance / viewing-angle tests, MapPoint::PredictScale, the radius search

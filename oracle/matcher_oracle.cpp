@@ -567,4 +567,68 @@ int orbo_search_for_triangulation(int N1, const KeyPoint* kps1, const uint8_t* d
     return nmatches;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (src/ORBmatcher.cc:765-905), NLeft == -1: like the
+// (KeyFrame, Frame) overload but both sides need a good map point, a KF2 feature is claimed once (vbMatched2), the threshold is STRICT
+// (bestDist1 < TH_LOW, :859) and the result is indexed by the KF1 feature.  point1 / point2: 0 no map point, 1 map point, 2 bad.
+int orbo_search_by_bow_kf(int N1, const KeyPoint* kps1, const uint8_t* desc1, const uint8_t* point1, int E1, const int* fvNode1, const int* fvFeat1,
+                          int N2, const KeyPoint* kps2, const uint8_t* desc2, const uint8_t* point2, int E2, const int* fvNode2, const int* fvFeat2,
+                          float nnratio, int checkOri, int* match12) {
+    static const int TH_LOW = 50;
+    for (int i = 0; i < N1; ++i) match12[i] = -1;
+    std::vector<uint8_t> vbMatched2(N2, 0);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int a = 0, b = 0;
+    while (a < E1 && b < E2) {
+        if (fvNode1[a] == fvNode2[b]) {
+            int a1 = a, b1 = b;
+            while (a1 < E1 && fvNode1[a1] == fvNode1[a]) ++a1;
+            while (b1 < E2 && fvNode2[b1] == fvNode2[b]) ++b1;
+            for (int i1 = a; i1 < a1; ++i1) {
+                const int idx1 = fvFeat1[i1];
+                if (point1[idx1] != 1) continue;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = b; i2 < b1; ++i2) {
+                    const int idx2 = fvFeat2[i2];
+                    if (vbMatched2[idx2] || point2[idx2] != 1) continue;
+                    const int dist = descriptor_distance(desc1 + (size_t)idx1 * 32, desc2 + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW && static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                    match12[idx1] = bestIdx2;
+                    vbMatched2[bestIdx2] = 1;
+                    if (checkOri) {
+                        float rot = kps1[idx1].angle - kps2[bestIdx2].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(idx1);
+                    }
+                    ++nmatches;
+                }
+            }
+            a = a1; b = b1;
+        } else if (fvNode1[a] < fvNode2[b]) { const int t = fvNode2[b]; while (a < E1 && fvNode1[a] < t) ++a; }
+        else { const int t = fvNode1[a]; while (b < E2 && fvNode2[b] < t) ++b; }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            const int sz = (int)rotHist[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rotHist[i]) { match12[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

@@ -11,6 +11,7 @@ RANGES = [
     ('matcher_local_map.inc', 'src/ORBmatcher.cc', 43, 221, 'int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>'),
     ('matcher_bow_kf_frame.inc', 'src/ORBmatcher.cc', 223, 425, 'int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F'),
     ('matcher_init.inc', 'src/ORBmatcher.cc', 648, 763, 'int ORBmatcher::SearchForInitialization'),
+    ('matcher_bow_kf_kf.inc', 'src/ORBmatcher.cc', 765, 905, 'int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint *> &vpMatches12)'),
     ('matcher_triangulation.inc', 'src/ORBmatcher.cc', 907, 1146, 'int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2'),
     ('pinhole_epipolar.inc', 'src/CameraModels/Pinhole.cpp', 107, 129, 'bool Pinhole::epipolarConstrain(GeometricCamera* pCamera2'),
     ('matcher_fuse.inc', 'src/ORBmatcher.cc', 1148, 1338, 'int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints'),

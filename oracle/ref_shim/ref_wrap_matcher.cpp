@@ -14,6 +14,7 @@ namespace ORB_SLAM3 {
 #include "matcher_init.inc"
 #include "matcher_fuse.inc"
 #include "matcher_triangulation.inc"
+#include "matcher_bow_kf_kf.inc"
 #include "matcher_last_frame.inc"
 #include "matcher_maxima_distance.inc"
 #include "pinhole_project.inc"
@@ -201,6 +202,30 @@ int ref_search_by_bow(int nKF, const cv::KeyPoint* kpsKF, const uint8_t* descKF,
     ORBmatcher matcher(nnratio, checkOri != 0);
     const int n = matcher.SearchByBoW(&KF, F, out);
     for (int i = 0; i < nF; ++i) matchF[i] = out[i] ? out[i]->index : -1;
+    return n;
+}
+
+// int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (src/ORBmatcher.cc:765-905; loop closing / merging).
+// point1 / point2 [N]: 0 no map point, 1 map point, 2 bad.  match12 [N1]: feature of KF2 whose map point is vpMatches12[idx1], -1 = NULL.
+int ref_search_by_bow_kf(int N1, const cv::KeyPoint* kps1, const uint8_t* desc1, const uint8_t* point1, int E1, const int* fvNode1, const int* fvFeat1,
+                         int N2, const cv::KeyPoint* kps2, const uint8_t* desc2, const uint8_t* point2, int E2, const int* fvNode2, const int* fvFeat2,
+                         float nnratio, int checkOri, int* match12) {
+    KeyFrame KF1, KF2;
+    std::vector<MapPoint> mps1(N1), mps2(N2);
+    auto fill = [](KeyFrame& KF, std::vector<MapPoint>& mps, int N, const cv::KeyPoint* kps, const uint8_t* desc, const uint8_t* point, int E, const int* fvNode, const int* fvFeat) {
+        KF.N = N; KF.NLeft = -1;
+        KF.mvpMapPoints.assign(N, (MapPoint*)nullptr);
+        for (int i = 0; i < N; ++i) { mps[i].index = i; mps[i].mbBad = point[i] == 2; if (point[i]) KF.mvpMapPoints[i] = &mps[i]; }
+        KF.mDescriptors = N ? cv::Mat(N, 32, CV_8UC1, (void*)desc, 32) : cv::Mat();
+        KF.mvKeysUn.assign(kps, kps + N); KF.mvKeys = KF.mvKeysUn;
+        for (int e = 0; e < E; ++e) KF.mFeatVec.addFeature(fvNode[e], fvFeat[e]);
+    };
+    fill(KF1, mps1, N1, kps1, desc1, point1, E1, fvNode1, fvFeat1);
+    fill(KF2, mps2, N2, kps2, desc2, point2, E2, fvNode2, fvFeat2);
+    std::vector<MapPoint*> out;
+    ORBmatcher matcher(nnratio, checkOri != 0);
+    const int n = matcher.SearchByBoW(&KF1, &KF2, out);
+    for (int i = 0; i < N1; ++i) match12[i] = out[i] ? out[i]->index : -1;
     return n;
 }
 

@@ -500,6 +500,23 @@ class ORBmatcher:
             raise OrbError(rc, 'orbm_fuse_search')
         return bi, bd
 
+    def SearchByBoWKF(self, k1, d1, point1, fv1, k2, d2, point2, fv2):
+        """``int ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)`` (src/ORBmatcher.cc:765-905): (nmatches, match12 [N1] = KF2 feature or -1)."""
+        class _BF(C.Structure):
+            _fields_ = [('N', C.c_int), ('keypoints', C.c_void_p), ('descriptors', C.c_void_p), ('nEntries', C.c_int), ('fvNode', C.c_void_p), ('fvFeature', C.c_void_p)]
+        keep = [_c(k1, KP_DTYPE), _c(d1, np.uint8), _c(fv1[0], np.int32), _c(fv1[1], np.int32), _c(k2, KP_DTYPE), _c(d2, np.uint8),
+                _c(fv2[0], np.int32), _c(fv2[1], np.int32), _c(point1, np.uint8), _c(point2, np.uint8)]
+        a = _BF(len(keep[0]), keep[0].ctypes.data, keep[1].ctypes.data, len(keep[2]), keep[2].ctypes.data, keep[3].ctypes.data)
+        b = _BF(len(keep[4]), keep[4].ctypes.data, keep[5].ctypes.data, len(keep[6]), keep[6].ctypes.data, keep[7].ctypes.data)
+        m12 = np.full(len(keep[0]), -1, np.int32)
+        n = C.c_int(0)
+        L = lib()
+        L.orbm_search_by_bow_kf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        rc = L.orbm_search_by_bow_kf(self._h, C.byref(a), _ptr(keep[8]), C.byref(b), _ptr(keep[9]), self.mfNNratio, int(self.mbCheckOrientation), _ptr(m12), C.byref(n))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_search_by_bow_kf')
+        return n.value, m12
+
     def SearchForTriangulation(self, kf1, kf2_list, scale_factors, level_sigma2, ep, F12, coarse=False):
         """``int ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, false, bCoarse)`` (src/ORBmatcher.cc:907-1146) for one keyframe against
         several neighbours.  A keyframe is a dict(kps, desc, has_mp, fv=(nodes, features)); ep [n, 2], F12 [n, 9].  Returns (nmatches [n], matches12 [n, N1])."""

@@ -648,12 +648,16 @@ struct BowMatchParams {
     const int *fvNodeKF, *fvFeatKF, *fvNodeF, *fvFeatF;
     float nnratio; int checkOri;
     int* match; int* nmatches; int* groupStart; uint8_t* evBin;   // match [nF]; scratch: groupStart [eKF + 1], evBin [nF]
+    // SearchByBoW(KeyFrame*, KeyFrame*) (src/ORBmatcher.cc:765-905): the second side is a keyframe too -- its features need a good map point
+    // (fPoint, null for a Frame), the distance test is strict (bestDist1 < TH_LOW, :859) and the result is indexed by the first side (match12)
+    const uint8_t* fPoint; int strictLow; int* match12;
 };
 constexpr int BM_NT = 256;
 __global__ void __launch_bounds__(BM_NT) bow_match_kernel(BowMatchParams Q) {
     __shared__ int s_hist[HISTO_LENGTH], s_ind[3], s_acc, s_rem, s_ng;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < Q.nF; i += BM_NT) { Q.match[i] = -1; Q.evBin[i] = 0; }
+    if (Q.match12) for (int i = tid; i < Q.nKF; i += BM_NT) Q.match12[i] = -1;
     if (tid < HISTO_LENGTH) s_hist[tid] = 0;
     if (tid == 0) { s_acc = 0; s_rem = 0; s_ng = 0; }
     __syncthreads();
@@ -685,6 +689,7 @@ __global__ void __launch_bounds__(BM_NT) bow_match_kernel(BowMatchParams Q) {
             for (int iF = b + lane; iF < b1; iF += 32) {
                 const int realIdxF = Q.fvFeatF[iF];
                 if (Q.match[realIdxF] >= 0) continue;            // already matched by an earlier keyframe feature of this node (:275-276)
+                if (Q.fPoint && Q.fPoint[realIdxF] != 1) continue;
                 const uint4* pf = reinterpret_cast<const uint4*>(Q.descF + (size_t)realIdxF * 32);
                 const uint4 f0 = __ldg(pf), f1 = __ldg(pf + 1);
                 const uint32_t dfw[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
@@ -692,9 +697,10 @@ __global__ void __launch_bounds__(BM_NT) bow_match_kernel(BowMatchParams Q) {
             }
             t.warp_merge();
             const int bestDist1 = t.i[0] >= 0 ? (int)(t.k[0] >> 32) : 256, bestDist2 = t.i[1] >= 0 ? (int)(t.k[1] >> 32) : 256;
-            if (bestDist1 <= TH_LOW && (float)bestDist1 < fmul(Q.nnratio, (float)bestDist2)) {
+            if ((Q.strictLow ? bestDist1 < TH_LOW : bestDist1 <= TH_LOW) && (float)bestDist1 < fmul(Q.nnratio, (float)bestDist2)) {
                 if (lane == 0) {
                     Q.match[t.i[0]] = realIdxKF;
+                    if (Q.match12) Q.match12[realIdxKF] = t.i[0];
                     if (Q.checkOri) {
                         const int bin = rot_bin(Q.kpsKF[realIdxKF].angle, Q.kpsF[t.i[0]].angle);
                         Q.evBin[t.i[0]] = (uint8_t)(bin + 1);
@@ -725,7 +731,7 @@ __global__ void __launch_bounds__(BM_NT) bow_match_kernel(BowMatchParams Q) {
         int rem = 0;
         for (int i = tid; i < Q.nF; i += BM_NT) {
             const int bb = (int)Q.evBin[i] - 1;
-            if (bb >= 0 && bb != s_ind[0] && bb != s_ind[1] && bb != s_ind[2]) { Q.match[i] = -1; ++rem; }
+            if (bb >= 0 && bb != s_ind[0] && bb != s_ind[1] && bb != s_ind[2]) { if (Q.match12) Q.match12[Q.match[i]] = -1; Q.match[i] = -1; ++rem; }
         }
         if (rem) atomicAdd(&s_rem, rem);
         __syncthreads();
@@ -1361,9 +1367,9 @@ int orbm_search_last_frame_batch_resident(orbm_handle* h, const OrbmBatchDevice*
     return search_last_frame_batch_host(h, in, th, checkOri, match, claimed, nmatches, true);
 }
 
-int orbm_search_by_bow(orbm_handle* h, const OrbmBowFrame* KF, const uint8_t* kfPoint, const OrbmBowFrame* F, float nnratio, int checkOrientation,
-                       int32_t* match, int* nmatches) {
-    if (!h || !KF || !F || !kfPoint || !match || !nmatches || KF->N < 0 || F->N < 0 || KF->nEntries < 0 || F->nEntries < 0 || KF->nEntries > KF->N ||
+static int search_by_bow_impl(orbm_handle* h, const OrbmBowFrame* KF, const uint8_t* kfPoint, const OrbmBowFrame* F, const uint8_t* fPoint, float nnratio,
+                              int checkOrientation, int32_t* match, int32_t* match12, int* nmatches) {
+    if (!h || !KF || !F || !kfPoint || (!match && !match12) || !nmatches || KF->N < 0 || F->N < 0 || KF->nEntries < 0 || F->nEntries < 0 || KF->nEntries > KF->N ||
         F->nEntries > F->N || KF->N > h->m.mcap || F->N > h->m.kcap) {
         set_error("orbm_search_by_bow: bad argument (KF.N <= max_mappoints, F.N <= max_keypoints of the handle)"); return ORB_ERR_ARG;
     }
@@ -1372,7 +1378,8 @@ int orbm_search_by_bow(orbm_handle* h, const OrbmBowFrame* KF, const uint8_t* kf
     Matcher& m = h->m;
     CK(cudaSetDevice(m.device));
     *nmatches = 0;
-    for (int i = 0; i < F->N; ++i) match[i] = -1;
+    if (match) for (int i = 0; i < F->N; ++i) match[i] = -1;
+    if (match12) for (int i = 0; i < KF->N; ++i) match12[i] = -1;
     if (F->N == 0 || KF->N == 0) return ORB_OK;
     Arena A(m.h_arena, m.d_arena, m.arenaBytes);
     BowMatchParams Q; memset(&Q, 0, sizeof(Q));
@@ -1381,21 +1388,35 @@ int orbm_search_by_bow(orbm_handle* h, const OrbmBowFrame* KF, const uint8_t* kf
               A.put(KF->fvNode, (size_t)KF->nEntries, &Q.fvNodeKF) && A.put(KF->fvFeature, (size_t)KF->nEntries, &Q.fvFeatKF) &&
               A.put(F->keypoints, (size_t)F->N, &Q.kpsF) && A.put(F->descriptors, (size_t)F->N * 32, &Q.descF) &&
               A.put(F->fvNode, (size_t)F->nEntries, &Q.fvNodeF) && A.put(F->fvFeature, (size_t)F->nEntries, &Q.fvFeatF);
+    if (fPoint) ok = ok && A.put(fPoint, (size_t)F->N, &Q.fPoint);
     const size_t inBytes = A.off;
-    const int *dMatch, *dN, *dGs; const uint8_t* dEv;
+    const int *dMatch, *dN, *dGs, *dM12 = nullptr; const uint8_t* dEv;
     ok = ok && A.put((const int*)nullptr, (size_t)F->N, &dMatch) && A.put((const int*)nullptr, (size_t)1, &dN) && A.put((const int*)nullptr, (size_t)KF->nEntries + 1, &dGs) &&
          A.put((const uint8_t*)nullptr, (size_t)F->N, &dEv);
+    if (match12) ok = ok && A.put((const int*)nullptr, (size_t)KF->N, &dM12);
     if (!ok) { set_error("matcher staging arena too small"); return ORB_ERR_CAPACITY; }
+    Q.match12 = const_cast<int*>(dM12); Q.strictLow = fPoint ? 1 : 0;
     Q.match = const_cast<int*>(dMatch); Q.nmatches = const_cast<int*>(dN); Q.groupStart = const_cast<int*>(dGs); Q.evBin = const_cast<uint8_t*>(dEv);
     cudaStream_t st = m.stream;
     CK(cudaMemcpyAsync(m.d_arena, m.h_arena, inBytes, cudaMemcpyHostToDevice, st));
     bow_match_kernel<<<1, BM_NT, 0, st>>>(Q);
     m.launches = 1;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(match, dMatch, 4 * (size_t)F->N, cudaMemcpyDeviceToHost, st));
+    if (match) CK(cudaMemcpyAsync(match, dMatch, 4 * (size_t)F->N, cudaMemcpyDeviceToHost, st));
+    if (match12) CK(cudaMemcpyAsync(match12, dM12, 4 * (size_t)KF->N, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(nmatches, dN, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return ORB_OK;
+}
+
+int orbm_search_by_bow(orbm_handle* h, const OrbmBowFrame* KF, const uint8_t* kfPoint, const OrbmBowFrame* F, float nnratio, int checkOrientation,
+                       int32_t* match, int* nmatches) {
+    return search_by_bow_impl(h, KF, kfPoint, F, nullptr, nnratio, checkOrientation, match, nullptr, nmatches);
+}
+int orbm_search_by_bow_kf(orbm_handle* h, const OrbmBowFrame* KF1, const uint8_t* point1, const OrbmBowFrame* KF2, const uint8_t* point2, float nnratio,
+                          int checkOrientation, int32_t* match12, int* nmatches) {
+    if (!point2 || !match12) { set_error("orbm_search_by_bow_kf: bad argument"); return ORB_ERR_ARG; }
+    return search_by_bow_impl(h, KF1, point1, KF2, point2, nnratio, checkOrientation, nullptr, match12, nmatches);
 }
 
 int orbm_fuse_search(orbm_handle* h, const OrbmFrame* KF, const float* invLevelSigma2, float logScaleFactor, const float* Tcw7, const float* Ow3,

@@ -488,3 +488,15 @@ def triangulation_geometry(sc):
     tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
     F12 = np.linalg.inv(K.T) @ tx @ R12 @ np.linalg.inv(K)
     return ep.astype(np.float32), F12.astype(np.float32).reshape(9)
+
+
+def search_by_bow_kf(k1, d1, point1, fv1, k2, d2, point2, fv2, nnratio=0.8, check_ori=True, _lib=None, _name='orbo_search_by_bow_kf'):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12): (nmatches, match12 [N1] = KF2 feature index or -1)."""
+    a = [_c(k1, KP_DTYPE), _c(d1, np.uint8), _c(point1, np.uint8), _c(fv1[0], np.int32), _c(fv1[1], np.int32)]
+    b = [_c(k2, KP_DTYPE), _c(d2, np.uint8), _c(point2, np.uint8), _c(fv2[0], np.int32), _c(fv2[1], np.int32)]
+    m12 = np.full(len(a[0]), -1, np.int32)
+    fn = getattr(_lib or lib(), _name)
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] * 2 + [C.c_float, C.c_int, C.c_void_p]
+    n = fn(len(a[0]), _p(a[0]), _p(a[1]), _p(a[2]), len(a[3]), _p(a[3]), _p(a[4]), len(b[0]), _p(b[0]), _p(b[1]), _p(b[2]), len(b[3]), _p(b[3]), _p(b[4]),
+           nnratio, int(check_ori), _p(m12))
+    return n, m12

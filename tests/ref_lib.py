@@ -253,3 +253,8 @@ def search_for_triangulation(sc, coarse=False, check_ori=True):
                                        len(b[0]), _p(b[0]), _p(b[1]), _p(b[2]), len(b[3]), _p(b[3]), _p(b[4]), _p(c[0]), _p(c[1]), len(c[0]),
                                        *[_p(v) for v in d], int(coarse), int(check_ori), _p(m12), _p(ep), _p(F12))
     return n, m12, ep, F12
+
+
+def search_by_bow_kf(*a, **kw):
+    import oracle_lib as O
+    return O.search_by_bow_kf(*a, _lib=lib(), _name='ref_search_by_bow_kf', **kw)

@@ -281,3 +281,17 @@ def test_search_for_triangulation(orb, t, dts, coarse, ori):
         on, om = O.search_for_triangulation(sc, geo[k][0], geo[k][1], coarse, ori)
         assert nm[k] == on and np.array_equal(m12[k], om), (k, nm[k], on)
         assert on > 30
+
+
+@pytest.mark.parametrize('t,dt,k,L,levelsup,ratio,ori', [(3, 1, 10, 4, 2, 0.8, True), (8, 2, 10, 3, 2, 0.75, True), (15, 1, 6, 4, 3, 0.9, False), (21, 3, 10, 3, 1, 0.8, True)])
+def test_search_by_bow_kf_kf(orb, t, dt, k, L, levelsup, ratio, ori):
+    """f2: ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*) vs the oracle (= the reference's own body, tests/test_ref_pins_oracle_cpu.py)."""
+    voc = O.synthetic_vocabulary(k, L, seed=k + L)
+    rng = np.random.default_rng(t)
+    k1, d1 = S.extract(t); k2, d2 = S.extract(t + dt)
+    fv1 = O.bow_transform(voc, d1, levelsup)[2:]; fv2 = O.bow_transform(voc, d2, levelsup)[2:]
+    p1 = rng.choice([0, 1, 1, 1, 1, 2], len(k1)).astype(np.uint8); p2 = rng.choice([0, 1, 1, 1, 1, 2], len(k2)).astype(np.uint8)
+    m = orb.ORBmatcher(ratio, ori, max_batch=1, max_keypoints=2048, max_mappoints=2048)
+    n, m12 = m.SearchByBoWKF(k1, d1, p1, fv1, k2, d2, p2, fv2)
+    on, om = O.search_by_bow_kf(k1, d1, p1, fv1, k2, d2, p2, fv2, nnratio=ratio, check_ori=ori)
+    assert n == on and np.array_equal(m12, om) and n > 20, (n, on)

@@ -272,3 +272,17 @@ def test_search_for_triangulation_equals_reference(t, dt, coarse, ori):
     assert n == on and np.array_equal(m12, om), (n, on, int((m12 != om).sum()))
     assert n > 30
     assert not sc['mp1'][m12 >= 0].any() and not sc['mp2'][m12[m12 >= 0]].any()
+
+
+@pytest.mark.parametrize('t,dt,k,L,levelsup,ratio,ori', [(3, 1, 10, 4, 2, 0.8, True), (8, 2, 10, 3, 2, 0.75, True), (15, 1, 6, 4, 3, 0.9, False), (21, 3, 10, 3, 1, 0.8, True)])
+def test_search_by_bow_kf_kf_equals_reference(t, dt, k, L, levelsup, ratio, ori):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:765-905): the reference's own body against the oracle."""
+    voc = O.synthetic_vocabulary(k, L, seed=k + L)
+    rng = np.random.default_rng(t)
+    k1, d1 = matcher_scenes.extract(t); k2, d2 = matcher_scenes.extract(t + dt)
+    fv1 = O.bow_transform(voc, d1, levelsup)[2:]; fv2 = O.bow_transform(voc, d2, levelsup)[2:]
+    p1 = rng.choice([0, 1, 1, 1, 1, 2], len(k1)).astype(np.uint8); p2 = rng.choice([0, 1, 1, 1, 1, 2], len(k2)).astype(np.uint8)
+    n, m = R.search_by_bow_kf(k1, d1, p1, fv1, k2, d2, p2, fv2, nnratio=ratio, check_ori=ori)
+    on, om = O.search_by_bow_kf(k1, d1, p1, fv1, k2, d2, p2, fv2, nnratio=ratio, check_ori=ori)
+    assert n == on and np.array_equal(m, om) and n > 20, (n, on)
+    assert (p1[m >= 0] == 1).all() and (p2[m[m >= 0]] == 1).all() and len(set(m[m >= 0].tolist())) == (m >= 0).sum()
