@@ -672,8 +672,35 @@ def main():
             # Mapping side, like the device-resident loop: the graphs of the next batch are uploaded and the results of the previous one
             # downloaded by a mapping thread WHILE the frames of the following rounds run; only the persistent kernel itself gets the
             # GPU to itself, between two rounds (it does not share SMs: see round_device).  Two handles alternate.
-            opt_pair = [opt, orb.Optimizer(max_poses=LBA_CFG['n_kf'], max_points=LBA_CFG['n_pts'], max_edges=LBA_CFG['n_pts'] * LBA_CFG['obs_per_pt'],
-                                           max_batch=NLBA * LR, device=local)]
+            SPLIT = max(1, int(os.environ.get('BENCH_E2E_SPLIT', '1')))
+
+            class OptSet:
+                """One batch of bundle adjustments served by SPLIT handles launched back to back on the mapping stream: each launch then owns only
+                its share of the SMs (clusters of 2 CTAs: 2 x problems SMs) and the frame kernels keep the rest."""
+                def __init__(self, first=None):
+                    n = NLBA * LR
+                    self.parts = [(k * n // SPLIT, (k + 1) * n // SPLIT) for k in range(SPLIT)]
+                    self.h = [first if (k == 0 and first is not None and SPLIT == 1) else
+                              orb.Optimizer(max_poses=LBA_CFG['n_kf'], max_points=LBA_CFG['n_pts'], max_edges=LBA_CFG['n_pts'] * LBA_CFG['obs_per_pt'],
+                                            max_batch=b - a, device=local) for k, (a, b) in enumerate(self.parts)]
+                    if SPLIT > 1:
+                        for h in self.h:
+                            h.set_cluster_size(2)
+
+                def upload(self, pr):
+                    for h, (a, b) in zip(self.h, self.parts):
+                        h.upload(pr[a:b])
+
+                def run_device(self, stream):
+                    for h in self.h:
+                        h.run_device(stream)
+
+                def download(self):
+                    out = []
+                    for h in self.h:
+                        out += h.download()
+                    return out
+            opt_pair = [OptSet(opt), OptSet()]
             up = [None, None]       # upload future per handle
             down = [None, None]     # download future per handle
             # Streams are independent SLAM instances: every group's host thread free-runs through its rounds (no join between rounds, so one

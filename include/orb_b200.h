@@ -285,6 +285,21 @@ typedef struct OrbmFusePoints {
 } OrbmFusePoints;
 int orbm_fuse_search(orbm_handle* h, const OrbmFrame* KF, const float* invLevelSigma2, float logScaleFactor, const float* Tcw7, const float* Ow3,
                      const float* cam4, const OrbmFusePoints* pts, float th, int32_t* bestIdx, int32_t* bestDist);
+/* int ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint)
+ * (include/ORBmatcher.h:102, src/ORBmatcher.cc:1340-1455; LoopClosing::SearchAndFuse): the search of orbm_fuse_search without the chi-square
+ * gate.  Tcw7 / Ow3: the caller's decomposition of Scw (:1349-1350: SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale()) and its
+ * inverse's translation).  state[i]: 1 = searched, 2 = isBad(), 3 = already among the keyframe's map points.  The caller applies :1436-1450
+ * (vpReplacePoint / AddObservation) to every bestDist[i] <= TH_LOW. */
+int orbm_fuse_search_sim3(orbm_handle* h, const OrbmFrame* KF, float logScaleFactor, const float* Tcw7, const float* Ow3, const float* cam4, const OrbmFusePoints* pts,
+                          float th, int32_t* bestIdx, int32_t* bestDist);
+/* int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const Sophus::Sim3f& S12, const float th)
+ * (include/ORBmatcher.h:95, src/ORBmatcher.cc:1457-1674): both projection searches and the agreement test.  One map-point slot per keyframe
+ * feature (pts.M == KF.K; state 0 = none, 1 = good, 2 = bad); pts1.worldPos holds the points of KF1 IN KF2's CAMERA FRAME
+ * (S12.inverse() * (T1w * p3Dw), :1507-1508), pts2.worldPos those of KF2 in KF1's (S12 * (T2w * p3Dw), :1586-1587) -- Sophus expressions the
+ * caller evaluates; normal is not read.  cam4 = pKF1's intrinsics (the reference uses them for both directions).  pre12[i1] = KF2 feature of
+ * an existing vpMatches12[i1] or -1; match12 = pre12 plus the new mutual matches, *nFound = the return value.  Host pointers. */
+int orbm_search_by_sim3(orbm_handle* h, const OrbmFrame* KF1, const OrbmFusePoints* pts1, const OrbmFrame* KF2, const OrbmFusePoints* pts2, float logScaleFactor,
+                        const float* cam4, float th, const int32_t* pre12, int32_t* match12, int* nFound);
 /* int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs, const bool bOnlyStereo,
  * const bool bCoarse) (include/ORBmatcher.h:84-85, src/ORBmatcher.cc:907-1146; monocular keyframes, bOnlyStereo = false) for ONE new keyframe
  * against nKF2 neighbours in one launch (LocalMapping::CreateNewMapPoints loops over vpNeighKFs, src/LocalMapping.cc:296-344).

@@ -430,14 +430,14 @@ int orbo_distinctive_descriptor(int n, const uint8_t* desc) {
     return BestIdx;
 }
 
-// ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th, bRight = false) (src/ORBmatcher.cc:1148-1338), monocular keyframe:
-// the SEARCH of every map point (projection, image / distance / viewing-angle tests, scale prediction, radius search with the chi-square gate,
-// best Hamming distance).  What Fuse then does with a hit (AddObservation / Replace, :1310-1330) mutates the pointer graph and stays with the
-// caller; no map point's search depends on it.  state[i]: 0 NULL, 1 ok, 2 bad, 3 already in the keyframe.  bestIdx -1 / bestDist 256: no candidate.
-// `ex*ex+ey*ey` (:1292) is one FMA in the reference's -O3 -march=native build (checked against oracle/_ref).
-void orbo_fuse_search(int K, const KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors, const float* invLevelSigma2, int nlevels,
-                      float logScaleFactor, const float* Tcw, const float* Ow, const float* cam, int M, const uint8_t* state, const float* xyz,
-                      const float* normal, const float* minDistance, const float* maxDistance, const uint8_t* mpDesc, float th, int* bestIdxOut, int* bestDistOut) {
+}  // extern "C"
+// mode 0: world point + keyframe pose + normal test (the two Fuse overloads; `gate` = the chi-square test of the plain one);
+// mode 2: the point is given in the keyframe's camera frame (SearchBySim3, :1506-1560): depth, projection `fx*x+cx` with x = X * (float)(1.0/Z)
+//         (one FMA in the reference build), distance = its norm, no normal test, no gate.
+static void project_search_impl(int K, const KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors, const float* invLevelSigma2, int nlevels,
+                                float logScaleFactor, const float* Tcw, const float* Ow, const float* cam, int M, const uint8_t* state, const float* xyz,
+                                const float* normal, const float* minDistance, const float* maxDistance, const uint8_t* mpDesc, float th, int mode, bool gate,
+                                int* bestIdxOut, int* bestDistOut) {
     FrameView F;
     F.K = K; F.kps = kps; F.desc = desc;
     F.minX = bounds[0]; F.minY = bounds[1]; F.maxX = bounds[2]; F.maxY = bounds[3];
@@ -445,25 +445,38 @@ void orbo_fuse_search(int K, const KeyPoint* kps, const uint8_t* desc, const flo
     F.gridHInv = (float)GRID_ROWS / (F.maxY - F.minY);
     F.scaleFactors = scaleFactors;
     F.build_grid();
-    const float qw = Tcw[0], qx = Tcw[1], qy = Tcw[2], qz = Tcw[3];
     std::vector<int> vIndices;
     for (int i = 0; i < M; ++i) {
         bestIdxOut[i] = -1; bestDistOut[i] = 256;
         if (state[i] != 1) continue;
         const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
-        float ux = qy * pz - qz * py, uy = qz * px - qx * pz, uz = qx * py - qy * px;
-        ux += ux; uy += uy; uz += uz;
-        const float cx_ = qy * uz - qz * uy, cy_ = qz * ux - qx * uz, cz_ = qx * uy - qy * ux;
-        const float xc = (px + qw * ux) + cx_ + Tcw[4], yc = (py + qw * uy) + cy_ + Tcw[5], zc = (pz + qw * uz) + cz_ + Tcw[6];
-        if (zc < 0.0f) continue;
-        const float u = cam[0] * xc / zc + cam[2], v = cam[1] * yc / zc + cam[3];
+        float u, v, dist3D;
+        if (mode == 0) {
+            const float qw = Tcw[0], qx = Tcw[1], qy = Tcw[2], qz = Tcw[3];
+            float ux = qy * pz - qz * py, uy = qz * px - qx * pz, uz = qx * py - qy * px;
+            ux += ux; uy += uy; uz += uz;
+            const float cx_ = qy * uz - qz * uy, cy_ = qz * ux - qx * uz, cz_ = qx * uy - qy * ux;
+            const float xc = (px + qw * ux) + cx_ + Tcw[4], yc = (py + qw * uy) + cy_ + Tcw[5], zc = (pz + qw * uz) + cz_ + Tcw[6];
+            if (zc < 0.0f) continue;
+            u = cam[0] * xc / zc + cam[2]; v = cam[1] * yc / zc + cam[3];
+        } else {
+            if (pz < 0.0) continue;
+            const float invz = 1.0 / pz;
+            const float x = px * invz, y = py * invz;
+            u = fmaf(cam[0], x, cam[2]); v = fmaf(cam[1], y, cam[3]);
+        }
         if (!(u >= F.minX && u < F.maxX && v >= F.minY && v < F.maxY)) continue;                    // KeyFrame::IsInImage
         const float maxD = 1.2f * maxDistance[i], minD = 0.8f * minDistance[i];
-        const float ox = px - Ow[0], oy = py - Ow[1], oz = pz - Ow[2];
-        const float dist3D = sqrtf((ox * ox + oy * oy) + oz * oz);
-        if (dist3D < minD || dist3D > maxD) continue;
-        const float dot = (ox * normal[3 * i] + oy * normal[3 * i + 1]) + oz * normal[3 * i + 2];
-        if (dot < 0.5 * dist3D) continue;
+        if (mode == 0) {
+            const float ox = px - Ow[0], oy = py - Ow[1], oz = pz - Ow[2];
+            dist3D = sqrtf((ox * ox + oy * oy) + oz * oz);
+            if (dist3D < minD || dist3D > maxD) continue;
+            const float dot = (ox * normal[3 * i] + oy * normal[3 * i + 1]) + oz * normal[3 * i + 2];
+            if (dot < 0.5 * dist3D) continue;
+        } else {
+            dist3D = sqrtf((px * px + py * py) + pz * pz);
+            if (dist3D < minD || dist3D > maxD) continue;
+        }
         const float ratio = maxDistance[i] / dist3D;
         int lvl = (int)std::ceil(std::log(ratio) / logScaleFactor);
         if (lvl < 0) lvl = 0; else if (lvl >= nlevels) lvl = nlevels - 1;
@@ -473,14 +486,64 @@ void orbo_fuse_search(int K, const KeyPoint* kps, const uint8_t* desc, const flo
         for (int idx : vIndices) {
             const int kpLevel = kps[idx].octave;
             if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
-            const float ex = u - kps[idx].x, ey = v - kps[idx].y;
-            const float e2 = fmaf(ex, ex, ey * ey);
-            if (e2 * invLevelSigma2[kpLevel] > 5.99) continue;
+            if (gate) {
+                const float ex = u - kps[idx].x, ey = v - kps[idx].y;
+                const float e2 = fmaf(ex, ex, ey * ey);
+                if (e2 * invLevelSigma2[kpLevel] > 5.99) continue;
+            }
             const int dist = descriptor_distance(mpDesc + (size_t)i * 32, desc + (size_t)idx * 32);
             if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
         }
         bestIdxOut[i] = bestIdx; bestDistOut[i] = bestDist;
     }
+}
+extern "C" {
+// ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th, bRight = false) (src/ORBmatcher.cc:1148-1338), monocular keyframe:
+// the SEARCH of every map point (projection, image / distance / viewing-angle tests, scale prediction, radius search with the chi-square gate,
+// best Hamming distance).  What Fuse then does with a hit (AddObservation / Replace, :1310-1330) mutates the pointer graph and stays with the
+// caller; no map point's search depends on it.  state[i]: 0 NULL, 1 ok, 2 bad, 3 already in the keyframe.  bestIdx -1 / bestDist 256: no candidate.
+// `ex*ex+ey*ey` (:1292) is one FMA in the reference's -O3 -march=native build (checked against oracle/_ref).
+void orbo_fuse_search(int K, const KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors, const float* invLevelSigma2, int nlevels,
+                      float logScaleFactor, const float* Tcw, const float* Ow, const float* cam, int M, const uint8_t* state, const float* xyz,
+                      const float* normal, const float* minDistance, const float* maxDistance, const uint8_t* mpDesc, float th, int* bestIdxOut, int* bestDistOut) {
+    project_search_impl(K, kps, desc, bounds, scaleFactors, invLevelSigma2, nlevels, logScaleFactor, Tcw, Ow, cam, M, state, xyz, normal, minDistance, maxDistance, mpDesc, th,
+                        0, true, bestIdxOut, bestDistOut);
+}
+// ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:1340-1455): the search of the plain overload
+// without the chi-square gate; Tcw / Ow are the caller's decomposition of Scw (:1349-1350).  The walk that fills vpReplacePoint / adds
+// observations (:1436-1450) stays with the caller.
+void orbo_fuse_search_sim3(int K, const KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors, int nlevels, float logScaleFactor, const float* Tcw,
+                           const float* Ow, const float* cam, int M, const uint8_t* state, const float* xyz, const float* normal, const float* minDistance,
+                           const float* maxDistance, const uint8_t* mpDesc, float th, int* bestIdxOut, int* bestDistOut) {
+    project_search_impl(K, kps, desc, bounds, scaleFactors, nullptr, nlevels, logScaleFactor, Tcw, Ow, cam, M, state, xyz, normal, minDistance, maxDistance, mpDesc, th,
+                        0, false, bestIdxOut, bestDistOut);
+}
+// ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1457-1674): both directions + the agreement test.  pc2of1 [N1][3]: the map points of KF1 in KF2's
+// camera frame (S21 * (T1w * p3Dw), :1507-1508), pc1of2 likewise (:1586-1587) -- Sophus expressions of the caller.  state: 0 no map point, 1 good,
+// 2 bad; pre12 [N1]: -1 or the KF2 feature already matched (vbAlreadyMatched1/2, :1478-1491).  match12 [N1] = pre12 plus the new agreements; returns nFound.
+int orbo_search_by_sim3(int nlevels, const float* scaleFactors, float logScaleFactor, const float* bounds, const float* cam,
+                        int N1, const KeyPoint* kps1, const uint8_t* desc1, const uint8_t* state1, const float* pc2of1, const float* min1, const float* max1, const uint8_t* mpDesc1,
+                        int N2, const KeyPoint* kps2, const uint8_t* desc2, const uint8_t* state2, const float* pc1of2, const float* min2, const float* max2, const uint8_t* mpDesc2,
+                        float th, const int* pre12, int* match12) {
+    std::vector<uint8_t> s1(N1), s2(N2);
+    for (int i = 0; i < N1; ++i) s1[i] = state1[i] == 1 && pre12[i] < 0;
+    for (int i = 0; i < N2; ++i) s2[i] = state2[i] == 1;
+    for (int i = 0; i < N1; ++i) if (pre12[i] >= 0 && pre12[i] < N2) s2[pre12[i]] = 0;
+    std::vector<int> m1(N1), d1(N1), m2(N2), d2(N2);
+    project_search_impl(N2, kps2, desc2, bounds, scaleFactors, nullptr, nlevels, logScaleFactor, nullptr, nullptr, cam, N1, s1.data(), pc2of1, nullptr, min1, max1, mpDesc1, th,
+                        2, false, m1.data(), d1.data());
+    project_search_impl(N1, kps1, desc1, bounds, scaleFactors, nullptr, nlevels, logScaleFactor, nullptr, nullptr, cam, N2, s2.data(), pc1of2, nullptr, min2, max2, mpDesc2, th,
+                        2, false, m2.data(), d2.data());
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; ++i1) {
+        match12[i1] = pre12[i1];
+        const int idx2 = d1[i1] <= TH_HIGH ? m1[i1] : -1;
+        if (idx2 >= 0) {
+            const int idx1 = d2[idx2] <= TH_HIGH ? m2[idx2] : -1;
+            if (idx1 == i1) { match12[i1] = idx2; ++nFound; }
+        }
+    }
+    return nFound;
 }
 
 // ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo = false, bCoarse) (src/ORBmatcher.cc:907-1146), monocular keyframes,

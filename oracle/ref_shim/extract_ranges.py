@@ -15,6 +15,9 @@ RANGES = [
     ('matcher_triangulation.inc', 'src/ORBmatcher.cc', 907, 1146, 'int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2'),
     ('pinhole_epipolar.inc', 'src/CameraModels/Pinhole.cpp', 107, 129, 'bool Pinhole::epipolarConstrain(GeometricCamera* pCamera2'),
     ('matcher_fuse.inc', 'src/ORBmatcher.cc', 1148, 1338, 'int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints'),
+    ('matcher_fuse_sim3.inc', 'src/ORBmatcher.cc', 1340, 1455, 'int ORBmatcher::Fuse(KeyFrame *pKF, Sophus::Sim3f &Scw, const vector<MapPoint *> &vpPoints'),
+    ('matcher_sim3.inc', 'src/ORBmatcher.cc', 1457, 1674, 'int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2'),
+    ('mappoint_index_in_kf.inc', 'src/MapPoint.cc', 411, 418, 'tuple<int,int> MapPoint::GetIndexInKeyFrame(KeyFrame *pKF)'),
     ('matcher_last_frame.inc', 'src/ORBmatcher.cc', 1676, 1887, 'int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame'),
     ('matcher_maxima_distance.inc', 'src/ORBmatcher.cc', 2012, 2074, 'void ORBmatcher::ComputeThreeMaxima'),
     ('frame_assign_grid.inc', 'src/Frame.cc', 385, 416, 'void Frame::AssignFeaturesToGrid()'),

@@ -5,6 +5,7 @@
 namespace Eigen {
 Vector3f Vector3f::operator+(const Vector3f& o) const { return Vector3f(v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]); }
 Vector3f Vector3f::operator-(const Vector3f& o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+Vector3f Vector3f::operator/(float d) const { return Vector3f(v[0] / d, v[1] / d, v[2] / d); }
 float Vector3f::dot(const Vector3f& o) const { return (v[0] * o.v[0] + v[1] * o.v[1]) + v[2] * o.v[2]; }
 float Vector3f::norm() const { return sqrtf((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]); }
 Vector3f Matrix3f::operator*(const Vector3f& p) const {
@@ -50,6 +51,25 @@ SE3f SE3f::inverse() const {
     r.t = Eigen::Vector3f(-rt.v[0], -rt.v[1], -rt.v[2]);
     return r;
 }
+SE3f::SE3(const Eigen::Matrix3f& R, const Eigen::Vector3f& trans) : t(trans) {     // Eigen::Quaternion from a rotation matrix (quaternionbase_assign_impl)
+    float tr = (R(0, 0) + R(1, 1)) + R(2, 2);
+    if (tr > 0) {
+        tr = sqrtf(tr + 1.0f);
+        qw = 0.5f * tr; tr = 0.5f / tr;
+        qx = (R(2, 1) - R(1, 2)) * tr; qy = (R(0, 2) - R(2, 0)) * tr; qz = (R(1, 0) - R(0, 1)) * tr;
+    } else {
+        int i = 0;
+        if (R(1, 1) > R(0, 0)) i = 1;
+        if (R(2, 2) > R(i, i)) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        tr = sqrtf(((R(i, i) - R(j, j)) - R(k, k)) + 1.0f);
+        float q[3];
+        q[i] = 0.5f * tr; tr = 0.5f / tr;
+        qw = (R(k, j) - R(j, k)) * tr;
+        q[j] = (R(j, i) + R(i, j)) * tr; q[k] = (R(k, i) + R(i, k)) * tr;
+        qx = q[0]; qy = q[1]; qz = q[2];
+    }
+}
 SE3f SE3f::operator*(const SE3f& o) const {
     SE3f r;
     r.qw = ((qw * o.qw - qx * o.qx) - qy * o.qy) - qz * o.qz;
@@ -68,6 +88,18 @@ Eigen::Matrix3f SE3f::rotationMatrix() const {     // Eigen::QuaternionBase::toR
     R(2, 0) = txz - twy; R(2, 1) = tyz + twx; R(2, 2) = 1 - (txx + tyy);
     return R;
 }
+static SE3f unit_of(const Sim3f& S) { SE3f r; r.qw = S.qw; r.qx = S.qx; r.qy = S.qy; r.qz = S.qz; return r; }
+Eigen::Vector3f Sim3f::operator*(const Eigen::Vector3f& p) const {
+    const Eigen::Vector3f r = unit_of(*this).rotate(p);
+    return Eigen::Vector3f(s * r.v[0] + t.v[0], s * r.v[1] + t.v[1], s * r.v[2] + t.v[2]);
+}
+Sim3f Sim3f::inverse() const {
+    Sim3f r; r.s = 1.0f / s; r.qw = qw; r.qx = -qx; r.qy = -qy; r.qz = -qz;
+    const Eigen::Vector3f rt = unit_of(r).rotate(t);
+    r.t = Eigen::Vector3f(-(r.s * rt.v[0]), -(r.s * rt.v[1]), -(r.s * rt.v[2]));
+    return r;
+}
+Eigen::Matrix3f Sim3f::rotationMatrix() const { return unit_of(*this).rotationMatrix(); }
 Eigen::Matrix3f SO3f::hat(const Eigen::Vector3f& w) {
     Eigen::Matrix3f O;
     O(0, 0) = 0; O(0, 1) = -w(2); O(0, 2) = w(1); O(1, 0) = w(2); O(1, 1) = 0; O(1, 2) = -w(0); O(2, 0) = -w(1); O(2, 1) = w(0); O(2, 2) = 0;

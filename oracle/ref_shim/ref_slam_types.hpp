@@ -38,6 +38,7 @@ template <> struct Matrix<float, 3, 1> {
     // out of line in ref_slam_types.cpp (compiled with -ffp-contract=off, see the header comment)
     Matrix operator+(const Matrix& o) const;
     Matrix operator-(const Matrix& o) const;
+    Matrix operator/(float d) const;
     float dot(const Matrix& o) const;
     float norm() const;
 };
@@ -72,6 +73,7 @@ template <> struct SE3<float> {
     float qw, qx, qy, qz;   // unit quaternion
     Eigen::Vector3f t;
     SE3() : qw(1), qx(0), qy(0), qz(0) {}
+    SE3(const Eigen::Matrix<float, 3, 3>& R, const Eigen::Vector3f& trans);   // se3.hpp:481: rotation matrix -> unit quaternion (Eigen's conversion)
     // so3.hpp:358-367 then se3.hpp:321-324 (+ translation)
     Eigen::Vector3f rotate(const Eigen::Vector3f& p) const;
     Eigen::Vector3f operator*(const Eigen::Vector3f& p) const;
@@ -84,7 +86,17 @@ typedef SE3<float> SE3f;
 template <typename T> struct SO3;
 template <> struct SO3<float> { static Eigen::Matrix3f hat(const Eigen::Vector3f& w); };   // so3.hpp:631-640
 typedef SO3<float> SO3f;
-template <typename T> struct Sim3 {};
+template <typename T> struct Sim3;
+template <> struct Sim3<float> {       // x -> s R x + t with R the rotation of the unit quaternion (Sophus keeps s inside the quaternion's norm)
+    float s, qw, qx, qy, qz;
+    Eigen::Vector3f t;
+    Sim3() : s(1), qw(1), qx(0), qy(0), qz(0) {}
+    Sim3 inverse() const;
+    Eigen::Vector3f operator*(const Eigen::Vector3f& p) const;
+    Eigen::Matrix<float, 3, 3> rotationMatrix() const;
+    const Eigen::Vector3f& translation() const { return t; }
+    float scale() const { return s; }
+};
 typedef Sim3<float> Sim3f;
 }  // namespace Sophus
 
@@ -151,6 +163,7 @@ public:
     bool IsInImage(const float& x, const float& y) const;                       // body: src/KeyFrame.cc:750-753
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;   // body: src/KeyFrame.cc:704-748
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    std::set<MapPoint*> GetMapPoints();                       // the good map points of the keyframe (src/KeyFrame.cc:317-330)
     void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
 };
 
@@ -159,6 +172,7 @@ public:
     std::map<KeyFrame*, std::tuple<int, int>> mObservations;
     std::mutex mMutexFeatures;
     void ComputeDistinctiveDescriptors();                      // body: src/MapPoint.cc:329-403
+    std::tuple<int, int> GetIndexInKeyFrame(KeyFrame* pKF);    // body: src/MapPoint.cc:411-418
     // flattened state (what the reference reads under mutexes)
     Eigen::Vector3f mWorldPos, mNormalVector;
     cv::Mat mDescriptor;
@@ -199,6 +213,7 @@ public:
     float mTrackViewCos = 0, mTrackViewCosR = 0;
 };
 
+inline std::set<MapPoint*> KeyFrame::GetMapPoints() { std::set<MapPoint*> s; for (MapPoint* p : mvpMapPoints) if (p && !p->isBad()) s.insert(p); return s; }
 inline void MapPoint::replace_in_keyframe(MapPoint* pMP) { slotKF->mvpMapPoints[slot] = pMP; }
 
 class Frame {
@@ -249,6 +264,8 @@ public:
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
     int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0, const bool bRight = false);
+    int Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const std::vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint);
+    int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const Sophus::Sim3f& S12, const float th);
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<pair<size_t, size_t>>& vMatchedPairs, const bool bOnlyStereo, const bool bCoarse = false);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     static const int TH_LOW;

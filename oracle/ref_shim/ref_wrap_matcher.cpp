@@ -13,6 +13,8 @@ namespace ORB_SLAM3 {
 #include "matcher_bow_kf_frame.inc"
 #include "matcher_init.inc"
 #include "matcher_fuse.inc"
+#include "matcher_fuse_sim3.inc"
+#include "matcher_sim3.inc"
 #include "matcher_triangulation.inc"
 #include "matcher_bow_kf_kf.inc"
 #include "matcher_last_frame.inc"
@@ -28,6 +30,7 @@ namespace ORB_SLAM3 {
 #include "frame_features_in_area.inc"
 #include "frame_stereo_matches.inc"
 #include "mappoint_distinctive.inc"
+#include "mappoint_index_in_kf.inc"
 #include "keyframe_features_in_area.inc"
 #include "mappoint_predict_scale_kf.inc"
 #include "mappoint_invariance.inc"
@@ -322,6 +325,110 @@ int ref_fuse(int K, const cv::KeyPoint* kps, const uint8_t* desc, const float* b
     const int nFused = matcher.Fuse(&KF, vp, th, false);
     for (int i = 0; i < M; ++i) { action[i] = 0; actionIdx[i] = -1; }
     for (int i = 0; i < M; ++i) { action[i] = mps[i].fuseAction; actionIdx[i] = mps[i].fuseIdx; }
+    return nFused;
+}
+
+// ---- the two Sim3 members (loop closing / map merging) ----
+static void fill_grid_kf(KeyFrame& KF, Pinhole& camera, int K, const cv::KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors, int nlevels,
+                         float logScaleFactor, const float* cam) {
+    KF.N = K; KF.NLeft = -1;
+    KF.mvKeysUn.assign(kps, kps + K); KF.mvKeys = KF.mvKeysUn;
+    KF.mvuRight.assign(K, -1.f);
+    KF.mDescriptors = K ? cv::Mat(K, 32, CV_8UC1, (void*)desc, 32) : cv::Mat();
+    KF.mnMinX = bounds[0]; KF.mnMinY = bounds[1]; KF.mnMaxX = bounds[2]; KF.mnMaxY = bounds[3];
+    KF.mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (KF.mnMaxX - KF.mnMinX);
+    KF.mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (KF.mnMaxY - KF.mnMinY);
+    KF.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    KF.mnScaleLevels = nlevels; KF.mfLogScaleFactor = logScaleFactor;
+    KF.fx = cam[0]; KF.fy = cam[1]; KF.cx = cam[2]; KF.cy = cam[3]; KF.mbf = 0.f;
+    camera.mvParameters.assign(cam, cam + 4); KF.mpCamera = &camera;
+    Frame F;
+    fill_frame(F, K, kps, desc, bounds, scaleFactors, nlevels);
+    KF.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+    for (int i = 0; i < FRAME_GRID_COLS; ++i) for (int j = 0; j < FRAME_GRID_ROWS; ++j) KF.mGrid[i][j] = F.mGrid[i][j];
+    KF.mGridRight = KF.mGrid;
+    KF.mvpMapPoints.assign(K, (MapPoint*)nullptr);
+}
+static void set_pose(Sophus::SE3f& T, const float* p) { T.qw = p[0]; T.qx = p[1]; T.qy = p[2]; T.qz = p[3]; T.t = Eigen::Vector3f(p[4], p[5], p[6]); }
+static void fill_points(std::vector<MapPoint>& mps, int M, const uint8_t* state, const float* xyz, const float* normal, const float* minD, const float* maxD, const uint8_t* desc) {
+    for (int i = 0; i < M; ++i) {
+        MapPoint& p = mps[i];
+        p.index = i; p.mbBad = state[i] == 2;
+        p.mWorldPos = Eigen::Vector3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        if (normal) p.mNormalVector = Eigen::Vector3f(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
+        p.mfMinDistance = minD[i]; p.mfMaxDistance = maxD[i];
+        p.mDescriptor = cv::Mat(1, 32, CV_8UC1, (void*)(desc + (size_t)i * 32), 32);
+    }
+}
+// int ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (src/ORBmatcher.cc:1457-1674).  The keyframes share camera and level tables; map
+// point i of keyframe k sits at its feature i (state 0 none, 1 good, 2 bad).  pre12 [N1]: -1 or the KF2 feature whose map point already is
+// vpMatches12[i].  S12 = (s, qw, qx, qy, qz, tx, ty, tz).  Out: match12 [N1] = KF2 feature of vpMatches12[i] afterwards; pc2of1 [N1][3] /
+// pc1of2 [N2][3]: the map points in the OTHER keyframe's camera frame as the body computes them (inputs of the C-ABI); returns nFound.
+int ref_search_by_sim3(int nlevels, const float* scaleFactors, float logScaleFactor, const float* bounds, const float* cam,
+                       int N1, const cv::KeyPoint* kps1, const uint8_t* desc1, const float* T1w, const uint8_t* state1, const float* xyz1, const float* min1, const float* max1, const uint8_t* mpDesc1,
+                       int N2, const cv::KeyPoint* kps2, const uint8_t* desc2, const float* T2w, const uint8_t* state2, const float* xyz2, const float* min2, const float* max2, const uint8_t* mpDesc2,
+                       const float* S12v, float th, const int* pre12, int* match12, float* pc2of1, float* pc1of2) {
+    KeyFrame KF1, KF2; Pinhole c1, c2;
+    fill_grid_kf(KF1, c1, N1, kps1, desc1, bounds, scaleFactors, nlevels, logScaleFactor, cam);
+    fill_grid_kf(KF2, c2, N2, kps2, desc2, bounds, scaleFactors, nlevels, logScaleFactor, cam);
+    set_pose(KF1.mTcw, T1w); set_pose(KF2.mTcw, T2w);
+    std::vector<MapPoint> mps1(N1), mps2(N2);
+    fill_points(mps1, N1, state1, xyz1, nullptr, min1, max1, mpDesc1);
+    fill_points(mps2, N2, state2, xyz2, nullptr, min2, max2, mpDesc2);
+    for (int i = 0; i < N1; ++i) if (state1[i]) { KF1.mvpMapPoints[i] = &mps1[i]; mps1[i].mObservations[&KF1] = std::make_tuple(i, -1); }
+    for (int i = 0; i < N2; ++i) if (state2[i]) { KF2.mvpMapPoints[i] = &mps2[i]; mps2[i].mObservations[&KF2] = std::make_tuple(i, -1); }
+    Sophus::Sim3f S12;
+    S12.s = S12v[0]; S12.qw = S12v[1]; S12.qx = S12v[2]; S12.qy = S12v[3]; S12.qz = S12v[4]; S12.t = Eigen::Vector3f(S12v[5], S12v[6], S12v[7]);
+    {
+        const Sophus::Sim3f S21 = S12.inverse();
+        for (int i = 0; i < N1; ++i) { const Eigen::Vector3f p = S21 * (KF1.GetPose() * mps1[i].mWorldPos); pc2of1[3 * i] = p(0); pc2of1[3 * i + 1] = p(1); pc2of1[3 * i + 2] = p(2); }
+        for (int i = 0; i < N2; ++i) { const Eigen::Vector3f p = S12 * (KF2.GetPose() * mps2[i].mWorldPos); pc1of2[3 * i] = p(0); pc1of2[3 * i + 1] = p(1); pc1of2[3 * i + 2] = p(2); }
+    }
+    std::vector<MapPoint*> vpMatches12(N1, (MapPoint*)nullptr);
+    for (int i = 0; i < N1; ++i) if (pre12[i] >= 0) vpMatches12[i] = &mps2[pre12[i]];
+    ORBmatcher matcher(0.75f, true);
+    const int n = matcher.SearchBySim3(&KF1, &KF2, vpMatches12, S12, th);
+    for (int i = 0; i < N1; ++i) match12[i] = vpMatches12[i] ? vpMatches12[i]->index : -1;
+    return n;
+}
+// int ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint)
+// (src/ORBmatcher.cc:1340-1455).  Points: state 1 ok, 2 bad, 3 already among the keyframe's map points (as kfPoint index: the point IS the
+// keyframe's point at feature found3[i]).  kfPoint [K]: 0 none, 1 good, 2 bad map point at that keyframe feature.  Out: action [M] 0 none,
+// 1 AddObservation at idx, 2 vpReplacePoint[i] = the keyframe's point at idx, 4 counted only (bad point there); Tcw7 / Ow: the decomposition the
+// body works with; returns nFused.
+int ref_fuse_sim3(int K, const cv::KeyPoint* kps, const uint8_t* desc, const float* bounds, const float* scaleFactors, int nlevels, float logScaleFactor, const float* cam,
+                  const uint8_t* kfPoint, const float* Scwv, int M, const uint8_t* state, const float* xyz, const float* normal, const float* minD, const float* maxD,
+                  const uint8_t* mpDesc, float th, int* action, int* actionIdx, float* Tcw7, float* Ow3) {
+    KeyFrame KF; Pinhole cam0;
+    fill_grid_kf(KF, cam0, K, kps, desc, bounds, scaleFactors, nlevels, logScaleFactor, cam);
+    std::vector<MapPoint> kfMps(K), mps(M);
+    for (int k = 0; k < K; ++k) if (kfPoint[k]) { kfMps[k].index = k; kfMps[k].mbBad = kfPoint[k] == 2; KF.mvpMapPoints[k] = &kfMps[k]; }
+    fill_points(mps, M, state, xyz, normal, minD, maxD, mpDesc);
+    std::vector<MapPoint*> vp(M), repl(M, (MapPoint*)nullptr);
+    int nextFree = 0;
+    for (int i = 0; i < M; ++i) {
+        vp[i] = &mps[i];
+        if (state[i] == 3) {                                    // the very object the keyframe already holds: hand in the keyframe's own point
+            while (nextFree < K && kfPoint[nextFree] != 1) ++nextFree;
+            if (nextFree < K) vp[i] = &kfMps[nextFree++];
+        }
+    }
+    Sophus::Sim3f Scw;
+    Scw.s = Scwv[0]; Scw.qw = Scwv[1]; Scw.qx = Scwv[2]; Scw.qy = Scwv[3]; Scw.qz = Scwv[4]; Scw.t = Eigen::Vector3f(Scwv[5], Scwv[6], Scwv[7]);
+    {
+        const Sophus::SE3f Tcw = Sophus::SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale());
+        const Eigen::Vector3f Ow = Tcw.inverse().translation();
+        Tcw7[0] = Tcw.qw; Tcw7[1] = Tcw.qx; Tcw7[2] = Tcw.qy; Tcw7[3] = Tcw.qz; Tcw7[4] = Tcw.t(0); Tcw7[5] = Tcw.t(1); Tcw7[6] = Tcw.t(2);
+        Ow3[0] = Ow(0); Ow3[1] = Ow(1); Ow3[2] = Ow(2);
+    }
+    ORBmatcher matcher(0.75f, true);
+    const int nFused = matcher.Fuse(&KF, Scw, vp, th, repl);
+    for (int i = 0; i < M; ++i) {
+        action[i] = 0; actionIdx[i] = -1;
+        if (vp[i] != &mps[i]) continue;
+        if (mps[i].fuseAction == 1) { action[i] = 1; actionIdx[i] = mps[i].fuseIdx; }
+        else if (repl[i]) { action[i] = 2; actionIdx[i] = (repl[i] >= kfMps.data() && repl[i] < kfMps.data() + K) ? repl[i]->index : repl[i]->fuseIdx; }
+    }
     return nFused;
 }
 

@@ -500,6 +500,50 @@ class ORBmatcher:
             raise OrbError(rc, 'orbm_fuse_search')
         return bi, bd
 
+    class _Fr(C.Structure):
+        _fields_ = [('K', C.c_int), ('keypoints', C.c_void_p), ('descriptors', C.c_void_p), ('minX', C.c_float), ('minY', C.c_float), ('maxX', C.c_float),
+                    ('maxY', C.c_float), ('scaleFactors', C.c_void_p), ('nlevels', C.c_int)]
+
+    class _Pt(C.Structure):
+        _fields_ = [('M', C.c_int)] + [(n, C.c_void_p) for n in ('state', 'worldPos', 'normal', 'minDistance', 'maxDistance', 'descriptors')]
+
+    def FuseSearchSim3(self, kf_kps, kf_desc, bounds, scale_factors, log_scale_factor, Tcw7, Ow, cam4, state, xyz, normal, min_d, max_d, mp_desc, th=3.0):
+        """The search of ``ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)`` (src/ORBmatcher.cc:1340-1455): (bestIdx, bestDist)."""
+        k = [_c(kf_kps, KP_DTYPE), _c(kf_desc, np.uint8), _c(scale_factors, np.float32)]
+        m = [_c(state, np.uint8), _c(xyz, np.float32), _c(normal, np.float32), _c(min_d, np.float32), _c(max_d, np.float32), _c(mp_desc, np.uint8)]
+        o = [_c(Tcw7, np.float32), _c(Ow, np.float32), _c(cam4, np.float32)]
+        fr = self._Fr(len(k[0]), k[0].ctypes.data, k[1].ctypes.data, *[float(b) for b in bounds], k[2].ctypes.data, len(k[2]))
+        pt = self._Pt(len(m[0]), *[a.ctypes.data for a in m])
+        bi = np.zeros(len(m[0]), np.int32); bd = np.zeros(len(m[0]), np.int32)
+        L = lib()
+        L.orbm_fuse_search_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+        rc = L.orbm_fuse_search_sim3(self._h, C.byref(fr), float(log_scale_factor), _ptr(o[0]), _ptr(o[1]), _ptr(o[2]), C.byref(pt), float(th), _ptr(bi), _ptr(bd))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_fuse_search_sim3')
+        return bi, bd
+
+    def SearchBySim3(self, kf1, kf2, bounds, scale_factors, log_scale_factor, cam4, pre12, th=7.5):
+        """``int ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th)`` (src/ORBmatcher.cc:1457-1674).  kf = dict(kps, desc, state, pcam (the map points
+        in the OTHER keyframe's camera frame), min_d, max_d, mp_desc).  Returns (nFound, match12)."""
+        keep = []
+
+        def side(kf):
+            a = [_c(kf['kps'], KP_DTYPE), _c(kf['desc'], np.uint8), _c(scale_factors, np.float32), _c(kf['state'], np.uint8), _c(kf['pcam'], np.float32),
+                 _c(kf['min_d'], np.float32), _c(kf['max_d'], np.float32), _c(kf['mp_desc'], np.uint8)]
+            keep.append(a)
+            fr = self._Fr(len(a[0]), a[0].ctypes.data, a[1].ctypes.data, *[float(b) for b in bounds], a[2].ctypes.data, len(a[2]))
+            pt = self._Pt(len(a[3]), a[3].ctypes.data, a[4].ctypes.data, None, a[5].ctypes.data, a[6].ctypes.data, a[7].ctypes.data)
+            return fr, pt
+        f1, p1 = side(kf1); f2, p2 = side(kf2)
+        cam = _c(cam4, np.float32); pre = _c(pre12, np.int32)
+        m12 = np.zeros(f1.K, np.int32); n = C.c_int(0)
+        L = lib()
+        L.orbm_search_by_sim3.argtypes = [C.c_void_p] * 5 + [C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = L.orbm_search_by_sim3(self._h, C.byref(f1), C.byref(p1), C.byref(f2), C.byref(p2), float(log_scale_factor), _ptr(cam), float(th), _ptr(pre), _ptr(m12), C.byref(n))
+        if rc != ORB_OK:
+            raise OrbError(rc, 'orbm_search_by_sim3')
+        return n.value, m12
+
     def SearchByBoWKF(self, k1, d1, point1, fv1, k2, d2, point2, fv2):
         """``int ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)`` (src/ORBmatcher.cc:765-905): (nmatches, match12 [N1] = KF2 feature or -1)."""
         class _BF(C.Structure):

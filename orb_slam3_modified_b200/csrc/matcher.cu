@@ -752,6 +752,7 @@ struct FuseParams {
     const uint8_t *state, *mpDesc;
     const float *xyz, *normal, *minD, *maxD, *invSigma2;
     float Tcw[7], Ow[3], logSF;
+    int mode, gate;         // mode 0: world point + pose + normal test (Fuse); 2: point given in the camera frame (SearchBySim3).  gate: chi-square test
     int *bestIdx, *bestDist;
 };
 __global__ void __launch_bounds__(MF_NT) fuse_search_kernel(FuseParams Q) {
@@ -767,25 +768,36 @@ __global__ void __launch_bounds__(MF_NT) fuse_search_kernel(FuseParams Q) {
         bool go = Q.state[i] == 1;
         float u = 0.f, v = 0.f, r = 0.f; int lvl = 0;
         if (go) {
-            const float qw = Q.Tcw[0], qx = Q.Tcw[1], qy = Q.Tcw[2], qz = Q.Tcw[3];
             const float px = Q.xyz[3 * i], py = Q.xyz[3 * i + 1], pz = Q.xyz[3 * i + 2];
-            float ux = fsub(fmul(qy, pz), fmul(qz, py)), uy = fsub(fmul(qz, px), fmul(qx, pz)), uz = fsub(fmul(qx, py), fmul(qy, px));
-            ux = fadd(ux, ux); uy = fadd(uy, uy); uz = fadd(uz, uz);
-            const float cx_ = fsub(fmul(qy, uz), fmul(qz, uy)), cy_ = fsub(fmul(qz, ux), fmul(qx, uz)), cz_ = fsub(fmul(qx, uy), fmul(qy, ux));
-            const float xc = fadd(fadd(fadd(px, fmul(qw, ux)), cx_), Q.Tcw[4]);
-            const float yc = fadd(fadd(fadd(py, fmul(qw, uy)), cy_), Q.Tcw[5]);
-            const float zc = fadd(fadd(fadd(pz, fmul(qw, uz)), cz_), Q.Tcw[6]);
-            go = !(zc < 0.0f);
-            u = fadd(fdiv(fmul(P.cam[0], xc), zc), P.cam[2]);
-            v = fadd(fdiv(fmul(P.cam[1], yc), zc), P.cam[3]);
-            go = go && (u >= P.minX && u < P.maxX && v >= P.minY && v < P.maxY);                                     // KeyFrame::IsInImage
             const float maxRaw = Q.maxD[i];
             const float maxDist = fmul(1.2f, maxRaw), minDist = fmul(0.8f, Q.minD[i]);
-            const float ox = fsub(px, Q.Ow[0]), oy = fsub(py, Q.Ow[1]), oz = fsub(pz, Q.Ow[2]);
-            const float dist3D = __fsqrt_rn(fadd(fadd(fmul(ox, ox), fmul(oy, oy)), fmul(oz, oz)));
-            go = go && !(dist3D < minDist || dist3D > maxDist);
-            const float dot = fadd(fadd(fmul(ox, Q.normal[3 * i]), fmul(oy, Q.normal[3 * i + 1])), fmul(oz, Q.normal[3 * i + 2]));
-            go = go && !((double)dot < 0.5 * (double)dist3D);
+            float dist3D;
+            if (Q.mode == 0) {
+                const float qw = Q.Tcw[0], qx = Q.Tcw[1], qy = Q.Tcw[2], qz = Q.Tcw[3];
+                float ux = fsub(fmul(qy, pz), fmul(qz, py)), uy = fsub(fmul(qz, px), fmul(qx, pz)), uz = fsub(fmul(qx, py), fmul(qy, px));
+                ux = fadd(ux, ux); uy = fadd(uy, uy); uz = fadd(uz, uz);
+                const float cx_ = fsub(fmul(qy, uz), fmul(qz, uy)), cy_ = fsub(fmul(qz, ux), fmul(qx, uz)), cz_ = fsub(fmul(qx, uy), fmul(qy, ux));
+                const float xc = fadd(fadd(fadd(px, fmul(qw, ux)), cx_), Q.Tcw[4]);
+                const float yc = fadd(fadd(fadd(py, fmul(qw, uy)), cy_), Q.Tcw[5]);
+                const float zc = fadd(fadd(fadd(pz, fmul(qw, uz)), cz_), Q.Tcw[6]);
+                go = !(zc < 0.0f);
+                u = fadd(fdiv(fmul(P.cam[0], xc), zc), P.cam[2]);
+                v = fadd(fdiv(fmul(P.cam[1], yc), zc), P.cam[3]);
+                go = go && (u >= P.minX && u < P.maxX && v >= P.minY && v < P.maxY);                                 // KeyFrame::IsInImage
+                const float ox = fsub(px, Q.Ow[0]), oy = fsub(py, Q.Ow[1]), oz = fsub(pz, Q.Ow[2]);
+                dist3D = __fsqrt_rn(fadd(fadd(fmul(ox, ox), fmul(oy, oy)), fmul(oz, oz)));
+                go = go && !(dist3D < minDist || dist3D > maxDist);
+                const float dot = fadd(fadd(fmul(ox, Q.normal[3 * i]), fmul(oy, Q.normal[3 * i + 1])), fmul(oz, Q.normal[3 * i + 2]));
+                go = go && !((double)dot < 0.5 * (double)dist3D);
+            } else {                                                   // src/ORBmatcher.cc:1510-1532 (and :1589-1611)
+                go = !(pz < 0.0f);
+                const float invz = (float)(1.0 / (double)pz);
+                u = __fmaf_rn(P.cam[0], fmul(px, invz), P.cam[2]);       // fx*x+cx: one FMA in the reference build, see oracle
+                v = __fmaf_rn(P.cam[1], fmul(py, invz), P.cam[3]);
+                go = go && (u >= P.minX && u < P.maxX && v >= P.minY && v < P.maxY);
+                dist3D = __fsqrt_rn(fadd(fadd(fmul(px, px), fmul(py, py)), fmul(pz, pz)));
+                go = go && !(dist3D < minDist || dist3D > maxDist);
+            }
             if (go) {
                 lvl = (int)ceilf(fdiv(orbx::logf_glibc(fdiv(maxRaw, dist3D)), Q.logSF));
                 if (lvl < 0) lvl = 0; else if (lvl >= P.nlevels) lvl = P.nlevels - 1;
@@ -798,7 +810,9 @@ __global__ void __launch_bounds__(MF_NT) fuse_search_kernel(FuseParams Q) {
             const uint4 a = __ldg(dp), b = __ldg(dp + 1);
             mpd[0] = a.x; mpd[1] = a.y; mpd[2] = a.z; mpd[3] = a.w; mpd[4] = b.x; mpd[5] = b.y; mpd[6] = b.z; mpd[7] = b.w;
             const float* isg = Q.invSigma2;
+            const bool gate = Q.gate != 0;
             const TopK<1> t = scan_candidates<1>(P, S, 0, u, v, r, lvl - 1, lvl, mpd, [&](int idx) {
+                if (!gate) return true;
                 const float ex = fsub(u, S.kx[idx]), ey = fsub(v, S.ky[idx]);
                 const float e2 = __fmaf_rn(ex, ex, fmul(ey, ey));                     // one FMA in the reference build, see oracle
                 return !((double)fmul(e2, isg[S.koct[idx]]) > 5.99);
@@ -1419,9 +1433,9 @@ int orbm_search_by_bow_kf(orbm_handle* h, const OrbmBowFrame* KF1, const uint8_t
     return search_by_bow_impl(h, KF1, point1, KF2, point2, nnratio, checkOrientation, nullptr, match12, nmatches);
 }
 
-int orbm_fuse_search(orbm_handle* h, const OrbmFrame* KF, const float* invLevelSigma2, float logScaleFactor, const float* Tcw7, const float* Ow3,
-                     const float* cam4, const OrbmFusePoints* pts, float th, int32_t* bestIdx, int32_t* bestDist) {
-    if (!h || !KF || !invLevelSigma2 || !Tcw7 || !Ow3 || !cam4 || !pts || !bestIdx || !bestDist || pts->M < 0 || KF->K < 0 || KF->K > h->m.kcap ||
+static int project_search_impl(orbm_handle* h, const OrbmFrame* KF, const float* invLevelSigma2, float logScaleFactor, const float* Tcw7, const float* Ow3,
+                               const float* cam4, const OrbmFusePoints* pts, float th, int mode, int32_t* bestIdx, int32_t* bestDist) {
+    if (!h || !KF || (mode == 0 && (!Tcw7 || !Ow3)) || !cam4 || !pts || !bestIdx || !bestDist || pts->M < 0 || KF->K < 0 || KF->K > h->m.kcap ||
         !KF->scaleFactors || KF->nlevels < 1 || KF->nlevels > 256 || !(KF->maxX > KF->minX) || !(KF->maxY > KF->minY)) {
         set_error("orbm_fuse_search: bad argument (KF.K <= max_keypoints of the handle)"); return ORB_ERR_ARG;
     }
@@ -1446,10 +1460,10 @@ int orbm_fuse_search(orbm_handle* h, const OrbmFrame* KF, const float* invLevelS
     CK(cudaMemcpyAsync(d + oKp, KF->keypoints, K * sizeof(OrbKeyPoint), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d + oDe, KF->descriptors, K * 32, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d + oSf, KF->scaleFactors, 4 * (size_t)KF->nlevels, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d + oIs, invLevelSigma2, 4 * (size_t)KF->nlevels, cudaMemcpyHostToDevice, st));
+    if (invLevelSigma2) CK(cudaMemcpyAsync(d + oIs, invLevelSigma2, 4 * (size_t)KF->nlevels, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d + oSt, pts->state, M, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d + oXy, pts->worldPos, 12 * M, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d + oNo, pts->normal, 12 * M, cudaMemcpyHostToDevice, st));
+    if (mode == 0) CK(cudaMemcpyAsync(d + oNo, pts->normal, 12 * M, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d + oMi, pts->minDistance, 4 * M, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d + oMa, pts->maxDistance, 4 * M, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d + oMd, pts->descriptors, 32 * M, cudaMemcpyHostToDevice, st));
@@ -1468,7 +1482,8 @@ int orbm_fuse_search(orbm_handle* h, const OrbmFrame* KF, const float* invLevelS
     if (rc) return rc;
     Q.K = (int)K; Q.M = (int)M; Q.state = d + oSt; Q.mpDesc = d + oMd; Q.xyz = (const float*)(d + oXy); Q.normal = (const float*)(d + oNo);
     Q.minD = (const float*)(d + oMi); Q.maxD = (const float*)(d + oMa); Q.invSigma2 = (const float*)(d + oIs);
-    memcpy(Q.Tcw, Tcw7, 28); memcpy(Q.Ow, Ow3, 12); Q.logSF = logScaleFactor;
+    if (mode == 0) { memcpy(Q.Tcw, Tcw7, 28); memcpy(Q.Ow, Ow3, 12); }
+    Q.logSF = logScaleFactor; Q.mode = mode; Q.gate = invLevelSigma2 ? 1 : 0;
     Q.bestIdx = (int*)(d + oBi); Q.bestDist = (int*)(d + oBd);
     const int grid = (int)std::min<size_t>(16, (M + 127) / 128);          // every CTA rebuilds the grid: a few CTAs, ~8 map points per warp
     fuse_search_kernel<<<grid, MF_NT, sm, st>>>(Q);
@@ -1477,6 +1492,46 @@ int orbm_fuse_search(orbm_handle* h, const OrbmFrame* KF, const float* invLevelS
     CK(cudaMemcpyAsync(bestIdx, d + oBi, 4 * M, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(bestDist, d + oBd, 4 * M, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_fuse_search(orbm_handle* h, const OrbmFrame* KF, const float* invLevelSigma2, float logScaleFactor, const float* Tcw7, const float* Ow3,
+                     const float* cam4, const OrbmFusePoints* pts, float th, int32_t* bestIdx, int32_t* bestDist) {
+    if (!invLevelSigma2 || !pts || !pts->normal) { set_error("orbm_fuse_search: bad argument"); return ORB_ERR_ARG; }
+    return project_search_impl(h, KF, invLevelSigma2, logScaleFactor, Tcw7, Ow3, cam4, pts, th, 0, bestIdx, bestDist);
+}
+int orbm_fuse_search_sim3(orbm_handle* h, const OrbmFrame* KF, float logScaleFactor, const float* Tcw7, const float* Ow3, const float* cam4, const OrbmFusePoints* pts,
+                          float th, int32_t* bestIdx, int32_t* bestDist) {
+    if (!pts || !pts->normal) { set_error("orbm_fuse_search_sim3: bad argument"); return ORB_ERR_ARG; }
+    return project_search_impl(h, KF, nullptr, logScaleFactor, Tcw7, Ow3, cam4, pts, th, 0, bestIdx, bestDist);
+}
+int orbm_search_by_sim3(orbm_handle* h, const OrbmFrame* KF1, const OrbmFusePoints* pts1, const OrbmFrame* KF2, const OrbmFusePoints* pts2, float logScaleFactor,
+                        const float* cam4, float th, const int32_t* pre12, int32_t* match12, int* nFound) {
+    if (!h || !KF1 || !KF2 || !pts1 || !pts2 || !pre12 || !match12 || !nFound || pts1->M != KF1->K || pts2->M != KF2->K) {
+        set_error("orbm_search_by_sim3: bad argument (one map-point slot per keyframe feature)"); return ORB_ERR_ARG;
+    }
+    const int N1 = KF1->K, N2 = KF2->K;
+    for (int i = 0; i < N1; ++i) if (pre12[i] >= N2) { set_error("orbm_search_by_sim3: pre12 out of range"); return ORB_ERR_ARG; }
+    // vbAlreadyMatched1 / 2 (:1478-1491) folded into the search flags
+    std::vector<uint8_t> s1(N1), s2(N2);
+    for (int i = 0; i < N1; ++i) s1[i] = pts1->state[i] == 1 && pre12[i] < 0;
+    for (int i = 0; i < N2; ++i) s2[i] = pts2->state[i] == 1;
+    for (int i = 0; i < N1; ++i) if (pre12[i] >= 0) s2[pre12[i]] = 0;
+    std::vector<int32_t> m1(N1), d1(N1), m2(N2), d2(N2);
+    OrbmFusePoints a = *pts1, b = *pts2;
+    a.state = s1.data(); b.state = s2.data();
+    int rc = project_search_impl(h, KF2, nullptr, logScaleFactor, nullptr, nullptr, cam4, &a, th, 2, m1.data(), d1.data());      // KF1's points in KF2 (:1497-1573)
+    if (rc) return rc;
+    rc = project_search_impl(h, KF1, nullptr, logScaleFactor, nullptr, nullptr, cam4, &b, th, 2, m2.data(), d2.data());          // KF2's points in KF1 (:1576-1652)
+    if (rc) return rc;
+    h->m.launches = 2;
+    int n = 0;
+    for (int i1 = 0; i1 < N1; ++i1) {                                                                                               // agreement (:1655-1671)
+        match12[i1] = pre12[i1];
+        const int idx2 = d1[i1] <= TH_HIGH ? m1[i1] : -1;
+        if (idx2 >= 0 && (d2[idx2] <= TH_HIGH ? m2[idx2] : -1) == i1) { match12[i1] = idx2; ++n; }
+    }
+    *nFound = n;
     return ORB_OK;
 }
 

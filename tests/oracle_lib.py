@@ -500,3 +500,77 @@ def search_by_bow_kf(k1, d1, point1, fv1, k2, d2, point2, fv2, nnratio=0.8, chec
     n = fn(len(a[0]), _p(a[0]), _p(a[1]), _p(a[2]), len(a[3]), _p(a[3]), _p(a[4]), len(b[0]), _p(b[0]), _p(b[1]), _p(b[2]), len(b[3]), _p(b[3]), _p(b[4]),
            nnratio, int(check_ori), _p(m12))
     return n, m12
+
+
+def fuse_search_sim3(sc, Tcw, Ow, th=3.0):
+    """The search of ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint): (bestIdx, bestDist); Tcw / Ow = the decomposition of Scw."""
+    M = len(sc['state'])
+    bi = np.zeros(M, np.int32); bd = np.zeros(M, np.int32)
+    L = lib()
+    L.orbo_fuse_search_sim3.restype = None
+    L.orbo_fuse_search_sim3.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_float] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_void_p, C.c_void_p]
+    a = [_c(sc['kps'], KP_DTYPE), _c(sc['desc'], np.uint8), _c(sc['bounds'], np.float32), _c(sc['sf'], np.float32)]
+    b = [_c(Tcw, np.float32), _c(Ow, np.float32), _c(sc['cam'], np.float32)]
+    c = [_c(sc['state'], np.uint8), _c(sc['xyz'], np.float32), _c(sc['normal'], np.float32), _c(sc['min_d'], np.float32), _c(sc['max_d'], np.float32), _c(sc['mp_desc'], np.uint8)]
+    L.orbo_fuse_search_sim3(len(a[0]), *[_p(v) for v in a], len(a[3]), float(sc['log_sf']), *[_p(v) for v in b], M, *[_p(v) for v in c], th, _p(bi), _p(bd))
+    return bi, bd
+
+
+def sim3_scene(t, dt=2, seed=0):
+    """Two keyframes with a map point at (most of) their features and a similarity S12 close to the true relative pose, for ORBmatcher::SearchBySim3."""
+    import matcher_scenes
+    from orb_slam3_modified_b200 import synth
+    rng = np.random.default_rng(seed + 7 * t + dt)
+    tab = OracleExtractor().tables()
+    out = dict(sf=tab['scale'], log_sf=np.float32(np.log(np.float32(1.2))), bounds=(0.0, 0.0, 640.0, 480.0), cam=synth.camera())
+    for k, tt in ((1, t), (2, t + dt)):
+        kp, de = matcher_scenes.extract(tt)
+        P = synth.backproject(np.stack([kp['x'], kp['y']], 1), tt) + rng.normal(0, 0.003, (len(kp), 3))
+        T = synth.pose(tt)
+        w, x, y, z = T[:4]
+        Rm = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                       [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        dist = np.linalg.norm(P - (-Rm.T @ T[4:]), axis=1)
+        dmax = (dist * 1.2 ** kp['octave'] * rng.uniform(0.9, 1.2, len(kp))).astype(np.float32)
+        out.update({'k%d' % k: kp, 'd%d' % k: de, 'T%dw' % k: T.astype(np.float32), 'R%d' % k: Rm, 't%d' % k: T[4:], 'state%d' % k: rng.choice([0, 1, 1, 1, 1, 1, 2], len(kp)).astype(np.uint8),
+                    'xyz%d' % k: P.astype(np.float32), 'max%d' % k: dmax, 'min%d' % k: (dmax / np.float32(1.2 ** 7)).astype(np.float32),
+                    'mpd%d' % k: de.copy()})
+    # S12: camera 2 -> camera 1 (scale 1 + a little), R12 = R1 R2^T, t12 = t1 - R12 t2
+    R12 = out['R1'] @ out['R2'].T
+    t12 = out['t1'] - R12 @ out['t2']
+    tr = np.trace(R12)
+    qw = np.sqrt(max(tr + 1, 1e-12)) / 2
+    q = np.array([qw, (R12[2, 1] - R12[1, 2]) / (4 * qw), (R12[0, 2] - R12[2, 0]) / (4 * qw), (R12[1, 0] - R12[0, 1]) / (4 * qw)])
+    out['S12'] = np.concatenate([[1.0 + 0.01 * rng.normal()], q / np.linalg.norm(q), t12 + rng.normal(0, 0.002, 3)]).astype(np.float32)
+    pre = np.full(len(out['k1']), -1, np.int32)
+    cand = np.flatnonzero(out['state1'] == 1)[:40]
+    good2 = np.flatnonzero(out['state2'] == 1)
+    pre[cand[::4]] = rng.choice(good2, len(cand[::4]), replace=False)
+    out['pre12'] = pre
+    return out
+
+
+def search_by_sim3(sc, pc2of1, pc1of2, th=7.5):
+    L = lib()
+    m12 = np.zeros(len(sc['k1']), np.int32)
+    L.orbo_search_by_sim3.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] + [C.c_void_p] * 7 + [C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p]
+    g = [_c(sc['sf'], np.float32), _c(sc['bounds'], np.float32), _c(sc['cam'], np.float32)]
+    a = [_c(sc['k1'], KP_DTYPE), _c(sc['d1'], np.uint8), _c(sc['state1'], np.uint8), _c(pc2of1, np.float32), _c(sc['min1'], np.float32), _c(sc['max1'], np.float32), _c(sc['mpd1'], np.uint8)]
+    b = [_c(sc['k2'], KP_DTYPE), _c(sc['d2'], np.uint8), _c(sc['state2'], np.uint8), _c(pc1of2, np.float32), _c(sc['min2'], np.float32), _c(sc['max2'], np.float32), _c(sc['mpd2'], np.uint8)]
+    pre = _c(sc['pre12'], np.int32)
+    n = L.orbo_search_by_sim3(len(g[0]), _p(g[0]), float(sc['log_sf']), _p(g[1]), _p(g[2]), len(a[0]), *[_p(v) for v in a], len(b[0]), *[_p(v) for v in b], th, _p(pre), _p(m12))
+    return n, m12
+
+
+def sim3_camera_points(sc):
+    """The map points of each keyframe in the other keyframe's camera frame (S21 * (T1w * p), S12 * (T2w * p); src/ORBmatcher.cc:1507-1508, :1586-1587)
+    in numpy float64, rounded to float32: inputs of the search (the reference evaluates them with Sophus)."""
+    s, q, t = float(sc['S12'][0]), sc['S12'][1:5].astype(np.float64), sc['S12'][5:].astype(np.float64)
+    w, x, y, z = q
+    R12 = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                    [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    c1 = sc['xyz1'].astype(np.float64) @ sc['R1'].T + sc['t1']
+    c2 = sc['xyz2'].astype(np.float64) @ sc['R2'].T + sc['t2']
+    p21 = ((c1 - t) @ R12) / s              # S21 = S12^-1
+    p12 = s * (c2 @ R12.T) + t
+    return p21.astype(np.float32), p12.astype(np.float32)

@@ -258,3 +258,31 @@ def search_for_triangulation(sc, coarse=False, check_ori=True):
 def search_by_bow_kf(*a, **kw):
     import oracle_lib as O
     return O.search_by_bow_kf(*a, _lib=lib(), _name='ref_search_by_bow_kf', **kw)
+
+
+def search_by_sim3(sc, th=7.5):
+    """ORBmatcher::SearchBySim3 itself: (nFound, match12, pc2of1, pc1of2) -- see ref_wrap_matcher.cpp."""
+    L = lib()
+    N1, N2 = len(sc['k1']), len(sc['k2'])
+    m12 = np.zeros(N1, np.int32); p21 = np.zeros((N1, 3), np.float32); p12 = np.zeros((N2, 3), np.float32)
+    L.ref_search_by_sim3.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + ([C.c_int] + [C.c_void_p] * 8) * 2 + [C.c_void_p, C.c_float] + [C.c_void_p] * 4
+    g = [_c(sc['sf'], np.float32), _c(sc['bounds'], np.float32), _c(sc['cam'], np.float32)]
+    side = lambda k: [_c(sc['k%d' % k], KP_DTYPE), _c(sc['d%d' % k], np.uint8), _c(sc['T%dw' % k], np.float32), _c(sc['state%d' % k], np.uint8), _c(sc['xyz%d' % k], np.float32),
+                      _c(sc['min%d' % k], np.float32), _c(sc['max%d' % k], np.float32), _c(sc['mpd%d' % k], np.uint8)]
+    a, b = side(1), side(2)
+    S = _c(sc['S12'], np.float32); pre = _c(sc['pre12'], np.int32)
+    n = L.ref_search_by_sim3(len(g[0]), _p(g[0]), float(sc['log_sf']), _p(g[1]), _p(g[2]), N1, *[_p(v) for v in a], N2, *[_p(v) for v in b], _p(S), th, _p(pre), _p(m12), _p(p21), _p(p12))
+    return n, m12, p21, p12
+
+
+def fuse_sim3(sc, Scw, kf_state, th=3.0):
+    """ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) itself: (nFused, action, action_idx, Tcw7, Ow)."""
+    L = lib()
+    M = len(sc['state'])
+    act = np.zeros(M, np.int32); idx = np.zeros(M, np.int32); T7 = np.zeros(7, np.float32); Ow = np.zeros(3, np.float32)
+    L.ref_fuse_sim3.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_float] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float] + [C.c_void_p] * 4
+    a = [_c(sc['kps'], KP_DTYPE), _c(sc['desc'], np.uint8), _c(sc['bounds'], np.float32), _c(sc['sf'], np.float32)]
+    b = [_c(sc['cam'], np.float32), _c(kf_state, np.uint8), _c(Scw, np.float32)]
+    c = [_c(sc['state'], np.uint8), _c(sc['xyz'], np.float32), _c(sc['normal'], np.float32), _c(sc['min_d'], np.float32), _c(sc['max_d'], np.float32), _c(sc['mp_desc'], np.uint8)]
+    n = L.ref_fuse_sim3(len(a[0]), *[_p(v) for v in a], len(a[3]), float(sc['log_sf']), *[_p(v) for v in b], M, *[_p(v) for v in c], th, _p(act), _p(idx), _p(T7), _p(Ow))
+    return n, act, idx, T7, Ow

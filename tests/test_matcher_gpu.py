@@ -295,3 +295,28 @@ def test_search_by_bow_kf_kf(orb, t, dt, k, L, levelsup, ratio, ori):
     n, m12 = m.SearchByBoWKF(k1, d1, p1, fv1, k2, d2, p2, fv2)
     on, om = O.search_by_bow_kf(k1, d1, p1, fv1, k2, d2, p2, fv2, nnratio=ratio, check_ori=ori)
     assert n == on and np.array_equal(m12, om) and n > 20, (n, on)
+
+
+@pytest.mark.parametrize('t,dt,th', [(5, 2, 7.5), (13, 3, 7.5), (20, 1, 4.0)])
+def test_search_by_sim3(orb, t, dt, th):
+    """f2: ORBmatcher::SearchBySim3 (both projection searches + agreement) vs the oracle (= the reference's own body, tests/test_ref_pins_oracle_cpu.py)."""
+    sc = O.sim3_scene(t, dt)
+    p21, p12 = O.sim3_camera_points(sc)
+    side = lambda k, pc: dict(kps=sc['k%d' % k], desc=sc['d%d' % k], state=sc['state%d' % k], pcam=pc, min_d=sc['min%d' % k], max_d=sc['max%d' % k], mp_desc=sc['mpd%d' % k])
+    m = orb.ORBmatcher(0.75, True, max_batch=1, max_keypoints=2048, max_mappoints=64)
+    n, m12 = m.SearchBySim3(side(1, p21), side(2, p12), sc['bounds'], sc['sf'], sc['log_sf'], sc['cam'], sc['pre12'], th)
+    on, om = O.search_by_sim3(sc, p21, p12, th)
+    assert n == on and np.array_equal(m12, om) and n > 50, (n, on)
+
+
+@pytest.mark.parametrize('t,th', [(6, 3.0), (14, 4.0)])
+def test_fuse_search_sim3(orb, t, th):
+    """f2: the search of ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) vs the oracle."""
+    sc = O.fuse_scene(t)
+    m = orb.ORBmatcher(0.6, True, max_batch=1, max_keypoints=2048, max_mappoints=64)
+    bi, bd = m.FuseSearchSim3(sc['kps'], sc['desc'], sc['bounds'], sc['sf'], sc['log_sf'], sc['Tcw'], sc['Ow'], sc['cam'], sc['state'], sc['xyz'], sc['normal'], sc['min_d'],
+                              sc['max_d'], sc['mp_desc'], th)
+    obi, obd = O.fuse_search_sim3(sc, sc['Tcw'], sc['Ow'], th)
+    assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and (bd <= 50).sum() > 100
+    gbi, gbd = O.fuse_search(sc, th)
+    assert (bd <= gbd).all() and (bd < gbd).any()          # without the chi-square gate the best candidate can only get closer

@@ -286,3 +286,36 @@ def test_search_by_bow_kf_kf_equals_reference(t, dt, k, L, levelsup, ratio, ori)
     on, om = O.search_by_bow_kf(k1, d1, p1, fv1, k2, d2, p2, fv2, nnratio=ratio, check_ori=ori)
     assert n == on and np.array_equal(m, om) and n > 20, (n, on)
     assert (p1[m >= 0] == 1).all() and (p2[m[m >= 0]] == 1).all() and len(set(m[m >= 0].tolist())) == (m >= 0).sum()
+
+
+@pytest.mark.parametrize('t,dt,th', [(5, 2, 7.5), (13, 3, 7.5), (20, 1, 4.0)])
+def test_search_by_sim3_equals_reference(t, dt, th):
+    """ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1457-1674): the reference's own body against the oracle, given the camera-frame points the body
+    computed from S12 / S21."""
+    sc = O.sim3_scene(t, dt)
+    n, m12, p21, p12 = R.search_by_sim3(sc, th)
+    on, om = O.search_by_sim3(sc, p21, p12, th)
+    assert n == on and np.array_equal(m12, om), (n, on, int((m12 != om).sum()))
+    assert n > 50 and (m12[sc['pre12'] >= 0] == sc['pre12'][sc['pre12'] >= 0]).all()
+
+
+@pytest.mark.parametrize('t,th', [(6, 3.0), (14, 4.0)])
+def test_fuse_sim3_search_equals_reference(t, th):
+    """ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:1340-1455): every action the reference body took names the oracle's
+    best keypoint, the return value is the number of oracle hits within TH_LOW."""
+    sc = O.fuse_scene(t)
+    rng = np.random.default_rng(t)
+    sc['state'] = np.where(sc['state'] == 0, 1, sc['state']).astype(np.uint8)          # this overload is never handed NULL points
+    kf_state = rng.choice([0, 0, 1, 1, 2], len(sc['kps'])).astype(np.uint8)
+    s = np.float32(1.0 + 0.02 * rng.normal())
+    Scw = np.concatenate([[s], sc['Tcw'][:4], sc['Tcw'][4:] * s]).astype(np.float32)
+    n, act, idx, T7, Ow = R.fuse_sim3(sc, Scw, kf_state, th)
+    bi, bd = O.fuse_search_sim3(sc, T7, Ow, th)
+    hit = bd <= 50
+    assert n == int(hit.sum()) and n > 100, (n, int(hit.sum()))
+    logged = act > 0
+    assert hit[logged].all() and np.array_equal(idx[logged], bi[logged])
+    # hits without a logged action: the keyframe's point at that keypoint is bad (counted, nothing done)
+    silent = hit & ~logged
+    assert (kf_state[bi[silent]] == 2).all() and {1, 2} <= set(act[hit].tolist())
+    assert not hit[sc['state'] != 1].any()
