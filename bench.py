@@ -409,7 +409,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the BASELINE configs[0] / configs[2] latency lines')
     ap.add_argument('--dev-groups', type=int, default=2, help='stream groups (own handles + CUDA stream) in the device-resident measurement')
-    ap.add_argument('--e2e-groups', type=int, default=4, help='stream groups (host threads with their own handles) in flight in the e2e measurement')
+    ap.add_argument('--e2e-groups', type=int, default=3, help='stream groups (host threads with their own handles) in flight in the e2e measurement')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -465,7 +465,7 @@ def main():
     probs = lba_problems(NLBA * LR, rank)   # the keyframes of LR rounds: one LocalBundleAdjustment each, solved by ONE kernel launch
     opt.upload(probs)                      # flattened graphs resident in HBM for the `value` measurement
     stream = torch.cuda.current_stream()
-    lba_stream = torch.cuda.Stream(device=dev, priority=-1 if os.environ.get('BENCH_LBA_PRIO') else 0)      # LocalMapping runs beside Tracking in the reference (src/System.cc:197)
+    lba_stream = torch.cuda.Stream(device=dev)      # LocalMapping runs beside Tracking in the reference (src/System.cc:197)
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
     # The B streams are served as DG groups, each with its own extractor / matcher handles on its own CUDA stream: the latency-bound
@@ -656,7 +656,6 @@ def main():
             exs = [orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, W, H, b1 - b0, local) for b0, b1 in hb]
             mts = [orb.ORBmatcher(0.9, True, max_batch=b1 - b0, max_keypoints=cap, max_mappoints=cap, device=local) for b0, b1 in hb]
             pool = ThreadPoolExecutor(G + 2)
-            E2E_EXCL = os.environ.get('BENCH_E2E_LBA', 'concurrent') == 'exclusive'
 
             def frames_job(g, i):
                 cur, lst = i & 1, (i + 1) & 1
@@ -669,38 +668,13 @@ def main():
                 mts[g].search_last_frame_batch(d, TH_PROJ, match_h[b0:b1], claimed_h[b0:b1], nmatch_h[b0:b1], resident=exs[g].resident_slabs())
                 return int(nK_h[b0:b1].sum())
 
-            # Mapping side, like the device-resident loop: the graphs of the next batch are uploaded and the results of the previous one
-            # downloaded by a mapping thread WHILE the frames of the following rounds run; only the persistent kernel itself gets the
-            # GPU to itself, between two rounds (it does not share SMs: see round_device).  Two handles alternate.
-            SPLIT = max(1, int(os.environ.get('BENCH_E2E_SPLIT', '1')))
-
-            class OptSet:
-                """One batch of bundle adjustments served by SPLIT handles launched back to back on the mapping stream: each launch then owns only
-                its share of the SMs (clusters of 2 CTAs: 2 x problems SMs) and the frame kernels keep the rest."""
-                def __init__(self, first=None):
-                    n = NLBA * LR
-                    self.parts = [(k * n // SPLIT, (k + 1) * n // SPLIT) for k in range(SPLIT)]
-                    self.h = [first if (k == 0 and first is not None and SPLIT == 1) else
-                              orb.Optimizer(max_poses=LBA_CFG['n_kf'], max_points=LBA_CFG['n_pts'], max_edges=LBA_CFG['n_pts'] * LBA_CFG['obs_per_pt'],
-                                            max_batch=b - a, device=local) for k, (a, b) in enumerate(self.parts)]
-                    if SPLIT > 1:
-                        for h in self.h:
-                            h.set_cluster_size(2)
-
-                def upload(self, pr):
-                    for h, (a, b) in zip(self.h, self.parts):
-                        h.upload(pr[a:b])
-
-                def run_device(self, stream):
-                    for h in self.h:
-                        h.run_device(stream)
-
-                def download(self):
-                    out = []
-                    for h in self.h:
-                        out += h.download()
-                    return out
-            opt_pair = [OptSet(opt), OptSet()]
+            # Mapping side: the graphs of a batch are uploaded and the results of the previous one downloaded by a mapping thread WHILE the frames
+            # of the following rounds run; two handles alternate.  Here the persistent kernel shares the GPU with the frame kernels: the loop is
+            # bound by the sum of the two kernel loads (about 5.6 ms of GPU time per round) whichever way they are interleaved -- gating the frame
+            # calls while a bundle-adjustment launch runs, splitting the launch into halves that own half of the SMs each, and a high-priority
+            # mapping stream were all measured and none was faster (tools/run_e2e_var.sh).
+            opt_pair = [opt, orb.Optimizer(max_poses=LBA_CFG['n_kf'], max_points=LBA_CFG['n_pts'], max_edges=LBA_CFG['n_pts'] * LBA_CFG['obs_per_pt'],
+                                           max_batch=NLBA * LR, device=local)]
             up = [None, None]       # upload future per handle
             down = [None, None]     # download future per handle
             # Streams are independent SLAM instances: every group's host thread free-runs through its rounds (no join between rounds, so one
@@ -711,19 +685,13 @@ def main():
             sys.setswitchinterval(float(os.environ.get('BENCH_SWITCH_INTERVAL', '5e-5')))
             cv = threading.Condition()
             done = [0] * G                                          # rounds finished per group (absolute round counter)
-            state = {'outs': None, 'nbatch': 0, 'err': None, 'lba_wants': False, 'frames_in_flight': 0}
+            state = {'outs': None, 'nbatch': 0, 'err': None}
 
             def group_loop(g, r0, r1):
                 try:
                     for i in range(r0, r1):
-                        if E2E_EXCL:                                # gate: no frame call starts while a bundle-adjustment launch owns the GPU
-                            with cv:
-                                cv.wait_for(lambda: not state['lba_wants'])
-                                state['frames_in_flight'] += 1
                         frames_job(g, i)
                         with cv:
-                            if E2E_EXCL:
-                                state['frames_in_flight'] -= 1
                             done[g] = i + 1
                             cv.notify_all()
                 except BaseException as exc:                       # surfaced by the main thread
@@ -746,16 +714,7 @@ def main():
                                 cv.wait_for(lambda: min(done) >= i + 1)     # the batch's keyframes exist
                             k = state['nbatch'] & 1
                             up[k].result()
-                            if E2E_EXCL:
-                                with cv:
-                                    state['lba_wants'] = True
-                                    cv.wait_for(lambda: state['frames_in_flight'] == 0)
                             opt_pair[k].run_device(lba_stream.cuda_stream)
-                            if E2E_EXCL:
-                                lba_stream.synchronize()
-                                with cv:
-                                    state['lba_wants'] = False
-                                    cv.notify_all()
                             down[k] = pool.submit(opt_pair[k].download)     # waits for the kernel on the device (event inside the library)
                             state['nbatch'] += 1
                 except BaseException as exc:
