@@ -75,4 +75,12 @@ __device__ __forceinline__ int hamming256(const uint32_t* a, const uint32_t* b) 
     return d;
 }
 
+// Wait for a stream from a host thread that has nothing else to do: through an event created with cudaEventBlockingSync the thread sleeps
+// instead of spinning in cudaStreamSynchronize (a server runs several such threads per GPU and several GPUs per host; spinning threads
+// take the cores the other ranks' threads need).  Used by the BATCH host entry points; single-frame calls keep the low-latency spin.
+inline cudaError_t wait_stream_blocking(cudaStream_t st, cudaEvent_t ev) {
+    cudaError_t e = cudaEventRecord(ev, st);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ev);
+}
+inline cudaError_t make_blocking_event(cudaEvent_t* ev) { return cudaEventCreateWithFlags(ev, cudaEventBlockingSync | cudaEventDisableTiming); }
 }  // namespace orbx

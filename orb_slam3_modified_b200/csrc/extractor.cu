@@ -89,6 +89,7 @@ struct Extractor {
     int* h_counts = nullptr;       // pinned: n[maxBatch], mono[maxBatch], status[maxBatch]
     int outCapInternal = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t evWait = nullptr;      // blocking-sync event: batch calls sleep on it instead of spinning (device_utils.cuh)
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     bool profiling = false; cudaEvent_t evStage[8] = {};   // pyramid | blur | fast | quadtree | assemble | describe
     float stageMs[6] = {0, 0, 0, 0, 0, 0};
@@ -111,6 +112,7 @@ struct Extractor {
         for (void* p : ptrs) if (p) cudaFree(p);
         if (h_counts) cudaFreeHost(h_counts);
         if (h_stereoStatus) cudaFreeHost(h_stereoStatus);
+        if (evWait) cudaEventDestroy(evWait);
         if (stream) cudaStreamDestroy(stream);
         if (stream2) cudaStreamDestroy(stream2);
         if (evFork) cudaEventDestroy(evFork);
@@ -314,6 +316,7 @@ struct Extractor {
         CK(cudaMallocHost(&h_stereoStatus, sizeof(int) * B));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+        CK(orbx::make_blocking_event(&evWait));
         CK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&evJoin, cudaEventDisableTiming));
         CK(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
@@ -540,7 +543,7 @@ int orbx_extract_batch(orbx_handle* h, const uint8_t* images, int batch, int row
         CK(cudaMemcpyAsync(kps, e.d_outKp, sizeof(OrbKeyPoint) * (size_t)icap * batch, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(desc, e.d_outDesc, (size_t)32 * icap * batch, cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaStreamSynchronize(st));
+    if (batch > 1) CK(orbx::wait_stream_blocking(st, e.evWait)); else CK(cudaStreamSynchronize(st));
     int worst = ORB_OK;
     for (int f = 0; f < batch; ++f) {
         n[f] = hn[f]; mono[f] = hm[f];

@@ -1186,6 +1186,7 @@ struct Solver {
     int* h_stop = nullptr; int* d_stop = nullptr;   // mapped pinned stop flags, one per problem
     int* h_status = nullptr; int* d_status = nullptr;   // mapped pinned status words of the structure kernel
     cudaEvent_t evDone = nullptr, evRun = nullptr;   // evRun: end of the last run, on whatever stream the caller launched it
+    cudaEvent_t evWait = nullptr;                    // blocking-sync event: upload / download sleep on it instead of spinning (device_utils.cuh)
     bool ranOnce = false;
     int nLoaded = 0, launches = 0, numSMs = 148;
     ~Solver() {
@@ -1197,6 +1198,7 @@ struct Solver {
         if (h_status) cudaFreeHost(h_status);
         if (evDone) cudaEventDestroy(evDone);
         if (evRun) cudaEventDestroy(evRun);
+        if (evWait) cudaEventDestroy(evWait);
         if (st) cudaStreamDestroy(st);
     }
     static size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -1240,6 +1242,7 @@ struct Solver {
         CK(cudaEventCreateWithFlags(&evDone, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&evRun, cudaEventDisableTiming));
+        CK(orbx::make_blocking_event(&evWait));
         h_probs.resize(maxBatch); packed.resize(maxBatch);
         return ORB_OK;
     }
@@ -1348,7 +1351,7 @@ struct Solver {
         for (int i = 0; i < count; ++i) h_status[i] = -1;
         lba_build_structure_kernel<<<count, BT, 0, st>>>(d_probs, d_status);     // BlockSolver::buildStructure, one CTA per problem
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(st));   // the resident copy must be complete before a run on any other stream
+        CK(orbx::wait_stream_blocking(st, evWait));   // the resident copy must be complete before a run on any other stream
         for (int i = 0; i < count; ++i) {
             if (h_status[i] == 0) continue;
             nLoaded = 0;
@@ -1417,7 +1420,7 @@ struct Solver {
         const size_t ob = outBlock(maxP, maxL, maxE);
         if (ranOnce) CK(cudaStreamWaitEvent(s, evRun, 0));    // the run may be on another stream than this copy
         CK(cudaMemcpy2DAsync(h_arena, perProblem, d_arena, perProblem, ob, (size_t)count, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(orbx::wait_stream_blocking(s, evWait));
         for (int i = 0; i < count; ++i) {
             const Packed& K = packed[i];
             LbaResult& R = res[i];

@@ -1009,6 +1009,7 @@ __global__ void hamming_pairs_kernel(const uint8_t* __restrict__ a, const uint8_
 struct Matcher {
     int device, maxBatch, kcap, mcap;
     cudaStream_t stream = nullptr;
+    cudaEvent_t evWait = nullptr;      // blocking-sync event of the batch host entry points (device_utils.cuh)
     // scratch
     float4* d_query = nullptr; int4 *d_resultIdx = nullptr, *d_resultDist = nullptr;
     int* d_status = nullptr;
@@ -1024,6 +1025,7 @@ struct Matcher {
         void* ptrs[] = {d_query, d_resultIdx, d_resultDist, d_status, d_arena, d_batch};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (h_arena) cudaFreeHost(h_arena);
+        if (evWait) cudaEventDestroy(evWait);
         if (stream) cudaStreamDestroy(stream);
     }
     int init() {
@@ -1050,6 +1052,7 @@ struct Matcher {
         batchBytes = B * ((size_t)kcap * (28 + 32 + 4 + 1) + (size_t)mcap * (1 + 12 + 4 + 4 + 1 + 32) + 28 + 16 + 13 * 256) + 4096;
         CK(cudaMalloc(&d_batch, batchBytes));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(orbx::make_blocking_event(&evWait));
         return ORB_OK;
     }
     // kUse / mUse: the largest keypoint / map-point count any frame of this call can have (the slab capacities when the
@@ -1326,7 +1329,7 @@ static int search_last_frame_batch_host(orbm_handle* h, const OrbmBatchDevice* i
     CK(cudaMemcpyAsync(match, dm, B * K * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(claimed, dc, B * K, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(nmatches, dn, B * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(orbx::wait_stream_blocking(st, m.evWait));
     return ORB_OK;
 }
 
