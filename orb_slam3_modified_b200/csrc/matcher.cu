@@ -590,6 +590,7 @@ __global__ void __launch_bounds__(MF_NT) init_match_kernel(MatchParams P) {
                 }
                 if (bIdx < 0 || bDist > TH_LOW) continue;             // :702
                 if (!((float)bDist < fmul((float)sDist, P.nnratio))) continue;    // :704
+                __syncwarp();                                         // every lane has read matchedDist[] for this keypoint before lane 0 updates it
                 if (lane == 0) {
                     const unsigned prev = m21[bIdx];
                     if (prev != NONE16) S.choice[prev] = (uint16_t)NONE16;        // :706-710
