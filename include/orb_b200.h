@@ -429,6 +429,19 @@ int imu_information_batch(int count, const float* preint, double* info9, double*
  * given, the Huber weight rho'(chi2) for huberDelta (sqrt(16.92) in LocalInertialBA, src/Optimizer.cc:540-542; <= 0: no kernel). */
 int imu_inertial_edges(int count, const float* preint, const double* states36, const double* info9, double huberDelta, double* err9, double* J9x24,
                        double* chi2, double* rho, int device);
+/* int Optimizer::PoseInertialOptimizationLastKeyFrame(Frame* pFrame, bool bRecInit) (include/Optimizer.h:66, src/Optimizer.cc:4491-4873),
+ * monocular frame: the inertial pose optimiser Tracking::TrackLocalMap runs per frame once the IMU is initialised and the map was updated
+ * (src/Tracking.cc:2985-2994), for `count` frames at once (one CTA per frame).  Per frame f (slots of `cap` entries, N[f] used):
+ *   Xw [count][cap][3] pMP->GetWorldPos(); obs [count][cap][2] mvKeysUn[i].pt; invSigma2 [count][cap] mvInvLevelSigma2[octave] / unc2;
+ *   trackDepth [count][cap] pMP->mTrackDepth (the 10 m "close" rule, :4730); cam4 [count][4]; extrinsics24: Rcb 9 | tcb 3 | Rbc 9 | tbc 3;
+ *   preint [count][IMU_PREINT_FLOATS]: pFrame->mpImuPreintegrated (from the last keyframe);
+ *   kfState21 / state21 [count][21]: Rwb 9 | twb 3 | velocity 3 | gyro bias 3 | acc bias 3 of the last keyframe (fixed) and of the frame
+ *   (in: VertexPose / Velocity / GyroBias / AccBias(pFrame); out: what SetImuPoseVelocity / mImuBias receive, :4813-4817).
+ * Out: outlier [count][cap] = mvbOutlier, H15 [count][225] = the Hessian handed to ConstraintPoseImu (:4819-4870, row-major, order pose 6 |
+ * velocity | gyro bias | acc bias), ret [count] = nInitialCorrespondences - nBad.  Host pointers. */
+int pose_inertial_optimization_last_kf_batch(int count, int cap, const int32_t* N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth,
+                                             const float* cam4, const double* extrinsics24, const float* preint, const double* kfState21, double* state21, int bRecInit,
+                                             uint8_t* outlier, double* H15, int32_t* ret, int device);
 /* EdgeMono (include/G2oTypes.h:342-385, src/G2oTypes.cc:349-373) over VertexPose = ImuCamPose (body pose + camera extrinsics, src/G2oTypes.cc:148-220). */
 typedef struct ImuMonoEdges {
     int nPoses;  const double* poses;       /* [nPoses][12]: Rwb 9 | twb 3 */

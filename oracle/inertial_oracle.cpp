@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace orbo {
 namespace imu {
@@ -362,6 +363,141 @@ void orbo_so3(int what, const double* in, double* out) {   // 0 Exp, 1 Log, 2 Ri
     else if (what == 2) right_jacobian(in, out, 1e-5);
     else if (what == 3) inv_right_jacobian(in, out);
     else normalize_rotation(in, out);
+}
+
+// int Optimizer::PoseInertialOptimizationLastKeyFrame(Frame* pFrame, bool bRecInit) (src/Optimizer.cc:4491-4873), monocular frame:
+// the tracking-side inertial pose optimiser (Tracking::TrackLocalMap, src/Tracking.cc:2985-2994).  Unknowns: the frame's VertexPose (6: rotation,
+// translation of ImuCamPose::Update), VertexVelocity, VertexGyroBias, VertexAccBias = 15; the last keyframe's four vertices are fixed.
+// Edges: EdgeMonoOnlyPose per map point (Huber sqrt(5.991), dropped after round 2), EdgeInertial (preintegration from the last keyframe,
+// biases of the keyframe), EdgeGyroRW, EdgeAccRW.  Four rounds of g2o Gauss-Newton (OptimizationAlgorithmGaussNewton::solve: computeActiveErrors,
+// buildSystem, dense LDLT, update; 10 iterations each, no restart of the estimate) with the chi2 re-classification of :4713-4778 (thresholds
+// 12 / 7.5 / 5.991 / 5.991, x1.5 for points closer than 10 m, stale errors for edges that were active, recomputed ones for outliers), the
+// recovery of :4783-4810, and the Hessian of the new prior (:4819-4867).
+// state15: Rwb 9 | twb 3 | v 3 | bg 3 | ba 3 (in/out for the frame; the keyframe's is read only).  Returns nInitialCorrespondences - nBad.
+static bool ldlt_solve(int n, const double* A, const double* b, double* x) {   // Eigen::LDLT + isPositive() (linear_solver_dense.h:111-118)
+    std::vector<double> L(A, A + (size_t)n * n), d(n), y(n);
+    for (int j = 0; j < n; ++j) {
+        double dj = L[j * n + j];
+        for (int k = 0; k < j; ++k) dj -= L[j * n + k] * L[j * n + k] * d[k];
+        if (!(dj > 0)) return false;
+        d[j] = dj;
+        for (int i = j + 1; i < n; ++i) {
+            double v = L[i * n + j];
+            for (int k = 0; k < j; ++k) v -= L[i * n + k] * L[j * n + k] * d[k];
+            L[i * n + j] = v / dj;
+        }
+    }
+    for (int i = 0; i < n; ++i) { double v = b[i]; for (int k = 0; k < i; ++k) v -= L[i * n + k] * y[k]; y[i] = v; }
+    for (int i = n - 1; i >= 0; --i) { double v = y[i] / d[i]; for (int k = i + 1; k < n; ++k) v -= L[k * n + i] * x[k]; x[i] = v; }
+    return true;
+}
+// `rounds` x `iters`: 4 x 10 in the reference; the tests also run a single Gauss-Newton step
+int orbo_pose_inertial_opt_last_kf_n(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24,
+                                     const float* P, const double* kfState15, double* state15, int bRecInit, uint8_t* outlier, double* H15, int rounds, int iters) {
+    const double *Rcb = extr24, *tcb = extr24 + 9, *Rbc = extr24 + 12, *tbc = extr24 + 21;
+    double *Rwb = state15, *twb = state15 + 9, *v = state15 + 12, *bg = state15 + 15, *ba = state15 + 18;
+    const double *Rwbk = kfState15, *twbk = kfState15 + 9, *vk = kfState15 + 12, *bgk = kfState15 + 15, *bak = kfState15 + 18;
+    double Info9[81], InfoG[9], InfoA[9];
+    orbo_imu_information(P, Info9, InfoG, InfoA);
+    const double delta = (double)sqrtf(5.991f), dsqr = delta * delta;      // const float thHuberMono = sqrt(5.991); rk->setDelta(thHuberMono)
+    std::vector<double> Xd(3 * (size_t)N), od(2 * (size_t)N), err(2 * (size_t)N, 0.0);
+    for (int i = 0; i < 3 * N; ++i) Xd[i] = (double)Xw[i];
+    for (int i = 0; i < 2 * N; ++i) od[i] = (double)obs[i];
+    std::vector<uint8_t> level(N, 0);
+    for (int i = 0; i < N; ++i) outlier[i] = 0;
+    bool robust = true;
+    int its = 0;                                                            // ImuCamPose::its
+    double x[15] = {0};
+    const float chi2Mono[4] = {12, 7.5, 5.991, 5.991};
+    int nBad = 0, nInliers = 0;
+    for (int it = 0; it < rounds; ++it) {
+        for (int iter = 0; iter < iters; ++iter) {
+            double H[225] = {0}, b[15] = {0};
+            for (int i = 0; i < N; ++i) {
+                if (level[i]) continue;
+                double Jpt[6], Jp[12];
+                orbo_imu_edge_mono(Rwb, twb, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], &err[2 * i], Jpt, Jp, nullptr);
+                const double om = (double)invSigma2[i];
+                const double c2 = om * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]);
+                double w = 1.0;
+                if (robust && c2 > dsqr) w = delta / std::sqrt(c2);
+                for (int a = 0; a < 6; ++a) {
+                    b[a] -= w * om * (Jp[a] * err[2 * i] + Jp[6 + a] * err[2 * i + 1]);
+                    for (int c = 0; c < 6; ++c) H[a * 15 + c] += w * om * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c]);
+                }
+            }
+            {   // EdgeInertial: only the Jacobians of the frame's pose (columns 15..20) and velocity (21..23) count, the keyframe is fixed
+                double e9[9], J[216], Jc[81], OJ[81];
+                orbo_imu_edge_inertial(P, Rwbk, twbk, vk, bgk, bak, Rwb, twb, v, e9, J);
+                for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) Jc[r * 9 + c] = J[r * 24 + 15 + c];
+                for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) { double s = 0; for (int k = 0; k < 9; ++k) s += Info9[r * 9 + k] * Jc[k * 9 + c]; OJ[r * 9 + c] = s; }
+                for (int a = 0; a < 9; ++a) {
+                    double s = 0;
+                    for (int r = 0; r < 9; ++r) s += OJ[r * 9 + a] * e9[r];            // J^T Omega e (Omega symmetric)
+                    b[a] -= s;
+                    for (int c = 0; c < 9; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += Jc[r * 9 + a] * OJ[r * 9 + c]; H[a * 15 + c] += h; }
+                }
+            }
+            for (int a = 0; a < 3; ++a) {                                   // EdgeGyroRW / EdgeAccRW: error = b2 - b1, Jacobian of the free vertex = I
+                double sg = 0, sa = 0;
+                for (int c = 0; c < 3; ++c) { sg += InfoG[a * 3 + c] * (bg[c] - bgk[c]); sa += InfoA[a * 3 + c] * (ba[c] - bak[c]); H[(9 + a) * 15 + 9 + c] += InfoG[a * 3 + c]; H[(12 + a) * 15 + 12 + c] += InfoA[a * 3 + c]; }
+                b[9 + a] -= sg; b[12 + a] -= sa;
+            }
+            const bool ok = ldlt_solve(15, H, b, x);                        // a failed solve leaves x from the previous iteration, update() still runs
+            orbo_imu_pose_update(Rwb, twb, x);
+            if (++its >= 3) { double Rn[9]; normalize_rotation(Rwb, Rn); for (int k = 0; k < 9; ++k) Rwb[k] = Rn[k]; its = 0; }
+            for (int k = 0; k < 3; ++k) { v[k] += x[6 + k]; bg[k] += x[9 + k]; ba[k] += x[12 + k]; }
+            if (!ok) break;
+        }
+        int nBadMono = 0, nInliersMono = 0;
+        const float chi2close = 1.5 * chi2Mono[it];
+        for (int i = 0; i < N; ++i) {
+            int dpos = 0;
+            double e2[2];
+            orbo_imu_edge_mono(Rwb, twb, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, nullptr, nullptr, &dpos);
+            if (outlier[i]) { err[2 * i] = e2[0]; err[2 * i + 1] = e2[1]; }     // e->computeError() only for the outliers; the others keep their last active error
+            const float chi2 = (float)((double)invSigma2[i] * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]));
+            const bool bClose = trackDepth[i] < 10.f;
+            if ((chi2 > chi2Mono[it] && !bClose) || (bClose && chi2 > chi2close) || !dpos) { outlier[i] = 1; level[i] = 1; ++nBadMono; }
+            else { outlier[i] = 0; level[i] = 0; ++nInliersMono; }
+        }
+        if (it == 2) robust = false;
+        nInliers = nInliersMono; nBad = nBadMono;
+        if (N + 3 < 10) break;                                              // optimizer.edges().size() < 10
+    }
+    if (nInliers < 30 && !bRecInit) {
+        nBad = 0;
+        for (int i = 0; i < N; ++i) {
+            double e2[2];
+            orbo_imu_edge_mono(Rwb, twb, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, nullptr, nullptr, nullptr);
+            err[2 * i] = e2[0]; err[2 * i + 1] = e2[1];
+            if ((double)invSigma2[i] * (e2[0] * e2[0] + e2[1] * e2[1]) < (double)18.f) outlier[i] = 0; else ++nBad;
+        }
+    }
+    // the prior of the next frame (:4819-4867): H = EdgeInertial::GetHessian2 + the two random-walk informations + the inliers' EdgeMonoOnlyPose Hessians
+    for (int i = 0; i < 225; ++i) H15[i] = 0;
+    {
+        double e9[9], J[216];
+        orbo_imu_edge_inertial(P, Rwbk, twbk, vk, bgk, bak, Rwb, twb, v, e9, J);
+        for (int a = 0; a < 9; ++a) for (int c = 0; c < 9; ++c) {
+            double h = 0;
+            for (int r = 0; r < 9; ++r) for (int k = 0; k < 9; ++k) h += J[r * 24 + 15 + a] * Info9[r * 9 + k] * J[k * 24 + 15 + c];
+            H15[a * 15 + c] += h;
+        }
+    }
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) { H15[(9 + a) * 15 + 9 + c] += InfoG[a * 3 + c]; H15[(12 + a) * 15 + 12 + c] += InfoA[a * 3 + c]; }
+    for (int i = 0; i < N; ++i) {
+        if (outlier[i]) continue;
+        double e2[2], Jpt[6], Jp[12];
+        orbo_imu_edge_mono(Rwb, twb, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, Jpt, Jp, nullptr);
+        const double om = (double)invSigma2[i];
+        for (int a = 0; a < 6; ++a) for (int c = 0; c < 6; ++c) H15[a * 15 + c] += om * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c]);
+    }
+    return N - nBad;
+}
+int orbo_pose_inertial_opt_last_kf(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24,
+                                   const float* P, const double* kfState15, double* state15, int bRecInit, uint8_t* outlier, double* H15) {
+    return orbo_pose_inertial_opt_last_kf_n(N, Xw, obs, invSigma2, trackDepth, cam4, extr24, P, kfState15, state15, bRecInit, outlier, H15, 4, 10);
 }
 
 }  // extern "C"

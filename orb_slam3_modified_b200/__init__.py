@@ -830,6 +830,29 @@ def imu_mono_edges(poses12, extrinsics24, cam, points, edge_point, edge_pose, ob
     return dict(err=err, Jpoint=Jp, Jpose=Jx, chi2=chi2, rho=rho, depth_pos=dp)
 
 
+def PoseInertialOptimizationLastKeyFrame(frames, extrinsics24, rec_init=False, device=0):
+    """``int Optimizer::PoseInertialOptimizationLastKeyFrame(Frame*, bool bRecInit)`` (src/Optimizer.cc:4491-4873) for a list of frames, one CTA each.
+    frame = dict(Xw [N,3], obs [N,2], inv_sigma2 [N], track_depth [N], cam [4], preint [IMU_PREINT_FLOATS], kf_state [21], state [21]).
+    Returns a list of dict(state [21], outlier [N], H [15,15], ret)."""
+    n = len(frames)
+    cap = max(1, max(len(f['Xw']) for f in frames))
+    N = np.array([len(f['Xw']) for f in frames], np.int32)
+    Xw = np.zeros((n, cap, 3), np.float32); ob = np.zeros((n, cap, 2), np.float32); isg = np.zeros((n, cap), np.float32); td = np.zeros((n, cap), np.float32)
+    for i, f in enumerate(frames):
+        Xw[i, :N[i]] = f['Xw']; ob[i, :N[i]] = f['obs']; isg[i, :N[i]] = f['inv_sigma2']; td[i, :N[i]] = f['track_depth']
+    cam = np.stack([_c(f['cam'], np.float32) for f in frames]); P = np.stack([_c(f['preint'], np.float32) for f in frames])
+    kf = np.stack([_c(f['kf_state'], np.float64) for f in frames]); st = np.stack([_c(f['state'], np.float64) for f in frames]).copy()
+    ex = _c(extrinsics24, np.float64)
+    out = np.zeros((n, cap), np.uint8); H = np.zeros((n, 15, 15)); ret = np.zeros(n, np.int32)
+    L = lib()
+    L.pose_inertial_optimization_last_kf_batch.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = L.pose_inertial_optimization_last_kf_batch(n, cap, _ptr(N), _ptr(Xw), _ptr(ob), _ptr(isg), _ptr(td), _ptr(cam), _ptr(ex), _ptr(P), _ptr(kf), _ptr(st), int(rec_init),
+                                                    _ptr(out), _ptr(H), _ptr(ret), device)
+    if rc != ORB_OK:
+        raise OrbError(rc, 'pose_inertial_optimization_last_kf_batch')
+    return [dict(state=st[i], outlier=out[i, :N[i]], H=H[i], ret=int(ret[i])) for i in range(n)]
+
+
 # =============================================================================================
 # DBoW2 vocabulary transform (reference Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h; SURVEY.md 8f rank 3)
 # =============================================================================================

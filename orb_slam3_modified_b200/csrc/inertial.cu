@@ -211,10 +211,7 @@ template <int N> __device__ bool invert_n(const double* A, double* out) {
     for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) out[i * N + j] = M[i * 2 * N + N + j];
     return true;
 }
-__global__ void imu_information_kernel(int count, const float* __restrict__ preint, double* __restrict__ info9, double* __restrict__ infoG, double* __restrict__ infoA) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= count) return;
-    const float* P = preint + (size_t)P_SIZE * e;
+__device__ void imu_information_dev(const float* __restrict__ P, double* __restrict__ I9, double* __restrict__ IG, double* __restrict__ IA) {
     double C9[81], A[81], V[81], w[9];
     for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) C9[i * 9 + j] = (double)P[P_C + i * 15 + j];
     invert_n<9>(C9, A);
@@ -237,12 +234,16 @@ __global__ void imu_information_kernel(int count, const float* __restrict__ prei
             }
     }
     for (int i = 0; i < 9; ++i) { w[i] = A[i * 9 + i]; if (w[i] < 1e-12) w[i] = 0; }
-    double* I9 = info9 + 81 * (size_t)e;
     for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) { double s = 0; for (int k = 0; k < 9; ++k) s += V[i * 9 + k] * w[k] * V[j * 9 + k]; I9[i * 9 + j] = s; }
     double G[9], Aa[9];
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { G[i * 3 + j] = (double)P[P_C + (9 + i) * 15 + 9 + j]; Aa[i * 3 + j] = (double)P[P_C + (12 + i) * 15 + 12 + j]; }
-    invert_n<3>(G, infoG + 9 * (size_t)e);
-    invert_n<3>(Aa, infoA + 9 * (size_t)e);
+    invert_n<3>(G, IG);
+    invert_n<3>(Aa, IA);
+}
+__global__ void imu_information_kernel(int count, const float* __restrict__ preint, double* __restrict__ info9, double* __restrict__ infoG, double* __restrict__ infoA) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    imu_information_dev(preint + (size_t)P_SIZE * e, info9 + 81 * (size_t)e, infoG + 9 * (size_t)e, infoA + 9 * (size_t)e);
 }
 
 // ---- SO3 helpers in double (src/G2oTypes.cc:777-861) ----
@@ -277,14 +278,8 @@ __device__ void inv_right_jacobian(const double* v, double* J) {
 
 // ---- EdgeInertial: residual, Jacobians, chi2 and robust weight; thread per edge.  states [count][36] doubles:
 //      Rwb1 9 | twb1 3 | v1 3 | bg 3 | ba 3 | Rwb2 9 | twb2 3 | v2 3 ----
-__global__ void inertial_edges_kernel(int count, const float* __restrict__ preint, const int* __restrict__ preintIndex, const double* __restrict__ states,
-                                      const double* __restrict__ info9, double huberDelta, double* __restrict__ errOut, double* __restrict__ Jout,
-                                      double* __restrict__ chi2Out, double* __restrict__ rhoOut) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= count) return;
-    const int pi = preintIndex ? preintIndex[e] : e;
-    const float* P = preint + (size_t)P_SIZE * pi;
-    const double* S = states + 36 * (size_t)e;
+// EdgeInertial::computeError + linearizeOplus for one edge: S = Rwb1 9 | twb1 3 | v1 3 | bg 3 | ba 3 | Rwb2 9 | twb2 3 | v2 3; err [9]; J [9][24] or null
+__device__ void edge_inertial_dev(const float* __restrict__ P, const double* S, double* err, double* J) {
     const double *Rwb1 = S, *twb1 = S + 9, *v1 = S + 12, *bg = S + 15, *ba = S + 18, *Rwb2 = S + 21, *twb2 = S + 30, *v2 = S + 33;
     // GetDeltaRotation / Velocity / Position(b1): float, like IMU::Preintegrated (src/ImuTypes.cc:283-307)
     const float b1[6] = {(float)ba[0], (float)ba[1], (float)ba[2], (float)bg[0], (float)bg[1], (float)bg[2]};
@@ -313,20 +308,11 @@ __global__ void inertial_edges_kernel(int count, const float* __restrict__ prein
     m3T(Rwb1, Rbw1); m3T(dR, dRt);
     m3mul(dRt, Rbw1, T); m3mul(T, Rwb2, eR);
     log_so3(eR, er);
-    double dv[3], dp[3], rv[3], rp[3], err[9];
+    double dv[3], dp[3], rv[3], rp[3];
     for (int i = 0; i < 3; ++i) { dv[i] = v2[i] - v1[i] - g[i] * dt; dp[i] = twb2[i] - twb1[i] - v1[i] * dt - g[i] * dt * dt / 2; }
     m3vec(Rbw1, dv, rv); m3vec(Rbw1, dp, rp);
     for (int i = 0; i < 3; ++i) { err[i] = er[i]; err[3 + i] = rv[i] - dV[i]; err[6 + i] = rp[i] - dP[i]; }
-    for (int i = 0; i < 9; ++i) errOut[9 * (size_t)e + i] = err[i];
-    if (info9) {   // chi2 = e^T Omega e, Huber rho' (RobustKernelHuber with delta = sqrt(16.92), src/Optimizer.cc:540-542)
-        const double* Om = info9 + 81 * (size_t)pi;
-        double c2 = 0;
-        for (int i = 0; i < 9; ++i) { double s = 0; for (int j = 0; j < 9; ++j) s += Om[i * 9 + j] * err[j]; c2 += err[i] * s; }
-        chi2Out[e] = c2;
-        if (rhoOut) { const double dsq = huberDelta * huberDelta; rhoOut[e] = (huberDelta <= 0 || c2 <= dsq) ? 1.0 : huberDelta / sqrt(c2); }
-    }
-    if (!Jout) return;
-    double* J = Jout + 216 * (size_t)e;
+    if (!J) return;
     for (int i = 0; i < 216; ++i) J[i] = 0;
     double invJr[9], A[9], H[9], Rwb2t[9];
     inv_right_jacobian(er, invJr);
@@ -358,6 +344,23 @@ __global__ void inertial_edges_kernel(int count, const float* __restrict__ prein
     put(0, 15, invJr, 1.0);
     m3mul(Rbw1, Rwb2, A); put(6, 18, A, 1.0);
     put(3, 21, Rbw1, 1.0);
+}
+__global__ void inertial_edges_kernel(int count, const float* __restrict__ preint, const int* __restrict__ preintIndex, const double* __restrict__ states,
+                                      const double* __restrict__ info9, double huberDelta, double* __restrict__ errOut, double* __restrict__ Jout,
+                                      double* __restrict__ chi2Out, double* __restrict__ rhoOut) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const int pi = preintIndex ? preintIndex[e] : e;
+    double err[9];
+    edge_inertial_dev(preint + (size_t)P_SIZE * pi, states + 36 * (size_t)e, err, Jout ? Jout + 216 * (size_t)e : nullptr);
+    for (int i = 0; i < 9; ++i) errOut[9 * (size_t)e + i] = err[i];
+    if (info9) {   // chi2 = e^T Omega e, Huber rho' (RobustKernelHuber with delta = sqrt(16.92), src/Optimizer.cc:540-542)
+        const double* Om = info9 + 81 * (size_t)pi;
+        double c2 = 0;
+        for (int i = 0; i < 9; ++i) { double s = 0; for (int j = 0; j < 9; ++j) s += Om[i * 9 + j] * err[j]; c2 += err[i] * s; }
+        chi2Out[e] = c2;
+        if (rhoOut) { const double dsq = huberDelta * huberDelta; rhoOut[e] = (huberDelta <= 0 || c2 <= dsq) ? 1.0 : huberDelta / sqrt(c2); }
+    }
 }
 
 // ---- EdgeMono with ImuCamPose (body pose + camera extrinsics): residual, Jacobians, chi2, depth sign; thread per edge ----
@@ -409,6 +412,265 @@ __global__ void mono_imu_edges_kernel(MonoParams Q) {
     for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) PR[i * 3 + j] = pj[i * 3] * Rcb[j] + pj[i * 3 + 1] * Rcb[3 + j] + pj[i * 3 + 2] * Rcb[6 + j];
     double* Jx = Q.Jpose + 12 * (size_t)e;
     for (int i = 0; i < 2; ++i) for (int j = 0; j < 6; ++j) Jx[i * 6 + j] = PR[i * 3] * Sd[j] + PR[i * 3 + 1] * Sd[6 + j] + PR[i * 3 + 2] * Sd[12 + j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// int Optimizer::PoseInertialOptimizationLastKeyFrame(Frame* pFrame, bool bRecInit) (src/Optimizer.cc:4491-4873), monocular frame: the
+// tracking-side inertial pose optimiser (Tracking::TrackLocalMap, src/Tracking.cc:2985-2994) for a batch of streams, one CTA per frame.
+// 15 unknowns (VertexPose 6, VertexVelocity 3, VertexGyroBias 3, VertexAccBias 3); the last keyframe's vertices are fixed.  Four rounds of
+// g2o Gauss-Newton x 10 iterations on the device: the EdgeMonoOnlyPose edges are spread over the threads (pose block: 21 + 6 ordered
+// block sums), thread 0 adds EdgeInertial and the two random-walk edges, factors the dense 15 x 15 system (LDLT, LinearSolverDense) and
+// applies the update (ImuCamPose::Update with its every-third-update NormalizeRotation); then the chi2 re-classification of :4713-4778 with
+// stale / recomputed errors exactly as g2o leaves them, the recovery of :4783-4810 and the Hessian of the next prior (:4819-4867).
+// ---------------------------------------------------------------------------------------------
+constexpr int PI_NT = 128;
+struct PoseInertialParams {
+    int count, cap, recInit;
+    const int* N;                       // [count]
+    const float *Xw, *obs, *invSigma2, *trackDepth;   // [count][cap][3], [..][2], [..], [..]
+    const float* cam4;                  // [count][4]
+    const double* extr;                 // [24]
+    const float* preint;                // [count][P_SIZE]
+    const double* kfState;              // [count][21]
+    double* state;                      // [count][21] in / out
+    double* err;                        // scratch [count][cap][2]
+    uint8_t* outlier;                   // [count][cap]
+    double* H15;                        // [count][225]
+    int* ret;                           // [count]
+};
+__device__ __forceinline__ double pi_block_sum(double v, double* sm) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0;
+#pragma unroll
+    for (int w = 0; w < PI_NT / 32; ++w) r += sm[w];
+    __syncthreads();
+    return r;
+}
+// EdgeMonoOnlyPose at the cached camera pose: residual, depth sign and (optionally) the 2 x 6 Jacobian (src/G2oTypes.cc:375-395)
+__device__ __forceinline__ void mono_only_pose(const double* Rcw, const double* tcw, const double* Rcb, const double* Rbc, const double* tbc, const float* cm,
+                                               const float* Xwf, const float* of, double& e0, double& e1, bool& depthPos, double* Jp) {
+    const double X[3] = {(double)Xwf[0], (double)Xwf[1], (double)Xwf[2]};
+    double Xc[3];
+    m3vec(Rcw, X, Xc);
+    for (int i = 0; i < 3; ++i) Xc[i] += tcw[i];
+    const double fx = cm[0], fy = cm[1], cx = cm[2], cy = cm[3];
+    e0 = (double)of[0] - (fx * Xc[0] / Xc[2] + cx);
+    e1 = (double)of[1] - (fy * Xc[1] / Xc[2] + cy);
+    depthPos = (Rcw[6] * X[0] + Rcw[7] * X[1] + Rcw[8] * X[2] + tcw[2]) > 0.0;
+    if (!Jp) return;
+    const double pj[6] = {fx / Xc[2], 0, -fx * Xc[0] / (Xc[2] * Xc[2]), 0, fy / Xc[2], -fy * Xc[1] / (Xc[2] * Xc[2])};
+    double Xb[3];
+    m3vec(Rbc, Xc, Xb);
+    for (int i = 0; i < 3; ++i) Xb[i] += tbc[i];
+    const double x = Xb[0], y = Xb[1], z = Xb[2];
+    const double Sd[18] = {0.0, z, -y, 1.0, 0.0, 0.0, -z, 0.0, x, 0.0, 1.0, 0.0, y, -x, 0.0, 0.0, 0.0, 1.0};
+    double PR[6];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) PR[i * 3 + j] = pj[i * 3] * Rcb[j] + pj[i * 3 + 1] * Rcb[3 + j] + pj[i * 3 + 2] * Rcb[6 + j];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 6; ++j) Jp[i * 6 + j] = PR[i * 3] * Sd[j] + PR[i * 3 + 1] * Sd[6 + j] + PR[i * 3 + 2] * Sd[12 + j];
+}
+__device__ void exp_so3_d(const double* w, double* R) {      // ExpSO3(double) with its NormalizeRotation (src/G2oTypes.cc:782-798)
+    const double d2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], d = sqrt(d2);
+    double W[9], W2[9], res[9];
+    hat(w, W); m3mul(W, W, W2);
+    for (int i = 0; i < 9; ++i) {
+        const double I = (i % 4 == 0) ? 1.0 : 0.0;
+        res[i] = d < 1e-5 ? I + W[i] + 0.5 * W2[i] : I + W[i] * sin(d) / d + W2[i] * (1.0 - cos(d)) / d2;
+    }
+    normalize_rotation(res, R);
+}
+__global__ void __launch_bounds__(PI_NT) pose_inertial_opt_kernel(PoseInertialParams Q) {
+    __shared__ double s_red[PI_NT / 32];
+    __shared__ double s_st[21], s_cam[12], s_info[81 + 9 + 9], s_x[15], s_H[225], s_b[15];
+    __shared__ int s_ok, s_cnt[2];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int N = min(Q.N[f], Q.cap);
+    const float* Xw = Q.Xw + 3 * (size_t)f * Q.cap; const float* ob = Q.obs + 2 * (size_t)f * Q.cap;
+    const float* is2 = Q.invSigma2 + (size_t)f * Q.cap; const float* td = Q.trackDepth + (size_t)f * Q.cap;
+    const float* cm = Q.cam4 + 4 * (size_t)f; const float* P = Q.preint + (size_t)P_SIZE * f;
+    const double* K = Q.kfState + 21 * (size_t)f;
+    double* err = Q.err + 2 * (size_t)f * Q.cap; uint8_t* outl = Q.outlier + (size_t)f * Q.cap;
+    const double *Rcb = Q.extr, *tcb = Q.extr + 9, *Rbc = Q.extr + 12, *tbc = Q.extr + 21;
+    double *Rcw = s_cam, *tcw = s_cam + 9;
+    if (tid < 21) s_st[tid] = Q.state[21 * (size_t)f + tid];
+    if (tid < 15) s_x[tid] = 0.0;
+    if (tid == 0) imu_information_dev(P, s_info, s_info + 81, s_info + 90);
+    for (int i = tid; i < N; i += PI_NT) { outl[i] = 0; err[2 * i] = 0; err[2 * i + 1] = 0; }
+    __syncthreads();
+    auto refresh_camera = [&]() {               // ImuCamPose::Update's camera part: Rcw = Rcb Rbw, tcw = Rcb tbw + tcb   (thread 0)
+        double Rbw[9], tbw[3];
+        m3T(s_st, Rbw); m3vec(Rbw, s_st + 9, tbw);
+        for (int i = 0; i < 3; ++i) tbw[i] = -tbw[i];
+        m3mul(Rcb, Rbw, Rcw); m3vec(Rcb, tbw, tcw);
+        for (int i = 0; i < 3; ++i) tcw[i] += tcb[i];
+    };
+    if (tid == 0) refresh_camera();
+    __syncthreads();
+    const double delta = (double)sqrtf(5.991f), dsqr = delta * delta;
+    const float chi2Mono[4] = {12.f, 7.5f, 5.991f, 5.991f};
+    bool robust = true;
+    int its = 0, nBad = 0, nInliers = 0;        // its: thread 0's copy of ImuCamPose::its
+    // level[i] lives in bit 1 of outl[] during the rounds (bit 0 = mvbOutlier): both are set together by the classification, so one flag does
+    for (int it = 0; it < 4; ++it) {
+        for (int iter = 0; iter < 10; ++iter) {
+            double acc[27];
+#pragma unroll
+            for (int k = 0; k < 27; ++k) acc[k] = 0;
+            for (int i = tid; i < N; i += PI_NT) {
+                if (outl[i]) continue;
+                double e0, e1, Jp[12]; bool dp;
+                mono_only_pose(Rcw, tcw, Rcb, Rbc, tbc, cm, Xw + 3 * i, ob + 2 * i, e0, e1, dp, Jp);
+                err[2 * i] = e0; err[2 * i + 1] = e1;
+                const double om = (double)is2[i], c2 = om * (e0 * e0 + e1 * e1);
+                const double w = (robust && c2 > dsqr) ? delta / sqrt(c2) : 1.0;
+                const double wo = w * om;
+                int t = 0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                    for (int c = a; c < 6; ++c) acc[t++] += wo * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c]);
+                }
+#pragma unroll
+                for (int a = 0; a < 6; ++a) acc[21 + a] -= wo * (Jp[a] * e0 + Jp[6 + a] * e1);
+            }
+            double tot[27];
+#pragma unroll
+            for (int k = 0; k < 27; ++k) tot[k] = pi_block_sum(acc[k], s_red);
+            if (tid == 0) {
+                for (int k = 0; k < 225; ++k) s_H[k] = 0;
+                for (int k = 0; k < 15; ++k) s_b[k] = 0;
+                int t = 0;
+                for (int a = 0; a < 6; ++a) for (int c = a; c < 6; ++c) { s_H[a * 15 + c] = tot[t]; s_H[c * 15 + a] = tot[t]; ++t; }
+                for (int a = 0; a < 6; ++a) s_b[a] = tot[21 + a];
+                {   // EdgeInertial: Jacobians of the frame's pose (columns 15..20) and velocity (21..23); the keyframe is fixed
+                    double S36[36], e9[9], J[216], OJ[81];
+                    for (int k = 0; k < 21; ++k) S36[k] = K[k];
+                    for (int k = 0; k < 15; ++k) S36[21 + k] = s_st[k];
+                    edge_inertial_dev(P, S36, e9, J);
+                    for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) { double sacc = 0; for (int k = 0; k < 9; ++k) sacc += s_info[r * 9 + k] * J[k * 24 + 15 + c]; OJ[r * 9 + c] = sacc; }
+                    for (int a = 0; a < 9; ++a) {
+                        double sacc = 0;
+                        for (int r = 0; r < 9; ++r) sacc += OJ[r * 9 + a] * e9[r];
+                        s_b[a] -= sacc;
+                        for (int c = 0; c < 9; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += J[r * 24 + 15 + a] * OJ[r * 9 + c]; s_H[a * 15 + c] += h; }
+                    }
+                }
+                for (int a = 0; a < 3; ++a) {       // EdgeGyroRW / EdgeAccRW
+                    double sg = 0, sa = 0;
+                    for (int c = 0; c < 3; ++c) {
+                        sg += s_info[81 + a * 3 + c] * (s_st[15 + c] - K[15 + c]); sa += s_info[90 + a * 3 + c] * (s_st[18 + c] - K[18 + c]);
+                        s_H[(9 + a) * 15 + 9 + c] += s_info[81 + a * 3 + c]; s_H[(12 + a) * 15 + 12 + c] += s_info[90 + a * 3 + c];
+                    }
+                    s_b[9 + a] -= sg; s_b[12 + a] -= sa;
+                }
+                // dense LDLT (Eigen::LDLT + isPositive(), linear_solver_dense.h:111-118); a failed solve leaves x of the previous iteration
+                double L[225], d[15], y[15];
+                for (int k = 0; k < 225; ++k) L[k] = s_H[k];
+                bool ok = true;
+                for (int j = 0; j < 15 && ok; ++j) {
+                    double dj = L[j * 15 + j];
+                    for (int k = 0; k < j; ++k) dj -= L[j * 15 + k] * L[j * 15 + k] * d[k];
+                    if (!(dj > 0)) { ok = false; break; }
+                    d[j] = dj;
+                    for (int i = j + 1; i < 15; ++i) {
+                        double v = L[i * 15 + j];
+                        for (int k = 0; k < j; ++k) v -= L[i * 15 + k] * L[j * 15 + k] * d[k];
+                        L[i * 15 + j] = v / dj;
+                    }
+                }
+                if (ok) {
+                    for (int i = 0; i < 15; ++i) { double v = s_b[i]; for (int k = 0; k < i; ++k) v -= L[i * 15 + k] * y[k]; y[i] = v; }
+                    for (int i = 14; i >= 0; --i) { double v = y[i] / d[i]; for (int k = i + 1; k < 15; ++k) v -= L[k * 15 + i] * s_x[k]; s_x[i] = v; }
+                }
+                // update: ImuCamPose::Update (twb += Rwb ut; Rwb = Rwb ExpSO3(ur); NormalizeRotation every third update), v / bg / ba += dx
+                double t3[3], E[9], Rn[9];
+                m3vec(s_st, s_x + 3, t3);
+                for (int i = 0; i < 3; ++i) s_st[9 + i] += t3[i];
+                exp_so3_d(s_x, E);
+                m3mul(s_st, E, Rn);
+                for (int i = 0; i < 9; ++i) s_st[i] = Rn[i];
+                if (++its >= 3) { normalize_rotation(s_st, Rn); for (int i = 0; i < 9; ++i) s_st[i] = Rn[i]; its = 0; }
+                for (int i = 0; i < 3; ++i) { s_st[12 + i] += s_x[6 + i]; s_st[15 + i] += s_x[9 + i]; s_st[18 + i] += s_x[12 + i]; }
+                refresh_camera();
+                s_ok = ok ? 1 : 0;
+            }
+            __syncthreads();
+            if (!s_ok) break;
+        }
+        // ---- re-classification (:4713-4778) ----
+        if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+        __syncthreads();
+        const float chi2close = (float)(1.5 * (double)chi2Mono[it]);
+        int bad = 0, good = 0;
+        for (int i = tid; i < N; i += PI_NT) {
+            double e0, e1; bool dp;
+            mono_only_pose(Rcw, tcw, Rcb, Rbc, tbc, cm, Xw + 3 * i, ob + 2 * i, e0, e1, dp, nullptr);
+            if (outl[i]) { err[2 * i] = e0; err[2 * i + 1] = e1; }          // e->computeError() only for the outliers
+            const float chi2 = (float)((double)is2[i] * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]));
+            const bool bClose = td[i] < 10.f;
+            if ((chi2 > chi2Mono[it] && !bClose) || (bClose && chi2 > chi2close) || !dp) { outl[i] = 1; ++bad; } else { outl[i] = 0; ++good; }
+        }
+        atomicAdd(&s_cnt[0], bad); atomicAdd(&s_cnt[1], good);
+        __syncthreads();
+        nBad = s_cnt[0]; nInliers = s_cnt[1];
+        __syncthreads();
+        if (it == 2) robust = false;
+        if (N + 3 < 10) break;                                              // optimizer.edges().size() < 10
+    }
+    if (nInliers < 30 && !Q.recInit) {                                       // :4783-4810
+        if (tid == 0) s_cnt[0] = 0;
+        __syncthreads();
+        int bad = 0;
+        for (int i = tid; i < N; i += PI_NT) {
+            double e0, e1; bool dp;
+            mono_only_pose(Rcw, tcw, Rcb, Rbc, tbc, cm, Xw + 3 * i, ob + 2 * i, e0, e1, dp, nullptr);
+            err[2 * i] = e0; err[2 * i + 1] = e1;
+            if ((double)is2[i] * (e0 * e0 + e1 * e1) < (double)18.f) outl[i] = 0; else ++bad;
+        }
+        atomicAdd(&s_cnt[0], bad);
+        __syncthreads();
+        nBad = s_cnt[0];
+        __syncthreads();
+    }
+    // ---- the prior of the next frame (:4819-4867) ----
+    double acc[21];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) acc[k] = 0;
+    for (int i = tid; i < N; i += PI_NT) {
+        if (outl[i]) continue;
+        double e0, e1, Jp[12]; bool dp;
+        mono_only_pose(Rcw, tcw, Rcb, Rbc, tbc, cm, Xw + 3 * i, ob + 2 * i, e0, e1, dp, Jp);
+        const double om = (double)is2[i];
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+#pragma unroll
+            for (int c = a; c < 6; ++c) acc[t++] += om * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c]);
+        }
+    }
+    double tot[21];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) tot[k] = pi_block_sum(acc[k], s_red);
+    if (tid == 0) {
+        double* H = Q.H15 + 225 * (size_t)f;
+        for (int k = 0; k < 225; ++k) H[k] = 0;
+        double S36[36], e9[9], J[216];
+        for (int k = 0; k < 21; ++k) S36[k] = K[k];
+        for (int k = 0; k < 15; ++k) S36[21 + k] = s_st[k];
+        edge_inertial_dev(P, S36, e9, J);
+        for (int a = 0; a < 9; ++a) for (int c = 0; c < 9; ++c) {
+            double h = 0;
+            for (int r = 0; r < 9; ++r) for (int k = 0; k < 9; ++k) h += J[r * 24 + 15 + a] * s_info[r * 9 + k] * J[k * 24 + 15 + c];
+            H[a * 15 + c] += h;
+        }
+        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) { H[(9 + a) * 15 + 9 + c] += s_info[81 + a * 3 + c]; H[(12 + a) * 15 + 12 + c] += s_info[90 + a * 3 + c]; }
+        int t = 0;
+        for (int a = 0; a < 6; ++a) for (int c = a; c < 6; ++c) { H[a * 15 + c] += tot[t]; if (c != a) H[c * 15 + a] += tot[t]; ++t; }
+        Q.ret[f] = N - nBad;
+    }
+    if (tid < 21) Q.state[21 * (size_t)f + tid] = s_st[tid];
 }
 
 // host plumbing: one device arena per host thread and device, grown on demand (these are static functions in the reference)
@@ -509,6 +771,45 @@ int imu_inertial_edges(int count, const float* preint, const double* states36, c
     if (J9x24) CK(cudaMemcpyAsync(J9x24, d + oJ, 1728 * C, cudaMemcpyDeviceToHost, st));
     if (info9) CK(cudaMemcpyAsync(chi2, d + oC, 8 * C, cudaMemcpyDeviceToHost, st));
     if (info9 && rho) CK(cudaMemcpyAsync(rho, d + oR, 8 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int pose_inertial_optimization_last_kf_batch(int count, int cap, const int32_t* N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth,
+                                             const float* cam4, const double* extrinsics24, const float* preint, const double* kfState21, double* state21, int bRecInit,
+                                             uint8_t* outlier, double* H15, int32_t* ret, int device) {
+    if (count < 1 || cap < 1 || !N || !Xw || !obs || !invSigma2 || !trackDepth || !cam4 || !extrinsics24 || !preint || !kfState21 || !state21 || !outlier || !H15 || !ret) {
+        set_error("pose_inertial_optimization_last_kf_batch: bad argument"); return ORB_ERR_ARG;
+    }
+    const size_t C = count, K = cap;
+    Bump B(nullptr);
+    const size_t oN = B.take(4 * C), oX = B.take(12 * C * K), oO = B.take(8 * C * K), oS = B.take(4 * C * K), oT = B.take(4 * C * K), oC = B.take(16 * C), oE = B.take(192),
+                 oP = B.take(4 * P_SIZE * C), oK = B.take(168 * C), oSt = B.take(168 * C), oEr = B.take(16 * C * K), oOut = B.take(C * K), oH = B.take(1800 * C), oR = B.take(4 * C);
+    Scratch* S;
+    int rc = scratch_for(device, B.off, &S);
+    if (rc) return rc;
+    uint8_t* d = S->d; cudaStream_t st = S->st;
+    CK(cudaMemcpyAsync(d + oN, N, 4 * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oX, Xw, 12 * C * K, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oO, obs, 8 * C * K, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oS, invSigma2, 4 * C * K, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oT, trackDepth, 4 * C * K, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oC, cam4, 16 * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oE, extrinsics24, 192, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oP, preint, 4 * P_SIZE * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oK, kfState21, 168 * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oSt, state21, 168 * C, cudaMemcpyHostToDevice, st));
+    PoseInertialParams Q;
+    Q.count = count; Q.cap = cap; Q.recInit = bRecInit;
+    Q.N = (const int*)(d + oN); Q.Xw = (const float*)(d + oX); Q.obs = (const float*)(d + oO); Q.invSigma2 = (const float*)(d + oS); Q.trackDepth = (const float*)(d + oT);
+    Q.cam4 = (const float*)(d + oC); Q.extr = (const double*)(d + oE); Q.preint = (const float*)(d + oP); Q.kfState = (const double*)(d + oK); Q.state = (double*)(d + oSt);
+    Q.err = (double*)(d + oEr); Q.outlier = d + oOut; Q.H15 = (double*)(d + oH); Q.ret = (int*)(d + oR);
+    pose_inertial_opt_kernel<<<count, PI_NT, 0, st>>>(Q);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(state21, d + oSt, 168 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(outlier, d + oOut, C * K, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(H15, d + oH, 1800 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ret, d + oR, 4 * C, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return ORB_OK;
 }

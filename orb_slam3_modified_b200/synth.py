@@ -271,3 +271,46 @@ def stereo_pair(t=0, width=640, height=480, seed=0, baseline_px=22.0):
     d = int(round(baseline_px))
     right = left[:, 32 + d:32 + d + width].astype(np.int16) + rng.integers(-2, 3, (height, width))
     return np.ascontiguousarray(left[:, 32:32 + width]), np.clip(right, 0, 255).astype(np.uint8)
+
+
+IMU_EXTRINSICS = None
+
+
+def imu_extrinsics():
+    """Tcb / Tbc of the synthetic rig (camera a few centimetres off the body, slightly rotated): Rcb 9 | tcb 3 | Rbc 9 | tbc 3."""
+    Rcb = _rodrigues(np.array([0.02, -0.015, 0.01])) @ np.array([[0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]])
+    tcb = np.array([0.03, -0.02, 0.01])
+    Rbc = Rcb.T
+    tbc = -Rbc @ tcb
+    return np.concatenate([Rcb.reshape(9), tcb, Rbc.reshape(9), tbc])
+
+
+def pose_inertial_problem(t0=1.0, t1=1.2, n=300, seed=0, outlier_frac=0.1, width=640, height=480, perturb=1.0, noise_px=0.7):
+    """One frame for Optimizer::PoseInertialOptimizationLastKeyFrame: the last keyframe at t0 (state known), the frame at t1 (state = ground truth + a
+    perturbation), the IMU samples between them, n map points seen by the frame's camera with noisy observations and a share of gross outliers."""
+    rng = np.random.default_rng(seed)
+    ex = imu_extrinsics()
+    Rcb, tcb = ex[:9].reshape(3, 3), ex[9:12]
+    R1, p1, v1, _, _ = imu_trajectory(t0)
+    R2, p2, v2, _, _ = imu_trajectory(t1)
+    bias = np.array([0.02, -0.01, 0.03, 0.002, -0.001, 0.0015])                     # bax.. bwx..
+    acc, gyr, dts = imu_interval(t0, t1, seed=seed, bias=tuple(bias))
+    cam = camera(width, height)
+    # points in front of the true camera
+    Rcw = Rcb @ R2.T
+    tcw = Rcb @ (-R2.T @ p2) + tcb
+    z = rng.uniform(2.0, 25.0, n)
+    u, v = rng.uniform(15, width - 15, n), rng.uniform(15, height - 15, n)
+    Xc = np.stack([(u - cam[2]) * z / cam[0], (v - cam[3]) * z / cam[1], z], 1)
+    Xw = (Xc - tcw) @ Rcw                                                            # Rcw^T (Xc - tcw)
+    octave = rng.integers(0, 8, n)
+    sig = 1.2 ** octave
+    obs = np.stack([u, v], 1) + rng.normal(0, noise_px, (n, 2)) * sig[:, None]
+    bad = rng.random(n) < outlier_frac
+    obs[bad] += rng.uniform(8, 40, (int(bad.sum()), 2)) * rng.choice([-1, 1], (int(bad.sum()), 2))
+    st = lambda R, p, v_, bg, ba: np.concatenate([R.reshape(9), p, v_, bg, ba]).astype(np.float64)
+    kf = st(R1, p1, v1, bias[3:], bias[:3])
+    fr = st(R2 @ _rodrigues(perturb * rng.normal(0, 0.01, 3)), p2 + perturb * rng.normal(0, 0.02, 3), v2 + perturb * rng.normal(0, 0.05, 3),
+            bias[3:] + perturb * rng.normal(0, 2e-4, 3), bias[:3] + perturb * rng.normal(0, 2e-3, 3))
+    return dict(Xw=Xw.astype(np.float32), obs=obs.astype(np.float32), inv_sigma2=(1.0 / 1.44 ** octave).astype(np.float32), track_depth=z.astype(np.float32), cam=cam,
+                extr=ex, acc=acc, gyr=gyr, dt=dts, bias6=bias.astype(np.float32), kf_state=kf, state=fr, truth=st(R2, p2, v2, bias[3:], bias[:3]), gross=bad)

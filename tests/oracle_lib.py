@@ -574,3 +574,19 @@ def sim3_camera_points(sc):
     p21 = ((c1 - t) @ R12) / s              # S21 = S12^-1
     p12 = s * (c2 @ R12.T) + t
     return p21.astype(np.float32), p12.astype(np.float32)
+
+
+def pose_inertial_opt_last_kf(pr, preint, rec_init=False, rounds=4, iters=10):
+    """Optimizer::PoseInertialOptimizationLastKeyFrame: returns dict(state [21], outlier [N], H [15,15], ret)."""
+    L = lib()
+    N = len(pr['Xw'])
+    st = _c(pr['state'], np.float64).copy(); out = np.zeros(N, np.uint8); H = np.zeros((15, 15))
+    L.orbo_pose_inertial_opt_last_kf_n.argtypes = [C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    a = [_c(pr['Xw'], np.float32), _c(pr['obs'], np.float32), _c(pr['inv_sigma2'], np.float32), _c(pr['track_depth'], np.float32), _c(pr['cam'], np.float32),
+         _c(pr['extr'], np.float64), _c(preint, np.float32), _c(pr['kf_state'], np.float64)]
+    ret = L.orbo_pose_inertial_opt_last_kf_n(N, *[_p(v) for v in a], _p(st), int(rec_init), _p(out), _p(H), rounds, iters)
+    return dict(state=st, outlier=out, H=H, ret=ret)
+
+
+def pose_inertial_opt_one_step(pr, preint):
+    return pose_inertial_opt_last_kf(pr, preint, rounds=1, iters=1)['state']
