@@ -500,4 +500,211 @@ int orbo_pose_inertial_opt_last_kf(int N, const float* Xw, const float* obs, con
     return orbo_pose_inertial_opt_last_kf_n(N, Xw, obs, invSigma2, trackDepth, cam4, extr24, P, kfState15, state15, bRecInit, outlier, H15, 4, 10);
 }
 
+// int Optimizer::PoseInertialOptimizationLastFrame(Frame* pFrame, bool bRecInit) (src/Optimizer.cc:4875-5289), monocular frame: like the
+// last-keyframe variant, but the PREVIOUS FRAME's four vertices are free too (30 unknowns), held by EdgePriorPoseImu (its ConstraintPoseImu:
+// state + 15 x 15 information, Huber delta 5; src/G2oTypes.cc:720-760); EdgeInertial uses mpImuPreintegratedFrame (frame to frame), the two
+// random-walk informations come from mpImuPreintegrated (since the last keyframe) (:5068-5078).  Thresholds 5.991 in all four rounds.
+// Afterwards the 30 x 30 Hessian is assembled in the order (previous 15 | current 15) and the previous frame is marginalised
+// (Optimizer::Marginalize, :2960-3043: Schur complement with the SVD pseudo-inverse, singular values <= 1e-6 dropped).
+// x layout here: current pose 6, v 3, bg 3, ba 3 | previous pose 6, v 3, bg 3, ba 3.
+static void sym_eig(int n, const double* Ain, double* V, double* w) {   // cyclic Jacobi, A = V diag(w) V^T
+    std::vector<double> A(Ain, Ain + (size_t)n * n);
+    for (int i = 0; i < n * n; ++i) V[i] = (i % (n + 1) == 0) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0, diag = 0;
+        for (int p = 0; p < n; ++p) { diag += A[p * n + p] * A[p * n + p]; for (int q = p + 1; q < n; ++q) off += A[p * n + q] * A[p * n + q]; }
+        if (off <= 1e-30 * diag || off < 1e-300) break;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[p * n + q];
+                if (apq == 0) continue;
+                const double theta = (A[q * n + q] - A[p * n + p]) / (2 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+                const double c = 1 / std::sqrt(t * t + 1), sn = t * c;
+                for (int k = 0; k < n; ++k) { const double akp = A[k * n + p], akq = A[k * n + q]; A[k * n + p] = c * akp - sn * akq; A[k * n + q] = sn * akp + c * akq; }
+                for (int k = 0; k < n; ++k) { const double apk = A[p * n + k], aqk = A[q * n + k]; A[p * n + k] = c * apk - sn * aqk; A[q * n + k] = sn * apk + c * aqk; }
+                for (int k = 0; k < n; ++k) { const double vkp = V[k * n + p], vkq = V[k * n + q]; V[k * n + p] = c * vkp - sn * vkq; V[k * n + q] = sn * vkp + c * vkq; }
+            }
+    }
+    for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
+}
+// ConstraintPoseImu's constructor (include/G2oTypes.h:711-722): symmetrise, clamp eigenvalues < 1e-12 to 0
+void orbo_constraint_pose_imu_information(const double* Hin, double* Hout) {
+    double S[225], V[225], w[15];
+    for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) S[i * 15 + j] = (Hin[i * 15 + j] + Hin[j * 15 + i]) / 2;
+    sym_eig(15, S, V, w);
+    for (int i = 0; i < 15; ++i) if (w[i] < 1e-12) w[i] = 0;
+    for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) { double a = 0; for (int k = 0; k < 15; ++k) a += V[i * 15 + k] * w[k] * V[j * 15 + k]; Hout[i * 15 + j] = a; }
+}
+// EdgePriorPoseImu: residual (15) and the diagonal-block Jacobian (15 x 15 wrt pose 6, v, bg, ba) of the previous frame
+static void prior_edge(const double* prior21, const double* st21, double* e15, double* J225) {
+    const double *Rp = prior21, *tp = prior21 + 9;
+    double Rpt[9], dR[9], er[3], d[3], et[3];
+    mat3_T(Rp, Rpt); mat3_mul(Rpt, st21, dR);
+    log_so3(dR, er);
+    for (int i = 0; i < 3; ++i) d[i] = st21[9 + i] - tp[i];
+    mat3_vec(Rpt, d, et);
+    for (int i = 0; i < 3; ++i) { e15[i] = er[i]; e15[3 + i] = et[i]; e15[6 + i] = st21[12 + i] - prior21[12 + i]; e15[9 + i] = st21[15 + i] - prior21[15 + i]; e15[12 + i] = st21[18 + i] - prior21[18 + i]; }
+    if (!J225) return;
+    for (int i = 0; i < 225; ++i) J225[i] = 0;
+    double iJ[9];
+    inv_right_jacobian(er, iJ);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { J225[i * 15 + j] = iJ[i * 3 + j]; J225[(3 + i) * 15 + 3 + j] = dR[i * 3 + j]; }
+    for (int i = 6; i < 15; ++i) J225[i * 15 + i] = 1.0;
+}
+int orbo_pose_inertial_opt_last_frame_n(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24,
+                                        const float* Pframe, const float* Pkf, const double* prior21, const double* priorH, double* prevState21, double* state21,
+                                        int bRecInit, uint8_t* outlier, double* H15, int rounds, int iters) {
+    const double *Rcb = extr24, *tcb = extr24 + 9, *Rbc = extr24 + 12, *tbc = extr24 + 21;
+    double* S[2] = {state21, prevState21};          // current, previous
+    double Info9[81], InfoG[9], InfoA[9], tmpI[81];
+    orbo_imu_information(Pframe, Info9, tmpI, tmpI);
+    orbo_imu_information(Pkf, tmpI, InfoG, InfoA);
+    const double delta = (double)sqrtf(5.991f), dsqr = delta * delta;
+    std::vector<double> Xd(3 * (size_t)N), od(2 * (size_t)N), err(2 * (size_t)N, 0.0);
+    for (int i = 0; i < 3 * N; ++i) Xd[i] = (double)Xw[i];
+    for (int i = 0; i < 2 * N; ++i) od[i] = (double)obs[i];
+    for (int i = 0; i < N; ++i) outlier[i] = 0;
+    bool robust = true;
+    int its[2] = {0, 0};
+    double x[30] = {0};
+    const float chi2Mono[4] = {5.991, 5.991, 5.991, 5.991};
+    int nBad = 0, nInliers = 0;
+    // column of x for column c of the EdgeInertial Jacobian (vertex order: previous pose, v, bg, ba, current pose, v)
+    auto xi = [](int c) { return c < 15 ? 15 + c : c - 15; };
+    auto inertial = [&](double* e9, double* J) { orbo_imu_edge_inertial(Pframe, S[1], S[1] + 9, S[1] + 12, S[1] + 15, S[1] + 18, S[0], S[0] + 9, S[0] + 12, e9, J); };
+    for (int it = 0; it < rounds; ++it) {
+        for (int iter = 0; iter < iters; ++iter) {
+            std::vector<double> H(900, 0.0); double b[30] = {0};
+            for (int i = 0; i < N; ++i) {
+                if (outlier[i]) continue;
+                double Jpt[6], Jp[12];
+                orbo_imu_edge_mono(S[0], S[0] + 9, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], &err[2 * i], Jpt, Jp, nullptr);
+                const double om = (double)invSigma2[i];
+                const double c2 = om * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]);
+                const double w = (robust && c2 > dsqr) ? delta / std::sqrt(c2) : 1.0;
+                for (int a = 0; a < 6; ++a) {
+                    b[a] -= w * om * (Jp[a] * err[2 * i] + Jp[6 + a] * err[2 * i + 1]);
+                    for (int c = 0; c < 6; ++c) H[a * 30 + c] += w * om * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c]);
+                }
+            }
+            {
+                double e9[9], J[216], OJ[216];
+                inertial(e9, J);
+                for (int r = 0; r < 9; ++r) for (int c = 0; c < 24; ++c) { double a = 0; for (int k = 0; k < 9; ++k) a += Info9[r * 9 + k] * J[k * 24 + c]; OJ[r * 24 + c] = a; }
+                for (int a = 0; a < 24; ++a) {
+                    double g = 0;
+                    for (int r = 0; r < 9; ++r) g += OJ[r * 24 + a] * e9[r];
+                    b[xi(a)] -= g;
+                    for (int c = 0; c < 24; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += J[r * 24 + a] * OJ[r * 24 + c]; H[xi(a) * 30 + xi(c)] += h; }
+                }
+            }
+            for (int a = 0; a < 3; ++a) {           // EdgeGyroRW (VGk, VG), EdgeAccRW (VAk, VA): error = b_cur - b_prev, Jacobians -I / +I
+                double sg = 0, sa = 0;
+                for (int c = 0; c < 3; ++c) {
+                    const double og = InfoG[a * 3 + c], oa = InfoA[a * 3 + c];
+                    sg += og * (S[0][15 + c] - S[1][15 + c]); sa += oa * (S[0][18 + c] - S[1][18 + c]);
+                    H[(9 + a) * 30 + 9 + c] += og; H[(24 + a) * 30 + 24 + c] += og; H[(9 + a) * 30 + 24 + c] -= og; H[(24 + a) * 30 + 9 + c] -= og;
+                    H[(12 + a) * 30 + 12 + c] += oa; H[(27 + a) * 30 + 27 + c] += oa; H[(12 + a) * 30 + 27 + c] -= oa; H[(27 + a) * 30 + 12 + c] -= oa;
+                }
+                b[9 + a] -= sg; b[24 + a] += sg; b[12 + a] -= sa; b[27 + a] += sa;
+            }
+            {   // EdgePriorPoseImu on the previous frame, Huber delta 5
+                double e15[15], J[225], OJ[225], Oe[15];
+                prior_edge(prior21, S[1], e15, J);
+                double c2 = 0;
+                for (int r = 0; r < 15; ++r) { double a = 0; for (int k = 0; k < 15; ++k) a += priorH[r * 15 + k] * e15[k]; Oe[r] = a; c2 += e15[r] * a; }
+                const double w = c2 > 25.0 ? 5.0 / std::sqrt(c2) : 1.0;
+                for (int r = 0; r < 15; ++r) for (int c = 0; c < 15; ++c) { double a = 0; for (int k = 0; k < 15; ++k) a += priorH[r * 15 + k] * J[k * 15 + c]; OJ[r * 15 + c] = a; }
+                for (int a = 0; a < 15; ++a) {
+                    double g = 0;
+                    for (int r = 0; r < 15; ++r) g += J[r * 15 + a] * Oe[r];
+                    b[15 + a] -= w * g;
+                    for (int c = 0; c < 15; ++c) { double h = 0; for (int r = 0; r < 15; ++r) h += J[r * 15 + a] * OJ[r * 15 + c]; H[(15 + a) * 30 + 15 + c] += w * h; }
+                }
+            }
+            const bool ok = ldlt_solve(30, H.data(), b, x);
+            for (int k = 0; k < 2; ++k) {
+                const double* dx = x + 15 * k;
+                orbo_imu_pose_update(S[k], S[k] + 9, dx);
+                if (++its[k] >= 3) { double Rn[9]; normalize_rotation(S[k], Rn); for (int q = 0; q < 9; ++q) S[k][q] = Rn[q]; its[k] = 0; }
+                for (int q = 0; q < 3; ++q) { S[k][12 + q] += dx[6 + q]; S[k][15 + q] += dx[9 + q]; S[k][18 + q] += dx[12 + q]; }
+            }
+            if (!ok) break;
+        }
+        int nBadMono = 0, nInliersMono = 0;
+        const float chi2close = 1.5 * chi2Mono[it];
+        for (int i = 0; i < N; ++i) {
+            int dpos = 0; double e2[2];
+            orbo_imu_edge_mono(S[0], S[0] + 9, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, nullptr, nullptr, &dpos);
+            if (outlier[i]) { err[2 * i] = e2[0]; err[2 * i + 1] = e2[1]; }
+            const float chi2 = (float)((double)invSigma2[i] * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]));
+            const bool bClose = trackDepth[i] < 10.f;
+            if ((chi2 > chi2Mono[it] && !bClose) || (bClose && chi2 > chi2close) || !dpos) { outlier[i] = 1; ++nBadMono; } else { outlier[i] = 0; ++nInliersMono; }
+        }
+        if (it == 2) robust = false;
+        nInliers = nInliersMono; nBad = nBadMono;
+        if (N + 4 < 10) break;                                              // optimizer.edges().size() < 10 (N mono + inertial + 2 random walk + prior)
+    }
+    if (nInliers < 30 && !bRecInit) {
+        nBad = 0;
+        for (int i = 0; i < N; ++i) {
+            double e2[2];
+            orbo_imu_edge_mono(S[0], S[0] + 9, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, nullptr, nullptr, nullptr);
+            if ((double)invSigma2[i] * (e2[0] * e2[0] + e2[1] * e2[1]) < (double)18.f) outlier[i] = 0; else ++nBad;
+        }
+    }
+    // 30 x 30 Hessian in the reference's order (previous 15 | current 15) (:5216-5266), then Marginalize(H, 0, 14) and the current 15 x 15 block
+    std::vector<double> Hf(900, 0.0);
+    {
+        double e9[9], J[216];
+        inertial(e9, J);
+        for (int a = 0; a < 24; ++a) for (int c = 0; c < 24; ++c) {
+            double h = 0;
+            for (int r = 0; r < 9; ++r) for (int k = 0; k < 9; ++k) h += J[r * 24 + a] * Info9[r * 9 + k] * J[k * 24 + c];
+            Hf[a * 30 + c] += h;
+        }
+        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) {
+            const double og = InfoG[a * 3 + c], oa = InfoA[a * 3 + c];
+            Hf[(9 + a) * 30 + 9 + c] += og; Hf[(9 + a) * 30 + 24 + c] -= og; Hf[(24 + a) * 30 + 9 + c] -= og; Hf[(24 + a) * 30 + 24 + c] += og;
+            Hf[(12 + a) * 30 + 12 + c] += oa; Hf[(12 + a) * 30 + 27 + c] -= oa; Hf[(27 + a) * 30 + 12 + c] -= oa; Hf[(27 + a) * 30 + 27 + c] += oa;
+        }
+        double e15[15], Jp[225];
+        prior_edge(prior21, S[1], e15, Jp);
+        for (int a = 0; a < 15; ++a) for (int c = 0; c < 15; ++c) {
+            double h = 0;
+            for (int r = 0; r < 15; ++r) for (int k = 0; k < 15; ++k) h += Jp[r * 15 + a] * priorH[r * 15 + k] * Jp[k * 15 + c];
+            Hf[a * 30 + c] += h;
+        }
+    }
+    for (int i = 0; i < N; ++i) {
+        if (outlier[i]) continue;
+        double e2[2], Jpt[6], Jp[12];
+        orbo_imu_edge_mono(S[0], S[0] + 9, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, Jpt, Jp, nullptr);
+        const double om = (double)invSigma2[i];
+        for (int a = 0; a < 6; ++a) for (int c = 0; c < 6; ++c) Hf[(15 + a) * 30 + 15 + c] += om * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c]);
+    }
+    {   // H_cc - H_cb pinv(H_bb) H_bc, pinv through the eigen-decomposition of the symmetrised block (= the SVD of a symmetric matrix)
+        double Hbb[225], V[225], w[15], pinv[225];
+        for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) Hbb[i * 15 + j] = (Hf[i * 30 + j] + Hf[j * 30 + i]) / 2;
+        sym_eig(15, Hbb, V, w);
+        for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) {
+            double a = 0;
+            for (int k = 0; k < 15; ++k) if (std::fabs(w[k]) > 1e-6) a += V[i * 15 + k] * V[j * 15 + k] / w[k];
+            pinv[i * 15 + j] = a;
+        }
+        for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) {
+            double a = 0;
+            for (int k = 0; k < 15; ++k) for (int l = 0; l < 15; ++l) a += Hf[(15 + i) * 30 + k] * pinv[k * 15 + l] * Hf[l * 30 + 15 + j];
+            H15[i * 15 + j] = Hf[(15 + i) * 30 + 15 + j] - a;
+        }
+    }
+    return N - nBad;
+}
+int orbo_pose_inertial_opt_last_frame(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24,
+                                      const float* Pframe, const float* Pkf, const double* prior21, const double* priorH, double* prevState21, double* state21,
+                                      int bRecInit, uint8_t* outlier, double* H15) {
+    return orbo_pose_inertial_opt_last_frame_n(N, Xw, obs, invSigma2, trackDepth, cam4, extr24, Pframe, Pkf, prior21, priorH, prevState21, state21, bRecInit, outlier, H15, 4, 10);
+}
+
 }  // extern "C"

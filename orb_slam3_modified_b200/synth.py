@@ -314,3 +314,24 @@ def pose_inertial_problem(t0=1.0, t1=1.2, n=300, seed=0, outlier_frac=0.1, width
             bias[3:] + perturb * rng.normal(0, 2e-4, 3), bias[:3] + perturb * rng.normal(0, 2e-3, 3))
     return dict(Xw=Xw.astype(np.float32), obs=obs.astype(np.float32), inv_sigma2=(1.0 / 1.44 ** octave).astype(np.float32), track_depth=z.astype(np.float32), cam=cam,
                 extr=ex, acc=acc, gyr=gyr, dt=dts, bias6=bias.astype(np.float32), kf_state=kf, state=fr, truth=st(R2, p2, v2, bias[3:], bias[:3]), gross=bad)
+
+
+def pose_inertial_problem_last_frame(t0=1.0, t1=1.15, t2=1.2, n=300, seed=0, outlier_frac=0.1, perturb=1.0, noise_px=0.7, prior_sigma=(2e-3, 5e-3, 2e-2, 1e-4, 1e-3)):
+    """One frame for Optimizer::PoseInertialOptimizationLastFrame: last keyframe at t0 (only its preintegration covariance is used), previous frame at
+    t1 (free, held by a prior = its true state + noise with a diagonal information), the frame at t2."""
+    pr = pose_inertial_problem(t1, t2, n=n, seed=seed, outlier_frac=outlier_frac, perturb=perturb, noise_px=noise_px)
+    rng = np.random.default_rng(seed + 991)
+    acc, gyr, dts = imu_interval(t0, t2, seed=seed + 1, bias=tuple(pr['bias6']))
+    pr['acc_kf'], pr['gyr_kf'], pr['dt_kf'] = acc, gyr, dts
+    truth_prev = pr['kf_state'].copy()                      # pose_inertial_problem's "keyframe" is the previous frame here
+    sr, st, sv, sg, sa = prior_sigma
+    prior = truth_prev.copy()
+    prior[:9] = (prior[:9].reshape(3, 3) @ _rodrigues(rng.normal(0, sr, 3))).reshape(9)
+    prior[9:12] += rng.normal(0, st, 3); prior[12:15] += rng.normal(0, sv, 3); prior[15:18] += rng.normal(0, sg, 3); prior[18:21] += rng.normal(0, sa, 3)
+    H = np.diag(np.concatenate([np.full(3, 1 / sr ** 2), np.full(3, 1 / st ** 2), np.full(3, 1 / sv ** 2), np.full(3, 1 / sg ** 2), np.full(3, 1 / sa ** 2)]))
+    A = rng.normal(0, 1, (15, 15)); Q, _ = np.linalg.qr(A)
+    M = np.eye(15) + 0.05 * (Q - np.eye(15))               # a mild mixing so that the information is not diagonal
+    pr['prior_state'] = prior; pr['prior_H'] = M.T @ H @ M
+    pr['prev_state'] = prior.copy()                         # VertexPose(pFp) etc.: the previous frame's current estimate
+    pr['truth_prev'] = truth_prev
+    return pr

@@ -590,3 +590,21 @@ def pose_inertial_opt_last_kf(pr, preint, rec_init=False, rounds=4, iters=10):
 
 def pose_inertial_opt_one_step(pr, preint):
     return pose_inertial_opt_last_kf(pr, preint, rounds=1, iters=1)['state']
+
+
+def pose_inertial_opt_last_frame(pr, P_frame, P_kf, rec_init=False, rounds=4, iters=10):
+    """Optimizer::PoseInertialOptimizationLastFrame: dict(state [21], prev_state [21], outlier [N], H [15,15], ret)."""
+    L = lib()
+    N = len(pr['Xw'])
+    st = _c(pr['state'], np.float64).copy(); pv = _c(pr['prev_state'], np.float64).copy(); out = np.zeros(N, np.uint8); H = np.zeros((15, 15))
+    L.orbo_pose_inertial_opt_last_frame_n.argtypes = [C.c_int] + [C.c_void_p] * 12 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    a = [_c(pr['Xw'], np.float32), _c(pr['obs'], np.float32), _c(pr['inv_sigma2'], np.float32), _c(pr['track_depth'], np.float32), _c(pr['cam'], np.float32),
+         _c(pr['extr'], np.float64), _c(P_frame, np.float32), _c(P_kf, np.float32), _c(pr['prior_state'], np.float64), _c(pr['prior_H'], np.float64)]
+    ret = L.orbo_pose_inertial_opt_last_frame_n(N, *[_p(v) for v in a], _p(pv), _p(st), int(rec_init), _p(out), _p(H), rounds, iters)
+    return dict(state=st, prev_state=pv, outlier=out, H=H, ret=ret)
+
+
+def constraint_pose_imu_information(H):
+    H = _c(H, np.float64); out = np.zeros((15, 15))
+    lib().orbo_constraint_pose_imu_information(_p(H), _p(out))
+    return out

@@ -162,7 +162,7 @@ def test_pose_inertial_opt_noise_free_fixed_point():
 def test_pose_inertial_opt_first_step_is_the_gauss_newton_step():
     """One Gauss-Newton step of the oracle = the dense normal-equation step built from NUMERICAL derivatives of the stacked, whitened residuals
     (mono edges without robust weight: inliers only, inertial edge, random-walk edges) under ImuCamPose::Update."""
-    pr = synth.pose_inertial_problem(seed=5, n=60, outlier_frac=0.0, perturb=0.3, noise_px=0.2)
+    pr = synth.pose_inertial_problem(seed=5, n=60, outlier_frac=0.0, perturb=0.05, noise_px=0.2)
     P = O.imu_preintegrate(pr['acc'], pr['gyr'], pr['dt'], pr['bias6'], synth.IMU_NOISE)
     info9, ig, ia = O.imu_information(P)
     ex = pr['extr']
@@ -189,6 +189,7 @@ def test_pose_inertial_opt_first_step_is_the_gauss_newton_step():
         return np.concatenate(out)
     s0 = pr['state']
     r0 = residuals(s0)
+    assert (r0[:2 * len(pr['Xw'])].reshape(-1, 2) ** 2).sum(1).max() < 5.99      # no Huber weight at the linearisation point
     J = np.zeros((len(r0), 15))
     for k in range(15):
         h = 1e-6
@@ -199,3 +200,83 @@ def test_pose_inertial_opt_first_step_is_the_gauss_newton_step():
     # the oracle with ONE iteration: emulate by comparing against its first update through a 1-iteration copy (huge Huber never active at this noise level)
     got = O.pose_inertial_opt_one_step(pr, P)
     assert np.allclose(got, want, rtol=0, atol=2e-6), np.abs(got - want).max()
+
+
+# ---- Optimizer::PoseInertialOptimizationLastFrame (src/Optimizer.cc:4875-5289) ----
+def _preints(pr):
+    return (O.imu_preintegrate(pr['acc'], pr['gyr'], pr['dt'], pr['bias6'], synth.IMU_NOISE),
+            O.imu_preintegrate(pr['acc_kf'], pr['gyr_kf'], pr['dt_kf'], pr['bias6'], synth.IMU_NOISE))
+
+
+def test_pose_inertial_opt_last_frame_recovers_the_state():
+    for seed in range(3):
+        pr = synth.pose_inertial_problem_last_frame(seed=seed, n=300, outlier_frac=0.1)
+        Pf, Pk = _preints(pr)
+        r = O.pose_inertial_opt_last_frame(pr, Pf, Pk)
+        e0, e1 = _pose_err(pr['state'], pr['truth']), _pose_err(r['state'], pr['truth'])
+        assert e1[0] < 2e-3 and e1[1] < 8e-3 and e1[0] < e0[0] and e1[1] < e0[1], (seed, e0, e1)
+        assert r['outlier'][pr['gross']].mean() > 0.95 and r['outlier'][~pr['gross']].mean() < 0.08 and r['ret'] == len(pr['Xw']) - int(r['outlier'].sum())
+        ep = _pose_err(r['prev_state'], pr['truth_prev'])
+        assert ep[0] < 6e-3 and ep[1] < 2e-2
+        H = r['H']
+        assert np.allclose(H, H.T, rtol=1e-8, atol=1e-7 * np.abs(H).max()) and np.linalg.eigvalsh((H + H.T) / 2).min() > -1e-6 * np.abs(H).max()
+        C2 = O.constraint_pose_imu_information(H)              # ConstraintPoseImu's constructor: symmetric, no negative eigenvalues, equal to H here
+        assert np.allclose(C2, (H + H.T) / 2, rtol=1e-8, atol=1e-8 * np.abs(H).max())
+
+
+def test_pose_inertial_opt_last_frame_with_a_rigid_prior_is_the_last_keyframe_variant():
+    """A prior so strong that the previous frame cannot move, at the previous frame's own state: the frame's result and the marginalised
+    Hessian must be those of PoseInertialOptimizationLastKeyFrame with the previous frame as the fixed keyframe."""
+    pr = synth.pose_inertial_problem_last_frame(seed=4, n=250, outlier_frac=0.1)
+    Pf, _ = _preints(pr)
+    pr['prior_state'] = pr['kf_state'].copy(); pr['prev_state'] = pr['kf_state'].copy(); pr['prior_H'] = 1e16 * np.eye(15)
+    a = O.pose_inertial_opt_last_frame(pr, Pf, Pf)
+    b = O.pose_inertial_opt_last_kf(pr, Pf)
+    assert np.array_equal(a['outlier'], b['outlier']) and a['ret'] == b['ret']
+    assert np.abs(a['state'] - b['state']).max() < 1e-7 and np.abs(a['prev_state'] - pr['kf_state']).max() < 1e-9
+    assert np.abs(a['H'] - b['H']).max() < 1e-4 * np.abs(b['H']).max()          # H_cc - H_cb H_bb^-1 H_bc with H_bb ~ 1e16
+
+
+def test_pose_inertial_opt_last_frame_first_step_is_the_gauss_newton_step():
+    pr = synth.pose_inertial_problem_last_frame(seed=6, n=50, outlier_frac=0.0, perturb=0.05, noise_px=0.2)
+    Pf, Pk = _preints(pr)
+    info9 = O.imu_information(Pf)[0]; _, ig, ia = O.imu_information(Pk)
+    ex = pr['extr']
+    Lp = np.linalg.cholesky(pr['prior_H'])
+
+    def apply(s, dx):
+        s = s.copy()
+        R, t = O.imu_pose_update(s[:9].reshape(3, 3), s[9:12], dx[:6])
+        s[:9] = R.reshape(9); s[9:12] = t; s[12:15] += dx[6:9]; s[15:18] += dx[9:12]; s[18:21] += dx[12:15]
+        return s
+
+    def residuals(sc, sp):
+        out = []
+        for i in range(len(pr['Xw'])):
+            e = O.imu_edge_mono(sc[:9].reshape(3, 3), sc[9:12], ex[:9], ex[9:12], ex[12:21], ex[21:24], pr['cam'], pr['Xw'][i].astype(np.float64),
+                                pr['obs'][i].astype(np.float64), jac=False)[0]
+            out.append(np.sqrt(float(pr['inv_sigma2'][i])) * e)
+        e9 = O.imu_edge_inertial(Pf, dict(Rwb1=sp[:9].reshape(3, 3), twb1=sp[9:12], v1=sp[12:15], bg=sp[15:18], ba=sp[18:21], Rwb2=sc[:9].reshape(3, 3), twb2=sc[9:12], v2=sc[12:15]),
+                                 jac=False)[0]
+        out.append(np.linalg.cholesky(info9 + 1e-18 * np.eye(9)).T @ e9)
+        out.append(np.linalg.cholesky(ig).T @ (sc[15:18] - sp[15:18]))
+        out.append(np.linalg.cholesky(ia).T @ (sc[18:21] - sp[18:21]))
+        q = pr['prior_state']
+        Rp = q[:9].reshape(3, 3)
+        e15 = np.concatenate([_log(Rp.T @ sp[:9].reshape(3, 3)), Rp.T @ (sp[9:12] - q[9:12]), sp[12:15] - q[12:15], sp[15:18] - q[15:18], sp[18:21] - q[18:21]])
+        chi2_prior.append(float(e15 @ pr['prior_H'] @ e15))
+        out.append(Lp.T @ e15)
+        return np.concatenate(out)
+    chi2_prior = []
+    c0, p0 = pr['state'], pr['prev_state']
+    r0 = residuals(c0, p0)
+    assert chi2_prior[0] < 25.0 and (r0[:2 * len(pr['Xw'])].reshape(-1, 2) ** 2).sum(1).max() < 5.99      # no Huber weight at the linearisation point
+    J = np.zeros((len(r0), 30))
+    for k in range(30):
+        h = 2e-3 if k % 15 >= 9 else 1e-6      # the preintegration applies bias changes in float (src/ImuTypes.cc:283-307): a bias step must stand out of its rounding
+        d = np.zeros(30); d[k] = h
+        J[:, k] = (residuals(apply(c0, d[:15]), apply(p0, d[15:])) - residuals(apply(c0, -d[:15]), apply(p0, -d[15:]))) / (2 * h)
+    dx = np.linalg.solve(J.T @ J, -J.T @ r0)
+    got = O.pose_inertial_opt_last_frame(pr, Pf, Pk, rounds=1, iters=1)
+    assert np.allclose(got['state'], apply(c0, dx[:15]), rtol=0, atol=3e-6), np.abs(got['state'] - apply(c0, dx[:15])).max()
+    assert np.allclose(got['prev_state'], apply(p0, dx[15:]), rtol=0, atol=3e-6), np.abs(got['prev_state'] - apply(p0, dx[15:])).max()
