@@ -442,6 +442,18 @@ int imu_inertial_edges(int count, const float* preint, const double* states36, c
 int pose_inertial_optimization_last_kf_batch(int count, int cap, const int32_t* N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth,
                                              const float* cam4, const double* extrinsics24, const float* preint, const double* kfState21, double* state21, int bRecInit,
                                              uint8_t* outlier, double* H15, int32_t* ret, int device);
+/* int Optimizer::PoseInertialOptimizationLastFrame(Frame* pFrame, bool bRecInit) (include/Optimizer.h:67, src/Optimizer.cc:4875-5289), monocular
+ * frame: the variant Tracking::TrackLocalMap runs when the map was NOT updated since the last frame (src/Tracking.cc:2985-2994).  The previous
+ * frame's pose / velocity / biases are free too (30 unknowns) and held by EdgePriorPoseImu: prior21 [count][21] = Rwb | twb | vwb | bg | ba and
+ * priorH [count][225] = pFp->mpcpi->H (what ConstraintPoseImu's constructor made of the Hessian the previous call returned: symmetrised,
+ * eigenvalues < 1e-12 clamped).  preintFrame = pFrame->mpImuPreintegratedFrame (EdgeInertial), preintKF = pFrame->mpImuPreintegrated (only the
+ * covariance blocks of the two random-walk edges, :5068-5078).  prevState21 in: VertexPose / Velocity / GyroBias / AccBias(pFp); out: their
+ * estimates afterwards (the reference does not write them back).  H15 = Marginalize(H, 0, 14).block<15,15>(15,15) (:5268-5270), the Hessian
+ * handed to the new ConstraintPoseImu.  Everything else as in pose_inertial_optimization_last_kf_batch. */
+int pose_inertial_optimization_last_frame_batch(int count, int cap, const int32_t* N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth,
+                                                const float* cam4, const double* extrinsics24, const float* preintFrame, const float* preintKF, const double* prior21,
+                                                const double* priorH, double* prevState21, double* state21, int bRecInit, uint8_t* outlier, double* H15, int32_t* ret,
+                                                int device);
 /* EdgeMono (include/G2oTypes.h:342-385, src/G2oTypes.cc:349-373) over VertexPose = ImuCamPose (body pose + camera extrinsics, src/G2oTypes.cc:148-220). */
 typedef struct ImuMonoEdges {
     int nPoses;  const double* poses;       /* [nPoses][12]: Rwb 9 | twb 3 */

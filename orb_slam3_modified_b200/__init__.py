@@ -853,6 +853,30 @@ def PoseInertialOptimizationLastKeyFrame(frames, extrinsics24, rec_init=False, d
     return [dict(state=st[i], outlier=out[i, :N[i]], H=H[i], ret=int(ret[i])) for i in range(n)]
 
 
+def PoseInertialOptimizationLastFrame(frames, extrinsics24, rec_init=False, device=0):
+    """``int Optimizer::PoseInertialOptimizationLastFrame(Frame*, bool bRecInit)`` (src/Optimizer.cc:4875-5289) for a list of frames.
+    frame = dict(Xw, obs, inv_sigma2, track_depth, cam, preint_frame, preint_kf, prior_state [21], prior_H [15,15], prev_state [21], state [21]).
+    Returns a list of dict(state, prev_state, outlier, H [15,15], ret)."""
+    n = len(frames)
+    cap = max(1, max(len(f['Xw']) for f in frames))
+    N = np.array([len(f['Xw']) for f in frames], np.int32)
+    Xw = np.zeros((n, cap, 3), np.float32); ob = np.zeros((n, cap, 2), np.float32); isg = np.zeros((n, cap), np.float32); td = np.zeros((n, cap), np.float32)
+    for i, f in enumerate(frames):
+        Xw[i, :N[i]] = f['Xw']; ob[i, :N[i]] = f['obs']; isg[i, :N[i]] = f['inv_sigma2']; td[i, :N[i]] = f['track_depth']
+    st64 = lambda k: np.stack([_c(f[k], np.float64).reshape(-1) for f in frames]).copy()
+    cam = np.stack([_c(f['cam'], np.float32) for f in frames]); Pf = np.stack([_c(f['preint_frame'], np.float32) for f in frames]); Pk = np.stack([_c(f['preint_kf'], np.float32) for f in frames])
+    prior, pH, pv, st = st64('prior_state'), st64('prior_H'), st64('prev_state'), st64('state')
+    ex = _c(extrinsics24, np.float64)
+    out = np.zeros((n, cap), np.uint8); H = np.zeros((n, 15, 15)); ret = np.zeros(n, np.int32)
+    L = lib()
+    L.pose_inertial_optimization_last_frame_batch.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 13 + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = L.pose_inertial_optimization_last_frame_batch(n, cap, _ptr(N), _ptr(Xw), _ptr(ob), _ptr(isg), _ptr(td), _ptr(cam), _ptr(ex), _ptr(Pf), _ptr(Pk), _ptr(prior), _ptr(pH),
+                                                       _ptr(pv), _ptr(st), int(rec_init), _ptr(out), _ptr(H), _ptr(ret), device)
+    if rc != ORB_OK:
+        raise OrbError(rc, 'pose_inertial_optimization_last_frame_batch')
+    return [dict(state=st[i], prev_state=pv[i], outlier=out[i, :N[i]], H=H[i], ret=int(ret[i])) for i in range(n)]
+
+
 # =============================================================================================
 # DBoW2 vocabulary transform (reference Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h; SURVEY.md 8f rank 3)
 # =============================================================================================

@@ -430,13 +430,17 @@ struct PoseInertialParams {
     const float *Xw, *obs, *invSigma2, *trackDepth;   // [count][cap][3], [..][2], [..], [..]
     const float* cam4;                  // [count][4]
     const double* extr;                 // [24]
-    const float* preint;                // [count][P_SIZE]
-    const double* kfState;              // [count][21]
+    const float* preint;                // [count][P_SIZE]: EdgeInertial (from the last keyframe / from the previous frame)
+    const double* kfState;              // [count][21]: the fixed last keyframe (last-keyframe variant)
     double* state;                      // [count][21] in / out
     double* err;                        // scratch [count][cap][2]
     uint8_t* outlier;                   // [count][cap]
     double* H15;                        // [count][225]
     int* ret;                           // [count]
+    // last-frame variant (src/Optimizer.cc:4875-5289): the previous frame is free and held by EdgePriorPoseImu
+    const float* preintKF;              // [count][P_SIZE]: mpImuPreintegrated, the source of the two random-walk informations (:5068-5078)
+    const double *prior, *priorH;       // [count][21], [count][225]: ConstraintPoseImu of the previous frame
+    double* prevState;                  // [count][21] in / out
 };
 __device__ __forceinline__ double pi_block_sum(double v, double* sm) {
 #pragma unroll
@@ -481,22 +485,73 @@ __device__ void exp_so3_d(const double* w, double* R) {      // ExpSO3(double) w
     }
     normalize_rotation(res, R);
 }
+// vertex updates of one frame: ImuCamPose::Update (twb += Rwb ut; Rwb = Rwb ExpSO3(ur); NormalizeRotation every third update), v / bg / ba += dx
+__device__ void apply_update15(double* st, const double* dx, int& its) {
+    double t3[3], E[9], Rn[9];
+    m3vec(st, dx + 3, t3);
+    for (int i = 0; i < 3; ++i) st[9 + i] += t3[i];
+    exp_so3_d(dx, E);
+    m3mul(st, E, Rn);
+    for (int i = 0; i < 9; ++i) st[i] = Rn[i];
+    if (++its >= 3) { normalize_rotation(st, Rn); for (int i = 0; i < 9; ++i) st[i] = Rn[i]; its = 0; }
+    for (int i = 0; i < 3; ++i) { st[12 + i] += dx[6 + i]; st[15 + i] += dx[9 + i]; st[18 + i] += dx[12 + i]; }
+}
+// EdgePriorPoseImu (src/G2oTypes.cc:731-760): residual 15 and Jacobian 15 x 15 (block diagonal) wrt the previous frame's pose 6, v, bg, ba
+__device__ void prior_edge_dev(const double* prior, const double* st, double* e15, double* J) {
+    double Rpt[9], dR[9], er[3], d[3], et[3], iJ[9];
+    m3T(prior, Rpt); m3mul(Rpt, st, dR);
+    log_so3(dR, er);
+    for (int i = 0; i < 3; ++i) d[i] = st[9 + i] - prior[9 + i];
+    m3vec(Rpt, d, et);
+    for (int i = 0; i < 3; ++i) { e15[i] = er[i]; e15[3 + i] = et[i]; e15[6 + i] = st[12 + i] - prior[12 + i]; e15[9 + i] = st[15 + i] - prior[15 + i]; e15[12 + i] = st[18 + i] - prior[18 + i]; }
+    for (int i = 0; i < 225; ++i) J[i] = 0;
+    inv_right_jacobian(er, iJ);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { J[i * 15 + j] = iJ[i * 3 + j]; J[(3 + i) * 15 + 3 + j] = dR[i * 3 + j]; }
+    for (int i = 6; i < 15; ++i) J[i * 15 + i] = 1.0;
+}
+// dense LDLT solve of the n x n system in H (row-major, leading dimension n), n <= 30: Eigen::LDLT + isPositive() (linear_solver_dense.h:111-118).
+// L: n*n scratch.  Returns false (x untouched) when a pivot is not positive.
+__device__ bool ldlt_solve_dev(int n, const double* H, const double* b, double* x, double* L) {
+    double d[30], y[30];
+    for (int k = 0; k < n * n; ++k) L[k] = H[k];
+    for (int j = 0; j < n; ++j) {
+        double dj = L[j * n + j];
+        for (int k = 0; k < j; ++k) dj -= L[j * n + k] * L[j * n + k] * d[k];
+        if (!(dj > 0)) return false;
+        d[j] = dj;
+        for (int i = j + 1; i < n; ++i) {
+            double v = L[i * n + j];
+            for (int k = 0; k < j; ++k) v -= L[i * n + k] * L[j * n + k] * d[k];
+            L[i * n + j] = v / dj;
+        }
+    }
+    for (int i = 0; i < n; ++i) { double v = b[i]; for (int k = 0; k < i; ++k) v -= L[i * n + k] * y[k]; y[i] = v; }
+    for (int i = n - 1; i >= 0; --i) { double v = y[i] / d[i]; for (int k = i + 1; k < n; ++k) v -= L[k * n + i] * x[k]; x[i] = v; }
+    return true;
+}
+// LF = false: PoseInertialOptimizationLastKeyFrame (15 unknowns); LF = true: PoseInertialOptimizationLastFrame (30 unknowns: current 15 | previous 15)
+template <bool LF>
 __global__ void __launch_bounds__(PI_NT) pose_inertial_opt_kernel(PoseInertialParams Q) {
+    constexpr int NX = LF ? 30 : 15;
     __shared__ double s_red[PI_NT / 32];
-    __shared__ double s_st[21], s_cam[12], s_info[81 + 9 + 9], s_x[15], s_H[225], s_b[15];
+    __shared__ double s_st[21], s_sp[21], s_cam[12], s_info[81 + 9 + 9], s_x[NX], s_H[NX * NX], s_b[NX], s_L[NX * NX];
     __shared__ int s_ok, s_cnt[2];
     const int f = blockIdx.x, tid = threadIdx.x;
     const int N = min(Q.N[f], Q.cap);
     const float* Xw = Q.Xw + 3 * (size_t)f * Q.cap; const float* ob = Q.obs + 2 * (size_t)f * Q.cap;
     const float* is2 = Q.invSigma2 + (size_t)f * Q.cap; const float* td = Q.trackDepth + (size_t)f * Q.cap;
     const float* cm = Q.cam4 + 4 * (size_t)f; const float* P = Q.preint + (size_t)P_SIZE * f;
-    const double* K = Q.kfState + 21 * (size_t)f;
     double* err = Q.err + 2 * (size_t)f * Q.cap; uint8_t* outl = Q.outlier + (size_t)f * Q.cap;
     const double *Rcb = Q.extr, *tcb = Q.extr + 9, *Rbc = Q.extr + 12, *tbc = Q.extr + 21;
+    const double* prior = LF ? Q.prior + 21 * (size_t)f : nullptr;
+    const double* priorH = LF ? Q.priorH + 225 * (size_t)f : nullptr;
     double *Rcw = s_cam, *tcw = s_cam + 9;
-    if (tid < 21) s_st[tid] = Q.state[21 * (size_t)f + tid];
-    if (tid < 15) s_x[tid] = 0.0;
-    if (tid == 0) imu_information_dev(P, s_info, s_info + 81, s_info + 90);
+    if (tid < 21) { s_st[tid] = Q.state[21 * (size_t)f + tid]; s_sp[tid] = LF ? Q.prevState[21 * (size_t)f + tid] : Q.kfState[21 * (size_t)f + tid]; }
+    if (tid < NX) s_x[tid] = 0.0;
+    if (tid == 0) {
+        if (LF) { imu_information_dev(Q.preintKF + (size_t)P_SIZE * f, s_H, s_info + 81, s_info + 90); imu_information_dev(P, s_info, s_H, s_H + 16); }
+        else imu_information_dev(P, s_info, s_info + 81, s_info + 90);
+    }
     for (int i = tid; i < N; i += PI_NT) { outl[i] = 0; err[2 * i] = 0; err[2 * i + 1] = 0; }
     __syncthreads();
     auto refresh_camera = [&]() {               // ImuCamPose::Update's camera part: Rcw = Rcb Rbw, tcw = Rcb tbw + tcb   (thread 0)
@@ -509,17 +564,18 @@ __global__ void __launch_bounds__(PI_NT) pose_inertial_opt_kernel(PoseInertialPa
     if (tid == 0) refresh_camera();
     __syncthreads();
     const double delta = (double)sqrtf(5.991f), dsqr = delta * delta;
-    const float chi2Mono[4] = {12.f, 7.5f, 5.991f, 5.991f};
+    const float chi2Mono[4] = {LF ? 5.991f : 12.f, LF ? 5.991f : 7.5f, 5.991f, 5.991f};
     bool robust = true;
-    int its = 0, nBad = 0, nInliers = 0;        // its: thread 0's copy of ImuCamPose::its
-    // level[i] lives in bit 1 of outl[] during the rounds (bit 0 = mvbOutlier): both are set together by the classification, so one flag does
+    int its = 0, itsPrev = 0, nBad = 0, nInliers = 0;        // its / itsPrev: thread 0's copies of ImuCamPose::its of the two VertexPose
+    // x column of column c of the EdgeInertial Jacobian (vertex order: previous pose, v, bg, ba | current pose, v)
+    auto xi = [](int c) { return c < 15 ? 15 + c : c - 15; };
     for (int it = 0; it < 4; ++it) {
         for (int iter = 0; iter < 10; ++iter) {
             double acc[27];
 #pragma unroll
             for (int k = 0; k < 27; ++k) acc[k] = 0;
             for (int i = tid; i < N; i += PI_NT) {
-                if (outl[i]) continue;
+                if (outl[i]) continue;                        // setLevel(1) and mvbOutlier are always set together (:4736-4747)
                 double e0, e1, Jp[12]; bool dp;
                 mono_only_pose(Rcw, tcw, Rcb, Rbc, tbc, cm, Xw + 3 * i, ob + 2 * i, e0, e1, dp, Jp);
                 err[2 * i] = e0; err[2 * i + 1] = e1;
@@ -539,67 +595,64 @@ __global__ void __launch_bounds__(PI_NT) pose_inertial_opt_kernel(PoseInertialPa
 #pragma unroll
             for (int k = 0; k < 27; ++k) tot[k] = pi_block_sum(acc[k], s_red);
             if (tid == 0) {
-                for (int k = 0; k < 225; ++k) s_H[k] = 0;
-                for (int k = 0; k < 15; ++k) s_b[k] = 0;
+                for (int k = 0; k < NX * NX; ++k) s_H[k] = 0;
+                for (int k = 0; k < NX; ++k) s_b[k] = 0;
                 int t = 0;
-                for (int a = 0; a < 6; ++a) for (int c = a; c < 6; ++c) { s_H[a * 15 + c] = tot[t]; s_H[c * 15 + a] = tot[t]; ++t; }
+                for (int a = 0; a < 6; ++a) for (int c = a; c < 6; ++c) { s_H[a * NX + c] = tot[t]; s_H[c * NX + a] = tot[t]; ++t; }
                 for (int a = 0; a < 6; ++a) s_b[a] = tot[21 + a];
-                {   // EdgeInertial: Jacobians of the frame's pose (columns 15..20) and velocity (21..23); the keyframe is fixed
-                    double S36[36], e9[9], J[216], OJ[81];
-                    for (int k = 0; k < 21; ++k) S36[k] = K[k];
+                {   // EdgeInertial (the keyframe's columns drop out in the last-keyframe variant: its vertices are fixed)
+                    double S36[36], e9[9], J[216], OJ[216];
+                    for (int k = 0; k < 21; ++k) S36[k] = s_sp[k];
                     for (int k = 0; k < 15; ++k) S36[21 + k] = s_st[k];
                     edge_inertial_dev(P, S36, e9, J);
-                    for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) { double sacc = 0; for (int k = 0; k < 9; ++k) sacc += s_info[r * 9 + k] * J[k * 24 + 15 + c]; OJ[r * 9 + c] = sacc; }
-                    for (int a = 0; a < 9; ++a) {
+                    const int c0 = LF ? 0 : 15;
+                    for (int r = 0; r < 9; ++r) for (int c = c0; c < 24; ++c) { double sacc = 0; for (int k = 0; k < 9; ++k) sacc += s_info[r * 9 + k] * J[k * 24 + c]; OJ[r * 24 + c] = sacc; }
+                    for (int a = c0; a < 24; ++a) {
                         double sacc = 0;
-                        for (int r = 0; r < 9; ++r) sacc += OJ[r * 9 + a] * e9[r];
-                        s_b[a] -= sacc;
-                        for (int c = 0; c < 9; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += J[r * 24 + 15 + a] * OJ[r * 9 + c]; s_H[a * 15 + c] += h; }
+                        for (int r = 0; r < 9; ++r) sacc += OJ[r * 24 + a] * e9[r];
+                        s_b[xi(a)] -= sacc;
+                        for (int c = c0; c < 24; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += J[r * 24 + a] * OJ[r * 24 + c]; s_H[xi(a) * NX + xi(c)] += h; }
                     }
                 }
-                for (int a = 0; a < 3; ++a) {       // EdgeGyroRW / EdgeAccRW
+                for (int a = 0; a < 3; ++a) {       // EdgeGyroRW / EdgeAccRW: error = b_cur - b_prev, Jacobians -I (previous, when free) / +I (current)
                     double sg = 0, sa = 0;
                     for (int c = 0; c < 3; ++c) {
-                        sg += s_info[81 + a * 3 + c] * (s_st[15 + c] - K[15 + c]); sa += s_info[90 + a * 3 + c] * (s_st[18 + c] - K[18 + c]);
-                        s_H[(9 + a) * 15 + 9 + c] += s_info[81 + a * 3 + c]; s_H[(12 + a) * 15 + 12 + c] += s_info[90 + a * 3 + c];
+                        const double og = s_info[81 + a * 3 + c], oa = s_info[90 + a * 3 + c];
+                        sg += og * (s_st[15 + c] - s_sp[15 + c]); sa += oa * (s_st[18 + c] - s_sp[18 + c]);
+                        s_H[(9 + a) * NX + 9 + c] += og; s_H[(12 + a) * NX + 12 + c] += oa;
+                        if (LF) {
+                            s_H[(24 + a) * NX + 24 + c] += og; s_H[(9 + a) * NX + 24 + c] -= og; s_H[(24 + a) * NX + 9 + c] -= og;
+                            s_H[(27 + a) * NX + 27 + c] += oa; s_H[(12 + a) * NX + 27 + c] -= oa; s_H[(27 + a) * NX + 12 + c] -= oa;
+                        }
                     }
                     s_b[9 + a] -= sg; s_b[12 + a] -= sa;
+                    if (LF) { s_b[24 + a] += sg; s_b[27 + a] += sa; }
                 }
-                // dense LDLT (Eigen::LDLT + isPositive(), linear_solver_dense.h:111-118); a failed solve leaves x of the previous iteration
-                double L[225], d[15], y[15];
-                for (int k = 0; k < 225; ++k) L[k] = s_H[k];
-                bool ok = true;
-                for (int j = 0; j < 15 && ok; ++j) {
-                    double dj = L[j * 15 + j];
-                    for (int k = 0; k < j; ++k) dj -= L[j * 15 + k] * L[j * 15 + k] * d[k];
-                    if (!(dj > 0)) { ok = false; break; }
-                    d[j] = dj;
-                    for (int i = j + 1; i < 15; ++i) {
-                        double v = L[i * 15 + j];
-                        for (int k = 0; k < j; ++k) v -= L[i * 15 + k] * L[j * 15 + k] * d[k];
-                        L[i * 15 + j] = v / dj;
+                if (LF) {                           // EdgePriorPoseImu on the previous frame, RobustKernelHuber delta 5 (:5084-5092)
+                    double e15[15], J[225], Oe[15];
+                    prior_edge_dev(prior, s_sp, e15, J);
+                    double c2 = 0;
+                    for (int r = 0; r < 15; ++r) { double sacc = 0; for (int k = 0; k < 15; ++k) sacc += priorH[r * 15 + k] * e15[k]; Oe[r] = sacc; c2 += e15[r] * sacc; }
+                    const double w = c2 > 25.0 ? 5.0 / sqrt(c2) : 1.0;
+                    double* OJ = s_L;               // 15 x 15 scratch (s_L is free until the factorisation)
+                    for (int r = 0; r < 15; ++r) for (int c = 0; c < 15; ++c) { double sacc = 0; for (int k = 0; k < 15; ++k) sacc += priorH[r * 15 + k] * J[k * 15 + c]; OJ[r * 15 + c] = sacc; }
+                    for (int a = 0; a < 15; ++a) {
+                        double g = 0;
+                        for (int r = 0; r < 15; ++r) g += J[r * 15 + a] * Oe[r];
+                        s_b[15 + a] -= w * g;
+                        for (int c = 0; c < 15; ++c) { double h = 0; for (int r = 0; r < 15; ++r) h += J[r * 15 + a] * OJ[r * 15 + c]; s_H[(15 + a) * NX + 15 + c] += w * h; }
                     }
                 }
-                if (ok) {
-                    for (int i = 0; i < 15; ++i) { double v = s_b[i]; for (int k = 0; k < i; ++k) v -= L[i * 15 + k] * y[k]; y[i] = v; }
-                    for (int i = 14; i >= 0; --i) { double v = y[i] / d[i]; for (int k = i + 1; k < 15; ++k) v -= L[k * 15 + i] * s_x[k]; s_x[i] = v; }
-                }
-                // update: ImuCamPose::Update (twb += Rwb ut; Rwb = Rwb ExpSO3(ur); NormalizeRotation every third update), v / bg / ba += dx
-                double t3[3], E[9], Rn[9];
-                m3vec(s_st, s_x + 3, t3);
-                for (int i = 0; i < 3; ++i) s_st[9 + i] += t3[i];
-                exp_so3_d(s_x, E);
-                m3mul(s_st, E, Rn);
-                for (int i = 0; i < 9; ++i) s_st[i] = Rn[i];
-                if (++its >= 3) { normalize_rotation(s_st, Rn); for (int i = 0; i < 9; ++i) s_st[i] = Rn[i]; its = 0; }
-                for (int i = 0; i < 3; ++i) { s_st[12 + i] += s_x[6 + i]; s_st[15 + i] += s_x[9 + i]; s_st[18 + i] += s_x[12 + i]; }
+                const bool ok = ldlt_solve_dev(NX, s_H, s_b, s_x, s_L);    // a failed solve leaves x of the previous iteration; update() still runs
+                apply_update15(s_st, s_x, its);
+                if (LF) apply_update15(s_sp, s_x + 15, itsPrev);
                 refresh_camera();
                 s_ok = ok ? 1 : 0;
             }
             __syncthreads();
             if (!s_ok) break;
         }
-        // ---- re-classification (:4713-4778) ----
+        // ---- re-classification (:4713-4778 / :5113-5180) ----
         if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
         __syncthreads();
         const float chi2close = (float)(1.5 * (double)chi2Mono[it]);
@@ -617,9 +670,9 @@ __global__ void __launch_bounds__(PI_NT) pose_inertial_opt_kernel(PoseInertialPa
         nBad = s_cnt[0]; nInliers = s_cnt[1];
         __syncthreads();
         if (it == 2) robust = false;
-        if (N + 3 < 10) break;                                              // optimizer.edges().size() < 10
+        if (N + (LF ? 4 : 3) < 10) break;                                   // optimizer.edges().size() < 10
     }
-    if (nInliers < 30 && !Q.recInit) {                                       // :4783-4810
+    if (nInliers < 30 && !Q.recInit) {                                       // :4783-4810 / :5183-5211
         if (tid == 0) s_cnt[0] = 0;
         __syncthreads();
         int bad = 0;
@@ -634,7 +687,7 @@ __global__ void __launch_bounds__(PI_NT) pose_inertial_opt_kernel(PoseInertialPa
         nBad = s_cnt[0];
         __syncthreads();
     }
-    // ---- the prior of the next frame (:4819-4867) ----
+    // ---- the prior of the next frame (:4819-4870 / :5216-5285) ----
     double acc[21];
 #pragma unroll
     for (int k = 0; k < 21; ++k) acc[k] = 0;
@@ -654,23 +707,80 @@ __global__ void __launch_bounds__(PI_NT) pose_inertial_opt_kernel(PoseInertialPa
 #pragma unroll
     for (int k = 0; k < 21; ++k) tot[k] = pi_block_sum(acc[k], s_red);
     if (tid == 0) {
-        double* H = Q.H15 + 225 * (size_t)f;
-        for (int k = 0; k < 225; ++k) H[k] = 0;
+        double* Hout = Q.H15 + 225 * (size_t)f;
         double S36[36], e9[9], J[216];
-        for (int k = 0; k < 21; ++k) S36[k] = K[k];
+        for (int k = 0; k < 21; ++k) S36[k] = s_sp[k];
         for (int k = 0; k < 15; ++k) S36[21 + k] = s_st[k];
         edge_inertial_dev(P, S36, e9, J);
-        for (int a = 0; a < 9; ++a) for (int c = 0; c < 9; ++c) {
-            double h = 0;
-            for (int r = 0; r < 9; ++r) for (int k = 0; k < 9; ++k) h += J[r * 24 + 15 + a] * s_info[r * 9 + k] * J[k * 24 + 15 + c];
-            H[a * 15 + c] += h;
+        if constexpr (!LF) {
+            for (int k = 0; k < 225; ++k) Hout[k] = 0;
+            for (int a = 0; a < 9; ++a) for (int c = 0; c < 9; ++c) {
+                double h = 0;
+                for (int r = 0; r < 9; ++r) for (int k = 0; k < 9; ++k) h += J[r * 24 + 15 + a] * s_info[r * 9 + k] * J[k * 24 + 15 + c];
+                Hout[a * 15 + c] += h;
+            }
+            for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) { Hout[(9 + a) * 15 + 9 + c] += s_info[81 + a * 3 + c]; Hout[(12 + a) * 15 + 12 + c] += s_info[90 + a * 3 + c]; }
+            int t = 0;
+            for (int a = 0; a < 6; ++a) for (int c = a; c < 6; ++c) { Hout[a * 15 + c] += tot[t]; if (c != a) Hout[c * 15 + a] += tot[t]; ++t; }
+        } else {
+            // 30 x 30 in the reference's order (previous 15 | current 15), then Optimizer::Marginalize(H, 0, 14): H_cc - H_cb pinv(H_bb) H_bc
+            double* Hf = s_H;
+            for (int k = 0; k < 900; ++k) Hf[k] = 0;
+            for (int a = 0; a < 24; ++a) for (int c = 0; c < 24; ++c) {
+                double h = 0;
+                for (int r = 0; r < 9; ++r) for (int k = 0; k < 9; ++k) h += J[r * 24 + a] * s_info[r * 9 + k] * J[k * 24 + c];
+                Hf[a * 30 + c] += h;
+            }
+            for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) {
+                const double og = s_info[81 + a * 3 + c], oa = s_info[90 + a * 3 + c];
+                Hf[(9 + a) * 30 + 9 + c] += og; Hf[(9 + a) * 30 + 24 + c] -= og; Hf[(24 + a) * 30 + 9 + c] -= og; Hf[(24 + a) * 30 + 24 + c] += og;
+                Hf[(12 + a) * 30 + 12 + c] += oa; Hf[(12 + a) * 30 + 27 + c] -= oa; Hf[(27 + a) * 30 + 12 + c] -= oa; Hf[(27 + a) * 30 + 27 + c] += oa;
+            }
+            {
+                double e15[15], Jp[225];
+                prior_edge_dev(prior, s_sp, e15, Jp);
+                for (int a = 0; a < 15; ++a) for (int c = 0; c < 15; ++c) {
+                    double h = 0;
+                    for (int r = 0; r < 15; ++r) for (int k = 0; k < 15; ++k) h += Jp[r * 15 + a] * priorH[r * 15 + k] * Jp[k * 15 + c];
+                    Hf[a * 30 + c] += h;
+                }
+            }
+            int t = 0;
+            for (int a = 0; a < 6; ++a) for (int c = a; c < 6; ++c) { Hf[(15 + a) * 30 + 15 + c] += tot[t]; if (c != a) Hf[(15 + c) * 30 + 15 + a] += tot[t]; ++t; }
+            // pseudo-inverse of the symmetrised H_bb through cyclic Jacobi (= the SVD of a symmetric matrix), eigenvalues with |w| <= 1e-6 dropped
+            double* A = s_L; double* V = s_L + 225; double* Pv = s_L + 450;     // 3 x 225 of the 900-double scratch
+            for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) { A[i * 15 + j] = (Hf[i * 30 + j] + Hf[j * 30 + i]) / 2; V[i * 15 + j] = i == j ? 1.0 : 0.0; }
+            for (int sweep = 0; sweep < 100; ++sweep) {
+                double off = 0, diag = 0;
+                for (int p = 0; p < 15; ++p) { diag += A[p * 15 + p] * A[p * 15 + p]; for (int q = p + 1; q < 15; ++q) off += A[p * 15 + q] * A[p * 15 + q]; }
+                if (off <= 1e-30 * diag || off < 1e-300) break;
+                for (int p = 0; p < 15; ++p)
+                    for (int q = p + 1; q < 15; ++q) {
+                        const double apq = A[p * 15 + q];
+                        if (apq == 0) continue;
+                        const double theta = (A[q * 15 + q] - A[p * 15 + p]) / (2 * apq);
+                        const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+                        const double cc = 1 / sqrt(tt * tt + 1), sn = tt * cc;
+                        for (int k = 0; k < 15; ++k) { const double akp = A[k * 15 + p], akq = A[k * 15 + q]; A[k * 15 + p] = cc * akp - sn * akq; A[k * 15 + q] = sn * akp + cc * akq; }
+                        for (int k = 0; k < 15; ++k) { const double apk = A[p * 15 + k], aqk = A[q * 15 + k]; A[p * 15 + k] = cc * apk - sn * aqk; A[q * 15 + k] = sn * apk + cc * aqk; }
+                        for (int k = 0; k < 15; ++k) { const double vkp = V[k * 15 + p], vkq = V[k * 15 + q]; V[k * 15 + p] = cc * vkp - sn * vkq; V[k * 15 + q] = sn * vkp + cc * vkq; }
+                    }
+            }
+            for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) {
+                double a = 0;
+                for (int k = 0; k < 15; ++k) { const double w = A[k * 15 + k]; if (fabs(w) > 1e-6) a += V[i * 15 + k] * V[j * 15 + k] / w; }
+                Pv[i * 15 + j] = a;
+            }
+            for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) {
+                double a = 0;
+                for (int k = 0; k < 15; ++k) for (int l = 0; l < 15; ++l) a += Hf[(15 + i) * 30 + k] * Pv[k * 15 + l] * Hf[l * 30 + 15 + j];
+                Hout[i * 15 + j] = Hf[(15 + i) * 30 + 15 + j] - a;
+            }
         }
-        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) { H[(9 + a) * 15 + 9 + c] += s_info[81 + a * 3 + c]; H[(12 + a) * 15 + 12 + c] += s_info[90 + a * 3 + c]; }
-        int t = 0;
-        for (int a = 0; a < 6; ++a) for (int c = a; c < 6; ++c) { H[a * 15 + c] += tot[t]; if (c != a) H[c * 15 + a] += tot[t]; ++t; }
         Q.ret[f] = N - nBad;
     }
-    if (tid < 21) Q.state[21 * (size_t)f + tid] = s_st[tid];
+    __syncthreads();
+    if (tid < 21) { Q.state[21 * (size_t)f + tid] = s_st[tid]; if (LF) Q.prevState[21 * (size_t)f + tid] = s_sp[tid]; }
 }
 
 // host plumbing: one device arena per host thread and device, grown on demand (these are static functions in the reference)
@@ -804,9 +914,57 @@ int pose_inertial_optimization_last_kf_batch(int count, int cap, const int32_t* 
     Q.N = (const int*)(d + oN); Q.Xw = (const float*)(d + oX); Q.obs = (const float*)(d + oO); Q.invSigma2 = (const float*)(d + oS); Q.trackDepth = (const float*)(d + oT);
     Q.cam4 = (const float*)(d + oC); Q.extr = (const double*)(d + oE); Q.preint = (const float*)(d + oP); Q.kfState = (const double*)(d + oK); Q.state = (double*)(d + oSt);
     Q.err = (double*)(d + oEr); Q.outlier = d + oOut; Q.H15 = (double*)(d + oH); Q.ret = (int*)(d + oR);
-    pose_inertial_opt_kernel<<<count, PI_NT, 0, st>>>(Q);
+    Q.preintKF = nullptr; Q.prior = nullptr; Q.priorH = nullptr; Q.prevState = nullptr;
+    pose_inertial_opt_kernel<false><<<count, PI_NT, 0, st>>>(Q);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(state21, d + oSt, 168 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(outlier, d + oOut, C * K, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(H15, d + oH, 1800 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ret, d + oR, 4 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int pose_inertial_optimization_last_frame_batch(int count, int cap, const int32_t* N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth,
+                                                const float* cam4, const double* extrinsics24, const float* preintFrame, const float* preintKF, const double* prior21,
+                                                const double* priorH, double* prevState21, double* state21, int bRecInit, uint8_t* outlier, double* H15, int32_t* ret,
+                                                int device) {
+    if (count < 1 || cap < 1 || !N || !Xw || !obs || !invSigma2 || !trackDepth || !cam4 || !extrinsics24 || !preintFrame || !preintKF || !prior21 || !priorH || !prevState21 ||
+        !state21 || !outlier || !H15 || !ret) {
+        set_error("pose_inertial_optimization_last_frame_batch: bad argument"); return ORB_ERR_ARG;
+    }
+    const size_t C = count, K = cap;
+    Bump B(nullptr);
+    const size_t oN = B.take(4 * C), oX = B.take(12 * C * K), oO = B.take(8 * C * K), oS = B.take(4 * C * K), oT = B.take(4 * C * K), oC = B.take(16 * C), oE = B.take(192),
+                 oP = B.take(4 * P_SIZE * C), oPk = B.take(4 * P_SIZE * C), oPr = B.take(168 * C), oPh = B.take(1800 * C), oPv = B.take(168 * C), oSt = B.take(168 * C),
+                 oEr = B.take(16 * C * K), oOut = B.take(C * K), oH = B.take(1800 * C), oR = B.take(4 * C);
+    Scratch* S;
+    int rc = scratch_for(device, B.off, &S);
+    if (rc) return rc;
+    uint8_t* d = S->d; cudaStream_t st = S->st;
+    CK(cudaMemcpyAsync(d + oN, N, 4 * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oX, Xw, 12 * C * K, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oO, obs, 8 * C * K, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oS, invSigma2, 4 * C * K, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oT, trackDepth, 4 * C * K, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oC, cam4, 16 * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oE, extrinsics24, 192, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oP, preintFrame, 4 * P_SIZE * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oPk, preintKF, 4 * P_SIZE * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oPr, prior21, 168 * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oPh, priorH, 1800 * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oPv, prevState21, 168 * C, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + oSt, state21, 168 * C, cudaMemcpyHostToDevice, st));
+    PoseInertialParams Q;
+    Q.count = count; Q.cap = cap; Q.recInit = bRecInit;
+    Q.N = (const int*)(d + oN); Q.Xw = (const float*)(d + oX); Q.obs = (const float*)(d + oO); Q.invSigma2 = (const float*)(d + oS); Q.trackDepth = (const float*)(d + oT);
+    Q.cam4 = (const float*)(d + oC); Q.extr = (const double*)(d + oE); Q.preint = (const float*)(d + oP); Q.kfState = nullptr; Q.state = (double*)(d + oSt);
+    Q.err = (double*)(d + oEr); Q.outlier = d + oOut; Q.H15 = (double*)(d + oH); Q.ret = (int*)(d + oR);
+    Q.preintKF = (const float*)(d + oPk); Q.prior = (const double*)(d + oPr); Q.priorH = (const double*)(d + oPh); Q.prevState = (double*)(d + oPv);
+    pose_inertial_opt_kernel<true><<<count, PI_NT, 0, st>>>(Q);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(state21, d + oSt, 168 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(prevState21, d + oPv, 168 * C, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(outlier, d + oOut, C * K, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(H15, d + oH, 1800 * C, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ret, d + oR, 4 * C, cudaMemcpyDeviceToHost, st));

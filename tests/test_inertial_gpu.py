@@ -137,3 +137,27 @@ def test_pose_inertial_optimization_last_keyframe(orb):
                                                          pr['obs'][i].astype(np.float64), jac=False)[0] for i in range(min(len(pr['Xw']), 60))])
             assert np.abs(res(g['state']) - res(want['state'])).max() < 1e-4          # px
             assert np.abs(g['H'] - want['H']).max() <= 1e-6 * np.abs(want['H']).max()
+
+
+def test_pose_inertial_optimization_last_frame(orb):
+    """f1: Optimizer::PoseInertialOptimizationLastFrame (30 unknowns, prior edge, marginalisation) for a batch of frames vs the oracle."""
+    from orb_slam3_modified_b200 import synth
+    cases = [dict(seed=0, n=300, outlier_frac=0.1), dict(seed=1, n=700, outlier_frac=0.2), dict(seed=2, n=40, outlier_frac=0.3), dict(seed=3, n=4, outlier_frac=0.0),
+             dict(seed=5, n=1000, outlier_frac=0.05, perturb=2.0), dict(seed=7, n=250, outlier_frac=0.1, prior_sigma=(2e-2, 5e-2, 1e-1, 1e-3, 1e-2))]
+    prs = [synth.pose_inertial_problem_last_frame(**c) for c in cases]
+    frames = []
+    for pr in prs:
+        Pf = O.imu_preintegrate(pr['acc'], pr['gyr'], pr['dt'], pr['bias6'], synth.IMU_NOISE)
+        Pk = O.imu_preintegrate(pr['acc_kf'], pr['gyr_kf'], pr['dt_kf'], pr['bias6'], synth.IMU_NOISE)
+        frames.append(dict(pr, preint_frame=Pf, preint_kf=Pk))
+    for rec in (False, True):
+        got = orb.PoseInertialOptimizationLastFrame(frames, prs[0]['extr'], rec_init=rec)
+        for pr, fr, g in zip(prs, frames, got):
+            want = O.pose_inertial_opt_last_frame(pr, fr['preint_frame'], fr['preint_kf'], rec_init=rec)
+            assert np.array_equal(g['outlier'], want['outlier']) and g['ret'] == want['ret'], (len(pr['Xw']), int((g['outlier'] != want['outlier']).sum()))
+            assert np.abs(g['state'] - want['state']).max() < 1e-6 and np.abs(g['prev_state'] - want['prev_state']).max() < 1e-6
+            ex = pr['extr']
+            res = lambda st: np.array([O.imu_edge_mono(st[:9].reshape(3, 3), st[9:12], ex[:9], ex[9:12], ex[12:21], ex[21:24], pr['cam'], pr['Xw'][i].astype(np.float64),
+                                                         pr['obs'][i].astype(np.float64), jac=False)[0] for i in range(min(len(pr['Xw']), 60))])
+            assert np.abs(res(g['state']) - res(want['state'])).max() < 1e-4          # px
+            assert np.abs(g['H'] - want['H']).max() <= 1e-5 * np.abs(want['H']).max()
