@@ -509,24 +509,36 @@ __device__ void prior_edge_dev(const double* prior, const double* st, double* e1
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { J[i * 15 + j] = iJ[i * 3 + j]; J[(3 + i) * 15 + 3 + j] = dR[i * 3 + j]; }
     for (int i = 6; i < 15; ++i) J[i * 15 + i] = 1.0;
 }
-// dense LDLT solve of the n x n system in H (row-major, leading dimension n), n <= 30: Eigen::LDLT + isPositive() (linear_solver_dense.h:111-118).
-// L: n*n scratch.  Returns false (x untouched) when a pivot is not positive.
-__device__ bool ldlt_solve_dev(int n, const double* H, const double* b, double* x, double* L) {
-    double d[30], y[30];
-    for (int k = 0; k < n * n; ++k) L[k] = H[k];
+// Dense LDLT solve of the n x n system in A (shared memory, row-major, n <= 30) by ONE WARP: Eigen::LDLT + isPositive()
+// (linear_solver_dense.h:111-118).  Left-looking by columns, lane = row of the column; substitutions column-oriented with the running
+// right-hand side in a register per lane.  A is overwritten by L (strictly lower part); d: n doubles of shared memory.
+// Returns false (x untouched) when a pivot is not positive.  All 32 lanes call.
+__device__ bool ldlt_solve_warp(int n, double* A, const double* b, double* x, double* d) {
+    const int lane = threadIdx.x & 31;
     for (int j = 0; j < n; ++j) {
-        double dj = L[j * n + j];
-        for (int k = 0; k < j; ++k) dj -= L[j * n + k] * L[j * n + k] * d[k];
-        if (!(dj > 0)) return false;
-        d[j] = dj;
-        for (int i = j + 1; i < n; ++i) {
-            double v = L[i * n + j];
-            for (int k = 0; k < j; ++k) v -= L[i * n + k] * L[j * n + k] * d[k];
-            L[i * n + j] = v / dj;
-        }
+        double dj = A[j * n + j];
+        for (int k = 0; k < j; ++k) dj -= A[j * n + k] * A[j * n + k] * d[k];
+        if (!(dj > 0)) return false;                         // every lane computed the same dj
+        const int i = j + 1 + lane;
+        double v = 0;
+        if (i < n) { v = A[i * n + j]; for (int k = 0; k < j; ++k) v -= A[i * n + k] * A[j * n + k] * d[k]; }
+        __syncwarp();
+        if (lane == 0) d[j] = dj;
+        if (i < n) A[i * n + j] = v / dj;
+        __syncwarp();
     }
-    for (int i = 0; i < n; ++i) { double v = b[i]; for (int k = 0; k < i; ++k) v -= L[i * n + k] * y[k]; y[i] = v; }
-    for (int i = n - 1; i >= 0; --i) { double v = y[i] / d[i]; for (int k = i + 1; k < n; ++k) v -= L[k * n + i] * x[k]; x[i] = v; }
+    double r = lane < n ? b[lane] : 0.0;                     // forward: L y = b
+    for (int k = 0; k < n; ++k) {
+        const double yk = __shfl_sync(0xffffffffu, r, k);
+        if (lane > k && lane < n) r -= A[lane * n + k] * yk;
+    }
+    r = lane < n ? r / d[lane] : 0.0;                        // D z = y
+    for (int k = n - 1; k >= 0; --k) {                       // backward: L^T x = z
+        const double xk = __shfl_sync(0xffffffffu, r, k);
+        if (lane < k) r -= A[k * n + lane] * xk;
+    }
+    if (lane < n) x[lane] = r;
+    __syncwarp();
     return true;
 }
 // LF = false: PoseInertialOptimizationLastKeyFrame (15 unknowns); LF = true: PoseInertialOptimizationLastFrame (30 unknowns: current 15 | previous 15)
@@ -534,7 +546,8 @@ template <bool LF>
 __global__ void __launch_bounds__(PI_NT) pose_inertial_opt_kernel(PoseInertialParams Q) {
     constexpr int NX = LF ? 30 : 15;
     __shared__ double s_red[PI_NT / 32];
-    __shared__ double s_st[21], s_sp[21], s_cam[12], s_info[81 + 9 + 9], s_x[NX], s_H[NX * NX], s_b[NX], s_L[NX * NX];
+    __shared__ double s_st[21], s_sp[21], s_cam[12], s_info[81 + 9 + 9], s_x[NX], s_H[NX * NX], s_b[NX], s_L[NX * NX], s_d[30];
+    __shared__ double s_J[216], s_OJ[216], s_e9[9], s_Jp[225], s_OJp[225], s_e15[15], s_Oe15[15];   // EdgeInertial / EdgePriorPoseImu: Jacobians, Omega J, residuals
     __shared__ int s_ok, s_cnt[2];
     const int f = blockIdx.x, tid = threadIdx.x;
     const int N = min(Q.N[f], Q.cap);
@@ -594,61 +607,70 @@ __global__ void __launch_bounds__(PI_NT) pose_inertial_opt_kernel(PoseInertialPa
             double tot[27];
 #pragma unroll
             for (int k = 0; k < 27; ++k) tot[k] = pi_block_sum(acc[k], s_red);
+            // (a) the two multi-vertex edges are linearised by two threads of different warps at the same time
             if (tid == 0) {
-                for (int k = 0; k < NX * NX; ++k) s_H[k] = 0;
-                for (int k = 0; k < NX; ++k) s_b[k] = 0;
-                int t = 0;
-                for (int a = 0; a < 6; ++a) for (int c = a; c < 6; ++c) { s_H[a * NX + c] = tot[t]; s_H[c * NX + a] = tot[t]; ++t; }
-                for (int a = 0; a < 6; ++a) s_b[a] = tot[21 + a];
-                {   // EdgeInertial (the keyframe's columns drop out in the last-keyframe variant: its vertices are fixed)
-                    double S36[36], e9[9], J[216], OJ[216];
-                    for (int k = 0; k < 21; ++k) S36[k] = s_sp[k];
-                    for (int k = 0; k < 15; ++k) S36[21 + k] = s_st[k];
-                    edge_inertial_dev(P, S36, e9, J);
-                    const int c0 = LF ? 0 : 15;
-                    for (int r = 0; r < 9; ++r) for (int c = c0; c < 24; ++c) { double sacc = 0; for (int k = 0; k < 9; ++k) sacc += s_info[r * 9 + k] * J[k * 24 + c]; OJ[r * 24 + c] = sacc; }
-                    for (int a = c0; a < 24; ++a) {
-                        double sacc = 0;
-                        for (int r = 0; r < 9; ++r) sacc += OJ[r * 24 + a] * e9[r];
-                        s_b[xi(a)] -= sacc;
-                        for (int c = c0; c < 24; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += J[r * 24 + a] * OJ[r * 24 + c]; s_H[xi(a) * NX + xi(c)] += h; }
-                    }
-                }
-                for (int a = 0; a < 3; ++a) {       // EdgeGyroRW / EdgeAccRW: error = b_cur - b_prev, Jacobians -I (previous, when free) / +I (current)
-                    double sg = 0, sa = 0;
-                    for (int c = 0; c < 3; ++c) {
-                        const double og = s_info[81 + a * 3 + c], oa = s_info[90 + a * 3 + c];
-                        sg += og * (s_st[15 + c] - s_sp[15 + c]); sa += oa * (s_st[18 + c] - s_sp[18 + c]);
-                        s_H[(9 + a) * NX + 9 + c] += og; s_H[(12 + a) * NX + 12 + c] += oa;
-                        if (LF) {
-                            s_H[(24 + a) * NX + 24 + c] += og; s_H[(9 + a) * NX + 24 + c] -= og; s_H[(24 + a) * NX + 9 + c] -= og;
-                            s_H[(27 + a) * NX + 27 + c] += oa; s_H[(12 + a) * NX + 27 + c] -= oa; s_H[(27 + a) * NX + 12 + c] -= oa;
-                        }
-                    }
-                    s_b[9 + a] -= sg; s_b[12 + a] -= sa;
-                    if (LF) { s_b[24 + a] += sg; s_b[27 + a] += sa; }
-                }
-                if (LF) {                           // EdgePriorPoseImu on the previous frame, RobustKernelHuber delta 5 (:5084-5092)
-                    double e15[15], J[225], Oe[15];
-                    prior_edge_dev(prior, s_sp, e15, J);
-                    double c2 = 0;
-                    for (int r = 0; r < 15; ++r) { double sacc = 0; for (int k = 0; k < 15; ++k) sacc += priorH[r * 15 + k] * e15[k]; Oe[r] = sacc; c2 += e15[r] * sacc; }
-                    const double w = c2 > 25.0 ? 5.0 / sqrt(c2) : 1.0;
-                    double* OJ = s_L;               // 15 x 15 scratch (s_L is free until the factorisation)
-                    for (int r = 0; r < 15; ++r) for (int c = 0; c < 15; ++c) { double sacc = 0; for (int k = 0; k < 15; ++k) sacc += priorH[r * 15 + k] * J[k * 15 + c]; OJ[r * 15 + c] = sacc; }
-                    for (int a = 0; a < 15; ++a) {
-                        double g = 0;
-                        for (int r = 0; r < 15; ++r) g += J[r * 15 + a] * Oe[r];
-                        s_b[15 + a] -= w * g;
-                        for (int c = 0; c < 15; ++c) { double h = 0; for (int r = 0; r < 15; ++r) h += J[r * 15 + a] * OJ[r * 15 + c]; s_H[(15 + a) * NX + 15 + c] += w * h; }
-                    }
-                }
-                const bool ok = ldlt_solve_dev(NX, s_H, s_b, s_x, s_L);    // a failed solve leaves x of the previous iteration; update() still runs
-                apply_update15(s_st, s_x, its);
-                if (LF) apply_update15(s_sp, s_x + 15, itsPrev);
-                refresh_camera();
-                s_ok = ok ? 1 : 0;
+                double S36[36];
+                for (int k = 0; k < 21; ++k) S36[k] = s_sp[k];
+                for (int k = 0; k < 15; ++k) S36[21 + k] = s_st[k];
+                edge_inertial_dev(P, S36, s_e9, s_J);
             }
+            if (LF && tid == 32) prior_edge_dev(prior, s_sp, s_e15, s_Jp);
+            __syncthreads();
+            // (b) Omega J, Omega e
+            for (int idx = tid; idx < 216; idx += PI_NT) { const int r = idx / 24, c = idx - r * 24; double a = 0; for (int k = 0; k < 9; ++k) a += s_info[r * 9 + k] * s_J[k * 24 + c]; s_OJ[idx] = a; }
+            if (LF) {
+                for (int idx = tid; idx < 225; idx += PI_NT) { const int r = idx / 15, c = idx - r * 15; double a = 0; for (int k = 0; k < 15; ++k) a += priorH[r * 15 + k] * s_Jp[k * 15 + c]; s_OJp[idx] = a; }
+                if (tid < 15) { double a = 0; for (int k = 0; k < 15; ++k) a += priorH[tid * 15 + k] * s_e15[k]; s_Oe15[tid] = a; }
+            }
+            __syncthreads();
+            // (c) the normal equations, one entry per thread.  x index -> column of the EdgeInertial Jacobian: current pose / velocity -> 15..23,
+            //     current biases -> none, previous 15 -> 0..14
+            double wPrior = 1.0;
+            if (LF) { double c2 = 0; for (int k = 0; k < 15; ++k) c2 += s_e15[k] * s_Oe15[k]; wPrior = c2 > 25.0 ? 5.0 / sqrt(c2) : 1.0; }   // RobustKernelHuber delta 5 (:5084-5092)
+            auto ecol = [](int i) { return i < 9 ? 15 + i : (i < 15 ? -1 : i - 15); };
+            for (int idx = tid; idx < NX * NX; idx += PI_NT) {
+                const int i = idx / NX, j = idx - i * NX;
+                double h = 0;
+                if (i < 6 && j < 6) { const int a = min(i, j), c = max(i, j); h += tot[a * 6 - a * (a - 1) / 2 + (c - a)]; }     // packed upper triangle of the mono block
+                const int ei = ecol(i), ej = ecol(j);
+                if (ei >= 0 && ej >= 0) { double a = 0; for (int r = 0; r < 9; ++r) a += s_J[r * 24 + ei] * s_OJ[r * 24 + ej]; h += a; }
+                // EdgeGyroRW / EdgeAccRW: error = b_cur - b_prev, Jacobians +I (current: x 9..14) and -I (previous, when free: x 24..29)
+                {
+                    const int bi = i >= 9 && i < 15 ? i - 9 : (LF && i >= 24 ? i - 24 : -1), bj = j >= 9 && j < 15 ? j - 9 : (LF && j >= 24 ? j - 24 : -1);
+                    if (bi >= 0 && bj >= 0 && (bi / 3) == (bj / 3)) {
+                        const double om = s_info[(bi < 3 ? 81 : 90) + (bi % 3) * 3 + (bj % 3)];
+                        h += ((i < 15) == (j < 15)) ? om : -om;
+                    }
+                }
+                if (LF && i >= 15 && j >= 15) { double a = 0; for (int r = 0; r < 15; ++r) a += s_Jp[r * 15 + i - 15] * s_OJp[r * 15 + j - 15]; h += wPrior * a; }
+                s_H[idx] = h;
+            }
+            if (tid < NX) {
+                const int i = tid;
+                double g = i < 6 ? tot[21 + i] : 0.0;
+                const int ei = ecol(i);
+                if (ei >= 0) { double a = 0; for (int r = 0; r < 9; ++r) a += s_OJ[r * 24 + ei] * s_e9[r]; g -= a; }
+                const int bi = i >= 9 && i < 15 ? i - 9 : (LF && i >= 24 ? i - 24 : -1);
+                if (bi >= 0) {
+                    double a = 0;
+                    for (int c = 0; c < 3; ++c) a += s_info[(bi < 3 ? 81 : 90) + (bi % 3) * 3 + c] * (s_st[(bi < 3 ? 15 : 18) + c] - s_sp[(bi < 3 ? 15 : 18) + c]);
+                    g += i < 15 ? -a : a;
+                }
+                if (LF && i >= 15) { double a = 0; for (int r = 0; r < 15; ++r) a += s_Jp[r * 15 + i - 15] * s_Oe15[r]; g -= wPrior * a; }
+                s_b[i] = g;
+            }
+            __syncthreads();
+            // (d) dense LDLT by warp 0; a failed solve leaves x of the previous iteration and update() still runs
+            if (tid < 32) {
+                for (int k = tid; k < NX * NX; k += 32) s_L[k] = s_H[k];
+                __syncwarp();
+                const bool ok = ldlt_solve_warp(NX, s_L, s_b, s_x, s_d);
+                if (tid == 0) s_ok = ok ? 1 : 0;
+            }
+            __syncthreads();
+            // (e) vertex updates, the two frames by two threads
+            if (tid == 0) { apply_update15(s_st, s_x, its); refresh_camera(); }
+            if (LF && tid == 32) apply_update15(s_sp, s_x + 15, itsPrev);
             __syncthreads();
             if (!s_ok) break;
         }

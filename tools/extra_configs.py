@@ -131,4 +131,30 @@ def measure(orb, synth, device=0, reps=40):
     c3['keypoints'], c3['in_view'], c3['matches'], c3['pose_inliers'] = int(len(state['kd'][0])), int(state['fr']['inView'].sum()), int(state['n']), int(state['po']['inliers'])
     c3['reference'] = 'Tracking::TrackLocalMap, src/Tracking.cc:2859-2974 + SearchLocalPoints :3346-3416'
     out['configs[2] 1280x720 tracking vs local map'] = c3
+    # ---------------- mono-inertial tracking: the per-frame inertial pose optimisers ----------------
+    # Tracking::TrackLocalMap calls PoseInertialOptimizationLastFrame / LastKeyFrame instead of PoseOptimization once the IMU is initialised
+    # (src/Tracking.cc:2985-2994): one frame alone (latency) and the frames of 240 streams in one call, 700 matched map points each
+    try:
+        def problems(n, npts):
+            prs = []
+            for k in range(n):
+                pr = synth.pose_inertial_problem_last_frame(seed=k % 8, n=npts, outlier_frac=0.1)
+                pre = lambda a, g, d: orb.imu_preintegrate(a[None], g[None], d[None], [len(d)], pr['bias6'][None], synth.IMU_NOISE, device)[0]
+                pr['preint_frame'] = pre(pr['acc'], pr['gyr'], pr['dt'])
+                pr['preint_kf'] = pre(pr['acc_kf'], pr['gyr_kf'], pr['dt_kf'])
+                pr['preint'] = pr['preint_frame']
+                prs.append(pr)
+            return prs
+        one, many = problems(1, 700), problems(8, 700) * 30
+        ex24 = one[0]['extr']
+        r1 = orb.PoseInertialOptimizationLastFrame(one, ex24, device=device)[0]
+        out['mono-inertial tracking: inertial pose optimisers (700 map points per frame)'] = {
+            'last_frame_1_frame_host_ms': _median_ms(lambda: orb.PoseInertialOptimizationLastFrame(one, ex24, device=device), 20),
+            'last_keyframe_1_frame_host_ms': _median_ms(lambda: orb.PoseInertialOptimizationLastKeyFrame(one, ex24, device=device), 20),
+            'last_frame_240_frames_host_ms': _median_ms(lambda: orb.PoseInertialOptimizationLastFrame(many, ex24, device=device), 5, warm=1),
+            'last_keyframe_240_frames_host_ms': _median_ms(lambda: orb.PoseInertialOptimizationLastKeyFrame(many, ex24, device=device), 5, warm=1),
+            'inliers_of_700': int(r1['ret']),
+            'reference': 'Optimizer::PoseInertialOptimizationLastFrame / LastKeyFrame, src/Optimizer.cc:4491-5289; includes the Python marshalling of the batch'}
+    except Exception as exc:          # the latency lines are informative; never fail the bench line over them
+        out['mono-inertial tracking: inertial pose optimisers (700 map points per frame)'] = {'error': repr(exc)[:200]}
     return out
