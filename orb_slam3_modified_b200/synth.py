@@ -335,3 +335,81 @@ def pose_inertial_problem_last_frame(t0=1.0, t1=1.15, t2=1.2, n=300, seed=0, out
     pr['prev_state'] = prior.copy()                         # VertexPose(pFp) etc.: the previous frame's current estimate
     pr['truth_prev'] = truth_prev
     return pr
+
+
+def local_inertial_ba_problem(n_opt=10, n_cov_fixed=3, n_pts=800, seed=0, kf_dt=0.25, t_end=6.0, width=640, height=480, outlier_frac=0.03, perturb=1.0,
+                              noise_px=0.7, float_inputs=True, rec_init=False, large=False):
+    """One Optimizer::LocalInertialBA graph (reference src/Optimizer.cc:2383-2958), flattened as the caller's graph walk leaves it:
+    keyframes [0, n_opt) = the temporal window, NEWEST FIRST (vpOptimizableKFs order); keyframe n_opt = the window's predecessor (fixed, linked by
+    the last EdgeInertial); n_cov_fixed older keyframes that only see points (fixed).  Inertial edge i links keyframe i+1 -> i; the one to the
+    fixed keyframe carries the Huber kernel and information * 1e-2 (:2633-2643), all carry the kernel with rec_init.  Points are seen by every keyframe in
+    whose image they fall.  States = ground truth + a seeded perturbation; with float_inputs they are rounded to float like KeyFrame storage and
+    the camera pose Tcw is rounded separately (ImuCamPose(KeyFrame*) loads both, src/G2oTypes.cc:25-47)."""
+    rng = np.random.default_rng(seed)
+    ex = imu_extrinsics()
+    Rcb, tcb = ex[:9].reshape(3, 3), ex[9:12]
+    nkf = n_opt + 1 + n_cov_fixed
+    times = [t_end - kf_dt * k for k in range(n_opt + 1)] + [t_end - kf_dt * (n_opt + 1) - 0.4 * (j + 1) for j in range(n_cov_fixed)]
+    bias = np.array([0.02, -0.01, 0.03, 0.002, -0.001, 0.0015])                      # bax.. bwx..
+    cam = camera(width, height)
+    truth = np.zeros((nkf, 21)); state = np.zeros((nkf, 21)); tcw12 = np.zeros((nkf, 12)); tcw_true = np.zeros((nkf, 12))
+
+    def cam_pose(R, p):
+        Rcw = Rcb @ R.T
+        return Rcw, Rcb @ (-R.T @ p) + tcb
+    for k, t in enumerate(times):
+        R, p, v, _, _ = imu_trajectory(t)
+        truth[k] = np.concatenate([R.reshape(9), p, v, bias[3:], bias[:3]])
+        Rc, tc = cam_pose(R, p)
+        tcw_true[k] = np.concatenate([Rc.reshape(9), tc])
+        if k < n_opt:
+            Rn = R @ _rodrigues(perturb * rng.normal(0, 0.004, 3)); pn = p + perturb * rng.normal(0, 0.01, 3)
+            state[k] = np.concatenate([Rn.reshape(9), pn, v + perturb * rng.normal(0, 0.03, 3), bias[3:] + perturb * rng.normal(0, 1e-4, 3),
+                                       bias[:3] + perturb * rng.normal(0, 2e-3, 3)])
+        else:
+            Rn, pn = R, p
+            state[k] = truth[k]
+        Rc, tc = cam_pose(Rn, pn)
+        tcw12[k] = np.concatenate([Rc.reshape(9), tc])
+    if float_inputs:
+        state = state.astype(np.float32).astype(np.float64)
+        tcw12 = tcw12.astype(np.float32).astype(np.float64)
+    # points in front of the newest camera, seen by every keyframe whose image contains them
+    Rc0, tc0 = tcw_true[0, :9].reshape(3, 3), tcw_true[0, 9:]
+    z = rng.uniform(2.0, 25.0, n_pts)
+    u, v = rng.uniform(-40, width + 40, n_pts), rng.uniform(-30, height + 30, n_pts)
+    Xc = np.stack([(u - cam[2]) * z / cam[0], (v - cam[3]) * z / cam[1], z], 1)
+    Xw = (Xc - tc0) @ Rc0
+    e_pt, e_kf, obs, isig = [], [], [], []
+    for j in range(n_pts):
+        for k in range(nkf):
+            Xk = tcw_true[k, :9].reshape(3, 3) @ Xw[j] + tcw_true[k, 9:]
+            if Xk[2] < 0.5:
+                continue
+            uu, vv = cam[0] * Xk[0] / Xk[2] + cam[2], cam[1] * Xk[1] / Xk[2] + cam[3]
+            if not (5 < uu < width - 5 and 5 < vv < height - 5) or rng.random() < 0.15:
+                continue
+            octv = int(rng.integers(0, 8))
+            o = np.array([uu, vv]) + rng.normal(0, noise_px, 2) * 1.2 ** octv
+            if rng.random() < outlier_frac:
+                o += rng.uniform(8, 40, 2) * rng.choice([-1, 1], 2)
+            e_pt.append(j); e_kf.append(k); obs.append(o); isig.append(1.0 / 1.44 ** octv)
+    e_pt = np.array(e_pt, np.int32); e_kf = np.array(e_kf, np.int32)
+    # drop points with fewer than two observations, re-index
+    cnt = np.bincount(e_pt, minlength=n_pts)
+    keep = cnt >= 2
+    remap = -np.ones(n_pts, np.int64); remap[keep] = np.arange(int(keep.sum()))
+    sel = keep[e_pt]
+    e_pt = remap[e_pt[sel]].astype(np.int32); e_kf = e_kf[sel]
+    obs = np.array(obs)[sel].astype(np.float32).astype(np.float64); isig = np.array(isig, np.float32)[sel]
+    pts_true = Xw[keep]
+    pts = pts_true + perturb * rng.normal(0, 0.02, pts_true.shape)
+    if float_inputs:
+        pts = pts.astype(np.float32).astype(np.float64)
+    imu = [imu_interval(times[i + 1], times[i], seed=seed * 100 + i, bias=tuple(bias)) for i in range(n_opt)]
+    return dict(n_kf=nkf, n_opt=n_opt, state=np.ascontiguousarray(state), tcw=np.ascontiguousarray(tcw12), cam=np.tile(cam, (nkf, 1)).astype(np.float32), extr=ex,
+                ie_kf1=np.arange(1, n_opt + 1, dtype=np.int32), ie_kf2=np.arange(0, n_opt, dtype=np.int32), imu=imu, bias6=bias.astype(np.float32),
+                ie_robust=np.array([1 if (i == n_opt - 1 or rec_init) else 0 for i in range(n_opt)], np.uint8),
+                ie_info_scale=np.array([1e-2 if i == n_opt - 1 else 1.0 for i in range(n_opt)]),
+                points=np.ascontiguousarray(pts), track_depth=z[keep].astype(np.float32), e_pt=e_pt, e_kf=e_kf, obs=np.ascontiguousarray(obs), inv_sigma2=isig,
+                iterations=4 if large else 10, lambda_init=1e-2 if large else 1.0, large=bool(large), truth=truth, points_true=pts_true, times=times)

@@ -608,3 +608,34 @@ def constraint_pose_imu_information(H):
     H = _c(H, np.float64); out = np.zeros((15, 15))
     lib().orbo_constraint_pose_imu_information(_p(H), _p(out))
     return out
+
+
+def liba_preints(pr):
+    """The IMU::Preintegrated of every inertial edge of a synth.local_inertial_ba_problem: [nI, 292] float32."""
+    from orb_slam3_modified_b200 import synth
+    return np.stack([imu_preintegrate(a, g, d, pr['bias6'], synth.IMU_NOISE) for a, g, d in pr['imu']])
+
+
+def local_inertial_ba(pr, preint, iterations=None, lambda_init=None):
+    """Optimizer::LocalInertialBA numeric core: dict(state [nKF,21], tcw [nKF,12], points [nL,3], erase [nE], chi2 [nE], iters, err, err_end, failed, lam, trials)."""
+    L = lib()
+    st = _c(pr['state'], np.float64).copy(); tc = _c(pr['tcw'], np.float64).copy(); pts = _c(pr['points'], np.float64).copy()
+    nE = len(pr['e_pt']); nI = len(pr['ie_kf1'])
+    erase = np.zeros(nE, np.uint8); chi2 = np.zeros(nE); stats = np.zeros(8)
+    a = dict(cam=_c(pr['cam'], np.float32), extr=_c(pr['extr'], np.float64), k1=_c(pr['ie_kf1'], np.int32), k2=_c(pr['ie_kf2'], np.int32), P=_c(preint, np.float32),
+             rob=_c(pr['ie_robust'], np.uint8), sc=_c(pr['ie_info_scale'], np.float64), td=_c(pr['track_depth'], np.float32), ep=_c(pr['e_pt'], np.int32),
+             ek=_c(pr['e_kf'], np.int32), obs=_c(pr['obs'], np.float64), isg=_c(pr['inv_sigma2'], np.float32))
+    L.orbo_local_inertial_ba.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + \
+        [C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    it = L.orbo_local_inertial_ba(pr['n_kf'], pr['n_opt'], _p(st), _p(tc), _p(a['cam']), _p(a['extr']), nI, _p(a['k1']), _p(a['k2']), _p(a['P']), _p(a['rob']), _p(a['sc']),
+                                  len(pts), _p(pts), _p(a['td']), nE, _p(a['ep']), _p(a['ek']), _p(a['obs']), _p(a['isg']),
+                                  pr['iterations'] if iterations is None else iterations, pr['lambda_init'] if lambda_init is None else lambda_init, int(pr['large']),
+                                  _p(erase), _p(chi2), _p(stats))
+    return dict(state=st, tcw=tc, points=pts, erase=erase, chi2=chi2, iters=it, err=stats[0], err_end=stats[1], failed=bool(stats[2]), lam=stats[3], trials=int(stats[4]))
+
+
+def local_inertial_ba_residuals(pr, tcw, points):
+    res = np.zeros((len(pr['e_pt']), 2))
+    tc = _c(tcw, np.float64); pts = _c(points, np.float64); ep = _c(pr['e_pt'], np.int32); ek = _c(pr['e_kf'], np.int32); cam = _c(pr['cam'], np.float32); obs = _c(pr['obs'], np.float64)
+    lib().orbo_local_inertial_ba_residuals(len(ep), _p(ep), _p(ek), _p(tc), _p(cam), _p(pts), _p(obs), _p(res))
+    return res
