@@ -468,6 +468,38 @@ typedef struct ImuMonoEdges {
 int imu_mono_edges(const ImuMonoEdges* in, double* err2, double* Jpoint2x3, double* Jpose2x6, double* chi2, double* rho, uint8_t* depthPositive, int device);
 
 
+/* void Optimizer::LocalInertialBA(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, int& num_fixedKF, int& num_OptKF, int& num_MPs, int& num_edges,
+ * bool bLarge, bool bRecInit) (include/Optimizer.h:62, src/Optimizer.cc:2383-2958; call site LocalMapping::Run, src/LocalMapping.cc:129-151),
+ * monocular-inertial: the numeric core between the graph set-up (:2385-2833, the caller's walk over keyframes / map points / observations) and the
+ * write-back (:2890-2957), for `count` local maps at once (one persistent CTA per map; LBA-style "replicas" across streams).
+ *   keyframes [0, nOpt): the temporal window vpOptimizableKFs (VertexPose + VertexVelocity + VertexGyroBias + VertexAccBias, all free);
+ *   keyframes [nOpt, nKF): lFixedKeyFrames (the window's predecessor first when it is linked by an EdgeInertial).
+ *   kfState21 [nKF][21]: Rwb 9 | twb 3 | velocity 3 | gyro bias 3 | acc bias 3 (GetImuRotation / GetImuPosition / GetVelocity / GetImuBias, as doubles);
+ *   kfTcw12 [nKF][12]: Rcw 9 | tcw 3 = the keyframe's own camera pose (GetRotation / GetTranslation): ImuCamPose(KeyFrame*) loads both and uses the
+ *   camera pose as it is until the vertex is first updated (src/G2oTypes.cc:25-47, :213-221);  cam4 [nKF][4];  extrinsics24: Rcb 9 | tcb 3 | Rbc 9 | tbc 3.
+ *   inertial edge i (:2593-2656): keyframes ieKf1[i] (mPrevKF) -> ieKf2[i], preint [nInertial][IMU_PREINT_FLOATS] = pKFi->mpImuPreintegrated,
+ *   ieRobust[i] = 1 for the Huber kernel sqrt(16.92) (i == N-1 || bRecInit), ieInfoScale[i] = 1e-2 for i == N-1, else 1.  Every inertial edge
+ *   brings its EdgeGyroRW and EdgeAccRW (informations from the preintegration covariance).
+ *   points3 [nPoints][3] = GetWorldPos(), trackDepth [nPoints] = mTrackDepth;  mono edge e (:2737-2763): edgePoint[e], edgeKf[e], obs2 = mvKeysUn[].pt,
+ *   invSigma2 = mvInvLevelSigma2[octave] / unc2; at most one edge per (point, keyframe) (monocular: no right-camera observations).
+ *   iterations = opt_it (10, or 4 with bLarge), lambdaInit = setUserLambdaInit's value (1e0, or 1e-2 with bLarge).
+ * Results (host pointers, per problem): the optimised kfState21 / kfTcw12 / points3 (what SetPose / SetVelocity / SetNewBias / SetWorldPos receive
+ * after the casts of :2905-2950), erase [nEdges] = 1 for the (keyframe, point) pairs of vToErase (:2848-2862), edgeChi2 [nEdges] = e->chi2(),
+ * stats8 = err, err_end (:2837-2839, as floats), failed (the "FAIL LOCAL-INERTIAL BA" test :2884: states and points are then returned unchanged),
+ * final lambda, LM trials, optimize()'s iteration count.  iterationsOut [count] (may be NULL). */
+typedef struct LocalInertialBAProblem {
+    int32_t nKF, nOpt;
+    const double* kfState21; const double* kfTcw12; const float* cam4; const double* extrinsics24;
+    int32_t nInertial; const int32_t* ieKf1; const int32_t* ieKf2; const float* preint; const uint8_t* ieRobust; const double* ieInfoScale;
+    int32_t nPoints; const double* points3; const float* trackDepth;
+    int32_t nEdges; const int32_t* edgePoint; const int32_t* edgeKf; const double* obs2; const float* invSigma2;
+    int32_t iterations; int32_t bLarge; double lambdaInit;
+} LocalInertialBAProblem;
+typedef struct LocalInertialBAResult {
+    double* kfState21; double* kfTcw12; double* points3; uint8_t* erase; double* edgeChi2; double* stats8;
+} LocalInertialBAResult;
+int local_inertial_ba_batch(int count, const LocalInertialBAProblem* problems, const LocalInertialBAResult* results, int32_t* iterationsOut, int device);
+
 /* ------------------------------------------------------------------------------------------
  * DBoW2 transform: Frame::ComputeBoW / KeyFrame::ComputeBoW (reference src/Frame.cc:738-745) call
  * ORBVocabulary::transform(vCurrentDesc, mBowVec, mFeatVec, 4) = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform

@@ -880,6 +880,59 @@ def PoseInertialOptimizationLastFrame(frames, extrinsics24, rec_init=False, devi
 # =============================================================================================
 # DBoW2 vocabulary transform (reference Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h)
 # =============================================================================================
+class _LocalInertialBAProblem(C.Structure):
+    _fields_ = [('nKF', C.c_int32), ('nOpt', C.c_int32), ('kfState21', C.c_void_p), ('kfTcw12', C.c_void_p), ('cam4', C.c_void_p), ('extrinsics24', C.c_void_p),
+                ('nInertial', C.c_int32), ('ieKf1', C.c_void_p), ('ieKf2', C.c_void_p), ('preint', C.c_void_p), ('ieRobust', C.c_void_p), ('ieInfoScale', C.c_void_p),
+                ('nPoints', C.c_int32), ('points3', C.c_void_p), ('trackDepth', C.c_void_p),
+                ('nEdges', C.c_int32), ('edgePoint', C.c_void_p), ('edgeKf', C.c_void_p), ('obs2', C.c_void_p), ('invSigma2', C.c_void_p),
+                ('iterations', C.c_int32), ('bLarge', C.c_int32), ('lambdaInit', C.c_double)]
+
+
+class _LocalInertialBAResult(C.Structure):
+    _fields_ = [('kfState21', C.c_void_p), ('kfTcw12', C.c_void_p), ('points3', C.c_void_p), ('erase', C.c_void_p), ('edgeChi2', C.c_void_p), ('stats8', C.c_void_p)]
+
+
+def _liba_marshal(probs):
+    """ctypes arrays of LocalInertialBAProblem / LocalInertialBAResult for a list of problem dicts (synth.local_inertial_ba_problem layout + 'preint')."""
+    n = len(probs)
+    P = (_LocalInertialBAProblem * n)(); R = (_LocalInertialBAResult * n)()
+    keep, outs = [], []
+    for i, pr in enumerate(probs):
+        a = dict(st=_c(pr['state'], np.float64), tc=_c(pr['tcw'], np.float64), cam=_c(pr['cam'], np.float32), ex=_c(pr['extr'], np.float64),
+                 k1=_c(pr['ie_kf1'], np.int32), k2=_c(pr['ie_kf2'], np.int32), pre=_c(pr['preint'], np.float32), rob=_c(pr['ie_robust'], np.uint8),
+                 sc=_c(pr['ie_info_scale'], np.float64), pts=_c(pr['points'], np.float64), td=_c(pr['track_depth'], np.float32), ep=_c(pr['e_pt'], np.int32),
+                 ek=_c(pr['e_kf'], np.int32), ob=_c(pr['obs'], np.float64), isg=_c(pr['inv_sigma2'], np.float32))
+        nE = len(a['ep'])
+        o = dict(state=np.zeros_like(a['st']), tcw=np.zeros_like(a['tc']), points=np.zeros_like(a['pts']), erase=np.zeros(nE, np.uint8), chi2=np.zeros(nE), stats=np.zeros(8))
+        P[i] = _LocalInertialBAProblem(int(pr['n_kf']), int(pr['n_opt']), a['st'].ctypes.data, a['tc'].ctypes.data, a['cam'].ctypes.data, a['ex'].ctypes.data, len(a['k1']), a['k1'].ctypes.data, a['k2'].ctypes.data,
+                                       a['pre'].ctypes.data, a['rob'].ctypes.data, a['sc'].ctypes.data, len(a['pts']), a['pts'].ctypes.data, a['td'].ctypes.data, nE, a['ep'].ctypes.data, a['ek'].ctypes.data,
+                                       a['ob'].ctypes.data, a['isg'].ctypes.data, int(pr['iterations']), int(bool(pr['large'])), float(pr['lambda_init']))
+        R[i] = _LocalInertialBAResult(o['state'].ctypes.data, o['tcw'].ctypes.data, o['points'].ctypes.data, o['erase'].ctypes.data, o['chi2'].ctypes.data, o['stats'].ctypes.data)
+        keep.append(a); outs.append(o)
+    return P, R, keep, outs
+
+
+def _liba_finish(outs, iters):
+    return [dict(state=o['state'], tcw=o['tcw'], points=o['points'], erase=o['erase'], chi2=o['chi2'], iters=int(iters[i]), err=float(o['stats'][0]),
+                 err_end=float(o['stats'][1]), failed=bool(o['stats'][2]), lam=float(o['stats'][3]), trials=int(o['stats'][4])) for i, o in enumerate(outs)]
+
+
+def LocalInertialBA(probs, device=0):
+    """``void Optimizer::LocalInertialBA(KeyFrame*, bool*, Map*, int&, int&, int&, int&, bool bLarge, bool bRecInit)`` (src/Optimizer.cc:2383-2958): the
+    numeric core for a list of local maps, one persistent CTA each (``local_inertial_ba_batch``).  A problem is the dict of
+    ``synth.local_inertial_ba_problem`` plus ``preint`` [nI, IMU_PREINT_FLOATS]: n_kf, n_opt, state [nKF,21], tcw [nKF,12], cam [nKF,4], extr [24], ie_kf1 / ie_kf2 /
+    ie_robust / ie_info_scale [nI], points [nL,3], track_depth [nL], e_pt / e_kf / obs / inv_sigma2 [nE], iterations, lambda_init, large.
+    Returns a list of dict(state, tcw, points, erase, chi2, iters, err, err_end, failed, lam, trials)."""
+    P, R, keep, outs = _liba_marshal(probs)
+    iters = np.zeros(len(probs), np.int32)
+    L = lib()
+    L.local_inertial_ba_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = L.local_inertial_ba_batch(len(probs), C.cast(P, C.c_void_p), C.cast(R, C.c_void_p), _ptr(iters), device)
+    if rc != ORB_OK:
+        raise OrbError(rc, 'local_inertial_ba_batch')
+    return _liba_finish(outs, iters)
+
+
 class _OrbVocabulary(C.Structure):
     _fields_ = [('nNodes', C.c_int), ('L', C.c_int), ('weighting', C.c_int), ('norm', C.c_int), ('childStart', C.c_void_p), ('children', C.c_void_p),
                 ('descriptors', C.c_void_p), ('weight', C.c_void_p), ('wordId', C.c_void_p)]

@@ -1,0 +1,141 @@
+// Optimizer::LocalInertialBA (reference src/Optimizer.cc:2383-2958) on the B200: local_inertial_ba_batch.
+// One persistent CTA (256 threads) per local map runs the whole g2o Levenberg-Marquardt loop of liba_core.cuh on the device; a batch
+// of maps (one per stream of a multi-stream server) fills the SMs.  The host side flattens the graph (liba_pack.h: layout, CSR lists),
+// uploads one packed input buffer, launches ONE kernel and downloads one packed output buffer.
+//
+// Why one CTA per map: the temporal window is 10 (25 with bLarge) keyframes x 15 unknowns, so the reduced system is a dense 150 (375)
+// square; per LM trial the work is ~10^4 EdgeMono evaluations, a Schur complement of ~10^5 6x3 * 3x6 products and a 150^3 / 3 flop
+// factorisation -- a dependent chain of small phases whose cost is barrier latency, not throughput.  A CTA barrier is ~20x cheaper than
+// a cluster or grid barrier, and the parallel dimension that fills the GPU is the batch of independent maps (the reference runs one
+// LocalMapping thread per map).  The working set of a map (~2-8 MB) lives in L2.
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/orb_b200.h"
+#include "device_utils.cuh"
+#include "liba_pack.h"
+
+using orbx::set_error;
+
+#define CK(call)                                                                   \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) {                                                   \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));         \
+            return ORB_ERR_CUDA;                                                   \
+        }                                                                          \
+    } while (0)
+
+namespace liba {
+
+// The executor of liba_core.cuh on the device: thread = threadIdx.x, barrier = __syncthreads, ordered CTA reductions.
+struct DeviceExec {
+    double* red;      // NT / 32 doubles of shared memory
+    template <class F> __device__ __forceinline__ void par(F f) { f((int)threadIdx.x); __syncthreads(); }
+    template <class F> __device__ __forceinline__ double sum(F f) {
+        double v = f((int)threadIdx.x);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        double total = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) total += red[w];      // every thread adds the warp sums in the same order
+        __syncthreads();
+        return total;
+    }
+    template <class F> __device__ __forceinline__ double max(F f) {
+        double v = f((int)threadIdx.x);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, off));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        double m = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) m = fmax(m, red[w]);
+        __syncthreads();
+        return m;
+    }
+};
+
+__global__ void __launch_bounds__(NT) local_inertial_ba_kernel(const Dev* __restrict__ probs) {
+    __shared__ double s_red[NT / 32];
+    __shared__ Dev s_D;
+    if (threadIdx.x == 0) s_D = probs[blockIdx.x];
+    __syncthreads();
+    DeviceExec ex{s_red};
+    run(s_D, ex);
+}
+
+// host plumbing: one arena per host thread and device, grown on demand; pinned staging for the packed input / output buffers
+struct Arena {
+    int device = -1;
+    uint8_t* d = nullptr; size_t dcap = 0;
+    uint8_t* h = nullptr; size_t hcap = 0;
+    cudaStream_t st = nullptr;
+    ~Arena() {
+        if (device >= 0) cudaSetDevice(device);
+        if (d) cudaFree(d);
+        if (h) cudaFreeHost(h);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+}  // namespace liba
+
+extern "C" int local_inertial_ba_batch(int count, const LocalInertialBAProblem* problems, const LocalInertialBAResult* results, int32_t* iterationsOut, int device) {
+    using namespace liba;
+    if (count < 1 || !problems || !results) { set_error("local_inertial_ba_batch: bad argument"); return ORB_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (this library has no CPU path)"); return ORB_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { set_error("bad device index"); return ORB_ERR_ARG; }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { set_error("device is not sm_100+ (Blackwell); this library has no other code path"); return ORB_ERR_CUDA; }
+
+    std::vector<Layout> lay(count);
+    std::vector<size_t> inOff(count), scOff(count), outOff(count);
+    size_t inTot = 0, scTot = 0, outTot = 0;
+    for (int i = 0; i < count; ++i) {
+        const std::string err = check(problems[i]);
+        if (!err.empty()) { set_error(err); return ORB_ERR_ARG; }
+        lay[i] = make_layout(problems[i]);
+        inOff[i] = inTot; scOff[i] = scTot; outOff[i] = outTot;
+        inTot += (lay[i].inBytes + 255) & ~(size_t)255; scTot += (lay[i].scBytes + 255) & ~(size_t)255; outTot += (lay[i].outBytes + 255) & ~(size_t)255;
+    }
+    const size_t devOff = inTot;                                   // the Dev array rides at the end of the input region
+    const size_t inAll = inTot + (((size_t)count * sizeof(Dev) + 255) & ~(size_t)255);
+    const size_t dBytes = inAll + scTot + outTot, hBytes = inAll + outTot;
+
+    thread_local Arena A;
+    if (A.device != device) {
+        if (A.device >= 0) { cudaSetDevice(A.device); if (A.d) cudaFree(A.d); if (A.h) cudaFreeHost(A.h); if (A.st) cudaStreamDestroy(A.st); A.d = A.h = nullptr; A.st = nullptr; A.dcap = A.hcap = 0; }
+        CK(cudaSetDevice(device));
+        A.device = device;
+    }
+    if (!A.st) CK(cudaStreamCreateWithFlags(&A.st, cudaStreamNonBlocking));
+    if (dBytes > A.dcap) { if (A.d) { cudaFree(A.d); A.d = nullptr; A.dcap = 0; } CK(cudaMalloc(&A.d, dBytes + dBytes / 4)); A.dcap = dBytes + dBytes / 4; }
+    if (hBytes > A.hcap) { if (A.h) { cudaFreeHost(A.h); A.h = nullptr; A.hcap = 0; } CK(cudaMallocHost(&A.h, hBytes + hBytes / 4)); A.hcap = hBytes + hBytes / 4; }
+
+    uint8_t* hIn = A.h; uint8_t* hOut = A.h + inAll;
+    uint8_t* dIn = A.d; uint8_t* dSc = A.d + inAll; uint8_t* dOut = A.d + inAll + scTot;
+    Dev* hDev = (Dev*)(hIn + devOff);
+    for (int i = 0; i < count; ++i) {
+        const std::string err = pack_inputs(problems[i], lay[i], hIn + inOff[i]);
+        if (!err.empty()) { set_error(err); return ORB_ERR_ARG; }
+        bind(hDev[i], problems[i], lay[i], dIn + inOff[i], dSc + scOff[i], dOut + outOff[i]);      // device addresses
+    }
+    CK(cudaMemcpyAsync(dIn, hIn, inAll, cudaMemcpyHostToDevice, A.st));
+    local_inertial_ba_kernel<<<count, NT, 0, A.st>>>((const Dev*)(dIn + devOff));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hOut, dOut, outTot, cudaMemcpyDeviceToHost, A.st));
+    CK(cudaStreamSynchronize(A.st));
+    for (int i = 0; i < count; ++i) {
+        const int it = unpack_outputs(problems[i], results[i], lay[i], hOut + outOff[i]);
+        if (iterationsOut) iterationsOut[i] = it;
+    }
+    return ORB_OK;
+}

@@ -116,3 +116,60 @@ def test_noise_free_ground_truth_is_a_fixed_point():
     r = O.local_inertial_ba(pr, P)
     assert not r['failed'] and r['erase'].sum() == 0
     assert np.abs(r['state'][:, 9:12] - pr['truth'][:, 9:12]).max() < 2e-3 and np.abs(r['points'] - pr['points_true']).max() < 2e-2
+
+
+# ---- the kernel's phase functions, run by a serial executor on the host (tests/liba_emulate.cpp), against the oracle ----
+def _emulate(pr, P):
+    import ctypes as C
+    import os
+    import subprocess
+    import orb_slam3_modified_b200 as orb
+    here = os.path.dirname(os.path.abspath(__file__))
+    so, src = os.path.join(here, 'libliba_emulate.so'), os.path.join(here, 'liba_emulate.cpp')
+    deps = [src] + [os.path.join(here, '..', 'orb_slam3_modified_b200', 'csrc', f) for f in ('liba_core.cuh', 'liba_pack.h', 'inertial_dev.cuh')]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-o', so, src])
+    L = C.CDLL(so)
+    q = dict(pr); q['preint'] = P
+    Pm, Rm, keep, outs = orb._liba_marshal([q])
+    err = C.create_string_buffer(256)
+    L.liba_emulate.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+    it = L.liba_emulate(C.cast(Pm, C.c_void_p), C.cast(Rm, C.c_void_p), err, 256)
+    assert it >= 0, err.value
+    return orb._liba_finish(outs, [it])[0]
+
+
+def _same_solve(a, b, pr, tol_state=1e-8):
+    assert a['iters'] == b['iters'] and a['trials'] == b['trials'] and a['failed'] == b['failed'], (a['iters'], b['iters'], a['trials'], b['trials'])
+    assert abs(a['err'] - b['err']) <= 1e-6 * abs(b['err']) and abs(a['err_end'] - b['err_end']) <= 1e-5 * abs(b['err_end']) + 1e-9
+    assert abs(a['lam'] - b['lam']) <= 1e-6 * abs(b['lam'])
+    assert np.abs(a['state'] - b['state']).max() < tol_state and np.abs(a['tcw'] - b['tcw']).max() < tol_state
+    ra = O.local_inertial_ba_residuals(pr, a['tcw'], a['points']); rb = O.local_inertial_ba_residuals(pr, b['tcw'], b['points'])
+    d = np.abs(ra - rb)
+    sane = np.abs(rb).max(1) < 1e3                         # unobservable outlier-only points can sit anywhere along their ray
+    assert d[sane].max() < 1e-4, d[sane].max()             # the north-star bar: reprojection residuals within 1e-4 px
+    assert np.array_equal(a['erase'], b['erase'])
+    assert np.allclose(a['chi2'][sane], b['chi2'][sane], rtol=1e-6, atol=1e-6)
+
+
+def test_kernel_phases_on_the_host_equal_the_oracle():
+    cases = [dict(n_opt=10, n_cov_fixed=3, n_pts=400, seed=1), dict(n_opt=14, n_cov_fixed=2, n_pts=300, seed=3, large=True), dict(n_opt=1, n_cov_fixed=2, n_pts=60, seed=5),
+             dict(n_opt=4, n_cov_fixed=0, n_pts=120, seed=6, rec_init=True), dict(n_opt=6, n_cov_fixed=1, n_pts=200, seed=7, perturb=4.0)]
+    for kw in cases:
+        pr = synth.local_inertial_ba_problem(**kw)
+        P = O.liba_preints(pr)
+        _same_solve(_emulate(pr, P), O.local_inertial_ba(pr, P), pr)
+
+
+def test_kernel_phases_default_lambda_and_rejected_steps():
+    pr = synth.local_inertial_ba_problem(n_opt=5, n_cov_fixed=1, n_pts=150, seed=8)
+    P = O.liba_preints(pr)
+    pr['lambda_init'] = 0.0                                 # computeLambdaInit's tau * max diagonal branch
+    _same_solve(_emulate(pr, P), O.local_inertial_ba(pr, P), pr)
+    pr['lambda_init'] = 1e-12                               # an (almost) undamped first step on a far-off start: rejected trials, lambda growth
+    pr2 = synth.local_inertial_ba_problem(n_opt=5, n_cov_fixed=1, n_pts=150, seed=9, perturb=12.0)
+    pr2['lambda_init'] = 1e-12
+    P2 = O.liba_preints(pr2)
+    a, b = _emulate(pr2, P2), O.local_inertial_ba(pr2, P2)
+    assert b['trials'] > b['iters']                         # at least one rejected trial happened
+    _same_solve(a, b, pr2, tol_state=1e-7)
