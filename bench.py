@@ -847,6 +847,18 @@ def main():
             try:
                 kind = _cpu_impl()[3]
                 fps1, dt1, sample, split, _ = run_cpu_arm(1, 1, 1, 24 * KF_INTERVAL)     # 240 frames + 24 LBAs: ~8 s of single-thread CPU work
+                try:      # the oracle port of Optimizer::LocalInertialBA on the map extra_configs times on the GPU (single thread, 3 runs)
+                    import numpy as np
+                    import oracle_lib as O
+                    from orb_slam3_modified_b200 import synth
+                    lpr = synth.local_inertial_ba_problem(n_opt=10, n_cov_fixed=6, n_pts=2500, seed=12)
+                    lP = O.liba_preints(lpr)
+                    ts = []
+                    for _ in range(3):
+                        t0 = time.perf_counter(); O.local_inertial_ba(lpr, lP); ts.append(time.perf_counter() - t0)
+                    split['local_inertial_ba_ms_per_map'] = 1e3 * float(np.median(ts))
+                except Exception as exc:
+                    split['local_inertial_ba_error'] = repr(exc)[:120]
                 out['cpu_baseline'] = {'value': fps1, 'unit': UNIT, 'cores': 1, 'kind': 'reference' if kind['extract'] == 'reference' else 'port',
                                        'kind_per_stage': kind, 'host': cpu_info(), 'sample': sample + ' (%.1f s)' % dt1, 'split': split}
             except Exception as exc:

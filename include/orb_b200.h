@@ -486,7 +486,7 @@ int imu_mono_edges(const ImuMonoEdges* in, double* err2, double* Jpoint2x3, doub
  * Results (host pointers, per problem): the optimised kfState21 / kfTcw12 / points3 (what SetPose / SetVelocity / SetNewBias / SetWorldPos receive
  * after the casts of :2905-2950), erase [nEdges] = 1 for the (keyframe, point) pairs of vToErase (:2848-2862), edgeChi2 [nEdges] = e->chi2(),
  * stats8 = err, err_end (:2837-2839, as floats), failed (the "FAIL LOCAL-INERTIAL BA" test :2884: states and points are then returned unchanged),
- * final lambda, LM trials, optimize()'s iteration count.  iterationsOut [count] (may be NULL). */
+ * final lambda, LM trials, optimize()'s iteration count, nanoseconds the map's CTA spent in the solver.  iterationsOut [count] (may be NULL). */
 typedef struct LocalInertialBAProblem {
     int32_t nKF, nOpt;
     const double* kfState21; const double* kfTcw12; const float* cam4; const double* extrinsics24;

@@ -914,7 +914,8 @@ def _liba_marshal(probs):
 
 def _liba_finish(outs, iters):
     return [dict(state=o['state'], tcw=o['tcw'], points=o['points'], erase=o['erase'], chi2=o['chi2'], iters=int(iters[i]), err=float(o['stats'][0]),
-                 err_end=float(o['stats'][1]), failed=bool(o['stats'][2]), lam=float(o['stats'][3]), trials=int(o['stats'][4])) for i, o in enumerate(outs)]
+                 err_end=float(o['stats'][1]), failed=bool(o['stats'][2]), lam=float(o['stats'][3]), trials=int(o['stats'][4]), kernel_ms=float(o['stats'][6]) * 1e-6)
+            for i, o in enumerate(outs)]
 
 
 def LocalInertialBA(probs, device=0):

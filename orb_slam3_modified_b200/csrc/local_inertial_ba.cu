@@ -66,7 +66,11 @@ __global__ void __launch_bounds__(NT) local_inertial_ba_kernel(const Dev* __rest
     if (threadIdx.x == 0) s_D = probs[blockIdx.x];
     __syncthreads();
     DeviceExec ex{s_red};
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     run(s_D, ex);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (threadIdx.x == 0) s_D.stats[6] = (double)(t1 - t0);      // nanoseconds this map's CTA spent in the solver
 }
 
 // host plumbing: one arena per host thread and device, grown on demand; pinned staging for the packed input / output buffers

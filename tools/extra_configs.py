@@ -157,4 +157,27 @@ def measure(orb, synth, device=0, reps=40):
             'reference': 'Optimizer::PoseInertialOptimizationLastFrame / LastKeyFrame, src/Optimizer.cc:4491-5289; includes the Python marshalling of the batch'}
     except Exception as exc:          # the latency lines are informative; never fail the bench line over them
         out['mono-inertial tracking: inertial pose optimisers (700 map points per frame)'] = {'error': repr(exc)[:200]}
+    # ---------------- mono-inertial mapping: Optimizer::LocalInertialBA ----------------
+    # LocalMapping::Run calls it instead of LocalBundleAdjustment once the IMU is initialised (src/LocalMapping.cc:129-151): 10 keyframes in the
+    # temporal window + 7 fixed, ~2100 points, ~24.5k EdgeMono; one map alone (latency) and one map per SM in a single launch
+    key = 'mono-inertial mapping: LocalInertialBA (10 + 7 keyframes, ~2100 points, ~24.5k edges)'
+    try:
+        def maps(n):
+            prs = []
+            for k in range(n):
+                pr = synth.local_inertial_ba_problem(n_opt=10, n_cov_fixed=6, n_pts=2500, seed=12 + k)
+                pr['preint'] = np.stack([orb.imu_preintegrate(a[None], g[None], d[None], [len(d)], pr['bias6'][None], synth.IMU_NOISE, device)[0] for a, g, d in pr['imu']])
+                prs.append(pr)
+            return prs
+        one = maps(1)
+        four = one + maps(4)[1:]
+        r1 = orb.LocalInertialBA(one, device=device)[0]
+        out[key] = {
+            '1_map_host_ms': _median_ms(lambda: orb.LocalInertialBA(one, device=device), 10),
+            '148_maps_host_ms': _median_ms(lambda: orb.LocalInertialBA(four * 37, device=device), 3, warm=1),
+            'edges': int(len(one[0]['e_pt'])), 'points': int(len(one[0]['points'])), 'iterations': int(r1['iters']), 'lm_trials': int(r1['trials']),
+            'erased_observations': int(r1['erase'].sum()),
+            'reference': 'Optimizer::LocalInertialBA, src/Optimizer.cc:2383-2958; host API incl. the Python marshalling and the packing of the graph'}
+    except Exception as exc:
+        out[key] = {'error': repr(exc)[:200]}
     return out
