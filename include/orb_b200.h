@@ -497,6 +497,7 @@ typedef struct LocalInertialBAProblem {
 } LocalInertialBAProblem;
 typedef struct LocalInertialBAResult {
     double* kfState21; double* kfTcw12; double* points3; uint8_t* erase; double* edgeChi2; double* stats8;
+    double* profile8;   /* may be NULL; diagnostic: nanoseconds in errors | buildSystem | Dinv, Y | Schur | LDL^T | point back-substitution | update / pop | rest */
 } LocalInertialBAResult;
 int local_inertial_ba_batch(int count, const LocalInertialBAProblem* problems, const LocalInertialBAResult* results, int32_t* iterationsOut, int device);
 

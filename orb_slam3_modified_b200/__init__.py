@@ -889,7 +889,7 @@ class _LocalInertialBAProblem(C.Structure):
 
 
 class _LocalInertialBAResult(C.Structure):
-    _fields_ = [('kfState21', C.c_void_p), ('kfTcw12', C.c_void_p), ('points3', C.c_void_p), ('erase', C.c_void_p), ('edgeChi2', C.c_void_p), ('stats8', C.c_void_p)]
+    _fields_ = [('kfState21', C.c_void_p), ('kfTcw12', C.c_void_p), ('points3', C.c_void_p), ('erase', C.c_void_p), ('edgeChi2', C.c_void_p), ('stats8', C.c_void_p), ('profile8', C.c_void_p)]
 
 
 def _liba_marshal(probs):
@@ -903,18 +903,18 @@ def _liba_marshal(probs):
                  sc=_c(pr['ie_info_scale'], np.float64), pts=_c(pr['points'], np.float64), td=_c(pr['track_depth'], np.float32), ep=_c(pr['e_pt'], np.int32),
                  ek=_c(pr['e_kf'], np.int32), ob=_c(pr['obs'], np.float64), isg=_c(pr['inv_sigma2'], np.float32))
         nE = len(a['ep'])
-        o = dict(state=np.zeros_like(a['st']), tcw=np.zeros_like(a['tc']), points=np.zeros_like(a['pts']), erase=np.zeros(nE, np.uint8), chi2=np.zeros(nE), stats=np.zeros(8))
+        o = dict(state=np.zeros_like(a['st']), tcw=np.zeros_like(a['tc']), points=np.zeros_like(a['pts']), erase=np.zeros(nE, np.uint8), chi2=np.zeros(nE), stats=np.zeros(8), prof=np.zeros(8))
         P[i] = _LocalInertialBAProblem(int(pr['n_kf']), int(pr['n_opt']), a['st'].ctypes.data, a['tc'].ctypes.data, a['cam'].ctypes.data, a['ex'].ctypes.data, len(a['k1']), a['k1'].ctypes.data, a['k2'].ctypes.data,
                                        a['pre'].ctypes.data, a['rob'].ctypes.data, a['sc'].ctypes.data, len(a['pts']), a['pts'].ctypes.data, a['td'].ctypes.data, nE, a['ep'].ctypes.data, a['ek'].ctypes.data,
                                        a['ob'].ctypes.data, a['isg'].ctypes.data, int(pr['iterations']), int(bool(pr['large'])), float(pr['lambda_init']))
-        R[i] = _LocalInertialBAResult(o['state'].ctypes.data, o['tcw'].ctypes.data, o['points'].ctypes.data, o['erase'].ctypes.data, o['chi2'].ctypes.data, o['stats'].ctypes.data)
+        R[i] = _LocalInertialBAResult(o['state'].ctypes.data, o['tcw'].ctypes.data, o['points'].ctypes.data, o['erase'].ctypes.data, o['chi2'].ctypes.data, o['stats'].ctypes.data, o['prof'].ctypes.data)
         keep.append(a); outs.append(o)
     return P, R, keep, outs
 
 
 def _liba_finish(outs, iters):
     return [dict(state=o['state'], tcw=o['tcw'], points=o['points'], erase=o['erase'], chi2=o['chi2'], iters=int(iters[i]), err=float(o['stats'][0]),
-                 err_end=float(o['stats'][1]), failed=bool(o['stats'][2]), lam=float(o['stats'][3]), trials=int(o['stats'][4]), kernel_ms=float(o['stats'][6]) * 1e-6)
+                 err_end=float(o['stats'][1]), failed=bool(o['stats'][2]), lam=float(o['stats'][3]), trials=int(o['stats'][4]), kernel_ms=float(o['stats'][6]) * 1e-6, phase_ms=o['prof'] * 1e-6)
             for i, o in enumerate(outs)]
 
 

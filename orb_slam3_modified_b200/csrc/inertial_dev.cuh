@@ -15,6 +15,17 @@
 
 namespace imu {
 
+// Product rounded on its own (never fused into a following addition) for the FLOAT arithmetic of IMU::Preintegrated: the bias-corrected
+// delta rotation / velocity / position are float in the reference (src/ImuTypes.cc:283-307) and every last-bit difference in them moves
+// the optimised states by ~1e-7, so the device evaluates them exactly like the CPU oracle (which is built with -ffp-contract=off).
+// Doubles are left to the compiler (their contraction changes results at the 1e-15 level only).
+template <class T> IMU_HD inline T pm(T a, T b) { return a * b; }
+#if defined(__CUDA_ARCH__)
+template <> __device__ inline float pm<float>(float a, float b) { return __fmul_rn(a, b); }
+#elif defined(__FMA__)
+template <> inline float pm<float>(float a, float b) { float r = a * b; asm volatile("" : "+x"(r)); return r; }
+#endif
+
 enum { P_DT = 0, P_DR = 1, P_DV = 10, P_DP = 13, P_JRG = 16, P_JVG = 25, P_JVA = 34, P_JPG = 43, P_JPA = 52, P_B = 61, P_C = 67, P_SIZE = 292 };
 
 template <class T> IMU_HD inline void m3mul(const T* A, const T* B, T* C) {
@@ -22,7 +33,7 @@ template <class T> IMU_HD inline void m3mul(const T* A, const T* B, T* C) {
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) r[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+        for (int j = 0; j < 3; ++j) r[i * 3 + j] = pm(A[i * 3], B[j]) + pm(A[i * 3 + 1], B[3 + j]) + pm(A[i * 3 + 2], B[6 + j]);
 #pragma unroll
     for (int i = 0; i < 9; ++i) C[i] = r[i];
 }
@@ -38,7 +49,7 @@ template <class T> IMU_HD inline void m3T(const T* A, T* B) {
 template <class T> IMU_HD inline void m3vec(const T* A, const T* v, T* o) {
     T r[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) r[i] = A[i * 3] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2];
+    for (int i = 0; i < 3; ++i) r[i] = pm(A[i * 3], v[0]) + pm(A[i * 3 + 1], v[1]) + pm(A[i * 3 + 2], v[2]);
 #pragma unroll
     for (int i = 0; i < 3; ++i) o[i] = r[i];
 }
@@ -59,19 +70,19 @@ template <class T> IMU_HD inline void normalize_rotation(const T* R, T* out) {
             for (int q = p + 1; q < 3; ++q) {
                 T alpha = 0, beta = 0, gamma = 0;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) { alpha += A[i * 3 + p] * A[i * 3 + p]; beta += A[i * 3 + q] * A[i * 3 + q]; gamma += A[i * 3 + p] * A[i * 3 + q]; }
+                for (int i = 0; i < 3; ++i) { alpha += pm(A[i * 3 + p], A[i * 3 + p]); beta += pm(A[i * 3 + q], A[i * 3 + q]); gamma += pm(A[i * 3 + p], A[i * 3 + q]); }
                 const T ab = alpha * beta, tiny = sizeof(T) == 4 ? (T)1e-30 : (T)1e-300;
                 off = fmax(off, (T)fabs(gamma) / (T)sqrt(ab > tiny ? ab : tiny));
                 if (gamma != 0) {
                     const T zeta = (beta - alpha) / (2 * gamma);
-                    const T t = (zeta >= 0 ? (T)1 : (T)-1) / ((T)fabs(zeta) + (T)sqrt(1 + zeta * zeta));
-                    const T c = 1 / (T)sqrt(1 + t * t), s = c * t;
+                    const T t = (zeta >= 0 ? (T)1 : (T)-1) / ((T)fabs(zeta) + (T)sqrt(1 + pm(zeta, zeta)));
+                    const T c = 1 / (T)sqrt(1 + pm(t, t)), s = c * t;
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         const T ap = A[i * 3 + p], aq = A[i * 3 + q];
-                        A[i * 3 + p] = c * ap - s * aq; A[i * 3 + q] = s * ap + c * aq;
+                        A[i * 3 + p] = pm(c, ap) - pm(s, aq); A[i * 3 + q] = pm(s, ap) + pm(c, aq);
                         const T vp = V[i * 3 + p], vq = V[i * 3 + q];
-                        V[i * 3 + p] = c * vp - s * vq; V[i * 3 + q] = s * vp + c * vq;
+                        V[i * 3 + p] = pm(c, vp) - pm(s, vq); V[i * 3 + q] = pm(s, vp) + pm(c, vq);
                     }
                 }
             }
@@ -82,7 +93,7 @@ template <class T> IMU_HD inline void normalize_rotation(const T* R, T* out) {
     for (int j = 0; j < 3; ++j) {
         T n = 0;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) n += A[i * 3 + j] * A[i * 3 + j];
+        for (int i = 0; i < 3; ++i) n += pm(A[i * 3 + j], A[i * 3 + j]);
         n = (T)sqrt(n);
 #pragma unroll
         for (int i = 0; i < 3; ++i) U[i * 3 + j] = n > 0 ? A[i * 3 + j] / n : (T)(i == j);
@@ -185,11 +196,11 @@ IMU_HD inline void edge_inertial_dev(const float* __restrict__ P, const double* 
     {
         float w[3], W[9], W2[9], E[9], M[9], Rn[9];
         m3vec(P + P_JRG, dbgf, w);
-        const float d2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], d = sqrtf(d2);
+        const float d2 = pm(w[0], w[0]) + pm(w[1], w[1]) + pm(w[2], w[2]), d = sqrtf(d2);
         hat(w, W); m3mul(W, W, W2);
         for (int i = 0; i < 9; ++i) {
             const float I = (i % 4 == 0) ? 1.f : 0.f;
-            E[i] = d < 1e-5f ? I + W[i] + 0.5f * W2[i] : I + W[i] * sinf(d) / d + W2[i] * (1.0f - cosf(d)) / d2;
+            E[i] = d < 1e-5f ? I + W[i] + pm(0.5f, W2[i]) : I + pm(W[i], sinf(d)) / d + pm(W2[i], 1.0f - cosf(d)) / d2;
         }
         m3mul(P + P_DR, E, M);
         normalize_rotation(M, Rn);

@@ -4,7 +4,9 @@
 //
 // The algorithm is written once, as a sequence of CTA-wide phases driven through an executor `Exec`:
 //     ex.par(f)   every thread t of the CTA runs f(t), then a CTA barrier;
-//     ex.sum(f)   CTA-wide ordered sum of f(t) (fixed reduction tree), the same value returned to every thread.
+//     ex.sum(f)   CTA-wide ordered sum of f(t) (fixed reduction tree), the same value returned to every thread;
+//     ex.tag(k)   marks the start of phase group k for the optional time profile (0 errors, 1 buildSystem, 2 Dinv / Y, 3 Schur, 4 LDL^T,
+//                 5 point back-substitution, 6 push / update / pop, 7 the rest).
 // Everything between two phases is uniform control flow (LM state replicated per thread).  On the GPU Exec is DeviceExec
 // (local_inertial_ba.cu: threadIdx + __syncthreads + shuffles); tests/liba_emulate.cpp instantiates the very same code with a serial
 // HostExec (g++), which checks the logic against the CPU oracle in this GPU-less container.  It is a test vehicle: the product library
@@ -23,9 +25,13 @@ namespace liba {
 
 using namespace imu;
 
-constexpr int NT = 256;          // threads per CTA
+#ifndef LIBA_NT
+#define LIBA_NT 256
+#endif
+constexpr int NT = LIBA_NT;      // threads per CTA
 constexpr int EJ = 21;           // per mono edge: A 2x3 | B 2x6 | w | r0 | r1
 constexpr int LW = 5;            // panel width of the blocked LDL^T (15 = 3 * 5)
+constexpr int SL = 32;           // slices of a keyframe's edge list in the Schur phase
 
 // One problem, device (or emulation) view.  Inputs are written by the host packer (liba_pack.h); scratch is uninitialised.
 struct Dev {
@@ -55,13 +61,15 @@ struct Dev {
     double *Hll, *bl, *Dinv, *db;           // [nL][9], [nL][3], [nL][9], [nL][3]
     double *H, *b, *Hs, *bs, *dvec, *x;     // [n][n], [n], [n][n], [n], [n], [n + 3 nL]
     double *He, *be;                        // [nI][900], [nI][30]
+    double *part, *partb;                   // [nPairs][SL][36], [nOpt][SL][6]: partial Schur sums
     double *kfBk, *tcwBk, *ptsBk;           // push() / pop()
     int *its, *itsBk;                       // ImuCamPose::its
     // ---- outputs ----
     double *outState, *outTcw, *outPts;     // [nKF][21], [nKF][12], [nL][3]
     uint8_t* erase;                         // [nE]
     double* chi2;                           // [nE]
-    double* stats;                          // [8]: err, err_end, failed, lambda, trials, iterations
+    double* stats;                          // [8]: err, err_end, failed, lambda, trials, iterations, solver ns
+    double* prof;                           // [8]: nanoseconds per phase group (ex.tag)
 };
 
 IMU_HD inline void huber(double e2, double delta, double& rho0, double& rho1) {      // RobustKernelHuber::robustify
@@ -96,6 +104,7 @@ IMU_HD inline void mono_camera_point(const Dev& D, int e, double* Xc) {
 
 // computeActiveErrors + activeRobustChi2
 template <class Exec> IMU_HD inline double compute_errors(const Dev& D, Exec& ex, double deltaMono, double deltaInertial) {
+    ex.tag(0);
     return ex.sum([&](int tid) {
         double v = 0;
         for (int e = tid; e < D.nE; e += NT) {
@@ -128,6 +137,7 @@ template <class Exec> IMU_HD inline double compute_errors(const Dev& D, Exec& ex
 
 // BlockSolver::buildSystem: linearizeOplus + constructQuadraticForm of every edge
 template <class Exec> IMU_HD inline void build_system(const Dev& D, Exec& ex, double deltaMono, double deltaInertial) {
+    ex.tag(1);
     const int n = 15 * D.nOpt;
     const double *Rcb = D.extr, *Rbc = D.extr + 12, *tbc = D.extr + 21;
     ex.par([&](int tid) {
@@ -216,19 +226,36 @@ template <class Exec> IMU_HD inline void build_system(const Dev& D, Exec& ex, do
             for (int k = 0; k < 9; ++k) D.Hll[9 * (size_t)p + k] = h[k];
             for (int k = 0; k < 3; ++k) D.bl[3 * (size_t)p + k] = b3[k];
         }
-        // keyframes: the 6 x 6 pose block (lower triangle, mirrored) and its b, one task per entry
-        for (int t = tid; t < D.nOpt * 27; t += NT) {
-            const int k = t / 27, q = t % 27;
-            int a = 0, c = 0;
-            if (q < 21) { int r = q; while (r > a) { r -= a + 1; ++a; } c = r; } else a = q - 21;
-            double acc = 0;
-            for (int j = D.kfStart[k]; j < D.kfStart[k + 1]; ++j) {
+        // keyframes, step 1: partial sums of the 6 x 6 pose block (lower triangle) and of its b over a slice of the keyframe's edge list
+        for (int t = tid; t < D.nOpt * SL; t += NT) {
+            const int k = t / SL, sl = t % SL;
+            double acc[27];
+            for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+            for (int j = D.kfStart[k] + sl; j < D.kfStart[k + 1]; j += SL) {
                 const double* J = D.ejac + (size_t)EJ * D.kfEdges[j];
                 const double* B = J + 6;
-                acc += q < 21 ? J[18] * (B[a] * B[c] + B[6 + a] * B[6 + c]) : B[a] * J[19] + B[6 + a] * J[20];
+                const double w = J[18], r0 = J[19], r1 = J[20];
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int c = 0; c <= a; ++c) acc[a * (a + 1) / 2 + c] += w * (B[a] * B[c] + B[6 + a] * B[6 + c]);
+#pragma unroll
+                for (int a = 0; a < 6; ++a) acc[21 + a] += B[a] * r0 + B[6 + a] * r1;
             }
-            if (q < 21) { D.H[(size_t)(15 * k + a) * n + 15 * k + c] = acc; D.H[(size_t)(15 * k + c) * n + 15 * k + a] = acc; }
-            else D.b[15 * k + a] = acc;
+            for (int q = 0; q < 27; ++q) D.part[27 * (size_t)t + q] = acc[q];
+        }
+    });
+    ex.par([&](int tid) {
+        // step 2: the slices in order; the block is mirrored
+        for (int t = tid; t < D.nOpt * 27; t += NT) {
+            const int k = t / 27, q = t % 27;
+            double acc = 0;
+            for (int sl = 0; sl < SL; ++sl) acc += D.part[27 * ((size_t)k * SL + sl) + q];
+            if (q < 21) {
+                int a = 0, r = q;
+                while (r > a) { r -= a + 1; ++a; }
+                D.H[(size_t)(15 * k + a) * n + 15 * k + r] = acc; D.H[(size_t)(15 * k + r) * n + 15 * k + a] = acc;
+            } else D.b[15 * k + q - 21] = acc;
         }
     });
     ex.par([&](int tid) {
@@ -271,6 +298,8 @@ template <class Exec> IMU_HD inline bool ldlt_solve(const Dev& D, Exec& ex) {
         }
         if (bad) return false;
         for (int c = 0; c < LW; ++c) { double v = y[k0 + c]; for (int j = 0; j < c; ++j) v -= L11[c * LW + j] * z[j]; z[c] = v; }
+        double dinv[LW];
+        for (int c = 0; c < LW; ++c) dinv[c] = 1.0 / d[c];
         ex.par([&](int tid) {
             // panel: X = A21 L11^-T (kept unscaled in place), y2 -= (X D^-1) z
             for (int i = k0 + LW + tid; i < n; i += NT) {
@@ -280,7 +309,7 @@ template <class Exec> IMU_HD inline bool ldlt_solve(const Dev& D, Exec& ex) {
                     double v = row[c];
                     for (int j = 0; j < c; ++j) v -= xr[j] * L11[c * LW + j];
                     xr[c] = v;
-                    s += v / d[c] * z[c];
+                    s += v * dinv[c] * z[c];
                 }
                 for (int c = 0; c < LW; ++c) row[c] = xr[c];
                 y[i] -= s;
@@ -304,7 +333,7 @@ template <class Exec> IMU_HD inline bool ldlt_solve(const Dev& D, Exec& ex) {
                     const double* xi = A + (size_t)(r0 + i) * n + k0;
                     const double* xj = A + (size_t)(r0 + j) * n + k0;
                     double s = 0;
-                    for (int c = 0; c < LW; ++c) s += xi[c] * xj[c] / d[c];
+                    for (int c = 0; c < LW; ++c) s += xi[c] * (xj[c] * dinv[c]);
                     A[(size_t)(r0 + i) * n + r0 + j] -= s;
                 }
             });
@@ -331,6 +360,7 @@ template <class Exec> IMU_HD inline bool ldlt_solve(const Dev& D, Exec& ex) {
 
 // BlockSolver::solve (Schur branch) with lambda folded into the diagonals of copies (setLambda / restoreDiagonal)
 template <class Exec> IMU_HD inline bool solve_system(const Dev& D, Exec& ex, double lambda) {
+    ex.tag(2);
     const int n = 15 * D.nOpt, nO = D.nOpt;
     ex.par([&](int tid) {
         for (int p = tid; p < D.nL; p += NT) {
@@ -342,7 +372,7 @@ template <class Exec> IMU_HD inline bool solve_system(const Dev& D, Exec& ex, do
             const double* b3 = D.bl + 3 * (size_t)p;
             for (int a = 0; a < 3; ++a) D.db[3 * (size_t)p + a] = Di[a * 3] * b3[0] + Di[a * 3 + 1] * b3[1] + Di[a * 3 + 2] * b3[2];
         }
-        for (size_t i = tid; i < (size_t)n * n; i += NT) D.Hs[i] = D.H[i] + ((i / n == i % n) ? lambda : 0.0);
+        for (int i = tid; i < n * n; i += NT) D.Hs[i] = D.H[i] + ((i / n == i % n) ? lambda : 0.0);
         for (int i = tid; i < n; i += NT) D.bs[i] = D.b[i];
     });
     ex.par([&](int tid) {
@@ -355,42 +385,68 @@ template <class Exec> IMU_HD inline bool solve_system(const Dev& D, Exec& ex, do
         }
     });
     const int nPairs = nO * (nO + 1) / 2;
+    ex.tag(3);
     ex.par([&](int tid) {
-        // Hschur: one task per (keyframe pair i1 <= i2, row a of the 6 x 6 block)
-        for (int t = tid; t < nPairs * 6; t += NT) {
-            int pidx = t / 6;
-            const int a = t % 6;
+        // Hschur, step 1: one task per (keyframe pair i1 <= i2, slice of keyframe i1's edge list): partial 6 x 6 blocks
+        for (int t = tid; t < nPairs * SL; t += NT) {
+            int pidx = t / SL;
+            const int sl = t % SL;
             int i1 = 0;
             while (pidx >= nO - i1) { pidx -= nO - i1; ++i1; }
             const int i2 = i1 + pidx;
-            double acc[6] = {0, 0, 0, 0, 0, 0};
-            for (int j = D.kfStart[i1]; j < D.kfStart[i1 + 1]; ++j) {
+            double acc[36];
+            for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+            for (int j = D.kfStart[i1] + sl; j < D.kfStart[i1 + 1]; j += SL) {
                 const int e1 = D.kfEdges[j];
-                const int e2 = D.pk[(size_t)D.ePt[e1] * nO + i2];
+                const int e2 = i1 == i2 ? e1 : D.pk[(size_t)D.ePt[e1] * nO + i2];
                 if (e2 < 0) continue;
-                const double* Yr = D.Y + 18 * (size_t)e1 + 3 * a;
+                const double* Y1 = D.Y + 18 * (size_t)e1;
                 const double* W2 = D.W + 18 * (size_t)e2;
-                for (int c = 0; c < 6; ++c) acc[c] += Yr[0] * W2[c * 3] + Yr[1] * W2[c * 3 + 1] + Yr[2] * W2[c * 3 + 2];
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) acc[a * 6 + c] += Y1[a * 3] * W2[c * 3] + Y1[a * 3 + 1] * W2[c * 3 + 1] + Y1[a * 3 + 2] * W2[c * 3 + 2];
             }
-            for (int c = 0; c < 6; ++c) {
-                D.Hs[(size_t)(15 * i1 + a) * n + 15 * i2 + c] -= acc[c];
-                if (i1 != i2) D.Hs[(size_t)(15 * i2 + c) * n + 15 * i1 + a] -= acc[c];
-            }
+            double* out = D.part + 36 * (size_t)t;
+            for (int k = 0; k < 36; ++k) out[k] = acc[k];
         }
-        // bschur
+        // bschur, step 1: (keyframe, slice)
+        for (int t = tid; t < nO * SL; t += NT) {
+            const int k = t / SL, sl = t % SL;
+            double acc[6] = {0, 0, 0, 0, 0, 0};
+            for (int j = D.kfStart[k] + sl; j < D.kfStart[k + 1]; j += SL) {
+                const int e = D.kfEdges[j];
+                const double* We = D.W + 18 * (size_t)e;
+                const double* d3 = D.db + 3 * (size_t)D.ePt[e];
+                for (int a = 0; a < 6; ++a) acc[a] += We[a * 3] * d3[0] + We[a * 3 + 1] * d3[1] + We[a * 3 + 2] * d3[2];
+            }
+            for (int a = 0; a < 6; ++a) D.partb[6 * (size_t)t + a] = acc[a];
+        }
+    });
+    ex.par([&](int tid) {
+        // step 2: the slices in order
+        for (int t = tid; t < nPairs * 36; t += NT) {
+            int pidx = t / 36;
+            const int q = t % 36, a = q / 6, c = q % 6;
+            const double* src = D.part + 36 * (size_t)pidx * SL + q;
+            double acc = 0;
+            for (int sl = 0; sl < SL; ++sl) acc += src[36 * sl];
+            int i1 = 0;
+            while (pidx >= nO - i1) { pidx -= nO - i1; ++i1; }
+            const int i2 = i1 + pidx;
+            D.Hs[(size_t)(15 * i1 + a) * n + 15 * i2 + c] -= acc;
+            if (i1 != i2) D.Hs[(size_t)(15 * i2 + c) * n + 15 * i1 + a] -= acc;
+        }
         for (int t = tid; t < nO * 6; t += NT) {
             const int k = t / 6, a = t % 6;
             double acc = 0;
-            for (int j = D.kfStart[k]; j < D.kfStart[k + 1]; ++j) {
-                const int e = D.kfEdges[j];
-                const double* Wr = D.W + 18 * (size_t)e + 3 * a;
-                const double* d3 = D.db + 3 * (size_t)D.ePt[e];
-                acc += Wr[0] * d3[0] + Wr[1] * d3[1] + Wr[2] * d3[2];
-            }
+            for (int sl = 0; sl < SL; ++sl) acc += D.partb[6 * ((size_t)k * SL + sl) + a];
             D.bs[15 * k + a] -= acc;
         }
     });
+    ex.tag(4);
     if (n > 0 && !ldlt_solve(D, ex)) return false;
+    ex.tag(5);
     ex.par([&](int tid) {
         // landmarks: xl = Dinv (bl - Hpl^T xp)
         for (int p = tid; p < D.nL; p += NT) {
@@ -411,6 +467,7 @@ template <class Exec> IMU_HD inline bool solve_system(const Dev& D, Exec& ex, do
 
 // push() + SparseOptimizer::update: VertexPose::oplusImpl = ImuCamPose::Update (src/G2oTypes.cc:192-221), additive velocity / biases / points
 template <class Exec> IMU_HD inline void push_and_update(const Dev& D, Exec& ex) {
+    ex.tag(6);
     const int n = 15 * D.nOpt;
     const double *Rcb = D.extr, *tcb = D.extr + 9;
     ex.par([&](int tid) {
@@ -439,6 +496,7 @@ template <class Exec> IMU_HD inline void push_and_update(const Dev& D, Exec& ex)
     });
 }
 template <class Exec> IMU_HD inline void pop(const Dev& D, Exec& ex) {
+    ex.tag(6);
     ex.par([&](int tid) {
         for (int i = tid; i < 21 * D.nOpt; i += NT) D.kfState[i] = D.kfBk[i];
         for (int i = tid; i < 12 * D.nOpt; i += NT) D.kfTcw[i] = D.tcwBk[i];
@@ -452,6 +510,7 @@ template <class Exec> IMU_HD inline void run(const Dev& D, Exec& ex) {
     const int n = 15 * D.nOpt, nO = D.nOpt;
     const double deltaMono = (double)sqrtf(5.991f);      // const float thHuberMono = sqrt(5.991)
     const double deltaInertial = sqrt(16.92);
+    ex.tag(7);
     ex.par([&](int tid) {
         for (int i = tid; i < D.nI; i += NT) {
             double* I9 = D.info9 + 81 * (size_t)i;
@@ -465,14 +524,17 @@ template <class Exec> IMU_HD inline void run(const Dev& D, Exec& ex) {
     ex.par([&](int tid) {
         for (int e = tid; e < D.nE; e += NT) if (D.eKf[e] < nO) D.pk[(size_t)D.ePt[e] * nO + D.eKf[e]] = e;
     });
-    const float err = (float)compute_errors(D, ex, deltaMono, deltaInertial);
+    double chiNow = compute_errors(D, ex, deltaMono, deltaInertial);      // the robust chi2 of the errors the edges hold for the current estimate
+    const float err = (float)chiNow;
 
     double lambda = -1, ni = 2;
     int nBad = 0, cj = 0, trials = 0;
     const int maxTrials = 10;
     bool ok = true;
     for (int it = 0; it < D.iterations && ok; ++it) {
-        double currentChi = compute_errors(D, ex, deltaMono, deltaInertial);
+        // solve() starts with computeActiveErrors(): the estimate has not changed since the last evaluation (the optimize() call itself, or the
+        // accepted trial that ended the previous iteration), so the edges already hold exactly these errors
+        double currentChi = chiNow;
         double tempChi = currentChi;
         const double iniChi = currentChi;
         build_system(D, ex, deltaMono, deltaInertial);
@@ -497,6 +559,7 @@ template <class Exec> IMU_HD inline void run(const Dev& D, Exec& ex) {
             tempChi = compute_errors(D, ex, deltaMono, deltaInertial);
             if (!ok2) tempChi = DBL_MAX;
             rho = currentChi - tempChi;
+            ex.tag(7);
             double scale = ex.sum([&](int tid) {
                 double s = 0;
                 for (int j = tid; j < n; j += NT) s += D.x[j] * (lambda * D.x[j] + D.b[j]);
@@ -511,6 +574,7 @@ template <class Exec> IMU_HD inline void run(const Dev& D, Exec& ex) {
                 lambda *= fmax(1. / 3., alpha);
                 ni = 2;
                 currentChi = tempChi;
+                chiNow = tempChi;
             } else {
                 lambda *= ni;
                 ni *= 2;
@@ -525,6 +589,7 @@ template <class Exec> IMU_HD inline void run(const Dev& D, Exec& ex) {
             if (nBad >= 3) ok = false;
         }
     }
+    ex.tag(7);
     // err_end = activeRobustChi2() of the errors the edges hold (those of a rejected last trial included)
     const float errEnd = (float)ex.sum([&](int tid) {
         double v = 0;

@@ -33,6 +33,16 @@ namespace liba {
 // The executor of liba_core.cuh on the device: thread = threadIdx.x, barrier = __syncthreads, ordered CTA reductions.
 struct DeviceExec {
     double* red;      // NT / 32 doubles of shared memory
+    double* prof;     // 8 doubles of shared memory: nanoseconds per phase group (thread 0 keeps the clock)
+    unsigned long long last; int cur;
+    __device__ __forceinline__ void tag(int k) {
+        if (threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            prof[cur] += (double)(t - last);
+            last = t; cur = k;
+        }
+    }
     template <class F> __device__ __forceinline__ void par(F f) { f((int)threadIdx.x); __syncthreads(); }
     template <class F> __device__ __forceinline__ double sum(F f) {
         double v = f((int)threadIdx.x);
@@ -65,12 +75,19 @@ __global__ void __launch_bounds__(NT) local_inertial_ba_kernel(const Dev* __rest
     __shared__ Dev s_D;
     if (threadIdx.x == 0) s_D = probs[blockIdx.x];
     __syncthreads();
-    DeviceExec ex{s_red};
+    __shared__ double s_prof[8];
+    if (threadIdx.x < 8) s_prof[threadIdx.x] = 0.0;
+    __syncthreads();
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    DeviceExec ex{s_red, s_prof, t0, 7};
     run(s_D, ex);
+    ex.tag(7);
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (threadIdx.x == 0) s_D.stats[6] = (double)(t1 - t0);      // nanoseconds this map's CTA spent in the solver
+    if (threadIdx.x == 0) {
+        s_D.stats[6] = (double)(t1 - t0);      // nanoseconds this map's CTA spent in the solver
+        for (int k = 0; k < 8; ++k) s_D.prof[k] = s_prof[k];
+    }
 }
 
 // host plumbing: one arena per host thread and device, grown on demand; pinned staging for the packed input / output buffers

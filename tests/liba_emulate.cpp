@@ -11,6 +11,7 @@
 
 namespace {
 struct HostExec {
+    void tag(int) {}
     template <class F> void par(F f) { for (int t = 0; t < liba::NT; ++t) f(t); }
     // the device's reduction tree: shuffle-down inside each warp (lane 0 holds the warp's sum), then the warp sums in order
     template <class F> double sum(F f) {

@@ -26,5 +26,5 @@ for name, kw in (('10+7 KF, ~2100 pts, ~24.5k edges', dict(n_opt=10, n_cov_fixed
     orb.LocalInertialBA(many)
     t0 = time.perf_counter(); gm = orb.LocalInertialBA(many); t_many = time.perf_counter() - t0
     print('%s: %d edges, %d iterations / %d trials | 1 map: solver %.2f ms, host API %.2f ms | 148 maps in one launch: solver %.2f ms per CTA, host API %.1f ms '
-          '(%.3f ms per map) | oracle, 1 thread: %.1f ms' % (name, len(pr['e_pt']), g['iters'], g['trials'], np.median(ks), 1e3 * np.median(ts),
-                                                          np.median([x['kernel_ms'] for x in gm]), 1e3 * t_many, 1e3 * t_many / 148, 1e3 * t_cpu))
+          '(%.3f ms per map) | oracle, 1 thread: %.1f ms | 1-map phases [errors, build, Dinv/Y, Schur, LDLT, points, update, rest] ms: %s' % (name, len(pr['e_pt']), g['iters'], g['trials'], np.median(ks), 1e3 * np.median(ts),
+                                                          np.median([x['kernel_ms'] for x in gm]), 1e3 * t_many, 1e3 * t_many / 148, 1e3 * t_cpu, np.round(g['phase_ms'], 2).tolist()))
