@@ -237,6 +237,29 @@ public:
                   "pose_optimization_batch");
         return inliers;
     }
+    // void static LocalInertialBA(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, int& num_fixedKF, int& num_OptKF, int& num_MPs, int& num_edges,
+    //                             bool bLarge = false, bool bRecInit = false)   (include/Optimizer.h:62, src/Optimizer.cc:2383-2958)
+    // The caller keeps the graph walk (:2385-2478, :2690-2833) and the write-back (:2890-2957); `graph` is the flattened window (LocalInertialBAProblem:
+    // the temporal window first, newest keyframe first like vpOptimizableKFs, then lFixedKeyFrames) and `out` receives what SetPose / SetVelocity /
+    // SetNewBias / SetWorldPos take plus the vToErase flags.  bLarge / bRecInit choose the iteration count, the initial lambda and which inertial
+    // edges carry the Huber kernel exactly as :2387-2394, :2497-2509, :2633-2643 do; the reference sets the stop flag only after optimize() (:2840),
+    // so pbStopFlag never interrupts this solve.  Returns false on "FAIL LOCAL-INERTIAL BA" (:2884-2888: nothing is to be written back).
+    static bool LocalInertialBA(LocalInertialBAProblem graph, LocalInertialBAResult& out, bool bLarge = false, bool bRecInit = false, int device = 0) {
+        const int N = graph.nInertial;
+        std::vector<uint8_t> robust((size_t)(N > 0 ? N : 1), 0);
+        std::vector<double> scale((size_t)(N > 0 ? N : 1), 1.0);
+        for (int i = 0; i < N; ++i) {                                  // i == N-1: the link to the fixed keyframe (vpOptimizableKFs order)
+            robust[i] = (i == N - 1 || bRecInit) ? 1 : 0;
+            scale[i] = (i == N - 1) ? 1e-2 : 1.0;
+        }
+        graph.ieRobust = robust.data(); graph.ieInfoScale = scale.data();
+        graph.iterations = bLarge ? 4 : 10; graph.lambdaInit = bLarge ? 1e-2 : 1e0; graph.bLarge = bLarge ? 1 : 0;
+        double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        LocalInertialBAResult r = out;
+        if (!r.stats8) r.stats8 = stats;
+        orb_check(local_inertial_ba_batch(1, &graph, &r, nullptr, device), "local_inertial_ba_batch");
+        return r.stats8[2] == 0.0;
+    }
 };
 
 }  // namespace ORB_SLAM3

@@ -26,7 +26,7 @@ namespace liba {
 using namespace imu;
 
 #ifndef LIBA_NT
-#define LIBA_NT 256
+#define LIBA_NT 512
 #endif
 constexpr int NT = LIBA_NT;      // threads per CTA
 constexpr int EJ = 21;           // per mono edge: A 2x3 | B 2x6 | w | r0 | r1
@@ -62,6 +62,7 @@ struct Dev {
     double *H, *b, *Hs, *bs, *dvec, *x;     // [n][n], [n], [n][n], [n], [n], [n + 3 nL]
     double *He, *be;                        // [nI][900], [nI][30]
     double *part, *partb;                   // [nPairs][SL][36], [nOpt][SL][6]: partial Schur sums
+    double *Jin, *OJ, *Oe, *win;            // [nI][216], [nI][216], [nI][9], [nI]: EdgeInertial Jacobians, Omega J, Omega e, robust weight
     double *kfBk, *tcwBk, *ptsBk;           // push() / pop()
     int *its, *itsBk;                       // ImuCamPose::its
     // ---- outputs ----
@@ -89,6 +90,38 @@ IMU_HD inline void inv3_cof(const double* m, double* o) {                       
     o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
     o[3] = c10 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
     o[6] = c20 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+// EdgeInertial's information matrix (src/G2oTypes.cc:499-507): inverse of the 9 x 9 covariance, symmetrised, then V diag(max(w, 0 if w < 1e-12)) V^T
+// of its eigen-decomposition.  The eigen step only changes the matrix when an eigenvalue is below 1e-12.  lambda_min(Info) = 1 / lambda_max(C) >=
+// 1 / trace(C), so for a positive definite Info (Cholesky succeeds) and trace(C) < 1e11 nothing is clamped and V diag(w) V^T reproduces the
+// symmetrised inverse up to rounding: the serial Jacobi sweeps (~3 ms on one thread) are then skipped.  Otherwise the full path runs.
+IMU_HD inline void information_matrices(const float* __restrict__ P, double* __restrict__ I9, double* __restrict__ IG, double* __restrict__ IA) {
+    double C9[81], A[81], Lc[81];
+    double trace = 0;
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) C9[i * 9 + j] = (double)P[P_C + i * 15 + j];
+    for (int i = 0; i < 9; ++i) trace += C9[i * 10];
+    bool ok = invert_n<9>(C9, A) && trace < 1e11;
+    if (ok) {
+        for (int i = 0; i < 9; ++i) for (int j = i; j < 9; ++j) { const double v = (A[i * 9 + j] + A[j * 9 + i]) / 2; A[i * 9 + j] = A[j * 9 + i] = v; }
+        for (int j = 0; j < 9 && ok; ++j) {                      // Cholesky: positive definite?
+            double dj = A[j * 9 + j];
+            for (int k = 0; k < j; ++k) dj -= Lc[j * 9 + k] * Lc[j * 9 + k];
+            if (!(dj > 0)) { ok = false; break; }
+            dj = sqrt(dj);
+            Lc[j * 9 + j] = dj;
+            for (int i = j + 1; i < 9; ++i) {
+                double v = A[i * 9 + j];
+                for (int k = 0; k < j; ++k) v -= Lc[i * 9 + k] * Lc[j * 9 + k];
+                Lc[i * 9 + j] = v / dj;
+            }
+        }
+    }
+    if (!ok) { imu_information_dev(P, I9, IG, IA); return; }
+    for (int i = 0; i < 81; ++i) I9[i] = A[i];
+    double G[9], Aa[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { G[i * 3 + j] = (double)P[P_C + (9 + i) * 15 + 9 + j]; Aa[i * 3 + j] = (double)P[P_C + (12 + i) * 15 + 12 + j]; }
+    invert_n<3>(G, IG);
+    invert_n<3>(Aa, IA);
 }
 IMU_HD inline void edge_states(const Dev& D, int i, double* S) {                     // the six vertices of EdgeInertial i
     const double* a = D.kfState + 21 * (size_t)D.ieKf1[i];
@@ -171,47 +204,29 @@ template <class Exec> IMU_HD inline void build_system(const Dev& D, Exec& ex, do
                 for (int a = 0; a < 6; ++a) for (int k = 0; k < 3; ++k) We[a * 3 + k] = w * (B[a] * A[k] + B[6 + a] * A[3 + k]);
             }
         }
-        // EdgeInertial (+ its EdgeGyroRW / EdgeAccRW): the local 30 x 30 Hessian over (keyframe 1's 15 | keyframe 2's 15) and its b
+        // EdgeInertial::linearizeOplus (one thread per edge; the products with the information matrix are spread over the CTA below)
         for (int i = tid; i < D.nI; i += NT) {
-            double S[36], e9[9], J[216], OJ[216], Oe[9];
+            double S[36], e9[9];
             edge_states(D, i, S);
-            edge_inertial_dev(D.preint + (size_t)P_SIZE * i, S, e9, J);
-            const double* Om = D.info9 + 81 * (size_t)i;
-            const double* er = D.errI + 9 * (size_t)i;
+            edge_inertial_dev(D.preint + (size_t)P_SIZE * i, S, e9, D.Jin + 216 * (size_t)i);
             double w = 1.0;
-            if (D.ieRobust[i]) { double r0; huber(quad<9>(Om, er), deltaInertial, r0, w); }
-            for (int r = 0; r < 9; ++r) {
-                double t = 0;
-                for (int k = 0; k < 9; ++k) t += Om[r * 9 + k] * er[k];
-                Oe[r] = t;
-                for (int c = 0; c < 24; ++c) { double s = 0; for (int k = 0; k < 9; ++k) s += Om[r * 9 + k] * J[k * 24 + c]; OJ[r * 24 + c] = s; }
-            }
-            double* He = D.He + 900 * (size_t)i; double* be = D.be + 30 * (size_t)i;
-            for (int k = 0; k < 900; ++k) He[k] = 0.0;
-            for (int k = 0; k < 30; ++k) be[k] = 0.0;
-            for (int a = 0; a < 24; ++a) {
-                double s = 0;
-                for (int r = 0; r < 9; ++r) s += J[r * 24 + a] * Oe[r];
-                be[a] = -w * s;
-                for (int c = 0; c < 24; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += J[r * 24 + a] * OJ[r * 24 + c]; He[a * 30 + c] = w * h; }
-            }
-            for (int which = 0; which < 2; ++which) {      // error = b2 - b1, Jacobians -I / +I (include/G2oTypes.h:635-700)
-                const double* Inf = which == 0 ? D.infoG + 9 * (size_t)i : D.infoA + 9 * (size_t)i;
-                const double* e3 = which == 0 ? D.errG + 3 * (size_t)i : D.errA + 3 * (size_t)i;
-                const int g1 = which == 0 ? 9 : 12, g2 = which == 0 ? 24 : 27;
-                for (int a = 0; a < 3; ++a) {
-                    double s = 0;
-                    for (int c = 0; c < 3; ++c) s += Inf[a * 3 + c] * e3[c];
-                    be[g1 + a] += s; be[g2 + a] -= s;
-                    for (int c = 0; c < 3; ++c) {
-                        He[(g1 + a) * 30 + g1 + c] += Inf[a * 3 + c]; He[(g2 + a) * 30 + g2 + c] += Inf[a * 3 + c];
-                        He[(g1 + a) * 30 + g2 + c] -= Inf[a * 3 + c]; He[(g2 + a) * 30 + g1 + c] -= Inf[c * 3 + a];
-                    }
-                }
-            }
+            if (D.ieRobust[i]) { double r0; huber(quad<9>(D.info9 + 81 * (size_t)i, D.errI + 9 * (size_t)i), deltaInertial, r0, w); }
+            D.win[i] = w;
         }
     });
     ex.par([&](int tid) {
+        // inertial edges: Omega J (one task per edge and Jacobian column) and Omega e
+        for (int t = tid; t < D.nI * 25; t += NT) {
+            const int i = t / 25, c = t % 25;
+            const double* Om = D.info9 + 81 * (size_t)i;
+            if (c < 24) {
+                const double* J = D.Jin + 216 * (size_t)i;
+                for (int r = 0; r < 9; ++r) { double sacc = 0; for (int k = 0; k < 9; ++k) sacc += Om[r * 9 + k] * J[k * 24 + c]; D.OJ[216 * (size_t)i + r * 24 + c] = sacc; }
+            } else {
+                const double* er = D.errI + 9 * (size_t)i;
+                for (int r = 0; r < 9; ++r) { double sacc = 0; for (int k = 0; k < 9; ++k) sacc += Om[r * 9 + k] * er[k]; D.Oe[9 * (size_t)i + r] = sacc; }
+            }
+        }
         // points: Hll, bl in the order of the point's edge list
         for (int p = tid; p < D.nL; p += NT) {
             double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b3[3] = {0, 0, 0};
@@ -246,6 +261,40 @@ template <class Exec> IMU_HD inline void build_system(const Dev& D, Exec& ex, do
         }
     });
     ex.par([&](int tid) {
+        // inertial edges: the local 30 x 30 Hessian over (keyframe 1's 15 | keyframe 2's 15) and its b, one task per row; EdgeGyroRW / EdgeAccRW
+        // (error = b2 - b1, Jacobians -I / +I, include/G2oTypes.h:635-700) add to the bias rows
+        for (int t = tid; t < D.nI * 30; t += NT) {
+            const int i = t / 30, a = t % 30;
+            const double* J = D.Jin + 216 * (size_t)i;
+            const double* OJ = D.OJ + 216 * (size_t)i;
+            const double w = D.win[i];
+            double* He = D.He + 900 * (size_t)i + 30 * a;
+            double bacc = 0;
+            for (int c = 0; c < 30; ++c) He[c] = 0.0;
+            if (a < 24) {
+                for (int r = 0; r < 9; ++r) bacc += J[r * 24 + a] * D.Oe[9 * (size_t)i + r];
+                bacc = -w * bacc;
+                for (int c = 0; c < 24; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += J[r * 24 + a] * OJ[r * 24 + c]; He[c] = w * h; }
+            }
+            const int blk = (a >= 9 && a < 15) ? (a - 9) / 3 : (a >= 24 ? (a - 24) / 3 : -1);      // 0 gyro, 1 acc
+            if (blk >= 0) {
+                const bool first = a < 15;                                                         // vertex 0 (Jacobian -I) or vertex 1 (+I)
+                const int q = (a - (first ? 9 : 24)) % 3;
+                const double* Inf = blk == 0 ? D.infoG + 9 * (size_t)i : D.infoA + 9 * (size_t)i;
+                const double* e3 = blk == 0 ? D.errG + 3 * (size_t)i : D.errA + 3 * (size_t)i;
+                const int g1 = blk == 0 ? 9 : 12, g2 = blk == 0 ? 24 : 27;
+                double sacc = 0;
+                for (int c = 0; c < 3; ++c) sacc += Inf[q * 3 + c] * e3[c];
+                if (first) {
+                    bacc += sacc;
+                    for (int c = 0; c < 3; ++c) { He[g1 + c] += Inf[q * 3 + c]; He[g2 + c] -= Inf[q * 3 + c]; }
+                } else {
+                    bacc -= sacc;
+                    for (int c = 0; c < 3; ++c) { He[g2 + c] += Inf[q * 3 + c]; He[g1 + c] -= Inf[c * 3 + q]; }
+                }
+            }
+            D.be[30 * (size_t)i + a] = bacc;
+        }
         // step 2: the slices in order; the block is mirrored
         for (int t = tid; t < D.nOpt * 27; t += NT) {
             const int k = t / 27, q = t % 27;
@@ -514,7 +563,7 @@ template <class Exec> IMU_HD inline void run(const Dev& D, Exec& ex) {
     ex.par([&](int tid) {
         for (int i = tid; i < D.nI; i += NT) {
             double* I9 = D.info9 + 81 * (size_t)i;
-            imu_information_dev(D.preint + (size_t)P_SIZE * i, I9, D.infoG + 9 * (size_t)i, D.infoA + 9 * (size_t)i);
+            information_matrices(D.preint + (size_t)P_SIZE * i, I9, D.infoG + 9 * (size_t)i, D.infoA + 9 * (size_t)i);
             for (int k = 0; k < 81; ++k) I9[k] *= D.ieInfoScale[i];      // vei[i]->setInformation(information() * 1e-2), :2641
         }
         for (int k = tid; k < nO; k += NT) D.its[k] = 0;

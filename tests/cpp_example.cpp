@@ -3,6 +3,7 @@
 //   track     Tracking::TrackWithMotionModel (src/Tracking.cc:2876-2897)    -> ORBmatcher(0.9,true).SearchByProjection(Current, Last, th, mono)
 //             + Optimizer::PoseOptimization (src/Tracking.cc:2919)
 //   lba       LocalMapping::Run (src/LocalMapping.cc:154)                    -> Optimizer::LocalBundleAdjustment(..., &mbAbortBA, ...)
+//   liba      LocalMapping::Run (src/LocalMapping.cc:129-151)                -> Optimizer::LocalInertialBA(..., bLarge, bRecInit)
 // Inputs are raw arrays written by tests/test_cpp_shim.py; results are printed as text for the test to compare with the oracle.
 #include <cstdio>
 #include <cstdlib>
@@ -100,6 +101,29 @@ int main(int argc, char** argv) {
             double sp = 0; for (double v : oposes) sp += v;
             double sx = 0; for (double v : opoints) sx += v;
             printf("lba%d %d %d %.12f %.9f %.9f\n", rep, r.iterations, r.trials, r.chi2, sp, sx);
+        }
+    }
+    // ---- LocalInertialBA (LocalMapping::Run once the IMU is initialised, src/LocalMapping.cc:129-151): plain, then with bRecInit ----
+    {
+        std::vector<double> st = load<double>(dir, "liba_state.raw"), tc = load<double>(dir, "liba_tcw.raw"), ex = load<double>(dir, "liba_extr.raw"),
+                            pts = load<double>(dir, "liba_points.raw"), lobs = load<double>(dir, "liba_obs.raw");
+        std::vector<float> lcam = load<float>(dir, "liba_cam.raw"), pre = load<float>(dir, "liba_preint.raw"), td = load<float>(dir, "liba_td.raw"), is2 = load<float>(dir, "liba_is2.raw");
+        std::vector<int32_t> k1 = load<int32_t>(dir, "liba_k1.raw"), k2 = load<int32_t>(dir, "liba_k2.raw"), ep = load<int32_t>(dir, "liba_ep.raw"), ek = load<int32_t>(dir, "liba_ek.raw");
+        LocalInertialBAProblem g; memset(&g, 0, sizeof(g));
+        g.nKF = (int)st.size() / 21; g.nOpt = (int)k1.size(); g.kfState21 = st.data(); g.kfTcw12 = tc.data(); g.cam4 = lcam.data(); g.extrinsics24 = ex.data();
+        g.nInertial = (int)k1.size(); g.ieKf1 = k1.data(); g.ieKf2 = k2.data(); g.preint = pre.data();
+        g.nPoints = (int)pts.size() / 3; g.points3 = pts.data(); g.trackDepth = td.data();
+        g.nEdges = (int)ep.size(); g.edgePoint = ep.data(); g.edgeKf = ek.data(); g.obs2 = lobs.data(); g.invSigma2 = is2.data();
+        for (int rec = 0; rec < 2; ++rec) {
+            std::vector<double> ost(st.size()), otc(tc.size()), opts(pts.size()), chi2(ep.size());
+            std::vector<uint8_t> erase(ep.size());
+            double stats[8];
+            LocalInertialBAResult r; memset(&r, 0, sizeof(r));
+            r.kfState21 = ost.data(); r.kfTcw12 = otc.data(); r.points3 = opts.data(); r.erase = erase.data(); r.edgeChi2 = chi2.data(); r.stats8 = stats;
+            const bool ok = Optimizer::LocalInertialBA(g, r, /*bLarge=*/false, /*bRecInit=*/rec == 1);
+            double ss = 0; for (int k = 0; k < g.nOpt * 21; ++k) ss += ost[k];
+            int ne = 0; for (uint8_t v : erase) ne += v;
+            printf("liba%d %d %d %d %d %.9f %.6f\n", rec, ok ? 1 : 0, (int)stats[5], (int)stats[4], ne, ss, stats[1]);
         }
     }
     return 0;

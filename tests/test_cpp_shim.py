@@ -1,7 +1,7 @@
 """The C++ host mirror (include/orb_b200/orb_slam3.hpp) compiles with plain g++ against the C-ABI (CPU test) and, run on the GPU,
 gives the oracle's results on every surface: ORBextractor::operator(), ORBmatcher::SearchByProjection (two stack temporaries),
-Optimizer::PoseOptimization and Optimizer::LocalBundleAdjustment (three calls on the per-thread arena, the last with the caller's
-bool abort flag set)."""
+Optimizer::PoseOptimization, Optimizer::LocalBundleAdjustment (three calls on the per-thread arena, the last with the caller's
+bool abort flag set) and Optimizer::LocalInertialBA (plain and with bRecInit)."""
 import os
 import subprocess
 
@@ -50,6 +50,13 @@ def test_cpp_shim_runs_like_the_oracle(tmp_path):
                           ('lba_fixed', p['fixed'], np.uint8), ('lba_cam', p['cam'], np.float32), ('lba_is2', p['inv_sigma2'], np.float32),
                           ('lba_ep', p['edge_point'], np.int32), ('lba_ek', p['edge_pose'], np.int32)):
         (tmp_path / (name + '.raw')).write_bytes(np.ascontiguousarray(arr, dt).tobytes())
+    lp = synth.local_inertial_ba_problem(n_opt=5, n_cov_fixed=2, n_pts=200, seed=31)
+    lP = O.liba_preints(lp)
+    for name, arr, dt in (('liba_state', lp['state'], np.float64), ('liba_tcw', lp['tcw'], np.float64), ('liba_extr', lp['extr'], np.float64), ('liba_points', lp['points'], np.float64),
+                          ('liba_obs', lp['obs'], np.float64), ('liba_cam', lp['cam'], np.float32), ('liba_preint', lP, np.float32), ('liba_td', lp['track_depth'], np.float32),
+                          ('liba_is2', lp['inv_sigma2'], np.float32), ('liba_k1', lp['ie_kf1'], np.int32), ('liba_k2', lp['ie_kf2'], np.int32), ('liba_ep', lp['e_pt'], np.int32),
+                          ('liba_ek', lp['e_kf'], np.int32)):
+        (tmp_path / (name + '.raw')).write_bytes(np.ascontiguousarray(arr, dt).tobytes())
     out = dict(l.split(' ', 1) for l in subprocess.check_output([EXE, str(tmp_path), '480', '640']).decode().strip().splitlines())
     # extract
     mono, kps, desc = O.OracleExtractor()(img, (0, 1000))
@@ -78,3 +85,11 @@ def test_cpp_shim_runs_like_the_oracle(tmp_path):
         assert abs(float(g[3]) - refl['poses'].sum()) < 1e-6 and abs(float(g[4]) - refl['points'].sum()) < 1e-5
     assert out['lba0'] == out['lba1']
     assert int(out['lba2'].split()[0]) == -1          # untouched result: the call returned at the stop-flag test
+    # LocalInertialBA: the mirror derives iterations / lambda / Huber flags from (bLarge, bRecInit) like src/Optimizer.cc:2387-2394,2497-2509,2633-2643
+    for rec in (0, 1):
+        q = dict(lp)
+        q['ie_robust'] = np.array([1 if (i == lp['n_opt'] - 1 or rec) else 0 for i in range(lp['n_opt'])], np.uint8)
+        w = O.local_inertial_ba(q, lP)
+        g = out['liba%d' % rec].split()
+        assert [int(v) for v in g[:4]] == [0 if w['failed'] else 1, w['iters'], w['trials'], int(w['erase'].sum())]
+        assert abs(float(g[4]) - w['state'][:lp['n_opt']].sum()) < 1e-6 and abs(float(g[5]) - w['err_end']) <= 1e-5 * w['err_end']
