@@ -29,6 +29,7 @@ RANGES = [
     ('mappoint_predict_scale_kf.inc', 'src/MapPoint.cc', 514, 529, 'int MapPoint::PredictScale(const float &currentDist, KeyFrame* pKF)'),
     ('mappoint_invariance.inc', 'src/MapPoint.cc', 502, 512, 'float MapPoint::GetMinDistanceInvariance()'),
     ('mappoint_predict_scale.inc', 'src/MapPoint.cc', 531, 546, 'int MapPoint::PredictScale(const float &currentDist, Frame* pF)'),
+    ('euroc_loaders.inc', 'Examples/Monocular-Inertial/mono_inertial_euroc.cc', 252, 310, 'void LoadImages(const string &strImagePath, const string &strPathTimes,'),
     ('pinhole_project.inc', 'src/CameraModels/Pinhole.cpp', 43, 49, 'Eigen::Vector2f Pinhole::project(const Eigen::Vector3f &v3D)'),
 ]
 
