@@ -29,7 +29,8 @@ using namespace imu;
 #define LIBA_NT 512
 #endif
 constexpr int NT = LIBA_NT;      // threads per CTA
-constexpr int EJ = 21;           // per mono edge: A 2x3 | B 2x6 | w | r0 | r1
+constexpr int EJ = 24;           // per mono edge: A 2x3 | B 2x6 | w | r0 | r1 | 3 pad (192 B = six 32-byte vectors)
+constexpr int WS = 20;           // per mono edge: the 6 x 3 block W (and Y) + 2 pad (160 B = five 32-byte vectors)
 constexpr int LW = 5;            // panel width of the blocked LDL^T (15 = 3 * 5)
 constexpr int SL = 32;           // slices of a keyframe's edge list in the Schur phase
 
@@ -57,7 +58,7 @@ struct Dev {
     int* pk;                      // [nL][nOpt] edge of (point, free keyframe) or -1
     double *info9, *infoG, *infoA;          // [nI][81], [nI][9], [nI][9]
     double *errM, *errI, *errG, *errA;      // the edges' _error
-    double *ejac, *W, *Y;                   // [nE][21], [nE][18], [nE][18]
+    double *ejac, *W, *Y;                   // [nE][EJ], [nE][WS], [nE][WS]
     double *Hll, *bl, *Dinv, *db;           // [nL][9], [nL][3], [nL][9], [nL][3]
     double *H, *b, *Hs, *bs, *dvec, *x;     // [n][n], [n], [n][n], [n], [n], [n + 3 nL]
     double *He, *be;                        // [nI][900], [nI][30]
@@ -73,6 +74,26 @@ struct Dev {
     double* prof;                           // [8]: nanoseconds per phase group (ex.tag)
 };
 
+// n32 consecutive 32-byte vectors (LDG.E.256 on the device: one L1 look-up per 32 bytes -- the gathers of the per-edge records are bound by
+// look-ups per instruction, not by bytes); p must be 32-byte aligned
+template <int N32> IMU_HD inline void ldvec(const double* p, double* r) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int k = 0; k < N32; ++k)
+        asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r[4 * k]), "=d"(r[4 * k + 1]), "=d"(r[4 * k + 2]), "=d"(r[4 * k + 3]) : "l"(p + 4 * k));
+#else
+    for (int k = 0; k < 4 * N32; ++k) r[k] = p[k];
+#endif
+}
+template <int N32> IMU_HD inline void stvec(double* p, const double* r) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int k = 0; k < N32; ++k)
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p + 4 * k), "d"(r[4 * k]), "d"(r[4 * k + 1]), "d"(r[4 * k + 2]), "d"(r[4 * k + 3]) : "memory");
+#else
+    for (int k = 0; k < 4 * N32; ++k) p[k] = r[k];
+#endif
+}
 IMU_HD inline void huber(double e2, double delta, double& rho0, double& rho1) {      // RobustKernelHuber::robustify
     const double dsqr = delta * delta;
     if (e2 <= dsqr) { rho0 = e2; rho1 = 1.0; }
@@ -184,7 +205,7 @@ template <class Exec> IMU_HD inline void build_system(const Dev& D, Exec& ex, do
             const float* c = D.cam + 4 * (size_t)D.eKf[e];
             const double fx = c[0], fy = c[1];
             const double pj[6] = {fx / Xc[2], 0, -fx * Xc[0] / (Xc[2] * Xc[2]), 0, fy / Xc[2], -fy * Xc[1] / (Xc[2] * Xc[2])};
-            double* J = D.ejac + (size_t)EJ * e;
+            double J[EJ];
             double* A = J; double* B = J + 6;
             for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) A[i * 3 + j] = -(pj[i * 3] * T[j] + pj[i * 3 + 1] * T[3 + j] + pj[i * 3 + 2] * T[6 + j]);
             double Xb[3];
@@ -198,10 +219,13 @@ template <class Exec> IMU_HD inline void build_system(const Dev& D, Exec& ex, do
             double r0, r1;
             huber(om * (e0 * e0 + e1 * e1), deltaMono, r0, r1);
             const double w = r1 * om;
-            J[18] = w; J[19] = -om * e0 * r1; J[20] = -om * e1 * r1;
+            J[18] = w; J[19] = -om * e0 * r1; J[20] = -om * e1 * r1; J[21] = 0.0; J[22] = 0.0; J[23] = 0.0;
+            stvec<6>(D.ejac + (size_t)EJ * e, J);
             if (D.eKf[e] < D.nOpt) {
-                double* We = D.W + 18 * (size_t)e;
+                double We[WS];
                 for (int a = 0; a < 6; ++a) for (int k = 0; k < 3; ++k) We[a * 3 + k] = w * (B[a] * A[k] + B[6 + a] * A[3 + k]);
+                We[18] = 0.0; We[19] = 0.0;
+                stvec<5>(D.W + WS * (size_t)e, We);
             }
         }
         // EdgeInertial::linearizeOplus (one thread per edge; the products with the information matrix are spread over the CTA below)
@@ -231,8 +255,10 @@ template <class Exec> IMU_HD inline void build_system(const Dev& D, Exec& ex, do
         for (int p = tid; p < D.nL; p += NT) {
             double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b3[3] = {0, 0, 0};
             for (int j = D.ptStart[p]; j < D.ptStart[p + 1]; ++j) {
-                const double* J = D.ejac + (size_t)EJ * D.ptEdges[j];
-                const double w = J[18], r0 = J[19], r1 = J[20];
+                double J[8], Jw[8];                              // record entries 0 .. 7 (A) and 16 .. 23 (w r0 r1 at 18 .. 20)
+                ldvec<2>(D.ejac + (size_t)EJ * D.ptEdges[j], J);
+                ldvec<2>(D.ejac + (size_t)EJ * D.ptEdges[j] + 16, Jw);
+                const double w = Jw[2], r0 = Jw[3], r1 = Jw[4];
                 for (int a = 0; a < 3; ++a) {
                     b3[a] += J[a] * r0 + J[3 + a] * r1;
                     for (int c = 0; c < 3; ++c) h[a * 3 + c] += w * (J[a] * J[c] + J[3 + a] * J[3 + c]);
@@ -247,9 +273,10 @@ template <class Exec> IMU_HD inline void build_system(const Dev& D, Exec& ex, do
             double acc[27];
             for (int q = 0; q < 27; ++q) acc[q] = 0.0;
             for (int j = D.kfStart[k] + sl; j < D.kfStart[k + 1]; j += SL) {
-                const double* J = D.ejac + (size_t)EJ * D.kfEdges[j];
-                const double* B = J + 6;
-                const double w = J[18], r0 = J[19], r1 = J[20];
+                double Jv[20];                                  // record entries 4 .. 23: A[4], A[5] | B 12 | w r0 r1 | pad
+                ldvec<5>(D.ejac + (size_t)EJ * D.kfEdges[j] + 4, Jv);
+                const double* B = Jv + 2;
+                const double w = Jv[14], r0 = Jv[15], r1 = Jv[16];
 #pragma unroll
                 for (int a = 0; a < 6; ++a)
 #pragma unroll
@@ -427,10 +454,12 @@ template <class Exec> IMU_HD inline bool solve_system(const Dev& D, Exec& ex, do
     ex.par([&](int tid) {
         for (int e = tid; e < D.nE; e += NT) {
             if (D.eKf[e] >= nO) continue;
-            const double* We = D.W + 18 * (size_t)e;
+            double We[WS], Ye[WS];
+            ldvec<5>(D.W + WS * (size_t)e, We);
             const double* Di = D.Dinv + 9 * (size_t)D.ePt[e];
-            double* Ye = D.Y + 18 * (size_t)e;
             for (int a = 0; a < 6; ++a) for (int c = 0; c < 3; ++c) Ye[a * 3 + c] = We[a * 3] * Di[c] + We[a * 3 + 1] * Di[3 + c] + We[a * 3 + 2] * Di[6 + c];
+            Ye[18] = 0.0; Ye[19] = 0.0;
+            stvec<5>(D.Y + WS * (size_t)e, Ye);
         }
     });
     const int nPairs = nO * (nO + 1) / 2;
@@ -445,12 +474,19 @@ template <class Exec> IMU_HD inline bool solve_system(const Dev& D, Exec& ex, do
             const int i2 = i1 + pidx;
             double acc[36];
             for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-            for (int j = D.kfStart[i1] + sl; j < D.kfStart[i1 + 1]; j += SL) {
-                const int e1 = D.kfEdges[j];
-                const int e2 = i1 == i2 ? e1 : D.pk[(size_t)D.ePt[e1] * nO + i2];
+            // the indices of the next pair are fetched before the blocks of the current one (two dependent look-ups hide behind the block loads)
+            int j = D.kfStart[i1] + sl;
+            const int jend = D.kfStart[i1 + 1];
+            int e1n = -1, e2n = -1;
+            if (j < jend) { e1n = D.kfEdges[j]; e2n = i1 == i2 ? e1n : D.pk[(size_t)D.ePt[e1n] * nO + i2]; }
+            while (j < jend) {
+                const int e1 = e1n, e2 = e2n;
+                j += SL;
+                if (j < jend) { e1n = D.kfEdges[j]; e2n = i1 == i2 ? e1n : D.pk[(size_t)D.ePt[e1n] * nO + i2]; }
                 if (e2 < 0) continue;
-                const double* Y1 = D.Y + 18 * (size_t)e1;
-                const double* W2 = D.W + 18 * (size_t)e2;
+                double Y1[WS], W2[WS];
+                ldvec<5>(D.Y + WS * (size_t)e1, Y1);
+                ldvec<5>(D.W + WS * (size_t)e2, W2);
 #pragma unroll
                 for (int a = 0; a < 6; ++a)
 #pragma unroll
@@ -465,7 +501,8 @@ template <class Exec> IMU_HD inline bool solve_system(const Dev& D, Exec& ex, do
             double acc[6] = {0, 0, 0, 0, 0, 0};
             for (int j = D.kfStart[k] + sl; j < D.kfStart[k + 1]; j += SL) {
                 const int e = D.kfEdges[j];
-                const double* We = D.W + 18 * (size_t)e;
+                double We[WS];
+                ldvec<5>(D.W + WS * (size_t)e, We);
                 const double* d3 = D.db + 3 * (size_t)D.ePt[e];
                 for (int a = 0; a < 6; ++a) acc[a] += We[a * 3] * d3[0] + We[a * 3 + 1] * d3[1] + We[a * 3 + 2] * d3[2];
             }
@@ -503,7 +540,8 @@ template <class Exec> IMU_HD inline bool solve_system(const Dev& D, Exec& ex, do
             for (int j = D.ptStart[p]; j < D.ptStart[p + 1]; ++j) {
                 const int e = D.ptEdges[j];
                 if (D.eKf[e] >= nO) continue;
-                const double* We = D.W + 18 * (size_t)e;
+                double We[WS];
+                ldvec<5>(D.W + WS * (size_t)e, We);
                 const double* xp = D.x + 15 * (size_t)D.eKf[e];
                 for (int c = 0; c < 3; ++c) for (int a = 0; a < 6; ++a) cl[c] -= We[a * 3 + c] * xp[a];
             }

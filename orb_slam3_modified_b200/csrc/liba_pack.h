@@ -20,7 +20,7 @@ struct Layout {
     int nFreeEdges;
 };
 
-inline size_t bump(size_t& off, size_t bytes) { const size_t at = off; off = (off + bytes + 15) & ~(size_t)15; return at; }
+inline size_t bump(size_t& off, size_t bytes) { const size_t at = off; off = (off + bytes + 31) & ~(size_t)31; return at; }   // 32-byte vector loads
 
 // returns an error text ("" = ok)
 inline std::string check(const LocalInertialBAProblem& p) {
@@ -52,7 +52,7 @@ inline Layout make_layout(const LocalInertialBAProblem& p) {
     o = 0;
     L.pk = bump(o, nL * nO * 4); L.info9 = bump(o, nI * 81 * 8); L.infoG = bump(o, nI * 9 * 8); L.infoA = bump(o, nI * 9 * 8);
     L.errM = bump(o, nE * 2 * 8); L.errI = bump(o, nI * 9 * 8); L.errG = bump(o, nI * 3 * 8); L.errA = bump(o, nI * 3 * 8);
-    L.ejac = bump(o, nE * EJ * 8); L.W = bump(o, nE * 18 * 8); L.Y = bump(o, nE * 18 * 8);
+    L.ejac = bump(o, nE * EJ * 8); L.W = bump(o, nE * WS * 8); L.Y = bump(o, nE * WS * 8);
     L.Hll = bump(o, nL * 9 * 8); L.bl = bump(o, nL * 3 * 8); L.Dinv = bump(o, nL * 9 * 8); L.db = bump(o, nL * 3 * 8);
     L.H = bump(o, n * n * 8); L.b = bump(o, n * 8); L.Hs = bump(o, n * n * 8); L.bs = bump(o, n * 8); L.dvec = bump(o, n * 8); L.x = bump(o, (n + 3 * nL) * 8);
     L.He = bump(o, nI * 900 * 8); L.be = bump(o, nI * 30 * 8);

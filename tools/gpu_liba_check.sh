@@ -1,15 +1,16 @@
 #!/bin/bash
-# One gpurun call for the LocalInertialBA kernel: its parity tests first, timing (+ thread-count variants), then the whole GPU suite, smoke, memcheck,
-# one ncu capture, the bench line.
+# One gpurun call for the LocalInertialBA kernel: its parity tests first (default library and thread-count variants), timing, then the whole GPU suite,
+# smoke, memcheck, one ncu capture, the bench line.
 set -u
 tag=${1:-r2b}
 out=gpurun_out
 mkdir -p $out
 timeout 600 python -m pytest tests/test_local_inertial_ba_gpu.py -q 2>&1 | tail -25 | tee $out/${tag}_pytest_liba.txt
 timeout 300 python tools/liba_time.py 2>&1 | tail -5 | tee $out/${tag}_liba_time.txt
-for v in nt512 nt128; do
+for v in nt256 nt512 nt128; do
   if [ -f build/liborb_$v.so ]; then
-    echo "== $v" | tee -a $out/${tag}_liba_time.txt
+    echo "== $v" | tee -a $out/${tag}_liba_time.txt $out/${tag}_pytest_liba.txt
+    ORB_B200_LIB=build/liborb_$v.so timeout 300 python -m pytest tests/test_local_inertial_ba_gpu.py -q 2>&1 | tail -5 | tee -a $out/${tag}_pytest_liba.txt
     ORB_B200_LIB=build/liborb_$v.so timeout 300 python tools/liba_time.py 2>&1 | tail -5 | tee -a $out/${tag}_liba_time.txt
   fi
 done
