@@ -10,6 +10,10 @@
 // LocalMapping thread per map).  The working set of a map (~2-8 MB) lives in L2.
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -113,9 +117,17 @@ extern "C" int local_inertial_ba_batch(int count, const LocalInertialBAProblem* 
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (this library has no CPU path)"); return ORB_ERR_CUDA; }
     if (device < 0 || device >= ndev) { set_error("bad device index"); return ORB_ERR_ARG; }
     CK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) { set_error("device is not sm_100+ (Blackwell); this library has no other code path"); return ORB_ERR_CUDA; }
+    {   // the architecture check is made once per device (cudaGetDeviceProperties costs milliseconds)
+        static int s_major[64];
+        static std::mutex s_mu;
+        std::lock_guard<std::mutex> lk(s_mu);
+        if (device < 64 && s_major[device] == 0) CK(cudaDeviceGetAttribute(&s_major[device], cudaDevAttrComputeCapabilityMajor, device));
+        const int major = device < 64 ? s_major[device] : 10;
+        if (major < 10) { set_error("device is not sm_100+ (Blackwell); this library has no other code path"); return ORB_ERR_CUDA; }
+    }
+    const bool trace = getenv("ORB_LIBA_TRACE") != nullptr;
+    const auto tStart = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
 
     std::vector<Layout> lay(count);
     std::vector<size_t> inOff(count), scOff(count), outOff(count);
@@ -149,14 +161,19 @@ extern "C" int local_inertial_ba_batch(int count, const LocalInertialBAProblem* 
         if (!err.empty()) { set_error(err); return ORB_ERR_ARG; }
         bind(hDev[i], problems[i], lay[i], dIn + inOff[i], dSc + scOff[i], dOut + outOff[i]);      // device addresses
     }
+    const double msPack = ms_since(tStart);
+    const auto tGpu = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(dIn, hIn, inAll, cudaMemcpyHostToDevice, A.st));
     local_inertial_ba_kernel<<<count, NT, 0, A.st>>>((const Dev*)(dIn + devOff));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(hOut, dOut, outTot, cudaMemcpyDeviceToHost, A.st));
     CK(cudaStreamSynchronize(A.st));
+    const double msGpu = ms_since(tGpu);
     for (int i = 0; i < count; ++i) {
         const int it = unpack_outputs(problems[i], results[i], lay[i], hOut + outOff[i]);
         if (iterationsOut) iterationsOut[i] = it;
     }
+    if (trace) fprintf(stderr, "local_inertial_ba_batch: %d maps, check + layout + pack %.3f ms (%zu bytes in), copy in + kernel + copy out %.3f ms (%zu bytes out), total %.3f ms\n",
+                       count, msPack, inAll, msGpu, outTot, ms_since(tStart));
     return ORB_OK;
 }
