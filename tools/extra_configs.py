@@ -175,9 +175,11 @@ def measure(orb, synth, device=0, reps=40):
         out[key] = {
             '1_map_host_ms': _median_ms(lambda: orb.LocalInertialBA(one, device=device), 10),
             '148_maps_host_ms': _median_ms(lambda: orb.LocalInertialBA(four * 37, device=device), 3, warm=1),
+            '1_map_solver_ms': float(np.median([orb.LocalInertialBA(one, device=device)[0]['kernel_ms'] for _ in range(5)])),
+            '148_maps_solver_ms_per_cta': float(np.median([r['kernel_ms'] for r in orb.LocalInertialBA(four * 37, device=device)])),
             'edges': int(len(one[0]['e_pt'])), 'points': int(len(one[0]['points'])), 'iterations': int(r1['iters']), 'lm_trials': int(r1['trials']),
             'erased_observations': int(r1['erase'].sum()),
-            'reference': 'Optimizer::LocalInertialBA, src/Optimizer.cc:2383-2958; host API incl. the Python marshalling and the packing of the graph'}
+            'reference': 'Optimizer::LocalInertialBA, src/Optimizer.cc:2383-2958; host = the API call incl. the Python marshalling and the packing of the graph, solver = the CTA\'s own globaltimer span'}
     except Exception as exc:
         out[key] = {'error': repr(exc)[:200]}
     return out
