@@ -5,6 +5,7 @@
 // The algorithm is written once, as a sequence of CTA-wide phases driven through an executor `Exec`:
 //     ex.par(f)   every thread t of the CTA runs f(t), then a CTA barrier;
 //     ex.sum(f)   CTA-wide ordered sum of f(t) (fixed reduction tree), the same value returned to every thread;
+//     ex.panel()  CTA-shared storage for the LDL^T panel (MAXN * LW doubles);
 //     ex.tag(k)   marks the start of phase group k for the optional time profile (0 errors, 1 buildSystem, 2 Dinv / Y, 3 Schur, 4 LDL^T,
 //                 5 point back-substitution, 6 push / update / pop, 7 the rest).
 // Everything between two phases is uniform control flow (LM state replicated per thread).  On the GPU Exec is DeviceExec
@@ -33,6 +34,7 @@ constexpr int EJ = 24;           // per mono edge: A 2x3 | B 2x6 | w | r0 | r1 |
 constexpr int WS = 20;           // per mono edge: the 6 x 3 block W (and Y) + 2 pad (160 B = five 32-byte vectors)
 constexpr int LW = 5;            // panel width of the blocked LDL^T (15 = 3 * 5)
 constexpr int SL = 32;           // slices of a keyframe's edge list in the Schur phase
+constexpr int MAXN = 15 * 64;    // largest reduced system (liba_pack.h: check() admits at most 64 keyframes in the window)
 
 // One problem, device (or emulation) view.  Inputs are written by the host packer (liba_pack.h); scratch is uninitialised.
 struct Dev {
@@ -357,6 +359,7 @@ template <class Exec> IMU_HD inline void build_system(const Dev& D, Exec& ex, do
 template <class Exec> IMU_HD inline bool ldlt_solve(const Dev& D, Exec& ex) {
     const int n = 15 * D.nOpt;
     double* A = D.Hs; double* y = D.bs;
+    double* P = ex.panel();             // (n - LW) x LW doubles of CTA-shared storage
     for (int k0 = 0; k0 < n; k0 += LW) {
         // uniform: factor the diagonal block, forward-substitute the block's right-hand side
         double L11[LW * LW], d[LW], z[LW];
@@ -387,7 +390,7 @@ template <class Exec> IMU_HD inline bool ldlt_solve(const Dev& D, Exec& ex) {
                     xr[c] = v;
                     s += v * dinv[c] * z[c];
                 }
-                for (int c = 0; c < LW; ++c) row[c] = xr[c];
+                for (int c = 0; c < LW; ++c) { row[c] = xr[c]; P[(i - k0 - LW) * LW + c] = xr[c]; }      // in place for the back-substitution, and in the CTA's panel buffer
                 y[i] -= s;
             }
         });
@@ -406,8 +409,8 @@ template <class Exec> IMU_HD inline bool ldlt_solve(const Dev& D, Exec& ex) {
                     while ((i + 1) * (i + 2) / 2 <= idx) ++i;
                     while (i * (i + 1) / 2 > idx) --i;
                     const int j = idx - i * (i + 1) / 2;
-                    const double* xi = A + (size_t)(r0 + i) * n + k0;
-                    const double* xj = A + (size_t)(r0 + j) * n + k0;
+                    const double* xi = P + i * LW;      // the panel rows come from shared memory (in A they are n doubles apart: 32 lanes = 32 lines per load)
+                    const double* xj = P + j * LW;
                     double s = 0;
                     for (int c = 0; c < LW; ++c) s += xi[c] * (xj[c] * dinv[c]);
                     A[(size_t)(r0 + i) * n + r0 + j] -= s;
@@ -484,13 +487,24 @@ template <class Exec> IMU_HD inline bool solve_system(const Dev& D, Exec& ex, do
                 j += SL;
                 if (j < jend) { e1n = D.kfEdges[j]; e2n = i1 == i2 ? e1n : D.pk[(size_t)D.ePt[e1n] * nO + i2]; }
                 if (e2 < 0) continue;
-                double Y1[WS], W2[WS];
+                // block += Y1 W2^T, with W2 consumed vector by vector (element m = 3 c + k of W2 meets column k of Y1): Y1, one vector of W2 and the
+                // 36 accumulators stay within the 128 registers a thread of a 512-thread CTA has
+                double Y1[WS];
                 ldvec<5>(D.Y + WS * (size_t)e1, Y1);
-                ldvec<5>(D.W + WS * (size_t)e2, W2);
+                const double* W2p = D.W + WS * (size_t)e2;
 #pragma unroll
-                for (int a = 0; a < 6; ++a)
+                for (int v = 0; v < 5; ++v) {
+                    double w4[4];
+                    ldvec<1>(W2p + 4 * v, w4);
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) acc[a * 6 + c] += Y1[a * 3] * W2[c * 3] + Y1[a * 3 + 1] * W2[c * 3 + 1] + Y1[a * 3 + 2] * W2[c * 3 + 2];
+                    for (int u = 0; u < 4; ++u) {
+                        const int m = 4 * v + u;
+                        if (m < 18) {
+#pragma unroll
+                            for (int a = 0; a < 6; ++a) acc[a * 6 + m / 3] += Y1[a * 3 + m % 3] * w4[u];
+                        }
+                    }
+                }
             }
             double* out = D.part + 36 * (size_t)t;
             for (int k = 0; k < 36; ++k) out[k] = acc[k];

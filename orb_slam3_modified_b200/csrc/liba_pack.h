@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/orb_b200.h"
@@ -92,6 +93,29 @@ inline std::string pack_inputs(const LocalInertialBAProblem& p, const Layout& L,
             if (seen[k] == (int)q) return "LocalInertialBA: two observations of one point in one keyframe (right-camera edges are not supported)";
             seen[k] = (int)q;
         }
+    return "";
+}
+
+// pack_inputs for a batch on up to 8 host threads (the copies into the pinned staging buffer dominate the host side of a many-map call);
+// returns the first error text ("" = ok)
+inline std::string pack_batch(int count, const LocalInertialBAProblem* problems, const Layout* lay, const size_t* inOff, uint8_t* hIn) {
+    size_t bytes = 0;
+    for (int i = 0; i < count; ++i) bytes += lay[i].inBytes;
+    int nth = (int)std::thread::hardware_concurrency();
+    if (nth > 8) nth = 8;
+    if (nth > count) nth = count;
+    if (nth < 2 || bytes < ((size_t)4 << 20)) {
+        for (int i = 0; i < count; ++i) { const std::string e = pack_inputs(problems[i], lay[i], hIn + inOff[i]); if (!e.empty()) return e; }
+        return "";
+    }
+    std::vector<std::string> err((size_t)nth);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; ++t)
+        th.emplace_back([&, t]() {
+            for (int i = t; i < count; i += nth) { const std::string e = pack_inputs(problems[i], lay[i], hIn + inOff[i]); if (!e.empty() && err[t].empty()) err[t] = e; }
+        });
+    for (auto& x : th) x.join();
+    for (const auto& e : err) if (!e.empty()) return e;
     return "";
 }
 

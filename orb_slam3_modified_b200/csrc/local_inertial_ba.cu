@@ -38,7 +38,9 @@ namespace liba {
 struct DeviceExec {
     double* red;      // NT / 32 doubles of shared memory
     double* prof;     // 8 doubles of shared memory: nanoseconds per phase group (thread 0 keeps the clock)
+    double* pnl;      // MAXN * LW doubles of shared memory: the LDL^T panel
     unsigned long long last; int cur;
+    __device__ __forceinline__ double* panel() const { return pnl; }
     __device__ __forceinline__ void tag(int k) {
         if (threadIdx.x == 0) {
             unsigned long long t;
@@ -80,11 +82,12 @@ __global__ void __launch_bounds__(NT) local_inertial_ba_kernel(const Dev* __rest
     if (threadIdx.x == 0) s_D = probs[blockIdx.x];
     __syncthreads();
     __shared__ double s_prof[8];
+    __shared__ double s_panel[MAXN * LW];      // 37.5 KB
     if (threadIdx.x < 8) s_prof[threadIdx.x] = 0.0;
     __syncthreads();
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    DeviceExec ex{s_red, s_prof, t0, 7};
+    DeviceExec ex{s_red, s_prof, s_panel, t0, 7};
     run(s_D, ex);
     ex.tag(7);
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -156,11 +159,11 @@ extern "C" int local_inertial_ba_batch(int count, const LocalInertialBAProblem* 
     uint8_t* hIn = A.h; uint8_t* hOut = A.h + inAll;
     uint8_t* dIn = A.d; uint8_t* dSc = A.d + inAll; uint8_t* dOut = A.d + inAll + scTot;
     Dev* hDev = (Dev*)(hIn + devOff);
-    for (int i = 0; i < count; ++i) {
-        const std::string err = pack_inputs(problems[i], lay[i], hIn + inOff[i]);
+    {
+        const std::string err = pack_batch(count, problems, lay.data(), inOff.data(), hIn);
         if (!err.empty()) { set_error(err); return ORB_ERR_ARG; }
-        bind(hDev[i], problems[i], lay[i], dIn + inOff[i], dSc + scOff[i], dOut + outOff[i]);      // device addresses
     }
+    for (int i = 0; i < count; ++i) bind(hDev[i], problems[i], lay[i], dIn + inOff[i], dSc + scOff[i], dOut + outOff[i]);      // device addresses
     const double msPack = ms_since(tStart);
     const auto tGpu = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(dIn, hIn, inAll, cudaMemcpyHostToDevice, A.st));

@@ -11,6 +11,8 @@
 
 namespace {
 struct HostExec {
+    std::vector<double> pnl = std::vector<double>((size_t)liba::MAXN * liba::LW, -1.0);
+    double* panel() { return pnl.data(); }
     void tag(int) {}
     template <class F> void par(F f) { for (int t = 0; t < liba::NT; ++t) f(t); }
     // the device's reduction tree: shuffle-down inside each warp (lane 0 holds the warp's sum), then the warp sums in order
@@ -44,4 +46,31 @@ extern "C" int liba_emulate(const LocalInertialBAProblem* p, const LocalInertial
     HostExec ex;
     liba::run(D, ex);
     return liba::unpack_outputs(*p, *r, L, out.data());
+}
+
+// The batch form of the host side (layout, threaded packing into ONE staging buffer, per-problem views) followed by the serial executor per map.
+extern "C" int liba_emulate_batch(int count, const LocalInertialBAProblem* p, const LocalInertialBAResult* r, int* iterations, char* errText, int errCap) {
+    std::vector<liba::Layout> lay(count);
+    std::vector<size_t> inOff(count);
+    size_t inTot = 0;
+    std::string err;
+    for (int i = 0; i < count && err.empty(); ++i) {
+        err = liba::check(p[i]);
+        if (!err.empty()) break;
+        lay[i] = liba::make_layout(p[i]);
+        inOff[i] = inTot;
+        inTot += (lay[i].inBytes + 255) & ~(size_t)255;
+    }
+    std::vector<uint8_t> in(inTot + 256, 0);
+    if (err.empty()) err = liba::pack_batch(count, p, lay.data(), inOff.data(), in.data());
+    if (!err.empty()) { if (errText && errCap > 0) { strncpy(errText, err.c_str(), errCap - 1); errText[errCap - 1] = 0; } return -1; }
+    for (int i = 0; i < count; ++i) {
+        std::vector<uint8_t> sc(lay[i].scBytes + 32, 0xAB), out(lay[i].outBytes + 32, 0);
+        liba::Dev D;
+        liba::bind(D, p[i], lay[i], in.data() + inOff[i], sc.data(), out.data());
+        HostExec ex;
+        liba::run(D, ex);
+        iterations[i] = liba::unpack_outputs(p[i], r[i], lay[i], out.data());
+    }
+    return 0;
 }

@@ -173,3 +173,24 @@ def test_kernel_phases_default_lambda_and_rejected_steps():
     a, b = _emulate(pr2, P2), O.local_inertial_ba(pr2, P2)
     assert b['trials'] > b['iters']                         # at least one rejected trial happened
     _same_solve(a, b, pr2, tol_state=1e-7)
+
+
+def test_threaded_batch_packing_equals_single_packing():
+    import ctypes as C
+    import os
+    import orb_slam3_modified_b200 as orb
+    prs = []
+    for sd in range(12):
+        pr = synth.local_inertial_ba_problem(n_opt=3 + sd % 4, n_cov_fixed=1 + sd % 3, n_pts=2500 if sd % 2 else 700, seed=40 + sd)
+        pr['preint'] = O.liba_preints(pr)
+        pr['iterations'] = 2                                # the packing is what is tested; two LM iterations keep the serial executor short
+        prs.append(pr)
+    singles = [_emulate(pr, pr['preint']) for pr in prs]    # (also builds the emulation library)
+    L = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libliba_emulate.so'))
+    Pm, Rm, keep, outs = orb._liba_marshal(prs)
+    its = np.zeros(len(prs), np.int32); err = C.create_string_buffer(256)
+    L.liba_emulate_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+    assert L.liba_emulate_batch(len(prs), C.cast(Pm, C.c_void_p), C.cast(Rm, C.c_void_p), its.ctypes.data, err, 256) == 0, err.value
+    got = orb._liba_finish(outs, its)
+    for a, b in zip(got, singles):
+        assert a['iters'] == b['iters'] and a['state'].tobytes() == b['state'].tobytes() and a['points'].tobytes() == b['points'].tobytes() and np.array_equal(a['erase'], b['erase'])
