@@ -445,7 +445,9 @@ int orbo_pose_inertial_opt_last_kf_n(int N, const float* Xw, const float* obs, c
             }
             const bool ok = ldlt_solve(15, H, b, x);                        // a failed solve leaves x from the previous iteration, update() still runs
             orbo_imu_pose_update(Rwb, twb, x);
-            if (++its >= 3) { double Rn[9]; normalize_rotation(Rwb, Rn); for (int k = 0; k < 9; ++k) Rwb[k] = Rn[k]; its = 0; }
+            // `NormalizeRotation(Rwb);` every third update (src/G2oTypes.cc:202-208) has no effect: the function (include/G2oTypes.h:67-71) returns the
+            // normalised matrix and the call discards it
+            if (++its >= 3) its = 0;
             for (int k = 0; k < 3; ++k) { v[k] += x[6 + k]; bg[k] += x[9 + k]; ba[k] += x[12 + k]; }
             if (!ok) break;
         }
@@ -627,7 +629,7 @@ int orbo_pose_inertial_opt_last_frame_n(int N, const float* Xw, const float* obs
             for (int k = 0; k < 2; ++k) {
                 const double* dx = x + 15 * k;
                 orbo_imu_pose_update(S[k], S[k] + 9, dx);
-                if (++its[k] >= 3) { double Rn[9]; normalize_rotation(S[k], Rn); for (int q = 0; q < 9; ++q) S[k][q] = Rn[q]; its[k] = 0; }
+                if (++its[k] >= 3) its[k] = 0;      // the reference's NormalizeRotation(Rwb) call discards its result (see the last-keyframe variant)
                 for (int q = 0; q < 3; ++q) { S[k][12 + q] += dx[6 + q]; S[k][15 + q] += dx[9 + q]; S[k][18 + q] += dx[12 + q]; }
             }
             if (!ok) break;

@@ -274,7 +274,7 @@ struct Problem {
             KF& f = kf[k];
             const double* u = &x[15 * (size_t)k];
             orbo_imu_pose_update(f.Rwb, f.twb, u);                          // twb += Rwb ut; Rwb = Rwb ExpSO3(ur)
-            if (++f.its >= 3) { double Rn[9]; orbo_so3(4, f.Rwb, Rn); std::memcpy(f.Rwb, Rn, sizeof(Rn)); f.its = 0; }
+            if (++f.its >= 3) f.its = 0;      // its `NormalizeRotation(Rwb);` (src/G2oTypes.cc:202-208) discards the returned matrix: Rwb is never renormalised
             double tbw[3];
             for (int i = 0; i < 3; ++i) tbw[i] = -(f.Rwb[i] * f.twb[0] + f.Rwb[3 + i] * f.twb[1] + f.Rwb[6 + i] * f.twb[2]);   // -Rbw twb
             for (int i = 0; i < 3; ++i) {

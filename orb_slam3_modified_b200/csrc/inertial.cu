@@ -196,7 +196,7 @@ __global__ void mono_imu_edges_kernel(MonoParams Q) {
 // 15 unknowns (VertexPose 6, VertexVelocity 3, VertexGyroBias 3, VertexAccBias 3); the last keyframe's vertices are fixed.  Four rounds of
 // g2o Gauss-Newton x 10 iterations on the device: the EdgeMonoOnlyPose edges are spread over the threads (pose block: 21 + 6 ordered
 // block sums), thread 0 adds EdgeInertial and the two random-walk edges, factors the dense 15 x 15 system (LDLT, LinearSolverDense) and
-// applies the update (ImuCamPose::Update with its every-third-update NormalizeRotation); then the chi2 re-classification of :4713-4778 with
+// applies the update (ImuCamPose::Update; its every-third-update NormalizeRotation call has no effect in the reference, see apply_update15); then the chi2 re-classification of :4713-4778 with
 // stale / recomputed errors exactly as g2o leaves them, the recovery of :4783-4810 and the Hessian of the next prior (:4819-4867).
 // ---------------------------------------------------------------------------------------------
 constexpr int PI_NT = 128;
@@ -251,7 +251,7 @@ __device__ __forceinline__ void mono_only_pose(const double* Rcw, const double* 
     for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) PR[i * 3 + j] = pj[i * 3] * Rcb[j] + pj[i * 3 + 1] * Rcb[3 + j] + pj[i * 3 + 2] * Rcb[6 + j];
     for (int i = 0; i < 2; ++i) for (int j = 0; j < 6; ++j) Jp[i * 6 + j] = PR[i * 3] * Sd[j] + PR[i * 3 + 1] * Sd[6 + j] + PR[i * 3 + 2] * Sd[12 + j];
 }
-// vertex updates of one frame: ImuCamPose::Update (twb += Rwb ut; Rwb = Rwb ExpSO3(ur); NormalizeRotation every third update), v / bg / ba += dx
+// vertex updates of one frame: ImuCamPose::Update (twb += Rwb ut; Rwb = Rwb ExpSO3(ur)), v / bg / ba += dx
 __device__ void apply_update15(double* st, const double* dx, int& its) {
     double t3[3], E[9], Rn[9];
     m3vec(st, dx + 3, t3);
@@ -259,7 +259,9 @@ __device__ void apply_update15(double* st, const double* dx, int& its) {
     exp_so3_d(dx, E);
     m3mul(st, E, Rn);
     for (int i = 0; i < 9; ++i) st[i] = Rn[i];
-    if (++its >= 3) { normalize_rotation(st, Rn); for (int i = 0; i < 9; ++i) st[i] = Rn[i]; its = 0; }
+    // ImuCamPose::Update's every-third-update `NormalizeRotation(Rwb);` (src/G2oTypes.cc:202-208) discards the return value of a function that leaves its
+    // argument alone (include/G2oTypes.h:67-71): the reference never renormalises Rwb, and neither does this
+    (void)its;
     for (int i = 0; i < 3; ++i) { st[12 + i] += dx[6 + i]; st[15 + i] += dx[9 + i]; st[18 + i] += dx[12 + i]; }
 }
 // EdgePriorPoseImu (src/G2oTypes.cc:731-760): residual 15 and Jacobian 15 x 15 (block diagonal) wrt the previous frame's pose 6, v, bg, ba

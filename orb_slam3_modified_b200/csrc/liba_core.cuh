@@ -67,7 +67,6 @@ struct Dev {
     double *part, *partb;                   // [nPairs][SL][36], [nOpt][SL][6]: partial Schur sums
     double *Jin, *OJ, *Oe, *win;            // [nI][216], [nI][216], [nI][9], [nI]: EdgeInertial Jacobians, Omega J, Omega e, robust weight
     double *kfBk, *tcwBk, *ptsBk;           // push() / pop()
-    int *its, *itsBk;                       // ImuCamPose::its
     // ---- outputs ----
     double *outState, *outTcw, *outPts;     // [nKF][21], [nKF][12], [nL][3]
     uint8_t* erase;                         // [nE]
@@ -576,7 +575,6 @@ template <class Exec> IMU_HD inline void push_and_update(const Dev& D, Exec& ex)
             double* st = D.kfState + 21 * (size_t)k; double* T = D.kfTcw + 12 * (size_t)k;
             for (int i = 0; i < 21; ++i) D.kfBk[21 * (size_t)k + i] = st[i];
             for (int i = 0; i < 12; ++i) D.tcwBk[12 * (size_t)k + i] = T[i];
-            D.itsBk[k] = D.its[k];
             const double* u = D.x + 15 * (size_t)k;
             double t3[3], E[9], Rn[9];
             m3vec(st, u + 3, t3);
@@ -584,7 +582,8 @@ template <class Exec> IMU_HD inline void push_and_update(const Dev& D, Exec& ex)
             exp_so3_d(u, E);
             m3mul(st, E, Rn);
             for (int i = 0; i < 9; ++i) st[i] = Rn[i];
-            if (++D.its[k] >= 3) { normalize_rotation(st, Rn); for (int i = 0; i < 9; ++i) st[i] = Rn[i]; D.its[k] = 0; }
+            // (ImuCamPose::Update's every-third-update `NormalizeRotation(Rwb);`, src/G2oTypes.cc:202-208, discards the function's return value -- the
+            //  template of include/G2oTypes.h:67-71 returns the normalised matrix and leaves its argument alone -- so the reference never renormalises Rwb)
             double tbw[3];
             for (int i = 0; i < 3; ++i) tbw[i] = -(st[i] * st[9] + st[3 + i] * st[10] + st[6 + i] * st[11]);
             for (int i = 0; i < 3; ++i) {
@@ -601,7 +600,6 @@ template <class Exec> IMU_HD inline void pop(const Dev& D, Exec& ex) {
     ex.par([&](int tid) {
         for (int i = tid; i < 21 * D.nOpt; i += NT) D.kfState[i] = D.kfBk[i];
         for (int i = tid; i < 12 * D.nOpt; i += NT) D.kfTcw[i] = D.tcwBk[i];
-        for (int i = tid; i < D.nOpt; i += NT) D.its[i] = D.itsBk[i];
         for (size_t i = tid; i < (size_t)3 * D.nL; i += NT) D.pts[i] = D.ptsBk[i];
     });
 }
@@ -618,7 +616,6 @@ template <class Exec> IMU_HD inline void run(const Dev& D, Exec& ex) {
             information_matrices(D.preint + (size_t)P_SIZE * i, I9, D.infoG + 9 * (size_t)i, D.infoA + 9 * (size_t)i);
             for (int k = 0; k < 81; ++k) I9[k] *= D.ieInfoScale[i];      // vei[i]->setInformation(information() * 1e-2), :2641
         }
-        for (int k = tid; k < nO; k += NT) D.its[k] = 0;
         for (size_t i = tid; i < (size_t)D.nL * nO; i += NT) D.pk[i] = -1;
         for (int i = tid; i < n + 3 * D.nL; i += NT) D.x[i] = 0.0;
     });

@@ -16,7 +16,7 @@ namespace liba {
 struct Layout {
     // byte offsets inside the three regions of one problem
     size_t kfState, kfTcw, cam, extr, ieKf1, ieKf2, preint, ieRobust, ieInfoScale, pts, trackDepth, ePt, eKf, obs, invSigma2, ptStart, ptEdges, kfStart, kfEdges, inBytes;
-    size_t pk, info9, infoG, infoA, errM, errI, errG, errA, ejac, W, Y, Hll, bl, Dinv, db, H, b, Hs, bs, dvec, x, He, be, part, partb, Jin, OJ, Oe, win, kfBk, tcwBk, ptsBk, its, itsBk, scBytes;
+    size_t pk, info9, infoG, infoA, errM, errI, errG, errA, ejac, W, Y, Hll, bl, Dinv, db, H, b, Hs, bs, dvec, x, He, be, part, partb, Jin, OJ, Oe, win, kfBk, tcwBk, ptsBk, scBytes;
     size_t outState, outTcw, outPts, erase, chi2, stats, prof, outBytes;
     int nFreeEdges;
 };
@@ -59,7 +59,7 @@ inline Layout make_layout(const LocalInertialBAProblem& p) {
     L.He = bump(o, nI * 900 * 8); L.be = bump(o, nI * 30 * 8);
     L.part = bump(o, nO * (nO + 1) / 2 * SL * 36 * 8); L.partb = bump(o, nO * SL * 6 * 8);
     L.Jin = bump(o, nI * 216 * 8); L.OJ = bump(o, nI * 216 * 8); L.Oe = bump(o, nI * 9 * 8); L.win = bump(o, nI * 8);
-    L.kfBk = bump(o, nO * 21 * 8); L.tcwBk = bump(o, nO * 12 * 8); L.ptsBk = bump(o, nL * 3 * 8); L.its = bump(o, nO * 4); L.itsBk = bump(o, nO * 4);
+    L.kfBk = bump(o, nO * 21 * 8); L.tcwBk = bump(o, nO * 12 * 8); L.ptsBk = bump(o, nL * 3 * 8);
     L.scBytes = o;
     o = 0;
     L.outState = bump(o, nKF * 21 * 8); L.outTcw = bump(o, nKF * 12 * 8); L.outPts = bump(o, nL * 3 * 8); L.erase = bump(o, nE); L.chi2 = bump(o, nE * 8); L.stats = bump(o, 8 * 8); L.prof = bump(o, 8 * 8);
@@ -133,7 +133,7 @@ inline void bind(Dev& D, const LocalInertialBAProblem& p, const Layout& L, uint8
     D.H = (double*)(sc + L.H); D.b = (double*)(sc + L.b); D.Hs = (double*)(sc + L.Hs); D.bs = (double*)(sc + L.bs); D.dvec = (double*)(sc + L.dvec); D.x = (double*)(sc + L.x);
     D.He = (double*)(sc + L.He); D.be = (double*)(sc + L.be); D.part = (double*)(sc + L.part); D.partb = (double*)(sc + L.partb);
     D.Jin = (double*)(sc + L.Jin); D.OJ = (double*)(sc + L.OJ); D.Oe = (double*)(sc + L.Oe); D.win = (double*)(sc + L.win);
-    D.kfBk = (double*)(sc + L.kfBk); D.tcwBk = (double*)(sc + L.tcwBk); D.ptsBk = (double*)(sc + L.ptsBk); D.its = (int*)(sc + L.its); D.itsBk = (int*)(sc + L.itsBk);
+    D.kfBk = (double*)(sc + L.kfBk); D.tcwBk = (double*)(sc + L.tcwBk); D.ptsBk = (double*)(sc + L.ptsBk);
     D.outState = (double*)(out + L.outState); D.outTcw = (double*)(out + L.outTcw); D.outPts = (double*)(out + L.outPts); D.erase = out + L.erase;
     D.chi2 = (double*)(out + L.chi2); D.stats = (double*)(out + L.stats); D.prof = (double*)(out + L.prof);
 }

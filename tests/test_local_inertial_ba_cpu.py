@@ -99,7 +99,7 @@ def test_recovers_the_window_and_flags_gross_outliers():
         for k in range(nO):
             R, p = r['state'][k, :9].reshape(3, 3), r['state'][k, 9:12]
             assert np.allclose(r['tcw'][k, :9].reshape(3, 3), Rcb @ R.T, atol=1e-12) and np.allclose(r['tcw'][k, 9:], Rcb @ (-R.T @ p) + tcb, atol=1e-12)
-            assert np.allclose(R.T @ R, np.eye(3), atol=1e-9)
+            assert np.allclose(R.T @ R, np.eye(3), atol=1e-6)       # the float rounding of the keyframe's Rwb stays: the reference never renormalises it (G2oTypes.cc:206 discards the result)
         # erased observations: residual test of :2848-2862 on the final state
         res = O.local_inertial_ba_residuals(pr, r['tcw'], r['points'])
         chi = pr['inv_sigma2'] * (res ** 2).sum(1)
