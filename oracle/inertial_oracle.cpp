@@ -8,9 +8,11 @@
 //   EdgeGyroRW / EdgeAccRW (include/G2oTypes.h:635-700): error = b2 - b1, information = inverse of the 3x3 walk covariance
 //   ExpSO3 / LogSO3 / RightJacobianSO3 / InverseRightJacobianSO3                                  :777-861
 //   ImuCamPose::Update (VertexPose::oplusImpl)                                                    :192-220
-// PARITY: G2oTypes / ImuTypes need Eigen and Sophus and cannot be compiled here (no oracle/_ref for them): the analytic Jacobians
+// PARITY: the double-precision edge functions below equal the reference's own function bodies compiled against a small Eigen stand-in
+// (oracle/ref_shim/ref_wrap_inertial.cpp -> oracle/_ref/libref_inertial.so, tests/test_ref_pins_inertial_cpu.py) to 1e-12; ImuTypes.cc needs Sophus::SO3f::exp
+// and Eigen::JacobiSVD and is not compiled.  Independently of that, the analytic Jacobians
 // below are pinned by numerical differentiation of the residuals under the reference's own update rules
-// (tests/test_inertial_cpu.py), the SVD / eigen pieces by their defining properties.  "parity unpinned" by the reference itself.
+// (tests/test_inertial_cpu.py), the SVD / eigen pieces by their defining properties.  The solver loops around these edges are "parity unpinned" by the reference itself.
 #include "oracle_common.h"
 
 #include <algorithm>

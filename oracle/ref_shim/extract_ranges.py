@@ -29,6 +29,15 @@ RANGES = [
     ('mappoint_predict_scale_kf.inc', 'src/MapPoint.cc', 514, 529, 'int MapPoint::PredictScale(const float &currentDist, KeyFrame* pKF)'),
     ('mappoint_invariance.inc', 'src/MapPoint.cc', 502, 512, 'float MapPoint::GetMinDistanceInvariance()'),
     ('mappoint_predict_scale.inc', 'src/MapPoint.cc', 531, 546, 'int MapPoint::PredictScale(const float &currentDist, Frame* pF)'),
+    ('g2o_imucampose_project.inc', 'src/G2oTypes.cc', 170, 175, 'Eigen::Vector2d ImuCamPose::Project(const Eigen::Vector3d &Xw, int cam_idx) const'),
+    ('g2o_imucampose_depth.inc', 'src/G2oTypes.cc', 187, 190, 'bool ImuCamPose::isDepthPositive(const Eigen::Vector3d &Xw, int cam_idx) const'),
+    ('g2o_imucampose_update.inc', 'src/G2oTypes.cc', 192, 220, 'void ImuCamPose::Update(const double *pu)'),
+    ('g2o_edge_mono.inc', 'src/G2oTypes.cc', 349, 395, 'void EdgeMono::linearizeOplus()'),
+    ('g2o_edge_inertial.inc', 'src/G2oTypes.cc', 514, 594, 'void EdgeInertial::computeError()'),
+    ('g2o_edge_prior.inc', 'src/G2oTypes.cc', 731, 760, 'void EdgePriorPoseImu::computeError()'),
+    ('g2o_so3.inc', 'src/G2oTypes.cc', 777, 861, 'Eigen::Matrix3d ExpSO3(const Eigen::Vector3d &w)'),
+    ('pinhole_project_d.inc', 'src/CameraModels/Pinhole.cpp', 35, 41, 'Eigen::Vector2d Pinhole::project(const Eigen::Vector3d &v3D)'),
+    ('pinhole_project_jac.inc', 'src/CameraModels/Pinhole.cpp', 71, 81, 'Eigen::Matrix<double, 2, 3> Pinhole::projectJac(const Eigen::Vector3d &v3D)'),
     ('euroc_loaders.inc', 'Examples/Monocular-Inertial/mono_inertial_euroc.cc', 252, 310, 'void LoadImages(const string &strImagePath, const string &strPathTimes,'),
     ('pinhole_project.inc', 'src/CameraModels/Pinhole.cpp', 43, 49, 'Eigen::Vector2f Pinhole::project(const Eigen::Vector3f &v3D)'),
 ]
