@@ -13,9 +13,9 @@
 // a dense LDL^T without pivoting (what SimplicialLDLT computes up to the fill-reducing permutation, i.e. up to rounding).
 // Summation order over edges is free (the reference's own order depends on pointer values, SURVEY.md 8a'); control
 // flow (accept/reject, lambda schedule, stop rules, stale errors after a rejected last trial) is reproduced exactly.
-// PARITY UNPINNED by the reference (no vectors, not buildable here); one LM step is checked against an independent dense solve
-// with numerical Jacobians (tests/test_lba_dense_cpu.py) and the whole LM loop against a second transcription
-// (tests/test_lba_lm_transcription_cpu.py).
+// PARITY: the edge errors / Jacobians, VertexSE3Expmap::oplusImpl, the Huber kernel and the LM control flow equal the reference's own text compiled into oracle/_ref
+// (tests/test_ref_pins_lba_edges_cpu.py, tests/test_ref_pins_lm_cpu.py); BlockSolver's Schur / linear solve (needs Eigen) stays pinned by an independent dense solve
+// with numerical Jacobians (tests/test_lba_dense_cpu.py), the whole LM loop additionally by a second transcription (tests/test_lba_lm_transcription_cpu.py).
 #include "oracle_common.h"
 
 #include <cfloat>
@@ -136,6 +136,17 @@ static bool ldlt_solve(std::vector<double>& A, int n, const double* b, double* x
     return true;
 }
 
+// EdgeSE3ProjectXYZ::linearizeOplus (src/OptimizableTypes.cpp:139-160) at the camera-frame point Xc = T.map(xyz)
+static void edge_jacobians(const Quat& q, const float* c, const double* Xc, double* A, double* B) {
+    const double x = Xc[0], y = Xc[1], z = Xc[2];
+    // -projectJac
+    const double J[6] = {-((double)c[0] / z), -0.0, -(-(double)c[0] * x / (z * z)), -0.0, -((double)c[1] / z), -(-(double)c[1] * y / (z * z))};
+    double R[9]; qtoR(q, R);
+    for (int r = 0; r < 2; ++r) for (int k = 0; k < 3; ++k) A[r * 3 + k] = J[r * 3] * R[k] + J[r * 3 + 1] * R[3 + k] + J[r * 3 + 2] * R[6 + k];      // 2x3 = J * R
+    const double S[18] = {0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1};
+    for (int r = 0; r < 2; ++r) for (int k = 0; k < 6; ++k) B[r * 6 + k] = J[r * 3] * S[k] + J[r * 3 + 1] * S[6 + k] + J[r * 3 + 2] * S[12 + k];   // 2x6 = J * SE3deriv
+}
+
 struct Lba {
     int nP, nL, nE;
     std::vector<Pose> poses, posesBk;
@@ -189,16 +200,8 @@ struct Lba {
             const int ip = ePt[e], ic = ePose[e], h = hidx[ic];
             double Xc[3], uv[2];
             project_edge(e, Xc, uv);
-            const float* c = cam + 4 * (size_t)ic;
-            const double x = Xc[0], y = Xc[1], z = Xc[2];
-            // -projectJac
-            const double J[6] = {-((double)c[0] / z), -0.0, -(-(double)c[0] * x / (z * z)), -0.0, -((double)c[1] / z), -(-(double)c[1] * y / (z * z))};
-            double R[9]; qtoR(poses[ic].q, R);
-            double A[6];   // 2x3 = J * R
-            for (int r = 0; r < 2; ++r) for (int k = 0; k < 3; ++k) A[r * 3 + k] = J[r * 3] * R[k] + J[r * 3 + 1] * R[3 + k] + J[r * 3 + 2] * R[6 + k];
-            const double S[18] = {0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1};
-            double B[12];  // 2x6 = J * SE3deriv
-            for (int r = 0; r < 2; ++r) for (int k = 0; k < 6; ++k) B[r * 6 + k] = J[r * 3] * S[k] + J[r * 3 + 1] * S[6 + k] + J[r * 3 + 2] * S[12 + k];
+            double A[6], B[12];   // _jacobianOplusXi (2x3), _jacobianOplusXj (2x6)
+            edge_jacobians(poses[ic].q, cam + 4 * (size_t)ic, Xc, A, B);
             double rho[3]; robustify(chi2(e), rho);
             const double w = rho[1] * (double)invSigma2[e];
             const double r0 = -(double)invSigma2[e] * err[2 * (size_t)e] * rho[1], r1 = -(double)invSigma2[e] * err[2 * (size_t)e + 1] * rho[1];
@@ -271,6 +274,8 @@ struct Lba {
 }  // namespace orbo
 
 using namespace orbo;
+
+static void only_pose_jacobian(const float* cam4, double x, double y, double z, double* B);
 
 extern "C" {
 
@@ -378,6 +383,92 @@ int orbo_lba_solve(int nP, double* posesInOut, const uint8_t* fixed, const float
     return cj;
 }
 
+// ---- the same state opened step by step (OrboLmBackend, oracle_common.h) ----
+namespace {
+struct LbaOpen {
+    Lba L;
+    std::vector<float> cam, is2; std::vector<int> ePt, ePose; std::vector<double> obs;
+    std::vector<double> bcat, diag;
+};
+void lbo_compute_errors(void* p) { ((LbaOpen*)p)->L.compute_errors(); }
+double lbo_robust_chi2(void* p) { return ((LbaOpen*)p)->L.robust_chi2(); }
+void lbo_build_system(void* p) {
+    LbaOpen* o = (LbaOpen*)p; Lba& L = o->L;
+    L.build_system();
+    const int n = 6 * L.nF;
+    o->bcat.assign(L.bp.begin(), L.bp.end()); o->bcat.insert(o->bcat.end(), L.bl.begin(), L.bl.end());
+    o->diag.clear();
+    for (int i = 0; i < n; ++i) o->diag.push_back(L.Hpp[(size_t)i * n + i]);
+    for (int q = 0; q < L.nL; ++q) for (int j = 0; j < 3; ++j) o->diag.push_back(L.Hll[9 * (size_t)q + 4 * j]);
+}
+int lbo_solve(void* p, double lambda) { return ((LbaOpen*)p)->L.solve(lambda) ? 1 : 0; }
+void lbo_update(void* p) { ((LbaOpen*)p)->L.update(); }
+void lbo_push(void* p) { Lba& L = ((LbaOpen*)p)->L; L.posesBk = L.poses; L.ptsBk = L.pts; }
+void lbo_pop(void* p) { Lba& L = ((LbaOpen*)p)->L; L.poses = L.posesBk; L.pts = L.ptsBk; }
+int lbo_vector_size(void* p) { Lba& L = ((LbaOpen*)p)->L; return 6 * L.nF + 3 * L.nL; }
+const double* lbo_x(void* p) { return ((LbaOpen*)p)->L.x.data(); }
+const double* lbo_b(void* p) { return ((LbaOpen*)p)->bcat.data(); }
+int lbo_n_diag(void* p) { return (int)((LbaOpen*)p)->diag.size(); }
+const double* lbo_diag(void* p) { return ((LbaOpen*)p)->diag.data(); }
+}  // namespace
+
+// arguments as orbo_lba_solve (copied: the caller's arrays need not outlive the call)
+void orbo_lba_backend_open(int nP, const double* poses7, const uint8_t* fixed, const float* cam4, int nL, const double* points3, int nE, const int* edgePoint, const int* edgePose,
+                           const double* obs2, const float* invSigma2, double huberDelta, OrboLmBackend* out) {
+    LbaOpen* o = new LbaOpen;
+    o->cam.assign(cam4, cam4 + 4 * (size_t)nP); o->is2.assign(invSigma2, invSigma2 + nE); o->ePt.assign(edgePoint, edgePoint + nE); o->ePose.assign(edgePose, edgePose + nE);
+    o->obs.assign(obs2, obs2 + 2 * (size_t)nE);
+    Lba& L = o->L;
+    L.nP = nP; L.nL = nL; L.nE = nE;
+    L.poses.resize(nP); L.fixed.assign(fixed, fixed + nP); L.hidx.assign(nP, -1);
+    for (int i = 0; i < nP; ++i) {
+        const double* p = poses7 + 7 * (size_t)i;
+        L.poses[i].q = {p[0], p[1], p[2], p[3]};
+        qnormalize(L.poses[i].q);
+        L.poses[i].t[0] = p[4]; L.poses[i].t[1] = p[5]; L.poses[i].t[2] = p[6];
+        if (!fixed[i]) L.hidx[i] = L.nF++;
+    }
+    L.pts.assign(points3, points3 + 3 * (size_t)nL);
+    L.cam = o->cam.data(); L.ePt = o->ePt.data(); L.ePose = o->ePose.data(); L.obs = o->obs.data(); L.invSigma2 = o->is2.data();
+    L.delta = huberDelta; L.dsqr = huberDelta * huberDelta; L.stop = nullptr;
+    L.err.assign(2 * (size_t)nE, 0.0);
+    const int n = 6 * L.nF;
+    L.Hpp.assign((size_t)n * n, 0.0); L.bp.assign(n, 0.0); L.Hll.assign(9 * (size_t)nL, 0.0); L.bl.assign(3 * (size_t)nL, 0.0);
+    L.W.assign(18 * (size_t)nE, 0.0); L.x.assign(n + 3 * (size_t)nL, 0.0); L.Dinv.assign(9 * (size_t)nL, 0.0);
+    *out = OrboLmBackend{o, lbo_compute_errors, lbo_robust_chi2, lbo_build_system, lbo_solve, lbo_update, lbo_push, lbo_pop, lbo_vector_size, lbo_x, lbo_b, lbo_n_diag, lbo_diag};
+}
+void orbo_lba_backend_close(OrboLmBackend* be, double* posesOut7, double* pointsOut3) {
+    LbaOpen* o = (LbaOpen*)be->self; Lba& L = o->L;
+    for (int i = 0; i < L.nP; ++i) {
+        double* p = posesOut7 + 7 * (size_t)i;
+        p[0] = L.poses[i].q.w; p[1] = L.poses[i].q.x; p[2] = L.poses[i].q.y; p[3] = L.poses[i].q.z; p[4] = L.poses[i].t[0]; p[5] = L.poses[i].t[1]; p[6] = L.poses[i].t[2];
+    }
+    std::memcpy(pointsOut3, L.pts.data(), sizeof(double) * 3 * (size_t)L.nL);
+    delete o;
+    be->self = nullptr;
+}
+
+// the per-edge numerics on their own, for tests/test_ref_pins_lba_edges_cpu.py (the functions the solvers above call)
+//   err [2] = obs - project(T.map(X)); Jpoint [2][3], Jpose [2][6] = EdgeSE3ProjectXYZ::linearizeOplus; JposeOnly [2][6] = EdgeSE3ProjectXYZOnlyPose::linearizeOplus
+void orbo_lba_edge(const double* pose7, const float* cam4, const double* X3, const double* obs2, double* err2, double* Jpoint, double* Jpose, double* JposeOnly, int* depthPositive) {
+    Quat q = {pose7[0], pose7[1], pose7[2], pose7[3]};
+    qnormalize(q);
+    double r[3]; qrot(q, X3, r);
+    const double Xc[3] = {r[0] + pose7[4], r[1] + pose7[5], r[2] + pose7[6]};
+    err2[0] = obs2[0] - ((double)cam4[0] * Xc[0] / Xc[2] + (double)cam4[2]);
+    err2[1] = obs2[1] - ((double)cam4[1] * Xc[1] / Xc[2] + (double)cam4[3]);
+    edge_jacobians(q, cam4, Xc, Jpoint, Jpose);
+    only_pose_jacobian(cam4, Xc[0], Xc[1], Xc[2], JposeOnly);
+    *depthPositive = Xc[2] > 0.0;
+}
+void orbo_huber(double delta, double e, double* rho3) { Lba L; L.delta = delta; L.dsqr = delta * delta; L.robustify(e, rho3); }
+// SE3Quat::exp(update) * T (VertexSE3Expmap::oplusImpl), pose7 in/out
+void orbo_lba_pose_oplus(double* pose7, const double* update6) {
+    Pose T; T.q = {pose7[0], pose7[1], pose7[2], pose7[3]}; qnormalize(T.q); T.t[0] = pose7[4]; T.t[1] = pose7[5]; T.t[2] = pose7[6];
+    pose_oplus(T, update6);
+    pose7[0] = T.q.w; pose7[1] = T.q.x; pose7[2] = T.q.y; pose7[3] = T.q.z; pose7[4] = T.t[0]; pose7[5] = T.t[1]; pose7[6] = T.t[2];
+}
+
 // reprojection residuals (obs - proj) of a state, for the 1e-4 px parity bar
 void orbo_lba_residuals(int nP, const double* poses7, const float* cam4, int nL, const double* points3, int nE, const int* edgePoint,
                         const int* edgePose, const double* obs2, double* res2) {
@@ -444,9 +535,8 @@ int orbo_pose_optimization(double* pose7, const float* cam4, int N, const double
                 if (level[e]) continue;
                 double r[3]; qrot(T.q, Xw3 + 3 * (size_t)e, r);
                 const double x = r[0] + T.t[0], y = r[1] + T.t[1], z = r[2] + T.t[2];
-                const double fx = cam4[0], fy = cam4[1];
-                const double J00 = -(fx / z), J02 = fx * x / (z * z), J11 = -(fy / z), J12 = fy * y / (z * z);
-                const double B[12] = {J02 * y, J00 * z - J02 * x, -J00 * y, J00, 0, J02, -J11 * z + J12 * y, -J12 * x, J11 * x, 0, J11, J12};
+                double B[12];
+                only_pose_jacobian(cam4, x, y, z, B);
                 double rho[2]; robustify(e, chi2(e), rho);
                 const double w = rho[1] * (double)invSigma2[e];
                 const double r0 = (double)invSigma2[e] * err[2 * (size_t)e], r1 = (double)invSigma2[e] * err[2 * (size_t)e + 1];
@@ -495,3 +585,11 @@ int orbo_pose_optimization(double* pose7, const float* cam4, int N, const double
 }
 
 }  // extern "C"
+
+// EdgeSE3ProjectXYZOnlyPose::linearizeOplus (src/OptimizableTypes.cpp:49-63): -projectJac * SE3deriv, written out
+static void only_pose_jacobian(const float* cam4, double x, double y, double z, double* B) {
+    const double fx = cam4[0], fy = cam4[1];
+    const double J00 = -(fx / z), J02 = fx * x / (z * z), J11 = -(fy / z), J12 = fy * y / (z * z);
+    const double v[12] = {J02 * y, J00 * z - J02 * x, -J00 * y, J00, 0, J02, -J11 * z + J12 * y, -J12 * x, J11 * x, 0, J11, J12};
+    for (int i = 0; i < 12; ++i) B[i] = v[i];
+}

@@ -421,6 +421,81 @@ int orbo_local_inertial_ba(int nKF, int nOpt, double* kfState21, double* kfTcw12
     return cj;
 }
 
+// ---- the same state opened step by step (OrboLmBackend, oracle_common.h) ----
+namespace {
+struct LibaOpen {
+    Problem L;
+    std::vector<float> cam, preint, is2; std::vector<double> extr, obs; std::vector<int> k1, k2, ePt, eKf; std::vector<uint8_t> rob;
+    std::vector<double> bcat, diag;
+};
+void lio_compute_errors(void* p) { ((LibaOpen*)p)->L.compute_errors(); }
+double lio_robust_chi2(void* p) { return ((LibaOpen*)p)->L.robust_chi2(); }
+void lio_build_system(void* p) {
+    LibaOpen* o = (LibaOpen*)p; Problem& L = o->L;
+    L.build_system();
+    const int n = 15 * L.nOpt;
+    o->bcat.assign(L.b.begin(), L.b.end()); o->bcat.insert(o->bcat.end(), L.bl.begin(), L.bl.end());
+    o->diag.clear();
+    for (int i = 0; i < n; ++i) o->diag.push_back(L.H[(size_t)i * n + i]);
+    for (int q = 0; q < L.nL; ++q) for (int j = 0; j < 3; ++j) o->diag.push_back(L.Hll[9 * (size_t)q + 4 * j]);
+}
+int lio_solve(void* p, double lambda) { return ((LibaOpen*)p)->L.solve(lambda) ? 1 : 0; }
+void lio_update(void* p) { ((LibaOpen*)p)->L.update(); }
+void lio_push(void* p) { Problem& L = ((LibaOpen*)p)->L; L.kfBk = L.kf; L.ptsBk = L.pts; }
+void lio_pop(void* p) { Problem& L = ((LibaOpen*)p)->L; L.kf = L.kfBk; L.pts = L.ptsBk; }
+int lio_vector_size(void* p) { Problem& L = ((LibaOpen*)p)->L; return 15 * L.nOpt + 3 * L.nL; }
+const double* lio_x(void* p) { return ((LibaOpen*)p)->L.x.data(); }
+const double* lio_b(void* p) { return ((LibaOpen*)p)->bcat.data(); }
+int lio_n_diag(void* p) { return (int)((LibaOpen*)p)->diag.size(); }
+const double* lio_diag(void* p) { return ((LibaOpen*)p)->diag.data(); }
+}  // namespace
+
+void orbo_liba_backend_open(int nKF, int nOpt, const double* kfState21, const double* kfTcw12, const float* cam4, const double* extr24, int nI, const int* ieKf1, const int* ieKf2,
+                            const float* preint, const uint8_t* ieRobust, const double* ieInfoScale, int nL, const double* points3, int nE, const int* ePt, const int* eKf,
+                            const double* obs2, const float* invSigma2, OrboLmBackend* out) {
+    LibaOpen* o = new LibaOpen;
+    o->cam.assign(cam4, cam4 + 4 * (size_t)nKF); o->extr.assign(extr24, extr24 + 24); o->k1.assign(ieKf1, ieKf1 + nI); o->k2.assign(ieKf2, ieKf2 + nI);
+    o->preint.assign(preint, preint + (size_t)P_SIZE * nI); o->rob.assign(ieRobust, ieRobust + nI); o->ePt.assign(ePt, ePt + nE); o->eKf.assign(eKf, eKf + nE);
+    o->obs.assign(obs2, obs2 + 2 * (size_t)nE); o->is2.assign(invSigma2, invSigma2 + nE);
+    Problem& L = o->L;
+    L.nKF = nKF; L.nOpt = nOpt; L.nI = nI; L.nL = nL; L.nE = nE;
+    L.kf.resize(nKF);
+    for (int k = 0; k < nKF; ++k) {
+        const double* s = kfState21 + 21 * (size_t)k;
+        KF& f = L.kf[k];
+        std::memcpy(f.Rwb, s, 9 * sizeof(double)); std::memcpy(f.twb, s + 9, 3 * sizeof(double)); std::memcpy(f.v, s + 12, 3 * sizeof(double));
+        std::memcpy(f.bg, s + 15, 3 * sizeof(double)); std::memcpy(f.ba, s + 18, 3 * sizeof(double));
+        std::memcpy(f.Rcw, kfTcw12 + 12 * (size_t)k, 9 * sizeof(double)); std::memcpy(f.tcw, kfTcw12 + 12 * (size_t)k + 9, 3 * sizeof(double));
+        f.its = 0;
+    }
+    L.pts.assign(points3, points3 + 3 * (size_t)nL);
+    L.cam = o->cam.data(); L.Rcb = o->extr.data(); L.tcb = o->extr.data() + 9; L.Rbc = o->extr.data() + 12; L.tbc = o->extr.data() + 21;
+    L.ieKf1 = o->k1.data(); L.ieKf2 = o->k2.data(); L.preint = o->preint.data(); L.ieRobust = o->rob.data();
+    L.info9.resize(81 * (size_t)nI); L.infoG.resize(9 * (size_t)nI); L.infoA.resize(9 * (size_t)nI);
+    for (int i = 0; i < nI; ++i) {
+        orbo_imu_information(L.preint + (size_t)P_SIZE * i, &L.info9[81 * (size_t)i], &L.infoG[9 * (size_t)i], &L.infoA[9 * (size_t)i]);
+        for (int k = 0; k < 81; ++k) L.info9[81 * (size_t)i + k] *= ieInfoScale[i];
+    }
+    L.ePt = o->ePt.data(); L.eKf = o->eKf.data(); L.obs = o->obs.data(); L.invSigma2 = o->is2.data();
+    L.deltaMono = (double)(float)std::sqrt(5.991); L.deltaInertial = std::sqrt(16.92);
+    L.errM.assign(2 * (size_t)nE, 0.0); L.errI.assign(9 * (size_t)nI, 0.0); L.errG.assign(3 * (size_t)nI, 0.0); L.errA.assign(3 * (size_t)nI, 0.0);
+    const int n = 15 * nOpt;
+    L.H.assign((size_t)n * n, 0.0); L.b.assign(n, 0.0); L.Hll.assign(9 * (size_t)nL, 0.0); L.bl.assign(3 * (size_t)nL, 0.0);
+    L.W.assign(18 * (size_t)nE, 0.0); L.x.assign(n + 3 * (size_t)nL, 0.0); L.Dinv.assign(9 * (size_t)nL, 0.0);
+    *out = OrboLmBackend{o, lio_compute_errors, lio_robust_chi2, lio_build_system, lio_solve, lio_update, lio_push, lio_pop, lio_vector_size, lio_x, lio_b, lio_n_diag, lio_diag};
+}
+void orbo_liba_backend_close(OrboLmBackend* be, double* kfStateOut21, double* pointsOut3) {
+    LibaOpen* o = (LibaOpen*)be->self; Problem& L = o->L;
+    for (int k = 0; k < L.nKF; ++k) {
+        double* s = kfStateOut21 + 21 * (size_t)k; const KF& f = L.kf[k];
+        std::memcpy(s, f.Rwb, 9 * sizeof(double)); std::memcpy(s + 9, f.twb, 3 * sizeof(double)); std::memcpy(s + 12, f.v, 3 * sizeof(double));
+        std::memcpy(s + 15, f.bg, 3 * sizeof(double)); std::memcpy(s + 18, f.ba, 3 * sizeof(double));
+    }
+    std::memcpy(pointsOut3, L.pts.data(), sizeof(double) * 3 * (size_t)L.nL);
+    delete o;
+    be->self = nullptr;
+}
+
 // reprojection residuals of a state (for the 1e-4 px bar): obs - project(Rcw X + tcw)
 void orbo_local_inertial_ba_residuals(int nE, const int* ePt, const int* eKf, const double* kfTcw12, const float* cam4, const double* points3, const double* obs2, double* res2) {
     for (int e = 0; e < nE; ++e) {

@@ -37,3 +37,24 @@ static inline int cvFloor(double v) { int i = (int)v; return i - (i > v); }
 static inline int cvCeil(double v) { int i = (int)v; return i + (i < v); }
 
 }  // namespace orbo
+
+// A solver state of the oracle (LocalBundleAdjustment or LocalInertialBA) opened step by step: the operations g2o's OptimizationAlgorithmLevenberg::solve and
+// SparseOptimizer::optimize call on their Solver / SparseOptimizer.  oracle/ref_shim/ref_wrap_g2o_lm.cpp drives these with the REFERENCE's own text of those two
+// functions, which pins the control flow of the oracle's Levenberg-Marquardt loops (tests/test_ref_pins_lm_cpu.py).
+extern "C" {
+typedef struct OrboLmBackend {
+    void* self;
+    void (*compute_errors)(void*);
+    double (*robust_chi2)(void*);
+    void (*build_system)(void*);
+    int (*solve)(void*, double lambda);           /* BlockSolver::setLambda + solve + restoreDiagonal; 0 = the factorisation failed */
+    void (*update)(void*);                        /* SparseOptimizer::update(solver->x()) */
+    void (*push)(void*);
+    void (*pop)(void*);
+    int (*vector_size)(void*);
+    const double* (*x)(void*);
+    const double* (*b)(void*);
+    int (*n_diag)(void*);
+    const double* (*diag)(void*);                 /* hessian(j, j) of every vertex in index-mapping order (computeLambdaInit) */
+} OrboLmBackend;
+}

@@ -38,6 +38,16 @@ RANGES = [
     ('g2o_so3.inc', 'src/G2oTypes.cc', 777, 861, 'Eigen::Matrix3d ExpSO3(const Eigen::Vector3d &w)'),
     ('pinhole_project_d.inc', 'src/CameraModels/Pinhole.cpp', 35, 41, 'Eigen::Vector2d Pinhole::project(const Eigen::Vector3d &v3D)'),
     ('pinhole_project_jac.inc', 'src/CameraModels/Pinhole.cpp', 71, 81, 'Eigen::Matrix<double, 2, 3> Pinhole::projectJac(const Eigen::Vector3d &v3D)'),
+    ('g2o_se3_skew.inc', 'Thirdparty/g2o/g2o/types/se3_ops.hpp', 27, 38, 'Matrix3d skew(const Vector3d&v)'),
+    ('g2o_se3quat_mul.inc', 'Thirdparty/g2o/g2o/types/se3quat.h', 104, 110, 'inline SE3Quat operator* (const SE3Quat& tr2) const{'),
+    ('g2o_se3quat_map.inc', 'Thirdparty/g2o/g2o/types/se3quat.h', 217, 220, 'Vector3d map(const Vector3d & xyz) const'),
+    ('g2o_se3quat_exp.inc', 'Thirdparty/g2o/g2o/types/se3quat.h', 223, 261, 'static SE3Quat exp(const Vector6d & update)'),
+    ('g2o_se3quat_normalize.inc', 'Thirdparty/g2o/g2o/types/se3quat.h', 284, 289, 'void normalizeRotation(){'),
+    ('edge_se3_only_pose.inc', 'src/OptimizableTypes.cpp', 49, 63, 'void EdgeSE3ProjectXYZOnlyPose::linearizeOplus() {'),
+    ('edge_se3_xyz.inc', 'src/OptimizableTypes.cpp', 139, 160, 'void EdgeSE3ProjectXYZ::linearizeOplus() {'),
+    ('g2o_huber.inc', 'Thirdparty/g2o/g2o/core/robust_kernel_impl.cpp', 78, 91, 'void RobustKernelHuber::robustify(double e, Eigen::Vector3d& rho) const'),
+    ('g2o_levenberg_solve.inc', 'Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp', 61, 194, 'OptimizationAlgorithm::SolverResult OptimizationAlgorithmLevenberg::solve(int iteration, bool online)'),
+    ('g2o_sparse_optimizer_optimize.inc', 'Thirdparty/g2o/g2o/core/sparse_optimizer.cpp', 354, 419, 'int SparseOptimizer::optimize(int iterations, bool online)'),
     ('euroc_loaders.inc', 'Examples/Monocular-Inertial/mono_inertial_euroc.cc', 252, 310, 'void LoadImages(const string &strImagePath, const string &strPathTimes,'),
     ('pinhole_project.inc', 'src/CameraModels/Pinhole.cpp', 43, 49, 'Eigen::Vector2f Pinhole::project(const Eigen::Vector3f &v3D)'),
 ]

@@ -34,6 +34,7 @@ template <typename T, int R, int C> struct Matrix {
     T& operator[](int i) { return m[i]; }
     const T& operator[](int i) const { return m[i]; }
     void setZero() { for (int i = 0; i < R * C; ++i) m[i] = 0; }
+    void fill(T v) { for (int i = 0; i < R * C; ++i) m[i] = v; }
     void setIdentity() { *this = Identity(); }
     Matrix<T, C, R> transpose() const { Matrix<T, C, R> r; for (int i = 0; i < R; ++i) for (int j = 0; j < C; ++j) r.m[j * R + i] = m[i * C + j]; return r; }
     template <typename U> Matrix<U, R, C> cast() const { Matrix<U, R, C> r; for (int i = 0; i < R * C; ++i) r.m[i] = (U)m[i]; return r; }
@@ -69,6 +70,58 @@ typedef Matrix<double, 3, 1> Vector3d;
 typedef Matrix<double, 2, 1> Vector2d;
 typedef Matrix<float, 3, 3> Matrix3f;
 typedef Matrix<float, 3, 1> Vector3f;
+
+// Eigen::Quaternion<double>, the operations g2o's SE3Quat uses; algorithms as in Eigen/src/Geometry/Quaternion.h (quaternion from a rotation matrix: Shepperd's
+// branches; v' = v + w t + q x t with t = 2 q x v; Hamilton product; toRotationMatrix)
+struct Coeffs4 { double* p; Coeffs4& operator*=(double s) { for (int i = 0; i < 4; ++i) p[i] *= s; return *this; } };
+struct Quaterniond {
+    double c[4];   // x, y, z, w (Eigen's coefficient order)
+    Quaterniond() : c{0, 0, 0, 1} {}
+    Quaterniond(double w, double x, double y, double z) : c{x, y, z, w} {}
+    explicit Quaterniond(const Matrix<double, 3, 3>& mat) {
+        double t = mat(0, 0) + mat(1, 1) + mat(2, 2);
+        if (t > 0) {
+            t = std::sqrt(t + 1.0);
+            c[3] = 0.5 * t; t = 0.5 / t;
+            c[0] = (mat(2, 1) - mat(1, 2)) * t; c[1] = (mat(0, 2) - mat(2, 0)) * t; c[2] = (mat(1, 0) - mat(0, 1)) * t;
+        } else {
+            int i = 0;
+            if (mat(1, 1) > mat(0, 0)) i = 1;
+            if (mat(2, 2) > mat(i, i)) i = 2;
+            const int j = (i + 1) % 3, k = (j + 1) % 3;
+            t = std::sqrt(mat(i, i) - mat(j, j) - mat(k, k) + 1.0);
+            c[i] = 0.5 * t; t = 0.5 / t;
+            c[3] = (mat(k, j) - mat(j, k)) * t;
+            c[j] = (mat(j, i) + mat(i, j)) * t;
+            c[k] = (mat(k, i) + mat(i, k)) * t;
+        }
+    }
+    double w() const { return c[3]; } double x() const { return c[0]; } double y() const { return c[1]; } double z() const { return c[2]; }
+    Coeffs4 coeffs() { return Coeffs4{c}; }
+    void normalize() { const double n = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2] + c[3] * c[3]); for (double& v : c) v /= n; }
+    Matrix<double, 3, 1> operator*(const Matrix<double, 3, 1>& v) const {
+        Matrix<double, 3, 1> uv, r;
+        uv[0] = c[1] * v[2] - c[2] * v[1]; uv[1] = c[2] * v[0] - c[0] * v[2]; uv[2] = c[0] * v[1] - c[1] * v[0];
+        uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+        r[0] = v[0] + c[3] * uv[0] + (c[1] * uv[2] - c[2] * uv[1]);
+        r[1] = v[1] + c[3] * uv[1] + (c[2] * uv[0] - c[0] * uv[2]);
+        r[2] = v[2] + c[3] * uv[2] + (c[0] * uv[1] - c[1] * uv[0]);
+        return r;
+    }
+    Quaterniond operator*(const Quaterniond& b) const {
+        return Quaterniond(w() * b.w() - x() * b.x() - y() * b.y() - z() * b.z(), w() * b.x() + x() * b.w() + y() * b.z() - z() * b.y(),
+                           w() * b.y() + y() * b.w() + z() * b.x() - x() * b.z(), w() * b.z() + z() * b.w() + x() * b.y() - y() * b.x());
+    }
+    Quaterniond& operator*=(const Quaterniond& b) { *this = *this * b; return *this; }
+    Matrix<double, 3, 3> toRotationMatrix() const {
+        Matrix<double, 3, 3> res;
+        const double tx = 2 * x(), ty = 2 * y(), tz = 2 * z(), twx = tx * w(), twy = ty * w(), twz = tz * w(), txx = tx * x(), txy = ty * x(), txz = tz * x(), tyy = ty * y(), tyz = tz * y(), tzz = tz * z();
+        res(0, 0) = 1 - (tyy + tzz); res(0, 1) = txy - twz; res(0, 2) = txz + twy;
+        res(1, 0) = txy + twz; res(1, 1) = 1 - (txx + tzz); res(1, 2) = tyz - twx;
+        res(2, 0) = txz - twy; res(2, 1) = tyz + twx; res(2, 2) = 1 - (txx + tyy);
+        return res;
+    }
+};
 
 // g2o's per-vertex Jacobian blocks are dynamic-size maps; the bodies only call setZero() and block<3,3>(r, c) = ...
 struct DynJacobian {

@@ -5,6 +5,9 @@
 //   EdgePriorPoseImu::computeError / linearizeOplus                     :731-760
 //   ExpSO3 / LogSO3 / InverseRightJacobianSO3 / RightJacobianSO3 / Skew :777-861
 //   Pinhole::project(Vector3d) / projectJac                             src/CameraModels/Pinhole.cpp:35-41, 71-81
+//   EdgeSE3ProjectXYZOnlyPose / EdgeSE3ProjectXYZ::linearizeOplus       src/OptimizableTypes.cpp:49-63, 139-160
+//   g2o::RobustKernelHuber::robustify                                   Thirdparty/g2o/g2o/core/robust_kernel_impl.cpp:78-91
+//   g2o::SE3Quat::operator* / map / exp / normalizeRotation, skew       Thirdparty/g2o/g2o/types/se3quat.h:104-110, 217-220, 223-261, 284-289, se3_ops.hpp:27-38
 // are cut out of the reference at build time (extract_ranges.py -> oracle/_ref/gen/*.inc) and compiled as they are against mini_eigen.hpp and the
 // class shells below (exactly the members those bodies touch, under the reference's names: include/G2oTypes.h).  What is NOT the reference's code:
 // IMU::Preintegrated::GetDelta* (float; Sophus::SO3f::exp and Eigen::JacobiSVD are unavailable -- they forward to the oracle's restatement) and
@@ -106,7 +109,43 @@ class VertexVelocity : public Vertex3<VertexVelocity> {};
 class VertexGyroBias : public Vertex3<VertexGyroBias> {};
 class VertexAccBias : public Vertex3<VertexAccBias> {};
 }  // namespace ORB_SLAM3
-namespace g2o { class VertexSBAPointXYZ : public ORB_SLAM3::Vertex3<VertexSBAPointXYZ> {}; }
+namespace g2o {
+class VertexSBAPointXYZ : public ORB_SLAM3::Vertex3<VertexSBAPointXYZ> {};
+using Eigen::Matrix3d; using Eigen::Vector3d; using Eigen::Quaterniond; using Eigen::Matrix;
+typedef Eigen::Matrix<double, 6, 1> Vector6d;
+#include "g2o_se3_skew.inc"
+class SE3Quat {                                         // Thirdparty/g2o/g2o/types/se3quat.h: the members the bodies below touch; the bodies are the reference's
+protected:
+    Quaterniond _r;
+    Vector3d _t;
+public:
+    SE3Quat() {}
+    SE3Quat(const Quaterniond& q, const Vector3d& t) : _r(q), _t(t) { normalizeRotation(); }   // :62-64
+    inline const Vector3d& translation() const { return _t; }
+    inline const Quaterniond& rotation() const { return _r; }
+#include "g2o_se3quat_mul.inc"
+#include "g2o_se3quat_map.inc"
+#include "g2o_se3quat_exp.inc"
+#include "g2o_se3quat_normalize.inc"
+};
+class VertexSE3Expmap : public ORB_SLAM3::VertexBase {   // types_six_dof_expmap.h:55-77
+public:
+    SE3Quat _estimate;
+    const SE3Quat& estimate() const { return _estimate; }
+    void setEstimate(const SE3Quat& e) { _estimate = e; }
+    void oplusImpl(const double* update_) {              // :73-76 (Eigen::Map replaced by a copy)
+        Vector6d update; for (int i = 0; i < 6; ++i) update[i] = update_[i];
+        setEstimate(SE3Quat::exp(update) * estimate());
+    }
+};
+class RobustKernelHuber {                               // core/robust_kernel_impl.h:54-67; setDelta as robust_kernel_impl.cpp:70-76
+public:
+    void setDelta(double delta) { dsqr = delta * delta; _delta = delta; }
+    void robustify(double e, Eigen::Vector3d& rho) const;
+    double _delta, dsqr;
+};
+#include "g2o_huber.inc"
+}  // namespace g2o
 namespace ORB_SLAM3 {
 
 class EdgeMono {                                        // include/G2oTypes.h:342-385
@@ -135,6 +174,39 @@ public:
     const int cam_idx;
 };
 #include "g2o_edge_mono.inc"
+
+class EdgeSE3ProjectXYZOnlyPose {                      // include/OptimizableTypes.h:31-57
+public:
+    void computeError() {                               // :41-45 (header-inline in the reference)
+        const g2o::VertexSE3Expmap* v1 = static_cast<const g2o::VertexSE3Expmap*>(_vertices[0]);
+        Eigen::Vector2d obs(_measurement);
+        _error = obs - pCamera->project(v1->estimate().map(Xw));
+    }
+    bool isDepthPositive() { const g2o::VertexSE3Expmap* v1 = static_cast<const g2o::VertexSE3Expmap*>(_vertices[0]); return (v1->estimate().map(Xw))(2) > 0.0; }   // :47-50
+    void linearizeOplus();
+    std::vector<VertexBase*> _vertices;
+    Eigen::Vector2d _measurement, _error;
+    Eigen::Matrix<double, 2, 6> _jacobianOplusXi;
+    Eigen::Vector3d Xw;
+    GeometricCamera* pCamera;
+};
+class EdgeSE3ProjectXYZ {                               // include/OptimizableTypes.h:89-115
+public:
+    void computeError() {                               // :99-104
+        const g2o::VertexSE3Expmap* v1 = static_cast<const g2o::VertexSE3Expmap*>(_vertices[1]);
+        const g2o::VertexSBAPointXYZ* v2 = static_cast<const g2o::VertexSBAPointXYZ*>(_vertices[0]);
+        Eigen::Vector2d obs(_measurement);
+        _error = obs - pCamera->project(v1->estimate().map(v2->estimate()));
+    }
+    void linearizeOplus();
+    std::vector<VertexBase*> _vertices;
+    Eigen::Vector2d _measurement, _error;
+    Eigen::Matrix<double, 2, 3> _jacobianOplusXi;
+    Eigen::Matrix<double, 2, 6> _jacobianOplusXj;
+    GeometricCamera* pCamera;
+};
+#include "edge_se3_only_pose.inc"
+#include "edge_se3_xyz.inc"
 
 class EdgeInertial {                                    // include/G2oTypes.h:488-560
 public:
@@ -254,6 +326,37 @@ void ref_edge_prior(const double* prior21, const double* st21, double* e15, doub
     const int col0[4] = {0, 6, 9, 12};
     for (int i = 0; i < 225; ++i) J225[i] = 0;
     for (int v = 0; v < 4; ++v) for (int r = 0; r < 15; ++r) for (int c = 0; c < e._jacobianOplus[v].cols; ++c) J225[r * 15 + col0[v] + c] = e._jacobianOplus[v](r, c);
+}
+
+// EdgeSE3ProjectXYZ / EdgeSE3ProjectXYZOnlyPose (LocalBundleAdjustment, PoseOptimization): error, Jacobians, depth sign; pose7 = qw qx qy qz tx ty tz
+void ref_lba_edge(const double* pose7, const float* cam4, const double* X3, const double* obs2, double* err2, double* Jpoint, double* Jpose, double* JposeOnly, int* depthPositive) {
+    Pinhole cam; cam.mvParameters.assign(cam4, cam4 + 4);
+    g2o::VertexSE3Expmap VP; Eigen::Vector3d t; set3(t, pose7 + 4);
+    VP._estimate = g2o::SE3Quat(Eigen::Quaterniond(pose7[0], pose7[1], pose7[2], pose7[3]), t);
+    g2o::VertexSBAPointXYZ VX; set3(VX._estimate, X3);
+    EdgeSE3ProjectXYZ e; e.pCamera = &cam; e._vertices = {&VX, &VP}; e._measurement[0] = obs2[0]; e._measurement[1] = obs2[1];
+    e.computeError(); e.linearizeOplus();
+    err2[0] = e._error[0]; err2[1] = e._error[1];
+    for (int i = 0; i < 6; ++i) Jpoint[i] = e._jacobianOplusXi.m[i];
+    for (int i = 0; i < 12; ++i) Jpose[i] = e._jacobianOplusXj.m[i];
+    EdgeSE3ProjectXYZOnlyPose eo; eo.pCamera = &cam; eo._vertices = {&VP}; eo.Xw = VX._estimate; eo._measurement = e._measurement;
+    eo.computeError(); eo.linearizeOplus();
+    for (int i = 0; i < 12; ++i) JposeOnly[i] = eo._jacobianOplusXi.m[i];
+    *depthPositive = eo.isDepthPositive() ? 1 : 0;
+}
+void ref_huber(double delta, double e, double* rho3) {
+    g2o::RobustKernelHuber k; k.setDelta(delta);
+    Eigen::Vector3d rho; k.robustify(e, rho);
+    for (int i = 0; i < 3; ++i) rho3[i] = rho[i];
+}
+// VertexSE3Expmap::oplusImpl = SE3Quat::exp(update) * estimate()
+void ref_lba_pose_oplus(double* pose7, const double* update6) {
+    g2o::VertexSE3Expmap VP; Eigen::Vector3d t; set3(t, pose7 + 4);
+    VP._estimate = g2o::SE3Quat(Eigen::Quaterniond(pose7[0], pose7[1], pose7[2], pose7[3]), t);
+    VP.oplusImpl(update6);
+    const Eigen::Quaterniond& q = VP._estimate.rotation();
+    pose7[0] = q.w(); pose7[1] = q.x(); pose7[2] = q.y(); pose7[3] = q.z();
+    for (int i = 0; i < 3; ++i) pose7[4 + i] = VP._estimate.translation()[i];
 }
 
 }  // extern "C"
