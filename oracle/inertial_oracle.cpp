@@ -359,6 +359,8 @@ void orbo_imu_pose_update(double* Rwb, double* twb, const double* pu) {
     mat3_mul(Rwb, E, Rwb);
 }
 
+void orbo_normalize_rotation_f(const float* R, float* out) { normalize_rotation(R, out); }   // IMU::NormalizeRotation (float), for oracle/ref_shim/ref_wrap_preint.cpp
+
 void orbo_so3(int what, const double* in, double* out) {   // 0 Exp, 1 Log, 2 RightJacobian, 3 InverseRightJacobian, 4 NormalizeRotation
     if (what == 0) exp_so3(in, out, true);
     else if (what == 1) log_so3(in, out);

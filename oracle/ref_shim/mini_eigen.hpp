@@ -17,12 +17,17 @@ template <typename T, int R, int C> struct CommaInit {
     CommaInit& operator,(T v) { m.m[k++] = v; return *this; }
     template <int N> CommaInit& operator,(const Matrix<T, N, 1>& v) { for (int i = 0; i < N; ++i) m.m[k++] = v.m[i]; return *this; }
 };
+template <typename T, int N> struct DiagonalMatrix;
 template <typename M, int BR, int BC> struct BlockRef {
     M& m; int r0, c0;
+    Matrix<typename M::Scalar, BR, BC> eval() const { Matrix<typename M::Scalar, BR, BC> o; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) o(i, j) = m(r0 + i, c0 + j); return o; }
+    template <typename T> BlockRef& operator=(const DiagonalMatrix<T, BR>& d) { for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(r0 + i, c0 + j) = i == j ? d.d[i] : 0; return *this; }
+    template <typename T, int N> BlockRef& operator+=(const DiagonalMatrix<T, N>& d) { for (int i = 0; i < N; ++i) m(r0 + i, c0 + i) += d.d[i]; return *this; }
     template <typename T> BlockRef& operator=(const Matrix<T, BR, BC>& v) { for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(r0 + i, c0 + j) = v(i, j); return *this; }
 };
 
 template <typename T, int R, int C> struct Matrix {
+    typedef T Scalar;
     T m[R * C];   // row-major
     Matrix() { for (int i = 0; i < R * C; ++i) m[i] = 0; }
     static Matrix Identity() { Matrix r; for (int i = 0; i < (R < C ? R : C); ++i) r.m[i * C + i] = 1; return r; }
@@ -44,10 +49,20 @@ template <typename T, int R, int C> struct Matrix {
     CommaInit<T, R, C> operator<<(T v) { m[0] = v; return CommaInit<T, R, C>{*this, 1}; }
     template <int N> CommaInit<T, R, C> operator<<(const Matrix<T, N, 1>& v) { for (int i = 0; i < N; ++i) m[i] = v.m[i]; return CommaInit<T, R, C>{*this, N}; }
     template <int BR, int BC> BlockRef<Matrix, BR, BC> block(int r, int c) { return BlockRef<Matrix, BR, BC>{*this, r, c}; }
+    template <int BR, int BC> Matrix<T, BR, BC> blockCopy(int r, int c) const { Matrix<T, BR, BC> o; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) o.m[i * BC + j] = m[(r + i) * C + c + j]; return o; }
     Matrix& operator+=(const Matrix& o) { for (int i = 0; i < R * C; ++i) m[i] += o.m[i]; return *this; }
     Matrix& operator-=(const Matrix& o) { for (int i = 0; i < R * C; ++i) m[i] -= o.m[i]; return *this; }
 };
 
+template <typename T, int N> struct DiagonalMatrix {
+    T d[N];
+    DiagonalMatrix() { for (int i = 0; i < N; ++i) d[i] = 0; }
+    DiagonalMatrix(T a, T b, T c) { static_assert(N == 3, "three-argument form"); d[0] = a; d[1] = b; d[2] = c; }
+    Matrix<T, N, 1>& diagonal() { return *reinterpret_cast<Matrix<T, N, 1>*>(d); }
+};
+template <typename T, int R, int N> Matrix<T, R, N> operator*(const Matrix<T, R, N>& a, const DiagonalMatrix<T, N>& d) {
+    Matrix<T, R, N> r; for (int i = 0; i < R; ++i) for (int j = 0; j < N; ++j) r.m[i * N + j] = a.m[i * N + j] * d.d[j]; return r;
+}
 template <typename T, int R, int C> Matrix<T, R, C> operator+(const Matrix<T, R, C>& a, const Matrix<T, R, C>& b) { Matrix<T, R, C> r; for (int i = 0; i < R * C; ++i) r.m[i] = a.m[i] + b.m[i]; return r; }
 template <typename T, int R, int C> Matrix<T, R, C> operator-(const Matrix<T, R, C>& a, const Matrix<T, R, C>& b) { Matrix<T, R, C> r; for (int i = 0; i < R * C; ++i) r.m[i] = a.m[i] - b.m[i]; return r; }
 template <typename T, int R, int C> Matrix<T, R, C> operator-(const Matrix<T, R, C>& a) { Matrix<T, R, C> r; for (int i = 0; i < R * C; ++i) r.m[i] = -a.m[i]; return r; }
@@ -56,6 +71,7 @@ template <typename T, int R, int K, int C> Matrix<T, R, C> operator*(const Matri
     for (int i = 0; i < R; ++i) for (int j = 0; j < C; ++j) { T s = 0; for (int k = 0; k < K; ++k) s += a.m[i * K + k] * b.m[k * C + j]; r.m[i * C + j] = s; }
     return r;
 }
+template <typename T, int R, int K, typename M, int C> Matrix<T, R, C> operator*(const Matrix<T, R, K>& a, const BlockRef<M, K, C>& b) { return a * b.eval(); }
 template <typename T, int R, int C, typename U, typename = typename std::enable_if<std::is_arithmetic<U>::value>::type>
 Matrix<T, R, C> operator*(const Matrix<T, R, C>& a, U s) { Matrix<T, R, C> r; for (int i = 0; i < R * C; ++i) r.m[i] = a.m[i] * (T)s; return r; }
 template <typename T, int R, int C, typename U, typename = typename std::enable_if<std::is_arithmetic<U>::value>::type>
@@ -125,6 +141,7 @@ struct Quaterniond {
 
 // g2o's per-vertex Jacobian blocks are dynamic-size maps; the bodies only call setZero() and block<3,3>(r, c) = ...
 struct DynJacobian {
+    typedef double Scalar;
     int rows, cols; double m[15 * 6];
     DynJacobian(int r = 0, int c = 0) : rows(r), cols(c) { for (double& v : m) v = 0; }
     void setZero() { for (double& v : m) v = 0; }

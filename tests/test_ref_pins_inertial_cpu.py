@@ -106,3 +106,31 @@ def test_edge_prior_pose_imu():
         want = np.concatenate([er, Rp.T @ (st[9:12] - prior[9:12]), st[12:15] - prior[12:15], st[15:18] - prior[15:18], st[18:21] - prior[18:21]])
         Jw = np.zeros((15, 15)); Jw[:3, :3] = O.so3('invJr', er); Jw[3:6, 3:6] = Rp.T @ R; Jw[6:, 6:] = np.eye(9)
         assert _close(e, want) and _close(J, Jw)
+
+
+def test_preintegration_equals_the_reference_text():
+    """IMU::Preintegrated::Initialize + IntegrateNewMeasurement (src/ImuTypes.cc:147-166, :177-236) and IntegratedRotation (:84-105), compiled verbatim into
+    oracle/_ref/libref_preint.so (float; NormalizeRotation is the oracle's polar factor on both sides): every field of the 292-float record -- dT, dR, dV, dP,
+    the five bias Jacobians and the 15 x 15 covariance -- of the oracle's preintegration equals it."""
+    so = os.path.join(ROOT, 'oracle', '_ref', 'libref_preint.so')
+    if not os.path.exists(so):
+        pytest.skip('oracle/_ref is not built here')
+    O.lib()
+    L = C.CDLL(so)
+    worst = 0.0
+    for seed in range(10):
+        t0 = 0.3 + 0.9 * seed
+        acc, gyr, dts = synth.imu_interval(t0, t0 + (0.04 if seed % 3 == 0 else 0.25 + 0.05 * seed), seed=seed, noise=seed % 2 == 0)
+        if seed == 7:
+            gyr[:] = np.float32(1e-7)                    # |w| dt below IMU::eps: the first-order branch of IntegratedRotation
+        bias = np.array([0.02, -0.01, 0.03, 0.002, -0.001, 0.0015], np.float32) * np.float32(1 + seed)
+        want = O.imu_preintegrate(acc, gyr, dts, bias, synth.IMU_NOISE)
+        got = np.zeros(292, np.float32)
+        a = [np.ascontiguousarray(x, np.float32) for x in (acc, gyr, dts, bias, np.array(synth.IMU_NOISE, np.float32))]
+        L.ref_imu_preintegrate(len(dts), *[_p(x) for x in a], _p(got))
+        for lo, hi in ((0, 1), (1, 10), (10, 13), (13, 16), (16, 25), (25, 34), (34, 43), (43, 52), (52, 61), (61, 67), (67, 292)):
+            g, w = got[lo:hi].astype(np.float64), want[lo:hi].astype(np.float64)
+            scale = max(np.abs(w).max(), 1e-30)
+            worst = max(worst, np.abs(g - w).max() / scale)
+            assert np.abs(g - w).max() <= 2e-6 * scale, (seed, lo, hi, np.abs(g - w).max(), scale)
+    print('worst relative difference per field group: %.2e' % worst)
