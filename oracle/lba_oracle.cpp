@@ -493,6 +493,60 @@ void orbo_lba_residuals(int nP, const double* poses7, const float* cam4, int nL,
 // (level 1) and can come back; the Huber kernel is removed after the third round (:1040-1041).
 // Returns nInitialCorrespondences - nBad.  pose7 in/out, outlier[N] out.
 // ---------------------------------------------------------------------------------------------------------
+}  // extern "C" (reopened below: the pose-only problem is a struct shared by the solver and its step-by-step form)
+
+namespace orbo {
+struct PoseOpt {
+    int N; const float* cam4; const double *Xw3, *obs2; const float* invSigma2; double delta, dsqr;
+    Pose T, Tbk;
+    std::vector<double> err; std::vector<uint8_t> level, robust;
+    double H[36], b[6], xs[6];      // xs: the solver's x vector keeps its previous content when the factorisation fails
+    void compute_error(int e) {
+        double r[3]; qrot(T.q, Xw3 + 3 * (size_t)e, r);
+        const double X = r[0] + T.t[0], Y = r[1] + T.t[1], Z = r[2] + T.t[2];
+        err[2 * (size_t)e] = obs2[2 * (size_t)e] - ((double)cam4[0] * X / Z + (double)cam4[2]);
+        err[2 * (size_t)e + 1] = obs2[2 * (size_t)e + 1] - ((double)cam4[1] * Y / Z + (double)cam4[3]);
+    }
+    double chi2(int e) const { return (double)invSigma2[e] * (err[2 * (size_t)e] * err[2 * (size_t)e] + err[2 * (size_t)e + 1] * err[2 * (size_t)e + 1]); }
+    void robustify(int e, double e2, double* rho) const {
+        if (!robust[e] || e2 <= dsqr) { rho[0] = e2; rho[1] = 1.; }
+        else { const double s = std::sqrt(e2); rho[0] = 2 * s * delta - dsqr; rho[1] = delta / s; }
+    }
+    void compute_active_errors() { for (int e = 0; e < N; ++e) if (!level[e]) compute_error(e); }
+    double active_chi2() const { double c = 0, rho[2]; for (int e = 0; e < N; ++e) if (!level[e]) { robustify(e, chi2(e), rho); c += rho[0]; } return c; }
+    int n_active() const { int n = 0; for (int e = 0; e < N; ++e) n += !level[e]; return n; }
+    void build() {
+        for (double& v : H) v = 0;
+        for (double& v : b) v = 0;
+        for (int e = 0; e < N; ++e) {
+            if (level[e]) continue;
+            double r[3]; qrot(T.q, Xw3 + 3 * (size_t)e, r);
+            const double x = r[0] + T.t[0], y = r[1] + T.t[1], z = r[2] + T.t[2];
+            double B[12];
+            only_pose_jacobian(cam4, x, y, z, B);
+            double rho[2]; robustify(e, chi2(e), rho);
+            const double w = rho[1] * (double)invSigma2[e];
+            const double r0 = (double)invSigma2[e] * err[2 * (size_t)e], r1 = (double)invSigma2[e] * err[2 * (size_t)e + 1];
+            for (int a = 0; a < 6; ++a) {
+                b[a] -= rho[1] * (B[a] * r0 + B[6 + a] * r1);
+                for (int c = 0; c < 6; ++c) H[a * 6 + c] += w * (B[a] * B[c] + B[6 + a] * B[6 + c]);
+            }
+        }
+    }
+    bool solve(double lambda) {         // LinearSolverDense: Eigen::LDLT + isPositive(); x untouched on failure
+        std::vector<double> A(H, H + 36); for (int a = 0; a < 6; ++a) A[a * 7] += lambda;
+        double x6[6] = {0, 0, 0, 0, 0, 0};
+        bool ok2 = ldlt_solve(A, 6, b, x6);
+        if (ok2) for (int a = 0; a < 6; ++a) if (A[a * 7] < 0) ok2 = false;
+        if (ok2) for (int a = 0; a < 6; ++a) xs[a] = x6[a];
+        return ok2;
+    }
+    void update() { pose_oplus(T, xs); }
+};
+}  // namespace orbo
+
+extern "C" {
+
 int orbo_pose_optimization(double* pose7, const float* cam4, int N, const double* Xw3, const double* obs2, const float* invSigma2,
                            double huberDelta, uint8_t* outlier, double* stats) {
     if (N < 3) {   // if(nInitialCorrespondences<3) return 0; (src/Optimizer.cc:996-997): the frame's pose is not touched
@@ -500,71 +554,39 @@ int orbo_pose_optimization(double* pose7, const float* cam4, int N, const double
         if (stats) stats[0] = 0;
         return 0;
     }
-    Quat q0 = {pose7[0], pose7[1], pose7[2], pose7[3]};
-    Pose T0; T0.q = q0; qnormalize(T0.q); T0.t[0] = pose7[4]; T0.t[1] = pose7[5]; T0.t[2] = pose7[6];
-    Pose T = T0;
-    std::vector<double> err(2 * (size_t)N, 0.0);
-    std::vector<uint8_t> level(N, 0), robust(N, 1);
+    PoseOpt P;
+    P.N = N; P.cam4 = cam4; P.Xw3 = Xw3; P.obs2 = obs2; P.invSigma2 = invSigma2; P.delta = huberDelta; P.dsqr = huberDelta * huberDelta;
+    Pose T0; T0.q = {pose7[0], pose7[1], pose7[2], pose7[3]}; qnormalize(T0.q); T0.t[0] = pose7[4]; T0.t[1] = pose7[5]; T0.t[2] = pose7[6];
+    P.T = T0;
+    P.err.assign(2 * (size_t)N, 0.0); P.level.assign(N, 0); P.robust.assign(N, 1);
+    for (double& v : P.xs) v = 0;
     for (int i = 0; i < N; ++i) outlier[i] = 0;
-    const double dsqr = huberDelta * huberDelta;
-    auto compute_error = [&](int e) {
-        double r[3]; qrot(T.q, Xw3 + 3 * (size_t)e, r);
-        const double X = r[0] + T.t[0], Y = r[1] + T.t[1], Z = r[2] + T.t[2];
-        err[2 * (size_t)e] = obs2[2 * (size_t)e] - ((double)cam4[0] * X / Z + (double)cam4[2]);
-        err[2 * (size_t)e + 1] = obs2[2 * (size_t)e + 1] - ((double)cam4[1] * Y / Z + (double)cam4[3]);
-    };
-    auto chi2 = [&](int e) { return (double)invSigma2[e] * (err[2 * (size_t)e] * err[2 * (size_t)e] + err[2 * (size_t)e + 1] * err[2 * (size_t)e + 1]); };
-    auto robustify = [&](int e, double e2, double* rho) {
-        if (!robust[e] || e2 <= dsqr) { rho[0] = e2; rho[1] = 1.; }
-        else { const double s = std::sqrt(e2); rho[0] = 2 * s * huberDelta - dsqr; rho[1] = huberDelta / s; }
-    };
-    auto active_chi2 = [&]() { double c = 0, rho[2]; for (int e = 0; e < N; ++e) if (!level[e]) { robustify(e, chi2(e), rho); c += rho[0]; } return c; };
     int nBad = 0, totalTrials = 0;
-    double xs[6] = {0, 0, 0, 0, 0, 0};   // the solver's x vector keeps its previous content when the factorisation fails
     for (int round = 0; round < 4; ++round) {
-        T = T0;
-        int nActive = 0;
-        for (int e = 0; e < N; ++e) nActive += !level[e];
+        P.T = T0;
+        const int nActive = P.n_active();
         // optimizer.optimize(10)
         double lambda = -1, ni = 2; int nBadLM = 0; bool ok = true;
         for (int it = 0; it < 10 && ok && nActive > 0; ++it) {
-            for (int e = 0; e < N; ++e) if (!level[e]) compute_error(e);
-            double currentChi = active_chi2(), tempChi = currentChi; const double iniChi = currentChi;
-            double H[36] = {0}, b[6] = {0};
-            for (int e = 0; e < N; ++e) {
-                if (level[e]) continue;
-                double r[3]; qrot(T.q, Xw3 + 3 * (size_t)e, r);
-                const double x = r[0] + T.t[0], y = r[1] + T.t[1], z = r[2] + T.t[2];
-                double B[12];
-                only_pose_jacobian(cam4, x, y, z, B);
-                double rho[2]; robustify(e, chi2(e), rho);
-                const double w = rho[1] * (double)invSigma2[e];
-                const double r0 = (double)invSigma2[e] * err[2 * (size_t)e], r1 = (double)invSigma2[e] * err[2 * (size_t)e + 1];
-                for (int a = 0; a < 6; ++a) {
-                    b[a] -= rho[1] * (B[a] * r0 + B[6 + a] * r1);
-                    for (int c = 0; c < 6; ++c) H[a * 6 + c] += w * (B[a] * B[c] + B[6 + a] * B[6 + c]);
-                }
-            }
-            if (it == 0) { double md = 0; for (int a = 0; a < 6; ++a) md = std::max(md, std::fabs(H[a * 7])); lambda = 1e-5 * md; ni = 2; nBadLM = 0; }
+            P.compute_active_errors();
+            double currentChi = P.active_chi2(), tempChi = currentChi; const double iniChi = currentChi;
+            P.build();
+            if (it == 0) { double md = 0; for (int a = 0; a < 6; ++a) md = std::max(md, std::fabs(P.H[a * 7])); lambda = 1e-5 * md; ni = 2; nBadLM = 0; }
             double rho = 0; int qmax = 0;
             do {
-                const Pose Tbk = T;
-                std::vector<double> A(H, H + 36); for (int a = 0; a < 6; ++a) A[a * 7] += lambda;
-                double x6[6] = {0, 0, 0, 0, 0, 0};
-                bool ok2 = ldlt_solve(A, 6, b, x6);
-                if (ok2) for (int a = 0; a < 6; ++a) if (A[a * 7] < 0) ok2 = false;     // Eigen::LDLT::isPositive()
-                if (ok2) for (int a = 0; a < 6; ++a) xs[a] = x6[a];
-                pose_oplus(T, ok2 ? x6 : xs);
-                for (int e = 0; e < N; ++e) if (!level[e]) compute_error(e);
-                tempChi = active_chi2();
+                P.Tbk = P.T;
+                const bool ok2 = P.solve(lambda);
+                P.update();
+                P.compute_active_errors();
+                tempChi = P.active_chi2();
                 if (!ok2) tempChi = DBL_MAX;
                 rho = currentChi - tempChi;
-                double scale = 0; for (int a = 0; a < 6; ++a) scale += (ok2 ? x6 : xs)[a] * (lambda * (ok2 ? x6 : xs)[a] + b[a]);
+                double scale = 0; for (int a = 0; a < 6; ++a) scale += P.xs[a] * (lambda * P.xs[a] + P.b[a]);
                 scale += 1e-3; rho /= scale;
                 if (rho > 0 && std::isfinite(tempChi)) {
                     double alpha = 1. - std::pow((2 * rho - 1), 3); alpha = std::min(alpha, 2. / 3.);
                     lambda *= std::max(1. / 3., alpha); ni = 2; currentChi = tempChi;
-                } else { lambda *= ni; ni *= 2; T = Tbk; }
+                } else { lambda *= ni; ni *= 2; P.T = P.Tbk; }
                 ++qmax; ++totalTrials;
             } while (rho < 0 && qmax < 10);
             if (qmax == 10 || rho == 0) ok = false;
@@ -572,17 +594,60 @@ int orbo_pose_optimization(double* pose7, const float* cam4, int N, const double
         }
         nBad = 0;
         for (int e = 0; e < N; ++e) {
-            if (outlier[e]) compute_error(e);
-            if ((float)chi2(e) > 5.991f) { outlier[e] = 1; level[e] = 1; ++nBad; }     // const float chi2 = e->chi2(); chi2 > chi2Mono[it] (:1025-1027)
-            else { outlier[e] = 0; level[e] = 0; }
-            if (round == 2) robust[e] = 0;
+            if (outlier[e]) P.compute_error(e);
+            if ((float)P.chi2(e) > 5.991f) { outlier[e] = 1; P.level[e] = 1; ++nBad; }     // const float chi2 = e->chi2(); chi2 > chi2Mono[it] (:1025-1027)
+            else { outlier[e] = 0; P.level[e] = 0; }
+            if (round == 2) P.robust[e] = 0;
         }
         if (N < 10) break;
     }
-    pose7[0] = T.q.w; pose7[1] = T.q.x; pose7[2] = T.q.y; pose7[3] = T.q.z; pose7[4] = T.t[0]; pose7[5] = T.t[1]; pose7[6] = T.t[2];
+    pose7[0] = P.T.q.w; pose7[1] = P.T.q.x; pose7[2] = P.T.q.y; pose7[3] = P.T.q.z; pose7[4] = P.T.t[0]; pose7[5] = P.T.t[1]; pose7[6] = P.T.t[2];
     if (stats) { stats[0] = totalTrials; }
     return N - nBad;
 }
+
+// ---- the pose-only problem opened step by step: OrboLmBackend for g2o's optimize() text + the per-edge operations the four-round loop of
+//      Optimizer::PoseOptimization (src/Optimizer.cc:1005-1104) performs (oracle/ref_shim/ref_wrap_g2o_lm.cpp compiles that loop verbatim) ----
+namespace {
+struct PoseOptOpen { PoseOpt P; std::vector<float> cam, is2; std::vector<double> X, obs; double diag[6]; };
+void ppo_compute_errors(void* p) { ((PoseOptOpen*)p)->P.compute_active_errors(); }
+double ppo_robust_chi2(void* p) { return ((PoseOptOpen*)p)->P.active_chi2(); }
+void ppo_build_system(void* p) { PoseOptOpen* o = (PoseOptOpen*)p; o->P.build(); for (int a = 0; a < 6; ++a) o->diag[a] = o->P.H[a * 7]; }
+int ppo_solve(void* p, double lambda) { return ((PoseOptOpen*)p)->P.solve(lambda) ? 1 : 0; }
+void ppo_update(void* p) { ((PoseOptOpen*)p)->P.update(); }
+void ppo_push(void* p) { PoseOpt& P = ((PoseOptOpen*)p)->P; P.Tbk = P.T; }
+void ppo_pop(void* p) { PoseOpt& P = ((PoseOptOpen*)p)->P; P.T = P.Tbk; }
+int ppo_vector_size(void*) { return 6; }
+const double* ppo_x(void* p) { return ((PoseOptOpen*)p)->P.xs; }
+const double* ppo_b(void* p) { return ((PoseOptOpen*)p)->P.b; }
+int ppo_n_diag(void*) { return 6; }
+const double* ppo_diag(void* p) { return ((PoseOptOpen*)p)->diag; }
+}  // namespace
+void orbo_poseopt_open(const float* cam4, int N, const double* Xw3, const double* obs2, const float* invSigma2, double huberDelta, OrboLmBackend* out) {
+    PoseOptOpen* o = new PoseOptOpen;
+    o->cam.assign(cam4, cam4 + 4); o->is2.assign(invSigma2, invSigma2 + N); o->X.assign(Xw3, Xw3 + 3 * (size_t)N); o->obs.assign(obs2, obs2 + 2 * (size_t)N);
+    PoseOpt& P = o->P;
+    P.N = N; P.cam4 = o->cam.data(); P.Xw3 = o->X.data(); P.obs2 = o->obs.data(); P.invSigma2 = o->is2.data(); P.delta = huberDelta; P.dsqr = huberDelta * huberDelta;
+    P.T.q = {1, 0, 0, 0}; P.T.t[0] = P.T.t[1] = P.T.t[2] = 0;
+    P.err.assign(2 * (size_t)N, 0.0); P.level.assign(N, 0); P.robust.assign(N, 1);
+    for (double& v : P.xs) v = 0;
+    for (double& v : o->diag) v = 0;
+    *out = OrboLmBackend{o, ppo_compute_errors, ppo_robust_chi2, ppo_build_system, ppo_solve, ppo_update, ppo_push, ppo_pop, ppo_vector_size, ppo_x, ppo_b, ppo_n_diag, ppo_diag};
+}
+void orbo_poseopt_set_estimate(void* h, const double* pose7) {      // vSE3->setEstimate(g2o::SE3Quat(q, t)): the constructor normalises
+    PoseOpt& P = ((PoseOptOpen*)h)->P;
+    P.T.q = {pose7[0], pose7[1], pose7[2], pose7[3]}; qnormalize(P.T.q); P.T.t[0] = pose7[4]; P.T.t[1] = pose7[5]; P.T.t[2] = pose7[6];
+}
+void orbo_poseopt_get_estimate(void* h, double* pose7) {
+    const PoseOpt& P = ((PoseOptOpen*)h)->P;
+    pose7[0] = P.T.q.w; pose7[1] = P.T.q.x; pose7[2] = P.T.q.y; pose7[3] = P.T.q.z; pose7[4] = P.T.t[0]; pose7[5] = P.T.t[1]; pose7[6] = P.T.t[2];
+}
+void orbo_poseopt_edge_compute_error(void* h, int e) { ((PoseOptOpen*)h)->P.compute_error(e); }
+double orbo_poseopt_edge_chi2(void* h, int e) { return ((PoseOptOpen*)h)->P.chi2(e); }
+void orbo_poseopt_edge_set_level(void* h, int e, int level) { ((PoseOptOpen*)h)->P.level[e] = (uint8_t)level; }
+void orbo_poseopt_edge_set_robust(void* h, int e, int on) { ((PoseOptOpen*)h)->P.robust[e] = (uint8_t)on; }
+int orbo_poseopt_active(void* h) { return ((PoseOptOpen*)h)->P.n_active(); }
+void orbo_poseopt_close(void* h) { delete (PoseOptOpen*)h; }
 
 }  // extern "C"
 

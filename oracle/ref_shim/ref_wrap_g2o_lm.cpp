@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- g2o's own Levenberg-Marquardt control flow driving the oracle's linear algebra:
 //   OptimizationAlgorithmLevenberg::solve / computeLambdaInit / computeScale      Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-194
 //   SparseOptimizer::optimize                                                     Thirdparty/g2o/g2o/core/sparse_optimizer.cpp:354-419
+//   the four rounds of Optimizer::PoseOptimization                                src/Optimizer.cc:996-1104
 // are cut out of the reference at build time (extract_ranges.py -> oracle/_ref/gen/*.inc) and compiled as they are against the class shells below, which
 // carry the members those bodies touch under g2o's names (optimization_algorithm_levenberg.h, optimization_algorithm_with_hessian.h, sparse_optimizer.h,
 // solver.h, property.h, batch_stats.h).  The shells' Solver and SparseOptimizer operations (buildSystem, solve, update, push / pop, computeActiveErrors,
@@ -127,6 +128,98 @@ public:
 #include "g2o_sparse_optimizer_optimize.inc"
 
 }  // namespace g2o
+
+// ---- Optimizer::PoseOptimization's four rounds (src/Optimizer.cc:996-1104: the early return, the pose reset, optimize(10), the chi2 re-classification with its
+//      stale-error rule, the level / robust-kernel switches, the fewer-than-10-edges exit), compiled verbatim; every object it touches is a shell over the oracle's
+//      pose-only state ----
+extern "C" {
+void orbo_poseopt_open(const float* cam4, int N, const double* Xw3, const double* obs2, const float* invSigma2, double huberDelta, OrboLmBackend* out);
+void orbo_poseopt_set_estimate(void* h, const double* pose7);
+void orbo_poseopt_get_estimate(void* h, double* pose7);
+void orbo_poseopt_edge_compute_error(void* h, int e);
+double orbo_poseopt_edge_chi2(void* h, int e);
+void orbo_poseopt_edge_set_level(void* h, int e, int level);
+void orbo_poseopt_edge_set_robust(void* h, int e, int on);
+int orbo_poseopt_active(void* h);
+void orbo_poseopt_close(void* h);
+}
+namespace Sophus {
+struct Quatd { double w, x, y, z; Quatd cast_double() const { return *this; } };
+struct Vec3d { double v[3]; };
+template <class T> struct Caster { T val; template <class U> T cast() const { return val; } };
+template <typename T> struct SE3 {                     // the frame's float pose: what the loop reads is unit_quaternion().cast<double>() and translation().cast<double>()
+    double p7[7];
+    Caster<Quatd> unit_quaternion() const { return Caster<Quatd>{Quatd{p7[0], p7[1], p7[2], p7[3]}}; }
+    Caster<Vec3d> translation() const { return Caster<Vec3d>{Vec3d{{p7[4], p7[5], p7[6]}}}; }
+};
+}  // namespace Sophus
+namespace g2o {
+struct SE3Quat { double p7[7]; SE3Quat(const Sophus::Quatd& q, const Sophus::Vec3d& t) : p7{q.w, q.x, q.y, q.z, t.v[0], t.v[1], t.v[2]} {} };
+struct VertexSE3Expmap { void* h; void setEstimate(const SE3Quat& e) { orbo_poseopt_set_estimate(h, e.p7); } };
+struct PoseEdgeShell {                                 // computeError / chi2 / setLevel / setRobustKernel of an only-pose edge
+    void* h; int idx;
+    void computeError() { orbo_poseopt_edge_compute_error(h, idx); }
+    double chi2() const { return orbo_poseopt_edge_chi2(h, idx); }
+    void setLevel(int l) { orbo_poseopt_edge_set_level(h, idx, l); }
+    void setRobustKernel(void* k) { orbo_poseopt_edge_set_robust(h, idx, k != nullptr); }
+};
+struct EdgeStereoSE3ProjectXYZOnlyPose : PoseEdgeShell {};
+struct PoseOptimizerShell : SparseOptimizer {          // optimizer.initializeOptimization(0) / optimize(n) / edges()
+    std::vector<int> _edges; void* h = nullptr; std::vector<OptimizableGraph::Vertex> _one;
+    const std::vector<int>& edges() const { return _edges; }
+    void initializeOptimization(int) {                 // the active set = the level-0 edges (kept by the oracle state); no active edge -> no active vertex
+        _ivMap.clear();
+        if (orbo_poseopt_active(h) > 0) for (size_t k = 0; k < _vstore.size(); ++k) _ivMap.push_back(&_vstore[k]);
+    }
+};
+}  // namespace g2o
+namespace ORB_SLAM3 {
+struct EdgeSE3ProjectXYZOnlyPose : g2o::PoseEdgeShell {};
+struct EdgeSE3ProjectXYZOnlyPoseToBody : g2o::PoseEdgeShell {};
+struct Frame {
+    Sophus::SE3<float> mTcw; std::vector<bool> mvbOutlier;
+    Sophus::SE3<float> GetPose() const { return mTcw; }
+};
+static int pose_optimization_rounds(Frame* pFrame, g2o::PoseOptimizerShell& optimizer, g2o::VertexSE3Expmap* vSE3, std::vector<EdgeSE3ProjectXYZOnlyPose*>& vpEdgesMono,
+                                    std::vector<size_t>& vnIndexEdgeMono, int nInitialCorrespondences) {
+    Sophus::SE3<float> Tcw = pFrame->GetPose();
+    std::vector<EdgeSE3ProjectXYZOnlyPoseToBody*> vpEdgesMono_FHR; std::vector<size_t> vnIndexEdgeRight;          // no right-camera / stereo observations (monocular frame)
+    std::vector<g2o::EdgeStereoSE3ProjectXYZOnlyPose*> vpEdgesStereo; std::vector<size_t> vnIndexEdgeStereo;
+#include "optimizer_pose_optimization_rounds.inc"
+    return nInitialCorrespondences - nBad;             // :1112
+}
+}  // namespace ORB_SLAM3
+
+extern "C" {
+// int Optimizer::PoseOptimization(Frame*) with the reference's own four-round loop + g2o's optimize() / Levenberg text over the oracle's pose-only state.
+// pose7 in/out (double, as the oracle's), outlier [N] out; returns nInitialCorrespondences - nBad.
+int ref_pose_optimization(double* pose7, const float* cam4, int N, const double* Xw3, const double* obs2, const float* invSigma2, double huberDelta, unsigned char* outlier) {
+    using namespace g2o;
+    OrboLmBackend be;
+    orbo_poseopt_open(cam4, N, Xw3, obs2, invSigma2, huberDelta, &be);
+    PoseOptimizerShell opt; opt.be = &be; opt.h = be.self;
+    Solver solver; solver.be = &be; solver._optimizer = &opt;
+    OptimizationAlgorithmLevenberg alg(&solver);
+    alg._optimizer = &opt;
+    opt._algorithm = &alg;
+    opt._vstore.assign(6, OptimizableGraph::Vertex{1, nullptr});
+    opt._edges.assign((size_t)N, 0);
+    ORB_SLAM3::Frame frame;
+    for (int i = 0; i < 7; ++i) frame.mTcw.p7[i] = pose7[i];
+    frame.mvbOutlier.assign((size_t)N, false);
+    VertexSE3Expmap vSE3{be.self};
+    std::vector<ORB_SLAM3::EdgeSE3ProjectXYZOnlyPose> store((size_t)N);
+    std::vector<ORB_SLAM3::EdgeSE3ProjectXYZOnlyPose*> edges; std::vector<size_t> index;
+    for (int i = 0; i < N; ++i) { store[i].h = be.self; store[i].idx = i; edges.push_back(&store[i]); index.push_back((size_t)i); }
+    int ret;
+    if (N < 3) ret = 0;                                 // (the early return is inside the extracted text too; the state set-up above is harmless)
+    else ret = ORB_SLAM3::pose_optimization_rounds(&frame, opt, &vSE3, edges, index, N);
+    if (N >= 3) orbo_poseopt_get_estimate(be.self, pose7);
+    for (int i = 0; i < N; ++i) outlier[i] = frame.mvbOutlier[i] ? 1 : 0;
+    orbo_poseopt_close(be.self);
+    return ret;
+}
+}
 
 extern "C" {
 // optimizer.optimize(iterations) with g2o's own text on the oracle state `be`.  stats [4]: final lambda, total Levenberg trials, last result of solve(), -.

@@ -96,3 +96,23 @@ def test_local_inertial_ba_loop():
         assert not want['failed']
         assert it == want['iters'] and int(stats[1]) == want['trials'] and stats[0] == want['lam'], (kw, it, want['iters'], stats, want['trials'], want['lam'])
         assert st.tobytes() == want['state'].tobytes() and pts.tobytes() == want['points'].tobytes()
+
+
+def test_pose_optimization_four_rounds():
+    """Optimizer::PoseOptimization: the reference's own four-round loop (src/Optimizer.cc:996-1104) + g2o's optimize() / Levenberg text over the oracle's
+    pose-only state == the oracle's orbo_pose_optimization: same return value, outlier flags and pose bit for bit (many outliers, few points, < 10 edges, < 3 edges)."""
+    L = C.CDLL(SO)
+    O.lib()
+    L.ref_pose_optimization.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    cases = [dict(n=300, seed=4), dict(n=700, seed=1, outlier_frac=0.35), dict(n=40, seed=2, outlier_frac=0.3), dict(n=9, seed=3, outlier_frac=0.0), dict(n=2, seed=5, outlier_frac=0.0),
+             dict(n=200, seed=6, pose_noise=(0.3, 10.0)), dict(n=12, seed=7, outlier_frac=0.6)]
+    for kw in cases:
+        fr = synth.pose_opt_problem(**kw)
+        want = O.pose_optimization(fr)
+        pose = np.ascontiguousarray(fr['pose'], np.float64).copy()
+        cam = np.ascontiguousarray(fr['cam'], np.float32); X = np.ascontiguousarray(fr['Xw'], np.float64); ob = np.ascontiguousarray(fr['obs'], np.float64)
+        isg = np.ascontiguousarray(fr['inv_sigma2'], np.float32)
+        out = np.zeros(len(X), np.uint8)
+        ret = L.ref_pose_optimization(_p(pose), _p(cam), len(X), _p(X), _p(ob), _p(isg), float(np.float32(np.sqrt(5.991))), _p(out))
+        assert ret == want['inliers'] and np.array_equal(out, want['outlier']), (kw, ret, want['inliers'])
+        assert pose.tobytes() == np.ascontiguousarray(want['pose'], np.float64).tobytes(), (kw, np.abs(pose - want['pose']).max())
