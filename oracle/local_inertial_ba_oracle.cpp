@@ -484,6 +484,15 @@ void orbo_liba_backend_open(int nKF, int nOpt, const double* kfState21, const do
     L.W.assign(18 * (size_t)nE, 0.0); L.x.assign(n + 3 * (size_t)nL, 0.0); L.Dinv.assign(9 * (size_t)nL, 0.0);
     *out = OrboLmBackend{o, lio_compute_errors, lio_robust_chi2, lio_build_system, lio_solve, lio_update, lio_push, lio_pop, lio_vector_size, lio_x, lio_b, lio_n_diag, lio_diag};
 }
+// per-edge accessors for the post-optimisation text of Optimizer::LocalInertialBA (src/Optimizer.cc:2840-2895), which oracle/ref_shim/ref_wrap_g2o_lm.cpp compiles verbatim
+double orbo_liba_edge_chi2(void* h, int e) { return ((LibaOpen*)h)->L.chi2_mono(e); }
+int orbo_liba_edge_depth_positive(void* h, int e) {
+    const Problem& L = ((LibaOpen*)h)->L;
+    const KF& k = L.kf[L.eKf[e]];
+    const double* X = &L.pts[3 * (size_t)L.ePt[e]];
+    return (k.Rcw[6] * X[0] + k.Rcw[7] * X[1] + k.Rcw[8] * X[2] + k.tcw[2]) > 0.0;
+}
+int orbo_liba_edge_point(void* h, int e) { return ((LibaOpen*)h)->L.ePt[e]; }
 void orbo_liba_backend_close(OrboLmBackend* be, double* kfStateOut21, double* pointsOut3) {
     LibaOpen* o = (LibaOpen*)be->self; Problem& L = o->L;
     for (int k = 0; k < L.nKF; ++k) {

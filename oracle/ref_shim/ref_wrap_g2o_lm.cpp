@@ -2,6 +2,7 @@
 //   OptimizationAlgorithmLevenberg::solve / computeLambdaInit / computeScale      Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-194
 //   SparseOptimizer::optimize                                                     Thirdparty/g2o/g2o/core/sparse_optimizer.cpp:354-419
 //   the four rounds of Optimizer::PoseOptimization                                src/Optimizer.cc:996-1104
+//   Optimizer::LocalInertialBA from initializeOptimization() to the FAIL test     src/Optimizer.cc:2840-2895
 // are cut out of the reference at build time (extract_ranges.py -> oracle/_ref/gen/*.inc) and compiled as they are against the class shells below, which
 // carry the members those bodies touch under g2o's names (optimization_algorithm_levenberg.h, optimization_algorithm_with_hessian.h, sparse_optimizer.h,
 // solver.h, property.h, batch_stats.h).  The shells' Solver and SparseOptimizer operations (buildSystem, solve, update, push / pop, computeActiveErrors,
@@ -12,6 +13,8 @@
 #include <cmath>
 #include <iostream>
 #include <limits>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../oracle_common.h"
@@ -218,6 +221,69 @@ int ref_pose_optimization(double* pose7, const float* cam4, int N, const double*
     for (int i = 0; i < N; ++i) outlier[i] = frame.mvbOutlier[i] ? 1 : 0;
     orbo_poseopt_close(be.self);
     return ret;
+}
+}
+
+// ---- Optimizer::LocalInertialBA between the graph set-up and the write-back (src/Optimizer.cc:2840-2895): initializeOptimization, err, optimize(opt_it), err_end, the
+//      chi2 / depth test that fills vToErase, the FAIL test -- compiled verbatim over shells of the optimizer, the edges and the map points ----
+extern "C" {
+double orbo_liba_edge_chi2(void* h, int e);
+int orbo_liba_edge_depth_positive(void* h, int e);
+}
+namespace ORB_SLAM3 {
+struct KeyFrame { int idx; };
+struct MapPoint { float mTrackDepth; bool isBad() { return false; } };
+struct Map { std::mutex mMutexMapUpdate; };
+struct EdgeMono { void* h; int idx; double chi2() const { return orbo_liba_edge_chi2(h, idx); } bool isDepthPositive() { return orbo_liba_edge_depth_positive(h, idx) != 0; } };
+struct EdgeStereo { double chi2() const { return 0; } };
+struct LibaOptimizerShell : g2o::SparseOptimizer {
+    void initializeOptimization() {}
+    void setForceStopFlag(bool* f) { _forceStopFlag = f; }
+};
+// `failed` is true on entry and cleared after the text: its `return;` (the FAIL branch) leaves it set
+static void local_inertial_ba_tail(LibaOptimizerShell& optimizer, int opt_it, bool* pbStopFlag, Map* pMap, bool bLarge, std::vector<EdgeMono*>& vpEdgesMono,
+                                   std::vector<MapPoint*>& vpMapPointEdgeMono, std::vector<KeyFrame*>& vpEdgeKFMono, std::vector<std::pair<KeyFrame*, MapPoint*> >& erased,
+                                   float* errOut, bool* failed) {
+    using namespace std;
+    const float chi2Mono2 = 5.991;                     // :2688
+    const float chi2Stereo2 = 7.815;                   // :2690
+    std::vector<EdgeStereo*> vpEdgesStereo; std::vector<MapPoint*> vpMapPointEdgeStereo; std::vector<KeyFrame*> vpEdgeKFStereo;
+    // the text's err / err_end / vToErase are handed out where it takes the map mutex (:2887), i.e. after the inlier check and before the FAIL test
+#define unique_lock errOut[0] = err; errOut[1] = err_end; erased = vToErase; unique_lock
+#include "optimizer_local_inertial_ba_tail.inc"
+#undef unique_lock
+    *failed = false;
+}
+}  // namespace ORB_SLAM3
+
+extern "C" {
+// stats [4]: err, err_end, failed, iterations-not-reported (the reference does not keep optimize()'s return value here); erase [nE]
+void ref_local_inertial_ba_tail(const OrboLmBackend* be, int nE, const int* edgePoint, const float* trackDepth, int nL, int opt_it, double userLambdaInit, int bLarge,
+                                unsigned char* erase, double* stats) {
+    using namespace g2o;
+    ORB_SLAM3::LibaOptimizerShell opt; opt.be = be;
+    Solver solver; solver.be = be; solver._optimizer = &opt;
+    OptimizationAlgorithmLevenberg alg(&solver);
+    alg._optimizer = &opt;
+    alg._userLambdaInit->setValue(userLambdaInit);
+    opt._algorithm = &alg;
+    be->build_system(be->self);
+    const int nd = be->n_diag(be->self);
+    opt._vstore.assign((size_t)nd, OptimizableGraph::Vertex{1, nullptr});
+    for (int k = 0; k < nd; ++k) opt._ivMap.push_back(&opt._vstore[k]);
+    std::vector<ORB_SLAM3::MapPoint> pts((size_t)nL);
+    for (int i = 0; i < nL; ++i) pts[i].mTrackDepth = trackDepth[i];
+    std::vector<ORB_SLAM3::EdgeMono> es((size_t)nE); std::vector<ORB_SLAM3::KeyFrame> kfs((size_t)nE);
+    std::vector<ORB_SLAM3::EdgeMono*> vpEdgesMono; std::vector<ORB_SLAM3::MapPoint*> vpMP; std::vector<ORB_SLAM3::KeyFrame*> vpKF;
+    for (int e = 0; e < nE; ++e) { es[e].h = be->self; es[e].idx = e; kfs[e].idx = e; vpEdgesMono.push_back(&es[e]); vpMP.push_back(&pts[edgePoint[e]]); vpKF.push_back(&kfs[e]); }
+    ORB_SLAM3::Map map;
+    std::vector<std::pair<ORB_SLAM3::KeyFrame*, ORB_SLAM3::MapPoint*> > erased;
+    float err2[2] = {0, 0};
+    bool failed = true;
+    ORB_SLAM3::local_inertial_ba_tail(opt, opt_it, nullptr, &map, bLarge != 0, vpEdgesMono, vpMP, vpKF, erased, err2, &failed);
+    for (int e = 0; e < nE; ++e) erase[e] = 0;
+    for (const auto& pr : erased) erase[pr.first->idx] = 1;      // the shell keyframe of edge e carries e
+    stats[0] = err2[0]; stats[1] = err2[1]; stats[2] = failed ? 1 : 0; stats[3] = alg._currentLambda;
 }
 }
 

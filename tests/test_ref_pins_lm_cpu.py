@@ -116,3 +116,41 @@ def test_pose_optimization_four_rounds():
         ret = L.ref_pose_optimization(_p(pose), _p(cam), len(X), _p(X), _p(ob), _p(isg), float(np.float32(np.sqrt(5.991))), _p(out))
         assert ret == want['inliers'] and np.array_equal(out, want['outlier']), (kw, ret, want['inliers'])
         assert pose.tobytes() == np.ascontiguousarray(want['pose'], np.float64).tobytes(), (kw, np.abs(pose - want['pose']).max())
+
+
+def test_local_inertial_ba_from_initialize_to_the_fail_test():
+    """Optimizer::LocalInertialBA's own text from optimizer.initializeOptimization() to the FAIL test (src/Optimizer.cc:2840-2895: err, optimize(opt_it), err_end, the chi2 /
+    depth test that fills vToErase, 2*err < err_end) over the oracle's state == orbo_local_inertial_ba: err, err_end, failed, erase flags, lambda."""
+    Lo = O.lib(); L = C.CDLL(SO)
+    L.ref_local_inertial_ba_tail.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    cases = [dict(n_opt=6, n_cov_fixed=2, n_pts=250, seed=21), dict(n_opt=10, n_cov_fixed=3, n_pts=400, seed=1), dict(n_opt=8, n_cov_fixed=1, n_pts=300, seed=3, large=True),
+             dict(n_opt=4, n_cov_fixed=1, n_pts=120, seed=33, nan_obs=True)]
+    seen_fail = False
+    for kw in cases:
+        nan_obs = kw.pop('nan_obs', False)
+        pr = synth.local_inertial_ba_problem(**kw)
+        if nan_obs:
+            pr['obs'][5, 0] = np.nan                     # isnan(err): the FAIL branch (:2891) -- an LM run itself never ends above twice its start
+        P = O.liba_preints(pr)
+        want = O.local_inertial_ba(pr, P)
+        c = lambda a, dt: np.ascontiguousarray(a, dt)
+        a = dict(st=c(pr['state'], np.float64), tc=c(pr['tcw'], np.float64), cam=c(pr['cam'], np.float32), ex=c(pr['extr'], np.float64), k1=c(pr['ie_kf1'], np.int32),
+                 k2=c(pr['ie_kf2'], np.int32), P=c(P, np.float32), rob=c(pr['ie_robust'], np.uint8), sc=c(pr['ie_info_scale'], np.float64), pts=c(pr['points'], np.float64),
+                 ep=c(pr['e_pt'], np.int32), ek=c(pr['e_kf'], np.int32), obs=c(pr['obs'], np.float64), isg=c(pr['inv_sigma2'], np.float32), td=c(pr['track_depth'], np.float32))
+        be = Backend()
+        Lo.orbo_liba_backend_open.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p]
+        Lo.orbo_liba_backend_open(pr['n_kf'], pr['n_opt'], _p(a['st']), _p(a['tc']), _p(a['cam']), _p(a['ex']), len(a['k1']), _p(a['k1']), _p(a['k2']), _p(a['P']), _p(a['rob']),
+                                  _p(a['sc']), len(a['pts']), _p(a['pts']), len(a['ep']), _p(a['ep']), _p(a['ek']), _p(a['obs']), _p(a['isg']), C.byref(be))
+        erase = np.zeros(len(a['ep']), np.uint8); stats = np.zeros(4)
+        L.ref_local_inertial_ba_tail(C.byref(be), len(a['ep']), _p(a['ep']), _p(a['td']), len(a['pts']), pr['iterations'], float(pr['lambda_init']), int(pr['large']), _p(erase), _p(stats))
+        st = np.zeros_like(a['st']); pts = np.zeros_like(a['pts'])
+        Lo.orbo_liba_backend_close.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        Lo.orbo_liba_backend_close(C.byref(be), _p(st), _p(pts))
+        same = lambda x, y: (x == y) or (np.isnan(x) and np.isnan(y))
+        assert same(stats[0], want['err']) and same(stats[1], want['err_end']) and bool(stats[2]) == want['failed'] and same(stats[3], want['lam']), (kw, stats, want['err'], want['err_end'], want['failed'])
+        seen_fail |= want['failed']
+        if not want['failed']:
+            assert np.array_equal(erase, want['erase']) and st.tobytes() == want['state'].tobytes()
+        else:                                                # the oracle hands the inputs back and clears the flags on FAIL; the text computed its vToErase before returning
+            assert np.array_equal(want['state'], pr['state']) and want['erase'].sum() == 0
+    assert seen_fail
