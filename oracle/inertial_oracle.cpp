@@ -395,64 +395,95 @@ static bool ldlt_solve(int n, const double* A, const double* b, double* x) {   /
     for (int i = n - 1; i >= 0; --i) { double v = y[i] / d[i]; for (int k = i + 1; k < n; ++k) v -= L[k * n + i] * x[k]; x[i] = v; }
     return true;
 }
+// the problem as a state with the operations g2o performs on it (shared by the solver below and by its step-by-step form, OrboLmBackend)
+struct PoseInertialKF {
+    int N; const float *invSigma2, *trackDepth, *cam4, *P; const double *Rcb, *tcb, *Rbc, *tbc;
+    const double *Rwbk, *twbk, *vk, *bgk, *bak;
+    double *Rwb, *twb, *v, *bg, *ba;
+    double Info9[81], InfoG[9], InfoA[9], delta, dsqr;
+    std::vector<double> Xd, od, err;
+    std::vector<uint8_t> level, robust;
+    int its = 0;                                                            // ImuCamPose::its
+    double x[15], H[225], b[15];
+    void edge_error(int i, double* e2, int* dpos) const { orbo_imu_edge_mono(Rwb, twb, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, nullptr, nullptr, dpos); }
+    void compute_error(int i) { edge_error(i, &err[2 * i], nullptr); }
+    double chi2(int i) const { return (double)invSigma2[i] * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]); }
+    void build() {                                                          // computeActiveErrors + buildSystem
+        for (double& q : H) q = 0;
+        for (double& q : b) q = 0;
+        for (int i = 0; i < N; ++i) {
+            if (level[i]) continue;
+            double Jpt[6], Jp[12];
+            orbo_imu_edge_mono(Rwb, twb, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], &err[2 * i], Jpt, Jp, nullptr);
+            const double om = (double)invSigma2[i];
+            const double c2 = om * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]);
+            double w = 1.0;
+            if (robust[i] && c2 > dsqr) w = delta / std::sqrt(c2);
+            for (int a = 0; a < 6; ++a) {
+                b[a] -= w * om * (Jp[a] * err[2 * i] + Jp[6 + a] * err[2 * i + 1]);
+                for (int c = 0; c < 6; ++c) H[a * 15 + c] += w * om * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c]);
+            }
+        }
+        {   // EdgeInertial: only the Jacobians of the frame's pose (columns 15..20) and velocity (21..23) count, the keyframe is fixed
+            double e9[9], J[216], Jc[81], OJ[81];
+            orbo_imu_edge_inertial(P, Rwbk, twbk, vk, bgk, bak, Rwb, twb, v, e9, J);
+            for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) Jc[r * 9 + c] = J[r * 24 + 15 + c];
+            for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) { double s = 0; for (int k = 0; k < 9; ++k) s += Info9[r * 9 + k] * Jc[k * 9 + c]; OJ[r * 9 + c] = s; }
+            for (int a = 0; a < 9; ++a) {
+                double s = 0;
+                for (int r = 0; r < 9; ++r) s += OJ[r * 9 + a] * e9[r];            // J^T Omega e (Omega symmetric)
+                b[a] -= s;
+                for (int c = 0; c < 9; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += Jc[r * 9 + a] * OJ[r * 9 + c]; H[a * 15 + c] += h; }
+            }
+        }
+        for (int a = 0; a < 3; ++a) {                                   // EdgeGyroRW / EdgeAccRW: error = b2 - b1, Jacobian of the free vertex = I
+            double sg = 0, sa = 0;
+            for (int c = 0; c < 3; ++c) { sg += InfoG[a * 3 + c] * (bg[c] - bgk[c]); sa += InfoA[a * 3 + c] * (ba[c] - bak[c]); H[(9 + a) * 15 + 9 + c] += InfoG[a * 3 + c]; H[(12 + a) * 15 + 12 + c] += InfoA[a * 3 + c]; }
+            b[9 + a] -= sg; b[12 + a] -= sa;
+        }
+    }
+    bool solve() { return ldlt_solve(15, H, b, x); }                    // a failed solve leaves x from the previous iteration, update() still runs
+    void update() {
+        orbo_imu_pose_update(Rwb, twb, x);
+        // `NormalizeRotation(Rwb);` every third update (src/G2oTypes.cc:202-208) has no effect: the function (include/G2oTypes.h:67-71) returns the
+        // normalised matrix and the call discards it
+        if (++its >= 3) its = 0;
+        for (int k = 0; k < 3; ++k) { v[k] += x[6 + k]; bg[k] += x[9 + k]; ba[k] += x[12 + k]; }
+    }
+    void init(int N_, const float* Xw, const float* obs, const float* invSigma2_, const float* trackDepth_, const float* cam4_, const double* extr24, const float* P_,
+              const double* kfState15, double* state15) {
+        N = N_; invSigma2 = invSigma2_; trackDepth = trackDepth_; cam4 = cam4_; P = P_;
+        Rcb = extr24; tcb = extr24 + 9; Rbc = extr24 + 12; tbc = extr24 + 21;
+        Rwb = state15; twb = state15 + 9; v = state15 + 12; bg = state15 + 15; ba = state15 + 18;
+        Rwbk = kfState15; twbk = kfState15 + 9; vk = kfState15 + 12; bgk = kfState15 + 15; bak = kfState15 + 18;
+        orbo_imu_information(P, Info9, InfoG, InfoA);
+        delta = (double)sqrtf(5.991f); dsqr = delta * delta;            // const float thHuberMono = sqrt(5.991); rk->setDelta(thHuberMono)
+        Xd.resize(3 * (size_t)N); od.resize(2 * (size_t)N); err.assign(2 * (size_t)N, 0.0);
+        for (int i = 0; i < 3 * N; ++i) Xd[i] = (double)Xw[i];
+        for (int i = 0; i < 2 * N; ++i) od[i] = (double)obs[i];
+        level.assign(N, 0); robust.assign(N, 1);
+        its = 0;
+        for (double& q : x) q = 0;
+    }
+};
 // `rounds` x `iters`: 4 x 10 in the reference; the tests also run a single Gauss-Newton step
 int orbo_pose_inertial_opt_last_kf_n(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24,
                                      const float* P, const double* kfState15, double* state15, int bRecInit, uint8_t* outlier, double* H15, int rounds, int iters) {
-    const double *Rcb = extr24, *tcb = extr24 + 9, *Rbc = extr24 + 12, *tbc = extr24 + 21;
-    double *Rwb = state15, *twb = state15 + 9, *v = state15 + 12, *bg = state15 + 15, *ba = state15 + 18;
-    const double *Rwbk = kfState15, *twbk = kfState15 + 9, *vk = kfState15 + 12, *bgk = kfState15 + 15, *bak = kfState15 + 18;
-    double Info9[81], InfoG[9], InfoA[9];
-    orbo_imu_information(P, Info9, InfoG, InfoA);
-    const double delta = (double)sqrtf(5.991f), dsqr = delta * delta;      // const float thHuberMono = sqrt(5.991); rk->setDelta(thHuberMono)
-    std::vector<double> Xd(3 * (size_t)N), od(2 * (size_t)N), err(2 * (size_t)N, 0.0);
-    for (int i = 0; i < 3 * N; ++i) Xd[i] = (double)Xw[i];
-    for (int i = 0; i < 2 * N; ++i) od[i] = (double)obs[i];
-    std::vector<uint8_t> level(N, 0);
+    PoseInertialKF S;
+    S.init(N, Xw, obs, invSigma2, trackDepth, cam4, extr24, P, kfState15, state15);
+    const double *Rcb = S.Rcb, *tcb = S.tcb, *Rbc = S.Rbc, *tbc = S.tbc;
+    double *Rwb = S.Rwb, *twb = S.twb, *v = S.v;
+    const double *Rwbk = S.Rwbk, *twbk = S.twbk, *vk = S.vk, *bgk = S.bgk, *bak = S.bak;
+    const double *Info9 = S.Info9, *InfoG = S.InfoG, *InfoA = S.InfoA;
+    const std::vector<double>&Xd = S.Xd, &od = S.od;
     for (int i = 0; i < N; ++i) outlier[i] = 0;
-    bool robust = true;
-    int its = 0;                                                            // ImuCamPose::its
-    double x[15] = {0};
     const float chi2Mono[4] = {12, 7.5, 5.991, 5.991};
     int nBad = 0, nInliers = 0;
     for (int it = 0; it < rounds; ++it) {
-        for (int iter = 0; iter < iters; ++iter) {
-            double H[225] = {0}, b[15] = {0};
-            for (int i = 0; i < N; ++i) {
-                if (level[i]) continue;
-                double Jpt[6], Jp[12];
-                orbo_imu_edge_mono(Rwb, twb, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], &err[2 * i], Jpt, Jp, nullptr);
-                const double om = (double)invSigma2[i];
-                const double c2 = om * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]);
-                double w = 1.0;
-                if (robust && c2 > dsqr) w = delta / std::sqrt(c2);
-                for (int a = 0; a < 6; ++a) {
-                    b[a] -= w * om * (Jp[a] * err[2 * i] + Jp[6 + a] * err[2 * i + 1]);
-                    for (int c = 0; c < 6; ++c) H[a * 15 + c] += w * om * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c]);
-                }
-            }
-            {   // EdgeInertial: only the Jacobians of the frame's pose (columns 15..20) and velocity (21..23) count, the keyframe is fixed
-                double e9[9], J[216], Jc[81], OJ[81];
-                orbo_imu_edge_inertial(P, Rwbk, twbk, vk, bgk, bak, Rwb, twb, v, e9, J);
-                for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) Jc[r * 9 + c] = J[r * 24 + 15 + c];
-                for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) { double s = 0; for (int k = 0; k < 9; ++k) s += Info9[r * 9 + k] * Jc[k * 9 + c]; OJ[r * 9 + c] = s; }
-                for (int a = 0; a < 9; ++a) {
-                    double s = 0;
-                    for (int r = 0; r < 9; ++r) s += OJ[r * 9 + a] * e9[r];            // J^T Omega e (Omega symmetric)
-                    b[a] -= s;
-                    for (int c = 0; c < 9; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += Jc[r * 9 + a] * OJ[r * 9 + c]; H[a * 15 + c] += h; }
-                }
-            }
-            for (int a = 0; a < 3; ++a) {                                   // EdgeGyroRW / EdgeAccRW: error = b2 - b1, Jacobian of the free vertex = I
-                double sg = 0, sa = 0;
-                for (int c = 0; c < 3; ++c) { sg += InfoG[a * 3 + c] * (bg[c] - bgk[c]); sa += InfoA[a * 3 + c] * (ba[c] - bak[c]); H[(9 + a) * 15 + 9 + c] += InfoG[a * 3 + c]; H[(12 + a) * 15 + 12 + c] += InfoA[a * 3 + c]; }
-                b[9 + a] -= sg; b[12 + a] -= sa;
-            }
-            const bool ok = ldlt_solve(15, H, b, x);                        // a failed solve leaves x from the previous iteration, update() still runs
-            orbo_imu_pose_update(Rwb, twb, x);
-            // `NormalizeRotation(Rwb);` every third update (src/G2oTypes.cc:202-208) has no effect: the function (include/G2oTypes.h:67-71) returns the
-            // normalised matrix and the call discards it
-            if (++its >= 3) its = 0;
-            for (int k = 0; k < 3; ++k) { v[k] += x[6 + k]; bg[k] += x[9 + k]; ba[k] += x[12 + k]; }
+        for (int iter = 0; iter < iters; ++iter) {                          // optimizer.optimize(its[it]) with OptimizationAlgorithmGaussNewton
+            S.build();
+            const bool ok = S.solve();
+            S.update();
             if (!ok) break;
         }
         int nBadMono = 0, nInliersMono = 0;
@@ -460,14 +491,14 @@ int orbo_pose_inertial_opt_last_kf_n(int N, const float* Xw, const float* obs, c
         for (int i = 0; i < N; ++i) {
             int dpos = 0;
             double e2[2];
-            orbo_imu_edge_mono(Rwb, twb, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, nullptr, nullptr, &dpos);
-            if (outlier[i]) { err[2 * i] = e2[0]; err[2 * i + 1] = e2[1]; }     // e->computeError() only for the outliers; the others keep their last active error
-            const float chi2 = (float)((double)invSigma2[i] * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]));
+            S.edge_error(i, e2, &dpos);
+            if (outlier[i]) { S.err[2 * i] = e2[0]; S.err[2 * i + 1] = e2[1]; }     // e->computeError() only for the outliers; the others keep their last active error
+            const float chi2 = (float)S.chi2(i);
             const bool bClose = trackDepth[i] < 10.f;
-            if ((chi2 > chi2Mono[it] && !bClose) || (bClose && chi2 > chi2close) || !dpos) { outlier[i] = 1; level[i] = 1; ++nBadMono; }
-            else { outlier[i] = 0; level[i] = 0; ++nInliersMono; }
+            if ((chi2 > chi2Mono[it] && !bClose) || (bClose && chi2 > chi2close) || !dpos) { outlier[i] = 1; S.level[i] = 1; ++nBadMono; }
+            else { outlier[i] = 0; S.level[i] = 0; ++nInliersMono; }
+            if (it == 2) S.robust[i] = 0;
         }
-        if (it == 2) robust = false;
         nInliers = nInliersMono; nBad = nBadMono;
         if (N + 3 < 10) break;                                              // optimizer.edges().size() < 10
     }
@@ -475,8 +506,8 @@ int orbo_pose_inertial_opt_last_kf_n(int N, const float* Xw, const float* obs, c
         nBad = 0;
         for (int i = 0; i < N; ++i) {
             double e2[2];
-            orbo_imu_edge_mono(Rwb, twb, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, nullptr, nullptr, nullptr);
-            err[2 * i] = e2[0]; err[2 * i + 1] = e2[1];
+            S.edge_error(i, e2, nullptr);
+            S.err[2 * i] = e2[0]; S.err[2 * i + 1] = e2[1];
             if ((double)invSigma2[i] * (e2[0] * e2[0] + e2[1] * e2[1]) < (double)18.f) outlier[i] = 0; else ++nBad;
         }
     }
@@ -501,6 +532,38 @@ int orbo_pose_inertial_opt_last_kf_n(int N, const float* Xw, const float* obs, c
     }
     return N - nBad;
 }
+// ---- the last-keyframe problem opened step by step: OrboLmBackend for g2o's Gauss-Newton / optimize() text + the per-edge operations the four rounds of
+//      Optimizer::PoseInertialOptimizationLastKeyFrame (src/Optimizer.cc:4698-4823) perform (oracle/ref_shim/ref_wrap_g2o_lm.cpp compiles that text verbatim) ----
+namespace {
+struct PiKfOpen { PoseInertialKF S; std::vector<float> Xw, obs, is2, td, cam, P; std::vector<double> extr, kf, st; double diag[15]; };
+void pik_compute_errors(void* p) { PoseInertialKF& S = ((PiKfOpen*)p)->S; for (int i = 0; i < S.N; ++i) if (!S.level[i]) S.compute_error(i); }
+double pik_robust_chi2(void*) { return 0.0; }                             // Gauss-Newton does not look at the cost
+void pik_build_system(void* p) { PiKfOpen* o = (PiKfOpen*)p; o->S.build(); for (int a = 0; a < 15; ++a) o->diag[a] = o->S.H[a * 16]; }
+int pik_solve(void* p, double) { return ((PiKfOpen*)p)->S.solve() ? 1 : 0; }
+void pik_update(void* p) { ((PiKfOpen*)p)->S.update(); }
+void pik_nop(void*) {}
+int pik_vector_size(void*) { return 15; }
+const double* pik_x(void* p) { return ((PiKfOpen*)p)->S.x; }
+const double* pik_b(void* p) { return ((PiKfOpen*)p)->S.b; }
+int pik_n_diag(void*) { return 15; }
+const double* pik_diag(void* p) { return ((PiKfOpen*)p)->diag; }
+}  // namespace
+void orbo_pikf_open(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24, const float* P,
+                    const double* kfState15, const double* state15, OrboLmBackend* out) {
+    PiKfOpen* o = new PiKfOpen;
+    o->Xw.assign(Xw, Xw + 3 * (size_t)N); o->obs.assign(obs, obs + 2 * (size_t)N); o->is2.assign(invSigma2, invSigma2 + N); o->td.assign(trackDepth, trackDepth + N);
+    o->cam.assign(cam4, cam4 + 4); o->P.assign(P, P + P_SIZE); o->extr.assign(extr24, extr24 + 24); o->kf.assign(kfState15, kfState15 + 21); o->st.assign(state15, state15 + 21);
+    o->S.init(N, o->Xw.data(), o->obs.data(), o->is2.data(), o->td.data(), o->cam.data(), o->extr.data(), o->P.data(), o->kf.data(), o->st.data());
+    for (double& d : o->diag) d = 0;
+    *out = OrboLmBackend{o, pik_compute_errors, pik_robust_chi2, pik_build_system, pik_solve, pik_update, pik_nop, pik_nop, pik_vector_size, pik_x, pik_b, pik_n_diag, pik_diag};
+}
+void orbo_pikf_edge_compute_error(void* h, int e) { ((PiKfOpen*)h)->S.compute_error(e); }
+double orbo_pikf_edge_chi2(void* h, int e) { return ((PiKfOpen*)h)->S.chi2(e); }
+int orbo_pikf_edge_depth_positive(void* h, int e) { double e2[2]; int d = 0; ((PiKfOpen*)h)->S.edge_error(e, e2, &d); return d; }
+void orbo_pikf_edge_set_level(void* h, int e, int level) { ((PiKfOpen*)h)->S.level[e] = (uint8_t)level; }
+void orbo_pikf_edge_set_robust(void* h, int e, int on) { ((PiKfOpen*)h)->S.robust[e] = (uint8_t)on; }
+void orbo_pikf_close(void* h, double* stateOut21) { PiKfOpen* o = (PiKfOpen*)h; for (int i = 0; i < 21; ++i) stateOut21[i] = o->st[i]; delete o; }
+
 int orbo_pose_inertial_opt_last_kf(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24,
                                    const float* P, const double* kfState15, double* state15, int bRecInit, uint8_t* outlier, double* H15) {
     return orbo_pose_inertial_opt_last_kf_n(N, Xw, obs, invSigma2, trackDepth, cam4, extr24, P, kfState15, state15, bRecInit, outlier, H15, 4, 10);

@@ -3,6 +3,8 @@
 //   SparseOptimizer::optimize                                                     Thirdparty/g2o/g2o/core/sparse_optimizer.cpp:354-419
 //   the four rounds of Optimizer::PoseOptimization                                src/Optimizer.cc:996-1104
 //   Optimizer::LocalInertialBA from initializeOptimization() to the FAIL test     src/Optimizer.cc:2840-2895
+//   OptimizationAlgorithmGaussNewton::solve                                       Thirdparty/g2o/g2o/core/optimization_algorithm_gauss_newton.cpp:50-93
+//   the four rounds + recovery of Optimizer::PoseInertialOptimizationLastKeyFrame  src/Optimizer.cc:4698-4823
 // are cut out of the reference at build time (extract_ranges.py -> oracle/_ref/gen/*.inc) and compiled as they are against the class shells below, which
 // carry the members those bodies touch under g2o's names (optimization_algorithm_levenberg.h, optimization_algorithm_with_hessian.h, sparse_optimizer.h,
 // solver.h, property.h, batch_stats.h).  The shells' Solver and SparseOptimizer operations (buildSystem, solve, update, push / pop, computeActiveErrors,
@@ -117,7 +119,7 @@ public:
     }
     bool verbose() const { return false; }
     void preIteration(int) {}
-    void postIteration(int) { static_cast<OptimizationAlgorithmLevenberg*>(_algorithm)->totalTrials += static_cast<OptimizationAlgorithmLevenberg*>(_algorithm)->_levenbergIterations; }
+    void postIteration(int);
     void computeActiveErrors() { be->compute_errors(be->self); }
     double activeRobustChi2() const { return be->robust_chi2(be->self); }
     void push() { be->push(be->self); }
@@ -127,7 +129,20 @@ public:
     int optimize(int iterations, bool online = false);
 };
 
+class OptimizationAlgorithmGaussNewton : public OptimizationAlgorithm {   // optimization_algorithm_gauss_newton.h
+public:
+    explicit OptimizationAlgorithmGaussNewton(Solver* solver) : _solver(solver) {}
+    bool init(bool = false) { return true; }
+    SolverResult solve(int iteration, bool online = false);
+    Solver* _solver;
+};
+
+inline void SparseOptimizer::postIteration(int) {
+    if (OptimizationAlgorithmLevenberg* lm = dynamic_cast<OptimizationAlgorithmLevenberg*>(_algorithm)) lm->totalTrials += lm->_levenbergIterations;
+}
+
 #include "g2o_levenberg_solve.inc"
+#include "g2o_gauss_newton_solve.inc"
 #include "g2o_sparse_optimizer_optimize.inc"
 
 }  // namespace g2o
@@ -284,6 +299,68 @@ void ref_local_inertial_ba_tail(const OrboLmBackend* be, int nE, const int* edge
     for (int e = 0; e < nE; ++e) erase[e] = 0;
     for (const auto& pr : erased) erase[pr.first->idx] = 1;      // the shell keyframe of edge e carries e
     stats[0] = err2[0]; stats[1] = err2[1]; stats[2] = failed ? 1 : 0; stats[3] = alg._currentLambda;
+}
+}
+
+// ---- Optimizer::PoseInertialOptimizationLastKeyFrame's four rounds + the recovery of not-too-bad points (src/Optimizer.cc:4698-4823), compiled verbatim; the optimizer
+//      runs g2o's Gauss-Newton text (optimization_algorithm_gauss_newton.cpp:50-93) ----
+extern "C" {
+void orbo_pikf_open(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24, const float* P,
+                    const double* kfState15, const double* state15, OrboLmBackend* out);
+void orbo_pikf_edge_compute_error(void* h, int e);
+double orbo_pikf_edge_chi2(void* h, int e);
+int orbo_pikf_edge_depth_positive(void* h, int e);
+void orbo_pikf_edge_set_level(void* h, int e, int level);
+void orbo_pikf_edge_set_robust(void* h, int e, int on);
+void orbo_pikf_close(void* h, double* stateOut21);
+}
+namespace ORB_SLAM3 {
+struct EdgeMonoOnlyPose {
+    void* h; int idx;
+    void computeError() { orbo_pikf_edge_compute_error(h, idx); }
+    double chi2() const { return orbo_pikf_edge_chi2(h, idx); }
+    bool isDepthPositive() { return orbo_pikf_edge_depth_positive(h, idx) != 0; }
+    void setLevel(int l) { orbo_pikf_edge_set_level(h, idx, l); }
+    void setRobustKernel(void* k) { orbo_pikf_edge_set_robust(h, idx, k != nullptr); }
+};
+struct EdgeStereoOnlyPose { void computeError() {} double chi2() const { return 0; } void setLevel(int) {} void setRobustKernel(void*) {} };
+struct InertialFrame { std::vector<bool> mvbOutlier; std::vector<MapPoint*> mvpMapPoints; };
+struct InertialOptimizerShell : g2o::SparseOptimizer {
+    std::vector<int> _edges;
+    const std::vector<int>& edges() const { return _edges; }
+    void initializeOptimization(int) {}
+};
+static int pose_inertial_kf_rounds(InertialFrame* pFrame, InertialOptimizerShell& optimizer, std::vector<EdgeMonoOnlyPose*>& vpEdgesMono, std::vector<size_t>& vnIndexEdgeMono, bool bRecInit) {
+    std::vector<EdgeStereoOnlyPose*> vpEdgesStereo; std::vector<size_t> vnIndexEdgeStereo;
+#include "optimizer_pose_inertial_kf_rounds.inc"
+    return nBad;
+}
+}  // namespace ORB_SLAM3
+
+extern "C" {
+// int Optimizer::PoseInertialOptimizationLastKeyFrame(Frame*, bool bRecInit) up to the recovery of the state: returns nInitialCorrespondences - nBad; state21 in/out, outlier [N] out
+int ref_pose_inertial_opt_last_kf(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24, const float* P,
+                                  const double* kfState21, double* state21, int bRecInit, unsigned char* outlier) {
+    using namespace g2o;
+    OrboLmBackend be;
+    orbo_pikf_open(N, Xw, obs, invSigma2, trackDepth, cam4, extr24, P, kfState21, state21, &be);
+    ORB_SLAM3::InertialOptimizerShell opt; opt.be = &be;
+    Solver solver; solver.be = &be; solver._optimizer = &opt;
+    OptimizationAlgorithmGaussNewton alg(&solver);
+    alg._optimizer = &opt;
+    opt._algorithm = &alg;
+    opt._vstore.assign(15, OptimizableGraph::Vertex{1, nullptr});
+    for (int k = 0; k < 15; ++k) opt._ivMap.push_back(&opt._vstore[k]);
+    opt._edges.assign((size_t)N + 3, 0);                 // the mono edges + EdgeInertial + EdgeGyroRW + EdgeAccRW
+    ORB_SLAM3::InertialFrame frame; frame.mvbOutlier.assign((size_t)N, false);
+    std::vector<ORB_SLAM3::MapPoint> mps((size_t)N);
+    std::vector<ORB_SLAM3::EdgeMonoOnlyPose> store((size_t)N);
+    std::vector<ORB_SLAM3::EdgeMonoOnlyPose*> edges; std::vector<size_t> index;
+    for (int i = 0; i < N; ++i) { mps[i].mTrackDepth = trackDepth[i]; frame.mvpMapPoints.push_back(&mps[i]); store[i].h = be.self; store[i].idx = i; edges.push_back(&store[i]); index.push_back((size_t)i); }
+    const int nBad = ORB_SLAM3::pose_inertial_kf_rounds(&frame, opt, edges, index, bRecInit != 0);
+    for (int i = 0; i < N; ++i) outlier[i] = frame.mvbOutlier[i] ? 1 : 0;
+    orbo_pikf_close(be.self, state21);
+    return N - nBad;
 }
 }
 

@@ -154,3 +154,25 @@ def test_local_inertial_ba_from_initialize_to_the_fail_test():
         else:                                                # the oracle hands the inputs back and clears the flags on FAIL; the text computed its vToErase before returning
             assert np.array_equal(want['state'], pr['state']) and want['erase'].sum() == 0
     assert seen_fail
+
+
+def test_pose_inertial_optimization_last_keyframe_rounds():
+    """Optimizer::PoseInertialOptimizationLastKeyFrame: the reference's own four rounds + recovery of not-too-bad points (src/Optimizer.cc:4698-4823) with g2o's
+    Gauss-Newton / optimize() text over the oracle's state == orbo_pose_inertial_opt_last_kf: return value, outlier flags and the frame's state bit for bit
+    (outliers, few points incl. fewer than 10 edges and the < 30 inliers recovery, bRecInit)."""
+    L = C.CDLL(SO)
+    L.ref_pose_inertial_opt_last_kf.argtypes = [C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_void_p]
+    cases = [dict(seed=0, n=300, outlier_frac=0.1), dict(seed=1, n=700, outlier_frac=0.2), dict(seed=2, n=40, outlier_frac=0.3), dict(seed=3, n=5, outlier_frac=0.0),
+             dict(seed=5, n=1000, outlier_frac=0.05, perturb=2.0), dict(seed=6, n=25, outlier_frac=0.4)]
+    for kw in cases:
+        pr = synth.pose_inertial_problem(**kw)
+        P = O.imu_preintegrate(pr['acc'], pr['gyr'], pr['dt'], pr['bias6'], synth.IMU_NOISE)
+        for rec in (False, True):
+            want = O.pose_inertial_opt_last_kf(pr, P, rec_init=rec)
+            c = lambda a, dt: np.ascontiguousarray(a, dt)
+            a = [c(pr['Xw'], np.float32), c(pr['obs'], np.float32), c(pr['inv_sigma2'], np.float32), c(pr['track_depth'], np.float32), c(pr['cam'], np.float32), c(pr['extr'], np.float64),
+                 c(P, np.float32), c(pr['kf_state'], np.float64)]
+            st = c(pr['state'], np.float64).copy(); out = np.zeros(len(a[0]), np.uint8)
+            ret = L.ref_pose_inertial_opt_last_kf(len(a[0]), *[_p(x) for x in a], _p(st), int(rec), _p(out))
+            assert ret == want['ret'] and np.array_equal(out, want['outlier']), (kw, rec, ret, want['ret'])
+            assert st.tobytes() == want['state'].tobytes(), (kw, rec, np.abs(st - want['state']).max())
