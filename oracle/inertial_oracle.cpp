@@ -621,97 +621,128 @@ static void prior_edge(const double* prior21, const double* st21, double* e15, d
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { J225[i * 15 + j] = iJ[i * 3 + j]; J225[(3 + i) * 15 + 3 + j] = dR[i * 3 + j]; }
     for (int i = 6; i < 15; ++i) J225[i * 15 + i] = 1.0;
 }
+// the problem as a state with the operations g2o performs on it (shared by the solver below and by its step-by-step form, OrboLmBackend); unknowns: current 15 | previous 15
+struct PoseInertialLF {
+    int N; const float *invSigma2, *trackDepth, *cam4, *Pframe; const double *Rcb, *tcb, *Rbc, *tbc, *prior21, *priorH;
+    double* S[2];                                    // current, previous
+    double Info9[81], InfoG[9], InfoA[9], delta, dsqr;
+    std::vector<double> Xd, od, err, H;
+    std::vector<uint8_t> level, robust;
+    int its[2];
+    double x[30], b[30];
+    static int xi(int c) { return c < 15 ? 15 + c : c - 15; }   // column of x for column c of the EdgeInertial Jacobian (vertex order: previous pose, v, bg, ba, current pose, v)
+    void inertial(double* e9, double* J) const { orbo_imu_edge_inertial(Pframe, S[1], S[1] + 9, S[1] + 12, S[1] + 15, S[1] + 18, S[0], S[0] + 9, S[0] + 12, e9, J); }
+    void edge_error(int i, double* e2, int* dpos) const { orbo_imu_edge_mono(S[0], S[0] + 9, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, nullptr, nullptr, dpos); }
+    void compute_error(int i) { edge_error(i, &err[2 * i], nullptr); }
+    double chi2(int i) const { return (double)invSigma2[i] * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]); }
+    void build() {
+        std::fill(H.begin(), H.end(), 0.0);
+        for (double& q : b) q = 0;
+        for (int i = 0; i < N; ++i) {
+            if (level[i]) continue;
+            double Jpt[6], Jp[12];
+            orbo_imu_edge_mono(S[0], S[0] + 9, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], &err[2 * i], Jpt, Jp, nullptr);
+            const double om = (double)invSigma2[i];
+            const double c2 = om * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]);
+            const double w = (robust[i] && c2 > dsqr) ? delta / std::sqrt(c2) : 1.0;
+            for (int a = 0; a < 6; ++a) {
+                b[a] -= w * om * (Jp[a] * err[2 * i] + Jp[6 + a] * err[2 * i + 1]);
+                for (int c = 0; c < 6; ++c) H[a * 30 + c] += w * om * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c]);
+            }
+        }
+        {
+            double e9[9], J[216], OJ[216];
+            inertial(e9, J);
+            for (int r = 0; r < 9; ++r) for (int c = 0; c < 24; ++c) { double a = 0; for (int k = 0; k < 9; ++k) a += Info9[r * 9 + k] * J[k * 24 + c]; OJ[r * 24 + c] = a; }
+            for (int a = 0; a < 24; ++a) {
+                double g = 0;
+                for (int r = 0; r < 9; ++r) g += OJ[r * 24 + a] * e9[r];
+                b[xi(a)] -= g;
+                for (int c = 0; c < 24; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += J[r * 24 + a] * OJ[r * 24 + c]; H[xi(a) * 30 + xi(c)] += h; }
+            }
+        }
+        for (int a = 0; a < 3; ++a) {           // EdgeGyroRW (VGk, VG), EdgeAccRW (VAk, VA): error = b_cur - b_prev, Jacobians -I / +I
+            double sg = 0, sa = 0;
+            for (int c = 0; c < 3; ++c) {
+                const double og = InfoG[a * 3 + c], oa = InfoA[a * 3 + c];
+                sg += og * (S[0][15 + c] - S[1][15 + c]); sa += oa * (S[0][18 + c] - S[1][18 + c]);
+                H[(9 + a) * 30 + 9 + c] += og; H[(24 + a) * 30 + 24 + c] += og; H[(9 + a) * 30 + 24 + c] -= og; H[(24 + a) * 30 + 9 + c] -= og;
+                H[(12 + a) * 30 + 12 + c] += oa; H[(27 + a) * 30 + 27 + c] += oa; H[(12 + a) * 30 + 27 + c] -= oa; H[(27 + a) * 30 + 12 + c] -= oa;
+            }
+            b[9 + a] -= sg; b[24 + a] += sg; b[12 + a] -= sa; b[27 + a] += sa;
+        }
+        {   // EdgePriorPoseImu on the previous frame, Huber delta 5
+            double e15[15], J[225], OJ[225], Oe[15];
+            prior_edge(prior21, S[1], e15, J);
+            double c2 = 0;
+            for (int r = 0; r < 15; ++r) { double a = 0; for (int k = 0; k < 15; ++k) a += priorH[r * 15 + k] * e15[k]; Oe[r] = a; c2 += e15[r] * a; }
+            const double w = c2 > 25.0 ? 5.0 / std::sqrt(c2) : 1.0;
+            for (int r = 0; r < 15; ++r) for (int c = 0; c < 15; ++c) { double a = 0; for (int k = 0; k < 15; ++k) a += priorH[r * 15 + k] * J[k * 15 + c]; OJ[r * 15 + c] = a; }
+            for (int a = 0; a < 15; ++a) {
+                double g = 0;
+                for (int r = 0; r < 15; ++r) g += J[r * 15 + a] * Oe[r];
+                b[15 + a] -= w * g;
+                for (int c = 0; c < 15; ++c) { double h = 0; for (int r = 0; r < 15; ++r) h += J[r * 15 + a] * OJ[r * 15 + c]; H[(15 + a) * 30 + 15 + c] += w * h; }
+            }
+        }
+    }
+    bool solve() { return ldlt_solve(30, H.data(), b, x); }
+    void update() {
+        for (int k = 0; k < 2; ++k) {
+            const double* dx = x + 15 * k;
+            orbo_imu_pose_update(S[k], S[k] + 9, dx);
+            if (++its[k] >= 3) its[k] = 0;      // the reference's NormalizeRotation(Rwb) call discards its result (see the last-keyframe variant)
+            for (int q = 0; q < 3; ++q) { S[k][12 + q] += dx[6 + q]; S[k][15 + q] += dx[9 + q]; S[k][18 + q] += dx[12 + q]; }
+        }
+    }
+    void init(int N_, const float* Xw, const float* obs, const float* invSigma2_, const float* trackDepth_, const float* cam4_, const double* extr24, const float* Pframe_,
+              const float* Pkf, const double* prior21_, const double* priorH_, double* prevState21, double* state21) {
+        N = N_; invSigma2 = invSigma2_; trackDepth = trackDepth_; cam4 = cam4_; Pframe = Pframe_; prior21 = prior21_; priorH = priorH_;
+        Rcb = extr24; tcb = extr24 + 9; Rbc = extr24 + 12; tbc = extr24 + 21;
+        S[0] = state21; S[1] = prevState21;
+        double tmpI[81];
+        orbo_imu_information(Pframe, Info9, tmpI, tmpI);
+        orbo_imu_information(Pkf, tmpI, InfoG, InfoA);
+        delta = (double)sqrtf(5.991f); dsqr = delta * delta;
+        Xd.resize(3 * (size_t)N); od.resize(2 * (size_t)N); err.assign(2 * (size_t)N, 0.0); H.assign(900, 0.0);
+        for (int i = 0; i < 3 * N; ++i) Xd[i] = (double)Xw[i];
+        for (int i = 0; i < 2 * N; ++i) od[i] = (double)obs[i];
+        level.assign(N, 0); robust.assign(N, 1);
+        its[0] = its[1] = 0;
+        for (double& q : x) q = 0;
+    }
+};
 int orbo_pose_inertial_opt_last_frame_n(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24,
                                         const float* Pframe, const float* Pkf, const double* prior21, const double* priorH, double* prevState21, double* state21,
                                         int bRecInit, uint8_t* outlier, double* H15, int rounds, int iters) {
-    const double *Rcb = extr24, *tcb = extr24 + 9, *Rbc = extr24 + 12, *tbc = extr24 + 21;
-    double* S[2] = {state21, prevState21};          // current, previous
-    double Info9[81], InfoG[9], InfoA[9], tmpI[81];
-    orbo_imu_information(Pframe, Info9, tmpI, tmpI);
-    orbo_imu_information(Pkf, tmpI, InfoG, InfoA);
-    const double delta = (double)sqrtf(5.991f), dsqr = delta * delta;
-    std::vector<double> Xd(3 * (size_t)N), od(2 * (size_t)N), err(2 * (size_t)N, 0.0);
-    for (int i = 0; i < 3 * N; ++i) Xd[i] = (double)Xw[i];
-    for (int i = 0; i < 2 * N; ++i) od[i] = (double)obs[i];
+    PoseInertialLF Q;
+    Q.init(N, Xw, obs, invSigma2, trackDepth, cam4, extr24, Pframe, Pkf, prior21, priorH, prevState21, state21);
+    const double *Rcb = Q.Rcb, *tcb = Q.tcb, *Rbc = Q.Rbc, *tbc = Q.tbc;
+    double** S = Q.S;
+    const double *Info9 = Q.Info9, *InfoG = Q.InfoG, *InfoA = Q.InfoA;
+    const std::vector<double>&Xd = Q.Xd, &od = Q.od;
+    auto inertial = [&](double* e9, double* J) { Q.inertial(e9, J); };
     for (int i = 0; i < N; ++i) outlier[i] = 0;
-    bool robust = true;
-    int its[2] = {0, 0};
-    double x[30] = {0};
     const float chi2Mono[4] = {5.991, 5.991, 5.991, 5.991};
     int nBad = 0, nInliers = 0;
-    // column of x for column c of the EdgeInertial Jacobian (vertex order: previous pose, v, bg, ba, current pose, v)
-    auto xi = [](int c) { return c < 15 ? 15 + c : c - 15; };
-    auto inertial = [&](double* e9, double* J) { orbo_imu_edge_inertial(Pframe, S[1], S[1] + 9, S[1] + 12, S[1] + 15, S[1] + 18, S[0], S[0] + 9, S[0] + 12, e9, J); };
     for (int it = 0; it < rounds; ++it) {
         for (int iter = 0; iter < iters; ++iter) {
-            std::vector<double> H(900, 0.0); double b[30] = {0};
-            for (int i = 0; i < N; ++i) {
-                if (outlier[i]) continue;
-                double Jpt[6], Jp[12];
-                orbo_imu_edge_mono(S[0], S[0] + 9, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], &err[2 * i], Jpt, Jp, nullptr);
-                const double om = (double)invSigma2[i];
-                const double c2 = om * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]);
-                const double w = (robust && c2 > dsqr) ? delta / std::sqrt(c2) : 1.0;
-                for (int a = 0; a < 6; ++a) {
-                    b[a] -= w * om * (Jp[a] * err[2 * i] + Jp[6 + a] * err[2 * i + 1]);
-                    for (int c = 0; c < 6; ++c) H[a * 30 + c] += w * om * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c]);
-                }
-            }
-            {
-                double e9[9], J[216], OJ[216];
-                inertial(e9, J);
-                for (int r = 0; r < 9; ++r) for (int c = 0; c < 24; ++c) { double a = 0; for (int k = 0; k < 9; ++k) a += Info9[r * 9 + k] * J[k * 24 + c]; OJ[r * 24 + c] = a; }
-                for (int a = 0; a < 24; ++a) {
-                    double g = 0;
-                    for (int r = 0; r < 9; ++r) g += OJ[r * 24 + a] * e9[r];
-                    b[xi(a)] -= g;
-                    for (int c = 0; c < 24; ++c) { double h = 0; for (int r = 0; r < 9; ++r) h += J[r * 24 + a] * OJ[r * 24 + c]; H[xi(a) * 30 + xi(c)] += h; }
-                }
-            }
-            for (int a = 0; a < 3; ++a) {           // EdgeGyroRW (VGk, VG), EdgeAccRW (VAk, VA): error = b_cur - b_prev, Jacobians -I / +I
-                double sg = 0, sa = 0;
-                for (int c = 0; c < 3; ++c) {
-                    const double og = InfoG[a * 3 + c], oa = InfoA[a * 3 + c];
-                    sg += og * (S[0][15 + c] - S[1][15 + c]); sa += oa * (S[0][18 + c] - S[1][18 + c]);
-                    H[(9 + a) * 30 + 9 + c] += og; H[(24 + a) * 30 + 24 + c] += og; H[(9 + a) * 30 + 24 + c] -= og; H[(24 + a) * 30 + 9 + c] -= og;
-                    H[(12 + a) * 30 + 12 + c] += oa; H[(27 + a) * 30 + 27 + c] += oa; H[(12 + a) * 30 + 27 + c] -= oa; H[(27 + a) * 30 + 12 + c] -= oa;
-                }
-                b[9 + a] -= sg; b[24 + a] += sg; b[12 + a] -= sa; b[27 + a] += sa;
-            }
-            {   // EdgePriorPoseImu on the previous frame, Huber delta 5
-                double e15[15], J[225], OJ[225], Oe[15];
-                prior_edge(prior21, S[1], e15, J);
-                double c2 = 0;
-                for (int r = 0; r < 15; ++r) { double a = 0; for (int k = 0; k < 15; ++k) a += priorH[r * 15 + k] * e15[k]; Oe[r] = a; c2 += e15[r] * a; }
-                const double w = c2 > 25.0 ? 5.0 / std::sqrt(c2) : 1.0;
-                for (int r = 0; r < 15; ++r) for (int c = 0; c < 15; ++c) { double a = 0; for (int k = 0; k < 15; ++k) a += priorH[r * 15 + k] * J[k * 15 + c]; OJ[r * 15 + c] = a; }
-                for (int a = 0; a < 15; ++a) {
-                    double g = 0;
-                    for (int r = 0; r < 15; ++r) g += J[r * 15 + a] * Oe[r];
-                    b[15 + a] -= w * g;
-                    for (int c = 0; c < 15; ++c) { double h = 0; for (int r = 0; r < 15; ++r) h += J[r * 15 + a] * OJ[r * 15 + c]; H[(15 + a) * 30 + 15 + c] += w * h; }
-                }
-            }
-            const bool ok = ldlt_solve(30, H.data(), b, x);
-            for (int k = 0; k < 2; ++k) {
-                const double* dx = x + 15 * k;
-                orbo_imu_pose_update(S[k], S[k] + 9, dx);
-                if (++its[k] >= 3) its[k] = 0;      // the reference's NormalizeRotation(Rwb) call discards its result (see the last-keyframe variant)
-                for (int q = 0; q < 3; ++q) { S[k][12 + q] += dx[6 + q]; S[k][15 + q] += dx[9 + q]; S[k][18 + q] += dx[12 + q]; }
-            }
+            Q.build();
+            const bool ok = Q.solve();
+            Q.update();
             if (!ok) break;
         }
         int nBadMono = 0, nInliersMono = 0;
         const float chi2close = 1.5 * chi2Mono[it];
         for (int i = 0; i < N; ++i) {
             int dpos = 0; double e2[2];
-            orbo_imu_edge_mono(S[0], S[0] + 9, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, nullptr, nullptr, &dpos);
-            if (outlier[i]) { err[2 * i] = e2[0]; err[2 * i + 1] = e2[1]; }
-            const float chi2 = (float)((double)invSigma2[i] * (err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1]));
+            Q.edge_error(i, e2, &dpos);
+            if (outlier[i]) { Q.err[2 * i] = e2[0]; Q.err[2 * i + 1] = e2[1]; }
+            const float chi2 = (float)Q.chi2(i);
             const bool bClose = trackDepth[i] < 10.f;
-            if ((chi2 > chi2Mono[it] && !bClose) || (bClose && chi2 > chi2close) || !dpos) { outlier[i] = 1; ++nBadMono; } else { outlier[i] = 0; ++nInliersMono; }
+            if ((chi2 > chi2Mono[it] && !bClose) || (bClose && chi2 > chi2close) || !dpos) { outlier[i] = 1; Q.level[i] = 1; ++nBadMono; } else { outlier[i] = 0; Q.level[i] = 0; ++nInliersMono; }
+            if (it == 2) Q.robust[i] = 0;
         }
-        if (it == 2) robust = false;
         nInliers = nInliersMono; nBad = nBadMono;
         if (N + 4 < 10) break;                                              // optimizer.edges().size() < 10 (N mono + inertial + 2 random walk + prior)
     }
@@ -719,7 +750,7 @@ int orbo_pose_inertial_opt_last_frame_n(int N, const float* Xw, const float* obs
         nBad = 0;
         for (int i = 0; i < N; ++i) {
             double e2[2];
-            orbo_imu_edge_mono(S[0], S[0] + 9, Rcb, tcb, Rbc, tbc, cam4, &Xd[3 * i], &od[2 * i], e2, nullptr, nullptr, nullptr);
+            Q.edge_error(i, e2, nullptr);
             if ((double)invSigma2[i] * (e2[0] * e2[0] + e2[1] * e2[1]) < (double)18.f) outlier[i] = 0; else ++nBad;
         }
     }
@@ -770,6 +801,38 @@ int orbo_pose_inertial_opt_last_frame_n(int N, const float* Xw, const float* obs
     }
     return N - nBad;
 }
+// ---- the last-frame problem opened step by step (as orbo_pikf_* for the last-keyframe variant): Optimizer.cc:5098-5221 ----
+namespace {
+struct PiLfOpen { PoseInertialLF Q; std::vector<float> Xw, obs, is2, td, cam, Pf, Pk; std::vector<double> extr, prior, priorH, prev, st; double diag[30]; };
+void pil_compute_errors(void* p) { PoseInertialLF& Q = ((PiLfOpen*)p)->Q; for (int i = 0; i < Q.N; ++i) if (!Q.level[i]) Q.compute_error(i); }
+double pil_robust_chi2(void*) { return 0.0; }
+void pil_build_system(void* p) { PiLfOpen* o = (PiLfOpen*)p; o->Q.build(); for (int a = 0; a < 30; ++a) o->diag[a] = o->Q.H[a * 31]; }
+int pil_solve(void* p, double) { return ((PiLfOpen*)p)->Q.solve() ? 1 : 0; }
+void pil_update(void* p) { ((PiLfOpen*)p)->Q.update(); }
+void pil_nop(void*) {}
+int pil_vector_size(void*) { return 30; }
+const double* pil_x(void* p) { return ((PiLfOpen*)p)->Q.x; }
+const double* pil_b(void* p) { return ((PiLfOpen*)p)->Q.b; }
+int pil_n_diag(void*) { return 30; }
+const double* pil_diag(void* p) { return ((PiLfOpen*)p)->diag; }
+}  // namespace
+void orbo_pilf_open(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24, const float* Pframe,
+                    const float* Pkf, const double* prior21, const double* priorH, const double* prevState21, const double* state21, OrboLmBackend* out) {
+    PiLfOpen* o = new PiLfOpen;
+    o->Xw.assign(Xw, Xw + 3 * (size_t)N); o->obs.assign(obs, obs + 2 * (size_t)N); o->is2.assign(invSigma2, invSigma2 + N); o->td.assign(trackDepth, trackDepth + N);
+    o->cam.assign(cam4, cam4 + 4); o->Pf.assign(Pframe, Pframe + P_SIZE); o->Pk.assign(Pkf, Pkf + P_SIZE); o->extr.assign(extr24, extr24 + 24);
+    o->prior.assign(prior21, prior21 + 21); o->priorH.assign(priorH, priorH + 225); o->prev.assign(prevState21, prevState21 + 21); o->st.assign(state21, state21 + 21);
+    o->Q.init(N, o->Xw.data(), o->obs.data(), o->is2.data(), o->td.data(), o->cam.data(), o->extr.data(), o->Pf.data(), o->Pk.data(), o->prior.data(), o->priorH.data(), o->prev.data(), o->st.data());
+    for (double& d : o->diag) d = 0;
+    *out = OrboLmBackend{o, pil_compute_errors, pil_robust_chi2, pil_build_system, pil_solve, pil_update, pil_nop, pil_nop, pil_vector_size, pil_x, pil_b, pil_n_diag, pil_diag};
+}
+void orbo_pilf_edge_compute_error(void* h, int e) { ((PiLfOpen*)h)->Q.compute_error(e); }
+double orbo_pilf_edge_chi2(void* h, int e) { return ((PiLfOpen*)h)->Q.chi2(e); }
+int orbo_pilf_edge_depth_positive(void* h, int e) { double e2[2]; int d = 0; ((PiLfOpen*)h)->Q.edge_error(e, e2, &d); return d; }
+void orbo_pilf_edge_set_level(void* h, int e, int level) { ((PiLfOpen*)h)->Q.level[e] = (uint8_t)level; }
+void orbo_pilf_edge_set_robust(void* h, int e, int on) { ((PiLfOpen*)h)->Q.robust[e] = (uint8_t)on; }
+void orbo_pilf_close(void* h, double* prevOut21, double* stateOut21) { PiLfOpen* o = (PiLfOpen*)h; for (int i = 0; i < 21; ++i) { prevOut21[i] = o->prev[i]; stateOut21[i] = o->st[i]; } delete o; }
+
 int orbo_pose_inertial_opt_last_frame(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24,
                                       const float* Pframe, const float* Pkf, const double* prior21, const double* priorH, double* prevState21, double* state21,
                                       int bRecInit, uint8_t* outlier, double* H15) {

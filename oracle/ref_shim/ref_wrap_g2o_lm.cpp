@@ -5,6 +5,7 @@
 //   Optimizer::LocalInertialBA from initializeOptimization() to the FAIL test     src/Optimizer.cc:2840-2895
 //   OptimizationAlgorithmGaussNewton::solve                                       Thirdparty/g2o/g2o/core/optimization_algorithm_gauss_newton.cpp:50-93
 //   the four rounds + recovery of Optimizer::PoseInertialOptimizationLastKeyFrame  src/Optimizer.cc:4698-4823
+//   the four rounds + recovery of Optimizer::PoseInertialOptimizationLastFrame     src/Optimizer.cc:5098-5221
 // are cut out of the reference at build time (extract_ranges.py -> oracle/_ref/gen/*.inc) and compiled as they are against the class shells below, which
 // carry the members those bodies touch under g2o's names (optimization_algorithm_levenberg.h, optimization_algorithm_with_hessian.h, sparse_optimizer.h,
 // solver.h, property.h, batch_stats.h).  The shells' Solver and SparseOptimizer operations (buildSystem, solve, update, push / pop, computeActiveErrors,
@@ -315,13 +316,14 @@ void orbo_pikf_edge_set_robust(void* h, int e, int on);
 void orbo_pikf_close(void* h, double* stateOut21);
 }
 namespace ORB_SLAM3 {
-struct EdgeMonoOnlyPose {
-    void* h; int idx;
-    void computeError() { orbo_pikf_edge_compute_error(h, idx); }
-    double chi2() const { return orbo_pikf_edge_chi2(h, idx); }
-    bool isDepthPositive() { return orbo_pikf_edge_depth_positive(h, idx) != 0; }
-    void setLevel(int l) { orbo_pikf_edge_set_level(h, idx, l); }
-    void setRobustKernel(void* k) { orbo_pikf_edge_set_robust(h, idx, k != nullptr); }
+struct EdgeOps { void (*ce)(void*, int); double (*chi2)(void*, int); int (*dp)(void*, int); void (*lvl)(void*, int, int); void (*rob)(void*, int, int); };
+struct EdgeMonoOnlyPose {                               // the operations of the loop on an only-pose edge, forwarded to the oracle state (last-keyframe or last-frame variant)
+    void* h; int idx; const EdgeOps* ops;
+    void computeError() { ops->ce(h, idx); }
+    double chi2() const { return ops->chi2(h, idx); }
+    bool isDepthPositive() { return ops->dp(h, idx) != 0; }
+    void setLevel(int l) { ops->lvl(h, idx, l); }
+    void setRobustKernel(void* k) { ops->rob(h, idx, k != nullptr); }
 };
 struct EdgeStereoOnlyPose { void computeError() {} double chi2() const { return 0; } void setLevel(int) {} void setRobustKernel(void*) {} };
 struct InertialFrame { std::vector<bool> mvbOutlier; std::vector<MapPoint*> mvpMapPoints; };
@@ -330,6 +332,11 @@ struct InertialOptimizerShell : g2o::SparseOptimizer {
     const std::vector<int>& edges() const { return _edges; }
     void initializeOptimization(int) {}
 };
+static int pose_inertial_lf_rounds(InertialFrame* pFrame, InertialOptimizerShell& optimizer, std::vector<EdgeMonoOnlyPose*>& vpEdgesMono, std::vector<size_t>& vnIndexEdgeMono, bool bRecInit) {
+    std::vector<EdgeStereoOnlyPose*> vpEdgesStereo; std::vector<size_t> vnIndexEdgeStereo;
+#include "optimizer_pose_inertial_lf_rounds.inc"
+    return nBad;
+}
 static int pose_inertial_kf_rounds(InertialFrame* pFrame, InertialOptimizerShell& optimizer, std::vector<EdgeMonoOnlyPose*>& vpEdgesMono, std::vector<size_t>& vnIndexEdgeMono, bool bRecInit) {
     std::vector<EdgeStereoOnlyPose*> vpEdgesStereo; std::vector<size_t> vnIndexEdgeStereo;
 #include "optimizer_pose_inertial_kf_rounds.inc"
@@ -356,10 +363,47 @@ int ref_pose_inertial_opt_last_kf(int N, const float* Xw, const float* obs, cons
     std::vector<ORB_SLAM3::MapPoint> mps((size_t)N);
     std::vector<ORB_SLAM3::EdgeMonoOnlyPose> store((size_t)N);
     std::vector<ORB_SLAM3::EdgeMonoOnlyPose*> edges; std::vector<size_t> index;
-    for (int i = 0; i < N; ++i) { mps[i].mTrackDepth = trackDepth[i]; frame.mvpMapPoints.push_back(&mps[i]); store[i].h = be.self; store[i].idx = i; edges.push_back(&store[i]); index.push_back((size_t)i); }
+    static const ORB_SLAM3::EdgeOps ops = {orbo_pikf_edge_compute_error, orbo_pikf_edge_chi2, orbo_pikf_edge_depth_positive, orbo_pikf_edge_set_level, orbo_pikf_edge_set_robust};
+    for (int i = 0; i < N; ++i) { mps[i].mTrackDepth = trackDepth[i]; frame.mvpMapPoints.push_back(&mps[i]); store[i].h = be.self; store[i].idx = i; store[i].ops = &ops; edges.push_back(&store[i]); index.push_back((size_t)i); }
     const int nBad = ORB_SLAM3::pose_inertial_kf_rounds(&frame, opt, edges, index, bRecInit != 0);
     for (int i = 0; i < N; ++i) outlier[i] = frame.mvbOutlier[i] ? 1 : 0;
     orbo_pikf_close(be.self, state21);
+    return N - nBad;
+}
+}
+
+extern "C" {
+void orbo_pilf_open(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24, const float* Pframe,
+                    const float* Pkf, const double* prior21, const double* priorH, const double* prevState21, const double* state21, OrboLmBackend* out);
+void orbo_pilf_edge_compute_error(void* h, int e);
+double orbo_pilf_edge_chi2(void* h, int e);
+int orbo_pilf_edge_depth_positive(void* h, int e);
+void orbo_pilf_edge_set_level(void* h, int e, int level);
+void orbo_pilf_edge_set_robust(void* h, int e, int on);
+void orbo_pilf_close(void* h, double* prevOut21, double* stateOut21);
+// int Optimizer::PoseInertialOptimizationLastFrame(Frame*, bool bRecInit): the four rounds + recovery (src/Optimizer.cc:5098-5221) up to the recovery of the states
+int ref_pose_inertial_opt_last_frame(int N, const float* Xw, const float* obs, const float* invSigma2, const float* trackDepth, const float* cam4, const double* extr24, const float* Pframe,
+                                     const float* Pkf, const double* prior21, const double* priorH, double* prevState21, double* state21, int bRecInit, unsigned char* outlier) {
+    using namespace g2o;
+    OrboLmBackend be;
+    orbo_pilf_open(N, Xw, obs, invSigma2, trackDepth, cam4, extr24, Pframe, Pkf, prior21, priorH, prevState21, state21, &be);
+    ORB_SLAM3::InertialOptimizerShell opt; opt.be = &be;
+    Solver solver; solver.be = &be; solver._optimizer = &opt;
+    OptimizationAlgorithmGaussNewton alg(&solver);
+    alg._optimizer = &opt;
+    opt._algorithm = &alg;
+    opt._vstore.assign(30, OptimizableGraph::Vertex{1, nullptr});
+    for (int k = 0; k < 30; ++k) opt._ivMap.push_back(&opt._vstore[k]);
+    opt._edges.assign((size_t)N + 4, 0);                 // the mono edges + EdgeInertial + EdgeGyroRW + EdgeAccRW + EdgePriorPoseImu
+    ORB_SLAM3::InertialFrame frame; frame.mvbOutlier.assign((size_t)N, false);
+    std::vector<ORB_SLAM3::MapPoint> mps((size_t)N);
+    std::vector<ORB_SLAM3::EdgeMonoOnlyPose> store((size_t)N);
+    std::vector<ORB_SLAM3::EdgeMonoOnlyPose*> edges; std::vector<size_t> index;
+    static const ORB_SLAM3::EdgeOps ops = {orbo_pilf_edge_compute_error, orbo_pilf_edge_chi2, orbo_pilf_edge_depth_positive, orbo_pilf_edge_set_level, orbo_pilf_edge_set_robust};
+    for (int i = 0; i < N; ++i) { mps[i].mTrackDepth = trackDepth[i]; frame.mvpMapPoints.push_back(&mps[i]); store[i].h = be.self; store[i].idx = i; store[i].ops = &ops; edges.push_back(&store[i]); index.push_back((size_t)i); }
+    const int nBad = ORB_SLAM3::pose_inertial_lf_rounds(&frame, opt, edges, index, bRecInit != 0);
+    for (int i = 0; i < N; ++i) outlier[i] = frame.mvbOutlier[i] ? 1 : 0;
+    orbo_pilf_close(be.self, prevState21, state21);
     return N - nBad;
 }
 }

@@ -176,3 +176,26 @@ def test_pose_inertial_optimization_last_keyframe_rounds():
             ret = L.ref_pose_inertial_opt_last_kf(len(a[0]), *[_p(x) for x in a], _p(st), int(rec), _p(out))
             assert ret == want['ret'] and np.array_equal(out, want['outlier']), (kw, rec, ret, want['ret'])
             assert st.tobytes() == want['state'].tobytes(), (kw, rec, np.abs(st - want['state']).max())
+
+
+def test_pose_inertial_optimization_last_frame_rounds():
+    """Optimizer::PoseInertialOptimizationLastFrame: the reference's own four rounds + recovery (src/Optimizer.cc:5098-5221) with g2o's Gauss-Newton text over the oracle's
+    30-unknown state (prior edge included) == orbo_pose_inertial_opt_last_frame: return value, outlier flags, both frames' states bit for bit.  (The marginalisation that
+    follows needs Eigen's JacobiSVD and stays with the oracle's own derivation.)"""
+    L = C.CDLL(SO)
+    L.ref_pose_inertial_opt_last_frame.argtypes = [C.c_int] + [C.c_void_p] * 12 + [C.c_int, C.c_void_p]
+    cases = [dict(seed=0, n=300, outlier_frac=0.1), dict(seed=1, n=700, outlier_frac=0.2), dict(seed=2, n=40, outlier_frac=0.3), dict(seed=3, n=4, outlier_frac=0.0),
+             dict(seed=5, n=1000, outlier_frac=0.05, perturb=2.0), dict(seed=7, n=250, outlier_frac=0.1, prior_sigma=(2e-2, 5e-2, 1e-1, 1e-3, 1e-2))]
+    for kw in cases:
+        pr = synth.pose_inertial_problem_last_frame(**kw)
+        Pf = O.imu_preintegrate(pr['acc'], pr['gyr'], pr['dt'], pr['bias6'], synth.IMU_NOISE)
+        Pk = O.imu_preintegrate(pr['acc_kf'], pr['gyr_kf'], pr['dt_kf'], pr['bias6'], synth.IMU_NOISE)
+        for rec in (False, True):
+            want = O.pose_inertial_opt_last_frame(pr, Pf, Pk, rec_init=rec)
+            c = lambda a, dt: np.ascontiguousarray(a, dt)
+            a = [c(pr['Xw'], np.float32), c(pr['obs'], np.float32), c(pr['inv_sigma2'], np.float32), c(pr['track_depth'], np.float32), c(pr['cam'], np.float32), c(pr['extr'], np.float64),
+                 c(Pf, np.float32), c(Pk, np.float32), c(pr['prior_state'], np.float64), c(pr['prior_H'], np.float64)]
+            pv = c(pr['prev_state'], np.float64).copy(); st = c(pr['state'], np.float64).copy(); out = np.zeros(len(a[0]), np.uint8)
+            ret = L.ref_pose_inertial_opt_last_frame(len(a[0]), *[_p(x) for x in a], _p(pv), _p(st), int(rec), _p(out))
+            assert ret == want['ret'] and np.array_equal(out, want['outlier']), (kw, rec, ret, want['ret'])
+            assert st.tobytes() == want['state'].tobytes() and pv.tobytes() == want['prev_state'].tobytes(), (kw, rec)
