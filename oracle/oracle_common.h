@@ -5,13 +5,16 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load it; the product (orb_slam3_modified_b200/) never does.
 //
-// PARITY PINNING: the reference ships no tests or golden vectors for this path
-//  and cannot be compiled here (needs OpenCV C++, Eigen,
-// Boost, Pangolin, PCL -- all absent).  The OpenCV primitives restated here
-// (resize, FAST, GaussianBlur, fastAtan2, BFMatcher) are pinned against the
-// independent cv2 4.13 wheel in tests/ (fixtures under tests/golden/ made by
-// tools/make_golden.py); everything downstream of them is "parity unpinned"
-// by the reference itself and rests on this line-by-line restatement.
+// PARITY PINNING: the reference ships no tests or golden vectors for this path and its own
+// build cannot run here (OpenCV C++, Eigen, Boost, Pangolin are absent).  What pins this restatement:
+//   * the OpenCV primitives (resize, FAST, GaussianBlur, fastAtan2, BFMatcher) against the independent cv2 4.13 wheel
+//     (fixtures under tests/golden/ made by tools/make_golden.py);
+//   * the reference's OWN SOURCE TEXT, compiled where it lies under /root/reference by oracle/Makefile into oracle/_ref/
+//     against minimal stand-in types (oracle/ref_shim/): src/ORBextractor.cc whole, the ORBmatcher / Frame / KeyFrame /
+//     MapPoint / DBoW2 function bodies (bit for bit), the g2o edge types and IMU preintegration (to rounding), g2o's
+//     Levenberg / Gauss-Newton / optimize() text and the optimiser loops of src/Optimizer.cc driving this oracle's
+//     linear algebra (bit for bit) -- tests/test_ref_pins_*_cpu.py, DESIGN.md section 2;
+//   * independent derivations (numerical Jacobians, dense solves, scipy) for what needs Eigen's solvers.
 #pragma once
 #include <cstdint>
 #include <cmath>
