@@ -60,8 +60,22 @@ inline void ImuSince(const std::vector<double>& vTimestampsImu, double tframe, s
     end = first_imu;
 }
 
+// The selection at the head of Tracking::PreintegrateIMU (src/Tracking.cc:1646-1672) on the queue Tracking::GrabImuData fills: the queue holds the samples
+// [front, queued) of the stream (queued = one past the last sample handed over so far); samples older than tPrev - imuPer are dropped, those before tCur - imuPer are
+// taken and consumed, the first one at or after tCur - imuPer is taken but STAYS at the front of the queue (it opens the next frame's interval).
+// sel receives the indices of mvImuFromLastFrame; imuPer is Tracking's mImuPer (0.001, :609).
+inline void SelectImuFromQueue(const std::vector<double>& t, std::size_t queued, std::size_t& front, double tPrev, double tCur, double imuPer, std::vector<std::size_t>& sel) {
+    sel.clear();
+    while (front < queued) {
+        if (t[front] < tPrev - imuPer) { ++front; continue; }
+        if (t[front] < tCur - imuPer) { sel.push_back(front); ++front; continue; }
+        sel.push_back(front);
+        break;
+    }
+}
+
 // Flatten the IMU samples between consecutive frames of `count` streams into imu_preintegrate_batch's arrays: stream s contributes the samples
-// [begin[s], end[s]) of its vectors; the integration steps follow Tracking::PreintegrateIMU (src/Tracking.cc:1680-1729): n-1 steps between
+// [begin[s], end[s]) of its vectors (= mvImuFromLastFrame, a contiguous run: see SelectImuFromQueue); the integration steps follow Tracking::PreintegrateIMU (src/Tracking.cc:1680-1729): n-1 steps between
 // consecutive samples, the first and last interpolated to the frame times tPrev[s] / tCur[s].
 // acc / gyr [count][maxMeas][3], dt [count][maxMeas], nMeas [count]; returns false when a stream has more than maxMeas steps.
 inline bool FlattenForPreintegration(int count, const std::vector<double>* const* tImu, const std::vector<Point3f>* const* vAcc, const std::vector<Point3f>* const* vGyro,

@@ -53,6 +53,8 @@ RANGES = [
     ('g2o_gauss_newton_solve.inc', 'Thirdparty/g2o/g2o/core/optimization_algorithm_gauss_newton.cpp', 50, 93, 'OptimizationAlgorithm::SolverResult OptimizationAlgorithmGaussNewton::solve(int iteration, bool online)'),
     ('optimizer_pose_inertial_kf_rounds.inc', 'src/Optimizer.cc', 4698, 4823, 'float chi2Mono[4]={12,7.5,5.991,5.991};'),
     ('optimizer_pose_inertial_lf_rounds.inc', 'src/Optimizer.cc', 5098, 5221, 'const float chi2Mono[4]={5.991,5.991,5.991,5.991};'),
+    ('tracking_preintegrate_select.inc', 'src/Tracking.cc', 1646, 1678, 'while(true)'),
+    ('tracking_preintegrate_steps.inc', 'src/Tracking.cc', 1680, 1729, 'const int n = mvImuFromLastFrame.size()-1;'),
     ('g2o_huber.inc', 'Thirdparty/g2o/g2o/core/robust_kernel_impl.cpp', 78, 91, 'void RobustKernelHuber::robustify(double e, Eigen::Vector3d& rho) const'),
     ('g2o_levenberg_solve.inc', 'Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp', 61, 194, 'OptimizationAlgorithm::SolverResult OptimizationAlgorithmLevenberg::solve(int iteration, bool online)'),
     ('g2o_sparse_optimizer_optimize.inc', 'Thirdparty/g2o/g2o/core/sparse_optimizer.cpp', 354, 419, 'int SparseOptimizer::optimize(int iterations, bool online)'),
