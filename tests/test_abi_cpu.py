@@ -11,7 +11,7 @@ def _declared():
     names = []
     for h in glob.glob(os.path.join(ROOT, 'include', '*.h')):
         src = re.sub(r'/\*.*?\*/', '', open(h).read(), flags=re.S)
-        names += re.findall(r'\b((?:orb|orbx|orbm|lba|pose)_[a-z0-9_]+)\s*\(', src)
+        names += re.findall(r'\b((?:orb|orbx|orbm|orbv|lba|pose|imu|local)_[a-z0-9_]+)\s*\(', src)
     return sorted(set(names))
 
 
@@ -34,6 +34,14 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip('GPU present')
     with pytest.raises(m.OrbError) as ei:
         m.ORBextractor(1000, 1.2, 8, 20, 7)
+    assert ei.value.code == m.ORB_ERR_CUDA
+    # the stateless entry points as well: LocalInertialBA on a well-formed problem
+    import oracle_lib as O
+    from orb_slam3_modified_b200 import synth
+    pr = synth.local_inertial_ba_problem(n_opt=2, n_cov_fixed=1, n_pts=20, seed=1)
+    pr['preint'] = O.liba_preints(pr)
+    with pytest.raises(m.OrbError) as ei:
+        m.LocalInertialBA([pr])
     assert ei.value.code == m.ORB_ERR_CUDA
 
 
