@@ -95,3 +95,44 @@ def test_one_lm_step_equals_dense_numeric_step():
     assert np.abs(ref['points'] - Xn).max() < 2e-6
     # and the step is a real one (so the comparison is not vacuous)
     assert np.abs(ref['points'] - X).max() > 1e-3
+
+
+def test_converged_solution_is_the_minimum_an_independent_optimizer_finds():
+    """The Schur machinery (a17-a19) checked at the level of its RESULT: g2o's Levenberg-Marquardt with Huber kernels is an iteratively re-weighted descent on
+    sum_e rho(chi2_e); scipy's trust-region solver minimising that same robust cost directly (residuals scaled by sqrt(rho / chi2), numerical Jacobian, its own
+    parametrisation T = exp(d) T0, p = p0 + d; gauge fixed by two fixed keyframes) must end at the same cost and the same reprojection residuals as the oracle."""
+    from scipy.optimize import least_squares
+    p = synth.lba_problem(n_kf=5, n_pts=40, obs_per_pt=4, n_fixed=2, seed=11, outlier_frac=0.05, pose_noise=(0.005, 0.2), point_noise=0.01)
+    nP, nL = len(p['poses']), len(p['points'])
+    free = [i for i in range(nP) if not p['fixed'][i]]
+    R0 = [_R(q[:4] / np.linalg.norm(q[:4])) for q in p['poses']]; t0 = [q[4:].copy() for q in p['poses']]
+    w = np.sqrt(p['inv_sigma2'].astype(np.float64))
+    delta = p['huber_delta']
+
+    def unpack(x):
+        Rs, ts = list(R0), list(t0)
+        for k, i in enumerate(free):
+            Re, te = _exp(x[6 * k:6 * k + 6])
+            Rs[i] = Re @ R0[i]; ts[i] = Re @ t0[i] + te
+        return Rs, ts, p['points'] + x[6 * len(free):].reshape(-1, 3)
+
+    def robust(e):                                                    # e: whitened residuals [nE, 2] -> scaled so that |.|^2 = rho(chi2)
+        c = (e ** 2).sum(1)
+        f = np.ones(len(c))
+        out = c > delta * delta
+        f[out] = np.sqrt((2 * delta * np.sqrt(c[out]) - delta * delta) / c[out])
+        return e * f[:, None]
+
+    def residuals(x):
+        Rs, ts, X = unpack(x)
+        return robust(_residuals(p, Rs, ts, X) * w[:, None]).reshape(-1)
+    n = 6 * len(free) + 3 * nL
+    sol = least_squares(residuals, np.zeros(n), method='trf', jac='2-point', xtol=1e-15, ftol=1e-15, gtol=1e-12, max_nfev=80)
+    got = O.lba_solve(p, iterations=60)
+    res_o = O.lba_residuals(p, got['poses'], got['points'])
+    ro = robust(res_o * w[:, None]).reshape(-1)
+    cost_o, cost_s = float(ro @ ro), float(sol.fun @ sol.fun)
+    assert ((res_o * w[:, None]) ** 2).sum(1).max() > delta * delta    # the kernel is active at the optimum (gross outliers present)
+    assert cost_s <= cost_o * (1 + 1e-9) and abs(cost_o - cost_s) < 1e-4 * cost_s, (cost_o, cost_s)   # measured 1.8e-5: g2o's stop rule (three iterations below 0.1 %) ends just short of the minimum
+    Rs, ts, X = unpack(sol.x)
+    assert np.abs(res_o - _residuals(p, Rs, ts, X)).max() < 0.25       # px (measured 0.1 on residuals of up to 20 px): two optimisers at the same minimum of the robust cost, one stopped by g2o's rule
