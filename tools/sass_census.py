@@ -5,7 +5,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else 'orb_slam3_modified_b200/liborb_b200
 out = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
 names = subprocess.run(['c++filt'], input='\n'.join(re.findall(r'Function : (\S+)', out)), capture_output=True, text=True).stdout.split('\n')
 want = ['UTMALDG', 'UBLKCP', 'SYNCS', 'UCGABAR', 'LDG.E.ENL2.256', 'DFMA', 'DADD', 'DMUL', 'SHFL', 'REDUX', 'VIADD', 'VIMNMX', 'VIMNMX3', 'LDS', 'STS', 'LDL', 'STL', 'BAR.SYNC', 'ATOMS', 'POPC',
-        'LDG.E.128', 'LDG.E.64', 'MUFU.RCP64H', 'FFMA', 'HMMA', 'UTCHMMA']
+        'STG.E.ENL2.256', 'LDG.E.128', 'LDG.E.64', 'MUFU.RCP64H', 'FFMA', 'HMMA', 'UTCHMMA']
 print('SASS instruction census of liborb_b200.so (cuobjdump -sass, sm_100a), per kernel: total instructions | selected mnemonics')
 print('(UTMALDG = TMA tensor load, SYNCS = mbarrier, UCGABAR = cluster barrier, REDUX = warp reduce, LDG.E.ENL2.256 = 256-bit global load,')
 print(' DFMA = FP64 FMA, VIADD/VIMNMX = packed-integer SIMD, LDL/STL = local-memory (spill) traffic)\n')
@@ -15,7 +15,7 @@ for i, blk in enumerate(out.split('Function : ')[1:]):
     c = collections.Counter()
     for m in ins:
         for w in want:
-            if m == w or m.startswith(w + '.') or m.startswith(w + '_') or (w == 'LDG.E.ENL2.256' and 'ENL2.256' in m):
+            if m == w or m.startswith(w + '.') or m.startswith(w + '_') or (w == 'LDG.E.ENL2.256' and m.startswith('LDG') and 'ENL2.256' in m) or (w == 'STG.E.ENL2.256' and m.startswith('STG') and '256' in m):
                 c[w] += 1
     name = names[i].split('(')[0]
     res.append((len(ins), name, c))
